@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Build the packed RRTMG/McICA/cloud-optics table blob from the reference's data + setup sources.
+
+Run in the authoring container (needs /root/reference):
+    python tools/extract_rrtmg_tables.py [--ref /root/reference] [--out ecrad_b200/data/rrtmg_tables.bin]
+
+What it replaces: the table-filling half of `setup_radiation` for the RRTMG configuration
+(radiation/radiation_interface.F90:37-156 -> radiation_ifs_rrtm.F90:34 setup_gas_optics ->
+SURRTPK/SURRTRF/RRTM_INIT_140GP/SRTM_INIT; radiation_cloud_optics.F90 setup_cloud_optics;
+radiation_pdf_sampler.F90:44 setup_pdf_sampler).  In a Fortran host the shim passes the very same arrays by
+pointer; the standalone bench/tests load this blob instead.
+
+Blob format ("ETB1"): see ecrad_b200/tables.py.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from minifortran import FArray, Interp  # noqa: E402
+from ecrad_b200.tables import write_blob  # noqa: E402
+
+NG_LW = [10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2]          # ifsrrtm/yoerrtm.F90:61-76
+NG_SW = [6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12]                  # ifsrrtm/yoesrtm.F90:43-56
+
+
+def rrtmg_tables(ref):
+    it = Interp([os.path.join(ref, "ifsrrtm"), os.path.join(ref, "ifsaux")], os.path.join(ref, "data"))
+    env = {"MPL_NPROC": lambda: 1, "MPL_MYRANK": lambda: 1, "CDIRECTORY": "."}
+    # radiation_ifs_rrtm.F90:91-99
+    it.run("SURRTPK")
+    it.run("SURRTRF")
+    it.run("RRTM_INIT_140GP", **env)
+    it.run("SRTM_INIT", **env)
+
+    out = {}
+
+    # ---- LW
+    for b in range(1, 17):
+        mod = it.module(f"YOERRTA{b}")
+        ng = NG_LW[b - 1]
+        for name, v in mod.items():
+            if name.startswith("__") or not isinstance(v, FArray):
+                continue
+            if name in ("ABSA", "ABSB"):
+                continue  # EQUIVALENCE'd with KA/KB (yoerrta*.F90), rebuilt below
+            a = v.a
+            if name.startswith("FRACREF"):
+                assert a.shape[0] == ng, (b, name, a.shape)   # FRACREFA(ng[,9]) : g-point first
+            else:
+                assert a.shape[-1] == ng, (b, name, a.shape)
+            if name in ("KA", "KB"):
+                a = a.reshape((-1, ng), order="F")  # = ABSA(65*nspa, ng) / ABSB(235*nspb, ng)
+                name = "ABSA" if name == "KA" else "ABSB"
+            out[f"lw{b}_{name}"] = a
+    wn = it.module("YOERRTWN")
+    out["lw_TOTPLNK"] = wn["TOTPLNK"].a
+    out["lw_DELWAVE"] = wn["DELWAVE"].a
+    out["lw_NSPA"] = wn["NSPA"].a.astype(np.int32)
+    out["lw_NSPB"] = wn["NSPB"].a.astype(np.int32)
+    rf = it.module("YOERRTRF")
+    out["lw_PREFLOG"] = rf["PREFLOG"].a
+    out["lw_TREF"] = rf["TREF"].a
+    out["lw_CHI_MLS"] = rf["CHI_MLS"].a
+    ftr = it.module("YOERRTFTR")
+    out["lw_NGB"] = ftr["NGB"].a[:140].astype(np.int32)
+    out["lw_NGC"] = ftr["NGC"].a.astype(np.int32)
+    assert list(out["lw_NGC"]) == NG_LW
+
+    # ---- SW
+    for b in range(16, 30):
+        mod = it.module(f"YOESRTA{b}")
+        ng = NG_SW[b - 16]
+        for name, v in mod.items():
+            if name.startswith("__") or name in ("ABSA", "ABSB", "JPG"):
+                continue
+            if isinstance(v, FArray):
+                # keep only the g-point-reduced ("C") arrays; the unreduced ones are setup intermediates
+                if not name.endswith("C"):
+                    continue
+                a = v.a
+                if name in ("KAC", "KBC"):
+                    a = a.reshape((-1, a.shape[-1]), order="F")[:, :ng]
+                    name = "ABSA" if name == "KAC" else "ABSB"
+                elif name in ("SFLUXREFC", "RAYLAC") and a.ndim == 2:
+                    a = a[:ng, :]
+                else:
+                    a = a[..., :ng] if a.ndim > 1 else a[:ng]
+                out[f"sw{b}_{name}"] = a
+            elif name in ("RAYL", "STRRAT", "STRRAT1", "GIVFAC", "SCALEKUR"):
+                out[f"sw{b}_{name}"] = np.array([float(v)])
+            elif name == "LAYREFFR":
+                out[f"sw{b}_{name}"] = np.array([int(v)], dtype=np.int32)
+    sw = it.module("YOESRTWN")
+    out["sw_PREFLOG"] = sw["PREFLOG"].a
+    out["sw_TREF"] = sw["TREF"].a
+    out["sw_NSPA"] = sw["NSPA"].a.astype(np.int32)
+    out["sw_NSPB"] = sw["NSPB"].a.astype(np.int32)
+    out["sw_NGC"] = sw["NGC"].a.astype(np.int32)
+    assert list(out["sw_NGC"]) == NG_SW
+    out["sw_NGBSW"] = it.module("YOESRTM")["NGBSW"].a[:112].astype(np.int32)
+    return out
+
+
+def nc_tables(ref):
+    """Cloud-optics coefficient files and the McICA PDF look-up table (netCDF-3 classic)."""
+    from scipy.io import netcdf_file
+
+    out = {}
+    d = os.path.join(ref, "data")
+    # radiation_cloud_optics.F90:46-110 (setup_cloud_optics): coeff arrays read as (nband, ncoeff)
+    with netcdf_file(os.path.join(d, "socrates_droplet_scattering_rrtm.nc"), mmap=False) as f:
+        out["liq_coeff_lw"] = np.array(f.variables["coeff_lw"][:], dtype=np.float64)
+        out["liq_coeff_sw"] = np.array(f.variables["coeff_sw"][:], dtype=np.float64)
+    with netcdf_file(os.path.join(d, "fu_ice_scattering_rrtm.nc"), mmap=False) as f:
+        out["ice_coeff_lw"] = np.array(f.variables["coeff_lw"][:], dtype=np.float64)
+        out["ice_coeff_sw"] = np.array(f.variables["coeff_sw"][:], dtype=np.float64)
+    # radiation_pdf_sampler.F90:44-107 (setup_pdf_sampler)
+    with netcdf_file(os.path.join(d, "mcica_gamma.nc"), mmap=False) as f:
+        out["pdf_val"] = np.array(f.variables["x"][:], dtype=np.float64).T.copy()  # val(ncdf, nfsd), radiation_pdf_sampler.F90:83-93
+        out["pdf_fsd"] = np.array(f.variables["fsd"][:], dtype=np.float64)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "ecrad_b200", "data", "rrtmg_tables.bin"))
+    args = ap.parse_args()
+    tabs = rrtmg_tables(args.ref)
+    tabs.update(nc_tables(args.ref))
+    write_blob(args.out, tabs)
+    tot = sum(v.nbytes for v in tabs.values())
+    print(f"wrote {args.out}: {len(tabs)} arrays, {tot/1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()
