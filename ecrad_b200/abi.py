@@ -1,0 +1,128 @@
+"""ctypes mirror of include/ecrad_b200.h (the C-ABI structs).  Field order/types must match the header."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+# enum values = the reference's `enum, bind(c)` blocks (radiation_config.F90:51-111, radiation_cloud_cover.F90:30-33)
+SOLVER = {"cloudless": 0, "homogeneous": 1, "mcica": 2, "spartacus": 3, "tripleclouds": 4}
+GAS_MODEL = {"monochromatic": 0, "rrtmg-ifs": 1, "ecckd": 2}
+OVERLAP = {"max-ran": 0, "exp-ran": 1, "exp-exp": 2}
+LIQ_MODEL = {"socrates": 1}
+ICE_MODEL = {"fu-ifs": 1}
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32),
+        ("i_solver_sw", C.c_int32), ("i_solver_lw", C.c_int32),
+        ("i_gas_model_sw", C.c_int32), ("i_gas_model_lw", C.c_int32),
+        ("i_overlap_scheme", C.c_int32),
+        ("i_liq_model", C.c_int32), ("i_ice_model", C.c_int32),
+        ("do_sw", C.c_int32), ("do_lw", C.c_int32), ("do_sw_direct", C.c_int32), ("do_clear", C.c_int32),
+        ("do_clouds", C.c_int32), ("use_aerosols", C.c_int32),
+        ("do_lw_cloud_scattering", C.c_int32), ("do_lw_aerosol_scattering", C.c_int32), ("do_lw_derivatives", C.c_int32),
+        ("do_sw_delta_scaling_with_gases", C.c_int32), ("do_fu_lw_ice_optics_bug", C.c_int32),
+        ("use_beta_overlap", C.c_int32), ("use_vectorizable_generator", C.c_int32),
+        ("do_surface_sw_spectral_flux", C.c_int32), ("do_canopy_fluxes_sw", C.c_int32),
+        ("do_canopy_fluxes_lw", C.c_int32), ("do_save_spectral_flux", C.c_int32),
+        ("do_nearest_spectral_sw_albedo", C.c_int32), ("do_nearest_spectral_lw_emiss", C.c_int32),
+        ("n_g_sw", C.c_int32), ("n_g_lw", C.c_int32), ("n_bands_sw", C.c_int32), ("n_bands_lw", C.c_int32),
+        ("n_albedo_sw", C.c_int32), ("n_emiss_lw", C.c_int32),
+        ("n_canopy_bands_sw", C.c_int32), ("n_canopy_bands_lw", C.c_int32),
+        ("reserved_i", C.c_int32 * 4),
+        ("cloud_fraction_threshold", C.c_double), ("cloud_mixing_ratio_threshold", C.c_double),
+        ("min_gas_od_lw", C.c_double), ("min_gas_od_sw", C.c_double),
+        ("cloud_inhom_decorr_scaling", C.c_double),
+        ("reserved_d", C.c_double * 4),
+    ]
+
+
+INPUT_ARRAYS = [
+    # name, dtype, shape-kind
+    ("cos_sza", "f8", "c"), ("skin_temperature", "f8", "c"),
+    ("sw_albedo", "f8", "ca"), ("sw_albedo_direct", "f8", "ca"), ("lw_emissivity", "f8", "ce"),
+    ("iseed", "i4", "c"),
+    ("pressure_hl", "f8", "ch"), ("temperature_hl", "f8", "ch"),
+    ("h2o_mmr", "f8", "cl"), ("co2_mmr", "f8", "cl"), ("o3_mmr", "f8", "cl"), ("n2o_mmr", "f8", "cl"),
+    ("ch4_mmr", "f8", "cl"), ("cfc11_mmr", "f8", "cl"), ("cfc12_mmr", "f8", "cl"), ("hcfc22_mmr", "f8", "cl"),
+    ("ccl4_mmr", "f8", "cl"),
+    ("cloud_fraction", "f8", "cl"), ("q_liq", "f8", "cl"), ("q_ice", "f8", "cl"), ("re_liq", "f8", "cl"),
+    ("re_ice", "f8", "cl"), ("overlap_param", "f8", "ci"), ("fractional_std", "f8", "cl"),
+]
+
+
+class Inputs(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32), ("solar_irradiance", C.c_double)] + [
+        (nm, c_ip if dt == "i4" else c_dp) for nm, dt, _ in INPUT_ARRAYS
+    ]
+
+
+# name, shape-kind: h = (ncol, nlev+1); c = (ncol); gl/gs = (ng, ncol); bs = (nbands_sw, ncol); as/al = canopy;
+# pl/ps = per-band profiles (nband, ncol, nlev+1)
+OUTPUT_ARRAYS = [
+    ("lw_up", "h"), ("lw_dn", "h"), ("lw_up_clear", "h"), ("lw_dn_clear", "h"),
+    ("sw_up", "h"), ("sw_dn", "h"), ("sw_dn_direct", "h"),
+    ("sw_up_clear", "h"), ("sw_dn_clear", "h"), ("sw_dn_direct_clear", "h"),
+    ("lw_derivatives", "h"),
+    ("cloud_cover_lw", "c"), ("cloud_cover_sw", "c"),
+    ("lw_dn_surf_g", "gl"), ("lw_dn_surf_clear_g", "gl"), ("lw_up_toa_g", "gl"), ("lw_up_toa_clear_g", "gl"),
+    ("sw_dn_diffuse_surf_g", "gs"), ("sw_dn_direct_surf_g", "gs"),
+    ("sw_dn_diffuse_surf_clear_g", "gs"), ("sw_dn_direct_surf_clear_g", "gs"),
+    ("sw_up_toa_g", "gs"), ("sw_up_toa_clear_g", "gs"),
+    ("sw_dn_surf_band", "bs"), ("sw_dn_direct_surf_band", "bs"),
+    ("sw_dn_surf_clear_band", "bs"), ("sw_dn_direct_surf_clear_band", "bs"),
+    ("sw_dn_diffuse_surf_canopy", "as"), ("sw_dn_direct_surf_canopy", "as"),
+    ("lw_dn_surf_canopy", "al"),
+    ("lw_up_band", "pl"), ("lw_dn_band", "pl"), ("sw_up_band", "ps"), ("sw_dn_band", "ps"), ("sw_dn_direct_band", "ps"),
+]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32)] + [(nm, c_dp) for nm, _ in OUTPUT_ARRAYS]
+
+
+def output_shape(kind, ncol, nlev, cfg):
+    """Fortran shape of a flux_type component (radiation_flux.F90:147-300)."""
+    return {
+        "h": (ncol, nlev + 1), "c": (ncol,), "gl": (cfg.n_g_lw, ncol), "gs": (cfg.n_g_sw, ncol),
+        "bs": (cfg.n_bands_sw, ncol), "as": (cfg.n_canopy_bands_sw, ncol), "al": (cfg.n_canopy_bands_lw, ncol),
+        "pl": (cfg.n_bands_lw, ncol, nlev + 1), "ps": (cfg.n_bands_sw, ncol, nlev + 1),
+    }[kind]
+
+
+def alloc_outputs(ncol, nlev, cfg, spectral_profiles=False, fill=np.nan):
+    """Allocate every flux component as a Fortran-ordered float64 array; returns (dict, Outputs struct)."""
+    arrs = {}
+    st = Outputs()
+    st.struct_bytes = C.sizeof(Outputs)
+    for nm, kind in OUTPUT_ARRAYS:
+        if kind in ("pl", "ps") and not spectral_profiles:
+            continue
+        a = np.full(output_shape(kind, ncol, nlev, cfg), fill, dtype=np.float64, order="F")
+        if nm.startswith("cloud_cover"):
+            a[...] = -1.0  # flux%allocate initial value seen in the golden files for night columns
+        arrs[nm] = a
+        setattr(st, nm, a.ctypes.data_as(c_dp))
+    return arrs, st
+
+
+def make_inputs(arrays, solar_irradiance):
+    """arrays: dict of Fortran-ordered numpy arrays keyed like INPUT_ARRAYS; returns (keepalive dict, Inputs)."""
+    st = Inputs()
+    st.struct_bytes = C.sizeof(Inputs)
+    st.solar_irradiance = float(solar_irradiance)
+    keep = {}
+    for nm, dt, _ in INPUT_ARRAYS:
+        a = arrays.get(nm)
+        if a is None:
+            continue
+        want = np.int32 if dt == "i4" else np.float64
+        a = np.asfortranarray(a, dtype=want)
+        keep[nm] = a
+        setattr(st, nm, a.ctypes.data_as(c_ip if dt == "i4" else c_dp))
+    return keep, st

@@ -1,0 +1,134 @@
+"""Host-side mirror of the part of `config_type` the hot path needs (radiation/radiation_config.F90:163-649).
+
+Key names are the reference's namelist keys (`&radiation`, radiation_config.F90:730-764); defaults are those of
+test/ifs/configCY49R1.nam with use_aerosols=false (the `noaer` ctest, BASELINE config 2).  `consolidate()` restates
+the two pieces of setup arithmetic whose results cross the C-ABI as tables:
+  * config%sw_albedo_weights        radiation_config.F90:1947-2019 -> radiation_spectral_definition.F90 calc_mapping_from_bands
+  * config%i_emiss_from_band_lw     radiation_config.F90:2025-2097
+In a Fortran host these come straight out of `config_type`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+
+# radiation_ifs_rrtm.F90:104-111 / :143-150 : RRTMG band limits (cm-1)
+SW_WN1 = np.array([2600, 3250, 4000, 4650, 5150, 6150, 7700, 8050, 12850, 16000, 22650, 29000, 38000, 820], dtype=np.float64)
+SW_WN2 = np.array([3250, 4000, 4650, 5150, 6150, 7700, 8050, 12850, 16000, 22650, 29000, 38000, 50000, 2600], dtype=np.float64)
+LW_WN1 = np.array([10, 350, 500, 630, 700, 820, 980, 1080, 1180, 1390, 1480, 1800, 2080, 2250, 2380, 2600], dtype=np.float64)
+LW_WN2 = np.array([350, 500, 630, 700, 820, 980, 1080, 1180, 1390, 1480, 1800, 2080, 2250, 2380, 2600, 3250], dtype=np.float64)
+SOLAR_REF_T = 5777.0        # radiation_spectral_definition.F90:27
+TERRESTRIAL_REF_T = 273.15  # radiation_spectral_definition.F90:28
+
+
+def _planck_wavenumber(wn, temperature):
+    """radiation_spectral_definition.F90 calc_planck_function_wavenumber (constants radiation_constants.F90)."""
+    c, kb, h = 299792458.0, 1.380648813e-23, 6.6260695729e-34
+    freq = 100.0 * c * np.asarray(wn, dtype=np.float64)
+    pf = 2.0 * h * freq**3 / (c**2 * (np.exp(h * freq / (kb * temperature)) - 1.0))
+    return pf * 100.0 * c
+
+
+def mapping_from_bands(wn1_band, wn2_band, ref_temperature, wavelength_bound, i_intervals):
+    """calc_mapping_from_bands(..., use_bands=.true.), radiation_spectral_definition.F90 (band branch).
+    Returns mapping(ninput, nband)."""
+    ninterval = len(i_intervals)
+    ninput = max(i_intervals)
+    nband = len(wn1_band)
+    mapping = np.zeros((ninput, nband))
+    weight = np.array([0.5, 1.0, 1.0, 1.0, 0.5])
+    for jb in range(nband):
+        for jint in range(1, ninterval + 1):
+            wn2 = wn2_band[jb] if jint == 1 else min(wn2_band[jb], 0.01 / wavelength_bound[jint - 2])
+            wn1 = wn1_band[jb] if jint == ninterval else max(wn1_band[jb], 0.01 / wavelength_bound[jint - 1])
+            if wn2 > wn1:
+                samp = wn1 + np.arange(5) * (wn2 - wn1) / 4.0
+                pl = _planck_wavenumber(samp, ref_temperature)
+                mapping[i_intervals[jint - 1] - 1, jb] += np.sum(pl * weight) * (wn2 - wn1)
+    for jb in range(nband):
+        mapping[:, jb] = mapping[:, jb] * (1.0 / np.sum(mapping[:, jb]))
+    return mapping
+
+
+@dataclass
+class RadiationConfig:
+    # names = namelist keys of &radiation (test/ifs/configCY49R1.nam)
+    do_sw: bool = True
+    do_lw: bool = True
+    do_sw_direct: bool = True
+    do_clear: bool = True
+    sw_solver_name: str = "McICA"
+    lw_solver_name: str = "McICA"
+    gas_model_name: str = "RRTMG-IFS"
+    liquid_model_name: str = "SOCRATES"
+    ice_model_name: str = "Fu-IFS"
+    overlap_scheme_name: str = "Exp-Ran"
+    cloud_fraction_threshold: float = 0.001e-3
+    cloud_mixing_ratio_threshold: float = 1.0e-9
+    do_lw_aerosol_scattering: bool = False
+    do_lw_cloud_scattering: bool = True
+    cloud_inhom_decorr_scaling: float = 0.5
+    use_beta_overlap: bool = False
+    use_vectorizable_generator: bool = False
+    use_aerosols: bool = False
+    do_save_spectral_flux: bool = True
+    do_lw_derivatives: bool = True
+    do_surface_sw_spectral_flux: bool = True
+    do_fu_lw_ice_optics_bug: bool = False
+    do_sw_delta_scaling_with_gases: bool = False
+    do_canopy_fluxes_lw: bool = True
+    do_canopy_fluxes_sw: bool = True
+    do_nearest_spectral_sw_albedo: bool = False
+    sw_albedo_wavelength_bound: tuple = (0.25e-6, 0.44e-6, 0.69e-6, 1.19e-6, 2.38e-6)
+    i_sw_albedo_index: tuple = (1, 2, 3, 4, 5, 6)
+    do_nearest_spectral_lw_emiss: bool = True
+    lw_emiss_wavelength_bound: tuple = (8.0e-6, 13.0e-6)
+    i_lw_emiss_index: tuple = (1, 2, 1)
+    min_gas_od_lw: float = 1.0e-15
+    min_gas_od_sw: float = 0.0
+    derived: dict = field(default_factory=dict)
+
+    def consolidate(self):
+        """Tables derived from the config (what `setup_radiation` stores in config_type)."""
+        w = mapping_from_bands(SW_WN1, SW_WN2, SOLAR_REF_T, self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
+        e = mapping_from_bands(LW_WN1, LW_WN2, TERRESTRIAL_REF_T, self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
+        self.derived = {
+            "sw_albedo_weights": np.asfortranarray(w),                                   # (n_albedo, 14)
+            "i_emiss_from_band_lw": (np.argmax(e, axis=0) + 1).astype(np.int32),         # maxloc(dim=1)
+            "lw_emiss_weights": np.asfortranarray(e),
+        }
+        return self
+
+    def to_struct(self) -> abi.Config:
+        if not self.derived:
+            self.consolidate()
+        c = abi.Config()
+        c.struct_bytes = C.sizeof(abi.Config)
+        c.i_solver_sw = abi.SOLVER[self.sw_solver_name.lower()]
+        c.i_solver_lw = abi.SOLVER[self.lw_solver_name.lower()]
+        c.i_gas_model_sw = c.i_gas_model_lw = abi.GAS_MODEL[self.gas_model_name.lower()]
+        c.i_overlap_scheme = abi.OVERLAP[self.overlap_scheme_name.lower()]
+        c.i_liq_model = abi.LIQ_MODEL[self.liquid_model_name.lower()]
+        c.i_ice_model = abi.ICE_MODEL[self.ice_model_name.lower()]
+        for k in ("do_sw", "do_lw", "do_sw_direct", "do_clear", "use_aerosols", "do_lw_cloud_scattering",
+                  "do_lw_aerosol_scattering", "do_lw_derivatives", "do_sw_delta_scaling_with_gases",
+                  "do_fu_lw_ice_optics_bug", "use_beta_overlap", "use_vectorizable_generator",
+                  "do_surface_sw_spectral_flux", "do_canopy_fluxes_sw", "do_canopy_fluxes_lw", "do_save_spectral_flux",
+                  "do_nearest_spectral_sw_albedo", "do_nearest_spectral_lw_emiss"):
+            setattr(c, k, int(getattr(self, k)))
+        # radiation_config.F90 consolidate: do_clouds is false only for the Cloudless solvers
+        c.do_clouds = int(not (c.i_solver_sw == 0 and c.i_solver_lw == 0))
+        c.n_g_sw, c.n_g_lw, c.n_bands_sw, c.n_bands_lw = 112, 140, 14, 16
+        c.n_albedo_sw = self.derived["sw_albedo_weights"].shape[0]
+        c.n_emiss_lw = max(self.i_lw_emiss_index)
+        c.n_canopy_bands_sw = max(self.i_sw_albedo_index)
+        c.n_canopy_bands_lw = max(self.i_lw_emiss_index)
+        c.cloud_fraction_threshold = self.cloud_fraction_threshold
+        c.cloud_mixing_ratio_threshold = self.cloud_mixing_ratio_threshold
+        c.min_gas_od_lw, c.min_gas_od_sw = self.min_gas_od_lw, self.min_gas_od_sw
+        c.cloud_inhom_decorr_scaling = self.cloud_inhom_decorr_scaling
+        return c

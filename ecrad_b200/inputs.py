@@ -1,0 +1,96 @@
+"""Column inputs for the hot path: reader for the reference's IFS-style netCDF input and the synthetic
+IFS-shaped generator used by bench.py.
+
+The arrays produced here are exactly what the reference's offline driver hands to `radiation()` after
+driver/ecrad_driver_read_input.F90:21 and `set_gas_units` (radiation_interface.F90:164 ->
+radiation_gas.F90 set_units_gas: vmr * M_gas/M_air), in Fortran memory order (column fastest).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SYNTH_BLOCK = 4096
+AIR_MOLAR_MASS = 28.970  # radiation_gas_constants.F90
+GAS_MOLAR_MASS = {"co2": 44.011, "n2o": 44.013, "ch4": 16.043, "cfc11": 137.3686, "cfc12": 120.914,
+                  "hcfc22": 86.469, "ccl4": 153.823}
+
+# variables copied from the reference input file into the small committed fixture
+NC_VARS = ["solar_irradiance", "skin_temperature", "cos_solar_zenith_angle", "sw_albedo", "sw_albedo_direct",
+           "lw_emissivity", "iseed", "pressure_hl", "temperature_hl", "q", "o3_mmr", "co2_vmr", "n2o_vmr", "ch4_vmr",
+           "cfc11_vmr", "cfc12_vmr", "hcfc22_vmr", "ccl4_vmr", "cloud_fraction", "q_liquid", "q_ice", "re_liquid",
+           "re_ice", "overlap_param", "fractional_std"]
+
+
+def read_ifs_netcdf(path):
+    """netCDF-3 classic reader (scipy) -> dict of raw file variables (float32 promoted exactly to float64)."""
+    from scipy.io import netcdf_file
+
+    raw = {}
+    with netcdf_file(path, mmap=False) as f:
+        for nm in NC_VARS:
+            raw[nm] = np.array(f.variables[nm][...], dtype=np.float64)
+    return raw
+
+
+def to_radiation_inputs(raw):
+    """File variables (C order: column slowest) -> radiation() inputs (Fortran order: column fastest)."""
+    F = np.asfortranarray
+    d = {
+        "cos_sza": raw["cos_solar_zenith_angle"].copy(),
+        "skin_temperature": raw["skin_temperature"].copy(),
+        "sw_albedo": F(raw["sw_albedo"]), "sw_albedo_direct": F(raw["sw_albedo_direct"]),
+        "lw_emissivity": F(raw["lw_emissivity"]),
+        "iseed": np.asarray(raw["iseed"]).astype(np.int64).astype(np.int32),
+        "pressure_hl": F(raw["pressure_hl"]), "temperature_hl": F(raw["temperature_hl"]),
+        "h2o_mmr": F(raw["q"]), "o3_mmr": F(raw["o3_mmr"]),
+        "cloud_fraction": F(raw["cloud_fraction"]), "q_liq": F(raw["q_liquid"]), "q_ice": F(raw["q_ice"]),
+        "re_liq": F(raw["re_liquid"]), "re_ice": F(raw["re_ice"]),
+        "overlap_param": F(raw["overlap_param"]), "fractional_std": F(raw["fractional_std"]),
+    }
+    for g, m in GAS_MOLAR_MASS.items():
+        sf = 1.0 * m / AIR_MOLAR_MASS  # radiation_gas.F90 set_units_gas: sf = sf*GasMolarMass/AirMolarMass
+        d[f"{g}_mmr"] = F(raw[f"{g}_vmr"] * sf)
+    d["solar_irradiance"] = float(raw["solar_irradiance"])
+    return d
+
+
+def synthetic_columns(base_raw, ncol, seed=20261017, first=0):
+    """IFS-shaped synthetic columns (BASELINE.md section 4 / SURVEY.md section 8d).
+
+    Column i (global index first+i) = column (i mod 32) of the 32-column test slice; columns >= 32 are perturbed:
+    T += U(-2,2) K, q *= exp N(0,0.1), o3 *= exp N(0,0.05), cloud fraction *= U(0.5,1.5) clipped to [0,1],
+    q_liq,q_ice *= exp N(0,0.3), cos_sza = U(-0.2,1), T_skin += U(-3,3), iseed = i+1.
+    Draws are made per block of 4096 global columns from a counter-based stream, so shards agree across ranks.
+    """
+    nbase = base_raw["pressure_hl"].shape[0]
+    idx = (first + np.arange(ncol)) % nbase
+    out = {}
+    for k, v in base_raw.items():
+        out[k] = v if np.ndim(v) == 0 else np.array(v[idx], dtype=np.float64)
+    gidx = first + np.arange(ncol)
+    pert = gidx >= nbase
+    if pert.any():
+        # perturbations are drawn per fixed block of global columns (counter-based Philox), so any shard
+        # [first, first+ncol) of the same global problem sees identical columns on every rank
+        B = SYNTH_BLOCK
+        draws = {k: np.empty(ncol) for k in ("dT", "q", "o3", "cf", "ql", "qi", "mu0", "dTs")}
+        for blk in range(first // B, (first + ncol - 1) // B + 1):
+            rng = np.random.Generator(np.random.Philox(key=seed, counter=[0, 0, 0, blk]))
+            b = {"dT": rng.uniform(-2.0, 2.0, B), "q": np.exp(rng.normal(0.0, 0.1, B)),
+                 "o3": np.exp(rng.normal(0.0, 0.05, B)), "cf": rng.uniform(0.5, 1.5, B),
+                 "ql": np.exp(rng.normal(0.0, 0.3, B)), "qi": np.exp(rng.normal(0.0, 0.3, B)),
+                 "mu0": rng.uniform(-0.2, 1.0, B), "dTs": rng.uniform(-3.0, 3.0, B)}
+            lo, hi = max(first, blk * B), min(first + ncol, (blk + 1) * B)
+            for k in draws:
+                draws[k][lo - first:hi - first] = b[k][lo - blk * B:hi - blk * B]
+        m = pert
+        out["temperature_hl"][m] += draws["dT"][m, None]
+        out["q"][m] *= draws["q"][m, None]
+        out["o3_mmr"][m] *= draws["o3"][m, None]
+        out["cloud_fraction"][m] = np.clip(out["cloud_fraction"][m] * draws["cf"][m, None], 0.0, 1.0)
+        out["q_liquid"][m] *= draws["ql"][m, None]
+        out["q_ice"][m] *= draws["qi"][m, None]
+        out["cos_solar_zenith_angle"][m] = draws["mu0"][m]
+        out["skin_temperature"][m] += draws["dTs"][m]
+        out["iseed"][m] = (gidx[m] + 1).astype(np.float64)
+    return out

@@ -1,0 +1,153 @@
+/* ecrad_b200.h -- C-ABI of the B200-native ecRad hot path (libecrad_b200.so).
+ *
+ * Drop-in boundary for the three public procedures of the reference's `module radiation_interface`
+ * (radiation/radiation_interface.F90:29):
+ *     setup_radiation(config)                     :37    -> ecrad_b200_setup      (called at its tail, :153)
+ *     radiation(ncol,nlev,istartcol,iendcol,...)  :200   -> ecrad_b200_radiation  (replaces the body :318-505)
+ *     (no finaliser in the reference)                    -> ecrad_b200_finalize
+ * The Fortran host keeps its derived types; a ~150-line ISO_C_BINDING shim passes c_loc()
+ * of their contiguous components.  No Fortran descriptors, no torch types: plain pointers, ints, doubles.
+ *
+ * Array conventions (identical to the reference's memory layout, so no host-side repacking):
+ *   - every (ncol, n) array is column-fastest ("Fortran order"): element (jcol, j) at [ (j-1)*ncol + (jcol-1) ]
+ *   - the leading dimension is always the FULL ncol; only columns istartcol..iendcol (1-based, inclusive,
+ *     exactly the reference's arguments) are read or written
+ *   - per-g-point outputs are (ng, ncol), g-point fastest, as in radiation_flux.F90:38-118
+ *   - levels are ordered top-of-atmosphere first (the shim keeps the reference's radiation_reverse in Fortran,
+ *     radiation_interface.F90:310-317)
+ *   - NULL output pointer == "component not allocated" (allocation rules radiation_flux.F90:147-300)
+ */
+#ifndef ECRAD_B200_H
+#define ECRAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Enumerations: numeric values are those of the reference's `enum, bind(c)` blocks. */
+enum { ECRAD_SOLVER_CLOUDLESS = 0, ECRAD_SOLVER_HOMOGENEOUS = 1, ECRAD_SOLVER_MCICA = 2,
+       ECRAD_SOLVER_SPARTACUS = 3, ECRAD_SOLVER_TRIPLECLOUDS = 4 };        /* radiation_config.F90:51-54   */
+enum { ECRAD_GAS_MONOCHROMATIC = 0, ECRAD_GAS_IFSRRTMG = 1, ECRAD_GAS_ECCKD = 2 }; /* radiation_config.F90:86-88 */
+enum { ECRAD_OVERLAP_MAX_RAN = 0, ECRAD_OVERLAP_EXP_RAN = 1, ECRAD_OVERLAP_EXP_EXP = 2 }; /* radiation_cloud_cover.F90:30-33 */
+enum { ECRAD_LIQ_SOCRATES = 1 };                                          /* radiation_config.F90:95-99  */
+enum { ECRAD_ICE_FU = 1 };                                                /* radiation_config.F90:107-111 */
+
+/* POD copy of the scalars of `config_type` (radiation_config.F90:163-649) that the hot path reads. */
+typedef struct ecrad_b200_config {
+  int32_t struct_bytes;              /* = sizeof(ecrad_b200_config), ABI check                           */
+  int32_t i_solver_sw, i_solver_lw;  /* config%i_solver_sw/lw                                            */
+  int32_t i_gas_model_sw, i_gas_model_lw;
+  int32_t i_overlap_scheme;
+  int32_t i_liq_model, i_ice_model;
+  int32_t do_sw, do_lw, do_sw_direct, do_clear, do_clouds, use_aerosols;
+  int32_t do_lw_cloud_scattering, do_lw_aerosol_scattering, do_lw_derivatives;
+  int32_t do_sw_delta_scaling_with_gases, do_fu_lw_ice_optics_bug;
+  int32_t use_beta_overlap, use_vectorizable_generator;
+  int32_t do_surface_sw_spectral_flux, do_canopy_fluxes_sw, do_canopy_fluxes_lw, do_save_spectral_flux;
+  int32_t do_nearest_spectral_sw_albedo, do_nearest_spectral_lw_emiss;
+  int32_t n_g_sw, n_g_lw, n_bands_sw, n_bands_lw;
+  int32_t n_albedo_sw;               /* size(config%sw_albedo_weights,1) == size(single_level%sw_albedo,2) */
+  int32_t n_emiss_lw;                /* size(single_level%lw_emissivity,2)                               */
+  int32_t n_canopy_bands_sw, n_canopy_bands_lw;
+  int32_t reserved_i[4];
+  double cloud_fraction_threshold;   /* config%cloud_fraction_threshold      (default 1e-6)              */
+  double cloud_mixing_ratio_threshold; /*                                     (default 1e-9)              */
+  double min_gas_od_lw, min_gas_od_sw; /* radiation_config.F90:244-245                                   */
+  double cloud_inhom_decorr_scaling;
+  double reserved_d[4];
+} ecrad_b200_config;
+
+/* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md
+ * ("table directory"); for the RRTMG path they are the module variables of ifsrrtm/yoerrta1..16.F90,
+ * yoesrta16..29.F90, yoerrtwn.F90, yoerrtrf.F90, yoesrtwn.F90 plus config%cloud_optics%*, config%pdf_sampler%*,
+ * config%sw_albedo_weights, config%i_emiss_from_band_lw.  Data are COPIED by ecrad_b200_setup. */
+typedef struct ecrad_b200_tables ecrad_b200_tables;
+ecrad_b200_tables* ecrad_b200_tables_create(void);
+/* dtype: 0 = float64, 1 = int32.  dims[ndim] in Fortran order (dims[0] fastest).  Returns 0 on success. */
+int  ecrad_b200_tables_add(ecrad_b200_tables* t, const char* name, int dtype, int ndim,
+                           const int64_t* dims, const void* data);
+/* Load an "ETB1" blob written by tools/extract_rrtmg_tables.py (stand-alone use without a Fortran host). */
+int  ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path);
+void ecrad_b200_tables_free(ecrad_b200_tables* t);
+
+/* Inputs of radiation(): components of single_level_type (radiation_single_level.F90:29-102),
+ * thermodynamics_type (radiation_thermodynamics.F90:29-49), gas_type (radiation_gas.F90:36-79; mass mixing
+ * ratios, i.e. after set_gas_units), cloud_type (radiation_cloud.F90:33-96). */
+typedef struct ecrad_b200_inputs {
+  int32_t struct_bytes;
+  int32_t reserved;
+  double solar_irradiance;            /* single_level%solar_irradiance                                   */
+  const double* cos_sza;              /* (ncol)                                                          */
+  const double* skin_temperature;     /* (ncol)                                                          */
+  const double* sw_albedo;            /* (ncol, n_albedo_sw)   diffuse                                   */
+  const double* sw_albedo_direct;     /* (ncol, n_albedo_sw)   or NULL -> same as diffuse                */
+  const double* lw_emissivity;        /* (ncol, n_emiss_lw)                                              */
+  const int32_t* iseed;               /* (ncol)                                                          */
+  const double* pressure_hl;          /* (ncol, nlev+1)  Pa                                              */
+  const double* temperature_hl;       /* (ncol, nlev+1)  K                                               */
+  /* gas%mixing_ratio(:,:,IGAS) slices, kg/kg, each (ncol, nlev); gas codes radiation_gas_constants.F90:26-39 */
+  const double* h2o_mmr; const double* co2_mmr; const double* o3_mmr; const double* n2o_mmr;
+  const double* ch4_mmr; const double* cfc11_mmr; const double* cfc12_mmr; const double* hcfc22_mmr;
+  const double* ccl4_mmr;
+  double*       cloud_fraction;       /* (ncol, nlev)  IN/OUT: cropped like cloud%crop_cloud_fraction    */
+  const double* q_liq;                /* (ncol, nlev)  cloud%mixing_ratio(:,:,1)                         */
+  const double* q_ice;                /* (ncol, nlev)  cloud%mixing_ratio(:,:,2)                         */
+  const double* re_liq;               /* (ncol, nlev)  cloud%effective_radius(:,:,1)  m                  */
+  const double* re_ice;               /* (ncol, nlev)  cloud%effective_radius(:,:,2)  m                  */
+  const double* overlap_param;        /* (ncol, nlev-1)                                                  */
+  const double* fractional_std;       /* (ncol, nlev)                                                    */
+} ecrad_b200_inputs;
+
+/* Outputs: components of flux_type (radiation_flux.F90:38-118).  Any pointer may be NULL. */
+typedef struct ecrad_b200_outputs {
+  int32_t struct_bytes;
+  int32_t reserved;
+  double *lw_up, *lw_dn, *lw_up_clear, *lw_dn_clear;                 /* (ncol, nlev+1) */
+  double *sw_up, *sw_dn, *sw_dn_direct;                              /* (ncol, nlev+1) */
+  double *sw_up_clear, *sw_dn_clear, *sw_dn_direct_clear;            /* (ncol, nlev+1) */
+  double *lw_derivatives;                                            /* (ncol, nlev+1) */
+  double *cloud_cover_lw, *cloud_cover_sw;                           /* (ncol)         */
+  double *lw_dn_surf_g, *lw_dn_surf_clear_g, *lw_up_toa_g, *lw_up_toa_clear_g;        /* (n_g_lw, ncol) */
+  double *sw_dn_diffuse_surf_g, *sw_dn_direct_surf_g;                                   /* (n_g_sw, ncol) */
+  double *sw_dn_diffuse_surf_clear_g, *sw_dn_direct_surf_clear_g;                       /* (n_g_sw, ncol) */
+  double *sw_up_toa_g, *sw_up_toa_clear_g;                                              /* (n_g_sw, ncol) */
+  double *sw_dn_surf_band, *sw_dn_direct_surf_band;                  /* (n_bands_sw, ncol) */
+  double *sw_dn_surf_clear_band, *sw_dn_direct_surf_clear_band;      /* (n_bands_sw, ncol) */
+  double *sw_dn_diffuse_surf_canopy, *sw_dn_direct_surf_canopy;      /* (n_canopy_bands_sw, ncol) */
+  double *lw_dn_surf_canopy;                                         /* (n_canopy_bands_lw, ncol) */
+  /* per-band profiles, only filled by the Cloudless solver when do_save_spectral_flux: (n_bands, ncol, nlev+1) */
+  double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;
+} ecrad_b200_outputs;
+
+/* Create the device-side state: copies `cfg` and the tables to the GPU selected by cudaGetDevice().
+ * Returns 0 on success; on failure *handle is NULL and ecrad_b200_last_error(NULL) describes why.
+ * There is NO CPU fallback: without a CUDA device this fails. */
+int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab, void** handle);
+
+/* Host-buffer entry: H2D of columns istartcol..iendcol, kernels, D2H into `out` (and the cropped
+ * cloud_fraction back into in->cloud_fraction).  Thread-safe per handle (internally serialised).
+ * Error convention: non-zero return + message (reference: radiation_abort, utilities/radiation_io.F90:45-73). */
+int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int iendcol,
+                         const ecrad_b200_inputs* in, ecrad_b200_outputs* out);
+
+/* Device-resident entry: every pointer in `in`/`out` is a DEVICE pointer with leading dimension `ncol`,
+ * all ncol columns are processed, work is enqueued on `cuda_stream` (a cudaStream_t) and not synchronised. */
+int ecrad_b200_radiation_device(void* handle, int ncol, int nlev,
+                                const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream);
+
+/* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
+int64_t ecrad_b200_kernel_launches(void* handle);
+/* Event-timed duration (ms) of the last call's kernels, by stage; returns number of stages written. */
+int ecrad_b200_last_stage_ms(void* handle, float* ms, int max_stages);
+const char* ecrad_b200_stage_name(int stage);
+
+void ecrad_b200_finalize(void* handle);
+const char* ecrad_b200_last_error(void* handle);
+const char* ecrad_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECRAD_B200_H */

@@ -1,0 +1,314 @@
+/* cloud.c -- oracle restatement of cloud optics and the McICA stochastic cloud generator.  TEST INFRASTRUCTURE.
+ * Follows radiation/radiation_cloud_optics.F90:218-523, radiation_liquid_optics_socrates.F90:40-80,
+ * radiation_ice_optics_fu.F90:42-138, radiation_delta_eddington.h:103-119, radiation_cloud_generator.F90:37-390,
+ * radiation_cloud_cover.F90:231-300, radiation_pdf_sampler.F90:126-150,
+ * utilities/radiation_random_numbers_mix.F90:142-309.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "oracle.h"
+
+static inline double dmin(double a, double b) { return a < b ? a : b; }
+static inline double dmax(double a, double b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* coeff(jb, k) of a (nb, ncoeff) Fortran array, jb 0-based, k 1-based */
+#define CO(c, nb, jb, k) ((c)[((k) - 1) * (nb) + (jb)])
+
+/* radiation_liquid_optics_socrates.F90:40-80 */
+static void liq_socrates(int nb, const double* c, double lwp, double re_in, double* od, double* scat_od, double* g) {
+  const double MinRe = (double)1.2e-6f, MaxRe = (double)50.0e-6f; /* default-kind literals in the source :31-32 */
+  double re = dmax(MinRe, dmin(re_in, MaxRe));
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = lwp * (CO(c, nb, jb, 1) + re * (CO(c, nb, jb, 2) + re * CO(c, nb, jb, 3))) /
+             (1.0 + re * (CO(c, nb, jb, 4) + re * (CO(c, nb, jb, 5) + re * CO(c, nb, jb, 6))));
+    scat_od[jb] = od[jb] * (1.0 - (CO(c, nb, jb, 7) + re * (CO(c, nb, jb, 8) + re * CO(c, nb, jb, 9))) /
+                                      (1.0 + re * (CO(c, nb, jb, 10) + re * CO(c, nb, jb, 11))));
+    g[jb] = (CO(c, nb, jb, 12) + re * (CO(c, nb, jb, 13) + re * CO(c, nb, jb, 14))) /
+            (1.0 + re * (CO(c, nb, jb, 15) + re * CO(c, nb, jb, 16)));
+  }
+}
+static const double MaxAsymmetryFactor = 1.0 - 10.0 * DBL_EPSILON; /* radiation_ice_optics_fu.F90:33 */
+/* radiation_ice_optics_fu.F90:42-84 */
+static void ice_fu_sw(int nb, const double* c, double iwp, double re, double* od, double* scat_od, double* g) {
+  double de_um = dmin(re, 100.0e-6) * (1.0e6 / 0.64952);
+  double inv_de_um = 1.0 / de_um;
+  double iwp_gm_2 = iwp * 1000.0;
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = iwp_gm_2 * (CO(c, nb, jb, 1) + CO(c, nb, jb, 2) * inv_de_um);
+    scat_od[jb] = od[jb] * (1.0 - (CO(c, nb, jb, 3) + de_um * (CO(c, nb, jb, 4) + de_um * (CO(c, nb, jb, 5) + de_um * CO(c, nb, jb, 6)))));
+    g[jb] = dmin(CO(c, nb, jb, 7) + de_um * (CO(c, nb, jb, 8) + de_um * (CO(c, nb, jb, 9) + de_um * CO(c, nb, jb, 10))), MaxAsymmetryFactor);
+  }
+}
+/* radiation_ice_optics_fu.F90:90-138 */
+static void ice_fu_lw(int nb, const double* c, double iwp, double re, double* od, double* scat_od, double* g) {
+  double de_um = dmin(re, 100.0e-6) * (1.0e6 / 0.64952);
+  double inv_de_um = 1.0 / de_um;
+  double iwp_gm_2 = iwp * 1000.0;
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = iwp_gm_2 * (CO(c, nb, jb, 1) + inv_de_um * (CO(c, nb, jb, 2) + inv_de_um * CO(c, nb, jb, 3)));
+    scat_od[jb] = od[jb] - iwp_gm_2 * inv_de_um * (CO(c, nb, jb, 4) + de_um * (CO(c, nb, jb, 5) + de_um * (CO(c, nb, jb, 6) + de_um * CO(c, nb, jb, 7))));
+    g[jb] = dmin(CO(c, nb, jb, 8) + de_um * (CO(c, nb, jb, 9) + de_um * (CO(c, nb, jb, 10) + de_um * CO(c, nb, jb, 11))), MaxAsymmetryFactor);
+  }
+}
+/* radiation_delta_eddington.h:103-119 */
+static void delta_eddington_scat_od(int n, double* od, double* scat_od, double* g) {
+  for (int i = 0; i < n; ++i) {
+    double f = g[i] * g[i];
+    od[i] = od[i] - scat_od[i] * f;
+    scat_od[i] = scat_od[i] * (1.0 - f);
+    g[i] = g[i] / (1.0 + g[i]);
+  }
+}
+
+/* radiation_cloud_optics.F90:218-523 for one column (SOCRATES liquid + Fu ice).  Outputs [nlev][nb]. */
+void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl,
+                      const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
+                      const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
+                      double* od_sw, double* ssa_sw, double* g_sw) {
+  const double AccelDueToGravity = 9.80665;
+  memset(od_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
+  memset(ssa_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
+  memset(g_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
+  memset(od_sw, 0, sizeof(double) * (size_t)nlev * NB_SW);
+  memset(ssa_sw, 0, sizeof(double) * (size_t)nlev * NB_SW);
+  memset(g_sw, 0, sizeof(double) * (size_t)nlev * NB_SW);
+  for (int jl = 0; jl < nlev; ++jl) {
+    if (!(frac[jl] > 0.0)) continue;
+    double od_lw_liq[NB_LW], scat_lw_liq[NB_LW], g_lw_liq[NB_LW], od_lw_ice[NB_LW], scat_lw_ice[NB_LW], g_lw_ice[NB_LW];
+    double od_sw_liq[NB_SW], scat_sw_liq[NB_SW], g_sw_liq[NB_SW], od_sw_ice[NB_SW], scat_sw_ice[NB_SW], g_sw_ice[NB_SW];
+    double factor = (p_hl[jl + 1] - p_hl[jl]) / (AccelDueToGravity * frac[jl]);
+    double lwp = factor * q_liq[jl], iwp = factor * q_ice[jl];
+    if (lwp > 0.0) {
+      liq_socrates(NB_LW, t->liq_coeff_lw, lwp, re_liq[jl], od_lw_liq, scat_lw_liq, g_lw_liq);
+      liq_socrates(NB_SW, t->liq_coeff_sw, lwp, re_liq[jl], od_sw_liq, scat_sw_liq, g_sw_liq);
+      if (!cfg->do_sw_delta_scaling_with_gases) delta_eddington_scat_od(NB_SW, od_sw_liq, scat_sw_liq, g_sw_liq);
+    } else {
+      memset(od_lw_liq, 0, sizeof od_lw_liq); memset(scat_lw_liq, 0, sizeof scat_lw_liq); memset(g_lw_liq, 0, sizeof g_lw_liq);
+      memset(od_sw_liq, 0, sizeof od_sw_liq); memset(scat_sw_liq, 0, sizeof scat_sw_liq); memset(g_sw_liq, 0, sizeof g_sw_liq);
+    }
+    if (iwp > 0.0) {
+      ice_fu_lw(NB_LW, t->ice_coeff_lw, iwp, re_ice[jl], od_lw_ice, scat_lw_ice, g_lw_ice);
+      if (cfg->do_fu_lw_ice_optics_bug) for (int b = 0; b < NB_LW; ++b) scat_lw_ice[b] = od_lw_ice[b] - scat_lw_ice[b];
+      ice_fu_sw(NB_SW, t->ice_coeff_sw, iwp, re_ice[jl], od_sw_ice, scat_sw_ice, g_sw_ice);
+      if (!cfg->do_sw_delta_scaling_with_gases) delta_eddington_scat_od(NB_SW, od_sw_ice, scat_sw_ice, g_sw_ice);
+      delta_eddington_scat_od(NB_LW, od_lw_ice, scat_lw_ice, g_lw_ice);
+    } else {
+      memset(od_lw_ice, 0, sizeof od_lw_ice); memset(scat_lw_ice, 0, sizeof scat_lw_ice); memset(g_lw_ice, 0, sizeof g_lw_ice);
+      memset(od_sw_ice, 0, sizeof od_sw_ice); memset(scat_sw_ice, 0, sizeof scat_sw_ice); memset(g_sw_ice, 0, sizeof g_sw_ice);
+    }
+    if (cfg->do_lw_cloud_scattering) {
+      for (int b = 0; b < NB_LW; ++b) {
+        od_lw[jl * NB_LW + b] = od_lw_liq[b] + od_lw_ice[b];
+        if (scat_lw_liq[b] + scat_lw_ice[b] > 0.0)
+          g_lw[jl * NB_LW + b] = (g_lw_liq[b] * scat_lw_liq[b] + g_lw_ice[b] * scat_lw_ice[b]) / (scat_lw_liq[b] + scat_lw_ice[b]);
+        else g_lw[jl * NB_LW + b] = 0.0;
+        ssa_lw[jl * NB_LW + b] = (scat_lw_liq[b] + scat_lw_ice[b]) / (od_lw_liq[b] + od_lw_ice[b]);
+      }
+    } else {
+      for (int b = 0; b < NB_LW; ++b) od_lw[jl * NB_LW + b] = od_lw_liq[b] - scat_lw_liq[b] + od_lw_ice[b] - scat_lw_ice[b];
+    }
+    for (int b = 0; b < NB_SW; ++b) {
+      od_sw[jl * NB_SW + b] = od_sw_liq[b] + od_sw_ice[b];
+      g_sw[jl * NB_SW + b] = (g_sw_liq[b] * scat_sw_liq[b] + g_sw_ice[b] * scat_sw_ice[b]) / (scat_sw_liq[b] + scat_sw_ice[b]);
+      ssa_sw[jl * NB_SW + b] = (scat_sw_liq[b] + scat_sw_ice[b]) / (od_sw_liq[b] + od_sw_ice[b]);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * utilities/radiation_random_numbers_mix.F90: 30-bit lagged-Fibonacci generator (p=273, q=607)
+ * ------------------------------------------------------------------------------------------------- */
+#define JPP 273
+#define JPQ 607
+#define JPS 105
+#define JPMM 30
+#define JPNUMSPLIT ((JPQ - 2) / (JPP - 1))
+#define JPLENSPLIT ((JPQ - JPP + JPNUMSPLIT - 1) / JPNUMSPLIT)
+typedef struct { int iused; int32_t ix[JPQ + 1]; double zrm; } rng_stream; /* ix[1..JPQ] */
+
+static inline int32_t lfsr_step(int32_t idum, int* top) {
+  uint32_t u = (uint32_t)idum;
+  *top = (u >> 31) & 1u;
+  if (*top) u = ((u ^ 87u) << 1) | 1u;  /* IBSET(ISHFT(IEOR(IDUM,87),1),0) */
+  else u = (u << 1) & ~1u;                /* IBCLR(ISHFT(IDUM,1),0)          */
+  return (int32_t)u;
+}
+static void rng_uniform(rng_stream* s, int n, double* px);
+
+/* radiation_random_numbers_mix.F90:142-231 */
+static void rng_init(int32_t kseed, rng_stream* s) {
+  const int32_t JPMASK = 123459876;
+  int32_t idum = kseed ^ JPMASK;
+  if (idum < 0) idum = (idum == INT32_MIN) ? idum : -idum; /* ABS */
+  if (idum == 0) idum = JPMASK;
+  int top;
+  for (int jj = 1; jj <= 64; ++jj) idum = lfsr_step(idum, &top);
+  for (int i = 1; i <= JPQ - 1; ++i) s->ix[i] = 0;
+  s->ix[2] = (int32_t)(((uint32_t)idum & ((1u << (JPMM - 1)) - 1u)) << 1);   /* ISHFT(IBITS(IDUM,0,JPMM-1),1) */
+  s->ix[JPQ] = (int32_t)(((uint32_t)idum >> (JPMM - 1)) & 7u);               /* IBITS(IDUM,JPMM-1,3)          */
+  for (int jbit = 1; jbit <= JPMM - 1; ++jbit) {
+    for (int jj = 3; jj <= JPQ - 1; ++jj) {
+      idum = lfsr_step(idum, &top);
+      if (top) s->ix[jj] |= (int32_t)(1u << jbit);
+    }
+  }
+  s->ix[JPQ - JPS] |= 1;
+  s->iused = JPQ;
+  s->zrm = 1.0 / (double)(1 << JPMM);
+  double warm[999];
+  rng_uniform(s, 999, warm);
+}
+
+/* radiation_random_numbers_mix.F90:261-309 */
+static void rng_uniform(rng_stream* s, int n, double* px) {
+  const int32_t IVAR = 0x3FFFFFFF;
+  int ifilled = 0;
+  int hi = imin(JPQ, n + s->iused);
+  for (int jj = s->iused + 1; jj <= hi; ++jj) {
+    px[jj - s->iused - 1] = s->ix[jj] * s->zrm;
+    ifilled++;
+  }
+  s->iused += ifilled;
+  if (ifilled == n) return;
+  while (ifilled < n) {
+    for (int jj = 1; jj <= JPP; ++jj) s->ix[jj] = IVAR & (s->ix[jj] + s->ix[jj - JPP + JPQ]);
+    for (int jk = 1; jk <= JPNUMSPLIT; ++jk)
+      for (int jj = 1 + JPP + (jk - 1) * JPLENSPLIT; jj <= imin(JPQ, JPP + jk * JPLENSPLIT); ++jj)
+        s->ix[jj] = IVAR & (s->ix[jj] + s->ix[jj - JPP]);
+    s->iused = imin(JPQ, n - ifilled);
+    for (int i = 1; i <= s->iused; ++i) px[ifilled + i - 1] = s->ix[i] * s->zrm;
+    ifilled += s->iused;
+  }
+}
+
+/* radiation_pdf_sampler.F90:126-150 sample_from_pdf */
+static double pdf_sample(const orc_tables* t, double fsd, double cdf) {
+  const int ncdf = t->pdf_ncdf, nfsd = t->pdf_nfsd;
+  double wcdf = cdf * (ncdf - 1) + 1.0;
+  int icdf = imax(1, imin((int)wcdf, ncdf - 1));
+  wcdf = dmax(0.0, dmin(wcdf - icdf, 1.0));
+  double wfsd = (fsd - t->pdf_fsd1) * t->pdf_inv_fsd_interval + 1.0;
+  int ifsd = imax(1, imin((int)wfsd, nfsd - 1));
+  wfsd = dmax(0.0, dmin(wfsd - ifsd, 1.0));
+#define VAL(i, j) (t->pdf_val[((j) - 1) * (size_t)ncdf + ((i) - 1)])
+  return (1.0 - wcdf) * (1.0 - wfsd) * VAL(icdf, ifsd) + (1.0 - wcdf) * wfsd * VAL(icdf, ifsd + 1) +
+         wcdf * (1.0 - wfsd) * VAL(icdf + 1, ifsd) + wcdf * wfsd * VAL(icdf + 1, ifsd + 1);
+#undef VAL
+}
+
+static const double MaxCloudFrac = 1.0 - DBL_EPSILON * 10.0; /* radiation_cloud_cover.F90:40 */
+
+/* radiation_cloud_cover.F90:53-69 */
+static double beta2alpha(double beta, double f1, double f2) {
+  if (beta < 1.0) {
+    double d = fabs(f1 - f2);
+    return beta + (1.0 - beta) * d / (d + 1.0 / beta - 1.0);
+  }
+  return 1.0;
+}
+/* radiation_cloud_cover.F90:231-300 cum_cloud_cover_exp_ran (1 column); arrays 0-based */
+static void cum_cloud_cover_exp_ran(int nlev, const double* frac, const double* overlap_param, int beta,
+                                    double* cum, double* pair) {
+  double cum_product = 1.0 - frac[0];
+  cum[0] = frac[0];
+  for (int jl = 0; jl < nlev - 1; ++jl) {
+    double alpha = beta ? beta2alpha(overlap_param[jl], frac[jl], frac[jl + 1]) : overlap_param[jl];
+    pair[jl] = alpha * dmax(frac[jl], frac[jl + 1]) + (1.0 - alpha) * (frac[jl] + frac[jl + 1] - frac[jl] * frac[jl + 1]);
+    if (frac[jl] >= MaxCloudFrac) cum_product = 0.0;
+    else cum_product = cum_product * (1.0 - pair[jl]) / (1.0 - frac[jl]);
+    cum[jl + 1] = 1.0 - cum_product;
+  }
+}
+/* radiation_cloud_cover.F90:169-225 cum_cloud_cover_max_ran */
+static void cum_cloud_cover_max_ran(int nlev, const double* frac, double* cum, double* pair) {
+  double cum_product = 1.0 - frac[0];
+  cum[0] = frac[0];
+  for (int jl = 0; jl < nlev - 1; ++jl) {
+    if (frac[jl] >= MaxCloudFrac) cum_product = 0.0;
+    else cum_product = cum_product * (1.0 - dmax(frac[jl], frac[jl + 1])) / (1.0 - frac[jl]);
+    cum[jl + 1] = 1.0 - cum_product;
+    pair[jl] = dmax(frac[jl], frac[jl + 1]);
+  }
+}
+
+/* radiation_cloud_generator.F90:262-390 generate_column_exp_ran; levels 1-based like the source via macros */
+static void generate_column_exp_ran(const orc_tables* t, int ng, int nlev, int ig, rng_stream* rs, const double* frac,
+                                    const double* pair, const double* cum, const double* overhang,
+                                    const double* fsd, const double* overlap_param_inhom, int itrigger, int iend,
+                                    double* od_scaling, double* rand_cloud, double* rand_inhom1, double* rand_inhom2) {
+#define F(a, l) ((a)[(l) - 1])
+  int n_layers_to_scale = 1;
+  int iy = 0;
+  (void)nlev;
+  rng_uniform(rs, iend + 1 - itrigger, rand_cloud);
+  for (int jlev = itrigger + 1; jlev <= iend + 1; ++jlev) {
+    int do_fill = 0;
+    if (jlev <= iend) {
+      iy++;
+      if (n_layers_to_scale > 0) {
+        if (rand_cloud[iy - 1] * F(frac, jlev - 1) < F(frac, jlev) + F(frac, jlev - 1) - F(pair, jlev - 1)) n_layers_to_scale++;
+        else do_fill = 1;
+      } else {
+        if (rand_cloud[iy - 1] * (F(cum, jlev - 1) - F(frac, jlev - 1)) < F(pair, jlev - 1) - F(overhang, jlev - 1) - F(frac, jlev - 1))
+          n_layers_to_scale = 1;
+      }
+    } else do_fill = 1;
+    if (do_fill) {
+      rng_uniform(rs, n_layers_to_scale, rand_inhom1);
+      rng_uniform(rs, n_layers_to_scale, rand_inhom2);
+      for (int jc = 2; jc <= n_layers_to_scale; ++jc)
+        if (rand_inhom2[jc - 1] < F(overlap_param_inhom, jlev - n_layers_to_scale + jc - 2)) rand_inhom1[jc - 1] = rand_inhom1[jc - 2];
+      for (int k = 0; k < n_layers_to_scale; ++k) {
+        int lev = jlev - n_layers_to_scale + k; /* 1-based level */
+        od_scaling[(size_t)(lev - 1) * ng + ig] = pdf_sample(t, F(fsd, lev), rand_inhom1[k]);
+      }
+      n_layers_to_scale = 0;
+    }
+  }
+#undef F
+}
+
+/* radiation_cloud_generator.F90:37-255 cloud_generator (Exp-Ran / Max-Ran, non-vectorizable RNG).
+ * od_scaling is [nlev][ng].  Exp-Exp and the vectorizable generator are not restated (out of the round-1 path). */
+void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_scheme, int32_t iseed,
+                         double frac_threshold, const double* frac, const double* overlap_param,
+                         double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,
+                         double* od_scaling, double* total_cloud_cover) {
+  double* cum = (double*)malloc(sizeof(double) * (size_t)nlev * 7);
+  double* pair = cum + nlev; double* overhang = pair + nlev; double* opi = overhang + nlev;
+  double* rand_cloud = opi + nlev; double* ri1 = rand_cloud + nlev; double* ri2 = ri1 + nlev;
+  if (i_overlap_scheme == ECRAD_OVERLAP_EXP_RAN) cum_cloud_cover_exp_ran(nlev, frac, overlap_param, use_beta_overlap, cum, pair);
+  else cum_cloud_cover_max_ran(nlev, frac, cum, pair);
+  double tcc = cum[nlev - 1];
+  for (int jl = 0; jl < nlev - 1; ++jl) overhang[jl] = cum[jl + 1] - cum[jl];
+  if (tcc < frac_threshold) {
+    tcc = 0.0;
+  } else {
+    int jlev = 1;
+    while (frac[jlev - 1] <= 0.0) jlev++;
+    int ibegin = jlev, iend = jlev;
+    for (jlev = jlev + 1; jlev <= nlev; ++jlev) if (frac[jlev - 1] > 0.0) iend = jlev;
+    for (int jl = 0; jl < nlev - 1; ++jl) opi[jl] = overlap_param[jl];
+    for (jlev = ibegin; jlev <= iend - 1; ++jlev)
+      if (overlap_param[jlev - 1] > 0.0) opi[jlev - 1] = pow(overlap_param[jlev - 1], 1.0 / decorrelation_scaling);
+    memset(od_scaling, 0, sizeof(double) * (size_t)ng * nlev);
+    rng_stream rs;
+    rng_init(iseed, &rs);
+    double* rand_top = (double*)malloc(sizeof(double) * (size_t)ng);
+    rng_uniform(&rs, ng, rand_top);
+    for (int jg = 0; jg < ng; ++jg) {
+      double trigger = rand_top[jg] * tcc;
+      jlev = ibegin;
+      while (trigger > cum[jlev - 1] && jlev < iend) jlev++;
+      generate_column_exp_ran(t, ng, nlev, jg, &rs, frac, pair, cum, overhang, fractional_std, opi, jlev, iend, od_scaling,
+                              rand_cloud, ri1, ri2);
+    }
+    free(rand_top);
+  }
+  *total_cloud_cover = tcc;
+  free(cum);
+}

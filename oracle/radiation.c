@@ -1,0 +1,553 @@
+/* radiation.c -- oracle restatement of radiation() and the McICA / Cloudless solvers.  TEST INFRASTRUCTURE.
+ * Follows radiation/radiation_interface.F90:200-510, radiation_single_level.F90:216-365 (get_albedos),
+ * radiation_ifs_rrtm.F90:216-613 (gas_optics) and :618-852 (planck_function_atmos/_surf),
+ * radiation_cloud.F90:700-740 (crop_cloud_fraction), radiation_mcica_lw.F90:39-419, radiation_mcica_sw.F90:41-408,
+ * radiation_cloudless_lw.F90, radiation_cloudless_sw.F90, radiation_lw_derivatives.F90:43-130,
+ * radiation_flux.F90:397-577 (calc_surface_spectral).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "oracle.h"
+
+#define A2(p, jcol, j) ((p)[(size_t)(j) * ncol + (jcol)]) /* (ncol, n) column-fastest, 0-based */
+
+typedef struct {
+  double *od_lw, *planck_hl, *lw_emission, *lw_albedo;         /* [nlev][140], [nlev+1][140], [140], [140] */
+  double *od_sw, *ssa_sw, *incoming_sw, *alb_dir, *alb_diff;   /* [nlev][112] x2, [112] x3 */
+  double *od_lw_cloud, *ssa_lw_cloud, *g_lw_cloud, *od_sw_cloud, *ssa_sw_cloud, *g_sw_cloud; /* [nlev][nb] */
+  double *w;  /* scratch pool */
+} col_work;
+
+/* get_albedos, radiation_single_level.F90:216-365 (paths used by test/ifs/configCY49R1.nam) */
+static int get_albedos(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int jcol,
+                       const ecrad_b200_inputs* in, double* alb_dir, double* alb_diff, double* lw_albedo) {
+  if (cfg->do_nearest_spectral_sw_albedo || !cfg->do_nearest_spectral_lw_emiss) return 1; /* not restated */
+  if (!t->sw_albedo_weights || !t->i_emiss_from_band_lw) return 2;
+  const int nalb = cfg->n_albedo_sw;
+  double band[NB_SW], band_dir[NB_SW];
+  for (int jb = 0; jb < NB_SW; ++jb) {
+    band[jb] = 0.0; band_dir[jb] = 0.0;
+    for (int ja = 0; ja < nalb; ++ja) {
+      double w = t->sw_albedo_weights[(size_t)jb * nalb + ja];
+      if (w != 0.0) {
+        band[jb] = band[jb] + w * A2(in->sw_albedo, jcol, ja);
+        if (in->sw_albedo_direct) band_dir[jb] = band_dir[jb] + w * A2(in->sw_albedo_direct, jcol, ja);
+      }
+    }
+  }
+  for (int g = 0; g < NG_SW; ++g) {
+    int jb = t->ngb_sw[g] - 16;
+    alb_diff[g] = band[jb];
+    alb_dir[g] = in->sw_albedo_direct ? band_dir[jb] : band[jb];
+  }
+  for (int g = 0; g < NG_LW; ++g) {
+    int jb = t->ngb_lw[g] - 1;
+    lw_albedo[g] = 1.0 - A2(in->lw_emissivity, jcol, t->i_emiss_from_band_lw[jb] - 1);
+  }
+  return 0;
+}
+
+/* Planck function at a temperature for all 16 bands: radiation_ifs_rrtm.F90:676-699 */
+static void planck_bands(const orc_tables* t, double temperature, double* store) {
+  const double zfluxfac = 2.0 * asin(1.0) * 1.0e4;
+  int ind; double frac;
+  if (temperature < 339.0 && temperature >= 160.0) {
+    ind = (int)(temperature - 159.0);
+    frac = temperature - (int)temperature;
+  } else if (temperature >= 339.0) {
+    ind = 180; frac = temperature - 339.0;
+  } else {
+    ind = 1; frac = 0.0;
+  }
+  for (int jb = 0; jb < NB_LW; ++jb) {
+    double factor = zfluxfac * t->delwave[jb];
+    const double* tp = t->totplnk + (size_t)jb * 181;
+    store[jb] = factor * (tp[ind - 1] + frac * (tp[ind] - tp[ind - 1]));
+  }
+}
+
+/* gas_optics for one column, radiation_ifs_rrtm.F90:216-613.  Outputs in ecRad level order (0 = top). */
+static void gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                              const ecrad_b200_inputs* in, const double* lw_albedo, double* od_lw, double* planck_hl,
+                              double* lw_emission, double* od_sw, double* ssa_sw, double* incoming_sw) {
+  double* buf = (double*)malloc(sizeof(double) * (size_t)(nlev + 1) * 16);
+  double *p_hl = buf, *t_hl = p_hl + (nlev + 1), *p_fl = t_hl + (nlev + 1), *t_fl = p_fl + nlev;
+  double* gas[9];
+  const double* src[9] = {in->h2o_mmr, in->co2_mmr, in->ch4_mmr, in->n2o_mmr, in->cfc11_mmr, in->cfc12_mmr,
+                          in->hcfc22_mmr, in->ccl4_mmr, in->o3_mmr};
+  for (int i = 0; i < 9; ++i) gas[i] = t_fl + nlev + (size_t)i * nlev;
+  for (int jl = 0; jl <= nlev; ++jl) { p_hl[jl] = A2(in->pressure_hl, jcol, jl); t_hl[jl] = A2(in->temperature_hl, jcol, jl); }
+  for (int jl = 0; jl < nlev; ++jl) {
+    p_fl[jl] = 0.5 * (p_hl[jl] + p_hl[jl + 1]);
+    t_fl[jl] = 0.5 * (t_hl[jl] + t_hl[jl + 1]);
+    for (int i = 0; i < 9; ++i) gas[i][jl] = A2(src[i], jcol, jl);
+  }
+  orc_lay_lw* lay = (orc_lay_lw*)malloc(sizeof(orc_lay_lw) * (size_t)nlev);
+  orc_prepare_gases(nlev, p_hl, t_hl, p_fl, t_fl, gas[0], gas[1], gas[2], gas[3], gas[4], gas[5], gas[6], gas[7], gas[8], lay);
+  if (cfg->do_lw) {
+    int laytrop;
+    double* tau = (double*)malloc(sizeof(double) * (size_t)nlev * NG_LW * 2);
+    double* pfrac = tau + (size_t)nlev * NG_LW;
+    orc_setcoef_lw(t, nlev, lay, &laytrop);
+    orc_taumol_lw(t, nlev, lay, laytrop, tau, pfrac);
+    /* planck_function_atmos :618-752 */
+    double store[NB_LW];
+    for (int jlev = 1; jlev <= nlev + 1; ++jlev) {
+      planck_bands(t, t_hl[jlev - 1], store);
+      int ilay = (jlev == 1) ? nlev : nlev + 2 - jlev; /* RRTMG layer (1-based) whose PFRAC is used */
+      for (int g = 0; g < NG_LW; ++g)
+        planck_hl[(size_t)(jlev - 1) * NG_LW + g] = store[t->ngb_lw[g] - 1] * pfrac[(size_t)(ilay - 1) * NG_LW + g];
+    }
+    /* planck_function_surf :757-852 and lw_emission :466 */
+    planck_bands(t, in->skin_temperature[jcol], store);
+    for (int g = 0; g < NG_LW; ++g) {
+      lw_emission[g] = store[t->ngb_lw[g] - 1] * pfrac[g];
+      lw_emission[g] = lw_emission[g] * (1.0 - lw_albedo[g]);
+    }
+    /* :506-511 un-reverse + clamp */
+    for (int jl = 1; jl <= nlev; ++jl)
+      for (int g = 0; g < NG_LW; ++g) {
+        double v = tau[(size_t)(nlev - jl) * NG_LW + g];
+        od_lw[(size_t)(jl - 1) * NG_LW + g] = v > cfg->min_gas_od_lw ? v : cfg->min_gas_od_lw;
+      }
+    free(tau);
+  }
+  if (cfg->do_sw) {
+    memset(od_sw, 0, sizeof(double) * (size_t)nlev * NG_SW);
+    memset(ssa_sw, 0, sizeof(double) * (size_t)nlev * NG_SW);
+    for (int g = 0; g < NG_SW; ++g) incoming_sw[g] = 0.0;
+    if (in->cos_sza[jcol] > 0.0) {
+      int laytrop;
+      orc_lay_sw* ls = (orc_lay_sw*)malloc(sizeof(orc_lay_sw) * (size_t)nlev);
+      double* zod = (double*)malloc(sizeof(double) * (size_t)nlev * NG_SW * 2);
+      double* zssa = zod + (size_t)nlev * NG_SW;
+      double incsol[NG_SW];
+      orc_setcoef_sw(t, nlev, lay, ls, &laytrop);
+      orc_taumol_sw(t, nlev, ls, laytrop, zod, zssa, incsol);
+      double sum = 0.0;
+      for (int g = 0; g < NG_SW; ++g) sum = sum + incsol[g];
+      double scale = in->solar_irradiance / sum;  /* :557-565 */
+      for (int jl = 1; jl <= nlev; ++jl)
+        for (int g = 0; g < NG_SW; ++g) {
+          double v = zod[(size_t)(jl - 1) * NG_SW + g];
+          od_sw[(size_t)(nlev - jl) * NG_SW + g] = v > cfg->min_gas_od_sw ? v : cfg->min_gas_od_sw;
+          ssa_sw[(size_t)(nlev - jl) * NG_SW + g] = zssa[(size_t)(jl - 1) * NG_SW + g];
+        }
+      for (int g = 0; g < NG_SW; ++g) incoming_sw[g] = scale * incsol[g];
+      free(zod); free(ls);
+    }
+  }
+  free(lay); free(buf);
+}
+
+int orc_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                          const ecrad_b200_inputs* in, double* od_lw, double* planck_hl, double* lw_emission,
+                          double* od_sw, double* ssa_sw, double* incoming_sw) {
+  double alb_dir[NG_SW], alb_diff[NG_SW], lw_albedo[NG_LW];
+  int rc = get_albedos(t, cfg, ncol, jcol - 1, in, alb_dir, alb_diff, lw_albedo);
+  if (rc) return rc;
+  gas_optics_column(t, cfg, ncol, nlev, jcol - 1, in, lw_albedo, od_lw, planck_hl, lw_emission, od_sw, ssa_sw, incoming_sw);
+  return 0;
+}
+
+/* radiation_lw_derivatives.F90:43-84 / :93-130 */
+static void lw_derivatives(int ng, int nlev, int ncol, int jcol, const double* trans, const double* flux_up_surf,
+                           double weight, int modify, double* out) {
+  double* dg = (double*)malloc(sizeof(double) * (size_t)ng);
+  double s = 0.0;
+  for (int g = 0; g < ng; ++g) s = s + flux_up_surf[g];
+  for (int g = 0; g < ng; ++g) dg[g] = flux_up_surf[g] / s;
+  A2(out, jcol, nlev) = 1.0;
+  for (int jl = nlev - 1; jl >= 0; --jl) {
+    double sum = 0.0;
+    for (int g = 0; g < ng; ++g) { dg[g] = dg[g] * trans[(size_t)jl * ng + g]; sum = sum + dg[g]; }
+    if (modify) A2(out, jcol, jl) = (1.0 - weight) * A2(out, jcol, jl) + weight * sum;
+    else A2(out, jcol, jl) = sum;
+  }
+  free(dg);
+}
+
+static void sum_g(int ng, int nlev1, const double* f, int ncol, int jcol, double* out) {
+  if (!out) return;
+  for (int jl = 0; jl < nlev1; ++jl) {
+    double s = 0.0;
+    for (int g = 0; g < ng; ++g) s = s + f[(size_t)jl * ng + g];
+    A2(out, jcol, jl) = s;
+  }
+}
+/* indexed_sum_profile, radiation_flux.F90:820-855: band profile (nband, ncol, nlev+1) */
+static void band_profile(int ng, int nb, int nlev1, const int32_t* ngb, int off, const double* f, int ncol, int jcol,
+                         double* out, int add) {
+  if (!out) return;
+  for (int jl = 0; jl < nlev1; ++jl) {
+    double* o = out + ((size_t)jl * ncol + jcol) * nb;
+    if (!add) for (int b = 0; b < nb; ++b) o[b] = 0.0;
+    for (int g = 0; g < ng; ++g) o[ngb[g] - off] = o[ngb[g] - off] + f[(size_t)jl * ng + g];
+  }
+}
+
+#define OUTG(p, ng, g) ((p)[(size_t)jcol * (ng) + (g)])
+
+/* ----- LW: radiation_mcica_lw.F90:39-419 and radiation_cloudless_lw.F90 ----- */
+static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                      const ecrad_b200_inputs* in, ecrad_b200_outputs* out, const col_work* w, const double* frac) {
+  const int ng = NG_LW;
+  const size_t nl = (size_t)nlev * ng, nl1 = (size_t)(nlev + 1) * ng;
+  double* pool = (double*)malloc(sizeof(double) * (8 * nl + 4 * nl1 + nl + 4 * ng));
+  double *ref_clear = pool, *trans_clear = ref_clear + nl, *ref = trans_clear + nl, *trans = ref + nl;
+  double *su_clear = trans + nl, *sd_clear = su_clear + nl, *su = sd_clear + nl, *sd = su + nl;
+  double *fu = sd + nl, *fd = fu + nl1, *fu_clear = fd + nl1, *fd_clear = fu_clear + nl1;
+  double *od_scaling = fd_clear + nl1, *od_total = od_scaling + nl, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
+  const double* planck = w->planck_hl;
+  /* clear sky: no-scattering (do_lw_aerosol_scattering = false) */
+  orc_calc_no_scattering_transmittance_lw(ng * nlev, w->od_lw, planck, planck + ng, trans_clear, su_clear, sd_clear);
+  memset(ref_clear, 0, sizeof(double) * nl);
+  orc_calc_fluxes_no_scattering_lw(ng, nlev, trans_clear, su_clear, sd_clear, w->lw_emission, w->lw_albedo, fu_clear, fd_clear);
+  sum_g(ng, nlev + 1, fu_clear, ncol, jcol, out->lw_up_clear);
+  sum_g(ng, nlev + 1, fd_clear, ncol, jcol, out->lw_dn_clear);
+  for (int g = 0; g < ng; ++g) {
+    if (out->lw_dn_surf_clear_g) OUTG(out->lw_dn_surf_clear_g, ng, g) = fd_clear[nl1 - ng + g];
+    if (out->lw_up_toa_clear_g) OUTG(out->lw_up_toa_clear_g, ng, g) = fu_clear[g];
+  }
+  if (cfg->i_solver_lw == ECRAD_SOLVER_CLOUDLESS) {
+    /* radiation_cloudless_lw.F90:118-160: all-sky = clear-sky */
+    sum_g(ng, nlev + 1, fu_clear, ncol, jcol, out->lw_up);
+    sum_g(ng, nlev + 1, fd_clear, ncol, jcol, out->lw_dn);
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = fd_clear[nl1 - ng + g];
+      if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = fu_clear[g];
+    }
+    band_profile(ng, NB_LW, nlev + 1, t->ngb_lw, 1, fu_clear, ncol, jcol, out->lw_up_band, 0);
+    band_profile(ng, NB_LW, nlev + 1, t->ngb_lw, 1, fd_clear, ncol, jcol, out->lw_dn_band, 0);
+    if (cfg->do_lw_derivatives && out->lw_derivatives)
+      lw_derivatives(ng, nlev, ncol, jcol, trans_clear, fu_clear + nl1 - ng, 0.0, 0, out->lw_derivatives);
+    free(pool);
+    return;
+  }
+  double tcc;
+  double *fsd = (double*)malloc(sizeof(double) * (size_t)nlev * 2), *op = fsd + nlev;
+  for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
+  for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
+  orc_cloud_generator(t, ng, nlev, cfg->i_overlap_scheme, in->iseed[jcol] + 997, cfg->cloud_fraction_threshold, frac, op,
+                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, od_scaling, &tcc);
+  free(fsd);
+  if (out->cloud_cover_lw) out->cloud_cover_lw[jcol] = tcc;
+  if (tcc >= cfg->cloud_fraction_threshold) {
+    int* is_clear = (int*)malloc(sizeof(int) * (size_t)nlev);
+    int i_cloud_top = nlev + 1;
+    for (int jl = 0; jl < nlev; ++jl) {
+      is_clear[jl] = 1;
+      if (frac[jl] >= cfg->cloud_fraction_threshold) {
+        is_clear[jl] = 0;
+        if (i_cloud_top > jl + 1) i_cloud_top = jl + 1;
+        for (int g = 0; g < ng; ++g) {
+          int jb = t->ngb_lw[g] - 1;
+          double od_cloud_new = od_scaling[(size_t)jl * ng + g] * w->od_lw_cloud[jl * NB_LW + jb];
+          od_total[g] = w->od_lw[(size_t)jl * ng + g] + od_cloud_new;
+          ssa_total[g] = 0.0; g_total[g] = 0.0;
+          if (cfg->do_lw_cloud_scattering) {
+            if (od_total[g] > 0.0) {
+              double scat_od = w->ssa_lw_cloud[jl * NB_LW + jb] * od_cloud_new;
+              ssa_total[g] = scat_od / od_total[g];
+              if (scat_od > 0.0) g_total[g] = w->g_lw_cloud[jl * NB_LW + jb] * w->ssa_lw_cloud[jl * NB_LW + jb] * od_cloud_new / scat_od;
+            }
+          }
+        }
+        if (cfg->do_lw_cloud_scattering)
+          orc_calc_ref_trans_lw(ng, od_total, ssa_total, g_total, planck + (size_t)jl * ng, planck + (size_t)(jl + 1) * ng,
+                                ref + (size_t)jl * ng, trans + (size_t)jl * ng, su + (size_t)jl * ng, sd + (size_t)jl * ng);
+        else
+          orc_calc_no_scattering_transmittance_lw(ng, od_total, planck + (size_t)jl * ng, planck + (size_t)(jl + 1) * ng,
+                                                  trans + (size_t)jl * ng, su + (size_t)jl * ng, sd + (size_t)jl * ng);
+      } else {
+        for (int g = 0; g < ng; ++g) {
+          size_t i = (size_t)jl * ng + g;
+          ref[i] = ref_clear[i]; trans[i] = trans_clear[i]; su[i] = su_clear[i]; sd[i] = sd_clear[i];
+        }
+      }
+    }
+    if (cfg->do_lw_cloud_scattering)
+      orc_fast_adding_ica_lw(ng, nlev, ref, trans, su, sd, w->lw_emission, w->lw_albedo, is_clear, i_cloud_top, fd_clear, fu, fd);
+    else
+      orc_calc_fluxes_no_scattering_lw(ng, nlev, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
+    free(is_clear);
+    for (int jl = 0; jl <= nlev; ++jl) {
+      double s_up = 0.0, s_dn = 0.0;
+      for (int g = 0; g < ng; ++g) { s_up = s_up + fu[(size_t)jl * ng + g]; s_dn = s_dn + fd[(size_t)jl * ng + g]; }
+      if (out->lw_up) A2(out->lw_up, jcol, jl) = tcc * s_up + (1.0 - tcc) * A2(out->lw_up_clear, jcol, jl);
+      if (out->lw_dn) A2(out->lw_dn, jcol, jl) = tcc * s_dn + (1.0 - tcc) * A2(out->lw_dn_clear, jcol, jl);
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = tcc * fd[nl1 - ng + g] + (1.0 - tcc) * fd_clear[nl1 - ng + g];
+      if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = tcc * fu[g] + (1.0 - tcc) * fu_clear[g];
+    }
+    if (cfg->do_lw_derivatives && out->lw_derivatives) {
+      lw_derivatives(ng, nlev, ncol, jcol, trans, fu + nl1 - ng, 0.0, 0, out->lw_derivatives);
+      if (tcc < 1.0 - cfg->cloud_fraction_threshold)
+        lw_derivatives(ng, nlev, ncol, jcol, trans_clear, fu_clear + nl1 - ng, 1.0 - tcc, 1, out->lw_derivatives);
+    }
+  } else {
+    for (int jl = 0; jl <= nlev; ++jl) {
+      if (out->lw_up) A2(out->lw_up, jcol, jl) = A2(out->lw_up_clear, jcol, jl);
+      if (out->lw_dn) A2(out->lw_dn, jcol, jl) = A2(out->lw_dn_clear, jcol, jl);
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = fd_clear[nl1 - ng + g];
+      if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = fu_clear[g];
+    }
+    if (cfg->do_lw_derivatives && out->lw_derivatives)
+      lw_derivatives(ng, nlev, ncol, jcol, trans_clear, fu_clear + nl1 - ng, 0.0, 0, out->lw_derivatives);
+  }
+  free(pool);
+}
+
+/* ----- SW: radiation_mcica_sw.F90:41-408 and radiation_cloudless_sw.F90 ----- */
+static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                      const ecrad_b200_inputs* in, ecrad_b200_outputs* out, const col_work* w, const double* frac) {
+  const int ng = NG_SW;
+  const size_t nl = (size_t)nlev * ng, nl1 = (size_t)(nlev + 1) * ng;
+  const double cos_sza = in->cos_sza[jcol];
+  if (!(cos_sza > 0.0)) {
+    for (int jl = 0; jl <= nlev; ++jl) {
+      if (out->sw_up) A2(out->sw_up, jcol, jl) = 0.0;
+      if (out->sw_dn) A2(out->sw_dn, jcol, jl) = 0.0;
+      if (out->sw_dn_direct) A2(out->sw_dn_direct, jcol, jl) = 0.0;
+      if (out->sw_up_clear) A2(out->sw_up_clear, jcol, jl) = 0.0;
+      if (out->sw_dn_clear) A2(out->sw_dn_clear, jcol, jl) = 0.0;
+      if (out->sw_dn_direct_clear) A2(out->sw_dn_direct_clear, jcol, jl) = 0.0;
+    }
+    double* gs[6] = {out->sw_dn_diffuse_surf_g, out->sw_dn_direct_surf_g, out->sw_up_toa_g,
+                     out->sw_dn_diffuse_surf_clear_g, out->sw_dn_direct_surf_clear_g, out->sw_up_toa_clear_g};
+    for (int k = 0; k < 6; ++k) if (gs[k]) for (int g = 0; g < ng; ++g) OUTG(gs[k], ng, g) = 0.0;
+    double* bs[3] = {out->sw_up_band, out->sw_dn_band, out->sw_dn_direct_band};
+    for (int k = 0; k < 3; ++k)
+      if (bs[k]) for (int jl = 0; jl <= nlev; ++jl) for (int b = 0; b < NB_SW; ++b) bs[k][((size_t)jl * ncol + jcol) * NB_SW + b] = 0.0;
+    return;
+  }
+  double* pool = (double*)malloc(sizeof(double) * (11 * nl + 3 * nl1 + 3 * ng));
+  double *ref_clear = pool, *trans_clear = ref_clear + nl, *ref = trans_clear + nl, *trans = ref + nl;
+  double *rdir_clear = trans + nl, *tdd_clear = rdir_clear + nl, *rdir = tdd_clear + nl, *tdd = rdir + nl;
+  double *tdir_clear = tdd + nl, *tdir = tdir_clear + nl, *od_scaling = tdir + nl;
+  double *fu = od_scaling + nl, *fdd = fu + nl1, *fdir = fdd + nl1;
+  double *od_total = fdir + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
+  double* gzero = (double*)calloc(nl, sizeof(double)); /* g_sw = 0 without aerosols, radiation_interface.F90:395 */
+  const int cloudless = (cfg->i_solver_sw == ECRAD_SOLVER_CLOUDLESS);
+  if (cloudless) {
+    for (int jl = 0; jl < nlev; ++jl)
+      orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, gzero,
+                                            ref_clear + (size_t)jl * ng, trans_clear + (size_t)jl * ng, rdir_clear + (size_t)jl * ng,
+                                            tdd_clear + (size_t)jl * ng, tdir_clear + (size_t)jl * ng);
+  } else {
+    orc_calc_ref_trans_sw(ng * nlev, cos_sza, w->od_sw, w->ssa_sw, gzero, ref_clear, trans_clear, rdir_clear, tdd_clear, tdir_clear);
+  }
+  orc_adding_ica_sw(ng, nlev, w->incoming_sw, w->alb_diff, w->alb_dir, cos_sza, ref_clear, trans_clear, rdir_clear, tdd_clear,
+                    tdir_clear, fu, fdd, fdir);
+  for (int jl = 0; jl <= nlev; ++jl) {
+    double s_up = 0.0, s_dd = 0.0, s_dir = 0.0;
+    for (int g = 0; g < ng; ++g) { s_up = s_up + fu[(size_t)jl * ng + g]; s_dd = s_dd + fdd[(size_t)jl * ng + g]; s_dir = s_dir + fdir[(size_t)jl * ng + g]; }
+    if (out->sw_up_clear) A2(out->sw_up_clear, jcol, jl) = s_up;
+    if (out->sw_dn_clear) A2(out->sw_dn_clear, jcol, jl) = s_dd + s_dir;
+    if (out->sw_dn_direct_clear) A2(out->sw_dn_direct_clear, jcol, jl) = s_dir;
+  }
+  for (int g = 0; g < ng; ++g) {
+    if (out->sw_dn_diffuse_surf_clear_g) OUTG(out->sw_dn_diffuse_surf_clear_g, ng, g) = fdd[nl1 - ng + g];
+    if (out->sw_dn_direct_surf_clear_g) OUTG(out->sw_dn_direct_surf_clear_g, ng, g) = fdir[nl1 - ng + g];
+    if (out->sw_up_toa_clear_g) OUTG(out->sw_up_toa_clear_g, ng, g) = fu[g];
+  }
+  if (cloudless) {
+    for (int jl = 0; jl <= nlev; ++jl) {
+      if (out->sw_up) A2(out->sw_up, jcol, jl) = A2(out->sw_up_clear, jcol, jl);
+      if (out->sw_dn) A2(out->sw_dn, jcol, jl) = A2(out->sw_dn_clear, jcol, jl);
+      if (out->sw_dn_direct) A2(out->sw_dn_direct, jcol, jl) = A2(out->sw_dn_direct_clear, jcol, jl);
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->sw_dn_diffuse_surf_g) OUTG(out->sw_dn_diffuse_surf_g, ng, g) = fdd[nl1 - ng + g];
+      if (out->sw_dn_direct_surf_g) OUTG(out->sw_dn_direct_surf_g, ng, g) = fdir[nl1 - ng + g];
+      if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = fu[g];
+    }
+    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fu, ncol, jcol, out->sw_up_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_direct_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdd, ncol, jcol, out->sw_dn_band, 1);
+    free(pool); free(gzero);
+    return;
+  }
+  double tcc;
+  double *fsd = (double*)malloc(sizeof(double) * (size_t)nlev * 2), *op = fsd + nlev;
+  for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
+  for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
+  orc_cloud_generator(t, ng, nlev, cfg->i_overlap_scheme, in->iseed[jcol], cfg->cloud_fraction_threshold, frac, op,
+                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, od_scaling, &tcc);
+  free(fsd);
+  if (out->cloud_cover_sw) out->cloud_cover_sw[jcol] = tcc;
+  if (tcc >= cfg->cloud_fraction_threshold) {
+    /* keep the clear-sky g-point surface/TOA fluxes before fu/fdd/fdir are overwritten */
+    double* keep = (double*)malloc(sizeof(double) * 3 * (size_t)ng);
+    for (int g = 0; g < ng; ++g) { keep[g] = fdd[nl1 - ng + g]; keep[ng + g] = fdir[nl1 - ng + g]; keep[2 * ng + g] = fu[g]; }
+    for (int jl = 0; jl < nlev; ++jl) {
+      if (frac[jl] >= cfg->cloud_fraction_threshold) {
+        for (int g = 0; g < ng; ++g) {
+          int jb = t->ngb_sw[g] - 16;
+          size_t i = (size_t)jl * ng + g;
+          double od_cloud_new = od_scaling[i] * w->od_sw_cloud[jl * NB_SW + jb];
+          od_total[g] = w->od_sw[i] + od_cloud_new;
+          ssa_total[g] = 0.0; g_total[g] = 0.0;
+          if (od_total[g] > 0.0) {
+            double scat_od = w->ssa_sw[i] * w->od_sw[i] + w->ssa_sw_cloud[jl * NB_SW + jb] * od_cloud_new;
+            ssa_total[g] = scat_od / od_total[g];
+            if (scat_od > 0.0)
+              g_total[g] = (gzero[i] * w->ssa_sw[i] * w->od_sw[i] + w->g_sw_cloud[jl * NB_SW + jb] * w->ssa_sw_cloud[jl * NB_SW + jb] * od_cloud_new) / scat_od;
+          }
+        }
+        orc_calc_ref_trans_sw(ng, cos_sza, od_total, ssa_total, g_total, ref + (size_t)jl * ng, trans + (size_t)jl * ng,
+                              rdir + (size_t)jl * ng, tdd + (size_t)jl * ng, tdir + (size_t)jl * ng);
+      } else {
+        for (int g = 0; g < ng; ++g) {
+          size_t i = (size_t)jl * ng + g;
+          ref[i] = ref_clear[i]; trans[i] = trans_clear[i]; rdir[i] = rdir_clear[i]; tdd[i] = tdd_clear[i]; tdir[i] = tdir_clear[i];
+        }
+      }
+    }
+    orc_adding_ica_sw(ng, nlev, w->incoming_sw, w->alb_diff, w->alb_dir, cos_sza, ref, trans, rdir, tdd, tdir, fu, fdd, fdir);
+    for (int jl = 0; jl <= nlev; ++jl) {
+      double s_up = 0.0, s_dd = 0.0, s_dir = 0.0;
+      for (int g = 0; g < ng; ++g) { s_up = s_up + fu[(size_t)jl * ng + g]; s_dd = s_dd + fdd[(size_t)jl * ng + g]; s_dir = s_dir + fdir[(size_t)jl * ng + g]; }
+      if (out->sw_up) A2(out->sw_up, jcol, jl) = tcc * s_up + (1.0 - tcc) * A2(out->sw_up_clear, jcol, jl);
+      if (out->sw_dn) A2(out->sw_dn, jcol, jl) = tcc * (s_dd + s_dir) + (1.0 - tcc) * A2(out->sw_dn_clear, jcol, jl);
+      if (out->sw_dn_direct) A2(out->sw_dn_direct, jcol, jl) = tcc * s_dir + (1.0 - tcc) * A2(out->sw_dn_direct_clear, jcol, jl);
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->sw_dn_diffuse_surf_g) OUTG(out->sw_dn_diffuse_surf_g, ng, g) = tcc * fdd[nl1 - ng + g] + (1.0 - tcc) * keep[g];
+      if (out->sw_dn_direct_surf_g) OUTG(out->sw_dn_direct_surf_g, ng, g) = tcc * fdir[nl1 - ng + g] + (1.0 - tcc) * keep[ng + g];
+      if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = tcc * fu[g] + (1.0 - tcc) * keep[2 * ng + g];
+    }
+    free(keep);
+  } else {
+    for (int jl = 0; jl <= nlev; ++jl) {
+      if (out->sw_up) A2(out->sw_up, jcol, jl) = A2(out->sw_up_clear, jcol, jl);
+      if (out->sw_dn) A2(out->sw_dn, jcol, jl) = A2(out->sw_dn_clear, jcol, jl);
+      if (out->sw_dn_direct) A2(out->sw_dn_direct, jcol, jl) = A2(out->sw_dn_direct_clear, jcol, jl);
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->sw_dn_diffuse_surf_g) OUTG(out->sw_dn_diffuse_surf_g, ng, g) = fdd[nl1 - ng + g];
+      if (out->sw_dn_direct_surf_g) OUTG(out->sw_dn_direct_surf_g, ng, g) = fdir[nl1 - ng + g];
+      if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = fu[g];
+    }
+  }
+  free(pool); free(gzero);
+}
+
+/* radiation_flux.F90:397-577 calc_surface_spectral (paths used by the test namelists) */
+static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, int jcol, ecrad_b200_outputs* out) {
+  if (cfg->do_sw && cfg->do_surface_sw_spectral_flux && out->sw_dn_surf_band && out->sw_dn_direct_surf_band &&
+      out->sw_dn_diffuse_surf_g && out->sw_dn_direct_surf_g) {
+    for (int pass = 0; pass < 2; ++pass) {
+      double *dirb = pass ? out->sw_dn_direct_surf_clear_band : out->sw_dn_direct_surf_band;
+      double *totb = pass ? out->sw_dn_surf_clear_band : out->sw_dn_surf_band;
+      const double *dirg = pass ? out->sw_dn_direct_surf_clear_g : out->sw_dn_direct_surf_g;
+      const double *difg = pass ? out->sw_dn_diffuse_surf_clear_g : out->sw_dn_diffuse_surf_g;
+      if (!dirb || !totb || !dirg || !difg || (pass && !cfg->do_clear)) continue;
+      double* db = dirb + (size_t)jcol * NB_SW; double* tb = totb + (size_t)jcol * NB_SW;
+      for (int b = 0; b < NB_SW; ++b) { db[b] = 0.0; tb[b] = 0.0; }
+      for (int g = 0; g < NG_SW; ++g) db[t->ngb_sw[g] - 16] = db[t->ngb_sw[g] - 16] + dirg[(size_t)jcol * NG_SW + g];
+      for (int g = 0; g < NG_SW; ++g) tb[t->ngb_sw[g] - 16] = tb[t->ngb_sw[g] - 16] + difg[(size_t)jcol * NG_SW + g];
+      for (int b = 0; b < NB_SW; ++b) tb[b] = tb[b] + db[b];
+    }
+  }
+  if (cfg->do_sw && cfg->do_canopy_fluxes_sw && out->sw_dn_diffuse_surf_canopy && out->sw_dn_direct_surf_canopy &&
+      out->sw_dn_surf_band && !cfg->do_nearest_spectral_sw_albedo && t->sw_albedo_weights) {
+    const int nalb = cfg->n_albedo_sw;
+    double* dif = out->sw_dn_diffuse_surf_canopy + (size_t)jcol * nalb;
+    double* dir = out->sw_dn_direct_surf_canopy + (size_t)jcol * nalb;
+    for (int a = 0; a < nalb; ++a) { dif[a] = 0.0; dir[a] = 0.0; }
+    for (int jb = 0; jb < NB_SW; ++jb)
+      for (int a = 0; a < nalb; ++a) {
+        double wgt = t->sw_albedo_weights[(size_t)jb * nalb + a];
+        if (wgt != 0.0) {
+          dif[a] = dif[a] + wgt * out->sw_dn_surf_band[(size_t)jcol * NB_SW + jb];
+          dir[a] = dir[a] + wgt * out->sw_dn_direct_surf_band[(size_t)jcol * NB_SW + jb];
+        }
+      }
+    for (int a = 0; a < nalb; ++a) dif[a] = dif[a] - dir[a];
+  }
+  if (cfg->do_lw && cfg->do_canopy_fluxes_lw && out->lw_dn_surf_canopy && out->lw_dn_surf_g &&
+      cfg->do_nearest_spectral_lw_emiss && t->i_emiss_from_band_lw) {
+    const int ne = cfg->n_canopy_bands_lw;
+    double* c = out->lw_dn_surf_canopy + (size_t)jcol * ne;
+    for (int a = 0; a < ne; ++a) c[a] = 0.0;
+    for (int g = 0; g < NG_LW; ++g) {
+      int a = t->i_emiss_from_band_lw[t->ngb_lw[g] - 1] - 1;
+      c[a] = c[a] + out->lw_dn_surf_g[(size_t)jcol * NG_LW + g];
+    }
+  }
+}
+
+static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                            const ecrad_b200_inputs* in, ecrad_b200_outputs* out) {
+  col_work w;
+  size_t n = (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 2 * (size_t)nlev * NG_SW + 3 * NG_SW +
+             3 * (size_t)nlev * NB_LW + 3 * (size_t)nlev * NB_SW + 6 * (size_t)nlev;
+  w.w = (double*)malloc(sizeof(double) * n);
+  double* p = w.w;
+  w.od_lw = p; p += (size_t)nlev * NG_LW;  w.planck_hl = p; p += (size_t)(nlev + 1) * NG_LW;
+  w.lw_emission = p; p += NG_LW;           w.lw_albedo = p; p += NG_LW;
+  w.od_sw = p; p += (size_t)nlev * NG_SW;  w.ssa_sw = p; p += (size_t)nlev * NG_SW;
+  w.incoming_sw = p; p += NG_SW; w.alb_dir = p; p += NG_SW; w.alb_diff = p; p += NG_SW;
+  w.od_lw_cloud = p; p += (size_t)nlev * NB_LW; w.ssa_lw_cloud = p; p += (size_t)nlev * NB_LW; w.g_lw_cloud = p; p += (size_t)nlev * NB_LW;
+  w.od_sw_cloud = p; p += (size_t)nlev * NB_SW; w.ssa_sw_cloud = p; p += (size_t)nlev * NB_SW; w.g_sw_cloud = p; p += (size_t)nlev * NB_SW;
+  double *frac = p, *qliq = frac + nlev, *qice = qliq + nlev, *rel = qice + nlev, *rei = rel + nlev, *phl = rei + nlev;
+  double* phl_full = (double*)malloc(sizeof(double) * (size_t)(nlev + 1));
+  (void)phl;
+  int rc = get_albedos(t, cfg, ncol, jcol, in, w.alb_dir, w.alb_diff, w.lw_albedo);
+  if (rc) { free(w.w); free(phl_full); return rc; }
+  gas_optics_column(t, cfg, ncol, nlev, jcol, in, w.lw_albedo, w.od_lw, w.planck_hl, w.lw_emission, w.od_sw, w.ssa_sw, w.incoming_sw);
+  for (int jl = 0; jl <= nlev; ++jl) phl_full[jl] = A2(in->pressure_hl, jcol, jl);
+  if (cfg->do_clouds) {
+    /* crop_cloud_fraction, radiation_cloud.F90:700-740 (mutates the caller's array) */
+    for (int jl = 0; jl < nlev; ++jl) {
+      double sum_mr = 0.0;
+      sum_mr = sum_mr + A2(in->q_liq, jcol, jl);
+      sum_mr = sum_mr + A2(in->q_ice, jcol, jl);
+      if (A2(in->cloud_fraction, jcol, jl) < cfg->cloud_fraction_threshold || sum_mr < cfg->cloud_mixing_ratio_threshold)
+        A2(in->cloud_fraction, jcol, jl) = 0.0;
+      frac[jl] = A2(in->cloud_fraction, jcol, jl);
+      qliq[jl] = A2(in->q_liq, jcol, jl); qice[jl] = A2(in->q_ice, jcol, jl);
+      rel[jl] = A2(in->re_liq, jcol, jl); rei[jl] = A2(in->re_ice, jcol, jl);
+    }
+    orc_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
+                     w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
+  } else {
+    for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
+  }
+  if (cfg->do_lw) solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac);
+  if (cfg->do_sw) solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac);
+  surface_spectral(t, cfg, jcol, out);
+  free(w.w); free(phl_full);
+  return 0;
+}
+
+int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
+                  const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
+  if (cfg->use_aerosols || cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator ||
+      cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP || cfg->do_sw_delta_scaling_with_gases) {
+    fprintf(stderr, "oracle: configuration outside the restated path\n");
+    return 10;
+  }
+  if (!out->lw_up_clear || !out->lw_dn_clear || !out->sw_up_clear || !out->sw_dn_clear || !out->sw_dn_direct_clear) {
+    fprintf(stderr, "oracle: clear-sky flux outputs are required (do_clear)\n");
+    return 11;
+  }
+  int err = 0;
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(| : err)
+#endif
+  for (int jcol = istartcol - 1; jcol < iendcol; ++jcol) err |= radiation_column(t, cfg, ncol, nlev, jcol, in, out);
+  (void)nthreads;
+  return err;
+}

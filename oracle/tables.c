@@ -1,0 +1,119 @@
+/* tables.c -- loader for the "ETB1" table blob (format: ecrad_b200/tables.py).  Oracle = test infrastructure.
+ * The arrays are what setup_radiation leaves in module storage (radiation_ifs_rrtm.F90:34-213 setup_gas_optics,
+ * ifsrrtm/yoerrta*.F90, yoesrta*.F90); indices below use the Fortran shapes. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "oracle.h"
+
+typedef struct { char name[48]; int32_t dtype; int32_t ndim; int64_t dims[4]; int64_t offset; } etb_entry;
+
+const orc_array* orc_find(const orc_tables* t, const char* name) {
+  for (int i = 0; i < t->n; ++i) if (!strcmp(t->arr[i].name, name)) return &t->arr[i];
+  return NULL;
+}
+
+int orc_tables_add(orc_tables* t, const char* name, int dtype, int ndim, const int64_t* dims, const void* data) {
+  t->arr = (orc_array*)realloc(t->arr, sizeof(orc_array) * (size_t)(t->n + 1));
+  orc_array* a = &t->arr[t->n++];
+  memset(a, 0, sizeof(*a));
+  strncpy(a->name, name, 47);
+  a->dtype = dtype; a->ndim = ndim;
+  for (int i = 0; i < 4; ++i) a->dims[i] = i < ndim ? dims[i] : 1;
+  a->data = data;
+  return 0;
+}
+
+static const double* D(const orc_tables* t, const char* fmt, int b) {
+  char nm[64]; snprintf(nm, sizeof nm, fmt, b);
+  const orc_array* a = orc_find(t, nm);
+  return a ? (const double*)a->data : NULL;
+}
+static const double* Dreq(const orc_tables* t, const char* nm, int* err) {
+  const orc_array* a = orc_find(t, nm);
+  if (!a) { fprintf(stderr, "oracle: missing table %s\n", nm); *err = 1; return NULL; }
+  return (const double*)a->data;
+}
+
+int orc_tables_resolve(orc_tables* t) {
+  int err = 0;
+  for (int b = 1; b <= 16; ++b) {
+    t->absa_lw[b] = D(t, "lw%d_ABSA", b);  t->absb_lw[b] = D(t, "lw%d_ABSB", b);
+    t->selfref_lw[b] = D(t, "lw%d_SELFREF", b); t->forref_lw[b] = D(t, "lw%d_FORREF", b);
+    t->fracrefa_lw[b] = D(t, "lw%d_FRACREFA", b); t->fracrefb_lw[b] = D(t, "lw%d_FRACREFB", b);
+  }
+  t->ka_mn2_1 = Dreq(t, "lw1_KA_MN2", &err);   t->kb_mn2_1 = Dreq(t, "lw1_KB_MN2", &err);
+  t->ka_mn2o_3 = Dreq(t, "lw3_KA_MN2O", &err); t->kb_mn2o_3 = Dreq(t, "lw3_KB_MN2O", &err);
+  t->ka_mo3_5 = Dreq(t, "lw5_KA_MO3", &err);   t->ccl4_5 = Dreq(t, "lw5_CCL4", &err);
+  t->cfc11adj_6 = Dreq(t, "lw6_CFC11ADJ", &err); t->cfc12_6 = Dreq(t, "lw6_CFC12", &err);
+  t->ka_mco2_6 = Dreq(t, "lw6_KA_MCO2", &err);
+  t->ka_mco2_7 = Dreq(t, "lw7_KA_MCO2", &err); t->kb_mco2_7 = Dreq(t, "lw7_KB_MCO2", &err);
+  t->ka_mco2_8 = Dreq(t, "lw8_KA_MCO2", &err); t->kb_mco2_8 = Dreq(t, "lw8_KB_MCO2", &err);
+  t->ka_mn2o_8 = Dreq(t, "lw8_KA_MN2O", &err); t->kb_mn2o_8 = Dreq(t, "lw8_KB_MN2O", &err);
+  t->ka_mo3_8 = Dreq(t, "lw8_KA_MO3", &err);   t->cfc12_8 = Dreq(t, "lw8_CFC12", &err);
+  t->cfc22adj_8 = Dreq(t, "lw8_CFC22ADJ", &err);
+  t->ka_mn2o_9 = Dreq(t, "lw9_KA_MN2O", &err); t->kb_mn2o_9 = Dreq(t, "lw9_KB_MN2O", &err);
+  t->ka_mo2_11 = Dreq(t, "lw11_KA_MO2", &err); t->kb_mo2_11 = Dreq(t, "lw11_KB_MO2", &err);
+  t->ka_mco2_13 = Dreq(t, "lw13_KA_MCO2", &err); t->ka_mco_13 = Dreq(t, "lw13_KA_MCO", &err);
+  t->kb_mo3_13 = Dreq(t, "lw13_KB_MO3", &err); t->ka_mn2_15 = Dreq(t, "lw15_KA_MN2", &err);
+  t->totplnk = Dreq(t, "lw_TOTPLNK", &err); t->delwave = Dreq(t, "lw_DELWAVE", &err);
+  t->preflog_lw = Dreq(t, "lw_PREFLOG", &err); t->tref_lw = Dreq(t, "lw_TREF", &err);
+  t->chi_mls = Dreq(t, "lw_CHI_MLS", &err);
+  t->ngb_lw = (const int32_t*)Dreq(t, "lw_NGB", &err); t->ngc_lw = (const int32_t*)Dreq(t, "lw_NGC", &err);
+  for (int b = 16; b <= 29; ++b) {
+    t->absa_sw[b] = D(t, "sw%d_ABSA", b); t->absb_sw[b] = D(t, "sw%d_ABSB", b);
+    t->selfref_sw[b] = D(t, "sw%d_SELFREFC", b); t->forref_sw[b] = D(t, "sw%d_FORREFC", b);
+    t->sfluxref_sw[b] = D(t, "sw%d_SFLUXREFC", b);
+    t->rayl_sw[b] = D(t, "sw%d_RAYL", b); t->raylc_sw[b] = D(t, "sw%d_RAYLC", b);
+    char nm[64]; snprintf(nm, sizeof nm, "sw%d_FORREFC", b);
+    const orc_array* a = orc_find(t, nm); t->nfor_sw[b] = a ? (int)a->dims[0] : 0;
+    const double* s = D(t, b == 16 ? "sw%d_STRRAT1" : "sw%d_STRRAT", b); t->strrat_sw[b] = s ? s[0] : 0.0;
+    snprintf(nm, sizeof nm, "sw%d_LAYREFFR", b);
+    a = orc_find(t, nm); t->layreffr_sw[b] = a ? ((const int32_t*)a->data)[0] : 0;
+  }
+  t->absch4_20 = Dreq(t, "sw20_ABSCH4C", &err);
+  t->abso3a_24 = Dreq(t, "sw24_ABSO3AC", &err); t->abso3b_24 = Dreq(t, "sw24_ABSO3BC", &err);
+  t->raylac_24 = Dreq(t, "sw24_RAYLAC", &err);  t->raylbc_24 = Dreq(t, "sw24_RAYLBC", &err);
+  t->abso3a_25 = Dreq(t, "sw25_ABSO3AC", &err); t->abso3b_25 = Dreq(t, "sw25_ABSO3BC", &err);
+  t->absco2_29 = Dreq(t, "sw29_ABSCO2C", &err); t->absh2o_29 = Dreq(t, "sw29_ABSH2OC", &err);
+  { const double* s = Dreq(t, "sw23_GIVFAC", &err); t->givfac_23 = s ? s[0] : 0; }
+  { const double* s = Dreq(t, "sw27_SCALEKUR", &err); t->scalekur_27 = s ? s[0] : 0; }
+  t->preflog_sw = Dreq(t, "sw_PREFLOG", &err); t->tref_sw = Dreq(t, "sw_TREF", &err);
+  t->ngb_sw = (const int32_t*)Dreq(t, "sw_NGBSW", &err); t->ngc_sw = (const int32_t*)Dreq(t, "sw_NGC", &err);
+  t->liq_coeff_lw = Dreq(t, "liq_coeff_lw", &err); t->liq_coeff_sw = Dreq(t, "liq_coeff_sw", &err);
+  t->ice_coeff_lw = Dreq(t, "ice_coeff_lw", &err); t->ice_coeff_sw = Dreq(t, "ice_coeff_sw", &err);
+  t->pdf_val = Dreq(t, "pdf_val", &err);
+  const orc_array* pv = orc_find(t, "pdf_val");
+  const double* fsd = Dreq(t, "pdf_fsd", &err);
+  if (pv && fsd) {
+    /* radiation_pdf_sampler.F90:83-93 */
+    t->pdf_ncdf = (int)pv->dims[0]; t->pdf_nfsd = (int)pv->dims[1];
+    t->pdf_fsd1 = fsd[0]; t->pdf_inv_fsd_interval = 1.0 / (fsd[1] - fsd[0]);
+  }
+  const orc_array* w = orc_find(t, "sw_albedo_weights");
+  t->sw_albedo_weights = w ? (const double*)w->data : NULL;
+  const orc_array* e = orc_find(t, "i_emiss_from_band_lw");
+  t->i_emiss_from_band_lw = e ? (const int32_t*)e->data : NULL;
+  return err;
+}
+
+orc_tables* orc_tables_load(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "oracle: cannot open %s\n", path); return NULL; }
+  fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+  char* buf = (char*)malloc((size_t)sz);
+  if (fread(buf, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(buf); return NULL; }
+  fclose(f);
+  if (memcmp(buf, "ETB1", 4)) { free(buf); fprintf(stderr, "oracle: %s is not ETB1\n", path); return NULL; }
+  uint32_t n; memcpy(&n, buf + 4, 4);
+  orc_tables* t = (orc_tables*)calloc(1, sizeof(orc_tables));
+  t->blob = buf;
+  const etb_entry* e = (const etb_entry*)(buf + 8);
+  for (uint32_t i = 0; i < n; ++i) orc_tables_add(t, e[i].name, e[i].dtype, e[i].ndim, e[i].dims, buf + e[i].offset);
+  return t;
+}
+
+void orc_tables_free(orc_tables* t) {
+  if (!t) return;
+  free(t->arr); free(t->blob); free(t);
+}

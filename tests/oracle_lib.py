@@ -1,0 +1,80 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so).  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ecrad_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+TABLES = os.path.join(ROOT, "ecrad_b200", "data", "rrtmg_tables.bin")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+    return os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+class Oracle:
+    def __init__(self, config):
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.orc_tables_load.restype = C.c_void_p
+        L.orc_tables_load.argtypes = [C.c_char_p]
+        L.orc_tables_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
+        L.orc_tables_resolve.argtypes = [C.c_void_p]
+        L.orc_tables_free.argtypes = [C.c_void_p]
+        L.orc_radiation.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_int]
+        L.orc_gas_optics_column.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(abi.Inputs)] + [abi.c_dp] * 6
+        self.config = config
+        self.cfg = config.to_struct()
+        self.t = L.orc_tables_load(TABLES.encode())
+        if not self.t:
+            raise RuntimeError("oracle: cannot load " + TABLES)
+        self._keep = []
+        for nm, arr in config.derived.items():
+            a = np.asfortranarray(arr)
+            code = 1 if a.dtype.kind in "iu" else 0
+            a = a.astype(np.int32 if code else np.float64, order="F")
+            self._keep.append(a)
+            dims = (C.c_int64 * 4)(*(list(a.shape) + [1] * (4 - a.ndim)))
+            L.orc_tables_add(self.t, nm.encode(), code, a.ndim, dims, a.ctypes.data_as(C.c_void_p))
+        if L.orc_tables_resolve(self.t):
+            raise RuntimeError("oracle: table blob incomplete")
+
+    def radiation(self, inputs, ncol, nlev, istartcol=1, iendcol=None, nthreads=0, spectral_profiles=False):
+        """inputs: dict from ecrad_b200.inputs.to_radiation_inputs (cloud_fraction is modified in place)."""
+        iendcol = ncol if iendcol is None else iendcol
+        keep, ist = abi.make_inputs(inputs, inputs["solar_irradiance"])
+        outs, ost = abi.alloc_outputs(ncol, nlev, self.cfg, spectral_profiles=spectral_profiles)
+        rc = self.lib.orc_radiation(self.t, C.byref(self.cfg), ncol, nlev, istartcol, iendcol, C.byref(ist), C.byref(ost), nthreads)
+        if rc:
+            raise RuntimeError(f"oracle radiation failed rc={rc}")
+        outs["cloud_fraction"] = keep["cloud_fraction"]
+        return outs
+
+    def gas_optics_column(self, inputs, ncol, nlev, jcol):
+        keep, ist = abi.make_inputs(inputs, inputs["solar_irradiance"])
+        od_lw = np.zeros((nlev, 140)); planck = np.zeros((nlev + 1, 140)); emis = np.zeros(140)
+        od_sw = np.zeros((nlev, 112)); ssa_sw = np.zeros((nlev, 112)); inc = np.zeros(112)
+        p = lambda a: a.ctypes.data_as(abi.c_dp)  # noqa: E731
+        rc = self.lib.orc_gas_optics_column(self.t, C.byref(self.cfg), ncol, nlev, jcol, C.byref(ist),
+                                            p(od_lw), p(planck), p(emis), p(od_sw), p(ssa_sw), p(inc))
+        if rc:
+            raise RuntimeError(f"oracle gas optics failed rc={rc}")
+        return dict(od_lw=od_lw, planck_hl=planck, lw_emission=emis, od_sw=od_sw, ssa_sw=ssa_sw, incoming_sw=inc)
+
+    def __del__(self):
+        try:
+            self.lib.orc_tables_free(self.t)
+        except Exception:
+            pass
