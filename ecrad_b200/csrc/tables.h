@@ -1,0 +1,215 @@
+// tables.h -- host-side named-array directory (what setup_radiation leaves in Fortran module storage) and the
+// packer that turns it into the GPU layout: per band one table of rows, g-point fastest (the transpose of the
+// reference's ABSA(row, ig) layout, so that lanes = g-points read contiguous memory).
+//
+// Host code only (runs once in ecrad_b200_setup).  No device code here.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "cloud_core.h"
+#include "gas_core.h"
+
+struct ecrad_b200_tables {
+  struct Arr { int dtype; int ndim; int64_t dims[4]; std::vector<char> data; };
+  std::map<std::string, Arr> a;
+
+  int add(const char* name, int dtype, int ndim, const int64_t* dims, const void* data) {
+    if (!name || ndim < 1 || ndim > 4 || (dtype != 0 && dtype != 1) || !data) return 1;
+    Arr x; x.dtype = dtype; x.ndim = ndim;
+    size_t n = 1;
+    for (int i = 0; i < 4; ++i) { x.dims[i] = i < ndim ? dims[i] : 1; n *= (size_t)x.dims[i]; }
+    x.data.assign((const char*)data, (const char*)data + n * (dtype == 0 ? 8 : 4));
+    a[name] = std::move(x);
+    return 0;
+  }
+  // "ETB1" blob written by tools/extract_rrtmg_tables.py (ecrad_b200/tables.py)
+  int load_file(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return 1;
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz);
+    if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return 2; }
+    fclose(f);
+    if (sz < 8 || memcmp(buf.data(), "ETB1", 4)) return 3;
+    uint32_t n; memcpy(&n, buf.data() + 4, 4);
+    struct Entry { char name[48]; int32_t dtype, ndim; int64_t dims[4]; int64_t offset; };
+    static_assert(sizeof(Entry) == 96, "ETB1 entry layout");
+    for (uint32_t i = 0; i < n; ++i) {
+      Entry e; memcpy(&e, buf.data() + 8 + (size_t)i * sizeof(Entry), sizeof(Entry));
+      char nm[49]; memcpy(nm, e.name, 48); nm[48] = 0;
+      if (add(nm, e.dtype, e.ndim, e.dims, buf.data() + e.offset)) return 4;
+    }
+    return 0;
+  }
+  const Arr* find(const std::string& n) const { auto it = a.find(n); return it == a.end() ? nullptr : &it->second; }
+  const Arr& req(const std::string& n) const {
+    const Arr* x = find(n);
+    if (!x) throw std::runtime_error("table '" + n + "' missing");
+    return *x;
+  }
+  const double* d(const std::string& n) const { const Arr& x = req(n); if (x.dtype != 0) throw std::runtime_error(n + ": not float64"); return (const double*)x.data.data(); }
+  const int32_t* i(const std::string& n) const { const Arr& x = req(n); if (x.dtype != 1) throw std::runtime_error(n + ": not int32"); return (const int32_t*)x.data.data(); }
+};
+
+namespace ecb {
+
+struct PackedTables {
+  GasMeta meta;
+  std::vector<double> lwtab, swtab;   // packed band tables
+  CloudMeta cloud;
+  std::vector<double> pdf_val;        // (ncdf, nfsd) Fortran order, as the reference stores it
+  std::vector<double> sw_albedo_weights;  // (n_albedo_sw, 14)
+  std::vector<int32_t> i_emiss_from_band_lw;  // (16) 1-based
+  int n_albedo_sw = 0;
+};
+
+namespace detail {
+struct BandPacker {
+  const ecrad_b200_tables& T;
+  std::vector<double>& tab;
+  BandMeta& B;
+  std::string prefix;
+  // Append `rows` rows of B.ng values; returns element offset of the first row.
+  int reserve(int rows) { int off = (int)tab.size(); tab.resize(tab.size() + (size_t)rows * B.ng, 0.0); return off; }
+  // array stored (rows..., ng) with rows fastest -> transpose
+  int rows_fast(const std::string& name) {
+    const auto& x = T.req(prefix + name);
+    size_t total = 1; for (int k = 0; k < x.ndim; ++k) total *= (size_t)x.dims[k];
+    if (x.dims[x.ndim - 1] != B.ng) throw std::runtime_error(prefix + name + ": last dim != ng");
+    int rows = (int)(total / B.ng);
+    int off = reserve(rows);
+    const double* s = (const double*)x.data.data();
+    for (int g = 0; g < B.ng; ++g) for (int r = 0; r < rows; ++r) tab[(size_t)off + (size_t)r * B.ng + g] = s[(size_t)g * rows + r];
+    return off;
+  }
+  // array stored (ng, rows) or (ng) -> as is
+  int g_fast(const std::string& name) {
+    const auto& x = T.req(prefix + name);
+    size_t total = 1; for (int k = 0; k < x.ndim; ++k) total *= (size_t)x.dims[k];
+    if (x.dims[0] != B.ng) throw std::runtime_error(prefix + name + ": first dim != ng");
+    int rows = (int)(total / B.ng);
+    int off = reserve(rows);
+    memcpy(&tab[off], x.data.data(), total * 8);
+    return off;
+  }
+  bool has(const std::string& name) const { return T.find(prefix + name) != nullptr; }
+};
+}  // namespace detail
+
+inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
+  GasMeta& M = P.meta;
+  memset(&M, 0, sizeof(M));
+  auto copy = [&](double* dst, const char* name, size_t n) {
+    const auto& x = T.req(name);
+    if (x.data.size() != n * 8) throw std::runtime_error(std::string(name) + ": unexpected size");
+    memcpy(dst, x.data.data(), n * 8);
+  };
+  copy(M.preflog_lw, "lw_PREFLOG", 59); copy(M.tref_lw, "lw_TREF", 59); copy(M.chi_mls, "lw_CHI_MLS", 7 * 59);
+  copy(M.preflog_sw, "sw_PREFLOG", 59); copy(M.tref_sw, "sw_TREF", 59);
+  copy(M.totplnk, "lw_TOTPLNK", 181 * 16); copy(M.delwave, "lw_DELWAVE", 16);
+  const int32_t* ngc_lw = T.i("lw_NGC");
+  const int32_t* ngc_sw = T.i("sw_NGC");
+  const int32_t* ngb_lw = T.i("lw_NGB");
+  const int32_t* ngb_sw = T.i("sw_NGBSW");
+  for (int g = 0; g < NG_LW; ++g) M.band_of_g_lw[g] = ngb_lw[g] - 1;
+  for (int g = 0; g < NG_SW; ++g) M.band_of_g_sw[g] = ngb_sw[g] - 16;
+
+  // ---- LW bands ----
+  static const char* lw_minor[16][5] = {
+      {"KA_MN2", "KB_MN2", 0, 0, 0}, {0, 0, 0, 0, 0}, {"KA_MN2O", "KB_MN2O", 0, 0, 0}, {0, 0, 0, 0, 0},
+      {"KA_MO3", 0, 0, 0, 0}, {"KA_MCO2", 0, 0, 0, 0}, {"KA_MCO2", "KB_MCO2", 0, 0, 0},
+      {"KA_MCO2", "KA_MO3", "KA_MN2O", "KB_MCO2", "KB_MN2O"}, {"KA_MN2O", "KB_MN2O", 0, 0, 0}, {0, 0, 0, 0, 0},
+      {"KA_MO2", "KB_MO2", 0, 0, 0}, {0, 0, 0, 0, 0}, {"KA_MCO2", 0, "KB_MO3", 0, 0}, {0, 0, 0, 0, 0},
+      {"KA_MN2", 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  static const char* lw_const[16][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {"CCL4", 0}, {"CFC11ADJ", "CFC12"}, {0, 0},
+                                        {"CFC12", "CFC22ADJ"}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  int g0 = 0;
+  for (int b = 0; b < NB_LW; ++b) {
+    BandMeta& B = M.lw[b];
+    B.ng = ngc_lw[b]; B.g0 = g0; g0 += B.ng;
+    for (int s = 0; s < 16; ++s) B.sec[s] = -1;
+    detail::BandPacker pk{T, P.lwtab, B, "lw" + std::to_string(b + 1) + "_"};
+    if (pk.has("ABSA")) B.sec[L_ABSA] = pk.rows_fast("ABSA");
+    if (pk.has("ABSB")) B.sec[L_ABSB] = pk.rows_fast("ABSB");
+    B.sec[L_SELF] = pk.rows_fast("SELFREF");
+    B.sec[L_FOR] = pk.rows_fast("FORREF");
+    B.sec[L_FRACA] = pk.g_fast("FRACREFA");
+    if (pk.has("FRACREFB")) B.sec[L_FRACB] = pk.g_fast("FRACREFB");
+    for (int m = 0; m < 5; ++m) if (lw_minor[b][m]) B.sec[L_M0 + m] = pk.rows_fast(lw_minor[b][m]);
+    for (int m = 0; m < 2; ++m) if (lw_const[b][m]) B.sec[L_C0 + m] = pk.g_fast(lw_const[b][m]);
+    if (b + 1 == 4 || b + 1 == 7) {
+      int off = pk.reserve(1);
+      for (int g = 0; g < B.ng; ++g) P.lwtab[off + g] = 1.0;
+      if (b + 1 == 4) {  // rrtm_taumol4.F90:283-289 (single-precision literals)
+        static const float f[7] = {0.92f, 0.88f, 1.07f, 1.1f, 0.99f, 0.88f, 0.943f};
+        for (int k = 0; k < 7; ++k) P.lwtab[off + 7 + k] = (double)f[k];
+      } else {           // rrtm_taumol7.F90 (double-precision literals)
+        static const double f[6] = {0.92, 0.88, 1.07, 1.1, 0.99, 0.855};
+        for (int k = 0; k < 6; ++k) P.lwtab[off + 5 + k] = f[k];
+      }
+      B.sec[L_POST] = off;
+    }
+  }
+  if (g0 != NG_LW) throw std::runtime_error("lw_NGC does not sum to 140");
+
+  // ---- SW bands ----
+  g0 = 0;
+  for (int b = 0; b < NB_SW; ++b) {
+    BandMeta& B = M.sw[b];
+    const int jb = b + 16;
+    B.ng = ngc_sw[b]; B.g0 = g0; g0 += B.ng;
+    for (int s = 0; s < 16; ++s) B.sec[s] = -1;
+    detail::BandPacker pk{T, P.swtab, B, "sw" + std::to_string(jb) + "_"};
+    if (pk.has("ABSA")) B.sec[S_ABSA] = pk.rows_fast("ABSA");
+    if (pk.has("ABSB")) B.sec[S_ABSB] = pk.rows_fast("ABSB");
+    if (pk.has("SELFREFC")) B.sec[S_SELF] = pk.rows_fast("SELFREFC");
+    if (pk.has("FORREFC")) { B.sec[S_FOR] = pk.rows_fast("FORREFC"); M.nfor_sw[b] = (int)T.req(pk.prefix + "FORREFC").dims[0]; }
+    B.sec[S_SFLUX] = pk.g_fast("SFLUXREFC");
+    if (pk.has("RAYLC")) B.sec[S_RAYA] = pk.g_fast("RAYLC");
+    if (pk.has("RAYLAC")) B.sec[S_RAYA] = pk.g_fast("RAYLAC");
+    if (pk.has("RAYLBC")) B.sec[S_RAYB] = pk.g_fast("RAYLBC");
+    if (jb == 20) B.sec[S_X0] = pk.g_fast("ABSCH4C");
+    if (jb == 24 || jb == 25) { B.sec[S_X0] = pk.g_fast("ABSO3AC"); B.sec[S_X1] = pk.g_fast("ABSO3BC"); }
+    if (jb == 29) { B.sec[S_X0] = pk.g_fast("ABSCO2C"); B.sec[S_X1] = pk.g_fast("ABSH2OC"); }
+    int off = pk.reserve(1);
+    for (int g = 0; g < B.ng; ++g) P.swtab[off + g] = 1.0;
+    B.sec[S_ONES] = off;
+    const auto* sr = T.find(pk.prefix + (jb == 16 ? "STRRAT1" : "STRRAT"));
+    M.strrat_sw[b] = sr ? ((const double*)sr->data.data())[0] : 0.0;
+    const auto* rl = T.find(pk.prefix + "RAYL");
+    M.rayl_sw[b] = rl ? ((const double*)rl->data.data())[0] : 0.0;
+    const auto* lr = T.find(pk.prefix + "LAYREFFR");
+    M.layreffr_sw[b] = lr ? ((const int32_t*)lr->data.data())[0] : 0;
+  }
+  if (g0 != NG_SW) throw std::runtime_error("sw_NGC does not sum to 112");
+  M.givfac_23 = T.d("sw23_GIVFAC")[0];
+  M.scalekur_27 = T.d("sw27_SCALEKUR")[0];
+
+  // ---- cloud optics coefficients, PDF look-up table, surface mappings ----
+  CloudMeta& C = P.cloud;
+  memset(&C, 0, sizeof(C));
+  copy(C.liq_lw, "liq_coeff_lw", 16 * 16); copy(C.liq_sw, "liq_coeff_sw", 14 * 16);
+  copy(C.ice_lw, "ice_coeff_lw", 16 * 11); copy(C.ice_sw, "ice_coeff_sw", 14 * 10);
+  const auto& pv = T.req("pdf_val");
+  const double* fsd = T.d("pdf_fsd");
+  C.pdf_ncdf = (int)pv.dims[0]; C.pdf_nfsd = (int)pv.dims[1];
+  C.pdf_fsd1 = fsd[0]; C.pdf_inv_fsd_interval = 1.0 / (fsd[1] - fsd[0]);  // radiation_pdf_sampler.F90:83-93
+  P.pdf_val.assign((const double*)pv.data.data(), (const double*)pv.data.data() + (size_t)C.pdf_ncdf * C.pdf_nfsd);
+  if (const auto* w = T.find("sw_albedo_weights")) {
+    P.n_albedo_sw = (int)w->dims[0];
+    if (w->dims[1] != NB_SW) throw std::runtime_error("sw_albedo_weights: second dim != 14");
+    P.sw_albedo_weights.assign((const double*)w->data.data(), (const double*)w->data.data() + (size_t)P.n_albedo_sw * NB_SW);
+  }
+  if (const auto* e = T.find("i_emiss_from_band_lw")) {
+    P.i_emiss_from_band_lw.assign((const int32_t*)e->data.data(), (const int32_t*)e->data.data() + NB_LW);
+  }
+}
+
+}  // namespace ecb
