@@ -1,0 +1,459 @@
+// api.cu -- the C-ABI of libecrad_b200.so (include/ecrad_b200.h): table directory, setup, radiation (host and
+// device-resident entries), finalize.  Host orchestration only: tiling of the column range, H2D/D2H staging
+// pipelined against the kernels on three streams, kernel launches.  There is NO CPU compute path in here.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ecrad_b200.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+using namespace ecb;
+
+namespace {
+
+thread_local std::string g_last_error;  // errors without a handle (setup failures)
+
+struct Buf {   // grow-only device buffer
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { N_IN = 25, N_OUT = 35, N_STAGE = 5 };
+const char* kStageNames[N_STAGE] = {"gas_optics_lw", "gas_optics_sw", "cloud_optics_generator", "solver_lw", "solver_sw"};
+
+struct Slot {            // device staging of one tile's inputs and outputs
+  Buf in[N_IN], out[N_OUT];
+  cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+  bool used = false;
+};
+
+struct Handle {
+  ecrad_b200_config cfg;
+  DevCfg dcfg;
+  DevTables T;
+  std::vector<void*> table_allocs;
+  int device = 0;
+  int tile_cols = 4096;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  Slot slot[2];
+  Buf work[24];
+  Work w;
+  int w_cols = 0, w_nlev = 0;
+  std::mutex mu;
+  std::string err;
+  int64_t launches = 0;
+  std::vector<cudaEvent_t> ev;       // stage boundary events of the last call: (N_STAGE+1) per tile
+  int ev_tiles = 0;
+};
+
+int fail(Handle* h, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf;
+  g_last_error = buf;
+  return 1;
+}
+#define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <class Tp>
+int upload(Handle* h, const Tp* src, size_t n, const Tp** dst) {
+  void* p = nullptr;
+  CK(h, cudaMalloc(&p, n * sizeof(Tp)));
+  h->table_allocs.push_back(p);
+  CK(h, cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  *dst = (const Tp*)p;
+  return 0;
+}
+
+// Which solver / model combinations have kernels.
+int check_config(Handle* h, const ecrad_b200_config& c) {
+  if (c.struct_bytes != (int32_t)sizeof(ecrad_b200_config)) return fail(h, "ecrad_b200_config: struct_bytes mismatch (ABI)");
+  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS; };
+  if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw)))
+    return fail(h, "solver not available in this build (McICA and Cloudless are)");
+  if ((c.do_sw && c.i_gas_model_sw != ECRAD_GAS_IFSRRTMG) || (c.do_lw && c.i_gas_model_lw != ECRAD_GAS_IFSRRTMG))
+    return fail(h, "gas model not available in this build (RRTMG-IFS is)");
+  if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN)
+    return fail(h, "overlap scheme not available in this build (Exp-Ran and Max-Ran are)");
+  if (c.use_aerosols || c.do_lw_aerosol_scattering) return fail(h, "aerosols are not available in this build");
+  if (c.use_vectorizable_generator) return fail(h, "use_vectorizable_generator is not available in this build");
+  if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
+  if (c.do_nearest_spectral_sw_albedo || !c.do_nearest_spectral_lw_emiss) return fail(h, "albedo/emissivity mapping mode not available");
+  if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
+  return 0;
+}
+
+int ensure_work(Handle* h, int cols, int nlev) {
+  if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
+  if (nlev != h->w_nlev) h->w_cols = 0;
+  const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
+  const size_t spc = scratch_doubles_per_column(nlev);
+  const size_t sz[] = {
+      8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
+      8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
+      8 * nc * nl * 3 * NB_LW, 8 * nc * nl * 3 * NB_SW,                                      // cl_lw cl_sw
+      8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
+      8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
+      4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
+      8 * nc * spc};                                                                         // scratch
+  for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
+  Work& w = h->w;
+  w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
+  w.od_sw = (double*)h->work[4].p; w.ssa_sw = (double*)h->work[5].p; w.incoming = (double*)h->work[6].p;
+  w.cl_lw = (double*)h->work[7].p; w.cl_sw = (double*)h->work[8].p;
+  w.cum = (double*)h->work[9].p; w.pair = (double*)h->work[10].p; w.opi = (double*)h->work[11].p;
+  w.tcc = (double*)h->work[12].p; w.ibegin = (int*)h->work[13].p; w.iend = (int*)h->work[14].p; w.ict = (int*)h->work[15].p;
+  w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
+  w.scr = (double*)h->work[18].p; w.scr_per_col = spc;
+  h->w_cols = cols; h->w_nlev = nlev;
+  return 0;
+}
+
+// Kernels of one tile; `in`/`out` are device views whose column 0 is the first column of the tile.
+int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev) {
+  const DevCfg& c = h->dcfg;
+  int n = 0;
+  if (ev) CK(h, cudaEventRecord(ev[0], st));
+  if (c.do_lw) n += launch_gas_lw(h->T, c, in, h->w, nc, nlev, st);
+  if (ev) CK(h, cudaEventRecord(ev[1], st));
+  if (c.do_sw) n += launch_gas_sw(h->T, c, in, h->w, nc, nlev, st);
+  if (ev) CK(h, cudaEventRecord(ev[2], st));
+  if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w, nc, nlev, st);
+  if (ev) CK(h, cudaEventRecord(ev[3], st));
+  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w, nc, nlev, st);
+  if (ev) CK(h, cudaEventRecord(ev[4], st));
+  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w, nc, nlev, st);
+  if (ev) CK(h, cudaEventRecord(ev[5], st));
+  CK(h, cudaGetLastError());
+  h->launches += n;
+  return 0;
+}
+
+int ensure_events(Handle* h, int tiles) {
+  while ((int)h->ev.size() < tiles * (N_STAGE + 1)) {
+    cudaEvent_t e; CK(h, cudaEventCreate(&e)); h->ev.push_back(e);
+  }
+  h->ev_tiles = tiles;
+  return 0;
+}
+
+struct InDesc { const void* host; int rows; int elem; };   // column-fastest (ncol, rows)
+struct OutDesc { double* host; int kind; int rows; };      // kind 0: (ncol, rows) profile; 1: (rows, ncol) per-column block; 2: (nb, ncol, nlev+1)
+
+int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in, const ecrad_b200_outputs* out) {
+  if (!in || !out) return fail(h, "null inputs/outputs");
+  if (in->struct_bytes != (int32_t)sizeof(ecrad_b200_inputs) || out->struct_bytes != (int32_t)sizeof(ecrad_b200_outputs))
+    return fail(h, "ecrad_b200_inputs/outputs: struct_bytes mismatch (ABI)");
+  if (ncol < 1 || nlev < 2 || nlev > 190 || istartcol < 1 || iendcol > ncol || iendcol < istartcol)
+    return fail(h, "bad dimensions ncol=%d nlev=%d istartcol=%d iendcol=%d (nlev <= 190)", ncol, nlev, istartcol, iendcol);
+  const ecrad_b200_config& c = h->cfg;
+  if (!in->pressure_hl || !in->temperature_hl || !in->h2o_mmr || !in->co2_mmr || !in->o3_mmr || !in->n2o_mmr || !in->ch4_mmr ||
+      !in->cfc11_mmr || !in->cfc12_mmr || !in->hcfc22_mmr || !in->ccl4_mmr)
+    return fail(h, "missing thermodynamics/gas input");
+  if (c.do_lw && (!in->skin_temperature || !in->lw_emissivity)) return fail(h, "missing LW surface input");
+  if (c.do_sw && (!in->cos_sza || !in->sw_albedo)) return fail(h, "missing SW surface input");
+  if (c.do_clouds && (!in->cloud_fraction || !in->q_liq || !in->q_ice || !in->re_liq || !in->re_ice || !in->overlap_param ||
+                      !in->fractional_std || !in->iseed))
+    return fail(h, "missing cloud input");
+  if (c.do_lw && (!out->lw_up || !out->lw_dn)) return fail(h, "flux%%lw_up/lw_dn must be allocated");
+  if (c.do_sw && (!out->sw_up || !out->sw_dn)) return fail(h, "flux%%sw_up/sw_dn must be allocated");
+  return 0;
+}
+
+void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* in, const ecrad_b200_outputs* out, InDesc* id, OutDesc* od) {
+  const int nl = nlev, nl1 = nlev + 1;
+  const InDesc ins[N_IN] = {
+      {in->cos_sza, 1, 8}, {in->skin_temperature, 1, 8}, {in->sw_albedo, c.n_albedo_sw, 8}, {in->sw_albedo_direct, c.n_albedo_sw, 8},
+      {in->lw_emissivity, c.n_emiss_lw, 8}, {in->iseed, 1, 4}, {in->pressure_hl, nl1, 8}, {in->temperature_hl, nl1, 8},
+      {in->h2o_mmr, nl, 8}, {in->co2_mmr, nl, 8}, {in->ch4_mmr, nl, 8}, {in->n2o_mmr, nl, 8}, {in->cfc11_mmr, nl, 8},
+      {in->cfc12_mmr, nl, 8}, {in->hcfc22_mmr, nl, 8}, {in->ccl4_mmr, nl, 8}, {in->o3_mmr, nl, 8},
+      {in->cloud_fraction, nl, 8}, {in->q_liq, nl, 8}, {in->q_ice, nl, 8}, {in->re_liq, nl, 8}, {in->re_ice, nl, 8},
+      {in->overlap_param, nl - 1, 8}, {in->fractional_std, nl, 8}, {nullptr, 0, 8}};
+  for (int i = 0; i < N_IN; ++i) id[i] = ins[i];
+  const OutDesc outs[N_OUT] = {
+      {out->lw_up, 0, nl1}, {out->lw_dn, 0, nl1}, {out->lw_up_clear, 0, nl1}, {out->lw_dn_clear, 0, nl1},
+      {out->sw_up, 0, nl1}, {out->sw_dn, 0, nl1}, {out->sw_dn_direct, 0, nl1},
+      {out->sw_up_clear, 0, nl1}, {out->sw_dn_clear, 0, nl1}, {out->sw_dn_direct_clear, 0, nl1},
+      {out->lw_derivatives, 0, nl1}, {out->cloud_cover_lw, 1, 1}, {out->cloud_cover_sw, 1, 1},
+      {out->lw_dn_surf_g, 1, NG_LW}, {out->lw_dn_surf_clear_g, 1, NG_LW}, {out->lw_up_toa_g, 1, NG_LW}, {out->lw_up_toa_clear_g, 1, NG_LW},
+      {out->sw_dn_diffuse_surf_g, 1, NG_SW}, {out->sw_dn_direct_surf_g, 1, NG_SW}, {out->sw_dn_diffuse_surf_clear_g, 1, NG_SW},
+      {out->sw_dn_direct_surf_clear_g, 1, NG_SW}, {out->sw_up_toa_g, 1, NG_SW}, {out->sw_up_toa_clear_g, 1, NG_SW},
+      {out->sw_dn_surf_band, 1, NB_SW}, {out->sw_dn_direct_surf_band, 1, NB_SW}, {out->sw_dn_surf_clear_band, 1, NB_SW},
+      {out->sw_dn_direct_surf_clear_band, 1, NB_SW},
+      {out->sw_dn_diffuse_surf_canopy, 1, c.n_canopy_bands_sw}, {out->sw_dn_direct_surf_canopy, 1, c.n_canopy_bands_sw},
+      {out->lw_dn_surf_canopy, 1, c.n_canopy_bands_lw},
+      {out->lw_up_band, 2, NB_LW}, {out->lw_dn_band, 2, NB_LW}, {out->sw_up_band, 2, NB_SW}, {out->sw_dn_band, 2, NB_SW},
+      {out->sw_dn_direct_band, 2, NB_SW}};
+  for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
+}
+
+// Build the kernel-facing views from 25 input / 35 output base pointers (device) with leading dimension ld.
+void make_views(void* const* ip, void* const* op, int ld, double solar_irradiance, DevIn& di, DevOut& dout) {
+  di.cos_sza = (const double*)ip[0]; di.skin_t = (const double*)ip[1]; di.sw_albedo = (const double*)ip[2];
+  di.sw_albedo_direct = (const double*)ip[3]; di.lw_emissivity = (const double*)ip[4]; di.iseed = (const int32_t*)ip[5];
+  di.p_hl = (const double*)ip[6]; di.t_hl = (const double*)ip[7];
+  for (int k = 0; k < 9; ++k) di.gas[k] = (const double*)ip[8 + k];
+  di.frac = (double*)ip[17]; di.q_liq = (const double*)ip[18]; di.q_ice = (const double*)ip[19];
+  di.re_liq = (const double*)ip[20]; di.re_ice = (const double*)ip[21]; di.overlap = (const double*)ip[22]; di.fsd = (const double*)ip[23];
+  di.solar_irradiance = solar_irradiance; di.ld = ld;
+  double** o = (double**)&dout;
+  for (int k = 0; k < N_OUT; ++k) o[k] = (double*)op[k];
+  dout.ld = ld;
+}
+static_assert(sizeof(DevOut) >= N_OUT * sizeof(double*) + sizeof(int), "DevOut layout");
+static_assert(offsetof(DevOut, sw_dn_direct_band) == (N_OUT - 1) * sizeof(double*), "DevOut must list the 35 outputs in ABI order");
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+ecrad_b200_tables* ecrad_b200_tables_create(void) { return new (std::nothrow) ecrad_b200_tables(); }
+int ecrad_b200_tables_add(ecrad_b200_tables* t, const char* name, int dtype, int ndim, const int64_t* dims, const void* data) {
+  if (!t) return 1;
+  return t->add(name, dtype, ndim, dims, data);
+}
+int ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path) {
+  if (!t || !path) return 1;
+  int rc = t->load_file(path);
+  if (rc) fail(nullptr, "cannot load table blob '%s' (rc=%d)", path, rc);
+  return rc;
+}
+void ecrad_b200_tables_free(ecrad_b200_tables* t) { delete t; }
+
+const char* ecrad_b200_version(void) { return "ecrad_b200 0.1 (sm_100a; RRTMG + McICA/Cloudless; fp64)"; }
+const char* ecrad_b200_last_error(void* handle) {
+  if (handle) return ((Handle*)handle)->err.c_str();
+  return g_last_error.c_str();
+}
+const char* ecrad_b200_stage_name(int stage) { return (stage >= 0 && stage < N_STAGE) ? kStageNames[stage] : ""; }
+
+int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab, void** handle) {
+  if (handle) *handle = nullptr;
+  if (!cfg || !tab || !handle) return fail(nullptr, "ecrad_b200_setup: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail(nullptr, "ecrad_b200_setup: no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) return fail(nullptr, "out of memory");
+  h->cfg = *cfg;
+  if (check_config(h, *cfg)) { delete h; return 1; }
+  PackedTables P;
+  try { pack_tables(*tab, P); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
+  if (P.sw_albedo_weights.empty() || P.n_albedo_sw != cfg->n_albedo_sw || P.i_emiss_from_band_lw.empty()) {
+    fail(nullptr, "tables 'sw_albedo_weights' (n_albedo_sw x 14) and 'i_emiss_from_band_lw' (16) are required"); delete h; return 1;
+  }
+  cudaGetDevice(&h->device);
+  int rc = 0;
+  rc |= upload(h, &P.meta, 1, &h->T.meta);
+  rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
+  rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
+  rc |= upload(h, &P.cloud, 1, &h->T.cloud);
+  rc |= upload(h, P.pdf_val.data(), P.pdf_val.size(), &h->T.pdf_val);
+  rc |= upload(h, P.sw_albedo_weights.data(), P.sw_albedo_weights.size(), &h->T.sw_albedo_weights);
+  rc |= upload(h, P.i_emiss_from_band_lw.data(), P.i_emiss_from_band_lw.size(), &h->T.i_emiss_from_band_lw);
+  if (rc) { g_last_error = h->err; ecrad_b200_finalize(h); return 1; }
+  DevCfg& d = h->dcfg;
+  d.solver_sw = cfg->i_solver_sw; d.solver_lw = cfg->i_solver_lw; d.overlap_scheme = cfg->i_overlap_scheme;
+  d.do_sw = cfg->do_sw; d.do_lw = cfg->do_lw; d.do_clouds = cfg->do_clouds;
+  d.do_lw_cloud_scattering = cfg->do_lw_cloud_scattering; d.do_lw_derivatives = cfg->do_lw_derivatives;
+  d.do_sw_delta_scaling_with_gases = cfg->do_sw_delta_scaling_with_gases; d.do_fu_lw_ice_optics_bug = cfg->do_fu_lw_ice_optics_bug;
+  d.use_beta_overlap = cfg->use_beta_overlap; d.do_surface_sw_spectral_flux = cfg->do_surface_sw_spectral_flux;
+  d.do_canopy_fluxes_sw = cfg->do_canopy_fluxes_sw; d.do_canopy_fluxes_lw = cfg->do_canopy_fluxes_lw; d.do_clear = cfg->do_clear;
+  d.n_albedo_sw = cfg->n_albedo_sw; d.n_emiss_lw = cfg->n_emiss_lw;
+  d.n_canopy_bands_sw = cfg->n_canopy_bands_sw; d.n_canopy_bands_lw = cfg->n_canopy_bands_lw;
+  d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
+  d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
+  d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
+  if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = v; }
+  if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(nullptr, "cannot create CUDA streams"); ecrad_b200_finalize(h); return 1;
+  }
+  for (auto& s : h->slot) {
+    cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
+  }
+  // generator thread stacks: 4.5 KB of private arrays per thread
+  cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+  *handle = h;
+  return 0;
+}
+
+void ecrad_b200_finalize(void* handle) {
+  Handle* h = (Handle*)handle;
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->table_allocs) cudaFree(p);
+  for (auto& b : h->work) b.release();
+  for (auto& s : h->slot) {
+    for (auto& b : s.in) b.release();
+    for (auto& b : s.out) b.release();
+    if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    if (s.compute_done) cudaEventDestroy(s.compute_done);
+    if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+  }
+  for (auto e : h->ev) cudaEventDestroy(e);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  delete h;
+}
+
+int64_t ecrad_b200_kernel_launches(void* handle) { return handle ? ((Handle*)handle)->launches : 0; }
+
+int ecrad_b200_last_stage_ms(void* handle, float* ms, int max_stages) {
+  Handle* h = (Handle*)handle;
+  if (!h || !ms) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->ev_tiles > 0) cudaEventSynchronize(h->ev[h->ev_tiles * (N_STAGE + 1) - 1]);
+  int n = max_stages < N_STAGE ? max_stages : N_STAGE;
+  for (int s = 0; s < n; ++s) ms[s] = 0.f;
+  for (int t = 0; t < h->ev_tiles; ++t)
+    for (int s = 0; s < n; ++s) {
+      float v = 0.f;
+      if (cudaEventElapsedTime(&v, h->ev[t * (N_STAGE + 1) + s], h->ev[t * (N_STAGE + 1) + s + 1]) == cudaSuccess) ms[s] += v;
+    }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer entry
+// ---------------------------------------------------------------------------------------------------------
+int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in,
+                         ecrad_b200_outputs* out) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_radiation: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (check_args(h, ncol, nlev, istartcol, iendcol, in, out)) return 1;
+  CK(h, cudaSetDevice(h->device));
+  const ecrad_b200_config& c = h->cfg;
+  const int c_first = istartcol - 1, ntot = iendcol - istartcol + 1;
+  const int cap = ntot < h->tile_cols ? ntot : h->tile_cols;
+  const int ntiles = (ntot + cap - 1) / cap;
+  if (ensure_work(h, cap, nlev)) return 1;
+  if (ensure_events(h, ntiles)) return 1;
+  InDesc id[N_IN]; OutDesc od[N_OUT];
+  fill_descs(c, nlev, in, out, id, od);
+  const bool mcica_sw = c.do_sw && c.i_solver_sw == ECRAD_SOLVER_MCICA, mcica_lw = c.do_lw && c.i_solver_lw == ECRAD_SOLVER_MCICA;
+  // outputs the kernels do not produce in this configuration are left untouched on the host
+  auto out_active = [&](int k) {
+    if (!od[k].host) return false;
+    const bool lw = (k <= 3) || k == 10 || k == 11 || (k >= 13 && k <= 16) || k == 29 || k == 30 || k == 31;
+    if (lw && !c.do_lw) return false;
+    if (!lw && !c.do_sw) return false;
+    if (k == 11) return mcica_lw;
+    if (k == 12) return mcica_sw;
+    if (k == 10) return c.do_lw_derivatives != 0;
+    if (k >= 23 && k <= 26) return c.do_surface_sw_spectral_flux != 0 && (k < 25 || c.do_clear);
+    if (k == 27 || k == 28) return c.do_canopy_fluxes_sw != 0;
+    if (k == 29) return c.do_canopy_fluxes_lw != 0;
+    if (k >= 30) return false;   // per-band profiles: not produced by this build
+    return true;
+  };
+  for (auto& s : h->slot) s.used = false;
+  for (int t = 0; t < ntiles; ++t) {
+    Slot& s = h->slot[t & 1];
+    const int c0 = c_first + t * cap, nt = (ntot - t * cap) < cap ? (ntot - t * cap) : cap;
+    void* ip[N_IN]; void* op[N_OUT];
+    // ---- H2D (this slot's buffers are free once the kernels and copies of tile t-2 are done) ----
+    if (s.used) { CK(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CK(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }
+    for (int k = 0; k < N_IN; ++k) {
+      ip[k] = nullptr;
+      if (!id[k].host || id[k].rows <= 0) continue;
+      const size_t el = (size_t)id[k].elem;
+      CK(h, s.in[k].reserve(el * cap * id[k].rows));
+      ip[k] = s.in[k].p;
+      CK(h, cudaMemcpy2DAsync(s.in[k].p, el * cap, (const char*)id[k].host + el * c0, el * ncol, el * nt, id[k].rows,
+                              cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    for (int k = 0; k < N_OUT; ++k) {
+      op[k] = nullptr;
+      if (!out_active(k)) continue;
+      const size_t per_col = od[k].kind == 0 ? (size_t)od[k].rows : od[k].kind == 1 ? (size_t)od[k].rows : (size_t)od[k].rows * (nlev + 1);
+      CK(h, s.out[k].reserve(8 * per_col * cap));
+      op[k] = s.out[k].p;
+    }
+    // night columns keep the caller's cloud_cover_sw (the reference does not touch it): stage the current values
+    if (op[12]) CK(h, cudaMemcpyAsync(op[12], od[12].host + c0, 8 * (size_t)nt, cudaMemcpyHostToDevice, h->s_h2d));
+    CK(h, cudaEventRecord(s.h2d_done, h->s_h2d));
+    // ---- kernels ----
+    DevIn di; DevOut dout;
+    make_views(ip, op, cap, in->solar_irradiance, di, dout);
+    CK(h, cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
+    if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp, s.d2h_done, 0));
+    if (run_tile(h, di, dout, nt, nlev, h->s_comp, &h->ev[t * (N_STAGE + 1)])) return 1;
+    CK(h, cudaEventRecord(s.compute_done, h->s_comp));
+    // ---- D2H ----
+    CK(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
+    for (int k = 0; k < N_OUT; ++k) {
+      if (!op[k]) continue;
+      if (od[k].kind == 0)
+        CK(h, cudaMemcpy2DAsync(od[k].host + c0, 8 * (size_t)ncol, op[k], 8 * (size_t)cap, 8 * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+      else if (od[k].kind == 1)
+        CK(h, cudaMemcpyAsync(od[k].host + (size_t)c0 * od[k].rows, op[k], 8 * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    if (c.do_clouds && ip[17])   // cropped cloud fraction back into the caller's array (cloud%crop_cloud_fraction)
+      CK(h, cudaMemcpy2DAsync(in->cloud_fraction + c0, 8 * (size_t)ncol, ip[17], 8 * (size_t)cap, 8 * (size_t)nt, nlev, cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(h, cudaEventRecord(s.d2h_done, h->s_d2h));
+    s.used = true;
+  }
+  CK(h, cudaStreamSynchronize(h->s_d2h));
+  CK(h, cudaStreamSynchronize(h->s_comp));
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-resident entry: all pointers are device pointers with leading dimension ncol; not synchronised
+// ---------------------------------------------------------------------------------------------------------
+int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_radiation_device: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (check_args(h, ncol, nlev, 1, ncol, in, out)) return 1;
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const ecrad_b200_config& c = h->cfg;
+  const int cap = ncol < h->tile_cols ? ncol : h->tile_cols;
+  const int ntiles = (ncol + cap - 1) / cap;
+  if (ensure_work(h, cap, nlev)) return 1;
+  if (ensure_events(h, ntiles)) return 1;
+  InDesc id[N_IN]; OutDesc od[N_OUT];
+  fill_descs(c, nlev, in, out, id, od);
+  for (int t = 0; t < ntiles; ++t) {
+    const int c0 = t * cap, nt = (ncol - c0) < cap ? (ncol - c0) : cap;
+    void* ip[N_IN]; void* op[N_OUT];
+    for (int k = 0; k < N_IN; ++k) ip[k] = id[k].host ? (void*)((const char*)id[k].host + (size_t)id[k].elem * c0) : nullptr;
+    for (int k = 0; k < N_OUT; ++k) {
+      op[k] = nullptr;
+      if (!od[k].host || od[k].kind == 2) continue;
+      op[k] = od[k].kind == 0 ? (void*)(od[k].host + c0) : (void*)(od[k].host + (size_t)c0 * od[k].rows);
+    }
+    DevIn di; DevOut dout;
+    make_views(ip, op, ncol, in->solar_irradiance, di, dout);
+    if (run_tile(h, di, dout, nt, nlev, st, &h->ev[t * (N_STAGE + 1)])) return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

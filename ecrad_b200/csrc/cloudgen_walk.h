@@ -17,7 +17,7 @@
 namespace ecb {
 
 struct GenColumn {
-  int nlev, stride, ibegin, iend;           // element l of an array: p[l * stride]; ibegin/iend 1-based
+  int nlev, fstride, stride, ibegin, iend;  // element l: frac[l*fstride]; cum/pair/opi[l*stride]; ibegin/iend 1-based
   const double *frac, *cum, *pair, *opi;
 };
 
@@ -31,7 +31,7 @@ HD double beta2alpha(double beta, double f1, double f2) {
 
 // scheme: 0 = Max-Ran, 1 = Exp-Ran.  Writes cum, pair, opi (strided); returns the total cloud cover
 // (0 if below the threshold, radiation_cloud_generator.F90:130-133).
-HD double gen_prepare(int scheme, int nlev, int stride, const double* frac, const double* overlap_param, bool beta,
+HD double gen_prepare(int scheme, int nlev, int fstride, int stride, const double* frac, const double* overlap_param, bool beta,
                       double decorr_scaling, double frac_threshold, double* cum, double* pair, double* opi,
                       int* ibegin_out, int* iend_out) {
   const double MaxCloudFrac = 1.0 - DBL_EPSILON * 10.0;
@@ -41,10 +41,10 @@ HD double gen_prepare(int scheme, int nlev, int stride, const double* frac, cons
   int ibegin = 0, iend = 0;
   if (f1 > 0.0) { ibegin = 1; iend = 1; }
   for (int jl = 0; jl < nlev - 1; ++jl) {
-    double f2 = frac[(size_t)(jl + 1) * stride];
+    double f2 = frac[(size_t)(jl + 1) * fstride];
     double pr;
     if (scheme == 1) {
-      double op = overlap_param[(size_t)jl * stride];
+      double op = overlap_param[(size_t)jl * fstride];
       double alpha = beta ? beta2alpha(op, f1, f2) : op;
       pr = add_rn(mul_rn(alpha, dmax(f1, f2)), mul_rn(sub_rn(1.0, alpha), sub_rn(add_rn(f1, f2), mul_rn(f1, f2))));
     } else {
@@ -62,7 +62,7 @@ HD double gen_prepare(int scheme, int nlev, int stride, const double* frac, cons
   if (tcc < frac_threshold || !ibegin) return 0.0;
   const double expo = 1.0 / decorr_scaling;
   for (int jl = 0; jl < nlev - 1; ++jl) {
-    double op = overlap_param[(size_t)jl * stride];
+    double op = overlap_param[(size_t)jl * fstride];
     if (jl + 1 >= ibegin && jl + 1 <= iend - 1 && op > 0.0)
       op = (expo == 2.0) ? mul_rn(op, op) : pow(op, expo);   // overlap_param ** (1/decorrelation_scaling)
     opi[(size_t)jl * stride] = op;
@@ -70,12 +70,12 @@ HD double gen_prepare(int scheme, int nlev, int stride, const double* frac, cons
   return tcc;
 }
 
-// rtop[ng], rcloud[nlev], ri1[nlev]: thread-private integer work arrays.  code: [ng][nlev] for this column,
+// rtop[ng], rcloud[nlev], ri1[nlev]: thread-private integer work arrays.  code: [ng][rowlen] for this column,
 // pre-zeroed; entry = 0x80000000 | rand30 for cloudy (g, layer).
 HD void gen_walk(const GenColumn& c, RngMix& rs, int32_t iseed, int ng, double tcc, int32_t* rtop, int32_t* rcloud,
-                 int32_t* ri1, uint32_t* code) {
+                 int32_t* ri1, uint32_t* code, int rowlen) {
   const double RM = 1.0 / 1073741824.0;  // 2^-30
-  const size_t st = (size_t)c.stride;
+  const size_t st = (size_t)c.stride, fs = (size_t)c.fstride;
   rs.init(iseed);
   for (int g = 0; g < ng; ++g) rtop[g] = rs.next_int();
   for (int g = 0; g < ng; ++g) {
@@ -86,14 +86,14 @@ HD void gen_walk(const GenColumn& c, RngMix& rs, int32_t iseed, int ng, double t
     const int nrand = c.iend + 1 - itrigger;
     for (int i = 0; i < nrand; ++i) rcloud[i] = rs.next_int();
     int n = 1, iy = 0;
-    uint32_t* out = code + (size_t)g * c.nlev;
+    uint32_t* out = code + (size_t)g * rowlen;
     for (jlev = itrigger + 1; jlev <= c.iend + 1; ++jlev) {
       bool fill = false;
       if (jlev <= c.iend) {
         double r = (double)rcloud[iy] * RM; ++iy;
-        double f_prev = c.frac[(size_t)(jlev - 2) * st], pr = c.pair[(size_t)(jlev - 2) * st];
+        double f_prev = c.frac[(size_t)(jlev - 2) * fs], pr = c.pair[(size_t)(jlev - 2) * st];
         if (n > 0) {
-          double f_cur = c.frac[(size_t)(jlev - 1) * st];
+          double f_cur = c.frac[(size_t)(jlev - 1) * fs];
           if (mul_rn(r, f_prev) < sub_rn(add_rn(f_cur, f_prev), pr)) ++n; else fill = true;
         } else {
           double cum_prev = c.cum[(size_t)(jlev - 2) * st];

@@ -1,0 +1,891 @@
+// kernels.cu -- sm_100a kernels of the ecRad hot path (RRTMG gas optics -> cloud optics / McICA generator ->
+// McICA & Cloudless two-stream solvers).  Double precision throughout.
+//
+// Mapping:
+//   gas_lw_kernel / gas_sw_kernel   one CTA per column; stage A = one thread per (layer, band) builds the
+//                                   interpolation stencil into shared memory, stage B = one lane per g-point
+//                                   evaluates it against the packed k-tables (rows contiguous in g -> coalesced).
+//   cloud_prep/optics/gen kernels   one thread per column (column-fastest inputs -> coalesced).
+//   solver_lw_kernel/solver_sw_kernel  one CTA per column, one thread per g-point marching the layers; layer
+//                                   two-stream solutions are computed in registers, the adding-method state that
+//                                   must survive between the upward and downward sweeps goes to a per-column
+//                                   scratch in global memory ([layer][g], coalesced), g-point sums are done through
+//                                   a shared-memory tile every LCH layers.
+#include <stdio.h>
+
+#include "cloudgen_walk.h"
+#include "kernels.cuh"
+#include "solver_core.h"
+
+namespace ecb {
+
+// ---------------------------------------------------------------------------------------------------------
+// tight packing of the per-(layer, band) stencil slots in shared memory
+// ---------------------------------------------------------------------------------------------------------
+__constant__ int c_lw_kmax[NB_LW] = {10, 8, 20, 16, 21, 12, 20, 16, 20, 8, 10, 16, 20, 8, 20, 16};
+__constant__ int c_lw_koff[NB_LW] = {0, 10, 18, 38, 54, 75, 87, 107, 123, 143, 151, 161, 177, 197, 205, 225};
+enum { LW_KTOT = 241 };
+__constant__ int c_sw_koff[NB_SW] = {0, 12, 24, 36, 48, 57, 69, 82, 90, 103, 108, 108, 112, 120};
+enum { SW_KTOT = 129 };
+
+enum { GAS_LC = 16, GAS_THREADS = 256 };
+
+#define LD_IN(p, c, j) ((p)[(size_t)(j) * in.ld + (c)])
+
+// =========================================================================================================
+// LW gas optics
+// =========================================================================================================
+struct GasLwSmem {
+  LwLev lev[1];  // [nlev] followed by the arrays below (carved manually)
+};
+
+__global__ void __launch_bounds__(GAS_THREADS, 2)
+gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const GasMeta& M = *T.meta;
+  // carve shared memory
+  LwLev* lev = reinterpret_cast<LwLev*>(smem_raw);
+  double* lc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][LW_KTOT]
+  double* pfc = lc + GAS_LC * LW_KTOT;                               // [GAS_LC][16][2]
+  double* plk = pfc + GAS_LC * NB_LW * 2;                            // [GAS_LC+1][16]
+  double* plk_surf = plk + (GAS_LC + 1) * NB_LW;                     // [16]
+  int* lo = reinterpret_cast<int*>(plk_surf + NB_LW);                // [GAS_LC][LW_KTOT]
+  int* ln = lo + GAS_LC * LW_KTOT;                                   // [GAS_LC][16]
+  int* lpost = ln + GAS_LC * NB_LW;                                  // [GAS_LC][16]
+  int* pfo = lpost + GAS_LC * NB_LW;                                 // [GAS_LC][16][2]
+  int* bog = pfo + GAS_LC * NB_LW * 2;                               // [140] band of g
+  int* g0b = bog + NG_LW;                                            // [140] in-band index of g
+
+  // ---- per-layer state (thread per layer) ----
+  int tropo = 0;
+  if (tid < nlev) {
+    LevGas G;
+    lev_prepare(LD_IN(in.p_hl, c, tid), LD_IN(in.p_hl, c, tid + 1), LD_IN(in.t_hl, c, tid), LD_IN(in.t_hl, c, tid + 1),
+                LD_IN(in.gas[0], c, tid), LD_IN(in.gas[1], c, tid), LD_IN(in.gas[2], c, tid), LD_IN(in.gas[3], c, tid),
+                LD_IN(in.gas[4], c, tid), LD_IN(in.gas[5], c, tid), LD_IN(in.gas[6], c, tid), LD_IN(in.gas[7], c, tid),
+                LD_IN(in.gas[8], c, tid), G);
+    LwLev L;
+    lw_setcoef(M, G, L);
+    lev[tid] = L;
+    tropo = L.tropo;
+  }
+  for (int g = tid; g < NG_LW; g += GAS_THREADS) { int b = M.band_of_g_lw[g]; bog[g] = b; g0b[g] = g - M.lw[b].g0; }
+  if (tid < NB_LW) plk_surf[tid] = planck_band(M, in.skin_t[c], tid);
+  const int laytrop = __syncthreads_count(tropo);
+
+  double* od_out = w.od_lw + (size_t)c * nlev * NG_LW;
+  double* pl_out = w.planck + (size_t)c * (nlev + 1) * NG_LW;
+
+  for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
+    const int nl = imin((int)GAS_LC, nlev - l0);
+    // ---- stage A: stencils of (layer, band) ----
+    {
+      const int b = tid >> 4, ll = tid & 15;   // GAS_LC == 16
+      if (ll < nl) {
+        const int l = l0 + ll;
+        const int il = nlev - l;               // RRTMG layer index (1 = bottom)
+        ListOut out;
+        out.c = lc + ll * LW_KTOT + c_lw_koff[b];
+        out.o = lo + ll * LW_KTOT + c_lw_koff[b];
+        out.n = 0;
+        int post;
+        PlanckFrac pf = lw_build_list(M, lev[l], b, il <= laytrop, out, &post);
+        ln[ll * NB_LW + b] = out.n;
+        lpost[ll * NB_LW + b] = post;
+        pfc[(ll * NB_LW + b) * 2] = pf.c0; pfc[(ll * NB_LW + b) * 2 + 1] = pf.c1;
+        pfo[(ll * NB_LW + b) * 2] = pf.o0; pfo[(ll * NB_LW + b) * 2 + 1] = pf.o1;
+      }
+    }
+    for (int i = tid; i < (nl + 1) * NB_LW; i += GAS_THREADS) {
+      int h = i >> 4, b = i & 15;
+      plk[i] = planck_band(M, LD_IN(in.t_hl, c, l0 + h), b);
+    }
+    __syncthreads();
+    // ---- stage B: one lane per g-point ----
+    const int items = nl * NG_LW;
+    for (int it = tid; it < items; it += GAS_THREADS) {
+      const int ll = it / NG_LW, g = it - ll * NG_LW;
+      const int l = l0 + ll;
+      const int b = bog[g], igb = g0b[g];
+      const int n = ln[ll * NB_LW + b];
+      const double* cc = lc + ll * LW_KTOT + c_lw_koff[b];
+      const int* oo = lo + ll * LW_KTOT + c_lw_koff[b];
+      double tau = 0.0;
+      for (int k = 0; k < n; ++k) tau = fma(cc[k], __ldg(T.lwtab + oo[k] + igb), tau);
+      const int post = lpost[ll * NB_LW + b];
+      if (post >= 0) tau *= __ldg(T.lwtab + post + igb);
+      const double pf = pfc[(ll * NB_LW + b) * 2] * __ldg(T.lwtab + pfo[(ll * NB_LW + b) * 2] + igb) +
+                        pfc[(ll * NB_LW + b) * 2 + 1] * __ldg(T.lwtab + pfo[(ll * NB_LW + b) * 2 + 1] + igb);
+      od_out[(size_t)l * NG_LW + g] = dmax(tau, cfg.min_gas_od_lw);       // radiation_ifs_rrtm.F90:506-511
+      pl_out[(size_t)(l + 1) * NG_LW + g] = plk[(ll + 1) * NB_LW + b] * pf; // half-level below uses this layer's PFRAC
+      if (l == 0) pl_out[g] = plk[b] * pf;                                 // TOA half-level: PFRAC of the top layer
+      if (l == nlev - 1) {
+        // surface: planck_function_surf :757-852, lw_emission = planck_surf * (1 - lw_albedo) :466
+        const double alb = 1.0 - LD_IN(in.lw_emissivity, c, T.i_emiss_from_band_lw[b] - 1);
+        w.lw_albedo[(size_t)c * NG_LW + g] = alb;
+        double em = plk_surf[b] * pf;
+        w.emission[(size_t)c * NG_LW + g] = em * (1.0 - alb);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =========================================================================================================
+// SW gas optics (sunlit columns only)
+// =========================================================================================================
+__global__ void __launch_bounds__(GAS_THREADS, 2)
+gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  if (!(in.cos_sza[c] > 0.0)) return;   // srtm only runs for sunlit columns (radiation_ifs_rrtm.F90:518-542)
+  const GasMeta& M = *T.meta;
+  SwLev* lev = reinterpret_cast<SwLev*>(smem_raw);
+  double* lc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][SW_KTOT]
+  double* rc = lc + GAS_LC * SW_KTOT;                                // [GAS_LC][14][2] Rayleigh coefficients
+  double* sc = rc + GAS_LC * NB_SW * 2;                              // [14][2]  solar-source coefficients
+  double* inc = sc + NB_SW * 2;                                      // [112]
+  int* lo = reinterpret_cast<int*>(inc + NG_SW);                     // [GAS_LC][SW_KTOT]
+  int* ln = lo + GAS_LC * SW_KTOT;                                   // [GAS_LC][14]
+  int* ro = ln + GAS_LC * NB_SW;                                     // [GAS_LC][14][2]
+  int* so = ro + GAS_LC * NB_SW * 2;                                 // [14][2]
+  int* lsol = so + NB_SW * 2;                                        // [14] ecRad layer index supplying the solar source (-1: none)
+  int* bog = lsol + NB_SW;                                           // [112]
+  int* g0b = bog + NG_SW;                                            // [112]
+  int* jps = g0b + NG_SW;                                            // [nlev] JP per layer (ecRad order)
+  __shared__ double s_scale;
+
+  int tropo = 0;
+  if (tid < nlev) {
+    LevGas G;
+    lev_prepare(LD_IN(in.p_hl, c, tid), LD_IN(in.p_hl, c, tid + 1), LD_IN(in.t_hl, c, tid), LD_IN(in.t_hl, c, tid + 1),
+                LD_IN(in.gas[0], c, tid), LD_IN(in.gas[1], c, tid), LD_IN(in.gas[2], c, tid), LD_IN(in.gas[3], c, tid),
+                LD_IN(in.gas[4], c, tid), LD_IN(in.gas[5], c, tid), LD_IN(in.gas[6], c, tid), LD_IN(in.gas[7], c, tid),
+                LD_IN(in.gas[8], c, tid), G);
+    SwLev L;
+    sw_setcoef(M, G, L);
+    lev[tid] = L;
+    jps[tid] = L.jp;
+    tropo = L.tropo;
+  }
+  for (int g = tid; g < NG_SW; g += GAS_THREADS) { int b = M.band_of_g_sw[g]; bog[g] = b; g0b[g] = g - M.sw[b].g0; inc[g] = 0.0; }
+  const int laytrop = __syncthreads_count(tropo);
+  if (tid < NB_SW) {
+    int il = sw_solar_layer(M, tid, nlev, laytrop, [&](int i) { return jps[nlev - i]; });
+    lsol[tid] = il > 0 ? nlev - il : -1;
+  }
+  __syncthreads();
+
+  double* od_out = w.od_sw + (size_t)c * nlev * NG_SW;
+  double* ssa_out = w.ssa_sw + (size_t)c * nlev * NG_SW;
+
+  for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
+    const int nl = imin((int)GAS_LC, nlev - l0);
+    {
+      const int b = tid >> 4, ll = tid & 15;
+      if (b < NB_SW && ll < nl) {
+        const int l = l0 + ll;
+        const int il = nlev - l;
+        ListOut out;
+        out.c = lc + ll * SW_KTOT + c_sw_koff[b];
+        out.o = lo + ll * SW_KTOT + c_sw_koff[b];
+        out.n = 0;
+        SwAux aux;
+        sw_build_list(M, lev[l], b, il <= laytrop, out, aux);
+        ln[ll * NB_SW + b] = out.n;
+        rc[(ll * NB_SW + b) * 2] = aux.rc0; rc[(ll * NB_SW + b) * 2 + 1] = aux.rc1;
+        ro[(ll * NB_SW + b) * 2] = aux.ro0; ro[(ll * NB_SW + b) * 2 + 1] = aux.ro1;
+        if (l == lsol[b]) { sc[b * 2] = aux.sc0; sc[b * 2 + 1] = aux.sc1; so[b * 2] = aux.so0; so[b * 2 + 1] = aux.so1; }
+      }
+    }
+    __syncthreads();
+    const int items = nl * NG_SW;
+    for (int it = tid; it < items; it += GAS_THREADS) {
+      const int ll = it / NG_SW, g = it - ll * NG_SW;
+      const int l = l0 + ll;
+      const int b = bog[g], igb = g0b[g];
+      const int n = ln[ll * NB_SW + b];
+      const double* cc = lc + ll * SW_KTOT + c_sw_koff[b];
+      const int* oo = lo + ll * SW_KTOT + c_sw_koff[b];
+      double taug = 0.0;
+      for (int k = 0; k < n; ++k) taug = fma(cc[k], __ldg(T.swtab + oo[k] + igb), taug);
+      const double taur = rc[(ll * NB_SW + b) * 2] * __ldg(T.swtab + ro[(ll * NB_SW + b) * 2] + igb) +
+                          rc[(ll * NB_SW + b) * 2 + 1] * __ldg(T.swtab + ro[(ll * NB_SW + b) * 2 + 1] + igb);
+      const double od = taur + taug;                                        // srtm_gas_optical_depth.F90:314-320
+      od_out[(size_t)l * NG_SW + g] = dmax(od, cfg.min_gas_od_sw);         // radiation_ifs_rrtm.F90:593
+      ssa_out[(size_t)l * NG_SW + g] = taur / od;
+      if (l == lsol[b]) inc[g] = sc[b * 2] * __ldg(T.swtab + so[b * 2] + igb) + sc[b * 2 + 1] * __ldg(T.swtab + so[b * 2 + 1] + igb);
+    }
+    __syncthreads();
+  }
+  // incoming_sw = ZINCSOL * solar_irradiance / sum(ZINCSOL): radiation_ifs_rrtm.F90:557-605
+  if (tid == 0) {
+    double s = 0.0;
+    for (int g = 0; g < NG_SW; ++g) s = s + inc[g];
+    s_scale = in.solar_irradiance / s;
+  }
+  __syncthreads();
+  for (int g = tid; g < NG_SW; g += GAS_THREADS) w.incoming[(size_t)c * NG_SW + g] = s_scale * inc[g];
+}
+
+// =========================================================================================================
+// clouds: crop, cumulative cover, band optics, McICA generator
+// =========================================================================================================
+__global__ void cloud_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  // crop_cloud_fraction, radiation_cloud.F90:700-740 (in place)
+  int ict = nlev;
+  for (int l = 0; l < nlev; ++l) {
+    double f = LD_IN(in.frac, c, l);
+    double sum_mr = 0.0;
+    sum_mr = sum_mr + LD_IN(in.q_liq, c, l);
+    sum_mr = sum_mr + LD_IN(in.q_ice, c, l);
+    if (f < cfg.cloud_fraction_threshold || sum_mr < cfg.cloud_mixing_ratio_threshold) { f = 0.0; LD_IN(in.frac, c, l) = 0.0; }
+    if (f >= cfg.cloud_fraction_threshold && ict == nlev) ict = l;
+  }
+  int ibegin, iend;
+  double tcc = gen_prepare(cfg.overlap_scheme, nlev, in.ld, nc, in.frac + c, in.overlap + c, cfg.use_beta_overlap != 0,
+                           cfg.cloud_inhom_decorr_scaling, cfg.cloud_fraction_threshold, w.cum + c, w.pair + c, w.opi + c,
+                           &ibegin, &iend);
+  w.tcc[c] = tcc;
+  w.ibegin[c] = ibegin; w.iend[c] = iend; w.ict[c] = ict;
+}
+
+__global__ void cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc * nlev) return;
+  const int c = i % nc, l = i / nc;
+  const double frac = LD_IN(in.frac, c, l);
+  if (!(frac > 0.0)) return;
+  const CloudMeta& C = *T.cloud;
+  const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / (9.80665 * frac);
+  const double lwp = factor * LD_IN(in.q_liq, c, l), iwp = factor * LD_IN(in.q_ice, c, l);
+  const double rel = LD_IN(in.re_liq, c, l), rei = LD_IN(in.re_ice, c, l);
+  if (cfg.do_lw) {
+    double* o = w.cl_lw + ((size_t)c * nlev + l) * 3 * NB_LW;
+    for (int b = 0; b < NB_LW; ++b) {
+      CloudBandOut r = cloud_optics_lw(C, b, lwp, iwp, rel, rei, cfg.do_lw_cloud_scattering != 0, cfg.do_fu_lw_ice_optics_bug != 0);
+      o[b] = r.od; o[NB_LW + b] = r.ssa; o[2 * NB_LW + b] = r.g;
+    }
+  }
+  if (cfg.do_sw) {
+    double* o = w.cl_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
+    for (int b = 0; b < NB_SW; ++b) {
+      CloudBandOut r = cloud_optics_sw(C, b, lwp, iwp, rel, rei, cfg.do_sw_delta_scaling_with_gases != 0);
+      o[b] = r.od; o[NB_SW + b] = r.ssa; o[2 * NB_SW + b] = r.g;
+    }
+  }
+}
+
+enum { GEN_MAXLEV = 192 };
+
+// one thread per (column, spectrum): spectrum 0 = SW (seed iseed), 1 = LW (seed iseed + 997, radiation_mcica_lw.F90:223)
+__global__ void __launch_bounds__(64)
+cloud_gen_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nc) return;
+  const int c = i % nc, spec = i / nc;
+  if (spec == 0 && (!cfg.do_sw || cfg.solver_sw != 2 || !(in.cos_sza[c] > 0.0))) return;
+  if (spec == 1 && (!cfg.do_lw || cfg.solver_lw != 2)) return;
+  const double tcc = w.tcc[c];
+  if (!(tcc > 0.0)) return;
+  int32_t ix[JPQ + 1], rtop[NG_LW], rcloud[GEN_MAXLEV], ri1[GEN_MAXLEV];
+  GenColumn gc;
+  gc.nlev = nlev; gc.fstride = in.ld; gc.stride = nc; gc.ibegin = w.ibegin[c]; gc.iend = w.iend[c];
+  gc.frac = in.frac + c; gc.cum = w.cum + c; gc.pair = w.pair + c; gc.opi = w.opi + c;
+  RngMix rs; rs.ix = ix; rs.iused = JPQ;
+  const int ng = spec ? NG_LW : NG_SW;
+  uint32_t* code = (spec ? w.code_lw : w.code_sw) + (size_t)c * ng * nlevp;
+  gen_walk(gc, rs, in.iseed[c] + (spec ? 997 : 0), ng, tcc, rtop, rcloud, ri1, code, nlevp);
+}
+
+// =========================================================================================================
+// solvers: shared helpers
+// =========================================================================================================
+enum { LCH = 16 };   // layers between two g-point reductions
+
+// Sum the rows of the shared-memory tile over g (4 threads per row) into sums[f][level].
+// Row (f, s), s < ns, holds level lfirst + dir*s of flux f.  Ends with a barrier so the tile can be refilled.
+__device__ __forceinline__ void flush_tile(const double* tile, int rs, int ng, int nf, int ns, double* const* dst, int lfirst, int dir) {
+  __syncthreads();
+  const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
+  const int nrows = nf * ns, rows_per_round = blockDim.x >> 2;
+  for (int r0 = 0; r0 < nrows; r0 += rows_per_round) {
+    const int r = r0 + row;
+    const bool valid = r < nrows;
+    int f = 0, s = 0;
+    double p = 0.0;
+    if (valid) {
+      f = r / ns; s = r - f * ns;
+      const double* t = tile + (size_t)(f * LCH + s) * rs;
+      for (int g = sub; g < ng; g += 4) p += t[g];
+    }
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    if (valid && sub == 0) dst[f][lfirst + dir * s] = p;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t pick4(const uint4& q, int k) { return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w; }
+
+// optical-depth scaling of this (g, layer) from the generator's code word
+__device__ __forceinline__ double od_scaling_from_code(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd) {
+  if (!code) return 0.0;
+  return pdf_sample(C, pdf_val, fsd, (double)(code & 0x3FFFFFFFu) * (1.0 / 1073741824.0));
+}
+
+// =========================================================================================================
+// LW solver: McICA (radiation_mcica_lw.F90:39-419) and Cloudless (radiation_cloudless_lw.F90)
+// =========================================================================================================
+enum { LW_THREADS = 160, LW_RS = 141 };
+
+__global__ void __launch_bounds__(LW_THREADS, 3)
+solver_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, g = threadIdx.x;
+  const bool act = g < NG_LW;
+  const int nl1 = nlev + 1;
+  double* sums = reinterpret_cast<double*>(smem_raw);   // [6][nl1]: dn_clear, up_clear, dn, up, deriv_clear, deriv
+  double* tile = sums + 6 * nl1;                         // [2][LCH][LW_RS]
+  double* fracs = tile + 2 * LCH * LW_RS;                // [nlev]
+  double* fsds = fracs + nlev;                           // [nlev]
+  double* s_dn_clear = sums, *s_up_clear = sums + nl1, *s_dn = sums + 2 * nl1, *s_up = sums + 3 * nl1;
+  double* s_dv_clear = sums + 4 * nl1, *s_dv = sums + 5 * nl1;
+
+  const bool mcica = cfg.solver_lw == 2;
+  for (int l = g; l < nlev; l += LW_THREADS) {
+    fracs[l] = mcica ? LD_IN(in.frac, c, l) : 0.0;
+    fsds[l] = mcica ? LD_IN(in.fsd, c, l) : 0.0;
+  }
+  const double tcc = mcica ? w.tcc[c] : 0.0;
+  const bool cloudy = tcc > 0.0;
+  const int ict = cloudy ? w.ict[c] : nlev;
+  const double thr = cfg.cloud_fraction_threshold;
+  const size_t n = (size_t)nlev * NG_LW;
+  const double* od = w.od_lw + (size_t)c * n;
+  const double* pl = w.planck + (size_t)c * nl1 * NG_LW;
+  double* scr = w.scr + (size_t)c * w.scr_per_col;
+  double *tr = scr, *su = scr + n, *sdc = scr + 2 * n, *sa = scr + 3 * n, *sb = scr + 4 * n, *sA = scr + 5 * n,
+         *sS = scr + 6 * n, *trc = scr + 7 * n;
+  const int gg = act ? g : 0;
+  const double emission = w.emission[(size_t)c * NG_LW + gg], albedo = w.lw_albedo[(size_t)c * NG_LW + gg];
+  __syncthreads();
+
+  // ---- pass 1: clear-sky layer properties and downward flux (calc_fluxes_no_scattering_lw, first loop) ----
+  double fd = 0.0, fd_ict = 0.0;
+  {
+    double* dst[1] = {s_dn_clear};
+    int slot = 0, lfirst = 0;
+    if (act) tile[slot * LW_RS + g] = 0.0;   // flux_dn at TOA
+    ++slot;
+    for (int l = 0; l < nlev; ++l) {
+      if (act) {
+        if (l == ict) fd_ict = fd;
+        const size_t i = (size_t)l * NG_LW + g;
+        LwLayer L = lw_no_scat(od[i], pl[i], pl[i + NG_LW]);
+        tr[i] = L.trans; su[i] = L.source_up; sdc[i] = L.source_dn;
+        fd = L.trans * fd + L.source_dn;
+        tile[slot * LW_RS + g] = fd;
+      }
+      ++slot;
+      if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+    }
+  }
+  const double fd_surf_clear = fd;
+  // ---- pass 2: clear-sky upward flux and the clear-sky derivative products ----
+  const double fu_surf_clear = emission + albedo * fd_surf_clear;
+  double fu = fu_surf_clear;
+  {
+    double* dst[2] = {s_up_clear, s_dv_clear};
+    int slot = 0, lfirst = nlev;
+    double prod = fu_surf_clear;
+    if (act) { tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod; }
+    ++slot;
+    for (int l = nlev - 1; l >= 0; --l) {
+      if (act) {
+        const size_t i = (size_t)l * NG_LW + g;
+        const double t = tr[i];
+        fu = t * fu + su[i];
+        prod = prod * t;
+        tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod;
+      }
+      ++slot;
+      if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
+    }
+  }
+  const double fu_toa_clear = fu;
+  double fd_surf = fd_surf_clear, fu_toa = fu_toa_clear;
+
+  if (cloudy) {
+    const CloudMeta& C = *T.cloud;
+    const int b = T.meta->band_of_g_lw[gg];
+    const uint4* codep = reinterpret_cast<const uint4*>(w.code_lw + ((size_t)c * NG_LW + gg) * nlevp);
+    const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
+    // ---- pass 3: upward sweep of albedo/source from the surface to cloud top (fast_adding_ica_lw) ----
+    if (act) {
+      double A = albedo, S = emission;
+      uint4 cq = make_uint4(0, 0, 0, 0);
+      for (int l = nlev - 1; l >= ict; --l) {
+        if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
+        const size_t i = (size_t)l * NG_LW + g;
+        double a_, b_, t_;
+        if (fracs[l] >= thr) {
+          const double scal = od_scaling_from_code(C, T.pdf_val, pick4(cq, l & 3), fsds[l]);
+          const double* clb = cl + (size_t)l * 3 * NB_LW;
+          const double od_cloud_new = scal * clb[b];
+          const double od_total = od[i] + od_cloud_new;
+          LwLayer L;
+          if (cfg.do_lw_cloud_scattering) {
+            double ssa_total = 0.0, g_total = 0.0;
+            if (od_total > 0.0) {
+              const double ssac = clb[NB_LW + b];
+              const double scat_od = ssac * od_cloud_new;
+              ssa_total = scat_od / od_total;
+              if (scat_od > 0.0) g_total = clb[2 * NB_LW + b] * ssac * od_cloud_new / scat_od;
+            }
+            L = lw_ref_trans(od_total, ssa_total, g_total, pl[i], pl[i + NG_LW]);
+          } else {
+            L = lw_no_scat(od_total, pl[i], pl[i + NG_LW]);
+          }
+          const double inv_den = 1.0 / (1.0 - A * L.ref);
+          a_ = L.trans * inv_den;
+          b_ = (L.ref * S + L.source_dn) * inv_den;
+          t_ = L.trans;
+          const double A_new = L.ref + L.trans * L.trans * A * inv_den;
+          const double S_new = L.source_up + L.trans * (S + A * L.source_dn) * inv_den;
+          sA[i] = A; sS[i] = S;   // albedo/source at the half-level below layer l
+          A = A_new; S = S_new;
+        } else {
+          const double t = tr[i], sd = sdc[i];
+          a_ = t; b_ = sd; t_ = t;
+          sA[i] = A; sS[i] = S;
+          const double A_new = t * t * A;
+          const double S_new = su[i] + t * (S + A * sd);
+          A = A_new; S = S_new;
+        }
+        sa[i] = a_; sb[i] = b_; trc[i] = t_;
+      }
+      fu = S + A * fd_ict;   // flux_up at cloud top
+    }
+    // ---- upward flux above cloud top ----
+    {
+      double* dst[1] = {s_up};
+      int slot = 0, lfirst = ict;
+      if (act) tile[slot * LW_RS + g] = fu;
+      ++slot;
+      for (int l = ict - 1; l >= 0; --l) {
+        if (act) { const size_t i = (size_t)l * NG_LW + g; fu = tr[i] * fu + su[i]; tile[slot * LW_RS + g] = fu; }
+        ++slot;
+        if (slot == LCH) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
+      }
+      if (slot) flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1);
+    }
+    fu_toa = fu;
+    // ---- downward sweep from cloud top to the surface ----
+    {
+      double* dst[2] = {s_dn, s_up};
+      int slot = 0, lfirst = ict + 1;
+      fd = fd_ict;
+      for (int l = ict; l < nlev; ++l) {
+        if (act) {
+          const size_t i = (size_t)l * NG_LW + g;
+          fd = sa[i] * fd + sb[i];
+          fu = sA[i] * fd + sS[i];
+          tile[slot * LW_RS + g] = fd; tile[(LCH + slot) * LW_RS + g] = fu;
+        }
+        ++slot;
+        if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+      }
+    }
+    fd_surf = fd;
+    // ---- derivative products of the cloudy sub-columns (calc_lw_derivatives_ica) ----
+    if (cfg.do_lw_derivatives && out.lw_derivatives) {
+      double* dst[1] = {s_dv};
+      int slot = 0, lfirst = nlev;
+      double prod = fu;   // flux_up at the surface of the cloudy sub-column
+      if (act) tile[slot * LW_RS + g] = prod;
+      ++slot;
+      for (int l = nlev - 1; l >= 0; --l) {
+        if (act) { const size_t i = (size_t)l * NG_LW + g; prod = prod * (l >= ict ? trc[i] : tr[i]); tile[slot * LW_RS + g] = prod; }
+        ++slot;
+        if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
+      }
+    }
+  }
+
+  // ---- outputs ----
+#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
+  const double wc = tcc, w1 = 1.0 - tcc;
+  for (int l = g; l < nl1; l += LW_THREADS) {
+    const double upc = s_up_clear[l], dnc = s_dn_clear[l];
+    if (out.lw_up_clear) OUT2(out.lw_up_clear, l) = upc;
+    if (out.lw_dn_clear) OUT2(out.lw_dn_clear, l) = dnc;
+    double up = upc, dn = dnc;
+    if (cloudy) {
+      up = wc * s_up[l] + w1 * upc;
+      dn = wc * (l <= ict ? dnc : s_dn[l]) + w1 * dnc;
+    }
+    if (out.lw_up) OUT2(out.lw_up, l) = up;
+    if (out.lw_dn) OUT2(out.lw_dn, l) = dn;
+    if (cfg.do_lw_derivatives && out.lw_derivatives) {
+      double dclear = l == nlev ? 1.0 : s_dv_clear[l] / s_up_clear[nlev];
+      double d = dclear;
+      if (cloudy) {
+        d = l == nlev ? 1.0 : s_dv[l] / s_up[nlev];
+        if (tcc < 1.0 - thr) d = l == nlev ? 1.0 : (1.0 - w1) * d + w1 * dclear;
+      }
+      OUT2(out.lw_derivatives, l) = d;
+    }
+  }
+  if (g == 0 && out.cloud_cover_lw && mcica) out.cloud_cover_lw[c] = tcc;
+  const double dn_surf_g = cloudy ? wc * fd_surf + w1 * fd_surf_clear : fd_surf_clear;
+  if (act) {
+    const size_t i = (size_t)c * NG_LW + g;
+    if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
+    if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fu_toa_clear;
+    if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
+    if (out.lw_up_toa_g) out.lw_up_toa_g[i] = cloudy ? wc * fu_toa + w1 * fu_toa_clear : fu_toa_clear;
+  }
+  // canopy fluxes, radiation_flux.F90 calc_surface_spectral (nearest-interval emissivity mapping)
+  if (cfg.do_canopy_fluxes_lw && out.lw_dn_surf_canopy) {
+    __syncthreads();
+    if (act) tile[g] = dn_surf_g;
+    __syncthreads();
+    if (g < cfg.n_canopy_bands_lw) {
+      double s = 0.0;
+      for (int k = 0; k < NG_LW; ++k)
+        if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) s = s + tile[k];
+      out.lw_dn_surf_canopy[(size_t)c * cfg.n_canopy_bands_lw + g] = s;
+    }
+  }
+#undef OUT2
+}
+
+// =========================================================================================================
+// SW solver: McICA (radiation_mcica_sw.F90:41-408) and Cloudless (radiation_cloudless_sw.F90)
+// =========================================================================================================
+enum { SW_THREADS = 128, SW_RS = 113 };
+
+struct SwPassResult { double fdir_surf, fdd_surf, fu_toa; };
+
+// One full adding-method solution (radiation_adding_ica_sw.F90:24-151) for the column held by this CTA.
+// CLOUDY: merge gas + scaled cloud properties in cloudy layers.  CLOUDLESS: use the Cloudless solver's two-stream pair.
+template <bool CLOUDY, bool CLOUDLESS>
+__device__ __forceinline__ SwPassResult sw_pass(const DevTables& T, const DevCfg& cfg, int c, int g, bool act, int nlev, int nlevp,
+                                                const Work& w, const double* fracs, const double* fsds, double mu0, double inc,
+                                                double alb_diff, double alb_dir, double* tile, double* s_dir, double* s_dn,
+                                                double* s_up) {
+  const size_t n = (size_t)nlev * NG_SW;
+  const double* od = w.od_sw + (size_t)c * n;
+  const double* ssa = w.ssa_sw + (size_t)c * n;
+  double* scr = w.scr + (size_t)c * w.scr_per_col;
+  double *sa = scr, *sb = scr + n, *sA = scr + 2 * n, *sS = scr + 3 * n, *sF = scr + 4 * n;
+  const CloudMeta& C = *T.cloud;
+  const int gg = act ? g : 0;
+  const int b = T.meta->band_of_g_sw[gg];
+  const uint4* codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)c * NG_SW + gg) * nlevp);
+  const double* cl = w.cl_sw + (size_t)c * nlev * 3 * NB_SW;
+  const double thr = cfg.cloud_fraction_threshold;
+  const double inv_mu0 = 1.0 / mu0;
+  SwPassResult R;
+
+  // total optical properties of (layer l, this g-point)
+  auto props = [&](int l, uint32_t code, double& odt, double& ssat, double& gt) {
+    const size_t i = (size_t)l * NG_SW + g;
+    odt = od[i]; ssat = ssa[i]; gt = 0.0;
+    if (CLOUDY && fracs[l] >= thr) {
+      const double scal = od_scaling_from_code(C, T.pdf_val, code, fsds[l]);
+      const double* clb = cl + (size_t)l * 3 * NB_SW;
+      const double od_cloud_new = scal * clb[b];
+      const double od_gas = odt, ssa_gas = ssat;
+      odt = od_gas + od_cloud_new;
+      ssat = 0.0;
+      if (odt > 0.0) {
+        const double ssac = clb[NB_SW + b];
+        const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
+        ssat = scat_od / odt;
+        if (scat_od > 0.0) gt = (clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
+      }
+    }
+  };
+
+  // ---- A: direct beam, top-down ----
+  {
+    double* dst[1] = {s_dir};
+    int slot = 0, lfirst = 0;
+    double fdir = inc;
+    uint4 cq = make_uint4(0, 0, 0, 0);
+    for (int l = 0; l < nlev; ++l) {
+      if (act) {
+        if (CLOUDY && (l & 3) == 0) cq = __ldg(codep + (l >> 2));
+        double odt, ssat, gt;
+        props(l, pick4(cq, l & 3), odt, ssat, gt);
+        double tdir;
+        if (CLOUDLESS) tdir = sw_ref_trans_cloudless(mu0, odt, ssat, gt).trans_dir_dir;
+        else tdir = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
+        sF[(size_t)l * NG_SW + g] = fdir;
+        tile[slot * SW_RS + g] = fdir;
+        fdir = fdir * tdir;
+      }
+      ++slot;
+      if (slot == LCH) { flush_tile(tile, SW_RS, NG_SW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+    }
+    if (act) tile[slot * SW_RS + g] = fdir;
+    ++slot;
+    flush_tile(tile, SW_RS, NG_SW, 1, slot, dst, lfirst, 1);
+    R.fdir_surf = fdir;
+  }
+  // ---- B: albedo / source of everything below each half-level, bottom-up ----
+  double S0 = 0.0;
+  if (act) {
+    double A = alb_diff, S = alb_dir * R.fdir_surf * mu0;
+    uint4 cq = make_uint4(0, 0, 0, 0);
+    for (int l = nlev - 1; l >= 0; --l) {
+      if (CLOUDY && (l == nlev - 1 || (l & 3) == 3)) cq = __ldg(codep + (l >> 2));
+      double odt, ssat, gt;
+      props(l, pick4(cq, l & 3), odt, ssat, gt);
+      const SwLayer L = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odt, ssat, gt) : sw_ref_trans(mu0, odt, ssat, gt);
+      const size_t i = (size_t)l * NG_SW + g;
+      const double fd_l = sF[i];
+      const double inv_den = 1.0 / (1.0 - A * L.ref);
+      sa[i] = L.trans * inv_den;
+      sb[i] = (L.ref * S + L.trans_dir_diff * fd_l) * inv_den;
+      sA[i] = A; sS[i] = S;
+      const double A_new = L.ref + L.trans * L.trans * A * inv_den;
+      const double S_new = L.ref_dir * fd_l + L.trans * (S + A * L.trans_dir_diff * fd_l) * inv_den;
+      A = A_new; S = S_new;
+    }
+    S0 = S;
+  }
+  R.fu_toa = S0;
+  // ---- C: fluxes, top-down ----
+  {
+    double* dst[2] = {s_dn, s_up};
+    int slot = 0, lfirst = 0;
+    double fdd = 0.0;
+    if (act) { tile[slot * SW_RS + g] = 0.0; tile[(LCH + slot) * SW_RS + g] = S0; }
+    ++slot;
+    for (int l = 0; l < nlev; ++l) {
+      if (act) {
+        const size_t i = (size_t)l * NG_SW + g;
+        fdd = sa[i] * fdd + sb[i];
+        const double fu = sA[i] * fdd + sS[i];
+        tile[slot * SW_RS + g] = fdd; tile[(LCH + slot) * SW_RS + g] = fu;
+      }
+      ++slot;
+      if (slot == LCH || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, 2, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+    }
+    R.fdd_surf = fdd;
+  }
+  return R;
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 3)
+solver_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, g = threadIdx.x;
+  const bool act = g < NG_SW;
+  const int nl1 = nlev + 1;
+  const double mu0 = in.cos_sza[c];
+#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
+  if (!(mu0 > 0.0)) {
+    // night column: radiation_mcica_sw.F90:380-401
+    for (int l = g; l < nl1; l += SW_THREADS) {
+      if (out.sw_up) OUT2(out.sw_up, l) = 0.0;
+      if (out.sw_dn) OUT2(out.sw_dn, l) = 0.0;
+      if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = 0.0;
+      if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = 0.0;
+      if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = 0.0;
+      if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = 0.0;
+    }
+    if (act) {
+      const size_t i = (size_t)c * NG_SW + g;
+      double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
+                       out.sw_dn_diffuse_surf_clear_g, out.sw_dn_direct_surf_clear_g, out.sw_up_toa_clear_g};
+      for (int k = 0; k < 6; ++k) if (gs[k]) gs[k][i] = 0.0;
+    }
+    if (g < NB_SW) {
+      double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
+      for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
+    }
+    if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
+      if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
+      if (out.sw_dn_direct_surf_canopy) out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
+    }
+    return;
+  }
+  double* sums = reinterpret_cast<double*>(smem_raw);   // [6][nl1]
+  double* tile = sums + 6 * nl1;                         // [2][LCH][SW_RS]
+  double* fracs = tile + 2 * LCH * SW_RS;                // [nlev]
+  double* fsds = fracs + nlev;                           // [nlev]
+  double* bandv = fsds + nlev;                           // [2][14] band albedos, later band fluxes
+  double *s_dir_c = sums, *s_dn_c = sums + nl1, *s_up_c = sums + 2 * nl1, *s_dir = sums + 3 * nl1, *s_dn = sums + 4 * nl1,
+         *s_up = sums + 5 * nl1;
+  const bool mcica = cfg.solver_sw == 2;
+  for (int l = g; l < nlev; l += SW_THREADS) {
+    fracs[l] = mcica ? LD_IN(in.frac, c, l) : 0.0;
+    fsds[l] = mcica ? LD_IN(in.fsd, c, l) : 0.0;
+  }
+  // get_albedos, radiation_single_level.F90:216-365 (weighted-interval mapping to bands)
+  if (g < NB_SW) {
+    double bd = 0.0, bdir = 0.0;
+    for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
+      const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
+      if (wgt != 0.0) {
+        bd = bd + wgt * LD_IN(in.sw_albedo, c, ja);
+        if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja);
+      }
+    }
+    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
+  }
+  __syncthreads();
+  const int gg = act ? g : 0;
+  const int bnd = T.meta->band_of_g_sw[gg];
+  const double alb_diff = bandv[bnd], alb_dir = bandv[NB_SW + bnd];
+  const double inc = w.incoming[(size_t)c * NG_SW + gg];
+  const double tcc = mcica ? w.tcc[c] : 0.0;
+  const bool cloudy = tcc > 0.0;
+
+  SwPassResult Rc, Ra;
+  if (mcica) Rc = sw_pass<false, false>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir_c, s_dn_c, s_up_c);
+  else Rc = sw_pass<false, true>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir_c, s_dn_c, s_up_c);
+  Ra = Rc;
+  if (cloudy) Ra = sw_pass<true, false>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir, s_dn, s_up);
+
+  const double wc = tcc, w1 = 1.0 - tcc;
+  for (int l = g; l < nl1; l += SW_THREADS) {
+    const double dirc = s_dir_c[l] * mu0, upc = s_up_c[l], dnc = s_dn_c[l] + dirc;
+    if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = upc;
+    if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = dnc;
+    if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = dirc;
+    double up = upc, dn = dnc, dir = dirc;
+    if (cloudy) {
+      const double dira = s_dir[l] * mu0;
+      up = wc * s_up[l] + w1 * upc;
+      dn = wc * (s_dn[l] + dira) + w1 * dnc;
+      dir = wc * dira + w1 * dirc;
+    }
+    if (out.sw_up) OUT2(out.sw_up, l) = up;
+    if (out.sw_dn) OUT2(out.sw_dn, l) = dn;
+    if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = dir;
+  }
+  if (g == 0 && out.cloud_cover_sw && mcica) out.cloud_cover_sw[c] = tcc;
+  // per-g surface / TOA fluxes
+  const double dif_c = Rc.fdd_surf, dir_c = Rc.fdir_surf * mu0, toa_c = Rc.fu_toa;
+  double dif_a = dif_c, dir_a = dir_c, toa_a = toa_c;
+  if (cloudy) {
+    dif_a = wc * Ra.fdd_surf + w1 * dif_c;
+    dir_a = wc * (Ra.fdir_surf * mu0) + w1 * dir_c;
+    toa_a = wc * Ra.fu_toa + w1 * toa_c;
+  }
+  if (act) {
+    const size_t i = (size_t)c * NG_SW + g;
+    if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
+    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
+    if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
+    if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
+    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
+    if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
+  }
+  // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral
+  if (cfg.do_surface_sw_spectral_flux || cfg.do_canopy_fluxes_sw) {
+    __syncthreads();
+    if (act) { tile[g] = dir_a; tile[SW_RS + g] = dif_a; tile[2 * SW_RS + g] = dir_c; tile[3 * SW_RS + g] = dif_c; }
+    __syncthreads();
+    double* bdir = tile + 4 * SW_RS;  // [14] all-sky direct band, [14] all-sky total band
+    if (g < NB_SW) {
+      const int g0 = T.meta->sw[g].g0, ngb = T.meta->sw[g].ng;
+      double d = 0.0, t = 0.0, dcl = 0.0, tcl = 0.0;
+      for (int k = g0; k < g0 + ngb; ++k) { d = d + tile[k]; t = t + tile[SW_RS + k]; dcl = dcl + tile[2 * SW_RS + k]; tcl = tcl + tile[3 * SW_RS + k]; }
+      t = t + d; tcl = tcl + dcl;
+      bdir[g] = d; bdir[NB_SW + g] = t;
+      if (cfg.do_surface_sw_spectral_flux) {
+        if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * NB_SW + g] = d;
+        if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * NB_SW + g] = t;
+        if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * NB_SW + g] = dcl;
+        if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * NB_SW + g] = tcl;
+      }
+    }
+    __syncthreads();
+    if (cfg.do_canopy_fluxes_sw && out.sw_dn_diffuse_surf_canopy && out.sw_dn_direct_surf_canopy && g < cfg.n_albedo_sw) {
+      double dif = 0.0, dir = 0.0;
+      for (int jb = 0; jb < NB_SW; ++jb) {
+        const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + g];
+        if (wgt != 0.0) { dif = dif + wgt * bdir[NB_SW + jb]; dir = dir + wgt * bdir[jb]; }
+      }
+      out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dif - dir;
+      out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dir;
+    }
+  }
+#undef OUT2
+}
+
+// =========================================================================================================
+// launchers
+// =========================================================================================================
+size_t scratch_doubles_per_column(int nlev) {
+  size_t lw = (size_t)LW_SCR_ARRAYS * nlev * NG_LW, sw = (size_t)SW_SCR_ARRAYS * nlev * NG_SW;
+  return lw > sw ? lw : sw;
+}
+
+static size_t gas_lw_smem(int nlev) {
+  return sizeof(LwLev) * nlev + sizeof(double) * (GAS_LC * LW_KTOT + GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
+         sizeof(int) * (GAS_LC * LW_KTOT + GAS_LC * NB_LW * 2 + GAS_LC * NB_LW * 2 + 2 * NG_LW) + 16;
+}
+static size_t gas_sw_smem(int nlev) {
+  return sizeof(SwLev) * nlev + sizeof(double) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
+         sizeof(int) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + nlev) + 16;
+}
+static size_t solver_lw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1) + 2 * LCH * LW_RS + 2 * nlev) + 16; }
+static size_t solver_sw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1) + 2 * LCH * SW_RS + 2 * nlev + 2 * NB_SW) + 16; }
+
+template <class K>
+static void allow_smem(K kernel, size_t bytes) {
+  static size_t granted = 0;   // per kernel instantiation
+  if (bytes > granted) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    granted = bytes;
+  }
+}
+
+int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  size_t sm = gas_lw_smem(nlev);
+  allow_smem(gas_lw_kernel, sm);
+  gas_lw_kernel<<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
+  return 1;
+}
+int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  size_t sm = gas_sw_smem(nlev);
+  allow_smem(gas_sw_kernel, sm);
+  gas_sw_kernel<<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
+  return 1;
+}
+int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const int nlevp = (nlev + 3) & ~3;
+  int n = 0;
+  cloud_prep_kernel<<<(nc + 127) / 128, 128, 0, st>>>(cfg, in, w, nc, nlev); ++n;
+  cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n;
+  if (cfg.do_lw && cfg.solver_lw == 2) cudaMemsetAsync(w.code_lw, 0, sizeof(uint32_t) * (size_t)nc * NG_LW * nlevp, st);
+  if (cfg.do_sw && cfg.solver_sw == 2) cudaMemsetAsync(w.code_sw, 0, sizeof(uint32_t) * (size_t)nc * NG_SW * nlevp, st);
+  if ((cfg.do_lw && cfg.solver_lw == 2) || (cfg.do_sw && cfg.solver_sw == 2)) {
+    cloud_gen_kernel<<<(2 * nc + 63) / 64, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
+  }
+  return n;
+}
+int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  size_t sm = solver_lw_smem(nlev);
+  allow_smem(solver_lw_kernel, sm);
+  solver_lw_kernel<<<nc, LW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev, (nlev + 3) & ~3);
+  return 1;
+}
+int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  size_t sm = solver_sw_smem(nlev);
+  allow_smem(solver_sw_kernel, sm);
+  solver_sw_kernel<<<nc, SW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev, (nlev + 3) & ~3);
+  return 1;
+}
+
+}  // namespace ecb

@@ -1,0 +1,82 @@
+// kernels.cuh -- launch interface between api.cu (host orchestration) and kernels.cu (sm_100a kernels).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cloud_core.h"
+#include "gas_core.h"
+
+namespace ecb {
+
+// Device view of the inputs of radiation(): column-fastest arrays with leading dimension ld, already offset to the
+// first column of the tile (element (c, j) at p[j*ld + c]).
+struct DevIn {
+  const double *cos_sza, *skin_t, *sw_albedo, *sw_albedo_direct, *lw_emissivity;
+  const int32_t* iseed;
+  const double *p_hl, *t_hl;
+  const double* gas[9];  // h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3 (mass mixing ratios)
+  double* frac;          // in/out (cropped)
+  const double *q_liq, *q_ice, *re_liq, *re_ice, *overlap, *fsd;
+  double solar_irradiance;
+  int ld;
+};
+
+// Device view of flux_type; NULL = not allocated.  Profiles (ld, nlev+1) column-fastest; *_g (ng, ld) g fastest.
+struct DevOut {
+  double *lw_up, *lw_dn, *lw_up_clear, *lw_dn_clear;
+  double *sw_up, *sw_dn, *sw_dn_direct, *sw_up_clear, *sw_dn_clear, *sw_dn_direct_clear;
+  double *lw_derivatives, *cloud_cover_lw, *cloud_cover_sw;
+  double *lw_dn_surf_g, *lw_dn_surf_clear_g, *lw_up_toa_g, *lw_up_toa_clear_g;
+  double *sw_dn_diffuse_surf_g, *sw_dn_direct_surf_g, *sw_dn_diffuse_surf_clear_g, *sw_dn_direct_surf_clear_g;
+  double *sw_up_toa_g, *sw_up_toa_clear_g;
+  double *sw_dn_surf_band, *sw_dn_direct_surf_band, *sw_dn_surf_clear_band, *sw_dn_direct_surf_clear_band;
+  double *sw_dn_diffuse_surf_canopy, *sw_dn_direct_surf_canopy, *lw_dn_surf_canopy;
+  double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;  // (nband, ld, nlev+1), Cloudless only
+  int ld;
+};
+
+// Read-only tables on the device.
+struct DevTables {
+  const GasMeta* meta;
+  const double *lwtab, *swtab;
+  const CloudMeta* cloud;
+  const double* pdf_val;
+  const double* sw_albedo_weights;     // (n_albedo_sw, 14)
+  const int32_t* i_emiss_from_band_lw; // (16), 1-based
+};
+
+// Scalars of config_type the kernels read.
+struct DevCfg {
+  int solver_sw, solver_lw, overlap_scheme;
+  int do_sw, do_lw, do_clouds, do_lw_cloud_scattering, do_lw_derivatives;
+  int do_sw_delta_scaling_with_gases, do_fu_lw_ice_optics_bug, use_beta_overlap;
+  int do_surface_sw_spectral_flux, do_canopy_fluxes_sw, do_canopy_fluxes_lw, do_clear;
+  int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
+  double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
+};
+
+enum { LW_SCR_ARRAYS = 8, SW_SCR_ARRAYS = 5 };
+
+// Per-tile scratch (nc = columns in the tile).
+struct Work {
+  double *od_lw, *planck, *emission, *lw_albedo;  // [nc][nlev][140], [nc][nlev+1][140], [nc][140], [nc][140]
+  double *od_sw, *ssa_sw, *incoming;              // [nc][nlev][112] x2, [nc][112]
+  double *cl_lw, *cl_sw;                          // cloud optics per band [nc][nlev][3][16], [nc][nlev][3][14]
+  double *cum, *pair, *opi;                       // [nlev][nc] column-fastest
+  double* tcc;                                    // [nc]
+  int *ibegin, *iend, *ict;                       // [nc]
+  uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
+  double* scr;                                    // [nc][scr_per_col]
+  size_t scr_per_col;
+};
+
+size_t scratch_doubles_per_column(int nlev);
+
+// Launchers.  All enqueue on `st` and return the number of kernels launched.
+int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+
+}  // namespace ecb

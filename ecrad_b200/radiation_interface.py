@@ -1,0 +1,143 @@
+"""Host-side mirror of `module radiation_interface` (radiation/radiation_interface.F90:29) over the C-ABI.
+
+    setup_radiation(config)                         radiation_interface.F90:37   -> ecrad_b200_setup
+    radiation(ncol, nlev, istartcol, iendcol, ...)  radiation_interface.F90:200  -> ecrad_b200_radiation
+
+This module only marshals numpy arrays into the POD structs of include/ecrad_b200.h and calls libecrad_b200.so.
+There is no Python/numpy compute path: if the CUDA library is missing or no GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .config import RadiationConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecrad_b200.so")
+DEFAULT_TABLES = os.path.join(_HERE, "data", "rrtmg_tables.bin")
+
+EXPORTS = [
+    "ecrad_b200_tables_create", "ecrad_b200_tables_add", "ecrad_b200_tables_load_file", "ecrad_b200_tables_free",
+    "ecrad_b200_setup", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_kernel_launches",
+    "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
+    "ecrad_b200_version",
+]
+
+_lib = None
+
+
+class RadiationError(RuntimeError):
+    """Raised where the reference would call radiation_abort (utilities/radiation_io.F90:45-73)."""
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RadiationError(f"{LIB_PATH} not built: run `make -C ecrad_b200/csrc` (or __graft_entry__.build()); "
+                             "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.ecrad_b200_tables_create.restype = C.c_void_p
+    L.ecrad_b200_tables_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
+    L.ecrad_b200_tables_load_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.ecrad_b200_tables_free.argtypes = [C.c_void_p]
+    L.ecrad_b200_setup.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ecrad_b200_radiation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
+    L.ecrad_b200_radiation_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
+    L.ecrad_b200_kernel_launches.restype = C.c_int64
+    L.ecrad_b200_kernel_launches.argtypes = [C.c_void_p]
+    L.ecrad_b200_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    L.ecrad_b200_stage_name.restype = C.c_char_p
+    L.ecrad_b200_stage_name.argtypes = [C.c_int]
+    L.ecrad_b200_finalize.argtypes = [C.c_void_p]
+    L.ecrad_b200_last_error.restype = C.c_char_p
+    L.ecrad_b200_last_error.argtypes = [C.c_void_p]
+    L.ecrad_b200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+class RadiationHandle:
+    """What `setup_radiation` leaves behind: the config plus the device-side tables (radiation_interface.F90:37-156)."""
+
+    def __init__(self, config: RadiationConfig, tables_path: str = DEFAULT_TABLES):
+        L = load_library()
+        self.lib = L
+        self.config = config
+        self.cfg = config.to_struct()
+        t = L.ecrad_b200_tables_create()
+        try:
+            if L.ecrad_b200_tables_load_file(t, tables_path.encode()):
+                raise RadiationError(L.ecrad_b200_last_error(None).decode())
+            # config%sw_albedo_weights, config%i_emiss_from_band_lw: the part of config_type that is a table
+            for nm, arr in config.derived.items():
+                a = np.asfortranarray(arr)
+                code = 1 if a.dtype.kind in "iu" else 0
+                a = a.astype(np.int32 if code else np.float64, order="F")
+                dims = (C.c_int64 * 4)(*(list(a.shape) + [1] * (4 - a.ndim)))
+                if L.ecrad_b200_tables_add(t, nm.encode(), code, a.ndim, dims, a.ctypes.data_as(C.c_void_p)):
+                    raise RadiationError(f"cannot add table {nm}")
+            h = C.c_void_p()
+            if L.ecrad_b200_setup(C.byref(self.cfg), t, C.byref(h)):
+                raise RadiationError(L.ecrad_b200_last_error(None).decode())
+            self.h = h
+        finally:
+            L.ecrad_b200_tables_free(t)
+
+    def _err(self):
+        return self.lib.ecrad_b200_last_error(self.h).decode()
+
+    def radiation(self, inputs, ncol, nlev, istartcol=1, iendcol=None, outputs=None, spectral_profiles=False):
+        """inputs: dict keyed like abi.INPUT_ARRAYS (+ 'solar_irradiance'); cloud_fraction is cropped in place like
+        cloud%crop_cloud_fraction.  Returns the dict of flux_type components (Fortran-ordered float64)."""
+        iendcol = ncol if iendcol is None else iendcol
+        keep, ist = abi.make_inputs(inputs, inputs["solar_irradiance"])
+        if outputs is None:
+            outs, ost = abi.alloc_outputs(ncol, nlev, self.cfg, spectral_profiles=spectral_profiles)
+        else:
+            outs, ost = outputs
+        rc = self.lib.ecrad_b200_radiation(self.h, ncol, nlev, istartcol, iendcol, C.byref(ist), C.byref(ost))
+        if rc:
+            raise RadiationError(self._err())
+        outs["cloud_fraction"] = keep.get("cloud_fraction")
+        return outs
+
+    def radiation_device(self, ncol, nlev, ist: abi.Inputs, ost: abi.Outputs, stream=0):
+        """Device-resident entry: every pointer in ist/ost is a device pointer with leading dimension ncol."""
+        rc = self.lib.ecrad_b200_radiation_device(self.h, ncol, nlev, C.byref(ist), C.byref(ost), C.c_void_p(stream))
+        if rc:
+            raise RadiationError(self._err())
+
+    def kernel_launches(self):
+        return int(self.lib.ecrad_b200_kernel_launches(self.h))
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 8)()
+        n = self.lib.ecrad_b200_last_stage_ms(self.h, buf, 8)
+        return {self.lib.ecrad_b200_stage_name(i).decode(): float(buf[i]) for i in range(n)}
+
+    def finalize(self):
+        if getattr(self, "h", None):
+            self.lib.ecrad_b200_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+
+def setup_radiation(config: RadiationConfig, tables_path: str = DEFAULT_TABLES) -> RadiationHandle:
+    if not config.derived:
+        config.consolidate()
+    return RadiationHandle(config, tables_path)
+
+
+def radiation(handle: RadiationHandle, ncol, nlev, istartcol, iendcol, inputs, **kw):
+    return handle.radiation(inputs, ncol, nlev, istartcol, iendcol, **kw)

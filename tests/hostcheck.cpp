@@ -104,14 +104,14 @@ int hc_cloud_generator(void* p, int ng, int nlev, int scheme, int32_t iseed, dou
   std::vector<uint32_t> code((size_t)ng * nlev, 0u);
   std::vector<int32_t> ix(JPQ + 1), rtop(ng), rcloud(nlev), ri1(nlev);
   GenColumn gc;
-  gc.nlev = nlev; gc.stride = 1; gc.frac = frac; gc.cum = cum.data(); gc.pair = pair.data(); gc.opi = opi.data();
-  double tcc = gen_prepare(scheme, nlev, 1, frac, overlap_param, use_beta != 0, decorr_scaling, frac_threshold, cum.data(),
+  gc.nlev = nlev; gc.stride = 1; gc.fstride = 1; gc.frac = frac; gc.cum = cum.data(); gc.pair = pair.data(); gc.opi = opi.data();
+  double tcc = gen_prepare(scheme, nlev, 1, 1, frac, overlap_param, use_beta != 0, decorr_scaling, frac_threshold, cum.data(),
                            pair.data(), opi.data(), &gc.ibegin, &gc.iend);
   *tcc_out = tcc;
   for (size_t i = 0; i < (size_t)ng * nlev; ++i) od_scaling[i] = 0.0;
   if (tcc > 0.0) {
     RngMix rs; rs.ix = ix.data();
-    gen_walk(gc, rs, iseed, ng, tcc, rtop.data(), rcloud.data(), ri1.data(), code.data());
+    gen_walk(gc, rs, iseed, ng, tcc, rtop.data(), rcloud.data(), ri1.data(), code.data(), nlev);
     for (int g = 0; g < ng; ++g)
       for (int l = 0; l < nlev; ++l) {
         uint32_t cd = code[(size_t)g * nlev + l];

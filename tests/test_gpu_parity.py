@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libecrad_b200.so), against the CPU oracle on the same
+seeded inputs, against the reference's golden files, and at BASELINE size through size-independent properties.
+
+Tolerance (BASELINE.json north_star): |flux - reference| <= 1e-6 W m-2 in double precision, on every flux component;
+integer / decision work (McICA cloud masks -> total cloud cover, cropped cloud fraction) must be bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from ecrad_b200 import inputs as I
+from ecrad_b200.config import RadiationConfig
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-6  # W m-2
+NLEV = 137
+FLUXES = ["lw_up", "lw_dn", "lw_up_clear", "lw_dn_clear", "sw_up", "sw_dn", "sw_dn_direct", "sw_up_clear", "sw_dn_clear",
+          "sw_dn_direct_clear"]
+OTHERS = ["lw_derivatives", "lw_dn_surf_g", "lw_dn_surf_clear_g", "lw_up_toa_g", "lw_up_toa_clear_g", "sw_dn_diffuse_surf_g",
+          "sw_dn_direct_surf_g", "sw_dn_diffuse_surf_clear_g", "sw_dn_direct_surf_clear_g", "sw_up_toa_g", "sw_up_toa_clear_g",
+          "sw_dn_surf_band", "sw_dn_direct_surf_band", "sw_dn_surf_clear_band", "sw_dn_direct_surf_clear_band",
+          "sw_dn_diffuse_surf_canopy", "sw_dn_direct_surf_canopy", "lw_dn_surf_canopy"]
+
+
+@pytest.fixture(scope="module")
+def handles():
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+
+    made = {}
+
+    def get(**kw):
+        key = tuple(sorted(kw.items()))
+        if key not in made:
+            cfg = RadiationConfig(**kw).consolidate()
+            made[key] = (setup_radiation(cfg), Oracle(cfg), cfg)
+        return made[key]
+
+    yield get
+    for h, _, _ in made.values():
+        h.finalize()
+
+
+def compare(out, ref, names, tol=TOL):
+    for nm in names:
+        a, b = out[nm], ref[nm]
+        assert a.shape == b.shape, nm
+        m = np.isfinite(b)
+        assert np.isfinite(a[m]).all(), f"{nm}: non-finite values"
+        err = np.abs(a[m] - b[m]).max() if m.any() else 0.0
+        assert err <= tol, f"{nm}: max |gpu - oracle| = {err:.3e} W m-2 > {tol}"
+
+
+def f32_ulp_err(a, g):
+    return np.abs(a - g.astype(np.float64)) / np.maximum(np.spacing(np.abs(g).astype(np.float32)).astype(np.float64), 1e-30)
+
+
+def test_mcica_meridian_vs_oracle(handles, meridian_raw):
+    h, orc, _ = handles()
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):  # night columns keep the caller's value (-1) in both
+        assert np.array_equal(out[nm], ref[nm]), nm
+    assert np.array_equal(out["cloud_fraction"], ref["cloud_fraction"])  # crop_cloud_fraction side effect
+
+
+def test_mcica_meridian_vs_reference_golden(handles, meridian_raw, golden_noaer):
+    """Direct check against the reference's own golden file (float32): within 1 float32 ulp of every stored value."""
+    h, _, _ = handles()
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    gmap = {"lw_up": "flux_up_lw", "lw_dn": "flux_dn_lw", "lw_up_clear": "flux_up_lw_clear", "lw_dn_clear": "flux_dn_lw_clear",
+            "sw_up": "flux_up_sw", "sw_dn": "flux_dn_sw", "sw_dn_direct": "flux_dn_direct_sw", "sw_up_clear": "flux_up_sw_clear",
+            "sw_dn_clear": "flux_dn_sw_clear", "sw_dn_direct_clear": "flux_dn_direct_sw_clear", "lw_derivatives": "lw_derivative",
+            "cloud_cover_lw": "cloud_cover_lw", "cloud_cover_sw": "cloud_cover_sw"}
+    for nm, gname in gmap.items():
+        assert f32_ulp_err(out[nm], golden_noaer[gname]).max() <= 1.0, nm
+    # and well inside the reference's own acceptance thresholds (test/ifs/CMakeLists.txt:18-19: LW 1e-3, SW 1e-1)
+    for nm, gname in gmap.items():
+        assert np.abs(out[nm] - golden_noaer[gname]).max() <= 1.0e-3, nm
+
+
+def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless):
+    h, orc, _ = handles(sw_solver_name="Cloudless", lw_solver_name="Cloudless")
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    for nm, gname in (("lw_up", "flux_up_lw"), ("lw_dn", "flux_dn_lw"), ("sw_up", "flux_up_sw"), ("sw_dn", "flux_dn_sw"),
+                      ("sw_dn_direct", "flux_dn_direct_sw")):
+        assert f32_ulp_err(out[nm], golden_cloudless[gname]).max() <= 1.0, nm
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(overlap_scheme_name="Max-Ran"), dict(do_lw_cloud_scattering=False),
+                                dict(use_beta_overlap=True)])
+def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
+    """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
+    n = 600
+    h, orc, _ = handles(**kw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+    assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
+    assert np.array_equal(out["cloud_fraction"], ref["cloud_fraction"])
+
+
+def test_column_range_and_untouched_columns(handles, meridian_raw):
+    """istartcol/iendcol semantics of radiation(): only that range is written (1-based inclusive)."""
+    h, orc, _ = handles()
+    n = 64
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV, istartcol=11, iendcol=40)
+    ref = orc.radiation(I.to_radiation_inputs(raw), n, NLEV, istartcol=11, iendcol=40)
+    for nm in FLUXES:
+        assert np.isnan(out[nm][:10]).all() and np.isnan(out[nm][40:]).all(), nm  # alloc_outputs fills with NaN
+        assert np.abs(out[nm][10:40] - ref[nm][10:40]).max() <= TOL, nm
+    assert np.isnan(out["sw_up_toa_g"][:, :10]).all() and np.isnan(out["sw_up_toa_g"][:, 40:]).all()
+    # single column, first and last
+    for j in (1, n):
+        o1 = h.radiation(I.to_radiation_inputs(raw), n, NLEV, istartcol=j, iendcol=j)
+        r1 = orc.radiation(I.to_radiation_inputs(raw), n, NLEV, istartcol=j, iendcol=j)
+        for nm in FLUXES:
+            assert np.abs(o1[nm][j - 1] - r1[nm][j - 1]).max() <= TOL
+
+
+def test_tiling_is_invisible(meridian_raw):
+    """Results do not depend on the internal column tile (ragged last tile included)."""
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    n = 333
+    raw = I.synthetic_columns(meridian_raw, n)
+    cfg = RadiationConfig().consolidate()
+    outs = []
+    for tile in ("4096", "100", "7"):
+        os.environ["ECRAD_B200_TILE"] = tile
+        try:
+            h = setup_radiation(cfg)
+        finally:
+            del os.environ["ECRAD_B200_TILE"]
+        outs.append(h.radiation(I.to_radiation_inputs(raw), n, NLEV))
+        h.finalize()
+    for nm in FLUXES + OTHERS + ["cloud_cover_sw", "cloud_cover_lw", "cloud_fraction"]:
+        assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
+        assert np.array_equal(outs[0][nm], outs[2][nm], equal_nan=True), nm
+
+
+def test_all_night_and_all_clear_edge_cases(handles, meridian_raw):
+    h, orc, _ = handles()
+    n = 40
+    raw = I.synthetic_columns(meridian_raw, n)
+    raw["cos_solar_zenith_angle"][:] = -0.1           # no sunlit column at all
+    raw["cloud_fraction"][: n // 2] = 0.0              # half the columns cloud free
+    raw["cloud_fraction"][n // 2:, 100:] = 1.0         # the rest overcast in the lowest layers (MaxCloudFrac branch)
+    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert (out["sw_dn"] == 0.0).all() and (out["cloud_cover_sw"] == -1.0).all()
+    assert np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+
+
+def test_full_size_properties_10000_columns(handles, meridian_raw, golden_noaer):
+    """BASELINE config 2 size (10 000 columns): column independence (permutation invariance, bit-exact), the first 32
+    columns reproduce the golden file, physical bounds, and an oracle spot check on a random subset."""
+    h, orc, _ = handles()
+    n = 10000
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    for nm in FLUXES:
+        assert np.isfinite(out[nm]).all(), nm
+    # (a) first 32 columns are the unperturbed test slice
+    assert f32_ulp_err(out["sw_dn"][:32], golden_noaer["flux_dn_sw"]).max() <= 1.0
+    assert f32_ulp_err(out["lw_up"][:32], golden_noaer["flux_up_lw"]).max() <= 1.0
+    # (b) permutation invariance: columns are independent, so shuffling them only shuffles the results
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(n)
+    rawp = {k: (v if np.ndim(v) == 0 else v[perm]) for k, v in raw.items()}
+    outp = h.radiation(I.to_radiation_inputs(rawp), n, NLEV)
+    for nm in FLUXES + ["cloud_cover_sw", "cloud_cover_lw", "lw_derivatives"]:
+        assert np.array_equal(outp[nm], out[nm][perm]), nm
+    # (c) physics: fluxes non-negative, direct <= total, TOA incoming = S0*mu0 for sunlit columns
+    assert (out["sw_dn"] >= -1e-9).all() and (out["sw_up"] >= -1e-9).all() and (out["lw_up"] > 0).all()
+    assert (out["sw_dn_direct"] <= out["sw_dn"] + 1e-9).all()
+    mu0 = raw["cos_solar_zenith_angle"]
+    sun = mu0 > 0
+    assert np.abs(out["sw_dn"][sun, 0] - raw["solar_irradiance"] * mu0[sun]).max() <= 1e-9 * 1400
+    assert (out["sw_dn"][~sun] == 0).all()
+    # (d) oracle on a random subset of 256 columns
+    idx = np.sort(rng.choice(n, 256, replace=False))
+    sub = {k: (v if np.ndim(v) == 0 else v[idx]) for k, v in raw.items()}
+    ref = orc.radiation(I.to_radiation_inputs(sub), len(idx), NLEV)
+    for nm in FLUXES:
+        assert np.abs(out[nm][idx] - ref[nm]).max() <= TOL, nm
+    assert np.array_equal(out["cloud_cover_sw"][idx], ref["cloud_cover_sw"])
+
+
+def test_device_resident_entry_matches_host_entry(handles, meridian_raw):
+    import ctypes as C
+
+    import torch
+
+    from ecrad_b200 import abi
+
+    h, _, cfg = handles()
+    n = 257
+    raw = I.synthetic_columns(meridian_raw, n)
+    inp = I.to_radiation_inputs(raw)
+    host = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    dev = torch.device("cuda:0")
+    ist = abi.Inputs(); ist.struct_bytes = C.sizeof(abi.Inputs); ist.solar_irradiance = inp["solar_irradiance"]
+    keep = {}
+    for nm, dt, _ in abi.INPUT_ARRAYS:
+        a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)   # (rows, ncol) C-order == (ncol, rows) Fortran order
+        keep[nm] = t
+        setattr(ist, nm, C.cast(t.data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
+    ost = abi.Outputs(); ost.struct_bytes = C.sizeof(abi.Outputs)
+    outs = {}
+    for nm in FLUXES:
+        t = torch.full((NLEV + 1, n), float("nan"), dtype=torch.float64, device=dev)
+        outs[nm] = t
+        setattr(ost, nm, C.cast(t.data_ptr(), abi.c_dp))
+    h.radiation_device(n, NLEV, ist, ost, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for nm in FLUXES:
+        assert np.array_equal(outs[nm].cpu().numpy().T, host[nm]), nm
+
+
+def test_error_behaviour(meridian_raw):
+    """Non-zero status + message instead of the reference's radiation_abort."""
+    from ecrad_b200.radiation_interface import RadiationError, setup_radiation
+
+    with pytest.raises(RadiationError, match="aerosols"):
+        setup_radiation(RadiationConfig(use_aerosols=True).consolidate())
+    h = setup_radiation(RadiationConfig().consolidate())
+    with pytest.raises(RadiationError, match="bad dimensions"):
+        h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, istartcol=5, iendcol=40)
+    h.finalize()
