@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- columns/s of the ecRad hot path (LW+SW, McICA + RRTMG 140+112 g-points, 137 levels) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--ncol C]          (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference [...]                                  (CPU arm: the oracle port on all host threads)
+
+One step = one pass of the whole hot path (gas optics -> cloud optics/generator -> LW and SW solvers) over one batch
+of synthetic IFS-shaped columns (BASELINE.json configs[1]: 10 000 columns per GPU).
+  value : whole-job columns/s with the inputs resident in HBM (device-resident C-ABI entry), CUDA-event timed on the
+          launching stream, max over ranks.
+  e2e   : the same through the host-buffer C-ABI entry ecrad_b200_radiation (what the Fortran shim calls), pinned host
+          buffers, H2D of every input and D2H of every flux_type component inside the timed region.
+Weak scaling: every rank owns `ncol` columns of one global synthetic problem (columns are independent; no data-path
+collective; the barrier/max-reduce of the timing go over NCCL).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLEV = 137
+B_MIN = 30924.0  # algorithmic bytes per column, fp64 (SURVEY.md section 8d / DESIGN.md "Roofline accounting")
+METRIC = "columns/sec LW+SW McICA+RRTMG 137-lev"
+
+
+def load_raw():
+    raw = dict(np.load(os.path.join(ROOT, "tests", "golden", "ecrad_meridian_inputs.npz")))
+    return {k: np.array(v, dtype=np.float64) for k, v in raw.items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(cfg, raw, ncol_sample, first, nthreads, reps):
+    """Times the oracle port (C, OpenMP over columns) on `ncol_sample` columns of the same synthetic workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ecrad_b200 import inputs as I
+    from oracle_lib import Oracle
+
+    orc = Oracle(cfg)
+    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol_sample, first=first))
+    orc.radiation(dict(inp), ncol_sample, NLEV, nthreads=nthreads)  # warm-up (page-in, thread pool)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.radiation(dict(inp), ncol_sample, NLEV, nthreads=nthreads)
+        ts.append(time.perf_counter() - t0)
+    return ncol_sample / float(np.mean(ts)), float(np.mean(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ncol", type=int, default=10000, help="columns per GPU (BASELINE config 2: 10 000)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="columns in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from ecrad_b200 import inputs as I
+    from ecrad_b200.config import RadiationConfig
+
+    cfg = RadiationConfig().consolidate()   # test/ifs/configCY49R1.nam with use_aerosols=false
+    raw = load_raw()
+    ncores = os.cpu_count() or 1
+    config = {"workload": f"McICA LW+SW, RRTMG 140+112 g-points, {NLEV} levels, {args.ncol} synthetic IFS columns per GPU "
+                          "(BASELINE.json configs[1])", "ncol_per_gpu": args.ncol, "nlev": NLEV, "namelist": "configCY49R1.nam, use_aerosols=false",
+              "sharding": f"columns x{world}, no data-path collective",
+              "l2": "inputs+scratch per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ CPU reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = args.cpu_sample or max(256, min(args.ncol, 16 * ncores))
+        warm = max(args.warmup, 1)
+        for _ in range(warm - 1):
+            cpu_arm(cfg, raw, sample, 0, ncores, 1)
+        v, sec = cpu_arm(cfg, raw, sample, 0, ncores, max(args.steps, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "columns/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "columns/s", "cores": ncores, "kind": "port",
+                                 "sample": f"{sample} columns of the same synthetic workload per step; C/OpenMP oracle port "
+                                           "(the Fortran reference cannot be built in this image: no Fortran compiler)"},
+                "e2e": {"value": v, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+
+    from ecrad_b200 import abi
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ncol = args.ncol
+    h = setup_radiation(cfg)
+    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol, first=rank * ncol))
+
+    # ---- host buffers (pinned) for the e2e path ----
+    pinned, host_in = {}, {}
+    for nm, dt, _ in abi.INPUT_ARRAYS:
+        a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory()   # (rows, ncol) C order == Fortran (ncol, rows)
+        pinned[nm] = t
+        host_in[nm] = t.numpy().T
+    host_in["solar_irradiance"] = inp["solar_irradiance"]
+    out_names = [(nm, kind) for nm, kind in abi.OUTPUT_ARRAYS if kind not in ("pl", "ps")]
+    host_out, ost_host = {}, abi.Outputs()
+    ost_host.struct_bytes = C.sizeof(abi.Outputs)
+    for nm, kind in out_names:
+        shp = abi.output_shape(kind, ncol, NLEV, h.cfg)
+        t = torch.empty(tuple(reversed(shp)), dtype=torch.float64).pin_memory()
+        t.fill_(-1.0 if nm.startswith("cloud_cover") else float("nan"))
+        host_out[nm] = t
+        setattr(ost_host, nm, C.cast(t.data_ptr(), abi.c_dp))
+    keep_h, ist_host = abi.make_inputs(host_in, inp["solar_irradiance"])
+    for nm, dt, _ in abi.INPUT_ARRAYS:   # make_inputs must not have copied: point at the pinned memory
+        setattr(ist_host, nm, C.cast(pinned[nm].data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values()) + ncol * 8
+    d2h_bytes = sum(t.numel() * 8 for t in host_out.values()) + ncol * NLEV * 8
+
+    # ---- device-resident buffers for the kernel-only path ----
+    dev_in, ist_dev = {}, abi.Inputs()
+    ist_dev.struct_bytes = C.sizeof(abi.Inputs)
+    ist_dev.solar_irradiance = inp["solar_irradiance"]
+    for nm, dt, _ in abi.INPUT_ARRAYS:
+        dev_in[nm] = pinned[nm].to(dev)
+        setattr(ist_dev, nm, C.cast(dev_in[nm].data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
+    dev_out, ost_dev = {}, abi.Outputs()
+    ost_dev.struct_bytes = C.sizeof(abi.Outputs)
+    for nm, kind in out_names:
+        shp = abi.output_shape(kind, ncol, NLEV, h.cfg)
+        dev_out[nm] = torch.zeros(tuple(reversed(shp)), dtype=torch.float64, device=dev)
+        setattr(ost_dev, nm, C.cast(dev_out[nm].data_ptr(), abi.c_dp))
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        # (cloud%crop_cloud_fraction is in place and idempotent, so repeated steps see the same effective input)
+        h.radiation_device(ncol, NLEV, ist_dev, ost_dev, stream=stream.cuda_stream)
+
+    def step_host():
+        rc = h.lib.ecrad_b200_radiation(h.h, ncol, NLEV, 1, ncol, C.byref(ist_host), C.byref(ost_host))
+        if rc:
+            raise RuntimeError(h._err())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = h.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    launches = h.kernel_launches() - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    stage_ms = h.last_stage_ms()   # kernels of the last step, CUDA events on the launching stream
+    ms_step = ms_total / args.steps
+    value = world * ncol / (ms_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer entry ----
+    for _ in range(max(args.warmup, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e_value = world * ncol / e2e_s
+    clocks = sampler.stop()
+
+    # parity guard: the timed outputs are the real thing (first 32 columns of rank 0 = the golden test slice)
+    if rank == 0:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ecrad_meridian_noaer_ref.npz"))
+        for nm, gn in (("sw_dn", "flux_dn_sw"), ("lw_up", "flux_up_lw")):
+            a = dev_out[nm].cpu().numpy().T[:32]
+            b = host_out[nm].numpy().T[:32]
+            err = np.abs(a - g[gn]).max()
+            assert err <= 1e-3 and np.array_equal(a, b), f"bench outputs are wrong: {nm} {err}"
+
+    # ---- roofline of the dominant kernel ----
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and dom:
+        tj = json.load(open(tpath))
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_column"] * ncol
+    roofline = None
+    if dom:
+        achieved = B_MIN * ncol / (stage_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
+                    "note": "fp64-ALU-bound path: algorithmic bytes are 30.9 kB/column against ~10 MFLOP/column (DESIGN.md)"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample = args.cpu_sample or max(256, min(ncol, 16 * ncores))
+            v, sec = cpu_arm(cfg, raw, sample, 0, ncores, 3)
+            cpu = {"value": v, "unit": "columns/s", "cores": ncores, "kind": "port",
+                   "sample": f"{sample} columns of the same workload, 3 repetitions ({sec:.2f} s each), C/OpenMP oracle port"}
+        line = {"metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_s * 1e3, "host_memory": "pinned"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    h.finalize()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -844,11 +844,8 @@ static size_t solver_sw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1)
 
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
-  static size_t granted = 0;   // per kernel instantiation
-  if (bytes > granted) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    granted = bytes;
-  }
+  // (kernels with the same signature share this template instantiation, so no caching by type here)
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
