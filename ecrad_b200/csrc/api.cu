@@ -158,8 +158,8 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
   if (!in || !out) return fail(h, "null inputs/outputs");
   if (in->struct_bytes != (int32_t)sizeof(ecrad_b200_inputs) || out->struct_bytes != (int32_t)sizeof(ecrad_b200_outputs))
     return fail(h, "ecrad_b200_inputs/outputs: struct_bytes mismatch (ABI)");
-  if (ncol < 1 || nlev < 2 || nlev > 190 || istartcol < 1 || iendcol > ncol || iendcol < istartcol)
-    return fail(h, "bad dimensions ncol=%d nlev=%d istartcol=%d iendcol=%d (nlev <= 190)", ncol, nlev, istartcol, iendcol);
+  if (ncol < 1 || nlev < 2 || nlev > 160 || istartcol < 1 || iendcol > ncol || iendcol < istartcol)
+    return fail(h, "bad dimensions ncol=%d nlev=%d istartcol=%d iendcol=%d (nlev <= 160)", ncol, nlev, istartcol, iendcol);
   const ecrad_b200_config& c = h->cfg;
   if (!in->pressure_hl || !in->temperature_hl || !in->h2o_mmr || !in->co2_mmr || !in->o3_mmr || !in->n2o_mmr || !in->ch4_mmr ||
       !in->cfc11_mmr || !in->cfc12_mmr || !in->hcfc22_mmr || !in->ccl4_mmr)
@@ -291,8 +291,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
   }
-  // generator thread stacks: 4.5 KB of private arrays per thread
-  cudaDeviceSetLimit(cudaLimitStackSize, 8192);
+  init_generator_constants();
   *handle = h;
   return 0;
 }

@@ -279,26 +279,229 @@ __global__ void cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, i
   }
 }
 
-enum { GEN_MAXLEV = 192 };
+// ---------------------------------------------------------------------------------------------------------
+// McICA cloud generator, warp-cooperative.  One CTA (2 warps) per column: warp 0 = SW stream (seed iseed), warp 1 =
+// LW stream (seed iseed + 997, radiation_mcica_lw.F90:223).  Same random stream, same decisions and same stream
+// consumption as radiation_cloud_generator.F90:202-390 + utilities/radiation_random_numbers_mix.F90 (the sequential
+// specification is gen_walk() in cloudgen_walk.h, which tests/ replays against the oracle), restructured so that
+// the 32 lanes work on one sub-column together:
+//   * seeding: the 29 x 604 serial LFSR steps of initialize_random_numbers are independent per bit plane once the
+//     LFSR (u' = u*x mod x^32+x^7+x^5+x^3+x^2+x+1 over GF(2)) is jumped ahead -> lane b fills bit plane b+1, a ballot
+//     assembles the words;
+//   * the lagged-Fibonacci stream s[t] = (s[t-607] + s[t-273]) mod 2^30 is produced 32 numbers per step into a
+//     1024-entry ring in shared memory and addressed by absolute stream position;
+//   * the cloudy/clear walk down the layers is a 2-state automaton: each layer's transition is an affine map over
+//     GF(2), composed with a warp prefix scan; run starts/ends, the offsets of the per-run random draws and the
+//     "reuse the previous layer's number" chain are further warp scans.
+// Output: code[g][layer] = 0 (clear) or 0x80000000 | rand30, consumed lane-parallel by the solvers (pdf_sample).
+// ---------------------------------------------------------------------------------------------------------
+enum { GW_MAXLEV = 160, GW_LPL = 5 };   // 32 lanes x 5 layers
 
-// one thread per (column, spectrum): spectrum 0 = SW (seed iseed), 1 = LW (seed iseed + 997, radiation_mcica_lw.F90:223)
+__constant__ uint32_t c_lfsr_jump[29];   // x^(604 b) mod P, b = 0..28
+
+__host__ __device__ __forceinline__ uint32_t lfsr_mul_x(uint32_t u) { return (u << 1) ^ ((u >> 31) ? 175u : 0u); }
+__host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+  for (int i = 31; i >= 0; --i) { r = lfsr_mul_x(r); if ((b >> i) & 1u) r ^= a; }
+  return r;
+}
+void init_generator_constants() {
+  uint32_t x604 = 1u;
+  for (int i = 0; i < 604; ++i) x604 = lfsr_mul_x(x604);
+  uint32_t c[29];
+  c[0] = 1u;
+  for (int b = 1; b < 29; ++b) c[b] = gf2_mulmod(c[b - 1], x604);
+  cudaMemcpyToSymbol(c_lfsr_jump, c, sizeof(c));
+}
+
 __global__ void __launch_bounds__(64)
-cloud_gen_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * nc) return;
-  const int c = i % nc, spec = i / nc;
-  if (spec == 0 && (!cfg.do_sw || cfg.solver_sw != 2 || !(in.cos_sza[c] > 0.0))) return;
-  if (spec == 1 && (!cfg.do_lw || cfg.solver_lw != 2)) return;
+cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp) {
+  __shared__ double sA1[GW_MAXLEV], sT1[GW_MAXLEV], sA2[GW_MAXLEV], sT2[GW_MAXLEV], sCUM[GW_MAXLEV], sOPI[GW_MAXLEV];
+  __shared__ int32_t sRing[2][1024];
+  __shared__ int32_t sTop[2][NG_LW];
+  const unsigned FULL = 0xffffffffu;
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double tcc = w.tcc[c];
   if (!(tcc > 0.0)) return;
-  int32_t ix[JPQ + 1], rtop[NG_LW], rcloud[GEN_MAXLEV], ri1[GEN_MAXLEV];
-  GenColumn gc;
-  gc.nlev = nlev; gc.fstride = in.ld; gc.stride = nc; gc.ibegin = w.ibegin[c]; gc.iend = w.iend[c];
-  gc.frac = in.frac + c; gc.cum = w.cum + c; gc.pair = w.pair + c; gc.opi = w.opi + c;
-  RngMix rs; rs.ix = ix; rs.iused = JPQ;
+  const int Lb = w.ibegin[c] - 1, Le = w.iend[c] - 1;   // first / last cloudy layer, 0-based
+  // per-layer constants of the two transition tests (same operations, same order as the reference's expressions)
+  for (int L = threadIdx.x; L < GW_MAXLEV; L += 64) {
+    double a1 = 0.0, t1 = 0.0, a2 = 0.0, t2 = 0.0, cu = 0.0, op = 0.0;
+    if (L < nlev) {
+      cu = w.cum[(size_t)L * nc + c];
+      if (L >= 1) {
+        const double f = LD_IN(in.frac, c, L), fp = LD_IN(in.frac, c, L - 1);
+        const double pr = w.pair[(size_t)(L - 1) * nc + c], cup = w.cum[(size_t)(L - 1) * nc + c];
+        a1 = fp;                                            // rand*frac(jlev-1) < frac(jlev)+frac(jlev-1)-pair(jlev-1)
+        t1 = sub_rn(add_rn(f, fp), pr);
+        a2 = sub_rn(cup, fp);                               // rand*(cum(jlev-1)-frac(jlev-1)) < pair(jlev-1)-overhang(jlev-1)-frac(jlev-1)
+        t2 = sub_rn(sub_rn(pr, sub_rn(cu, cup)), fp);
+        op = w.opi[(size_t)(L - 1) * nc + c];               // overlap_param_inhom between layers L-1 and L
+      }
+    }
+    sA1[L] = a1; sT1[L] = t1; sA2[L] = a2; sT2[L] = t2; sCUM[L] = cu; sOPI[L] = op;
+  }
+  __syncthreads();
+  const int spec = warp;
+  const bool mine = spec == 0 ? (cfg.do_sw && cfg.solver_sw == 2 && in.cos_sza[c] > 0.0) : (cfg.do_lw && cfg.solver_lw == 2);
+  if (!mine) return;
   const int ng = spec ? NG_LW : NG_SW;
   uint32_t* code = (spec ? w.code_lw : w.code_sw) + (size_t)c * ng * nlevp;
-  gen_walk(gc, rs, in.iseed[c] + (spec ? 997 : 0), ng, tcc, rtop, rcloud, ri1, code, nlevp);
+  int32_t* ring = sRing[warp];
+  int32_t* rtop = sTop[warp];
+  const double RM = 1.0 / 1073741824.0;
+
+  // ---- initialize_random_numbers (radiation_random_numbers_mix.F90:142-231) ----
+  {
+    const int32_t JPMASK = 123459876;
+    int32_t idum = (in.iseed[c] + (spec ? 997 : 0)) ^ JPMASK;
+    if (idum < 0) idum = (idum == INT32_MIN) ? idum : -idum;
+    if (idum == 0) idum = JPMASK;
+    uint32_t u = (uint32_t)idum;
+    for (int k = 0; k < 64; ++k) u = lfsr_mul_x(u);
+    for (int i = lane; i < 1024; i += 32) ring[i] = 0;
+    __syncwarp();
+    // state word ix(jj) is stream element s[jj-608]; ring index = stream index mod 1024
+    if (lane == 0) {
+      ring[(2 - 608) & 1023] = (int32_t)((u & ((1u << (JPMM - 1)) - 1u)) << 1);
+      ring[(607 - 608) & 1023] = (int32_t)((u >> (JPMM - 1)) & 7u);
+    }
+    uint32_t v = lane < 29 ? gf2_mulmod(u, c_lfsr_jump[lane]) : 0u;
+    for (int jj = 3; jj <= JPQ - 1; ++jj) {
+      const uint32_t word = __ballot_sync(FULL, v >> 31);     // bit b = top bit of plane b+1 before the step
+      v = lfsr_mul_x(v);
+      if (lane == (jj & 31)) ring[(jj - 608) & 1023] = (int32_t)((word & 0x1FFFFFFFu) << 1);
+    }
+    __syncwarp();
+    if (lane == 0) ring[(JPQ - JPS - 608) & 1023] |= 1;
+    __syncwarp();
+  }
+  int tgen = 0;   // stream elements [tgen-607, tgen) are in the ring
+  auto gen_to = [&](int target) {
+    while (tgen < target) {
+      const int t = tgen + lane;
+      ring[t & 1023] = 0x3FFFFFFF & (ring[(t - 607) & 1023] + ring[(t - 273) & 1023]);
+      __syncwarp();
+      tgen += 32;
+    }
+  };
+  gen_to(999 + ng);                                   // 999 warm-up numbers, then rand_top(1:ng)
+  for (int g = lane; g < ng; g += 32) rtop[g] = ring[(999 + g) & 1023];
+  __syncwarp();
+  int pos = 999 + ng;
+
+  for (int g = 0; g < ng; ++g) {
+    gen_to(pos + 416);   // one sub-column consumes at most nlev + 2*nlev numbers
+    // ---- cloud-top trigger: first layer whose cumulative cover reaches rand_top*total_cloud_cover ----
+    const double trigger = mul_rn((double)rtop[g] * RM, tcc);
+    int first = 1 << 30;
+#pragma unroll
+    for (int m = GW_LPL - 1; m >= 0; --m) {
+      const int L = lane * GW_LPL + m;
+      if (L >= Lb && L <= Le && !(trigger > sCUM[L])) first = L;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) first = min(first, __shfl_xor_sync(FULL, first, d));
+    const int Lt = min(first, Le);
+    const int N = Le - Lt + 1;
+    // ---- transition maps s' = a*s ^ b of every layer (s = 1: cloudy) ----
+    uint32_t am = 0, bm = 0;
+#pragma unroll
+    for (int m = 0; m < GW_LPL; ++m) {
+      const int L = lane * GW_LPL + m;
+      uint32_t a = 0, b = 0;
+      if (L == Lt) b = 1;
+      else if (L > Lt && L <= Le) {
+        const double r = (double)ring[(pos + (L - Lt - 1)) & 1023] * RM;
+        const bool c1 = mul_rn(r, sA1[L]) < sT1[L];   // cloudy above -> stays cloudy
+        const bool c2 = mul_rn(r, sA2[L]) < sT2[L];   // clear above  -> becomes cloudy
+        a = (uint32_t)(c1 != c2); b = (uint32_t)c2;
+      }
+      am |= a << m; bm |= b << m;
+    }
+    uint32_t A = 1, B = 0;
+#pragma unroll
+    for (int m = 0; m < GW_LPL; ++m) { const uint32_t a = (am >> m) & 1u, b = (bm >> m) & 1u; B = (a & B) ^ b; A = a & A; }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t Ap = __shfl_up_sync(FULL, A, d), Bp = __shfl_up_sync(FULL, B, d);
+      if (lane >= d) { B = (A & Bp) ^ B; A = A & Ap; }
+    }
+    uint32_t sin = __shfl_up_sync(FULL, B, 1);
+    if (lane == 0) sin = 0;
+    uint32_t cl = 0;
+    {
+      uint32_t s = sin;
+#pragma unroll
+      for (int m = 0; m < GW_LPL; ++m) { s = (((am >> m) & 1u) & s) ^ ((bm >> m) & 1u); cl |= s << m; }
+    }
+    // ---- number of cloudy layers above each layer ----
+    const int cnt = __popc(cl);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    const int C = __shfl_sync(FULL, incl, 31);
+    const int cntb_lane = incl - cnt;
+    // ---- first and last layer of the contiguous cloudy run each layer belongs to ----
+    const uint32_t isstart = cl & ~((cl << 1) | sin) & 31u;
+    int sc = isstart ? lane * GW_LPL + (31 - __clz((int)isstart)) : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc = max(sc, t); }
+    int rs_in = __shfl_up_sync(FULL, sc, 1);
+    if (lane == 0) rs_in = -1;
+    uint32_t nextfirst = __shfl_down_sync(FULL, cl & 1u, 1);
+    if (lane == 31) nextfirst = 0;
+    const uint32_t isend = cl & ~((cl >> 1) | (nextfirst << (GW_LPL - 1))) & 31u;
+    int ec = isend ? lane * GW_LPL + (__ffs((int)isend) - 1) : (1 << 30);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_down_sync(FULL, ec, d); if (lane + d < 32) ec = min(ec, t); }
+    int re_in = __shfl_down_sync(FULL, ec, 1);
+    if (lane == 31) re_in = 1 << 30;
+    int rsv[GW_LPL], rev[GW_LPL];
+    {
+      int cur = rs_in;
+#pragma unroll
+      for (int m = 0; m < GW_LPL; ++m) { if ((isstart >> m) & 1u) cur = lane * GW_LPL + m; rsv[m] = cur; }
+      cur = re_in;
+#pragma unroll
+      for (int m = GW_LPL - 1; m >= 0; --m) { if ((isend >> m) & 1u) cur = lane * GW_LPL + m; rev[m] = cur; }
+    }
+    // ---- per-run random draws: run r takes n numbers (rand_inhom1) then n numbers (rand_inhom2), runs in order ----
+    int offv[GW_LPL];
+    uint32_t fresh = 0;
+#pragma unroll
+    for (int m = 0; m < GW_LPL; ++m) {
+      offv[m] = 0;
+      if ((cl >> m) & 1u) {
+        const int L = lane * GW_LPL + m;
+        const int p = L - rsv[m], n = rev[m] - rsv[m] + 1;
+        const int cb = cntb_lane + __popc(cl & ((1u << m) - 1u));
+        const int off = pos + N + 2 * (cb - p);
+        offv[m] = off;
+        const double r2 = (double)ring[(off + n + p) & 1023] * RM;
+        if (p == 0 || !(r2 < sOPI[L])) fresh |= 1u << m;   // else: reuse the number of the layer above
+      }
+    }
+    int qc = fresh ? lane * GW_LPL + (31 - __clz((int)fresh)) : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, qc, d); if (lane >= d) qc = max(qc, t); }
+    int q_in = __shfl_up_sync(FULL, qc, 1);
+    if (lane == 0) q_in = -1;
+    uint32_t* row = code + (size_t)g * nlevp;
+    {
+      int cur = q_in;
+#pragma unroll
+      for (int m = 0; m < GW_LPL; ++m) {
+        const int L = lane * GW_LPL + m;
+        uint32_t word = 0;
+        if ((fresh >> m) & 1u) cur = L;
+        if ((cl >> m) & 1u) word = 0x80000000u | (uint32_t)ring[(offv[m] + (cur - rsv[m])) & 1023];
+        if (L < nlevp) row[L] = word;
+      }
+    }
+    pos += N + 2 * C;
+    __syncwarp();
+  }
 }
 
 // =========================================================================================================
@@ -865,10 +1068,8 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
   int n = 0;
   cloud_prep_kernel<<<(nc + 127) / 128, 128, 0, st>>>(cfg, in, w, nc, nlev); ++n;
   cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n;
-  if (cfg.do_lw && cfg.solver_lw == 2) cudaMemsetAsync(w.code_lw, 0, sizeof(uint32_t) * (size_t)nc * NG_LW * nlevp, st);
-  if (cfg.do_sw && cfg.solver_sw == 2) cudaMemsetAsync(w.code_sw, 0, sizeof(uint32_t) * (size_t)nc * NG_SW * nlevp, st);
   if ((cfg.do_lw && cfg.solver_lw == 2) || (cfg.do_sw && cfg.solver_sw == 2)) {
-    cloud_gen_kernel<<<(2 * nc + 63) / 64, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
+    cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
   }
   return n;
 }

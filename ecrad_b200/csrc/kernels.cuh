@@ -71,6 +71,7 @@ struct Work {
 };
 
 size_t scratch_doubles_per_column(int nlev);
+void init_generator_constants();   // once per process/device, before the first generator launch
 
 // Launchers.  All enqueue on `st` and return the number of kernels launched.
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
