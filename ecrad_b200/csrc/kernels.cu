@@ -15,7 +15,7 @@
 
 #include "cloudgen_walk.h"
 #include "kernels.cuh"
-#include "solver_core.h"
+#include "solver_common.cuh"
 
 namespace ecb {
 
@@ -30,7 +30,6 @@ enum { SW_KTOT = 129 };
 
 enum { GAS_LC = 16, GAS_THREADS = 256 };
 
-#define LD_IN(p, c, j) ((p)[(size_t)(j) * in.ld + (c)])
 
 // =========================================================================================================
 // LW gas optics
@@ -505,42 +504,6 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
 }
 
 // =========================================================================================================
-// solvers: shared helpers
-// =========================================================================================================
-enum { LCH = 16 };   // layers between two g-point reductions
-
-// Sum the rows of the shared-memory tile over g (4 threads per row) into sums[f][level].
-// Row (f, s), s < ns, holds level lfirst + dir*s of flux f.  Ends with a barrier so the tile can be refilled.
-__device__ __forceinline__ void flush_tile(const double* tile, int rs, int ng, int nf, int ns, double* const* dst, int lfirst, int dir) {
-  __syncthreads();
-  const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
-  const int nrows = nf * ns, rows_per_round = blockDim.x >> 2;
-  for (int r0 = 0; r0 < nrows; r0 += rows_per_round) {
-    const int r = r0 + row;
-    const bool valid = r < nrows;
-    int f = 0, s = 0;
-    double p = 0.0;
-    if (valid) {
-      f = r / ns; s = r - f * ns;
-      const double* t = tile + (size_t)(f * LCH + s) * rs;
-      for (int g = sub; g < ng; g += 4) p += t[g];
-    }
-    p += __shfl_xor_sync(0xffffffffu, p, 1);
-    p += __shfl_xor_sync(0xffffffffu, p, 2);
-    if (valid && sub == 0) dst[f][lfirst + dir * s] = p;
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ uint32_t pick4(const uint4& q, int k) { return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w; }
-
-// optical-depth scaling of this (g, layer) from the generator's code word
-__device__ __forceinline__ double od_scaling_from_code(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd) {
-  if (!code) return 0.0;
-  return pdf_sample(C, pdf_val, fsd, (double)(code & 0x3FFFFFFFu) * (1.0 / 1073741824.0));
-}
-
-// =========================================================================================================
 // LW solver: McICA (radiation_mcica_lw.F90:39-419) and Cloudless (radiation_cloudless_lw.F90)
 // =========================================================================================================
 enum { LW_THREADS = 160, LW_RS = 141 };
@@ -768,265 +731,6 @@ solver_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev
 }
 
 // =========================================================================================================
-// SW solver: McICA (radiation_mcica_sw.F90:41-408) and Cloudless (radiation_cloudless_sw.F90)
-// =========================================================================================================
-enum { SW_THREADS = 128, SW_RS = 113 };
-
-struct SwPassResult { double fdir_surf, fdd_surf, fu_toa; };
-
-// One full adding-method solution (radiation_adding_ica_sw.F90:24-151) for the column held by this CTA.
-// CLOUDY: merge gas + scaled cloud properties in cloudy layers.  CLOUDLESS: use the Cloudless solver's two-stream pair.
-template <bool CLOUDY, bool CLOUDLESS>
-__device__ __forceinline__ SwPassResult sw_pass(const DevTables& T, const DevCfg& cfg, int c, int g, bool act, int nlev, int nlevp,
-                                                const Work& w, const double* fracs, const double* fsds, double mu0, double inc,
-                                                double alb_diff, double alb_dir, double* tile, double* s_dir, double* s_dn,
-                                                double* s_up) {
-  const size_t n = (size_t)nlev * NG_SW;
-  const double* od = w.od_sw + (size_t)c * n;
-  const double* ssa = w.ssa_sw + (size_t)c * n;
-  double* scr = w.scr + (size_t)c * w.scr_per_col;
-  double *sa = scr, *sb = scr + n, *sA = scr + 2 * n, *sS = scr + 3 * n, *sF = scr + 4 * n;
-  const CloudMeta& C = *T.cloud;
-  const int gg = act ? g : 0;
-  const int b = T.meta->band_of_g_sw[gg];
-  const uint4* codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)c * NG_SW + gg) * nlevp);
-  const double* cl = w.cl_sw + (size_t)c * nlev * 3 * NB_SW;
-  const double thr = cfg.cloud_fraction_threshold;
-  const double inv_mu0 = 1.0 / mu0;
-  SwPassResult R;
-
-  // total optical properties of (layer l, this g-point)
-  auto props = [&](int l, uint32_t code, double& odt, double& ssat, double& gt) {
-    const size_t i = (size_t)l * NG_SW + g;
-    odt = od[i]; ssat = ssa[i]; gt = 0.0;
-    if (CLOUDY && fracs[l] >= thr) {
-      const double scal = od_scaling_from_code(C, T.pdf_val, code, fsds[l]);
-      const double* clb = cl + (size_t)l * 3 * NB_SW;
-      const double od_cloud_new = scal * clb[b];
-      const double od_gas = odt, ssa_gas = ssat;
-      odt = od_gas + od_cloud_new;
-      ssat = 0.0;
-      if (odt > 0.0) {
-        const double ssac = clb[NB_SW + b];
-        const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
-        ssat = scat_od / odt;
-        if (scat_od > 0.0) gt = (clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
-      }
-    }
-  };
-
-  // ---- A: direct beam, top-down ----
-  {
-    double* dst[1] = {s_dir};
-    int slot = 0, lfirst = 0;
-    double fdir = inc;
-    uint4 cq = make_uint4(0, 0, 0, 0);
-    for (int l = 0; l < nlev; ++l) {
-      if (act) {
-        if (CLOUDY && (l & 3) == 0) cq = __ldg(codep + (l >> 2));
-        double odt, ssat, gt;
-        props(l, pick4(cq, l & 3), odt, ssat, gt);
-        double tdir;
-        if (CLOUDLESS) tdir = sw_ref_trans_cloudless(mu0, odt, ssat, gt).trans_dir_dir;
-        else tdir = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
-        sF[(size_t)l * NG_SW + g] = fdir;
-        tile[slot * SW_RS + g] = fdir;
-        fdir = fdir * tdir;
-      }
-      ++slot;
-      if (slot == LCH) { flush_tile(tile, SW_RS, NG_SW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
-    }
-    if (act) tile[slot * SW_RS + g] = fdir;
-    ++slot;
-    flush_tile(tile, SW_RS, NG_SW, 1, slot, dst, lfirst, 1);
-    R.fdir_surf = fdir;
-  }
-  // ---- B: albedo / source of everything below each half-level, bottom-up ----
-  double S0 = 0.0;
-  if (act) {
-    double A = alb_diff, S = alb_dir * R.fdir_surf * mu0;
-    uint4 cq = make_uint4(0, 0, 0, 0);
-    for (int l = nlev - 1; l >= 0; --l) {
-      if (CLOUDY && (l == nlev - 1 || (l & 3) == 3)) cq = __ldg(codep + (l >> 2));
-      double odt, ssat, gt;
-      props(l, pick4(cq, l & 3), odt, ssat, gt);
-      const SwLayer L = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odt, ssat, gt) : sw_ref_trans(mu0, odt, ssat, gt);
-      const size_t i = (size_t)l * NG_SW + g;
-      const double fd_l = sF[i];
-      const double inv_den = 1.0 / (1.0 - A * L.ref);
-      sa[i] = L.trans * inv_den;
-      sb[i] = (L.ref * S + L.trans_dir_diff * fd_l) * inv_den;
-      sA[i] = A; sS[i] = S;
-      const double A_new = L.ref + L.trans * L.trans * A * inv_den;
-      const double S_new = L.ref_dir * fd_l + L.trans * (S + A * L.trans_dir_diff * fd_l) * inv_den;
-      A = A_new; S = S_new;
-    }
-    S0 = S;
-  }
-  R.fu_toa = S0;
-  // ---- C: fluxes, top-down ----
-  {
-    double* dst[2] = {s_dn, s_up};
-    int slot = 0, lfirst = 0;
-    double fdd = 0.0;
-    if (act) { tile[slot * SW_RS + g] = 0.0; tile[(LCH + slot) * SW_RS + g] = S0; }
-    ++slot;
-    for (int l = 0; l < nlev; ++l) {
-      if (act) {
-        const size_t i = (size_t)l * NG_SW + g;
-        fdd = sa[i] * fdd + sb[i];
-        const double fu = sA[i] * fdd + sS[i];
-        tile[slot * SW_RS + g] = fdd; tile[(LCH + slot) * SW_RS + g] = fu;
-      }
-      ++slot;
-      if (slot == LCH || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, 2, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
-    }
-    R.fdd_surf = fdd;
-  }
-  return R;
-}
-
-__global__ void __launch_bounds__(SW_THREADS, 3)
-solver_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int c = blockIdx.x, g = threadIdx.x;
-  const bool act = g < NG_SW;
-  const int nl1 = nlev + 1;
-  const double mu0 = in.cos_sza[c];
-#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
-  if (!(mu0 > 0.0)) {
-    // night column: radiation_mcica_sw.F90:380-401
-    for (int l = g; l < nl1; l += SW_THREADS) {
-      if (out.sw_up) OUT2(out.sw_up, l) = 0.0;
-      if (out.sw_dn) OUT2(out.sw_dn, l) = 0.0;
-      if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = 0.0;
-      if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = 0.0;
-      if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = 0.0;
-      if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = 0.0;
-    }
-    if (act) {
-      const size_t i = (size_t)c * NG_SW + g;
-      double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
-                       out.sw_dn_diffuse_surf_clear_g, out.sw_dn_direct_surf_clear_g, out.sw_up_toa_clear_g};
-      for (int k = 0; k < 6; ++k) if (gs[k]) gs[k][i] = 0.0;
-    }
-    if (g < NB_SW) {
-      double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
-      for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
-    }
-    if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
-      if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
-      if (out.sw_dn_direct_surf_canopy) out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
-    }
-    return;
-  }
-  double* sums = reinterpret_cast<double*>(smem_raw);   // [6][nl1]
-  double* tile = sums + 6 * nl1;                         // [2][LCH][SW_RS]
-  double* fracs = tile + 2 * LCH * SW_RS;                // [nlev]
-  double* fsds = fracs + nlev;                           // [nlev]
-  double* bandv = fsds + nlev;                           // [2][14] band albedos, later band fluxes
-  double *s_dir_c = sums, *s_dn_c = sums + nl1, *s_up_c = sums + 2 * nl1, *s_dir = sums + 3 * nl1, *s_dn = sums + 4 * nl1,
-         *s_up = sums + 5 * nl1;
-  const bool mcica = cfg.solver_sw == 2;
-  for (int l = g; l < nlev; l += SW_THREADS) {
-    fracs[l] = mcica ? LD_IN(in.frac, c, l) : 0.0;
-    fsds[l] = mcica ? LD_IN(in.fsd, c, l) : 0.0;
-  }
-  // get_albedos, radiation_single_level.F90:216-365 (weighted-interval mapping to bands)
-  if (g < NB_SW) {
-    double bd = 0.0, bdir = 0.0;
-    for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
-      const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
-      if (wgt != 0.0) {
-        bd = bd + wgt * LD_IN(in.sw_albedo, c, ja);
-        if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja);
-      }
-    }
-    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
-  }
-  __syncthreads();
-  const int gg = act ? g : 0;
-  const int bnd = T.meta->band_of_g_sw[gg];
-  const double alb_diff = bandv[bnd], alb_dir = bandv[NB_SW + bnd];
-  const double inc = w.incoming[(size_t)c * NG_SW + gg];
-  const double tcc = mcica ? w.tcc[c] : 0.0;
-  const bool cloudy = tcc > 0.0;
-
-  SwPassResult Rc, Ra;
-  if (mcica) Rc = sw_pass<false, false>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir_c, s_dn_c, s_up_c);
-  else Rc = sw_pass<false, true>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir_c, s_dn_c, s_up_c);
-  Ra = Rc;
-  if (cloudy) Ra = sw_pass<true, false>(T, cfg, c, g, act, nlev, nlevp, w, fracs, fsds, mu0, inc, alb_diff, alb_dir, tile, s_dir, s_dn, s_up);
-
-  const double wc = tcc, w1 = 1.0 - tcc;
-  for (int l = g; l < nl1; l += SW_THREADS) {
-    const double dirc = s_dir_c[l] * mu0, upc = s_up_c[l], dnc = s_dn_c[l] + dirc;
-    if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = upc;
-    if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = dnc;
-    if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = dirc;
-    double up = upc, dn = dnc, dir = dirc;
-    if (cloudy) {
-      const double dira = s_dir[l] * mu0;
-      up = wc * s_up[l] + w1 * upc;
-      dn = wc * (s_dn[l] + dira) + w1 * dnc;
-      dir = wc * dira + w1 * dirc;
-    }
-    if (out.sw_up) OUT2(out.sw_up, l) = up;
-    if (out.sw_dn) OUT2(out.sw_dn, l) = dn;
-    if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = dir;
-  }
-  if (g == 0 && out.cloud_cover_sw && mcica) out.cloud_cover_sw[c] = tcc;
-  // per-g surface / TOA fluxes
-  const double dif_c = Rc.fdd_surf, dir_c = Rc.fdir_surf * mu0, toa_c = Rc.fu_toa;
-  double dif_a = dif_c, dir_a = dir_c, toa_a = toa_c;
-  if (cloudy) {
-    dif_a = wc * Ra.fdd_surf + w1 * dif_c;
-    dir_a = wc * (Ra.fdir_surf * mu0) + w1 * dir_c;
-    toa_a = wc * Ra.fu_toa + w1 * toa_c;
-  }
-  if (act) {
-    const size_t i = (size_t)c * NG_SW + g;
-    if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
-    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
-    if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
-    if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
-    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
-    if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
-  }
-  // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral
-  if (cfg.do_surface_sw_spectral_flux || cfg.do_canopy_fluxes_sw) {
-    __syncthreads();
-    if (act) { tile[g] = dir_a; tile[SW_RS + g] = dif_a; tile[2 * SW_RS + g] = dir_c; tile[3 * SW_RS + g] = dif_c; }
-    __syncthreads();
-    double* bdir = tile + 4 * SW_RS;  // [14] all-sky direct band, [14] all-sky total band
-    if (g < NB_SW) {
-      const int g0 = T.meta->sw[g].g0, ngb = T.meta->sw[g].ng;
-      double d = 0.0, t = 0.0, dcl = 0.0, tcl = 0.0;
-      for (int k = g0; k < g0 + ngb; ++k) { d = d + tile[k]; t = t + tile[SW_RS + k]; dcl = dcl + tile[2 * SW_RS + k]; tcl = tcl + tile[3 * SW_RS + k]; }
-      t = t + d; tcl = tcl + dcl;
-      bdir[g] = d; bdir[NB_SW + g] = t;
-      if (cfg.do_surface_sw_spectral_flux) {
-        if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * NB_SW + g] = d;
-        if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * NB_SW + g] = t;
-        if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * NB_SW + g] = dcl;
-        if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * NB_SW + g] = tcl;
-      }
-    }
-    __syncthreads();
-    if (cfg.do_canopy_fluxes_sw && out.sw_dn_diffuse_surf_canopy && out.sw_dn_direct_surf_canopy && g < cfg.n_albedo_sw) {
-      double dif = 0.0, dir = 0.0;
-      for (int jb = 0; jb < NB_SW; ++jb) {
-        const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + g];
-        if (wgt != 0.0) { dif = dif + wgt * bdir[NB_SW + jb]; dir = dir + wgt * bdir[jb]; }
-      }
-      out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dif - dir;
-      out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dir;
-    }
-  }
-#undef OUT2
-}
-
-// =========================================================================================================
 // launchers
 // =========================================================================================================
 size_t scratch_doubles_per_column(int nlev) {
@@ -1043,7 +747,6 @@ static size_t gas_sw_smem(int nlev) {
          sizeof(int) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + nlev) + 16;
 }
 static size_t solver_lw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1) + 2 * LCH * LW_RS + 2 * nlev) + 16; }
-static size_t solver_sw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1) + 2 * LCH * SW_RS + 2 * nlev + 2 * NB_SW) + 16; }
 
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
@@ -1079,11 +782,4 @@ int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   solver_lw_kernel<<<nc, LW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev, (nlev + 3) & ~3);
   return 1;
 }
-int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  size_t sm = solver_sw_smem(nlev);
-  allow_smem(solver_sw_kernel, sm);
-  solver_sw_kernel<<<nc, SW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev, (nlev + 3) & ~3);
-  return 1;
-}
-
 }  // namespace ecb

@@ -1,0 +1,363 @@
+// solver_sw.cu -- shortwave McICA (radiation_mcica_sw.F90:41-408) and Cloudless (radiation_cloudless_sw.F90) solvers.
+//
+// One CTA per sunlit column, one thread per g-point.  The clear-sky and the cloudy (McICA sub-column) solutions of
+// the adding method (radiation_adding_ica_sw.F90:24-151) are advanced TOGETHER by the same thread: layers in which
+// this column has no cloud share one two-stream evaluation (in the reference the cloudy arrays are copies of the
+// clear-sky ones there, radiation_mcica_sw.F90:287-297), and the two independent recurrences give the instruction-level
+// parallelism that hides the fp64 latencies.  Three kernels, so that each runs at the occupancy it needs:
+//   sw_direct_kernel   top-down: direct beam (1 exp per layer)                      -> fdir per layer, g-sums of fdir
+//   sw_adding_kernel   bottom-up: two-stream (calc_ref_trans_sw) + albedo/source     -> a, b, albedo, source per layer
+//   sw_flux_kernel     top-down: flux recurrence, g-point sums, flux_type outputs    (pure streaming)
+// State between the kernels lives in the per-column scratch ([layer][g], coalesced): 2 + 8 arrays.
+#include "solver_common.cuh"
+
+namespace ecb {
+
+enum { SW_THREADS = 128, SW_RS = 113, SW_LCH_FLUX = 8 };
+
+// total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
+__device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd, const double* clb,
+                                                int b, double od_gas, double ssa_gas, double& odt, double& ssat, double& gt) {
+  const double scal = od_scaling_from_code(C, pdf_val, code, fsd);
+  const double od_cloud_new = scal * clb[b];
+  odt = od_gas + od_cloud_new;
+  ssat = 0.0; gt = 0.0;
+  if (odt > 0.0) {
+    const double ssac = clb[NB_SW + b];
+    const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
+    ssat = scat_od / odt;
+    if (scat_od > 0.0) gt = (clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
+  }
+}
+
+struct SwColumn {
+  int c, g, gg, b; bool act, cloudy; double mu0, tcc, thr;
+  size_t n;
+  const double *od, *ssa, *cl; const uint4* codep;
+  double* scr;
+};
+
+__device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nlev, int nlevp) {
+  SwColumn s;
+  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < NG_SW; s.gg = s.act ? s.g : 0;
+  s.mu0 = in.cos_sza[s.c];
+  s.tcc = cfg.solver_sw == 2 ? w.tcc[s.c] : 0.0;
+  s.cloudy = s.tcc > 0.0;
+  s.thr = cfg.cloud_fraction_threshold;
+  s.n = (size_t)nlev * NG_SW;
+  s.od = w.od_sw + (size_t)s.c * s.n;
+  s.ssa = w.ssa_sw + (size_t)s.c * s.n;
+  s.cl = w.cl_sw + (size_t)s.c * nlev * 3 * NB_SW;
+  s.b = T.meta->band_of_g_sw[s.gg];
+  s.codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)s.c * NG_SW + s.gg) * nlevp);
+  s.scr = w.scr + (size_t)s.c * w.scr_per_col;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A: direct beam, top-down (radiation_adding_ica_sw.F90:85-88)
+// ---------------------------------------------------------------------------------------------------------
+template <bool CLOUDLESS>
+__global__ void __launch_bounds__(SW_THREADS, 6)
+sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  if (!(s.mu0 > 0.0)) return;
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LCH][SW_RS]
+  double* fracs = tile + 2 * LCH * SW_RS;               // [nlev]
+  double* fsds = fracs + nlev;                          // [nlev]
+  for (int l = s.g; l < nlev; l += SW_THREADS) {
+    fracs[l] = s.cloudy ? LD_IN(in.frac, s.c, l) : 0.0;
+    fsds[l] = s.cloudy ? LD_IN(in.fsd, s.c, l) : 0.0;
+  }
+  __syncthreads();
+  const CloudMeta& C = *T.cloud;
+  const int g = s.g, nl1 = nlev + 1;
+  double *sFc = s.scr, *sFa = s.scr + s.n;
+  double* sums = w.sw_sums + (size_t)s.c * 6 * nl1;
+  double* dst[2] = {sums, sums + 3 * nl1};
+  const int nf = s.cloudy ? 2 : 1;
+  const double inv_mu0 = 1.0 / s.mu0;
+  double fc = w.incoming[(size_t)s.c * NG_SW + s.gg], fa = fc;
+  int slot = 0, lfirst = 0;
+  uint4 cq = make_uint4(0, 0, 0, 0);
+  for (int l = 0; l < nlev; ++l) {
+    if (s.act) {
+      const size_t i = (size_t)l * NG_SW + g;
+      const double odg = s.od[i];
+      double tdir_c;
+      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, s.ssa[i], 0.0).trans_dir_dir;
+      else tdir_c = exp(dmax(-dmax(odg * inv_mu0, 0.0), -1000.0));
+      double tdir_a = tdir_c;
+      if (s.cloudy) {
+        if ((l & 3) == 0) cq = __ldg(s.codep + (l >> 2));
+        if (fracs[l] >= s.thr) {
+          double odt, ssat, gt;
+          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, s.ssa[i], odt, ssat, gt);
+          tdir_a = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
+        }
+        sFa[i] = fa;
+        tile[(LCH + slot) * SW_RS + g] = fa;
+      }
+      sFc[i] = fc;
+      tile[slot * SW_RS + g] = fc;
+      fc = fc * tdir_c;
+      fa = fa * tdir_a;
+    }
+    ++slot;
+    if (slot == LCH) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+  }
+  if (s.act) { tile[slot * SW_RS + g] = fc; tile[(LCH + slot) * SW_RS + g] = fa; }
+  ++slot;
+  flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1);
+  if (s.act) {
+    double* carry = w.sw_carry + (size_t)s.c * 4 * NG_SW;
+    carry[g] = fc; carry[NG_SW + g] = fa;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B: two-stream layer solutions and the upward sweep of albedo / source (radiation_adding_ica_sw.F90:90-121)
+// ---------------------------------------------------------------------------------------------------------
+template <bool CLOUDLESS>
+__global__ void __launch_bounds__(SW_THREADS, 3)
+sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  if (!(s.mu0 > 0.0)) return;
+  double* fracs = reinterpret_cast<double*>(smem_raw);   // [nlev]
+  double* fsds = fracs + nlev;                           // [nlev]
+  double* bandv = fsds + nlev;                           // [2][14] band albedos
+  const int g = s.g, c = s.c;
+  for (int l = g; l < nlev; l += SW_THREADS) {
+    fracs[l] = s.cloudy ? LD_IN(in.frac, c, l) : 0.0;
+    fsds[l] = s.cloudy ? LD_IN(in.fsd, c, l) : 0.0;
+  }
+  // get_albedos, radiation_single_level.F90:216-365 (weighted-interval mapping to bands)
+  if (g < NB_SW) {
+    double bd = 0.0, bdir = 0.0;
+    for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
+      const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
+      if (wgt != 0.0) {
+        bd = bd + wgt * LD_IN(in.sw_albedo, c, ja);
+        if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja);
+      }
+    }
+    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
+  }
+  __syncthreads();
+  if (!s.act) return;
+  const CloudMeta& C = *T.cloud;
+  const size_t n = s.n;
+  const double* sFc = s.scr; const double* sFa = s.scr + n;
+  double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
+  double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
+  double* carry = w.sw_carry + (size_t)c * 4 * NG_SW;
+  const double alb_diff = bandv[s.b], alb_dir = bandv[NB_SW + s.b];
+  const double mu0 = s.mu0;
+  double A_c = alb_diff, S_c = alb_dir * carry[g] * mu0;
+  double A_a = alb_diff, S_a = alb_dir * carry[NG_SW + g] * mu0;
+  uint4 cq = make_uint4(0, 0, 0, 0);
+  // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
+  size_t i = (size_t)(nlev - 1) * NG_SW + g;
+  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0;
+  for (int l = nlev - 1; l >= 0; --l) {
+    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n;
+    i = (size_t)l * NG_SW + g;
+    if (l > 0) {
+      const size_t ip = i - NG_SW;
+      od_n = s.od[ip]; ssa_n = s.ssa[ip]; fc_n = sFc[ip];
+      if (s.cloudy) fa_n = sFa[ip];
+    }
+    const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, 0.0) : sw_ref_trans(mu0, odg, ssag, 0.0);
+    {
+      const double inv_den = 1.0 / (1.0 - A_c * Lc.ref);
+      ac[i] = Lc.trans * inv_den;
+      bc[i] = (Lc.ref * S_c + Lc.trans_dir_diff * fd_c) * inv_den;
+      Ac[i] = A_c; Sc[i] = S_c;   // albedo / source of everything below the half-level under layer l
+      const double A_new = Lc.ref + Lc.trans * Lc.trans * A_c * inv_den;
+      const double S_new = Lc.ref_dir * fd_c + Lc.trans * (S_c + A_c * Lc.trans_dir_diff * fd_c) * inv_den;
+      A_c = A_new; S_c = S_new;
+    }
+    if (s.cloudy) {
+      if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(s.codep + (l >> 2));
+      SwLayer La = Lc;
+      if (fracs[l] >= s.thr) {
+        double odt, ssat, gt;
+        sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, odt, ssat, gt);
+        La = sw_ref_trans(mu0, odt, ssat, gt);
+      }
+      const double inv_den = 1.0 / (1.0 - A_a * La.ref);
+      aa[i] = La.trans * inv_den;
+      ba[i] = (La.ref * S_a + La.trans_dir_diff * fd_a) * inv_den;
+      Aa[i] = A_a; Sa[i] = S_a;
+      const double A_new = La.ref + La.trans * La.trans * A_a * inv_den;
+      const double S_new = La.ref_dir * fd_a + La.trans * (S_a + A_a * La.trans_dir_diff * fd_a) * inv_den;
+      A_a = A_new; S_a = S_new;
+    }
+  }
+  carry[2 * NG_SW + g] = S_c;   // flux_up at TOA = source(1)
+  carry[3 * NG_SW + g] = S_a;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C: fluxes top-down (radiation_adding_ica_sw.F90:134-146), g-point sums, blending and the flux_type outputs
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SW_THREADS, 6)
+sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  const int c = s.c, g = s.g, nl1 = nlev + 1;
+  const bool act = s.act;
+  const double mu0 = s.mu0;
+#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
+  if (!(mu0 > 0.0)) {
+    // night column: radiation_mcica_sw.F90:380-401
+    for (int l = g; l < nl1; l += SW_THREADS) {
+      if (out.sw_up) OUT2(out.sw_up, l) = 0.0;
+      if (out.sw_dn) OUT2(out.sw_dn, l) = 0.0;
+      if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = 0.0;
+      if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = 0.0;
+      if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = 0.0;
+      if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = 0.0;
+    }
+    if (act) {
+      const size_t i = (size_t)c * NG_SW + g;
+      double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
+                       out.sw_dn_diffuse_surf_clear_g, out.sw_dn_direct_surf_clear_g, out.sw_up_toa_clear_g};
+      for (int k = 0; k < 6; ++k) if (gs[k]) gs[k][i] = 0.0;
+    }
+    if (g < NB_SW) {
+      double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
+      for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
+    }
+    if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
+      if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
+      if (out.sw_dn_direct_surf_canopy) out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
+    }
+    return;
+  }
+  double* ssum = reinterpret_cast<double*>(smem_raw);    // [4][nl1]: dn_c, up_c, dn_a, up_a
+  double* tile = ssum + 4 * nl1;                          // [4][SW_LCH_FLUX][SW_RS]
+  double *s_dn_c = ssum, *s_up_c = ssum + nl1, *s_dn = ssum + 2 * nl1, *s_up = ssum + 3 * nl1;
+  const double* gsum = w.sw_sums + (size_t)c * 6 * nl1;   // direct-beam sums from sw_direct_kernel
+  const double *s_dir_c = gsum, *s_dir = gsum + 3 * nl1;
+  const size_t n = s.n;
+  const double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
+  const double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
+  const double* carry = w.sw_carry + (size_t)c * 4 * NG_SW;
+  const bool cloudy = s.cloudy;
+  const double toa_c = carry[2 * NG_SW + s.gg], toa_a0 = carry[3 * NG_SW + s.gg];
+  double fdd_c = 0.0, fdd_a = 0.0;
+  {
+    double* dst[4] = {s_dn_c, s_up_c, s_dn, s_up};
+    const int nf = cloudy ? 4 : 2;
+    int slot = 0, lfirst = 0;
+    if (act) {
+      tile[slot * SW_RS + g] = 0.0; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = toa_c;
+      tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = 0.0; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = toa_a0;
+    }
+    ++slot;
+#pragma unroll 4
+    for (int l = 0; l < nlev; ++l) {
+      if (act) {
+        const size_t i = (size_t)l * NG_SW + g;
+        fdd_c = ac[i] * fdd_c + bc[i];
+        const double fu_c = Ac[i] * fdd_c + Sc[i];
+        tile[slot * SW_RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = fu_c;
+        if (cloudy) {
+          fdd_a = aa[i] * fdd_a + ba[i];
+          const double fu_a = Aa[i] * fdd_a + Sa[i];
+          tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = fu_a;
+        }
+      }
+      ++slot;
+      if (slot == SW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0; }
+    }
+  }
+  const double tcc = s.tcc;
+  const double wc = tcc, w1 = 1.0 - tcc;
+  for (int l = g; l < nl1; l += SW_THREADS) {
+    const double dirc = s_dir_c[l] * mu0, upc = s_up_c[l], dnc = s_dn_c[l] + dirc;
+    if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = upc;
+    if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = dnc;
+    if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = dirc;
+    double up = upc, dn = dnc, dir = dirc;
+    if (cloudy) {
+      const double dira = s_dir[l] * mu0;
+      up = wc * s_up[l] + w1 * upc;
+      dn = wc * (s_dn[l] + dira) + w1 * dnc;
+      dir = wc * dira + w1 * dirc;
+    }
+    if (out.sw_up) OUT2(out.sw_up, l) = up;
+    if (out.sw_dn) OUT2(out.sw_dn, l) = dn;
+    if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = dir;
+  }
+  if (g == 0 && out.cloud_cover_sw && cfg.solver_sw == 2) out.cloud_cover_sw[c] = tcc;
+  // per-g surface / TOA fluxes
+  const double dif_c = fdd_c, dir_c = carry[s.gg] * mu0;
+  double dif_a = dif_c, dir_a = dir_c, toa_a = toa_c;
+  if (cloudy) {
+    dif_a = wc * fdd_a + w1 * dif_c;
+    dir_a = wc * (carry[NG_SW + s.gg] * mu0) + w1 * dir_c;
+    toa_a = wc * toa_a0 + w1 * toa_c;
+  }
+  if (act) {
+    const size_t i = (size_t)c * NG_SW + g;
+    if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
+    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
+    if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
+    if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
+    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
+    if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
+  }
+  // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral
+  if (cfg.do_surface_sw_spectral_flux || cfg.do_canopy_fluxes_sw) {
+    __syncthreads();
+    if (act) { tile[g] = dir_a; tile[SW_RS + g] = dif_a; tile[2 * SW_RS + g] = dir_c; tile[3 * SW_RS + g] = dif_c; }
+    __syncthreads();
+    double* bdir = tile + 4 * SW_RS;  // [14] all-sky direct band, [14] all-sky total band
+    if (g < NB_SW) {
+      const int g0 = T.meta->sw[g].g0, ngb = T.meta->sw[g].ng;
+      double d = 0.0, t = 0.0, dcl = 0.0, tcl = 0.0;
+      for (int k = g0; k < g0 + ngb; ++k) { d = d + tile[k]; t = t + tile[SW_RS + k]; dcl = dcl + tile[2 * SW_RS + k]; tcl = tcl + tile[3 * SW_RS + k]; }
+      t = t + d; tcl = tcl + dcl;
+      bdir[g] = d; bdir[NB_SW + g] = t;
+      if (cfg.do_surface_sw_spectral_flux) {
+        if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * NB_SW + g] = d;
+        if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * NB_SW + g] = t;
+        if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * NB_SW + g] = dcl;
+        if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * NB_SW + g] = tcl;
+      }
+    }
+    __syncthreads();
+    if (cfg.do_canopy_fluxes_sw && out.sw_dn_diffuse_surf_canopy && out.sw_dn_direct_surf_canopy && g < cfg.n_albedo_sw) {
+      double dif = 0.0, dir = 0.0;
+      for (int jb = 0; jb < NB_SW; ++jb) {
+        const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + g];
+        if (wgt != 0.0) { dif = dif + wgt * bdir[NB_SW + jb]; dir = dir + wgt * bdir[jb]; }
+      }
+      out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dif - dir;
+      out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dir;
+    }
+  }
+#undef OUT2
+}
+
+int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const int nlevp = (nlev + 3) & ~3;
+  const size_t smA = sizeof(double) * (2 * LCH * SW_RS + 2 * nlev) + 16;
+  const size_t smB = sizeof(double) * (2 * nlev + 2 * NB_SW) + 16;
+  const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SW_RS) + 16;
+  if (cfg.solver_sw == 2) {
+    sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_adding_kernel<false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+  } else {
+    sw_direct_kernel<true><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_adding_kernel<true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+  }
+  sw_flux_kernel<<<nc, SW_THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
+  return 3;
+}
+
+}  // namespace ecb
