@@ -110,7 +110,8 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
       8 * nc * spc,                                                                          // scratch
-      8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW};                                            // sw_sums sw_carry
+      8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
+      8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW};                                            // lw_sums lw_carry
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
@@ -121,6 +122,7 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
   w.scr = (double*)h->work[18].p; w.scr_per_col = spc;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
+  w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
   return 0;
 }

@@ -504,233 +504,6 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
 }
 
 // =========================================================================================================
-// LW solver: McICA (radiation_mcica_lw.F90:39-419) and Cloudless (radiation_cloudless_lw.F90)
-// =========================================================================================================
-enum { LW_THREADS = 160, LW_RS = 141 };
-
-__global__ void __launch_bounds__(LW_THREADS, 3)
-solver_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int c = blockIdx.x, g = threadIdx.x;
-  const bool act = g < NG_LW;
-  const int nl1 = nlev + 1;
-  double* sums = reinterpret_cast<double*>(smem_raw);   // [6][nl1]: dn_clear, up_clear, dn, up, deriv_clear, deriv
-  double* tile = sums + 6 * nl1;                         // [2][LCH][LW_RS]
-  double* fracs = tile + 2 * LCH * LW_RS;                // [nlev]
-  double* fsds = fracs + nlev;                           // [nlev]
-  double* s_dn_clear = sums, *s_up_clear = sums + nl1, *s_dn = sums + 2 * nl1, *s_up = sums + 3 * nl1;
-  double* s_dv_clear = sums + 4 * nl1, *s_dv = sums + 5 * nl1;
-
-  const bool mcica = cfg.solver_lw == 2;
-  for (int l = g; l < nlev; l += LW_THREADS) {
-    fracs[l] = mcica ? LD_IN(in.frac, c, l) : 0.0;
-    fsds[l] = mcica ? LD_IN(in.fsd, c, l) : 0.0;
-  }
-  const double tcc = mcica ? w.tcc[c] : 0.0;
-  const bool cloudy = tcc > 0.0;
-  const int ict = cloudy ? w.ict[c] : nlev;
-  const double thr = cfg.cloud_fraction_threshold;
-  const size_t n = (size_t)nlev * NG_LW;
-  const double* od = w.od_lw + (size_t)c * n;
-  const double* pl = w.planck + (size_t)c * nl1 * NG_LW;
-  double* scr = w.scr + (size_t)c * w.scr_per_col;
-  double *tr = scr, *su = scr + n, *sdc = scr + 2 * n, *sa = scr + 3 * n, *sb = scr + 4 * n, *sA = scr + 5 * n,
-         *sS = scr + 6 * n, *trc = scr + 7 * n;
-  const int gg = act ? g : 0;
-  const double emission = w.emission[(size_t)c * NG_LW + gg], albedo = w.lw_albedo[(size_t)c * NG_LW + gg];
-  __syncthreads();
-
-  // ---- pass 1: clear-sky layer properties and downward flux (calc_fluxes_no_scattering_lw, first loop) ----
-  double fd = 0.0, fd_ict = 0.0;
-  {
-    double* dst[1] = {s_dn_clear};
-    int slot = 0, lfirst = 0;
-    if (act) tile[slot * LW_RS + g] = 0.0;   // flux_dn at TOA
-    ++slot;
-    for (int l = 0; l < nlev; ++l) {
-      if (act) {
-        if (l == ict) fd_ict = fd;
-        const size_t i = (size_t)l * NG_LW + g;
-        LwLayer L = lw_no_scat(od[i], pl[i], pl[i + NG_LW]);
-        tr[i] = L.trans; su[i] = L.source_up; sdc[i] = L.source_dn;
-        fd = L.trans * fd + L.source_dn;
-        tile[slot * LW_RS + g] = fd;
-      }
-      ++slot;
-      if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
-    }
-  }
-  const double fd_surf_clear = fd;
-  // ---- pass 2: clear-sky upward flux and the clear-sky derivative products ----
-  const double fu_surf_clear = emission + albedo * fd_surf_clear;
-  double fu = fu_surf_clear;
-  {
-    double* dst[2] = {s_up_clear, s_dv_clear};
-    int slot = 0, lfirst = nlev;
-    double prod = fu_surf_clear;
-    if (act) { tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod; }
-    ++slot;
-    for (int l = nlev - 1; l >= 0; --l) {
-      if (act) {
-        const size_t i = (size_t)l * NG_LW + g;
-        const double t = tr[i];
-        fu = t * fu + su[i];
-        prod = prod * t;
-        tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod;
-      }
-      ++slot;
-      if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
-    }
-  }
-  const double fu_toa_clear = fu;
-  double fd_surf = fd_surf_clear, fu_toa = fu_toa_clear;
-
-  if (cloudy) {
-    const CloudMeta& C = *T.cloud;
-    const int b = T.meta->band_of_g_lw[gg];
-    const uint4* codep = reinterpret_cast<const uint4*>(w.code_lw + ((size_t)c * NG_LW + gg) * nlevp);
-    const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
-    // ---- pass 3: upward sweep of albedo/source from the surface to cloud top (fast_adding_ica_lw) ----
-    if (act) {
-      double A = albedo, S = emission;
-      uint4 cq = make_uint4(0, 0, 0, 0);
-      for (int l = nlev - 1; l >= ict; --l) {
-        if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
-        const size_t i = (size_t)l * NG_LW + g;
-        double a_, b_, t_;
-        if (fracs[l] >= thr) {
-          const double scal = od_scaling_from_code(C, T.pdf_val, pick4(cq, l & 3), fsds[l]);
-          const double* clb = cl + (size_t)l * 3 * NB_LW;
-          const double od_cloud_new = scal * clb[b];
-          const double od_total = od[i] + od_cloud_new;
-          LwLayer L;
-          if (cfg.do_lw_cloud_scattering) {
-            double ssa_total = 0.0, g_total = 0.0;
-            if (od_total > 0.0) {
-              const double ssac = clb[NB_LW + b];
-              const double scat_od = ssac * od_cloud_new;
-              ssa_total = scat_od / od_total;
-              if (scat_od > 0.0) g_total = clb[2 * NB_LW + b] * ssac * od_cloud_new / scat_od;
-            }
-            L = lw_ref_trans(od_total, ssa_total, g_total, pl[i], pl[i + NG_LW]);
-          } else {
-            L = lw_no_scat(od_total, pl[i], pl[i + NG_LW]);
-          }
-          const double inv_den = 1.0 / (1.0 - A * L.ref);
-          a_ = L.trans * inv_den;
-          b_ = (L.ref * S + L.source_dn) * inv_den;
-          t_ = L.trans;
-          const double A_new = L.ref + L.trans * L.trans * A * inv_den;
-          const double S_new = L.source_up + L.trans * (S + A * L.source_dn) * inv_den;
-          sA[i] = A; sS[i] = S;   // albedo/source at the half-level below layer l
-          A = A_new; S = S_new;
-        } else {
-          const double t = tr[i], sd = sdc[i];
-          a_ = t; b_ = sd; t_ = t;
-          sA[i] = A; sS[i] = S;
-          const double A_new = t * t * A;
-          const double S_new = su[i] + t * (S + A * sd);
-          A = A_new; S = S_new;
-        }
-        sa[i] = a_; sb[i] = b_; trc[i] = t_;
-      }
-      fu = S + A * fd_ict;   // flux_up at cloud top
-    }
-    // ---- upward flux above cloud top ----
-    {
-      double* dst[1] = {s_up};
-      int slot = 0, lfirst = ict;
-      if (act) tile[slot * LW_RS + g] = fu;
-      ++slot;
-      for (int l = ict - 1; l >= 0; --l) {
-        if (act) { const size_t i = (size_t)l * NG_LW + g; fu = tr[i] * fu + su[i]; tile[slot * LW_RS + g] = fu; }
-        ++slot;
-        if (slot == LCH) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
-      }
-      if (slot) flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1);
-    }
-    fu_toa = fu;
-    // ---- downward sweep from cloud top to the surface ----
-    {
-      double* dst[2] = {s_dn, s_up};
-      int slot = 0, lfirst = ict + 1;
-      fd = fd_ict;
-      for (int l = ict; l < nlev; ++l) {
-        if (act) {
-          const size_t i = (size_t)l * NG_LW + g;
-          fd = sa[i] * fd + sb[i];
-          fu = sA[i] * fd + sS[i];
-          tile[slot * LW_RS + g] = fd; tile[(LCH + slot) * LW_RS + g] = fu;
-        }
-        ++slot;
-        if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
-      }
-    }
-    fd_surf = fd;
-    // ---- derivative products of the cloudy sub-columns (calc_lw_derivatives_ica) ----
-    if (cfg.do_lw_derivatives && out.lw_derivatives) {
-      double* dst[1] = {s_dv};
-      int slot = 0, lfirst = nlev;
-      double prod = fu;   // flux_up at the surface of the cloudy sub-column
-      if (act) tile[slot * LW_RS + g] = prod;
-      ++slot;
-      for (int l = nlev - 1; l >= 0; --l) {
-        if (act) { const size_t i = (size_t)l * NG_LW + g; prod = prod * (l >= ict ? trc[i] : tr[i]); tile[slot * LW_RS + g] = prod; }
-        ++slot;
-        if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
-      }
-    }
-  }
-
-  // ---- outputs ----
-#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
-  const double wc = tcc, w1 = 1.0 - tcc;
-  for (int l = g; l < nl1; l += LW_THREADS) {
-    const double upc = s_up_clear[l], dnc = s_dn_clear[l];
-    if (out.lw_up_clear) OUT2(out.lw_up_clear, l) = upc;
-    if (out.lw_dn_clear) OUT2(out.lw_dn_clear, l) = dnc;
-    double up = upc, dn = dnc;
-    if (cloudy) {
-      up = wc * s_up[l] + w1 * upc;
-      dn = wc * (l <= ict ? dnc : s_dn[l]) + w1 * dnc;
-    }
-    if (out.lw_up) OUT2(out.lw_up, l) = up;
-    if (out.lw_dn) OUT2(out.lw_dn, l) = dn;
-    if (cfg.do_lw_derivatives && out.lw_derivatives) {
-      double dclear = l == nlev ? 1.0 : s_dv_clear[l] / s_up_clear[nlev];
-      double d = dclear;
-      if (cloudy) {
-        d = l == nlev ? 1.0 : s_dv[l] / s_up[nlev];
-        if (tcc < 1.0 - thr) d = l == nlev ? 1.0 : (1.0 - w1) * d + w1 * dclear;
-      }
-      OUT2(out.lw_derivatives, l) = d;
-    }
-  }
-  if (g == 0 && out.cloud_cover_lw && mcica) out.cloud_cover_lw[c] = tcc;
-  const double dn_surf_g = cloudy ? wc * fd_surf + w1 * fd_surf_clear : fd_surf_clear;
-  if (act) {
-    const size_t i = (size_t)c * NG_LW + g;
-    if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
-    if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fu_toa_clear;
-    if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
-    if (out.lw_up_toa_g) out.lw_up_toa_g[i] = cloudy ? wc * fu_toa + w1 * fu_toa_clear : fu_toa_clear;
-  }
-  // canopy fluxes, radiation_flux.F90 calc_surface_spectral (nearest-interval emissivity mapping)
-  if (cfg.do_canopy_fluxes_lw && out.lw_dn_surf_canopy) {
-    __syncthreads();
-    if (act) tile[g] = dn_surf_g;
-    __syncthreads();
-    if (g < cfg.n_canopy_bands_lw) {
-      double s = 0.0;
-      for (int k = 0; k < NG_LW; ++k)
-        if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) s = s + tile[k];
-      out.lw_dn_surf_canopy[(size_t)c * cfg.n_canopy_bands_lw + g] = s;
-    }
-  }
-#undef OUT2
-}
-
-// =========================================================================================================
 // launchers
 // =========================================================================================================
 size_t scratch_doubles_per_column(int nlev) {
@@ -746,7 +519,6 @@ static size_t gas_sw_smem(int nlev) {
   return sizeof(SwLev) * nlev + sizeof(double) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
          sizeof(int) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + nlev) + 16;
 }
-static size_t solver_lw_smem(int nlev) { return sizeof(double) * (6 * (nlev + 1) + 2 * LCH * LW_RS + 2 * nlev) + 16; }
 
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
@@ -775,11 +547,5 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
     cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
   }
   return n;
-}
-int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  size_t sm = solver_lw_smem(nlev);
-  allow_smem(solver_lw_kernel, sm);
-  solver_lw_kernel<<<nc, LW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev, (nlev + 3) & ~3);
-  return 1;
 }
 }  // namespace ecb

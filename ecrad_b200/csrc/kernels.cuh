@@ -55,7 +55,7 @@ struct DevCfg {
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
 };
 
-enum { LW_SCR_ARRAYS = 8, SW_SCR_ARRAYS = 10 };
+enum { LW_SCR_ARRAYS = 5, SW_SCR_ARRAYS = 10 };
 
 // Per-tile scratch (nc = columns in the tile).
 struct Work {
@@ -67,6 +67,7 @@ struct Work {
   int *ibegin, *iend, *ict;                       // [nc]
   uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
   double* scr;                                    // [nc][scr_per_col]
+  double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
   size_t scr_per_col;
 };

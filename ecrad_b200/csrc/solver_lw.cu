@@ -1,0 +1,285 @@
+// solver_lw.cu -- longwave McICA (radiation_mcica_lw.F90:39-419) and Cloudless (radiation_cloudless_lw.F90) solvers.
+//
+// One CTA per column, one thread per g-point.  Clear-sky layers are no-scattering (radiation_two_stream.F90:342-409:
+// one exp and one division per layer and g-point), so their transmittance/sources are RECOMPUTED in every sweep
+// instead of being stored: the fp64 pipe is idle in these memory-bound sweeps and 32 bytes per element are saved.
+//   lw_down_kernel   top-down: clear-sky downward flux (calc_fluxes_no_scattering_lw, first loop)
+//   lw_up_kernel     bottom-up: clear-sky upward flux + derivative products, and -- in the same sweep -- the cloudy
+//                    sub-column: two-stream of cloudy layers (calc_ref_trans_lw), albedo/source up to cloud top
+//                    (fast_adding_ica_lw), then the upward flux above cloud top
+//   lw_flux_kernel   top-down from cloud top: cloudy fluxes; derivative sums (calc_lw_derivatives_ica); outputs
+#include "solver_common.cuh"
+
+namespace ecb {
+
+enum { LW_THREADS = 160, LW_RS = 141, LW_LCH_FLUX = 8 };
+enum { LWS_DN_C = 0, LWS_UP_C = 1, LWS_DV_C = 2, LWS_UP_A = 3, LWS_DN_A = 4, LWS_DV_A = 5 };
+
+struct LwColumn {
+  int c, g, gg, ict; bool act, mcica, cloudy; double tcc, thr;
+  size_t n;
+  const double *od, *pl;
+  double *scr, *sums, *carry;
+};
+
+__device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, int nlev) {
+  LwColumn s;
+  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < NG_LW; s.gg = s.act ? s.g : 0;
+  s.mcica = cfg.solver_lw == 2;
+  s.tcc = s.mcica ? w.tcc[s.c] : 0.0;
+  s.cloudy = s.tcc > 0.0;
+  s.ict = s.cloudy ? w.ict[s.c] : nlev;
+  s.thr = cfg.cloud_fraction_threshold;
+  s.n = (size_t)nlev * NG_LW;
+  s.od = w.od_lw + (size_t)s.c * s.n;
+  s.pl = w.planck + (size_t)s.c * (nlev + 1) * NG_LW;
+  s.scr = w.scr + (size_t)s.c * w.scr_per_col;
+  s.sums = w.lw_sums + (size_t)s.c * 6 * (nlev + 1);
+  s.carry = w.lw_carry + (size_t)s.c * 4 * NG_LW;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// clear-sky downward flux
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_THREADS, 6)
+lw_down_kernel(DevCfg cfg, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const LwColumn s = lw_column(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [1][LCH][LW_RS]
+  const int g = s.g, nl1 = nlev + 1;
+  double* dst[1] = {s.sums + LWS_DN_C * nl1};
+  double fd = 0.0, fd_ict = 0.0;
+  int slot = 0, lfirst = 0;
+  if (s.act) tile[g] = 0.0;   // flux_dn at TOA
+  ++slot;
+  double pt = s.act ? s.pl[g] : 0.0;
+  for (int l = 0; l < nlev; ++l) {
+    if (s.act) {
+      if (l == s.ict) fd_ict = fd;
+      const size_t i = (size_t)l * NG_LW + g;
+      const double pb = s.pl[i + NG_LW];
+      const LwLayer L = lw_no_scat(s.od[i], pt, pb);
+      pt = pb;
+      fd = L.trans * fd + L.source_dn;
+      tile[slot * LW_RS + g] = fd;
+    }
+    ++slot;
+    if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+  }
+  if (s.act) { s.carry[g] = fd_ict; s.carry[NG_LW + g] = fd; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// upward sweep: clear-sky flux_up and derivative products; cloudy albedo/source below cloud top, flux_up above
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_THREADS, 3)
+lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const LwColumn s = lw_column(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LCH][LW_RS]
+  double* fracs = tile + 3 * LCH * LW_RS;               // [nlev]
+  double* fsds = fracs + nlev;                          // [nlev]
+  const int c = s.c, g = s.g, nl1 = nlev + 1;
+  for (int l = g; l < nlev; l += LW_THREADS) {
+    fracs[l] = s.cloudy ? LD_IN(in.frac, c, l) : 0.0;
+    fsds[l] = s.cloudy ? LD_IN(in.fsd, c, l) : 0.0;
+  }
+  __syncthreads();
+  const CloudMeta& C = *T.cloud;
+  const size_t n = s.n;
+  double *sa = s.scr, *sb = s.scr + n, *sA = s.scr + 2 * n, *sS = s.scr + 3 * n, *sP = s.scr + 4 * n;
+  const double emission = w.emission[(size_t)c * NG_LW + s.gg], albedo = w.lw_albedo[(size_t)c * NG_LW + s.gg];
+  const int b = T.meta->band_of_g_lw[s.gg];
+  const uint4* codep = reinterpret_cast<const uint4*>(w.code_lw + ((size_t)c * NG_LW + s.gg) * nlevp);
+  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
+  const bool cloudy = s.cloudy;
+  const int ict = s.ict;
+  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[NG_LW + s.gg];
+  double* dst[3] = {s.sums + LWS_UP_C * nl1, s.sums + LWS_DV_C * nl1, s.sums + LWS_UP_A * nl1};
+  const int nf = cloudy ? 3 : 2;
+  // surface
+  double fu = emission + albedo * fd_surf_clear;   // clear-sky flux_up at the surface
+  double prod = fu;                                 // flux_up(surface) * prod(trans) : calc_lw_derivatives_ica
+  double A = albedo, S = emission;                  // cloudy sub-column: albedo / source of everything below
+  double fu_a = 0.0, pa = 1.0;                      // cloudy flux_up (above cloud top), product of transmittances
+  int slot = 0, lfirst = nlev;
+  if (s.act) { tile[g] = fu; tile[LCH * LW_RS + g] = prod; tile[2 * LCH * LW_RS + g] = 0.0; }
+  ++slot;
+  uint4 cq = make_uint4(0, 0, 0, 0);
+  double pb = s.act ? s.pl[(size_t)nlev * NG_LW + g] : 0.0;
+  for (int l = nlev - 1; l >= 0; --l) {
+    if (s.act) {
+      const size_t i = (size_t)l * NG_LW + g;
+      const double odg = s.od[i], pt = s.pl[i];
+      const LwLayer Lc = lw_no_scat(odg, pt, pb);
+      fu = Lc.trans * fu + Lc.source_up;
+      prod = prod * Lc.trans;
+      tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod;
+      if (cloudy) {
+        if (l >= ict) {
+          if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
+          double a_, b_, t_;
+          if (fracs[l] >= s.thr) {
+            // radiation_mcica_lw.F90:248-294: gas + scaled cloud
+            const double scal = od_scaling_from_code(C, T.pdf_val, pick4(cq, l & 3), fsds[l]);
+            const double* clb = cl + (size_t)l * 3 * NB_LW;
+            const double od_cloud_new = scal * clb[b];
+            const double od_total = odg + od_cloud_new;
+            LwLayer L;
+            if (cfg.do_lw_cloud_scattering) {
+              double ssa_total = 0.0, g_total = 0.0;
+              if (od_total > 0.0) {
+                const double ssac = clb[NB_LW + b];
+                const double scat_od = ssac * od_cloud_new;
+                ssa_total = scat_od / od_total;
+                if (scat_od > 0.0) g_total = clb[2 * NB_LW + b] * ssac * od_cloud_new / scat_od;
+              }
+              L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
+            } else {
+              L = lw_no_scat(od_total, pt, pb);
+            }
+            const double inv_den = 1.0 / (1.0 - A * L.ref);
+            a_ = L.trans * inv_den;
+            b_ = (L.ref * S + L.source_dn) * inv_den;
+            t_ = L.trans;
+            const double A_new = L.ref + L.trans * L.trans * A * inv_den;
+            const double S_new = L.source_up + L.trans * (S + A * L.source_dn) * inv_den;
+            sA[i] = A; sS[i] = S;   // albedo/source at the half-level below layer l
+            A = A_new; S = S_new;
+          } else {
+            a_ = Lc.trans; b_ = Lc.source_dn; t_ = Lc.trans;
+            sA[i] = A; sS[i] = S;
+            const double A_new = t_ * t_ * A;
+            const double S_new = Lc.source_up + t_ * (S + A * Lc.source_dn);
+            A = A_new; S = S_new;
+          }
+          sa[i] = a_; sb[i] = b_;
+          pa = pa * t_;
+          if (l == ict) fu_a = S + A * fd_ict;   // flux_up at cloud top
+        } else {
+          fu_a = Lc.trans * fu_a + Lc.source_up;
+          pa = pa * Lc.trans;
+        }
+        sP[i] = pa;
+        tile[(2 * LCH + slot) * LW_RS + g] = l <= ict ? fu_a : 0.0;
+      }
+    }
+    ++slot;
+    if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
+    pb = s.act ? s.pl[(size_t)l * NG_LW + g] : 0.0;
+  }
+  if (s.act) { s.carry[2 * NG_LW + g] = fu; s.carry[3 * NG_LW + g] = fu_a; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cloudy fluxes from cloud top down, derivative sums, and the flux_type outputs
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_THREADS, 6)
+lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const LwColumn s = lw_column(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LW_LCH_FLUX][LW_RS]
+  const int c = s.c, g = s.g, nl1 = nlev + 1;
+  const bool act = s.act, cloudy = s.cloudy;
+  const int ict = s.ict;
+  const size_t n = s.n;
+  const double *sa = s.scr, *sb = s.scr + n, *sA = s.scr + 2 * n, *sS = s.scr + 3 * n, *sP = s.scr + 4 * n;
+  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[NG_LW + s.gg];
+  const double fu_toa_clear = s.carry[2 * NG_LW + s.gg], fu_toa_a = s.carry[3 * NG_LW + s.gg];
+  double fd_surf = fd_surf_clear;
+  const bool want_dv = cfg.do_lw_derivatives && out.lw_derivatives;
+  if (cloudy) {
+    double fd = fd_ict, fu = 0.0;
+    {
+      double* dst[2] = {s.sums + LWS_DN_A * nl1, s.sums + LWS_UP_A * nl1};
+      int slot = 0, lfirst = ict + 1;
+#pragma unroll 4
+      for (int l = ict; l < nlev; ++l) {
+        if (act) {
+          const size_t i = (size_t)l * NG_LW + g;
+          fd = sa[i] * fd + sb[i];
+          fu = sA[i] * fd + sS[i];
+          tile[slot * LW_RS + g] = fd; tile[(LW_LCH_FLUX + slot) * LW_RS + g] = fu;
+        }
+        ++slot;
+        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+      }
+    }
+    fd_surf = fd;
+    if (want_dv) {
+      // derivative of flux_up at each half-level w.r.t. the surface emission: sum_g flux_up_surf(g) * prod(trans)
+      double* dst[1] = {s.sums + LWS_DV_A * nl1};
+      int slot = 0, lfirst = 0;
+#pragma unroll 4
+      for (int l = 0; l < nlev; ++l) {
+        if (act) tile[slot * LW_RS + g] = fu * sP[(size_t)l * NG_LW + g];
+        ++slot;
+        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- outputs ----
+#define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
+  const double *s_dn_clear = s.sums + LWS_DN_C * nl1, *s_up_clear = s.sums + LWS_UP_C * nl1, *s_dv_clear = s.sums + LWS_DV_C * nl1;
+  const double *s_up = s.sums + LWS_UP_A * nl1, *s_dn = s.sums + LWS_DN_A * nl1, *s_dv = s.sums + LWS_DV_A * nl1;
+  const double tcc = s.tcc, wc = tcc, w1 = 1.0 - tcc;
+  for (int l = g; l < nl1; l += LW_THREADS) {
+    const double upc = s_up_clear[l], dnc = s_dn_clear[l];
+    if (out.lw_up_clear) OUT2(out.lw_up_clear, l) = upc;
+    if (out.lw_dn_clear) OUT2(out.lw_dn_clear, l) = dnc;
+    double up = upc, dn = dnc;
+    if (cloudy) {
+      up = wc * s_up[l] + w1 * upc;
+      dn = wc * (l <= ict ? dnc : s_dn[l]) + w1 * dnc;
+    }
+    if (out.lw_up) OUT2(out.lw_up, l) = up;
+    if (out.lw_dn) OUT2(out.lw_dn, l) = dn;
+    if (want_dv) {
+      const double dclear = l == nlev ? 1.0 : s_dv_clear[l] / s_up_clear[nlev];
+      double d = dclear;
+      if (cloudy) {
+        d = l == nlev ? 1.0 : s_dv[l] / s_up[nlev];
+        if (tcc < 1.0 - s.thr) d = l == nlev ? 1.0 : (1.0 - w1) * d + w1 * dclear;
+      }
+      OUT2(out.lw_derivatives, l) = d;
+    }
+  }
+  if (g == 0 && out.cloud_cover_lw && s.mcica) out.cloud_cover_lw[c] = tcc;
+  const double dn_surf_g = cloudy ? wc * fd_surf + w1 * fd_surf_clear : fd_surf_clear;
+  if (act) {
+    const size_t i = (size_t)c * NG_LW + g;
+    if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
+    if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fu_toa_clear;
+    if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
+    if (out.lw_up_toa_g) out.lw_up_toa_g[i] = cloudy ? wc * fu_toa_a + w1 * fu_toa_clear : fu_toa_clear;
+  }
+  // canopy fluxes, radiation_flux.F90 calc_surface_spectral (nearest-interval emissivity mapping)
+  if (cfg.do_canopy_fluxes_lw && out.lw_dn_surf_canopy) {
+    __syncthreads();
+    if (act) tile[g] = dn_surf_g;
+    __syncthreads();
+    if (g < cfg.n_canopy_bands_lw) {
+      double sum = 0.0;
+      for (int k = 0; k < NG_LW; ++k)
+        if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) sum = sum + tile[k];
+      out.lw_dn_surf_canopy[(size_t)c * cfg.n_canopy_bands_lw + g] = sum;
+    }
+  }
+#undef OUT2
+}
+
+int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const int nlevp = (nlev + 3) & ~3;
+  const size_t sm1 = sizeof(double) * (LCH * LW_RS) + 16;
+  const size_t sm2 = sizeof(double) * (3 * LCH * LW_RS + 2 * nlev) + 16;
+  const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * LW_RS) + 16;
+  cudaFuncSetAttribute(lw_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(cfg, w, nlev);
+  lw_up_kernel<<<nc, LW_THREADS, sm2, st>>>(T, cfg, in, w, nlev, nlevp);
+  lw_flux_kernel<<<nc, LW_THREADS, sm3, st>>>(T, cfg, out, w, nlev);
+  return 3;
+}
+
+}  // namespace ecb
