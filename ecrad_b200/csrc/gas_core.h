@@ -41,6 +41,9 @@ struct GasMeta {
   double preflog_lw[59], tref_lw[59], chi_mls[7 * 59];
   double preflog_sw[59], tref_sw[59];
   double totplnk[181 * 16], delwave[16];
+  // CHI_MLS(i,jp)/CHI_MLS(j,jp) for the species pairs the binary-species bands use (rrtm_setcoef_140gp.F90:169-182),
+  // tabulated once on the host with the same IEEE division: [pair][jp-1], pairs: h2o/co2 h2o/o3 h2o/n2o h2o/ch4 n2o/co2 o3/co2
+  double chi_rat[6][59];
   double strrat_sw[NB_SW], rayl_sw[NB_SW], givfac_23, scalekur_27;
   int layreffr_sw[NB_SW], nfor_sw[NB_SW];
   int band_of_g_lw[NG_LW], band_of_g_sw[NG_SW];  // 0-based band of each g-point
@@ -87,9 +90,13 @@ struct LwLev {
   double fac00, fac01, fac10, fac11, forfac, forfrac, selffac, selffrac, scaleminor, scaleminorn2, minorfrac;
   double colh2o, colco2, colo3, coln2o, colch4, colo2, colbrd, coldry, pavel;
   double wx1, wx2, wx3, wx4;
+  double pad_;   // sizeof = 29 doubles: odd stride => conflict-free shared-memory access across layers
 };
+static_assert(sizeof(LwLev) % 16 == 8, "LwLev stride must be an odd number of doubles");
 
 #define ECB_CHI(i, j) (M.chi_mls[((j) - 1) * 7 + ((i) - 1)])
+enum { RAT_H2OCO2 = 0, RAT_H2OO3 = 1, RAT_H2ON2O = 2, RAT_H2OCH4 = 3, RAT_N2OCO2 = 4, RAT_O3CO2 = 5 };
+#define ECB_RAT(pair, j) (M.chi_rat[pair][(j) - 1])
 
 HD void lw_setcoef(const GasMeta& M, const LevGas& G, LwLev& L) {
   const double stpfac = 296.0 / 1013.0;
@@ -148,11 +155,12 @@ HD void lw_setcoef(const GasMeta& M, const LevGas& G, LwLev& L) {
 // ---------------------------------------------------------------------------------------------------------
 // list emitters
 // ---------------------------------------------------------------------------------------------------------
+struct Term { double c; int o; int pad; };   // 16 bytes: coefficient, element offset of the table row (add the in-band g index)
 struct ListOut {
-  double* c;  // coefficients
-  int* o;     // element offsets of the table rows (add the in-band g index)
+  Term* t;
   int n;
-  HD void add(double coef, int off) { c[n] = coef; o[n] = off; ++n; }
+  HD void add(double coef, int off) { t[n].c = coef; t[n].o = off; ++n; }
+  HD void pad4() { while (n & 3) { t[n].c = 0.0; t[n].o = 0; ++n; } }   // zero terms so that consumers can unroll by 4
 };
 
 struct Spec { double speccomb, specparm, fs; int js; };
@@ -280,13 +288,13 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
         emit_lin(out, B.sec[L_M1], ng, indm, mf, scalen2);
         pf = pf_const(FB);
       }
-      for (int k = 0; k < out.n; ++k) out.c[k] = corradj * out.c[k];
+      for (int k = 0; k < out.n; ++k) out.t[k].c = corradj * out.t[k].c;
     } break;
     case 2: {  // rrtm_taumol2.F90: H2O / H2O
       if (low) {
         double corradj = 1.0 - .05 * (L.pavel - 100.0) / 900.0;
         MAJ1A(L.colh2o); SELF_(); FOR_();
-        for (int k = 0; k < out.n; ++k) out.c[k] = corradj * out.c[k];
+        for (int k = 0; k < out.n; ++k) out.t[k].c = corradj * out.t[k].c;
         pf = pf_const(FA);
       } else {
         MAJ1B(L.colh2o); FOR_();
@@ -295,17 +303,17 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 3: {  // rrtm_taumol3.F90: H2O,CO2 / H2O,CO2; minor N2O
       double adjcoln2o = adjcol(L.coln2o, L.coldry, ECB_CHI(4, jp + 1), 1.5, 0.5, 0.65);
-      double rat = ECB_CHI(1, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(2, jp + 1);
+      double rat = ECB_RAT(RAT_H2OCO2, jp), rat1 = ECB_RAT(RAT_H2OCO2, jp + 1);
       if (low) {
         Spec s = mkspec(L.colh2o, rat, L.colco2, 8.0), s1 = mkspec(L.colh2o, rat1, L.colco2, 8.0);
-        Spec sm = mkspec(L.colh2o, ECB_CHI(1, 3) / ECB_CHI(2, 3), L.colco2, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 9) / ECB_CHI(2, 9), L.colco2, 8.0);
+        Spec sm = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 3), L.colco2, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 9), L.colco2, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         emit_minor2(out, B.sec[L_M0], ng, 9, sm.js, sm.fs, indm, mf, adjcoln2o);
         pf = pf_interp(FA, ng, sp);
       } else {
         Spec s = mkspec(L.colh2o, rat, L.colco2, 4.0), s1 = mkspec(L.colh2o, rat1, L.colco2, 4.0);
-        Spec sm = mkspec(L.colh2o, ECB_CHI(1, 13) / ECB_CHI(2, 13), L.colco2, 4.0);
+        Spec sm = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 13), L.colco2, 4.0);
         MAJ5(s, s1); FOR_();
         emit_minor2(out, B.sec[L_M1], ng, 5, sm.js, sm.fs, indm, mf, adjcoln2o);
         pf = pf_interp(FB, ng, sm);
@@ -313,15 +321,15 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 4: {  // rrtm_taumol4.F90: H2O,CO2 / O3,CO2
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_H2OCO2, jp), rat1 = ECB_RAT(RAT_H2OCO2, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.colco2, 8.0), s1 = mkspec(L.colh2o, rat1, L.colco2, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 11) / ECB_CHI(2, 11), L.colco2, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 11), L.colco2, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         pf = pf_interp(FA, ng, sp);
       } else {
-        double rat = ECB_CHI(3, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(3, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_O3CO2, jp), rat1 = ECB_RAT(RAT_O3CO2, jp + 1);
         Spec s = mkspec(L.colo3, rat, L.colco2, 4.0), s1 = mkspec(L.colo3, rat1, L.colco2, 4.0);
-        Spec sp = mkspec(L.colo3, ECB_CHI(3, 13) / ECB_CHI(2, 13), L.colco2, 4.0);
+        Spec sp = mkspec(L.colo3, ECB_RAT(RAT_O3CO2, 13), L.colco2, 4.0);
         MAJ5(s, s1);
         pf = pf_interp(FB, ng, sp);
         *post = B.sec[L_POST];  // empirical stratospheric multipliers, rrtm_taumol4.F90:283-289
@@ -329,18 +337,18 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 5: {  // rrtm_taumol5.F90: H2O,CO2 / O3,CO2; minor O3, CCl4
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_H2OCO2, jp), rat1 = ECB_RAT(RAT_H2OCO2, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.colco2, 8.0), s1 = mkspec(L.colh2o, rat1, L.colco2, 8.0);
-        Spec sm = mkspec(L.colh2o, ECB_CHI(1, 7) / ECB_CHI(2, 7), L.colco2, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 5) / ECB_CHI(2, 5), L.colco2, 8.0);
+        Spec sm = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 7), L.colco2, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 5), L.colco2, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         emit_minor2(out, B.sec[L_M0], ng, 9, sm.js, sm.fs, indm, mf, L.colo3);
         out.add(L.wx1, B.sec[L_C0]);
         pf = pf_interp(FA, ng, sp);
       } else {
-        double rat = ECB_CHI(3, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(3, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_O3CO2, jp), rat1 = ECB_RAT(RAT_O3CO2, jp + 1);
         Spec s = mkspec(L.colo3, rat, L.colco2, 4.0), s1 = mkspec(L.colo3, rat1, L.colco2, 4.0);
-        Spec sp = mkspec(L.colo3, ECB_CHI(3, 43) / ECB_CHI(2, 43), L.colco2, 4.0);
+        Spec sp = mkspec(L.colo3, ECB_RAT(RAT_O3CO2, 43), L.colco2, 4.0);
         MAJ5(s, s1);
         out.add(L.wx1, B.sec[L_C0]);
         pf = pf_interp(FB, ng, sp);
@@ -359,9 +367,9 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 7: {  // rrtm_taumol7.F90: H2O,O3 / O3; minor CO2
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(3, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(3, jp + 1);
+        double rat = ECB_RAT(RAT_H2OO3, jp), rat1 = ECB_RAT(RAT_H2OO3, jp + 1);
         Spec s = mkspec7(L.colh2o, rat, L.colo3, 8.0), s1 = mkspec7(L.colh2o, rat1, L.colo3, 8.0);
-        Spec sm = mkspec7(L.colh2o, ECB_CHI(1, 3) / ECB_CHI(3, 3), L.colo3, 8.0);
+        Spec sm = mkspec7(L.colh2o, ECB_RAT(RAT_H2OO3, 3), L.colo3, 8.0);
         double adjcolco2 = adjcol(L.colco2, L.coldry, ECB_CHI(2, jp + 1), 3.0, 3.0, 0.79);
         MAJ9(s, s1); SELF_(); FOR_();
         emit_minor2(out, B.sec[L_M0], ng, 9, sm.js, sm.fs, indm, mf, adjcolco2);
@@ -394,10 +402,10 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     case 9: {  // rrtm_taumol9.F90: H2O,CH4 / CH4; minor N2O
       double adjcoln2o = adjcol(L.coln2o, L.coldry, ECB_CHI(4, jp + 1), 1.5, 0.5, 0.65);
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(6, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(6, jp + 1);
+        double rat = ECB_RAT(RAT_H2OCH4, jp), rat1 = ECB_RAT(RAT_H2OCH4, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.colch4, 8.0), s1 = mkspec(L.colh2o, rat1, L.colch4, 8.0);
-        Spec sm = mkspec(L.colh2o, ECB_CHI(1, 3) / ECB_CHI(6, 3), L.colch4, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 9) / ECB_CHI(6, 9), L.colch4, 8.0);
+        Spec sm = mkspec(L.colh2o, ECB_RAT(RAT_H2OCH4, 3), L.colch4, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCH4, 9), L.colch4, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         emit_minor2(out, B.sec[L_M0], ng, 9, sm.js, sm.fs, indm, mf, adjcoln2o);
         pf = pf_interp(FA, ng, sp);
@@ -418,19 +426,19 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 12: {  // rrtm_taumol12.F90: H2O,CO2 / -
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_H2OCO2, jp), rat1 = ECB_RAT(RAT_H2OCO2, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.colco2, 8.0), s1 = mkspec(L.colh2o, rat1, L.colco2, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 10) / ECB_CHI(2, 10), L.colco2, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCO2, 10), L.colco2, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         pf = pf_interp(FA, ng, sp);
       }
     } break;
     case 13: {  // rrtm_taumol13.F90: H2O,N2O / -; minor CO2, CO (column amount 0 in the IFS), O3
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(4, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(4, jp + 1);
+        double rat = ECB_RAT(RAT_H2ON2O, jp), rat1 = ECB_RAT(RAT_H2ON2O, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.coln2o, 8.0), s1 = mkspec(L.colh2o, rat1, L.coln2o, 8.0);
-        Spec smco2 = mkspec(L.colh2o, ECB_CHI(1, 1) / ECB_CHI(4, 1), L.coln2o, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 5) / ECB_CHI(4, 5), L.coln2o, 8.0);
+        Spec smco2 = mkspec(L.colh2o, ECB_RAT(RAT_H2ON2O, 1), L.coln2o, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2ON2O, 5), L.coln2o, 8.0);
         double adjcolco2;
         {  // reference CO2 mixing ratio is the constant 3.55e-4 (second occurrence single precision in the source)
           double chi_co2 = L.colco2 / L.coldry;
@@ -454,9 +462,9 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 15: {  // rrtm_taumol15.F90: N2O,CO2 / -; minor N2
       if (low) {
-        double rat = ECB_CHI(4, jp) / ECB_CHI(2, jp), rat1 = ECB_CHI(4, jp + 1) / ECB_CHI(2, jp + 1);
+        double rat = ECB_RAT(RAT_N2OCO2, jp), rat1 = ECB_RAT(RAT_N2OCO2, jp + 1);
         Spec s = mkspec(L.coln2o, rat, L.colco2, 8.0), s1 = mkspec(L.coln2o, rat1, L.colco2, 8.0);
-        Spec sm = mkspec(L.coln2o, ECB_CHI(4, 1) / ECB_CHI(2, 1), L.colco2, 8.0);
+        Spec sm = mkspec(L.coln2o, ECB_RAT(RAT_N2OCO2, 1), L.colco2, 8.0);
         double scalen2 = L.colbrd * L.scaleminor;
         MAJ9(s, s1); SELF_(); FOR_();
         emit_minor2(out, B.sec[L_M0], ng, 9, sm.js, sm.fs, indm, mf, scalen2);
@@ -465,9 +473,9 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
     } break;
     case 16: {  // rrtm_taumol16.F90: H2O,CH4 / CH4
       if (low) {
-        double rat = ECB_CHI(1, jp) / ECB_CHI(6, jp), rat1 = ECB_CHI(1, jp + 1) / ECB_CHI(6, jp + 1);
+        double rat = ECB_RAT(RAT_H2OCH4, jp), rat1 = ECB_RAT(RAT_H2OCH4, jp + 1);
         Spec s = mkspec(L.colh2o, rat, L.colch4, 8.0), s1 = mkspec(L.colh2o, rat1, L.colch4, 8.0);
-        Spec sp = mkspec(L.colh2o, ECB_CHI(1, 6) / ECB_CHI(6, 6), L.colch4, 8.0);
+        Spec sp = mkspec(L.colh2o, ECB_RAT(RAT_H2OCH4, 6), L.colch4, 8.0);
         MAJ9(s, s1); SELF_(); FOR_();
         pf = pf_interp(FA, ng, sp);
       } else {
@@ -511,6 +519,7 @@ struct SwLev {
   double fac00, fac01, fac10, fac11, forfac, forfrac, selffac, selffrac;
   double colh2o, colco2, colo3, colch4, colo2, colmol;
 };
+static_assert(sizeof(SwLev) % 16 == 8, "SwLev stride must be an odd number of doubles");
 
 HD void sw_setcoef(const GasMeta& M, const LevGas& G, SwLev& L) {
   const double stpfac = 296.0 / 1013.0;

@@ -22,14 +22,32 @@ namespace ecb {
 // ---------------------------------------------------------------------------------------------------------
 // tight packing of the per-(layer, band) stencil slots in shared memory
 // ---------------------------------------------------------------------------------------------------------
-__constant__ int c_lw_kmax[NB_LW] = {10, 8, 20, 16, 21, 12, 20, 16, 20, 8, 10, 16, 20, 8, 20, 16};
-__constant__ int c_lw_koff[NB_LW] = {0, 10, 18, 38, 54, 75, 87, 107, 123, 143, 151, 161, 177, 197, 205, 225};
-enum { LW_KTOT = 241 };
-__constant__ int c_sw_koff[NB_SW] = {0, 12, 24, 36, 48, 57, 69, 82, 90, 103, 108, 108, 112, 120};
-enum { SW_KTOT = 129 };
+// slots per band = max number of terms rounded up to a multiple of 4 (lists are zero-padded so stage B unrolls by 4)
+//                                 band:  1   2   3   4   5   6   7   8   9  10  11  12  13  14  15  16
+__constant__ int c_lw_koff[NB_LW] = {0, 12, 20, 40, 56, 80, 92, 112, 128, 148, 156, 168, 184, 204, 212, 232};
+enum { LW_KTOT = 249 };   // 248 slots + 1: per-layer stride of 249 x 16 B keeps stage A's stores off a single bank
+//                                 band: 16  17  18  19  20  21  22  23  24  25  26  27  28  29
+__constant__ int c_sw_koff[NB_SW] = {0, 12, 24, 36, 48, 60, 72, 88, 96, 112, 120, 120, 124, 132};
+enum { SW_KTOT = 145 };   // 144 slots + 1 (bank spread, as above)
 
 enum { GAS_LC = 16, GAS_THREADS = 256 };
 
+// sum_k coef_k * tab_g[off_k] over a zero-padded list of n (multiple of 4) packed terms in shared memory.
+// tab_g = table base + in-band g index (hoisted: one 64-bit pointer per item; offsets are unsigned 32-bit, so each
+// address is a single IMAD.WIDE.U32).
+__device__ __forceinline__ double stencil_dot(const Term* tt, int n, const double* __restrict__ tab_g) {
+  double acc0 = 0.0, acc1 = 0.0;
+  const uint4* q = reinterpret_cast<const uint4*>(tt);
+  for (int k = 0; k < n; k += 4) {
+    const uint4 t0 = q[k], t1 = q[k + 1], t2 = q[k + 2], t3 = q[k + 3];
+    const double v0 = __ldg(tab_g + t0.z), v1 = __ldg(tab_g + t1.z), v2 = __ldg(tab_g + t2.z), v3 = __ldg(tab_g + t3.z);
+    acc0 = fma(__hiloint2double((int)t0.y, (int)t0.x), v0, acc0);
+    acc1 = fma(__hiloint2double((int)t1.y, (int)t1.x), v1, acc1);
+    acc0 = fma(__hiloint2double((int)t2.y, (int)t2.x), v2, acc0);
+    acc1 = fma(__hiloint2double((int)t3.y, (int)t3.x), v3, acc1);
+  }
+  return acc0 + acc1;
+}
 
 // =========================================================================================================
 // LW gas optics
@@ -44,17 +62,18 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const int c = blockIdx.x, tid = threadIdx.x;
   const GasMeta& M = *T.meta;
   // carve shared memory
-  LwLev* lev = reinterpret_cast<LwLev*>(smem_raw);
-  double* lc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][LW_KTOT]
-  double* pfc = lc + GAS_LC * LW_KTOT;                               // [GAS_LC][16][2]
+  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [GAS_LC][LW_KTOT] (16-byte aligned)
+  LwLev* lev = reinterpret_cast<LwLev*>(lt + GAS_LC * LW_KTOT);      // [nlev]
+  double* pfc = reinterpret_cast<double*>(lev + nlev);               // [GAS_LC][16][2]
   double* plk = pfc + GAS_LC * NB_LW * 2;                            // [GAS_LC+1][16]
   double* plk_surf = plk + (GAS_LC + 1) * NB_LW;                     // [16]
-  int* lo = reinterpret_cast<int*>(plk_surf + NB_LW);                // [GAS_LC][LW_KTOT]
-  int* ln = lo + GAS_LC * LW_KTOT;                                   // [GAS_LC][16]
+  int* ln = reinterpret_cast<int*>(plk_surf + NB_LW);                // [GAS_LC][16]
   int* lpost = ln + GAS_LC * NB_LW;                                  // [GAS_LC][16]
   int* pfo = lpost + GAS_LC * NB_LW;                                 // [GAS_LC][16][2]
   int* bog = pfo + GAS_LC * NB_LW * 2;                               // [140] band of g
   int* g0b = bog + NG_LW;                                            // [140] in-band index of g
+  int* sng = g0b + NG_LW;                                            // [16] g-points per band
+  float* srn = reinterpret_cast<float*>(sng + NB_LW);                // [16] 1 / g-points per band
 
   // ---- per-layer state (thread per layer) ----
   int tropo = 0;
@@ -70,6 +89,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     tropo = L.tropo;
   }
   for (int g = tid; g < NG_LW; g += GAS_THREADS) { int b = M.band_of_g_lw[g]; bog[g] = b; g0b[g] = g - M.lw[b].g0; }
+  if (tid < NB_LW) { sng[tid] = M.lw[tid].ng; srn[tid] = 1.0f / (float)M.lw[tid].ng; }
   if (tid < NB_LW) plk_surf[tid] = planck_band(M, in.skin_t[c], tid);
   const int laytrop = __syncthreads_count(tropo);
 
@@ -85,11 +105,11 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         const int l = l0 + ll;
         const int il = nlev - l;               // RRTMG layer index (1 = bottom)
         ListOut out;
-        out.c = lc + ll * LW_KTOT + c_lw_koff[b];
-        out.o = lo + ll * LW_KTOT + c_lw_koff[b];
+        out.t = lt + ll * LW_KTOT + c_lw_koff[b];
         out.n = 0;
         int post;
         PlanckFrac pf = lw_build_list(M, lev[l], b, il <= laytrop, out, &post);
+        out.pad4();
         ln[ll * NB_LW + b] = out.n;
         lpost[ll * NB_LW + b] = post;
         pfc[(ll * NB_LW + b) * 2] = pf.c0; pfc[(ll * NB_LW + b) * 2 + 1] = pf.c1;
@@ -101,21 +121,25 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       plk[i] = planck_band(M, LD_IN(in.t_hl, c, l0 + h), b);
     }
     __syncthreads();
-    // ---- stage B: one lane per g-point ----
+    // ---- stage B: one lane per (layer, g-point), items ordered band-major: [band][layer][g in band], so that the
+    //      whole CTA works on one or two bands at a time (table rows stay in L1, lanes of a warp share the term count)
     const int items = nl * NG_LW;
     for (int it = tid; it < items; it += GAS_THREADS) {
-      const int ll = it / NG_LW, g = it - ll * NG_LW;
+      const int gq = nl == GAS_LC ? it >> 4 : it / nl;
+      const int b = bog[gq];
+      const int g0 = gq - g0b[gq];
+      const int j = it - nl * g0;
+      const int ll = __float2int_rz(((float)j + 0.5f) * srn[b]);
+      const int igb = j - ll * sng[b];
+      const int g = g0 + igb;
       const int l = l0 + ll;
-      const int b = bog[g], igb = g0b[g];
       const int n = ln[ll * NB_LW + b];
-      const double* cc = lc + ll * LW_KTOT + c_lw_koff[b];
-      const int* oo = lo + ll * LW_KTOT + c_lw_koff[b];
-      double tau = 0.0;
-      for (int k = 0; k < n; ++k) tau = fma(cc[k], __ldg(T.lwtab + oo[k] + igb), tau);
+      const double* tab_g = T.lwtab + igb;
+      double tau = stencil_dot(lt + ll * LW_KTOT + c_lw_koff[b], n, tab_g);
       const int post = lpost[ll * NB_LW + b];
-      if (post >= 0) tau *= __ldg(T.lwtab + post + igb);
-      const double pf = pfc[(ll * NB_LW + b) * 2] * __ldg(T.lwtab + pfo[(ll * NB_LW + b) * 2] + igb) +
-                        pfc[(ll * NB_LW + b) * 2 + 1] * __ldg(T.lwtab + pfo[(ll * NB_LW + b) * 2 + 1] + igb);
+      if (post >= 0) tau *= __ldg(tab_g + (unsigned)post);
+      const double pf = pfc[(ll * NB_LW + b) * 2] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2]) +
+                        pfc[(ll * NB_LW + b) * 2 + 1] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2 + 1]);
       od_out[(size_t)l * NG_LW + g] = dmax(tau, cfg.min_gas_od_lw);       // radiation_ifs_rrtm.F90:506-511
       pl_out[(size_t)(l + 1) * NG_LW + g] = plk[(ll + 1) * NB_LW + b] * pf; // half-level below uses this layer's PFRAC
       if (l == 0) pl_out[g] = plk[b] * pf;                                 // TOA half-level: PFRAC of the top layer
@@ -140,19 +164,20 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const int c = blockIdx.x, tid = threadIdx.x;
   if (!(in.cos_sza[c] > 0.0)) return;   // srtm only runs for sunlit columns (radiation_ifs_rrtm.F90:518-542)
   const GasMeta& M = *T.meta;
-  SwLev* lev = reinterpret_cast<SwLev*>(smem_raw);
-  double* lc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][SW_KTOT]
-  double* rc = lc + GAS_LC * SW_KTOT;                                // [GAS_LC][14][2] Rayleigh coefficients
+  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [GAS_LC][SW_KTOT] (16-byte aligned)
+  SwLev* lev = reinterpret_cast<SwLev*>(lt + GAS_LC * SW_KTOT);      // [nlev]
+  double* rc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][14][2] Rayleigh coefficients
   double* sc = rc + GAS_LC * NB_SW * 2;                              // [14][2]  solar-source coefficients
   double* inc = sc + NB_SW * 2;                                      // [112]
-  int* lo = reinterpret_cast<int*>(inc + NG_SW);                     // [GAS_LC][SW_KTOT]
-  int* ln = lo + GAS_LC * SW_KTOT;                                   // [GAS_LC][14]
+  int* ln = reinterpret_cast<int*>(inc + NG_SW);                     // [GAS_LC][14]
   int* ro = ln + GAS_LC * NB_SW;                                     // [GAS_LC][14][2]
   int* so = ro + GAS_LC * NB_SW * 2;                                 // [14][2]
   int* lsol = so + NB_SW * 2;                                        // [14] ecRad layer index supplying the solar source (-1: none)
   int* bog = lsol + NB_SW;                                           // [112]
   int* g0b = bog + NG_SW;                                            // [112]
-  int* jps = g0b + NG_SW;                                            // [nlev] JP per layer (ecRad order)
+  int* sng = g0b + NG_SW;                                            // [14]
+  float* srn = reinterpret_cast<float*>(sng + NB_SW);                // [14]
+  int* jps = reinterpret_cast<int*>(srn + NB_SW);                    // [nlev] JP per layer (ecRad order)
   __shared__ double s_scale;
 
   int tropo = 0;
@@ -169,6 +194,7 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     tropo = L.tropo;
   }
   for (int g = tid; g < NG_SW; g += GAS_THREADS) { int b = M.band_of_g_sw[g]; bog[g] = b; g0b[g] = g - M.sw[b].g0; inc[g] = 0.0; }
+  if (tid < NB_SW) { sng[tid] = M.sw[tid].ng; srn[tid] = 1.0f / (float)M.sw[tid].ng; }
   const int laytrop = __syncthreads_count(tropo);
   if (tid < NB_SW) {
     int il = sw_solar_layer(M, tid, nlev, laytrop, [&](int i) { return jps[nlev - i]; });
@@ -187,11 +213,11 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         const int l = l0 + ll;
         const int il = nlev - l;
         ListOut out;
-        out.c = lc + ll * SW_KTOT + c_sw_koff[b];
-        out.o = lo + ll * SW_KTOT + c_sw_koff[b];
+        out.t = lt + ll * SW_KTOT + c_sw_koff[b];
         out.n = 0;
         SwAux aux;
         sw_build_list(M, lev[l], b, il <= laytrop, out, aux);
+        out.pad4();
         ln[ll * NB_SW + b] = out.n;
         rc[(ll * NB_SW + b) * 2] = aux.rc0; rc[(ll * NB_SW + b) * 2 + 1] = aux.rc1;
         ro[(ll * NB_SW + b) * 2] = aux.ro0; ro[(ll * NB_SW + b) * 2 + 1] = aux.ro1;
@@ -199,22 +225,25 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       }
     }
     __syncthreads();
-    const int items = nl * NG_SW;
+    const int items = nl * NG_SW;   // band-major item order, as in gas_lw_kernel
     for (int it = tid; it < items; it += GAS_THREADS) {
-      const int ll = it / NG_SW, g = it - ll * NG_SW;
+      const int gq = nl == GAS_LC ? it >> 4 : it / nl;
+      const int b = bog[gq];
+      const int g0 = gq - g0b[gq];
+      const int j = it - nl * g0;
+      const int ll = __float2int_rz(((float)j + 0.5f) * srn[b]);
+      const int igb = j - ll * sng[b];
+      const int g = g0 + igb;
       const int l = l0 + ll;
-      const int b = bog[g], igb = g0b[g];
       const int n = ln[ll * NB_SW + b];
-      const double* cc = lc + ll * SW_KTOT + c_sw_koff[b];
-      const int* oo = lo + ll * SW_KTOT + c_sw_koff[b];
-      double taug = 0.0;
-      for (int k = 0; k < n; ++k) taug = fma(cc[k], __ldg(T.swtab + oo[k] + igb), taug);
-      const double taur = rc[(ll * NB_SW + b) * 2] * __ldg(T.swtab + ro[(ll * NB_SW + b) * 2] + igb) +
-                          rc[(ll * NB_SW + b) * 2 + 1] * __ldg(T.swtab + ro[(ll * NB_SW + b) * 2 + 1] + igb);
+      const double* tab_g = T.swtab + igb;
+      const double taug = stencil_dot(lt + ll * SW_KTOT + c_sw_koff[b], n, tab_g);
+      const double taur = rc[(ll * NB_SW + b) * 2] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2]) +
+                          rc[(ll * NB_SW + b) * 2 + 1] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2 + 1]);
       const double od = taur + taug;                                        // srtm_gas_optical_depth.F90:314-320
       od_out[(size_t)l * NG_SW + g] = dmax(od, cfg.min_gas_od_sw);         // radiation_ifs_rrtm.F90:593
       ssa_out[(size_t)l * NG_SW + g] = taur / od;
-      if (l == lsol[b]) inc[g] = sc[b * 2] * __ldg(T.swtab + so[b * 2] + igb) + sc[b * 2 + 1] * __ldg(T.swtab + so[b * 2 + 1] + igb);
+      if (l == lsol[b]) inc[g] = sc[b * 2] * __ldg(tab_g + (unsigned)so[b * 2]) + sc[b * 2 + 1] * __ldg(tab_g + (unsigned)so[b * 2 + 1]);
     }
     __syncthreads();
   }
@@ -512,14 +541,13 @@ size_t scratch_doubles_per_column(int nlev) {
 }
 
 static size_t gas_lw_smem(int nlev) {
-  return sizeof(LwLev) * nlev + sizeof(double) * (GAS_LC * LW_KTOT + GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
-         sizeof(int) * (GAS_LC * LW_KTOT + GAS_LC * NB_LW * 2 + GAS_LC * NB_LW * 2 + 2 * NG_LW) + 16;
+  return sizeof(Term) * GAS_LC * LW_KTOT + sizeof(LwLev) * nlev + sizeof(double) * (GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
+         sizeof(int) * (GAS_LC * NB_LW * 2 + GAS_LC * NB_LW * 2 + 2 * NG_LW + 2 * NB_LW) + 16;
 }
 static size_t gas_sw_smem(int nlev) {
-  return sizeof(SwLev) * nlev + sizeof(double) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
-         sizeof(int) * (GAS_LC * SW_KTOT + GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + nlev) + 16;
+  return sizeof(Term) * GAS_LC * SW_KTOT + sizeof(SwLev) * nlev + sizeof(double) * (GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
+         sizeof(int) * (GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + 2 * NB_SW + nlev) + 16;
 }
-
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
   // (kernels with the same signature share this template instantiation, so no caching by type here)

@@ -114,6 +114,11 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
   copy(M.preflog_lw, "lw_PREFLOG", 59); copy(M.tref_lw, "lw_TREF", 59); copy(M.chi_mls, "lw_CHI_MLS", 7 * 59);
   copy(M.preflog_sw, "sw_PREFLOG", 59); copy(M.tref_sw, "sw_TREF", 59);
   copy(M.totplnk, "lw_TOTPLNK", 181 * 16); copy(M.delwave, "lw_DELWAVE", 16);
+  {
+    static const int pr[6][2] = {{1, 2}, {1, 3}, {1, 4}, {1, 6}, {4, 2}, {3, 2}};
+    for (int k = 0; k < 6; ++k)
+      for (int j = 0; j < 59; ++j) M.chi_rat[k][j] = M.chi_mls[j * 7 + pr[k][0] - 1] / M.chi_mls[j * 7 + pr[k][1] - 1];
+  }
   const int32_t* ngc_lw = T.i("lw_NGC");
   const int32_t* ngc_sw = T.i("sw_NGC");
   const int32_t* ngb_lw = T.i("lw_NGB");

@@ -44,18 +44,18 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
     laytrop_sw += SL[jl].tropo;
   }
   *kmax_lw = 0; *kmax_sw = 0;
-  double c[64]; int o[64];
+  Term tt[64];
   for (int jl = 0; jl < nlev; ++jl) {
     const int il = nlev - jl;  // RRTMG layer index (1 = bottom)
     for (int b = 0; b < NB_LW; ++b) {
-      ListOut out{c, o, 0};
+      ListOut out{tt, 0};
       int post;
       PlanckFrac pf = lw_build_list(M, LL[jl], b, il <= laytrop_lw, out, &post);
       if (out.n > *kmax_lw) *kmax_lw = out.n;
       const BandMeta& B = M.lw[b];
       for (int ig = 0; ig < B.ng; ++ig) {
         double tau = 0.0;
-        for (int k = 0; k < out.n; ++k) tau += c[k] * P->lwtab[o[k] + ig];
+        for (int k = 0; k < out.n; ++k) tau += tt[k].c * P->lwtab[tt[k].o + ig];
         if (post >= 0) tau *= P->lwtab[post + ig];
         od_lw[(size_t)jl * NG_LW + B.g0 + ig] = tau;
         pfrac[(size_t)jl * NG_LW + B.g0 + ig] = pf.c0 * P->lwtab[pf.o0 + ig] + pf.c1 * P->lwtab[pf.o1 + ig];
@@ -75,13 +75,13 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
     for (int ig = 0; ig < B.ng; ++ig) incsol[B.g0 + ig] = 0.0;
     for (int jl = 0; jl < nlev; ++jl) {
       const int il = nlev - jl;
-      ListOut out{c, o, 0};
+      ListOut out{tt, 0};
       SwAux aux;
       sw_build_list(M, SL[jl], b, il <= laytrop_sw, out, aux);
       if (out.n > *kmax_sw) *kmax_sw = out.n;
       for (int ig = 0; ig < B.ng; ++ig) {
         double taug = 0.0;
-        for (int k = 0; k < out.n; ++k) taug += c[k] * P->swtab[o[k] + ig];
+        for (int k = 0; k < out.n; ++k) taug += tt[k].c * P->swtab[tt[k].o + ig];
         double taur = aux.rc0 * P->swtab[aux.ro0 + ig] + aux.rc1 * P->swtab[aux.ro1 + ig];
         double od = taur + taug;
         od_sw[(size_t)jl * NG_SW + B.g0 + ig] = od;
