@@ -238,7 +238,13 @@ def main():
     barrier()
     launches = h.kernel_launches() - l0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    stage_ms = h.last_stage_ms()   # kernels of the last step, CUDA events on the launching stream
+    # per-stage kernel durations for the roofline: one extra pass with the three chains serialised on the launching stream
+    # (in the timed region they overlap on three streams, so per-kernel durations are not separable there)
+    h.set_option("serial", 1)
+    step_device(); step_device()
+    torch.cuda.synchronize()
+    stage_ms = h.last_stage_ms()
+    h.set_option("serial", 0)
     ms_step = ms_total / args.steps
     value = world * ncol / (ms_step * 1e-3)
 
@@ -280,7 +286,7 @@ def main():
     if dom:
         achieved = B_MIN * ncol / (stage_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms, "stage_ms_mode": "serialised extra pass (CUDA events on the launching stream)",
                     "note": "fp64-ALU-bound path: algorithmic bytes are 30.9 kB/column against ~10 MFLOP/column (DESIGN.md)"}
 
     if rank == 0:

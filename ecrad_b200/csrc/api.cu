@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <string>
@@ -48,7 +49,9 @@ struct Handle {
   std::vector<void*> table_allocs;
   int device = 0;
   int tile_cols = 4096;
-  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_aux1 = nullptr, s_aux2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
+  int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
   Buf work[24];
   Work w;
@@ -101,7 +104,6 @@ int ensure_work(Handle* h, int cols, int nlev) {
   if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
   if (nlev != h->w_nlev) h->w_cols = 0;
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
-  const size_t spc = scratch_doubles_per_column(nlev);
   const size_t sz[] = {
       8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
@@ -109,9 +111,10 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
-      8 * nc * spc,                                                                          // scratch
+      8 * nc * LW_SCR_ARRAYS * nl * NG_LW,                                                   // scr_lw
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
-      8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW};                                            // lw_sums lw_carry
+      8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
+      8 * nc * SW_SCR_ARRAYS * nl * NG_SW};                                                  // scr_sw
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
@@ -120,7 +123,7 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.cum = (double*)h->work[9].p; w.pair = (double*)h->work[10].p; w.opi = (double*)h->work[11].p;
   w.tcc = (double*)h->work[12].p; w.ibegin = (int*)h->work[13].p; w.iend = (int*)h->work[14].p; w.ict = (int*)h->work[15].p;
   w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
-  w.scr = (double*)h->work[18].p; w.scr_per_col = spc;
+  w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
   w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
@@ -128,27 +131,51 @@ int ensure_work(Handle* h, int cols, int nlev) {
 }
 
 // Kernels of one tile; `in`/`out` are device views whose column 0 is the first column of the tile.
+// Three independent chains: cloud (prep -> optics -> generator), LW (gas -> down -> up -> flux), SW (gas -> direct ->
+// adding -> flux); the solvers wait for the cloud chain.  With serial == 0 they run on three streams forked from and
+// joined into `st`, so that latency-bound and fp64-bound kernels share the SMs.
+// ev: 2 events per stage (start, end), stages = gas_lw, gas_sw, cloud, solver_lw, solver_sw.
 int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev) {
   const DevCfg& c = h->dcfg;
   int n = 0;
-  if (ev) CK(h, cudaEventRecord(ev[0], st));
-  if (c.do_lw) n += launch_gas_lw(h->T, c, in, h->w, nc, nlev, st);
-  if (ev) CK(h, cudaEventRecord(ev[1], st));
-  if (c.do_sw) n += launch_gas_sw(h->T, c, in, h->w, nc, nlev, st);
-  if (ev) CK(h, cudaEventRecord(ev[2], st));
-  if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w, nc, nlev, st);
-  if (ev) CK(h, cudaEventRecord(ev[3], st));
-  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w, nc, nlev, st);
-  if (ev) CK(h, cudaEventRecord(ev[4], st));
-  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w, nc, nlev, st);
-  if (ev) CK(h, cudaEventRecord(ev[5], st));
+  const bool par = !h->serial;
+  cudaStream_t s_lw = st, s_sw = par ? h->s_aux1 : st, s_cl = par ? h->s_aux2 : st;
+  if (par) {
+    CK(h, cudaEventRecord(h->ev_fork, st));
+    CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork, 0));
+    CK(h, cudaStreamWaitEvent(s_cl, h->ev_fork, 0));
+  }
+  // cloud chain
+  CK(h, cudaEventRecord(ev[4], s_cl));
+  if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w, nc, nlev, s_cl);
+  CK(h, cudaEventRecord(ev[5], s_cl));
+  if (par) CK(h, cudaEventRecord(h->ev_cloud, s_cl));
+  // LW chain
+  CK(h, cudaEventRecord(ev[0], s_lw));
+  if (c.do_lw) n += launch_gas_lw(h->T, c, in, h->w, nc, nlev, s_lw);
+  CK(h, cudaEventRecord(ev[1], s_lw));
+  // SW chain
+  CK(h, cudaEventRecord(ev[2], s_sw));
+  if (c.do_sw) n += launch_gas_sw(h->T, c, in, h->w, nc, nlev, s_sw);
+  CK(h, cudaEventRecord(ev[3], s_sw));
+  if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud, 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud, 0)); }
+  CK(h, cudaEventRecord(ev[6], s_lw));
+  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w, nc, nlev, s_lw);
+  CK(h, cudaEventRecord(ev[7], s_lw));
+  CK(h, cudaEventRecord(ev[8], s_sw));
+  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w, nc, nlev, s_sw);
+  CK(h, cudaEventRecord(ev[9], s_sw));
+  if (par) {
+    CK(h, cudaEventRecord(h->ev_sw_done, s_sw));
+    CK(h, cudaStreamWaitEvent(st, h->ev_sw_done, 0));
+  }
   CK(h, cudaGetLastError());
   h->launches += n;
   return 0;
 }
 
 int ensure_events(Handle* h, int tiles) {
-  while ((int)h->ev.size() < tiles * (N_STAGE + 1)) {
+  while ((int)h->ev.size() < tiles * 2 * N_STAGE) {
     cudaEvent_t e; CK(h, cudaEventCreate(&e)); h->ev.push_back(e);
   }
   h->ev_tiles = tiles;
@@ -287,7 +314,9 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = v; }
   if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux1, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux2, cudaStreamNonBlocking) != cudaSuccess) {
     fail(nullptr, "cannot create CUDA streams"); ecrad_b200_finalize(h); return 1;
   }
   for (auto& s : h->slot) {
@@ -295,6 +324,10 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_cloud, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_sw_done, cudaEventDisableTiming);
+  if (const char* s2 = getenv("ECRAD_B200_SERIAL")) h->serial = atoi(s2) != 0;
   init_generator_constants();
   *handle = h;
   return 0;
@@ -318,6 +351,9 @@ void ecrad_b200_finalize(void* handle) {
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  if (h->s_aux1) cudaStreamDestroy(h->s_aux1);
+  if (h->s_aux2) cudaStreamDestroy(h->s_aux2);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_cloud, h->ev_sw_done}) if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -328,15 +364,24 @@ int ecrad_b200_last_stage_ms(void* handle, float* ms, int max_stages) {
   if (!h || !ms) return 0;
   std::lock_guard<std::mutex> lk(h->mu);
   cudaSetDevice(h->device);
-  if (h->ev_tiles > 0) cudaEventSynchronize(h->ev[h->ev_tiles * (N_STAGE + 1) - 1]);
+  cudaDeviceSynchronize();
   int n = max_stages < N_STAGE ? max_stages : N_STAGE;
   for (int s = 0; s < n; ++s) ms[s] = 0.f;
   for (int t = 0; t < h->ev_tiles; ++t)
     for (int s = 0; s < n; ++s) {
       float v = 0.f;
-      if (cudaEventElapsedTime(&v, h->ev[t * (N_STAGE + 1) + s], h->ev[t * (N_STAGE + 1) + s + 1]) == cudaSuccess) ms[s] += v;
+      if (cudaEventElapsedTime(&v, h->ev[(t * N_STAGE + s) * 2], h->ev[(t * N_STAGE + s) * 2 + 1]) == cudaSuccess) ms[s] += v;
     }
   return n;
+}
+
+int ecrad_b200_set_option(void* handle, const char* key, int value) {
+  Handle* h = (Handle*)handle;
+  if (!h || !key) return 1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!strcmp(key, "serial")) { h->serial = value != 0; return 0; }
+  if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
+  return fail(h, "unknown option '%s'", key);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -404,7 +449,7 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     make_views(ip, op, cap, in->solar_irradiance, di, dout);
     CK(h, cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
     if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp, s.d2h_done, 0));
-    if (run_tile(h, di, dout, nt, nlev, h->s_comp, &h->ev[t * (N_STAGE + 1)])) return 1;
+    if (run_tile(h, di, dout, nt, nlev, h->s_comp, &h->ev[t * 2 * N_STAGE])) return 1;
     CK(h, cudaEventRecord(s.compute_done, h->s_comp));
     // ---- D2H ----
     CK(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
@@ -454,7 +499,7 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b2
     }
     DevIn di; DevOut dout;
     make_views(ip, op, ncol, in->solar_irradiance, di, dout);
-    if (run_tile(h, di, dout, nt, nlev, st, &h->ev[t * (N_STAGE + 1)])) return 1;
+    if (run_tile(h, di, dout, nt, nlev, st, &h->ev[t * 2 * N_STAGE])) return 1;
   }
   return 0;
 }

@@ -535,11 +535,6 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
 // =========================================================================================================
 // launchers
 // =========================================================================================================
-size_t scratch_doubles_per_column(int nlev) {
-  size_t lw = (size_t)LW_SCR_ARRAYS * nlev * NG_LW, sw = (size_t)SW_SCR_ARRAYS * nlev * NG_SW;
-  return lw > sw ? lw : sw;
-}
-
 static size_t gas_lw_smem(int nlev) {
   return sizeof(Term) * GAS_LC * LW_KTOT + sizeof(LwLev) * nlev + sizeof(double) * (GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
          sizeof(int) * (GAS_LC * NB_LW * 2 + GAS_LC * NB_LW * 2 + 2 * NG_LW + 2 * NB_LW) + 16;

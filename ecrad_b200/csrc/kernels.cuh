@@ -66,13 +66,11 @@ struct Work {
   double* tcc;                                    // [nc]
   int *ibegin, *iend, *ict;                       // [nc]
   uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
-  double* scr;                                    // [nc][scr_per_col]
+  double *scr_lw, *scr_sw;                        // [nc][LW_SCR_ARRAYS*nlev*140], [nc][SW_SCR_ARRAYS*nlev*112] (separate: LW and SW chains run concurrently)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
-  size_t scr_per_col;
 };
 
-size_t scratch_doubles_per_column(int nlev);
 void init_generator_constants();   // once per process/device, before the first generator launch
 
 // Launchers.  All enqueue on `st` and return the number of kernels launched.

@@ -33,7 +33,7 @@ __device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, 
   s.n = (size_t)nlev * NG_LW;
   s.od = w.od_lw + (size_t)s.c * s.n;
   s.pl = w.planck + (size_t)s.c * (nlev + 1) * NG_LW;
-  s.scr = w.scr + (size_t)s.c * w.scr_per_col;
+  s.scr = w.scr_lw + (size_t)s.c * LW_SCR_ARRAYS * s.n;
   s.sums = w.lw_sums + (size_t)s.c * 6 * (nlev + 1);
   s.carry = w.lw_carry + (size_t)s.c * 4 * NG_LW;
   return s;

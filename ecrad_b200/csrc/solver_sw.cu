@@ -50,7 +50,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
   s.cl = w.cl_sw + (size_t)s.c * nlev * 3 * NB_SW;
   s.b = T.meta->band_of_g_sw[s.gg];
   s.codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)s.c * NG_SW + s.gg) * nlevp);
-  s.scr = w.scr + (size_t)s.c * w.scr_per_col;
+  s.scr = w.scr_sw + (size_t)s.c * SW_SCR_ARRAYS * s.n;
   return s;
 }
 

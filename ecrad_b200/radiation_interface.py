@@ -22,7 +22,7 @@ DEFAULT_TABLES = os.path.join(_HERE, "data", "rrtmg_tables.bin")
 
 EXPORTS = [
     "ecrad_b200_tables_create", "ecrad_b200_tables_add", "ecrad_b200_tables_load_file", "ecrad_b200_tables_free",
-    "ecrad_b200_setup", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_kernel_launches",
+    "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_kernel_launches",
     "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
     "ecrad_b200_version",
 ]
@@ -49,6 +49,7 @@ def load_library():
     L.ecrad_b200_setup.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.POINTER(C.c_void_p)]
     L.ecrad_b200_radiation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
     L.ecrad_b200_radiation_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
+    L.ecrad_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.ecrad_b200_kernel_launches.restype = C.c_int64
     L.ecrad_b200_kernel_launches.argtypes = [C.c_void_p]
     L.ecrad_b200_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
@@ -111,6 +112,10 @@ class RadiationHandle:
         """Device-resident entry: every pointer in ist/ost is a device pointer with leading dimension ncol."""
         rc = self.lib.ecrad_b200_radiation_device(self.h, ncol, nlev, C.byref(ist), C.byref(ost), C.c_void_p(stream))
         if rc:
+            raise RadiationError(self._err())
+
+    def set_option(self, key, value):
+        if self.lib.ecrad_b200_set_option(self.h, key.encode(), int(value)):
             raise RadiationError(self._err())
 
     def kernel_launches(self):

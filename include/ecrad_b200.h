@@ -137,6 +137,10 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
 int ecrad_b200_radiation_device(void* handle, int ncol, int nlev,
                                 const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream);
 
+/* Tuning/diagnostic options: "serial" (0/1: run a tile's kernels on one stream instead of the three overlapping chains;
+ * needed for per-kernel timing), "tile_cols" (columns per internal tile).  Returns 0 on success. */
+int ecrad_b200_set_option(void* handle, const char* key, int value);
+
 /* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t ecrad_b200_kernel_launches(void* handle);
 /* Event-timed duration (ms) of the last call's kernels, by stage; returns number of stages written. */
