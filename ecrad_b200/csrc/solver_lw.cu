@@ -54,12 +54,14 @@ lw_down_kernel(DevCfg cfg, Work w, int nlev) {
   if (s.act) tile[g] = 0.0;   // flux_dn at TOA
   ++slot;
   double pt = s.act ? s.pl[g] : 0.0;
+  // software pipeline: the loads of layer l+1 are issued before the exp/div of layer l
+  double od_n = s.act ? s.od[g] : 0.0, pb_n = s.act ? s.pl[NG_LW + g] : 0.0;
   for (int l = 0; l < nlev; ++l) {
     if (s.act) {
       if (l == s.ict) fd_ict = fd;
-      const size_t i = (size_t)l * NG_LW + g;
-      const double pb = s.pl[i + NG_LW];
-      const LwLayer L = lw_no_scat(s.od[i], pt, pb);
+      const double odg = od_n, pb = pb_n;
+      if (l + 1 < nlev) { const size_t i1 = (size_t)(l + 1) * NG_LW + g; od_n = s.od[i1]; pb_n = s.pl[i1 + NG_LW]; }
+      const LwLayer L = lw_no_scat(odg, pt, pb);
       pt = pb;
       fd = L.trans * fd + L.source_dn;
       tile[slot * LW_RS + g] = fd;
@@ -108,10 +110,13 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   ++slot;
   uint4 cq = make_uint4(0, 0, 0, 0);
   double pb = s.act ? s.pl[(size_t)nlev * NG_LW + g] : 0.0;
+  // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
+  double od_n = s.act ? s.od[(size_t)(nlev - 1) * NG_LW + g] : 0.0, pt_n = s.act ? s.pl[(size_t)(nlev - 1) * NG_LW + g] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
     if (s.act) {
       const size_t i = (size_t)l * NG_LW + g;
-      const double odg = s.od[i], pt = s.pl[i];
+      const double odg = od_n, pt = pt_n;
+      if (l > 0) { od_n = s.od[i - NG_LW]; pt_n = s.pl[i - NG_LW]; }
       const LwLayer Lc = lw_no_scat(odg, pt, pb);
       fu = Lc.trans * fu + Lc.source_up;
       prod = prod * Lc.trans;
@@ -164,10 +169,10 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
         sP[i] = pa;
         tile[(2 * LCH + slot) * LW_RS + g] = l <= ict ? fu_a : 0.0;
       }
+      pb = pt;
     }
     ++slot;
     if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
-    pb = s.act ? s.pl[(size_t)l * NG_LW + g] : 0.0;
   }
   if (s.act) { s.carry[2 * NG_LW + g] = fu; s.carry[3 * NG_LW + g] = fu_a; }
 }
@@ -194,16 +199,24 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
     {
       double* dst[2] = {s.sums + LWS_DN_A * nl1, s.sums + LWS_UP_A * nl1};
       int slot = 0, lfirst = ict + 1;
-#pragma unroll 4
-      for (int l = ict; l < nlev; ++l) {
-        if (act) {
-          const size_t i = (size_t)l * NG_LW + g;
-          fd = sa[i] * fd + sb[i];
-          fu = sA[i] * fd + sS[i];
-          tile[slot * LW_RS + g] = fd; tile[(LW_LCH_FLUX + slot) * LW_RS + g] = fu;
+      for (int l0 = ict; l0 < nlev; l0 += 4) {
+        double va[4], vb[4], vA[4], vS[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (act && l0 + k < nlev) { const size_t i = (size_t)(l0 + k) * NG_LW + g; va[k] = sa[i]; vb[k] = sb[i]; vA[k] = sA[i]; vS[k] = sS[i]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int l = l0 + k;
+          if (l < nlev) {
+            if (act) {
+              fd = va[k] * fd + vb[k];
+              fu = vA[k] * fd + vS[k];
+              tile[slot * LW_RS + g] = fd; tile[(LW_LCH_FLUX + slot) * LW_RS + g] = fu;
+            }
+            ++slot;
+            if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+          }
         }
-        ++slot;
-        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
       }
     }
     fd_surf = fd;

@@ -81,19 +81,23 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   double fc = w.incoming[(size_t)s.c * NG_SW + s.gg], fa = fc;
   int slot = 0, lfirst = 0;
   uint4 cq = make_uint4(0, 0, 0, 0);
+  // software pipeline: od (and ssa where needed) of layer l+1 are loaded before the exp of layer l
+  const bool need_ssa = CLOUDLESS || s.cloudy;
+  double od_n = s.act ? s.od[g] : 0.0, ssa_n = (s.act && need_ssa) ? s.ssa[g] : 0.0;
   for (int l = 0; l < nlev; ++l) {
     if (s.act) {
       const size_t i = (size_t)l * NG_SW + g;
-      const double odg = s.od[i];
+      const double odg = od_n, ssag = ssa_n;
+      if (l + 1 < nlev) { od_n = s.od[i + NG_SW]; if (need_ssa) ssa_n = s.ssa[i + NG_SW]; }
       double tdir_c;
-      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, s.ssa[i], 0.0).trans_dir_dir;
+      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, ssag, 0.0).trans_dir_dir;
       else tdir_c = exp(dmax(-dmax(odg * inv_mu0, 0.0), -1000.0));
       double tdir_a = tdir_c;
       if (s.cloudy) {
         if ((l & 3) == 0) cq = __ldg(s.codep + (l >> 2));
         if (fracs[l] >= s.thr) {
           double odt, ssat, gt;
-          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, s.ssa[i], odt, ssat, gt);
+          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, odt, ssat, gt);
           tdir_a = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
         }
         sFa[i] = fa;
@@ -203,7 +207,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
 // ---------------------------------------------------------------------------------------------------------
 // C: fluxes top-down (radiation_adding_ica_sw.F90:134-146), g-point sums, blending and the flux_type outputs
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SW_THREADS, 6)
+__global__ void __launch_bounds__(SW_THREADS, 5)
 sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
@@ -258,21 +262,33 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
       tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = 0.0; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = toa_a0;
     }
     ++slot;
-#pragma unroll 4
-    for (int l = 0; l < nlev; ++l) {
-      if (act) {
-        const size_t i = (size_t)l * NG_SW + g;
-        fdd_c = ac[i] * fdd_c + bc[i];
-        const double fu_c = Ac[i] * fdd_c + Sc[i];
-        tile[slot * SW_RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = fu_c;
-        if (cloudy) {
-          fdd_a = aa[i] * fdd_a + ba[i];
-          const double fu_a = Aa[i] * fdd_a + Sa[i];
-          tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = fu_a;
+    for (int l0 = 0; l0 < nlev; l0 += 4) {
+      double ca[4], cb[4], cA[4], cS[4], da[4], db[4], dA[4], dS[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (act && l0 + k < nlev) {
+          const size_t i = (size_t)(l0 + k) * NG_SW + g;
+          ca[k] = ac[i]; cb[k] = bc[i]; cA[k] = Ac[i]; cS[k] = Sc[i];
+          if (cloudy) { da[k] = aa[i]; db[k] = ba[i]; dA[k] = Aa[i]; dS[k] = Sa[i]; }
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int l = l0 + k;
+        if (l < nlev) {
+          if (act) {
+            fdd_c = ca[k] * fdd_c + cb[k];
+            const double fu_c = cA[k] * fdd_c + cS[k];
+            tile[slot * SW_RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = fu_c;
+            if (cloudy) {
+              fdd_a = da[k] * fdd_a + db[k];
+              const double fu_a = dA[k] * fdd_a + dS[k];
+              tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = fu_a;
+            }
+          }
+          ++slot;
+          if (slot == SW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0; }
         }
       }
-      ++slot;
-      if (slot == SW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0; }
     }
   }
   const double tcc = s.tcc;
