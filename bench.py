@@ -129,7 +129,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_sample or max(256, min(args.ncol, 16 * ncores))
+        sample = args.cpu_sample or min(args.ncol, 10000)
         warm = max(args.warmup, 1)
         for _ in range(warm - 1):
             cpu_arm(cfg, raw, sample, 0, ncores, 1)
@@ -172,7 +172,12 @@ def main():
         return float(t.item())
 
     ncol = args.ncol
-    h = setup_radiation(cfg)
+    blob = None
+    if dist is not None:   # rank 0 reads the optics tables, one NCCL broadcast hands them to every GPU
+        from ecrad_b200.radiation_interface import DEFAULT_TABLES
+        from ecrad_b200.sharding import broadcast_table_blob
+        blob = broadcast_table_blob(DEFAULT_TABLES, dist, device=dev)
+    h = setup_radiation(cfg, tables_blob=blob)
     inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol, first=rank * ncol))
 
     # ---- host buffers (pinned) for the e2e path ----
@@ -260,6 +265,21 @@ def main():
     e2e_value = world * ncol / e2e_s
     clocks = sampler.stop()
 
+    # optional exchange step of a host model: gather the 10 broadband flux profiles on rank 0 over NVLink (not in the timed
+    # region: the path itself needs no collective; reported for information)
+    gather_ms = None
+    if dist is not None:
+        from ecrad_b200.sharding import gather_profiles
+        prof = [nm for nm, kind in out_names if kind == "h"][:10]
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for nm in prof:
+            gather_profiles(dev_out[nm], world * ncol, dist)
+        g1.record()
+        barrier()
+        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+
     # parity guard: the timed outputs are the real thing (first 32 columns of rank 0 = the golden test slice)
     if rank == 0:
         g = np.load(os.path.join(ROOT, "tests", "golden", "ecrad_meridian_noaer_ref.npz"))
@@ -292,7 +312,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            sample = args.cpu_sample or max(256, min(ncol, 16 * ncores))
+            sample = args.cpu_sample or min(ncol, 10000)
             v, sec = cpu_arm(cfg, raw, sample, 0, ncores, 3)
             cpu = {"value": v, "unit": "columns/s", "cores": ncores, "kind": "port",
                    "sample": f"{sample} columns of the same workload, 3 repetitions ({sec:.2f} s each), C/OpenMP oracle port"}
@@ -302,6 +322,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_s * 1e3, "host_memory": "pinned"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if gather_ms is not None:
+            line["gather_profiles_ms"] = gather_ms
         print(json.dumps(line))
     h.finalize()
     if dist is not None:

@@ -264,6 +264,12 @@ int ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path) {
   if (rc) fail(nullptr, "cannot load table blob '%s' (rc=%d)", path, rc);
   return rc;
 }
+int ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_t nbytes) {
+  if (!t || !blob || nbytes < 8) return 1;
+  int rc = t->load_memory((const char*)blob, (size_t)nbytes);
+  if (rc) fail(nullptr, "table blob in memory is not a valid ETB1 image (rc=%d)", rc);
+  return rc;
+}
 void ecrad_b200_tables_free(ecrad_b200_tables* t) { delete t; }
 
 const char* ecrad_b200_version(void) { return "ecrad_b200 0.1 (sm_100a; RRTMG + McICA/Cloudless; fp64)"; }

@@ -37,14 +37,19 @@ struct ecrad_b200_tables {
     std::vector<char> buf((size_t)sz);
     if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return 2; }
     fclose(f);
-    if (sz < 8 || memcmp(buf.data(), "ETB1", 4)) return 3;
-    uint32_t n; memcpy(&n, buf.data() + 4, 4);
+    return load_memory(buf.data(), (size_t)sz);
+  }
+  int load_memory(const char* buf, size_t sz) {
+    if (sz < 8 || memcmp(buf, "ETB1", 4)) return 3;
+    uint32_t n; memcpy(&n, buf + 4, 4);
     struct Entry { char name[48]; int32_t dtype, ndim; int64_t dims[4]; int64_t offset; };
     static_assert(sizeof(Entry) == 96, "ETB1 entry layout");
+    if (8 + (size_t)n * sizeof(Entry) > sz) return 3;
     for (uint32_t i = 0; i < n; ++i) {
-      Entry e; memcpy(&e, buf.data() + 8 + (size_t)i * sizeof(Entry), sizeof(Entry));
+      Entry e; memcpy(&e, buf + 8 + (size_t)i * sizeof(Entry), sizeof(Entry));
       char nm[49]; memcpy(nm, e.name, 48); nm[48] = 0;
-      if (add(nm, e.dtype, e.ndim, e.dims, buf.data() + e.offset)) return 4;
+      if (e.offset < 0 || (size_t)e.offset >= sz) return 4;
+      if (add(nm, e.dtype, e.ndim, e.dims, buf + e.offset)) return 4;
     }
     return 0;
   }

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libecrad_b200.so")
 DEFAULT_TABLES = os.path.join(_HERE, "data", "rrtmg_tables.bin")
 
 EXPORTS = [
-    "ecrad_b200_tables_create", "ecrad_b200_tables_add", "ecrad_b200_tables_load_file", "ecrad_b200_tables_free",
+    "ecrad_b200_tables_create", "ecrad_b200_tables_add", "ecrad_b200_tables_load_file", "ecrad_b200_tables_load_memory", "ecrad_b200_tables_free",
     "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_kernel_launches",
     "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
     "ecrad_b200_version",
@@ -45,6 +45,7 @@ def load_library():
     L.ecrad_b200_tables_create.restype = C.c_void_p
     L.ecrad_b200_tables_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
     L.ecrad_b200_tables_load_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.ecrad_b200_tables_load_memory.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.ecrad_b200_tables_free.argtypes = [C.c_void_p]
     L.ecrad_b200_setup.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.POINTER(C.c_void_p)]
     L.ecrad_b200_radiation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
@@ -66,14 +67,16 @@ def load_library():
 class RadiationHandle:
     """What `setup_radiation` leaves behind: the config plus the device-side tables (radiation_interface.F90:37-156)."""
 
-    def __init__(self, config: RadiationConfig, tables_path: str = DEFAULT_TABLES):
+    def __init__(self, config: RadiationConfig, tables_path: str = DEFAULT_TABLES, tables_blob: bytes = None):
         L = load_library()
         self.lib = L
         self.config = config
         self.cfg = config.to_struct()
         t = L.ecrad_b200_tables_create()
         try:
-            if L.ecrad_b200_tables_load_file(t, tables_path.encode()):
+            rc = (L.ecrad_b200_tables_load_memory(t, tables_blob, len(tables_blob)) if tables_blob is not None
+                  else L.ecrad_b200_tables_load_file(t, tables_path.encode()))
+            if rc:
                 raise RadiationError(L.ecrad_b200_last_error(None).decode())
             # config%sw_albedo_weights, config%i_emiss_from_band_lw: the part of config_type that is a table
             for nm, arr in config.derived.items():
@@ -138,10 +141,11 @@ class RadiationHandle:
             pass
 
 
-def setup_radiation(config: RadiationConfig, tables_path: str = DEFAULT_TABLES) -> RadiationHandle:
+def setup_radiation(config: RadiationConfig, tables_path: str = DEFAULT_TABLES, tables_blob: bytes = None) -> RadiationHandle:
+    """tables_blob: the ETB1 image as bytes (e.g. received by a broadcast) instead of a file path."""
     if not config.derived:
         config.consolidate()
-    return RadiationHandle(config, tables_path)
+    return RadiationHandle(config, tables_path, tables_blob)
 
 
 def radiation(handle: RadiationHandle, ncol, nlev, istartcol, iendcol, inputs, **kw):

@@ -1,0 +1,60 @@
+"""Column sharding across GPUs (one process per GPU, torch.distributed for the plumbing).
+
+Columns are independent end to end (the reference already block-decomposes by istartcol:iendcol,
+driver/ecrad_driver.F90:345-354), so the data path needs no collective: rank r owns a contiguous column range and
+writes its own slice of flux_type.  The only exchange steps are the ones the reference's MPL layer has
+(ifsrrtm/rrtm_kgb*.F90: rank 0 reads the tables, MPL_BROADCAST) and, where the host model wants all fluxes in one place,
+a gather of the flux profiles; both are provided here over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(ncol_total: int, rank: int, world: int):
+    """1-based inclusive (istartcol, iendcol) of rank `rank`: contiguous blocks of ceil(N/G) columns, like the offline
+    driver's blocks.  Returns (1, 0) for ranks beyond the data."""
+    per = -(-ncol_total // world)
+    start = rank * per + 1
+    end = min((rank + 1) * per, ncol_total)
+    return (start, end) if start <= end else (1, 0)
+
+
+def broadcast_table_blob(path: str, dist, device=None) -> bytes:
+    """Rank 0 reads the packed ETB1 table blob, every rank receives the same bytes (one broadcast of ~2.5 MB)."""
+    import torch
+
+    rank = dist.get_rank()
+    n = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == 0:
+        raw = np.fromfile(path, dtype=np.uint8)
+        n[0] = raw.size
+    dist.broadcast(n, src=0)
+    buf = torch.empty(int(n.item()), dtype=torch.uint8, device=device)
+    if rank == 0:
+        buf.copy_(torch.from_numpy(raw))
+    dist.broadcast(buf, src=0)
+    return buf.cpu().numpy().tobytes()
+
+
+def gather_profiles(local, ncol_total: int, dist, dst: int = 0):
+    """Gather a (nrows, ncol_local) tensor of flux profiles (row = half-level, column fastest: the reference layout of
+    flux%lw_up etc.) from every rank's contiguous column range into (nrows, ncol_total) on rank `dst`.
+    Ragged last shard is handled by padding to the common shard width."""
+    import torch
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = -(-ncol_total // world)
+    nrows = local.shape[0]
+    send = torch.zeros((nrows, per), dtype=local.dtype, device=local.device)
+    send[:, : local.shape[1]] = local
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty((nrows, ncol_total), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        s, e = shard_range(ncol_total, r, world)
+        if e >= s:
+            out[:, s - 1:e] = recv[r][:, : e - s + 1]
+    return out

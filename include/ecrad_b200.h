@@ -70,6 +70,9 @@ int  ecrad_b200_tables_add(ecrad_b200_tables* t, const char* name, int dtype, in
                            const int64_t* dims, const void* data);
 /* Load an "ETB1" blob written by tools/extract_rrtmg_tables.py (stand-alone use without a Fortran host). */
 int  ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path);
+/* Same from memory (e.g. the blob received by an MPI/NCCL broadcast from the rank that read it; mirrors MPL_BROADCAST in
+ * ifsrrtm/rrtm_kgb1.F90:38-51). */
+int  ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_t nbytes);
 void ecrad_b200_tables_free(ecrad_b200_tables* t);
 
 /* Inputs of radiation(): components of single_level_type (radiation_single_level.F90:29-102),
