@@ -53,7 +53,7 @@ struct Handle {
   cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
-  Buf work[24];
+  Buf work[28];
   Work w;
   int w_cols = 0, w_nlev = 0;
   std::mutex mu;
@@ -114,7 +114,8 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc * LW_SCR_ARRAYS * nl * NG_LW,                                                   // scr_lw
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
-      8 * nc * SW_SCR_ARRAYS * nl * NG_SW};                                                  // scr_sw
+      8 * nc * SW_SCR_ARRAYS * nl * NG_SW,                                                   // scr_sw
+      sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl};                                     // lev_lw lev_sw
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
@@ -124,6 +125,7 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.tcc = (double*)h->work[12].p; w.ibegin = (int*)h->work[13].p; w.iend = (int*)h->work[14].p; w.ict = (int*)h->work[15].p;
   w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
   w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
+  w.lev_lw = (LwLev*)h->work[24].p; w.lev_sw = (SwLev*)h->work[25].p;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
   w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
@@ -140,6 +142,7 @@ int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cu
   int n = 0;
   const bool par = !h->serial;
   cudaStream_t s_lw = st, s_sw = par ? h->s_aux1 : st, s_cl = par ? h->s_aux2 : st;
+  n += launch_gas_prep(h->T, c, in, h->w, nc, nlev, st);   // shared by the LW and SW gas-optics kernels
   if (par) {
     CK(h, cudaEventRecord(h->ev_fork, st));
     CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork, 0));

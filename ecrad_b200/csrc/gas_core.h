@@ -155,12 +155,13 @@ HD void lw_setcoef(const GasMeta& M, const LevGas& G, LwLev& L) {
 // ---------------------------------------------------------------------------------------------------------
 // list emitters
 // ---------------------------------------------------------------------------------------------------------
-struct Term { double c; int o; int pad; };   // 16 bytes: coefficient, element offset of the table row (add the in-band g index)
+struct alignas(16) Term { double c; int o; int pad; };   // 16 bytes: coefficient, element offset of the table row (add the in-band g index)
 struct ListOut {
-  Term* t;
+  Term* t;      // term k lives at t[k * stride] (the kernels interleave the lists of 16 layers: stride = 16)
   int n;
-  HD void add(double coef, int off) { t[n].c = coef; t[n].o = off; ++n; }
-  HD void pad4() { while (n & 3) { t[n].c = 0.0; t[n].o = 0; ++n; } }   // zero terms so that consumers can unroll by 4
+  int stride;
+  HD void add(double coef, int off) { Term x; x.c = coef; x.o = off; x.pad = 0; t[n * stride] = x; ++n; }   // one 128-bit store
+  HD void pad4() { while (n & 3) add(0.0, 0); }   // zero terms so that consumers can unroll by 4
 };
 
 struct Spec { double speccomb, specparm, fs; int js; };
@@ -288,13 +289,13 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
         emit_lin(out, B.sec[L_M1], ng, indm, mf, scalen2);
         pf = pf_const(FB);
       }
-      for (int k = 0; k < out.n; ++k) out.t[k].c = corradj * out.t[k].c;
+      for (int k = 0; k < out.n; ++k) out.t[k * out.stride].c = corradj * out.t[k * out.stride].c;
     } break;
     case 2: {  // rrtm_taumol2.F90: H2O / H2O
       if (low) {
         double corradj = 1.0 - .05 * (L.pavel - 100.0) / 900.0;
         MAJ1A(L.colh2o); SELF_(); FOR_();
-        for (int k = 0; k < out.n; ++k) out.t[k].c = corradj * out.t[k].c;
+        for (int k = 0; k < out.n; ++k) out.t[k * out.stride].c = corradj * out.t[k * out.stride].c;
         pf = pf_const(FA);
       } else {
         MAJ1B(L.colh2o); FOR_();

@@ -25,10 +25,10 @@ namespace ecb {
 // slots per band = max number of terms rounded up to a multiple of 4 (lists are zero-padded so stage B unrolls by 4)
 //                                 band:  1   2   3   4   5   6   7   8   9  10  11  12  13  14  15  16
 __constant__ int c_lw_koff[NB_LW] = {0, 12, 20, 40, 56, 80, 92, 112, 128, 148, 156, 168, 184, 204, 212, 232};
-enum { LW_KTOT = 249 };   // 248 slots + 1: per-layer stride of 249 x 16 B keeps stage A's stores off a single bank
+enum { LW_KTOT = 248 };
 //                                 band: 16  17  18  19  20  21  22  23  24  25  26  27  28  29
 __constant__ int c_sw_koff[NB_SW] = {0, 12, 24, 36, 48, 60, 72, 88, 96, 112, 120, 120, 124, 132};
-enum { SW_KTOT = 145 };   // 144 slots + 1 (bank spread, as above)
+enum { SW_KTOT = 144 };
 
 enum { GAS_LC = 16, GAS_THREADS = 256 };
 
@@ -36,10 +36,12 @@ enum { GAS_LC = 16, GAS_THREADS = 256 };
 // tab_g = table base + in-band g index (hoisted: one 64-bit pointer per item; offsets are unsigned 32-bit, so each
 // address is a single IMAD.WIDE.U32).
 __device__ __forceinline__ double stencil_dot(const Term* tt, int n, const double* __restrict__ tab_g) {
+  // term k of this (layer, band) list is tt[k * GAS_LC]: the lists of the chunk's 16 layers are interleaved, so stage A's
+  // 128-bit stores (lanes = layers) and stage B's 128-bit loads (a quarter-warp reads <= 2 distinct terms) are conflict-free
   double acc0 = 0.0, acc1 = 0.0;
   const uint4* q = reinterpret_cast<const uint4*>(tt);
   for (int k = 0; k < n; k += 4) {
-    const uint4 t0 = q[k], t1 = q[k + 1], t2 = q[k + 2], t3 = q[k + 3];
+    const uint4 t0 = q[k * GAS_LC], t1 = q[(k + 1) * GAS_LC], t2 = q[(k + 2) * GAS_LC], t3 = q[(k + 3) * GAS_LC];
     const double v0 = __ldg(tab_g + t0.z), v1 = __ldg(tab_g + t1.z), v2 = __ldg(tab_g + t2.z), v3 = __ldg(tab_g + t3.z);
     acc0 = fma(__hiloint2double((int)t0.y, (int)t0.x), v0, acc0);
     acc1 = fma(__hiloint2double((int)t1.y, (int)t1.x), v1, acc1);
@@ -47,6 +49,24 @@ __device__ __forceinline__ double stencil_dot(const Term* tt, int n, const doubl
     acc1 = fma(__hiloint2double((int)t3.y, (int)t3.x), v3, acc1);
   }
   return acc0 + acc1;
+}
+
+// =========================================================================================================
+// per-layer state of both spectra (rrtm_prepare_gases + rrtm_setcoef_140gp + srtm_setcoef): one thread per (column, layer),
+// column fastest so that the reference-layout inputs are read coalesced
+// =========================================================================================================
+__global__ void gas_prep_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc * nlev) return;
+  const int c = i % nc, l = i / nc;
+  const GasMeta& M = *T.meta;
+  LevGas G;
+  lev_prepare(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1),
+              LD_IN(in.gas[0], c, l), LD_IN(in.gas[1], c, l), LD_IN(in.gas[2], c, l), LD_IN(in.gas[3], c, l),
+              LD_IN(in.gas[4], c, l), LD_IN(in.gas[5], c, l), LD_IN(in.gas[6], c, l), LD_IN(in.gas[7], c, l),
+              LD_IN(in.gas[8], c, l), G);
+  if (cfg.do_lw) { LwLev L; lw_setcoef(M, G, L); L.pad_ = 0.0; w.lev_lw[(size_t)c * nlev + l] = L; }
+  if (cfg.do_sw && in.cos_sza[c] > 0.0) { SwLev L; sw_setcoef(M, G, L); w.lev_sw[(size_t)c * nlev + l] = L; }
 }
 
 // =========================================================================================================
@@ -62,9 +82,8 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const int c = blockIdx.x, tid = threadIdx.x;
   const GasMeta& M = *T.meta;
   // carve shared memory
-  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [GAS_LC][LW_KTOT] (16-byte aligned)
-  LwLev* lev = reinterpret_cast<LwLev*>(lt + GAS_LC * LW_KTOT);      // [nlev]
-  double* pfc = reinterpret_cast<double*>(lev + nlev);               // [GAS_LC][16][2]
+  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [LW_KTOT][GAS_LC] (16-byte aligned)
+  double* pfc = reinterpret_cast<double*>(lt + GAS_LC * LW_KTOT);    // [GAS_LC][16][2]
   double* plk = pfc + GAS_LC * NB_LW * 2;                            // [GAS_LC+1][16]
   double* plk_surf = plk + (GAS_LC + 1) * NB_LW;                     // [16]
   int* ln = reinterpret_cast<int*>(plk_surf + NB_LW);                // [GAS_LC][16]
@@ -75,19 +94,9 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   int* sng = g0b + NG_LW;                                            // [16] g-points per band
   float* srn = reinterpret_cast<float*>(sng + NB_LW);                // [16] 1 / g-points per band
 
-  // ---- per-layer state (thread per layer) ----
-  int tropo = 0;
-  if (tid < nlev) {
-    LevGas G;
-    lev_prepare(LD_IN(in.p_hl, c, tid), LD_IN(in.p_hl, c, tid + 1), LD_IN(in.t_hl, c, tid), LD_IN(in.t_hl, c, tid + 1),
-                LD_IN(in.gas[0], c, tid), LD_IN(in.gas[1], c, tid), LD_IN(in.gas[2], c, tid), LD_IN(in.gas[3], c, tid),
-                LD_IN(in.gas[4], c, tid), LD_IN(in.gas[5], c, tid), LD_IN(in.gas[6], c, tid), LD_IN(in.gas[7], c, tid),
-                LD_IN(in.gas[8], c, tid), G);
-    LwLev L;
-    lw_setcoef(M, G, L);
-    lev[tid] = L;
-    tropo = L.tropo;
-  }
+  // per-layer state was prepared by gas_prep_kernel; LAYTROP = number of layers with plog > 4.56
+  const LwLev* lev = w.lev_lw + (size_t)c * nlev;
+  const int tropo = tid < nlev ? lev[tid].tropo : 0;
   for (int g = tid; g < NG_LW; g += GAS_THREADS) { int b = M.band_of_g_lw[g]; bog[g] = b; g0b[g] = g - M.lw[b].g0; }
   if (tid < NB_LW) { sng[tid] = M.lw[tid].ng; srn[tid] = 1.0f / (float)M.lw[tid].ng; }
   if (tid < NB_LW) plk_surf[tid] = planck_band(M, in.skin_t[c], tid);
@@ -105,8 +114,8 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         const int l = l0 + ll;
         const int il = nlev - l;               // RRTMG layer index (1 = bottom)
         ListOut out;
-        out.t = lt + ll * LW_KTOT + c_lw_koff[b];
-        out.n = 0;
+        out.t = lt + c_lw_koff[b] * GAS_LC + ll;
+        out.n = 0; out.stride = GAS_LC;
         int post;
         PlanckFrac pf = lw_build_list(M, lev[l], b, il <= laytrop, out, &post);
         out.pad4();
@@ -135,7 +144,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       const int l = l0 + ll;
       const int n = ln[ll * NB_LW + b];
       const double* tab_g = T.lwtab + igb;
-      double tau = stencil_dot(lt + ll * LW_KTOT + c_lw_koff[b], n, tab_g);
+      double tau = stencil_dot(lt + c_lw_koff[b] * GAS_LC + ll, n, tab_g);
       const int post = lpost[ll * NB_LW + b];
       if (post >= 0) tau *= __ldg(tab_g + (unsigned)post);
       const double pf = pfc[(ll * NB_LW + b) * 2] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2]) +
@@ -164,9 +173,8 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const int c = blockIdx.x, tid = threadIdx.x;
   if (!(in.cos_sza[c] > 0.0)) return;   // srtm only runs for sunlit columns (radiation_ifs_rrtm.F90:518-542)
   const GasMeta& M = *T.meta;
-  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [GAS_LC][SW_KTOT] (16-byte aligned)
-  SwLev* lev = reinterpret_cast<SwLev*>(lt + GAS_LC * SW_KTOT);      // [nlev]
-  double* rc = reinterpret_cast<double*>(lev + nlev);                // [GAS_LC][14][2] Rayleigh coefficients
+  Term* lt = reinterpret_cast<Term*>(smem_raw);                      // [SW_KTOT][GAS_LC] (16-byte aligned)
+  double* rc = reinterpret_cast<double*>(lt + GAS_LC * SW_KTOT);     // [GAS_LC][14][2] Rayleigh coefficients
   double* sc = rc + GAS_LC * NB_SW * 2;                              // [14][2]  solar-source coefficients
   double* inc = sc + NB_SW * 2;                                      // [112]
   int* ln = reinterpret_cast<int*>(inc + NG_SW);                     // [GAS_LC][14]
@@ -180,19 +188,9 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   int* jps = reinterpret_cast<int*>(srn + NB_SW);                    // [nlev] JP per layer (ecRad order)
   __shared__ double s_scale;
 
+  const SwLev* lev = w.lev_sw + (size_t)c * nlev;
   int tropo = 0;
-  if (tid < nlev) {
-    LevGas G;
-    lev_prepare(LD_IN(in.p_hl, c, tid), LD_IN(in.p_hl, c, tid + 1), LD_IN(in.t_hl, c, tid), LD_IN(in.t_hl, c, tid + 1),
-                LD_IN(in.gas[0], c, tid), LD_IN(in.gas[1], c, tid), LD_IN(in.gas[2], c, tid), LD_IN(in.gas[3], c, tid),
-                LD_IN(in.gas[4], c, tid), LD_IN(in.gas[5], c, tid), LD_IN(in.gas[6], c, tid), LD_IN(in.gas[7], c, tid),
-                LD_IN(in.gas[8], c, tid), G);
-    SwLev L;
-    sw_setcoef(M, G, L);
-    lev[tid] = L;
-    jps[tid] = L.jp;
-    tropo = L.tropo;
-  }
+  if (tid < nlev) { jps[tid] = lev[tid].jp; tropo = lev[tid].tropo; }
   for (int g = tid; g < NG_SW; g += GAS_THREADS) { int b = M.band_of_g_sw[g]; bog[g] = b; g0b[g] = g - M.sw[b].g0; inc[g] = 0.0; }
   if (tid < NB_SW) { sng[tid] = M.sw[tid].ng; srn[tid] = 1.0f / (float)M.sw[tid].ng; }
   const int laytrop = __syncthreads_count(tropo);
@@ -213,8 +211,8 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         const int l = l0 + ll;
         const int il = nlev - l;
         ListOut out;
-        out.t = lt + ll * SW_KTOT + c_sw_koff[b];
-        out.n = 0;
+        out.t = lt + c_sw_koff[b] * GAS_LC + ll;
+        out.n = 0; out.stride = GAS_LC;
         SwAux aux;
         sw_build_list(M, lev[l], b, il <= laytrop, out, aux);
         out.pad4();
@@ -237,7 +235,7 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       const int l = l0 + ll;
       const int n = ln[ll * NB_SW + b];
       const double* tab_g = T.swtab + igb;
-      const double taug = stencil_dot(lt + ll * SW_KTOT + c_sw_koff[b], n, tab_g);
+      const double taug = stencil_dot(lt + c_sw_koff[b] * GAS_LC + ll, n, tab_g);
       const double taur = rc[(ll * NB_SW + b) * 2] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2]) +
                           rc[(ll * NB_SW + b) * 2 + 1] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2 + 1]);
       const double od = taur + taug;                                        // srtm_gas_optical_depth.F90:314-320
@@ -535,12 +533,12 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
 // =========================================================================================================
 // launchers
 // =========================================================================================================
-static size_t gas_lw_smem(int nlev) {
-  return sizeof(Term) * GAS_LC * LW_KTOT + sizeof(LwLev) * nlev + sizeof(double) * (GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
+static size_t gas_lw_smem(int) {
+  return sizeof(Term) * GAS_LC * LW_KTOT + sizeof(double) * (GAS_LC * NB_LW * 2 + (GAS_LC + 1) * NB_LW + NB_LW) +
          sizeof(int) * (GAS_LC * NB_LW * 2 + GAS_LC * NB_LW * 2 + 2 * NG_LW + 2 * NB_LW) + 16;
 }
 static size_t gas_sw_smem(int nlev) {
-  return sizeof(Term) * GAS_LC * SW_KTOT + sizeof(SwLev) * nlev + sizeof(double) * (GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
+  return sizeof(Term) * GAS_LC * SW_KTOT + sizeof(double) * (GAS_LC * NB_SW * 2 + NB_SW * 2 + NG_SW) +
          sizeof(int) * (GAS_LC * NB_SW + GAS_LC * NB_SW * 2 + NB_SW * 2 + NB_SW + 2 * NG_SW + 2 * NB_SW + nlev) + 16;
 }
 template <class K>
@@ -549,6 +547,10 @@ static void allow_smem(K kernel, size_t bytes) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  gas_prep_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev);
+  return 1;
+}
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   size_t sm = gas_lw_smem(nlev);
   allow_smem(gas_lw_kernel, sm);

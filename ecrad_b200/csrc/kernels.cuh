@@ -67,6 +67,7 @@ struct Work {
   int *ibegin, *iend, *ict;                       // [nc]
   uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
   double *scr_lw, *scr_sw;                        // [nc][LW_SCR_ARRAYS*nlev*140], [nc][SW_SCR_ARRAYS*nlev*112] (separate: LW and SW chains run concurrently)
+  LwLev* lev_lw; SwLev* lev_sw;                   // [nc][nlev] per-layer gas-optics state (gas_prep_kernel)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
 };
@@ -74,6 +75,7 @@ struct Work {
 void init_generator_constants();   // once per process/device, before the first generator launch
 
 // Launchers.  All enqueue on `st` and return the number of kernels launched.
+int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);

@@ -48,7 +48,7 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
   for (int jl = 0; jl < nlev; ++jl) {
     const int il = nlev - jl;  // RRTMG layer index (1 = bottom)
     for (int b = 0; b < NB_LW; ++b) {
-      ListOut out{tt, 0};
+      ListOut out{tt, 0, 1};
       int post;
       PlanckFrac pf = lw_build_list(M, LL[jl], b, il <= laytrop_lw, out, &post);
       if (out.n > *kmax_lw) *kmax_lw = out.n;
@@ -75,7 +75,7 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
     for (int ig = 0; ig < B.ng; ++ig) incsol[B.g0 + ig] = 0.0;
     for (int jl = 0; jl < nlev; ++jl) {
       const int il = nlev - jl;
-      ListOut out{tt, 0};
+      ListOut out{tt, 0, 1};
       SwAux aux;
       sw_build_list(M, SL[jl], b, il <= laytrop_sw, out, aux);
       if (out.n > *kmax_sw) *kmax_sw = out.n;
