@@ -34,7 +34,8 @@ class Config(C.Structure):
         ("n_g_sw", C.c_int32), ("n_g_lw", C.c_int32), ("n_bands_sw", C.c_int32), ("n_bands_lw", C.c_int32),
         ("n_albedo_sw", C.c_int32), ("n_emiss_lw", C.c_int32),
         ("n_canopy_bands_sw", C.c_int32), ("n_canopy_bands_lw", C.c_int32),
-        ("reserved_i", C.c_int32 * 4),
+        ("n_aerosol_types", C.c_int32),
+        ("reserved_i", C.c_int32 * 3),
         ("cloud_fraction_threshold", C.c_double), ("cloud_mixing_ratio_threshold", C.c_double),
         ("min_gas_od_lw", C.c_double), ("min_gas_od_sw", C.c_double),
         ("cloud_inhom_decorr_scaling", C.c_double),
@@ -53,6 +54,7 @@ INPUT_ARRAYS = [
     ("ccl4_mmr", "f8", "cl"),
     ("cloud_fraction", "f8", "cl"), ("q_liq", "f8", "cl"), ("q_ice", "f8", "cl"), ("re_liq", "f8", "cl"),
     ("re_ice", "f8", "cl"), ("overlap_param", "f8", "ci"), ("fractional_std", "f8", "cl"),
+    ("aerosol_mmr", "f8", "clt"), ("h2o_sat_liq", "f8", "cl"),
 ]
 
 

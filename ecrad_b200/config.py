@@ -88,6 +88,9 @@ class RadiationConfig:
     do_nearest_spectral_lw_emiss: bool = True
     lw_emiss_wavelength_bound: tuple = (8.0e-6, 13.0e-6)
     i_lw_emiss_index: tuple = (1, 2, 1)
+    use_general_aerosol_optics: bool = True
+    n_aerosol_types: int = 12
+    i_aerosol_type_map: tuple = (-1, -2, -3, 7, 8, 9, -4, 10, 11, 11, -5, 14)
     min_gas_od_lw: float = 1.0e-15
     min_gas_od_sw: float = 0.0
     derived: dict = field(default_factory=dict)
@@ -101,6 +104,11 @@ class RadiationConfig:
             "i_emiss_from_band_lw": (np.argmax(e, axis=0) + 1).astype(np.int32),         # maxloc(dim=1)
             "lw_emiss_weights": np.asfortranarray(e),
         }
+        if self.use_aerosols:
+            # aerosol_optics%set_types (radiation_aerosol_optics_data.F90:605-633): >0 hydrophobic, <0 hydrophilic, 0 ignored
+            m = np.array(self.i_aerosol_type_map[: self.n_aerosol_types], dtype=np.int32)
+            self.derived["aerosol_iclass"] = np.where(m > 0, 1, np.where(m < 0, 2, 0)).astype(np.int32)
+            self.derived["aerosol_itype"] = np.abs(m).astype(np.int32)
         return self
 
     def to_struct(self) -> abi.Config:
@@ -127,6 +135,7 @@ class RadiationConfig:
         c.n_emiss_lw = max(self.i_lw_emiss_index)
         c.n_canopy_bands_sw = max(self.i_sw_albedo_index)
         c.n_canopy_bands_lw = max(self.i_lw_emiss_index)
+        c.n_aerosol_types = self.n_aerosol_types if self.use_aerosols else 0
         c.cloud_fraction_threshold = self.cloud_fraction_threshold
         c.cloud_mixing_ratio_threshold = self.cloud_mixing_ratio_threshold
         c.min_gas_od_lw, c.min_gas_od_sw = self.min_gas_od_lw, self.min_gas_od_sw

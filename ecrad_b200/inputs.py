@@ -18,7 +18,7 @@ GAS_MOLAR_MASS = {"co2": 44.011, "n2o": 44.013, "ch4": 16.043, "cfc11": 137.3686
 NC_VARS = ["solar_irradiance", "skin_temperature", "cos_solar_zenith_angle", "sw_albedo", "sw_albedo_direct",
            "lw_emissivity", "iseed", "pressure_hl", "temperature_hl", "q", "o3_mmr", "co2_vmr", "n2o_vmr", "ch4_vmr",
            "cfc11_vmr", "cfc12_vmr", "hcfc22_vmr", "ccl4_vmr", "cloud_fraction", "q_liquid", "q_ice", "re_liquid",
-           "re_ice", "overlap_param", "fractional_std"]
+           "re_ice", "overlap_param", "fractional_std", "aerosol_mmr"]
 
 
 def read_ifs_netcdf(path):
@@ -51,7 +51,20 @@ def to_radiation_inputs(raw):
         sf = 1.0 * m / AIR_MOLAR_MASS  # radiation_gas.F90 set_units_gas: sf = sf*GasMolarMass/AirMolarMass
         d[f"{g}_mmr"] = F(raw[f"{g}_vmr"] * sf)
     d["solar_irradiance"] = float(raw["solar_irradiance"])
+    if "aerosol_mmr" in raw:
+        # file (column, type, level) -> aerosol%mixing_ratio(ncol, nlev, ntype)  (driver/ecrad_driver_read_input.F90:546)
+        d["aerosol_mmr"] = F(np.transpose(raw["aerosol_mmr"], (0, 2, 1)))
+        d["h2o_sat_liq"] = F(saturation_wrt_liquid(raw["pressure_hl"], raw["temperature_hl"]))
     return d
+
+
+def saturation_wrt_liquid(pressure_hl, temperature_hl):
+    """thermodynamics%calc_saturation_wrt_liquid (radiation_thermodynamics.F90:118-158): driver-side preparation of the
+    saturation mass mixing ratio used for the aerosol relative-humidity index (driver/ecrad_driver.F90:301)."""
+    p = 0.5 * (pressure_hl[:, :-1] + pressure_hl[:, 1:])
+    t = 0.5 * (temperature_hl[:, :-1] + temperature_hl[:, 1:])
+    e_sat = 6.11e2 * np.exp(17.269 * (t - 273.16) / (t - 35.86))
+    return np.minimum(1.0, 0.622 * e_sat / p)
 
 
 def synthetic_columns(base_raw, ncol, seed=20261017, first=0):

@@ -51,7 +51,8 @@ typedef struct ecrad_b200_config {
   int32_t n_albedo_sw;               /* size(config%sw_albedo_weights,1) == size(single_level%sw_albedo,2) */
   int32_t n_emiss_lw;                /* size(single_level%lw_emissivity,2)                               */
   int32_t n_canopy_bands_sw, n_canopy_bands_lw;
-  int32_t reserved_i[4];
+  int32_t n_aerosol_types;           /* config%n_aerosol_types == size(aerosol%mixing_ratio,3); 0 without aerosols  */
+  int32_t reserved_i[3];
   double cloud_fraction_threshold;   /* config%cloud_fraction_threshold      (default 1e-6)              */
   double cloud_mixing_ratio_threshold; /*                                     (default 1e-9)              */
   double min_gas_od_lw, min_gas_od_sw; /* radiation_config.F90:244-245                                   */
@@ -62,7 +63,8 @@ typedef struct ecrad_b200_config {
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md
  * ("table directory"); for the RRTMG path they are the module variables of ifsrrtm/yoerrta1..16.F90,
  * yoesrta16..29.F90, yoerrtwn.F90, yoerrtrf.F90, yoesrtwn.F90 plus config%cloud_optics%*, config%pdf_sampler%*,
- * config%sw_albedo_weights, config%i_emiss_from_band_lw.  Data are COPIED by ecrad_b200_setup. */
+ * config%sw_albedo_weights, config%i_emiss_from_band_lw, and (with aerosols) config%aerosol_optics%{mass_ext,ssa,g}_{sw,lw}_
+ * {phobic,philic}, %rh_lower, %iclass, %itype ("aer_*", "aerosol_iclass", "aerosol_itype").  Data are COPIED by ecrad_b200_setup. */
 typedef struct ecrad_b200_tables ecrad_b200_tables;
 ecrad_b200_tables* ecrad_b200_tables_create(void);
 /* dtype: 0 = float64, 1 = int32.  dims[ndim] in Fortran order (dims[0] fastest).  Returns 0 on success. */
@@ -101,6 +103,9 @@ typedef struct ecrad_b200_inputs {
   const double* re_ice;               /* (ncol, nlev)  cloud%effective_radius(:,:,2)  m                  */
   const double* overlap_param;        /* (ncol, nlev-1)                                                  */
   const double* fractional_std;       /* (ncol, nlev)                                                    */
+  /* aerosol_type (radiation_aerosol.F90) and thermodynamics%h2o_sat_liq; only read when cfg.use_aerosols */
+  const double* aerosol_mmr;          /* (ncol, nlev, n_aerosol_types)  aerosol%mixing_ratio, levels 1..nlev */
+  const double* h2o_sat_liq;          /* (ncol, nlev)  saturation mass mixing ratio w.r.t. liquid (calc_saturation_wrt_liquid) */
 } ecrad_b200_inputs;
 
 /* Outputs: components of flux_type (radiation_flux.F90:38-118).  Any pointer may be NULL. */

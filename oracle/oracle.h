@@ -39,6 +39,11 @@ typedef struct orc_tables {
   const int32_t *ngb_sw, *ngc_sw;
   const double *liq_coeff_lw, *liq_coeff_sw, *ice_coeff_lw, *ice_coeff_sw;
   const double *pdf_val; int pdf_ncdf, pdf_nfsd; double pdf_fsd1, pdf_inv_fsd_interval;
+  /* aerosol optics per band (config%aerosol_optics): phobic (nband, ntype), philic (nband, nrh, ntype) */
+  const double *aer_me_sw_phobic, *aer_ssa_sw_phobic, *aer_g_sw_phobic, *aer_me_lw_phobic, *aer_ssa_lw_phobic, *aer_g_lw_phobic;
+  const double *aer_me_sw_philic, *aer_ssa_sw_philic, *aer_g_sw_philic, *aer_me_lw_philic, *aer_ssa_lw_philic, *aer_g_lw_philic;
+  const double *aer_rh_lower; int aer_nrh;
+  const int32_t *aer_iclass, *aer_itype;  /* (n_aerosol_types): 0 ignored / 1 hydrophobic / 2 hydrophilic; 1-based type */
   const double *sw_albedo_weights;      /* (n_albedo_sw, 14) */
   const int32_t *i_emiss_from_band_lw;  /* (16), 1-based */
 } orc_tables;

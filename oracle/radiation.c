@@ -18,7 +18,7 @@
 
 typedef struct {
   double *od_lw, *planck_hl, *lw_emission, *lw_albedo;         /* [nlev][140], [nlev+1][140], [140], [140] */
-  double *od_sw, *ssa_sw, *incoming_sw, *alb_dir, *alb_diff;   /* [nlev][112] x2, [112] x3 */
+  double *od_sw, *ssa_sw, *g_sw, *incoming_sw, *alb_dir, *alb_diff;   /* [nlev][112] x3, [112] x3 */
   double *od_lw_cloud, *ssa_lw_cloud, *g_lw_cloud, *od_sw_cloud, *ssa_sw_cloud, *g_sw_cloud; /* [nlev][nb] */
   double *w;  /* scratch pool */
 } col_work;
@@ -153,6 +153,79 @@ int orc_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int
   if (rc) return rc;
   gas_optics_column(t, cfg, ncol, nlev, jcol - 1, in, lw_albedo, od_lw, planck_hl, lw_emission, od_sw, ssa_sw, incoming_sw);
   return 0;
+}
+
+/* add_aerosol_optics, radiation_aerosol_optics.F90:487-826 (band-wise aerosol properties, no LW aerosol scattering,
+ * do_cloud_aerosol_per_*_g_point = false).  Modifies od_sw, ssa_sw, g_sw, od_lw of one column in place. */
+static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                               const ecrad_b200_inputs* in, double* od_lw, double* od_sw, double* ssa_sw, double* g_sw) {
+  const int ntype = cfg->n_aerosol_types, nrh = t->aer_nrh;
+  const double OneOverAccelDueToGravity = 1.0 / 9.80665;
+  double* od_sw_aer = (double*)calloc((size_t)nlev * (3 * NB_SW + NB_LW), sizeof(double));
+  double *scat_sw_aer = od_sw_aer + (size_t)nlev * NB_SW, *scat_g_sw_aer = scat_sw_aer + (size_t)nlev * NB_SW;
+  double* od_lw_aer = scat_g_sw_aer + (size_t)nlev * NB_SW;
+  int* irhs = (int*)malloc(sizeof(int) * (size_t)nlev);
+  double* factor = (double*)malloc(sizeof(double) * (size_t)nlev);
+  for (size_t i = 0; i < (size_t)nlev * NG_SW; ++i) g_sw[i] = 0.0;
+  for (int jl = 0; jl < nlev; ++jl) {
+    double rh = A2(in->h2o_mmr, jcol, jl) / A2(in->h2o_sat_liq, jcol, jl);
+    int irh;   /* calc_rh_index, radiation_aerosol_optics_data.F90:640-664 (1-based) */
+    if (rh > t->aer_rh_lower[nrh - 1]) irh = nrh;
+    else { irh = 1; while (rh > t->aer_rh_lower[irh]) irh++; }
+    irhs[jl] = irh;
+    factor[jl] = (A2(in->pressure_hl, jcol, jl + 1) - A2(in->pressure_hl, jcol, jl)) * OneOverAccelDueToGravity;
+  }
+  for (int jt = 0; jt < ntype; ++jt) {
+    const int itype = t->aer_itype[jt] - 1, iclass = t->aer_iclass[jt];
+    if (iclass == 0) continue;
+    for (int jl = 0; jl < nlev; ++jl) {
+      const double mixing_ratio = in->aerosol_mmr[((size_t)jt * nlev + jl) * ncol + jcol];
+      const size_t isw = iclass == 1 ? (size_t)itype * NB_SW : ((size_t)itype * nrh + (irhs[jl] - 1)) * NB_SW;
+      const size_t ilw = iclass == 1 ? (size_t)itype * NB_LW : ((size_t)itype * nrh + (irhs[jl] - 1)) * NB_LW;
+      const double *me_sw = (iclass == 1 ? t->aer_me_sw_phobic : t->aer_me_sw_philic) + isw;
+      const double *ss_sw = (iclass == 1 ? t->aer_ssa_sw_phobic : t->aer_ssa_sw_philic) + isw;
+      const double *gg_sw = (iclass == 1 ? t->aer_g_sw_phobic : t->aer_g_sw_philic) + isw;
+      const double *me_lw = (iclass == 1 ? t->aer_me_lw_phobic : t->aer_me_lw_philic) + ilw;
+      const double *ss_lw = (iclass == 1 ? t->aer_ssa_lw_phobic : t->aer_ssa_lw_philic) + ilw;
+      for (int jb = 0; jb < NB_SW; ++jb) {
+        double local_od_sw = factor[jl] * mixing_ratio * me_sw[jb];
+        od_sw_aer[jl * NB_SW + jb] = od_sw_aer[jl * NB_SW + jb] + local_od_sw;
+        scat_sw_aer[jl * NB_SW + jb] = scat_sw_aer[jl * NB_SW + jb] + local_od_sw * ss_sw[jb];
+        scat_g_sw_aer[jl * NB_SW + jb] = scat_g_sw_aer[jl * NB_SW + jb] + local_od_sw * ss_sw[jb] * gg_sw[jb];
+      }
+      for (int jb = 0; jb < NB_LW; ++jb)
+        od_lw_aer[jl * NB_LW + jb] = od_lw_aer[jl * NB_LW + jb] + factor[jl] * mixing_ratio * me_lw[jb] * (1.0 - ss_lw[jb]);
+    }
+  }
+  if (!cfg->do_sw_delta_scaling_with_gases) {
+    /* delta_eddington_extensive_vec, radiation_delta_eddington.h:74-96 (1.0e-24 is a default-kind literal) */
+    for (int i = 0; i < nlev * NB_SW; ++i) {
+      double den = scat_sw_aer[i] > (double)1.0e-24f ? scat_sw_aer[i] : (double)1.0e-24f;
+      double g = scat_g_sw_aer[i] / den;
+      double f = g * g;
+      od_sw_aer[i] = od_sw_aer[i] - scat_sw_aer[i] * f;
+      scat_sw_aer[i] = scat_sw_aer[i] * (1.0 - f);
+      scat_g_sw_aer[i] = scat_sw_aer[i] * g / (1.0 + g);
+    }
+  }
+  if (cfg->do_sw)
+    for (int jl = 0; jl < nlev; ++jl)
+      for (int g = 0; g < NG_SW; ++g) {
+        const int ib = t->ngb_sw[g] - 16;
+        const size_t i = (size_t)jl * NG_SW + g;
+        double local_od = od_sw[i] + od_sw_aer[jl * NB_SW + ib];
+        if (local_od > 0.0 && od_sw_aer[jl * NB_SW + ib] > 0.0) {
+          double local_scat = ssa_sw[i] * od_sw[i] + scat_sw_aer[jl * NB_SW + ib];
+          if (local_scat > 0.0) g_sw[i] = scat_g_sw_aer[jl * NB_SW + ib] / local_scat;
+          ssa_sw[i] = local_scat / local_od;
+          od_sw[i] = local_od;
+        }
+      }
+  if (cfg->do_lw)
+    for (int jl = 0; jl < nlev; ++jl)
+      for (int g = 0; g < NG_LW; ++g)
+        od_lw[(size_t)jl * NG_LW + g] = od_lw[(size_t)jl * NG_LW + g] + od_lw_aer[jl * NB_LW + (t->ngb_lw[g] - 1)];
+  free(od_sw_aer); free(irhs); free(factor);
 }
 
 /* radiation_lw_derivatives.F90:43-84 / :93-130 */
@@ -335,7 +408,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   double *tdir_clear = tdd + nl, *tdir = tdir_clear + nl, *od_scaling = tdir + nl;
   double *fu = od_scaling + nl, *fdd = fu + nl1, *fdir = fdd + nl1;
   double *od_total = fdir + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
-  double* gzero = (double*)calloc(nl, sizeof(double)); /* g_sw = 0 without aerosols, radiation_interface.F90:395 */
+  const double* gzero = w->g_sw;   /* g_sw: zero without aerosols (radiation_interface.F90:395), else from add_aerosol_optics */
   const int cloudless = (cfg->i_solver_sw == ECRAD_SOLVER_CLOUDLESS);
   if (cloudless) {
     for (int jl = 0; jl < nlev; ++jl)
@@ -374,7 +447,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
     band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_direct_band, 0);
     band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_band, 0);
     band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdd, ncol, jcol, out->sw_dn_band, 1);
-    free(pool); free(gzero);
+    free(pool);
     return;
   }
   double tcc;
@@ -439,7 +512,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = fu[g];
     }
   }
-  free(pool); free(gzero);
+  free(pool);
 }
 
 /* radiation_flux.F90:397-577 calc_surface_spectral (paths used by the test namelists) */
@@ -490,13 +563,13 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
 static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                             const ecrad_b200_inputs* in, ecrad_b200_outputs* out) {
   col_work w;
-  size_t n = (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 2 * (size_t)nlev * NG_SW + 3 * NG_SW +
+  size_t n = (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 3 * (size_t)nlev * NG_SW + 3 * NG_SW +
              3 * (size_t)nlev * NB_LW + 3 * (size_t)nlev * NB_SW + 6 * (size_t)nlev;
   w.w = (double*)malloc(sizeof(double) * n);
   double* p = w.w;
   w.od_lw = p; p += (size_t)nlev * NG_LW;  w.planck_hl = p; p += (size_t)(nlev + 1) * NG_LW;
   w.lw_emission = p; p += NG_LW;           w.lw_albedo = p; p += NG_LW;
-  w.od_sw = p; p += (size_t)nlev * NG_SW;  w.ssa_sw = p; p += (size_t)nlev * NG_SW;
+  w.od_sw = p; p += (size_t)nlev * NG_SW;  w.ssa_sw = p; p += (size_t)nlev * NG_SW;  w.g_sw = p; p += (size_t)nlev * NG_SW;
   w.incoming_sw = p; p += NG_SW; w.alb_dir = p; p += NG_SW; w.alb_diff = p; p += NG_SW;
   w.od_lw_cloud = p; p += (size_t)nlev * NB_LW; w.ssa_lw_cloud = p; p += (size_t)nlev * NB_LW; w.g_lw_cloud = p; p += (size_t)nlev * NB_LW;
   w.od_sw_cloud = p; p += (size_t)nlev * NB_SW; w.ssa_sw_cloud = p; p += (size_t)nlev * NB_SW; w.g_sw_cloud = p; p += (size_t)nlev * NB_SW;
@@ -506,6 +579,8 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   int rc = get_albedos(t, cfg, ncol, jcol, in, w.alb_dir, w.alb_diff, w.lw_albedo);
   if (rc) { free(w.w); free(phl_full); return rc; }
   gas_optics_column(t, cfg, ncol, nlev, jcol, in, w.lw_albedo, w.od_lw, w.planck_hl, w.lw_emission, w.od_sw, w.ssa_sw, w.incoming_sw);
+  for (size_t i = 0; i < (size_t)nlev * NG_SW; ++i) w.g_sw[i] = 0.0;
+  if (cfg->use_aerosols) add_aerosol_optics(t, cfg, ncol, nlev, jcol, in, w.od_lw, w.od_sw, w.ssa_sw, w.g_sw);
   for (int jl = 0; jl <= nlev; ++jl) phl_full[jl] = A2(in->pressure_hl, jcol, jl);
   if (cfg->do_clouds) {
     /* crop_cloud_fraction, radiation_cloud.F90:700-740 (mutates the caller's array) */
@@ -533,7 +608,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  if (cfg->use_aerosols || cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator ||
+  if (cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator ||
       cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP || cfg->do_sw_delta_scaling_with_gases) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
@@ -541,6 +616,10 @@ int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, i
   if (!out->lw_up_clear || !out->lw_dn_clear || !out->sw_up_clear || !out->sw_dn_clear || !out->sw_dn_direct_clear) {
     fprintf(stderr, "oracle: clear-sky flux outputs are required (do_clear)\n");
     return 11;
+  }
+  if (cfg->use_aerosols && (!in->aerosol_mmr || !in->h2o_sat_liq || !t->aer_me_sw_phobic || !t->aer_iclass || !t->aer_itype)) {
+    fprintf(stderr, "oracle: aerosol inputs/tables missing\n");
+    return 12;
   }
   int err = 0;
 #ifdef _OPENMP

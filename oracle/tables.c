@@ -90,6 +90,19 @@ int orc_tables_resolve(orc_tables* t) {
     t->pdf_ncdf = (int)pv->dims[0]; t->pdf_nfsd = (int)pv->dims[1];
     t->pdf_fsd1 = fsd[0]; t->pdf_inv_fsd_interval = 1.0 / (fsd[1] - fsd[0]);
   }
+  {
+    const char* nm[12] = {"aer_mass_ext_sw_phobic", "aer_ssa_sw_phobic", "aer_g_sw_phobic", "aer_mass_ext_lw_phobic", "aer_ssa_lw_phobic",
+                          "aer_g_lw_phobic", "aer_mass_ext_sw_philic", "aer_ssa_sw_philic", "aer_g_sw_philic", "aer_mass_ext_lw_philic",
+                          "aer_ssa_lw_philic", "aer_g_lw_philic"};
+    const double** dst[12] = {&t->aer_me_sw_phobic, &t->aer_ssa_sw_phobic, &t->aer_g_sw_phobic, &t->aer_me_lw_phobic, &t->aer_ssa_lw_phobic,
+                              &t->aer_g_lw_phobic, &t->aer_me_sw_philic, &t->aer_ssa_sw_philic, &t->aer_g_sw_philic, &t->aer_me_lw_philic,
+                              &t->aer_ssa_lw_philic, &t->aer_g_lw_philic};
+    for (int i = 0; i < 12; ++i) { const orc_array* a = orc_find(t, nm[i]); *dst[i] = a ? (const double*)a->data : NULL; }
+    const orc_array* rh = orc_find(t, "aer_rh_lower");
+    t->aer_rh_lower = rh ? (const double*)rh->data : NULL; t->aer_nrh = rh ? (int)rh->dims[0] : 0;
+    const orc_array* ic = orc_find(t, "aerosol_iclass"); t->aer_iclass = ic ? (const int32_t*)ic->data : NULL;
+    const orc_array* it = orc_find(t, "aerosol_itype");  t->aer_itype = it ? (const int32_t*)it->data : NULL;
+  }
   const orc_array* w = orc_find(t, "sw_albedo_weights");
   t->sw_albedo_weights = w ? (const double*)w->data : NULL;
   const orc_array* e = orc_find(t, "i_emiss_from_band_lw");

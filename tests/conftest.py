@@ -31,3 +31,13 @@ def golden_noaer():
 @pytest.fixture(scope="session")
 def golden_cloudless():
     return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_cloudless_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_default():
+    return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_default_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_expexp():
+    return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_expexp_ref.npz")))

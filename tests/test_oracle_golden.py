@@ -59,6 +59,20 @@ def test_oracle_mcica_noaer_matches_reference_golden(meridian_raw, golden_noaer)
             assert np.abs(a - g).max() <= tol, (nm, np.abs(a - g).max())
 
 
+def test_oracle_mcica_with_aerosols_matches_reference_default_golden(meridian_raw, golden_default):
+    """test/ifs `default` ctest: McICA + RRTMG + general aerosol optics (12 IFS aerosol types); also pins the setup-time
+    spectral averaging restated in tools/extract_rrtmg_tables.py (aerosol_tables)."""
+    _, out = _run(meridian_raw, use_aerosols=True)
+    for nm, gname in PROFILES.items():
+        err = f32_ulp_err(out[nm], golden_default[gname])
+        assert err.max() <= 0.51, (nm, err.max())
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):
+        assert f32_ulp_err(out[nm], golden_default[nm]).max() <= 0.51, nm
+    assert f32_ulp_err(out["lw_derivatives"], golden_default["lw_derivative"]).max() <= 0.51
+    for nm, gname in (("sw_dn_surf_band", "spectral_flux_dn_sw_surf"), ("sw_dn_direct_surf_band", "spectral_flux_dn_direct_sw_surf")):
+        assert f32_ulp_err(out[nm].T, golden_default[gname]).max() <= 0.51, nm
+
+
 def test_oracle_cloudless_matches_reference_golden(meridian_raw, golden_cloudless):
     _, out = _run(meridian_raw, sw_solver_name="Cloudless", lw_solver_name="Cloudless")
     for nm, gname in PROFILES.items():

@@ -125,6 +125,69 @@ def nc_tables(ref):
     return out
 
 
+def calc_mapping_bands(wavenumber, wn1_band, wn2_band, reference_temperature):
+    """radiation_spectral_definition.F90:222-338 calc_mapping, use_bands=.true. branch: mapping(nband, nwav)."""
+    from ecrad_b200.config import _planck_wavenumber
+
+    nwav, nband = len(wavenumber), len(wn1_band)
+    planck_weight = _planck_wavenumber(wavenumber, reference_temperature)
+    mapping = np.zeros((nband, nwav))
+    for jb in range(nband):
+        weight = np.zeros(nwav)
+        for jw in range(nwav):
+            if wn1_band[jb] <= wavenumber[jw] <= wn2_band[jb]:
+                w1 = max(wn1_band[jb], 0.5 * (wavenumber[jw - 1] + wavenumber[jw])) if jw > 0 else wn1_band[jb]
+                w2 = min(wn2_band[jb], 0.5 * (wavenumber[jw] + wavenumber[jw + 1])) if jw < nwav - 1 else wn2_band[jb]
+                weight[jw] = (w2 - w1) * planck_weight[jw]
+        if weight.sum() <= 0.0:
+            if wavenumber[0] >= wn2_band[jb]:
+                weight[0] = 1.0
+            elif wavenumber[-1] <= wn1_band[jb]:
+                weight[-1] = 1.0
+            else:
+                iw = 1
+                while wavenumber[iw] < wn2_band[jb]:
+                    iw += 1
+                mid = 0.5 * (wn2_band[jb] + wn1_band[jb])
+                weight[iw - 1] = planck_weight[iw - 1] * (wavenumber[iw] - mid)
+                weight[iw] = planck_weight[iw] * (-wavenumber[iw - 1] + mid)
+        mapping[jb, :] = weight / weight.sum()
+    return mapping
+
+
+def aerosol_tables(ref):
+    """Band-averaged aerosol optical properties for the RRTMG bands: setup_general_aerosol_optics,
+    radiation/radiation_aerosol_optics.F90:96-338, applied to data/aerosol_ifs_49R1_20230119.nc (the default of
+    use_general_aerosol_optics=true, radiation_config.F90:1221-1240).  Arrays keep the reference's Fortran shapes:
+    *_phobic(nband, ntype), *_philic(nband, nrh, ntype)."""
+    from scipy.io import netcdf_file
+
+    from ecrad_b200.config import LW_WN1, LW_WN2, SOLAR_REF_T, SW_WN1, SW_WN2, TERRESTRIAL_REF_T
+
+    out = {}
+    with netcdf_file(os.path.join(ref, "data", "aerosol_ifs_49R1_20230119.nc"), mmap=False) as f:
+        g = lambda n: np.array(f.variables[n][:], dtype=np.float64)  # noqa: E731
+        wn = g("wavenumber")
+        phobic = {k: g(f"{k}_hydrophobic").T for k in ("mass_ext", "ssa", "asymmetry")}          # (nwav, ntype)
+        philic = {k: np.transpose(g(f"{k}_hydrophilic"), (2, 1, 0)) for k in ("mass_ext", "ssa", "asymmetry")}  # (nwav, nrh, ntype)
+        out["aer_rh_lower"] = g("relative_humidity1")
+    for spec, wn1, wn2, tref in (("sw", SW_WN1, SW_WN2, SOLAR_REF_T), ("lw", LW_WN1, LW_WN2, TERRESTRIAL_REF_T)):
+        m = calc_mapping_bands(wn, wn1, wn2, tref)
+        me = m @ phobic["mass_ext"]
+        ssa = (m @ (phobic["mass_ext"] * phobic["ssa"])) / me
+        gg = (m @ (phobic["mass_ext"] * phobic["ssa"] * phobic["asymmetry"])) / (me * ssa)
+        out[f"aer_mass_ext_{spec}_phobic"], out[f"aer_ssa_{spec}_phobic"], out[f"aer_g_{spec}_phobic"] = me, ssa, gg
+        nrh, nty = philic["mass_ext"].shape[1:]
+        me3 = np.zeros((len(wn1), nrh, nty)); ssa3 = np.zeros_like(me3); g3 = np.zeros_like(me3)
+        for jt in range(nty):
+            e, s_, a = (philic[k][:, :, jt] for k in ("mass_ext", "ssa", "asymmetry"))
+            me3[:, :, jt] = m @ e
+            ssa3[:, :, jt] = (m @ (e * s_)) / me3[:, :, jt]
+            g3[:, :, jt] = (m @ (e * s_ * a)) / (me3[:, :, jt] * ssa3[:, :, jt])
+        out[f"aer_mass_ext_{spec}_philic"], out[f"aer_ssa_{spec}_philic"], out[f"aer_g_{spec}_philic"] = me3, ssa3, g3
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -132,6 +195,7 @@ def main():
     args = ap.parse_args()
     tabs = rrtmg_tables(args.ref)
     tabs.update(nc_tables(args.ref))
+    tabs.update(aerosol_tables(args.ref))
     write_blob(args.out, tabs)
     tot = sum(v.nbytes for v in tabs.values())
     print(f"wrote {args.out}: {len(tabs)} arrays, {tot/1e6:.2f} MB")
