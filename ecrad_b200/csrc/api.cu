@@ -33,7 +33,7 @@ struct Buf {   // grow-only device buffer
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { N_IN = 25, N_OUT = 35, N_STAGE = 5 };
+enum { N_IN = 26, N_OUT = 35, N_STAGE = 5 };
 const char* kStageNames[N_STAGE] = {"gas_optics_lw", "gas_optics_sw", "cloud_optics_generator", "solver_lw", "solver_sw"};
 
 struct Slot {            // device staging of one tile's inputs and outputs
@@ -53,7 +53,7 @@ struct Handle {
   cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
-  Buf work[28];
+  Buf work[32];
   Work w;
   int w_cols = 0, w_nlev = 0;
   std::mutex mu;
@@ -92,7 +92,8 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "gas model not available in this build (RRTMG-IFS is)");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN)
     return fail(h, "overlap scheme not available in this build (Exp-Ran and Max-Ran are)");
-  if (c.use_aerosols || c.do_lw_aerosol_scattering) return fail(h, "aerosols are not available in this build");
+  if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
+  if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator) return fail(h, "use_vectorizable_generator is not available in this build");
   if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
   if (c.do_nearest_spectral_sw_albedo || !c.do_nearest_spectral_lw_emiss) return fail(h, "albedo/emissivity mapping mode not available");
@@ -115,7 +116,9 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
       8 * nc * SW_SCR_ARRAYS * nl * NG_SW,                                                   // scr_sw
-      sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl};                                     // lev_lw lev_sw
+      sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl,                                      // lev_lw lev_sw
+      h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, h->cfg.use_aerosols ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
+      h->cfg.use_aerosols ? 8 * nc * nl * NB_LW : 0};                                        // aer_lw
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
@@ -126,6 +129,7 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
   w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
   w.lev_lw = (LwLev*)h->work[24].p; w.lev_sw = (SwLev*)h->work[25].p;
+  w.g_sw = (double*)h->work[26].p; w.aer_sw = (double*)h->work[27].p; w.aer_lw = (double*)h->work[28].p;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
   w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
@@ -143,6 +147,7 @@ int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cu
   const bool par = !h->serial;
   cudaStream_t s_lw = st, s_sw = par ? h->s_aux1 : st, s_cl = par ? h->s_aux2 : st;
   n += launch_gas_prep(h->T, c, in, h->w, nc, nlev, st);   // shared by the LW and SW gas-optics kernels
+  if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w, nc, nlev, st);
   if (par) {
     CK(h, cudaEventRecord(h->ev_fork, st));
     CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork, 0));
@@ -203,6 +208,7 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
   if (c.do_clouds && (!in->cloud_fraction || !in->q_liq || !in->q_ice || !in->re_liq || !in->re_ice || !in->overlap_param ||
                       !in->fractional_std || !in->iseed))
     return fail(h, "missing cloud input");
+  if (c.use_aerosols && (!in->aerosol_mmr || !in->h2o_sat_liq)) return fail(h, "missing aerosol input (aerosol_mmr, h2o_sat_liq)");
   if (c.do_lw && (!out->lw_up || !out->lw_dn)) return fail(h, "flux%%lw_up/lw_dn must be allocated");
   if (c.do_sw && (!out->sw_up || !out->sw_dn)) return fail(h, "flux%%sw_up/sw_dn must be allocated");
   return 0;
@@ -216,7 +222,8 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
       {in->h2o_mmr, nl, 8}, {in->co2_mmr, nl, 8}, {in->ch4_mmr, nl, 8}, {in->n2o_mmr, nl, 8}, {in->cfc11_mmr, nl, 8},
       {in->cfc12_mmr, nl, 8}, {in->hcfc22_mmr, nl, 8}, {in->ccl4_mmr, nl, 8}, {in->o3_mmr, nl, 8},
       {in->cloud_fraction, nl, 8}, {in->q_liq, nl, 8}, {in->q_ice, nl, 8}, {in->re_liq, nl, 8}, {in->re_ice, nl, 8},
-      {in->overlap_param, nl - 1, 8}, {in->fractional_std, nl, 8}, {nullptr, 0, 8}};
+      {in->overlap_param, nl - 1, 8}, {in->fractional_std, nl, 8},
+      {c.use_aerosols ? in->aerosol_mmr : nullptr, nl * c.n_aerosol_types, 8}, {c.use_aerosols ? in->h2o_sat_liq : nullptr, nl, 8}};
   for (int i = 0; i < N_IN; ++i) id[i] = ins[i];
   const OutDesc outs[N_OUT] = {
       {out->lw_up, 0, nl1}, {out->lw_dn, 0, nl1}, {out->lw_up_clear, 0, nl1}, {out->lw_dn_clear, 0, nl1},
@@ -243,6 +250,7 @@ void make_views(void* const* ip, void* const* op, int ld, double solar_irradianc
   for (int k = 0; k < 9; ++k) di.gas[k] = (const double*)ip[8 + k];
   di.frac = (double*)ip[17]; di.q_liq = (const double*)ip[18]; di.q_ice = (const double*)ip[19];
   di.re_liq = (const double*)ip[20]; di.re_ice = (const double*)ip[21]; di.overlap = (const double*)ip[22]; di.fsd = (const double*)ip[23];
+  di.aerosol_mmr = (const double*)ip[24]; di.h2o_sat_liq = (const double*)ip[25];
   di.solar_irradiance = solar_irradiance; di.ld = ld;
   double** o = (double**)&dout;
   for (int k = 0; k < N_OUT; ++k) o[k] = (double*)op[k];
@@ -307,6 +315,14 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   rc |= upload(h, P.pdf_val.data(), P.pdf_val.size(), &h->T.pdf_val);
   rc |= upload(h, P.sw_albedo_weights.data(), P.sw_albedo_weights.size(), &h->T.sw_albedo_weights);
   rc |= upload(h, P.i_emiss_from_band_lw.data(), P.i_emiss_from_band_lw.size(), &h->T.i_emiss_from_band_lw);
+  h->T.aer = nullptr; h->T.aertab = nullptr;
+  if (cfg->use_aerosols) {
+    if (P.aer.ntype != cfg->n_aerosol_types || P.aertab.empty()) {
+      fail(nullptr, "use_aerosols: tables 'aerosol_iclass'/'aerosol_itype' (n_aerosol_types) and 'aer_*' are required"); ecrad_b200_finalize(h); return 1;
+    }
+    rc |= upload(h, &P.aer, 1, &h->T.aer);
+    rc |= upload(h, P.aertab.data(), P.aertab.size(), &h->T.aertab);
+  }
   if (rc) { g_last_error = h->err; ecrad_b200_finalize(h); return 1; }
   DevCfg& d = h->dcfg;
   d.solver_sw = cfg->i_solver_sw; d.solver_lw = cfg->i_solver_lw; d.overlap_scheme = cfg->i_overlap_scheme;
@@ -317,6 +333,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.do_canopy_fluxes_sw = cfg->do_canopy_fluxes_sw; d.do_canopy_fluxes_lw = cfg->do_canopy_fluxes_lw; d.do_clear = cfg->do_clear;
   d.n_albedo_sw = cfg->n_albedo_sw; d.n_emiss_lw = cfg->n_emiss_lw;
   d.n_canopy_bands_sw = cfg->n_canopy_bands_sw; d.n_canopy_bands_lw = cfg->n_canopy_bands_lw;
+  d.use_aerosols = cfg->use_aerosols; d.n_aerosol_types = cfg->n_aerosol_types;
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;

@@ -70,6 +70,66 @@ __global__ void gas_prep_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int n
 }
 
 // =========================================================================================================
+// aerosol optics per band: add_aerosol_optics, radiation_aerosol_optics.F90:487-750 (band-wise properties, no LW aerosol
+// scattering).  One thread per (column, layer); the merge into the g-point arrays happens in stage B of the gas kernels.
+// =========================================================================================================
+__global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc * nlev) return;
+  const int c = i % nc, l = i / nc;
+  const AerMeta& A = *T.aer;
+  const double* tab = T.aertab;
+  const double rh = LD_IN(in.gas[0], c, l) / LD_IN(in.h2o_sat_liq, c, l);
+  int irh;   // calc_rh_index (1-based), radiation_aerosol_optics_data.F90:640-664
+  if (rh > A.rh_lower[A.nrh - 1]) irh = A.nrh;
+  else { irh = 1; while (rh > A.rh_lower[irh]) ++irh; }
+  const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) * (1.0 / 9.80665);
+  double od_sw[NB_SW], sc_sw[NB_SW], sg_sw[NB_SW], od_lw[NB_LW];
+#pragma unroll
+  for (int b = 0; b < NB_SW; ++b) { od_sw[b] = 0.0; sc_sw[b] = 0.0; sg_sw[b] = 0.0; }
+#pragma unroll
+  for (int b = 0; b < NB_LW; ++b) od_lw[b] = 0.0;
+  for (int jt = 0; jt < A.ntype; ++jt) {
+    const int iclass = A.iclass[jt];
+    if (iclass == 0) continue;
+    const int itype = A.itype[jt] - 1;
+    const double mr = in.aerosol_mmr[((size_t)jt * nlev + l) * in.ld + c];
+    const int isw = iclass == 1 ? itype * NB_SW : (itype * A.nrh + (irh - 1)) * NB_SW;
+    const int ilw = iclass == 1 ? itype * NB_LW : (itype * A.nrh + (irh - 1)) * NB_LW;
+    const double* me_sw = tab + (iclass == 1 ? A.me_sw_phobic : A.me_sw_philic) + isw;
+    const double* ss_sw = tab + (iclass == 1 ? A.ssa_sw_phobic : A.ssa_sw_philic) + isw;
+    const double* gg_sw = tab + (iclass == 1 ? A.g_sw_phobic : A.g_sw_philic) + isw;
+    const double* me_lw = tab + (iclass == 1 ? A.me_lw_phobic : A.me_lw_philic) + ilw;
+    const double* ss_lw = tab + (iclass == 1 ? A.ssa_lw_phobic : A.ssa_lw_philic) + ilw;
+#pragma unroll
+    for (int b = 0; b < NB_SW; ++b) {
+      const double local_od = factor * mr * me_sw[b];
+      od_sw[b] = od_sw[b] + local_od;
+      sc_sw[b] = sc_sw[b] + local_od * ss_sw[b];
+      sg_sw[b] = sg_sw[b] + local_od * ss_sw[b] * gg_sw[b];
+    }
+#pragma unroll
+    for (int b = 0; b < NB_LW; ++b) od_lw[b] = od_lw[b] + factor * mr * me_lw[b] * (1.0 - ss_lw[b]);
+  }
+  double* osw = w.aer_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
+#pragma unroll
+  for (int b = 0; b < NB_SW; ++b) {
+    double od = od_sw[b], sc = sc_sw[b], sg = sg_sw[b];
+    if (!cfg.do_sw_delta_scaling_with_gases) {   // delta_eddington_extensive_vec, radiation_delta_eddington.h:74-96
+      const double g = sg / dmax(sc, (double)1.0e-24f);
+      const double f = g * g;
+      od = od - sc * f;
+      sc = sc * (1.0 - f);
+      sg = sc * g / (1.0 + g);
+    }
+    osw[b] = od; osw[NB_SW + b] = sc; osw[2 * NB_SW + b] = sg;
+  }
+  double* olw = w.aer_lw + ((size_t)c * nlev + l) * NB_LW;
+#pragma unroll
+  for (int b = 0; b < NB_LW; ++b) olw[b] = od_lw[b];
+}
+
+// =========================================================================================================
 // LW gas optics
 // =========================================================================================================
 struct GasLwSmem {
@@ -149,7 +209,9 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       if (post >= 0) tau *= __ldg(tab_g + (unsigned)post);
       const double pf = pfc[(ll * NB_LW + b) * 2] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2]) +
                         pfc[(ll * NB_LW + b) * 2 + 1] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2 + 1]);
-      od_out[(size_t)l * NG_LW + g] = dmax(tau, cfg.min_gas_od_lw);       // radiation_ifs_rrtm.F90:506-511
+      double odv = dmax(tau, cfg.min_gas_od_lw);                           // radiation_ifs_rrtm.F90:506-511
+      if (cfg.use_aerosols) odv = odv + w.aer_lw[((size_t)c * nlev + l) * NB_LW + b];   // radiation_aerosol_optics.F90:806-812
+      od_out[(size_t)l * NG_LW + g] = odv;
       pl_out[(size_t)(l + 1) * NG_LW + g] = plk[(ll + 1) * NB_LW + b] * pf; // half-level below uses this layer's PFRAC
       if (l == 0) pl_out[g] = plk[b] * pf;                                 // TOA half-level: PFRAC of the top layer
       if (l == nlev - 1) {
@@ -239,8 +301,22 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       const double taur = rc[(ll * NB_SW + b) * 2] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2]) +
                           rc[(ll * NB_SW + b) * 2 + 1] * __ldg(tab_g + (unsigned)ro[(ll * NB_SW + b) * 2 + 1]);
       const double od = taur + taug;                                        // srtm_gas_optical_depth.F90:314-320
-      od_out[(size_t)l * NG_SW + g] = dmax(od, cfg.min_gas_od_sw);         // radiation_ifs_rrtm.F90:593
-      ssa_out[(size_t)l * NG_SW + g] = taur / od;
+      double odv = dmax(od, cfg.min_gas_od_sw), ssav = taur / od;          // radiation_ifs_rrtm.F90:593
+      if (cfg.use_aerosols) {
+        // merge aerosol and gas per g-point: radiation_aerosol_optics.F90:765-781
+        const double* a = w.aer_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
+        const double od_a = a[b], local_od = odv + od_a;
+        double gv = 0.0;
+        if (local_od > 0.0 && od_a > 0.0) {
+          const double local_scat = ssav * odv + a[NB_SW + b];
+          if (local_scat > 0.0) gv = a[2 * NB_SW + b] / local_scat;
+          ssav = local_scat / local_od;
+          odv = local_od;
+        }
+        w.g_sw[((size_t)c * nlev + l) * NG_SW + g] = gv;
+      }
+      od_out[(size_t)l * NG_SW + g] = odv;
+      ssa_out[(size_t)l * NG_SW + g] = ssav;
       if (l == lsol[b]) inc[g] = sc[b * 2] * __ldg(tab_g + (unsigned)so[b * 2]) + sc[b * 2 + 1] * __ldg(tab_g + (unsigned)so[b * 2 + 1]);
     }
     __syncthreads();
@@ -549,6 +625,10 @@ static void allow_smem(K kernel, size_t bytes) {
 
 int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   gas_prep_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev);
+  return 1;
+}
+int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  aerosol_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev);
   return 1;
 }
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {

@@ -17,6 +17,7 @@ struct DevIn {
   const double* gas[9];  // h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3 (mass mixing ratios)
   double* frac;          // in/out (cropped)
   const double *q_liq, *q_ice, *re_liq, *re_ice, *overlap, *fsd;
+  const double *aerosol_mmr, *h2o_sat_liq;   // (ld, nlev, ntype), (ld, nlev); only with aerosols
   double solar_irradiance;
   int ld;
 };
@@ -43,6 +44,8 @@ struct DevTables {
   const double* pdf_val;
   const double* sw_albedo_weights;     // (n_albedo_sw, 14)
   const int32_t* i_emiss_from_band_lw; // (16), 1-based
+  const AerMeta* aer;                  // aerosol optics (NULL tables if no aerosols)
+  const double* aertab;
 };
 
 // Scalars of config_type the kernels read.
@@ -52,6 +55,7 @@ struct DevCfg {
   int do_sw_delta_scaling_with_gases, do_fu_lw_ice_optics_bug, use_beta_overlap;
   int do_surface_sw_spectral_flux, do_canopy_fluxes_sw, do_canopy_fluxes_lw, do_clear;
   int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
+  int use_aerosols, n_aerosol_types;
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
 };
 
@@ -61,6 +65,8 @@ enum { LW_SCR_ARRAYS = 5, SW_SCR_ARRAYS = 10 };
 struct Work {
   double *od_lw, *planck, *emission, *lw_albedo;  // [nc][nlev][140], [nc][nlev+1][140], [nc][140], [nc][140]
   double *od_sw, *ssa_sw, *incoming;              // [nc][nlev][112] x2, [nc][112]
+  double *g_sw;                                   // [nc][nlev][112] asymmetry factor of gas+aerosol (NULL without aerosols: g = 0)
+  double *aer_sw, *aer_lw;                        // aerosol band optics [nc][nlev][3][14] (od, scat, scat*g), [nc][nlev][16] (absorption od)
   double *cl_lw, *cl_sw;                          // cloud optics per band [nc][nlev][3][16], [nc][nlev][3][14]
   double *cum, *pair, *opi;                       // [nlev][nc] column-fastest
   double* tcc;                                    // [nc]
@@ -76,6 +82,7 @@ void init_generator_constants();   // once per process/device, before the first 
 
 // Launchers.  All enqueue on `st` and return the number of kernels launched.
 int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);

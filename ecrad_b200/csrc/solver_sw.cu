@@ -17,7 +17,7 @@ enum { SW_THREADS = 128, SW_RS = 113, SW_LCH_FLUX = 8 };
 
 // total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
 __device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd, const double* clb,
-                                                int b, double od_gas, double ssa_gas, double& odt, double& ssat, double& gt) {
+                                                int b, double od_gas, double ssa_gas, double g_gas, double& odt, double& ssat, double& gt) {
   const double scal = od_scaling_from_code(C, pdf_val, code, fsd);
   const double od_cloud_new = scal * clb[b];
   odt = od_gas + od_cloud_new;
@@ -26,14 +26,14 @@ __device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double
     const double ssac = clb[NB_SW + b];
     const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
     ssat = scat_od / odt;
-    if (scat_od > 0.0) gt = (clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
+    if (scat_od > 0.0) gt = (g_gas * ssa_gas * od_gas + clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
   }
 }
 
 struct SwColumn {
   int c, g, gg, b; bool act, cloudy; double mu0, tcc, thr;
   size_t n;
-  const double *od, *ssa, *cl; const uint4* codep;
+  const double *od, *ssa, *gas_g, *cl; const uint4* codep;   // gas_g: asymmetry factor of gas + aerosol, NULL = 0
   double* scr;
 };
 
@@ -47,6 +47,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
   s.n = (size_t)nlev * NG_SW;
   s.od = w.od_sw + (size_t)s.c * s.n;
   s.ssa = w.ssa_sw + (size_t)s.c * s.n;
+  s.gas_g = (cfg.use_aerosols && w.g_sw) ? w.g_sw + (size_t)s.c * s.n : nullptr;
   s.cl = w.cl_sw + (size_t)s.c * nlev * 3 * NB_SW;
   s.b = T.meta->band_of_g_sw[s.gg];
   s.codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)s.c * NG_SW + s.gg) * nlevp);
@@ -90,14 +91,15 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       const double odg = od_n, ssag = ssa_n;
       if (l + 1 < nlev) { od_n = s.od[i + NG_SW]; if (need_ssa) ssa_n = s.ssa[i + NG_SW]; }
       double tdir_c;
-      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, ssag, 0.0).trans_dir_dir;
+      const double gg_gas = (need_ssa && s.gas_g) ? s.gas_g[i] : 0.0;
+      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, ssag, gg_gas).trans_dir_dir;
       else tdir_c = exp(dmax(-dmax(odg * inv_mu0, 0.0), -1000.0));
       double tdir_a = tdir_c;
       if (s.cloudy) {
         if ((l & 3) == 0) cq = __ldg(s.codep + (l >> 2));
         if (fracs[l] >= s.thr) {
           double odt, ssat, gt;
-          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, odt, ssat, gt);
+          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, gg_gas, odt, ssat, gt);
           tdir_a = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
         }
         sFa[i] = fa;
@@ -164,16 +166,17 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   uint4 cq = make_uint4(0, 0, 0, 0);
   // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
   size_t i = (size_t)(nlev - 1) * NG_SW + g;
-  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0;
+  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0, gg_n = s.gas_g ? s.gas_g[i] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
-    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n;
+    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n, gg_gas = gg_n;
     i = (size_t)l * NG_SW + g;
     if (l > 0) {
       const size_t ip = i - NG_SW;
       od_n = s.od[ip]; ssa_n = s.ssa[ip]; fc_n = sFc[ip];
       if (s.cloudy) fa_n = sFa[ip];
+      if (s.gas_g) gg_n = s.gas_g[ip];
     }
-    const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, 0.0) : sw_ref_trans(mu0, odg, ssag, 0.0);
+    const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
     {
       const double inv_den = 1.0 / (1.0 - A_c * Lc.ref);
       ac[i] = Lc.trans * inv_den;
@@ -188,7 +191,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       SwLayer La = Lc;
       if (fracs[l] >= s.thr) {
         double odt, ssat, gt;
-        sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, odt, ssat, gt);
+        sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, gg_gas, odt, ssat, gt);
         La = sw_ref_trans(mu0, odt, ssat, gt);
       }
       const double inv_den = 1.0 / (1.0 - A_a * La.ref);

@@ -72,6 +72,8 @@ struct PackedTables {
   std::vector<double> pdf_val;        // (ncdf, nfsd) Fortran order, as the reference stores it
   std::vector<double> sw_albedo_weights;  // (n_albedo_sw, 14)
   std::vector<int32_t> i_emiss_from_band_lw;  // (16) 1-based
+  AerMeta aer;                        // aer.ntype == 0: no aerosol tables
+  std::vector<double> aertab;
   int n_albedo_sw = 0;
 };
 
@@ -216,6 +218,39 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     P.n_albedo_sw = (int)w->dims[0];
     if (w->dims[1] != NB_SW) throw std::runtime_error("sw_albedo_weights: second dim != 14");
     P.sw_albedo_weights.assign((const double*)w->data.data(), (const double*)w->data.data() + (size_t)P.n_albedo_sw * NB_SW);
+  }
+  // ---- aerosol optics (only if the host registered the type map) ----
+  memset(&P.aer, 0, sizeof(P.aer));
+  if (T.find("aerosol_iclass") && T.find("aerosol_itype")) {
+    AerMeta& A = P.aer;
+    const auto& ic = T.req("aerosol_iclass");
+    A.ntype = (int)ic.dims[0];
+    if (A.ntype > 32) throw std::runtime_error("more than 32 aerosol types");
+    memcpy(A.iclass, T.i("aerosol_iclass"), 4 * A.ntype);
+    memcpy(A.itype, T.i("aerosol_itype"), 4 * A.ntype);
+    const auto& rh = T.req("aer_rh_lower");
+    A.nrh = (int)rh.dims[0];
+    if (A.nrh > 16) throw std::runtime_error("more than 16 aerosol humidity bins");
+    memcpy(A.rh_lower, rh.data.data(), 8 * A.nrh);
+    A.n_phobic = (int)T.req("aer_mass_ext_sw_phobic").dims[1];
+    A.n_philic = (int)T.req("aer_mass_ext_sw_philic").dims[2];
+    auto put = [&](const char* nm, size_t expect) {
+      const auto& x = T.req(nm);
+      if (x.data.size() != expect * 8) throw std::runtime_error(std::string(nm) + ": unexpected size");
+      int off = (int)P.aertab.size();
+      P.aertab.insert(P.aertab.end(), (const double*)x.data.data(), (const double*)x.data.data() + expect);
+      return off;
+    };
+    const size_t pb_sw = (size_t)NB_SW * A.n_phobic, pb_lw = (size_t)NB_LW * A.n_phobic;
+    const size_t pl_sw = (size_t)NB_SW * A.nrh * A.n_philic, pl_lw = (size_t)NB_LW * A.nrh * A.n_philic;
+    A.me_sw_phobic = put("aer_mass_ext_sw_phobic", pb_sw); A.ssa_sw_phobic = put("aer_ssa_sw_phobic", pb_sw); A.g_sw_phobic = put("aer_g_sw_phobic", pb_sw);
+    A.me_lw_phobic = put("aer_mass_ext_lw_phobic", pb_lw); A.ssa_lw_phobic = put("aer_ssa_lw_phobic", pb_lw);
+    A.me_sw_philic = put("aer_mass_ext_sw_philic", pl_sw); A.ssa_sw_philic = put("aer_ssa_sw_philic", pl_sw); A.g_sw_philic = put("aer_g_sw_philic", pl_sw);
+    A.me_lw_philic = put("aer_mass_ext_lw_philic", pl_lw); A.ssa_lw_philic = put("aer_ssa_lw_philic", pl_lw);
+    for (int k = 0; k < A.ntype; ++k) {
+      if (A.iclass[k] == 1 && (A.itype[k] < 1 || A.itype[k] > A.n_phobic)) throw std::runtime_error("hydrophobic aerosol type out of range");
+      if (A.iclass[k] == 2 && (A.itype[k] < 1 || A.itype[k] > A.n_philic)) throw std::runtime_error("hydrophilic aerosol type out of range");
+    }
   }
   if (const auto* e = T.find("i_emiss_from_band_lw")) {
     P.i_emiss_from_band_lw.assign((const int32_t*)e->data.data(), (const int32_t*)e->data.data() + NB_LW);

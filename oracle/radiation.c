@@ -412,7 +412,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   const int cloudless = (cfg->i_solver_sw == ECRAD_SOLVER_CLOUDLESS);
   if (cloudless) {
     for (int jl = 0; jl < nlev; ++jl)
-      orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, gzero,
+      orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, gzero + (size_t)jl * ng,
                                             ref_clear + (size_t)jl * ng, trans_clear + (size_t)jl * ng, rdir_clear + (size_t)jl * ng,
                                             tdd_clear + (size_t)jl * ng, tdir_clear + (size_t)jl * ng);
   } else {

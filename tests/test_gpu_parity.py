@@ -82,6 +82,19 @@ def test_mcica_meridian_vs_reference_golden(handles, meridian_raw, golden_noaer)
         assert np.abs(out[nm] - golden_noaer[gname]).max() <= 1.0e-3, nm
 
 
+def test_mcica_with_aerosols_vs_reference_default_golden(handles, meridian_raw, golden_default):
+    """The reference's `default` ctest (McICA + RRTMG + 12 IFS aerosol types): within 1 float32 ulp of its golden file."""
+    h, orc, _ = handles(use_aerosols=True)
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    gmap = {"lw_up": "flux_up_lw", "lw_dn": "flux_dn_lw", "sw_up": "flux_up_sw", "sw_dn": "flux_dn_sw", "sw_dn_direct": "flux_dn_direct_sw",
+            "sw_up_clear": "flux_up_sw_clear", "sw_dn_clear": "flux_dn_sw_clear", "lw_up_clear": "flux_up_lw_clear",
+            "lw_derivatives": "lw_derivative", "cloud_cover_sw": "cloud_cover_sw"}
+    for nm, gname in gmap.items():
+        assert f32_ulp_err(out[nm], golden_default[gname]).max() <= 1.0, nm
+
+
 def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless):
     h, orc, _ = handles(sw_solver_name="Cloudless", lw_solver_name="Cloudless")
     out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
@@ -93,7 +106,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(overlap_scheme_name="Max-Ran"), dict(do_lw_cloud_scattering=False),
-                                dict(use_beta_overlap=True)])
+                                dict(use_beta_overlap=True), dict(use_aerosols=True),
+                                dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless")])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
@@ -232,8 +246,8 @@ def test_error_behaviour(meridian_raw):
     """Non-zero status + message instead of the reference's radiation_abort."""
     from ecrad_b200.radiation_interface import RadiationError, setup_radiation
 
-    with pytest.raises(RadiationError, match="aerosols"):
-        setup_radiation(RadiationConfig(use_aerosols=True).consolidate())
+    with pytest.raises(RadiationError, match="do_lw_aerosol_scattering"):
+        setup_radiation(RadiationConfig(do_lw_aerosol_scattering=True).consolidate())
     h = setup_radiation(RadiationConfig().consolidate())
     with pytest.raises(RadiationError, match="bad dimensions"):
         h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, istartcol=5, iendcol=40)

@@ -18,7 +18,7 @@ ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 solver = sys.argv[2] if len(sys.argv) > 2 else "McICA"
 raw = {k: np.array(v, dtype=np.float64) for k, v in np.load(os.path.join(ROOT, "tests/golden/ecrad_meridian_inputs.npz")).items()}
 raw = I.synthetic_columns(raw, ncol)
-cfg = RadiationConfig(sw_solver_name=solver, lw_solver_name=solver).consolidate()
+cfg = RadiationConfig(sw_solver_name=solver, lw_solver_name=solver, use_aerosols=len(sys.argv) > 3).consolidate()
 h = setup_radiation(cfg)
 for rep in range(2):
     t = time.time()
