@@ -90,8 +90,8 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "solver not available in this build (McICA and Cloudless are)");
   if ((c.do_sw && c.i_gas_model_sw != ECRAD_GAS_IFSRRTMG) || (c.do_lw && c.i_gas_model_lw != ECRAD_GAS_IFSRRTMG))
     return fail(h, "gas model not available in this build (RRTMG-IFS is)");
-  if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN)
-    return fail(h, "overlap scheme not available in this build (Exp-Ran and Max-Ran are)");
+  if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
+    return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator) return fail(h, "use_vectorizable_generator is not available in this build");

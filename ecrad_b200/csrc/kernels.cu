@@ -569,12 +569,22 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
       for (int m = GW_LPL - 1; m >= 0; --m) { if ((isend >> m) & 1u) cur = lane * GW_LPL + m; rev[m] = cur; }
     }
     // ---- per-run random draws: run r takes n numbers (rand_inhom1) then n numbers (rand_inhom2), runs in order ----
+    // (Exp-Exp, generate_column_exp_exp: one "run" = the whole range Lt..Le whether cloudy or not: N + N numbers)
+    const bool exp_exp = cfg.overlap_scheme == 2;
     int offv[GW_LPL];
     uint32_t fresh = 0;
 #pragma unroll
     for (int m = 0; m < GW_LPL; ++m) {
       offv[m] = 0;
-      if ((cl >> m) & 1u) {
+      if (exp_exp) {
+        const int L = lane * GW_LPL + m;
+        if (L >= Lt && L <= Le) {
+          rsv[m] = Lt;
+          offv[m] = pos + N;
+          const double r2 = (double)ring[(pos + 2 * N + (L - Lt)) & 1023] * RM;
+          if (L == Lt || !(r2 < sOPI[L])) fresh |= 1u << m;
+        }
+      } else if ((cl >> m) & 1u) {
         const int L = lane * GW_LPL + m;
         const int p = L - rsv[m], n = rev[m] - rsv[m] + 1;
         const int cb = cntb_lane + __popc(cl & ((1u << m) - 1u));
@@ -601,7 +611,7 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
         if (L < nlevp) row[L] = word;
       }
     }
-    pos += N + 2 * C;
+    pos += exp_exp ? 3 * N : N + 2 * C;
     __syncwarp();
   }
 }

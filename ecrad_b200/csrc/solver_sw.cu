@@ -125,7 +125,7 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
 // ---------------------------------------------------------------------------------------------------------
 // B: two-stream layer solutions and the upward sweep of albedo / source (radiation_adding_ica_sw.F90:90-121)
 // ---------------------------------------------------------------------------------------------------------
-template <bool CLOUDLESS>
+template <bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
 __global__ void __launch_bounds__(SW_THREADS, 3)
 sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,15 +166,15 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   uint4 cq = make_uint4(0, 0, 0, 0);
   // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
   size_t i = (size_t)(nlev - 1) * NG_SW + g;
-  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0, gg_n = s.gas_g ? s.gas_g[i] : 0.0;
+  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0, gg_n = AER ? s.gas_g[i] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
-    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n, gg_gas = gg_n;
+    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n, gg_gas = AER ? gg_n : 0.0;
     i = (size_t)l * NG_SW + g;
     if (l > 0) {
       const size_t ip = i - NG_SW;
       od_n = s.od[ip]; ssa_n = s.ssa[ip]; fc_n = sFc[ip];
       if (s.cloudy) fa_n = sFa[ip];
-      if (s.gas_g) gg_n = s.gas_g[ip];
+      if (AER) gg_n = s.gas_g[ip];
     }
     const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
     {
@@ -368,12 +368,15 @@ int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   const size_t smA = sizeof(double) * (2 * LCH * SW_RS + 2 * nlev) + 16;
   const size_t smB = sizeof(double) * (2 * nlev + 2 * NB_SW) + 16;
   const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SW_RS) + 16;
+  const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
     sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
-    sw_adding_kernel<false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    if (aer) sw_adding_kernel<false, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    else sw_adding_kernel<false, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   } else {
     sw_direct_kernel<true><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
-    sw_adding_kernel<true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    if (aer) sw_adding_kernel<true, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    else sw_adding_kernel<true, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   }
   sw_flux_kernel<<<nc, SW_THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
   return 3;

@@ -235,6 +235,116 @@ static void cum_cloud_cover_max_ran(int nlev, const double* frac, double* cum, d
   }
 }
 
+/* radiation_cloud_cover.F90:339-623 cum_cloud_cover_exp_exp (1 column); arrays 0-based, object indices 1-based as in
+ * the source */
+static void cum_cloud_cover_exp_exp(int nlev, const double* frac, const double* overlap_param, int beta,
+                                    double* cum, double* pair) {
+  const double min_frac = 1.0e-6;
+  int* i_top = (int*)malloc(sizeof(int) * (size_t)(nlev + 2) * 4);
+  int *i_max = i_top + nlev + 2, *i_base = i_max + nlev + 2, *i_next = i_base + nlev + 2;
+  double* cc_obj = (double*)malloc(sizeof(double) * (size_t)(nlev + 2) * 3);
+  double *alpha_obj = cc_obj + nlev + 2, *alpha = alpha_obj + nlev + 2;
+#define FR(l) frac[(l) - 1]
+#define CUM(l) cum[(l) - 1]
+#define PAIR(l) pair[(l) - 1]
+  int jlev = 1, nobj = 0;
+  while (jlev <= nlev) {
+    if (FR(jlev) > min_frac) {
+      nobj++;
+      i_top[nobj] = jlev;
+      jlev++;
+      while (jlev <= nlev) { if (FR(jlev) < FR(jlev - 1)) break; jlev++; }
+      i_max[nobj] = jlev - 1;
+      while (jlev <= nlev) { if (FR(jlev) > FR(jlev - 1) || FR(jlev) <= min_frac) break; jlev++; }
+      i_base[nobj] = jlev - 1;
+      i_next[nobj] = nobj + 1;
+    } else jlev++;
+  }
+  for (int l = 0; l < nlev; ++l) cum[l] = 0.0;
+  for (int l = 0; l < nlev - 1; ++l) pair[l] = 0.0;
+  if (nobj > 0) {
+    for (int l = 1; l <= nlev - 1; ++l) {
+      alpha[l] = beta ? beta2alpha(overlap_param[l - 1], FR(l), FR(l + 1)) : overlap_param[l - 1];
+      PAIR(l) = alpha[l] * dmax(FR(l), FR(l + 1)) + (1.0 - alpha[l]) * (FR(l) + FR(l + 1) - FR(l) * FR(l + 1));
+    }
+    for (int jobj = 1; jobj <= nobj - 1; ++jobj) {
+      double prod = 1.0;
+      for (int l = i_max[jobj]; l <= i_max[jobj + 1] - 1; ++l) prod = prod * alpha[l];
+      alpha_obj[jobj] = prod;
+    }
+    for (int jobj = 1; jobj <= nobj; ++jobj) {
+      CUM(i_top[jobj]) = FR(i_top[jobj]);
+      for (int l = i_top[jobj]; l <= i_base[jobj] - 1; ++l) {
+        if (FR(l) >= MaxCloudFrac) CUM(l + 1) = 1.0;
+        else CUM(l + 1) = 1.0 - (1.0 - CUM(l)) * (1.0 - PAIR(l)) / (1.0 - FR(l));
+      }
+      cc_obj[jobj] = CUM(i_base[jobj]);
+    }
+    int iobj1 = 1;
+    while (nobj > 1) {
+      double alpha_max = 0.0;
+      iobj1 = 1;
+      int jobj = 1, count = 1;
+      /* "do while (jobj < nobj)" walks the linked list; the source compares the list index with the remaining count */
+      while (jobj < nobj) {
+        if (alpha_obj[jobj] > alpha_max) { alpha_max = alpha_obj[jobj]; iobj1 = jobj; }
+        jobj = i_next[jobj];
+        (void)count;
+      }
+      int iobj2 = i_next[iobj1];
+      for (int l = i_base[iobj1] + 1; l <= i_top[iobj2] - 1; ++l) CUM(l) = CUM(i_base[iobj1]);
+      double cc_pair = alpha_obj[iobj1] * dmax(cc_obj[iobj1], cc_obj[iobj2]) +
+                       (1.0 - alpha_obj[iobj1]) * (cc_obj[iobj1] + cc_obj[iobj2] - cc_obj[iobj1] * cc_obj[iobj2]);
+      double scaling = dmin(dmax((cc_pair - cc_obj[iobj1]) / dmax(min_frac, cc_obj[iobj2]), 0.0), 1.0);
+      for (int l = i_top[iobj2]; l <= i_base[iobj2]; ++l) CUM(l) = CUM(i_base[iobj1]) + CUM(l) * scaling;
+      cc_obj[iobj1] = cc_pair;
+      i_base[iobj1] = i_base[iobj2];
+      i_next[iobj1] = i_next[iobj2];
+      alpha_obj[iobj1] = alpha_obj[iobj2];
+      nobj--;
+    }
+    for (int l = i_base[iobj1] + 1; l <= nlev; ++l) CUM(l) = CUM(i_base[iobj1]);
+    for (int l = 1; l <= nlev - 1; ++l) PAIR(l) = dmax(PAIR(l), FR(l) + CUM(l + 1) - CUM(l));
+    for (int l = 1; l <= nlev; ++l) CUM(l) = dmin(CUM(l), 1.0);
+  }
+#undef FR
+#undef CUM
+#undef PAIR
+  free(i_top); free(cc_obj);
+}
+
+/* radiation_cloud_generator.F90:396-530 generate_column_exp_exp */
+static void generate_column_exp_exp(const orc_tables* t, int ng, int nlev, int ig, rng_stream* rs, const double* frac,
+                                    const double* pair, const double* cum, const double* overhang, const double* fsd,
+                                    const double* overlap_param_inhom, int itrigger, int iend, double* od_scaling,
+                                    double* rand_cloud, double* rand_inhom1, double* rand_inhom2) {
+#define F(a, l) ((a)[(l) - 1])
+  int* is_cloudy = (int*)calloc((size_t)nlev + 2, sizeof(int));
+  int iy = 0;
+  is_cloudy[itrigger] = 1;
+  rng_uniform(rs, iend + 1 - itrigger, rand_cloud);
+  for (int jlev = itrigger + 1; jlev <= iend; ++jlev) {
+    iy++;
+    if (is_cloudy[jlev - 1]) {
+      if (rand_cloud[iy - 1] * F(frac, jlev - 1) < F(frac, jlev) + F(frac, jlev - 1) - F(pair, jlev - 1)) is_cloudy[jlev] = 1;
+    } else {
+      if (rand_cloud[iy - 1] * (F(cum, jlev - 1) - F(frac, jlev - 1)) < F(pair, jlev - 1) - F(overhang, jlev - 1) - F(frac, jlev - 1))
+        is_cloudy[jlev] = 1;
+    }
+  }
+  const int n = iend + 1 - itrigger;
+  rng_uniform(rs, n, rand_inhom1);
+  rng_uniform(rs, n, rand_inhom2);
+  for (int jc = 2; jc <= n; ++jc)
+    if (rand_inhom2[jc - 1] < F(overlap_param_inhom, iend - n + jc - 1)) rand_inhom1[jc - 1] = rand_inhom1[jc - 2];
+  for (int k = 0; k < n; ++k) {
+    int lev = itrigger + k;
+    od_scaling[(size_t)(lev - 1) * ng + ig] = is_cloudy[lev] ? pdf_sample(t, F(fsd, lev), rand_inhom1[k]) : 0.0;
+  }
+  free(is_cloudy);
+#undef F
+}
+
 /* radiation_cloud_generator.F90:262-390 generate_column_exp_ran; levels 1-based like the source via macros */
 static void generate_column_exp_ran(const orc_tables* t, int ng, int nlev, int ig, rng_stream* rs, const double* frac,
                                     const double* pair, const double* cum, const double* overhang,
@@ -282,6 +392,7 @@ void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_sc
   double* pair = cum + nlev; double* overhang = pair + nlev; double* opi = overhang + nlev;
   double* rand_cloud = opi + nlev; double* ri1 = rand_cloud + nlev; double* ri2 = ri1 + nlev;
   if (i_overlap_scheme == ECRAD_OVERLAP_EXP_RAN) cum_cloud_cover_exp_ran(nlev, frac, overlap_param, use_beta_overlap, cum, pair);
+  else if (i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP) cum_cloud_cover_exp_exp(nlev, frac, overlap_param, use_beta_overlap, cum, pair);
   else cum_cloud_cover_max_ran(nlev, frac, cum, pair);
   double tcc = cum[nlev - 1];
   for (int jl = 0; jl < nlev - 1; ++jl) overhang[jl] = cum[jl + 1] - cum[jl];
@@ -304,8 +415,12 @@ void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_sc
       double trigger = rand_top[jg] * tcc;
       jlev = ibegin;
       while (trigger > cum[jlev - 1] && jlev < iend) jlev++;
-      generate_column_exp_ran(t, ng, nlev, jg, &rs, frac, pair, cum, overhang, fractional_std, opi, jlev, iend, od_scaling,
-                              rand_cloud, ri1, ri2);
+      if (i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)
+        generate_column_exp_exp(t, ng, nlev, jg, &rs, frac, pair, cum, overhang, fractional_std, opi, jlev, iend, od_scaling,
+                                rand_cloud, ri1, ri2);
+      else
+        generate_column_exp_ran(t, ng, nlev, jg, &rs, frac, pair, cum, overhang, fractional_std, opi, jlev, iend, od_scaling,
+                                rand_cloud, ri1, ri2);
     }
     free(rand_top);
   }

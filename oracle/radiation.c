@@ -608,8 +608,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  if (cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator ||
-      cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP || cfg->do_sw_delta_scaling_with_gases) {
+  if (cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator || cfg->do_sw_delta_scaling_with_gases) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
   }

@@ -111,7 +111,7 @@ int hc_cloud_generator(void* p, int ng, int nlev, int scheme, int32_t iseed, dou
   for (size_t i = 0; i < (size_t)ng * nlev; ++i) od_scaling[i] = 0.0;
   if (tcc > 0.0) {
     RngMix rs; rs.ix = ix.data();
-    gen_walk(gc, rs, iseed, ng, tcc, rtop.data(), rcloud.data(), ri1.data(), code.data(), nlev);
+    gen_walk(gc, rs, iseed, ng, tcc, rtop.data(), rcloud.data(), ri1.data(), code.data(), nlev, scheme == 2);
     for (int g = 0; g < ng; ++g)
       for (int l = 0; l < nlev; ++l) {
         uint32_t cd = code[(size_t)g * nlev + l];

@@ -49,7 +49,7 @@ def test_stencil_gas_optics_matches_oracle(env, meridian_raw):
         assert v < 1e-12, (k, v)   # re-association only: ~1e-15 relative
 
 
-@pytest.mark.parametrize("scheme,beta", [(1, 0), (0, 0), (1, 1)])
+@pytest.mark.parametrize("scheme,beta", [(1, 0), (0, 0), (1, 1), (2, 0), (2, 1)])
 def test_generator_walk_is_bit_exact(env, meridian_raw, scheme, beta):
     lib, h, orc, _ = env
     L = orc.lib

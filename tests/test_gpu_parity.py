@@ -95,6 +95,15 @@ def test_mcica_with_aerosols_vs_reference_default_golden(handles, meridian_raw, 
         assert f32_ulp_err(out[nm], golden_default[gname]).max() <= 1.0, nm
 
 
+def test_expexp_vs_reference_golden(handles, meridian_raw, golden_expexp):
+    """The reference's `expexp` ctest (Exp-Exp overlap + aerosols): within 1 float32 ulp of its golden file."""
+    h, _, _ = handles(use_aerosols=True, overlap_scheme_name="Exp-Exp")
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    for nm, gname in (("lw_up", "flux_up_lw"), ("lw_dn", "flux_dn_lw"), ("sw_up", "flux_up_sw"), ("sw_dn", "flux_dn_sw"),
+                      ("sw_dn_direct", "flux_dn_direct_sw"), ("cloud_cover_sw", "cloud_cover_sw"), ("cloud_cover_lw", "cloud_cover_lw")):
+        assert f32_ulp_err(out[nm], golden_expexp[gname]).max() <= 1.0, nm
+
+
 def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless):
     h, orc, _ = handles(sw_solver_name="Cloudless", lw_solver_name="Cloudless")
     out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
@@ -106,7 +115,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(overlap_scheme_name="Max-Ran"), dict(do_lw_cloud_scattering=False),
-                                dict(use_beta_overlap=True), dict(use_aerosols=True),
+                                dict(use_beta_overlap=True), dict(use_aerosols=True), dict(overlap_scheme_name="Exp-Exp"),
+                                dict(overlap_scheme_name="Exp-Exp", use_beta_overlap=True),
                                 dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless")])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""

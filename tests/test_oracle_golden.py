@@ -73,6 +73,16 @@ def test_oracle_mcica_with_aerosols_matches_reference_default_golden(meridian_ra
         assert f32_ulp_err(out[nm].T, golden_default[gname]).max() <= 0.51, nm
 
 
+def test_oracle_expexp_matches_reference_golden(meridian_raw, golden_expexp):
+    """test/ifs `expexp` ctest: as `default` with overlap_scheme_name='Exp-Exp' (cum_cloud_cover_exp_exp + generate_column_exp_exp)."""
+    _, out = _run(meridian_raw, use_aerosols=True, overlap_scheme_name="Exp-Exp")
+    for nm, gname in PROFILES.items():
+        err = f32_ulp_err(out[nm], golden_expexp[gname])
+        assert err.max() <= 0.51, (nm, err.max())
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):
+        assert f32_ulp_err(out[nm], golden_expexp[nm]).max() <= 0.51, nm
+
+
 def test_oracle_cloudless_matches_reference_golden(meridian_raw, golden_cloudless):
     _, out = _run(meridian_raw, sw_solver_name="Cloudless", lw_solver_name="Cloudless")
     for nm, gname in PROFILES.items():
