@@ -117,6 +117,23 @@ void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_sc
                          double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,
                          double* od_scaling /*[nlev][ng]*/, double* total_cloud_cover);
 
+/* tripleclouds.c */
+typedef struct {
+  double cloud_cover;
+  double *up, *dn, *dn_direct, *up_clear, *dn_clear, *dn_direct_clear;                   /* [nlev+1] sums over g */
+  double *up_toa_g, *up_toa_clear_g, *dn_diffuse_surf_g, *dn_direct_surf_g, *dn_diffuse_surf_clear_g, *dn_direct_surf_clear_g; /* [ng] */
+  double *up_g_prof, *dn_dif_g_prof, *dn_dir_g_prof;   /* optional [nlev+1][ng]: per-g totals over regions (band profiles) */
+  double *lw_deriv;                                    /* optional [nlev+1] */
+} orc_tc_out;
+void orc_tripleclouds_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, double mu0, const double* frac,
+                         const double* fsd, const double* overlap_param, const double* od, const double* ssa, const double* g,
+                         const double* od_cloud, const double* ssa_cloud, const double* g_cloud, const double* incoming,
+                         const double* alb_diff, const double* alb_dir, orc_tc_out* o);
+void orc_tripleclouds_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* frac, const double* fsd,
+                         const double* overlap_param, const double* od, const double* planck_hl, const double* od_cloud,
+                         const double* ssa_cloud, const double* g_cloud, const double* emission, const double* albedo,
+                         orc_tc_out* o);
+
 /* radiation.c */
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads);

@@ -515,6 +515,87 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   free(pool);
 }
 
+/* ----- Tripleclouds wrappers: scatter the per-column results of tripleclouds.c into flux_type ----- */
+static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol, const ecrad_b200_inputs* in,
+                      ecrad_b200_outputs* out, const col_work* w, const double* frac, int sw) {
+  const int ng = sw ? NG_SW : NG_LW, nb = sw ? NB_SW : NB_LW, nl1 = nlev + 1;
+  double* buf = (double*)calloc((size_t)7 * nl1 + 6 * ng + 3 * (size_t)nl1 * ng + 2 * nlev, sizeof(double));
+  orc_tc_out o; memset(&o, 0, sizeof o);
+  o.up = buf; o.dn = o.up + nl1; o.dn_direct = o.dn + nl1; o.up_clear = o.dn_direct + nl1; o.dn_clear = o.up_clear + nl1;
+  o.dn_direct_clear = o.dn_clear + nl1; o.lw_deriv = o.dn_direct_clear + nl1;
+  o.up_toa_g = o.lw_deriv + nl1; o.up_toa_clear_g = o.up_toa_g + ng; o.dn_diffuse_surf_g = o.up_toa_clear_g + ng;
+  o.dn_direct_surf_g = o.dn_diffuse_surf_g + ng; o.dn_diffuse_surf_clear_g = o.dn_direct_surf_g + ng; o.dn_direct_surf_clear_g = o.dn_diffuse_surf_clear_g + ng;
+  o.up_g_prof = o.dn_direct_surf_clear_g + ng; o.dn_dif_g_prof = o.up_g_prof + (size_t)nl1 * ng; o.dn_dir_g_prof = o.dn_dif_g_prof + (size_t)nl1 * ng;
+  double *fsd = o.dn_dir_g_prof + (size_t)nl1 * ng, *op = fsd + nlev;
+  for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
+  for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
+  if (!sw) {
+    orc_tripleclouds_lw(t, cfg, nlev, frac, fsd, op, w->od_lw, w->planck_hl, w->od_lw_cloud, w->ssa_lw_cloud, w->g_lw_cloud,
+                        w->lw_emission, w->lw_albedo, &o);
+    if (out->cloud_cover_lw) out->cloud_cover_lw[jcol] = o.cloud_cover;
+    for (int jl = 0; jl < nl1; ++jl) {
+      if (out->lw_up) A2(out->lw_up, jcol, jl) = o.up[jl];
+      if (out->lw_dn) A2(out->lw_dn, jcol, jl) = o.dn[jl];
+      if (out->lw_up_clear) A2(out->lw_up_clear, jcol, jl) = o.up_clear[jl];
+      if (out->lw_dn_clear) A2(out->lw_dn_clear, jcol, jl) = o.dn_clear[jl];
+      if (cfg->do_lw_derivatives && out->lw_derivatives) A2(out->lw_derivatives, jcol, jl) = o.lw_deriv[jl];
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = o.dn_diffuse_surf_g[g];
+      if (out->lw_dn_surf_clear_g) OUTG(out->lw_dn_surf_clear_g, ng, g) = o.dn_diffuse_surf_clear_g[g];
+      if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = o.up_toa_g[g];
+      if (out->lw_up_toa_clear_g) OUTG(out->lw_up_toa_clear_g, ng, g) = o.up_toa_clear_g[g];
+    }
+    band_profile(ng, nb, nl1, t->ngb_lw, 1, o.up_g_prof, ncol, jcol, out->lw_up_band, 0);
+    band_profile(ng, nb, nl1, t->ngb_lw, 1, o.dn_dif_g_prof, ncol, jcol, out->lw_dn_band, 0);
+  } else {
+    const double mu0 = in->cos_sza[jcol];
+    if (mu0 < 1.0e-10) {
+      /* night: fluxes zeroed; cloud_cover_sw is still the overlap-matrix value (computed before the column loop) */
+      double (*reg)[3] = malloc(sizeof(double[3]) * nlev), (*ods)[3] = malloc(sizeof(double[3]) * nlev);
+      double (*U)[3][3] = malloc(sizeof(double[3][3]) * nl1), (*V)[3][3] = malloc(sizeof(double[3][3]) * nl1);
+      extern void orc_region_properties(int, const double*, const double*, double, double (*)[3], double (*)[3]);
+      extern void orc_overlap_matrices(int, double (*)[3], const double*, double, double, double (*)[3][3], double (*)[3][3], double*);
+      orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+      orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, U, V, &o.cloud_cover);
+      free(reg); free(ods); free(U); free(V);
+    } else {
+      orc_tripleclouds_sw(t, cfg, nlev, mu0, frac, fsd, op, w->od_sw, w->ssa_sw, w->g_sw, w->od_sw_cloud, w->ssa_sw_cloud, w->g_sw_cloud,
+                          w->incoming_sw, w->alb_diff, w->alb_dir, &o);
+    }
+    if (out->cloud_cover_sw) out->cloud_cover_sw[jcol] = o.cloud_cover;
+    for (int jl = 0; jl < nl1; ++jl) {
+      if (out->sw_up) A2(out->sw_up, jcol, jl) = o.up[jl];
+      if (out->sw_dn) A2(out->sw_dn, jcol, jl) = o.dn[jl];
+      if (out->sw_dn_direct) A2(out->sw_dn_direct, jcol, jl) = o.dn_direct[jl];
+      if (out->sw_up_clear) A2(out->sw_up_clear, jcol, jl) = o.up_clear[jl];
+      if (out->sw_dn_clear) A2(out->sw_dn_clear, jcol, jl) = o.dn_clear[jl];
+      if (out->sw_dn_direct_clear) A2(out->sw_dn_direct_clear, jcol, jl) = o.dn_direct_clear[jl];
+    }
+    for (int g = 0; g < ng; ++g) {
+      if (out->sw_dn_diffuse_surf_g) OUTG(out->sw_dn_diffuse_surf_g, ng, g) = o.dn_diffuse_surf_g[g];
+      if (out->sw_dn_direct_surf_g) OUTG(out->sw_dn_direct_surf_g, ng, g) = o.dn_direct_surf_g[g];
+      if (out->sw_dn_diffuse_surf_clear_g) OUTG(out->sw_dn_diffuse_surf_clear_g, ng, g) = o.dn_diffuse_surf_clear_g[g];
+      if (out->sw_dn_direct_surf_clear_g) OUTG(out->sw_dn_direct_surf_clear_g, ng, g) = o.dn_direct_surf_clear_g[g];
+      if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = o.up_toa_g[g];
+      if (out->sw_up_toa_clear_g) OUTG(out->sw_up_toa_clear_g, ng, g) = o.up_toa_clear_g[g];
+    }
+    /* band profiles: up; dn = mu0*direct + diffuse; dn_direct = mu0*direct (radiation_tripleclouds_sw.F90:604-624) */
+    if (out->sw_up_band || out->sw_dn_band || out->sw_dn_direct_band) {
+      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.up_g_prof, ncol, jcol, out->sw_up_band, 0);
+      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_direct_band, 0);
+      if (out->sw_dn_direct_band)
+        for (int jl = 0; jl < nl1; ++jl) for (int b = 0; b < nb; ++b) out->sw_dn_direct_band[((size_t)jl * ncol + jcol) * nb + b] *= mu0;
+      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_band, 0);
+      if (out->sw_dn_band) {
+        for (int jl = 0; jl < nl1; ++jl) for (int b = 0; b < nb; ++b) out->sw_dn_band[((size_t)jl * ncol + jcol) * nb + b] *= mu0;
+        band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dif_g_prof, ncol, jcol, out->sw_dn_band, 1);
+      }
+    }
+  }
+  free(buf);
+}
+
 /* radiation_flux.F90:397-577 calc_surface_spectral (paths used by the test namelists) */
 static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, int jcol, ecrad_b200_outputs* out) {
   if (cfg->do_sw && cfg->do_surface_sw_spectral_flux && out->sw_dn_surf_band && out->sw_dn_direct_surf_band &&
@@ -599,8 +680,8 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }
-  if (cfg->do_lw) solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac);
-  if (cfg->do_sw) solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac);
+  if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
+  if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   surface_spectral(t, cfg, jcol, out);
   free(w.w); free(phl_full);
   return 0;

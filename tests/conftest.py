@@ -41,3 +41,8 @@ def golden_default():
 @pytest.fixture(scope="session")
 def golden_expexp():
     return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_expexp_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_tripleclouds():
+    return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_tripleclouds_ref.npz")))

@@ -26,11 +26,11 @@ def f32_ulp_err(a, g):
     return np.abs(a - g64) / np.maximum(np.spacing(np.abs(g).astype(np.float32)).astype(np.float64), 1e-30)
 
 
-def _run(raw, **cfgkw):
+def _run(raw, spectral=False, **cfgkw):
     cfg = RadiationConfig(**cfgkw).consolidate()
     inp = I.to_radiation_inputs(raw)
     ncol, nlev = inp["pressure_hl"].shape[0], inp["pressure_hl"].shape[1] - 1
-    out = Oracle(cfg).radiation(inp, ncol, nlev, spectral_profiles=cfg.sw_solver_name == "Cloudless")
+    out = Oracle(cfg).radiation(inp, ncol, nlev, spectral_profiles=spectral or cfg.sw_solver_name == "Cloudless")
     return cfg, out
 
 
@@ -81,6 +81,22 @@ def test_oracle_expexp_matches_reference_golden(meridian_raw, golden_expexp):
         assert err.max() <= 0.51, (nm, err.max())
     for nm in ("cloud_cover_lw", "cloud_cover_sw"):
         assert f32_ulp_err(out[nm], golden_expexp[nm]).max() <= 0.51, nm
+
+
+def test_oracle_tripleclouds_matches_reference_golden(meridian_raw, golden_tripleclouds):
+    """test/ifs `tripleclouds` ctest: Tripleclouds LW+SW (3 regions, gamma PDF) + RRTMG + aerosols, incl. per-band profiles."""
+    _, out = _run(meridian_raw, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", spectral=True)
+    for nm, gname in PROFILES.items():
+        err = f32_ulp_err(out[nm], golden_tripleclouds[gname])
+        assert err.max() <= 0.51, (nm, err.max())
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):
+        assert f32_ulp_err(out[nm], golden_tripleclouds[nm]).max() <= 0.51, nm
+    assert f32_ulp_err(out["lw_derivatives"], golden_tripleclouds["lw_derivative"]).max() <= 0.51
+    lev = golden_tripleclouds["band_levels"]
+    for nm, gname in (("lw_up_band", "spectral_flux_up_lw"), ("lw_dn_band", "spectral_flux_dn_lw"), ("sw_up_band", "spectral_flux_up_sw"),
+                      ("sw_dn_band", "spectral_flux_dn_sw"), ("sw_dn_direct_band", "spectral_flux_dn_direct_sw")):
+        a = np.transpose(out[nm], (1, 2, 0))[:, lev, :]
+        assert f32_ulp_err(a, golden_tripleclouds[gname]).max() <= 0.51, nm
 
 
 def test_oracle_cloudless_matches_reference_golden(meridian_raw, golden_cloudless):

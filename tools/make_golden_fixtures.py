@@ -24,7 +24,7 @@ BAND_LEVELS = [0, 20, 40, 60, 80, 100, 120, 137]
 os.makedirs(OUT, exist_ok=True)
 with netcdf_file(f"{REF}/test/ifs/ecrad_meridian.nc", mmap=False) as f:
     np.savez_compressed(f"{OUT}/ecrad_meridian_inputs.npz", **{k: np.array(f.variables[k][...]) for k in NC_VARS})
-for name in ("noaer", "cloudless", "default", "expexp"):
+for name in ("noaer", "cloudless", "default", "expexp", "tripleclouds"):
     with netcdf_file(f"{REF}/test/ifs/ecrad_meridian_{name}_out_REFERENCE.nc", mmap=False) as f:
         d = {}
         for k, v in f.variables.items():
