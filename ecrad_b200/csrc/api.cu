@@ -53,7 +53,7 @@ struct Handle {
   cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
-  Buf work[32];
+  Buf work[36];
   Work w;
   int w_cols = 0, w_nlev = 0;
   std::mutex mu;
@@ -85,9 +85,11 @@ int upload(Handle* h, const Tp* src, size_t n, const Tp** dst) {
 // Which solver / model combinations have kernels.
 int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.struct_bytes != (int32_t)sizeof(ecrad_b200_config)) return fail(h, "ecrad_b200_config: struct_bytes mismatch (ABI)");
-  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS; };
+  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS || s == ECRAD_SOLVER_TRIPLECLOUDS; };
   if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw)))
-    return fail(h, "solver not available in this build (McICA and Cloudless are)");
+    return fail(h, "solver not available in this build (McICA, Tripleclouds and Cloudless are)");
+  if (c.use_beta_overlap && ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS)))
+    return fail(h, "use_beta_overlap is not available with the Tripleclouds solver in this build");
   if ((c.do_sw && c.i_gas_model_sw != ECRAD_GAS_IFSRRTMG) || (c.do_lw && c.i_gas_model_lw != ECRAD_GAS_IFSRRTMG))
     return fail(h, "gas model not available in this build (RRTMG-IFS is)");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
@@ -105,6 +107,8 @@ int ensure_work(Handle* h, int cols, int nlev) {
   if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
   if (nlev != h->w_nlev) h->w_cols = 0;
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
+  const bool tc_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS, tc_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
+  const bool tc = tc_lw || tc_sw;
   const size_t sz[] = {
       8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
@@ -112,13 +116,14 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
-      8 * nc * LW_SCR_ARRAYS * nl * NG_LW,                                                   // scr_lw
+      8 * nc * (tc_lw ? tc_scratch_doubles_lw(nlev) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
-      8 * nc * SW_SCR_ARRAYS * nl * NG_SW,                                                   // scr_sw
+      8 * nc * (tc_sw ? tc_scratch_doubles_sw(nlev) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
       sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl,                                      // lev_lw lev_sw
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, h->cfg.use_aerosols ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
-      h->cfg.use_aerosols ? 8 * nc * nl * NB_LW : 0};                                        // aer_lw
+      h->cfg.use_aerosols ? 8 * nc * nl * NB_LW : 0,                                         // aer_lw
+      tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0};  // tc_reg tc_ods tc_u tc_v tc_cc
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
@@ -130,6 +135,8 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
   w.lev_lw = (LwLev*)h->work[24].p; w.lev_sw = (SwLev*)h->work[25].p;
   w.g_sw = (double*)h->work[26].p; w.aer_sw = (double*)h->work[27].p; w.aer_lw = (double*)h->work[28].p;
+  w.tc_reg = (double*)h->work[29].p; w.tc_ods = (double*)h->work[30].p; w.tc_u = (double*)h->work[31].p;
+  w.tc_v = (double*)h->work[32].p; w.tc_cc = (double*)h->work[33].p;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
   w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
@@ -156,6 +163,8 @@ int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cu
   // cloud chain
   CK(h, cudaEventRecord(ev[4], s_cl));
   if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w, nc, nlev, s_cl);
+  if ((c.do_lw && c.solver_lw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_sw && c.solver_sw == ECRAD_SOLVER_TRIPLECLOUDS))
+    n += launch_tc_prep(c, in, h->w, nc, nlev, s_cl);
   CK(h, cudaEventRecord(ev[5], s_cl));
   if (par) CK(h, cudaEventRecord(h->ev_cloud, s_cl));
   // LW chain
@@ -435,8 +444,8 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     const bool lw = (k <= 3) || k == 10 || k == 11 || (k >= 13 && k <= 16) || k == 29 || k == 30 || k == 31;
     if (lw && !c.do_lw) return false;
     if (!lw && !c.do_sw) return false;
-    if (k == 11) return mcica_lw;
-    if (k == 12) return mcica_sw;
+    if (k == 11) return mcica_lw || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS);
+    if (k == 12) return mcica_sw || (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS);
     if (k == 10) return c.do_lw_derivatives != 0;
     if (k >= 23 && k <= 26) return c.do_surface_sw_spectral_flux != 0 && (k < 25 || c.do_clear);
     if (k == 27 || k == 28) return c.do_canopy_fluxes_sw != 0;

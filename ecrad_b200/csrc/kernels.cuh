@@ -73,6 +73,7 @@ struct Work {
   int *ibegin, *iend, *ict;                       // [nc]
   uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
   double *scr_lw, *scr_sw;                        // [nc][LW_SCR_ARRAYS*nlev*140], [nc][SW_SCR_ARRAYS*nlev*112] (separate: LW and SW chains run concurrently)
+  double *tc_reg, *tc_ods, *tc_u, *tc_v, *tc_cc;  // Tripleclouds: [nc][nlev][3] x2, [nc][nlev+1][9] x2, [nc]
   LwLev* lev_lw; SwLev* lev_sw;                   // [nc][nlev] per-layer gas-optics state (gas_prep_kernel)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
@@ -86,6 +87,11 @@ int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+size_t tc_scratch_doubles_lw(int nlev);
+size_t tc_scratch_doubles_sw(int nlev);
+int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 

@@ -28,7 +28,7 @@ __device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, 
   s.mcica = cfg.solver_lw == 2;
   s.tcc = s.mcica ? w.tcc[s.c] : 0.0;
   s.cloudy = s.tcc > 0.0;
-  s.ict = s.cloudy ? w.ict[s.c] : nlev;
+  s.ict = (s.cloudy || cfg.solver_lw == 4) ? w.ict[s.c] : nlev;   // 4 = Tripleclouds: needs the clear-sky flux_dn at cloud top too
   s.thr = cfg.cloud_fraction_threshold;
   s.n = (size_t)nlev * NG_LW;
   s.od = w.od_lw + (size_t)s.c * s.n;
@@ -268,18 +268,7 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
     if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
     if (out.lw_up_toa_g) out.lw_up_toa_g[i] = cloudy ? wc * fu_toa_a + w1 * fu_toa_clear : fu_toa_clear;
   }
-  // canopy fluxes, radiation_flux.F90 calc_surface_spectral (nearest-interval emissivity mapping)
-  if (cfg.do_canopy_fluxes_lw && out.lw_dn_surf_canopy) {
-    __syncthreads();
-    if (act) tile[g] = dn_surf_g;
-    __syncthreads();
-    if (g < cfg.n_canopy_bands_lw) {
-      double sum = 0.0;
-      for (int k = 0; k < NG_LW; ++k)
-        if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) sum = sum + tile[k];
-      out.lw_dn_surf_canopy[(size_t)c * cfg.n_canopy_bands_lw + g] = sum;
-    }
-  }
+  lw_surface_canopy(T, cfg, out, c, g, act, tile, dn_surf_g);
 #undef OUT2
 }
 
@@ -288,8 +277,9 @@ int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   const size_t sm1 = sizeof(double) * (LCH * LW_RS) + 16;
   const size_t sm2 = sizeof(double) * (3 * LCH * LW_RS + 2 * nlev) + 16;
   const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * LW_RS) + 16;
-  cudaFuncSetAttribute(lw_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
   lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(cfg, w, nlev);
+  if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
+  cudaFuncSetAttribute(lw_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
   lw_up_kernel<<<nc, LW_THREADS, sm2, st>>>(T, cfg, in, w, nlev, nlevp);
   lw_flux_kernel<<<nc, LW_THREADS, sm3, st>>>(T, cfg, out, w, nlev);
   return 3;

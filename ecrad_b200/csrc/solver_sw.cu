@@ -330,36 +330,7 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
     if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
   }
-  // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral
-  if (cfg.do_surface_sw_spectral_flux || cfg.do_canopy_fluxes_sw) {
-    __syncthreads();
-    if (act) { tile[g] = dir_a; tile[SW_RS + g] = dif_a; tile[2 * SW_RS + g] = dir_c; tile[3 * SW_RS + g] = dif_c; }
-    __syncthreads();
-    double* bdir = tile + 4 * SW_RS;  // [14] all-sky direct band, [14] all-sky total band
-    if (g < NB_SW) {
-      const int g0 = T.meta->sw[g].g0, ngb = T.meta->sw[g].ng;
-      double d = 0.0, t = 0.0, dcl = 0.0, tcl = 0.0;
-      for (int k = g0; k < g0 + ngb; ++k) { d = d + tile[k]; t = t + tile[SW_RS + k]; dcl = dcl + tile[2 * SW_RS + k]; tcl = tcl + tile[3 * SW_RS + k]; }
-      t = t + d; tcl = tcl + dcl;
-      bdir[g] = d; bdir[NB_SW + g] = t;
-      if (cfg.do_surface_sw_spectral_flux) {
-        if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * NB_SW + g] = d;
-        if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * NB_SW + g] = t;
-        if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * NB_SW + g] = dcl;
-        if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * NB_SW + g] = tcl;
-      }
-    }
-    __syncthreads();
-    if (cfg.do_canopy_fluxes_sw && out.sw_dn_diffuse_surf_canopy && out.sw_dn_direct_surf_canopy && g < cfg.n_albedo_sw) {
-      double dif = 0.0, dir = 0.0;
-      for (int jb = 0; jb < NB_SW; ++jb) {
-        const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + g];
-        if (wgt != 0.0) { dif = dif + wgt * bdir[NB_SW + jb]; dir = dir + wgt * bdir[jb]; }
-      }
-      out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dif - dir;
-      out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dir;
-    }
-  }
+  sw_surface_spectral(T, cfg, out, c, g, act, tile, SW_RS, dir_a, dif_a, dir_c, dif_c);
 #undef OUT2
 }
 
@@ -368,6 +339,7 @@ int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   const size_t smA = sizeof(double) * (2 * LCH * SW_RS + 2 * nlev) + 16;
   const size_t smB = sizeof(double) * (2 * nlev + 2 * NB_SW) + 16;
   const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SW_RS) + 16;
+  if (cfg.solver_sw == 4) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
   const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
     sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);

@@ -1,0 +1,427 @@
+// solver_tc.cu -- Tripleclouds solvers (3 regions: clear, optically thin cloud, optically thick cloud).
+//
+// Reference: radiation/radiation_tripleclouds_sw.F90:42-661, radiation_tripleclouds_lw.F90:38-605,
+// radiation_regions.F90, radiation_overlap.F90, radiation_lw_derivatives.F90:200-290 (calc_lw_derivatives_region).
+// One CTA per column, one thread per g-point holding the three regions' albedo/source (upward sweep) and fluxes
+// (downward sweep) in registers; the 3x3 overlap matrices of every half-level sit in shared memory.  What the downward
+// sweep needs from the upward one goes to the per-column scratch, pre-combined per region:
+//   SW:  a = T/(1-R*A), b = (Tdir*Adir*R + Tdirdif)/(1-R*A), Tdir, A, Adir       (A, Adir: albedos of everything below)
+//   LW:  a = T/(1-R*A), b = (R*S + src_dn)/(1-R*A), A, S, T                       (S: source of everything below)
+// First version: one kernel per spectrum (not yet split/tuned like the McICA path).
+#include "solver_common.cuh"
+#include "tc_core.h"
+
+namespace ecb {
+
+enum { TC_SW_THREADS = 128, TC_SW_RS = 113, TC_LW_THREADS = 160, TC_LW_RS = 141, TC_LCH = 8 };
+enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
+
+// ---------------------------------------------------------------------------------------------------------
+// region fractions, optical-depth scalings and overlap matrices: one thread per column
+// ---------------------------------------------------------------------------------------------------------
+__global__ void tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double* reg = w.tc_reg + (size_t)c * nlev * 3;
+  double* ods = w.tc_ods + (size_t)c * nlev * 3;
+  double* U = w.tc_u + (size_t)c * (nlev + 1) * 9;
+  double* V = w.tc_v + (size_t)c * (nlev + 1) * 9;
+  w.tc_cc[c] = tc_prepare_column(nlev, in.ld, in.frac + c, in.fsd + c, in.overlap + c, cfg.cloud_inhom_decorr_scaling,
+                                 cfg.cloud_fraction_threshold, reg, ods, U, V);
+}
+
+struct TcShared {
+  double *reg, *ods, *U, *V;
+  int* clear;   // is_clear_sky_layer(0:nlev+1)
+};
+
+// loads the column's region data into shared memory (block-wide, ends with a barrier)
+__device__ __forceinline__ TcShared tc_load_shared(unsigned char* base, const Work& w, const DevIn& in, int c, int nlev, int nthreads) {
+  TcShared s;
+  s.reg = reinterpret_cast<double*>(base);
+  s.ods = s.reg + nlev * 3;
+  s.U = s.ods + nlev * 3;
+  s.V = s.U + (nlev + 1) * 9;
+  s.clear = reinterpret_cast<int*>(s.V + (nlev + 1) * 9);
+  const int t = threadIdx.x;
+  for (int i = t; i < nlev * 3; i += nthreads) { s.reg[i] = w.tc_reg[(size_t)c * nlev * 3 + i]; s.ods[i] = w.tc_ods[(size_t)c * nlev * 3 + i]; }
+  for (int i = t; i < (nlev + 1) * 9; i += nthreads) { s.U[i] = w.tc_u[(size_t)c * (nlev + 1) * 9 + i]; s.V[i] = w.tc_v[(size_t)c * (nlev + 1) * 9 + i]; }
+  for (int i = t; i < nlev + 2; i += nthreads) s.clear[i] = (i == 0 || i == nlev + 1) ? 1 : !(LD_IN(in.frac, c, i - 1) > 0.0);
+  __syncthreads();
+  return s;
+}
+static size_t tc_shared_bytes(int nlev) { return sizeof(double) * (6 * nlev + 18 * (nlev + 1)) + sizeof(int) * (nlev + 2) + 16; }
+
+// out[j1] = sum_j2 A[j1][j2] * x[j2]   (singlemat_x_vec, radiation_matrix.F90:110-136)
+__device__ __forceinline__ void mat3_x_vec(const double* A, double* x) {
+  double o[3];
+#pragma unroll
+  for (int j1 = 0; j1 < 3; ++j1) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j2 = 0; j2 < 3; ++j2) acc = acc + A[j1 * 3 + j2] * x[j2];
+    o[j1] = acc;
+  }
+  x[0] = o[0]; x[1] = o[1]; x[2] = o[2];
+}
+
+// =========================================================================================================
+// SW
+// =========================================================================================================
+__global__ void __launch_bounds__(TC_SW_THREADS, 2)
+tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
+  const bool act = g < NG_SW;
+  const int gg = act ? g : 0;
+  const double mu0 = in.cos_sza[c];
+  if (g == 0 && out.cloud_cover_sw) out.cloud_cover_sw[c] = w.tc_cc[c];   // set for every column, also at night
+  if (mu0 < 1.0e-10) { sw_night_column(cfg, out, c, g, act, nl1, TC_SW_THREADS); return; }
+  double* sums = reinterpret_cast<double*>(smem_raw);     // [6][nl1]: up, dn_dif, dn_dir, up_c, dn_dif_c, dn_dir_c
+  double* tile = sums + 6 * nl1;                           // [6][TC_LCH][TC_SW_RS]
+  double* bandv = tile + 6 * TC_LCH * TC_SW_RS;            // [2][14]
+  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(bandv + 2 * NB_SW), w, in, c, nlev, TC_SW_THREADS);
+  if (g < NB_SW) {   // get_albedos, radiation_single_level.F90:216-365
+    double bd = 0.0, bdir = 0.0;
+    for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
+      const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
+      if (wgt != 0.0) { bd = bd + wgt * LD_IN(in.sw_albedo, c, ja); if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja); }
+    }
+    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
+  }
+  __syncthreads();
+  const size_t n = (size_t)nlev * NG_SW;
+  const double* od = w.od_sw + (size_t)c * n;
+  const double* ssa = w.ssa_sw + (size_t)c * n;
+  const double* gas_g = (cfg.use_aerosols && w.g_sw) ? w.g_sw + (size_t)c * n : nullptr;
+  const double* cl = w.cl_sw + (size_t)c * nlev * 3 * NB_SW;
+  double* scr = w.scr_sw + (size_t)c * TC_SW_ARRAYS * n;
+#define SCR(set, f, i) scr[(size_t)((set) * 5 + (f)) * n + (i)]   // sets: 0 clear-sky, 1..3 regions; fields: a b tdir talb talbdir
+  const int b = T.meta->band_of_g_sw[gg];
+  const double alb_diff = bandv[b], alb_dir = bandv[NB_SW + b];
+  const double inc = w.incoming[(size_t)c * NG_SW + gg];
+
+  // ---- upward sweep: total albedos of everything below each half-level (radiation_tripleclouds_sw.F90:322-420) ----
+  double ta[3] = {alb_diff, 0.0, 0.0}, td[3] = {mu0 * alb_dir, 0.0, 0.0};
+  if (!S.clear[nlev]) { ta[1] = ta[0]; ta[2] = ta[0]; td[1] = td[0]; td[2] = td[0]; }
+  double tac = ta[0], tdc = td[0];
+  if (act) {
+    for (int l = nlev - 1; l >= 0; --l) {
+      const int jl = l + 1;
+      const size_t i = (size_t)l * NG_SW + g;
+      const double odg = od[i], ssag = ssa[i], gg_gas = gas_g ? gas_g[i] : 0.0;
+      const SwLayer Lc = sw_ref_trans(mu0, odg, ssag, gg_gas);
+      {   // clear-sky column
+        const double id = 1.0 / (1.0 - tac * Lc.ref);
+        SCR(0, 0, i) = Lc.trans * id;
+        SCR(0, 1, i) = (Lc.trans_dir_dir * tdc * Lc.ref + Lc.trans_dir_diff) * id;
+        SCR(0, 2, i) = Lc.trans_dir_dir; SCR(0, 3, i) = tac; SCR(0, 4, i) = tdc;
+        const double tac_new = Lc.ref + Lc.trans * Lc.trans * tac * id;
+        tdc = Lc.ref_dir + (Lc.trans_dir_dir * tdc + Lc.trans_dir_diff * tac) * Lc.trans * id;
+        tac = tac_new;
+      }
+      double below[3] = {0.0, 0.0, 0.0}, belowd[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int jr = 0; jr < 3; ++jr) {
+        if (jr > 0 && S.clear[jl]) continue;
+        SwLayer L = Lc;
+        if (jr > 0) {   // cloudy region: gas/aerosol + scaled cloud (radiation_tripleclouds_sw.F90:286-302)
+          const double* clb = cl + (size_t)l * 3 * NB_SW;
+          const double scal = S.ods[l * 3 + jr];
+          const double scat_od = odg * ssag;
+          const double scat_od_cloud = clb[b] * clb[NB_SW + b] * scal;
+          const double od_total = odg + clb[b] * scal;
+          const double ssa_total = (scat_od + scat_od_cloud) / od_total;
+          const double g_total = (scat_od * gg_gas + scat_od_cloud * clb[2 * NB_SW + b]) / (scat_od + scat_od_cloud);
+          L = sw_ref_trans(mu0, od_total, ssa_total, g_total);
+        }
+        const double id = 1.0 / (1.0 - ta[jr] * L.ref);
+        SCR(1 + jr, 0, i) = L.trans * id;
+        SCR(1 + jr, 1, i) = (L.trans_dir_dir * td[jr] * L.ref + L.trans_dir_diff) * id;
+        SCR(1 + jr, 2, i) = L.trans_dir_dir; SCR(1 + jr, 3, i) = ta[jr]; SCR(1 + jr, 4, i) = td[jr];
+        below[jr] = L.ref + L.trans * L.trans * ta[jr] * id;
+        belowd[jr] = L.ref_dir + (L.trans_dir_dir * td[jr] + L.trans_dir_diff * ta[jr]) * L.trans * id;
+      }
+      if (S.clear[jl] && S.clear[jl - 1]) {
+#pragma unroll
+        for (int jr = 0; jr < 3; ++jr) { ta[jr] = below[jr]; td[jr] = belowd[jr]; }
+      } else {
+        const double* V = S.V + l * 9;   // v_matrix(:,:,jlev)
+#pragma unroll
+        for (int jr = 0; jr < 3; ++jr) {
+          double a = 0.0, d = 0.0;
+#pragma unroll
+          for (int jr2 = 0; jr2 < 3; ++jr2) { a = a + below[jr2] * V[jr2 * 3 + jr]; d = d + belowd[jr2] * V[jr2 * 3 + jr]; }
+          ta[jr] = a; td[jr] = d;
+        }
+      }
+    }
+  }
+  // ---- downward sweep: fluxes (radiation_tripleclouds_sw.F90:424-645) ----
+  double ddn[3], fdn[3] = {0.0, 0.0, 0.0}, fup[3];
+#pragma unroll
+  for (int jr = 0; jr < 3; ++jr) { ddn[jr] = inc * S.reg[jr]; fup[jr] = ddn[jr] * td[jr]; }
+  double ddc = inc, fdc = 0.0, fuc = ddc * tdc;
+  const double toa_a = fup[0] + fup[1] + fup[2], toa_c = fuc;
+  double* dst[6] = {sums, sums + nl1, sums + 2 * nl1, sums + 3 * nl1, sums + 4 * nl1, sums + 5 * nl1};
+  int slot = 0, lfirst = 0;
+#define PUT_ROWS()                                                                                        \
+  if (act) {                                                                                              \
+    tile[(0 * TC_LCH + slot) * TC_SW_RS + g] = fup[0] + fup[1] + fup[2];                                  \
+    tile[(1 * TC_LCH + slot) * TC_SW_RS + g] = fdn[0] + fdn[1] + fdn[2];                                  \
+    tile[(2 * TC_LCH + slot) * TC_SW_RS + g] = ddn[0] + ddn[1] + ddn[2];                                  \
+    tile[(3 * TC_LCH + slot) * TC_SW_RS + g] = fuc;                                                       \
+    tile[(4 * TC_LCH + slot) * TC_SW_RS + g] = fdc;                                                       \
+    tile[(5 * TC_LCH + slot) * TC_SW_RS + g] = ddc;                                                       \
+  }                                                                                                       \
+  ++slot;
+  PUT_ROWS();
+  for (int l = 0; l < nlev; ++l) {
+    const int jl = l + 1;
+    if (act) {
+      const size_t i = (size_t)l * NG_SW + g;
+      fdc = SCR(0, 0, i) * fdc + SCR(0, 1, i) * ddc;
+      ddc = SCR(0, 2, i) * ddc;
+      fuc = ddc * SCR(0, 4, i) + fdc * SCR(0, 3, i);
+#pragma unroll
+      for (int jr = 0; jr < 3; ++jr) {
+        if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; ddn[jr] = 0.0; continue; }
+        fdn[jr] = SCR(1 + jr, 0, i) * fdn[jr] + SCR(1 + jr, 1, i) * ddn[jr];
+        ddn[jr] = SCR(1 + jr, 2, i) * ddn[jr];
+        fup[jr] = ddn[jr] * SCR(1 + jr, 4, i) + fdn[jr] * SCR(1 + jr, 3, i);
+      }
+      if (!(S.clear[jl] && S.clear[jl + 1])) {
+        const double* V = S.V + jl * 9;   // v_matrix(:,:,jlev+1)
+        mat3_x_vec(V, fdn);
+        mat3_x_vec(V, ddn);
+      }
+    }
+    PUT_ROWS();
+    if (slot == TC_LCH || l == nlev - 1) { flush_tile(tile, TC_SW_RS, NG_SW, 6, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0; }
+  }
+#undef PUT_ROWS
+#undef SCR
+  // ---- outputs ----
+  for (int l = g; l < nl1; l += TC_SW_THREADS) {
+    const double dir = mu0 * sums[2 * nl1 + l], dirc = mu0 * sums[5 * nl1 + l];
+    const size_t o = (size_t)l * out.ld + c;
+    if (out.sw_up) out.sw_up[o] = sums[l];
+    if (out.sw_dn) out.sw_dn[o] = l == 0 ? dir : dir + sums[nl1 + l];
+    if (out.sw_dn_direct) out.sw_dn_direct[o] = dir;
+    if (out.sw_up_clear) out.sw_up_clear[o] = sums[3 * nl1 + l];
+    if (out.sw_dn_clear) out.sw_dn_clear[o] = l == 0 ? dirc : dirc + sums[4 * nl1 + l];
+    if (out.sw_dn_direct_clear) out.sw_dn_direct_clear[o] = dirc;
+  }
+  const double dif_a = fdn[0] + fdn[1] + fdn[2], dir_a = mu0 * (ddn[0] + ddn[1] + ddn[2]), dif_c = fdc, dir_c = mu0 * ddc;
+  if (act) {
+    const size_t i = (size_t)c * NG_SW + g;
+    if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
+    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
+    if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
+    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
+    if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
+    if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
+  }
+  sw_surface_spectral(T, cfg, out, c, g, act, tile, TC_SW_RS, dir_a, dif_a, dir_c, dif_c);
+}
+
+// =========================================================================================================
+// LW (after lw_down_kernel: clear-sky flux_dn sums, flux_dn at cloud top and at the surface per g-point)
+// =========================================================================================================
+__global__ void __launch_bounds__(TC_LW_THREADS, 2)
+tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
+  const bool act = g < NG_LW;
+  const int gg = act ? g : 0;
+  double* sums = reinterpret_cast<double*>(smem_raw);     // [4][nl1]: up_clear, up, dn, deriv
+  double* tile = sums + 4 * nl1;                           // [2][TC_LCH][TC_LW_RS]
+  double* red = tile + 2 * TC_LCH * TC_LW_RS;              // [8] block reduction scratch
+  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(red + 8), w, in, c, nlev, TC_LW_THREADS);
+  const size_t n = (size_t)nlev * NG_LW;
+  const double* od = w.od_lw + (size_t)c * n;
+  const double* pl = w.planck + (size_t)c * nl1 * NG_LW;
+  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
+  const double* gsum = w.lw_sums + (size_t)c * 6 * nl1;     // row 0: clear-sky flux_dn sums (lw_down_kernel)
+  const double* carry = w.lw_carry + (size_t)c * 4 * NG_LW;
+  double* scr = w.scr_lw + (size_t)c * TC_LW_ARRAYS * n;
+#define SCR(jr, f, i) scr[(size_t)((jr) * 5 + (f)) * n + (i)]   // fields: a b talb tsrc trans
+  const int ict = w.ict[c];                                  // first cloudy layer (0-based), nlev if none
+  const int b = T.meta->band_of_g_lw[gg];
+  const double emission = w.emission[(size_t)c * NG_LW + gg], albedo = w.lw_albedo[(size_t)c * NG_LW + gg];
+  const double fd_surf_clear = carry[NG_LW + gg];
+  const double fd_ict = ict < nlev ? carry[gg] : fd_surf_clear;   // clear-sky flux_dn at the cloud-top half-level
+  double* s_up_c = sums, *s_up = sums + nl1, *s_dn = sums + 2 * nl1, *s_dv = sums + 3 * nl1;
+
+  // ---- upward sweep (radiation_tripleclouds_lw.F90:215-420) ----
+  double ta[3] = {albedo, albedo, albedo}, ts[3];
+#pragma unroll
+  for (int jr = 0; jr < 3; ++jr) ts[jr] = S.reg[(nlev - 1) * 3 + jr] * emission;
+  double fuc = emission + albedo * fd_surf_clear;           // clear-sky flux_up at the surface
+  double fu = ts[0] + ta[0] * fd_ict;                       // all-sky flux_up at cloud top (valid as is if no cloud)
+  const double fuc_surf = fuc;
+  {
+    double* dst[2] = {s_up_c, s_up};
+    int slot = 0, lfirst = nlev;
+    if (act) { tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = fu; }
+    ++slot;
+    double pb = act ? pl[(size_t)nlev * NG_LW + g] : 0.0;
+    for (int l = nlev - 1; l >= 0; --l) {
+      const int jl = l + 1;
+      if (act) {
+        const size_t i = (size_t)l * NG_LW + g;
+        const double odg = od[i], pt = pl[i];
+        const LwLayer Lc = lw_no_scat(odg, pt, pb);
+        fuc = Lc.trans * fuc + Lc.source_up;
+        if (l >= ict) {
+          const bool cloudy_layer = !S.clear[jl];
+          double below[3] = {0.0, 0.0, 0.0}, sbelow[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int jr = 0; jr < 3; ++jr) {
+            if (jr > 0 && !cloudy_layer) { SCR(jr, 4, i) = 1.0; continue; }
+            LwLayer L = Lc;
+            if (jr > 0) {   // radiation_tripleclouds_lw.F90:247-300
+              const double* clb = cl + (size_t)l * 3 * NB_LW;
+              const double od_cloud_new = clb[b] * S.ods[l * 3 + jr];
+              const double od_total = odg + od_cloud_new;
+              if (cfg.do_lw_cloud_scattering) {
+                double ssa_total = 0.0, g_total = 0.0;
+                if (od_total > 0.0) ssa_total = clb[NB_LW + b] * od_cloud_new / od_total;
+                if (ssa_total > 0.0 && od_total > 0.0) g_total = clb[2 * NB_LW + b] * clb[NB_LW + b] * od_cloud_new / (ssa_total * od_total);
+                L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
+              } else {
+                L = lw_no_scat(od_total, pt, pb);
+              }
+            }
+            double su = L.source_up, sd = L.source_dn;
+            if (cloudy_layer) { su = S.reg[l * 3 + jr] * su; sd = S.reg[l * 3 + jr] * sd; }
+            const double id = 1.0 / (1.0 - ta[jr] * L.ref);
+            SCR(jr, 0, i) = L.trans * id;
+            SCR(jr, 1, i) = (L.ref * ts[jr] + sd) * id;
+            SCR(jr, 2, i) = ta[jr]; SCR(jr, 3, i) = ts[jr]; SCR(jr, 4, i) = L.trans;
+            below[jr] = L.ref + L.trans * L.trans * ta[jr] * id;
+            sbelow[jr] = su + L.trans * (ts[jr] + ta[jr] * sd) * id;
+          }
+          if (S.clear[jl] && S.clear[jl - 1]) {
+#pragma unroll
+            for (int jr = 0; jr < 3; ++jr) { ta[jr] = below[jr]; ts[jr] = sbelow[jr]; }
+          } else {
+            const double* U = S.U + l * 9; const double* V = S.V + l * 9;
+#pragma unroll
+            for (int j1 = 0; j1 < 3; ++j1) {
+              double a = 0.0, sacc = 0.0;
+#pragma unroll
+              for (int j2 = 0; j2 < 3; ++j2) { sacc = sacc + U[j1 * 3 + j2] * sbelow[j2]; a = a + below[j2] * V[j2 * 3 + j1]; }
+              ts[j1] = sacc; ta[j1] = a;
+            }
+          }
+          if (l == ict) fu = ts[0] + ta[0] * fd_ict;   // flux_up(:,1) at cloud top
+        } else {
+          fu = Lc.trans * fu + Lc.source_up;            // above cloud top
+        }
+        pb = pt;
+        tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = l <= ict ? fu : 0.0;
+      }
+      ++slot;
+      if (slot == TC_LCH || l == 0) { flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
+    }
+  }
+  const double fu_toa = fu, fuc_toa = fuc;
+  // ---- downward sweep from cloud top (radiation_tripleclouds_lw.F90:470-540) ----
+  double fdn[3], fup[3] = {fu, 0.0, 0.0};
+#pragma unroll
+  for (int jr = 0; jr < 3; ++jr) fdn[jr] = S.V[ict * 9 + jr * 3 + 0] * fd_ict;
+  if (ict < nlev) {
+    double* dst[2] = {s_up, s_dn};
+    int slot = 0, lfirst = ict + 1;
+    for (int l = ict; l < nlev; ++l) {
+      const int jl = l + 1;
+      if (act) {
+        const size_t i = (size_t)l * NG_LW + g;
+#pragma unroll
+        for (int jr = 0; jr < 3; ++jr) {
+          if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
+          fdn[jr] = SCR(jr, 0, i) * fdn[jr] + SCR(jr, 1, i);
+          fup[jr] = SCR(jr, 3, i) + fdn[jr] * SCR(jr, 2, i);
+        }
+        if (!(S.clear[jl] && S.clear[jl + 1])) mat3_x_vec(S.V + jl * 9, fdn);
+        tile[slot * TC_LW_RS + g] = fup[0] + fup[1] + fup[2];
+        tile[(TC_LCH + slot) * TC_LW_RS + g] = fdn[0] + fdn[1] + fdn[2];
+      }
+      ++slot;
+      if (slot == TC_LCH || l == nlev - 1) { flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0; }
+    }
+  }
+  const double dn_surf_g = fdn[0] + fdn[1] + fdn[2];
+  // ---- derivatives: calc_lw_derivatives_region (weights = last flux_up, i.e. the surface one unless the column is cloud free) ----
+  const bool want_dv = cfg.do_lw_derivatives && out.lw_derivatives;
+  if (want_dv) {
+    const double fus = fup[0] + fup[1] + fup[2];
+    // block sum of fus (same order of partial sums as flush_tile is not required: only a normalisation)
+    __syncthreads();
+    if (act) tile[g] = fus;
+    __syncthreads();
+    if (g == 0) { double s = 0.0; for (int k = 0; k < NG_LW; ++k) s = s + tile[k]; red[0] = s; }
+    __syncthreads();
+    double d[3] = {fus / red[0], 0.0, 0.0};
+    double* dst[1] = {s_dv};
+    int slot = 0, lfirst = nlev - 1;
+    for (int l = nlev - 1; l >= 0; --l) {
+      const int jl = l + 1;
+      if (act) {
+        const size_t i = (size_t)l * NG_LW + g;
+        mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1)
+        if (l >= ict) { d[0] = d[0] * SCR(0, 4, i); d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
+        else d[0] = d[0] * exp(-ECB_LW_DIFFUSIVITY * od[i]);   // regions 2,3: transmittance = 1 above cloud top
+        tile[slot * TC_LW_RS + g] = d[0] + d[1] + d[2];
+      }
+      ++slot;
+      if (slot == TC_LCH || l == 0) { flush_tile(tile, TC_LW_RS, NG_LW, 1, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
+    }
+  }
+#undef SCR
+  __syncthreads();
+  // ---- outputs ----
+  for (int l = g; l < nl1; l += TC_LW_THREADS) {
+    const size_t o = (size_t)l * out.ld + c;
+    const double dnc = gsum[l];
+    if (out.lw_up_clear) out.lw_up_clear[o] = s_up_c[l];
+    if (out.lw_dn_clear) out.lw_dn_clear[o] = dnc;
+    if (out.lw_up) out.lw_up[o] = s_up[l];
+    if (out.lw_dn) out.lw_dn[o] = l <= ict ? dnc : s_dn[l];
+    if (want_dv) out.lw_derivatives[o] = l == nlev ? 1.0 : s_dv[l];
+  }
+  if (g == 0 && out.cloud_cover_lw) out.cloud_cover_lw[c] = w.tc_cc[c];
+  if (act) {
+    const size_t i = (size_t)c * NG_LW + g;
+    if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
+    if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fuc_toa;
+    if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
+    if (out.lw_up_toa_g) out.lw_up_toa_g[i] = fu_toa;
+  }
+  (void)fuc_surf;
+  lw_surface_canopy(T, cfg, out, c, g, act, tile, dn_surf_g);
+}
+
+// =========================================================================================================
+size_t tc_scratch_doubles_lw(int nlev) { return (size_t)TC_LW_ARRAYS * nlev * NG_LW; }
+size_t tc_scratch_doubles_sw(int nlev) { return (size_t)TC_SW_ARRAYS * nlev * NG_SW; }
+
+int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  tc_prep_kernel<<<(nc + 63) / 64, 64, 0, st>>>(cfg, in, w, nc, nlev);
+  return 1;
+}
+int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const size_t sm = sizeof(double) * (6 * (nlev + 1) + 6 * TC_LCH * TC_SW_RS + 2 * NB_SW) + tc_shared_bytes(nlev);
+  cudaFuncSetAttribute(tc_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  tc_sw_kernel<<<nc, TC_SW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+  return 1;
+}
+int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const size_t sm = sizeof(double) * (4 * (nlev + 1) + 2 * TC_LCH * TC_LW_RS + 8) + tc_shared_bytes(nlev);
+  cudaFuncSetAttribute(tc_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  tc_lw_kernel<<<nc, TC_LW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+  return 1;
+}
+
+}  // namespace ecb

@@ -104,6 +104,19 @@ def test_expexp_vs_reference_golden(handles, meridian_raw, golden_expexp):
         assert f32_ulp_err(out[nm], golden_expexp[gname]).max() <= 1.0, nm
 
 
+def test_tripleclouds_vs_reference_golden(handles, meridian_raw, golden_tripleclouds):
+    """The reference's `tripleclouds` ctest (Tripleclouds LW+SW + RRTMG + aerosols): within 1 float32 ulp of its golden file."""
+    h, orc, _ = handles(use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"]) and np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+    for nm, gname in (("lw_up", "flux_up_lw"), ("lw_dn", "flux_dn_lw"), ("sw_up", "flux_up_sw"), ("sw_dn", "flux_dn_sw"),
+                      ("sw_dn_direct", "flux_dn_direct_sw"), ("lw_up_clear", "flux_up_lw_clear"), ("sw_dn_clear", "flux_dn_sw_clear"),
+                      ("cloud_cover_sw", "cloud_cover_sw"), ("lw_derivatives", "lw_derivative")):
+        assert f32_ulp_err(out[nm], golden_tripleclouds[gname]).max() <= 1.0, nm
+
+
 def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless):
     h, orc, _ = handles(sw_solver_name="Cloudless", lw_solver_name="Cloudless")
     out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
@@ -117,6 +130,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
 @pytest.mark.parametrize("kw", [dict(), dict(overlap_scheme_name="Max-Ran"), dict(do_lw_cloud_scattering=False),
                                 dict(use_beta_overlap=True), dict(use_aerosols=True), dict(overlap_scheme_name="Exp-Exp"),
                                 dict(overlap_scheme_name="Exp-Exp", use_beta_overlap=True),
+                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True, do_lw_cloud_scattering=False),
                                 dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless")])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
