@@ -12,7 +12,7 @@
 
 namespace ecb {
 
-enum { LW_THREADS = 160, LW_RS = 141, LW_LCH_FLUX = 8 };
+enum { LW_THREADS = 160, LW_RS = 141, LW_LCH_FLUX = 8, LW_LCH_UP = 8 };
 enum { LWS_DN_C = 0, LWS_UP_C = 1, LWS_DV_C = 2, LWS_UP_A = 3, LWS_DN_A = 4, LWS_DV_A = 5 };
 
 struct LwColumn {
@@ -75,12 +75,12 @@ lw_down_kernel(DevCfg cfg, Work w, int nlev) {
 // ---------------------------------------------------------------------------------------------------------
 // upward sweep: clear-sky flux_up and derivative products; cloudy albedo/source below cloud top, flux_up above
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LW_THREADS, 3)
+__global__ void __launch_bounds__(LW_THREADS, 4)
 lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LwColumn s = lw_column(cfg, w, nlev);
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LCH][LW_RS]
-  double* fracs = tile + 3 * LCH * LW_RS;               // [nlev]
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LW_LCH_UP][LW_RS]
+  double* fracs = tile + 3 * LW_LCH_UP * LW_RS;               // [nlev]
   double* fsds = fracs + nlev;                          // [nlev]
   const int c = s.c, g = s.g, nl1 = nlev + 1;
   for (int l = g; l < nlev; l += LW_THREADS) {
@@ -106,7 +106,7 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   double A = albedo, S = emission;                  // cloudy sub-column: albedo / source of everything below
   double fu_a = 0.0, pa = 1.0;                      // cloudy flux_up (above cloud top), product of transmittances
   int slot = 0, lfirst = nlev;
-  if (s.act) { tile[g] = fu; tile[LCH * LW_RS + g] = prod; tile[2 * LCH * LW_RS + g] = 0.0; }
+  if (s.act) { tile[g] = fu; tile[LW_LCH_UP * LW_RS + g] = prod; tile[2 * LW_LCH_UP * LW_RS + g] = 0.0; }
   ++slot;
   uint4 cq = make_uint4(0, 0, 0, 0);
   double pb = s.act ? s.pl[(size_t)nlev * NG_LW + g] : 0.0;
@@ -120,7 +120,7 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
       const LwLayer Lc = lw_no_scat(odg, pt, pb);
       fu = Lc.trans * fu + Lc.source_up;
       prod = prod * Lc.trans;
-      tile[slot * LW_RS + g] = fu; tile[(LCH + slot) * LW_RS + g] = prod;
+      tile[slot * LW_RS + g] = fu; tile[(LW_LCH_UP + slot) * LW_RS + g] = prod;
       if (cloudy) {
         if (l >= ict) {
           if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
@@ -167,12 +167,12 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
           pa = pa * Lc.trans;
         }
         sP[i] = pa;
-        tile[(2 * LCH + slot) * LW_RS + g] = l <= ict ? fu_a : 0.0;
+        tile[(2 * LW_LCH_UP + slot) * LW_RS + g] = l <= ict ? fu_a : 0.0;
       }
       pb = pt;
     }
     ++slot;
-    if (slot == LCH || l == 0) { flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1); lfirst -= slot; slot = 0; }
+    if (slot == LW_LCH_UP || l == 0) { flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0; }
   }
   if (s.act) { s.carry[2 * NG_LW + g] = fu; s.carry[3 * NG_LW + g] = fu_a; }
 }
@@ -275,7 +275,7 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
   const size_t sm1 = sizeof(double) * (LCH * LW_RS) + 16;
-  const size_t sm2 = sizeof(double) * (3 * LCH * LW_RS + 2 * nlev) + 16;
+  const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * LW_RS + 2 * nlev) + 16;
   const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * LW_RS) + 16;
   lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(cfg, w, nlev);
   if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
