@@ -123,6 +123,7 @@ int ensure_work(Handle* h, int cols, int nlev) {
       sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl,                                      // lev_lw lev_sw
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, h->cfg.use_aerosols ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
       h->cfg.use_aerosols ? 8 * nc * nl * NB_LW : 0,                                         // aer_lw
+      (h->cfg.do_save_spectral_flux && h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_CLOUDLESS) ? 8 * nc * (nl + 1) * NB_SW : 0,   // sw_band_dir
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0};  // tc_reg tc_ods tc_u tc_v tc_cc
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
@@ -135,8 +136,9 @@ int ensure_work(Handle* h, int cols, int nlev) {
   w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
   w.lev_lw = (LwLev*)h->work[24].p; w.lev_sw = (SwLev*)h->work[25].p;
   w.g_sw = (double*)h->work[26].p; w.aer_sw = (double*)h->work[27].p; w.aer_lw = (double*)h->work[28].p;
-  w.tc_reg = (double*)h->work[29].p; w.tc_ods = (double*)h->work[30].p; w.tc_u = (double*)h->work[31].p;
-  w.tc_v = (double*)h->work[32].p; w.tc_cc = (double*)h->work[33].p;
+  w.sw_band_dir = (double*)h->work[29].p;
+  w.tc_reg = (double*)h->work[30].p; w.tc_ods = (double*)h->work[31].p; w.tc_u = (double*)h->work[32].p;
+  w.tc_v = (double*)h->work[33].p; w.tc_cc = (double*)h->work[34].p;
   w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
   w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
   h->w_cols = cols; h->w_nlev = nlev;
@@ -343,6 +345,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.n_albedo_sw = cfg->n_albedo_sw; d.n_emiss_lw = cfg->n_emiss_lw;
   d.n_canopy_bands_sw = cfg->n_canopy_bands_sw; d.n_canopy_bands_lw = cfg->n_canopy_bands_lw;
   d.use_aerosols = cfg->use_aerosols; d.n_aerosol_types = cfg->n_aerosol_types;
+  d.do_save_spectral_flux = cfg->do_save_spectral_flux;
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
@@ -450,7 +453,10 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     if (k >= 23 && k <= 26) return c.do_surface_sw_spectral_flux != 0 && (k < 25 || c.do_clear);
     if (k == 27 || k == 28) return c.do_canopy_fluxes_sw != 0;
     if (k == 29) return c.do_canopy_fluxes_lw != 0;
-    if (k >= 30) return false;   // per-band profiles: not produced by this build
+    if (k >= 30) {   // per-band profiles: Cloudless and Tripleclouds solvers with do_save_spectral_flux
+      const int sol = k <= 31 ? c.i_solver_lw : c.i_solver_sw;
+      return c.do_save_spectral_flux != 0 && (sol == ECRAD_SOLVER_CLOUDLESS || sol == ECRAD_SOLVER_TRIPLECLOUDS);
+    }
     return true;
   };
   for (auto& s : h->slot) s.used = false;
@@ -494,6 +500,9 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
         CK(h, cudaMemcpy2DAsync(od[k].host + c0, 8 * (size_t)ncol, op[k], 8 * (size_t)cap, 8 * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
       else if (od[k].kind == 1)
         CK(h, cudaMemcpyAsync(od[k].host + (size_t)c0 * od[k].rows, op[k], 8 * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+      else   // (nband, ncol, nlev+1): row = half-level, nt*nband contiguous values per row
+        CK(h, cudaMemcpy2DAsync(od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)ncol * od[k].rows, op[k], 8 * (size_t)cap * od[k].rows,
+                                8 * (size_t)nt * od[k].rows, nlev + 1, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     if (c.do_clouds && ip[17])   // cropped cloud fraction back into the caller's array (cloud%crop_cloud_fraction)
       CK(h, cudaMemcpy2DAsync(in->cloud_fraction + c0, 8 * (size_t)ncol, ip[17], 8 * (size_t)cap, 8 * (size_t)nt, nlev, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -529,7 +538,7 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b2
     for (int k = 0; k < N_IN; ++k) ip[k] = id[k].host ? (void*)((const char*)id[k].host + (size_t)id[k].elem * c0) : nullptr;
     for (int k = 0; k < N_OUT; ++k) {
       op[k] = nullptr;
-      if (!od[k].host || od[k].kind == 2) continue;
+      if (!od[k].host) continue;
       op[k] = od[k].kind == 0 ? (void*)(od[k].host + c0) : (void*)(od[k].host + (size_t)c0 * od[k].rows);
     }
     DevIn di; DevOut dout;

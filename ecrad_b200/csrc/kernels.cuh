@@ -56,6 +56,7 @@ struct DevCfg {
   int do_surface_sw_spectral_flux, do_canopy_fluxes_sw, do_canopy_fluxes_lw, do_clear;
   int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
   int use_aerosols, n_aerosol_types;
+  int do_save_spectral_flux;
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
 };
 
@@ -73,6 +74,7 @@ struct Work {
   int *ibegin, *iend, *ict;                       // [nc]
   uint32_t *code_lw, *code_sw;                    // [nc][ng][nlev]
   double *scr_lw, *scr_sw;                        // [nc][LW_SCR_ARRAYS*nlev*140], [nc][SW_SCR_ARRAYS*nlev*112] (separate: LW and SW chains run concurrently)
+  double *sw_band_dir;                            // [nc][nlev+1][14] mu0 * per-band direct-beam sums (spectral flux profiles)
   double *tc_reg, *tc_ods, *tc_u, *tc_v, *tc_cc;  // Tripleclouds: [nc][nlev][3] x2, [nc][nlev+1][9] x2, [nc]
   LwLev* lev_lw; SwLev* lev_sw;                   // [nc][nlev] per-layer gas-optics state (gas_prep_kernel)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)

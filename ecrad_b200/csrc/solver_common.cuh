@@ -33,6 +33,35 @@ __device__ __forceinline__ void flush_tile(const double* tile, int rs, int ng, i
   __syncthreads();
 }
 
+// Per-band sums of tile rows (do_save_spectral_flux: flux%*_band(nband, ncol, nlev+1), radiation_flux.F90 indexed_sum_profile).
+// Output k (k < nout) = sa[k] * sum_{g in band} row(fa[k]) [+ sb[k] * sum_{g in band} row(fb[k]) if fb[k] >= 0] [+ add[k][...]],
+// written to dst[k][((level * ld) + c) * nb + band]; g-points are summed in ascending order like the reference.
+// Call BEFORE flush_tile (it starts with a barrier; the tile is only read here).
+struct BandOut { double* dst; int ld; int fa, fb; double sa, sb; const double* add; int add_ld; };   // add: optional addend, same layout with its own ld
+__device__ __forceinline__ void flush_bands(const double* tile, int rs, int lch, int ns, const BandOut* bo, int nout, int lfirst, int dir,
+                                            int c, int nb, const BandMeta* bands) {
+  __syncthreads();
+  const int ntask = nout * ns * nb;
+  for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
+    const int k = t / (ns * nb), r = t - k * ns * nb, s = r / nb, b = r - s * nb;
+    const BandOut& o = bo[k];
+    if (!o.dst) continue;
+    const int g0 = bands[b].g0, ng = bands[b].ng, level = lfirst + dir * s;
+    const double* ra = tile + (size_t)(o.fa * lch + s) * rs + g0;
+    double acc = 0.0;
+    for (int g = 0; g < ng; ++g) acc = acc + ra[g];
+    double v = o.sa * acc;
+    if (o.fb >= 0) {
+      const double* rb = tile + (size_t)(o.fb * lch + s) * rs + g0;
+      double accb = 0.0;
+      for (int g = 0; g < ng; ++g) accb = accb + rb[g];
+      v = v + o.sb * accb;
+    }
+    if (o.add) v = v + o.add[((size_t)level * o.add_ld + c) * nb + b];
+    o.dst[((size_t)level * o.ld + c) * nb + b] = v;
+  }
+}
+
 __device__ __forceinline__ uint32_t pick4(const uint4& q, int k) { return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w; }
 
 // optical-depth scaling of this (g, layer) from the generator's code word
@@ -106,6 +135,11 @@ __device__ __forceinline__ void sw_night_column(const DevCfg& cfg, const DevOut&
   if (g < NB_SW) {
     double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
     for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
+  }
+  if (cfg.do_save_spectral_flux && cfg.solver_sw != 2) {
+    double* pb[3] = {out.sw_up_band, out.sw_dn_band, out.sw_dn_direct_band};
+    for (int k = 0; k < 3; ++k)
+      if (pb[k]) for (int i = g; i < nl1 * NB_SW; i += nthreads) pb[k][((size_t)(i / NB_SW) * out.ld + c) * NB_SW + (i % NB_SW)] = 0.0;
   }
   if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
     if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;

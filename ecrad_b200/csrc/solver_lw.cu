@@ -43,12 +43,14 @@ __device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, 
 // clear-sky downward flux
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LW_THREADS, 6)
-lw_down_kernel(DevCfg cfg, Work w, int nlev) {
+lw_down_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LwColumn s = lw_column(cfg, w, nlev);
   double* tile = reinterpret_cast<double*>(smem_raw);   // [1][LCH][LW_RS]
   const int g = s.g, nl1 = nlev + 1;
   double* dst[1] = {s.sums + LWS_DN_C * nl1};
+  // per-band profile of flux_dn: clear-sky = all-sky for Cloudless; Tripleclouds overwrites the levels below cloud top
+  const BandOut bo[1] = {{(cfg.do_save_spectral_flux && !s.mcica) ? out.lw_dn_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0}};
   double fd = 0.0, fd_ict = 0.0;
   int slot = 0, lfirst = 0;
   if (s.act) tile[g] = 0.0;   // flux_dn at TOA
@@ -67,7 +69,10 @@ lw_down_kernel(DevCfg cfg, Work w, int nlev) {
       tile[slot * LW_RS + g] = fd;
     }
     ++slot;
-    if (slot == LCH || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+    if (slot == LCH || l == nlev - 1) {
+      if (bo[0].dst) flush_bands(tile, LW_RS, LCH, slot, bo, 1, lfirst, 1, s.c, NB_LW, T.meta->lw);
+      flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
+    }
   }
   if (s.act) { s.carry[g] = fd_ict; s.carry[NG_LW + g] = fd; }
 }
@@ -76,7 +81,7 @@ lw_down_kernel(DevCfg cfg, Work w, int nlev) {
 // upward sweep: clear-sky flux_up and derivative products; cloudy albedo/source below cloud top, flux_up above
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LW_THREADS, 4)
-lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
+lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const LwColumn s = lw_column(cfg, w, nlev);
   double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LW_LCH_UP][LW_RS]
@@ -100,6 +105,7 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[NG_LW + s.gg];
   double* dst[3] = {s.sums + LWS_UP_C * nl1, s.sums + LWS_DV_C * nl1, s.sums + LWS_UP_A * nl1};
   const int nf = cloudy ? 3 : 2;
+  const BandOut bo[1] = {{(cfg.do_save_spectral_flux && cfg.solver_lw == 0) ? out.lw_up_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0}};   // Cloudless
   // surface
   double fu = emission + albedo * fd_surf_clear;   // clear-sky flux_up at the surface
   double prod = fu;                                 // flux_up(surface) * prod(trans) : calc_lw_derivatives_ica
@@ -172,7 +178,10 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
       pb = pt;
     }
     ++slot;
-    if (slot == LW_LCH_UP || l == 0) { flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0; }
+    if (slot == LW_LCH_UP || l == 0) {
+      if (bo[0].dst) flush_bands(tile, LW_RS, LW_LCH_UP, slot, bo, 1, lfirst, -1, c, NB_LW, T.meta->lw);
+      flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0;
+    }
   }
   if (s.act) { s.carry[2 * NG_LW + g] = fu; s.carry[3 * NG_LW + g] = fu_a; }
 }
@@ -277,10 +286,10 @@ int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   const size_t sm1 = sizeof(double) * (LCH * LW_RS) + 16;
   const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * LW_RS + 2 * nlev) + 16;
   const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * LW_RS) + 16;
-  lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(cfg, w, nlev);
+  lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(T, cfg, out, w, nlev);
   if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
   cudaFuncSetAttribute(lw_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  lw_up_kernel<<<nc, LW_THREADS, sm2, st>>>(T, cfg, in, w, nlev, nlevp);
+  lw_up_kernel<<<nc, LW_THREADS, sm2, st>>>(T, cfg, in, out, w, nlev, nlevp);
   lw_flux_kernel<<<nc, LW_THREADS, sm3, st>>>(T, cfg, out, w, nlev);
   return 3;
 }

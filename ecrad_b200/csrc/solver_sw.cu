@@ -60,7 +60,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 // ---------------------------------------------------------------------------------------------------------
 template <bool CLOUDLESS>
 __global__ void __launch_bounds__(SW_THREADS, 6)
-sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
+sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
   if (!(s.mu0 > 0.0)) return;
@@ -78,6 +78,10 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   double* sums = w.sw_sums + (size_t)s.c * 6 * nl1;
   double* dst[2] = {sums, sums + 3 * nl1};
   const int nf = s.cloudy ? 2 : 1;
+  // Cloudless + do_save_spectral_flux: per-band direct beam (x mu0); also kept in scratch for sw_dn_band (sw_flux_kernel)
+  const bool bands = CLOUDLESS && cfg.do_save_spectral_flux && (out.sw_dn_direct_band || out.sw_dn_band);
+  const BandOut bo[2] = {{bands ? out.sw_dn_direct_band : nullptr, out.ld, 0, -1, s.mu0, 0.0, nullptr, 0},
+                         {bands ? w.sw_band_dir : nullptr, (int)gridDim.x, 0, -1, s.mu0, 0.0, nullptr, 0}};
   const double inv_mu0 = 1.0 / s.mu0;
   double fc = w.incoming[(size_t)s.c * NG_SW + s.gg], fa = fc;
   int slot = 0, lfirst = 0;
@@ -111,10 +115,14 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       fa = fa * tdir_a;
     }
     ++slot;
-    if (slot == LCH) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0; }
+    if (slot == LCH) {
+      if (bands) flush_bands(tile, SW_RS, LCH, slot, bo, 2, lfirst, 1, s.c, NB_SW, T.meta->sw);
+      flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
+    }
   }
   if (s.act) { tile[slot * SW_RS + g] = fc; tile[(LCH + slot) * SW_RS + g] = fa; }
   ++slot;
+  if (bands) flush_bands(tile, SW_RS, LCH, slot, bo, 2, lfirst, 1, s.c, NB_SW, T.meta->sw);
   flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1);
   if (s.act) {
     double* carry = w.sw_carry + (size_t)s.c * 4 * NG_SW;
@@ -228,6 +236,11 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
       if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = 0.0;
       if (out.sw_dn_direct_clear) OUT2(out.sw_dn_direct_clear, l) = 0.0;
     }
+    if (cfg.solver_sw == 0 && cfg.do_save_spectral_flux) {   // Cloudless: per-band profiles (radiation_cloudless_sw.F90)
+      double* pb[3] = {out.sw_up_band, out.sw_dn_band, out.sw_dn_direct_band};
+      for (int k = 0; k < 3; ++k)
+        if (pb[k]) for (int i = g; i < nl1 * NB_SW; i += SW_THREADS) pb[k][((size_t)(i / NB_SW) * out.ld + c) * NB_SW + (i % NB_SW)] = 0.0;
+    }
     if (act) {
       const size_t i = (size_t)c * NG_SW + g;
       double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
@@ -259,6 +272,10 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
   {
     double* dst[4] = {s_dn_c, s_up_c, s_dn, s_up};
     const int nf = cloudy ? 4 : 2;
+    // Cloudless + do_save_spectral_flux: sw_up_band = band sums of flux_up; sw_dn_band = mu0 * direct (scratch) + diffuse
+    const bool bands = cfg.solver_sw == 0 && cfg.do_save_spectral_flux && (out.sw_up_band || out.sw_dn_band);
+    const BandOut bo[2] = {{bands ? out.sw_up_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0},
+                           {bands ? out.sw_dn_band : nullptr, out.ld, 0, -1, 1.0, 0.0, w.sw_band_dir, (int)gridDim.x}};
     int slot = 0, lfirst = 0;
     if (act) {
       tile[slot * SW_RS + g] = 0.0; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = toa_c;
@@ -289,7 +306,10 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
             }
           }
           ++slot;
-          if (slot == SW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0; }
+          if (slot == SW_LCH_FLUX || l == nlev - 1) {
+            if (bands) flush_bands(tile, SW_RS, SW_LCH_FLUX, slot, bo, 2, lfirst, 1, c, NB_SW, T.meta->sw);
+            flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0;
+          }
         }
       }
     }
@@ -342,11 +362,11 @@ int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, con
   if (cfg.solver_sw == 4) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
   const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
-    sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
     if (aer) sw_adding_kernel<false, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
     else sw_adding_kernel<false, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   } else {
-    sw_direct_kernel<true><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_direct_kernel<true><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
     if (aer) sw_adding_kernel<true, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
     else sw_adding_kernel<true, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   }

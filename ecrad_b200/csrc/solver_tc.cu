@@ -164,6 +164,10 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   double ddc = inc, fdc = 0.0, fuc = ddc * tdc;
   const double toa_a = fup[0] + fup[1] + fup[2], toa_c = fuc;
   double* dst[6] = {sums, sums + nl1, sums + 2 * nl1, sums + 3 * nl1, sums + 4 * nl1, sums + 5 * nl1};
+  // do_save_spectral_flux: per-band all-sky profiles (radiation_tripleclouds_sw.F90:604-624)
+  const bool bands = cfg.do_save_spectral_flux && (out.sw_up_band || out.sw_dn_band || out.sw_dn_direct_band);
+  const BandOut bo[3] = {{out.sw_up_band, out.ld, 0, -1, 1.0, 0.0, nullptr, 0}, {out.sw_dn_direct_band, out.ld, 2, -1, mu0, 0.0, nullptr, 0},
+                         {out.sw_dn_band, out.ld, 2, 1, mu0, 1.0, nullptr, 0}};
   int slot = 0, lfirst = 0;
 #define PUT_ROWS()                                                                                        \
   if (act) {                                                                                              \
@@ -197,7 +201,10 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
       }
     }
     PUT_ROWS();
-    if (slot == TC_LCH || l == nlev - 1) { flush_tile(tile, TC_SW_RS, NG_SW, 6, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0; }
+    if (slot == TC_LCH || l == nlev - 1) {
+      if (bands) flush_bands(tile, TC_SW_RS, TC_LCH, slot, bo, 3, lfirst, 1, c, NB_SW, T.meta->sw);
+      flush_tile(tile, TC_SW_RS, NG_SW, 6, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
+    }
   }
 #undef PUT_ROWS
 #undef SCR
@@ -262,6 +269,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   const double fuc_surf = fuc;
   {
     double* dst[2] = {s_up_c, s_up};
+    const BandOut bo[1] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = nlev;
     if (act) { tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = fu; }
     ++slot;
@@ -323,7 +331,10 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = l <= ict ? fu : 0.0;
       }
       ++slot;
-      if (slot == TC_LCH || l == 0) { flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
+      if (slot == TC_LCH || l == 0) {
+        if (bo[0].dst) flush_bands(tile, TC_LW_RS, TC_LCH, slot, bo, 1, lfirst, -1, c, NB_LW, T.meta->lw);
+        flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0;
+      }
     }
   }
   const double fu_toa = fu, fuc_toa = fuc;
@@ -333,6 +344,8 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   for (int jr = 0; jr < 3; ++jr) fdn[jr] = S.V[ict * 9 + jr * 3 + 0] * fd_ict;
   if (ict < nlev) {
     double* dst[2] = {s_up, s_dn};
+    const BandOut bo[2] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0},
+                           {cfg.do_save_spectral_flux ? out.lw_dn_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = ict + 1;
     for (int l = ict; l < nlev; ++l) {
       const int jl = l + 1;
@@ -349,7 +362,10 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         tile[(TC_LCH + slot) * TC_LW_RS + g] = fdn[0] + fdn[1] + fdn[2];
       }
       ++slot;
-      if (slot == TC_LCH || l == nlev - 1) { flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0; }
+      if (slot == TC_LCH || l == nlev - 1) {
+        if (bo[0].dst || bo[1].dst) flush_bands(tile, TC_LW_RS, TC_LCH, slot, bo, 2, lfirst, 1, c, NB_LW, T.meta->lw);
+        flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
+      }
     }
   }
   const double dn_surf_g = fdn[0] + fdn[1] + fdn[2];

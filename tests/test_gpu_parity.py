@@ -22,6 +22,20 @@ OTHERS = ["lw_derivatives", "lw_dn_surf_g", "lw_dn_surf_clear_g", "lw_up_toa_g",
           "sw_dn_direct_surf_g", "sw_dn_diffuse_surf_clear_g", "sw_dn_direct_surf_clear_g", "sw_up_toa_g", "sw_up_toa_clear_g",
           "sw_dn_surf_band", "sw_dn_direct_surf_band", "sw_dn_surf_clear_band", "sw_dn_direct_surf_clear_band",
           "sw_dn_diffuse_surf_canopy", "sw_dn_direct_surf_canopy", "lw_dn_surf_canopy"]
+BANDS = ["lw_up_band", "lw_dn_band", "sw_up_band", "sw_dn_band", "sw_dn_direct_band"]   # flux%*_band(nband, ncol, nlev+1)
+BANDS_GOLDEN = {"lw_up_band": "spectral_flux_up_lw", "lw_dn_band": "spectral_flux_dn_lw", "sw_up_band": "spectral_flux_up_sw",
+                "sw_dn_band": "spectral_flux_dn_sw", "sw_dn_direct_band": "spectral_flux_dn_direct_sw"}
+
+
+def check_band_profiles(out, ref, golden):
+    """Per-band profiles (do_save_spectral_flux): vs the oracle, vs the golden file's stored half-levels, and band sums = broadband."""
+    compare(out, ref, BANDS)
+    lev = golden["band_levels"]
+    for nm, gname in BANDS_GOLDEN.items():
+        a = np.transpose(out[nm], (1, 2, 0))[:, lev, :]   # (nband, ncol, nlev+1) -> (ncol, levels, nband)
+        assert f32_ulp_err(a, golden[gname]).max() <= 1.0, nm
+    for nm in BANDS:
+        assert np.abs(out[nm].sum(axis=0) - out[nm[:-5]]).max() <= 1e-9, nm
 
 
 @pytest.fixture(scope="module")
@@ -107,9 +121,10 @@ def test_expexp_vs_reference_golden(handles, meridian_raw, golden_expexp):
 def test_tripleclouds_vs_reference_golden(handles, meridian_raw, golden_tripleclouds):
     """The reference's `tripleclouds` ctest (Tripleclouds LW+SW + RRTMG + aerosols): within 1 float32 ulp of its golden file."""
     h, orc, _ = handles(use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")
-    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
-    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, spectral_profiles=True)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, spectral_profiles=True)
     compare(out, ref, FLUXES + OTHERS)
+    check_band_profiles(out, ref, golden_tripleclouds)
     assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"]) and np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
     for nm, gname in (("lw_up", "flux_up_lw"), ("lw_dn", "flux_dn_lw"), ("sw_up", "flux_up_sw"), ("sw_dn", "flux_dn_sw"),
                       ("sw_dn_direct", "flux_dn_direct_sw"), ("lw_up_clear", "flux_up_lw_clear"), ("sw_dn_clear", "flux_dn_sw_clear"),
@@ -119,9 +134,10 @@ def test_tripleclouds_vs_reference_golden(handles, meridian_raw, golden_triplecl
 
 def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless):
     h, orc, _ = handles(sw_solver_name="Cloudless", lw_solver_name="Cloudless")
-    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
-    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV)
+    out = h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, spectral_profiles=True)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, spectral_profiles=True)
     compare(out, ref, FLUXES + OTHERS)
+    check_band_profiles(out, ref, golden_cloudless)
     for nm, gname in (("lw_up", "flux_up_lw"), ("lw_dn", "flux_dn_lw"), ("sw_up", "flux_up_sw"), ("sw_dn", "flux_dn_sw"),
                       ("sw_dn_direct", "flux_dn_direct_sw")):
         assert f32_ulp_err(out[nm], golden_cloudless[gname]).max() <= 1.0, nm
@@ -184,6 +200,34 @@ def test_tiling_is_invisible(meridian_raw):
     for nm in FLUXES + OTHERS + ["cloud_cover_sw", "cloud_cover_lw", "cloud_fraction"]:
         assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
         assert np.array_equal(outs[0][nm], outs[2][nm], equal_nan=True), nm
+
+
+@pytest.mark.parametrize("solver", ["Tripleclouds", "Cloudless"])
+def test_band_profiles_synthetic_and_tiled(handles, meridian_raw, solver):
+    """Per-band profiles on perturbed columns (night columns included), and the same through ragged column tiles."""
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    n = 150
+    raw = I.synthetic_columns(meridian_raw, n)
+    h, orc, cfg = handles(sw_solver_name=solver, lw_solver_name=solver, use_aerosols=True)
+    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV, spectral_profiles=True)
+    ref = orc.radiation(I.to_radiation_inputs(raw), n, NLEV, spectral_profiles=True)
+    compare(out, ref, FLUXES + BANDS)
+    os.environ["ECRAD_B200_TILE"] = "64"
+    try:
+        h2 = setup_radiation(cfg)
+    finally:
+        del os.environ["ECRAD_B200_TILE"]
+    out2 = h2.radiation(I.to_radiation_inputs(raw), n, NLEV, spectral_profiles=True)
+    h2.finalize()
+    for nm in FLUXES + BANDS:
+        assert np.array_equal(out[nm], out2[nm]), nm
+    # do_save_spectral_flux = false: the band arrays are left untouched
+    h3 = setup_radiation(RadiationConfig(sw_solver_name=solver, lw_solver_name=solver, do_save_spectral_flux=False).consolidate())
+    out3 = h3.radiation(I.to_radiation_inputs(raw), n, NLEV, spectral_profiles=True)
+    h3.finalize()
+    for nm in BANDS:
+        assert np.isnan(out3[nm]).all(), nm
 
 
 def test_all_night_and_all_clear_edge_cases(handles, meridian_raw):
