@@ -12,6 +12,8 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 
 from . import abi
@@ -93,12 +95,45 @@ class RadiationConfig:
     i_aerosol_type_map: tuple = (-1, -2, -3, 7, 8, 9, -4, 10, 11, 11, -5, 14)
     min_gas_od_lw: float = 1.0e-15
     min_gas_od_sw: float = 0.0
+    # gas_model_name = "ECCKD": table blob made by tools/extract_ecckd_tables.py (file name inside ecrad_b200/data/, or a
+    # path); stands for gas_optics_{sw,lw}_override_file_name + the general cloud / aerosol optics files.  Cloud and
+    # aerosol optics are per g-point (do_cloud_aerosol_per_{sw,lw}_g_point = true, radiation_config.F90 defaults for ecCKD).
+    ecckd_tables: str = "ecckd_tables_32b.bin"
     derived: dict = field(default_factory=dict)
+    n_g: tuple = (112, 140)      # (n_g_sw, n_g_lw), set by consolidate()
+    n_bands: tuple = (14, 16)    # (n_bands_sw, n_bands_lw)
+
+    @property
+    def is_ecckd(self):
+        return self.gas_model_name.lower() == "ecckd"
+
+    def tables_path(self):
+        """The table blob `setup_radiation` loads for this configuration."""
+        here = os.path.dirname(os.path.abspath(__file__))
+        if not self.is_ecckd:
+            return os.path.join(here, "data", "rrtmg_tables.bin")
+        return self.ecckd_tables if os.path.isabs(self.ecckd_tables) else os.path.join(here, "data", self.ecckd_tables)
 
     def consolidate(self):
         """Tables derived from the config (what `setup_radiation` stores in config_type)."""
-        w = mapping_from_bands(SW_WN1, SW_WN2, SOLAR_REF_T, self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
-        e = mapping_from_bands(LW_WN1, LW_WN2, TERRESTRIAL_REF_T, self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
+        if self.do_canopy_fluxes_sw:   # radiation_config.F90:1119-1124
+            self.do_surface_sw_spectral_flux = True
+        if self.is_ecckd:
+            # consolidate_sw_albedo_intervals / consolidate_lw_emiss_intervals (radiation_config.F90:1947-2100) with the
+            # model's own spectral definition, one weight vector per g-point; bands == g-points
+            # (radiation_ecckd_interface.F90:46-76)
+            from .spectral import SpectralDefinition
+            from .tables import read_blob
+            tabs = read_blob(self.tables_path())
+            sd_sw, sd_lw = SpectralDefinition.from_tables(tabs, "ckd_sw_"), SpectralDefinition.from_tables(tabs, "ckd_lw_")
+            w = sd_sw.calc_mapping_from_bands(self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
+            e = sd_lw.calc_mapping_from_bands(self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
+            self.n_g = (sd_sw.ng, sd_lw.ng)
+            self.n_bands = (sd_sw.ng, sd_lw.ng)
+        else:
+            w = mapping_from_bands(SW_WN1, SW_WN2, SOLAR_REF_T, self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
+            e = mapping_from_bands(LW_WN1, LW_WN2, TERRESTRIAL_REF_T, self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
+            self.n_g, self.n_bands = (112, 140), (14, 16)
         self.derived = {
             "sw_albedo_weights": np.asfortranarray(w),                                   # (n_albedo, 14)
             "i_emiss_from_band_lw": (np.argmax(e, axis=0) + 1).astype(np.int32),         # maxloc(dim=1)
@@ -130,7 +165,8 @@ class RadiationConfig:
             setattr(c, k, int(getattr(self, k)))
         # radiation_config.F90 consolidate: do_clouds is false only for the Cloudless solvers
         c.do_clouds = int(not (c.i_solver_sw == 0 and c.i_solver_lw == 0))
-        c.n_g_sw, c.n_g_lw, c.n_bands_sw, c.n_bands_lw = 112, 140, 14, 16
+        c.n_g_sw, c.n_g_lw = self.n_g
+        c.n_bands_sw, c.n_bands_lw = self.n_bands
         c.n_albedo_sw = self.derived["sw_albedo_weights"].shape[0]
         c.n_emiss_lw = max(self.i_lw_emiss_index)
         c.n_canopy_bands_sw = max(self.i_sw_albedo_index)

@@ -32,9 +32,14 @@ def read_ifs_netcdf(path):
     return raw
 
 
-def to_radiation_inputs(raw):
-    """File variables (C order: column slowest) -> radiation() inputs (Fortran order: column fastest)."""
+def to_radiation_inputs(raw, config=None):
+    """File variables (C order: column slowest) -> radiation() inputs (Fortran order: column fastest).
+
+    Gas arrays are what gas%mixing_ratio holds after set_gas_units (radiation_interface.F90:164-193): mass mixing ratios
+    for RRTMG (radiation_ifs_rrtm.F90 set_gas_units), volume mixing ratios for ecCKD (radiation_ecckd_interface.F90:148-163);
+    pass the RadiationConfig to get the latter.  The dict keys stay the C-ABI field names (`*_mmr`)."""
     F = np.asfortranarray
+    vmr = config is not None and getattr(config, "is_ecckd", False)
     d = {
         "cos_sza": raw["cos_solar_zenith_angle"].copy(),
         "skin_temperature": raw["skin_temperature"].copy(),
@@ -47,9 +52,13 @@ def to_radiation_inputs(raw):
         "re_liq": F(raw["re_liquid"]), "re_ice": F(raw["re_ice"]),
         "overlap_param": F(raw["overlap_param"]), "fractional_std": F(raw["fractional_std"]),
     }
+    if vmr:
+        # radiation_gas.F90:444-451 set_units_gas: sf = 1*AirMolarMass/GasMolarMass for the two gases given as mass mixing ratio
+        d["h2o_mmr"] = F(raw["q"] * (1.0 * AIR_MOLAR_MASS / 18.0152833))
+        d["o3_mmr"] = F(raw["o3_mmr"] * (1.0 * AIR_MOLAR_MASS / 47.9982))
     for g, m in GAS_MOLAR_MASS.items():
         sf = 1.0 * m / AIR_MOLAR_MASS  # radiation_gas.F90 set_units_gas: sf = sf*GasMolarMass/AirMolarMass
-        d[f"{g}_mmr"] = F(raw[f"{g}_vmr"] * sf)
+        d[f"{g}_mmr"] = F(raw[f"{g}_vmr"]) if vmr else F(raw[f"{g}_vmr"] * sf)
     d["solar_irradiance"] = float(raw["solar_irradiance"])
     if "aerosol_mmr" in raw:
         # file (column, type, level) -> aerosol%mixing_ratio(ncol, nlev, ntype)  (driver/ecrad_driver_read_input.F90:546)

@@ -67,10 +67,11 @@ def load_library():
 class RadiationHandle:
     """What `setup_radiation` leaves behind: the config plus the device-side tables (radiation_interface.F90:37-156)."""
 
-    def __init__(self, config: RadiationConfig, tables_path: str = DEFAULT_TABLES, tables_blob: bytes = None):
+    def __init__(self, config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None):
         L = load_library()
         self.lib = L
         self.config = config
+        tables_path = tables_path or config.tables_path()
         self.cfg = config.to_struct()
         t = L.ecrad_b200_tables_create()
         try:
@@ -141,7 +142,7 @@ class RadiationHandle:
             pass
 
 
-def setup_radiation(config: RadiationConfig, tables_path: str = DEFAULT_TABLES, tables_blob: bytes = None) -> RadiationHandle:
+def setup_radiation(config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None) -> RadiationHandle:
     """tables_blob: the ETB1 image as bytes (e.g. received by a broadcast) instead of a file path."""
     if not config.derived:
         config.consolidate()

@@ -20,6 +20,22 @@
 #define NB_LW 16
 #define NB_SW 14
 
+/* ---- ecCKD model (radiation_ecckd.F90:34-118 ckd_model_type, radiation_ecckd_gas.F90:38-72 ckd_gas_type) ---- */
+enum { ORC_CONC_NONE = 0, ORC_CONC_LINEAR = 1, ORC_CONC_LUT = 2, ORC_CONC_RELATIVE_LINEAR = 3 };
+typedef struct {
+  int code, dep, n_mole_frac;       /* code: radiation_gas_constants.F90:26-39, 0 = composite of well-mixed gases */
+  double reference_mole_frac, log_mole_frac1, d_log_mole_frac;
+  const double* molar_abs;          /* (ng, npress, ntemp [, n_mole_frac]) */
+} orc_ckd_gas;
+typedef struct {
+  int ng, npress, ntemp, nplanck, ngas, is_sw;
+  double log_pressure1, d_log_pressure, d_temperature, temperature1_planck, d_temperature_planck;
+  const double *temperature1, *planck_function /*(ng, nplanck)*/, *norm_solar_irradiance, *rayleigh_molar_scat;
+  orc_ckd_gas gas[16];
+} orc_ckd_model;
+/* generalised cloud optics of one cloud type (radiation_general_cloud_optics_data.F90:33-62) */
+typedef struct { int nre; double re0, dre; const double *mass_ext, *ssa, *asymmetry; /* (ng, nre) */ } orc_gco;
+
 /* ---- named-array tables (ETB1 blob) ---- */
 typedef struct { char name[48]; int dtype; int ndim; int64_t dims[4]; const void* data; } orc_array;
 typedef struct orc_tables {
@@ -44,8 +60,15 @@ typedef struct orc_tables {
   const double *aer_me_sw_philic, *aer_ssa_sw_philic, *aer_g_sw_philic, *aer_me_lw_philic, *aer_ssa_lw_philic, *aer_g_lw_philic;
   const double *aer_rh_lower; int aer_nrh;
   const int32_t *aer_iclass, *aer_itype;  /* (n_aerosol_types): 0 ignored / 1 hydrophobic / 2 hydrophilic; 1-based type */
-  const double *sw_albedo_weights;      /* (n_albedo_sw, 14) */
-  const int32_t *i_emiss_from_band_lw;  /* (16), 1-based */
+  const double *sw_albedo_weights;      /* (n_albedo_sw, n_bands_sw) */
+  const int32_t *i_emiss_from_band_lw;  /* (n_bands_lw), 1-based */
+  const double *lw_emiss_weights;       /* (n_emiss_lw, n_bands_lw), used when !do_nearest_spectral_lw_emiss */
+  /* 0-based band of each g-point: RRTMG ngb-1 / ngb-16; ecCKD with per-g-point cloud/aerosol optics: identity */
+  int32_t band_lw[256], band_sw[256];
+  /* ecCKD gas optics + generalised cloud optics (blob of tools/extract_ecckd_tables.py) */
+  int is_ecckd;
+  orc_ckd_model ckd_lw, ckd_sw;
+  orc_gco gco_lw[2], gco_sw[2];         /* cloud types: 0 liquid (mie_droplet), 1 ice (baum-general-habit-mixture) */
 } orc_tables;
 
 orc_tables* orc_tables_load(const char* path);
@@ -116,6 +139,15 @@ void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_sc
                          double frac_threshold, const double* frac, const double* overlap_param,
                          double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,
                          double* od_scaling /*[nlev][ng]*/, double* total_cloud_cover);
+
+/* ecckd.c */
+void orc_ecckd_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
+                                 const ecrad_b200_inputs* in, const double* lw_albedo, double* od_lw, double* planck_hl,
+                                 double* lw_emission, double* od_sw, double* ssa_sw, double* incoming_sw);
+void orc_general_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl,
+                              const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
+                              const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
+                              double* od_sw, double* ssa_sw, double* g_sw);
 
 /* tripleclouds.c */
 typedef struct {

@@ -16,6 +16,16 @@
 
 #define A2(p, jcol, j) ((p)[(size_t)(j) * ncol + (jcol)]) /* (ncol, n) column-fastest, 0-based */
 
+/* spectral sizes come from the configuration here (RRTMG 140/112 g-points in 16/14 bands; ecCKD: bands == g-points) */
+#undef NG_LW
+#undef NG_SW
+#undef NB_LW
+#undef NB_SW
+#define NG_LW (cfg->n_g_lw)
+#define NG_SW (cfg->n_g_sw)
+#define NB_LW (cfg->n_bands_lw)
+#define NB_SW (cfg->n_bands_sw)
+
 typedef struct {
   double *od_lw, *planck_hl, *lw_emission, *lw_albedo;         /* [nlev][140], [nlev+1][140], [140], [140] */
   double *od_sw, *ssa_sw, *g_sw, *incoming_sw, *alb_dir, *alb_diff;   /* [nlev][112] x3, [112] x3 */
@@ -26,8 +36,8 @@ typedef struct {
 /* get_albedos, radiation_single_level.F90:216-365 (paths used by test/ifs/configCY49R1.nam) */
 static int get_albedos(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int jcol,
                        const ecrad_b200_inputs* in, double* alb_dir, double* alb_diff, double* lw_albedo) {
-  if (cfg->do_nearest_spectral_sw_albedo || !cfg->do_nearest_spectral_lw_emiss) return 1; /* not restated */
-  if (!t->sw_albedo_weights || !t->i_emiss_from_band_lw) return 2;
+  if (cfg->do_nearest_spectral_sw_albedo) return 1; /* not restated */
+  if (!t->sw_albedo_weights) return 2;
   const int nalb = cfg->n_albedo_sw;
   double band[NB_SW], band_dir[NB_SW];
   for (int jb = 0; jb < NB_SW; ++jb) {
@@ -41,13 +51,27 @@ static int get_albedos(const orc_tables* t, const ecrad_b200_config* cfg, int nc
     }
   }
   for (int g = 0; g < NG_SW; ++g) {
-    int jb = t->ngb_sw[g] - 16;
+    int jb = t->band_sw[g];
     alb_diff[g] = band[jb];
     alb_dir[g] = in->sw_albedo_direct ? band_dir[jb] : band[jb];
   }
-  for (int g = 0; g < NG_LW; ++g) {
-    int jb = t->ngb_lw[g] - 1;
-    lw_albedo[g] = 1.0 - A2(in->lw_emissivity, jcol, t->i_emiss_from_band_lw[jb] - 1);
+  if (cfg->do_nearest_spectral_lw_emiss) {
+    if (!t->i_emiss_from_band_lw) return 2;
+    for (int g = 0; g < NG_LW; ++g)
+      lw_albedo[g] = 1.0 - A2(in->lw_emissivity, jcol, t->i_emiss_from_band_lw[t->band_lw[g]] - 1);
+  } else {
+    /* weighted emissivity intervals, radiation_single_level.F90:322-345 */
+    if (!t->lw_emiss_weights) return 2;
+    const int nem = cfg->n_emiss_lw;
+    double lband[NB_LW];
+    for (int jb = 0; jb < NB_LW; ++jb) {
+      lband[jb] = 0.0;
+      for (int ja = 0; ja < nem; ++ja) {
+        double w = t->lw_emiss_weights[(size_t)jb * nem + ja];
+        if (w != 0.0) lband[jb] = lband[jb] + w * (1.0 - A2(in->lw_emissivity, jcol, ja));
+      }
+    }
+    for (int g = 0; g < NG_LW; ++g) lw_albedo[g] = lband[t->band_lw[g]];
   }
   return 0;
 }
@@ -64,7 +88,7 @@ static void planck_bands(const orc_tables* t, double temperature, double* store)
   } else {
     ind = 1; frac = 0.0;
   }
-  for (int jb = 0; jb < NB_LW; ++jb) {
+  for (int jb = 0; jb < 16; ++jb) {
     double factor = zfluxfac * t->delwave[jb];
     const double* tp = t->totplnk + (size_t)jb * 181;
     store[jb] = factor * (tp[ind - 1] + frac * (tp[ind] - tp[ind - 1]));
@@ -75,6 +99,10 @@ static void planck_bands(const orc_tables* t, double temperature, double* store)
 static void gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                               const ecrad_b200_inputs* in, const double* lw_albedo, double* od_lw, double* planck_hl,
                               double* lw_emission, double* od_sw, double* ssa_sw, double* incoming_sw) {
+  if (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) {
+    orc_ecckd_gas_optics_column(t, cfg, ncol, nlev, jcol, in, lw_albedo, od_lw, planck_hl, lw_emission, od_sw, ssa_sw, incoming_sw);
+    return;
+  }
   double* buf = (double*)malloc(sizeof(double) * (size_t)(nlev + 1) * 16);
   double *p_hl = buf, *t_hl = p_hl + (nlev + 1), *p_fl = t_hl + (nlev + 1), *t_fl = p_fl + nlev;
   double* gas[9];
@@ -96,17 +124,17 @@ static void gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg,
     orc_setcoef_lw(t, nlev, lay, &laytrop);
     orc_taumol_lw(t, nlev, lay, laytrop, tau, pfrac);
     /* planck_function_atmos :618-752 */
-    double store[NB_LW];
+    double store[16];
     for (int jlev = 1; jlev <= nlev + 1; ++jlev) {
       planck_bands(t, t_hl[jlev - 1], store);
       int ilay = (jlev == 1) ? nlev : nlev + 2 - jlev; /* RRTMG layer (1-based) whose PFRAC is used */
       for (int g = 0; g < NG_LW; ++g)
-        planck_hl[(size_t)(jlev - 1) * NG_LW + g] = store[t->ngb_lw[g] - 1] * pfrac[(size_t)(ilay - 1) * NG_LW + g];
+        planck_hl[(size_t)(jlev - 1) * NG_LW + g] = store[t->band_lw[g]] * pfrac[(size_t)(ilay - 1) * NG_LW + g];
     }
     /* planck_function_surf :757-852 and lw_emission :466 */
     planck_bands(t, in->skin_temperature[jcol], store);
     for (int g = 0; g < NG_LW; ++g) {
-      lw_emission[g] = store[t->ngb_lw[g] - 1] * pfrac[g];
+      lw_emission[g] = store[t->band_lw[g]] * pfrac[g];
       lw_emission[g] = lw_emission[g] * (1.0 - lw_albedo[g]);
     }
     /* :506-511 un-reverse + clamp */
@@ -168,7 +196,10 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
   double* factor = (double*)malloc(sizeof(double) * (size_t)nlev);
   for (size_t i = 0; i < (size_t)nlev * NG_SW; ++i) g_sw[i] = 0.0;
   for (int jl = 0; jl < nlev; ++jl) {
-    double rh = A2(in->h2o_mmr, jcol, jl) / A2(in->h2o_sat_liq, jcol, jl);
+    /* gas%mixing_ratio(:,:,IH2O) is a volume mixing ratio under ecCKD: radiation_aerosol_optics.F90:590-600 converts */
+    double h2o = A2(in->h2o_mmr, jcol, jl);
+    if (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) h2o = h2o * (18.0152833 / 28.970);
+    double rh = h2o / A2(in->h2o_sat_liq, jcol, jl);
     int irh;   /* calc_rh_index, radiation_aerosol_optics_data.F90:640-664 (1-based) */
     if (rh > t->aer_rh_lower[nrh - 1]) irh = nrh;
     else { irh = 1; while (rh > t->aer_rh_lower[irh]) irh++; }
@@ -211,7 +242,7 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
   if (cfg->do_sw)
     for (int jl = 0; jl < nlev; ++jl)
       for (int g = 0; g < NG_SW; ++g) {
-        const int ib = t->ngb_sw[g] - 16;
+        const int ib = t->band_sw[g];
         const size_t i = (size_t)jl * NG_SW + g;
         double local_od = od_sw[i] + od_sw_aer[jl * NB_SW + ib];
         if (local_od > 0.0 && od_sw_aer[jl * NB_SW + ib] > 0.0) {
@@ -224,7 +255,7 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
   if (cfg->do_lw)
     for (int jl = 0; jl < nlev; ++jl)
       for (int g = 0; g < NG_LW; ++g)
-        od_lw[(size_t)jl * NG_LW + g] = od_lw[(size_t)jl * NG_LW + g] + od_lw_aer[jl * NB_LW + (t->ngb_lw[g] - 1)];
+        od_lw[(size_t)jl * NG_LW + g] = od_lw[(size_t)jl * NG_LW + g] + od_lw_aer[jl * NB_LW + (t->band_lw[g])];
   free(od_sw_aer); free(irhs); free(factor);
 }
 
@@ -254,13 +285,13 @@ static void sum_g(int ng, int nlev1, const double* f, int ncol, int jcol, double
   }
 }
 /* indexed_sum_profile, radiation_flux.F90:820-855: band profile (nband, ncol, nlev+1) */
-static void band_profile(int ng, int nb, int nlev1, const int32_t* ngb, int off, const double* f, int ncol, int jcol,
+static void band_profile(int ng, int nb, int nlev1, const int32_t* band, const double* f, int ncol, int jcol,
                          double* out, int add) {
   if (!out) return;
   for (int jl = 0; jl < nlev1; ++jl) {
     double* o = out + ((size_t)jl * ncol + jcol) * nb;
     if (!add) for (int b = 0; b < nb; ++b) o[b] = 0.0;
-    for (int g = 0; g < ng; ++g) o[ngb[g] - off] = o[ngb[g] - off] + f[(size_t)jl * ng + g];
+    for (int g = 0; g < ng; ++g) o[band[g]] = o[band[g]] + f[(size_t)jl * ng + g];
   }
 }
 
@@ -295,8 +326,8 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = fd_clear[nl1 - ng + g];
       if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = fu_clear[g];
     }
-    band_profile(ng, NB_LW, nlev + 1, t->ngb_lw, 1, fu_clear, ncol, jcol, out->lw_up_band, 0);
-    band_profile(ng, NB_LW, nlev + 1, t->ngb_lw, 1, fd_clear, ncol, jcol, out->lw_dn_band, 0);
+    band_profile(ng, NB_LW, nlev + 1, t->band_lw, fu_clear, ncol, jcol, out->lw_up_band, 0);
+    band_profile(ng, NB_LW, nlev + 1, t->band_lw, fd_clear, ncol, jcol, out->lw_dn_band, 0);
     if (cfg->do_lw_derivatives && out->lw_derivatives)
       lw_derivatives(ng, nlev, ncol, jcol, trans_clear, fu_clear + nl1 - ng, 0.0, 0, out->lw_derivatives);
     free(pool);
@@ -319,7 +350,7 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
         is_clear[jl] = 0;
         if (i_cloud_top > jl + 1) i_cloud_top = jl + 1;
         for (int g = 0; g < ng; ++g) {
-          int jb = t->ngb_lw[g] - 1;
+          int jb = t->band_lw[g];
           double od_cloud_new = od_scaling[(size_t)jl * ng + g] * w->od_lw_cloud[jl * NB_LW + jb];
           od_total[g] = w->od_lw[(size_t)jl * ng + g] + od_cloud_new;
           ssa_total[g] = 0.0; g_total[g] = 0.0;
@@ -443,10 +474,10 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       if (out->sw_dn_direct_surf_g) OUTG(out->sw_dn_direct_surf_g, ng, g) = fdir[nl1 - ng + g];
       if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = fu[g];
     }
-    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fu, ncol, jcol, out->sw_up_band, 0);
-    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_direct_band, 0);
-    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdir, ncol, jcol, out->sw_dn_band, 0);
-    band_profile(ng, NB_SW, nlev + 1, t->ngb_sw, 16, fdd, ncol, jcol, out->sw_dn_band, 1);
+    band_profile(ng, NB_SW, nlev + 1, t->band_sw, fu, ncol, jcol, out->sw_up_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->band_sw, fdir, ncol, jcol, out->sw_dn_direct_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->band_sw, fdir, ncol, jcol, out->sw_dn_band, 0);
+    band_profile(ng, NB_SW, nlev + 1, t->band_sw, fdd, ncol, jcol, out->sw_dn_band, 1);
     free(pool);
     return;
   }
@@ -465,7 +496,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
     for (int jl = 0; jl < nlev; ++jl) {
       if (frac[jl] >= cfg->cloud_fraction_threshold) {
         for (int g = 0; g < ng; ++g) {
-          int jb = t->ngb_sw[g] - 16;
+          int jb = t->band_sw[g];
           size_t i = (size_t)jl * ng + g;
           double od_cloud_new = od_scaling[i] * w->od_sw_cloud[jl * NB_SW + jb];
           od_total[g] = w->od_sw[i] + od_cloud_new;
@@ -546,8 +577,8 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = o.up_toa_g[g];
       if (out->lw_up_toa_clear_g) OUTG(out->lw_up_toa_clear_g, ng, g) = o.up_toa_clear_g[g];
     }
-    band_profile(ng, nb, nl1, t->ngb_lw, 1, o.up_g_prof, ncol, jcol, out->lw_up_band, 0);
-    band_profile(ng, nb, nl1, t->ngb_lw, 1, o.dn_dif_g_prof, ncol, jcol, out->lw_dn_band, 0);
+    band_profile(ng, nb, nl1, t->band_lw, o.up_g_prof, ncol, jcol, out->lw_up_band, 0);
+    band_profile(ng, nb, nl1, t->band_lw, o.dn_dif_g_prof, ncol, jcol, out->lw_dn_band, 0);
   } else {
     const double mu0 = in->cos_sza[jcol];
     if (mu0 < 1.0e-10) {
@@ -582,14 +613,14 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
     }
     /* band profiles: up; dn = mu0*direct + diffuse; dn_direct = mu0*direct (radiation_tripleclouds_sw.F90:604-624) */
     if (out->sw_up_band || out->sw_dn_band || out->sw_dn_direct_band) {
-      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.up_g_prof, ncol, jcol, out->sw_up_band, 0);
-      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_direct_band, 0);
+      band_profile(ng, nb, nl1, t->band_sw, o.up_g_prof, ncol, jcol, out->sw_up_band, 0);
+      band_profile(ng, nb, nl1, t->band_sw, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_direct_band, 0);
       if (out->sw_dn_direct_band)
         for (int jl = 0; jl < nl1; ++jl) for (int b = 0; b < nb; ++b) out->sw_dn_direct_band[((size_t)jl * ncol + jcol) * nb + b] *= mu0;
-      band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_band, 0);
+      band_profile(ng, nb, nl1, t->band_sw, o.dn_dir_g_prof, ncol, jcol, out->sw_dn_band, 0);
       if (out->sw_dn_band) {
         for (int jl = 0; jl < nl1; ++jl) for (int b = 0; b < nb; ++b) out->sw_dn_band[((size_t)jl * ncol + jcol) * nb + b] *= mu0;
-        band_profile(ng, nb, nl1, t->ngb_sw, 16, o.dn_dif_g_prof, ncol, jcol, out->sw_dn_band, 1);
+        band_profile(ng, nb, nl1, t->band_sw, o.dn_dif_g_prof, ncol, jcol, out->sw_dn_band, 1);
       }
     }
   }
@@ -608,8 +639,8 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
       if (!dirb || !totb || !dirg || !difg || (pass && !cfg->do_clear)) continue;
       double* db = dirb + (size_t)jcol * NB_SW; double* tb = totb + (size_t)jcol * NB_SW;
       for (int b = 0; b < NB_SW; ++b) { db[b] = 0.0; tb[b] = 0.0; }
-      for (int g = 0; g < NG_SW; ++g) db[t->ngb_sw[g] - 16] = db[t->ngb_sw[g] - 16] + dirg[(size_t)jcol * NG_SW + g];
-      for (int g = 0; g < NG_SW; ++g) tb[t->ngb_sw[g] - 16] = tb[t->ngb_sw[g] - 16] + difg[(size_t)jcol * NG_SW + g];
+      for (int g = 0; g < NG_SW; ++g) db[t->band_sw[g]] = db[t->band_sw[g]] + dirg[(size_t)jcol * NG_SW + g];
+      for (int g = 0; g < NG_SW; ++g) tb[t->band_sw[g]] = tb[t->band_sw[g]] + difg[(size_t)jcol * NG_SW + g];
       for (int b = 0; b < NB_SW; ++b) tb[b] = tb[b] + db[b];
     }
   }
@@ -635,9 +666,24 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
     double* c = out->lw_dn_surf_canopy + (size_t)jcol * ne;
     for (int a = 0; a < ne; ++a) c[a] = 0.0;
     for (int g = 0; g < NG_LW; ++g) {
-      int a = t->i_emiss_from_band_lw[t->ngb_lw[g] - 1] - 1;
+      int a = t->i_emiss_from_band_lw[t->band_lw[g]] - 1;
       c[a] = c[a] + out->lw_dn_surf_g[(size_t)jcol * NG_LW + g];
     }
+  }
+  if (cfg->do_lw && cfg->do_canopy_fluxes_lw && out->lw_dn_surf_canopy && out->lw_dn_surf_g &&
+      !cfg->do_nearest_spectral_lw_emiss && t->lw_emiss_weights) {
+    /* radiation_flux.F90:545-571: band sums of lw_dn_surf_g, then the emissivity-interval weights */
+    const int ne = cfg->n_emiss_lw;
+    double lband[NB_LW];
+    for (int b = 0; b < NB_LW; ++b) lband[b] = 0.0;
+    for (int g = 0; g < NG_LW; ++g) lband[t->band_lw[g]] = lband[t->band_lw[g]] + out->lw_dn_surf_g[(size_t)jcol * NG_LW + g];
+    double* c = out->lw_dn_surf_canopy + (size_t)jcol * ne;
+    for (int a = 0; a < ne; ++a) c[a] = 0.0;
+    for (int jb = 0; jb < NB_LW; ++jb)
+      for (int a = 0; a < ne; ++a) {
+        double wgt = t->lw_emiss_weights[(size_t)jb * ne + a];
+        if (wgt != 0.0) c[a] = c[a] + wgt * lband[jb];
+      }
   }
 }
 
@@ -675,8 +721,12 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
       qliq[jl] = A2(in->q_liq, jcol, jl); qice[jl] = A2(in->q_ice, jcol, jl);
       rel[jl] = A2(in->re_liq, jcol, jl); rei[jl] = A2(in->re_ice, jcol, jl);
     }
-    orc_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
-                     w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
+    if (t->is_ecckd)   /* use_general_cloud_optics */
+      orc_general_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
+                               w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
+    else
+      orc_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
+                       w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }

@@ -35,8 +35,55 @@ static const double* Dreq(const orc_tables* t, const char* nm, int* err) {
   return (const double*)a->data;
 }
 
+static void resolve_common(orc_tables* t, int* perr);
+
+/* ecCKD blob (tools/extract_ecckd_tables.py): "ckd_{lw,sw}_*", "gco_{lw,sw}_{0,1}_*" */
+static void resolve_ckd_model(orc_tables* t, const char* pre, orc_ckd_model* m, int* err) {
+  char nm[64];
+  snprintf(nm, sizeof nm, "%smeta", pre);
+  const double* meta = Dreq(t, nm, err);
+  if (!meta) return;
+  m->ng = (int)meta[0]; m->npress = (int)meta[1]; m->ntemp = (int)meta[2]; m->nplanck = (int)meta[3]; m->ngas = (int)meta[4];
+  m->log_pressure1 = meta[5]; m->d_log_pressure = meta[6]; m->d_temperature = meta[7];
+  m->temperature1_planck = meta[8]; m->d_temperature_planck = meta[9]; m->is_sw = meta[10] != 0.0;
+  snprintf(nm, sizeof nm, "%stemperature1", pre); m->temperature1 = Dreq(t, nm, err);
+  if (m->is_sw) {
+    snprintf(nm, sizeof nm, "%snorm_solar_irradiance", pre); m->norm_solar_irradiance = Dreq(t, nm, err);
+    snprintf(nm, sizeof nm, "%srayleigh_molar_scat", pre); m->rayleigh_molar_scat = Dreq(t, nm, err);
+  } else {
+    snprintf(nm, sizeof nm, "%splanck_function", pre); m->planck_function = Dreq(t, nm, err);
+  }
+  snprintf(nm, sizeof nm, "%sgas_meta", pre);
+  const double* gm = Dreq(t, nm, err);
+  for (int j = 0; gm && j < m->ngas && j < 16; ++j) {
+    orc_ckd_gas* g = &m->gas[j];
+    g->code = (int)gm[6 * j]; g->dep = (int)gm[6 * j + 1]; g->reference_mole_frac = gm[6 * j + 2];
+    g->n_mole_frac = (int)gm[6 * j + 3]; g->log_mole_frac1 = gm[6 * j + 4]; g->d_log_mole_frac = gm[6 * j + 5];
+    snprintf(nm, sizeof nm, "%sgas%d_molar_abs", pre, j); g->molar_abs = Dreq(t, nm, err);
+  }
+}
+
 int orc_tables_resolve(orc_tables* t) {
   int err = 0;
+  t->is_ecckd = orc_find(t, "ckd_lw_meta") != NULL;
+  if (t->is_ecckd) {
+    resolve_ckd_model(t, "ckd_lw_", &t->ckd_lw, &err);
+    resolve_ckd_model(t, "ckd_sw_", &t->ckd_sw, &err);
+    for (int jt = 0; jt < 2; ++jt)
+      for (int sw = 0; sw < 2; ++sw) {
+        orc_gco* c = sw ? &t->gco_sw[jt] : &t->gco_lw[jt];
+        char nm[64];
+        snprintf(nm, sizeof nm, "gco_%s_%d_meta", sw ? "sw" : "lw", jt);
+        const double* meta = Dreq(t, nm, &err);
+        if (meta) { c->nre = (int)meta[0]; c->re0 = meta[1]; c->dre = meta[2]; }
+        snprintf(nm, sizeof nm, "gco_%s_%d_mass_ext", sw ? "sw" : "lw", jt); c->mass_ext = Dreq(t, nm, &err);
+        snprintf(nm, sizeof nm, "gco_%s_%d_ssa", sw ? "sw" : "lw", jt); c->ssa = Dreq(t, nm, &err);
+        snprintf(nm, sizeof nm, "gco_%s_%d_asymmetry", sw ? "sw" : "lw", jt); c->asymmetry = Dreq(t, nm, &err);
+      }
+    for (int g = 0; g < 256; ++g) { t->band_lw[g] = g; t->band_sw[g] = g; }   /* radiation_ecckd_interface.F90:60-63 */
+    resolve_common(t, &err);
+    return err;
+  }
   for (int b = 1; b <= 16; ++b) {
     t->absa_lw[b] = D(t, "lw%d_ABSA", b);  t->absb_lw[b] = D(t, "lw%d_ABSB", b);
     t->selfref_lw[b] = D(t, "lw%d_SELFREF", b); t->forref_lw[b] = D(t, "lw%d_FORREF", b);
@@ -82,6 +129,15 @@ int orc_tables_resolve(orc_tables* t) {
   t->ngb_sw = (const int32_t*)Dreq(t, "sw_NGBSW", &err); t->ngc_sw = (const int32_t*)Dreq(t, "sw_NGC", &err);
   t->liq_coeff_lw = Dreq(t, "liq_coeff_lw", &err); t->liq_coeff_sw = Dreq(t, "liq_coeff_sw", &err);
   t->ice_coeff_lw = Dreq(t, "ice_coeff_lw", &err); t->ice_coeff_sw = Dreq(t, "ice_coeff_sw", &err);
+  if (t->ngb_lw) for (int g = 0; g < NG_LW; ++g) t->band_lw[g] = t->ngb_lw[g] - 1;
+  if (t->ngb_sw) for (int g = 0; g < NG_SW; ++g) t->band_sw[g] = t->ngb_sw[g] - 16;
+  resolve_common(t, &err);
+  return err;
+}
+
+/* tables shared by both gas models: McICA PDF look-up table, aerosol optics, config-derived surface weights */
+static void resolve_common(orc_tables* t, int* perr) {
+  int err = 0;
   t->pdf_val = Dreq(t, "pdf_val", &err);
   const orc_array* pv = orc_find(t, "pdf_val");
   const double* fsd = Dreq(t, "pdf_fsd", &err);
@@ -107,7 +163,9 @@ int orc_tables_resolve(orc_tables* t) {
   t->sw_albedo_weights = w ? (const double*)w->data : NULL;
   const orc_array* e = orc_find(t, "i_emiss_from_band_lw");
   t->i_emiss_from_band_lw = e ? (const int32_t*)e->data : NULL;
-  return err;
+  const orc_array* ew = orc_find(t, "lw_emiss_weights");
+  t->lw_emiss_weights = ew ? (const double*)ew->data : NULL;
+  if (err) *perr = 1;
 }
 
 orc_tables* orc_tables_load(const char* path) {

@@ -9,6 +9,16 @@
 #include <string.h>
 #include "oracle.h"
 
+/* spectral sizes from the configuration (RRTMG or ecCKD) */
+#undef NG_LW
+#undef NG_SW
+#undef NB_LW
+#undef NB_SW
+#define NG_LW (cfg->n_g_lw)
+#define NG_SW (cfg->n_g_sw)
+#define NB_LW (cfg->n_bands_lw)
+#define NB_SW (cfg->n_bands_sw)
+
 #define NREG 3
 static inline double dmin(double a, double b) { return a < b ? a : b; }
 static inline double dmax(double a, double b) { return a > b ? a : b; }
@@ -113,7 +123,7 @@ void orc_tripleclouds_sw(const orc_tables* t, const ecrad_b200_config* cfg, int 
     if (clear[jl]) continue;
     for (int jr = 1; jr < NREG; ++jr) {
       for (int jg = 0; jg < ng; ++jg) {
-        const int ib = t->ngb_sw[jg] - 16;
+        const int ib = t->band_sw[jg];
         const size_t i = (size_t)(jl - 1) * ng + jg;
         double scat_od = od[i] * ssa[i];
         double scat_od_cloud = od_cloud[(jl - 1) * NB_SW + ib] * ssa_cloud[(jl - 1) * NB_SW + ib] * ods[jl - 1][jr];
@@ -301,7 +311,7 @@ void orc_tripleclouds_lw(const orc_tables* t, const ecrad_b200_config* cfg, int 
     } else {
       for (int jr = 1; jr < NREG; ++jr) {
         for (int jg = 0; jg < ng; ++jg) {
-          const int ib = t->ngb_lw[jg] - 1;
+          const int ib = t->band_lw[jg];
           double od_cloud_new = od_cloud[l * NB_LW + ib] * ods[l][jr];
           od_total[jg] = A2L(od, l, jg) + od_cloud_new;
           ssa_total[jg] = 0.0; g_total[jg] = 0.0;

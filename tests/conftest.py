@@ -46,3 +46,13 @@ def golden_expexp():
 @pytest.fixture(scope="session")
 def golden_tripleclouds():
     return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_tripleclouds_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_ecckd_mcica():
+    return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_ecckd_mcica_ref.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_ecckd_tc():
+    return dict(np.load(os.path.join(GOLDEN, "ecrad_meridian_ecckd_tc_ref.npz")))

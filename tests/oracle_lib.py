@@ -37,9 +37,10 @@ class Oracle:
                                             C.POINTER(abi.Inputs)] + [abi.c_dp] * 6
         self.config = config
         self.cfg = config.to_struct()
-        self.t = L.orc_tables_load(TABLES.encode())
+        tables = config.tables_path()
+        self.t = L.orc_tables_load(tables.encode())
         if not self.t:
-            raise RuntimeError("oracle: cannot load " + TABLES)
+            raise RuntimeError("oracle: cannot load " + tables)
         self._keep = []
         for nm, arr in config.derived.items():
             a = np.asfortranarray(arr)

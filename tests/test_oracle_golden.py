@@ -114,6 +114,48 @@ def test_oracle_cloudless_matches_reference_golden(meridian_raw, golden_cloudles
         assert err.max() <= 0.51, (nm, err.max())
 
 
+ECCKD = dict(gas_model_name="ECCKD", use_aerosols=True, do_nearest_spectral_lw_emiss=False)   # test/ifs/configCY49R1_ecckd.nam
+CANOPY = (("lw_dn_surf_canopy", "canopy_flux_dn_lw_surf"), ("sw_dn_diffuse_surf_canopy", "canopy_flux_dn_diffuse_sw_surf"),
+          ("sw_dn_direct_surf_canopy", "canopy_flux_dn_direct_sw_surf"))
+
+
+def _run_ecckd(raw, spectral=False, **kw):
+    cfg = RadiationConfig(**ECCKD, **kw).consolidate()
+    return cfg, Oracle(cfg).radiation(I.to_radiation_inputs(raw, cfg), 32, 137, spectral_profiles=spectral)
+
+
+def test_oracle_ecckd_tripleclouds_matches_reference_golden(meridian_raw, golden_ecckd_tc):
+    """test/ifs `ecckd_tc` ctest: ecCKD 32-term gas optics (LW fsck-32b, SW rgb-32b) + generalised cloud optics (thick
+    averaging) + generalised aerosol optics, all per g-point, weighted albedo/emissivity intervals, Tripleclouds."""
+    cfg, out = _run_ecckd(meridian_raw, spectral=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")
+    assert (cfg.n_g, cfg.n_bands) == ((32, 32), (32, 32))
+    for nm, gname in PROFILES.items():
+        assert f32_ulp_err(out[nm], golden_ecckd_tc[gname]).max() <= 0.51, nm
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):
+        assert f32_ulp_err(out[nm], golden_ecckd_tc[nm]).max() <= 0.51, nm
+    assert f32_ulp_err(out["lw_derivatives"], golden_ecckd_tc["lw_derivative"]).max() <= 0.51
+    for nm, gname in CANOPY:
+        assert f32_ulp_err(out[nm].T, golden_ecckd_tc[gname]).max() <= 0.51, nm
+    lev = golden_ecckd_tc["band_levels"]   # per-g-point profiles pin every k-term separately
+    for nm, gname in (("lw_up_band", "spectral_flux_up_lw"), ("lw_dn_band", "spectral_flux_dn_lw"), ("sw_up_band", "spectral_flux_up_sw"),
+                      ("sw_dn_band", "spectral_flux_dn_sw"), ("sw_dn_direct_band", "spectral_flux_dn_direct_sw")):
+        a = np.transpose(out[nm], (1, 2, 0))[:, lev, :]
+        assert f32_ulp_err(a, golden_ecckd_tc[gname]).max() <= 0.51, nm
+
+
+def test_oracle_ecckd_mcica_matches_reference_golden(meridian_raw, golden_ecckd_mcica):
+    """test/ifs `ecckd_mcica` ctest: same optics, McICA solvers (32 g-point streams per spectrum)."""
+    _, out = _run_ecckd(meridian_raw, sw_solver_name="McICA", lw_solver_name="McICA")
+    for nm, gname in PROFILES.items():
+        assert f32_ulp_err(out[nm], golden_ecckd_mcica[gname]).max() <= 0.51, nm
+    for nm in ("cloud_cover_lw", "cloud_cover_sw"):
+        assert f32_ulp_err(out[nm], golden_ecckd_mcica[nm]).max() <= 0.51, nm
+    assert f32_ulp_err(out["lw_derivatives"], golden_ecckd_mcica["lw_derivative"]).max() <= 0.51
+    for nm, gname in CANOPY + (("sw_dn_surf_band", "spectral_flux_dn_sw_surf"), ("sw_dn_direct_surf_band", "spectral_flux_dn_direct_sw_surf"),
+                               ("sw_dn_surf_clear_band", "spectral_flux_dn_sw_surf_clear")):
+        assert f32_ulp_err(out[nm].T, golden_ecckd_mcica[gname]).max() <= 0.51, nm
+
+
 def test_oracle_crop_cloud_fraction_side_effect(meridian_raw):
     """radiation_cloud.F90:700-740: fraction below threshold (or with negligible water) is zeroed in the caller's array."""
     cfg = RadiationConfig().consolidate()

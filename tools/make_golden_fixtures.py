@@ -5,6 +5,7 @@ Run in the authoring container (needs /root/reference); the GPU box only sees th
   inputs : test/ifs/ecrad_meridian.nc                          -> tests/golden/ecrad_meridian_inputs.npz
   golden : test/ifs/ecrad_meridian_noaer_out_REFERENCE.nc      -> tests/golden/ecrad_meridian_noaer_ref.npz
            test/ifs/ecrad_meridian_cloudless_out_REFERENCE.nc  -> tests/golden/ecrad_meridian_cloudless_ref.npz
+           ... and the default, expexp, tripleclouds, ecckd_mcica, ecckd_tc reference outputs likewise
 The golden outputs are float32 as written by the reference driver (do_write_double_precision=false); the
 per-band profiles of the cloudless file are kept at 8 half-levels only to keep the fixture small.
 """
@@ -24,7 +25,7 @@ BAND_LEVELS = [0, 20, 40, 60, 80, 100, 120, 137]
 os.makedirs(OUT, exist_ok=True)
 with netcdf_file(f"{REF}/test/ifs/ecrad_meridian.nc", mmap=False) as f:
     np.savez_compressed(f"{OUT}/ecrad_meridian_inputs.npz", **{k: np.array(f.variables[k][...]) for k in NC_VARS})
-for name in ("noaer", "cloudless", "default", "expexp", "tripleclouds"):
+for name in ("noaer", "cloudless", "default", "expexp", "tripleclouds", "ecckd_mcica", "ecckd_tc"):
     with netcdf_file(f"{REF}/test/ifs/ecrad_meridian_{name}_out_REFERENCE.nc", mmap=False) as f:
         d = {}
         for k, v in f.variables.items():
