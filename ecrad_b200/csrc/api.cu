@@ -90,16 +90,26 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "solver not available in this build (McICA, Tripleclouds and Cloudless are)");
   if (c.use_beta_overlap && ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS)))
     return fail(h, "use_beta_overlap is not available with the Tripleclouds solver in this build");
-  if ((c.do_sw && c.i_gas_model_sw != ECRAD_GAS_IFSRRTMG) || (c.do_lw && c.i_gas_model_lw != ECRAD_GAS_IFSRRTMG))
-    return fail(h, "gas model not available in this build (RRTMG-IFS is)");
+  const int gm = c.do_lw ? c.i_gas_model_lw : c.i_gas_model_sw;
+  if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
+    return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
     return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator) return fail(h, "use_vectorizable_generator is not available in this build");
-  if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
-  if (c.do_nearest_spectral_sw_albedo || !c.do_nearest_spectral_lw_emiss) return fail(h, "albedo/emissivity mapping mode not available");
-  if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
+  if (c.do_nearest_spectral_sw_albedo) return fail(h, "do_nearest_spectral_sw_albedo is not available in this build");
+  if (gm == ECRAD_GAS_IFSRRTMG) {
+    if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
+    if (!c.do_nearest_spectral_lw_emiss) return fail(h, "weighted emissivity intervals are only available with the ECCKD gas model in this build");
+    if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
+  } else {
+    // generalised cloud + aerosol optics per g-point (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points
+    auto ok = [](int n) { return n == 32 || n == 64 || n == 96; };
+    if (!ok(c.n_g_lw) || !ok(c.n_g_sw) || c.n_bands_lw != c.n_g_lw || c.n_bands_sw != c.n_g_sw)
+      return fail(h, "ECCKD: models with 32, 64 or 96 g-points and cloud/aerosol optics per g-point (n_bands == n_g) are built in");
+    if (c.do_sw_delta_scaling_with_gases) return fail(h, "do_sw_delta_scaling_with_gases is not available in this build");
+  }
   return 0;
 }
 
@@ -109,6 +119,8 @@ int ensure_work(Handle* h, int cols, int nlev) {
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
   const bool tc_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS, tc_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
   const bool tc = tc_lw || tc_sw;
+  const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
+  const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
   const size_t sz[] = {
       8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
@@ -116,13 +128,13 @@ int ensure_work(Handle* h, int cols, int nlev) {
       8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
-      8 * nc * (tc_lw ? tc_scratch_doubles_lw(nlev) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
+      8 * nc * (tc_lw ? tc_scratch_doubles_lw(nlev, (int)NG_LW) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
-      8 * nc * (tc_sw ? tc_scratch_doubles_sw(nlev) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
-      sizeof(LwLev) * nc * nl, sizeof(SwLev) * nc * nl,                                      // lev_lw lev_sw
-      h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, h->cfg.use_aerosols ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
-      h->cfg.use_aerosols ? 8 * nc * nl * NB_LW : 0,                                         // aer_lw
+      8 * nc * (tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
+      ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
+      h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
+      (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       (h->cfg.do_save_spectral_flux && h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_CLOUDLESS) ? 8 * nc * (nl + 1) * NB_SW : 0,   // sw_band_dir
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0};  // tc_reg tc_ods tc_u tc_v tc_cc
   for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
@@ -155,8 +167,11 @@ int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cu
   int n = 0;
   const bool par = !h->serial;
   cudaStream_t s_lw = st, s_sw = par ? h->s_aux1 : st, s_cl = par ? h->s_aux2 : st;
-  n += launch_gas_prep(h->T, c, in, h->w, nc, nlev, st);   // shared by the LW and SW gas-optics kernels
-  if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w, nc, nlev, st);
+  const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
+  if (!ckd) {
+    n += launch_gas_prep(h->T, c, in, h->w, nc, nlev, st);   // shared by the LW and SW gas-optics kernels
+    if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w, nc, nlev, st);
+  }
   if (par) {
     CK(h, cudaEventRecord(h->ev_fork, st));
     CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork, 0));
@@ -171,11 +186,11 @@ int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cu
   if (par) CK(h, cudaEventRecord(h->ev_cloud, s_cl));
   // LW chain
   CK(h, cudaEventRecord(ev[0], s_lw));
-  if (c.do_lw) n += launch_gas_lw(h->T, c, in, h->w, nc, nlev, s_lw);
+  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w, nc, nlev, s_lw) : launch_gas_lw(h->T, c, in, h->w, nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[1], s_lw));
   // SW chain
   CK(h, cudaEventRecord(ev[2], s_sw));
-  if (c.do_sw) n += launch_gas_sw(h->T, c, in, h->w, nc, nlev, s_sw);
+  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w, nc, nlev, s_sw) : launch_gas_sw(h->T, c, in, h->w, nc, nlev, s_sw);
   CK(h, cudaEventRecord(ev[3], s_sw));
   if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud, 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud, 0)); }
   CK(h, cudaEventRecord(ev[6], s_lw));
@@ -241,15 +256,15 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
       {out->sw_up, 0, nl1}, {out->sw_dn, 0, nl1}, {out->sw_dn_direct, 0, nl1},
       {out->sw_up_clear, 0, nl1}, {out->sw_dn_clear, 0, nl1}, {out->sw_dn_direct_clear, 0, nl1},
       {out->lw_derivatives, 0, nl1}, {out->cloud_cover_lw, 1, 1}, {out->cloud_cover_sw, 1, 1},
-      {out->lw_dn_surf_g, 1, NG_LW}, {out->lw_dn_surf_clear_g, 1, NG_LW}, {out->lw_up_toa_g, 1, NG_LW}, {out->lw_up_toa_clear_g, 1, NG_LW},
-      {out->sw_dn_diffuse_surf_g, 1, NG_SW}, {out->sw_dn_direct_surf_g, 1, NG_SW}, {out->sw_dn_diffuse_surf_clear_g, 1, NG_SW},
-      {out->sw_dn_direct_surf_clear_g, 1, NG_SW}, {out->sw_up_toa_g, 1, NG_SW}, {out->sw_up_toa_clear_g, 1, NG_SW},
-      {out->sw_dn_surf_band, 1, NB_SW}, {out->sw_dn_direct_surf_band, 1, NB_SW}, {out->sw_dn_surf_clear_band, 1, NB_SW},
-      {out->sw_dn_direct_surf_clear_band, 1, NB_SW},
+      {out->lw_dn_surf_g, 1, c.n_g_lw}, {out->lw_dn_surf_clear_g, 1, c.n_g_lw}, {out->lw_up_toa_g, 1, c.n_g_lw}, {out->lw_up_toa_clear_g, 1, c.n_g_lw},
+      {out->sw_dn_diffuse_surf_g, 1, c.n_g_sw}, {out->sw_dn_direct_surf_g, 1, c.n_g_sw}, {out->sw_dn_diffuse_surf_clear_g, 1, c.n_g_sw},
+      {out->sw_dn_direct_surf_clear_g, 1, c.n_g_sw}, {out->sw_up_toa_g, 1, c.n_g_sw}, {out->sw_up_toa_clear_g, 1, c.n_g_sw},
+      {out->sw_dn_surf_band, 1, c.n_bands_sw}, {out->sw_dn_direct_surf_band, 1, c.n_bands_sw}, {out->sw_dn_surf_clear_band, 1, c.n_bands_sw},
+      {out->sw_dn_direct_surf_clear_band, 1, c.n_bands_sw},
       {out->sw_dn_diffuse_surf_canopy, 1, c.n_canopy_bands_sw}, {out->sw_dn_direct_surf_canopy, 1, c.n_canopy_bands_sw},
       {out->lw_dn_surf_canopy, 1, c.n_canopy_bands_lw},
-      {out->lw_up_band, 2, NB_LW}, {out->lw_dn_band, 2, NB_LW}, {out->sw_up_band, 2, NB_SW}, {out->sw_dn_band, 2, NB_SW},
-      {out->sw_dn_direct_band, 2, NB_SW}};
+      {out->lw_up_band, 2, c.n_bands_lw}, {out->lw_dn_band, 2, c.n_bands_lw}, {out->sw_up_band, 2, c.n_bands_sw}, {out->sw_dn_band, 2, c.n_bands_sw},
+      {out->sw_dn_direct_band, 2, c.n_bands_sw}};
   for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
 }
 
@@ -294,7 +309,7 @@ int ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_
 }
 void ecrad_b200_tables_free(ecrad_b200_tables* t) { delete t; }
 
-const char* ecrad_b200_version(void) { return "ecrad_b200 0.1 (sm_100a; RRTMG + McICA/Cloudless; fp64)"; }
+const char* ecrad_b200_version(void) { return "ecrad_b200 0.2 (sm_100a; RRTMG-IFS / ecCKD gas optics; McICA, Tripleclouds, Cloudless; fp64)"; }
 const char* ecrad_b200_last_error(void* handle) {
   if (handle) return ((Handle*)handle)->err.c_str();
   return g_last_error.c_str();
@@ -314,18 +329,35 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   if (check_config(h, *cfg)) { delete h; return 1; }
   PackedTables P;
   try { pack_tables(*tab, P); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
-  if (P.sw_albedo_weights.empty() || P.n_albedo_sw != cfg->n_albedo_sw || P.i_emiss_from_band_lw.empty()) {
-    fail(nullptr, "tables 'sw_albedo_weights' (n_albedo_sw x 14) and 'i_emiss_from_band_lw' (16) are required"); delete h; return 1;
+  if (P.is_ecckd != (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD)) {
+    fail(nullptr, "the table directory holds %s tables but the configuration asks for the other gas model", P.is_ecckd ? "ecCKD" : "RRTMG"); delete h; return 1;
+  }
+  if (P.is_ecckd && ((cfg->do_lw && P.ng_lw != cfg->n_g_lw) || (cfg->do_sw && P.ng_sw != cfg->n_g_sw))) {
+    fail(nullptr, "ecCKD tables have %d/%d g-points (LW/SW), the configuration says %d/%d", P.ng_lw, P.ng_sw, cfg->n_g_lw, cfg->n_g_sw); delete h; return 1;
+  }
+  if (P.sw_albedo_weights.empty() || P.n_albedo_sw != cfg->n_albedo_sw) {
+    fail(nullptr, "table 'sw_albedo_weights' (n_albedo_sw x n_bands_sw) is required"); delete h; return 1;
+  }
+  if (cfg->do_nearest_spectral_lw_emiss ? P.i_emiss_from_band_lw.empty() : (P.lw_emiss_weights.empty() || P.n_emiss_lw != cfg->n_emiss_lw)) {
+    fail(nullptr, "table 'i_emiss_from_band_lw' (n_bands_lw) or 'lw_emiss_weights' (n_emiss_lw x n_bands_lw) is required"); delete h; return 1;
   }
   cudaGetDevice(&h->device);
   int rc = 0;
   rc |= upload(h, &P.meta, 1, &h->T.meta);
-  rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
-  rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
+  h->T.lwtab = h->T.swtab = nullptr; h->T.ckd = nullptr; h->T.ckdtab = nullptr;
+  h->T.i_emiss_from_band_lw = nullptr; h->T.lw_emiss_weights = nullptr;
+  if (P.is_ecckd) {
+    rc |= upload(h, &P.ckd, 1, &h->T.ckd);
+    rc |= upload(h, P.ckdtab.data(), P.ckdtab.size(), &h->T.ckdtab);
+  } else {
+    rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
+    rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
+  }
   rc |= upload(h, &P.cloud, 1, &h->T.cloud);
   rc |= upload(h, P.pdf_val.data(), P.pdf_val.size(), &h->T.pdf_val);
   rc |= upload(h, P.sw_albedo_weights.data(), P.sw_albedo_weights.size(), &h->T.sw_albedo_weights);
-  rc |= upload(h, P.i_emiss_from_band_lw.data(), P.i_emiss_from_band_lw.size(), &h->T.i_emiss_from_band_lw);
+  if (!P.i_emiss_from_band_lw.empty()) rc |= upload(h, P.i_emiss_from_band_lw.data(), P.i_emiss_from_band_lw.size(), &h->T.i_emiss_from_band_lw);
+  if (!P.lw_emiss_weights.empty()) rc |= upload(h, P.lw_emiss_weights.data(), P.lw_emiss_weights.size(), &h->T.lw_emiss_weights);
   h->T.aer = nullptr; h->T.aertab = nullptr;
   if (cfg->use_aerosols) {
     if (P.aer.ntype != cfg->n_aerosol_types || P.aertab.empty()) {
@@ -346,6 +378,9 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.n_canopy_bands_sw = cfg->n_canopy_bands_sw; d.n_canopy_bands_lw = cfg->n_canopy_bands_lw;
   d.use_aerosols = cfg->use_aerosols; d.n_aerosol_types = cfg->n_aerosol_types;
   d.do_save_spectral_flux = cfg->do_save_spectral_flux;
+  d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
+  d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;

@@ -22,7 +22,19 @@
 
 namespace ecb {
 
-enum { NG_LW = 140, NG_SW = 112, NB_LW = 16, NB_SW = 14 };
+enum { NG_LW = 140, NG_SW = 112, NB_LW = 16, NB_SW = 14 };   // RRTMG
+
+// Spectral sizes of a solver instantiation: g-points, bands (cloud/aerosol optics resolution), threads of the one-CTA-per-
+// column kernels (one thread per g-point), row stride of the shared-memory reduction tiles.
+template <int NG_, int NB_> struct SpecDims { enum { NG = NG_, NB = NB_, THREADS = (NG_ + 31) / 32 * 32, RS = NG_ + 1 }; };
+typedef SpecDims<NG_LW, NB_LW> LwRrtmg;
+typedef SpecDims<NG_SW, NB_SW> SwRrtmg;
+// ecCKD models: cloud and aerosol optics per g-point, i.e. bands == g-points (radiation_ecckd_interface.F90:46-76)
+typedef SpecDims<32, 32> Ckd32;
+typedef SpecDims<64, 64> Ckd64;
+typedef SpecDims<96, 96> Ckd96;
+// minimum resident CTAs per SM that keeps the register budget of a kernel tuned as __launch_bounds__(t0, b0)
+constexpr int scaled_min_blocks(int threads, int t0, int b0) { return (t0 * b0 / threads) > 32 ? 32 : (t0 * b0 / threads); }
 enum { LW_KMAX = 22, SW_KMAX = 14 };
 
 // Sections of a band's packed table (rows of ng doubles, g-point fastest).
@@ -37,7 +49,7 @@ struct BandMeta {
 
 // Small read-only tables and per-band scalars (device global memory; ~36 KB).
 struct GasMeta {
-  BandMeta lw[NB_LW], sw[NB_SW];
+  BandMeta lw[NG_LW], sw[NG_SW];   // RRTMG: 16 / 14 bands; ecCKD: one single-g-point band per g-point
   double preflog_lw[59], tref_lw[59], chi_mls[7 * 59];
   double preflog_sw[59], tref_sw[59];
   double totplnk[181 * 16], delwave[16];

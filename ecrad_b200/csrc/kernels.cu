@@ -447,7 +447,7 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
   const int spec = warp;
   const bool mine = spec == 0 ? (cfg.do_sw && cfg.solver_sw == 2 && in.cos_sza[c] > 0.0) : (cfg.do_lw && cfg.solver_lw == 2);
   if (!mine) return;
-  const int ng = spec ? NG_LW : NG_SW;
+  const int ng = spec ? cfg.ng_lw : cfg.ng_sw;
   uint32_t* code = (spec ? w.code_lw : w.code_sw) + (size_t)c * ng * nlevp;
   int32_t* ring = sRing[warp];
   int32_t* rtop = sTop[warp];
@@ -657,7 +657,8 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
   const int nlevp = (nlev + 3) & ~3;
   int n = 0;
   cloud_prep_kernel<<<(nc + 127) / 128, 128, 0, st>>>(cfg, in, w, nc, nlev); ++n;
-  cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n;
+  if (cfg.gas_model == 2) n += launch_general_cloud_optics(T, cfg, in, w, nc, nlev, st);   // ECRAD_GAS_ECCKD: use_general_cloud_optics
+  else { cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n; }
   if ((cfg.do_lw && cfg.solver_lw == 2) || (cfg.do_sw && cfg.solver_sw == 2)) {
     cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
   }

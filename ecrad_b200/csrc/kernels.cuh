@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "cloud_core.h"
+#include "ecckd_core.h"
 #include "gas_core.h"
 
 namespace ecb {
@@ -14,7 +15,7 @@ struct DevIn {
   const double *cos_sza, *skin_t, *sw_albedo, *sw_albedo_direct, *lw_emissivity;
   const int32_t* iseed;
   const double *p_hl, *t_hl;
-  const double* gas[9];  // h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3 (mass mixing ratios)
+  const double* gas[9];  // h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3 (mass mixing ratios with RRTMG, mole fractions with ecCKD)
   double* frac;          // in/out (cropped)
   const double *q_liq, *q_ice, *re_liq, *re_ice, *overlap, *fsd;
   const double *aerosol_mmr, *h2o_sat_liq;   // (ld, nlev, ntype), (ld, nlev); only with aerosols
@@ -43,9 +44,12 @@ struct DevTables {
   const CloudMeta* cloud;
   const double* pdf_val;
   const double* sw_albedo_weights;     // (n_albedo_sw, 14)
-  const int32_t* i_emiss_from_band_lw; // (16), 1-based
+  const int32_t* i_emiss_from_band_lw; // (n_bands_lw), 1-based; do_nearest_spectral_lw_emiss
+  const double* lw_emiss_weights;      // (n_emiss_lw, n_bands_lw); !do_nearest_spectral_lw_emiss
   const AerMeta* aer;                  // aerosol optics (NULL tables if no aerosols)
   const double* aertab;
+  const CkdMeta* ckd;                  // ecCKD gas optics + generalised cloud optics (NULL with RRTMG)
+  const double* ckdtab;
 };
 
 // Scalars of config_type the kernels read.
@@ -57,6 +61,9 @@ struct DevCfg {
   int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
   int use_aerosols, n_aerosol_types;
   int do_save_spectral_flux;
+  int do_nearest_spectral_lw_emiss;
+  int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
+  int ng_lw, ng_sw, nb_lw, nb_sw;   // spectral sizes: RRTMG 140/112/16/14; ecCKD ng = nb = 32/64/96
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
 };
 
@@ -88,9 +95,13 @@ int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, cons
 int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+// ecCKD gas optics (+ per-g-point aerosol merge), generalised cloud optics: ecckd.cu
+int launch_ckd_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_ckd_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_general_cloud_optics(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
-size_t tc_scratch_doubles_lw(int nlev);
-size_t tc_scratch_doubles_sw(int nlev);
+size_t tc_scratch_doubles_lw(int nlev, int ng);
+size_t tc_scratch_doubles_sw(int nlev, int ng);
 int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);

@@ -73,6 +73,7 @@ __device__ __forceinline__ double od_scaling_from_code(const CloudMeta& C, const
 
 // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral.  Block-wide (contains barriers);
 // tile: >= 4*rs + 28 doubles of shared memory; dir/dif: per-g direct and diffuse surface fluxes (all-sky, clear-sky).
+template <class SD>
 __device__ __forceinline__ void sw_surface_spectral(const DevTables& T, const DevCfg& cfg, const DevOut& out, int c, int g, bool act,
                                                     double* tile, int rs, double dir_a, double dif_a, double dir_c, double dif_c) {
   if (!(cfg.do_surface_sw_spectral_flux || cfg.do_canopy_fluxes_sw)) return;
@@ -80,32 +81,34 @@ __device__ __forceinline__ void sw_surface_spectral(const DevTables& T, const De
   if (act) { tile[g] = dir_a; tile[rs + g] = dif_a; tile[2 * rs + g] = dir_c; tile[3 * rs + g] = dif_c; }
   __syncthreads();
   double* bdir = tile + 4 * rs;  // [14] all-sky direct band, [14] all-sky total band
-  if (g < NB_SW) {
+  if (g < SD::NB) {
     const int g0 = T.meta->sw[g].g0, ngb = T.meta->sw[g].ng;
     double d = 0.0, t = 0.0, dcl = 0.0, tcl = 0.0;
     for (int k = g0; k < g0 + ngb; ++k) { d = d + tile[k]; t = t + tile[rs + k]; dcl = dcl + tile[2 * rs + k]; tcl = tcl + tile[3 * rs + k]; }
     t = t + d; tcl = tcl + dcl;
-    bdir[g] = d; bdir[NB_SW + g] = t;
+    bdir[g] = d; bdir[SD::NB + g] = t;
     if (cfg.do_surface_sw_spectral_flux) {
-      if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * NB_SW + g] = d;
-      if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * NB_SW + g] = t;
-      if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * NB_SW + g] = dcl;
-      if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * NB_SW + g] = tcl;
+      if (out.sw_dn_direct_surf_band) out.sw_dn_direct_surf_band[(size_t)c * SD::NB + g] = d;
+      if (out.sw_dn_surf_band) out.sw_dn_surf_band[(size_t)c * SD::NB + g] = t;
+      if (cfg.do_clear && out.sw_dn_direct_surf_clear_band) out.sw_dn_direct_surf_clear_band[(size_t)c * SD::NB + g] = dcl;
+      if (cfg.do_clear && out.sw_dn_surf_clear_band) out.sw_dn_surf_clear_band[(size_t)c * SD::NB + g] = tcl;
     }
   }
   __syncthreads();
   if (cfg.do_canopy_fluxes_sw && out.sw_dn_diffuse_surf_canopy && out.sw_dn_direct_surf_canopy && g < cfg.n_albedo_sw) {
     double dif = 0.0, dir = 0.0;
-    for (int jb = 0; jb < NB_SW; ++jb) {
+    for (int jb = 0; jb < SD::NB; ++jb) {
       const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + g];
-      if (wgt != 0.0) { dif = dif + wgt * bdir[NB_SW + jb]; dir = dir + wgt * bdir[jb]; }
+      if (wgt != 0.0) { dif = dif + wgt * bdir[SD::NB + jb]; dir = dir + wgt * bdir[jb]; }
     }
     out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dif - dir;
     out.sw_dn_direct_surf_canopy[(size_t)c * cfg.n_albedo_sw + g] = dir;
   }
 }
 
-// LW canopy fluxes (nearest-interval emissivity mapping), radiation_flux.F90 calc_surface_spectral.  Block-wide.
+// LW canopy fluxes, radiation_flux.F90:529-572 calc_surface_spectral: nearest-interval mapping (i_emiss_from_band_lw) or the
+// weighted emissivity intervals (lw_emiss_weights applied to the band sums of lw_dn_surf_g).  Block-wide.
+template <class SD>
 __device__ __forceinline__ void lw_surface_canopy(const DevTables& T, const DevCfg& cfg, const DevOut& out, int c, int g, bool act,
                                                   double* tile, double dn_surf_g) {
   if (!(cfg.do_canopy_fluxes_lw && out.lw_dn_surf_canopy)) return;
@@ -114,32 +117,45 @@ __device__ __forceinline__ void lw_surface_canopy(const DevTables& T, const DevC
   __syncthreads();
   if (g < cfg.n_canopy_bands_lw) {
     double sum = 0.0;
-    for (int k = 0; k < NG_LW; ++k)
-      if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) sum = sum + tile[k];
+    if (cfg.do_nearest_spectral_lw_emiss) {
+      for (int k = 0; k < SD::NG; ++k)
+        if (T.i_emiss_from_band_lw[T.meta->band_of_g_lw[k]] - 1 == g) sum = sum + tile[k];
+    } else {
+      for (int jb = 0; jb < SD::NB; ++jb) {
+        const double wgt = T.lw_emiss_weights[jb * cfg.n_emiss_lw + g];
+        if (wgt != 0.0) {
+          double band = 0.0;
+          const int g0 = T.meta->lw[jb].g0, ngb = T.meta->lw[jb].ng;
+          for (int k = g0; k < g0 + ngb; ++k) band = band + tile[k];
+          sum = sum + wgt * band;
+        }
+      }
+    }
     out.lw_dn_surf_canopy[(size_t)c * cfg.n_canopy_bands_lw + g] = sum;
   }
 }
 
 // night column of a SW solver: radiation_mcica_sw.F90:380-401 / radiation_tripleclouds_sw.F90:236-280
+template <class SD>
 __device__ __forceinline__ void sw_night_column(const DevCfg& cfg, const DevOut& out, int c, int g, bool act, int nl1, int nthreads) {
   for (int l = g; l < nl1; l += nthreads) {
     double* p[6] = {out.sw_up, out.sw_dn, out.sw_dn_direct, out.sw_up_clear, out.sw_dn_clear, out.sw_dn_direct_clear};
     for (int k = 0; k < 6; ++k) if (p[k]) p[k][(size_t)l * out.ld + c] = 0.0;
   }
   if (act) {
-    const size_t i = (size_t)c * NG_SW + g;
+    const size_t i = (size_t)c * SD::NG + g;
     double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
                      out.sw_dn_diffuse_surf_clear_g, out.sw_dn_direct_surf_clear_g, out.sw_up_toa_clear_g};
     for (int k = 0; k < 6; ++k) if (gs[k]) gs[k][i] = 0.0;
   }
-  if (g < NB_SW) {
+  if (g < SD::NB) {
     double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
-    for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
+    for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * SD::NB + g] = 0.0;
   }
   if (cfg.do_save_spectral_flux && cfg.solver_sw != 2) {
     double* pb[3] = {out.sw_up_band, out.sw_dn_band, out.sw_dn_direct_band};
     for (int k = 0; k < 3; ++k)
-      if (pb[k]) for (int i = g; i < nl1 * NB_SW; i += nthreads) pb[k][((size_t)(i / NB_SW) * out.ld + c) * NB_SW + (i % NB_SW)] = 0.0;
+      if (pb[k]) for (int i = g; i < nl1 * SD::NB; i += nthreads) pb[k][((size_t)(i / SD::NB) * out.ld + c) * SD::NB + (i % SD::NB)] = 0.0;
   }
   if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
     if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;

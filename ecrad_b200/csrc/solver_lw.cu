@@ -12,7 +12,7 @@
 
 namespace ecb {
 
-enum { LW_THREADS = 160, LW_RS = 141, LW_LCH_FLUX = 8, LW_LCH_UP = 8 };
+enum { LW_LCH_FLUX = 8, LW_LCH_UP = 8 };
 enum { LWS_DN_C = 0, LWS_UP_C = 1, LWS_DV_C = 2, LWS_UP_A = 3, LWS_DN_A = 4, LWS_DV_A = 5 };
 
 struct LwColumn {
@@ -22,31 +22,33 @@ struct LwColumn {
   double *scr, *sums, *carry;
 };
 
+template <class SD>
 __device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, int nlev) {
   LwColumn s;
-  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < NG_LW; s.gg = s.act ? s.g : 0;
+  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < SD::NG; s.gg = s.act ? s.g : 0;
   s.mcica = cfg.solver_lw == 2;
   s.tcc = s.mcica ? w.tcc[s.c] : 0.0;
   s.cloudy = s.tcc > 0.0;
   s.ict = (s.cloudy || cfg.solver_lw == 4) ? w.ict[s.c] : nlev;   // 4 = Tripleclouds: needs the clear-sky flux_dn at cloud top too
   s.thr = cfg.cloud_fraction_threshold;
-  s.n = (size_t)nlev * NG_LW;
+  s.n = (size_t)nlev * SD::NG;
   s.od = w.od_lw + (size_t)s.c * s.n;
-  s.pl = w.planck + (size_t)s.c * (nlev + 1) * NG_LW;
+  s.pl = w.planck + (size_t)s.c * (nlev + 1) * SD::NG;
   s.scr = w.scr_lw + (size_t)s.c * LW_SCR_ARRAYS * s.n;
   s.sums = w.lw_sums + (size_t)s.c * 6 * (nlev + 1);
-  s.carry = w.lw_carry + (size_t)s.c * 4 * NG_LW;
+  s.carry = w.lw_carry + (size_t)s.c * 4 * SD::NG;
   return s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // clear-sky downward flux
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LW_THREADS, 6)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 6))
 lw_down_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const LwColumn s = lw_column(cfg, w, nlev);
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [1][LCH][LW_RS]
+  const LwColumn s = lw_column<SD>(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [1][LCH][SD::RS]
   const int g = s.g, nl1 = nlev + 1;
   double* dst[1] = {s.sums + LWS_DN_C * nl1};
   // per-band profile of flux_dn: clear-sky = all-sky for Cloudless; Tripleclouds overwrites the levels below cloud top
@@ -57,38 +59,39 @@ lw_down_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   ++slot;
   double pt = s.act ? s.pl[g] : 0.0;
   // software pipeline: the loads of layer l+1 are issued before the exp/div of layer l
-  double od_n = s.act ? s.od[g] : 0.0, pb_n = s.act ? s.pl[NG_LW + g] : 0.0;
+  double od_n = s.act ? s.od[g] : 0.0, pb_n = s.act ? s.pl[SD::NG + g] : 0.0;
   for (int l = 0; l < nlev; ++l) {
     if (s.act) {
       if (l == s.ict) fd_ict = fd;
       const double odg = od_n, pb = pb_n;
-      if (l + 1 < nlev) { const size_t i1 = (size_t)(l + 1) * NG_LW + g; od_n = s.od[i1]; pb_n = s.pl[i1 + NG_LW]; }
+      if (l + 1 < nlev) { const size_t i1 = (size_t)(l + 1) * SD::NG + g; od_n = s.od[i1]; pb_n = s.pl[i1 + SD::NG]; }
       const LwLayer L = lw_no_scat(odg, pt, pb);
       pt = pb;
       fd = L.trans * fd + L.source_dn;
-      tile[slot * LW_RS + g] = fd;
+      tile[slot * SD::RS + g] = fd;
     }
     ++slot;
     if (slot == LCH || l == nlev - 1) {
-      if (bo[0].dst) flush_bands(tile, LW_RS, LCH, slot, bo, 1, lfirst, 1, s.c, NB_LW, T.meta->lw);
-      flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
+      if (bo[0].dst) flush_bands(tile, SD::RS, LCH, slot, bo, 1, lfirst, 1, s.c, SD::NB, T.meta->lw);
+      flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
     }
   }
-  if (s.act) { s.carry[g] = fd_ict; s.carry[NG_LW + g] = fd; }
+  if (s.act) { s.carry[g] = fd_ict; s.carry[SD::NG + g] = fd; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // upward sweep: clear-sky flux_up and derivative products; cloudy albedo/source below cloud top, flux_up above
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LW_THREADS, 4)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 4))
 lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const LwColumn s = lw_column(cfg, w, nlev);
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LW_LCH_UP][LW_RS]
-  double* fracs = tile + 3 * LW_LCH_UP * LW_RS;               // [nlev]
+  const LwColumn s = lw_column<SD>(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [3][LW_LCH_UP][SD::RS]
+  double* fracs = tile + 3 * LW_LCH_UP * SD::RS;               // [nlev]
   double* fsds = fracs + nlev;                          // [nlev]
   const int c = s.c, g = s.g, nl1 = nlev + 1;
-  for (int l = g; l < nlev; l += LW_THREADS) {
+  for (int l = g; l < nlev; l += SD::THREADS) {
     fracs[l] = s.cloudy ? LD_IN(in.frac, c, l) : 0.0;
     fsds[l] = s.cloudy ? LD_IN(in.fsd, c, l) : 0.0;
   }
@@ -96,13 +99,13 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
   const CloudMeta& C = *T.cloud;
   const size_t n = s.n;
   double *sa = s.scr, *sb = s.scr + n, *sA = s.scr + 2 * n, *sS = s.scr + 3 * n, *sP = s.scr + 4 * n;
-  const double emission = w.emission[(size_t)c * NG_LW + s.gg], albedo = w.lw_albedo[(size_t)c * NG_LW + s.gg];
+  const double emission = w.emission[(size_t)c * SD::NG + s.gg], albedo = w.lw_albedo[(size_t)c * SD::NG + s.gg];
   const int b = T.meta->band_of_g_lw[s.gg];
-  const uint4* codep = reinterpret_cast<const uint4*>(w.code_lw + ((size_t)c * NG_LW + s.gg) * nlevp);
-  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
+  const uint4* codep = reinterpret_cast<const uint4*>(w.code_lw + ((size_t)c * SD::NG + s.gg) * nlevp);
+  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * SD::NB;
   const bool cloudy = s.cloudy;
   const int ict = s.ict;
-  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[NG_LW + s.gg];
+  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[SD::NG + s.gg];
   double* dst[3] = {s.sums + LWS_UP_C * nl1, s.sums + LWS_DV_C * nl1, s.sums + LWS_UP_A * nl1};
   const int nf = cloudy ? 3 : 2;
   const BandOut bo[1] = {{(cfg.do_save_spectral_flux && cfg.solver_lw == 0) ? out.lw_up_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0}};   // Cloudless
@@ -112,21 +115,21 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
   double A = albedo, S = emission;                  // cloudy sub-column: albedo / source of everything below
   double fu_a = 0.0, pa = 1.0;                      // cloudy flux_up (above cloud top), product of transmittances
   int slot = 0, lfirst = nlev;
-  if (s.act) { tile[g] = fu; tile[LW_LCH_UP * LW_RS + g] = prod; tile[2 * LW_LCH_UP * LW_RS + g] = 0.0; }
+  if (s.act) { tile[g] = fu; tile[LW_LCH_UP * SD::RS + g] = prod; tile[2 * LW_LCH_UP * SD::RS + g] = 0.0; }
   ++slot;
   uint4 cq = make_uint4(0, 0, 0, 0);
-  double pb = s.act ? s.pl[(size_t)nlev * NG_LW + g] : 0.0;
+  double pb = s.act ? s.pl[(size_t)nlev * SD::NG + g] : 0.0;
   // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
-  double od_n = s.act ? s.od[(size_t)(nlev - 1) * NG_LW + g] : 0.0, pt_n = s.act ? s.pl[(size_t)(nlev - 1) * NG_LW + g] : 0.0;
+  double od_n = s.act ? s.od[(size_t)(nlev - 1) * SD::NG + g] : 0.0, pt_n = s.act ? s.pl[(size_t)(nlev - 1) * SD::NG + g] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
     if (s.act) {
-      const size_t i = (size_t)l * NG_LW + g;
+      const size_t i = (size_t)l * SD::NG + g;
       const double odg = od_n, pt = pt_n;
-      if (l > 0) { od_n = s.od[i - NG_LW]; pt_n = s.pl[i - NG_LW]; }
+      if (l > 0) { od_n = s.od[i - SD::NG]; pt_n = s.pl[i - SD::NG]; }
       const LwLayer Lc = lw_no_scat(odg, pt, pb);
       fu = Lc.trans * fu + Lc.source_up;
       prod = prod * Lc.trans;
-      tile[slot * LW_RS + g] = fu; tile[(LW_LCH_UP + slot) * LW_RS + g] = prod;
+      tile[slot * SD::RS + g] = fu; tile[(LW_LCH_UP + slot) * SD::RS + g] = prod;
       if (cloudy) {
         if (l >= ict) {
           if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
@@ -134,17 +137,17 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
           if (fracs[l] >= s.thr) {
             // radiation_mcica_lw.F90:248-294: gas + scaled cloud
             const double scal = od_scaling_from_code(C, T.pdf_val, pick4(cq, l & 3), fsds[l]);
-            const double* clb = cl + (size_t)l * 3 * NB_LW;
+            const double* clb = cl + (size_t)l * 3 * SD::NB;
             const double od_cloud_new = scal * clb[b];
             const double od_total = odg + od_cloud_new;
             LwLayer L;
             if (cfg.do_lw_cloud_scattering) {
               double ssa_total = 0.0, g_total = 0.0;
               if (od_total > 0.0) {
-                const double ssac = clb[NB_LW + b];
+                const double ssac = clb[SD::NB + b];
                 const double scat_od = ssac * od_cloud_new;
                 ssa_total = scat_od / od_total;
-                if (scat_od > 0.0) g_total = clb[2 * NB_LW + b] * ssac * od_cloud_new / scat_od;
+                if (scat_od > 0.0) g_total = clb[2 * SD::NB + b] * ssac * od_cloud_new / scat_od;
               }
               L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
             } else {
@@ -173,34 +176,35 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
           pa = pa * Lc.trans;
         }
         sP[i] = pa;
-        tile[(2 * LW_LCH_UP + slot) * LW_RS + g] = l <= ict ? fu_a : 0.0;
+        tile[(2 * LW_LCH_UP + slot) * SD::RS + g] = l <= ict ? fu_a : 0.0;
       }
       pb = pt;
     }
     ++slot;
     if (slot == LW_LCH_UP || l == 0) {
-      if (bo[0].dst) flush_bands(tile, LW_RS, LW_LCH_UP, slot, bo, 1, lfirst, -1, c, NB_LW, T.meta->lw);
-      flush_tile(tile, LW_RS, NG_LW, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0;
+      if (bo[0].dst) flush_bands(tile, SD::RS, LW_LCH_UP, slot, bo, 1, lfirst, -1, c, SD::NB, T.meta->lw);
+      flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0;
     }
   }
-  if (s.act) { s.carry[2 * NG_LW + g] = fu; s.carry[3 * NG_LW + g] = fu_a; }
+  if (s.act) { s.carry[2 * SD::NG + g] = fu; s.carry[3 * SD::NG + g] = fu_a; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // cloudy fluxes from cloud top down, derivative sums, and the flux_type outputs
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LW_THREADS, 6)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 6))
 lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const LwColumn s = lw_column(cfg, w, nlev);
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LW_LCH_FLUX][LW_RS]
+  const LwColumn s = lw_column<SD>(cfg, w, nlev);
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LW_LCH_FLUX][SD::RS]
   const int c = s.c, g = s.g, nl1 = nlev + 1;
   const bool act = s.act, cloudy = s.cloudy;
   const int ict = s.ict;
   const size_t n = s.n;
   const double *sa = s.scr, *sb = s.scr + n, *sA = s.scr + 2 * n, *sS = s.scr + 3 * n, *sP = s.scr + 4 * n;
-  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[NG_LW + s.gg];
-  const double fu_toa_clear = s.carry[2 * NG_LW + s.gg], fu_toa_a = s.carry[3 * NG_LW + s.gg];
+  const double fd_ict = s.carry[s.gg], fd_surf_clear = s.carry[SD::NG + s.gg];
+  const double fu_toa_clear = s.carry[2 * SD::NG + s.gg], fu_toa_a = s.carry[3 * SD::NG + s.gg];
   double fd_surf = fd_surf_clear;
   const bool want_dv = cfg.do_lw_derivatives && out.lw_derivatives;
   if (cloudy) {
@@ -212,7 +216,7 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
         double va[4], vb[4], vA[4], vS[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (act && l0 + k < nlev) { const size_t i = (size_t)(l0 + k) * NG_LW + g; va[k] = sa[i]; vb[k] = sb[i]; vA[k] = sA[i]; vS[k] = sS[i]; }
+          if (act && l0 + k < nlev) { const size_t i = (size_t)(l0 + k) * SD::NG + g; va[k] = sa[i]; vb[k] = sb[i]; vA[k] = sA[i]; vS[k] = sS[i]; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int l = l0 + k;
@@ -220,10 +224,10 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
             if (act) {
               fd = va[k] * fd + vb[k];
               fu = vA[k] * fd + vS[k];
-              tile[slot * LW_RS + g] = fd; tile[(LW_LCH_FLUX + slot) * LW_RS + g] = fu;
+              tile[slot * SD::RS + g] = fd; tile[(LW_LCH_FLUX + slot) * SD::RS + g] = fu;
             }
             ++slot;
-            if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+            if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
           }
         }
       }
@@ -235,9 +239,9 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
       int slot = 0, lfirst = 0;
 #pragma unroll 4
       for (int l = 0; l < nlev; ++l) {
-        if (act) tile[slot * LW_RS + g] = fu * sP[(size_t)l * NG_LW + g];
+        if (act) tile[slot * SD::RS + g] = fu * sP[(size_t)l * SD::NG + g];
         ++slot;
-        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, LW_RS, NG_LW, 1, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
       }
     }
   }
@@ -247,7 +251,7 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   const double *s_dn_clear = s.sums + LWS_DN_C * nl1, *s_up_clear = s.sums + LWS_UP_C * nl1, *s_dv_clear = s.sums + LWS_DV_C * nl1;
   const double *s_up = s.sums + LWS_UP_A * nl1, *s_dn = s.sums + LWS_DN_A * nl1, *s_dv = s.sums + LWS_DV_A * nl1;
   const double tcc = s.tcc, wc = tcc, w1 = 1.0 - tcc;
-  for (int l = g; l < nl1; l += LW_THREADS) {
+  for (int l = g; l < nl1; l += SD::THREADS) {
     const double upc = s_up_clear[l], dnc = s_dn_clear[l];
     if (out.lw_up_clear) OUT2(out.lw_up_clear, l) = upc;
     if (out.lw_dn_clear) OUT2(out.lw_dn_clear, l) = dnc;
@@ -271,27 +275,38 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   if (g == 0 && out.cloud_cover_lw && s.mcica) out.cloud_cover_lw[c] = tcc;
   const double dn_surf_g = cloudy ? wc * fd_surf + w1 * fd_surf_clear : fd_surf_clear;
   if (act) {
-    const size_t i = (size_t)c * NG_LW + g;
+    const size_t i = (size_t)c * SD::NG + g;
     if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
     if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fu_toa_clear;
     if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
     if (out.lw_up_toa_g) out.lw_up_toa_g[i] = cloudy ? wc * fu_toa_a + w1 * fu_toa_clear : fu_toa_clear;
   }
-  lw_surface_canopy(T, cfg, out, c, g, act, tile, dn_surf_g);
+  lw_surface_canopy<SD>(T, cfg, out, c, g, act, tile, dn_surf_g);
 #undef OUT2
 }
 
-int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+template <class SD>
+static int launch_solver_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
-  const size_t sm1 = sizeof(double) * (LCH * LW_RS) + 16;
-  const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * LW_RS + 2 * nlev) + 16;
-  const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * LW_RS) + 16;
-  lw_down_kernel<<<nc, LW_THREADS, sm1, st>>>(T, cfg, out, w, nlev);
+  const size_t sm1 = sizeof(double) * (LCH * SD::RS) + 16;
+  const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * SD::RS + 2 * nlev) + 16;
+  const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
+  lw_down_kernel<SD><<<nc, SD::THREADS, sm1, st>>>(T, cfg, out, w, nlev);
   if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
-  cudaFuncSetAttribute(lw_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  lw_up_kernel<<<nc, LW_THREADS, sm2, st>>>(T, cfg, in, out, w, nlev, nlevp);
-  lw_flux_kernel<<<nc, LW_THREADS, sm3, st>>>(T, cfg, out, w, nlev);
+  cudaFuncSetAttribute(lw_up_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  lw_up_kernel<SD><<<nc, SD::THREADS, sm2, st>>>(T, cfg, in, out, w, nlev, nlevp);
+  lw_flux_kernel<SD><<<nc, SD::THREADS, sm3, st>>>(T, cfg, out, w, nlev);
   return 3;
+}
+
+int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  switch (cfg.ng_lw) {
+    case NG_LW: return launch_solver_lw_t<LwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
+    case 32: return launch_solver_lw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);
+    case 64: return launch_solver_lw_t<Ckd64>(T, cfg, in, out, w, nc, nlev, st);
+    case 96: return launch_solver_lw_t<Ckd96>(T, cfg, in, out, w, nc, nlev, st);
+  }
+  return -1;   // check_config refuses other spectral sizes
 }
 
 }  // namespace ecb

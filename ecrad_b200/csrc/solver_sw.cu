@@ -13,9 +13,10 @@
 
 namespace ecb {
 
-enum { SW_THREADS = 128, SW_RS = 113, SW_LCH_FLUX = 8 };
+enum { SW_LCH_FLUX = 8 };
 
 // total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
+template <class SD>
 __device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd, const double* clb,
                                                 int b, double od_gas, double ssa_gas, double g_gas, double& odt, double& ssat, double& gt) {
   const double scal = od_scaling_from_code(C, pdf_val, code, fsd);
@@ -23,10 +24,10 @@ __device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double
   odt = od_gas + od_cloud_new;
   ssat = 0.0; gt = 0.0;
   if (odt > 0.0) {
-    const double ssac = clb[NB_SW + b];
+    const double ssac = clb[SD::NB + b];
     const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
     ssat = scat_od / odt;
-    if (scat_od > 0.0) gt = (g_gas * ssa_gas * od_gas + clb[2 * NB_SW + b] * ssac * od_cloud_new) / scat_od;
+    if (scat_od > 0.0) gt = (g_gas * ssa_gas * od_gas + clb[2 * SD::NB + b] * ssac * od_cloud_new) / scat_od;
   }
 }
 
@@ -37,20 +38,21 @@ struct SwColumn {
   double* scr;
 };
 
+template <class SD>
 __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nlev, int nlevp) {
   SwColumn s;
-  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < NG_SW; s.gg = s.act ? s.g : 0;
+  s.c = blockIdx.x; s.g = threadIdx.x; s.act = s.g < SD::NG; s.gg = s.act ? s.g : 0;
   s.mu0 = in.cos_sza[s.c];
   s.tcc = cfg.solver_sw == 2 ? w.tcc[s.c] : 0.0;
   s.cloudy = s.tcc > 0.0;
   s.thr = cfg.cloud_fraction_threshold;
-  s.n = (size_t)nlev * NG_SW;
+  s.n = (size_t)nlev * SD::NG;
   s.od = w.od_sw + (size_t)s.c * s.n;
   s.ssa = w.ssa_sw + (size_t)s.c * s.n;
   s.gas_g = (cfg.use_aerosols && w.g_sw) ? w.g_sw + (size_t)s.c * s.n : nullptr;
-  s.cl = w.cl_sw + (size_t)s.c * nlev * 3 * NB_SW;
+  s.cl = w.cl_sw + (size_t)s.c * nlev * 3 * SD::NB;
   s.b = T.meta->band_of_g_sw[s.gg];
-  s.codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)s.c * NG_SW + s.gg) * nlevp);
+  s.codep = reinterpret_cast<const uint4*>(w.code_sw + ((size_t)s.c * SD::NG + s.gg) * nlevp);
   s.scr = w.scr_sw + (size_t)s.c * SW_SCR_ARRAYS * s.n;
   return s;
 }
@@ -58,16 +60,16 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 // ---------------------------------------------------------------------------------------------------------
 // A: direct beam, top-down (radiation_adding_ica_sw.F90:85-88)
 // ---------------------------------------------------------------------------------------------------------
-template <bool CLOUDLESS>
-__global__ void __launch_bounds__(SW_THREADS, 6)
+template <class SD, bool CLOUDLESS>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 6))
 sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  const SwColumn s = sw_column<SD>(T, cfg, in, w, nlev, nlevp);
   if (!(s.mu0 > 0.0)) return;
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LCH][SW_RS]
-  double* fracs = tile + 2 * LCH * SW_RS;               // [nlev]
+  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LCH][SD::RS]
+  double* fracs = tile + 2 * LCH * SD::RS;               // [nlev]
   double* fsds = fracs + nlev;                          // [nlev]
-  for (int l = s.g; l < nlev; l += SW_THREADS) {
+  for (int l = s.g; l < nlev; l += SD::THREADS) {
     fracs[l] = s.cloudy ? LD_IN(in.frac, s.c, l) : 0.0;
     fsds[l] = s.cloudy ? LD_IN(in.fsd, s.c, l) : 0.0;
   }
@@ -83,7 +85,7 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev
   const BandOut bo[2] = {{bands ? out.sw_dn_direct_band : nullptr, out.ld, 0, -1, s.mu0, 0.0, nullptr, 0},
                          {bands ? w.sw_band_dir : nullptr, (int)gridDim.x, 0, -1, s.mu0, 0.0, nullptr, 0}};
   const double inv_mu0 = 1.0 / s.mu0;
-  double fc = w.incoming[(size_t)s.c * NG_SW + s.gg], fa = fc;
+  double fc = w.incoming[(size_t)s.c * SD::NG + s.gg], fa = fc;
   int slot = 0, lfirst = 0;
   uint4 cq = make_uint4(0, 0, 0, 0);
   // software pipeline: od (and ssa where needed) of layer l+1 are loaded before the exp of layer l
@@ -91,9 +93,9 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev
   double od_n = s.act ? s.od[g] : 0.0, ssa_n = (s.act && need_ssa) ? s.ssa[g] : 0.0;
   for (int l = 0; l < nlev; ++l) {
     if (s.act) {
-      const size_t i = (size_t)l * NG_SW + g;
+      const size_t i = (size_t)l * SD::NG + g;
       const double odg = od_n, ssag = ssa_n;
-      if (l + 1 < nlev) { od_n = s.od[i + NG_SW]; if (need_ssa) ssa_n = s.ssa[i + NG_SW]; }
+      if (l + 1 < nlev) { od_n = s.od[i + SD::NG]; if (need_ssa) ssa_n = s.ssa[i + SD::NG]; }
       double tdir_c;
       const double gg_gas = (need_ssa && s.gas_g) ? s.gas_g[i] : 0.0;
       if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, ssag, gg_gas).trans_dir_dir;
@@ -103,52 +105,52 @@ sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev
         if ((l & 3) == 0) cq = __ldg(s.codep + (l >> 2));
         if (fracs[l] >= s.thr) {
           double odt, ssat, gt;
-          sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, gg_gas, odt, ssat, gt);
+          sw_cloudy_props<SD>(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * SD::NB, s.b, odg, ssag, gg_gas, odt, ssat, gt);
           tdir_a = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
         }
         sFa[i] = fa;
-        tile[(LCH + slot) * SW_RS + g] = fa;
+        tile[(LCH + slot) * SD::RS + g] = fa;
       }
       sFc[i] = fc;
-      tile[slot * SW_RS + g] = fc;
+      tile[slot * SD::RS + g] = fc;
       fc = fc * tdir_c;
       fa = fa * tdir_a;
     }
     ++slot;
     if (slot == LCH) {
-      if (bands) flush_bands(tile, SW_RS, LCH, slot, bo, 2, lfirst, 1, s.c, NB_SW, T.meta->sw);
-      flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
+      if (bands) flush_bands(tile, SD::RS, LCH, slot, bo, 2, lfirst, 1, s.c, SD::NB, T.meta->sw);
+      flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
     }
   }
-  if (s.act) { tile[slot * SW_RS + g] = fc; tile[(LCH + slot) * SW_RS + g] = fa; }
+  if (s.act) { tile[slot * SD::RS + g] = fc; tile[(LCH + slot) * SD::RS + g] = fa; }
   ++slot;
-  if (bands) flush_bands(tile, SW_RS, LCH, slot, bo, 2, lfirst, 1, s.c, NB_SW, T.meta->sw);
-  flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1);
+  if (bands) flush_bands(tile, SD::RS, LCH, slot, bo, 2, lfirst, 1, s.c, SD::NB, T.meta->sw);
+  flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1);
   if (s.act) {
-    double* carry = w.sw_carry + (size_t)s.c * 4 * NG_SW;
-    carry[g] = fc; carry[NG_SW + g] = fa;
+    double* carry = w.sw_carry + (size_t)s.c * 4 * SD::NG;
+    carry[g] = fc; carry[SD::NG + g] = fa;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // B: two-stream layer solutions and the upward sweep of albedo / source (radiation_adding_ica_sw.F90:90-121)
 // ---------------------------------------------------------------------------------------------------------
-template <bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
-__global__ void __launch_bounds__(SW_THREADS, 3)
+template <class SD, bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 3))
 sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  const SwColumn s = sw_column<SD>(T, cfg, in, w, nlev, nlevp);
   if (!(s.mu0 > 0.0)) return;
   double* fracs = reinterpret_cast<double*>(smem_raw);   // [nlev]
   double* fsds = fracs + nlev;                           // [nlev]
   double* bandv = fsds + nlev;                           // [2][14] band albedos
   const int g = s.g, c = s.c;
-  for (int l = g; l < nlev; l += SW_THREADS) {
+  for (int l = g; l < nlev; l += SD::THREADS) {
     fracs[l] = s.cloudy ? LD_IN(in.frac, c, l) : 0.0;
     fsds[l] = s.cloudy ? LD_IN(in.fsd, c, l) : 0.0;
   }
   // get_albedos, radiation_single_level.F90:216-365 (weighted-interval mapping to bands)
-  if (g < NB_SW) {
+  if (g < SD::NB) {
     double bd = 0.0, bdir = 0.0;
     for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
       const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
@@ -157,7 +159,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
         if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja);
       }
     }
-    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
+    bandv[g] = bd; bandv[SD::NB + g] = in.sw_albedo_direct ? bdir : bd;
   }
   __syncthreads();
   if (!s.act) return;
@@ -166,20 +168,20 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   const double* sFc = s.scr; const double* sFa = s.scr + n;
   double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
   double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
-  double* carry = w.sw_carry + (size_t)c * 4 * NG_SW;
-  const double alb_diff = bandv[s.b], alb_dir = bandv[NB_SW + s.b];
+  double* carry = w.sw_carry + (size_t)c * 4 * SD::NG;
+  const double alb_diff = bandv[s.b], alb_dir = bandv[SD::NB + s.b];
   const double mu0 = s.mu0;
   double A_c = alb_diff, S_c = alb_dir * carry[g] * mu0;
-  double A_a = alb_diff, S_a = alb_dir * carry[NG_SW + g] * mu0;
+  double A_a = alb_diff, S_a = alb_dir * carry[SD::NG + g] * mu0;
   uint4 cq = make_uint4(0, 0, 0, 0);
   // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
-  size_t i = (size_t)(nlev - 1) * NG_SW + g;
+  size_t i = (size_t)(nlev - 1) * SD::NG + g;
   double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0, gg_n = AER ? s.gas_g[i] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
     const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n, gg_gas = AER ? gg_n : 0.0;
-    i = (size_t)l * NG_SW + g;
+    i = (size_t)l * SD::NG + g;
     if (l > 0) {
-      const size_t ip = i - NG_SW;
+      const size_t ip = i - SD::NG;
       od_n = s.od[ip]; ssa_n = s.ssa[ip]; fc_n = sFc[ip];
       if (s.cloudy) fa_n = sFa[ip];
       if (AER) gg_n = s.gas_g[ip];
@@ -199,7 +201,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       SwLayer La = Lc;
       if (fracs[l] >= s.thr) {
         double odt, ssat, gt;
-        sw_cloudy_props(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * NB_SW, s.b, odg, ssag, gg_gas, odt, ssat, gt);
+        sw_cloudy_props<SD>(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * SD::NB, s.b, odg, ssag, gg_gas, odt, ssat, gt);
         La = sw_ref_trans(mu0, odt, ssat, gt);
       }
       const double inv_den = 1.0 / (1.0 - A_a * La.ref);
@@ -211,24 +213,25 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       A_a = A_new; S_a = S_new;
     }
   }
-  carry[2 * NG_SW + g] = S_c;   // flux_up at TOA = source(1)
-  carry[3 * NG_SW + g] = S_a;
+  carry[2 * SD::NG + g] = S_c;   // flux_up at TOA = source(1)
+  carry[3 * SD::NG + g] = S_a;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // C: fluxes top-down (radiation_adding_ica_sw.F90:134-146), g-point sums, blending and the flux_type outputs
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SW_THREADS, 5)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 5))
 sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SwColumn s = sw_column(T, cfg, in, w, nlev, nlevp);
+  const SwColumn s = sw_column<SD>(T, cfg, in, w, nlev, nlevp);
   const int c = s.c, g = s.g, nl1 = nlev + 1;
   const bool act = s.act;
   const double mu0 = s.mu0;
 #define OUT2(p, l) ((p)[(size_t)(l) * out.ld + c])
   if (!(mu0 > 0.0)) {
     // night column: radiation_mcica_sw.F90:380-401
-    for (int l = g; l < nl1; l += SW_THREADS) {
+    for (int l = g; l < nl1; l += SD::THREADS) {
       if (out.sw_up) OUT2(out.sw_up, l) = 0.0;
       if (out.sw_dn) OUT2(out.sw_dn, l) = 0.0;
       if (out.sw_dn_direct) OUT2(out.sw_dn_direct, l) = 0.0;
@@ -239,17 +242,17 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     if (cfg.solver_sw == 0 && cfg.do_save_spectral_flux) {   // Cloudless: per-band profiles (radiation_cloudless_sw.F90)
       double* pb[3] = {out.sw_up_band, out.sw_dn_band, out.sw_dn_direct_band};
       for (int k = 0; k < 3; ++k)
-        if (pb[k]) for (int i = g; i < nl1 * NB_SW; i += SW_THREADS) pb[k][((size_t)(i / NB_SW) * out.ld + c) * NB_SW + (i % NB_SW)] = 0.0;
+        if (pb[k]) for (int i = g; i < nl1 * SD::NB; i += SD::THREADS) pb[k][((size_t)(i / SD::NB) * out.ld + c) * SD::NB + (i % SD::NB)] = 0.0;
     }
     if (act) {
-      const size_t i = (size_t)c * NG_SW + g;
+      const size_t i = (size_t)c * SD::NG + g;
       double* gs[6] = {out.sw_dn_diffuse_surf_g, out.sw_dn_direct_surf_g, out.sw_up_toa_g,
                        out.sw_dn_diffuse_surf_clear_g, out.sw_dn_direct_surf_clear_g, out.sw_up_toa_clear_g};
       for (int k = 0; k < 6; ++k) if (gs[k]) gs[k][i] = 0.0;
     }
-    if (g < NB_SW) {
+    if (g < SD::NB) {
       double* bs[4] = {out.sw_dn_surf_band, out.sw_dn_direct_surf_band, out.sw_dn_surf_clear_band, out.sw_dn_direct_surf_clear_band};
-      for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * NB_SW + g] = 0.0;
+      for (int k = 0; k < 4; ++k) if (bs[k] && cfg.do_surface_sw_spectral_flux) bs[k][(size_t)c * SD::NB + g] = 0.0;
     }
     if (g < cfg.n_canopy_bands_sw && cfg.do_canopy_fluxes_sw) {
       if (out.sw_dn_diffuse_surf_canopy) out.sw_dn_diffuse_surf_canopy[(size_t)c * cfg.n_canopy_bands_sw + g] = 0.0;
@@ -258,16 +261,16 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     return;
   }
   double* ssum = reinterpret_cast<double*>(smem_raw);    // [4][nl1]: dn_c, up_c, dn_a, up_a
-  double* tile = ssum + 4 * nl1;                          // [4][SW_LCH_FLUX][SW_RS]
+  double* tile = ssum + 4 * nl1;                          // [4][SW_LCH_FLUX][SD::RS]
   double *s_dn_c = ssum, *s_up_c = ssum + nl1, *s_dn = ssum + 2 * nl1, *s_up = ssum + 3 * nl1;
   const double* gsum = w.sw_sums + (size_t)c * 6 * nl1;   // direct-beam sums from sw_direct_kernel
   const double *s_dir_c = gsum, *s_dir = gsum + 3 * nl1;
   const size_t n = s.n;
   const double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
   const double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
-  const double* carry = w.sw_carry + (size_t)c * 4 * NG_SW;
+  const double* carry = w.sw_carry + (size_t)c * 4 * SD::NG;
   const bool cloudy = s.cloudy;
-  const double toa_c = carry[2 * NG_SW + s.gg], toa_a0 = carry[3 * NG_SW + s.gg];
+  const double toa_c = carry[2 * SD::NG + s.gg], toa_a0 = carry[3 * SD::NG + s.gg];
   double fdd_c = 0.0, fdd_a = 0.0;
   {
     double* dst[4] = {s_dn_c, s_up_c, s_dn, s_up};
@@ -278,8 +281,8 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
                            {bands ? out.sw_dn_band : nullptr, out.ld, 0, -1, 1.0, 0.0, w.sw_band_dir, (int)gridDim.x}};
     int slot = 0, lfirst = 0;
     if (act) {
-      tile[slot * SW_RS + g] = 0.0; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = toa_c;
-      tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = 0.0; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = toa_a0;
+      tile[slot * SD::RS + g] = 0.0; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = toa_c;
+      tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = 0.0; tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = toa_a0;
     }
     ++slot;
     for (int l0 = 0; l0 < nlev; l0 += 4) {
@@ -287,7 +290,7 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (act && l0 + k < nlev) {
-          const size_t i = (size_t)(l0 + k) * NG_SW + g;
+          const size_t i = (size_t)(l0 + k) * SD::NG + g;
           ca[k] = ac[i]; cb[k] = bc[i]; cA[k] = Ac[i]; cS[k] = Sc[i];
           if (cloudy) { da[k] = aa[i]; db[k] = ba[i]; dA[k] = Aa[i]; dS[k] = Sa[i]; }
         }
@@ -298,17 +301,17 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
           if (act) {
             fdd_c = ca[k] * fdd_c + cb[k];
             const double fu_c = cA[k] * fdd_c + cS[k];
-            tile[slot * SW_RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SW_RS + g] = fu_c;
+            tile[slot * SD::RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = fu_c;
             if (cloudy) {
               fdd_a = da[k] * fdd_a + db[k];
               const double fu_a = dA[k] * fdd_a + dS[k];
-              tile[(2 * SW_LCH_FLUX + slot) * SW_RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SW_RS + g] = fu_a;
+              tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = fu_a;
             }
           }
           ++slot;
           if (slot == SW_LCH_FLUX || l == nlev - 1) {
-            if (bands) flush_bands(tile, SW_RS, SW_LCH_FLUX, slot, bo, 2, lfirst, 1, c, NB_SW, T.meta->sw);
-            flush_tile(tile, SW_RS, NG_SW, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0;
+            if (bands) flush_bands(tile, SD::RS, SW_LCH_FLUX, slot, bo, 2, lfirst, 1, c, SD::NB, T.meta->sw);
+            flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0;
           }
         }
       }
@@ -316,7 +319,7 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
   }
   const double tcc = s.tcc;
   const double wc = tcc, w1 = 1.0 - tcc;
-  for (int l = g; l < nl1; l += SW_THREADS) {
+  for (int l = g; l < nl1; l += SD::THREADS) {
     const double dirc = s_dir_c[l] * mu0, upc = s_up_c[l], dnc = s_dn_c[l] + dirc;
     if (out.sw_up_clear) OUT2(out.sw_up_clear, l) = upc;
     if (out.sw_dn_clear) OUT2(out.sw_dn_clear, l) = dnc;
@@ -338,11 +341,11 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
   double dif_a = dif_c, dir_a = dir_c, toa_a = toa_c;
   if (cloudy) {
     dif_a = wc * fdd_a + w1 * dif_c;
-    dir_a = wc * (carry[NG_SW + s.gg] * mu0) + w1 * dir_c;
+    dir_a = wc * (carry[SD::NG + s.gg] * mu0) + w1 * dir_c;
     toa_a = wc * toa_a0 + w1 * toa_c;
   }
   if (act) {
-    const size_t i = (size_t)c * NG_SW + g;
+    const size_t i = (size_t)c * SD::NG + g;
     if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
     if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
     if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
@@ -350,28 +353,39 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
     if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
   }
-  sw_surface_spectral(T, cfg, out, c, g, act, tile, SW_RS, dir_a, dif_a, dir_c, dif_c);
+  sw_surface_spectral<SD>(T, cfg, out, c, g, act, tile, SD::RS, dir_a, dif_a, dir_c, dif_c);
 #undef OUT2
 }
 
-int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+template <class SD>
+static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
-  const size_t smA = sizeof(double) * (2 * LCH * SW_RS + 2 * nlev) + 16;
-  const size_t smB = sizeof(double) * (2 * nlev + 2 * NB_SW) + 16;
-  const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SW_RS) + 16;
-  if (cfg.solver_sw == 4) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
+  const size_t smA = sizeof(double) * (2 * LCH * SD::RS + 2 * nlev) + 16;
+  const size_t smB = sizeof(double) * (2 * nlev + 2 * SD::NB) + 16;
+  const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
   const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
-    sw_direct_kernel<false><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
-    if (aer) sw_adding_kernel<false, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
-    else sw_adding_kernel<false, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_direct_kernel<SD, false><<<nc, SD::THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
+    if (aer) sw_adding_kernel<SD, false, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    else sw_adding_kernel<SD, false, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   } else {
-    sw_direct_kernel<true><<<nc, SW_THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
-    if (aer) sw_adding_kernel<true, true><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
-    else sw_adding_kernel<true, false><<<nc, SW_THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    sw_direct_kernel<SD, true><<<nc, SD::THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
+    if (aer) sw_adding_kernel<SD, true, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    else sw_adding_kernel<SD, true, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   }
-  sw_flux_kernel<<<nc, SW_THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
+  sw_flux_kernel<SD><<<nc, SD::THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
   return 3;
+}
+
+int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  if (cfg.solver_sw == 4) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
+  switch (cfg.ng_sw) {
+    case NG_SW: return launch_solver_sw_t<SwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
+    case 32: return launch_solver_sw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);
+    case 64: return launch_solver_sw_t<Ckd64>(T, cfg, in, out, w, nc, nlev, st);
+    case 96: return launch_solver_sw_t<Ckd96>(T, cfg, in, out, w, nc, nlev, st);
+  }
+  return -1;   // check_config refuses other spectral sizes
 }
 
 }  // namespace ecb

@@ -13,7 +13,7 @@
 
 namespace ecb {
 
-enum { TC_SW_THREADS = 128, TC_SW_RS = 113, TC_LW_THREADS = 160, TC_LW_RS = 141, TC_LCH = 8 };
+enum { TC_LCH = 8 };
 enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -68,38 +68,39 @@ __device__ __forceinline__ void mat3_x_vec(const double* A, double* x) {
 // =========================================================================================================
 // SW
 // =========================================================================================================
-__global__ void __launch_bounds__(TC_SW_THREADS, 2)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 2))
 tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
-  const bool act = g < NG_SW;
+  const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   const double mu0 = in.cos_sza[c];
   if (g == 0 && out.cloud_cover_sw) out.cloud_cover_sw[c] = w.tc_cc[c];   // set for every column, also at night
-  if (mu0 < 1.0e-10) { sw_night_column(cfg, out, c, g, act, nl1, TC_SW_THREADS); return; }
+  if (mu0 < 1.0e-10) { sw_night_column<SD>(cfg, out, c, g, act, nl1, SD::THREADS); return; }
   double* sums = reinterpret_cast<double*>(smem_raw);     // [6][nl1]: up, dn_dif, dn_dir, up_c, dn_dif_c, dn_dir_c
-  double* tile = sums + 6 * nl1;                           // [6][TC_LCH][TC_SW_RS]
-  double* bandv = tile + 6 * TC_LCH * TC_SW_RS;            // [2][14]
-  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(bandv + 2 * NB_SW), w, in, c, nlev, TC_SW_THREADS);
-  if (g < NB_SW) {   // get_albedos, radiation_single_level.F90:216-365
+  double* tile = sums + 6 * nl1;                           // [6][TC_LCH][SD::RS]
+  double* bandv = tile + 6 * TC_LCH * SD::RS;            // [2][14]
+  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(bandv + 2 * SD::NB), w, in, c, nlev, SD::THREADS);
+  if (g < SD::NB) {   // get_albedos, radiation_single_level.F90:216-365
     double bd = 0.0, bdir = 0.0;
     for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
       const double wgt = T.sw_albedo_weights[g * cfg.n_albedo_sw + ja];
       if (wgt != 0.0) { bd = bd + wgt * LD_IN(in.sw_albedo, c, ja); if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja); }
     }
-    bandv[g] = bd; bandv[NB_SW + g] = in.sw_albedo_direct ? bdir : bd;
+    bandv[g] = bd; bandv[SD::NB + g] = in.sw_albedo_direct ? bdir : bd;
   }
   __syncthreads();
-  const size_t n = (size_t)nlev * NG_SW;
+  const size_t n = (size_t)nlev * SD::NG;
   const double* od = w.od_sw + (size_t)c * n;
   const double* ssa = w.ssa_sw + (size_t)c * n;
   const double* gas_g = (cfg.use_aerosols && w.g_sw) ? w.g_sw + (size_t)c * n : nullptr;
-  const double* cl = w.cl_sw + (size_t)c * nlev * 3 * NB_SW;
+  const double* cl = w.cl_sw + (size_t)c * nlev * 3 * SD::NB;
   double* scr = w.scr_sw + (size_t)c * TC_SW_ARRAYS * n;
 #define SCR(set, f, i) scr[(size_t)((set) * 5 + (f)) * n + (i)]   // sets: 0 clear-sky, 1..3 regions; fields: a b tdir talb talbdir
   const int b = T.meta->band_of_g_sw[gg];
-  const double alb_diff = bandv[b], alb_dir = bandv[NB_SW + b];
-  const double inc = w.incoming[(size_t)c * NG_SW + gg];
+  const double alb_diff = bandv[b], alb_dir = bandv[SD::NB + b];
+  const double inc = w.incoming[(size_t)c * SD::NG + gg];
 
   // ---- upward sweep: total albedos of everything below each half-level (radiation_tripleclouds_sw.F90:322-420) ----
   double ta[3] = {alb_diff, 0.0, 0.0}, td[3] = {mu0 * alb_dir, 0.0, 0.0};
@@ -108,7 +109,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   if (act) {
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
-      const size_t i = (size_t)l * NG_SW + g;
+      const size_t i = (size_t)l * SD::NG + g;
       const double odg = od[i], ssag = ssa[i], gg_gas = gas_g ? gas_g[i] : 0.0;
       const SwLayer Lc = sw_ref_trans(mu0, odg, ssag, gg_gas);
       {   // clear-sky column
@@ -126,13 +127,13 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         if (jr > 0 && S.clear[jl]) continue;
         SwLayer L = Lc;
         if (jr > 0) {   // cloudy region: gas/aerosol + scaled cloud (radiation_tripleclouds_sw.F90:286-302)
-          const double* clb = cl + (size_t)l * 3 * NB_SW;
+          const double* clb = cl + (size_t)l * 3 * SD::NB;
           const double scal = S.ods[l * 3 + jr];
           const double scat_od = odg * ssag;
-          const double scat_od_cloud = clb[b] * clb[NB_SW + b] * scal;
+          const double scat_od_cloud = clb[b] * clb[SD::NB + b] * scal;
           const double od_total = odg + clb[b] * scal;
           const double ssa_total = (scat_od + scat_od_cloud) / od_total;
-          const double g_total = (scat_od * gg_gas + scat_od_cloud * clb[2 * NB_SW + b]) / (scat_od + scat_od_cloud);
+          const double g_total = (scat_od * gg_gas + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
           L = sw_ref_trans(mu0, od_total, ssa_total, g_total);
         }
         const double id = 1.0 / (1.0 - ta[jr] * L.ref);
@@ -171,19 +172,19 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   int slot = 0, lfirst = 0;
 #define PUT_ROWS()                                                                                        \
   if (act) {                                                                                              \
-    tile[(0 * TC_LCH + slot) * TC_SW_RS + g] = fup[0] + fup[1] + fup[2];                                  \
-    tile[(1 * TC_LCH + slot) * TC_SW_RS + g] = fdn[0] + fdn[1] + fdn[2];                                  \
-    tile[(2 * TC_LCH + slot) * TC_SW_RS + g] = ddn[0] + ddn[1] + ddn[2];                                  \
-    tile[(3 * TC_LCH + slot) * TC_SW_RS + g] = fuc;                                                       \
-    tile[(4 * TC_LCH + slot) * TC_SW_RS + g] = fdc;                                                       \
-    tile[(5 * TC_LCH + slot) * TC_SW_RS + g] = ddc;                                                       \
+    tile[(0 * TC_LCH + slot) * SD::RS + g] = fup[0] + fup[1] + fup[2];                                  \
+    tile[(1 * TC_LCH + slot) * SD::RS + g] = fdn[0] + fdn[1] + fdn[2];                                  \
+    tile[(2 * TC_LCH + slot) * SD::RS + g] = ddn[0] + ddn[1] + ddn[2];                                  \
+    tile[(3 * TC_LCH + slot) * SD::RS + g] = fuc;                                                       \
+    tile[(4 * TC_LCH + slot) * SD::RS + g] = fdc;                                                       \
+    tile[(5 * TC_LCH + slot) * SD::RS + g] = ddc;                                                       \
   }                                                                                                       \
   ++slot;
   PUT_ROWS();
   for (int l = 0; l < nlev; ++l) {
     const int jl = l + 1;
     if (act) {
-      const size_t i = (size_t)l * NG_SW + g;
+      const size_t i = (size_t)l * SD::NG + g;
       fdc = SCR(0, 0, i) * fdc + SCR(0, 1, i) * ddc;
       ddc = SCR(0, 2, i) * ddc;
       fuc = ddc * SCR(0, 4, i) + fdc * SCR(0, 3, i);
@@ -202,14 +203,14 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     }
     PUT_ROWS();
     if (slot == TC_LCH || l == nlev - 1) {
-      if (bands) flush_bands(tile, TC_SW_RS, TC_LCH, slot, bo, 3, lfirst, 1, c, NB_SW, T.meta->sw);
-      flush_tile(tile, TC_SW_RS, NG_SW, 6, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
+      if (bands) flush_bands(tile, SD::RS, TC_LCH, slot, bo, 3, lfirst, 1, c, SD::NB, T.meta->sw);
+      flush_tile(tile, SD::RS, SD::NG, 6, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
     }
   }
 #undef PUT_ROWS
 #undef SCR
   // ---- outputs ----
-  for (int l = g; l < nl1; l += TC_SW_THREADS) {
+  for (int l = g; l < nl1; l += SD::THREADS) {
     const double dir = mu0 * sums[2 * nl1 + l], dirc = mu0 * sums[5 * nl1 + l];
     const size_t o = (size_t)l * out.ld + c;
     if (out.sw_up) out.sw_up[o] = sums[l];
@@ -221,7 +222,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   }
   const double dif_a = fdn[0] + fdn[1] + fdn[2], dir_a = mu0 * (ddn[0] + ddn[1] + ddn[2]), dif_c = fdc, dir_c = mu0 * ddc;
   if (act) {
-    const size_t i = (size_t)c * NG_SW + g;
+    const size_t i = (size_t)c * SD::NG + g;
     if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
     if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
     if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
@@ -229,34 +230,35 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
     if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
   }
-  sw_surface_spectral(T, cfg, out, c, g, act, tile, TC_SW_RS, dir_a, dif_a, dir_c, dif_c);
+  sw_surface_spectral<SD>(T, cfg, out, c, g, act, tile, SD::RS, dir_a, dif_a, dir_c, dif_c);
 }
 
 // =========================================================================================================
 // LW (after lw_down_kernel: clear-sky flux_dn sums, flux_dn at cloud top and at the surface per g-point)
 // =========================================================================================================
-__global__ void __launch_bounds__(TC_LW_THREADS, 2)
+template <class SD>
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 2))
 tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
-  const bool act = g < NG_LW;
+  const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   double* sums = reinterpret_cast<double*>(smem_raw);     // [4][nl1]: up_clear, up, dn, deriv
-  double* tile = sums + 4 * nl1;                           // [2][TC_LCH][TC_LW_RS]
-  double* red = tile + 2 * TC_LCH * TC_LW_RS;              // [8] block reduction scratch
-  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(red + 8), w, in, c, nlev, TC_LW_THREADS);
-  const size_t n = (size_t)nlev * NG_LW;
+  double* tile = sums + 4 * nl1;                           // [2][TC_LCH][SD::RS]
+  double* red = tile + 2 * TC_LCH * SD::RS;              // [8] block reduction scratch
+  const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(red + 8), w, in, c, nlev, SD::THREADS);
+  const size_t n = (size_t)nlev * SD::NG;
   const double* od = w.od_lw + (size_t)c * n;
-  const double* pl = w.planck + (size_t)c * nl1 * NG_LW;
-  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * NB_LW;
+  const double* pl = w.planck + (size_t)c * nl1 * SD::NG;
+  const double* cl = w.cl_lw + (size_t)c * nlev * 3 * SD::NB;
   const double* gsum = w.lw_sums + (size_t)c * 6 * nl1;     // row 0: clear-sky flux_dn sums (lw_down_kernel)
-  const double* carry = w.lw_carry + (size_t)c * 4 * NG_LW;
+  const double* carry = w.lw_carry + (size_t)c * 4 * SD::NG;
   double* scr = w.scr_lw + (size_t)c * TC_LW_ARRAYS * n;
 #define SCR(jr, f, i) scr[(size_t)((jr) * 5 + (f)) * n + (i)]   // fields: a b talb tsrc trans
   const int ict = w.ict[c];                                  // first cloudy layer (0-based), nlev if none
   const int b = T.meta->band_of_g_lw[gg];
-  const double emission = w.emission[(size_t)c * NG_LW + gg], albedo = w.lw_albedo[(size_t)c * NG_LW + gg];
-  const double fd_surf_clear = carry[NG_LW + gg];
+  const double emission = w.emission[(size_t)c * SD::NG + gg], albedo = w.lw_albedo[(size_t)c * SD::NG + gg];
+  const double fd_surf_clear = carry[SD::NG + gg];
   const double fd_ict = ict < nlev ? carry[gg] : fd_surf_clear;   // clear-sky flux_dn at the cloud-top half-level
   double* s_up_c = sums, *s_up = sums + nl1, *s_dn = sums + 2 * nl1, *s_dv = sums + 3 * nl1;
 
@@ -271,13 +273,13 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     double* dst[2] = {s_up_c, s_up};
     const BandOut bo[1] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = nlev;
-    if (act) { tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = fu; }
+    if (act) { tile[slot * SD::RS + g] = fuc; tile[(TC_LCH + slot) * SD::RS + g] = fu; }
     ++slot;
-    double pb = act ? pl[(size_t)nlev * NG_LW + g] : 0.0;
+    double pb = act ? pl[(size_t)nlev * SD::NG + g] : 0.0;
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
-        const size_t i = (size_t)l * NG_LW + g;
+        const size_t i = (size_t)l * SD::NG + g;
         const double odg = od[i], pt = pl[i];
         const LwLayer Lc = lw_no_scat(odg, pt, pb);
         fuc = Lc.trans * fuc + Lc.source_up;
@@ -289,13 +291,13 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
             if (jr > 0 && !cloudy_layer) { SCR(jr, 4, i) = 1.0; continue; }
             LwLayer L = Lc;
             if (jr > 0) {   // radiation_tripleclouds_lw.F90:247-300
-              const double* clb = cl + (size_t)l * 3 * NB_LW;
+              const double* clb = cl + (size_t)l * 3 * SD::NB;
               const double od_cloud_new = clb[b] * S.ods[l * 3 + jr];
               const double od_total = odg + od_cloud_new;
               if (cfg.do_lw_cloud_scattering) {
                 double ssa_total = 0.0, g_total = 0.0;
-                if (od_total > 0.0) ssa_total = clb[NB_LW + b] * od_cloud_new / od_total;
-                if (ssa_total > 0.0 && od_total > 0.0) g_total = clb[2 * NB_LW + b] * clb[NB_LW + b] * od_cloud_new / (ssa_total * od_total);
+                if (od_total > 0.0) ssa_total = clb[SD::NB + b] * od_cloud_new / od_total;
+                if (ssa_total > 0.0 && od_total > 0.0) g_total = clb[2 * SD::NB + b] * clb[SD::NB + b] * od_cloud_new / (ssa_total * od_total);
                 L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
               } else {
                 L = lw_no_scat(od_total, pt, pb);
@@ -328,12 +330,12 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           fu = Lc.trans * fu + Lc.source_up;            // above cloud top
         }
         pb = pt;
-        tile[slot * TC_LW_RS + g] = fuc; tile[(TC_LCH + slot) * TC_LW_RS + g] = l <= ict ? fu : 0.0;
+        tile[slot * SD::RS + g] = fuc; tile[(TC_LCH + slot) * SD::RS + g] = l <= ict ? fu : 0.0;
       }
       ++slot;
       if (slot == TC_LCH || l == 0) {
-        if (bo[0].dst) flush_bands(tile, TC_LW_RS, TC_LCH, slot, bo, 1, lfirst, -1, c, NB_LW, T.meta->lw);
-        flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0;
+        if (bo[0].dst) flush_bands(tile, SD::RS, TC_LCH, slot, bo, 1, lfirst, -1, c, SD::NB, T.meta->lw);
+        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0;
       }
     }
   }
@@ -350,7 +352,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     for (int l = ict; l < nlev; ++l) {
       const int jl = l + 1;
       if (act) {
-        const size_t i = (size_t)l * NG_LW + g;
+        const size_t i = (size_t)l * SD::NG + g;
 #pragma unroll
         for (int jr = 0; jr < 3; ++jr) {
           if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
@@ -358,13 +360,13 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           fup[jr] = SCR(jr, 3, i) + fdn[jr] * SCR(jr, 2, i);
         }
         if (!(S.clear[jl] && S.clear[jl + 1])) mat3_x_vec(S.V + jl * 9, fdn);
-        tile[slot * TC_LW_RS + g] = fup[0] + fup[1] + fup[2];
-        tile[(TC_LCH + slot) * TC_LW_RS + g] = fdn[0] + fdn[1] + fdn[2];
+        tile[slot * SD::RS + g] = fup[0] + fup[1] + fup[2];
+        tile[(TC_LCH + slot) * SD::RS + g] = fdn[0] + fdn[1] + fdn[2];
       }
       ++slot;
       if (slot == TC_LCH || l == nlev - 1) {
-        if (bo[0].dst || bo[1].dst) flush_bands(tile, TC_LW_RS, TC_LCH, slot, bo, 2, lfirst, 1, c, NB_LW, T.meta->lw);
-        flush_tile(tile, TC_LW_RS, NG_LW, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
+        if (bo[0].dst || bo[1].dst) flush_bands(tile, SD::RS, TC_LCH, slot, bo, 2, lfirst, 1, c, SD::NB, T.meta->lw);
+        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
       }
     }
   }
@@ -377,7 +379,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     __syncthreads();
     if (act) tile[g] = fus;
     __syncthreads();
-    if (g == 0) { double s = 0.0; for (int k = 0; k < NG_LW; ++k) s = s + tile[k]; red[0] = s; }
+    if (g == 0) { double s = 0.0; for (int k = 0; k < SD::NG; ++k) s = s + tile[k]; red[0] = s; }
     __syncthreads();
     double d[3] = {fus / red[0], 0.0, 0.0};
     double* dst[1] = {s_dv};
@@ -385,20 +387,20 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
-        const size_t i = (size_t)l * NG_LW + g;
+        const size_t i = (size_t)l * SD::NG + g;
         mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1)
         if (l >= ict) { d[0] = d[0] * SCR(0, 4, i); d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
         else d[0] = d[0] * exp(-ECB_LW_DIFFUSIVITY * od[i]);   // regions 2,3: transmittance = 1 above cloud top
-        tile[slot * TC_LW_RS + g] = d[0] + d[1] + d[2];
+        tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
       }
       ++slot;
-      if (slot == TC_LCH || l == 0) { flush_tile(tile, TC_LW_RS, NG_LW, 1, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
+      if (slot == TC_LCH || l == 0) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
     }
   }
 #undef SCR
   __syncthreads();
   // ---- outputs ----
-  for (int l = g; l < nl1; l += TC_LW_THREADS) {
+  for (int l = g; l < nl1; l += SD::THREADS) {
     const size_t o = (size_t)l * out.ld + c;
     const double dnc = gsum[l];
     if (out.lw_up_clear) out.lw_up_clear[o] = s_up_c[l];
@@ -409,35 +411,55 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   }
   if (g == 0 && out.cloud_cover_lw) out.cloud_cover_lw[c] = w.tc_cc[c];
   if (act) {
-    const size_t i = (size_t)c * NG_LW + g;
+    const size_t i = (size_t)c * SD::NG + g;
     if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;
     if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = fuc_toa;
     if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;
     if (out.lw_up_toa_g) out.lw_up_toa_g[i] = fu_toa;
   }
   (void)fuc_surf;
-  lw_surface_canopy(T, cfg, out, c, g, act, tile, dn_surf_g);
+  lw_surface_canopy<SD>(T, cfg, out, c, g, act, tile, dn_surf_g);
 }
 
 // =========================================================================================================
-size_t tc_scratch_doubles_lw(int nlev) { return (size_t)TC_LW_ARRAYS * nlev * NG_LW; }
-size_t tc_scratch_doubles_sw(int nlev) { return (size_t)TC_SW_ARRAYS * nlev * NG_SW; }
+size_t tc_scratch_doubles_lw(int nlev, int ng) { return (size_t)TC_LW_ARRAYS * nlev * ng; }
+size_t tc_scratch_doubles_sw(int nlev, int ng) { return (size_t)TC_SW_ARRAYS * nlev * ng; }
 
 int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   tc_prep_kernel<<<(nc + 63) / 64, 64, 0, st>>>(cfg, in, w, nc, nlev);
   return 1;
 }
-int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  const size_t sm = sizeof(double) * (6 * (nlev + 1) + 6 * TC_LCH * TC_SW_RS + 2 * NB_SW) + tc_shared_bytes(nlev);
-  cudaFuncSetAttribute(tc_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  tc_sw_kernel<<<nc, TC_SW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+template <class SD>
+static int launch_tc_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const size_t sm = sizeof(double) * (6 * (nlev + 1) + 6 * TC_LCH * SD::RS + 2 * SD::NB) + tc_shared_bytes(nlev);
+  cudaFuncSetAttribute(tc_sw_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  tc_sw_kernel<SD><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
   return 1;
 }
-int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  const size_t sm = sizeof(double) * (4 * (nlev + 1) + 2 * TC_LCH * TC_LW_RS + 8) + tc_shared_bytes(nlev);
-  cudaFuncSetAttribute(tc_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  tc_lw_kernel<<<nc, TC_LW_THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+template <class SD>
+static int launch_tc_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  const size_t sm = sizeof(double) * (4 * (nlev + 1) + 2 * TC_LCH * SD::RS + 8) + tc_shared_bytes(nlev);
+  cudaFuncSetAttribute(tc_lw_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  tc_lw_kernel<SD><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
   return 1;
+}
+int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  switch (cfg.ng_sw) {
+    case NG_SW: return launch_tc_sw_t<SwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
+    case 32: return launch_tc_sw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);
+    case 64: return launch_tc_sw_t<Ckd64>(T, cfg, in, out, w, nc, nlev, st);
+    case 96: return launch_tc_sw_t<Ckd96>(T, cfg, in, out, w, nc, nlev, st);
+  }
+  return -1;
+}
+int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
+  switch (cfg.ng_lw) {
+    case NG_LW: return launch_tc_lw_t<LwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
+    case 32: return launch_tc_lw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);
+    case 64: return launch_tc_lw_t<Ckd64>(T, cfg, in, out, w, nc, nlev, st);
+    case 96: return launch_tc_lw_t<Ckd96>(T, cfg, in, out, w, nc, nlev, st);
+  }
+  return -1;
 }
 
 }  // namespace ecb

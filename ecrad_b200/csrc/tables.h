@@ -13,7 +13,10 @@
 #include <string>
 #include <vector>
 
+#include <math.h>
+
 #include "cloud_core.h"
+#include "ecckd_core.h"
 #include "gas_core.h"
 
 struct ecrad_b200_tables {
@@ -70,8 +73,14 @@ struct PackedTables {
   std::vector<double> lwtab, swtab;   // packed band tables
   CloudMeta cloud;
   std::vector<double> pdf_val;        // (ncdf, nfsd) Fortran order, as the reference stores it
-  std::vector<double> sw_albedo_weights;  // (n_albedo_sw, 14)
-  std::vector<int32_t> i_emiss_from_band_lw;  // (16) 1-based
+  std::vector<double> sw_albedo_weights;  // (n_albedo_sw, n_bands_sw)
+  std::vector<int32_t> i_emiss_from_band_lw;  // (n_bands_lw) 1-based
+  std::vector<double> lw_emiss_weights;   // (n_emiss_lw, n_bands_lw)
+  int n_emiss_lw = 0;
+  bool is_ecckd = false;
+  int ng_lw = NG_LW, ng_sw = NG_SW, nb_lw = NB_LW, nb_sw = NB_SW;
+  CkdMeta ckd;                        // ecCKD gas optics + generalised cloud optics
+  std::vector<double> ckdtab;
   AerMeta aer;                        // aer.ntype == 0: no aerosol tables
   std::vector<double> aertab;
   int n_albedo_sw = 0;
@@ -110,7 +119,71 @@ struct BandPacker {
 };
 }  // namespace detail
 
+inline void pack_common(const ecrad_b200_tables& T, PackedTables& P);
+
+// ecCKD blob of tools/extract_ecckd_tables.py: "ckd_{lw,sw}_*" (read_ckd_model, radiation_ecckd.F90:128-226) and
+// "gco_{lw,sw}_{0,1}_*" (setup_general_cloud_optics, radiation_general_cloud_optics_data.F90:71-243)
+inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
+  memset(&P.meta, 0, sizeof(P.meta));
+  memset(&P.ckd, 0, sizeof(P.ckd));
+  auto put = [&](const std::string& nm, size_t expect) {
+    const auto& x = T.req(nm);
+    if (x.dtype != 0 || x.data.size() != expect * 8) throw std::runtime_error(nm + ": unexpected size");
+    size_t off = P.ckdtab.size();
+    P.ckdtab.insert(P.ckdtab.end(), (const double*)x.data.data(), (const double*)x.data.data() + expect);
+    return off;
+  };
+  static const int slot_of_code[13] = {-1, 0, 1, 8, 3, -1, 2, -1, 4, 5, 6, 7, -1};   // DevIn::gas order: h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3
+  for (int sw = 0; sw < 2; ++sw) {
+    const std::string pre = sw ? "ckd_sw_" : "ckd_lw_";
+    CkdModel& m = sw ? P.ckd.sw : P.ckd.lw;
+    const double* meta = T.d(pre + "meta");
+    m.ng = (int)meta[0]; m.npress = (int)meta[1]; m.ntemp = (int)meta[2]; m.nplanck = (int)meta[3]; m.ngas = (int)meta[4];
+    m.log_pressure1 = meta[5]; m.d_log_pressure = meta[6]; m.d_temperature = meta[7];
+    m.temperature1_planck = meta[8]; m.d_temperature_planck = meta[9];
+    if ((meta[10] != 0.0) != (sw != 0)) throw std::runtime_error(pre + "meta: longwave/shortwave model mismatch");
+    if (m.ngas > CKD_MAXGAS) throw std::runtime_error("more than 12 ecCKD gases");
+    if (m.ng != 32 && m.ng != 64 && m.ng != 96) throw std::runtime_error("ecCKD models with 32, 64 or 96 g-points are built in");
+    m.off_temperature1 = put(pre + "temperature1", (size_t)m.npress);
+    if (sw) {
+      m.off_solar = put(pre + "norm_solar_irradiance", (size_t)m.ng);
+      m.off_rayleigh = put(pre + "rayleigh_molar_scat", (size_t)m.ng);
+    } else {
+      m.off_planck = put(pre + "planck_function", (size_t)m.ng * m.nplanck);
+    }
+    const double* gm = T.d(pre + "gas_meta");
+    for (int j = 0; j < m.ngas; ++j) {
+      CkdGas& g = m.gas[j];
+      const int code = (int)gm[6 * j];
+      g.dep = (int)gm[6 * j + 1]; g.reference_mole_frac = gm[6 * j + 2]; g.n_mole_frac = (int)gm[6 * j + 3];
+      g.log_mole_frac1 = gm[6 * j + 4]; g.d_log_mole_frac = gm[6 * j + 5];
+      g.mole_frac1 = exp(g.log_mole_frac1);
+      g.slot = (code >= 0 && code <= 12) ? slot_of_code[code] : -1;
+      const size_t n = (size_t)m.ng * m.npress * m.ntemp * (g.dep == CKD_CONC_LUT ? g.n_mole_frac : 1);
+      g.off = put(pre + "gas" + std::to_string(j) + "_molar_abs", n);
+    }
+    for (int jt = 0; jt < 2; ++jt) {
+      GcoType& c = sw ? P.ckd.gco_sw[jt] : P.ckd.gco_lw[jt];
+      const std::string gp = std::string("gco_") + (sw ? "sw_" : "lw_") + std::to_string(jt) + "_";
+      const double* cm = T.d(gp + "meta");
+      c.nre = (int)cm[0]; c.re0 = cm[1]; c.dre = cm[2];
+      c.off_me = put(gp + "mass_ext", (size_t)m.ng * c.nre);
+      c.off_ssa = put(gp + "ssa", (size_t)m.ng * c.nre);
+      c.off_g = put(gp + "asymmetry", (size_t)m.ng * c.nre);
+    }
+  }
+  P.is_ecckd = true;
+  P.ng_lw = P.nb_lw = P.ckd.lw.ng;
+  P.ng_sw = P.nb_sw = P.ckd.sw.ng;
+  // bands == g-points (radiation_ecckd_interface.F90:60-63, :95-98)
+  for (int g = 0; g < P.ng_lw; ++g) { P.meta.band_of_g_lw[g] = g; P.meta.lw[g].ng = 1; P.meta.lw[g].g0 = g; }
+  for (int g = 0; g < P.ng_sw; ++g) { P.meta.band_of_g_sw[g] = g; P.meta.sw[g].ng = 1; P.meta.sw[g].g0 = g; }
+  memset(&P.cloud, 0, sizeof(P.cloud));
+  pack_common(T, P);
+}
+
 inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
+  if (T.find("ckd_lw_meta")) { pack_ecckd(T, P); return; }
   GasMeta& M = P.meta;
   memset(&M, 0, sizeof(M));
   auto copy = [&](double* dst, const char* name, size_t n) {
@@ -209,6 +282,13 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
   memset(&C, 0, sizeof(C));
   copy(C.liq_lw, "liq_coeff_lw", 16 * 16); copy(C.liq_sw, "liq_coeff_sw", 14 * 16);
   copy(C.ice_lw, "ice_coeff_lw", 16 * 11); copy(C.ice_sw, "ice_coeff_sw", 14 * 10);
+  pack_common(T, P);
+}
+
+// tables both gas models share: McICA PDF look-up table, surface albedo / emissivity mappings, aerosol optics
+inline void pack_common(const ecrad_b200_tables& T, PackedTables& P) {
+  CloudMeta& C = P.cloud;
+  const int NB_SW = P.nb_sw, NB_LW = P.nb_lw;   // shadow the RRTMG constants: bands of this configuration
   const auto& pv = T.req("pdf_val");
   const double* fsd = T.d("pdf_fsd");
   C.pdf_ncdf = (int)pv.dims[0]; C.pdf_nfsd = (int)pv.dims[1];
@@ -216,7 +296,7 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
   P.pdf_val.assign((const double*)pv.data.data(), (const double*)pv.data.data() + (size_t)C.pdf_ncdf * C.pdf_nfsd);
   if (const auto* w = T.find("sw_albedo_weights")) {
     P.n_albedo_sw = (int)w->dims[0];
-    if (w->dims[1] != NB_SW) throw std::runtime_error("sw_albedo_weights: second dim != 14");
+    if (w->dims[1] != NB_SW) throw std::runtime_error("sw_albedo_weights: second dim != number of shortwave bands");
     P.sw_albedo_weights.assign((const double*)w->data.data(), (const double*)w->data.data() + (size_t)P.n_albedo_sw * NB_SW);
   }
   // ---- aerosol optics (only if the host registered the type map) ----
@@ -253,7 +333,13 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     }
   }
   if (const auto* e = T.find("i_emiss_from_band_lw")) {
+    if (e->dims[0] != NB_LW) throw std::runtime_error("i_emiss_from_band_lw: size != number of longwave bands");
     P.i_emiss_from_band_lw.assign((const int32_t*)e->data.data(), (const int32_t*)e->data.data() + NB_LW);
+  }
+  if (const auto* e = T.find("lw_emiss_weights")) {
+    if (e->dims[1] != NB_LW) throw std::runtime_error("lw_emiss_weights: second dim != number of longwave bands");
+    P.n_emiss_lw = (int)e->dims[0];
+    P.lw_emiss_weights.assign((const double*)e->data.data(), (const double*)e->data.data() + (size_t)P.n_emiss_lw * NB_LW);
   }
 }
 

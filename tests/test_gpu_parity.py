@@ -202,6 +202,82 @@ def test_tiling_is_invisible(meridian_raw):
         assert np.array_equal(outs[0][nm], outs[2][nm], equal_nan=True), nm
 
 
+ECCKD = dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False)   # test/ifs/configCY49R1_ecckd.nam
+CANOPY = (("lw_dn_surf_canopy", "canopy_flux_dn_lw_surf"), ("sw_dn_diffuse_surf_canopy", "canopy_flux_dn_diffuse_sw_surf"),
+          ("sw_dn_direct_surf_canopy", "canopy_flux_dn_direct_sw_surf"))
+GOLDEN_PROFILES = {"lw_up": "flux_up_lw", "lw_dn": "flux_dn_lw", "lw_up_clear": "flux_up_lw_clear", "lw_dn_clear": "flux_dn_lw_clear",
+                   "sw_up": "flux_up_sw", "sw_dn": "flux_dn_sw", "sw_dn_direct": "flux_dn_direct_sw", "sw_up_clear": "flux_up_sw_clear",
+                   "sw_dn_clear": "flux_dn_sw_clear", "sw_dn_direct_clear": "flux_dn_direct_sw_clear", "lw_derivatives": "lw_derivative",
+                   "cloud_cover_lw": "cloud_cover_lw", "cloud_cover_sw": "cloud_cover_sw"}
+
+
+def test_ecckd_tripleclouds_vs_reference_golden(handles, meridian_raw, golden_ecckd_tc):
+    """The reference's `ecckd_tc` ctest: ecCKD 32-term gas optics, generalised cloud + aerosol optics per g-point,
+    Tripleclouds; per-g-point flux profiles included.  Within 1 float32 ulp of the golden file, <= 1e-6 W m-2 of the oracle."""
+    h, orc, cfg = handles(**ECCKD, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")
+    out = h.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV, spectral_profiles=True)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV, spectral_profiles=True)
+    compare(out, ref, FLUXES + OTHERS)
+    check_band_profiles(out, ref, golden_ecckd_tc)
+    for nm, gname in GOLDEN_PROFILES.items():
+        assert f32_ulp_err(out[nm], golden_ecckd_tc[gname]).max() <= 1.0, nm
+    for nm, gname in CANOPY:
+        assert f32_ulp_err(out[nm].T, golden_ecckd_tc[gname]).max() <= 1.0, nm
+
+
+def test_ecckd_mcica_vs_reference_golden(handles, meridian_raw, golden_ecckd_mcica):
+    """The reference's `ecckd_mcica` ctest (McICA over 32 + 32 g-points)."""
+    h, orc, cfg = handles(**ECCKD, use_aerosols=True)
+    out = h.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"]) and np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+    for nm, gname in GOLDEN_PROFILES.items():
+        assert f32_ulp_err(out[nm], golden_ecckd_mcica[gname]).max() <= 1.0, nm
+    for nm, gname in CANOPY + (("sw_dn_surf_band", "spectral_flux_dn_sw_surf"), ("sw_dn_direct_surf_band", "spectral_flux_dn_direct_sw_surf")):
+        assert f32_ulp_err(out[nm].T, golden_ecckd_mcica[gname]).max() <= 1.0, nm
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_aerosols=True), dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(sw_solver_name="Cloudless", lw_solver_name="Cloudless", use_aerosols=True),
+                                dict(do_lw_cloud_scattering=False, overlap_scheme_name="Exp-Exp"),
+                                dict(do_nearest_spectral_lw_emiss=True, overlap_scheme_name="Max-Ran"),
+                                dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True),
+                                dict(ecckd_tables="ecckd_tables_64b.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+def test_ecckd_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
+    """ecCKD configurations (32- and 64-term models; BASELINE configs 1 and 3 have no golden file) on 300 perturbed columns."""
+    n = 300
+    cfgkw = dict(ECCKD); cfgkw.update(kw)
+    h, orc, cfg = handles(**cfgkw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV, spectral_profiles=True)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV, spectral_profiles=True)
+    compare(out, ref, FLUXES + OTHERS)
+    if cfg.sw_solver_name != "McICA":
+        compare(out, ref, BANDS)
+    for nm in ("cloud_cover_lw", "cloud_cover_sw", "cloud_fraction"):
+        assert np.array_equal(out[nm], ref[nm]), nm
+
+
+def test_ecckd_tiling_is_invisible(meridian_raw):
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    n = 150
+    raw = I.synthetic_columns(meridian_raw, n)
+    cfg = RadiationConfig(**ECCKD, use_aerosols=True).consolidate()
+    outs = []
+    for tile in ("4096", "37"):
+        os.environ["ECRAD_B200_TILE"] = tile
+        try:
+            h = setup_radiation(cfg)
+        finally:
+            del os.environ["ECRAD_B200_TILE"]
+        outs.append(h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV))
+        h.finalize()
+    for nm in FLUXES + OTHERS + ["cloud_cover_sw", "cloud_cover_lw"]:
+        assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
+
+
 @pytest.mark.parametrize("solver", ["Tripleclouds", "Cloudless"])
 def test_band_profiles_synthetic_and_tiled(handles, meridian_raw, solver):
     """Per-band profiles on perturbed columns (night columns included), and the same through ragged column tiles."""
