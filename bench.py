@@ -90,7 +90,7 @@ def cpu_arm(cfg, raw, ncol_sample, first, nthreads, reps):
     from oracle_lib import Oracle
 
     orc = Oracle(cfg)
-    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol_sample, first=first))
+    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol_sample, first=first), cfg)
     orc.radiation(dict(inp), ncol_sample, NLEV, nthreads=nthreads)  # warm-up (page-in, thread pool)
     ts = []
     for _ in range(reps):
@@ -100,12 +100,28 @@ def cpu_arm(cfg, raw, ncol_sample, first, nthreads, reps):
     return ncol_sample / float(np.mean(ts)), float(np.mean(ts))
 
 
+# --workload: BASELINE.json configs (the default, configs[1], is the one the metric is quoted on; the others are extra lines)
+WORKLOADS = {
+    "mcica_rrtmg": (dict(), 10000, "McICA LW+SW, RRTMG 140+112 g-points", "configCY49R1.nam, use_aerosols=false", "BASELINE.json configs[1]"),
+    "cloudless_ecckd32": (dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
+                          10000, "Cloudless LW+SW, ecCKD 32+32 g-points", "configCY49R1_ecckd.nam, Cloudless, use_aerosols=false", "BASELINE.json configs[0] on the GPU"),
+    "mcica_ecckd32": (dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False), 10000, "McICA LW+SW, ecCKD 32+32 g-points",
+                      "configCY49R1_ecckd.nam, McICA, use_aerosols=false", "extra"),
+    "tripleclouds_ecckd64": (dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds",
+                                  ecckd_tables="ecckd_tables_64b.bin"), 100000, "Tripleclouds LW+SW, ecCKD 64+64 g-points",
+                             "configCY49R1_ecckd.nam + 64-term models, use_aerosols=false", "BASELINE.json configs[2]"),
+    "tripleclouds_rrtmg": (dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"), 10000, "Tripleclouds LW+SW, RRTMG 140+112 g-points",
+                           "configCY49R1.nam, Tripleclouds, use_aerosols=false", "extra"),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="mcica_rrtmg", choices=sorted(WORKLOADS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--ncol", type=int, default=10000, help="columns per GPU (BASELINE config 2: 10 000)")
+    ap.add_argument("--ncol", type=int, default=0, help="columns per GPU (default: the workload's, 10 000 for BASELINE configs[1])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -117,11 +133,13 @@ def main():
     from ecrad_b200 import inputs as I
     from ecrad_b200.config import RadiationConfig
 
-    cfg = RadiationConfig().consolidate()   # test/ifs/configCY49R1.nam with use_aerosols=false
+    wkw, wncol, wname, wnam, wref = WORKLOADS[args.workload]
+    args.ncol = args.ncol or wncol
+    cfg = RadiationConfig(**wkw).consolidate()   # default: test/ifs/configCY49R1.nam with use_aerosols=false
     raw = load_raw()
     ncores = os.cpu_count() or 1
-    config = {"workload": f"McICA LW+SW, RRTMG 140+112 g-points, {NLEV} levels, {args.ncol} synthetic IFS columns per GPU "
-                          "(BASELINE.json configs[1])", "ncol_per_gpu": args.ncol, "nlev": NLEV, "namelist": "configCY49R1.nam, use_aerosols=false",
+    config = {"workload": f"{wname}, {NLEV} levels, {args.ncol} synthetic IFS columns per GPU ({wref})",
+              "ncol_per_gpu": args.ncol, "nlev": NLEV, "namelist": wnam,
               "sharding": f"columns x{world}, no data-path collective",
               "l2": "inputs+scratch per step (>3 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -174,11 +192,10 @@ def main():
     ncol = args.ncol
     blob = None
     if dist is not None:   # rank 0 reads the optics tables, one NCCL broadcast hands them to every GPU
-        from ecrad_b200.radiation_interface import DEFAULT_TABLES
         from ecrad_b200.sharding import broadcast_table_blob
-        blob = broadcast_table_blob(DEFAULT_TABLES, dist, device=dev)
+        blob = broadcast_table_blob(cfg.tables_path(), dist, device=dev)
     h = setup_radiation(cfg, tables_blob=blob)
-    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol, first=rank * ncol))
+    inp = I.to_radiation_inputs(I.synthetic_columns(raw, ncol, first=rank * ncol), cfg)
 
     # ---- host buffers (pinned) for the e2e path ----
     pinned, host_in = {}, {}
@@ -286,8 +303,9 @@ def main():
         for nm, gn in (("sw_dn", "flux_dn_sw"), ("lw_up", "flux_up_lw")):
             a = dev_out[nm].cpu().numpy().T[:32]
             b = host_out[nm].numpy().T[:32]
-            err = np.abs(a - g[gn]).max()
-            assert err <= 1e-3 and np.array_equal(a, b), f"bench outputs are wrong: {nm} {err}"
+            # the golden file is the RRTMG one: other gas models / solvers differ from it by physics (a few W m-2), not by bugs
+            err = np.abs(a - g[gn]).max() if args.workload == "mcica_rrtmg" else 0.0
+            assert err <= 1e-3 and np.array_equal(a, b) and np.isfinite(a).all(), f"bench outputs are wrong: {nm} {err}"
 
     # ---- roofline of the dominant kernel ----
     dom = max(stage_ms, key=stage_ms.get) if stage_ms else None

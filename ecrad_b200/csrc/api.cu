@@ -48,7 +48,8 @@ struct Handle {
   DevTables T;
   std::vector<void*> table_allocs;
   int device = 0;
-  int tile_cols = 4096;
+  int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
+  int tile_cols_device = 16384;  // device entry: only bounds the scratch (about 3 MB per column); bigger tiles = fewer partial waves
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_aux1 = nullptr, s_aux2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
@@ -113,15 +114,15 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   return 0;
 }
 
-int ensure_work(Handle* h, int cols, int nlev) {
-  if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
-  if (nlev != h->w_nlev) h->w_cols = 0;
+enum { N_WORK = 35 };
+// bytes of every per-tile scratch array for `cols` columns (all linear in cols)
+void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
   const bool tc_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS, tc_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
   const bool tc = tc_lw || tc_sw;
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
   const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
-  const size_t sz[] = {
+  const size_t sz[N_WORK] = {
       8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
       8 * nc * nl * 3 * NB_LW, 8 * nc * nl * 3 * NB_SW,                                      // cl_lw cl_sw
@@ -137,7 +138,21 @@ int ensure_work(Handle* h, int cols, int nlev) {
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       (h->cfg.do_save_spectral_flux && h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_CLOUDLESS) ? 8 * nc * (nl + 1) * NB_SW : 0,   // sw_band_dir
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0};  // tc_reg tc_ods tc_u tc_v tc_cc
-  for (size_t i = 0; i < sizeof(sz) / sizeof(sz[0]); ++i) CK(h, h->work[i].reserve(sz[i]));
+  for (int i = 0; i < N_WORK; ++i) out[i] = sz[i];
+}
+size_t work_bytes_per_column(const Handle* h, int nlev) {
+  size_t sz[N_WORK], tot = 0;
+  work_sizes(h, 1, nlev, sz);
+  for (int i = 0; i < N_WORK; ++i) tot += sz[i];
+  return tot;
+}
+
+int ensure_work(Handle* h, int cols, int nlev) {
+  if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
+  if (nlev != h->w_nlev) h->w_cols = 0;
+  size_t sz[N_WORK];
+  work_sizes(h, cols, nlev, sz);
+  for (int i = 0; i < N_WORK; ++i) CK(h, h->work[i].reserve(sz[i]));
   Work& w = h->w;
   w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
   w.od_sw = (double*)h->work[4].p; w.ssa_sw = (double*)h->work[5].p; w.incoming = (double*)h->work[6].p;
@@ -381,10 +396,11 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
   d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;
+  d.ckd_ngas_lw = P.ckd.lw.ngas; d.ckd_nlut_lw = P.ckd.lw.nlut; d.ckd_ngas_sw = P.ckd.sw.ngas; d.ckd_nlut_sw = P.ckd.sw.nlut;
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
-  if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = v; }
+  if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = h->tile_cols_device = v; }
   if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
@@ -454,6 +470,7 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (!strcmp(key, "serial")) { h->serial = value != 0; return 0; }
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
+  if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);
 }
 
@@ -469,8 +486,8 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
   CK(h, cudaSetDevice(h->device));
   const ecrad_b200_config& c = h->cfg;
   const int c_first = istartcol - 1, ntot = iendcol - istartcol + 1;
-  const int cap = ntot < h->tile_cols ? ntot : h->tile_cols;
-  const int ntiles = (ntot + cap - 1) / cap;
+  const int ntiles = (ntot + h->tile_cols - 1) / h->tile_cols;
+  const int cap = (ntot + ntiles - 1) / ntiles;   // balanced tiles: no short last tile
   if (ensure_work(h, cap, nlev)) return 1;
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];
@@ -561,8 +578,17 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b2
   CK(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const ecrad_b200_config& c = h->cfg;
-  const int cap = ncol < h->tile_cols ? ncol : h->tile_cols;
-  const int ntiles = (ncol + cap - 1) / cap;
+  int tile = h->tile_cols_device;
+  if (ncol > h->w_cols || nlev != h->w_nlev) {   // growing the scratch: stay within a third of the memory that is free now
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+      const size_t per_col = work_bytes_per_column(h, nlev);
+      const size_t fit = (fr / 3 + (size_t)h->w_cols * per_col) / (per_col ? per_col : 1);
+      if ((size_t)tile > fit) tile = fit < 256 ? 256 : (int)fit;
+    }
+  }
+  const int ntiles = (ncol + tile - 1) / tile;
+  const int cap = (ncol + ntiles - 1) / ntiles;
   if (ensure_work(h, cap, nlev)) return 1;
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];

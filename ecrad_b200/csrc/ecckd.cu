@@ -17,16 +17,33 @@ namespace ecb {
 
 enum { CKD_THREADS = 128, CKD_WARPS = 4 };
 
-struct CkdLay {                 // interpolation state of one layer (calc_optical_depth_ckd_model :531-556)
-  int ip1, it1;                 // 1-based lower corner in pressure / temperature
-  double pw1, pw2, tw1, tw2;
-  double simple_multiplier;     // mol of dry air per m2 in the layer
-  double mult[CKD_MAXGAS];      // per gas: multiplier of the interpolated molar absorption
-  int ic1[CKD_MAXGAS];          // concentration corner (look-up-table gases)
-  double cw1[CKD_MAXGAS], cw2[CKD_MAXGAS];
+// Interpolation state of one layer (calc_optical_depth_ckd_model :531-556), carved from shared memory as structure of arrays
+// sized by the model (ngas multipliers per layer, one concentration corner per look-up-table gas):
+struct CkdLayers {
+  int2* corner;        // [nlev] (ip1, it1): 1-based lower corner in pressure / temperature
+  double* pw2;         // [nlev] upper weights (the lower ones are 1 - w, as in the reference)
+  double* tw2;         // [nlev]
+  double* smult;       // [nlev] simple_multiplier: mol of dry air per m2 in the layer
+  double* mult;        // [nlev][ngas] multiplier of the interpolated molar absorption of each gas
+  int* ic1;            // [nlev][nlut] concentration corner of the look-up-table gases
+  double* cw2;         // [nlev][nlut]
+  int ngas, nlut;
 };
+__host__ __device__ inline size_t ckd_layers_bytes(int nlev, int ngas, int nlut) {
+  return (size_t)nlev * (sizeof(int2) + 3 * sizeof(double) + ngas * sizeof(double) + nlut * (sizeof(double) + sizeof(int))) + 32;
+}
+__device__ __forceinline__ unsigned char* ckd_layers_carve(unsigned char* base, int nlev, const CkdModel& m, CkdLayers& L) {
+  L.ngas = m.ngas; L.nlut = m.nlut;
+  double* d = reinterpret_cast<double*>(base);
+  L.pw2 = d; d += nlev; L.tw2 = d; d += nlev; L.smult = d; d += nlev;
+  L.mult = d; d += (size_t)nlev * m.ngas;
+  L.cw2 = d; d += (size_t)nlev * m.nlut;
+  L.corner = reinterpret_cast<int2*>(d);
+  L.ic1 = reinterpret_cast<int*>(L.corner + nlev);
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(L.ic1 + (size_t)nlev * m.nlut) + 15) & ~(uintptr_t)15);
+}
 
-__device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double* __restrict__ tab, const DevIn& in, int c, int l, CkdLay& L) {
+__device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double* __restrict__ tab, const DevIn& in, int c, int l, const CkdLayers& L) {
   const double global_multiplier = 1.0 / (9.80665 * 0.001 * 28.970);   // 1 / (AccelDueToGravity * 0.001 * AirMolarMass)
   const double p1 = LD_IN(in.p_hl, c, l), p2 = LD_IN(in.p_hl, c, l + 1);
   const double t1 = LD_IN(in.t_hl, c, l), t2 = LD_IN(in.t_hl, c, l + 1);
@@ -34,66 +51,80 @@ __device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double*
   const double log_pressure_fl = log(0.5 * (p1 + p2));
   double pindex1 = (log_pressure_fl - m.log_pressure1) / m.d_log_pressure;
   pindex1 = 1.0 + dmax(0.0, dmin(pindex1, m.npress - 1.0001));
-  L.ip1 = (int)pindex1;
-  L.pw2 = pindex1 - L.ip1; L.pw1 = 1.0 - L.pw2;
+  const int ip1 = (int)pindex1;
+  const double pw2 = pindex1 - ip1, pw1 = 1.0 - pw2;
   const double* tt = tab + m.off_temperature1;
-  const double temperature1 = L.pw1 * tt[L.ip1 - 1] + L.pw2 * tt[L.ip1];
+  const double temperature1 = pw1 * tt[ip1 - 1] + pw2 * tt[ip1];
   double tindex1 = (temperature_fl - temperature1) / m.d_temperature;
   tindex1 = 1.0 + dmax(0.0, dmin(tindex1, m.ntemp - 1.0001));
-  L.it1 = (int)tindex1;
-  L.tw2 = tindex1 - L.it1; L.tw1 = 1.0 - L.tw2;
-  L.simple_multiplier = global_multiplier * (p2 - p1);
+  const int it1 = (int)tindex1;
+  L.corner[l] = make_int2(ip1, it1);
+  L.pw2[l] = pw2; L.tw2[l] = tindex1 - it1;
+  const double simple_multiplier = global_multiplier * (p2 - p1);
+  L.smult[l] = simple_multiplier;
   for (int j = 0; j < m.ngas; ++j) {
     const CkdGas& G = m.gas[j];
     const double mf = G.slot >= 0 ? LD_IN(in.gas[G.slot], c, l) : 0.0;
-    L.ic1[j] = 1; L.cw1[j] = 1.0; L.cw2[j] = 0.0;
-    if (G.dep == CKD_CONC_LINEAR) L.mult[j] = L.simple_multiplier * mf * 1.0;
-    else if (G.dep == CKD_CONC_RELATIVE_LINEAR) L.mult[j] = L.simple_multiplier * (mf * 1.0 - G.reference_mole_frac);
+    double mult;
+    if (G.dep == CKD_CONC_LINEAR) mult = simple_multiplier * mf * 1.0;
+    else if (G.dep == CKD_CONC_RELATIVE_LINEAR) mult = simple_multiplier * (mf * 1.0 - G.reference_mole_frac);
     else if (G.dep == CKD_CONC_LUT) {
       const double log_conc = log(dmax(mf * 1.0, G.mole_frac1));
       double cindex1 = (log_conc - G.log_mole_frac1) / G.d_log_mole_frac;
       cindex1 = 1.0 + dmax(0.0, dmin(cindex1, G.n_mole_frac - 1.0001));
-      L.ic1[j] = (int)cindex1;
-      L.cw2[j] = cindex1 - L.ic1[j]; L.cw1[j] = 1.0 - L.cw2[j];
-      L.mult[j] = L.simple_multiplier * mf * 1.0;
-    } else L.mult[j] = L.simple_multiplier;
+      const int ic1 = (int)cindex1;
+      L.ic1[(size_t)l * m.nlut + G.lut] = ic1;
+      L.cw2[(size_t)l * m.nlut + G.lut] = cindex1 - ic1;
+      mult = simple_multiplier * mf * 1.0;
+    } else mult = simple_multiplier;
+    L.mult[(size_t)l * m.ngas + j] = mult;
   }
 }
 
 // absorption optical depth of one (layer, g-point): sum over the gases, clamped at zero (:558-639)
-__device__ __forceinline__ double ckd_optical_depth(const CkdModel& m, const double* __restrict__ tab, const CkdLay& L, int g) {
+__device__ __forceinline__ double ckd_optical_depth(const CkdModel& m, const double* __restrict__ tab, const CkdLayers& L, int l, int g) {
   const size_t sp = (size_t)m.ng, st = (size_t)m.ng * m.npress, sc = st * m.ntemp;
-  const size_t corner = (size_t)(L.ip1 - 1) * sp + (size_t)(L.it1 - 1) * st + g;
+  const int2 cr = L.corner[l];
+  const double pw2 = L.pw2[l], pw1 = 1.0 - pw2, tw2 = L.tw2[l], tw1 = 1.0 - tw2;
+  const size_t corner = (size_t)(cr.x - 1) * sp + (size_t)(cr.y - 1) * st + g;
+  const double* mult = L.mult + (size_t)l * m.ngas;
   double od = 0.0;
   for (int j = 0; j < m.ngas; ++j) {
     const CkdGas& G = m.gas[j];
     const double* k00 = tab + G.off + corner;
     if (G.dep == CKD_CONC_LUT) {
-      const size_t c0 = (size_t)(L.ic1[j] - 1) * sc, c1 = c0 + sc;
-      const double cw1 = L.cw1[j], cw2 = L.cw2[j];
-      od = od + L.mult[j] * ((cw1 * L.tw1 * L.pw1) * __ldg(k00 + c0) + (cw1 * L.tw1 * L.pw2) * __ldg(k00 + c0 + sp) +
-                             (cw1 * L.tw2 * L.pw1) * __ldg(k00 + c0 + st) + (cw1 * L.tw2 * L.pw2) * __ldg(k00 + c0 + sp + st) +
-                             (cw2 * L.tw1 * L.pw1) * __ldg(k00 + c1) + (cw2 * L.tw1 * L.pw2) * __ldg(k00 + c1 + sp) +
-                             (cw2 * L.tw2 * L.pw1) * __ldg(k00 + c1 + st) + (cw2 * L.tw2 * L.pw2) * __ldg(k00 + c1 + sp + st));
+      const int ic1 = L.ic1[(size_t)l * m.nlut + G.lut];
+      const double cw2 = L.cw2[(size_t)l * m.nlut + G.lut], cw1 = 1.0 - cw2;
+      const size_t c0 = (size_t)(ic1 - 1) * sc, c1 = c0 + sc;
+      od = od + mult[j] * ((cw1 * tw1 * pw1) * __ldg(k00 + c0) + (cw1 * tw1 * pw2) * __ldg(k00 + c0 + sp) +
+                           (cw1 * tw2 * pw1) * __ldg(k00 + c0 + st) + (cw1 * tw2 * pw2) * __ldg(k00 + c0 + sp + st) +
+                           (cw2 * tw1 * pw1) * __ldg(k00 + c1) + (cw2 * tw1 * pw2) * __ldg(k00 + c1 + sp) +
+                           (cw2 * tw2 * pw1) * __ldg(k00 + c1 + st) + (cw2 * tw2 * pw2) * __ldg(k00 + c1 + sp + st));
     } else {
-      od = od + L.mult[j] * (L.tw1 * (L.pw1 * __ldg(k00) + L.pw2 * __ldg(k00 + sp)) + L.tw2 * (L.pw1 * __ldg(k00 + st) + L.pw2 * __ldg(k00 + sp + st)));
+      od = od + mult[j] * (tw1 * (pw1 * __ldg(k00) + pw2 * __ldg(k00 + sp)) + tw2 * (pw1 * __ldg(k00 + st) + pw2 * __ldg(k00 + sp + st)));
     }
   }
   return dmax(0.0, od);
 }
 
 // aerosol state of one layer: humidity bin and (layer mass) x (mixing ratio) of every type (add_aerosol_optics :623-700)
-struct AerLay { int irh; double fm[32]; };
-__device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& in, int c, int l, int nlev, AerLay& a) {
+struct AerLayers { int* irh; double* fm; int ntype; };   // [nlev], [nlev][ntype]
+__host__ __device__ inline size_t aer_layers_bytes(int nlev, int ntype) { return (size_t)nlev * (sizeof(int) + ntype * sizeof(double)) + 16; }
+__device__ __forceinline__ void aer_layers_carve(unsigned char* base, int nlev, int ntype, AerLayers& a) {
+  a.ntype = ntype;
+  a.fm = reinterpret_cast<double*>(base);
+  a.irh = reinterpret_cast<int*>(a.fm + (size_t)nlev * ntype);
+}
+__device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& in, int c, int l, int nlev, const AerLayers& a) {
   // gas%mixing_ratio(:,:,IH2O) is a mole fraction under ecCKD: gas%get(IH2O, IMassMixingRatio) (:611, radiation_gas.F90:603-616)
   const double h2o_mmr = LD_IN(in.gas[0], c, l) * (18.0152833 / 28.970);
   const double rh = h2o_mmr / LD_IN(in.h2o_sat_liq, c, l);
   int irh;
   if (rh > A.rh_lower[A.nrh - 1]) irh = A.nrh;
   else { irh = 1; while (rh > A.rh_lower[irh]) ++irh; }
-  a.irh = irh;
+  a.irh[l] = irh;
   const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) * (1.0 / 9.80665);
-  for (int jt = 0; jt < A.ntype; ++jt) a.fm[jt] = factor * in.aerosol_mmr[((size_t)jt * nlev + l) * in.ld + c];
+  for (int jt = 0; jt < A.ntype; ++jt) a.fm[(size_t)l * A.ntype + jt] = factor * in.aerosol_mmr[((size_t)jt * nlev + l) * in.ld + c];
 }
 
 // =========================================================================================================
@@ -106,13 +137,14 @@ ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const CkdModel& m = T.ckd->lw;
   const double* tab = T.ckdtab;
-  CkdLay* lay = reinterpret_cast<CkdLay*>(smem_raw);                                    // [nlev]
-  double* ptw = reinterpret_cast<double*>(lay + nlev);                                  // [nlev+2][2]: Planck interpolation (tw2, it1 or -1)
-  AerLay* aer = reinterpret_cast<AerLay*>(ptw + 2 * (nlev + 2));                        // [nlev] (with aerosols)
+  CkdLayers lay;
+  double* ptw = reinterpret_cast<double*>(ckd_layers_carve(smem_raw, nlev, m, lay));   // [nlev+2][2]: Planck interpolation (tw2, it1 or -1)
   const bool do_aer = cfg.use_aerosols && T.aer;
+  AerLayers aer;
+  if (do_aer) aer_layers_carve(reinterpret_cast<unsigned char*>(ptw + 2 * (nlev + 2)), nlev, T.aer->ntype, aer);
   for (int l = tid; l < nlev; l += CKD_THREADS) {
-    ckd_layer_state(m, tab, in, c, l, lay[l]);
-    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer[l]);
+    ckd_layer_state(m, tab, in, c, l, lay);
+    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer);
   }
   for (int k = tid; k < nlev + 2; k += CKD_THREADS) {   // half-levels 0..nlev, then the skin temperature
     const double temperature = k <= nlev ? LD_IN(in.t_hl, c, k) : in.skin_t[c];
@@ -139,17 +171,17 @@ ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     for (int g = lane; g < SD::NG; g += 32) {
       pl_out[(size_t)l * SD::NG + g] = planck(l, g);
       if (l < nlev) {
-        double od = ckd_optical_depth(m, tab, lay[l], g);
+        double od = ckd_optical_depth(m, tab, lay, l, g);
         if (do_aer) {   // absorption optical depth of the aerosol mixture in this g-point (:700-722, no LW aerosol scattering)
           const AerMeta& A = *T.aer;
           double od_aer = 0.0;
           for (int jt = 0; jt < A.ntype; ++jt) {
             const int iclass = A.iclass[jt];
             if (iclass == 0) continue;
-            const int row = iclass == 1 ? (A.itype[jt] - 1) : ((A.itype[jt] - 1) * A.nrh + (aer[l].irh - 1));
+            const int row = iclass == 1 ? (A.itype[jt] - 1) : ((A.itype[jt] - 1) * A.nrh + (aer.irh[l] - 1));
             const double me = __ldg(T.aertab + (iclass == 1 ? A.me_lw_phobic : A.me_lw_philic) + (size_t)row * SD::NB + g);
             const double ss = __ldg(T.aertab + (iclass == 1 ? A.ssa_lw_phobic : A.ssa_lw_philic) + (size_t)row * SD::NB + g);
-            od_aer = od_aer + aer[l].fm[jt] * me * (1.0 - ss);
+            od_aer = od_aer + aer.fm[(size_t)l * A.ntype + jt] * me * (1.0 - ss);
           }
           od = od + od_aer;
         }
@@ -185,12 +217,14 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   if (!(in.cos_sza[c] > 0.0)) return;   // night column: the solvers do not read the optical properties
   const CkdModel& m = T.ckd->sw;
   const double* tab = T.ckdtab;
-  CkdLay* lay = reinterpret_cast<CkdLay*>(smem_raw);
-  AerLay* aer = reinterpret_cast<AerLay*>(lay + nlev);
+  CkdLayers lay;
+  unsigned char* rest = ckd_layers_carve(smem_raw, nlev, m, lay);
   const bool do_aer = cfg.use_aerosols && T.aer;
+  AerLayers aer;
+  if (do_aer) aer_layers_carve(rest, nlev, T.aer->ntype, aer);
   for (int l = tid; l < nlev; l += CKD_THREADS) {
-    ckd_layer_state(m, tab, in, c, l, lay[l]);
-    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer[l]);
+    ckd_layer_state(m, tab, in, c, l, lay);
+    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer);
   }
   __syncthreads();
   const size_t n = (size_t)nlev * SD::NG;
@@ -200,8 +234,8 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const double* rayl = tab + m.off_rayleigh;
   for (int l = warp; l < nlev; l += CKD_WARPS) {
     for (int g = lane; g < SD::NG; g += 32) {
-      double od = ckd_optical_depth(m, tab, lay[l], g);
-      const double rayleigh = lay[l].simple_multiplier * __ldg(rayl + g);      // :642-647
+      double od = ckd_optical_depth(m, tab, lay, l, g);
+      const double rayleigh = lay.smult[l] * __ldg(rayl + g);      // :642-647
       od = od + rayleigh;                                                       // radiation_ecckd_interface.F90:272-279
       double ssa = rayleigh / od;
       double gg = 0.0;
@@ -211,11 +245,11 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         for (int jt = 0; jt < A.ntype; ++jt) {
           const int iclass = A.iclass[jt];
           if (iclass == 0) continue;
-          const size_t row = iclass == 1 ? (size_t)(A.itype[jt] - 1) : (size_t)((A.itype[jt] - 1) * A.nrh + (aer[l].irh - 1));
+          const size_t row = iclass == 1 ? (size_t)(A.itype[jt] - 1) : (size_t)((A.itype[jt] - 1) * A.nrh + (aer.irh[l] - 1));
           const double me = __ldg(T.aertab + (iclass == 1 ? A.me_sw_phobic : A.me_sw_philic) + row * SD::NB + g);
           const double ss = __ldg(T.aertab + (iclass == 1 ? A.ssa_sw_phobic : A.ssa_sw_philic) + row * SD::NB + g);
           const double ga = __ldg(T.aertab + (iclass == 1 ? A.g_sw_phobic : A.g_sw_philic) + row * SD::NB + g);
-          const double local_od = aer[l].fm[jt] * me;
+          const double local_od = aer.fm[(size_t)l * A.ntype + jt] * me;
           od_aer = od_aer + local_od;
           scat = scat + local_od * ss;
           scat_g = scat_g + local_od * ss * ga;
@@ -328,19 +362,19 @@ general_cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, i
 // =========================================================================================================
 // launchers
 // =========================================================================================================
-static size_t ckd_smem(int nlev, bool aer, bool lw) {
-  return sizeof(CkdLay) * nlev + (lw ? sizeof(double) * 2 * (nlev + 2) : 0) + (aer ? sizeof(AerLay) * nlev : 0) + 16;
+static size_t ckd_smem(int nlev, int ngas, int nlut, int n_aerosol_types, bool lw) {
+  return ckd_layers_bytes(nlev, ngas, nlut) + (lw ? sizeof(double) * 2 * (nlev + 2) : 0) + (n_aerosol_types ? aer_layers_bytes(nlev, n_aerosol_types) : 0) + 16;
 }
 template <class SD>
 static int launch_ckd_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
-  const size_t sm = ckd_smem(nlev, cfg.use_aerosols && T.aer, true);
+  const size_t sm = ckd_smem(nlev, cfg.ckd_ngas_lw, cfg.ckd_nlut_lw, (cfg.use_aerosols && T.aer) ? cfg.n_aerosol_types : 0, true);
   cudaFuncSetAttribute(ckd_lw_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   ckd_lw_kernel<SD><<<nc, CKD_THREADS, sm, st>>>(T, cfg, in, w, nlev);
   return 1;
 }
 template <class SD>
 static int launch_ckd_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
-  const size_t sm = ckd_smem(nlev, cfg.use_aerosols && T.aer, false);
+  const size_t sm = ckd_smem(nlev, cfg.ckd_ngas_sw, cfg.ckd_nlut_sw, (cfg.use_aerosols && T.aer) ? cfg.n_aerosol_types : 0, false);
   cudaFuncSetAttribute(ckd_sw_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   ckd_sw_kernel<SD><<<nc, CKD_THREADS, sm, st>>>(T, cfg, in, w, nlev);
   return 1;

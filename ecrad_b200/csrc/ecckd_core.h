@@ -19,13 +19,14 @@ struct CkdGas {
   int dep;            // concentration dependence
   int slot;           // index into DevIn::gas[] of this gas' mole-fraction array, -1: composite / not provided (zero)
   int n_mole_frac;
+  int lut;            // index among the look-up-table gases of the model (dep == CKD_CONC_LUT), else -1
   double reference_mole_frac, log_mole_frac1, d_log_mole_frac;
   double mole_frac1;  // exp(log_mole_frac1), evaluated once on the host (radiation_ecckd.F90:586)
   size_t off;         // molar_abs
 };
 
 struct CkdModel {
-  int ng, npress, ntemp, nplanck, ngas;
+  int ng, npress, ntemp, nplanck, ngas, nlut;
   double log_pressure1, d_log_pressure, d_temperature, temperature1_planck, d_temperature_planck;
   size_t off_temperature1, off_planck, off_solar, off_rayleigh;
   CkdGas gas[CKD_MAXGAS];

@@ -13,7 +13,7 @@
 
 namespace ecb {
 
-enum { TC_LCH = 8 };
+enum { TC_LCH = 4 };   // layers between two g-point reductions (small: the tile competes with resident CTAs for shared memory)
 enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -31,26 +31,28 @@ __global__ void tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
 }
 
 struct TcShared {
-  double *reg, *ods, *U, *V;
-  int* clear;   // is_clear_sky_layer(0:nlev+1)
+  double *reg, *ods;        // shared memory: region fractions and optical-depth scalings [nlev][3]
+  const double *U, *V;      // global memory (uniform, L1-resident broadcast loads): overlap matrices [nlev+1][3][3]
+  int* clear;               // is_clear_sky_layer(0:nlev+1)
 };
 
-// loads the column's region data into shared memory (block-wide, ends with a barrier)
+// loads the column's region data into shared memory (block-wide, ends with a barrier).  The 3x3 overlap matrices stay in
+// global memory: every thread of the CTA reads the same 9 values per half-level, one L1 transaction per warp, and keeping
+// their 20 KB out of shared memory doubles the resident CTAs of these kernels.
 __device__ __forceinline__ TcShared tc_load_shared(unsigned char* base, const Work& w, const DevIn& in, int c, int nlev, int nthreads) {
   TcShared s;
   s.reg = reinterpret_cast<double*>(base);
   s.ods = s.reg + nlev * 3;
-  s.U = s.ods + nlev * 3;
-  s.V = s.U + (nlev + 1) * 9;
-  s.clear = reinterpret_cast<int*>(s.V + (nlev + 1) * 9);
+  s.clear = reinterpret_cast<int*>(s.ods + nlev * 3);
+  s.U = w.tc_u + (size_t)c * (nlev + 1) * 9;
+  s.V = w.tc_v + (size_t)c * (nlev + 1) * 9;
   const int t = threadIdx.x;
   for (int i = t; i < nlev * 3; i += nthreads) { s.reg[i] = w.tc_reg[(size_t)c * nlev * 3 + i]; s.ods[i] = w.tc_ods[(size_t)c * nlev * 3 + i]; }
-  for (int i = t; i < (nlev + 1) * 9; i += nthreads) { s.U[i] = w.tc_u[(size_t)c * (nlev + 1) * 9 + i]; s.V[i] = w.tc_v[(size_t)c * (nlev + 1) * 9 + i]; }
   for (int i = t; i < nlev + 2; i += nthreads) s.clear[i] = (i == 0 || i == nlev + 1) ? 1 : !(LD_IN(in.frac, c, i - 1) > 0.0);
   __syncthreads();
   return s;
 }
-static size_t tc_shared_bytes(int nlev) { return sizeof(double) * (6 * nlev + 18 * (nlev + 1)) + sizeof(int) * (nlev + 2) + 16; }
+static size_t tc_shared_bytes(int nlev) { return sizeof(double) * (6 * nlev) + sizeof(int) * (nlev + 2) + 16; }
 
 // out[j1] = sum_j2 A[j1][j2] * x[j2]   (singlemat_x_vec, radiation_matrix.F90:110-136)
 __device__ __forceinline__ void mat3_x_vec(const double* A, double* x) {

@@ -79,7 +79,7 @@ struct PackedTables {
   int n_emiss_lw = 0;
   bool is_ecckd = false;
   int ng_lw = NG_LW, ng_sw = NG_SW, nb_lw = NB_LW, nb_sw = NB_SW;
-  CkdMeta ckd;                        // ecCKD gas optics + generalised cloud optics
+  CkdMeta ckd{};                      // ecCKD gas optics + generalised cloud optics
   std::vector<double> ckdtab;
   AerMeta aer;                        // aer.ntype == 0: no aerosol tables
   std::vector<double> aertab;
@@ -158,6 +158,7 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
       g.dep = (int)gm[6 * j + 1]; g.reference_mole_frac = gm[6 * j + 2]; g.n_mole_frac = (int)gm[6 * j + 3];
       g.log_mole_frac1 = gm[6 * j + 4]; g.d_log_mole_frac = gm[6 * j + 5];
       g.mole_frac1 = exp(g.log_mole_frac1);
+      g.lut = g.dep == CKD_CONC_LUT ? m.nlut++ : -1;
       g.slot = (code >= 0 && code <= 12) ? slot_of_code[code] : -1;
       const size_t n = (size_t)m.ng * m.npress * m.ntemp * (g.dep == CKD_CONC_LUT ? g.n_mole_frac : 1);
       g.off = put(pre + "gas" + std::to_string(j) + "_molar_abs", n);

@@ -63,14 +63,19 @@ typedef struct ecrad_b200_config {
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md
  * ("table directory"); for the RRTMG path they are the module variables of ifsrrtm/yoerrta1..16.F90,
  * yoesrta16..29.F90, yoerrtwn.F90, yoerrtrf.F90, yoesrtwn.F90 plus config%cloud_optics%*, config%pdf_sampler%*,
- * config%sw_albedo_weights, config%i_emiss_from_band_lw, and (with aerosols) config%aerosol_optics%{mass_ext,ssa,g}_{sw,lw}_
+ * config%sw_albedo_weights, config%i_emiss_from_band_lw or config%lw_emiss_weights ("lw_emiss_weights", when
+ * do_nearest_spectral_lw_emiss is false), and (with aerosols) config%aerosol_optics%{mass_ext,ssa,g}_{sw,lw}_
  * {phobic,philic}, %rh_lower, %iclass, %itype ("aer_*", "aerosol_iclass", "aerosol_itype").  Data are COPIED by ecrad_b200_setup. */
 typedef struct ecrad_b200_tables ecrad_b200_tables;
 ecrad_b200_tables* ecrad_b200_tables_create(void);
 /* dtype: 0 = float64, 1 = int32.  dims[ndim] in Fortran order (dims[0] fastest).  Returns 0 on success. */
 int  ecrad_b200_tables_add(ecrad_b200_tables* t, const char* name, int dtype, int ndim,
                            const int64_t* dims, const void* data);
-/* Load an "ETB1" blob written by tools/extract_rrtmg_tables.py (stand-alone use without a Fortran host). */
+/* For the ECCKD gas model the directory holds config%gas_optics_{lw,sw} ("ckd_lw_*", "ckd_sw_*": look-up-table grids,
+ * molar_abs per gas, planck_function, norm_solar_irradiance, rayleigh_molar_scat), config%cloud_optics_{lw,sw}(1:2)
+ * ("gco_*": mass_ext, ssa, asymmetry per g-point and effective radius) and the aerosol arrays per g-point; names and
+ * shapes in tools/extract_ecckd_tables.py.
+ * Load an "ETB1" blob written by tools/extract_rrtmg_tables.py / extract_ecckd_tables.py (stand-alone use without a Fortran host). */
 int  ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path);
 /* Same from memory (e.g. the blob received by an MPI/NCCL broadcast from the rank that read it; mirrors MPL_BROADCAST in
  * ifsrrtm/rrtm_kgb1.F90:38-51). */
@@ -92,7 +97,9 @@ typedef struct ecrad_b200_inputs {
   const int32_t* iseed;               /* (ncol)                                                          */
   const double* pressure_hl;          /* (ncol, nlev+1)  Pa                                              */
   const double* temperature_hl;       /* (ncol, nlev+1)  K                                               */
-  /* gas%mixing_ratio(:,:,IGAS) slices, kg/kg, each (ncol, nlev); gas codes radiation_gas_constants.F90:26-39 */
+  /* gas%mixing_ratio(:,:,IGAS) slices AFTER set_gas_units (radiation_interface.F90:164-193), each (ncol, nlev); gas codes
+   * radiation_gas_constants.F90:26-39.  RRTMG-IFS: mass mixing ratios, kg/kg (radiation_ifs_rrtm.F90 set_gas_units);
+   * ECCKD: volume mixing ratios, mol/mol (radiation_ecckd_interface.F90:148-163) -- the field names keep the RRTMG spelling. */
   const double* h2o_mmr; const double* co2_mmr; const double* o3_mmr; const double* n2o_mmr;
   const double* ch4_mmr; const double* cfc11_mmr; const double* cfc12_mmr; const double* hcfc22_mmr;
   const double* ccl4_mmr;
@@ -125,7 +132,8 @@ typedef struct ecrad_b200_outputs {
   double *sw_dn_surf_clear_band, *sw_dn_direct_surf_clear_band;      /* (n_bands_sw, ncol) */
   double *sw_dn_diffuse_surf_canopy, *sw_dn_direct_surf_canopy;      /* (n_canopy_bands_sw, ncol) */
   double *lw_dn_surf_canopy;                                         /* (n_canopy_bands_lw, ncol) */
-  /* per-band profiles, only filled by the Cloudless solver when do_save_spectral_flux: (n_bands, ncol, nlev+1) */
+  /* per-band profiles (n_bands, ncol, nlev+1), filled by the Cloudless and Tripleclouds solvers when do_save_spectral_flux
+   * (the McICA solver has none in the reference either); with ECCKD n_bands == n_g, i.e. one profile per g-point */
   double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;
 } ecrad_b200_outputs;
 
