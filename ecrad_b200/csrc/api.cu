@@ -49,6 +49,7 @@ struct Handle {
   std::vector<void*> table_allocs;
   int device = 0;
   int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
+  int edge_cols = 1024;          // host entry: at most this many columns in the first and the last tile
   int tile_cols_device = 16384;  // device entry: only bounds the scratch (about 3 MB per column); bigger tiles = fewer partial waves
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_aux1 = nullptr, s_aux2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
@@ -401,6 +402,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
   if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = h->tile_cols_device = v; }
+  if (const char* s = getenv("ECRAD_B200_EDGE")) { int v = atoi(s); if (v > 0) h->edge_cols = v; }
   if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
@@ -486,8 +488,26 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
   CK(h, cudaSetDevice(h->device));
   const ecrad_b200_config& c = h->cfg;
   const int c_first = istartcol - 1, ntot = iendcol - istartcol + 1;
-  const int ntiles = (ntot + h->tile_cols - 1) / h->tile_cols;
-  const int cap = (ntot + ntiles - 1) / ntiles;   // balanced tiles: no short last tile
+  // Tile schedule.  The first tile's H2D and the last tile's D2H are the only copies that cannot hide behind kernels, so both
+  // edge tiles are short (a quarter of tile_cols); the columns in between are split into equal tiles of at most tile_cols.
+  std::vector<int> tile_first, tile_n;
+  {
+    const int edge = h->tile_cols / 4 < h->edge_cols ? h->tile_cols / 4 : h->edge_cols;
+    int pos = 0;
+    auto push = [&](int n) { tile_first.push_back(pos); tile_n.push_back(n); pos += n; };
+    if (edge >= 64 && ntot >= 2 * edge + h->tile_cols / 2) {
+      push(edge);
+      const int rest = ntot - 2 * edge, k = (rest + h->tile_cols - 1) / h->tile_cols;
+      for (int i = 0; i < k; ++i) push(rest / k + (i < rest % k ? 1 : 0));
+      push(edge);
+    } else {
+      const int k = (ntot + h->tile_cols - 1) / h->tile_cols;
+      for (int i = 0; i < k; ++i) push(ntot / k + (i < ntot % k ? 1 : 0));
+    }
+  }
+  const int ntiles = (int)tile_n.size();
+  int cap = 0;
+  for (int n : tile_n) cap = n > cap ? n : cap;
   if (ensure_work(h, cap, nlev)) return 1;
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];
@@ -514,7 +534,7 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
   for (auto& s : h->slot) s.used = false;
   for (int t = 0; t < ntiles; ++t) {
     Slot& s = h->slot[t & 1];
-    const int c0 = c_first + t * cap, nt = (ntot - t * cap) < cap ? (ntot - t * cap) : cap;
+    const int c0 = c_first + tile_first[t], nt = tile_n[t];
     void* ip[N_IN]; void* op[N_OUT];
     // ---- H2D (this slot's buffers are free once the kernels and copies of tile t-2 are done) ----
     if (s.used) { CK(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CK(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }

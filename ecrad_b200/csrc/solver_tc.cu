@@ -13,7 +13,9 @@
 
 namespace ecb {
 
-enum { TC_LCH = 4 };   // layers between two g-point reductions (small: the tile competes with resident CTAs for shared memory)
+// layers between two g-point reductions: rows per flush (6 x 4 in the SW, 2 x 16 in the LW) ~ the 32-40 row slots of flush_tile;
+// the tile competes with resident CTAs for shared memory
+enum { TC_LCH = 4, TC_LCH_LW = 16 };
 enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -246,8 +248,8 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   double* sums = reinterpret_cast<double*>(smem_raw);     // [4][nl1]: up_clear, up, dn, deriv
-  double* tile = sums + 4 * nl1;                           // [2][TC_LCH][SD::RS]
-  double* red = tile + 2 * TC_LCH * SD::RS;              // [8] block reduction scratch
+  double* tile = sums + 4 * nl1;                           // [2][TC_LCH_LW][SD::RS]
+  double* red = tile + 2 * TC_LCH_LW * SD::RS;              // [8] block reduction scratch
   const TcShared S = tc_load_shared(reinterpret_cast<unsigned char*>(red + 8), w, in, c, nlev, SD::THREADS);
   const size_t n = (size_t)nlev * SD::NG;
   const double* od = w.od_lw + (size_t)c * n;
@@ -275,7 +277,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     double* dst[2] = {s_up_c, s_up};
     const BandOut bo[1] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = nlev;
-    if (act) { tile[slot * SD::RS + g] = fuc; tile[(TC_LCH + slot) * SD::RS + g] = fu; }
+    if (act) { tile[slot * SD::RS + g] = fuc; tile[(TC_LCH_LW + slot) * SD::RS + g] = fu; }
     ++slot;
     double pb = act ? pl[(size_t)nlev * SD::NG + g] : 0.0;
     for (int l = nlev - 1; l >= 0; --l) {
@@ -332,12 +334,12 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           fu = Lc.trans * fu + Lc.source_up;            // above cloud top
         }
         pb = pt;
-        tile[slot * SD::RS + g] = fuc; tile[(TC_LCH + slot) * SD::RS + g] = l <= ict ? fu : 0.0;
+        tile[slot * SD::RS + g] = fuc; tile[(TC_LCH_LW + slot) * SD::RS + g] = l <= ict ? fu : 0.0;
       }
       ++slot;
-      if (slot == TC_LCH || l == 0) {
-        if (bo[0].dst) flush_bands(tile, SD::RS, TC_LCH, slot, bo, 1, lfirst, -1, c, SD::NB, T.meta->lw);
-        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0;
+      if (slot == TC_LCH_LW || l == 0) {
+        if (bo[0].dst) flush_bands(tile, SD::RS, TC_LCH_LW, slot, bo, 1, lfirst, -1, c, SD::NB, T.meta->lw);
+        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, -1, TC_LCH_LW); lfirst -= slot; slot = 0;
       }
     }
   }
@@ -363,12 +365,12 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         }
         if (!(S.clear[jl] && S.clear[jl + 1])) mat3_x_vec(S.V + jl * 9, fdn);
         tile[slot * SD::RS + g] = fup[0] + fup[1] + fup[2];
-        tile[(TC_LCH + slot) * SD::RS + g] = fdn[0] + fdn[1] + fdn[2];
+        tile[(TC_LCH_LW + slot) * SD::RS + g] = fdn[0] + fdn[1] + fdn[2];
       }
       ++slot;
-      if (slot == TC_LCH || l == nlev - 1) {
-        if (bo[0].dst || bo[1].dst) flush_bands(tile, SD::RS, TC_LCH, slot, bo, 2, lfirst, 1, c, SD::NB, T.meta->lw);
-        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, 1, TC_LCH); lfirst += slot; slot = 0;
+      if (slot == TC_LCH_LW || l == nlev - 1) {
+        if (bo[0].dst || bo[1].dst) flush_bands(tile, SD::RS, TC_LCH_LW, slot, bo, 2, lfirst, 1, c, SD::NB, T.meta->lw);
+        flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, 1, TC_LCH_LW); lfirst += slot; slot = 0;
       }
     }
   }
@@ -396,7 +398,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
       }
       ++slot;
-      if (slot == TC_LCH || l == 0) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, -1, TC_LCH); lfirst -= slot; slot = 0; }
+      if (slot == TC_LCH_LW || l == 0) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, -1, TC_LCH_LW); lfirst -= slot; slot = 0; }
     }
   }
 #undef SCR
@@ -440,7 +442,7 @@ static int launch_tc_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in
 }
 template <class SD>
 static int launch_tc_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  const size_t sm = sizeof(double) * (4 * (nlev + 1) + 2 * TC_LCH * SD::RS + 8) + tc_shared_bytes(nlev);
+  const size_t sm = sizeof(double) * (4 * (nlev + 1) + 2 * TC_LCH_LW * SD::RS + 8) + tc_shared_bytes(nlev);
   cudaFuncSetAttribute(tc_lw_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   tc_lw_kernel<SD><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
   return 1;
