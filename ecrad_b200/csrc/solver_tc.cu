@@ -19,17 +19,47 @@ enum { TC_LCH = 4, TC_LCH_LW = 16 };
 enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
 
 // ---------------------------------------------------------------------------------------------------------
-// region fractions, optical-depth scalings and overlap matrices: one thread per column
+// region fractions, optical-depth scalings and overlap matrices (calc_region_properties + calc_overlap_matrices): one CTA
+// per column, one thread per half-level -- an interface only needs the regions of the two layers it separates, which each
+// thread recomputes (tc_region is a handful of operations); the total cloud cover 1 - prod v_matrix(1,1,:) is then
+// multiplied up in interface order by one thread, as the reference does.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
+enum { TC_PREP_THREADS = 160 };
+__global__ void __launch_bounds__(TC_PREP_THREADS)
+tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  __shared__ double v11[TC_PREP_THREADS + 8];
+  const int c = blockIdx.x;
   double* reg = w.tc_reg + (size_t)c * nlev * 3;
   double* ods = w.tc_ods + (size_t)c * nlev * 3;
-  double* U = w.tc_u + (size_t)c * (nlev + 1) * 9;
-  double* V = w.tc_v + (size_t)c * (nlev + 1) * 9;
-  w.tc_cc[c] = tc_prepare_column(nlev, in.ld, in.frac + c, in.fsd + c, in.overlap + c, cfg.cloud_inhom_decorr_scaling,
-                                 cfg.cloud_fraction_threshold, reg, ods, U, V);
+  const double expo = 1.0 / cfg.cloud_inhom_decorr_scaling, thr = cfg.cloud_fraction_threshold;
+  for (int jlev = 1 + (int)threadIdx.x; jlev <= nlev + 1; jlev += TC_PREP_THREADS) {   // interface above layer jlev (1-based)
+    double fu[3] = {1.0, 0.0, 0.0}, fl[3] = {1.0, 0.0, 0.0}, o_[3], M[3][3];
+    if (jlev > 1) tc_region(LD_IN(in.frac, c, jlev - 2), LD_IN(in.fsd, c, jlev - 2), thr, fu, o_);
+    if (jlev <= nlev) {
+      tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_);
+      for (int r = 0; r < 3; ++r) { reg[(jlev - 1) * 3 + r] = fl[r]; ods[(jlev - 1) * 3 + r] = o_[r]; }
+    }
+    double op1 = 1.0, op2 = 1.0;
+    if (jlev > 1 && jlev <= nlev) {
+      op1 = LD_IN(in.overlap, c, jlev - 2);
+      op2 = op1 >= 0.0 ? (expo == 2.0 ? mul_rn(op1, op1) : pow(op1, expo)) : op1;
+    }
+    tc_alpha_overlap_matrix(op1, op2, fu, fl, M);
+    double* u = w.tc_u + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
+    double* v = w.tc_v + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
+    for (int ju = 0; ju < 3; ++ju)
+      for (int jw = 0; jw < 3; ++jw) {
+        u[ju * 3 + jw] = fl[jw] >= thr ? M[ju][jw] / fl[jw] : 0.0;
+        v[jw * 3 + ju] = fu[ju] >= thr ? M[ju][jw] / fu[ju] : 0.0;
+      }
+    if (jlev - 1 < TC_PREP_THREADS + 8) v11[jlev - 1] = v[0];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double prod = 1.0;
+    for (int k = 0; k <= nlev; ++k) prod = prod * v11[k];
+    w.tc_cc[c] = 1.0 - prod;
+  }
 }
 
 struct TcShared {
@@ -430,7 +460,7 @@ size_t tc_scratch_doubles_lw(int nlev, int ng) { return (size_t)TC_LW_ARRAYS * n
 size_t tc_scratch_doubles_sw(int nlev, int ng) { return (size_t)TC_SW_ARRAYS * nlev * ng; }
 
 int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
-  tc_prep_kernel<<<(nc + 63) / 64, 64, 0, st>>>(cfg, in, w, nc, nlev);
+  tc_prep_kernel<<<nc, TC_PREP_THREADS, 0, st>>>(cfg, in, w, nc, nlev);
   return 1;
 }
 template <class SD>

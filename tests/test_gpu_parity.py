@@ -306,6 +306,68 @@ def test_band_profiles_synthetic_and_tiled(handles, meridian_raw, solver):
         assert np.isnan(out3[nm]).all(), nm
 
 
+def coarsen_levels(raw, nlev_new):
+    """Column set on fewer model levels: keep nlev_new+1 of the 138 half-levels (TOA and surface included); each new layer takes
+    the composition/cloud of the first old layer it spans.  Only the array shapes matter for the test."""
+    hl = np.unique(np.round(np.linspace(0, 137, nlev_new + 1)).astype(int))
+    assert len(hl) == nlev_new + 1
+    lay = hl[:-1]
+    out = {}
+    for k, v in raw.items():
+        if np.ndim(v) < 2:
+            out[k] = v
+        elif k == "aerosol_mmr":
+            out[k] = v[:, :, lay]
+        elif v.shape[1] == 138:
+            out[k] = v[:, hl]
+        elif v.shape[1] == 137:
+            out[k] = v[:, lay]
+        elif v.shape[1] == 136:
+            out[k] = v[:, lay[:-1]]
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("nlev,kw", [(60, dict()), (91, dict(use_aerosols=True, overlap_scheme_name="Exp-Exp")),
+                                     (19, dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")),
+                                     (50, dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_aerosols=True)),
+                                     (33, dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds",
+                                               lw_solver_name="Tripleclouds"))])
+def test_other_level_counts(handles, meridian_raw, nlev, kw):
+    """The reference takes any nlev; the kernels stage per-layer state in shared memory sized by nlev (odd counts, not a multiple of 4)."""
+    n = 96
+    h, orc, cfg = handles(**kw)
+    raw = coarsen_levels(I.synthetic_columns(meridian_raw, n), nlev)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+    compare(out, ref, FLUXES + OTHERS)
+    for nm in ("cloud_cover_lw", "cloud_cover_sw", "cloud_fraction"):
+        assert np.array_equal(out[nm], ref[nm]), nm
+
+
+@pytest.mark.parametrize("kw", [dict(do_sw=False), dict(do_lw=False), dict(do_sw=False, gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False),
+                                dict(do_lw=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+def test_one_spectrum_only_and_single_column(handles, meridian_raw, kw):
+    """do_sw = false / do_lw = false: the other spectrum's outputs stay untouched; ncol = 1 and a 1-column range work."""
+    n = 40
+    h, orc, cfg = handles(**kw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    on = [nm for nm in FLUXES + OTHERS if nm.startswith("lw" if cfg.do_lw else "sw")]
+    off = [nm for nm in FLUXES if nm.startswith("sw" if cfg.do_lw else "lw")]
+    compare(out, ref, on)
+    for nm in off:
+        assert np.isnan(out[nm]).all(), nm
+    one = {k: (v if np.ndim(v) == 0 else v[7:8]) for k, v in raw.items()}
+    out1 = h.radiation(I.to_radiation_inputs(one, cfg), 1, NLEV)
+    for nm in on:
+        a = out1[nm]
+        b = out[nm][7:8] if a.shape[0] == 1 else out[nm][:, 7:8]
+        assert np.array_equal(a, b, equal_nan=True), nm
+
+
 def test_all_night_and_all_clear_edge_cases(handles, meridian_raw):
     h, orc, _ = handles()
     n = 40
