@@ -141,10 +141,14 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   if (!S.clear[nlev]) { ta[1] = ta[0]; ta[2] = ta[0]; td[1] = td[0]; td[2] = td[0]; }
   double tac = ta[0], tdc = td[0];
   if (act) {
+    // software pipeline: the gas optical properties of layer l-1 are loaded before the two-stream arithmetic of layer l
+    size_t in_ = (size_t)(nlev - 1) * SD::NG + g;
+    double od_n = od[in_], ssa_n = ssa[in_], gg_n = gas_g ? gas_g[in_] : 0.0;
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       const size_t i = (size_t)l * SD::NG + g;
-      const double odg = od[i], ssag = ssa[i], gg_gas = gas_g ? gas_g[i] : 0.0;
+      const double odg = od_n, ssag = ssa_n, gg_gas = gg_n;
+      if (l > 0) { od_n = od[i - SD::NG]; ssa_n = ssa[i - SD::NG]; if (gas_g) gg_n = gas_g[i - SD::NG]; }
       const SwLayer Lc = sw_ref_trans(mu0, odg, ssag, gg_gas);
       {   // clear-sky column
         const double id = 1.0 / (1.0 - tac * Lc.ref);
@@ -310,11 +314,13 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     if (act) { tile[slot * SD::RS + g] = fuc; tile[(TC_LCH_LW + slot) * SD::RS + g] = fu; }
     ++slot;
     double pb = act ? pl[(size_t)nlev * SD::NG + g] : 0.0;
+    double od_n = act ? od[(size_t)(nlev - 1) * SD::NG + g] : 0.0, pt_n = act ? pl[(size_t)(nlev - 1) * SD::NG + g] : 0.0;   // software pipeline
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
         const size_t i = (size_t)l * SD::NG + g;
-        const double odg = od[i], pt = pl[i];
+        const double odg = od_n, pt = pt_n;
+        if (l > 0) { od_n = od[i - SD::NG]; pt_n = pl[i - SD::NG]; }
         const LwLayer Lc = lw_no_scat(odg, pt, pb);
         fuc = Lc.trans * fuc + Lc.source_up;
         if (l >= ict) {
