@@ -90,8 +90,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS || s == ECRAD_SOLVER_TRIPLECLOUDS; };
   if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw)))
     return fail(h, "solver not available in this build (McICA, Tripleclouds and Cloudless are)");
-  if (c.use_beta_overlap && ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS)))
-    return fail(h, "use_beta_overlap is not available with the Tripleclouds solver in this build");
   const int gm = c.do_lw ? c.i_gas_model_lw : c.i_gas_model_sw;
   if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
     return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");

@@ -44,7 +44,8 @@ tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
       op1 = LD_IN(in.overlap, c, jlev - 2);
       op2 = op1 >= 0.0 ? (expo == 2.0 ? mul_rn(op1, op1) : pow(op1, expo)) : op1;
     }
-    tc_alpha_overlap_matrix(op1, op2, fu, fl, M);
+    if (cfg.use_beta_overlap) { const double op[3] = {op1, op2, op2}; tc_beta_overlap_matrix(op, fu, fl, thr, M); }
+    else tc_alpha_overlap_matrix(op1, op2, fu, fl, M);
     double* u = w.tc_u + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
     double* v = w.tc_v + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
     for (int ju = 0; ju < 3; ++ju)

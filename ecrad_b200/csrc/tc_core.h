@@ -49,6 +49,23 @@ HD void tc_alpha_overlap_matrix(double op, double op_inhom, const double* fu, co
   M[2][2] = frac_both * (cf_upper + cf_lower - pair_cloud_cover);
 }
 
+// calc_beta_overlap_matrix, radiation_overlap.F90:63-122: one "beta" overlap parameter per region (Shonk et al. 2010)
+HD void tc_beta_overlap_matrix(const double* op, const double* fu, const double* fl, double frac_threshold, double M[3][3]) {
+  double denominator = 1.0, op_x_frac_min[3];
+  for (int r = 0; r < 3; ++r) {
+    op_x_frac_min[r] = op[r] * dmin(fu[r], fl[r]);
+    denominator = denominator - op_x_frac_min[r];
+  }
+  if (denominator >= frac_threshold) {
+    const double factor = 1.0 / denominator;
+    for (int ju = 0; ju < 3; ++ju)
+      for (int jw = 0; jw < 3; ++jw) M[ju][jw] = factor * (fl[jw] - op_x_frac_min[jw]) * (fu[ju] - op_x_frac_min[ju]);
+  } else {
+    for (int ju = 0; ju < 3; ++ju) for (int jw = 0; jw < 3; ++jw) M[ju][jw] = 0.0;
+  }
+  for (int r = 0; r < 3; ++r) M[r][r] = M[r][r] + op_x_frac_min[r];
+}
+
 // One column: reg/ods [nlev][3], U/V [nlev+1][3][3] with U[hl][jupper][jlower] = u_matrix(jupper,jlower,hl+1) and
 // V[hl][a][b] = v_matrix(a,b,hl+1); returns the total cloud cover 1 - prod v_matrix(1,1,:).
 // frac/fsd/overlap_param are strided by `fstride` (reference layout, column fastest).

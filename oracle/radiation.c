@@ -586,9 +586,9 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       double (*reg)[3] = malloc(sizeof(double[3]) * nlev), (*ods)[3] = malloc(sizeof(double[3]) * nlev);
       double (*U)[3][3] = malloc(sizeof(double[3][3]) * nl1), (*V)[3][3] = malloc(sizeof(double[3][3]) * nl1);
       extern void orc_region_properties(int, const double*, const double*, double, double (*)[3], double (*)[3]);
-      extern void orc_overlap_matrices(int, double (*)[3], const double*, double, double, double (*)[3][3], double (*)[3][3], double*);
+      extern void orc_overlap_matrices(int, double (*)[3], const double*, double, double, int, double (*)[3][3], double (*)[3][3], double*);
       orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
-      orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, U, V, &o.cloud_cover);
+      orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o.cloud_cover);
       free(reg); free(ods); free(U); free(V);
     } else {
       orc_tripleclouds_sw(t, cfg, nlev, mu0, frac, fsd, op, w->od_sw, w->ssa_sw, w->g_sw, w->od_sw_cloud, w->ssa_sw_cloud, w->g_sw_cloud,

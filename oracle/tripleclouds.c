@@ -67,10 +67,27 @@ static void alpha_overlap_matrix(double op, double op_inhom, const double* fu, c
   M[2][2] = frac_both * (cf_upper + cf_lower - pair_cloud_cover);
 }
 
+/* calc_beta_overlap_matrix, radiation_overlap.F90:63-122 (Shonk et al. 2010 "beta" overlap parameter per region) */
+static void beta_overlap_matrix(const double* op, const double* fu, const double* fl, double frac_threshold, double M[NREG][NREG]) {
+  double denominator = 1.0, op_x_frac_min[NREG];
+  for (int r = 0; r < NREG; ++r) {
+    op_x_frac_min[r] = op[r] * dmin(fu[r], fl[r]);
+    denominator = denominator - op_x_frac_min[r];
+  }
+  if (denominator >= frac_threshold) {
+    const double factor = 1.0 / denominator;
+    for (int ju = 0; ju < NREG; ++ju)
+      for (int jw = 0; jw < NREG; ++jw) M[ju][jw] = factor * (fl[jw] - op_x_frac_min[jw]) * (fu[ju] - op_x_frac_min[ju]);
+  } else {
+    for (int ju = 0; ju < NREG; ++ju) for (int jw = 0; jw < NREG; ++jw) M[ju][jw] = 0.0;
+  }
+  for (int r = 0; r < NREG; ++r) M[r][r] = M[r][r] + op_x_frac_min[r];
+}
+
 /* radiation_overlap.F90:280-457.  U[jlev][jupper][jlower] = u_matrix(jupper,jlower,jlev); V[jlev][a][b] = v_matrix(a,b,jlev);
  * jlev = 0..nlev (half-levels). */
 void orc_overlap_matrices(int nlev, double (*reg_fracs)[NREG], const double* overlap_param, double decorrelation_scaling,
-                          double frac_threshold, double (*U)[NREG][NREG], double (*V)[NREG][NREG], double* cloud_cover) {
+                          double frac_threshold, int use_beta_overlap, double (*U)[NREG][NREG], double (*V)[NREG][NREG], double* cloud_cover) {
   double frac_upper[NREG] = {1.0, 0.0, 0.0}, frac_lower[NREG], M[NREG][NREG];
   for (int jlev = 1; jlev <= nlev + 1; ++jlev) {
     if (jlev > nlev) { frac_lower[0] = 1.0; frac_lower[1] = 0.0; frac_lower[2] = 0.0; }
@@ -81,7 +98,8 @@ void orc_overlap_matrices(int nlev, double (*reg_fracs)[NREG], const double* ove
       op1 = overlap_param[jlev - 2];
       op2 = op1 >= 0.0 ? pow(op1, 1.0 / decorrelation_scaling) : op1;
     }
-    alpha_overlap_matrix(op1, op2, frac_upper, frac_lower, M);
+    if (use_beta_overlap) { const double op[NREG] = {op1, op2, op2}; beta_overlap_matrix(op, frac_upper, frac_lower, frac_threshold, M); }
+    else alpha_overlap_matrix(op1, op2, frac_upper, frac_lower, M);
     for (int ju = 0; ju < NREG; ++ju)
       for (int jw = 0; jw < NREG; ++jw) {
         U[jlev - 1][ju][jw] = frac_lower[jw] >= frac_threshold ? M[ju][jw] / frac_lower[jw] : 0.0;
@@ -106,7 +124,7 @@ void orc_tripleclouds_sw(const orc_tables* t, const ecrad_b200_config* cfg, int 
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
   orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
-  orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, U, V, &o->cloud_cover);
+  orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));   /* is_clear_sky_layer(0:nlev+1) */
   clear[0] = 1; clear[nlev + 1] = 1;
   for (int jl = 1; jl <= nlev; ++jl) clear[jl] = !(frac[jl - 1] > 0.0);
@@ -275,7 +293,7 @@ void orc_tripleclouds_lw(const orc_tables* t, const ecrad_b200_config* cfg, int 
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
   orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
-  orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, U, V, &o->cloud_cover);
+  orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));
   clear[0] = 1; clear[nlev + 1] = 1;
   int i_cloud_top = nlev + 1;

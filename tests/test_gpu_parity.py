@@ -148,7 +148,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(overlap_scheme_name="Exp-Exp", use_beta_overlap=True),
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True, do_lw_cloud_scattering=False),
-                                dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless")])
+                                dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
+                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_beta_overlap=True)])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
