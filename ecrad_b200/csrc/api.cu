@@ -97,7 +97,8 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
-  if (c.use_vectorizable_generator) return fail(h, "use_vectorizable_generator is not available in this build");
+  if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
+    return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
   if (c.do_nearest_spectral_sw_albedo) return fail(h, "do_nearest_spectral_sw_albedo is not available in this build");
   if (gm == ECRAD_GAS_IFSRRTMG) {
     if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
@@ -367,6 +368,8 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
     rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
   }
+  if (cfg->use_vectorizable_generator) { P.cloud.gen_mask = 0x7FFFFFFFu; P.cloud.gen_scale = 1.0 / 2147483647.0; }
+  else { P.cloud.gen_mask = 0x3FFFFFFFu; P.cloud.gen_scale = 1.0 / 1073741824.0; }
   rc |= upload(h, &P.cloud, 1, &h->T.cloud);
   rc |= upload(h, P.pdf_val.data(), P.pdf_val.size(), &h->T.pdf_val);
   rc |= upload(h, P.sw_albedo_weights.data(), P.sw_albedo_weights.size(), &h->T.sw_albedo_weights);
@@ -392,6 +395,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.n_canopy_bands_sw = cfg->n_canopy_bands_sw; d.n_canopy_bands_lw = cfg->n_canopy_bands_lw;
   d.use_aerosols = cfg->use_aerosols; d.n_aerosol_types = cfg->n_aerosol_types;
   d.do_save_spectral_flux = cfg->do_save_spectral_flux;
+  d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
   d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;

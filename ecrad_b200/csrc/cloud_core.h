@@ -22,6 +22,10 @@ struct CloudMeta {
   double ice_lw[16 * 11], ice_sw[14 * 10];
   int pdf_ncdf, pdf_nfsd;
   double pdf_fsd1, pdf_inv_fsd_interval;
+  // decoding of the generator's code words into uniform deviates: (code & gen_mask) * gen_scale
+  //   default generator: 30-bit numbers of radiation_random_numbers_mix (mask 0x3FFFFFFF, scale 2^-30)
+  //   vectorizable generator: MINSTD states 1..2^31-2 of radiation_random_numbers (mask 0x7FFFFFFF, scale 1/(2^31-1))
+  unsigned gen_mask; double gen_scale;
 };
 
 // Aerosol optics per band (config%aerosol_optics): offsets into one packed device array; phobic (nband, ntype),

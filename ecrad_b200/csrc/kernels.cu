@@ -616,6 +616,101 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// "Vectorizable" McICA generator (use_vectorizable_generator): radiation_cloud_generator.F90:587-734 with the vector
+// MINSTD generator of radiation_random_numbers.F90 -- one independent Lehmer stream s' = 48271 s mod (2^31-1) per g-point,
+// and a fixed consumption pattern: 1 number for the cloud-top trigger, one block per cloudy layer (rand_cloud), one
+// block per layer of ibegin-1..iend (rand_inhom), one block per cloudy layer (rand_inhom2).  On a GPU that is one thread per
+// (spectrum, g-point): the three blocks a layer needs are three positions of the thread's own stream, reached by jump-ahead
+// (A^k mod M), so the walk down the layers needs no communication at all.  Output code word = the 31-bit stream state
+// of the number that sets the optical-depth scaling (never 0), 0 = clear.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t minstd_next(uint32_t s) { return (uint32_t)((48271ull * s) % 2147483647ull); }
+__device__ __forceinline__ uint32_t minstd_mulmod(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) % 2147483647ull); }
+__device__ __forceinline__ uint32_t minstd_pow(int k) {   // 48271^k mod (2^31-1)
+  uint32_t r = 1u, a = 48271u;
+  while (k > 0) { if (k & 1) r = minstd_mulmod(r, a); a = minstd_mulmod(a, a); k >>= 1; }
+  return r;
+}
+
+__global__ void __launch_bounds__(320)
+cloud_gen_vec_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp, int threads_sw) {
+  __shared__ double sA1[GW_MAXLEV], sT1[GW_MAXLEV], sA2[GW_MAXLEV], sT2[GW_MAXLEV], sCUM[GW_MAXLEV], sOPI[GW_MAXLEV];
+  __shared__ unsigned char sCLD[GW_MAXLEV];
+  __shared__ int sNcl;
+  const int c = blockIdx.x;
+  const double tcc = w.tcc[c];
+  if (!(tcc > 0.0)) return;
+  const int Lb = w.ibegin[c] - 1, Le = w.iend[c] - 1;   // first / last layer with cloud, 0-based
+  for (int L = threadIdx.x; L < GW_MAXLEV; L += blockDim.x) {   // same per-layer constants as cloud_gen_warp_kernel
+    double a1 = 0.0, t1 = 0.0, a2 = 0.0, t2 = 0.0, cu = 0.0, op = 0.0;
+    unsigned char cld = 0;
+    if (L < nlev) {
+      cu = w.cum[(size_t)L * nc + c];
+      const double f = LD_IN(in.frac, c, L);
+      cld = (L >= Lb && L <= Le && f >= cfg.cloud_fraction_threshold) ? 1 : 0;
+      if (L >= 1) {
+        const double fp = LD_IN(in.frac, c, L - 1);
+        const double pr = w.pair[(size_t)(L - 1) * nc + c], cup = w.cum[(size_t)(L - 1) * nc + c];
+        a1 = fp; t1 = sub_rn(add_rn(f, fp), pr);
+        a2 = sub_rn(cup, fp); t2 = sub_rn(sub_rn(pr, sub_rn(cu, cup)), fp);
+        op = w.opi[(size_t)(L - 1) * nc + c];
+      }
+    }
+    sA1[L] = a1; sT1[L] = t1; sA2[L] = a2; sT2[L] = t2; sCUM[L] = cu; sOPI[L] = op; sCLD[L] = cld;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { int n = 0; for (int L = Lb; L <= Le; ++L) n += sCLD[L]; sNcl = n; }
+  __syncthreads();
+  const int spec = (int)threadIdx.x >= threads_sw;   // 0: SW stream (seed iseed), 1: LW stream (seed iseed + 997)
+  const int g = spec ? (int)threadIdx.x - threads_sw : (int)threadIdx.x;
+  const int ng = spec ? cfg.ng_lw : cfg.ng_sw;
+  const bool mine = spec == 0 ? (cfg.do_sw && cfg.solver_sw == 2 && in.cos_sza[c] > 0.0) : (cfg.do_lw && cfg.solver_lw == 2);
+  if (!mine || g >= ng) return;
+  uint32_t* row = (spec ? w.code_lw : w.code_sw) + ((size_t)c * ng + g) * nlevp;
+  const double SCALE = 1.0 / 2147483647.0;
+  // rng_type%initialize (radiation_random_numbers.F90:96-150), stream jstr = g + 1
+  const int32_t seed = in.iseed[c] + (spec ? 997 : 0);
+  const double rseed = fabs((double)seed);
+  const int jstr = g + 1;
+  const double x = mul_rn(mul_rn(mul_rn(rseed, (double)jstr), add_rn(sub_rn(1.0, mul_rn(0.05, (double)jstr)), mul_rn(0.005, (double)(jstr * jstr)))), 16807.0);
+  uint32_t s = (uint32_t)llround(fmod(x, 2147483647.0));
+  s = minstd_next(s);
+  s = minstd_next(s);                                   // trigger(jg)
+  const double trigger = mul_rn((double)s * SCALE, tcc);
+  const int n = Le - Lb + 1, ncl = sNcl;
+  uint32_t s_rc = s;                                    // rand_cloud: one number per cloudy layer
+  uint32_t s_ri = minstd_mulmod(s, minstd_pow(ncl));    // rand_inhom: layers ibegin-1 .. iend
+  uint32_t s_r2 = minstd_mulmod(s, minstd_pow(ncl + n + 1));   // rand_inhom2: one number per cloudy layer
+  s_ri = minstd_next(s_ri);                             // rand_inhom(ibegin-1)
+  uint32_t ri_above = s_ri;
+  bool is_cloud = false, found = false;
+  for (int L = 0; L < Lb && L < nlevp; ++L) row[L] = 0u;
+  for (int L = Lb; L <= Le; ++L) {
+    s_ri = minstd_next(s_ri);
+    uint32_t ri = s_ri, word = 0u;
+    if (sCLD[L]) {
+      s_rc = minstd_next(s_rc); s_r2 = minstd_next(s_r2);
+      const bool prev = is_cloud;
+      const bool first = !(trigger > sCUM[L]) && !found;
+      found = found || first;
+      const double rc = (double)s_rc * SCALE;
+      const bool test = prev ? (mul_rn(rc, sA1[L]) < sT1[L]) : (mul_rn(rc, sA2[L]) < sT2[L]);
+      is_cloud = first || (found && L >= 1 && test);
+      if (is_cloud) {
+        if (L >= 1 && prev && ((double)s_r2 * SCALE < sOPI[L])) ri = ri_above;
+        word = ri;
+      }
+    } else {
+      is_cloud = false;
+    }
+    ri_above = is_cloud ? ri : s_ri;   // rand_inhom(jg, jlev) as left in the array (a clear layer's value is never reused)
+    row[L] = word;
+  }
+  for (int L = Le + 1; L < nlevp; ++L) row[L] = 0u;
+}
+
 // =========================================================================================================
 // launchers
 // =========================================================================================================
@@ -660,7 +755,13 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
   if (cfg.gas_model == 2) n += launch_general_cloud_optics(T, cfg, in, w, nc, nlev, st);   // ECRAD_GAS_ECCKD: use_general_cloud_optics
   else { cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n; }
   if ((cfg.do_lw && cfg.solver_lw == 2) || (cfg.do_sw && cfg.solver_sw == 2)) {
-    cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp); ++n;
+    if (cfg.use_vectorizable_generator) {
+      const int tsw = (cfg.ng_sw + 31) / 32 * 32, tlw = (cfg.ng_lw + 31) / 32 * 32;
+      cloud_gen_vec_kernel<<<nc, tsw + tlw, 0, st>>>(cfg, in, w, nc, nlev, nlevp, tsw);
+    } else {
+      cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp);
+    }
+    ++n;
   }
   return n;
 }

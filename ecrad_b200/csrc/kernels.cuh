@@ -61,6 +61,7 @@ struct DevCfg {
   int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
   int use_aerosols, n_aerosol_types;
   int do_save_spectral_flux;
+  int use_vectorizable_generator;
   int do_nearest_spectral_lw_emiss;
   int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
   int ckd_ngas_lw, ckd_nlut_lw, ckd_ngas_sw, ckd_nlut_sw;   // ecCKD: gases / look-up-table gases per model (shared-memory sizing)

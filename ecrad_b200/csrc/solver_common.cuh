@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t pick4(const uint4& q, int k) { return k == 0
 // optical-depth scaling of this (g, layer) from the generator's code word
 __device__ __forceinline__ double od_scaling_from_code(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd) {
   if (!code) return 0.0;
-  return pdf_sample(C, pdf_val, fsd, (double)(code & 0x3FFFFFFFu) * (1.0 / 1073741824.0));
+  return pdf_sample(C, pdf_val, fsd, (double)(code & C.gen_mask) * C.gen_scale);
 }
 
 

@@ -382,12 +382,78 @@ static void generate_column_exp_ran(const orc_tables* t, int ng, int nlev, int i
 #undef F
 }
 
-/* radiation_cloud_generator.F90:37-255 cloud_generator (Exp-Ran / Max-Ran, non-vectorizable RNG).
- * od_scaling is [nlev][ng].  Exp-Exp and the vectorizable generator are not restated (out of the round-1 path). */
+/* ---- vectorizable generator: radiation_random_numbers.F90 (rng_type, IRngMinstdVector) + radiation_cloud_generator.F90:587-734 ---- */
+#define MINSTD_A 48271.0
+#define MINSTD_M 2147483647.0
+#define MINSTD_A0 16807.0
+
+/* rng_type%initialize, radiation_random_numbers.F90:96-150 (state kept in double precision, USE_REAL_RNG_STATE) */
+static void minstd_init(int32_t iseed, int nstreams, double* istate) {
+  const double rseed = fabs((double)iseed);
+  for (int jstr = 1; jstr <= nstreams; ++jstr)
+    istate[jstr - 1] = (double)llround(fmod(rseed * jstr * (1.0 - 0.05 * jstr + 0.005 * (double)(jstr * jstr)) * MINSTD_A0, MINSTD_M));
+  for (int jstr = 0; jstr < nstreams; ++jstr) istate[jstr] = fmod(MINSTD_A * istate[jstr], MINSTD_M);
+}
+/* one block of nstreams numbers (uniform_distribution_1d / one jblock of _2d), :157-176 */
+static void minstd_block(int nstreams, double* istate, double* randnum) {
+  const double scale = 1.0 / MINSTD_M;
+  for (int i = 0; i < nstreams; ++i) {
+    istate[i] = fmod(MINSTD_A * istate[i], MINSTD_M);
+    randnum[i] = scale * istate[i];
+  }
+}
+
+/* generate_columns_exp_ran: all g-points at once; ibegin/iend 1-based; od_scaling [nlev][ng] (already zero) */
+static void generate_columns_exp_ran(const orc_tables* t, int ng, int nlev, int32_t iseed, double total_cloud_cover, double frac_threshold,
+                                     const double* frac, const double* pair, const double* cum, const double* overhang,
+                                     const double* fsd, const double* opi, int ibegin, int iend, double* od_scaling) {
+  (void)nlev;
+  const int n = iend - ibegin + 1;
+  double* istate = (double*)malloc(sizeof(double) * (size_t)ng * (3 * (size_t)n + 3));
+  double* trigger = istate + ng;
+  double* rand_cloud = trigger + ng;                  /* [n][ng]   levels ibegin..iend */
+  double* rand_inhom = rand_cloud + (size_t)n * ng;   /* [n+1][ng] levels ibegin-1..iend */
+  double* rand_inhom2 = rand_inhom + (size_t)(n + 1) * ng;
+  char *is_cloud = (char*)calloc((size_t)ng * 2, 1), *found_cloud = is_cloud + ng;
+  minstd_init(iseed, ng, istate);
+  minstd_block(ng, istate, trigger);
+  for (int jl = ibegin; jl <= iend; ++jl) if (frac[jl - 1] >= frac_threshold) minstd_block(ng, istate, rand_cloud + (size_t)(jl - ibegin) * ng);
+  for (int k = 0; k <= n; ++k) minstd_block(ng, istate, rand_inhom + (size_t)k * ng);
+  for (int jl = ibegin; jl <= iend; ++jl) if (frac[jl - 1] >= frac_threshold) minstd_block(ng, istate, rand_inhom2 + (size_t)(jl - ibegin) * ng);
+  for (int g = 0; g < ng; ++g) trigger[g] = trigger[g] * total_cloud_cover;
+  for (int jl = ibegin; jl <= iend; ++jl) {
+    if (frac[jl - 1] >= frac_threshold) {
+      const double* rc = rand_cloud + (size_t)(jl - ibegin) * ng;
+      const double* r2 = rand_inhom2 + (size_t)(jl - ibegin) * ng;
+      double* ri = rand_inhom + (size_t)(jl - ibegin + 1) * ng;   /* this level */
+      const double* ri_above = ri - ng;
+      for (int g = 0; g < ng; ++g) {
+        const int prev_cloud = is_cloud[g];
+        const int first_cloud = (trigger[g] <= cum[jl - 1]) && !found_cloud[g];
+        found_cloud[g] = found_cloud[g] || first_cloud;
+        int test = 0;
+        if (jl >= 2) {   /* (the reference evaluates this at jl = ibegin = 1 with out-of-range indices; it cannot matter there: found implies first) */
+          test = prev_cloud ? (rc[g] * frac[jl - 2] < frac[jl - 1] + frac[jl - 2] - pair[jl - 2])
+                            : (rc[g] * (cum[jl - 2] - frac[jl - 2]) < pair[jl - 2] - overhang[jl - 2] - frac[jl - 2]);
+        }
+        is_cloud[g] = first_cloud || (found_cloud[g] && test);
+        if (is_cloud[g]) { if (jl >= 2 && r2[g] < opi[jl - 2] && prev_cloud) ri[g] = ri_above[g]; }
+        else ri[g] = 0.0;
+      }
+      /* sample_from_pdf_masked_block, radiation_pdf_sampler.F90:267-310 */
+      for (int g = 0; g < ng; ++g) od_scaling[(size_t)(jl - 1) * ng + g] = ri[g] > 0.0 ? pdf_sample(t, fsd[jl - 1], ri[g]) : 0.0;
+    } else {
+      for (int g = 0; g < ng; ++g) is_cloud[g] = 0;
+    }
+  }
+  free(istate); free(is_cloud);
+}
+
+/* radiation_cloud_generator.F90:37-255 cloud_generator.  od_scaling is [nlev][ng]. */
 void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_scheme, int32_t iseed,
                          double frac_threshold, const double* frac, const double* overlap_param,
                          double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,
-                         double* od_scaling, double* total_cloud_cover) {
+                         int use_vectorizable_generator, double* od_scaling, double* total_cloud_cover) {
   double* cum = (double*)malloc(sizeof(double) * (size_t)nlev * 7);
   double* pair = cum + nlev; double* overhang = pair + nlev; double* opi = overhang + nlev;
   double* rand_cloud = opi + nlev; double* ri1 = rand_cloud + nlev; double* ri2 = ri1 + nlev;
@@ -407,6 +473,12 @@ void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_sc
     for (jlev = ibegin; jlev <= iend - 1; ++jlev)
       if (overlap_param[jlev - 1] > 0.0) opi[jlev - 1] = pow(overlap_param[jlev - 1], 1.0 / decorrelation_scaling);
     memset(od_scaling, 0, sizeof(double) * (size_t)ng * nlev);
+    if (use_vectorizable_generator) {   /* :235-249 (not available with Exp-Exp: refused by orc_radiation) */
+      generate_columns_exp_ran(t, ng, nlev, iseed, tcc, frac_threshold, frac, pair, cum, overhang, fractional_std, opi, ibegin, iend, od_scaling);
+      *total_cloud_cover = tcc;
+      free(cum);
+      return;
+    }
     rng_stream rs;
     rng_init(iseed, &rs);
     double* rand_top = (double*)malloc(sizeof(double) * (size_t)ng);

@@ -138,7 +138,7 @@ void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nle
 void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_scheme, int32_t iseed,
                          double frac_threshold, const double* frac, const double* overlap_param,
                          double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,
-                         double* od_scaling /*[nlev][ng]*/, double* total_cloud_cover);
+                         int use_vectorizable_generator, double* od_scaling /*[nlev][ng]*/, double* total_cloud_cover);
 
 /* ecckd.c */
 void orc_ecckd_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,

@@ -338,7 +338,7 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
   for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
   orc_cloud_generator(t, ng, nlev, cfg->i_overlap_scheme, in->iseed[jcol] + 997, cfg->cloud_fraction_threshold, frac, op,
-                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, od_scaling, &tcc);
+                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, cfg->use_vectorizable_generator, od_scaling, &tcc);
   free(fsd);
   if (out->cloud_cover_lw) out->cloud_cover_lw[jcol] = tcc;
   if (tcc >= cfg->cloud_fraction_threshold) {
@@ -486,7 +486,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
   for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
   orc_cloud_generator(t, ng, nlev, cfg->i_overlap_scheme, in->iseed[jcol], cfg->cloud_fraction_threshold, frac, op,
-                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, od_scaling, &tcc);
+                      cfg->cloud_inhom_decorr_scaling, fsd, cfg->use_beta_overlap, cfg->use_vectorizable_generator, od_scaling, &tcc);
   free(fsd);
   if (out->cloud_cover_sw) out->cloud_cover_sw[jcol] = tcc;
   if (tcc >= cfg->cloud_fraction_threshold) {
@@ -739,7 +739,8 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  if (cfg->do_lw_aerosol_scattering || cfg->use_vectorizable_generator || cfg->do_sw_delta_scaling_with_gases) {
+  if (cfg->do_lw_aerosol_scattering || cfg->do_sw_delta_scaling_with_gases ||
+      (cfg->use_vectorizable_generator && cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
   }

@@ -54,7 +54,7 @@ def test_generator_walk_is_bit_exact(env, meridian_raw, scheme, beta):
     lib, h, orc, _ = env
     L = orc.lib
     L.orc_cloud_generator.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_double, C.POINTER(C.c_double),
-                                      C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]
     raw = I.synthetic_columns(meridian_raw, 96)
     inp = I.to_radiation_inputs(raw)
@@ -64,6 +64,6 @@ def test_generator_walk_is_bit_exact(env, meridian_raw, scheme, beta):
         op = np.ascontiguousarray(inp["overlap_param"][c]); fsd = np.ascontiguousarray(inp["fractional_std"][c])
         for ng, seed in ((112, int(inp["iseed"][c])), (140, int(inp["iseed"][c]) + 997)):
             a = np.zeros((NLEV, ng)); b = np.zeros((NLEV, ng)); ta, tb = C.c_double(), C.c_double()
-            L.orc_cloud_generator(orc.t, ng, NLEV, scheme, seed, 1e-6, dp(fr), dp(op), 0.5, dp(fsd), beta, dp(a), C.byref(ta))
+            L.orc_cloud_generator(orc.t, ng, NLEV, scheme, seed, 1e-6, dp(fr), dp(op), 0.5, dp(fsd), beta, 0, dp(a), C.byref(ta))
             lib.hc_cloud_generator(h, ng, NLEV, scheme, seed, 1e-6, dp(fr), dp(op), 0.5, dp(fsd), beta, dp(b), C.byref(tb))
             assert ta.value == tb.value and np.array_equal(a, b), (c, ng)

@@ -149,7 +149,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True, do_lw_cloud_scattering=False),
                                 dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
-                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_beta_overlap=True)])
+                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_beta_overlap=True),
+                                dict(use_vectorizable_generator=True), dict(use_vectorizable_generator=True, overlap_scheme_name="Max-Ran", use_aerosols=True)])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
@@ -243,7 +244,7 @@ def test_ecckd_mcica_vs_reference_golden(handles, meridian_raw, golden_ecckd_mci
                                 dict(sw_solver_name="Cloudless", lw_solver_name="Cloudless", use_aerosols=True),
                                 dict(do_lw_cloud_scattering=False, overlap_scheme_name="Exp-Exp"),
                                 dict(do_nearest_spectral_lw_emiss=True, overlap_scheme_name="Max-Ran"),
-                                dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True),
+                                dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True), dict(use_vectorizable_generator=True),
                                 dict(ecckd_tables="ecckd_tables_64b.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
 def test_ecckd_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """ecCKD configurations (32- and 64-term models; BASELINE configs 1 and 3 have no golden file) on 300 perturbed columns."""

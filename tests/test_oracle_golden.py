@@ -156,6 +156,24 @@ def test_oracle_ecckd_mcica_matches_reference_golden(meridian_raw, golden_ecckd_
         assert f32_ulp_err(out[nm].T, golden_ecckd_mcica[gname]).max() <= 0.51, nm
 
 
+def test_oracle_vectorizable_generator_is_statistically_consistent(meridian_raw):
+    """use_vectorizable_generator (ctest `vec`) has no reference output: it draws other random numbers (vector MINSTD streams,
+    radiation_random_numbers.F90), so it can only agree with the default generator in the mean.  Same cloud cover and clear-sky
+    fluxes exactly; all-sky fluxes differ by McICA noise with a mean well below 1 W m-2 over 600 columns."""
+    n = 600
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = {}
+    for vec in (False, True):
+        cfg = RadiationConfig(use_vectorizable_generator=vec).consolidate()
+        out[vec] = Oracle(cfg).radiation(I.to_radiation_inputs(raw), n, 137)
+    assert np.array_equal(out[0]["cloud_cover_sw"], out[1]["cloud_cover_sw"])
+    assert np.array_equal(out[0]["sw_up_clear"], out[1]["sw_up_clear"]) and np.array_equal(out[0]["lw_dn_clear"], out[1]["lw_dn_clear"])
+    for nm in ("sw_up", "sw_dn", "lw_up", "lw_dn"):
+        d = out[1][nm] - out[0][nm]
+        assert np.abs(d).max() > 1.0, nm                      # it really is another sample of sub-columns
+        assert abs(d.mean()) < 1.0 and np.sqrt((d ** 2).mean()) < 30.0, (nm, d.mean())
+
+
 def test_oracle_crop_cloud_fraction_side_effect(meridian_raw):
     """radiation_cloud.F90:700-740: fraction below threshold (or with negligible water) is zeroed in the caller's array."""
     cfg = RadiationConfig().consolidate()
