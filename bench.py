@@ -282,12 +282,13 @@ def main():
     e2e_value = world * ncol / e2e_s
     clocks = sampler.stop()
 
-    # optional exchange step of a host model: gather the 10 broadband flux profiles on rank 0 over NVLink (not in the timed
-    # region: the path itself needs no collective; reported for information)
-    gather_ms = None
+    # Exchange step of a host model that wants all fluxes on one GPU.  Not part of `value` (the path itself needs
+    # no collective).  Two ways: (1) NCCL gather of the profiles after the step; (2) no gather at all -- every rank's flux kernels
+    # store their column slice straight into rank 0's arrays over NVLink (peer-mapped memory, ecrad_b200_radiation_device_ld).
+    gather = None
     if dist is not None:
-        from ecrad_b200.sharding import gather_profiles
-        prof = [nm for nm, kind in out_names if kind == "h"][:10]
+        from ecrad_b200.sharding import PeerFluxArrays, gather_profiles
+        prof = [nm for nm, kind in out_names if kind == "h"]
         gather_profiles(dev_out[prof[0]], world * ncol, dist)   # warm-up: NCCL sets up its channels on the first collective
         barrier()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
@@ -296,7 +297,44 @@ def main():
             gather_profiles(dev_out[nm], world * ncol, dist)
         g1.record()
         barrier()
-        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+        nccl_ms = max_over_ranks(g0.elapsed_time(g1))
+        peer = PeerFluxArrays(prof, NLEV + 1, world * ncol, dist, dst=0)
+        ost_peer = abi.Outputs()
+        C.memmove(C.byref(ost_peer), C.byref(ost_dev), C.sizeof(abi.Outputs))
+        for nm in prof:
+            setattr(ost_peer, nm, C.cast(peer.pointer(nm, rank * ncol), abi.c_dp))
+
+        def step_peer():
+            h.radiation_device_ld(ncol, NLEV, ncol, world * ncol, ist_dev, ost_peer, stream=stream.cuda_stream)
+
+        for _ in range(3):
+            step_peer()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            step_peer()
+        p1.record(stream)
+        barrier()
+        peer_ms = max_over_ranks(p0.elapsed_time(p1)) / args.steps
+        # every rank's slice must have arrived bit-exact: compare on rank 0 against checksums of the local results
+        # (checksum = sum of the bit patterns as int64: exact and independent of the order of summation)
+        sums = torch.stack([dev_out[nm].view(torch.int64).sum() for nm in prof])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        ok = True
+        if rank == 0:
+            for k, nm in enumerate(prof):
+                full = peer.tensor(nm)
+                for r in range(world):
+                    ok = ok and bool(full[:, r * ncol:(r + 1) * ncol].contiguous().view(torch.int64).sum() == allsums[r][k])
+                ok = ok and bool(torch.equal(full[:, :ncol], dev_out[nm]))
+            assert ok, "peer-written flux arrays differ from the local results"
+        peer.close()
+        gather = {"profiles": len(prof), "bytes_per_step": len(prof) * (NLEV + 1) * world * ncol * 8,
+                  "nccl_gather_after_step_ms": nccl_ms,
+                  "fused_p2p_stores": {"ms_per_step": peer_ms, "value": world * ncol / (peer_ms * 1e-3), "unit": "columns/s",
+                                       "how": "flux kernels of every rank write their column slice into rank 0's arrays over NVLink (CUDA IPC peer mapping), checked bit-exact"}}
 
     # parity guard: the timed outputs are the real thing (first 32 columns of rank 0 = the golden test slice)
     if rank == 0:
@@ -344,8 +382,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_s * 1e3, "host_memory": "pinned"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        if gather_ms is not None:
-            line["gather_profiles_ms"] = gather_ms
+        if gather is not None:
+            line["gather"] = gather
         print(json.dumps(line))
     h.finalize()
     if dist is not None:

@@ -284,7 +284,7 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
 }
 
 // Build the kernel-facing views from 25 input / 35 output base pointers (device) with leading dimension ld.
-void make_views(void* const* ip, void* const* op, int ld, double solar_irradiance, DevIn& di, DevOut& dout) {
+void make_views(void* const* ip, void* const* op, int ld, int ld_out, double solar_irradiance, DevIn& di, DevOut& dout) {
   di.cos_sza = (const double*)ip[0]; di.skin_t = (const double*)ip[1]; di.sw_albedo = (const double*)ip[2];
   di.sw_albedo_direct = (const double*)ip[3]; di.lw_emissivity = (const double*)ip[4]; di.iseed = (const int32_t*)ip[5];
   di.p_hl = (const double*)ip[6]; di.t_hl = (const double*)ip[7];
@@ -295,7 +295,7 @@ void make_views(void* const* ip, void* const* op, int ld, double solar_irradianc
   di.solar_irradiance = solar_irradiance; di.ld = ld;
   double** o = (double**)&dout;
   for (int k = 0; k < N_OUT; ++k) o[k] = (double*)op[k];
-  dout.ld = ld;
+  dout.ld = ld_out;
 }
 static_assert(sizeof(DevOut) >= N_OUT * sizeof(double*) + sizeof(int), "DevOut layout");
 static_assert(offsetof(DevOut, sw_dn_direct_band) == (N_OUT - 1) * sizeof(double*), "DevOut must list the 35 outputs in ABI order");
@@ -561,7 +561,7 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     CK(h, cudaEventRecord(s.h2d_done, h->s_h2d));
     // ---- kernels ----
     DevIn di; DevOut dout;
-    make_views(ip, op, cap, in->solar_irradiance, di, dout);
+    make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
     CK(h, cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
     if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp, s.d2h_done, 0));
     if (run_tile(h, di, dout, nt, nlev, h->s_comp, &h->ev[t * 2 * N_STAGE])) return 1;
@@ -593,10 +593,16 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
 // device-resident entry: all pointers are device pointers with leading dimension ncol; not synchronised
 // ---------------------------------------------------------------------------------------------------------
 int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream) {
+  return ecrad_b200_radiation_device_ld(handle, ncol, nlev, ncol, ncol, in, out, cuda_stream);
+}
+
+int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, int ld_out, const ecrad_b200_inputs* in,
+                                   ecrad_b200_outputs* out, void* cuda_stream) {
   Handle* h = (Handle*)handle;
   if (!h) return fail(nullptr, "ecrad_b200_radiation_device: null handle");
   std::lock_guard<std::mutex> lk(h->mu);
   if (check_args(h, ncol, nlev, 1, ncol, in, out)) return 1;
+  if (ld_in < ncol || ld_out < ncol) return fail(h, "leading dimensions (%d, %d) smaller than ncol = %d", ld_in, ld_out, ncol);
   CK(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const ecrad_b200_config& c = h->cfg;
@@ -625,7 +631,7 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b2
       op[k] = od[k].kind == 0 ? (void*)(od[k].host + c0) : (void*)(od[k].host + (size_t)c0 * od[k].rows);
     }
     DevIn di; DevOut dout;
-    make_views(ip, op, ncol, in->solar_irradiance, di, dout);
+    make_views(ip, op, ld_in, ld_out, in->solar_irradiance, di, dout);
     if (run_tile(h, di, dout, nt, nlev, st, &h->ev[t * 2 * N_STAGE])) return 1;
   }
   return 0;

@@ -22,7 +22,8 @@ DEFAULT_TABLES = os.path.join(_HERE, "data", "rrtmg_tables.bin")
 
 EXPORTS = [
     "ecrad_b200_tables_create", "ecrad_b200_tables_add", "ecrad_b200_tables_load_file", "ecrad_b200_tables_load_memory", "ecrad_b200_tables_free",
-    "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_kernel_launches",
+    "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_radiation_device_ld",
+    "ecrad_b200_kernel_launches",
     "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
     "ecrad_b200_version",
 ]
@@ -50,6 +51,7 @@ def load_library():
     L.ecrad_b200_setup.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.POINTER(C.c_void_p)]
     L.ecrad_b200_radiation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
     L.ecrad_b200_radiation_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
+    L.ecrad_b200_radiation_device_ld.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
     L.ecrad_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.ecrad_b200_kernel_launches.restype = C.c_int64
     L.ecrad_b200_kernel_launches.argtypes = [C.c_void_p]
@@ -115,6 +117,12 @@ class RadiationHandle:
     def radiation_device(self, ncol, nlev, ist: abi.Inputs, ost: abi.Outputs, stream=0):
         """Device-resident entry: every pointer in ist/ost is a device pointer with leading dimension ncol."""
         rc = self.lib.ecrad_b200_radiation_device(self.h, ncol, nlev, C.byref(ist), C.byref(ost), C.c_void_p(stream))
+        if rc:
+            raise RadiationError(self._err())
+
+    def radiation_device_ld(self, ncol, nlev, ld_in, ld_out, ist: abi.Inputs, ost: abi.Outputs, stream=0):
+        """As radiation_device with separate leading dimensions (outputs may be a column slice of peer-GPU arrays)."""
+        rc = self.lib.ecrad_b200_radiation_device_ld(self.h, ncol, nlev, ld_in, ld_out, C.byref(ist), C.byref(ost), C.c_void_p(stream))
         if rc:
             raise RadiationError(self._err())
 

@@ -58,3 +58,69 @@ def gather_profiles(local, ncol_total: int, dist, dst: int = 0):
         if e >= s:
             out[:, s - 1:e] = recv[r][:, : e - s + 1]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Gather fused into the flux kernels: every rank stores its column slice straight into arrays that live on one GPU
+# ---------------------------------------------------------------------------------------------------------
+class PeerFluxArrays:
+    """Flux profiles of ALL columns in the memory of rank `dst`, writable by every rank of the node over NVLink.
+
+    Rank `dst` allocates one device arena holding `names` arrays of shape (nrows, ncol_total) (row = half-level, column
+    fastest: the reference layout of flux%lw_up etc.); its CUDA IPC handle goes to the other ranks with one broadcast; each
+    rank opens it (cudaIpcOpenMemHandle maps the peer memory into its address space) and hands
+    `ecrad_b200_radiation_device_ld` pointers to the column slice it owns, with ld_out = ncol_total.  The kernels that produce
+    the fluxes then write them where the host model wants them -- the reference's block decomposition
+    (driver/ecrad_driver.F90:345-354) without a gather step.  No data-path collective; one barrier tells `dst` the step is done.
+    """
+
+    def __init__(self, names, nrows, ncol_total, dist, dst=0):
+        import torch
+        from cuda.bindings import runtime as rt
+
+        self.rt, self.dist, self.dst = rt, dist, dst
+        self.names, self.nrows, self.ncol_total = list(names), int(nrows), int(ncol_total)
+        self.rank = dist.get_rank()
+        self.plane = self.nrows * self.ncol_total * 8
+        nbytes = self.plane * len(self.names)
+        self.owner = self.rank == dst
+        if self.owner:
+            err, ptr = rt.cudaMalloc(nbytes)
+            assert err == rt.cudaError_t.cudaSuccess, err
+            rt.cudaMemset(ptr, 0xFF, nbytes)   # NaN pattern: unwritten columns would show
+            err, handle = rt.cudaIpcGetMemHandle(ptr)
+            assert err == rt.cudaError_t.cudaSuccess, err
+            payload = [bytes(handle.reserved)]
+        else:
+            payload = [None]
+        dist.broadcast_object_list(payload, src=dst)
+        if not self.owner:
+            handle = rt.cudaIpcMemHandle_t()
+            handle.reserved = payload[0]
+            err, ptr = rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)
+            assert err == rt.cudaError_t.cudaSuccess, err
+        self.base = int(ptr)
+        self._torch = torch
+
+    def pointer(self, name, first_col):
+        """Device address of element (row 0, column first_col) of array `name` (0-based column in the global numbering)."""
+        return self.base + self.names.index(name) * self.plane + 8 * int(first_col)
+
+    def tensor(self, name):
+        """The whole (nrows, ncol_total) array as a torch tensor (owner rank only)."""
+        assert self.owner
+        torch = self._torch
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.nrows, self.ncol_total), "typestr": "<f8", "version": 3,
+                                        "data": (self.base + self.names.index(name) * self.plane, False)}
+        return torch.as_tensor(raw, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def close(self):
+        self.dist.barrier()
+        if self.owner:
+            self.rt.cudaFree(self.base)
+        else:
+            self.rt.cudaIpcCloseMemHandle(self.base)

@@ -153,6 +153,15 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
 int ecrad_b200_radiation_device(void* handle, int ncol, int nlev,
                                 const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream);
 
+/* Same with separate leading dimensions: input arrays are (ld_in, n), output arrays (ld_out, n) / (n, ld_out) / (nband, ld_out,
+ * nlev+1), every pointer already offset to the caller's first column; ncol columns are processed.  This is the multi-GPU
+ * entry of a host model that wants all fluxes in one place: rank r passes pointers into the column slice it owns of arrays
+ * that live on ANOTHER GPU of the NVLink domain (peer-mapped: cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess), and the flux
+ * kernels store their results straight into that slice over NVLink -- the gather of the reference's block decomposition
+ * (driver/ecrad_driver.F90:345-354) fused into the kernels that produce the fluxes, no separate collective. */
+int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, int ld_out,
+                                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream);
+
 /* Tuning/diagnostic options: "serial" (0/1: run a tile's kernels on one stream instead of the three overlapping chains;
  * needed for per-kernel timing), "tile_cols" (columns per internal tile).  Returns 0 on success. */
 int ecrad_b200_set_option(void* handle, const char* key, int value);
