@@ -136,7 +136,7 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
-      (h->cfg.do_save_spectral_flux && h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_CLOUDLESS) ? 8 * nc * (nl + 1) * NB_SW : 0,   // sw_band_dir
+      0,                                                                                     // (sw_band_dir: no longer used)
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0};  // tc_reg tc_ods tc_u tc_v tc_cc
   for (int i = 0; i < N_WORK; ++i) out[i] = sz[i];
 }

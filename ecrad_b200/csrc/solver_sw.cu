@@ -13,7 +13,7 @@
 
 namespace ecb {
 
-enum { SW_LCH_FLUX = 8 };
+enum { SW_LCH_FLUX = 4, SW_BATCH = 2 };   // layers per g-point reduction / per batch of loads in sw_flux_kernel
 
 // total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
 template <class SD>
@@ -58,82 +58,13 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// A: direct beam, top-down (radiation_adding_ica_sw.F90:85-88)
-// ---------------------------------------------------------------------------------------------------------
-template <class SD, bool CLOUDLESS>
-__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 6))
-sw_direct_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, int nlevp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SwColumn s = sw_column<SD>(T, cfg, in, w, nlev, nlevp);
-  if (!(s.mu0 > 0.0)) return;
-  double* tile = reinterpret_cast<double*>(smem_raw);   // [2][LCH][SD::RS]
-  double* fracs = tile + 2 * LCH * SD::RS;               // [nlev]
-  double* fsds = fracs + nlev;                          // [nlev]
-  for (int l = s.g; l < nlev; l += SD::THREADS) {
-    fracs[l] = s.cloudy ? LD_IN(in.frac, s.c, l) : 0.0;
-    fsds[l] = s.cloudy ? LD_IN(in.fsd, s.c, l) : 0.0;
-  }
-  __syncthreads();
-  const CloudMeta& C = *T.cloud;
-  const int g = s.g, nl1 = nlev + 1;
-  double *sFc = s.scr, *sFa = s.scr + s.n;
-  double* sums = w.sw_sums + (size_t)s.c * 6 * nl1;
-  double* dst[2] = {sums, sums + 3 * nl1};
-  const int nf = s.cloudy ? 2 : 1;
-  // Cloudless + do_save_spectral_flux: per-band direct beam (x mu0); also kept in scratch for sw_dn_band (sw_flux_kernel)
-  const bool bands = CLOUDLESS && cfg.do_save_spectral_flux && (out.sw_dn_direct_band || out.sw_dn_band);
-  const BandOut bo[2] = {{bands ? out.sw_dn_direct_band : nullptr, out.ld, 0, -1, s.mu0, 0.0, nullptr, 0},
-                         {bands ? w.sw_band_dir : nullptr, (int)gridDim.x, 0, -1, s.mu0, 0.0, nullptr, 0}};
-  const double inv_mu0 = 1.0 / s.mu0;
-  double fc = w.incoming[(size_t)s.c * SD::NG + s.gg], fa = fc;
-  int slot = 0, lfirst = 0;
-  uint4 cq = make_uint4(0, 0, 0, 0);
-  // software pipeline: od (and ssa where needed) of layer l+1 are loaded before the exp of layer l
-  const bool need_ssa = CLOUDLESS || s.cloudy;
-  double od_n = s.act ? s.od[g] : 0.0, ssa_n = (s.act && need_ssa) ? s.ssa[g] : 0.0;
-  for (int l = 0; l < nlev; ++l) {
-    if (s.act) {
-      const size_t i = (size_t)l * SD::NG + g;
-      const double odg = od_n, ssag = ssa_n;
-      if (l + 1 < nlev) { od_n = s.od[i + SD::NG]; if (need_ssa) ssa_n = s.ssa[i + SD::NG]; }
-      double tdir_c;
-      const double gg_gas = (need_ssa && s.gas_g) ? s.gas_g[i] : 0.0;
-      if (CLOUDLESS) tdir_c = sw_ref_trans_cloudless(s.mu0, odg, ssag, gg_gas).trans_dir_dir;
-      else tdir_c = exp(dmax(-dmax(odg * inv_mu0, 0.0), -1000.0));
-      double tdir_a = tdir_c;
-      if (s.cloudy) {
-        if ((l & 3) == 0) cq = __ldg(s.codep + (l >> 2));
-        if (fracs[l] >= s.thr) {
-          double odt, ssat, gt;
-          sw_cloudy_props<SD>(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * SD::NB, s.b, odg, ssag, gg_gas, odt, ssat, gt);
-          tdir_a = exp(dmax(-dmax(odt * inv_mu0, 0.0), -1000.0));
-        }
-        sFa[i] = fa;
-        tile[(LCH + slot) * SD::RS + g] = fa;
-      }
-      sFc[i] = fc;
-      tile[slot * SD::RS + g] = fc;
-      fc = fc * tdir_c;
-      fa = fa * tdir_a;
-    }
-    ++slot;
-    if (slot == LCH) {
-      if (bands) flush_bands(tile, SD::RS, LCH, slot, bo, 2, lfirst, 1, s.c, SD::NB, T.meta->sw);
-      flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1); lfirst += slot; slot = 0;
-    }
-  }
-  if (s.act) { tile[slot * SD::RS + g] = fc; tile[(LCH + slot) * SD::RS + g] = fa; }
-  ++slot;
-  if (bands) flush_bands(tile, SD::RS, LCH, slot, bo, 2, lfirst, 1, s.c, SD::NB, T.meta->sw);
-  flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1);
-  if (s.act) {
-    double* carry = w.sw_carry + (size_t)s.c * 4 * SD::NG;
-    carry[g] = fc; carry[SD::NG + g] = fa;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// B: two-stream layer solutions and the upward sweep of albedo / source (radiation_adding_ica_sw.F90:90-121)
+// A: two-stream layer solutions and the upward sweep (radiation_adding_ica_sw.F90:90-121).
+// The reference carries the albedo A and a source S = (direct albedo) x (direct flux at that half-level), which needs the
+// direct beam first (its loop :85-88).  S is linear in the direct flux, so the sweep here carries the direct albedo D
+// itself (S = D * Fdir, the form radiation_tripleclouds_sw.F90:322-420 uses): D' = Rdir + (Tdir*D + Tdirdif*A) * T / (1 - A*R),
+// and the direct beam is marched by the downward kernel together with the fluxes.  No separate direct-beam pass, no second
+// evaluation of the cloudy layers' optical properties.  Stored per layer and sub-column (clear / cloudy):
+//   a = T/(1-A*R), b = (Tdir*D*R + Tdirdif)/(1-A*R), t = Tdir, A, D      (A, D: of everything below the layer)
 // ---------------------------------------------------------------------------------------------------------
 template <class SD, bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
 __global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 3))
@@ -143,7 +74,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   if (!(s.mu0 > 0.0)) return;
   double* fracs = reinterpret_cast<double*>(smem_raw);   // [nlev]
   double* fsds = fracs + nlev;                           // [nlev]
-  double* bandv = fsds + nlev;                           // [2][14] band albedos
+  double* bandv = fsds + nlev;                           // [2][nb] band albedos
   const int g = s.g, c = s.c;
   for (int l = g; l < nlev; l += SD::THREADS) {
     fracs[l] = s.cloudy ? LD_IN(in.frac, c, l) : 0.0;
@@ -165,36 +96,33 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
   if (!s.act) return;
   const CloudMeta& C = *T.cloud;
   const size_t n = s.n;
-  const double* sFc = s.scr; const double* sFa = s.scr + n;
-  double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
-  double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
+  double *ac = s.scr, *bc = s.scr + n, *tc = s.scr + 2 * n, *Ac = s.scr + 3 * n, *Dc = s.scr + 4 * n;
+  double *aa = s.scr + 5 * n, *ba = s.scr + 6 * n, *ta = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Da = s.scr + 9 * n;
   double* carry = w.sw_carry + (size_t)c * 4 * SD::NG;
-  const double alb_diff = bandv[s.b], alb_dir = bandv[SD::NB + s.b];
   const double mu0 = s.mu0;
-  double A_c = alb_diff, S_c = alb_dir * carry[g] * mu0;
-  double A_a = alb_diff, S_a = alb_dir * carry[SD::NG + g] * mu0;
+  double A_c = bandv[s.b], D_c = mu0 * bandv[SD::NB + s.b];   // surface: diffuse albedo, direct albedo x cos_sza (:95-96)
+  double A_a = A_c, D_a = D_c;
   uint4 cq = make_uint4(0, 0, 0, 0);
   // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
   size_t i = (size_t)(nlev - 1) * SD::NG + g;
-  double od_n = s.od[i], ssa_n = s.ssa[i], fc_n = sFc[i], fa_n = s.cloudy ? sFa[i] : 0.0, gg_n = AER ? s.gas_g[i] : 0.0;
+  double od_n = s.od[i], ssa_n = s.ssa[i], gg_n = AER ? s.gas_g[i] : 0.0;
   for (int l = nlev - 1; l >= 0; --l) {
-    const double odg = od_n, ssag = ssa_n, fd_c = fc_n, fd_a = fa_n, gg_gas = AER ? gg_n : 0.0;
+    const double odg = od_n, ssag = ssa_n, gg_gas = AER ? gg_n : 0.0;
     i = (size_t)l * SD::NG + g;
     if (l > 0) {
       const size_t ip = i - SD::NG;
-      od_n = s.od[ip]; ssa_n = s.ssa[ip]; fc_n = sFc[ip];
-      if (s.cloudy) fa_n = sFa[ip];
+      od_n = s.od[ip]; ssa_n = s.ssa[ip];
       if (AER) gg_n = s.gas_g[ip];
     }
     const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
     {
       const double inv_den = 1.0 / (1.0 - A_c * Lc.ref);
       ac[i] = Lc.trans * inv_den;
-      bc[i] = (Lc.ref * S_c + Lc.trans_dir_diff * fd_c) * inv_den;
-      Ac[i] = A_c; Sc[i] = S_c;   // albedo / source of everything below the half-level under layer l
+      bc[i] = (Lc.trans_dir_dir * D_c * Lc.ref + Lc.trans_dir_diff) * inv_den;
+      tc[i] = Lc.trans_dir_dir; Ac[i] = A_c; Dc[i] = D_c;   // albedos of everything below the half-level under layer l
       const double A_new = Lc.ref + Lc.trans * Lc.trans * A_c * inv_den;
-      const double S_new = Lc.ref_dir * fd_c + Lc.trans * (S_c + A_c * Lc.trans_dir_diff * fd_c) * inv_den;
-      A_c = A_new; S_c = S_new;
+      D_c = Lc.ref_dir + (Lc.trans_dir_dir * D_c + Lc.trans_dir_diff * A_c) * Lc.trans * inv_den;
+      A_c = A_new;
     }
     if (s.cloudy) {
       if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(s.codep + (l >> 2));
@@ -206,19 +134,19 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       }
       const double inv_den = 1.0 / (1.0 - A_a * La.ref);
       aa[i] = La.trans * inv_den;
-      ba[i] = (La.ref * S_a + La.trans_dir_diff * fd_a) * inv_den;
-      Aa[i] = A_a; Sa[i] = S_a;
+      ba[i] = (La.trans_dir_dir * D_a * La.ref + La.trans_dir_diff) * inv_den;
+      ta[i] = La.trans_dir_dir; Aa[i] = A_a; Da[i] = D_a;
       const double A_new = La.ref + La.trans * La.trans * A_a * inv_den;
-      const double S_new = La.ref_dir * fd_a + La.trans * (S_a + A_a * La.trans_dir_diff * fd_a) * inv_den;
-      A_a = A_new; S_a = S_new;
+      D_a = La.ref_dir + (La.trans_dir_dir * D_a + La.trans_dir_diff * A_a) * La.trans * inv_den;
+      A_a = A_new;
     }
   }
-  carry[2 * SD::NG + g] = S_c;   // flux_up at TOA = source(1)
-  carry[3 * SD::NG + g] = S_a;
+  carry[g] = D_c;             // direct albedo of the whole atmosphere + surface: flux_up(TOA) = D * incoming
+  carry[SD::NG + g] = D_a;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// C: fluxes top-down (radiation_adding_ica_sw.F90:134-146), g-point sums, blending and the flux_type outputs
+// B: direct beam and fluxes top-down (radiation_adding_ica_sw.F90:85-88, :134-146), g-point sums, blending, flux_type outputs
 // ---------------------------------------------------------------------------------------------------------
 template <class SD>
 __global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 5))
@@ -260,57 +188,59 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     }
     return;
   }
-  double* ssum = reinterpret_cast<double*>(smem_raw);    // [4][nl1]: dn_c, up_c, dn_a, up_a
-  double* tile = ssum + 4 * nl1;                          // [4][SW_LCH_FLUX][SD::RS]
-  double *s_dn_c = ssum, *s_up_c = ssum + nl1, *s_dn = ssum + 2 * nl1, *s_up = ssum + 3 * nl1;
-  const double* gsum = w.sw_sums + (size_t)c * 6 * nl1;   // direct-beam sums from sw_direct_kernel
-  const double *s_dir_c = gsum, *s_dir = gsum + 3 * nl1;
+  double* ssum = reinterpret_cast<double*>(smem_raw);    // [6][nl1]: dir_c, dn_c, up_c, dir_a, dn_a, up_a  (dir: per unit area normal to the beam)
+  double* tile = ssum + 6 * nl1;                          // [6][SW_LCH_FLUX][SD::RS]
+  double *s_dir_c = ssum, *s_dn_c = ssum + nl1, *s_up_c = ssum + 2 * nl1, *s_dir = ssum + 3 * nl1, *s_dn = ssum + 4 * nl1, *s_up = ssum + 5 * nl1;
   const size_t n = s.n;
-  const double *ac = s.scr + 2 * n, *bc = s.scr + 3 * n, *Ac = s.scr + 4 * n, *Sc = s.scr + 5 * n;
-  const double *aa = s.scr + 6 * n, *ba = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Sa = s.scr + 9 * n;
+  const double *ac = s.scr, *bc = s.scr + n, *tc = s.scr + 2 * n, *Ac = s.scr + 3 * n, *Dc = s.scr + 4 * n;
+  const double *aa = s.scr + 5 * n, *ba = s.scr + 6 * n, *ta = s.scr + 7 * n, *Aa = s.scr + 8 * n, *Da = s.scr + 9 * n;
   const double* carry = w.sw_carry + (size_t)c * 4 * SD::NG;
   const bool cloudy = s.cloudy;
-  const double toa_c = carry[2 * SD::NG + s.gg], toa_a0 = carry[3 * SD::NG + s.gg];
-  double fdd_c = 0.0, fdd_a = 0.0;
+  const double inc = w.incoming[(size_t)c * SD::NG + s.gg];
+  double dir_c = inc, dir_a = inc, fdd_c = 0.0, fdd_a = 0.0;
+  const double toa_c = dir_c * carry[s.gg], toa_a0 = dir_a * carry[SD::NG + s.gg];
   {
-    double* dst[4] = {s_dn_c, s_up_c, s_dn, s_up};
-    const int nf = cloudy ? 4 : 2;
-    // Cloudless + do_save_spectral_flux: sw_up_band = band sums of flux_up; sw_dn_band = mu0 * direct (scratch) + diffuse
-    const bool bands = cfg.solver_sw == 0 && cfg.do_save_spectral_flux && (out.sw_up_band || out.sw_dn_band);
-    const BandOut bo[2] = {{bands ? out.sw_up_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0},
-                           {bands ? out.sw_dn_band : nullptr, out.ld, 0, -1, 1.0, 0.0, w.sw_band_dir, (int)gridDim.x}};
+    double* dst[6] = {s_dir_c, s_dn_c, s_up_c, s_dir, s_dn, s_up};
+    const int nf = cloudy ? 6 : 3;
+    // Cloudless + do_save_spectral_flux (radiation_cloudless_sw.F90): per-band up, direct (x mu0) and total down profiles
+    const bool bands = cfg.solver_sw == 0 && cfg.do_save_spectral_flux && (out.sw_up_band || out.sw_dn_band || out.sw_dn_direct_band);
+    const BandOut bo[3] = {{out.sw_up_band, out.ld, 2, -1, 1.0, 0.0, nullptr, 0}, {out.sw_dn_direct_band, out.ld, 0, -1, mu0, 0.0, nullptr, 0},
+                           {out.sw_dn_band, out.ld, 0, 1, mu0, 1.0, nullptr, 0}};
     int slot = 0, lfirst = 0;
     if (act) {
-      tile[slot * SD::RS + g] = 0.0; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = toa_c;
-      tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = 0.0; tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = toa_a0;
+      tile[slot * SD::RS + g] = dir_c; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = 0.0; tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = toa_c;
+      tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = dir_a; tile[(4 * SW_LCH_FLUX + slot) * SD::RS + g] = 0.0; tile[(5 * SW_LCH_FLUX + slot) * SD::RS + g] = toa_a0;
     }
     ++slot;
-    for (int l0 = 0; l0 < nlev; l0 += 4) {
-      double ca[4], cb[4], cA[4], cS[4], da[4], db[4], dA[4], dS[4];
+    for (int l0 = 0; l0 < nlev; l0 += SW_BATCH) {
+      double ca[SW_BATCH], cb[SW_BATCH], ct[SW_BATCH], cA[SW_BATCH], cD[SW_BATCH], da[SW_BATCH], db[SW_BATCH], dt[SW_BATCH], dA[SW_BATCH], dD[SW_BATCH];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < SW_BATCH; ++k)
         if (act && l0 + k < nlev) {
           const size_t i = (size_t)(l0 + k) * SD::NG + g;
-          ca[k] = ac[i]; cb[k] = bc[i]; cA[k] = Ac[i]; cS[k] = Sc[i];
-          if (cloudy) { da[k] = aa[i]; db[k] = ba[i]; dA[k] = Aa[i]; dS[k] = Sa[i]; }
+          ca[k] = ac[i]; cb[k] = bc[i]; ct[k] = tc[i]; cA[k] = Ac[i]; cD[k] = Dc[i];
+          if (cloudy) { da[k] = aa[i]; db[k] = ba[i]; dt[k] = ta[i]; dA[k] = Aa[i]; dD[k] = Da[i]; }
         }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < SW_BATCH; ++k) {
         const int l = l0 + k;
         if (l < nlev) {
           if (act) {
-            fdd_c = ca[k] * fdd_c + cb[k];
-            const double fu_c = cA[k] * fdd_c + cS[k];
-            tile[slot * SD::RS + g] = fdd_c; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = fu_c;
+            fdd_c = ca[k] * fdd_c + cb[k] * dir_c;
+            dir_c = ct[k] * dir_c;
+            const double fu_c = dir_c * cD[k] + fdd_c * cA[k];
+            tile[slot * SD::RS + g] = dir_c; tile[(SW_LCH_FLUX + slot) * SD::RS + g] = fdd_c; tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = fu_c;
             if (cloudy) {
-              fdd_a = da[k] * fdd_a + db[k];
-              const double fu_a = dA[k] * fdd_a + dS[k];
-              tile[(2 * SW_LCH_FLUX + slot) * SD::RS + g] = fdd_a; tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = fu_a;
+              fdd_a = da[k] * fdd_a + db[k] * dir_a;
+              dir_a = dt[k] * dir_a;
+              const double fu_a = dir_a * dD[k] + fdd_a * dA[k];
+              tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = dir_a; tile[(4 * SW_LCH_FLUX + slot) * SD::RS + g] = fdd_a;
+              tile[(5 * SW_LCH_FLUX + slot) * SD::RS + g] = fu_a;
             }
           }
           ++slot;
           if (slot == SW_LCH_FLUX || l == nlev - 1) {
-            if (bands) flush_bands(tile, SD::RS, SW_LCH_FLUX, slot, bo, 2, lfirst, 1, c, SD::NB, T.meta->sw);
+            if (bands) flush_bands(tile, SD::RS, SW_LCH_FLUX, slot, bo, 3, lfirst, 1, c, SD::NB, T.meta->sw);
             flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0;
           }
         }
@@ -337,44 +267,42 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
   }
   if (g == 0 && out.cloud_cover_sw && cfg.solver_sw == 2) out.cloud_cover_sw[c] = tcc;
   // per-g surface / TOA fluxes
-  const double dif_c = fdd_c, dir_c = carry[s.gg] * mu0;
-  double dif_a = dif_c, dir_a = dir_c, toa_a = toa_c;
+  const double dif_c = fdd_c, dir_cs = dir_c * mu0;
+  double dif_a = dif_c, dir_as = dir_cs, toa_a = toa_c;
   if (cloudy) {
     dif_a = wc * fdd_a + w1 * dif_c;
-    dir_a = wc * (carry[SD::NG + s.gg] * mu0) + w1 * dir_c;
+    dir_as = wc * (dir_a * mu0) + w1 * dir_cs;
     toa_a = wc * toa_a0 + w1 * toa_c;
   }
   if (act) {
     const size_t i = (size_t)c * SD::NG + g;
     if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
-    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
+    if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_cs;
     if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
     if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
-    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
+    if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_as;
     if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
   }
-  sw_surface_spectral<SD>(T, cfg, out, c, g, act, tile, SD::RS, dir_a, dif_a, dir_c, dif_c);
+  sw_surface_spectral<SD>(T, cfg, out, c, g, act, tile, SD::RS, dir_as, dif_a, dir_cs, dif_c);
 #undef OUT2
 }
 
 template <class SD>
 static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
-  const size_t smA = sizeof(double) * (2 * LCH * SD::RS + 2 * nlev) + 16;
   const size_t smB = sizeof(double) * (2 * nlev + 2 * SD::NB) + 16;
-  const size_t smC = sizeof(double) * (4 * (nlev + 1) + 4 * SW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
+  const size_t smC = sizeof(double) * (6 * (nlev + 1) + 6 * SW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
   const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
-    sw_direct_kernel<SD, false><<<nc, SD::THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
     if (aer) sw_adding_kernel<SD, false, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
     else sw_adding_kernel<SD, false, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   } else {
-    sw_direct_kernel<SD, true><<<nc, SD::THREADS, smA, st>>>(T, cfg, in, out, w, nlev, nlevp);
     if (aer) sw_adding_kernel<SD, true, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
     else sw_adding_kernel<SD, true, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
   }
+  cudaFuncSetAttribute(sw_flux_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smC);
   sw_flux_kernel<SD><<<nc, SD::THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
-  return 3;
+  return 2;
 }
 
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
