@@ -51,13 +51,16 @@ struct Handle {
   int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
   int edge_cols = 1024;          // host entry: at most this many columns in the first and the last tile
   int tile_cols_device = 16384;  // device entry: only bounds the scratch (about 3 MB per column); bigger tiles = fewer partial waves
-  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_aux1 = nullptr, s_aux2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_cloud = nullptr, ev_sw_done = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  // Two compute sets (scratch + three streams + fork/join events): consecutive tiles of the host entry alternate between them,
+  // so the kernels of tile t+1 fill the SMs that the tail of tile t leaves idle.
+  cudaStream_t s_comp[2] = {nullptr, nullptr}, s_aux1[2] = {nullptr, nullptr}, s_aux2[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_cloud[2] = {nullptr, nullptr}, ev_sw_done[2] = {nullptr, nullptr};
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
-  Buf work[36];
-  Work w;
-  int w_cols = 0, w_nlev = 0;
+  Buf work[2][36];
+  Work w[2];
+  int w_cols[2] = {0, 0}, w_nlev[2] = {0, 0};
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
@@ -147,28 +150,28 @@ size_t work_bytes_per_column(const Handle* h, int nlev) {
   return tot;
 }
 
-int ensure_work(Handle* h, int cols, int nlev) {
-  if (cols <= h->w_cols && nlev == h->w_nlev) return 0;
-  if (nlev != h->w_nlev) h->w_cols = 0;
+int ensure_work(Handle* h, int set, int cols, int nlev) {
+  if (cols <= h->w_cols[set] && nlev == h->w_nlev[set]) return 0;
+  if (nlev != h->w_nlev[set]) h->w_cols[set] = 0;
   size_t sz[N_WORK];
   work_sizes(h, cols, nlev, sz);
-  for (int i = 0; i < N_WORK; ++i) CK(h, h->work[i].reserve(sz[i]));
-  Work& w = h->w;
-  w.od_lw = (double*)h->work[0].p; w.planck = (double*)h->work[1].p; w.emission = (double*)h->work[2].p; w.lw_albedo = (double*)h->work[3].p;
-  w.od_sw = (double*)h->work[4].p; w.ssa_sw = (double*)h->work[5].p; w.incoming = (double*)h->work[6].p;
-  w.cl_lw = (double*)h->work[7].p; w.cl_sw = (double*)h->work[8].p;
-  w.cum = (double*)h->work[9].p; w.pair = (double*)h->work[10].p; w.opi = (double*)h->work[11].p;
-  w.tcc = (double*)h->work[12].p; w.ibegin = (int*)h->work[13].p; w.iend = (int*)h->work[14].p; w.ict = (int*)h->work[15].p;
-  w.code_lw = (uint32_t*)h->work[16].p; w.code_sw = (uint32_t*)h->work[17].p;
-  w.scr_lw = (double*)h->work[18].p; w.scr_sw = (double*)h->work[23].p;
-  w.lev_lw = (LwLev*)h->work[24].p; w.lev_sw = (SwLev*)h->work[25].p;
-  w.g_sw = (double*)h->work[26].p; w.aer_sw = (double*)h->work[27].p; w.aer_lw = (double*)h->work[28].p;
-  w.sw_band_dir = (double*)h->work[29].p;
-  w.tc_reg = (double*)h->work[30].p; w.tc_ods = (double*)h->work[31].p; w.tc_u = (double*)h->work[32].p;
-  w.tc_v = (double*)h->work[33].p; w.tc_cc = (double*)h->work[34].p;
-  w.sw_sums = (double*)h->work[19].p; w.sw_carry = (double*)h->work[20].p;
-  w.lw_sums = (double*)h->work[21].p; w.lw_carry = (double*)h->work[22].p;
-  h->w_cols = cols; h->w_nlev = nlev;
+  for (int i = 0; i < N_WORK; ++i) CK(h, h->work[set][i].reserve(sz[i]));
+  Work& w = h->w[set];
+  w.od_lw = (double*)h->work[set][0].p; w.planck = (double*)h->work[set][1].p; w.emission = (double*)h->work[set][2].p; w.lw_albedo = (double*)h->work[set][3].p;
+  w.od_sw = (double*)h->work[set][4].p; w.ssa_sw = (double*)h->work[set][5].p; w.incoming = (double*)h->work[set][6].p;
+  w.cl_lw = (double*)h->work[set][7].p; w.cl_sw = (double*)h->work[set][8].p;
+  w.cum = (double*)h->work[set][9].p; w.pair = (double*)h->work[set][10].p; w.opi = (double*)h->work[set][11].p;
+  w.tcc = (double*)h->work[set][12].p; w.ibegin = (int*)h->work[set][13].p; w.iend = (int*)h->work[set][14].p; w.ict = (int*)h->work[set][15].p;
+  w.code_lw = (uint32_t*)h->work[set][16].p; w.code_sw = (uint32_t*)h->work[set][17].p;
+  w.scr_lw = (double*)h->work[set][18].p; w.scr_sw = (double*)h->work[set][23].p;
+  w.lev_lw = (LwLev*)h->work[set][24].p; w.lev_sw = (SwLev*)h->work[set][25].p;
+  w.g_sw = (double*)h->work[set][26].p; w.aer_sw = (double*)h->work[set][27].p; w.aer_lw = (double*)h->work[set][28].p;
+  w.sw_band_dir = (double*)h->work[set][29].p;
+  w.tc_reg = (double*)h->work[set][30].p; w.tc_ods = (double*)h->work[set][31].p; w.tc_u = (double*)h->work[set][32].p;
+  w.tc_v = (double*)h->work[set][33].p; w.tc_cc = (double*)h->work[set][34].p;
+  w.sw_sums = (double*)h->work[set][19].p; w.sw_carry = (double*)h->work[set][20].p;
+  w.lw_sums = (double*)h->work[set][21].p; w.lw_carry = (double*)h->work[set][22].p;
+  h->w_cols[set] = cols; h->w_nlev[set] = nlev;
   return 0;
 }
 
@@ -177,46 +180,46 @@ int ensure_work(Handle* h, int cols, int nlev) {
 // adding -> flux); the solvers wait for the cloud chain.  With serial == 0 they run on three streams forked from and
 // joined into `st`, so that latency-bound and fp64-bound kernels share the SMs.
 // ev: 2 events per stage (start, end), stages = gas_lw, gas_sw, cloud, solver_lw, solver_sw.
-int run_tile(Handle* h, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev) {
+int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev) {
   const DevCfg& c = h->dcfg;
   int n = 0;
   const bool par = !h->serial;
-  cudaStream_t s_lw = st, s_sw = par ? h->s_aux1 : st, s_cl = par ? h->s_aux2 : st;
+  cudaStream_t s_lw = st, s_sw = par ? h->s_aux1[set] : st, s_cl = par ? h->s_aux2[set] : st;
   const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
   if (!ckd) {
-    n += launch_gas_prep(h->T, c, in, h->w, nc, nlev, st);   // shared by the LW and SW gas-optics kernels
-    if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w, nc, nlev, st);
+    n += launch_gas_prep(h->T, c, in, h->w[set], nc, nlev, st);   // shared by the LW and SW gas-optics kernels
+    if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w[set], nc, nlev, st);
   }
   if (par) {
-    CK(h, cudaEventRecord(h->ev_fork, st));
-    CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork, 0));
-    CK(h, cudaStreamWaitEvent(s_cl, h->ev_fork, 0));
+    CK(h, cudaEventRecord(h->ev_fork[set], st));
+    CK(h, cudaStreamWaitEvent(s_sw, h->ev_fork[set], 0));
+    CK(h, cudaStreamWaitEvent(s_cl, h->ev_fork[set], 0));
   }
   // cloud chain
   CK(h, cudaEventRecord(ev[4], s_cl));
-  if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w, nc, nlev, s_cl);
+  if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w[set], nc, nlev, s_cl);
   if ((c.do_lw && c.solver_lw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_sw && c.solver_sw == ECRAD_SOLVER_TRIPLECLOUDS))
-    n += launch_tc_prep(c, in, h->w, nc, nlev, s_cl);
+    n += launch_tc_prep(c, in, h->w[set], nc, nlev, s_cl);
   CK(h, cudaEventRecord(ev[5], s_cl));
-  if (par) CK(h, cudaEventRecord(h->ev_cloud, s_cl));
+  if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
   // LW chain
   CK(h, cudaEventRecord(ev[0], s_lw));
-  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w, nc, nlev, s_lw) : launch_gas_lw(h->T, c, in, h->w, nc, nlev, s_lw);
+  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : launch_gas_lw(h->T, c, in, h->w[set], nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[1], s_lw));
   // SW chain
   CK(h, cudaEventRecord(ev[2], s_sw));
-  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w, nc, nlev, s_sw) : launch_gas_sw(h->T, c, in, h->w, nc, nlev, s_sw);
+  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w[set], nc, nlev, s_sw) : launch_gas_sw(h->T, c, in, h->w[set], nc, nlev, s_sw);
   CK(h, cudaEventRecord(ev[3], s_sw));
-  if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud, 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud, 0)); }
+  if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud[set], 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud[set], 0)); }
   CK(h, cudaEventRecord(ev[6], s_lw));
-  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w, nc, nlev, s_lw);
+  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w[set], nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[7], s_lw));
   CK(h, cudaEventRecord(ev[8], s_sw));
-  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w, nc, nlev, s_sw);
+  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w[set], nc, nlev, s_sw);
   CK(h, cudaEventRecord(ev[9], s_sw));
   if (par) {
-    CK(h, cudaEventRecord(h->ev_sw_done, s_sw));
-    CK(h, cudaStreamWaitEvent(st, h->ev_sw_done, 0));
+    CK(h, cudaEventRecord(h->ev_sw_done[set], s_sw));
+    CK(h, cudaStreamWaitEvent(st, h->ev_sw_done[set], 0));
   }
   CK(h, cudaGetLastError());
   h->launches += n;
@@ -403,13 +406,23 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
+  {
+    // host-entry tile (measured, two overlapping compute sets): 2048 columns for the RRTMG-sized spectra, 4096 for the ecCKD
+    // ones (less work per column; their end-to-end time is PCIe-bound and wants more, not bigger, tiles); short first/last tiles
+    const int ngs = (cfg->do_lw ? cfg->n_g_lw : 0) + (cfg->do_sw ? cfg->n_g_sw : 0);
+    const int t = ngs >= 200 ? 2048 : 4096;
+    h->tile_cols = t; h->edge_cols = t / 4;
+  }
   if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = h->tile_cols_device = v; }
   if (const char* s = getenv("ECRAD_B200_EDGE")) { int v = atoi(s); if (v > 0) h->edge_cols = v; }
   if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_comp[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_comp[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux1[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux2[1], cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_aux1, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->s_aux2, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->s_aux1[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->s_aux2[0], cudaStreamNonBlocking) != cudaSuccess) {
     fail(nullptr, "cannot create CUDA streams"); ecrad_b200_finalize(h); return 1;
   }
   for (auto& s : h->slot) {
@@ -417,9 +430,11 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming);
   }
-  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_cloud, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_sw_done, cudaEventDisableTiming);
+  for (int k = 0; k < 2; ++k) {
+    cudaEventCreateWithFlags(&h->ev_fork[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_cloud[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_sw_done[k], cudaEventDisableTiming);
+  }
   if (const char* s2 = getenv("ECRAD_B200_SERIAL")) h->serial = atoi(s2) != 0;
   init_generator_constants();
   *handle = h;
@@ -432,7 +447,7 @@ void ecrad_b200_finalize(void* handle) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->table_allocs) cudaFree(p);
-  for (auto& b : h->work) b.release();
+  for (auto& ws : h->work) for (auto& b : ws) b.release();
   for (auto& s : h->slot) {
     for (auto& b : s.in) b.release();
     for (auto& b : s.out) b.release();
@@ -442,11 +457,9 @@ void ecrad_b200_finalize(void* handle) {
   }
   for (auto e : h->ev) cudaEventDestroy(e);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
-  if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  for (cudaStream_t q : {h->s_comp[0], h->s_comp[1], h->s_aux1[0], h->s_aux1[1], h->s_aux2[0], h->s_aux2[1]}) if (q) cudaStreamDestroy(q);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
-  if (h->s_aux1) cudaStreamDestroy(h->s_aux1);
-  if (h->s_aux2) cudaStreamDestroy(h->s_aux2);
-  for (cudaEvent_t e : {h->ev_fork, h->ev_cloud, h->ev_sw_done}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_fork[0], h->ev_cloud[0], h->ev_sw_done[0], h->ev_fork[1], h->ev_cloud[1], h->ev_sw_done[1]}) if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -510,7 +523,8 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
   const int ntiles = (int)tile_n.size();
   int cap = 0;
   for (int n : tile_n) cap = n > cap ? n : cap;
-  if (ensure_work(h, cap, nlev)) return 1;
+  if (ensure_work(h, 0, cap, nlev)) return 1;
+  if (ntiles > 1 && ensure_work(h, 1, cap, nlev)) return 1;
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];
   fill_descs(c, nlev, in, out, id, od);
@@ -562,10 +576,11 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     // ---- kernels ----
     DevIn di; DevOut dout;
     make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
-    CK(h, cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
-    if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp, s.d2h_done, 0));
-    if (run_tile(h, di, dout, nt, nlev, h->s_comp, &h->ev[t * 2 * N_STAGE])) return 1;
-    CK(h, cudaEventRecord(s.compute_done, h->s_comp));
+    const int set = t & 1;   // staging slot and compute set alternate together
+    CK(h, cudaStreamWaitEvent(h->s_comp[set], s.h2d_done, 0));
+    if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp[set], s.d2h_done, 0));
+    if (run_tile(h, set, di, dout, nt, nlev, h->s_comp[set], &h->ev[t * 2 * N_STAGE])) return 1;
+    CK(h, cudaEventRecord(s.compute_done, h->s_comp[set]));
     // ---- D2H ----
     CK(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
     for (int k = 0; k < N_OUT; ++k) {
@@ -584,7 +599,8 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     s.used = true;
   }
   CK(h, cudaStreamSynchronize(h->s_d2h));
-  CK(h, cudaStreamSynchronize(h->s_comp));
+  CK(h, cudaStreamSynchronize(h->s_comp[0]));
+  CK(h, cudaStreamSynchronize(h->s_comp[1]));
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -607,17 +623,17 @@ int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, 
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const ecrad_b200_config& c = h->cfg;
   int tile = h->tile_cols_device;
-  if (ncol > h->w_cols || nlev != h->w_nlev) {   // growing the scratch: stay within a third of the memory that is free now
+  if (ncol > h->w_cols[0] || nlev != h->w_nlev[0]) {   // growing the scratch: stay within a third of the memory that is free now
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
       const size_t per_col = work_bytes_per_column(h, nlev);
-      const size_t fit = (fr / 3 + (size_t)h->w_cols * per_col) / (per_col ? per_col : 1);
+      const size_t fit = (fr / 3 + (size_t)h->w_cols[0] * per_col) / (per_col ? per_col : 1);
       if ((size_t)tile > fit) tile = fit < 256 ? 256 : (int)fit;
     }
   }
   const int ntiles = (ncol + tile - 1) / tile;
   const int cap = (ncol + ntiles - 1) / ntiles;
-  if (ensure_work(h, cap, nlev)) return 1;
+  if (ensure_work(h, 0, cap, nlev)) return 1;
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];
   fill_descs(c, nlev, in, out, id, od);
@@ -632,7 +648,7 @@ int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, 
     }
     DevIn di; DevOut dout;
     make_views(ip, op, ld_in, ld_out, in->solar_irradiance, di, dout);
-    if (run_tile(h, di, dout, nt, nlev, st, &h->ev[t * 2 * N_STAGE])) return 1;
+    if (run_tile(h, 0, di, dout, nt, nlev, st, &h->ev[t * 2 * N_STAGE])) return 1;
   }
   return 0;
 }
