@@ -9,11 +9,13 @@
 //   sw_adding_kernel   bottom-up: two-stream (calc_ref_trans_sw) + albedo/source     -> a, b, albedo, source per layer
 //   sw_flux_kernel     top-down: flux recurrence, g-point sums, flux_type outputs    (pure streaming)
 // State between the kernels lives in the per-column scratch ([layer][g], coalesced): 2 + 8 arrays.
+#include "bulk_pipe.cuh"
 #include "solver_common.cuh"
 
 namespace ecb {
 
-enum { SW_LCH_FLUX = 4, SW_BATCH = 2 };   // layers per g-point reduction / per batch of loads in sw_flux_kernel
+enum { SW_LCH_FLUX = 4, SW_BATCH = 2, SW_NST = 2 };   // sw_flux_kernel: layers per g-point reduction, layers per TMA stage, stages in the ring
+typedef BulkRing<SW_NST, SW_BATCH, 10> SwRing;
 
 // total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
 template <class SD>
@@ -212,15 +214,29 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
       tile[(3 * SW_LCH_FLUX + slot) * SD::RS + g] = dir_a; tile[(4 * SW_LCH_FLUX + slot) * SD::RS + g] = 0.0; tile[(5 * SW_LCH_FLUX + slot) * SD::RS + g] = toa_a0;
     }
     ++slot;
-    for (int l0 = 0; l0 < nlev; l0 += SW_BATCH) {
+    // The 5 (clear) or 10 (clear + cloudy) scratch arrays are streamed through a ring of shared-memory stages filled by the TMA
+    // unit, SW_BATCH layers per stage, requested two stages ahead by thread 0: the copies run while the CTA reduces.
+    SwRing ring;
+    ring.carve(reinterpret_cast<unsigned char*>(tile + 6 * SW_LCH_FLUX * SD::RS), SD::NG);
+    ring.init(SD::THREADS);
+    const double* src[10] = {ac, bc, tc, Ac, Dc, aa, ba, ta, Aa, Da};
+    const int narr = cloudy ? 10 : 5, nstage = (nlev + SW_BATCH - 1) / SW_BATCH;
+    if (threadIdx.x == 0)
+      for (int j = 0; j < SW_NST && j < nstage; ++j) ring.issue(j, src, narr, j * SW_BATCH, imin((int)SW_BATCH, nlev - j * SW_BATCH));
+    for (int j = 0; j < nstage; ++j) {
+      const int l0 = j * SW_BATCH, st = j % SW_NST;
       double ca[SW_BATCH], cb[SW_BATCH], ct[SW_BATCH], cA[SW_BATCH], cD[SW_BATCH], da[SW_BATCH], db[SW_BATCH], dt[SW_BATCH], dA[SW_BATCH], dD[SW_BATCH];
+      ring.wait_full(j);
 #pragma unroll
       for (int k = 0; k < SW_BATCH; ++k)
         if (act && l0 + k < nlev) {
-          const size_t i = (size_t)(l0 + k) * SD::NG + g;
-          ca[k] = ac[i]; cb[k] = bc[i]; ct[k] = tc[i]; cA[k] = Ac[i]; cD[k] = Dc[i];
-          if (cloudy) { da[k] = aa[i]; db[k] = ba[i]; dt[k] = ta[i]; dA[k] = Aa[i]; dD[k] = Da[i]; }
+          const int o = k * SD::NG + g;
+          ca[k] = ring.stage(st, 0)[o]; cb[k] = ring.stage(st, 1)[o]; ct[k] = ring.stage(st, 2)[o]; cA[k] = ring.stage(st, 3)[o]; cD[k] = ring.stage(st, 4)[o];
+          if (cloudy) { da[k] = ring.stage(st, 5)[o]; db[k] = ring.stage(st, 6)[o]; dt[k] = ring.stage(st, 7)[o]; dA[k] = ring.stage(st, 8)[o]; dD[k] = ring.stage(st, 9)[o]; }
         }
+      ring.release(j);
+      if (threadIdx.x == 0 && j + SW_NST < nstage)
+        ring.issue(j + SW_NST, src, narr, (j + SW_NST) * SW_BATCH, imin((int)SW_BATCH, nlev - (j + SW_NST) * SW_BATCH));
 #pragma unroll
       for (int k = 0; k < SW_BATCH; ++k) {
         const int l = l0 + k;
@@ -291,7 +307,7 @@ template <class SD>
 static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
   const size_t smB = sizeof(double) * (2 * nlev + 2 * SD::NB) + 16;
-  const size_t smC = sizeof(double) * (6 * (nlev + 1) + 6 * SW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
+  const size_t smC = sizeof(double) * (6 * (nlev + 1) + 6 * SW_LCH_FLUX * SD::RS) + sizeof(double) * SW_NST * 10 * SW_BATCH * SD::NG + 2 * SW_NST * sizeof(uint64_t) + 16;
   const bool aer = cfg.use_aerosols && w.g_sw;
   if (cfg.solver_sw == 2) {
     if (aer) sw_adding_kernel<SD, false, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);

@@ -245,7 +245,9 @@ def test_ecckd_mcica_vs_reference_golden(handles, meridian_raw, golden_ecckd_mci
                                 dict(do_lw_cloud_scattering=False, overlap_scheme_name="Exp-Exp"),
                                 dict(do_nearest_spectral_lw_emiss=True, overlap_scheme_name="Max-Ran"),
                                 dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True), dict(use_vectorizable_generator=True),
-                                dict(ecckd_tables="ecckd_tables_64b.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+                                dict(ecckd_tables="ecckd_tables_64b.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(ecckd_tables="ecckd_tables_lw32_sw96.bin", use_aerosols=True),
+                                dict(ecckd_tables="ecckd_tables_lw32_sw96.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
 def test_ecckd_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """ecCKD configurations (32- and 64-term models; BASELINE configs 1 and 3 have no golden file) on 300 perturbed columns."""
     n = 300

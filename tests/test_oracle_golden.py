@@ -156,6 +156,24 @@ def test_oracle_ecckd_mcica_matches_reference_golden(meridian_raw, golden_ecckd_
         assert f32_ulp_err(out[nm].T, golden_ecckd_mcica[gname]).max() <= 0.51, nm
 
 
+def test_oracle_unpinned_ecckd_models_agree_with_the_pinned_one(meridian_raw):
+    """The 64-term pair (BASELINE configs[2]) and the 96-term SW model have no golden file (SURVEY section 8c gaps): same code,
+    other tables.  Cross-model check: their clear-sky fluxes agree with the pinned 32-term models within 1.5 W m-2 (and all of
+    them with RRTMG within 6 W m-2, the known inter-model spread)."""
+    out = {}
+    for tabs in ("ecckd_tables_32b.bin", "ecckd_tables_64b.bin", "ecckd_tables_lw32_sw96.bin"):
+        cfg = RadiationConfig(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, ecckd_tables=tabs,
+                              sw_solver_name="Cloudless", lw_solver_name="Cloudless").consolidate()
+        out[tabs] = Oracle(cfg).radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, 137)
+    cfg = RadiationConfig(sw_solver_name="Cloudless", lw_solver_name="Cloudless").consolidate()
+    rrtmg = Oracle(cfg).radiation(I.to_radiation_inputs(meridian_raw), 32, 137)
+    ref = out["ecckd_tables_32b.bin"]
+    for tabs, o in out.items():
+        for nm, lev in (("sw_dn", -1), ("sw_up", 0), ("lw_up", 0), ("lw_dn", -1)):
+            assert np.abs(o[nm][:, lev] - ref[nm][:, lev]).max() < 1.5, (tabs, nm)
+            assert np.abs(o[nm][:, lev] - rrtmg[nm][:, lev]).max() < 6.0, (tabs, nm)
+
+
 def test_oracle_vectorizable_generator_is_statistically_consistent(meridian_raw):
     """use_vectorizable_generator (ctest `vec`) has no reference output: it draws other random numbers (vector MINSTD streams,
     radiation_random_numbers.F90), so it can only agree with the default generator in the mean.  Same cloud cover and clear-sky
