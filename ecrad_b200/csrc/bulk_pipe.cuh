@@ -69,6 +69,8 @@ struct BulkRing {
     for (int k = 0; k < narr; ++k) bulk_g2s(stage(s, k), src[k] + (size_t)l0 * rowlen, one, &full[s]);
   }
   __device__ __forceinline__ void wait_full(int j) { mbar_wait(&full[j % NST], (j / NST) & 1); }
+  // Call AFTER the values read from the stage have been used in arithmetic (or stored): the arrive must not overtake shared-memory
+  // loads that are still in flight, or the refill could land under them (seen as one wrong element in ~10^6 stages).
   __device__ __forceinline__ void release(int j) { mbar_arrive(&empty[j % NST]); }
 };
 

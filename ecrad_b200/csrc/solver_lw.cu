@@ -8,11 +8,13 @@
 //                    sub-column: two-stream of cloudy layers (calc_ref_trans_lw), albedo/source up to cloud top
 //                    (fast_adding_ica_lw), then the upward flux above cloud top
 //   lw_flux_kernel   top-down from cloud top: cloudy fluxes; derivative sums (calc_lw_derivatives_ica); outputs
+#include "bulk_pipe.cuh"
 #include "solver_common.cuh"
 
 namespace ecb {
 
-enum { LW_LCH_FLUX = 8, LW_LCH_UP = 8 };
+enum { LW_LCH_FLUX = 8, LW_LCH_UP = 8, LW_FLUX_NL = 2, LW_FLUX_NST = 2 };   // lw_flux_kernel: layers per TMA stage, stages in the ring
+typedef BulkRing<LW_FLUX_NST, LW_FLUX_NL, 4> LwRing;
 enum { LWS_DN_C = 0, LWS_UP_C = 1, LWS_DV_C = 2, LWS_UP_A = 3, LWS_DN_A = 4, LWS_DV_A = 5 };
 
 struct LwColumn {
@@ -209,16 +211,30 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
   const bool want_dv = cfg.do_lw_derivatives && out.lw_derivatives;
   if (cloudy) {
     double fd = fd_ict, fu = 0.0;
+    // scratch arrays streamed through a ring of shared-memory stages filled by the TMA unit (bulk_pipe.cuh), two stages ahead
+    LwRing ring;
+    ring.carve(reinterpret_cast<unsigned char*>(tile + 2 * LW_LCH_FLUX * SD::RS), SD::NG);
+    ring.init(SD::THREADS);
+    int jbase = 0;
     {
       double* dst[2] = {s.sums + LWS_DN_A * nl1, s.sums + LWS_UP_A * nl1};
+      const double* src[4] = {sa, sb, sA, sS};
+      const int nstage = (nlev - ict + LW_FLUX_NL - 1) / LW_FLUX_NL;
+      if (threadIdx.x == 0)
+        for (int j = 0; j < LW_FLUX_NST && j < nstage; ++j) ring.issue(j, src, 4, ict + j * LW_FLUX_NL, imin((int)LW_FLUX_NL, nlev - ict - j * LW_FLUX_NL));
       int slot = 0, lfirst = ict + 1;
-      for (int l0 = ict; l0 < nlev; l0 += 4) {
-        double va[4], vb[4], vA[4], vS[4];
+      for (int j = 0; j < nstage; ++j) {
+        const int l0 = ict + j * LW_FLUX_NL, st = j % LW_FLUX_NST;
+        double va[LW_FLUX_NL], vb[LW_FLUX_NL], vA[LW_FLUX_NL], vS[LW_FLUX_NL];
+        ring.wait_full(j);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (act && l0 + k < nlev) { const size_t i = (size_t)(l0 + k) * SD::NG + g; va[k] = sa[i]; vb[k] = sb[i]; vA[k] = sA[i]; vS[k] = sS[i]; }
+        for (int k = 0; k < LW_FLUX_NL; ++k)
+          if (act && l0 + k < nlev) {
+            const int o = k * SD::NG + g;
+            va[k] = ring.stage(st, 0)[o]; vb[k] = ring.stage(st, 1)[o]; vA[k] = ring.stage(st, 2)[o]; vS[k] = ring.stage(st, 3)[o];
+          }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < LW_FLUX_NL; ++k) {
           const int l = l0 + k;
           if (l < nlev) {
             if (act) {
@@ -227,21 +243,47 @@ lw_flux_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
               tile[slot * SD::RS + g] = fd; tile[(LW_LCH_FLUX + slot) * SD::RS + g] = fu;
             }
             ++slot;
+            if (k == LW_FLUX_NL - 1 || l == nlev - 1) {   // all values of the stage consumed (loads complete): hand it back, request the next
+              ring.release(j);
+              if (threadIdx.x == 0 && j + LW_FLUX_NST < nstage)
+                ring.issue(j + LW_FLUX_NST, src, 4, ict + (j + LW_FLUX_NST) * LW_FLUX_NL, imin((int)LW_FLUX_NL, nlev - ict - (j + LW_FLUX_NST) * LW_FLUX_NL));
+            }
             if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SD::RS, SD::NG, 2, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
           }
         }
       }
+      jbase = nstage;
     }
     fd_surf = fd;
     if (want_dv) {
       // derivative of flux_up at each half-level w.r.t. the surface emission: sum_g flux_up_surf(g) * prod(trans)
       double* dst[1] = {s.sums + LWS_DV_A * nl1};
+      const double* src[1] = {sP};
+      const int nstage = (nlev + LW_FLUX_NL - 1) / LW_FLUX_NL;
+      if (threadIdx.x == 0)
+        for (int j = 0; j < LW_FLUX_NST && j < nstage; ++j) ring.issue(jbase + j, src, 1, j * LW_FLUX_NL, imin((int)LW_FLUX_NL, nlev - j * LW_FLUX_NL));
       int slot = 0, lfirst = 0;
-#pragma unroll 4
-      for (int l = 0; l < nlev; ++l) {
-        if (act) tile[slot * SD::RS + g] = fu * sP[(size_t)l * SD::NG + g];
-        ++slot;
-        if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+      for (int j = 0; j < nstage; ++j) {
+        const int l0 = j * LW_FLUX_NL, st = (jbase + j) % LW_FLUX_NST;
+        double vP[LW_FLUX_NL];
+        ring.wait_full(jbase + j);
+#pragma unroll
+        for (int k = 0; k < LW_FLUX_NL; ++k)
+          if (act && l0 + k < nlev) vP[k] = ring.stage(st, 0)[k * SD::NG + g];
+#pragma unroll
+        for (int k = 0; k < LW_FLUX_NL; ++k) {
+          const int l = l0 + k;
+          if (l < nlev) {
+            if (act) tile[slot * SD::RS + g] = fu * vP[k];
+            ++slot;
+            if (k == LW_FLUX_NL - 1 || l == nlev - 1) {
+              ring.release(jbase + j);
+              if (threadIdx.x == 0 && j + LW_FLUX_NST < nstage)
+                ring.issue(jbase + j + LW_FLUX_NST, src, 1, (j + LW_FLUX_NST) * LW_FLUX_NL, imin((int)LW_FLUX_NL, nlev - (j + LW_FLUX_NST) * LW_FLUX_NL));
+            }
+            if (slot == LW_LCH_FLUX || l == nlev - 1) { flush_tile(tile, SD::RS, SD::NG, 1, slot, dst, lfirst, 1, LW_LCH_FLUX); lfirst += slot; slot = 0; }
+          }
+        }
       }
     }
   }
@@ -290,11 +332,12 @@ static int launch_solver_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn
   const int nlevp = (nlev + 3) & ~3;
   const size_t sm1 = sizeof(double) * (LCH * SD::RS) + 16;
   const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * SD::RS + 2 * nlev) + 16;
-  const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * SD::RS + 2 * SD::NB) + 16;
+  const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * SD::RS + 2 * SD::NB) + sizeof(double) * LW_FLUX_NST * 4 * LW_FLUX_NL * SD::NG + 2 * LW_FLUX_NST * sizeof(uint64_t) + 32;
   lw_down_kernel<SD><<<nc, SD::THREADS, sm1, st>>>(T, cfg, out, w, nlev);
   if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
   cudaFuncSetAttribute(lw_up_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
   lw_up_kernel<SD><<<nc, SD::THREADS, sm2, st>>>(T, cfg, in, out, w, nlev, nlevp);
+  cudaFuncSetAttribute(lw_flux_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
   lw_flux_kernel<SD><<<nc, SD::THREADS, sm3, st>>>(T, cfg, out, w, nlev);
   return 3;
 }

@@ -14,7 +14,7 @@
 
 namespace ecb {
 
-enum { SW_LCH_FLUX = 4, SW_BATCH = 2, SW_NST = 2 };   // sw_flux_kernel: layers per g-point reduction, layers per TMA stage, stages in the ring
+enum { SW_LCH_FLUX = 2, SW_BATCH = 2, SW_NST = 2 };   // sw_flux_kernel: layers per g-point reduction, layers per TMA stage, stages in the ring
 typedef BulkRing<SW_NST, SW_BATCH, 10> SwRing;
 
 // total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
@@ -234,9 +234,6 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
           ca[k] = ring.stage(st, 0)[o]; cb[k] = ring.stage(st, 1)[o]; ct[k] = ring.stage(st, 2)[o]; cA[k] = ring.stage(st, 3)[o]; cD[k] = ring.stage(st, 4)[o];
           if (cloudy) { da[k] = ring.stage(st, 5)[o]; db[k] = ring.stage(st, 6)[o]; dt[k] = ring.stage(st, 7)[o]; dA[k] = ring.stage(st, 8)[o]; dD[k] = ring.stage(st, 9)[o]; }
         }
-      ring.release(j);
-      if (threadIdx.x == 0 && j + SW_NST < nstage)
-        ring.issue(j + SW_NST, src, narr, (j + SW_NST) * SW_BATCH, imin((int)SW_BATCH, nlev - (j + SW_NST) * SW_BATCH));
 #pragma unroll
       for (int k = 0; k < SW_BATCH; ++k) {
         const int l = l0 + k;
@@ -255,6 +252,13 @@ sw_flux_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
             }
           }
           ++slot;
+          if (k == SW_BATCH - 1 || l == nlev - 1) {
+            // every value of this stage has gone through the arithmetic above (so its shared-memory loads have completed): hand
+            // the stage back and request the one after next before the reduction starts
+            ring.release(j);
+            if (threadIdx.x == 0 && j + SW_NST < nstage)
+              ring.issue(j + SW_NST, src, narr, (j + SW_NST) * SW_BATCH, imin((int)SW_BATCH, nlev - (j + SW_NST) * SW_BATCH));
+          }
           if (slot == SW_LCH_FLUX || l == nlev - 1) {
             if (bands) flush_bands(tile, SD::RS, SW_LCH_FLUX, slot, bo, 3, lfirst, 1, c, SD::NB, T.meta->sw);
             flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, 1, SW_LCH_FLUX); lfirst += slot; slot = 0;

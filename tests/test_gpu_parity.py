@@ -421,6 +421,20 @@ def test_full_size_properties_10000_columns(handles, meridian_raw, golden_noaer)
     assert np.array_equal(out["cloud_cover_sw"][idx], ref["cloud_cover_sw"])
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_aerosols=True)])
+def test_repeated_runs_are_bit_identical(handles, meridian_raw, kw):
+    """Race detector for the asynchronous pieces (TMA bulk-copy rings in the flux kernels, overlapping column tiles, three
+    concurrent kernel chains): the same 10 000 columns, run repeatedly, must reproduce every output bit for bit."""
+    h, _, cfg = handles(**kw)
+    n = 10000
+    raw = I.synthetic_columns(meridian_raw, n)
+    ref = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    for _ in range(8):
+        out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+        for nm in FLUXES + OTHERS + ["cloud_cover_sw", "cloud_cover_lw"]:
+            assert np.array_equal(out[nm], ref[nm], equal_nan=True), nm
+
+
 def test_device_resident_entry_matches_host_entry(handles, meridian_raw):
     import ctypes as C
 
