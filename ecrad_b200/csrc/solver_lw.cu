@@ -15,6 +15,8 @@ namespace ecb {
 
 enum { LW_LCH_FLUX = 8, LW_LCH_UP = 8, LW_FLUX_NL = 2, LW_FLUX_NST = 2 };   // lw_flux_kernel: layers per TMA stage, stages in the ring
 typedef BulkRing<LW_FLUX_NST, LW_FLUX_NL, 4> LwRing;
+enum { LW_UP_NL = 4, LW_UP_NST = 2 };   // lw_up_kernel: optical depth + Planck function streamed bottom-up, 4 layers per stage
+typedef BulkRing<LW_UP_NST, LW_UP_NL, 2> LwUpRing;
 enum { LWS_DN_C = 0, LWS_UP_C = 1, LWS_DV_C = 2, LWS_UP_A = 3, LWS_DN_A = 4, LWS_DV_A = 5 };
 
 struct LwColumn {
@@ -121,13 +123,23 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
   ++slot;
   uint4 cq = make_uint4(0, 0, 0, 0);
   double pb = s.act ? s.pl[(size_t)nlev * SD::NG + g] : 0.0;
-  // software pipeline: the loads of layer l-1 are issued before the arithmetic of layer l
-  double od_n = s.act ? s.od[(size_t)(nlev - 1) * SD::NG + g] : 0.0, pt_n = s.act ? s.pl[(size_t)(nlev - 1) * SD::NG + g] : 0.0;
-  for (int l = nlev - 1; l >= 0; --l) {
+  // optical depth and Planck function (top of layer) come through a ring of shared-memory stages filled by the TMA unit
+  // (bulk_pipe.cuh), LW_UP_NL layers per stage from the surface upwards, requested two stages ahead
+  LwUpRing ring;
+  ring.carve(reinterpret_cast<unsigned char*>(fsds + nlev), SD::NG);
+  ring.init(SD::THREADS);
+  const double* src[2] = {s.od, s.pl};
+  const int nstage = (nlev + LW_UP_NL - 1) / LW_UP_NL;
+  auto stage_l0 = [&](int j) { const int hi = nlev - j * LW_UP_NL; return hi - LW_UP_NL > 0 ? hi - LW_UP_NL : 0; };
+  if (threadIdx.x == 0)
+    for (int j = 0; j < LW_UP_NST && j < nstage; ++j) ring.issue(j, src, 2, stage_l0(j), nlev - j * LW_UP_NL - stage_l0(j));
+  for (int js = 0; js < nstage; ++js) {
+   const int sl0 = stage_l0(js), snl = nlev - js * LW_UP_NL - sl0, sst = js % LW_UP_NST;
+   ring.wait_full(js);
+   for (int l = sl0 + snl - 1; l >= sl0; --l) {
     if (s.act) {
       const size_t i = (size_t)l * SD::NG + g;
-      const double odg = od_n, pt = pt_n;
-      if (l > 0) { od_n = s.od[i - SD::NG]; pt_n = s.pl[i - SD::NG]; }
+      const double odg = ring.stage(sst, 0)[(l - sl0) * SD::NG + g], pt = ring.stage(sst, 1)[(l - sl0) * SD::NG + g];
       const LwLayer Lc = lw_no_scat(odg, pt, pb);
       fu = Lc.trans * fu + Lc.source_up;
       prod = prod * Lc.trans;
@@ -183,10 +195,16 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
       pb = pt;
     }
     ++slot;
+    if (l == sl0) {   // the stage's values have all been used: hand it back, request the stage after next
+      ring.release(js);
+      if (threadIdx.x == 0 && js + LW_UP_NST < nstage)
+        ring.issue(js + LW_UP_NST, src, 2, stage_l0(js + LW_UP_NST), nlev - (js + LW_UP_NST) * LW_UP_NL - stage_l0(js + LW_UP_NST));
+    }
     if (slot == LW_LCH_UP || l == 0) {
       if (bo[0].dst) flush_bands(tile, SD::RS, LW_LCH_UP, slot, bo, 1, lfirst, -1, c, SD::NB, T.meta->lw);
       flush_tile(tile, SD::RS, SD::NG, nf, slot, dst, lfirst, -1, LW_LCH_UP); lfirst -= slot; slot = 0;
     }
+   }
   }
   if (s.act) { s.carry[2 * SD::NG + g] = fu; s.carry[3 * SD::NG + g] = fu_a; }
 }
@@ -331,7 +349,7 @@ template <class SD>
 static int launch_solver_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
   const size_t sm1 = sizeof(double) * (LCH * SD::RS) + 16;
-  const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * SD::RS + 2 * nlev) + 16;
+  const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * SD::RS + 2 * nlev) + sizeof(double) * LW_UP_NST * 2 * LW_UP_NL * SD::NG + 2 * LW_UP_NST * sizeof(uint64_t) + 32;
   const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * SD::RS + 2 * SD::NB) + sizeof(double) * LW_FLUX_NST * 4 * LW_FLUX_NL * SD::NG + 2 * LW_FLUX_NST * sizeof(uint64_t) + 32;
   lw_down_kernel<SD><<<nc, SD::THREADS, sm1, st>>>(T, cfg, out, w, nlev);
   if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
