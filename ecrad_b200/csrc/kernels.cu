@@ -416,6 +416,152 @@ void init_generator_constants() {
   cudaMemcpyToSymbol(c_lfsr_jump, c, sizeof(c));
 }
 
+// One sub-column (g-point) of the walk, the 32 lanes covering the cloudy range Lb..Le with LPL consecutive layers each
+// (LPL = ceil((Le-Lb+1)/32): the median cloudy range of IFS columns is ~40 layers, so most columns run with LPL = 1 or 2
+// instead of the 5 that cover a whole 137-level profile).
+__device__ __forceinline__ void gen_to(int32_t* ring, int& tgen, int lane, int target) {
+  while (tgen < target) {
+    const int t = tgen + lane;
+    ring[t & 1023] = 0x3FFFFFFF & (ring[(t - 607) & 1023] + ring[(t - 273) & 1023]);
+    __syncwarp();
+    tgen += 32;
+  }
+}
+
+template <int LPL>
+__device__ __forceinline__ void gen_walk_warp(const DevCfg& cfg, int32_t* ring, const int32_t* rtop, uint32_t* code, int ng, int nlevp, int lane,
+                                              int Lb, int Le, double tcc, const double* sA1, const double* sT1, const double* sA2,
+                                              const double* sT2, const double* sCUM, const double* sOPI, int& tgen, int& pos) {
+  const unsigned FULL = 0xffffffffu;
+  const double RM = 1.0 / 1073741824.0;
+  const uint32_t MASK = (1u << LPL) - 1u;
+  const int L0 = Lb + lane * LPL;   // first layer of this lane
+  for (int g = 0; g < ng; ++g) {
+    gen_to(ring, tgen, lane, pos + 3 * GW_MAXLEV);   // one sub-column consumes at most 3 numbers per layer
+    // ---- cloud-top trigger: first layer whose cumulative cover reaches rand_top*total_cloud_cover ----
+    const double trigger = mul_rn((double)rtop[g] * RM, tcc);
+    int first = 1 << 30;
+#pragma unroll
+    for (int m = LPL - 1; m >= 0; --m) {
+      const int L = L0 + m;
+      if (L >= Lb && L <= Le && !(trigger > sCUM[L])) first = L;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) first = min(first, __shfl_xor_sync(FULL, first, d));
+    const int Lt = min(first, Le);
+    const int N = Le - Lt + 1;
+    // ---- transition maps s' = a*s ^ b of every layer (s = 1: cloudy) ----
+    uint32_t am = 0, bm = 0;
+#pragma unroll
+    for (int m = 0; m < LPL; ++m) {
+      const int L = L0 + m;
+      uint32_t a = 0, b = 0;
+      if (L == Lt) b = 1;
+      else if (L > Lt && L <= Le) {
+        const double r = (double)ring[(pos + (L - Lt - 1)) & 1023] * RM;
+        const bool c1 = mul_rn(r, sA1[L]) < sT1[L];   // cloudy above -> stays cloudy
+        const bool c2 = mul_rn(r, sA2[L]) < sT2[L];   // clear above  -> becomes cloudy
+        a = (uint32_t)(c1 != c2); b = (uint32_t)c2;
+      }
+      am |= a << m; bm |= b << m;
+    }
+    uint32_t A = 1, B = 0;
+#pragma unroll
+    for (int m = 0; m < LPL; ++m) { const uint32_t a = (am >> m) & 1u, b = (bm >> m) & 1u; B = (a & B) ^ b; A = a & A; }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t Ap = __shfl_up_sync(FULL, A, d), Bp = __shfl_up_sync(FULL, B, d);
+      if (lane >= d) { B = (A & Bp) ^ B; A = A & Ap; }
+    }
+    uint32_t sin = __shfl_up_sync(FULL, B, 1);
+    if (lane == 0) sin = 0;
+    uint32_t cl = 0;
+    {
+      uint32_t s = sin;
+#pragma unroll
+      for (int m = 0; m < LPL; ++m) { s = (((am >> m) & 1u) & s) ^ ((bm >> m) & 1u); cl |= s << m; }
+    }
+    // ---- number of cloudy layers above each layer ----
+    const int cnt = __popc(cl);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    const int C = __shfl_sync(FULL, incl, 31);
+    const int cntb_lane = incl - cnt;
+    // ---- first and last layer of the contiguous cloudy run each layer belongs to ----
+    const uint32_t isstart = cl & ~((cl << 1) | sin) & MASK;
+    int sc = isstart ? L0 + (31 - __clz((int)isstart)) : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc = max(sc, t); }
+    int rs_in = __shfl_up_sync(FULL, sc, 1);
+    if (lane == 0) rs_in = -1;
+    uint32_t nextfirst = __shfl_down_sync(FULL, cl & 1u, 1);
+    if (lane == 31) nextfirst = 0;
+    const uint32_t isend = cl & ~((cl >> 1) | (nextfirst << (LPL - 1))) & MASK;
+    int ec = isend ? L0 + (__ffs((int)isend) - 1) : (1 << 30);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_down_sync(FULL, ec, d); if (lane + d < 32) ec = min(ec, t); }
+    int re_in = __shfl_down_sync(FULL, ec, 1);
+    if (lane == 31) re_in = 1 << 30;
+    int rsv[LPL], rev[LPL];
+    {
+      int cur = rs_in;
+#pragma unroll
+      for (int m = 0; m < LPL; ++m) { if ((isstart >> m) & 1u) cur = L0 + m; rsv[m] = cur; }
+      cur = re_in;
+#pragma unroll
+      for (int m = LPL - 1; m >= 0; --m) { if ((isend >> m) & 1u) cur = L0 + m; rev[m] = cur; }
+    }
+    // ---- per-run random draws: run r takes n numbers (rand_inhom1) then n numbers (rand_inhom2), runs in order ----
+    // (Exp-Exp, generate_column_exp_exp: one "run" = the whole range Lt..Le whether cloudy or not: N + N numbers)
+    const bool exp_exp = cfg.overlap_scheme == 2;
+    int offv[LPL];
+    uint32_t fresh = 0;
+#pragma unroll
+    for (int m = 0; m < LPL; ++m) {
+      offv[m] = 0;
+      if (exp_exp) {
+        const int L = L0 + m;
+        if (L >= Lt && L <= Le) {
+          rsv[m] = Lt;
+          offv[m] = pos + N;
+          const double r2 = (double)ring[(pos + 2 * N + (L - Lt)) & 1023] * RM;
+          if (L == Lt || !(r2 < sOPI[L])) fresh |= 1u << m;
+        }
+      } else if ((cl >> m) & 1u) {
+        const int L = L0 + m;
+        const int p = L - rsv[m], n = rev[m] - rsv[m] + 1;
+        const int cb = cntb_lane + __popc(cl & ((1u << m) - 1u));
+        const int off = pos + N + 2 * (cb - p);
+        offv[m] = off;
+        const double r2 = (double)ring[(off + n + p) & 1023] * RM;
+        if (p == 0 || !(r2 < sOPI[L])) fresh |= 1u << m;   // else: reuse the number of the layer above
+      }
+    }
+    int qc = fresh ? L0 + (31 - __clz((int)fresh)) : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, qc, d); if (lane >= d) qc = max(qc, t); }
+    int q_in = __shfl_up_sync(FULL, qc, 1);
+    if (lane == 0) q_in = -1;
+    uint32_t* row = code + (size_t)g * nlevp;
+    {
+      int cur = q_in;
+#pragma unroll
+      for (int m = 0; m < LPL; ++m) {
+        const int L = L0 + m;
+        uint32_t word = 0;
+        if ((fresh >> m) & 1u) cur = L;
+        if ((cl >> m) & 1u) word = 0x80000000u | (uint32_t)ring[(offv[m] + (cur - rsv[m])) & 1023];
+        if (L < nlevp) row[L] = word;
+      }
+    }
+    pos += exp_exp ? 3 * N : N + 2 * C;
+    __syncwarp();
+    // layers outside the range the lanes cover are clear
+    for (int L = lane; L < nlevp; L += 32) if (L < Lb || L >= Lb + 32 * LPL) row[L] = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(64)
 cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp) {
   __shared__ double sA1[GW_MAXLEV], sT1[GW_MAXLEV], sA2[GW_MAXLEV], sT2[GW_MAXLEV], sCUM[GW_MAXLEV], sOPI[GW_MAXLEV];
@@ -479,143 +625,20 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
     __syncwarp();
   }
   int tgen = 0;   // stream elements [tgen-607, tgen) are in the ring
-  auto gen_to = [&](int target) {
-    while (tgen < target) {
-      const int t = tgen + lane;
-      ring[t & 1023] = 0x3FFFFFFF & (ring[(t - 607) & 1023] + ring[(t - 273) & 1023]);
-      __syncwarp();
-      tgen += 32;
-    }
-  };
-  gen_to(999 + ng);                                   // 999 warm-up numbers, then rand_top(1:ng)
+  gen_to(ring, tgen, lane, 999 + ng);                                   // 999 warm-up numbers, then rand_top(1:ng)
   for (int g = lane; g < ng; g += 32) rtop[g] = ring[(999 + g) & 1023];
   __syncwarp();
   int pos = 999 + ng;
 
-  for (int g = 0; g < ng; ++g) {
-    gen_to(pos + 416);   // one sub-column consumes at most nlev + 2*nlev numbers
-    // ---- cloud-top trigger: first layer whose cumulative cover reaches rand_top*total_cloud_cover ----
-    const double trigger = mul_rn((double)rtop[g] * RM, tcc);
-    int first = 1 << 30;
-#pragma unroll
-    for (int m = GW_LPL - 1; m >= 0; --m) {
-      const int L = lane * GW_LPL + m;
-      if (L >= Lb && L <= Le && !(trigger > sCUM[L])) first = L;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) first = min(first, __shfl_xor_sync(FULL, first, d));
-    const int Lt = min(first, Le);
-    const int N = Le - Lt + 1;
-    // ---- transition maps s' = a*s ^ b of every layer (s = 1: cloudy) ----
-    uint32_t am = 0, bm = 0;
-#pragma unroll
-    for (int m = 0; m < GW_LPL; ++m) {
-      const int L = lane * GW_LPL + m;
-      uint32_t a = 0, b = 0;
-      if (L == Lt) b = 1;
-      else if (L > Lt && L <= Le) {
-        const double r = (double)ring[(pos + (L - Lt - 1)) & 1023] * RM;
-        const bool c1 = mul_rn(r, sA1[L]) < sT1[L];   // cloudy above -> stays cloudy
-        const bool c2 = mul_rn(r, sA2[L]) < sT2[L];   // clear above  -> becomes cloudy
-        a = (uint32_t)(c1 != c2); b = (uint32_t)c2;
-      }
-      am |= a << m; bm |= b << m;
-    }
-    uint32_t A = 1, B = 0;
-#pragma unroll
-    for (int m = 0; m < GW_LPL; ++m) { const uint32_t a = (am >> m) & 1u, b = (bm >> m) & 1u; B = (a & B) ^ b; A = a & A; }
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t Ap = __shfl_up_sync(FULL, A, d), Bp = __shfl_up_sync(FULL, B, d);
-      if (lane >= d) { B = (A & Bp) ^ B; A = A & Ap; }
-    }
-    uint32_t sin = __shfl_up_sync(FULL, B, 1);
-    if (lane == 0) sin = 0;
-    uint32_t cl = 0;
-    {
-      uint32_t s = sin;
-#pragma unroll
-      for (int m = 0; m < GW_LPL; ++m) { s = (((am >> m) & 1u) & s) ^ ((bm >> m) & 1u); cl |= s << m; }
-    }
-    // ---- number of cloudy layers above each layer ----
-    const int cnt = __popc(cl);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-    const int C = __shfl_sync(FULL, incl, 31);
-    const int cntb_lane = incl - cnt;
-    // ---- first and last layer of the contiguous cloudy run each layer belongs to ----
-    const uint32_t isstart = cl & ~((cl << 1) | sin) & 31u;
-    int sc = isstart ? lane * GW_LPL + (31 - __clz((int)isstart)) : -1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc = max(sc, t); }
-    int rs_in = __shfl_up_sync(FULL, sc, 1);
-    if (lane == 0) rs_in = -1;
-    uint32_t nextfirst = __shfl_down_sync(FULL, cl & 1u, 1);
-    if (lane == 31) nextfirst = 0;
-    const uint32_t isend = cl & ~((cl >> 1) | (nextfirst << (GW_LPL - 1))) & 31u;
-    int ec = isend ? lane * GW_LPL + (__ffs((int)isend) - 1) : (1 << 30);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_down_sync(FULL, ec, d); if (lane + d < 32) ec = min(ec, t); }
-    int re_in = __shfl_down_sync(FULL, ec, 1);
-    if (lane == 31) re_in = 1 << 30;
-    int rsv[GW_LPL], rev[GW_LPL];
-    {
-      int cur = rs_in;
-#pragma unroll
-      for (int m = 0; m < GW_LPL; ++m) { if ((isstart >> m) & 1u) cur = lane * GW_LPL + m; rsv[m] = cur; }
-      cur = re_in;
-#pragma unroll
-      for (int m = GW_LPL - 1; m >= 0; --m) { if ((isend >> m) & 1u) cur = lane * GW_LPL + m; rev[m] = cur; }
-    }
-    // ---- per-run random draws: run r takes n numbers (rand_inhom1) then n numbers (rand_inhom2), runs in order ----
-    // (Exp-Exp, generate_column_exp_exp: one "run" = the whole range Lt..Le whether cloudy or not: N + N numbers)
-    const bool exp_exp = cfg.overlap_scheme == 2;
-    int offv[GW_LPL];
-    uint32_t fresh = 0;
-#pragma unroll
-    for (int m = 0; m < GW_LPL; ++m) {
-      offv[m] = 0;
-      if (exp_exp) {
-        const int L = lane * GW_LPL + m;
-        if (L >= Lt && L <= Le) {
-          rsv[m] = Lt;
-          offv[m] = pos + N;
-          const double r2 = (double)ring[(pos + 2 * N + (L - Lt)) & 1023] * RM;
-          if (L == Lt || !(r2 < sOPI[L])) fresh |= 1u << m;
-        }
-      } else if ((cl >> m) & 1u) {
-        const int L = lane * GW_LPL + m;
-        const int p = L - rsv[m], n = rev[m] - rsv[m] + 1;
-        const int cb = cntb_lane + __popc(cl & ((1u << m) - 1u));
-        const int off = pos + N + 2 * (cb - p);
-        offv[m] = off;
-        const double r2 = (double)ring[(off + n + p) & 1023] * RM;
-        if (p == 0 || !(r2 < sOPI[L])) fresh |= 1u << m;   // else: reuse the number of the layer above
-      }
-    }
-    int qc = fresh ? lane * GW_LPL + (31 - __clz((int)fresh)) : -1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, qc, d); if (lane >= d) qc = max(qc, t); }
-    int q_in = __shfl_up_sync(FULL, qc, 1);
-    if (lane == 0) q_in = -1;
-    uint32_t* row = code + (size_t)g * nlevp;
-    {
-      int cur = q_in;
-#pragma unroll
-      for (int m = 0; m < GW_LPL; ++m) {
-        const int L = lane * GW_LPL + m;
-        uint32_t word = 0;
-        if ((fresh >> m) & 1u) cur = L;
-        if ((cl >> m) & 1u) word = 0x80000000u | (uint32_t)ring[(offv[m] + (cur - rsv[m])) & 1023];
-        if (L < nlevp) row[L] = word;
-      }
-    }
-    pos += exp_exp ? 3 * N : N + 2 * C;
-    __syncwarp();
+  const int lpl = (Le - Lb + 1 + 31) / 32;
+  switch (lpl) {
+    case 1: gen_walk_warp<1>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    case 2: gen_walk_warp<2>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    case 3: gen_walk_warp<3>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    case 4: gen_walk_warp<4>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    default: gen_walk_warp<5>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // "Vectorizable" McICA generator (use_vectorizable_generator): radiation_cloud_generator.F90:587-734 with the vector
