@@ -229,7 +229,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
 // =========================================================================================================
 // SW gas optics (sunlit columns only)
 // =========================================================================================================
-__global__ void __launch_bounds__(GAS_THREADS, 2)
+__global__ void __launch_bounds__(GAS_THREADS, 3)
 gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, tid = threadIdx.x;

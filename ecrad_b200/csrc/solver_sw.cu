@@ -69,7 +69,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 //   a = T/(1-A*R), b = (Tdir*D*R + Tdirdif)/(1-A*R), t = Tdir, A, D      (A, D: of everything below the layer)
 // ---------------------------------------------------------------------------------------------------------
 template <class SD, bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
-__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 3))
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 6))
 sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SwColumn s = sw_column<SD>(T, cfg, in, w, nlev, nlevp);
