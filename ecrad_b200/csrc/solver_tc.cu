@@ -104,7 +104,7 @@ __device__ __forceinline__ void mat3_x_vec(const double* A, double* x) {
 // SW
 // =========================================================================================================
 template <class SD>
-__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 2))
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 5))
 tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
@@ -276,7 +276,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
 // LW (after lw_down_kernel: clear-sky flux_dn sums, flux_dn at cloud top and at the surface per g-point)
 // =========================================================================================================
 template <class SD>
-__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 2))
+__global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 160, 4))
 tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
