@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence of one measurement round (run on the GPU box through gpurun): launch lists + --set full captures.
 #   tools/profile_round.sh <tag>      -> gpurun_out/launches_<tag>.csv, launches_<tag>_ecckd.csv, prof_<kernel>_<tag>.ncu-rep
-TAG=${1:-r1f}
+TAG=${1:-r1g}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --clock-control none"
