@@ -131,7 +131,7 @@ __device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& i
 // LW: optical depth, Planck function at half-levels, surface emission and albedo per g-point
 // =========================================================================================================
 template <class SD>
-__global__ void __launch_bounds__(CKD_THREADS)
+__global__ void __launch_bounds__(CKD_THREADS, 10)
 ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,7 +210,7 @@ ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
 // SW: absorption + Rayleigh -> od / ssa, incoming flux per g-point, aerosol merge (od, ssa, g)
 // =========================================================================================================
 template <class SD>
-__global__ void __launch_bounds__(CKD_THREADS)
+__global__ void __launch_bounds__(CKD_THREADS, 10)
 ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -53,7 +53,7 @@ def table(paths):
     """One markdown row per capture: ms, DRAM R+W (GB), DRAM %, fp64 %, warps %, issue %, regs, L1 hit, L2 hit, top stalls."""
     print("| capture | ms | DRAM R+W GB | DRAM % | fp64 % | warps % | issue % | regs | L1 hit % | L2 hit % | stalls (per issue) |\n|---|---|---|---|---|---|---|---|---|---|---|")
     for p in paths:
-        out = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        out = open(p).read() if p.endswith(".csv") else subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         r = list(csv.reader(out.splitlines()))
         hdr, units, vals = r[0], r[1], r[2]
         d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
@@ -65,7 +65,7 @@ def table(paths):
             return x * m * scale
         st = {k.split("stalled_")[1].split("_per_issue")[0]: f(k) for k in d if "issue_stalled" in k and k.endswith("per_issue_active.ratio")}
         top = ", ".join(f"{k} {v:.1f}" for k, v in sorted(st.items(), key=lambda x: -x[1])[:3])
-        name = p.split("/")[-1].replace(".ncu-rep", "").replace("prof_", "")
+        name = p.split("/")[-1].replace(".ncu-rep", "").replace("_raw.csv", "").replace("prof_", "")
         print(f"| {name} | {f('gpu__time_duration.sum'):.2f} | {f('dram__bytes_read.sum'):.2f} + {f('dram__bytes_write.sum'):.2f} | "
               f"{f('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {f('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
               f"{f('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {f('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
