@@ -84,21 +84,32 @@ class PeerFluxArrays:
         self.plane = self.nrows * self.ncol_total * 8
         nbytes = self.plane * len(self.names)
         self.owner = self.rank == dst
+        # every step is followed by an agreement over the process group, so that a failure on one rank (no peer access, IPC
+        # not permitted in a sandbox, ...) makes ALL ranks raise instead of leaving the others in a barrier
+        def agree(ok, what):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                raise RuntimeError("PeerFluxArrays: " + what + " failed on at least one rank")
+
+        ptr, payload, ok = 0, [None], True
         if self.owner:
             err, ptr = rt.cudaMalloc(nbytes)
-            assert err == rt.cudaError_t.cudaSuccess, err
-            rt.cudaMemset(ptr, 0xFF, nbytes)   # NaN pattern: unwritten columns would show
-            err, handle = rt.cudaIpcGetMemHandle(ptr)
-            assert err == rt.cudaError_t.cudaSuccess, err
-            payload = [bytes(handle.reserved)]
-        else:
-            payload = [None]
+            ok = err == rt.cudaError_t.cudaSuccess
+            if ok:
+                rt.cudaMemset(ptr, 0xFF, nbytes)   # NaN pattern: unwritten columns would show
+                err, handle = rt.cudaIpcGetMemHandle(ptr)
+                ok = err == rt.cudaError_t.cudaSuccess
+                if ok:
+                    payload = [bytes(handle.reserved)]
+        agree(ok, "allocation / cudaIpcGetMemHandle")
         dist.broadcast_object_list(payload, src=dst)
         if not self.owner:
             handle = rt.cudaIpcMemHandle_t()
             handle.reserved = payload[0]
             err, ptr = rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)
-            assert err == rt.cudaError_t.cudaSuccess, err
+            ok = err == rt.cudaError_t.cudaSuccess
+        agree(ok, "cudaIpcOpenMemHandle")
         self.base = int(ptr)
         self._torch = torch
 
