@@ -467,6 +467,40 @@ def test_device_resident_entry_matches_host_entry(handles, meridian_raw):
         assert np.array_equal(outs[nm].cpu().numpy().T, host[nm]), nm
 
 
+def test_device_entry_with_separate_leading_dimensions(handles, meridian_raw):
+    """ecrad_b200_radiation_device_ld: two column ranges write their slices of ONE set of output arrays (ld_out = total columns),
+    as the ranks of a multi-GPU run do with peer-mapped arrays; result = the host entry on all columns, bit for bit."""
+    import ctypes as C
+
+    import torch
+
+    from ecrad_b200 import abi
+
+    h, _, cfg = handles()
+    n, n1 = 300, 130   # ranges [0, 130) and [130, 300)
+    raw = I.synthetic_columns(meridian_raw, n)
+    inp = I.to_radiation_inputs(raw)
+    host = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    dev = torch.device("cuda:0")
+    keep = {}
+    for nm, dt, _ in abi.INPUT_ARRAYS:
+        a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
+        keep[nm] = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)   # (rows, n): leading dimension n
+    outs = {nm: torch.full((NLEV + 1, n), float("nan"), dtype=torch.float64, device=dev) for nm in FLUXES}
+    for c0, nc in ((0, n1), (n1, n - n1)):
+        ist = abi.Inputs(); ist.struct_bytes = C.sizeof(abi.Inputs); ist.solar_irradiance = inp["solar_irradiance"]
+        for nm, dt, _ in abi.INPUT_ARRAYS:
+            esz = 4 if dt == "i4" else 8
+            setattr(ist, nm, C.cast(keep[nm].data_ptr() + esz * c0, abi.c_ip if dt == "i4" else abi.c_dp))
+        ost = abi.Outputs(); ost.struct_bytes = C.sizeof(abi.Outputs)
+        for nm in FLUXES:
+            setattr(ost, nm, C.cast(outs[nm].data_ptr() + 8 * c0, abi.c_dp))
+        h.radiation_device_ld(nc, NLEV, n, n, ist, ost, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for nm in FLUXES:
+        assert np.array_equal(outs[nm].cpu().numpy().T, host[nm]), nm
+
+
 def test_error_behaviour(meridian_raw):
     """Non-zero status + message instead of the reference's radiation_abort."""
     from ecrad_b200.radiation_interface import RadiationError, setup_radiation
