@@ -14,6 +14,8 @@ GAS_MODEL = {"monochromatic": 0, "rrtmg-ifs": 1, "ecckd": 2}
 OVERLAP = {"max-ran": 0, "exp-ran": 1, "exp-exp": 2}
 LIQ_MODEL = {"socrates": 1}
 ICE_MODEL = {"fu-ifs": 1}
+# sw_entrapment_name (radiation_config.F90:69-84)
+ENTRAPMENT = {"zero": 0, "edge-only": 1, "explicit": 2, "non-fractal": 3, "maximum": 4}
 
 
 class Config(C.Structure):
@@ -35,11 +37,14 @@ class Config(C.Structure):
         ("n_albedo_sw", C.c_int32), ("n_emiss_lw", C.c_int32),
         ("n_canopy_bands_sw", C.c_int32), ("n_canopy_bands_lw", C.c_int32),
         ("n_aerosol_types", C.c_int32),
-        ("reserved_i", C.c_int32 * 3),
+        ("do_3d_effects", C.c_int32), ("i_3d_sw_entrapment", C.c_int32), ("do_3d_lw_multilayer_effects", C.c_int32),
         ("cloud_fraction_threshold", C.c_double), ("cloud_mixing_ratio_threshold", C.c_double),
         ("min_gas_od_lw", C.c_double), ("min_gas_od_sw", C.c_double),
         ("cloud_inhom_decorr_scaling", C.c_double),
-        ("reserved_d", C.c_double * 4),
+        ("max_gas_od_3d", C.c_double), ("max_cloud_od", C.c_double), ("max_3d_transfer_rate", C.c_double),
+        ("min_cloud_effective_size", C.c_double),
+        ("overhead_sun_factor", C.c_double), ("overhang_factor", C.c_double), ("clear_to_thick_fraction", C.c_double),
+        ("do_lw_side_emissivity", C.c_int32), ("use_expm_everywhere", C.c_int32),
     ]
 
 
@@ -55,6 +60,7 @@ INPUT_ARRAYS = [
     ("cloud_fraction", "f8", "cl"), ("q_liq", "f8", "cl"), ("q_ice", "f8", "cl"), ("re_liq", "f8", "cl"),
     ("re_ice", "f8", "cl"), ("overlap_param", "f8", "ci"), ("fractional_std", "f8", "cl"),
     ("aerosol_mmr", "f8", "clt"), ("h2o_sat_liq", "f8", "cl"),
+    ("inv_cloud_effective_size", "f8", "cl"), ("inv_inhom_effective_size", "f8", "cl"),
 ]
 
 

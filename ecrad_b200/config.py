@@ -95,6 +95,19 @@ class RadiationConfig:
     i_aerosol_type_map: tuple = (-1, -2, -3, 7, 8, 9, -4, 10, 11, 11, -5, 14)
     min_gas_od_lw: float = 1.0e-15
     min_gas_od_sw: float = 0.0
+    # SPARTACUS (radiation_config.F90:225-411 defaults; test/ifs `test_spartacus` sets do_3d_effects = true)
+    do_3d_effects: bool = False
+    sw_entrapment_name: str = "Explicit"
+    do_3d_lw_multilayer_effects: bool = False
+    do_lw_side_emissivity: bool = True
+    use_expm_everywhere: bool = False
+    max_gas_od_3d: float = 8.0
+    max_cloud_od: float = 16.0
+    max_3d_transfer_rate: float = 10.0
+    min_cloud_effective_size: float = 100.0
+    overhead_sun_factor: float = 0.0
+    overhang_factor: float = 0.0
+    clear_to_thick_fraction: float = 0.0
     # gas_model_name = "ECCKD": table blob made by tools/extract_ecckd_tables.py (file name inside ecrad_b200/data/, or a
     # path); stands for gas_optics_{sw,lw}_override_file_name + the general cloud / aerosol optics files.  Cloud and
     # aerosol optics are per g-point (do_cloud_aerosol_per_{sw,lw}_g_point = true, radiation_config.F90 defaults for ecCKD).
@@ -161,8 +174,14 @@ class RadiationConfig:
                   "do_lw_aerosol_scattering", "do_lw_derivatives", "do_sw_delta_scaling_with_gases",
                   "do_fu_lw_ice_optics_bug", "use_beta_overlap", "use_vectorizable_generator",
                   "do_surface_sw_spectral_flux", "do_canopy_fluxes_sw", "do_canopy_fluxes_lw", "do_save_spectral_flux",
-                  "do_nearest_spectral_sw_albedo", "do_nearest_spectral_lw_emiss"):
+                  "do_nearest_spectral_sw_albedo", "do_nearest_spectral_lw_emiss",
+                  "do_3d_effects", "do_3d_lw_multilayer_effects", "do_lw_side_emissivity", "use_expm_everywhere"):
             setattr(c, k, int(getattr(self, k)))
+        c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
+        for k in ("max_gas_od_3d", "max_cloud_od", "max_3d_transfer_rate", "overhead_sun_factor", "overhang_factor",
+                  "clear_to_thick_fraction"):
+            setattr(c, k, float(getattr(self, k)))
+        c.min_cloud_effective_size = max(1.0e-6, self.min_cloud_effective_size)   # radiation_config.F90:970
         # radiation_config.F90 consolidate: do_clouds is false only for the Cloudless solvers
         c.do_clouds = int(not (c.i_solver_sw == 0 and c.i_solver_lw == 0))
         c.n_g_sw, c.n_g_lw = self.n_g

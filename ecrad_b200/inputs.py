@@ -64,7 +64,27 @@ def to_radiation_inputs(raw, config=None):
         # file (column, type, level) -> aerosol%mixing_ratio(ncol, nlev, ntype)  (driver/ecrad_driver_read_input.F90:546)
         d["aerosol_mmr"] = F(np.transpose(raw["aerosol_mmr"], (0, 2, 1)))
         d["h2o_sat_liq"] = F(saturation_wrt_liquid(raw["pressure_hl"], raw["temperature_hl"]))
+    if config is not None and "spartacus" in (config.sw_solver_name.lower(), config.lw_solver_name.lower()):
+        ic, ii = cloud_effective_separation_eta(raw["pressure_hl"], raw["cloud_fraction"])
+        d["inv_cloud_effective_size"], d["inv_inhom_effective_size"] = F(ic), F(ii)
     return d
+
+
+def cloud_effective_separation_eta(pressure_hl, cloud_fraction, separation_surf=2500.0, separation_toa=14000.0, power=3.5,
+                                   inhom_separation_factor=0.75):
+    """cloud%param_cloud_effective_separation_eta (radiation_cloud.F90:602-690) with the driver's namelist values of
+    test/ifs/configCY49R1.nam (cloud_separation_scale_surface/_toa/_power, cloud_inhom_separation_factor;
+    driver/ecrad_driver_read_input.F90:333-353): the inverse cloud and inhomogeneity effective sizes (m-1) the SPARTACUS
+    solvers read, (ncol, nlev) each.  Arguments in file order (column slowest), levels top-down."""
+    coeff_e = 1.0 - np.exp(-1.0)
+    coeff_b = (separation_toa - separation_surf) / coeff_e
+    coeff_a = separation_toa - coeff_b
+    eta = (pressure_hl[:, :-1] + pressure_hl[:, 1:]) * (0.5 / pressure_hl[:, -1:])
+    eff_separation = coeff_a + coeff_b * np.exp(-eta**power)
+    f = cloud_fraction
+    inv_cloud = 1.0 / (eff_separation * np.sqrt(np.maximum(1.0e-5, f * (1.0 - f))))
+    inv_inhom = 1.0 / (eff_separation * inhom_separation_factor * np.sqrt(np.maximum(1.0e-5, 0.5 * f * (1.0 - 0.5 * f))))
+    return inv_cloud, inv_inhom
 
 
 def saturation_wrt_liquid(pressure_hl, temperature_hl):

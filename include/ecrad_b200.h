@@ -33,6 +33,9 @@ enum { ECRAD_GAS_MONOCHROMATIC = 0, ECRAD_GAS_IFSRRTMG = 1, ECRAD_GAS_ECCKD = 2 
 enum { ECRAD_OVERLAP_MAX_RAN = 0, ECRAD_OVERLAP_EXP_RAN = 1, ECRAD_OVERLAP_EXP_EXP = 2 }; /* radiation_cloud_cover.F90:30-33 */
 enum { ECRAD_LIQ_SOCRATES = 1 };                                          /* radiation_config.F90:95-99  */
 enum { ECRAD_ICE_FU = 1 };                                                /* radiation_config.F90:107-111 */
+/* SPARTACUS shortwave entrapment, config%i_3d_sw_entrapment (radiation_config.F90:69-77) */
+enum { ECRAD_ENTRAPMENT_ZERO = 0, ECRAD_ENTRAPMENT_EDGE_ONLY = 1, ECRAD_ENTRAPMENT_EXPLICIT = 2,
+       ECRAD_ENTRAPMENT_EXPLICIT_NON_FRACTAL = 3, ECRAD_ENTRAPMENT_MAXIMUM = 4 };
 
 /* POD copy of the scalars of `config_type` (radiation_config.F90:163-649) that the hot path reads. */
 typedef struct ecrad_b200_config {
@@ -52,12 +55,15 @@ typedef struct ecrad_b200_config {
   int32_t n_emiss_lw;                /* size(single_level%lw_emissivity,2)                               */
   int32_t n_canopy_bands_sw, n_canopy_bands_lw;
   int32_t n_aerosol_types;           /* config%n_aerosol_types == size(aerosol%mixing_ratio,3); 0 without aerosols  */
-  int32_t reserved_i[3];
+  /* SPARTACUS (radiation_config.F90:225-411); nregions is fixed to 3 */
+  int32_t do_3d_effects, i_3d_sw_entrapment, do_3d_lw_multilayer_effects;
   double cloud_fraction_threshold;   /* config%cloud_fraction_threshold      (default 1e-6)              */
   double cloud_mixing_ratio_threshold; /*                                     (default 1e-9)              */
   double min_gas_od_lw, min_gas_od_sw; /* radiation_config.F90:244-245                                   */
   double cloud_inhom_decorr_scaling;
-  double reserved_d[4];
+  double max_gas_od_3d, max_cloud_od, max_3d_transfer_rate, min_cloud_effective_size;  /* defaults 8, 16, 10, 100 m */
+  double overhead_sun_factor, overhang_factor, clear_to_thick_fraction;                /* defaults 0, 0, 0          */
+  int32_t do_lw_side_emissivity, use_expm_everywhere;                                  /* defaults 1, 0             */
 } ecrad_b200_config;
 
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md
@@ -113,6 +119,10 @@ typedef struct ecrad_b200_inputs {
   /* aerosol_type (radiation_aerosol.F90) and thermodynamics%h2o_sat_liq; only read when cfg.use_aerosols */
   const double* aerosol_mmr;          /* (ncol, nlev, n_aerosol_types)  aerosol%mixing_ratio, levels 1..nlev */
   const double* h2o_sat_liq;          /* (ncol, nlev)  saturation mass mixing ratio w.r.t. liquid (calc_saturation_wrt_liquid) */
+  /* cloud%inv_cloud_effective_size, cloud%inv_inhom_effective_size (radiation_cloud.F90:74-88), m-1; only read by the
+   * SPARTACUS solvers; NULL = not allocated (no 3D effects / inhomogeneity size = cloud size) */
+  const double* inv_cloud_effective_size;   /* (ncol, nlev) */
+  const double* inv_inhom_effective_size;   /* (ncol, nlev) */
 } ecrad_b200_inputs;
 
 /* Outputs: components of flux_type (radiation_flux.F90:38-118).  Any pointer may be NULL. */

@@ -560,7 +560,21 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   double *fsd = o.dn_dir_g_prof + (size_t)nl1 * ng, *op = fsd + nlev;
   for (int jl = 0; jl < nlev; ++jl) fsd[jl] = A2(in->fractional_std, jcol, jl);
   for (int jl = 0; jl < nlev - 1; ++jl) op[jl] = A2(in->overlap_param, jcol, jl);
+  /* SPARTACUS also reads the half-level pressure/temperature (layer depth) and the cloud effective sizes */
+  const int spartacus = (sw ? cfg->i_solver_sw : cfg->i_solver_lw) == ECRAD_SOLVER_SPARTACUS;
+  double *sp = NULL, *p_hl = NULL, *t_hl = NULL, *ics = NULL, *iis = NULL;
+  if (spartacus) {
+    sp = (double*)malloc(sizeof(double) * (2 * (size_t)nl1 + 2 * (size_t)nlev));
+    p_hl = sp; t_hl = p_hl + nl1;
+    for (int jl = 0; jl < nl1; ++jl) { p_hl[jl] = A2(in->pressure_hl, jcol, jl); t_hl[jl] = A2(in->temperature_hl, jcol, jl); }
+    if (in->inv_cloud_effective_size) { ics = t_hl + nl1; for (int jl = 0; jl < nlev; ++jl) ics[jl] = A2(in->inv_cloud_effective_size, jcol, jl); }
+    if (in->inv_inhom_effective_size) { iis = t_hl + nl1 + nlev; for (int jl = 0; jl < nlev; ++jl) iis[jl] = A2(in->inv_inhom_effective_size, jcol, jl); }
+  }
   if (!sw) {
+    if (spartacus)
+      orc_spartacus_lw(t, cfg, nlev, p_hl, t_hl, frac, fsd, op, ics, iis, w->od_lw, w->planck_hl, w->od_lw_cloud, w->ssa_lw_cloud,
+                       w->g_lw_cloud, w->lw_emission, w->lw_albedo, &o);
+    else
     orc_tripleclouds_lw(t, cfg, nlev, frac, fsd, op, w->od_lw, w->planck_hl, w->od_lw_cloud, w->ssa_lw_cloud, w->g_lw_cloud,
                         w->lw_emission, w->lw_albedo, &o);
     if (out->cloud_cover_lw) out->cloud_cover_lw[jcol] = o.cloud_cover;
@@ -590,6 +604,9 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
       orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o.cloud_cover);
       free(reg); free(ods); free(U); free(V);
+    } else if (spartacus) {
+      orc_spartacus_sw(t, cfg, nlev, mu0, p_hl, t_hl, frac, fsd, op, ics, iis, w->od_sw, w->ssa_sw, w->g_sw, w->od_sw_cloud, w->ssa_sw_cloud,
+                       w->g_sw_cloud, w->incoming_sw, w->alb_diff, w->alb_dir, &o);
     } else {
       orc_tripleclouds_sw(t, cfg, nlev, mu0, frac, fsd, op, w->od_sw, w->ssa_sw, w->g_sw, w->od_sw_cloud, w->ssa_sw_cloud, w->g_sw_cloud,
                           w->incoming_sw, w->alb_diff, w->alb_dir, &o);
@@ -624,7 +641,7 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       }
     }
   }
-  free(buf);
+  free(buf); free(sp);
 }
 
 /* radiation_flux.F90:397-577 calc_surface_spectral (paths used by the test namelists) */
@@ -730,8 +747,8 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }
-  if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
-  if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
+  if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
+  if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   surface_spectral(t, cfg, jcol, out);
   free(w.w); free(phl_full);
   return 0;
