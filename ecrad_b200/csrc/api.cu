@@ -33,7 +33,7 @@ struct Buf {   // grow-only device buffer
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { N_IN = 26, N_OUT = 35, N_STAGE = 5 };
+enum { N_IN = 28, N_OUT = 35, N_STAGE = 5 };
 const char* kStageNames[N_STAGE] = {"gas_optics_lw", "gas_optics_sw", "cloud_optics_generator", "solver_lw", "solver_sw"};
 
 struct Slot {            // device staging of one tile's inputs and outputs
@@ -90,9 +90,18 @@ int upload(Handle* h, const Tp* src, size_t n, const Tp** dst) {
 // Which solver / model combinations have kernels.
 int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.struct_bytes != (int32_t)sizeof(ecrad_b200_config)) return fail(h, "ecrad_b200_config: struct_bytes mismatch (ABI)");
-  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS || s == ECRAD_SOLVER_TRIPLECLOUDS; };
+  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS || s == ECRAD_SOLVER_TRIPLECLOUDS || s == ECRAD_SOLVER_SPARTACUS; };
   if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw)))
-    return fail(h, "solver not available in this build (McICA, Tripleclouds and Cloudless are)");
+    return fail(h, "solver not available in this build (McICA, Tripleclouds, SPARTACUS and Cloudless are)");
+  if ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS)) {
+    if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN)   // radiation_config.F90:1134-1141
+      return fail(h, "SPARTACUS/Tripleclouds solvers can only do Exponential-Random overlap");
+    if (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS && c.do_sw_delta_scaling_with_gases)   // radiation_config.F90:1336-1339
+      return fail(h, "SW delta-Eddington scaling with gases not possible with SPARTACUS solver");
+    if (c.use_expm_everywhere) return fail(h, "use_expm_everywhere is not available in this build");
+    if (c.i_3d_sw_entrapment < ECRAD_ENTRAPMENT_ZERO || c.i_3d_sw_entrapment > ECRAD_ENTRAPMENT_MAXIMUM) return fail(h, "unknown sw_entrapment");
+    if (!(c.min_cloud_effective_size > 0.0) || !(c.max_cloud_od > 0.0)) return fail(h, "SPARTACUS: min_cloud_effective_size and max_cloud_od must be positive");
+  }
   const int gm = c.do_lw ? c.i_gas_model_lw : c.i_gas_model_sw;
   if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
     return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");
@@ -122,7 +131,8 @@ enum { N_WORK = 35 };
 void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
   const bool tc_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS, tc_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
-  const bool tc = tc_lw || tc_sw;
+  const bool sp_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_SPARTACUS, sp_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_SPARTACUS;
+  const bool tc = tc_lw || tc_sw || sp_lw || sp_sw;   // region fractions and overlap matrices (tc_prep_kernel)
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
   const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
   const size_t sz[N_WORK] = {
@@ -132,10 +142,10 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
-      8 * nc * (tc_lw ? tc_scratch_doubles_lw(nlev, (int)NG_LW) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
+      8 * nc * (sp_lw ? sp_scratch_doubles_lw(nlev, (int)NG_LW) : tc_lw ? tc_scratch_doubles_lw(nlev, (int)NG_LW) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
-      8 * nc * (tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
+      8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
       ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
@@ -198,7 +208,8 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   // cloud chain
   CK(h, cudaEventRecord(ev[4], s_cl));
   if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w[set], nc, nlev, s_cl);
-  if ((c.do_lw && c.solver_lw == ECRAD_SOLVER_TRIPLECLOUDS) || (c.do_sw && c.solver_sw == ECRAD_SOLVER_TRIPLECLOUDS))
+  if ((c.do_lw && (c.solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || c.solver_lw == ECRAD_SOLVER_SPARTACUS)) ||
+      (c.do_sw && (c.solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || c.solver_sw == ECRAD_SOLVER_SPARTACUS)))
     n += launch_tc_prep(c, in, h->w[set], nc, nlev, s_cl);
   CK(h, cudaEventRecord(ev[5], s_cl));
   if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
@@ -253,6 +264,9 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
                       !in->fractional_std || !in->iseed))
     return fail(h, "missing cloud input");
   if (c.use_aerosols && (!in->aerosol_mmr || !in->h2o_sat_liq)) return fail(h, "missing aerosol input (aerosol_mmr, h2o_sat_liq)");
+  if (c.do_3d_effects && ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS)) &&
+      !in->inv_cloud_effective_size)
+    return fail(h, "SPARTACUS with do_3d_effects needs cloud%%inv_cloud_effective_size");
   if (c.do_lw && (!out->lw_up || !out->lw_dn)) return fail(h, "flux%%lw_up/lw_dn must be allocated");
   if (c.do_sw && (!out->sw_up || !out->sw_dn)) return fail(h, "flux%%sw_up/sw_dn must be allocated");
   return 0;
@@ -260,6 +274,7 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
 
 void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* in, const ecrad_b200_outputs* out, InDesc* id, OutDesc* od) {
   const int nl = nlev, nl1 = nlev + 1;
+  const bool sp = (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS);
   const InDesc ins[N_IN] = {
       {in->cos_sza, 1, 8}, {in->skin_temperature, 1, 8}, {in->sw_albedo, c.n_albedo_sw, 8}, {in->sw_albedo_direct, c.n_albedo_sw, 8},
       {in->lw_emissivity, c.n_emiss_lw, 8}, {in->iseed, 1, 4}, {in->pressure_hl, nl1, 8}, {in->temperature_hl, nl1, 8},
@@ -267,7 +282,8 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
       {in->cfc12_mmr, nl, 8}, {in->hcfc22_mmr, nl, 8}, {in->ccl4_mmr, nl, 8}, {in->o3_mmr, nl, 8},
       {in->cloud_fraction, nl, 8}, {in->q_liq, nl, 8}, {in->q_ice, nl, 8}, {in->re_liq, nl, 8}, {in->re_ice, nl, 8},
       {in->overlap_param, nl - 1, 8}, {in->fractional_std, nl, 8},
-      {c.use_aerosols ? in->aerosol_mmr : nullptr, nl * c.n_aerosol_types, 8}, {c.use_aerosols ? in->h2o_sat_liq : nullptr, nl, 8}};
+      {c.use_aerosols ? in->aerosol_mmr : nullptr, nl * c.n_aerosol_types, 8}, {c.use_aerosols ? in->h2o_sat_liq : nullptr, nl, 8},
+      {sp ? in->inv_cloud_effective_size : nullptr, nl, 8}, {sp ? in->inv_inhom_effective_size : nullptr, nl, 8}};
   for (int i = 0; i < N_IN; ++i) id[i] = ins[i];
   const OutDesc outs[N_OUT] = {
       {out->lw_up, 0, nl1}, {out->lw_dn, 0, nl1}, {out->lw_up_clear, 0, nl1}, {out->lw_dn_clear, 0, nl1},
@@ -286,7 +302,7 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
   for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
 }
 
-// Build the kernel-facing views from 25 input / 35 output base pointers (device) with leading dimension ld.
+// Build the kernel-facing views from 28 input / 35 output base pointers (device) with leading dimension ld.
 void make_views(void* const* ip, void* const* op, int ld, int ld_out, double solar_irradiance, DevIn& di, DevOut& dout) {
   di.cos_sza = (const double*)ip[0]; di.skin_t = (const double*)ip[1]; di.sw_albedo = (const double*)ip[2];
   di.sw_albedo_direct = (const double*)ip[3]; di.lw_emissivity = (const double*)ip[4]; di.iseed = (const int32_t*)ip[5];
@@ -295,6 +311,7 @@ void make_views(void* const* ip, void* const* op, int ld, int ld_out, double sol
   di.frac = (double*)ip[17]; di.q_liq = (const double*)ip[18]; di.q_ice = (const double*)ip[19];
   di.re_liq = (const double*)ip[20]; di.re_ice = (const double*)ip[21]; di.overlap = (const double*)ip[22]; di.fsd = (const double*)ip[23];
   di.aerosol_mmr = (const double*)ip[24]; di.h2o_sat_liq = (const double*)ip[25];
+  di.inv_cloud_size = (const double*)ip[26]; di.inv_inhom_size = (const double*)ip[27];
   di.solar_irradiance = solar_irradiance; di.ld = ld;
   double** o = (double**)&dout;
   for (int k = 0; k < N_OUT; ++k) o[k] = (double*)op[k];
@@ -327,7 +344,7 @@ int ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_
 }
 void ecrad_b200_tables_free(ecrad_b200_tables* t) { delete t; }
 
-const char* ecrad_b200_version(void) { return "ecrad_b200 0.2 (sm_100a; RRTMG-IFS / ecCKD gas optics; McICA, Tripleclouds, Cloudless; fp64)"; }
+const char* ecrad_b200_version(void) { return "ecrad_b200 0.3 (sm_100a; RRTMG-IFS / ecCKD gas optics; McICA, Tripleclouds, SPARTACUS, Cloudless; fp64)"; }
 const char* ecrad_b200_last_error(void* handle) {
   if (handle) return ((Handle*)handle)->err.c_str();
   return g_last_error.c_str();
@@ -406,11 +423,18 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
+  d.sp.do_3d_effects = cfg->do_3d_effects; d.sp.entrapment = cfg->i_3d_sw_entrapment;
+  d.sp.do_3d_lw_multilayer_effects = cfg->do_3d_lw_multilayer_effects; d.sp.do_lw_side_emissivity = cfg->do_lw_side_emissivity;
+  d.sp.max_gas_od_3d = cfg->max_gas_od_3d; d.sp.max_cloud_od = cfg->max_cloud_od; d.sp.max_3d_transfer_rate = cfg->max_3d_transfer_rate;
+  d.sp.min_cloud_effective_size = cfg->min_cloud_effective_size; d.sp.overhead_sun_factor = cfg->overhead_sun_factor;
+  d.sp.overhang_factor = cfg->overhang_factor; d.sp.clear_to_thick_fraction = cfg->clear_to_thick_fraction;
   {
     // host-entry tile (measured, two overlapping compute sets): 2048 columns for the RRTMG-sized spectra, 4096 for the ecCKD
     // ones (less work per column; their end-to-end time is PCIe-bound and wants more, not bigger, tiles); short first/last tiles
     const int ngs = (cfg->do_lw ? cfg->n_g_lw : 0) + (cfg->do_sw ? cfg->n_g_sw : 0);
-    const int t = ngs >= 200 ? 2048 : 4096;
+    int t = ngs >= 200 ? 2048 : 4096;
+    // SPARTACUS keeps 3x3 matrices per (layer, g-point) between its kernels: about 5x the scratch per column
+    if ((cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS)) t /= 4;
     h->tile_cols = t; h->edge_cols = t / 4;
   }
   if (const char* s = getenv("ECRAD_B200_TILE")) { int v = atoi(s); if (v > 0) h->tile_cols = h->tile_cols_device = v; }
@@ -535,15 +559,15 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     const bool lw = (k <= 3) || k == 10 || k == 11 || (k >= 13 && k <= 16) || k == 29 || k == 30 || k == 31;
     if (lw && !c.do_lw) return false;
     if (!lw && !c.do_sw) return false;
-    if (k == 11) return mcica_lw || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS);
-    if (k == 12) return mcica_sw || (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS);
+    if (k == 11) return mcica_lw || (c.do_lw && (c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || c.i_solver_lw == ECRAD_SOLVER_SPARTACUS));
+    if (k == 12) return mcica_sw || (c.do_sw && (c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || c.i_solver_sw == ECRAD_SOLVER_SPARTACUS));
     if (k == 10) return c.do_lw_derivatives != 0;
     if (k >= 23 && k <= 26) return c.do_surface_sw_spectral_flux != 0 && (k < 25 || c.do_clear);
     if (k == 27 || k == 28) return c.do_canopy_fluxes_sw != 0;
     if (k == 29) return c.do_canopy_fluxes_lw != 0;
     if (k >= 30) {   // per-band profiles: Cloudless and Tripleclouds solvers with do_save_spectral_flux
       const int sol = k <= 31 ? c.i_solver_lw : c.i_solver_sw;
-      return c.do_save_spectral_flux != 0 && (sol == ECRAD_SOLVER_CLOUDLESS || sol == ECRAD_SOLVER_TRIPLECLOUDS);
+      return c.do_save_spectral_flux != 0 && (sol == ECRAD_SOLVER_CLOUDLESS || sol == ECRAD_SOLVER_TRIPLECLOUDS || sol == ECRAD_SOLVER_SPARTACUS);
     }
     return true;
   };

@@ -6,6 +6,7 @@
 #include "cloud_core.h"
 #include "ecckd_core.h"
 #include "gas_core.h"
+#include "sp_core.h"
 
 namespace ecb {
 
@@ -19,6 +20,7 @@ struct DevIn {
   double* frac;          // in/out (cropped)
   const double *q_liq, *q_ice, *re_liq, *re_ice, *overlap, *fsd;
   const double *aerosol_mmr, *h2o_sat_liq;   // (ld, nlev, ntype), (ld, nlev); only with aerosols
+  const double *inv_cloud_size, *inv_inhom_size;   // (ld, nlev) cloud%inv_cloud_effective_size / inv_inhom_effective_size (SPARTACUS); may be NULL
   double solar_irradiance;
   int ld;
 };
@@ -67,6 +69,7 @@ struct DevCfg {
   int ckd_ngas_lw, ckd_nlut_lw, ckd_ngas_sw, ckd_nlut_sw;   // ecCKD: gases / look-up-table gases per model (shared-memory sizing)
   int ng_lw, ng_sw, nb_lw, nb_sw;   // spectral sizes: RRTMG 140/112/16/14; ecCKD ng = nb = 32/64/96
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
+  SpCfg sp;                      // SPARTACUS scalars
 };
 
 enum { LW_SCR_ARRAYS = 5, SW_SCR_ARRAYS = 10 };
@@ -107,6 +110,11 @@ size_t tc_scratch_doubles_sw(int nlev, int ng);
 int launch_tc_prep(const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_tc_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_tc_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+// SPARTACUS: solver_sp.cu
+size_t sp_scratch_doubles_lw(int nlev, int ng);
+size_t sp_scratch_doubles_sw(int nlev, int ng);
+int launch_sp_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../ecrad_b200/csrc/tables.h"
+#include "../ecrad_b200/csrc/sp_core.h"
 
 using namespace ecb;
 
@@ -120,5 +121,15 @@ int hc_cloud_generator(void* p, int ng, int nlev, int scheme, int32_t iseed, dou
   }
   return 0;
 }
+
+// SPARTACUS matrix routines of sp_core.h (what the CUDA kernels inline), one matrix in C row-major order
+void hc_expm(int m, double* a, int sw_pattern) {
+  double W[5 * 81];
+  if (m == 9 && sw_pattern) sp_expm<9, true>(a, W);
+  else if (m == 9) sp_expm<9, false>(a, W);
+  else if (m == 6) sp_expm<6, false>(a, W);
+}
+void hc_fast_expm_exchange_3(double a, double b, double c, double d, double* r) { sp_fast_expm_exchange_3(a, b, c, d, r); }
+void hc_m3_solve_mat(const double* A, const double* B, double* X) { m3_solve_mat(A, B, X); }
 
 }  // extern "C"

@@ -22,6 +22,9 @@ def load():
     lib.hc_gas_column.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, C.c_double] + [dp] * 7 + [ip, ip]
     lib.hc_cloud_generator.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_double, dp, dp, C.c_double, dp, C.c_int, dp, dp]
     lib.hc_table_sizes.argtypes = [C.c_void_p, ip, ip]
+    lib.hc_expm.argtypes = [C.c_int, dp, C.c_int]
+    lib.hc_fast_expm_exchange_3.argtypes = [C.c_double] * 4 + [dp]
+    lib.hc_m3_solve_mat.argtypes = [dp, dp, dp]
     h = lib.hc_load(TABLES.encode())
     assert h, "hostcheck: cannot pack tables"
     return lib, h

@@ -35,6 +35,8 @@ class Oracle:
                                     C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_int]
         L.orc_gas_optics_column.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int,
                                             C.POINTER(abi.Inputs)] + [abi.c_dp] * 6
+        L.orc_expm.argtypes = [C.c_int, abi.c_dp, C.c_int]
+        L.orc_fast_expm_exchange_3.argtypes = [C.c_double] * 4 + [abi.c_dp]
         self.config = config
         self.cfg = config.to_struct()
         tables = config.tables_path()

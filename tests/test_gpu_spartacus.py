@@ -1,0 +1,133 @@
+"""GPU parity of the SPARTACUS solvers (solver_sp.cu, through the C-ABI) against the CPU oracle (oracle/spartacus.c).
+
+The reference ships no SPARTACUS output (its ctest targets `spartacus*` are XFAIL_VALIDATION without a reference file), so the
+oracle is pinned indirectly (tests/test_oracle_spartacus.py) and the bar here is the fp64 tolerance of BASELINE.json's north_star:
+|flux - oracle| <= 1e-6 W m-2 on every flux component, cloud cover and cropped fraction bit-exact.
+"""
+import numpy as np
+import pytest
+
+from ecrad_b200 import inputs as I
+from ecrad_b200.config import RadiationConfig
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-6  # W m-2
+NLEV = 137
+FLUXES = ["lw_up", "lw_dn", "lw_up_clear", "lw_dn_clear", "sw_up", "sw_dn", "sw_dn_direct", "sw_up_clear", "sw_dn_clear",
+          "sw_dn_direct_clear"]
+OTHERS = ["lw_derivatives", "lw_dn_surf_g", "lw_dn_surf_clear_g", "lw_up_toa_g", "lw_up_toa_clear_g", "sw_dn_diffuse_surf_g",
+          "sw_dn_direct_surf_g", "sw_dn_diffuse_surf_clear_g", "sw_dn_direct_surf_clear_g", "sw_up_toa_g", "sw_up_toa_clear_g",
+          "sw_dn_surf_band", "sw_dn_direct_surf_band", "sw_dn_surf_clear_band", "sw_dn_direct_surf_clear_band",
+          "sw_dn_diffuse_surf_canopy", "sw_dn_direct_surf_canopy", "lw_dn_surf_canopy"]
+BANDS = ["lw_up_band", "lw_dn_band", "sw_up_band", "sw_dn_band", "sw_dn_direct_band"]
+SP = dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)
+
+
+def run_pair(kw, raw, n, nlev=NLEV, spectral_profiles=False):
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+
+    cfg = RadiationConfig(**kw).consolidate()
+    h = setup_radiation(cfg)
+    try:
+        out = h.radiation(I.to_radiation_inputs(raw, cfg), n, nlev, spectral_profiles=spectral_profiles)
+    finally:
+        h.finalize()
+    ref = Oracle(cfg).radiation(I.to_radiation_inputs(raw, cfg), n, nlev, spectral_profiles=spectral_profiles)
+    return out, ref
+
+
+def compare(out, ref, names, tol=TOL):
+    worst = {}
+    for nm in names:
+        a, b = out[nm], ref[nm]
+        assert a.shape == b.shape, nm
+        m = np.isfinite(b)
+        assert np.isfinite(a[m]).all(), f"{nm}: non-finite values"
+        worst[nm] = np.abs(a[m] - b[m]).max() if m.any() else 0.0
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, f"max |gpu - oracle| (W m-2) above {tol}: {bad}"
+    return worst
+
+
+def check_exact(out, ref):
+    assert np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+    assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
+    assert np.array_equal(out["cloud_fraction"], ref["cloud_fraction"])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sw_entrapment_name="Maximum"), dict(sw_entrapment_name="Zero"),
+                                dict(sw_entrapment_name="Edge-only"), dict(sw_entrapment_name="Non-fractal"),
+                                dict(do_3d_effects=False), dict(do_3d_lw_multilayer_effects=True),
+                                dict(do_lw_side_emissivity=False, clear_to_thick_fraction=0.3),
+                                dict(use_aerosols=True, do_lw_cloud_scattering=False)])
+def test_spartacus_meridian_vs_oracle(meridian_raw, kw):
+    """The reference's own 32-column slice (the input of its `spartacus` / `spartacus_maxentr` ctest targets)."""
+    out, ref = run_pair({**SP, **kw}, meridian_raw, 32, spectral_profiles=True)
+    compare(out, ref, FLUXES + OTHERS + BANDS)
+    check_exact(out, ref)
+    for nm in BANDS:   # band sums = broadband
+        assert np.abs(out[nm].sum(axis=0) - out[nm[:-5]]).max() <= 1e-9, nm
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sw_entrapment_name="Maximum", use_beta_overlap=True)])
+def test_spartacus_synthetic_columns_vs_oracle(meridian_raw, kw):
+    """300 perturbed columns: other cloud profiles and sun angles (incl. night columns and very low sun)."""
+    n = 300
+    raw = I.synthetic_columns(meridian_raw, n)
+    out, ref = run_pair({**SP, **kw}, raw, n)
+    compare(out, ref, FLUXES + OTHERS)
+    check_exact(out, ref)
+
+
+def test_spartacus_ecckd_vs_oracle(meridian_raw):
+    """SPARTACUS on the 32-term ecCKD spectra (per-g-point cloud optics): the same kernels, other spectral sizes."""
+    kw = dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, **SP)
+    out, ref = run_pair(kw, meridian_raw, 32)
+    compare(out, ref, FLUXES + OTHERS)
+    check_exact(out, ref)
+
+
+def test_spartacus_without_3d_is_tripleclouds(meridian_raw):
+    """Physical cross-check on the GPU alone: with 3D effects off SPARTACUS and Tripleclouds solve the same SW equations."""
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    res = {}
+    for name in ("SPARTACUS", "Tripleclouds"):
+        cfg = RadiationConfig(sw_solver_name=name, lw_solver_name=name, do_3d_effects=False).consolidate()
+        h = setup_radiation(cfg)
+        res[name] = h.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+        h.finalize()
+    for nm in ("sw_up", "sw_dn", "sw_dn_direct"):
+        assert np.abs(res["SPARTACUS"][nm] - res["Tripleclouds"][nm]).max() < 1e-5, nm
+
+
+def test_spartacus_tiling_and_column_range(meridian_raw):
+    """Host-entry tiles must not show: 700 columns in one tile == tiles of 128; istartcol:iendcol leaves the rest untouched."""
+    from ecrad_b200.radiation_interface import setup_radiation
+
+    n = 700
+    cfg = RadiationConfig(**SP).consolidate()
+    raw = I.synthetic_columns(meridian_raw, n)
+    h = setup_radiation(cfg)
+    h.set_option("tile_cols", 1024)
+    a = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    h.set_option("tile_cols", 128)
+    b = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    for nm in FLUXES + OTHERS:
+        assert np.array_equal(a[nm], b[nm], equal_nan=True), nm
+    c = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV, istartcol=101, iendcol=400)
+    h.finalize()
+    for nm in FLUXES:
+        assert np.array_equal(c[nm][100:400], a[nm][100:400]), nm
+        assert np.isnan(c[nm][:100]).all() and np.isnan(c[nm][400:]).all(), nm
+
+
+def test_spartacus_error_behaviour():
+    from ecrad_b200.radiation_interface import RadiationError, setup_radiation
+
+    with pytest.raises(RadiationError, match="Exponential-Random"):
+        setup_radiation(RadiationConfig(overlap_scheme_name="Max-Ran", **SP).consolidate())
+    with pytest.raises(RadiationError, match="use_expm_everywhere"):
+        setup_radiation(RadiationConfig(use_expm_everywhere=True, **SP).consolidate())
