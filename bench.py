@@ -112,6 +112,9 @@ WORKLOADS = {
                              "configCY49R1_ecckd.nam + 64-term models, use_aerosols=false", "BASELINE.json configs[2]"),
     "tripleclouds_rrtmg": (dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"), 10000, "Tripleclouds LW+SW, RRTMG 140+112 g-points",
                            "configCY49R1.nam, Tripleclouds, use_aerosols=false", "extra"),
+    "spartacus_rrtmg": (dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True), 50000,
+                        "SPARTACUS LW+SW 3 regions with 3D effects, RRTMG 140+112 g-points",
+                        "configCY49R1.nam, SPARTACUS, do_3d_effects=true, use_aerosols=false (ctest `spartacus`)", "BASELINE.json configs[4]"),
 }
 
 
@@ -147,7 +150,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_sample or min(args.ncol, 10000)
+        sample = args.cpu_sample or min(args.ncol, 2000 if args.workload.startswith("spartacus") else 10000)
         warm = max(args.warmup, 1)
         for _ in range(warm - 1):
             cpu_arm(cfg, raw, sample, 0, ncores, 1)
@@ -199,7 +202,8 @@ def main():
 
     # ---- host buffers (pinned) for the e2e path ----
     pinned, host_in = {}, {}
-    for nm, dt, _ in abi.INPUT_ARRAYS:
+    in_arrays = [(nm, dt) for nm, dt, _ in abi.INPUT_ARRAYS if nm in inp]   # optional inputs (aerosols, cloud sizes) may be absent
+    for nm, dt in in_arrays:
         a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
         t = torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory()   # (rows, ncol) C order == Fortran (ncol, rows)
         pinned[nm] = t
@@ -215,7 +219,7 @@ def main():
         host_out[nm] = t
         setattr(ost_host, nm, C.cast(t.data_ptr(), abi.c_dp))
     keep_h, ist_host = abi.make_inputs(host_in, inp["solar_irradiance"])
-    for nm, dt, _ in abi.INPUT_ARRAYS:   # make_inputs must not have copied: point at the pinned memory
+    for nm, dt in in_arrays:   # make_inputs must not have copied: point at the pinned memory
         setattr(ist_host, nm, C.cast(pinned[nm].data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
     h2d_bytes = sum(t.numel() * t.element_size() for t in pinned.values()) + ncol * 8
     d2h_bytes = sum(t.numel() * 8 for t in host_out.values()) + ncol * NLEV * 8
@@ -224,7 +228,7 @@ def main():
     dev_in, ist_dev = {}, abi.Inputs()
     ist_dev.struct_bytes = C.sizeof(abi.Inputs)
     ist_dev.solar_irradiance = inp["solar_irradiance"]
-    for nm, dt, _ in abi.INPUT_ARRAYS:
+    for nm, dt in in_arrays:
         dev_in[nm] = pinned[nm].to(dev)
         setattr(ist_dev, nm, C.cast(dev_in[nm].data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
     dev_out, ost_dev = {}, abi.Outputs()
@@ -378,7 +382,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            sample = args.cpu_sample or min(ncol, 10000)
+            sample = args.cpu_sample or min(ncol, 2000 if args.workload.startswith("spartacus") else 10000)
             v, sec = cpu_arm(cfg, raw, sample, 0, ncores, 3)
             cpu = {"value": v, "unit": "columns/s", "cores": ncores, "kind": "port",
                    "sample": f"{sample} columns of the same workload, 3 repetitions ({sec:.2f} s each), C/OpenMP oracle port"}

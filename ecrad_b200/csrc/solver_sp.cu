@@ -51,8 +51,8 @@ __device__ __forceinline__ int sp_first_thick_g(int* s_first, bool act, int g, i
 // =========================================================================================================
 // SW: layer properties (radiation_spartacus_sw.F90:420-835)
 // =========================================================================================================
-template <class SD>
-__global__ void __launch_bounds__(SD::THREADS)
+template <class SD, int MINB>
+__global__ void __launch_bounds__(SD::THREADS, MINB)
 sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   __shared__ int s_first;
   const int l = blockIdx.x, c = blockIdx.y, g = threadIdx.x;
@@ -118,7 +118,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   }
   // ---- 9x9 matrix exponential (:658-770) ----
   const double one_over_mu0 = 1.0 / mu0;
-  double G[81], W[5 * 81];
+  double G[81], W[3 * 81];
   for (int k = 0; k < 81; ++k) G[k] = 0.0;
 #pragma unroll
   for (int jr = 0; jr < 3; ++jr) {
@@ -216,8 +216,8 @@ __device__ __forceinline__ void sp_load_m3(const double* __restrict__ p, double*
 // =========================================================================================================
 // SW: albedo matrices upward, fluxes downward (radiation_spartacus_sw.F90:837-1590)
 // =========================================================================================================
-template <class SD>
-__global__ void __launch_bounds__(SD::THREADS)
+template <class SD, int MINB>
+__global__ void __launch_bounds__(SD::THREADS, MINB)
 sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
@@ -505,8 +505,8 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
 // =========================================================================================================
 // LW: layer properties (radiation_spartacus_lw.F90:349-780); no LW aerosol scattering: clear-region ssa = g = 0
 // =========================================================================================================
-template <class SD>
-__global__ void __launch_bounds__(SD::THREADS)
+template <class SD, int MINB>
+__global__ void __launch_bounds__(SD::THREADS, MINB)
 sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   __shared__ int s_first;
   const int l = blockIdx.x, c = blockIdx.y, g = threadIdx.x;
@@ -565,7 +565,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     return;
   }
   // ---- 6x6 matrix exponential (:596-727) ----
-  double G[36], W[5 * 36], planck_top[6], planck_diff[6], solution0[6], solution_diff[6];
+  double G[36], W[3 * 36], planck_top[6], planck_diff[6], solution0[6], solution_diff[6];
   for (int k = 0; k < 36; ++k) G[k] = 0.0;
 #pragma unroll
   for (int jr = 0; jr < 3; ++jr) {
@@ -651,8 +651,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
 // =========================================================================================================
 // LW: albedo/source upward, fluxes downward, derivatives (radiation_spartacus_lw.F90:782-1060)
 // =========================================================================================================
-template <class SD>
-__global__ void __launch_bounds__(SD::THREADS)
+template <class SD, int MINB>
+__global__ void __launch_bounds__(SD::THREADS, MINB)
 sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x, g = threadIdx.x, nl1 = nlev + 1;
@@ -885,20 +885,32 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
 }
 
 // =========================================================================================================
+// resident CTAs per SM asked of the compiler (register budget = 65536 / (MINB * threads)); tuning knobs for the measurement scripts
+static int sp_minb(const char* env, int dflt) {
+  const char* s = getenv(env);
+  const int v = s ? atoi(s) : dflt;
+  return v <= 2 ? 2 : 4;
+}
+// measured on the B200 (tools/sp_minb_sweep.sh, 20 000 columns): 2/2 -> 97 k, 4/2 -> 104 k, 2/4 -> 107 k, 4/4 -> 115 k columns/s
+#define SP_DISPATCH_MINB(minb, CALL) \
+  switch (minb) { case 2: { constexpr int MB = 2; CALL; } break; default: { constexpr int MB = 4; CALL; } break; }
+
 template <class SD>
 static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  sp_sw_layer_kernel<SD><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  SP_DISPATCH_MINB(mb_layer, (sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev)));
   const size_t sm = sizeof(double) * (6 * (nlev + 1) + 6 * SP_LCH * SD::RS + 2 * SD::NB) + sp_shared_bytes(nlev);
-  cudaFuncSetAttribute(sp_sw_sweep_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  sp_sw_sweep_kernel<SD><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+  SP_DISPATCH_MINB(mb_sweep, (cudaFuncSetAttribute(sp_sw_sweep_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
+                              sp_sw_sweep_kernel<SD, MB><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev)));
   return 2;
 }
 template <class SD>
 static int launch_sp_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  sp_lw_layer_kernel<SD><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  SP_DISPATCH_MINB(mb_layer, (sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev)));
   const size_t sm = sizeof(double) * (5 * (nlev + 1) + 4 * SP_LCH_LW * SD::RS) + tc_shared_bytes(nlev);
-  cudaFuncSetAttribute(sp_lw_sweep_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  sp_lw_sweep_kernel<SD><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev);
+  SP_DISPATCH_MINB(mb_sweep, (cudaFuncSetAttribute(sp_lw_sweep_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
+                              sp_lw_sweep_kernel<SD, MB><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev)));
   return 2;
 }
 int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {

@@ -100,11 +100,13 @@ HDN void sp_lu_subst(const double* LU, double* X, int ncols, int ldx) {
   }
 }
 
-// Matrix exponential of A (M x M, M = 6 or 9) in place; W: 5 * M * M doubles of thread-local work space.
+// Matrix exponential of A (M x M, M = 6 or 9) in place; W: 3 * M * M doubles of thread-local work space.  Four matrices are
+// live at any time (A and the three of W): the two Pade polynomials overwrite A^6 and A^4 element by element, the product
+// U = A * (b7 A^6 + b5 A^4 + b3 A^2 + b1 I) overwrites A^2, and the squarings ping-pong between A and that buffer.
 template <int M, bool SWP>
 HD void sp_expm(double* A, double* W) {
   constexpr int MM = M * M;
-  double *A2 = W, *A4 = W + MM, *A6 = W + 2 * MM, *U = W + 3 * MM, *V = W + 4 * MM;
+  double *A2 = W, *A4 = W + MM, *A6 = W + 2 * MM;
   double normA = 0.0;
   for (int j3 = 0; j3 < M; ++j3) {
     double sum_column = 0.0;
@@ -120,21 +122,19 @@ HD void sp_expm(double* A, double* W) {
   sp_matmul<M, SWP>(A, A, A2);
   sp_matmul<M, SWP>(A2, A2, A4);
   sp_matmul<M, SWP>(A2, A4, A6);
-  for (int i = 0; i < MM; ++i) V[i] = 1.0 * A6[i] + 1512.0 * A4[i] + 277200.0 * A2[i];
-  for (int j = 0; j < M; ++j) V[j * M + j] = V[j * M + j] + 8648640.0;
-  sp_matmul<M, SWP>(A, V, U);
   for (int i = 0; i < MM; ++i) {
-    double v = 56.0 * A6[i] + 25200.0 * A4[i] + 1995840.0 * A2[i];
-    if (i % (M + 1) == 0) v = v + 17297280.0;
-    V[i] = v - U[i];
-    U[i] = 2.0 * U[i];
+    const double a2 = A2[i], a4 = A4[i], a6 = A6[i];
+    double w1 = 1.0 * a6 + 1512.0 * a4 + 277200.0 * a2;        // c(8) A6 + c(6) A4 + c(4) A2
+    double v = 56.0 * a6 + 25200.0 * a4 + 1995840.0 * a2;      // c(7) A6 + c(5) A4 + c(3) A2
+    if (i % (M + 1) == 0) { w1 = w1 + 8648640.0; v = v + 17297280.0; }
+    A6[i] = w1; A4[i] = v;
   }
-  sp_lu<M>(V);
-  sp_lu_subst<M>(V, U, M, M);
-  for (int i = 0; i < MM; ++i) A[i] = U[i];
-  for (int j = 0; j < M; ++j) A[j * M + j] = A[j * M + j] + 1.0;
-  // repeated squaring, ping-pong between A and A2
-  double *src = A, *dst = A2;
+  sp_matmul<M, SWP>(A, A6, A2);                                  // U
+  for (int i = 0; i < MM; ++i) { A4[i] = A4[i] - A2[i]; A2[i] = 2.0 * A2[i]; }   // V - U, 2 U
+  sp_lu<M>(A4);
+  sp_lu_subst<M>(A4, A2, M, M);
+  for (int j = 0; j < M; ++j) A2[j * M + j] = A2[j * M + j] + 1.0;
+  double *src = A2, *dst = A;
   for (int k = 0; k < expo; ++k) {
     sp_matmul<M, SWP>(src, src, dst);
     double* t = src; src = dst; dst = t;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # one bench line per extra workload (stage times from the serialised pass)
-for w in "$@"; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+for w in "$@"; do python bench.py --workload $w --steps ${STEPS:-5} --warmup 3 --no-cpu-baseline ${EXTRA} 2>&1 | tail -1 | python -c "
 import json,sys
 for l in sys.stdin:
     try: d=json.loads(l)
