@@ -451,6 +451,8 @@ def test_device_resident_entry_matches_host_entry(handles, meridian_raw):
     ist = abi.Inputs(); ist.struct_bytes = C.sizeof(abi.Inputs); ist.solar_irradiance = inp["solar_irradiance"]
     keep = {}
     for nm, dt, _ in abi.INPUT_ARRAYS:
+        if nm not in inp:   # optional inputs (cloud effective sizes: SPARTACUS only)
+            continue
         a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
         t = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)   # (rows, ncol) C-order == (ncol, rows) Fortran order
         keep[nm] = t
@@ -484,12 +486,16 @@ def test_device_entry_with_separate_leading_dimensions(handles, meridian_raw):
     dev = torch.device("cuda:0")
     keep = {}
     for nm, dt, _ in abi.INPUT_ARRAYS:
+        if nm not in inp:   # optional inputs (cloud effective sizes: SPARTACUS only)
+            continue
         a = np.asfortranarray(inp[nm], dtype=np.int32 if dt == "i4" else np.float64)
         keep[nm] = torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)   # (rows, n): leading dimension n
     outs = {nm: torch.full((NLEV + 1, n), float("nan"), dtype=torch.float64, device=dev) for nm in FLUXES}
     for c0, nc in ((0, n1), (n1, n - n1)):
         ist = abi.Inputs(); ist.struct_bytes = C.sizeof(abi.Inputs); ist.solar_irradiance = inp["solar_irradiance"]
         for nm, dt, _ in abi.INPUT_ARRAYS:
+            if nm not in keep:
+                continue
             esz = 4 if dt == "i4" else 8
             setattr(ist, nm, C.cast(keep[nm].data_ptr() + esz * c0, abi.c_ip if dt == "i4" else abi.c_dp))
         ost = abi.Outputs(); ost.struct_bytes = C.sizeof(abi.Outputs)

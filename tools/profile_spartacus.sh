@@ -1,7 +1,7 @@
 #!/bin/bash
 # SPARTACUS measurement round (run on the GPU box through gpurun): bench line, ncu launch list, --set full captures of the
 # four SPARTACUS kernels.   tools/profile_spartacus.sh <tag> [ncol]
-TAG=${1:-r1h}
+TAG=${1:-r1i}
 NCOL=${2:-50000}
 OUT=gpurun_out
 mkdir -p $OUT
