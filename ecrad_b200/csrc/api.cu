@@ -90,9 +90,12 @@ int upload(Handle* h, const Tp* src, size_t n, const Tp** dst) {
 // Which solver / model combinations have kernels.
 int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.struct_bytes != (int32_t)sizeof(ecrad_b200_config)) return fail(h, "ecrad_b200_config: struct_bytes mismatch (ABI)");
-  auto solver_ok = [](int s) { return s == ECRAD_SOLVER_MCICA || s == ECRAD_SOLVER_CLOUDLESS || s == ECRAD_SOLVER_TRIPLECLOUDS || s == ECRAD_SOLVER_SPARTACUS; };
-  if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw)))
-    return fail(h, "solver not available in this build (McICA, Tripleclouds, SPARTACUS and Cloudless are)");
+  auto solver_ok = [](int s) { return s >= ECRAD_SOLVER_CLOUDLESS && s <= ECRAD_SOLVER_TRIPLECLOUDS; };
+  if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw))) return fail(h, "unknown solver");
+  if (c.do_lw && c.do_sw && ((c.i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) != (c.i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS)))   // radiation_config.F90:1341-1349
+    return fail(h, "if one solver is \"Homogeneous\" then the other must be");
+  if (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS && c.do_sw_delta_scaling_with_gases)
+    return fail(h, "do_sw_delta_scaling_with_gases is not available in this build");
   if ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS)) {
     if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN)   // radiation_config.F90:1134-1141
       return fail(h, "SPARTACUS/Tripleclouds solvers can only do Exponential-Random overlap");
@@ -130,7 +133,9 @@ enum { N_WORK = 35 };
 // bytes of every per-tile scratch array for `cols` columns (all linear in cols)
 void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
-  const bool tc_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS, tc_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
+  // the Homogeneous solvers run on the Tripleclouds kernels
+  const bool tc_lw = h->cfg.do_lw && (h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || h->cfg.i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS),
+             tc_sw = h->cfg.do_sw && (h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || h->cfg.i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS);
   const bool sp_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_SPARTACUS, sp_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_SPARTACUS;
   const bool tc = tc_lw || tc_sw || sp_lw || sp_sw;   // region fractions and overlap matrices (tc_prep_kernel)
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
@@ -208,8 +213,8 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   // cloud chain
   CK(h, cudaEventRecord(ev[4], s_cl));
   if (c.do_clouds) n += launch_cloud(h->T, c, in, h->w[set], nc, nlev, s_cl);
-  if ((c.do_lw && (c.solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || c.solver_lw == ECRAD_SOLVER_SPARTACUS)) ||
-      (c.do_sw && (c.solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || c.solver_sw == ECRAD_SOLVER_SPARTACUS)))
+  auto regions = [](int s) { return s == ECRAD_SOLVER_TRIPLECLOUDS || s == ECRAD_SOLVER_SPARTACUS || s == ECRAD_SOLVER_HOMOGENEOUS; };
+  if ((c.do_lw && regions(c.solver_lw)) || (c.do_sw && regions(c.solver_sw)))
     n += launch_tc_prep(c, in, h->w[set], nc, nlev, s_cl);
   CK(h, cudaEventRecord(ev[5], s_cl));
   if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
@@ -344,7 +349,7 @@ int ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_
 }
 void ecrad_b200_tables_free(ecrad_b200_tables* t) { delete t; }
 
-const char* ecrad_b200_version(void) { return "ecrad_b200 0.3 (sm_100a; RRTMG-IFS / ecCKD gas optics; McICA, Tripleclouds, SPARTACUS, Cloudless; fp64)"; }
+const char* ecrad_b200_version(void) { return "ecrad_b200 0.3 (sm_100a; RRTMG-IFS / ecCKD gas optics; McICA, Tripleclouds, SPARTACUS, Homogeneous, Cloudless; fp64)"; }
 const char* ecrad_b200_last_error(void* handle) {
   if (handle) return ((Handle*)handle)->err.c_str();
   return g_last_error.c_str();
@@ -418,6 +423,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.is_homogeneous = (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS);   // radiation_config.F90:1351-1356
   d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;
   d.ckd_ngas_lw = P.ckd.lw.ngas; d.ckd_nlut_lw = P.ckd.lw.nlut; d.ckd_ngas_sw = P.ckd.sw.ngas; d.ckd_nlut_sw = P.ckd.sw.nlut;
   d.cloud_fraction_threshold = cfg->cloud_fraction_threshold; d.cloud_mixing_ratio_threshold = cfg->cloud_mixing_ratio_threshold;
@@ -567,7 +573,7 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     if (k == 29) return c.do_canopy_fluxes_lw != 0;
     if (k >= 30) {   // per-band profiles: Cloudless and Tripleclouds solvers with do_save_spectral_flux
       const int sol = k <= 31 ? c.i_solver_lw : c.i_solver_sw;
-      return c.do_save_spectral_flux != 0 && (sol == ECRAD_SOLVER_CLOUDLESS || sol == ECRAD_SOLVER_TRIPLECLOUDS || sol == ECRAD_SOLVER_SPARTACUS);
+      return c.do_save_spectral_flux != 0 && sol != ECRAD_SOLVER_MCICA;   // every solver but McICA stores per-band profiles
     }
     return true;
   };

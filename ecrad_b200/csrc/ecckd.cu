@@ -327,7 +327,7 @@ general_cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, i
   const CkdMeta& M = *T.ckd;
   const double* tab = T.ckdtab;
   const double dp = LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l);
-  const double inv = 1.0 / (9.80665 * dmax(cfg.cloud_fraction_threshold, frac));   // radiation_general_cloud_optics.F90:191-197
+  const double inv = cfg.is_homogeneous ? 1.0 / 9.80665 : 1.0 / (9.80665 * dmax(cfg.cloud_fraction_threshold, frac));   // radiation_general_cloud_optics.F90:191-205
   const double wp_liq = LD_IN(in.q_liq, c, l) * dp * inv, wp_ice = LD_IN(in.q_ice, c, l) * dp * inv;
   const double rel = LD_IN(in.re_liq, c, l), rei = LD_IN(in.re_ice, c, l);
   if (cfg.do_lw) {

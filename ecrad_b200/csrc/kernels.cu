@@ -362,7 +362,9 @@ __global__ void cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, i
   const double frac = LD_IN(in.frac, c, l);
   if (!(frac > 0.0)) return;
   const CloudMeta& C = *T.cloud;
-  const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / (9.80665 * frac);
+  // config%is_homogeneous (radiation_cloud_optics.F90:318-327): gridbox-mean water path for the Homogeneous solvers
+  const double factor = cfg.is_homogeneous ? (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / 9.80665
+                                           : (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / (9.80665 * frac);
   const double lwp = factor * LD_IN(in.q_liq, c, l), iwp = factor * LD_IN(in.q_ice, c, l);
   const double rel = LD_IN(in.re_liq, c, l), rei = LD_IN(in.re_ice, c, l);
   if (cfg.do_lw) {

@@ -33,7 +33,7 @@ __device__ __forceinline__ LwColumn lw_column(const DevCfg& cfg, const Work& w, 
   s.mcica = cfg.solver_lw == 2;
   s.tcc = s.mcica ? w.tcc[s.c] : 0.0;
   s.cloudy = s.tcc > 0.0;
-  s.ict = (s.cloudy || cfg.solver_lw == 4) ? w.ict[s.c] : nlev;   // 4 = Tripleclouds: needs the clear-sky flux_dn at cloud top too
+  s.ict = (s.cloudy || cfg.solver_lw == 4 || cfg.solver_lw == 1) ? w.ict[s.c] : nlev;   // 4 = Tripleclouds (1 = Homogeneous runs on its kernels): needs the clear-sky flux_dn at cloud top too
   s.thr = cfg.cloud_fraction_threshold;
   s.n = (size_t)nlev * SD::NG;
   s.od = w.od_lw + (size_t)s.c * s.n;
@@ -352,7 +352,7 @@ static int launch_solver_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn
   const size_t sm2 = sizeof(double) * (3 * LW_LCH_UP * SD::RS + 2 * nlev) + sizeof(double) * LW_UP_NST * 2 * LW_UP_NL * SD::NG + 2 * LW_UP_NST * sizeof(uint64_t) + 32;
   const size_t sm3 = sizeof(double) * (2 * LW_LCH_FLUX * SD::RS + 2 * SD::NB) + sizeof(double) * LW_FLUX_NST * 4 * LW_FLUX_NL * SD::NG + 2 * LW_FLUX_NST * sizeof(uint64_t) + 32;
   lw_down_kernel<SD><<<nc, SD::THREADS, sm1, st>>>(T, cfg, out, w, nlev);
-  if (cfg.solver_lw == 4) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
+  if (cfg.solver_lw == 4 || cfg.solver_lw == 1) return 1 + launch_tc_lw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds, Homogeneous
   cudaFuncSetAttribute(lw_up_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
   lw_up_kernel<SD><<<nc, SD::THREADS, sm2, st>>>(T, cfg, in, out, w, nlev, nlevp);
   cudaFuncSetAttribute(lw_flux_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);

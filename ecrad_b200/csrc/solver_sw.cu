@@ -326,7 +326,7 @@ static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn
 }
 
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  if (cfg.solver_sw == 4) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds
+  if (cfg.solver_sw == 4 || cfg.solver_sw == 1) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds, Homogeneous
   if (cfg.solver_sw == 3) return launch_sp_sw(T, cfg, in, out, w, nc, nlev, st);   // SPARTACUS
   switch (cfg.ng_sw) {
     case NG_SW: return launch_solver_sw_t<SwRrtmg>(T, cfg, in, out, w, nc, nlev, st);

@@ -8,6 +8,11 @@
 //   SW:  a = T/(1-R*A), b = (Tdir*Adir*R + Tdirdif)/(1-R*A), Tdir, A, Adir       (A, Adir: albedos of everything below)
 //   LW:  a = T/(1-R*A), b = (R*S + src_dn)/(1-R*A), A, S, T                       (S: source of everything below)
 // First version: one kernel per spectrum (not yet split/tuned like the McICA path).
+//
+// The Homogeneous solvers (radiation_homogeneous_sw.F90, radiation_homogeneous_lw.F90: every cloudy layer is overcast with the
+// gridbox-mean cloud) run on the same kernels: tc_prep_kernel then puts the whole layer into region 2 with unit optical-depth
+// scaling and maximum overlap, so every overlap matrix is an exact permutation of 0s and 1s and the unused regions carry exact
+// zeros; the SW two-stream solution is the gammas + calc_reflectance_transmittance_sw pair that solver uses.
 #include "solver_common.cuh"
 #include "tc_core.h"
 #include "tc_shared.cuh"
@@ -35,17 +40,18 @@ tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
   const double expo = 1.0 / cfg.cloud_inhom_decorr_scaling, thr = cfg.cloud_fraction_threshold;
   for (int jlev = 1 + (int)threadIdx.x; jlev <= nlev + 1; jlev += TC_PREP_THREADS) {   // interface above layer jlev (1-based)
     double fu[3] = {1.0, 0.0, 0.0}, fl[3] = {1.0, 0.0, 0.0}, o_[3], M[3][3];
-    if (jlev > 1) tc_region(LD_IN(in.frac, c, jlev - 2), LD_IN(in.fsd, c, jlev - 2), thr, fu, o_);
+    const bool homog = cfg.is_homogeneous != 0;
+    if (jlev > 1) { if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 2), thr, fu, o_); else tc_region(LD_IN(in.frac, c, jlev - 2), LD_IN(in.fsd, c, jlev - 2), thr, fu, o_); }
     if (jlev <= nlev) {
-      tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_);
+      if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 1), thr, fl, o_); else tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_);
       for (int r = 0; r < 3; ++r) { reg[(jlev - 1) * 3 + r] = fl[r]; ods[(jlev - 1) * 3 + r] = o_[r]; }
     }
     double op1 = 1.0, op2 = 1.0;
-    if (jlev > 1 && jlev <= nlev) {
+    if (jlev > 1 && jlev <= nlev && !homog) {
       op1 = LD_IN(in.overlap, c, jlev - 2);
       op2 = op1 >= 0.0 ? (expo == 2.0 ? mul_rn(op1, op1) : pow(op1, expo)) : op1;
     }
-    if (cfg.use_beta_overlap) { const double op[3] = {op1, op2, op2}; tc_beta_overlap_matrix(op, fu, fl, thr, M); }
+    if (cfg.use_beta_overlap && !homog) { const double op[3] = {op1, op2, op2}; tc_beta_overlap_matrix(op, fu, fl, thr, M); }
     else tc_alpha_overlap_matrix(op1, op2, fu, fl, M);
     double* u = w.tc_u + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
     double* v = w.tc_v + ((size_t)c * (nlev + 1) + (jlev - 1)) * 9;
@@ -75,8 +81,9 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   const double mu0 = in.cos_sza[c];
-  if (g == 0 && out.cloud_cover_sw) out.cloud_cover_sw[c] = w.tc_cc[c];   // set for every column, also at night
-  if (mu0 < 1.0e-10) { sw_night_column<SD>(cfg, out, c, g, act, nl1, SD::THREADS); return; }
+  const bool homog = cfg.is_homogeneous != 0;   // Homogeneous: no cloud cover output, night is cos_sza <= 0 (radiation_homogeneous_sw.F90:118)
+  if (g == 0 && out.cloud_cover_sw && !homog) out.cloud_cover_sw[c] = w.tc_cc[c];   // set for every column, also at night
+  if (homog ? !(mu0 > 0.0) : mu0 < 1.0e-10) { sw_night_column<SD>(cfg, out, c, g, act, nl1, SD::THREADS); return; }
   double* sums = reinterpret_cast<double*>(smem_raw);     // [6][nl1]: up, dn_dif, dn_dir, up_c, dn_dif_c, dn_dir_c
   double* tile = sums + 6 * nl1;                           // [6][TC_LCH][SD::RS]
   double* bandv = tile + 6 * TC_LCH * SD::RS;            // [2][14]
@@ -114,7 +121,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
       const size_t i = (size_t)l * SD::NG + g;
       const double odg = od_n, ssag = ssa_n, gg_gas = gg_n;
       if (l > 0) { od_n = od[i - SD::NG]; ssa_n = ssa[i - SD::NG]; if (gas_g) gg_n = gas_g[i - SD::NG]; }
-      const SwLayer Lc = sw_ref_trans(mu0, odg, ssag, gg_gas);
+      const SwLayer Lc = homog ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
       {   // clear-sky column
         const double id = 1.0 / (1.0 - tac * Lc.ref);
         SCR(0, 0, i) = Lc.trans * id;
@@ -137,7 +144,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           const double od_total = odg + clb[b] * scal;
           const double ssa_total = (scat_od + scat_od_cloud) / od_total;
           const double g_total = (scat_od * gg_gas + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
-          L = sw_ref_trans(mu0, od_total, ssa_total, g_total);
+          L = homog ? sw_ref_trans_cloudless(mu0, od_total, ssa_total, g_total) : sw_ref_trans(mu0, od_total, ssa_total, g_total);
         }
         const double id = 1.0 / (1.0 - ta[jr] * L.ref);
         SCR(1 + jr, 0, i) = L.trans * id;
@@ -379,7 +386,9 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   // ---- derivatives: calc_lw_derivatives_region (weights = last flux_up, i.e. the surface one unless the column is cloud free) ----
   const bool want_dv = cfg.do_lw_derivatives && out.lw_derivatives;
   if (want_dv) {
-    const double fus = fup[0] + fup[1] + fup[2];
+    // (Tripleclouds: in a cloud-free column the reference's flux_up still holds the top-of-atmosphere values at this point and the
+    // oracle follows it; the Homogeneous solver weights with the surface flux in every column, calc_lw_derivatives_ica)
+    const double fus = (cfg.is_homogeneous && ict >= nlev) ? fuc_surf : fup[0] + fup[1] + fup[2];
     // block sum of fus (same order of partial sums as flush_tile is not required: only a normalisation)
     __syncthreads();
     if (act) tile[g] = fus;
@@ -414,7 +423,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     if (out.lw_dn) out.lw_dn[o] = l <= ict ? dnc : s_dn[l];
     if (want_dv) out.lw_derivatives[o] = l == nlev ? 1.0 : s_dv[l];
   }
-  if (g == 0 && out.cloud_cover_lw) out.cloud_cover_lw[c] = w.tc_cc[c];
+  if (g == 0 && out.cloud_cover_lw && !cfg.is_homogeneous) out.cloud_cover_lw[c] = w.tc_cc[c];
   if (act) {
     const size_t i = (size_t)c * SD::NG + g;
     if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fd_surf_clear;

@@ -28,6 +28,14 @@ HD void tc_region(double frac, double fsd, double frac_threshold, double* reg, d
   }
 }
 
+// Homogeneous solvers on the Tripleclouds kernels: a cloudy layer (cropped fraction >= threshold) is entirely region 2 with the
+// unscaled gridbox-mean cloud (radiation_homogeneous_sw.F90:218-260), a clear layer entirely region 1
+HD void tc_region_homogeneous(double frac, double frac_threshold, double* reg, double* ods) {
+  const bool cloudy = frac >= frac_threshold;
+  reg[0] = cloudy ? 0.0 : 1.0; reg[1] = cloudy ? 1.0 : 0.0; reg[2] = 0.0;
+  ods[0] = 0.0; ods[1] = 1.0; ods[2] = 1.0;
+}
+
 // overlap matrix M[jupper][jlower] between the region fractions above (fu) and below (fl) an interface
 HD void tc_alpha_overlap_matrix(double op, double op_inhom, const double* fu, const double* fl, double M[3][3]) {
   double cf_upper = fu[1] + fu[2], cf_lower = fl[1] + fl[2];

@@ -80,7 +80,9 @@ void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nle
     if (!(frac[jl] > 0.0)) continue;
     double od_lw_liq[NB_LW], scat_lw_liq[NB_LW], g_lw_liq[NB_LW], od_lw_ice[NB_LW], scat_lw_ice[NB_LW], g_lw_ice[NB_LW];
     double od_sw_liq[NB_SW], scat_sw_liq[NB_SW], g_sw_liq[NB_SW], od_sw_ice[NB_SW], scat_sw_ice[NB_SW], g_sw_ice[NB_SW];
-    double factor = (p_hl[jl + 1] - p_hl[jl]) / (AccelDueToGravity * frac[jl]);
+    /* config%is_homogeneous (radiation_cloud_optics.F90:318-327): the Homogeneous solvers take gridbox-mean water paths */
+    const int is_homogeneous = (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS);
+    double factor = is_homogeneous ? (p_hl[jl + 1] - p_hl[jl]) / AccelDueToGravity : (p_hl[jl + 1] - p_hl[jl]) / (AccelDueToGravity * frac[jl]);
     double lwp = factor * q_liq[jl], iwp = factor * q_ice[jl];
     if (lwp > 0.0) {
       liq_socrates(NB_LW, t->liq_coeff_lw, lwp, re_liq[jl], od_lw_liq, scat_lw_liq, g_lw_liq);

@@ -193,7 +193,9 @@ void orc_general_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg,
     const double* q = jt ? q_ice : q_liq;
     const double* re = jt ? re_ice : re_liq;
     for (int jl = 0; jl < nlev; ++jl)   /* in-cloud water path, :191-197 */
-      water_path[jl] = q[jl] * (p_hl[jl + 1] - p_hl[jl]) * (1.0 / (AccelDueToGravity * dmax(cfg->cloud_fraction_threshold, frac[jl])));
+      water_path[jl] = ((cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS))
+                           ? q[jl] * (p_hl[jl + 1] - p_hl[jl]) * (1.0 / AccelDueToGravity)   /* config%is_homogeneous */
+                           : q[jl] * (p_hl[jl + 1] - p_hl[jl]) * (1.0 / (AccelDueToGravity * dmax(cfg->cloud_fraction_threshold, frac[jl])));
     if (cfg->do_lw) {
       if (cfg->do_lw_cloud_scattering) gco_add(&t->gco_lw[jt], nlw, nlev, frac, water_path, re, od_lw, ssa_lw, g_lw);
       else gco_add_absorption(&t->gco_lw[jt], nlw, nlev, water_path, re, od_lw);

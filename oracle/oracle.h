@@ -125,6 +125,8 @@ void orc_adding_ica_sw(int ng, int nlev, const double* incoming, const double* a
 void orc_calc_fluxes_no_scattering_lw(int ng, int nlev, const double* trans, const double* source_up,
                        const double* source_dn, const double* emission, const double* albedo,
                        double* flux_up, double* flux_dn);
+void orc_adding_ica_lw(int ng, int nlev, const double* ref, const double* trans, const double* source_up, const double* source_dn,
+                       const double* emission, const double* albedo_surf, double* flux_up, double* flux_dn);
 void orc_fast_adding_ica_lw(int ng, int nlev, const double* ref, const double* trans, const double* source_up,
                        const double* source_dn, const double* emission, const double* albedo,
                        const int* is_clear_sky_layer, int i_cloud_top, const double* flux_dn_clear,

@@ -546,6 +546,139 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   free(pool);
 }
 
+/* ----- Homogeneous solvers: radiation_homogeneous_sw.F90:36-379, radiation_homogeneous_lw.F90:36-319.  Clouds fill the gridbox in
+ * every layer whose (cropped) fraction reaches the threshold; cloud_optics has then computed gridbox-mean water paths
+ * (config%is_homogeneous, radiation_cloud_optics.F90:318-327).  No LW aerosol scattering, no SW delta scaling with gases. ----- */
+static void solver_homog(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol, const ecrad_b200_inputs* in,
+                         ecrad_b200_outputs* out, const col_work* w, const double* frac, int sw) {
+  const int ng = sw ? NG_SW : NG_LW, nb = sw ? NB_SW : NB_LW, nl1n = nlev + 1;
+  const size_t nl = (size_t)nlev * ng, nl1 = (size_t)nl1n * ng;
+  const int32_t* band = sw ? t->band_sw : t->band_lw;
+  int is_cloudy_profile = 0;
+  for (int jl = 0; jl < nlev; ++jl) if (frac[jl] >= cfg->cloud_fraction_threshold) is_cloudy_profile = 1;
+  if (sw) {
+    const double cos_sza = in->cos_sza[jcol];
+    double* prof[6] = {out->sw_up, out->sw_dn, out->sw_dn_direct, out->sw_up_clear, out->sw_dn_clear, out->sw_dn_direct_clear};
+    double* gs[6] = {out->sw_dn_diffuse_surf_g, out->sw_dn_direct_surf_g, out->sw_up_toa_g,
+                     out->sw_dn_diffuse_surf_clear_g, out->sw_dn_direct_surf_clear_g, out->sw_up_toa_clear_g};
+    double* bs[3] = {out->sw_up_band, out->sw_dn_band, out->sw_dn_direct_band};
+    if (!(cos_sza > 0.0)) {
+      for (int k = 0; k < 6; ++k) if (prof[k]) for (int jl = 0; jl <= nlev; ++jl) A2(prof[k], jcol, jl) = 0.0;
+      for (int k = 0; k < 6; ++k) if (gs[k]) for (int g = 0; g < ng; ++g) OUTG(gs[k], ng, g) = 0.0;
+      for (int k = 0; k < 3; ++k)
+        if (bs[k]) for (int jl = 0; jl <= nlev; ++jl) for (int b = 0; b < nb; ++b) bs[k][((size_t)jl * ncol + jcol) * nb + b] = 0.0;
+      return;
+    }
+    double* pool = (double*)malloc(sizeof(double) * (5 * nl + 3 * nl1 + 3 * (size_t)ng));
+    double *ref = pool, *trans = ref + nl, *rdir = trans + nl, *tdd = rdir + nl, *tdir = tdd + nl;
+    double *fu = tdir + nl, *fdd = fu + nl1, *fdir = fdd + nl1, *od_total = fdir + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
+    for (int jl = 0; jl < nlev; ++jl)
+      orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, w->g_sw + (size_t)jl * ng,
+                                            ref + (size_t)jl * ng, trans + (size_t)jl * ng, rdir + (size_t)jl * ng, tdd + (size_t)jl * ng,
+                                            tdir + (size_t)jl * ng);
+    for (int pass = 0; pass < 2; ++pass) {   /* 0: clear sky, 1: all sky */
+      if (pass == 1) {
+        if (!is_cloudy_profile) {   /* all-sky = clear-sky */
+          for (int k = 0; k < 3; ++k) if (prof[k] && prof[k + 3]) for (int jl = 0; jl <= nlev; ++jl) A2(prof[k], jcol, jl) = A2(prof[k + 3], jcol, jl);
+          for (int k = 0; k < 3; ++k) if (gs[k] && gs[k + 3]) for (int g = 0; g < ng; ++g) OUTG(gs[k], ng, g) = OUTG(gs[k + 3], ng, g);
+          /* (band profiles: same sums as below on the unchanged clear-sky arrays) */
+        } else {
+          for (int jl = 0; jl < nlev; ++jl) {
+            if (!(frac[jl] >= cfg->cloud_fraction_threshold)) continue;
+            for (int g = 0; g < ng; ++g) {
+              const size_t i = (size_t)jl * ng + g;
+              const int ib = band[g];
+              const double od_cloud_g = w->od_sw_cloud[jl * nb + ib];
+              od_total[g] = w->od_sw[i] + od_cloud_g;
+              ssa_total[g] = 0.0; g_total[g] = 0.0;
+              if (od_total[g] > 0.0) ssa_total[g] = (w->ssa_sw[i] * w->od_sw[i] + w->ssa_sw_cloud[jl * nb + ib] * od_cloud_g) / od_total[g];
+              if (ssa_total[g] > 0.0 && od_total[g] > 0.0)
+                g_total[g] = (w->g_sw[i] * w->ssa_sw[i] * w->od_sw[i] + w->g_sw_cloud[jl * nb + ib] * w->ssa_sw_cloud[jl * nb + ib] * od_cloud_g) /
+                             (ssa_total[g] * od_total[g]);
+            }
+            orc_calc_reflectance_transmittance_sw(ng, cos_sza, od_total, ssa_total, g_total, ref + (size_t)jl * ng, trans + (size_t)jl * ng,
+                                                  rdir + (size_t)jl * ng, tdd + (size_t)jl * ng, tdir + (size_t)jl * ng);
+          }
+        }
+      }
+      if (pass == 1 && !is_cloudy_profile) { /* fluxes of the clear-sky pass are still in fu/fdd/fdir */ }
+      else orc_adding_ica_sw(ng, nlev, w->incoming_sw, w->alb_diff, w->alb_dir, cos_sza, ref, trans, rdir, tdd, tdir, fu, fdd, fdir);
+      if (!(pass == 1 && !is_cloudy_profile)) {
+        double *o_up = prof[pass ? 0 : 3], *o_dn = prof[pass ? 1 : 4], *o_dir = prof[pass ? 2 : 5];
+        for (int jl = 0; jl <= nlev; ++jl) {
+          double s_up = 0.0, s_dd = 0.0, s_dir = 0.0;
+          for (int g = 0; g < ng; ++g) { s_up = s_up + fu[(size_t)jl * ng + g]; s_dd = s_dd + fdd[(size_t)jl * ng + g]; s_dir = s_dir + fdir[(size_t)jl * ng + g]; }
+          if (o_up) A2(o_up, jcol, jl) = s_up;
+          if (o_dn) A2(o_dn, jcol, jl) = s_dd + s_dir;
+          if (o_dir) A2(o_dir, jcol, jl) = s_dir;
+        }
+        for (int g = 0; g < ng; ++g) {
+          if (gs[pass ? 0 : 3]) OUTG(gs[pass ? 0 : 3], ng, g) = fdd[nl1 - ng + g];
+          if (gs[pass ? 1 : 4]) OUTG(gs[pass ? 1 : 4], ng, g) = fdir[nl1 - ng + g];
+          if (gs[pass ? 2 : 5]) OUTG(gs[pass ? 2 : 5], ng, g) = fu[g];
+        }
+      }
+      if (pass == 1) {   /* all-sky band profiles (the clear-sky ones are not part of the C-ABI) */
+        band_profile(ng, nb, nl1n, band, fu, ncol, jcol, out->sw_up_band, 0);
+        band_profile(ng, nb, nl1n, band, fdir, ncol, jcol, out->sw_dn_direct_band, 0);
+        band_profile(ng, nb, nl1n, band, fdir, ncol, jcol, out->sw_dn_band, 0);
+        band_profile(ng, nb, nl1n, band, fdd, ncol, jcol, out->sw_dn_band, 1);
+      }
+    }
+    free(pool);
+  } else {
+    double* pool = (double*)malloc(sizeof(double) * (4 * nl + 2 * nl1 + 3 * (size_t)ng));
+    double *ref = pool, *trans = ref + nl, *su = trans + nl, *sd = su + nl, *fu = sd + nl, *fd = fu + nl1;
+    double *od_total = fd + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
+    const double* planck = w->planck_hl;
+    orc_calc_no_scattering_transmittance_lw(ng * nlev, w->od_lw, planck, planck + ng, trans, su, sd);
+    memset(ref, 0, sizeof(double) * nl);
+    orc_calc_fluxes_no_scattering_lw(ng, nlev, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
+    sum_g(ng, nl1n, fu, ncol, jcol, out->lw_up_clear);
+    sum_g(ng, nl1n, fd, ncol, jcol, out->lw_dn_clear);
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_clear_g) OUTG(out->lw_dn_surf_clear_g, ng, g) = fd[nl1 - ng + g];
+      if (out->lw_up_toa_clear_g) OUTG(out->lw_up_toa_clear_g, ng, g) = fu[g];
+    }
+    if (is_cloudy_profile) {
+      for (int jl = 0; jl < nlev; ++jl) {
+        if (!(frac[jl] >= cfg->cloud_fraction_threshold)) continue;
+        for (int g = 0; g < ng; ++g) {
+          const size_t i = (size_t)jl * ng + g;
+          const int ib = band[g];
+          const double od_cloud_g = w->od_lw_cloud[jl * nb + ib];
+          od_total[g] = w->od_lw[i] + od_cloud_g;
+          ssa_total[g] = 0.0; g_total[g] = 0.0;
+          if (cfg->do_lw_cloud_scattering) {
+            if (od_total[g] > 0.0) ssa_total[g] = w->ssa_lw_cloud[jl * nb + ib] * od_cloud_g / od_total[g];
+            if (ssa_total[g] > 0.0 && od_total[g] > 0.0)
+              g_total[g] = w->g_lw_cloud[jl * nb + ib] * w->ssa_lw_cloud[jl * nb + ib] * od_cloud_g / (ssa_total[g] * od_total[g]);
+          }
+        }
+        if (cfg->do_lw_cloud_scattering)
+          orc_calc_ref_trans_lw(ng, od_total, ssa_total, g_total, planck + (size_t)jl * ng, planck + (size_t)(jl + 1) * ng, ref + (size_t)jl * ng,
+                                trans + (size_t)jl * ng, su + (size_t)jl * ng, sd + (size_t)jl * ng);
+        else
+          orc_calc_no_scattering_transmittance_lw(ng, od_total, planck + (size_t)jl * ng, planck + (size_t)(jl + 1) * ng, trans + (size_t)jl * ng,
+                                                  su + (size_t)jl * ng, sd + (size_t)jl * ng);
+      }
+      if (cfg->do_lw_cloud_scattering) orc_adding_ica_lw(ng, nlev, ref, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
+      else orc_calc_fluxes_no_scattering_lw(ng, nlev, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
+    }
+    sum_g(ng, nl1n, fu, ncol, jcol, out->lw_up);
+    sum_g(ng, nl1n, fd, ncol, jcol, out->lw_dn);
+    for (int g = 0; g < ng; ++g) {
+      if (out->lw_dn_surf_g) OUTG(out->lw_dn_surf_g, ng, g) = fd[nl1 - ng + g];
+      if (out->lw_up_toa_g) OUTG(out->lw_up_toa_g, ng, g) = fu[g];
+    }
+    band_profile(ng, nb, nl1n, band, fu, ncol, jcol, out->lw_up_band, 0);
+    band_profile(ng, nb, nl1n, band, fd, ncol, jcol, out->lw_dn_band, 0);
+    if (cfg->do_lw_derivatives && out->lw_derivatives) lw_derivatives(ng, nlev, ncol, jcol, trans, fu + nl1 - ng, 0.0, 0, out->lw_derivatives);
+    free(pool);
+  }
+  (void)in;
+}
+
 /* ----- Tripleclouds wrappers: scatter the per-column results of tripleclouds.c into flux_type ----- */
 static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol, const ecrad_b200_inputs* in,
                       ecrad_b200_outputs* out, const col_work* w, const double* frac, int sw) {
@@ -747,8 +880,10 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }
-  if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
-  if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
+  if (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0);
+  else if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
+  if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1);
+  else if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   surface_spectral(t, cfg, jcol, out);
   free(w.w); free(phl_full);
   return 0;

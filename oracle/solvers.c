@@ -239,3 +239,27 @@ void orc_fast_adding_ica_lw(int ng, int nlev, const double* ref, const double* t
   }
   free(albedo); free(source); free(inv_den);
 }
+
+/* radiation_adding_ica_lw.F90:32-131 adding_ica_lw (full adding method, used by the Homogeneous solver). */
+void orc_adding_ica_lw(int ng, int nlev, const double* ref, const double* trans, const double* source_up, const double* source_dn,
+                       const double* emission, const double* albedo_surf, double* flux_up, double* flux_dn) {
+  double* albedo = (double*)malloc(sizeof(double) * (size_t)(2 * (nlev + 1) + nlev) * ng);
+  double* source = albedo + (size_t)(nlev + 1) * ng;
+  double* inv_denominator = source + (size_t)(nlev + 1) * ng;
+  for (int g = 0; g < ng; ++g) { albedo[IX(nlev, g)] = albedo_surf[g]; source[IX(nlev, g)] = emission[g]; }
+  for (int jl = nlev - 1; jl >= 0; --jl)
+    for (int g = 0; g < ng; ++g) {
+      inv_denominator[IX(jl, g)] = 1.0 / (1.0 - albedo[IX(jl + 1, g)] * ref[IX(jl, g)]);
+      albedo[IX(jl, g)] = ref[IX(jl, g)] + trans[IX(jl, g)] * trans[IX(jl, g)] * albedo[IX(jl + 1, g)] * inv_denominator[IX(jl, g)];
+      source[IX(jl, g)] = source_up[IX(jl, g)] +
+                          trans[IX(jl, g)] * (source[IX(jl + 1, g)] + albedo[IX(jl + 1, g)] * source_dn[IX(jl, g)]) * inv_denominator[IX(jl, g)];
+    }
+  for (int g = 0; g < ng; ++g) { flux_dn[IX(0, g)] = 0.0; flux_up[IX(0, g)] = source[IX(0, g)]; }
+  for (int jl = 0; jl < nlev; ++jl)
+    for (int g = 0; g < ng; ++g) {
+      flux_dn[IX(jl + 1, g)] = (trans[IX(jl, g)] * flux_dn[IX(jl, g)] + ref[IX(jl, g)] * source[IX(jl + 1, g)] + source_dn[IX(jl, g)]) *
+                               inv_denominator[IX(jl, g)];
+      flux_up[IX(jl + 1, g)] = albedo[IX(jl + 1, g)] * flux_dn[IX(jl + 1, g)] + source[IX(jl + 1, g)];
+    }
+  free(albedo);
+}

@@ -150,7 +150,9 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True, do_lw_cloud_scattering=False),
                                 dict(use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_beta_overlap=True),
-                                dict(use_vectorizable_generator=True), dict(use_vectorizable_generator=True, overlap_scheme_name="Max-Ran", use_aerosols=True)])
+                                dict(use_vectorizable_generator=True), dict(use_vectorizable_generator=True, overlap_scheme_name="Max-Ran", use_aerosols=True),
+                                dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"),
+                                dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", use_aerosols=True, do_lw_cloud_scattering=False)])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
@@ -282,7 +284,7 @@ def test_ecckd_tiling_is_invisible(meridian_raw):
         assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
 
 
-@pytest.mark.parametrize("solver", ["Tripleclouds", "Cloudless"])
+@pytest.mark.parametrize("solver", ["Tripleclouds", "Cloudless", "Homogeneous"])
 def test_band_profiles_synthetic_and_tiled(handles, meridian_raw, solver):
     """Per-band profiles on perturbed columns (night columns included), and the same through ragged column tiles."""
     from ecrad_b200.radiation_interface import setup_radiation

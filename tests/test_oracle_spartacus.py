@@ -132,3 +132,19 @@ def test_spartacus_3d_invariants(meridian_raw, entr):
     if cloud_free.any():
         assert d[cloud_free].max() < 1e-5
     assert np.abs(sp["lw_up"][:, 0] - tc["lw_up"][:, 0]).max() < 2.0
+
+
+def test_homogeneous_oracle_invariants(meridian_raw):
+    """Homogeneous solvers (radiation_homogeneous_{sw,lw}.F90; no reference output exists): clear-sky part = the Cloudless solver,
+    cloud-free columns have all-sky = clear-sky, overcast plane-parallel clouds are brighter / colder at TOA than McICA's on average."""
+    hm = run(meridian_raw, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous")
+    cl = run(meridian_raw, sw_solver_name="Cloudless", lw_solver_name="Cloudless")
+    mc = run(meridian_raw)
+    for nm in ("lw_up_clear", "lw_dn_clear", "sw_up_clear", "sw_dn_clear", "sw_dn_direct_clear"):
+        assert np.array_equal(hm[nm], cl[nm]), nm
+    cloud_free = ~(np.asarray(hm["cloud_fraction"]) > 0).any(axis=1)
+    assert cloud_free.any()
+    for nm in ("lw_up", "lw_dn", "sw_up", "sw_dn"):
+        assert np.isfinite(hm[nm]).all()
+        assert np.array_equal(hm[nm][cloud_free], hm[nm + "_clear"][cloud_free]), nm
+    assert hm["sw_up"][:, 0].mean() > mc["sw_up"][:, 0].mean() and hm["lw_up"][:, 0].mean() < mc["lw_up"][:, 0].mean()
