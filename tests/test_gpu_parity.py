@@ -339,7 +339,9 @@ def coarsen_levels(raw, nlev_new):
                                      (19, dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")),
                                      (50, dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_aerosols=True)),
                                      (33, dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds",
-                                               lw_solver_name="Tripleclouds"))])
+                                               lw_solver_name="Tripleclouds")),
+                                     (45, dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)),
+                                     (27, dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"))])
 def test_other_level_counts(handles, meridian_raw, nlev, kw):
     """The reference takes any nlev; the kernels stage per-layer state in shared memory sized by nlev (odd counts, not a multiple of 4)."""
     n = 96
@@ -353,7 +355,10 @@ def test_other_level_counts(handles, meridian_raw, nlev, kw):
 
 
 @pytest.mark.parametrize("kw", [dict(do_sw=False), dict(do_lw=False), dict(do_sw=False, gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False),
-                                dict(do_lw=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+                                dict(do_lw=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(do_sw=False, sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True),
+                                dict(do_lw=False, sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True),
+                                dict(do_lw=False, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous")])
 def test_one_spectrum_only_and_single_column(handles, meridian_raw, kw):
     """do_sw = false / do_lw = false: the other spectrum's outputs stay untouched; ncol = 1 and a 1-column range work."""
     n = 40
@@ -437,18 +442,19 @@ def test_repeated_runs_are_bit_identical(handles, meridian_raw, kw):
             assert np.array_equal(out[nm], ref[nm], equal_nan=True), nm
 
 
-def test_device_resident_entry_matches_host_entry(handles, meridian_raw):
+@pytest.mark.parametrize("kw", [dict(), dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)])
+def test_device_resident_entry_matches_host_entry(handles, meridian_raw, kw):
     import ctypes as C
 
     import torch
 
     from ecrad_b200 import abi
 
-    h, _, cfg = handles()
+    h, _, cfg = handles(**kw)
     n = 257
     raw = I.synthetic_columns(meridian_raw, n)
-    inp = I.to_radiation_inputs(raw)
-    host = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    inp = I.to_radiation_inputs(raw, cfg)
+    host = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
     dev = torch.device("cuda:0")
     ist = abi.Inputs(); ist.struct_bytes = C.sizeof(abi.Inputs); ist.solar_irradiance = inp["solar_irradiance"]
     keep = {}
