@@ -131,3 +131,42 @@ def test_spartacus_error_behaviour():
         setup_radiation(RadiationConfig(overlap_scheme_name="Max-Ran", **SP).consolidate())
     with pytest.raises(RadiationError, match="use_expm_everywhere"):
         setup_radiation(RadiationConfig(use_expm_everywhere=True, **SP).consolidate())
+
+
+def test_spartacus_full_size_properties(meridian_raw):
+    """5000 columns through the tiled host entry (10 tiles, two overlapping compute sets): column independence (permutation
+    invariance, bit-exact), bit-identical repeated runs (race detector), physical bounds, oracle spot check on a random subset."""
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+
+    n = 5000
+    cfg = RadiationConfig(**SP).consolidate()
+    raw = I.synthetic_columns(meridian_raw, n)
+    h = setup_radiation(cfg)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    for nm in FLUXES:
+        assert np.isfinite(out[nm]).all(), nm
+    again = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    for nm in FLUXES + OTHERS:
+        assert np.array_equal(again[nm], out[nm], equal_nan=True), nm
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(n)
+    rawp = {k: (v if np.ndim(v) == 0 else v[perm]) for k, v in raw.items()}
+    outp = h.radiation(I.to_radiation_inputs(rawp, cfg), n, NLEV)
+    h.finalize()
+    for nm in FLUXES + ["cloud_cover_sw", "cloud_cover_lw", "lw_derivatives"]:
+        assert np.array_equal(outp[nm], out[nm][perm]), nm
+    mu0 = raw["cos_solar_zenith_angle"]
+    sun = mu0 >= 1e-10
+    assert (out["sw_dn"] >= -1e-9).all() and (out["sw_up"] >= -1e-9).all() and (out["lw_up"] > 0).all()
+    assert (out["sw_dn_direct"] <= out["sw_dn"] + 1e-9).all()
+    assert np.abs(out["sw_dn"][sun, 0] - raw["solar_irradiance"] * mu0[sun]).max() <= 1e-9 * 1400
+    assert (out["sw_dn"][~sun] == 0).all()
+    net = out["sw_dn"] - out["sw_up"]
+    assert (np.diff(net[sun], axis=1) <= 1e-6).all()          # absorption only: the SW net flux decreases downwards
+    idx = np.sort(rng.choice(n, 128, replace=False))
+    sub = {k: (v if np.ndim(v) == 0 else v[idx]) for k, v in raw.items()}
+    ref = Oracle(cfg).radiation(I.to_radiation_inputs(sub, cfg), len(idx), NLEV)
+    for nm in FLUXES:
+        assert np.abs(out[nm][idx] - ref[nm]).max() <= TOL, nm
+    assert np.array_equal(out["cloud_cover_sw"][idx], ref["cloud_cover_sw"])
