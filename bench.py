@@ -365,8 +365,9 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and dom and args.workload == "mcica_rrtmg":   # ncu figures of the default workload
+    if os.path.exists(tpath) and dom and args.workload in ("mcica_rrtmg", "spartacus_rrtmg"):   # ncu figures exist for these two
         tj = json.load(open(tpath))
+        tj = tj if args.workload == "mcica_rrtmg" else tj.get(args.workload, {})
         if dom in tj:
             traffic = tj[dom]["dram_bytes_per_column"] * ncol
     roofline = None
@@ -377,7 +378,7 @@ def main():
                     # the same stage on the DRAM bytes it really moves (ncu): how close the adding-method scratch traffic runs to the HBM peak
                     "dram_achieved": (traffic / (stage_ms[dom] * 1e-3) / 1e9) if traffic else None,
                     "dram_frac": (traffic / (stage_ms[dom] * 1e-3) / 1e9 / peak) if traffic else None, "peak_source": peak_src, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms, "stage_ms_mode": "serialised extra pass (CUDA events on the launching stream)",
-                    "note": "fp64-ALU-bound path: algorithmic bytes are 30.9 kB/column against ~10 MFLOP/column (DESIGN.md)"}
+                    "note": "fp64-ALU-bound path: algorithmic bytes are 30.9 kB/column against ~10 MFLOP/column (~70 MFLOP with SPARTACUS) (DESIGN.md)"}
 
     if rank == 0:
         cpu = None
