@@ -52,13 +52,7 @@ def to_radiation_inputs(raw, config=None):
         "re_liq": F(raw["re_liquid"]), "re_ice": F(raw["re_ice"]),
         "overlap_param": F(raw["overlap_param"]), "fractional_std": F(raw["fractional_std"]),
     }
-    if vmr:
-        # radiation_gas.F90:444-451 set_units_gas: sf = 1*AirMolarMass/GasMolarMass for the two gases given as mass mixing ratio
-        d["h2o_mmr"] = F(raw["q"] * (1.0 * AIR_MOLAR_MASS / 18.0152833))
-        d["o3_mmr"] = F(raw["o3_mmr"] * (1.0 * AIR_MOLAR_MASS / 47.9982))
-    for g, m in GAS_MOLAR_MASS.items():
-        sf = 1.0 * m / AIR_MOLAR_MASS  # radiation_gas.F90 set_units_gas: sf = sf*GasMolarMass/AirMolarMass
-        d[f"{g}_mmr"] = F(raw[f"{g}_vmr"]) if vmr else F(raw[f"{g}_vmr"] * sf)
+    d.update(set_gas_units(raw, vmr))
     d["solar_irradiance"] = float(raw["solar_irradiance"])
     if "aerosol_mmr" in raw:
         # file (column, type, level) -> aerosol%mixing_ratio(ncol, nlev, ntype)  (driver/ecrad_driver_read_input.F90:546)
@@ -67,6 +61,23 @@ def to_radiation_inputs(raw, config=None):
     if config is not None and "spartacus" in (config.sw_solver_name.lower(), config.lw_solver_name.lower()):
         ic, ii = cloud_effective_separation_eta(raw["pressure_hl"], raw["cloud_fraction"])
         d["inv_cloud_effective_size"], d["inv_inhom_effective_size"] = F(ic), F(ii)
+    return d
+
+
+def set_gas_units(raw, want_vmr):
+    """What `set_gas_units` (radiation_interface.F90:164-193 -> gas%set_units, radiation_gas.F90:392-461) leaves in
+    gas%mixing_ratio for the gases the hot path reads: mass mixing ratios for RRTMG-IFS (radiation_ifs_rrtm.F90 set_gas_units),
+    volume mixing ratios for ecCKD (radiation_ecckd_interface.F90:148-163).  The input file gives H2O and O3 as mass mixing ratios
+    (`q`, `o3_mmr`) and the well-mixed gases as volume mixing ratios (`*_vmr`).  Keys are the C-ABI field names (`*_mmr`)."""
+    F = np.asfortranarray
+    d = {"h2o_mmr": F(raw["q"]), "o3_mmr": F(raw["o3_mmr"])}
+    if want_vmr:
+        # radiation_gas.F90:444-451 set_units_gas: sf = 1*AirMolarMass/GasMolarMass for the two gases given as mass mixing ratio
+        d["h2o_mmr"] = F(raw["q"] * (1.0 * AIR_MOLAR_MASS / 18.0152833))
+        d["o3_mmr"] = F(raw["o3_mmr"] * (1.0 * AIR_MOLAR_MASS / 47.9982))
+    for g, m in GAS_MOLAR_MASS.items():
+        sf = 1.0 * m / AIR_MOLAR_MASS  # radiation_gas.F90 set_units_gas: sf = sf*GasMolarMass/AirMolarMass
+        d[f"{g}_mmr"] = F(raw[f"{g}_vmr"]) if want_vmr else F(raw[f"{g}_vmr"] * sf)
     return d
 
 

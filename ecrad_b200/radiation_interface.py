@@ -1,6 +1,7 @@
 """Host-side mirror of `module radiation_interface` (radiation/radiation_interface.F90:29) over the C-ABI.
 
     setup_radiation(config)                         radiation_interface.F90:37   -> ecrad_b200_setup
+    set_gas_units(config, gas)                      radiation_interface.F90:164  -> host side only (ecrad_b200.inputs.set_gas_units)
     radiation(ncol, nlev, istartcol, iendcol, ...)  radiation_interface.F90:200  -> ecrad_b200_radiation
 
 This module only marshals numpy arrays into the POD structs of include/ecrad_b200.h and calls libecrad_b200.so.
@@ -155,6 +156,14 @@ def setup_radiation(config: RadiationConfig, tables_path: str = None, tables_blo
     if not config.derived:
         config.consolidate()
     return RadiationHandle(config, tables_path, tables_blob)
+
+
+def set_gas_units(config: RadiationConfig, gas: dict) -> dict:
+    """Scale the gas concentrations to the units the configured gas-optics model wants (radiation_interface.F90:164-193); stays on
+    the host, like the reference's.  `gas`: file variables (`q`, `o3_mmr`, `*_vmr`); returns the C-ABI gas arrays."""
+    from .inputs import set_gas_units as _set
+
+    return _set(gas, config.is_ecckd)
 
 
 def radiation(handle: RadiationHandle, ncol, nlev, istartcol, iendcol, inputs, **kw):
