@@ -101,7 +101,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
       return fail(h, "SPARTACUS/Tripleclouds solvers can only do Exponential-Random overlap");
     if (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS && c.do_sw_delta_scaling_with_gases)   // radiation_config.F90:1336-1339
       return fail(h, "SW delta-Eddington scaling with gases not possible with SPARTACUS solver");
-    if (c.use_expm_everywhere) return fail(h, "use_expm_everywhere is not available in this build");
     if (c.i_3d_sw_entrapment < ECRAD_ENTRAPMENT_ZERO || c.i_3d_sw_entrapment > ECRAD_ENTRAPMENT_MAXIMUM) return fail(h, "unknown sw_entrapment");
     if (!(c.min_cloud_effective_size > 0.0) || !(c.max_cloud_od > 0.0)) return fail(h, "SPARTACUS: min_cloud_effective_size and max_cloud_od must be positive");
   }
@@ -430,7 +429,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.min_gas_od_lw = cfg->min_gas_od_lw; d.min_gas_od_sw = cfg->min_gas_od_sw;
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
   d.sp.do_3d_effects = cfg->do_3d_effects; d.sp.entrapment = cfg->i_3d_sw_entrapment;
-  d.sp.do_3d_lw_multilayer_effects = cfg->do_3d_lw_multilayer_effects; d.sp.do_lw_side_emissivity = cfg->do_lw_side_emissivity;
+  d.sp.do_3d_lw_multilayer_effects = cfg->do_3d_lw_multilayer_effects; d.sp.do_lw_side_emissivity = cfg->do_lw_side_emissivity; d.sp.use_expm_everywhere = cfg->use_expm_everywhere;
   d.sp.max_gas_od_3d = cfg->max_gas_od_3d; d.sp.max_cloud_od = cfg->max_cloud_od; d.sp.max_3d_transfer_rate = cfg->max_3d_transfer_rate;
   d.sp.min_cloud_effective_size = cfg->min_cloud_effective_size; d.sp.overhead_sun_factor = cfg->overhead_sun_factor;
   d.sp.overhang_factor = cfg->overhang_factor; d.sp.clear_to_thick_fraction = cfg->clear_to_thick_fraction;

@@ -73,19 +73,24 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     clr[0 * n + i] = Lc.ref; clr[1 * n + i] = Lc.trans; clr[2 * n + i] = Lc.ref_dir; clr[3 * n + i] = Lc.trans_dir_diff; clr[4 * n + i] = Lc.trans_dir_dir;
   }
   const double frac = LD_IN(in.frac, c, l);
-  if (!(frac > 0.0)) return;   // clear-sky layer: the (1,1) elements are the clear-sky values
-  // ---- cloudy layer ----
+  const bool cloudy = frac > 0.0;
+  // clear-sky layer: the (1,1) elements are the clear-sky values, unless use_expm_everywhere asks for the matrix exponential there too
+  if (!cloudy && !sc.use_expm_everywhere) return;
+  const int nra = cloudy ? 3 : 1;   // nregactive
+  // ---- cloudy layer (or a clear one treated with the matrix exponential) ----
   const double* reg = w.tc_reg + ((size_t)c * nlev + l) * 3;
   const double* ods = w.tc_ods + ((size_t)c * nlev + l) * 3;
-  double edge[3], rate_dir[9], rate_dif[9];
-  const bool has3d = in.inv_cloud_size && sp_edge_lengths(sc, reg, LD_IN(in.inv_cloud_size, c, l), in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
+  double edge[3] = {0.0, 0.0, 0.0}, rate_dir[9], rate_dif[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { rate_dir[k] = 0.0; rate_dif[k] = 0.0; }
+  const bool has3d = cloudy && in.inv_cloud_size && sp_edge_lengths(sc, reg, LD_IN(in.inv_cloud_size, c, l), in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
   if (has3d) {
     const SpGeom q = sp_geometry(sc, mu0);
     const double dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     sp_transfer_rates(sc, dz, edge, reg, q.tan_sza, rate_dir);
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate_dif);
   }
-  const int ng3d = has3d ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
+  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
   if (!act) return;
   // optical properties of the regions (:606-655)
   const int b = T.meta->band_of_g_sw[g];
@@ -95,6 +100,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const double scat_od = odg * ssag;
 #pragma unroll
   for (int jr = 1; jr < 3; ++jr) {
+    if (!cloudy) { od_r[jr] = 0.0; ssa_r[jr] = 0.0; g_r[jr] = 0.0; continue; }
     const double scat_od_cloud = clb[b] * clb[SD::NB + b] * ods[jr];
     od_r[jr] = odg + clb[b] * ods[jr];
     ssa_r[jr] = (scat_od + scat_od_cloud) / od_r[jr];
@@ -107,7 +113,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     for (int k = 0; k < 9; ++k) {
       const int jr = k / 4;
       SwLayer L = {0.0, 0.0, 0.0, 0.0, 0.0};
-      if (k % 4 == 0) L = jr == 0 ? Lc : sw_ref_trans_cloudless(mu0, od_r[jr], ssa_r[jr], g_r[jr]);
+      if (k % 4 == 0 && jr < nra) L = jr == 0 ? Lc : sw_ref_trans_cloudless(mu0, od_r[jr], ssa_r[jr], g_r[jr]);
       mats[(size_t)(0 + k) * SD::NG + g] = L.ref;
       mats[(size_t)(9 + k) * SD::NG + g] = L.trans;
       mats[(size_t)(18 + k) * SD::NG + g] = L.ref_dir;
@@ -122,6 +128,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   for (int k = 0; k < 81; ++k) G[k] = 0.0;
 #pragma unroll
   for (int jr = 0; jr < 3; ++jr) {
+    if (jr >= nra) continue;
     const double factor = 0.75 * g_r[jr];   // calc_two_stream_gammas_sw
     const double gamma1 = 2.0 - ssa_r[jr] * (1.25 + factor), gamma2 = ssa_r[jr] * (0.75 - factor), gamma3 = 0.5 - mu0 * factor;
     G[jr * 9 + jr] = od_r[jr] * gamma1;
@@ -132,6 +139,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   }
 #pragma unroll
   for (int jr = 0; jr < 2; ++jr) {
+    if (jr + 1 >= nra) continue;
     G[jr * 9 + jr] = G[jr * 9 + jr] + rate_dif[jr * 3 + jr + 1];
     G[(jr + 1) * 9 + jr + 1] = G[(jr + 1) * 9 + jr + 1] + rate_dif[(jr + 1) * 3 + jr];
     G[(jr + 1) * 9 + jr] = -rate_dif[jr * 3 + jr + 1];
@@ -151,10 +159,10 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     G[8 * 9 + 6] = rate_dir[2];
     G[6 * 9 + 8] = rate_dir[6];
   }
-  for (int a = 0; a < 3; ++a)
-    for (int bb = 0; bb < 3; ++bb) G[(3 + a) * 9 + 3 + bb] = -G[a * 9 + bb];
-  for (int a = 0; a < 3; ++a)
-    for (int bb = 0; bb < 3; ++bb) G[a * 9 + 3 + bb] = -G[(3 + a) * 9 + bb];
+  for (int a = 0; a < nra; ++a)
+    for (int bb = 0; bb < nra; ++bb) G[(3 + a) * 9 + 3 + bb] = -G[a * 9 + bb];
+  for (int a = 0; a < nra; ++a)
+    for (int bb = 0; bb < nra; ++bb) G[a * 9 + 3 + bb] = -G[(3 + a) * 9 + bb];
   sp_expm<9, true>(G, W);
   double E11[9], E21[9], X[9], R[9];
 #pragma unroll
@@ -290,7 +298,8 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       if (clear_l) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) { R[k] = 0.0; Tm[k] = 0.0; RD[k] = 0.0; TDD[k] = 0.0; TD[k] = 0.0; }
-        R[0] = rc; Tm[0] = trc; RD[0] = rdc; TDD[0] = tddc; TD[0] = tdrc;
+        if (sc.use_expm_everywhere) { R[0] = MAT(l, 0); Tm[0] = MAT(l, 9); RD[0] = MAT(l, 18); TDD[0] = MAT(l, 27); TD[0] = MAT(l, 36); }
+        else { R[0] = rc; Tm[0] = trc; RD[0] = rdc; TDD[0] = tddc; TD[0] = tdrc; }
         const double inv_denom = 1.0 / (1.0 - TA[0] * R[0]);
         below[0] = R[0] + Tm[0] * Tm[0] * TA[0] * inv_denom;
         belowd[0] = RD[0] + (TD[0] * TAD[0] + TDD[0] * TA[0]) * Tm[0] * inv_denom;
@@ -435,9 +444,11 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       }
       if (clear_l) {
         const double ta0 = ALB(jl, 0), tad0 = ALB(jl, 9);
-        const double source_dn = tddc * ddn[0];
-        const double dabove = tdrc * ddn[0];
-        fdn[0] = (trc * fdn[0] + rc * tad0 * dabove + source_dn) / (1.0 - rc * ta0);
+        const bool ev = sc.use_expm_everywhere != 0;   // all-sky (1,1) elements from the matrix exponential also in clear layers
+        const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc, tdd0 = ev ? MAT(l, 27) : tddc, td0 = ev ? MAT(l, 36) : tdrc;
+        const double source_dn = tdd0 * ddn[0];
+        const double dabove = td0 * ddn[0];
+        fdn[0] = (t0 * fdn[0] + r0 * tad0 * dabove + source_dn) / (1.0 - r0 * ta0);
         fup[0] = tad0 * dabove + ta0 * fdn[0];
         ddn[0] = dabove;
         fdn[1] = 0.0; fdn[2] = 0.0; fup[1] = 0.0; fup[2] = 0.0; ddn[1] = 0.0; ddn[2] = 0.0;
@@ -522,17 +533,21 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   const LwLayer Lc = lw_ref_trans(odg, 0.0, 0.0, pt, pb);
   if (act) { clr[i] = Lc.ref; clr[n + i] = Lc.trans; clr[2 * n + i] = Lc.source_up; clr[3 * n + i] = Lc.source_dn; }
   const double frac = LD_IN(in.frac, c, l);
-  if (!(frac > 0.0)) return;
+  const bool cloudy = frac > 0.0;
+  if (!cloudy && !sc.use_expm_everywhere) return;
+  const int nra = cloudy ? 3 : 1;   // nregActive
   const double* reg = w.tc_reg + ((size_t)c * nlev + l) * 3;
   const double* ods = w.tc_ods + ((size_t)c * nlev + l) * 3;
-  double edge[3], rate[9], dz = 1.0;
+  double edge[3] = {0.0, 0.0, 0.0}, rate[9], dz = 1.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rate[k] = 0.0;
   const double inv_size = in.inv_cloud_size ? LD_IN(in.inv_cloud_size, c, l) : 0.0;
-  const bool has3d = in.inv_cloud_size && sp_edge_lengths(sc, reg, inv_size, in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
+  const bool has3d = cloudy && in.inv_cloud_size && sp_edge_lengths(sc, reg, inv_size, in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
   if (has3d) {
     dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate);
   }
-  const int ng3d = has3d ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
+  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
   if (!act) return;
   const int b = T.meta->band_of_g_lw[g];
   const double* clb = w.cl_lw + ((size_t)c * nlev + l) * 3 * SD::NB;
@@ -540,6 +555,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   od_r[0] = odg;
 #pragma unroll
   for (int jr = 1; jr < 3; ++jr) {
+    if (!cloudy) { od_r[jr] = 0.0; continue; }
     od_r[jr] = odg + clb[b] * ods[jr];
     if (cfg.do_lw_cloud_scattering) {
       const double scat_od_cloud = clb[b] * clb[SD::NB + b] * ods[jr];   // scat_od of the clear region is zero
@@ -555,7 +571,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       LwLayer L = {0.0, 0.0, 0.0, 0.0};
       if (k % 4 == 0) {
         if (jr == 0) { L = Lc; L.source_up = reg[0] * Lc.source_up; L.source_dn = reg[0] * Lc.source_dn; }
-        else L = lw_ref_trans(od_r[jr], ssa_r[jr], g_r[jr], reg[jr] * pt, reg[jr] * pb);
+        else if (jr < nra) L = lw_ref_trans(od_r[jr], ssa_r[jr], g_r[jr], reg[jr] * pt, reg[jr] * pb);
         mats[(size_t)(18 + jr) * SD::NG + g] = L.source_up;
         mats[(size_t)(21 + jr) * SD::NG + g] = L.source_dn;
       }
@@ -568,7 +584,10 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   double G[36], W[3 * 36], planck_top[6], planck_diff[6], solution0[6], solution_diff[6];
   for (int k = 0; k < 36; ++k) G[k] = 0.0;
 #pragma unroll
+  for (int k = 0; k < 6; ++k) { planck_top[k] = 0.0; planck_diff[k] = 0.0; }
+#pragma unroll
   for (int jr = 0; jr < 3; ++jr) {
+    if (jr >= nra) continue;
     const double factor = (ECB_LW_DIFFUSIVITY * 0.5) * ssa_r[jr];   // calc_two_stream_gammas_lw
     const double gamma1 = ECB_LW_DIFFUSIVITY - factor * (1.0 + g_r[jr]), gamma2 = factor * (1.0 - g_r[jr]);
     G[jr * 6 + jr] = od_r[jr] * gamma1;
@@ -578,6 +597,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     planck_diff[3 + jr] = od_r[jr] * (1.0 - ssa_r[jr]) * reg[jr] * (pb - pt) * ECB_LW_DIFFUSIVITY;
     planck_diff[jr] = -planck_diff[3 + jr];
   }
+  // non-zeros in the empty cloudy regions of a clear layer, to avoid NaNs (:622-630)
+  for (int jr = nra; jr < 3; ++jr) { G[jr * 6 + jr] = G[0]; G[(3 + jr) * 6 + jr] = G[3 * 6 + 0]; }
   double side_emiss = 1.0;
   if (sc.do_lw_side_emissivity && reg[0] > 0.0 && reg[1] > 0.0 && sc.do_3d_effects && inv_size > 0.0) {
     const double aspect_ratio = 1.0 / (dmin(inv_size, 1.0 / sc.min_cloud_effective_size) * reg[0] * dz);
@@ -591,6 +612,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   }
 #pragma unroll
   for (int jr = 0; jr < 2; ++jr) {
+    if (jr + 1 >= nra) continue;
     G[jr * 6 + jr] = G[jr * 6 + jr] + rate[jr * 3 + jr + 1];
     G[(jr + 1) * 6 + jr] = -rate[jr * 3 + jr + 1];
     if (jr > 0) {
@@ -706,10 +728,12 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
 #pragma unroll
       for (int k = 0; k < 9; ++k) below[k] = 0.0;
       if (clear_l) {
-        const double su0 = S.reg[l * 3] * suc, sd0 = S.reg[l * 3] * sdc;
-        const double inv_denom = 1.0 / (1.0 - TA[0] * rc);
-        below[0] = rc + trc * trc * TA[0] * inv_denom;
-        sbelow[0] = su0 + trc * (TS[0] + TA[0] * sd0) * inv_denom;
+        const bool ev = sc.use_expm_everywhere != 0;
+        const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc;
+        const double su0 = ev ? MAT(l, 18) : S.reg[l * 3] * suc, sd0 = ev ? MAT(l, 21) : S.reg[l * 3] * sdc;
+        const double inv_denom = 1.0 / (1.0 - TA[0] * r0);
+        below[0] = r0 + t0 * t0 * TA[0] * inv_denom;
+        sbelow[0] = su0 + t0 * (TS[0] + TA[0] * sd0) * inv_denom;
       } else {
         double R[9], Tm[9], SU[3], SDn[3];
 #pragma unroll
@@ -790,8 +814,10 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       fdc = (trc * fdc + rc * tscb + sdc) / (1.0 - rc * tacb);
       fuc = tscb + tacb * fdc;
       if (clear_l) {
-        const double ta0 = ALB(jl, 0), ts0 = ALB(jl, 9), sd0 = S.reg[l * 3] * sdc;
-        fdn[0] = (trc * fdn[0] + rc * ts0 + sd0) / (1.0 - rc * ta0);
+        const bool ev = sc.use_expm_everywhere != 0;
+        const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc;
+        const double ta0 = ALB(jl, 0), ts0 = ALB(jl, 9), sd0 = ev ? MAT(l, 21) : S.reg[l * 3] * sdc;
+        fdn[0] = (t0 * fdn[0] + r0 * ts0 + sd0) / (1.0 - r0 * ta0);
         fup[0] = ts0 + ta0 * fdn[0];
         fdn[1] = 0.0; fdn[2] = 0.0; fup[1] = 0.0; fup[2] = 0.0;
       } else {
@@ -846,7 +872,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         sp_load_m3(Ug + jl * 9, U);   // u_matrix(:,:,jlev+1)
         m3_x_vec(U, d, d);
         if (S.clear[jl]) {
-          const double trc = clr[n + (size_t)l * SD::NG + g];
+          const double trc = sc.use_expm_everywhere ? MAT(l, 9) : clr[n + (size_t)l * SD::NG + g];
           d[0] = trc * d[0]; d[1] = 0.0; d[2] = 0.0;
         } else {
           double Tm[9];

@@ -254,7 +254,7 @@ HD void sp_fast_expm_exchange_3(double a, double b, double c, double d, double* 
 
 // Scalars of config_type the SPARTACUS kernels read.
 struct SpCfg {
-  int do_3d_effects, entrapment, do_3d_lw_multilayer_effects, do_lw_side_emissivity;
+  int do_3d_effects, entrapment, do_3d_lw_multilayer_effects, do_lw_side_emissivity, use_expm_everywhere;
   double max_gas_od_3d, max_cloud_od, max_3d_transfer_rate, min_cloud_effective_size, overhead_sun_factor, overhang_factor,
       clear_to_thick_fraction;
 };

@@ -61,7 +61,8 @@ def check_exact(out, ref):
                                 dict(sw_entrapment_name="Edge-only"), dict(sw_entrapment_name="Non-fractal"),
                                 dict(do_3d_effects=False), dict(do_3d_lw_multilayer_effects=True),
                                 dict(do_lw_side_emissivity=False, clear_to_thick_fraction=0.3),
-                                dict(use_aerosols=True, do_lw_cloud_scattering=False)])
+                                dict(use_aerosols=True, do_lw_cloud_scattering=False),
+                                dict(use_expm_everywhere=True), dict(use_expm_everywhere=True, do_3d_effects=False)])
 def test_spartacus_meridian_vs_oracle(meridian_raw, kw):
     """The reference's own 32-column slice (the input of its `spartacus` / `spartacus_maxentr` ctest targets)."""
     out, ref = run_pair({**SP, **kw}, meridian_raw, 32, spectral_profiles=True)
@@ -129,8 +130,8 @@ def test_spartacus_error_behaviour():
 
     with pytest.raises(RadiationError, match="Exponential-Random"):
         setup_radiation(RadiationConfig(overlap_scheme_name="Max-Ran", **SP).consolidate())
-    with pytest.raises(RadiationError, match="use_expm_everywhere"):
-        setup_radiation(RadiationConfig(use_expm_everywhere=True, **SP).consolidate())
+    with pytest.raises(RadiationError, match="delta-Eddington scaling with gases"):
+        setup_radiation(RadiationConfig(do_sw_delta_scaling_with_gases=True, **SP).consolidate())
 
 
 def test_spartacus_full_size_properties(meridian_raw):
