@@ -62,6 +62,15 @@ HD LwLayer lw_ref_trans(double od, double ssa, double asym, double planck_top, d
 
 struct SwLayer { double ref, trans, ref_dir, trans_dir_diff, trans_dir_dir; };
 
+// delta_eddington, radiation_delta_eddington.h:20-37: with do_sw_delta_scaling_with_gases the solvers scale the gas-aerosol(-cloud)
+// mixture instead of the cloud and aerosol optics on their own
+HD void sw_delta_eddington(double& od, double& ssa, double& g) {
+  const double f = g * g;
+  od = od * (1.0 - ssa * f);
+  ssa = ssa * (1.0 - f) / (1.0 - ssa * f);
+  g = g / (1.0 + g);
+}
+
 HD SwLayer sw_ref_trans(double mu0, double od, double ssa, double asym) {
   SwLayer r;
   const double eps = DBL_EPSILON;

@@ -68,7 +68,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 // evaluation of the cloudy layers' optical properties.  Stored per layer and sub-column (clear / cloudy):
 //   a = T/(1-A*R), b = (Tdir*D*R + Tdirdif)/(1-A*R), t = Tdir, A, D      (A, D: of everything below the layer)
 // ---------------------------------------------------------------------------------------------------------
-template <class SD, bool CLOUDLESS, bool AER>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory
+template <class SD, bool CLOUDLESS, bool AER, bool DELTA>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory; DELTA: do_sw_delta_scaling_with_gases
 __global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 6))
 sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,7 +116,14 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       od_n = s.od[ip]; ssa_n = s.ssa[ip];
       if (AER) gg_n = s.gas_g[ip];
     }
-    const SwLayer Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
+    SwLayer Lc;
+    if (DELTA && AER) {   // radiation_mcica_sw.F90:165-180 (a no-op when g = 0, i.e. without aerosols)
+      double odc = odg, ssac = ssag, gc = gg_gas;
+      sw_delta_eddington(odc, ssac, gc);
+      Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odc, ssac, gc) : sw_ref_trans(mu0, odc, ssac, gc);
+    } else {
+      Lc = CLOUDLESS ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
+    }
     {
       const double inv_den = 1.0 / (1.0 - A_c * Lc.ref);
       ac[i] = Lc.trans * inv_den;
@@ -132,6 +139,7 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       if (fracs[l] >= s.thr) {
         double odt, ssat, gt;
         sw_cloudy_props<SD>(C, T.pdf_val, pick4(cq, l & 3), fsds[l], s.cl + (size_t)l * 3 * SD::NB, s.b, odg, ssag, gg_gas, odt, ssat, gt);
+        if (DELTA) sw_delta_eddington(odt, ssat, gt);   // radiation_mcica_sw.F90:274-278
         La = sw_ref_trans(mu0, odt, ssat, gt);
       }
       const double inv_den = 1.0 / (1.0 - A_a * La.ref);
@@ -313,13 +321,17 @@ static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn
   const size_t smB = sizeof(double) * (2 * nlev + 2 * SD::NB) + 16;
   const size_t smC = sizeof(double) * (6 * (nlev + 1) + 6 * SW_LCH_FLUX * SD::RS) + sizeof(double) * SW_NST * 10 * SW_BATCH * SD::NG + 2 * SW_NST * sizeof(uint64_t) + 16;
   const bool aer = cfg.use_aerosols && w.g_sw;
+  const bool delta = cfg.do_sw_delta_scaling_with_gases != 0;
+#define SW_ADDING(CL, AE, DE) sw_adding_kernel<SD, CL, AE, DE><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp)
   if (cfg.solver_sw == 2) {
-    if (aer) sw_adding_kernel<SD, false, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
-    else sw_adding_kernel<SD, false, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
-  } else {
-    if (aer) sw_adding_kernel<SD, true, true><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
-    else sw_adding_kernel<SD, true, false><<<nc, SD::THREADS, smB, st>>>(T, cfg, in, w, nlev, nlevp);
+    if (delta) { if (aer) SW_ADDING(false, true, true); else SW_ADDING(false, false, true); }
+    else { if (aer) SW_ADDING(false, true, false); else SW_ADDING(false, false, false); }
+  } else {   // Cloudless: only the gas-aerosol mixture can need the scaling
+    if (aer && delta) SW_ADDING(true, true, true);
+    else if (aer) SW_ADDING(true, true, false);
+    else SW_ADDING(true, false, false);
   }
+#undef SW_ADDING
   cudaFuncSetAttribute(sw_flux_kernel<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smC);
   sw_flux_kernel<SD><<<nc, SD::THREADS, smC, st>>>(T, cfg, in, out, w, nlev, nlevp);
   return 2;

@@ -121,7 +121,11 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
       const size_t i = (size_t)l * SD::NG + g;
       const double odg = od_n, ssag = ssa_n, gg_gas = gg_n;
       if (l > 0) { od_n = od[i - SD::NG]; ssa_n = ssa[i - SD::NG]; if (gas_g) gg_n = gas_g[i - SD::NG]; }
-      const SwLayer Lc = homog ? sw_ref_trans_cloudless(mu0, odg, ssag, gg_gas) : sw_ref_trans(mu0, odg, ssag, gg_gas);
+      // do_sw_delta_scaling_with_gases: the Homogeneous solver scales the clear-sky mixture too (radiation_homogeneous_sw.F90:145-175),
+      // Tripleclouds only its cloudy regions (radiation_tripleclouds_sw.F90:269 vs :298-302)
+      double odc = odg, ssac = ssag, gc = gg_gas;
+      if (homog && cfg.do_sw_delta_scaling_with_gases) sw_delta_eddington(odc, ssac, gc);
+      const SwLayer Lc = homog ? sw_ref_trans_cloudless(mu0, odc, ssac, gc) : sw_ref_trans(mu0, odg, ssag, gg_gas);
       {   // clear-sky column
         const double id = 1.0 / (1.0 - tac * Lc.ref);
         SCR(0, 0, i) = Lc.trans * id;
@@ -144,7 +148,9 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           const double od_total = odg + clb[b] * scal;
           const double ssa_total = (scat_od + scat_od_cloud) / od_total;
           const double g_total = (scat_od * gg_gas + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
-          L = homog ? sw_ref_trans_cloudless(mu0, od_total, ssa_total, g_total) : sw_ref_trans(mu0, od_total, ssa_total, g_total);
+          double odt = od_total, ssat = ssa_total, gt = g_total;
+          if (cfg.do_sw_delta_scaling_with_gases) sw_delta_eddington(odt, ssat, gt);
+          L = homog ? sw_ref_trans_cloudless(mu0, odt, ssat, gt) : sw_ref_trans(mu0, odt, ssat, gt);
         }
         const double id = 1.0 / (1.0 - ta[jr] * L.ref);
         SCR(1 + jr, 0, i) = L.trans * id;

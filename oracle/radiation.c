@@ -410,6 +410,17 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   free(pool);
 }
 
+/* delta_eddington, radiation_delta_eddington.h:20-37 (do_sw_delta_scaling_with_gases: applied to the gas-aerosol(-cloud) mixture
+ * inside the solver instead of to the aerosol and cloud parts on their own) */
+static void delta_eddington_vec(int n, double* od, double* ssa, double* g) {
+  for (int i = 0; i < n; ++i) {
+    const double f = g[i] * g[i];
+    od[i] = od[i] * (1.0 - ssa[i] * f);
+    ssa[i] = ssa[i] * (1.0 - f) / (1.0 - ssa[i] * f);
+    g[i] = g[i] / (1.0 + g[i]);
+  }
+}
+
 /* ----- SW: radiation_mcica_sw.F90:41-408 and radiation_cloudless_sw.F90 ----- */
 static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                       const ecrad_b200_inputs* in, ecrad_b200_outputs* out, const col_work* w, const double* frac) {
@@ -441,7 +452,19 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   double *od_total = fdir + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
   const double* gzero = w->g_sw;   /* g_sw: zero without aerosols (radiation_interface.F90:395), else from add_aerosol_optics */
   const int cloudless = (cfg->i_solver_sw == ECRAD_SOLVER_CLOUDLESS);
-  if (cloudless) {
+  if (cfg->do_sw_delta_scaling_with_gases) {
+    /* radiation_mcica_sw.F90:165-180 / radiation_cloudless_sw.F90:126-146: scale the gas-aerosol mixture layer by layer */
+    for (int jl = 0; jl < nlev; ++jl) {
+      for (int g = 0; g < ng; ++g) { od_total[g] = w->od_sw[(size_t)jl * ng + g]; ssa_total[g] = w->ssa_sw[(size_t)jl * ng + g]; g_total[g] = gzero[(size_t)jl * ng + g]; }
+      delta_eddington_vec(ng, od_total, ssa_total, g_total);
+      if (cloudless)
+        orc_calc_reflectance_transmittance_sw(ng, cos_sza, od_total, ssa_total, g_total, ref_clear + (size_t)jl * ng, trans_clear + (size_t)jl * ng,
+                                              rdir_clear + (size_t)jl * ng, tdd_clear + (size_t)jl * ng, tdir_clear + (size_t)jl * ng);
+      else
+        orc_calc_ref_trans_sw(ng, cos_sza, od_total, ssa_total, g_total, ref_clear + (size_t)jl * ng, trans_clear + (size_t)jl * ng,
+                              rdir_clear + (size_t)jl * ng, tdd_clear + (size_t)jl * ng, tdir_clear + (size_t)jl * ng);
+    }
+  } else if (cloudless) {
     for (int jl = 0; jl < nlev; ++jl)
       orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, gzero + (size_t)jl * ng,
                                             ref_clear + (size_t)jl * ng, trans_clear + (size_t)jl * ng, rdir_clear + (size_t)jl * ng,
@@ -508,6 +531,7 @@ static void solver_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
               g_total[g] = (gzero[i] * w->ssa_sw[i] * w->od_sw[i] + w->g_sw_cloud[jl * NB_SW + jb] * w->ssa_sw_cloud[jl * NB_SW + jb] * od_cloud_new) / scat_od;
           }
         }
+        if (cfg->do_sw_delta_scaling_with_gases) delta_eddington_vec(ng, od_total, ssa_total, g_total);   /* radiation_mcica_sw.F90:274-278 */
         orc_calc_ref_trans_sw(ng, cos_sza, od_total, ssa_total, g_total, ref + (size_t)jl * ng, trans + (size_t)jl * ng,
                               rdir + (size_t)jl * ng, tdd + (size_t)jl * ng, tdir + (size_t)jl * ng);
       } else {
@@ -572,10 +596,12 @@ static void solver_homog(const orc_tables* t, const ecrad_b200_config* cfg, int 
     double* pool = (double*)malloc(sizeof(double) * (5 * nl + 3 * nl1 + 3 * (size_t)ng));
     double *ref = pool, *trans = ref + nl, *rdir = trans + nl, *tdd = rdir + nl, *tdir = tdd + nl;
     double *fu = tdir + nl, *fdd = fu + nl1, *fdir = fdd + nl1, *od_total = fdir + nl1, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
-    for (int jl = 0; jl < nlev; ++jl)
-      orc_calc_reflectance_transmittance_sw(ng, cos_sza, w->od_sw + (size_t)jl * ng, w->ssa_sw + (size_t)jl * ng, w->g_sw + (size_t)jl * ng,
-                                            ref + (size_t)jl * ng, trans + (size_t)jl * ng, rdir + (size_t)jl * ng, tdd + (size_t)jl * ng,
-                                            tdir + (size_t)jl * ng);
+    for (int jl = 0; jl < nlev; ++jl) {
+      for (int g = 0; g < ng; ++g) { od_total[g] = w->od_sw[(size_t)jl * ng + g]; ssa_total[g] = w->ssa_sw[(size_t)jl * ng + g]; g_total[g] = w->g_sw[(size_t)jl * ng + g]; }
+      if (cfg->do_sw_delta_scaling_with_gases) delta_eddington_vec(ng, od_total, ssa_total, g_total);   /* radiation_homogeneous_sw.F90:145-175 */
+      orc_calc_reflectance_transmittance_sw(ng, cos_sza, od_total, ssa_total, g_total, ref + (size_t)jl * ng, trans + (size_t)jl * ng,
+                                            rdir + (size_t)jl * ng, tdd + (size_t)jl * ng, tdir + (size_t)jl * ng);
+    }
     for (int pass = 0; pass < 2; ++pass) {   /* 0: clear sky, 1: all sky */
       if (pass == 1) {
         if (!is_cloudy_profile) {   /* all-sky = clear-sky */
@@ -596,6 +622,7 @@ static void solver_homog(const orc_tables* t, const ecrad_b200_config* cfg, int 
                 g_total[g] = (w->g_sw[i] * w->ssa_sw[i] * w->od_sw[i] + w->g_sw_cloud[jl * nb + ib] * w->ssa_sw_cloud[jl * nb + ib] * od_cloud_g) /
                              (ssa_total[g] * od_total[g]);
             }
+            if (cfg->do_sw_delta_scaling_with_gases) delta_eddington_vec(ng, od_total, ssa_total, g_total);   /* :257-259 */
             orc_calc_reflectance_transmittance_sw(ng, cos_sza, od_total, ssa_total, g_total, ref + (size_t)jl * ng, trans + (size_t)jl * ng,
                                                   rdir + (size_t)jl * ng, tdd + (size_t)jl * ng, tdir + (size_t)jl * ng);
           }
@@ -891,7 +918,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  if (cfg->do_lw_aerosol_scattering || cfg->do_sw_delta_scaling_with_gases ||
+  if (cfg->do_lw_aerosol_scattering || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
       (cfg->use_vectorizable_generator && cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;

@@ -149,6 +149,13 @@ void orc_tripleclouds_sw(const orc_tables* t, const ecrad_b200_config* cfg, int 
         ssa_total[jg] = (scat_od + scat_od_cloud) / od_total[jg];
         g_total[jg] = (scat_od * g[i] + scat_od_cloud * g_cloud[(jl - 1) * NB_SW + ib]) / (scat_od + scat_od_cloud);
       }
+      if (cfg->do_sw_delta_scaling_with_gases)   /* radiation_tripleclouds_sw.F90:298-302: cloudy regions only, the clear region is not scaled */
+        for (int jg = 0; jg < ng; ++jg) {
+          const double f = g_total[jg] * g_total[jg];
+          od_total[jg] = od_total[jg] * (1.0 - ssa_total[jg] * f);
+          ssa_total[jg] = ssa_total[jg] * (1.0 - f) / (1.0 - ssa_total[jg] * f);
+          g_total[jg] = g_total[jg] / (1.0 + g_total[jg]);
+        }
       orc_calc_ref_trans_sw(ng, mu0, od_total, ssa_total, g_total, &A3(ref, jl - 1, jr, 0), &A3(tr, jl - 1, jr, 0),
                             &A3(rdir, jl - 1, jr, 0), &A3(tdd, jl - 1, jr, 0), &A3(tdir, jl - 1, jr, 0));
     }

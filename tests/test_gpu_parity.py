@@ -152,7 +152,11 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_beta_overlap=True),
                                 dict(use_vectorizable_generator=True), dict(use_vectorizable_generator=True, overlap_scheme_name="Max-Ran", use_aerosols=True),
                                 dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"),
-                                dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", use_aerosols=True, do_lw_cloud_scattering=False)])
+                                dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", use_aerosols=True, do_lw_cloud_scattering=False),
+                                dict(do_sw_delta_scaling_with_gases=True), dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True),
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous")])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
