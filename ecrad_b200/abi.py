@@ -15,6 +15,7 @@ OVERLAP = {"max-ran": 0, "exp-ran": 1, "exp-exp": 2}
 LIQ_MODEL = {"socrates": 1}
 ICE_MODEL = {"fu-ifs": 1}
 # sw_entrapment_name (radiation_config.F90:69-84)
+PDF_SHAPE = {"lognormal": 0, "gamma": 1}   # cloud_pdf_shape_name (radiation_config.F90:134-142)
 ENTRAPMENT = {"zero": 0, "edge-only": 1, "explicit": 2, "non-fractal": 3, "maximum": 4}
 
 
@@ -45,6 +46,7 @@ class Config(C.Structure):
         ("min_cloud_effective_size", C.c_double),
         ("overhead_sun_factor", C.c_double), ("overhang_factor", C.c_double), ("clear_to_thick_fraction", C.c_double),
         ("do_lw_side_emissivity", C.c_int32), ("use_expm_everywhere", C.c_int32),
+        ("i_cloud_pdf_shape", C.c_int32),
     ]
 
 

@@ -74,6 +74,8 @@ class RadiationConfig:
     do_lw_aerosol_scattering: bool = False
     do_lw_cloud_scattering: bool = True
     cloud_inhom_decorr_scaling: float = 0.5
+    cloud_pdf_shape_name: str = "Gamma"   # shape of the sub-grid cloud water PDF: regions of Tripleclouds / SPARTACUS (the McICA
+                                          # look-up table of the shipped blob is the gamma one, data/mcica_gamma.nc)
     use_beta_overlap: bool = False
     use_vectorizable_generator: bool = False
     use_aerosols: bool = False
@@ -178,6 +180,10 @@ class RadiationConfig:
                   "do_3d_effects", "do_3d_lw_multilayer_effects", "do_lw_side_emissivity", "use_expm_everywhere"):
             setattr(c, k, int(getattr(self, k)))
         c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
+        c.i_cloud_pdf_shape = abi.PDF_SHAPE[self.cloud_pdf_shape_name.lower()]
+        if c.i_cloud_pdf_shape == 0 and "mcica" in (self.sw_solver_name.lower(), self.lw_solver_name.lower()):
+            raise ValueError("the shipped table blob holds the gamma PDF look-up table of the McICA generator (mcica_gamma.nc); "
+                             "a lognormal McICA run needs 'pdf_val' from mcica_lognormal.nc")
         for k in ("max_gas_od_3d", "max_cloud_od", "max_3d_transfer_rate", "overhead_sun_factor", "overhang_factor",
                   "clear_to_thick_fraction"):
             setattr(c, k, float(getattr(self, k)))

@@ -105,6 +105,7 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   const int gm = c.do_lw ? c.i_gas_model_lw : c.i_gas_model_sw;
   if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
     return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");
+  if (c.i_cloud_pdf_shape != ECRAD_PDF_GAMMA && c.i_cloud_pdf_shape != ECRAD_PDF_LOGNORMAL) return fail(h, "unknown cloud PDF shape");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
     return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
@@ -420,6 +421,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.pdf_gamma = cfg->i_cloud_pdf_shape == ECRAD_PDF_GAMMA;
   d.is_homogeneous = (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS);   // radiation_config.F90:1351-1356
   d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;
   d.ckd_ngas_lw = P.ckd.lw.ngas; d.ckd_nlut_lw = P.ckd.lw.nlut; d.ckd_ngas_sw = P.ckd.sw.ngas; d.ckd_nlut_sw = P.ckd.sw.nlut;

@@ -66,6 +66,7 @@ struct DevCfg {
   int use_vectorizable_generator;
   int do_nearest_spectral_lw_emiss;
   int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
+  int pdf_gamma;                 // config%i_cloud_pdf_shape == IPdfShapeGamma (regions of Tripleclouds / SPARTACUS)
   int is_homogeneous;            // config%is_homogeneous: Homogeneous solvers (gridbox-mean cloud water paths, clouds fill the box)
   int ckd_ngas_lw, ckd_nlut_lw, ckd_ngas_sw, ckd_nlut_sw;   // ecCKD: gases / look-up-table gases per model (shared-memory sizing)
   int ng_lw, ng_sw, nb_lw, nb_sw;   // spectral sizes: RRTMG 140/112/16/14; ecCKD ng = nb = 32/64/96

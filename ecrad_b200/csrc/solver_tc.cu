@@ -41,9 +41,9 @@ tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
   for (int jlev = 1 + (int)threadIdx.x; jlev <= nlev + 1; jlev += TC_PREP_THREADS) {   // interface above layer jlev (1-based)
     double fu[3] = {1.0, 0.0, 0.0}, fl[3] = {1.0, 0.0, 0.0}, o_[3], M[3][3];
     const bool homog = cfg.is_homogeneous != 0;
-    if (jlev > 1) { if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 2), thr, fu, o_); else tc_region(LD_IN(in.frac, c, jlev - 2), LD_IN(in.fsd, c, jlev - 2), thr, fu, o_); }
+    if (jlev > 1) { if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 2), thr, fu, o_); else tc_region(LD_IN(in.frac, c, jlev - 2), LD_IN(in.fsd, c, jlev - 2), thr, fu, o_, cfg.pdf_gamma != 0); }
     if (jlev <= nlev) {
-      if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 1), thr, fl, o_); else tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_);
+      if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 1), thr, fl, o_); else tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_, cfg.pdf_gamma != 0);
       for (int r = 0; r < 3; ++r) { reg[(jlev - 1) * 3 + r] = fl[r]; ods[(jlev - 1) * 3 + r] = o_[r]; }
     }
     double op1 = 1.0, op2 = 1.0;

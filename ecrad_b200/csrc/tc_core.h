@@ -11,7 +11,17 @@ namespace ecb {
 enum { TC_NREG = 3 };
 
 // region fractions reg[3] and optical-depth scalings ods[3] (ods[0] unused) of one layer
-HD void tc_region(double frac, double fsd, double frac_threshold, double* reg, double* ods) {
+HD void tc_region(double frac, double fsd, double frac_threshold, double* reg, double* ods, bool do_gamma = true) {
+  if (!do_gamma) {   // lognormal PDF: two cloudy regions of equal size (radiation_regions.F90:110-126)
+    ods[0] = 0.0;
+    if (frac < frac_threshold) { reg[0] = 1.0; reg[1] = 0.0; reg[2] = 0.0; ods[1] = 1.0; ods[2] = 1.0; }
+    else {
+      reg[0] = 1.0 - frac; reg[1] = frac * 0.5; reg[2] = frac * 0.5;
+      ods[1] = exp(-sqrt(log(fsd * fsd + 1.0))) / sqrt(fsd * fsd + 1.0);
+      ods[2] = 2.0 - ods[1];
+    }
+    return;
+  }
   const double MinGammaODScaling = 0.025, MinLowerFrac = 0.5, MaxLowerFrac = 0.9, FSDAtMinLowerFrac = 1.5, FSDAtMaxLowerFrac = 3.725;
   const double LowerFracFSDGradient = (MaxLowerFrac - MinLowerFrac) / (FSDAtMaxLowerFrac - FSDAtMinLowerFrac);
   const double LowerFracFSDIntercept = MinLowerFrac - FSDAtMinLowerFrac * LowerFracFSDGradient;

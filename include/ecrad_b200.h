@@ -33,6 +33,7 @@ enum { ECRAD_GAS_MONOCHROMATIC = 0, ECRAD_GAS_IFSRRTMG = 1, ECRAD_GAS_ECCKD = 2 
 enum { ECRAD_OVERLAP_MAX_RAN = 0, ECRAD_OVERLAP_EXP_RAN = 1, ECRAD_OVERLAP_EXP_EXP = 2 }; /* radiation_cloud_cover.F90:30-33 */
 enum { ECRAD_LIQ_SOCRATES = 1 };                                          /* radiation_config.F90:95-99  */
 enum { ECRAD_ICE_FU = 1 };                                                /* radiation_config.F90:107-111 */
+enum { ECRAD_PDF_LOGNORMAL = 0, ECRAD_PDF_GAMMA = 1 };                    /* radiation_config.F90:134-138 */
 /* SPARTACUS shortwave entrapment, config%i_3d_sw_entrapment (radiation_config.F90:69-77) */
 enum { ECRAD_ENTRAPMENT_ZERO = 0, ECRAD_ENTRAPMENT_EDGE_ONLY = 1, ECRAD_ENTRAPMENT_EXPLICIT = 2,
        ECRAD_ENTRAPMENT_EXPLICIT_NON_FRACTAL = 3, ECRAD_ENTRAPMENT_MAXIMUM = 4 };
@@ -64,6 +65,8 @@ typedef struct ecrad_b200_config {
   double max_gas_od_3d, max_cloud_od, max_3d_transfer_rate, min_cloud_effective_size;  /* defaults 8, 16, 10, 100 m */
   double overhead_sun_factor, overhang_factor, clear_to_thick_fraction;                /* defaults 0, 0, 0          */
   int32_t do_lw_side_emissivity, use_expm_everywhere;                                  /* defaults 1, 0             */
+  int32_t i_cloud_pdf_shape;         /* config%i_cloud_pdf_shape (radiation_config.F90:134-138): 0 lognormal, 1 gamma (default); shapes the
+                                      * two cloudy regions of Tripleclouds / SPARTACUS; McICA takes it through the 'pdf_val' table */
 } ecrad_b200_config;
 
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md

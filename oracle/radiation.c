@@ -923,6 +923,7 @@ int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, i
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
   }
+  { extern void orc_set_region_pdf(int); orc_set_region_pdf(cfg->i_cloud_pdf_shape); }
   if (!out->lw_up_clear || !out->lw_dn_clear || !out->sw_up_clear || !out->sw_dn_clear || !out->sw_dn_direct_clear) {
     fprintf(stderr, "oracle: clear-sky flux outputs are required (do_clear)\n");
     return 11;

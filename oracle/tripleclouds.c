@@ -24,6 +24,8 @@ static inline double dmin(double a, double b) { return a < b ? a : b; }
 static inline double dmax(double a, double b) { return a > b ? a : b; }
 
 /* radiation_regions.F90:35-199, nreg = 3, do_gamma = .true. (config%i_cloud_pdf_shape default) */
+static int g_region_lognormal = 0;   /* set per call by orc_set_region_pdf (threads share the configuration) */
+void orc_set_region_pdf(int i_cloud_pdf_shape) { g_region_lognormal = (i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL); }
 void orc_region_properties(int nlev, const double* frac, const double* fsd, double frac_threshold,
                            double (*reg_fracs)[NREG], double (*od_scaling)[NREG]) {
   const double MinGammaODScaling = 0.025, MinLowerFrac = 0.5, MaxLowerFrac = 0.9, FSDAtMinLowerFrac = 1.5,
@@ -34,6 +36,11 @@ void orc_region_properties(int nlev, const double* frac, const double* fsd, doub
     if (frac[jl] < frac_threshold) {
       reg_fracs[jl][0] = 1.0; reg_fracs[jl][1] = 0.0; reg_fracs[jl][2] = 0.0;
       od_scaling[jl][1] = 1.0; od_scaling[jl][2] = 1.0;
+    } else if (g_region_lognormal) {   /* radiation_regions.F90:110-126 */
+      reg_fracs[jl][0] = 1.0 - frac[jl];
+      reg_fracs[jl][1] = frac[jl] * 0.5; reg_fracs[jl][2] = frac[jl] * 0.5;
+      od_scaling[jl][1] = exp(-sqrt(log(fsd[jl] * fsd[jl] + 1.0))) / sqrt(fsd[jl] * fsd[jl] + 1.0);
+      od_scaling[jl][2] = 2.0 - od_scaling[jl][1];
     } else {
       reg_fracs[jl][0] = 1.0 - frac[jl];
       reg_fracs[jl][1] = frac[jl] * dmax(MinLowerFrac, dmin(MaxLowerFrac, LowerFracFSDIntercept + fsd[jl] * LowerFracFSDGradient));

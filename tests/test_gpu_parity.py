@@ -153,6 +153,8 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(use_vectorizable_generator=True), dict(use_vectorizable_generator=True, overlap_scheme_name="Max-Ran", use_aerosols=True),
                                 dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"),
                                 dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", use_aerosols=True, do_lw_cloud_scattering=False),
+                                dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", cloud_pdf_shape_name="Lognormal"),
+                                dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, cloud_pdf_shape_name="Lognormal"),
                                 dict(do_sw_delta_scaling_with_gases=True), dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
@@ -160,10 +162,10 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600
-    h, orc, _ = handles(**kw)
+    h, orc, cfg = handles(**kw)
     raw = I.synthetic_columns(meridian_raw, n)
-    out = h.radiation(I.to_radiation_inputs(raw), n, NLEV)
-    ref = orc.radiation(I.to_radiation_inputs(raw), n, NLEV)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
     compare(out, ref, FLUXES + OTHERS)
     assert np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
     assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
