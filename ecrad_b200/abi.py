@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("min_cloud_effective_size", C.c_double),
         ("overhead_sun_factor", C.c_double), ("overhang_factor", C.c_double), ("clear_to_thick_fraction", C.c_double),
         ("do_lw_side_emissivity", C.c_int32), ("use_expm_everywhere", C.c_int32),
-        ("i_cloud_pdf_shape", C.c_int32),
+        ("do_toa_spectral_flux", C.c_int32), ("i_cloud_pdf_shape", C.c_int32),
     ]
 
 
@@ -89,6 +89,8 @@ OUTPUT_ARRAYS = [
     ("sw_dn_diffuse_surf_canopy", "as"), ("sw_dn_direct_surf_canopy", "as"),
     ("lw_dn_surf_canopy", "al"),
     ("lw_up_band", "pl"), ("lw_dn_band", "pl"), ("sw_up_band", "ps"), ("sw_dn_band", "ps"), ("sw_dn_direct_band", "ps"),
+    ("sw_dn_toa_g", "gs"), ("sw_dn_toa_band", "bs"), ("sw_up_toa_band", "bs"), ("sw_up_toa_clear_band", "bs"),
+    ("lw_up_toa_band", "bl"), ("lw_up_toa_clear_band", "bl"),
 ]
 
 
@@ -100,7 +102,7 @@ def output_shape(kind, ncol, nlev, cfg):
     """Fortran shape of a flux_type component (radiation_flux.F90:147-300)."""
     return {
         "h": (ncol, nlev + 1), "c": (ncol,), "gl": (cfg.n_g_lw, ncol), "gs": (cfg.n_g_sw, ncol),
-        "bs": (cfg.n_bands_sw, ncol), "as": (cfg.n_canopy_bands_sw, ncol), "al": (cfg.n_canopy_bands_lw, ncol),
+        "bs": (cfg.n_bands_sw, ncol), "bl": (cfg.n_bands_lw, ncol), "as": (cfg.n_canopy_bands_sw, ncol), "al": (cfg.n_canopy_bands_lw, ncol),
         "pl": (cfg.n_bands_lw, ncol, nlev + 1), "ps": (cfg.n_bands_sw, ncol, nlev + 1),
     }[kind]
 

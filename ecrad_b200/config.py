@@ -82,6 +82,7 @@ class RadiationConfig:
     do_save_spectral_flux: bool = True
     do_lw_derivatives: bool = True
     do_surface_sw_spectral_flux: bool = True
+    do_toa_spectral_flux: bool = False
     do_fu_lw_ice_optics_bug: bool = False
     do_sw_delta_scaling_with_gases: bool = False
     do_canopy_fluxes_lw: bool = True
@@ -177,7 +178,7 @@ class RadiationConfig:
                   "do_fu_lw_ice_optics_bug", "use_beta_overlap", "use_vectorizable_generator",
                   "do_surface_sw_spectral_flux", "do_canopy_fluxes_sw", "do_canopy_fluxes_lw", "do_save_spectral_flux",
                   "do_nearest_spectral_sw_albedo", "do_nearest_spectral_lw_emiss",
-                  "do_3d_effects", "do_3d_lw_multilayer_effects", "do_lw_side_emissivity", "use_expm_everywhere"):
+                  "do_3d_effects", "do_3d_lw_multilayer_effects", "do_lw_side_emissivity", "use_expm_everywhere", "do_toa_spectral_flux"):
             setattr(c, k, int(getattr(self, k)))
         c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
         c.i_cloud_pdf_shape = abi.PDF_SHAPE[self.cloud_pdf_shape_name.lower()]

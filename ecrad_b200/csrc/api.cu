@@ -33,7 +33,7 @@ struct Buf {   // grow-only device buffer
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { N_IN = 28, N_OUT = 35, N_STAGE = 5 };
+enum { N_IN = 28, N_OUT = 41, N_STAGE = 5 };
 const char* kStageNames[N_STAGE] = {"gas_optics_lw", "gas_optics_sw", "cloud_optics_generator", "solver_lw", "solver_sw"};
 
 struct Slot {            // device staging of one tile's inputs and outputs
@@ -227,9 +227,11 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud[set], 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud[set], 0)); }
   CK(h, cudaEventRecord(ev[6], s_lw));
   if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w[set], nc, nlev, s_lw);
+  if (c.do_lw && c.do_toa_spectral_flux) n += launch_toa_spectral(h->T, c, in, out, nc, false, s_lw);
   CK(h, cudaEventRecord(ev[7], s_lw));
   CK(h, cudaEventRecord(ev[8], s_sw));
   if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w[set], nc, nlev, s_sw);
+  if (c.do_sw && c.do_toa_spectral_flux) n += launch_toa_spectral(h->T, c, in, out, nc, true, s_sw);
   CK(h, cudaEventRecord(ev[9], s_sw));
   if (par) {
     CK(h, cudaEventRecord(h->ev_sw_done[set], s_sw));
@@ -272,6 +274,8 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
     return fail(h, "SPARTACUS with do_3d_effects needs cloud%%inv_cloud_effective_size");
   if (c.do_lw && (!out->lw_up || !out->lw_dn)) return fail(h, "flux%%lw_up/lw_dn must be allocated");
   if (c.do_sw && (!out->sw_up || !out->sw_dn)) return fail(h, "flux%%sw_up/sw_dn must be allocated");
+  if (c.do_toa_spectral_flux && ((c.do_sw && out->sw_up_toa_band && !out->sw_up_toa_g) || (c.do_lw && out->lw_up_toa_band && !out->lw_up_toa_g)))
+    return fail(h, "do_toa_spectral_flux: flux%%sw_up_toa_g / lw_up_toa_g must be allocated");
   return 0;
 }
 
@@ -301,7 +305,9 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
       {out->sw_dn_diffuse_surf_canopy, 1, c.n_canopy_bands_sw}, {out->sw_dn_direct_surf_canopy, 1, c.n_canopy_bands_sw},
       {out->lw_dn_surf_canopy, 1, c.n_canopy_bands_lw},
       {out->lw_up_band, 2, c.n_bands_lw}, {out->lw_dn_band, 2, c.n_bands_lw}, {out->sw_up_band, 2, c.n_bands_sw}, {out->sw_dn_band, 2, c.n_bands_sw},
-      {out->sw_dn_direct_band, 2, c.n_bands_sw}};
+      {out->sw_dn_direct_band, 2, c.n_bands_sw},
+      {out->sw_dn_toa_g, 1, c.n_g_sw}, {out->sw_dn_toa_band, 1, c.n_bands_sw}, {out->sw_up_toa_band, 1, c.n_bands_sw},
+      {out->sw_up_toa_clear_band, 1, c.n_bands_sw}, {out->lw_up_toa_band, 1, c.n_bands_lw}, {out->lw_up_toa_clear_band, 1, c.n_bands_lw}};
   for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
 }
 
@@ -321,7 +327,7 @@ void make_views(void* const* ip, void* const* op, int ld, int ld_out, double sol
   dout.ld = ld_out;
 }
 static_assert(sizeof(DevOut) >= N_OUT * sizeof(double*) + sizeof(int), "DevOut layout");
-static_assert(offsetof(DevOut, sw_dn_direct_band) == (N_OUT - 1) * sizeof(double*), "DevOut must list the 35 outputs in ABI order");
+static_assert(offsetof(DevOut, lw_up_toa_clear_band) == (N_OUT - 1) * sizeof(double*), "DevOut must list the 41 outputs in ABI order");
 
 }  // namespace
 
@@ -421,6 +427,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.do_toa_spectral_flux = cfg->do_toa_spectral_flux;
   d.pdf_gamma = cfg->i_cloud_pdf_shape == ECRAD_PDF_GAMMA;
   d.is_homogeneous = (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS);   // radiation_config.F90:1351-1356
   d.ng_lw = cfg->n_g_lw; d.ng_sw = cfg->n_g_sw; d.nb_lw = cfg->n_bands_lw; d.nb_sw = cfg->n_bands_sw;
@@ -561,7 +568,7 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
   // outputs the kernels do not produce in this configuration are left untouched on the host
   auto out_active = [&](int k) {
     if (!od[k].host) return false;
-    const bool lw = (k <= 3) || k == 10 || k == 11 || (k >= 13 && k <= 16) || k == 29 || k == 30 || k == 31;
+    const bool lw = (k <= 3) || k == 10 || k == 11 || (k >= 13 && k <= 16) || k == 29 || k == 30 || k == 31 || k == 39 || k == 40;
     if (lw && !c.do_lw) return false;
     if (!lw && !c.do_sw) return false;
     if (k == 11) return mcica_lw || (c.do_lw && (c.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || c.i_solver_lw == ECRAD_SOLVER_SPARTACUS));
@@ -570,6 +577,9 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     if (k >= 23 && k <= 26) return c.do_surface_sw_spectral_flux != 0 && (k < 25 || c.do_clear);
     if (k == 27 || k == 28) return c.do_canopy_fluxes_sw != 0;
     if (k == 29) return c.do_canopy_fluxes_lw != 0;
+    if (k == 35) return c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;                                  // sw_dn_toa_g: only Tripleclouds sets it
+    if (k == 36) return c.do_toa_spectral_flux != 0 && c.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS;
+    if (k >= 37) return c.do_toa_spectral_flux != 0 && (c.do_clear || (k != 38 && k != 40));
     if (k >= 30) {   // per-band profiles: Cloudless and Tripleclouds solvers with do_save_spectral_flux
       const int sol = k <= 31 ? c.i_solver_lw : c.i_solver_sw;
       return c.do_save_spectral_flux != 0 && sol != ECRAD_SOLVER_MCICA;   // every solver but McICA stores per-band profiles
@@ -601,6 +611,9 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     }
     // night columns keep the caller's cloud_cover_sw (the reference does not touch it): stage the current values
     if (op[12]) CK(h, cudaMemcpyAsync(op[12], od[12].host + c0, 8 * (size_t)nt, cudaMemcpyHostToDevice, h->s_h2d));
+    // likewise sw_dn_toa_g / sw_dn_toa_band of night columns (Tripleclouds sets them for sunlit columns only)
+    for (int k = 35; k <= 36; ++k)
+      if (op[k]) CK(h, cudaMemcpyAsync(op[k], od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)nt * od[k].rows, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(s.h2d_done, h->s_h2d));
     // ---- kernels ----
     DevIn di; DevOut dout;

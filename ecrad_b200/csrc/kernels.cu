@@ -773,6 +773,29 @@ int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const 
   gas_sw_kernel<<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
   return 1;
 }
+// flux%calc_toa_spectral (radiation_flux.F90:579-660): band sums of the per-g-point top-of-atmosphere fluxes, one thread per
+// (column, band), g-points added in ascending order like indexed_sum
+__global__ void toa_spectral_kernel(DevTables T, DevOut out, const double* mu0_of, int nc, int ng, int nb, int sw, int do_clear, int with_dn) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * nb) return;
+  const int c = t / nb, b = t - c * nb;
+  const BandMeta& B = sw ? T.meta->sw[b] : T.meta->lw[b];
+  const double* src[3] = {sw ? out.sw_up_toa_g : out.lw_up_toa_g, sw ? out.sw_up_toa_clear_g : out.lw_up_toa_clear_g, sw ? out.sw_dn_toa_g : nullptr};
+  double* dst[3] = {sw ? out.sw_up_toa_band : out.lw_up_toa_band, sw ? out.sw_up_toa_clear_band : out.lw_up_toa_clear_band, sw ? out.sw_dn_toa_band : nullptr};
+  for (int k = 0; k < 3; ++k) {
+    if (!src[k] || !dst[k] || (k == 1 && !do_clear) || (k == 2 && !with_dn)) continue;
+    if (k == 2 && mu0_of && mu0_of[c] < 1.0e-10) continue;   // night column: sw_dn_toa_g was not set, leave its band sums alone
+    double acc = 0.0;
+    for (int g = B.g0; g < B.g0 + B.ng; ++g) acc = acc + src[k][(size_t)c * ng + g];
+    dst[k][(size_t)c * nb + b] = acc;
+  }
+}
+int launch_toa_spectral(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, int nc, bool sw, cudaStream_t st) {
+  const int ng = sw ? cfg.ng_sw : cfg.ng_lw, nb = sw ? cfg.nb_sw : cfg.nb_lw;
+  // sw_dn_toa_g is only set by the Tripleclouds solver (radiation_tripleclouds_sw.F90:444), so only then is its band sum defined
+  toa_spectral_kernel<<<(nc * nb + 127) / 128, 128, 0, st>>>(T, out, sw ? in.cos_sza : nullptr, nc, ng, nb, sw ? 1 : 0, cfg.do_clear, sw && cfg.solver_sw == 4);
+  return 1;
+}
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
   int n = 0;

@@ -35,7 +35,9 @@ struct DevOut {
   double *sw_up_toa_g, *sw_up_toa_clear_g;
   double *sw_dn_surf_band, *sw_dn_direct_surf_band, *sw_dn_surf_clear_band, *sw_dn_direct_surf_clear_band;
   double *sw_dn_diffuse_surf_canopy, *sw_dn_direct_surf_canopy, *lw_dn_surf_canopy;
-  double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;  // (nband, ld, nlev+1), Cloudless only
+  double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;  // (nband, ld, nlev+1)
+  double *sw_dn_toa_g;                                                            // (ng_sw, ld), Tripleclouds only
+  double *sw_dn_toa_band, *sw_up_toa_band, *sw_up_toa_clear_band, *lw_up_toa_band, *lw_up_toa_clear_band;   // (nband, ld): calc_toa_spectral
   int ld;
 };
 
@@ -66,6 +68,7 @@ struct DevCfg {
   int use_vectorizable_generator;
   int do_nearest_spectral_lw_emiss;
   int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
+  int do_toa_spectral_flux;
   int pdf_gamma;                 // config%i_cloud_pdf_shape == IPdfShapeGamma (regions of Tripleclouds / SPARTACUS)
   int is_homogeneous;            // config%is_homogeneous: Homogeneous solvers (gridbox-mean cloud water paths, clouds fill the box)
   int ckd_ngas_lw, ckd_nlut_lw, ckd_ngas_sw, ckd_nlut_sw;   // ecCKD: gases / look-up-table gases per model (shared-memory sizing)
@@ -117,6 +120,7 @@ size_t sp_scratch_doubles_lw(int nlev, int ng);
 size_t sp_scratch_doubles_sw(int nlev, int ng);
 int launch_sp_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_toa_spectral(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, int nc, bool sw, cudaStream_t st);   // flux%calc_toa_spectral
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 

@@ -245,6 +245,7 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     if (out.sw_dn_direct_surf_clear_g) out.sw_dn_direct_surf_clear_g[i] = dir_c;
     if (out.sw_up_toa_g) out.sw_up_toa_g[i] = toa_a;
     if (out.sw_up_toa_clear_g) out.sw_up_toa_clear_g[i] = toa_c;
+    if (out.sw_dn_toa_g && !homog) out.sw_dn_toa_g[i] = inc * mu0;   // radiation_tripleclouds_sw.F90:444
   }
   sw_surface_spectral<SD>(T, cfg, out, c, g, act, tile, SD::RS, dir_a, dif_a, dir_c, dif_c);
 }

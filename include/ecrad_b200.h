@@ -65,6 +65,7 @@ typedef struct ecrad_b200_config {
   double max_gas_od_3d, max_cloud_od, max_3d_transfer_rate, min_cloud_effective_size;  /* defaults 8, 16, 10, 100 m */
   double overhead_sun_factor, overhang_factor, clear_to_thick_fraction;                /* defaults 0, 0, 0          */
   int32_t do_lw_side_emissivity, use_expm_everywhere;                                  /* defaults 1, 0             */
+  int32_t do_toa_spectral_flux;      /* config%do_toa_spectral_flux (default 0) */
   int32_t i_cloud_pdf_shape;         /* config%i_cloud_pdf_shape (radiation_config.F90:134-138): 0 lognormal, 1 gamma (default); shapes the
                                       * two cloudy regions of Tripleclouds / SPARTACUS; McICA takes it through the 'pdf_val' table */
 } ecrad_b200_config;
@@ -148,6 +149,12 @@ typedef struct ecrad_b200_outputs {
   /* per-band profiles (n_bands, ncol, nlev+1), filled by the Cloudless and Tripleclouds solvers when do_save_spectral_flux
    * (the McICA solver has none in the reference either); with ECCKD n_bands == n_g, i.e. one profile per g-point */
   double *lw_up_band, *lw_dn_band, *sw_up_band, *sw_dn_band, *sw_dn_direct_band;
+  /* top-of-atmosphere spectral fluxes, flux%calc_toa_spectral (radiation_flux.F90:579-660) when cfg.do_toa_spectral_flux: band sums of
+   * the *_toa_g arrays above (which must then be allocated).  sw_dn_toa_g (n_g_sw, ncol) is only set by the Tripleclouds solver
+   * in the reference (radiation_tripleclouds_sw.F90:444), and so is sw_dn_toa_band here. */
+  double *sw_dn_toa_g;                                               /* (n_g_sw, ncol) */
+  double *sw_dn_toa_band, *sw_up_toa_band, *sw_up_toa_clear_band;    /* (n_bands_sw, ncol) */
+  double *lw_up_toa_band, *lw_up_toa_clear_band;                     /* (n_bands_lw, ncol) */
 } ecrad_b200_outputs;
 
 /* Create the device-side state: copies `cfg` and the tables to the GPU selected by cudaGetDevice().

@@ -787,6 +787,8 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       if (out->sw_dn_direct_surf_clear_g) OUTG(out->sw_dn_direct_surf_clear_g, ng, g) = o.dn_direct_surf_clear_g[g];
       if (out->sw_up_toa_g) OUTG(out->sw_up_toa_g, ng, g) = o.up_toa_g[g];
       if (out->sw_up_toa_clear_g) OUTG(out->sw_up_toa_clear_g, ng, g) = o.up_toa_clear_g[g];
+      /* radiation_tripleclouds_sw.F90:444 (sunlit columns only; the other solvers never set it) */
+      if (out->sw_dn_toa_g && !spartacus && !(mu0 < 1.0e-10)) OUTG(out->sw_dn_toa_g, ng, g) = w->incoming_sw[g] * mu0;
     }
     /* band profiles: up; dn = mu0*direct + diffuse; dn_direct = mu0*direct (radiation_tripleclouds_sw.F90:604-624) */
     if (out->sw_up_band || out->sw_dn_band || out->sw_dn_direct_band) {
@@ -802,6 +804,25 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
     }
   }
   free(buf); free(sp);
+}
+
+/* radiation_flux.F90:579-660 calc_toa_spectral: band sums (indexed_sum) of the per-g-point top-of-atmosphere fluxes.  sw_dn_toa_g is only
+ * set by the Tripleclouds solver (radiation_tripleclouds_sw.F90:444); for the other solvers the reference sums an array it never wrote. */
+static void toa_spectral(const orc_tables* t, const ecrad_b200_config* cfg, int jcol, double mu0, ecrad_b200_outputs* out) {
+  if (!cfg->do_toa_spectral_flux) return;
+  for (int k = 0; k < 5; ++k) {
+    const int sw = k < 3;
+    if (sw ? !cfg->do_sw : !cfg->do_lw) continue;
+    const double* src = k == 0 ? out->sw_dn_toa_g : k == 1 ? out->sw_up_toa_g : k == 2 ? out->sw_up_toa_clear_g : k == 3 ? out->lw_up_toa_g : out->lw_up_toa_clear_g;
+    double* dst = k == 0 ? out->sw_dn_toa_band : k == 1 ? out->sw_up_toa_band : k == 2 ? out->sw_up_toa_clear_band : k == 3 ? out->lw_up_toa_band : out->lw_up_toa_clear_band;
+    if (!src || !dst || ((k == 2 || k == 4) && !cfg->do_clear) || (k == 0 && cfg->i_solver_sw != ECRAD_SOLVER_TRIPLECLOUDS)) continue;
+    if (k == 0 && mu0 < 1.0e-10) continue;   /* night column: sw_dn_toa_g was never set */
+    const int ng = sw ? NG_SW : NG_LW, nb = sw ? NB_SW : NB_LW;
+    const int32_t* band = sw ? t->band_sw : t->band_lw;
+    double* o = dst + (size_t)jcol * nb;
+    for (int b = 0; b < nb; ++b) o[b] = 0.0;
+    for (int g = 0; g < ng; ++g) o[band[g]] = o[band[g]] + src[(size_t)jcol * ng + g];
+  }
 }
 
 /* radiation_flux.F90:397-577 calc_surface_spectral (paths used by the test namelists) */
@@ -912,6 +933,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1);
   else if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   surface_spectral(t, cfg, jcol, out);
+  toa_spectral(t, cfg, jcol, (cfg->do_sw && in->cos_sza) ? in->cos_sza[jcol] : 1.0, out);
   free(w.w); free(phl_full);
   return 0;
 }

@@ -290,6 +290,33 @@ def test_ecckd_tiling_is_invisible(meridian_raw):
         assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
 
 
+TOA = ["sw_dn_toa_g", "sw_dn_toa_band", "sw_up_toa_band", "sw_up_toa_clear_band", "lw_up_toa_band", "lw_up_toa_clear_band"]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True),
+                                dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+def test_toa_spectral_fluxes(handles, meridian_raw, kw):
+    """flux%calc_toa_spectral (do_toa_spectral_flux): band sums of the per-g-point TOA fluxes; sw_dn_toa_g / sw_dn_toa_band exist for
+    the Tripleclouds solver only (the reference's other solvers never set sw_dn_toa_g) and stay untouched otherwise."""
+    n = 200
+    h, orc, cfg = handles(do_toa_spectral_flux=True, **kw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS + TOA)
+    tc = cfg.sw_solver_name == "Tripleclouds"
+    sun = raw["cos_solar_zenith_angle"] >= 1e-10
+    for nm in ("sw_dn_toa_g", "sw_dn_toa_band"):
+        assert np.array_equal(np.isnan(out[nm]), np.isnan(ref[nm])), nm
+        assert np.isnan(out[nm]).all() != tc, nm
+    if tc:
+        assert np.abs(out["sw_dn_toa_band"][:, sun].sum(axis=0) - out["sw_dn"][sun, 0]).max() <= 1e-9
+    assert np.abs(out["sw_up_toa_band"].sum(axis=0) - out["sw_up"][:, 0]).max() <= 1e-9
+    assert np.abs(out["lw_up_toa_band"].sum(axis=0) - out["lw_up"][:, 0]).max() <= 1e-9
+    assert np.abs(out["lw_up_toa_clear_band"].sum(axis=0) - out["lw_up_clear"][:, 0]).max() <= 1e-9
+
+
 @pytest.mark.parametrize("solver", ["Tripleclouds", "Cloudless", "Homogeneous"])
 def test_band_profiles_synthetic_and_tiled(handles, meridian_raw, solver):
     """Per-band profiles on perturbed columns (night columns included), and the same through ragged column tiles."""
