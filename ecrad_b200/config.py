@@ -155,6 +155,8 @@ class RadiationConfig:
             "i_emiss_from_band_lw": (np.argmax(e, axis=0) + 1).astype(np.int32),         # maxloc(dim=1)
             "lw_emiss_weights": np.asfortranarray(e),
         }
+        if self.do_nearest_spectral_sw_albedo:   # radiation_config.F90:1994-1997: maxloc(sw_albedo_weights, dim=1)
+            self.derived["i_albedo_from_band_sw"] = (np.argmax(w, axis=0) + 1).astype(np.int32)
         if self.use_aerosols:
             # aerosol_optics%set_types (radiation_aerosol_optics_data.F90:605-633): >0 hydrophobic, <0 hydrophilic, 0 ignored
             m = np.array(self.i_aerosol_type_map[: self.n_aerosol_types], dtype=np.int32)

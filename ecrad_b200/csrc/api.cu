@@ -112,7 +112,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
-  if (c.do_nearest_spectral_sw_albedo) return fail(h, "do_nearest_spectral_sw_albedo is not available in this build");
   if (gm == ECRAD_GAS_IFSRRTMG) {
     if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
     if (!c.do_nearest_spectral_lw_emiss) return fail(h, "weighted emissivity intervals are only available with the ECCKD gas model in this build");
@@ -378,6 +377,20 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   }
   if (P.is_ecckd && ((cfg->do_lw && P.ng_lw != cfg->n_g_lw) || (cfg->do_sw && P.ng_sw != cfg->n_g_sw))) {
     fail(nullptr, "ecCKD tables have %d/%d g-points (LW/SW), the configuration says %d/%d", P.ng_lw, P.ng_sw, cfg->n_g_lw, cfg->n_g_sw); delete h; return 1;
+  }
+  if (cfg->do_nearest_spectral_sw_albedo) {
+    // Nearest-interval mapping (get_albedos, radiation_single_level.F90:266-285; calc_surface_spectral, radiation_flux.F90:479-497) is the
+    // weighted mapping with a single weight of 1 per band: 0 + 1*albedo is exact, and the canopy fluxes collect the same bands.
+    if ((int)P.i_albedo_from_band_sw.size() != cfg->n_bands_sw || cfg->n_albedo_sw < 1) {
+      fail(nullptr, "do_nearest_spectral_sw_albedo: table 'i_albedo_from_band_sw' (n_bands_sw) is required"); delete h; return 1;
+    }
+    P.n_albedo_sw = cfg->n_albedo_sw;
+    P.sw_albedo_weights.assign((size_t)P.n_albedo_sw * cfg->n_bands_sw, 0.0);
+    for (int jb = 0; jb < cfg->n_bands_sw; ++jb) {
+      const int ia = P.i_albedo_from_band_sw[jb];
+      if (ia < 1 || ia > P.n_albedo_sw) { fail(nullptr, "i_albedo_from_band_sw out of range"); delete h; return 1; }
+      P.sw_albedo_weights[(size_t)jb * P.n_albedo_sw + ia - 1] = 1.0;
+    }
   }
   if (P.sw_albedo_weights.empty() || P.n_albedo_sw != cfg->n_albedo_sw) {
     fail(nullptr, "table 'sw_albedo_weights' (n_albedo_sw x n_bands_sw) is required"); delete h; return 1;

@@ -74,6 +74,7 @@ struct PackedTables {
   CloudMeta cloud;
   std::vector<double> pdf_val;        // (ncdf, nfsd) Fortran order, as the reference stores it
   std::vector<double> sw_albedo_weights;  // (n_albedo_sw, n_bands_sw)
+  std::vector<int32_t> i_albedo_from_band_sw;  // (n_bands_sw) 1-based; do_nearest_spectral_sw_albedo
   std::vector<int32_t> i_emiss_from_band_lw;  // (n_bands_lw) 1-based
   std::vector<double> lw_emiss_weights;   // (n_emiss_lw, n_bands_lw)
   int n_emiss_lw = 0;
@@ -299,6 +300,11 @@ inline void pack_common(const ecrad_b200_tables& T, PackedTables& P) {
     P.n_albedo_sw = (int)w->dims[0];
     if (w->dims[1] != NB_SW) throw std::runtime_error("sw_albedo_weights: second dim != number of shortwave bands");
     P.sw_albedo_weights.assign((const double*)w->data.data(), (const double*)w->data.data() + (size_t)P.n_albedo_sw * NB_SW);
+  }
+  // do_nearest_spectral_sw_albedo: config%i_albedo_from_band_sw(n_bands_sw), 1-based (radiation_config.F90:1994-1997)
+  if (const auto* ia = T.find("i_albedo_from_band_sw")) {
+    if (ia->dims[0] != NB_SW) throw std::runtime_error("i_albedo_from_band_sw: size != number of shortwave bands");
+    P.i_albedo_from_band_sw.assign((const int32_t*)ia->data.data(), (const int32_t*)ia->data.data() + NB_SW);
   }
   // ---- aerosol optics (only if the host registered the type map) ----
   memset(&P.aer, 0, sizeof(P.aer));

@@ -73,7 +73,8 @@ typedef struct ecrad_b200_config {
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md
  * ("table directory"); for the RRTMG path they are the module variables of ifsrrtm/yoerrta1..16.F90,
  * yoesrta16..29.F90, yoerrtwn.F90, yoerrtrf.F90, yoesrtwn.F90 plus config%cloud_optics%*, config%pdf_sampler%*,
- * config%sw_albedo_weights, config%i_emiss_from_band_lw or config%lw_emiss_weights ("lw_emiss_weights", when
+ * config%sw_albedo_weights (or, with do_nearest_spectral_sw_albedo, config%i_albedo_from_band_sw as "i_albedo_from_band_sw"),
+ * config%i_emiss_from_band_lw or config%lw_emiss_weights ("lw_emiss_weights", when
  * do_nearest_spectral_lw_emiss is false), and (with aerosols) config%aerosol_optics%{mass_ext,ssa,g}_{sw,lw}_
  * {phobic,philic}, %rh_lower, %iclass, %itype ("aer_*", "aerosol_iclass", "aerosol_itype").  Data are COPIED by ecrad_b200_setup. */
 typedef struct ecrad_b200_tables ecrad_b200_tables;

@@ -62,6 +62,7 @@ typedef struct orc_tables {
   const int32_t *aer_iclass, *aer_itype;  /* (n_aerosol_types): 0 ignored / 1 hydrophobic / 2 hydrophilic; 1-based type */
   const double *sw_albedo_weights;      /* (n_albedo_sw, n_bands_sw) */
   const int32_t *i_emiss_from_band_lw;  /* (n_bands_lw), 1-based */
+  const int32_t *i_albedo_from_band_sw; /* (n_bands_sw), 1-based; do_nearest_spectral_sw_albedo */
   const double *lw_emiss_weights;       /* (n_emiss_lw, n_bands_lw), used when !do_nearest_spectral_lw_emiss */
   /* 0-based band of each g-point: RRTMG ngb-1 / ngb-16; ecCKD with per-g-point cloud/aerosol optics: identity */
   int32_t band_lw[256], band_sw[256];

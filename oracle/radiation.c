@@ -36,10 +36,15 @@ typedef struct {
 /* get_albedos, radiation_single_level.F90:216-365 (paths used by test/ifs/configCY49R1.nam) */
 static int get_albedos(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int jcol,
                        const ecrad_b200_inputs* in, double* alb_dir, double* alb_diff, double* lw_albedo) {
-  if (cfg->do_nearest_spectral_sw_albedo) return 1; /* not restated */
-  if (!t->sw_albedo_weights) return 2;
+  if (cfg->do_nearest_spectral_sw_albedo ? !t->i_albedo_from_band_sw : !t->sw_albedo_weights) return 2;
   const int nalb = cfg->n_albedo_sw;
   double band[NB_SW], band_dir[NB_SW];
+  if (cfg->do_nearest_spectral_sw_albedo)   /* radiation_single_level.F90:266-285: albedo of the nearest interval */
+    for (int jb = 0; jb < NB_SW; ++jb) {
+      band[jb] = A2(in->sw_albedo, jcol, t->i_albedo_from_band_sw[jb] - 1);
+      band_dir[jb] = in->sw_albedo_direct ? A2(in->sw_albedo_direct, jcol, t->i_albedo_from_band_sw[jb] - 1) : band[jb];
+    }
+  else
   for (int jb = 0; jb < NB_SW; ++jb) {
     band[jb] = 0.0; band_dir[jb] = 0.0;
     for (int ja = 0; ja < nalb; ++ja) {
@@ -857,6 +862,19 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
         }
       }
     for (int a = 0; a < nalb; ++a) dif[a] = dif[a] - dir[a];
+  }
+  if (cfg->do_sw && cfg->do_canopy_fluxes_sw && out->sw_dn_diffuse_surf_canopy && out->sw_dn_direct_surf_canopy &&
+      cfg->do_nearest_spectral_sw_albedo && t->i_albedo_from_band_sw && out->sw_dn_diffuse_surf_g && out->sw_dn_direct_surf_g) {
+    /* radiation_flux.F90:479-497: indexed_sum of the per-g-point surface fluxes into the albedo intervals */
+    const int nalb = cfg->n_canopy_bands_sw;
+    double* dif = out->sw_dn_diffuse_surf_canopy + (size_t)jcol * nalb;
+    double* dir = out->sw_dn_direct_surf_canopy + (size_t)jcol * nalb;
+    for (int a = 0; a < nalb; ++a) { dif[a] = 0.0; dir[a] = 0.0; }
+    for (int g = 0; g < NG_SW; ++g) {
+      const int a = t->i_albedo_from_band_sw[t->band_sw[g]] - 1;
+      dir[a] = dir[a] + out->sw_dn_direct_surf_g[(size_t)jcol * NG_SW + g];
+      dif[a] = dif[a] + out->sw_dn_diffuse_surf_g[(size_t)jcol * NG_SW + g];
+    }
   }
   if (cfg->do_lw && cfg->do_canopy_fluxes_lw && out->lw_dn_surf_canopy && out->lw_dn_surf_g &&
       cfg->do_nearest_spectral_lw_emiss && t->i_emiss_from_band_lw) {

@@ -161,6 +161,7 @@ static void resolve_common(orc_tables* t, int* perr) {
   }
   const orc_array* w = orc_find(t, "sw_albedo_weights");
   t->sw_albedo_weights = w ? (const double*)w->data : NULL;
+  { const orc_array* ia = orc_find(t, "i_albedo_from_band_sw"); t->i_albedo_from_band_sw = ia ? (const int32_t*)ia->data : NULL; }
   const orc_array* e = orc_find(t, "i_emiss_from_band_lw");
   t->i_emiss_from_band_lw = e ? (const int32_t*)e->data : NULL;
   const orc_array* ew = orc_find(t, "lw_emiss_weights");
