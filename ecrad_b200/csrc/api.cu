@@ -114,7 +114,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
   if (gm == ECRAD_GAS_IFSRRTMG) {
     if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
-    if (!c.do_nearest_spectral_lw_emiss) return fail(h, "weighted emissivity intervals are only available with the ECCKD gas model in this build");
     if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
   } else {
     // generalised cloud + aerosol optics per g-point (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points

@@ -216,7 +216,16 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       if (l == 0) pl_out[g] = plk[b] * pf;                                 // TOA half-level: PFRAC of the top layer
       if (l == nlev - 1) {
         // surface: planck_function_surf :757-852, lw_emission = planck_surf * (1 - lw_albedo) :466
-        const double alb = 1.0 - LD_IN(in.lw_emissivity, c, T.i_emiss_from_band_lw[b] - 1);
+        double alb;
+        if (cfg.do_nearest_spectral_lw_emiss) {
+          alb = 1.0 - LD_IN(in.lw_emissivity, c, T.i_emiss_from_band_lw[b] - 1);
+        } else {   // weighted emissivity intervals (get_albedos, radiation_single_level.F90:330-352)
+          alb = 0.0;
+          for (int ja = 0; ja < cfg.n_emiss_lw; ++ja) {
+            const double wgt = T.lw_emiss_weights[b * cfg.n_emiss_lw + ja];
+            if (wgt != 0.0) alb = alb + wgt * (1.0 - LD_IN(in.lw_emissivity, c, ja));
+          }
+        }
         w.lw_albedo[(size_t)c * NG_LW + g] = alb;
         double em = plk_surf[b] * pf;
         w.emission[(size_t)c * NG_LW + g] = em * (1.0 - alb);

@@ -157,6 +157,7 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, cloud_pdf_shape_name="Lognormal"),
                                 dict(do_nearest_spectral_sw_albedo=True), dict(do_nearest_spectral_sw_albedo=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(do_nearest_spectral_sw_albedo=True, gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False),
+                                dict(do_nearest_spectral_lw_emiss=False), dict(do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(do_sw_delta_scaling_with_gases=True), dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
