@@ -136,6 +136,7 @@ struct GasLwSmem {
   LwLev lev[1];  // [nlev] followed by the arrays below (carved manually)
 };
 
+template <bool WEIGHTED_EMISS>   // !do_nearest_spectral_lw_emiss (a template so that the default instantiation is the code that was tuned)
 __global__ void __launch_bounds__(GAS_THREADS, 2)
 gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,7 +218,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       if (l == nlev - 1) {
         // surface: planck_function_surf :757-852, lw_emission = planck_surf * (1 - lw_albedo) :466
         double alb;
-        if (cfg.do_nearest_spectral_lw_emiss) {
+        if (!WEIGHTED_EMISS) {
           alb = 1.0 - LD_IN(in.lw_emissivity, c, T.i_emiss_from_band_lw[b] - 1);
         } else {   // weighted emissivity intervals (get_albedos, radiation_single_level.F90:330-352)
           alb = 0.0;
@@ -772,8 +773,13 @@ int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const
 }
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   size_t sm = gas_lw_smem(nlev);
-  allow_smem(gas_lw_kernel, sm);
-  gas_lw_kernel<<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
+  if (cfg.do_nearest_spectral_lw_emiss) {
+    allow_smem(gas_lw_kernel<false>, sm);
+    gas_lw_kernel<false><<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
+  } else {
+    allow_smem(gas_lw_kernel<true>, sm);
+    gas_lw_kernel<true><<<nc, GAS_THREADS, sm, st>>>(T, cfg, in, w, nlev);
+  }
   return 1;
 }
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
