@@ -1,0 +1,83 @@
+"""CPU checks of the oracle's option branches added late in round 1 (no reference output exists for any of them: invariants only).
+
+  do_sw_delta_scaling_with_gases   radiation_mcica_sw.F90:156-180, :274-278 (+ cloudless / tripleclouds / homogeneous)
+  do_toa_spectral_flux             radiation_flux.F90:579-660 calc_toa_spectral
+  do_nearest_spectral_sw_albedo    radiation_single_level.F90:266-285, radiation_flux.F90:479-497
+  do_nearest_spectral_lw_emiss     radiation_single_level.F90:310-355 (weighted intervals with RRTMG)
+  cloud_pdf_shape_name             radiation_regions.F90:110-126 (lognormal regions)
+"""
+import numpy as np
+import pytest
+
+from ecrad_b200 import inputs as I
+from ecrad_b200.config import RadiationConfig
+from oracle_lib import Oracle
+
+NLEV = 137
+TC = dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")
+
+
+def run(raw, n=32, **kw):
+    cfg = RadiationConfig(**kw).consolidate()
+    return Oracle(cfg).radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+
+
+def test_delta_scaling_with_gases(meridian_raw):
+    base = run(meridian_raw)
+    dsg = run(meridian_raw, do_sw_delta_scaling_with_gases=True)
+    # without aerosols the clear-sky mixture has g = 0: the scaling is the identity there, and it never touches the longwave
+    for nm in ("sw_up_clear", "sw_dn_clear", "sw_dn_direct_clear", "lw_up", "lw_dn"):
+        assert np.array_equal(dsg[nm], base[nm]), nm
+    # scaling the gas-cloud mixture instead of the cloud alone is a small change of the cloudy fluxes, not a different answer
+    d = np.abs(dsg["sw_up"] - base["sw_up"]).max()
+    assert 0.0 < d < 10.0
+    aer = run(meridian_raw, use_aerosols=True, do_sw_delta_scaling_with_gases=True)
+    aer0 = run(meridian_raw, use_aerosols=True)
+    assert 0.0 < np.abs(aer["sw_up_clear"] - aer0["sw_up_clear"]).max() < 5.0
+    # Tripleclouds does not scale its clear-sky region (radiation_tripleclouds_sw.F90:269)
+    t1, t0 = run(meridian_raw, use_aerosols=True, do_sw_delta_scaling_with_gases=True, **TC), run(meridian_raw, use_aerosols=True, **TC)
+    assert np.abs(t1["sw_up"] - t0["sw_up"]).max() > 0.0
+
+
+@pytest.mark.parametrize("kw", [dict(), TC])
+def test_toa_spectral_flux(meridian_raw, kw):
+    out = run(meridian_raw, do_toa_spectral_flux=True, **kw)
+    assert np.abs(out["sw_up_toa_band"].sum(axis=0) - out["sw_up"][:, 0]).max() <= 1e-9
+    assert np.abs(out["sw_up_toa_clear_band"].sum(axis=0) - out["sw_up_clear"][:, 0]).max() <= 1e-9
+    assert np.abs(out["lw_up_toa_band"].sum(axis=0) - out["lw_up"][:, 0]).max() <= 1e-9
+    assert np.abs(out["lw_up_toa_clear_band"].sum(axis=0) - out["lw_up_clear"][:, 0]).max() <= 1e-9
+    sun = np.asarray(meridian_raw["cos_solar_zenith_angle"]) >= 1e-10
+    if kw:   # only the Tripleclouds solver sets sw_dn_toa_g (sunlit columns)
+        assert np.abs(out["sw_dn_toa_band"][:, sun].sum(axis=0) - out["sw_dn"][sun, 0]).max() <= 1e-9
+        assert np.isnan(out["sw_dn_toa_g"][:, ~sun]).all()
+    else:
+        assert np.isnan(out["sw_dn_toa_g"]).all() and np.isnan(out["sw_dn_toa_band"]).all()
+    off = run(meridian_raw, **kw)
+    assert np.isnan(off["sw_up_toa_band"]).all() and np.isnan(off["lw_up_toa_band"]).all()
+
+
+def test_nearest_albedo_and_weighted_emissivity(meridian_raw):
+    near = run(meridian_raw, do_nearest_spectral_sw_albedo=True)
+    wgt = run(meridian_raw)
+    # canopy fluxes partition the surface downwelling flux whichever mapping is used
+    for o in (near, wgt):
+        tot = o["sw_dn_diffuse_surf_canopy"].sum(axis=0) + o["sw_dn_direct_surf_canopy"].sum(axis=0)
+        assert np.abs(tot - o["sw_dn"][:, -1]).max() <= 1e-9
+    assert np.isfinite(near["sw_up"]).all() and np.abs(near["sw_up"] - wgt["sw_up"]).max() < 40.0
+    assert np.array_equal(near["lw_up"], wgt["lw_up"])
+    we = run(meridian_raw, do_nearest_spectral_lw_emiss=False)
+    assert np.array_equal(we["sw_up"], wgt["sw_up"])
+    assert np.abs(we["lw_dn_surf_canopy"].sum(axis=0) - we["lw_dn"][:, -1]).max() <= 1e-9
+    assert 0.0 < np.abs(we["lw_up"] - wgt["lw_up"]).max() < 3.0
+
+
+def test_lognormal_regions(meridian_raw):
+    gam = run(meridian_raw, **TC)
+    logn = run(meridian_raw, cloud_pdf_shape_name="Lognormal", **TC)
+    # the overlap of the cloud boundaries does not depend on how the cloudy part is split: same cloud cover, same clear-sky fluxes
+    assert np.array_equal(logn["cloud_cover_sw"], gam["cloud_cover_sw"])
+    for nm in ("sw_up_clear", "lw_up_clear"):
+        assert np.array_equal(logn[nm], gam[nm]), nm
+    assert np.isfinite(logn["sw_up"]).all() and 0.0 < np.abs(logn["sw_up"] - gam["sw_up"]).max() < 60.0
+    with pytest.raises(ValueError, match="gamma PDF"):
+        RadiationConfig(cloud_pdf_shape_name="Lognormal").consolidate().to_struct()
