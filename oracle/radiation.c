@@ -764,9 +764,9 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       /* night: fluxes zeroed; cloud_cover_sw is still the overlap-matrix value (computed before the column loop) */
       double (*reg)[3] = malloc(sizeof(double[3]) * nlev), (*ods)[3] = malloc(sizeof(double[3]) * nlev);
       double (*U)[3][3] = malloc(sizeof(double[3][3]) * nl1), (*V)[3][3] = malloc(sizeof(double[3][3]) * nl1);
-      extern void orc_region_properties(int, const double*, const double*, double, double (*)[3], double (*)[3]);
+      extern void orc_region_properties(int, const double*, const double*, double, int, double (*)[3], double (*)[3]);
       extern void orc_overlap_matrices(int, double (*)[3], const double*, double, double, int, double (*)[3][3], double (*)[3][3], double*);
-      orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+      orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
       orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o.cloud_cover);
       free(reg); free(ods); free(U); free(V);
     } else if (spartacus) {
@@ -963,7 +963,6 @@ int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, i
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
   }
-  { extern void orc_set_region_pdf(int); orc_set_region_pdf(cfg->i_cloud_pdf_shape); }
   if (!out->lw_up_clear || !out->lw_dn_clear || !out->sw_up_clear || !out->sw_dn_clear || !out->sw_dn_direct_clear) {
     fprintf(stderr, "oracle: clear-sky flux outputs are required (do_clear)\n");
     return 11;

@@ -33,7 +33,7 @@
 static inline double dmin(double a, double b) { return a < b ? a : b; }
 static inline double dmax(double a, double b) { return a > b ? a : b; }
 
-void orc_region_properties(int nlev, const double* frac, const double* fsd, double frac_threshold, double (*reg_fracs)[NREG],
+void orc_region_properties(int nlev, const double* frac, const double* fsd, double frac_threshold, int lognormal, double (*reg_fracs)[NREG],
                            double (*od_scaling)[NREG]);
 void orc_overlap_matrices(int nlev, double (*reg_fracs)[NREG], const double* overlap_param, double decorrelation_scaling,
                           double frac_threshold, int use_beta_overlap, double (*U)[NREG][NREG], double (*V)[NREG][NREG], double* cloud_cover);
@@ -428,7 +428,7 @@ void orc_spartacus_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
   const double tan_diffuse_angle_3d = Pi * 0.5, min_mu0_3d = 0.004625;
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
-  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
 
   const double one_over_mu0 = 1.0 / mu0;
@@ -804,7 +804,7 @@ void orc_spartacus_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
   const double tan_diffuse_angle_3d = Pi * 0.5, side_emiss_thin = 1.4107;
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
-  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));
   for (int i = 0; i < nlev + 2; ++i) clear[i] = 1;

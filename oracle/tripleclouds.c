@@ -24,9 +24,7 @@ static inline double dmin(double a, double b) { return a < b ? a : b; }
 static inline double dmax(double a, double b) { return a > b ? a : b; }
 
 /* radiation_regions.F90:35-199, nreg = 3, do_gamma = .true. (config%i_cloud_pdf_shape default) */
-static int g_region_lognormal = 0;   /* set per call by orc_set_region_pdf (threads share the configuration) */
-void orc_set_region_pdf(int i_cloud_pdf_shape) { g_region_lognormal = (i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL); }
-void orc_region_properties(int nlev, const double* frac, const double* fsd, double frac_threshold,
+void orc_region_properties(int nlev, const double* frac, const double* fsd, double frac_threshold, int lognormal,
                            double (*reg_fracs)[NREG], double (*od_scaling)[NREG]) {
   const double MinGammaODScaling = 0.025, MinLowerFrac = 0.5, MaxLowerFrac = 0.9, FSDAtMinLowerFrac = 1.5,
                FSDAtMaxLowerFrac = 3.725;
@@ -36,7 +34,7 @@ void orc_region_properties(int nlev, const double* frac, const double* fsd, doub
     if (frac[jl] < frac_threshold) {
       reg_fracs[jl][0] = 1.0; reg_fracs[jl][1] = 0.0; reg_fracs[jl][2] = 0.0;
       od_scaling[jl][1] = 1.0; od_scaling[jl][2] = 1.0;
-    } else if (g_region_lognormal) {   /* radiation_regions.F90:110-126 */
+    } else if (lognormal) {   /* radiation_regions.F90:110-126 */
       reg_fracs[jl][0] = 1.0 - frac[jl];
       reg_fracs[jl][1] = frac[jl] * 0.5; reg_fracs[jl][2] = frac[jl] * 0.5;
       od_scaling[jl][1] = exp(-sqrt(log(fsd[jl] * fsd[jl] + 1.0))) / sqrt(fsd[jl] * fsd[jl] + 1.0);
@@ -130,7 +128,7 @@ void orc_tripleclouds_sw(const orc_tables* t, const ecrad_b200_config* cfg, int 
   const int ng = NG_SW;
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
-  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));   /* is_clear_sky_layer(0:nlev+1) */
   clear[0] = 1; clear[nlev + 1] = 1;
@@ -306,7 +304,7 @@ void orc_tripleclouds_lw(const orc_tables* t, const ecrad_b200_config* cfg, int 
   const int ng = NG_LW;
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
-  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, reg, ods);
+  orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));
   clear[0] = 1; clear[nlev + 1] = 1;
