@@ -94,9 +94,12 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if ((c.do_sw && !solver_ok(c.i_solver_sw)) || (c.do_lw && !solver_ok(c.i_solver_lw))) return fail(h, "unknown solver");
   if (c.do_lw && c.do_sw && ((c.i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) != (c.i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS)))   // radiation_config.F90:1341-1349
     return fail(h, "if one solver is \"Homogeneous\" then the other must be");
-  if ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS)) {
-    if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN)   // radiation_config.F90:1134-1141
+  {   // radiation_config.F90:1134-1141
+    auto regions = [](int s) { return s == ECRAD_SOLVER_SPARTACUS || s == ECRAD_SOLVER_TRIPLECLOUDS; };
+    if (((c.do_sw && regions(c.i_solver_sw)) || (c.do_lw && regions(c.i_solver_lw))) && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN)
       return fail(h, "SPARTACUS/Tripleclouds solvers can only do Exponential-Random overlap");
+  }
+  if ((c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (c.do_lw && c.i_solver_lw == ECRAD_SOLVER_SPARTACUS)) {
     if (c.do_sw && c.i_solver_sw == ECRAD_SOLVER_SPARTACUS && c.do_sw_delta_scaling_with_gases)   // radiation_config.F90:1336-1339
       return fail(h, "SW delta-Eddington scaling with gases not possible with SPARTACUS solver");
     if (c.i_3d_sw_entrapment < ECRAD_ENTRAPMENT_ZERO || c.i_3d_sw_entrapment > ECRAD_ENTRAPMENT_MAXIMUM) return fail(h, "unknown sw_entrapment");

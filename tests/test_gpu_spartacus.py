@@ -130,6 +130,10 @@ def test_spartacus_error_behaviour():
 
     with pytest.raises(RadiationError, match="Exponential-Random"):
         setup_radiation(RadiationConfig(overlap_scheme_name="Max-Ran", **SP).consolidate())
+    with pytest.raises(RadiationError, match="Exponential-Random"):
+        setup_radiation(RadiationConfig(overlap_scheme_name="Exp-Exp", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds").consolidate())
+    with pytest.raises(RadiationError, match="Homogeneous"):
+        setup_radiation(RadiationConfig(sw_solver_name="Homogeneous").consolidate())
     with pytest.raises(RadiationError, match="delta-Eddington scaling with gases"):
         setup_radiation(RadiationConfig(do_sw_delta_scaling_with_gases=True, **SP).consolidate())
 
