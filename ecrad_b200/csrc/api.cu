@@ -312,7 +312,7 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
   for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
 }
 
-// Build the kernel-facing views from 28 input / 35 output base pointers (device) with leading dimension ld.
+// Build the kernel-facing views from 28 input / 41 output base pointers (device) with leading dimension ld.
 void make_views(void* const* ip, void* const* op, int ld, int ld_out, double solar_irradiance, DevIn& di, DevOut& dout) {
   di.cos_sza = (const double*)ip[0]; di.skin_t = (const double*)ip[1]; di.sw_albedo = (const double*)ip[2];
   di.sw_albedo_direct = (const double*)ip[3]; di.lw_emissivity = (const double*)ip[4]; di.iseed = (const int32_t*)ip[5];
