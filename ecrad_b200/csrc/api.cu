@@ -56,11 +56,12 @@ struct Handle {
   // so the kernels of tile t+1 fill the SMs that the tail of tile t leaves idle.
   cudaStream_t s_comp[2] = {nullptr, nullptr}, s_aux1[2] = {nullptr, nullptr}, s_aux2[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_cloud[2] = {nullptr, nullptr}, ev_sw_done[2] = {nullptr, nullptr};
+  int scan_solvers = 1;   // McICA / Cloudless solvers as warp scans (solver_scan.cu); 0: the lanes-are-g-points kernels (solver_sw.cu, solver_lw.cu)
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
   Buf work[2][36];
   Work w[2];
-  int w_cols[2] = {0, 0}, w_nlev[2] = {0, 0};
+  int w_cols[2] = {0, 0}, w_nlev[2] = {0, 0}, w_scan[2] = {-1, -1};
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
@@ -129,9 +130,20 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
 }
 
 enum { N_WORK = 35 };
+// Which spectra run the scan solvers (and therefore want their gas optical properties laid out [column][g][layer]).
+bool use_scan(const Handle* h, bool sw, int nlev) {
+  const ecrad_b200_config& c = h->cfg;
+  if (!h->scan_solvers || !(sw ? c.do_sw : c.do_lw)) return false;
+  const int sol = sw ? c.i_solver_sw : c.i_solver_lw;
+  if (sol != ECRAD_SOLVER_MCICA && sol != ECRAD_SOLVER_CLOUDLESS) return false;
+  if (sol == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux) return false;   // per-band profiles: the band-summing kernels
+  if (h->dcfg.gas_model != ECRAD_GAS_IFSRRTMG) return false;
+  return nlev <= scan_max_levels();
+}
 // bytes of every per-tile scratch array for `cols` columns (all linear in cols)
 void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
-  const size_t nc = (size_t)cols, nl = (size_t)nlev, nlp = (size_t)((nlev + 3) & ~3);
+  const size_t nc = (size_t)cols, nlp = (size_t)((nlev + 3) & ~3);
+  const size_t nl = (size_t)((nlev + 1 + 3) & ~3);   // row stride of the [g][layer] layout; also covers [layer][g] with nlev + 1 levels
   // the Homogeneous solvers run on the Tripleclouds kernels
   const bool tc_lw = h->cfg.do_lw && (h->cfg.i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || h->cfg.i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS),
              tc_sw = h->cfg.do_sw && (h->cfg.i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || h->cfg.i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS);
@@ -140,16 +152,16 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
   const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
   const size_t sz[N_WORK] = {
-      8 * nc * nl * NG_LW, 8 * nc * (nl + 1) * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,        // od_lw planck emission lw_albedo
+      8 * nc * nl * NG_LW, 8 * nc * nl * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,              // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
       8 * nc * nl * 3 * NB_LW, 8 * nc * nl * 3 * NB_SW,                                      // cl_lw cl_sw
       8 * nc * nl, 8 * nc * nl, 8 * nc * nl,                                                 // cum pair opi
       8 * nc, 4 * nc, 4 * nc, 4 * nc,                                                        // tcc ibegin iend ict
       4 * nc * NG_LW * nlp, 4 * nc * NG_SW * nlp,                                            // code_lw code_sw
-      8 * nc * (sp_lw ? sp_scratch_doubles_lw(nlev, (int)NG_LW) : tc_lw ? tc_scratch_doubles_lw(nlev, (int)NG_LW) : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw
+      8 * nc * (sp_lw ? sp_scratch_doubles_lw(nlev, (int)NG_LW) : tc_lw ? tc_scratch_doubles_lw(nlev, (int)NG_LW) : use_scan(h, false, nlev) ? 0 : LW_SCR_ARRAYS * nl * NG_LW),            // scr_lw (the scan solvers keep the adding-method state in registers)
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
-      8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
+      8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : use_scan(h, true, nlev) ? 0 : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
       ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
@@ -165,8 +177,13 @@ size_t work_bytes_per_column(const Handle* h, int nlev) {
 }
 
 int ensure_work(Handle* h, int set, int cols, int nlev) {
-  if (cols <= h->w_cols[set] && nlev == h->w_nlev[set]) return 0;
-  if (nlev != h->w_nlev[set]) h->w_cols[set] = 0;
+  if (cols <= h->w_cols[set] && nlev == h->w_nlev[set] && h->scan_solvers == h->w_scan[set]) return 0;
+  if (nlev != h->w_nlev[set] || h->scan_solvers != h->w_scan[set]) {   // different array sizes per column: start over
+    cudaDeviceSynchronize();
+    for (auto& b : h->work[set]) b.release();
+    h->w_cols[set] = 0;
+  }
+  h->w_scan[set] = h->scan_solvers;
   size_t sz[N_WORK];
   work_sizes(h, cols, nlev, sz);
   for (int i = 0; i < N_WORK; ++i) CK(h, h->work[set][i].reserve(sz[i]));
@@ -185,6 +202,7 @@ int ensure_work(Handle* h, int set, int cols, int nlev) {
   w.tc_v = (double*)h->work[set][33].p; w.tc_cc = (double*)h->work[set][34].p;
   w.sw_sums = (double*)h->work[set][19].p; w.sw_carry = (double*)h->work[set][20].p;
   w.lw_sums = (double*)h->work[set][21].p; w.lw_carry = (double*)h->work[set][22].p;
+  w.ls = (nlev + 1 + 3) & ~3;
   h->w_cols[set] = cols; h->w_nlev[set] = nlev;
   return 0;
 }
@@ -198,6 +216,8 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   const DevCfg& c = h->dcfg;
   int n = 0;
   const bool par = !h->serial;
+  h->w[set].layout_b_lw = use_scan(h, false, nlev);
+  h->w[set].layout_b_sw = use_scan(h, true, nlev);
   cudaStream_t s_lw = st, s_sw = par ? h->s_aux1[set] : st, s_cl = par ? h->s_aux2[set] : st;
   const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
   if (!ckd) {
@@ -487,6 +507,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     cudaEventCreateWithFlags(&h->ev_sw_done[k], cudaEventDisableTiming);
   }
   if (const char* s2 = getenv("ECRAD_B200_SERIAL")) h->serial = atoi(s2) != 0;
+  if (const char* s2 = getenv("ECRAD_B200_SCAN")) h->scan_solvers = atoi(s2) != 0;
   init_generator_constants();
   *handle = h;
   return 0;
@@ -537,6 +558,7 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   if (!h || !key) return 1;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!strcmp(key, "serial")) { h->serial = value != 0; return 0; }
+  if (!strcmp(key, "scan_solvers")) { h->scan_solvers = value != 0; return 0; }
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
   if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);

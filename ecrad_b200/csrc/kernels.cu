@@ -163,8 +163,11 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   if (tid < NB_LW) plk_surf[tid] = planck_band(M, in.skin_t[c], tid);
   const int laytrop = __syncthreads_count(tropo);
 
-  double* od_out = w.od_lw + (size_t)c * nlev * NG_LW;
-  double* pl_out = w.planck + (size_t)c * (nlev + 1) * NG_LW;
+  // output layout (kernels.cuh, Work): [layer][g] or [g][ls]
+  const bool lb = w.layout_b_lw != 0;
+  const size_t sg = lb ? (size_t)w.ls : 1, sl = lb ? 1 : (size_t)NG_LW;
+  double* od_out = w.od_lw + (size_t)c * (lb ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW);
+  double* pl_out = w.planck + (size_t)c * (lb ? (size_t)NG_LW * w.ls : (size_t)(nlev + 1) * NG_LW);
 
   for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
     const int nl = imin((int)GAS_LC, nlev - l0);
@@ -212,9 +215,9 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
                         pfc[(ll * NB_LW + b) * 2 + 1] * __ldg(tab_g + (unsigned)pfo[(ll * NB_LW + b) * 2 + 1]);
       double odv = dmax(tau, cfg.min_gas_od_lw);                           // radiation_ifs_rrtm.F90:506-511
       if (cfg.use_aerosols) odv = odv + w.aer_lw[((size_t)c * nlev + l) * NB_LW + b];   // radiation_aerosol_optics.F90:806-812
-      od_out[(size_t)l * NG_LW + g] = odv;
-      pl_out[(size_t)(l + 1) * NG_LW + g] = plk[(ll + 1) * NB_LW + b] * pf; // half-level below uses this layer's PFRAC
-      if (l == 0) pl_out[g] = plk[b] * pf;                                 // TOA half-level: PFRAC of the top layer
+      od_out[l * sl + g * sg] = odv;
+      pl_out[(l + 1) * sl + g * sg] = plk[(ll + 1) * NB_LW + b] * pf;      // half-level below uses this layer's PFRAC
+      if (l == 0) pl_out[g * sg] = plk[b] * pf;                            // TOA half-level: PFRAC of the top layer
       if (l == nlev - 1) {
         // surface: planck_function_surf :757-852, lw_emission = planck_surf * (1 - lw_albedo) :466
         double alb;
@@ -272,8 +275,11 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   }
   __syncthreads();
 
-  double* od_out = w.od_sw + (size_t)c * nlev * NG_SW;
-  double* ssa_out = w.ssa_sw + (size_t)c * nlev * NG_SW;
+  const bool lb = w.layout_b_sw != 0;
+  const size_t sg = lb ? (size_t)w.ls : 1, sl = lb ? 1 : (size_t)NG_SW;
+  const size_t cbase = (size_t)c * (lb ? (size_t)NG_SW * w.ls : (size_t)nlev * NG_SW);
+  double* od_out = w.od_sw + cbase;
+  double* ssa_out = w.ssa_sw + cbase;
 
   for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
     const int nl = imin((int)GAS_LC, nlev - l0);
@@ -323,10 +329,10 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
           ssav = local_scat / local_od;
           odv = local_od;
         }
-        w.g_sw[((size_t)c * nlev + l) * NG_SW + g] = gv;
+        w.g_sw[cbase + l * sl + g * sg] = gv;
       }
-      od_out[(size_t)l * NG_SW + g] = odv;
-      ssa_out[(size_t)l * NG_SW + g] = ssav;
+      od_out[l * sl + g * sg] = odv;
+      ssa_out[l * sl + g * sg] = ssav;
       if (l == lsol[b]) inc[g] = sc[b * 2] * __ldg(tab_g + (unsigned)so[b * 2]) + sc[b * 2 + 1] * __ldg(tab_g + (unsigned)so[b * 2 + 1]);
     }
     __syncthreads();

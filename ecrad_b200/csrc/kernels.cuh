@@ -96,6 +96,10 @@ struct Work {
   LwLev* lev_lw; SwLev* lev_sw;                   // [nc][nlev] per-layer gas-optics state (gas_prep_kernel)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
+  // Layout of the gas optical properties (od_*, ssa_sw, g_sw, planck), per spectrum: 0 = [column][layer][g] (g fastest: the
+  // lanes-are-g-points kernels), 1 = [column][g][ls] (layer fastest, row stride ls >= nlev+1, a multiple of 4: the scan solvers,
+  // whose warps read one contiguous row per g-point)
+  int layout_b_lw, layout_b_sw, ls;
 };
 
 void init_generator_constants();   // once per process/device, before the first generator launch
@@ -121,6 +125,9 @@ size_t sp_scratch_doubles_sw(int nlev, int ng);
 int launch_sp_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_toa_spectral(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, int nc, bool sw, cudaStream_t st);   // flux%calc_toa_spectral
+int scan_max_levels();   // most layers the scan solvers take (32 lanes x layers per lane)
+int launch_solver_lw_scan(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_solver_sw_scan(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 

@@ -71,6 +71,22 @@ __device__ __forceinline__ double od_scaling_from_code(const CloudMeta& C, const
 }
 
 
+// total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
+template <class SD>
+__device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd, const double* clb,
+                                                int b, double od_gas, double ssa_gas, double g_gas, double& odt, double& ssat, double& gt) {
+  const double scal = od_scaling_from_code(C, pdf_val, code, fsd);
+  const double od_cloud_new = scal * clb[b];
+  odt = od_gas + od_cloud_new;
+  ssat = 0.0; gt = 0.0;
+  if (odt > 0.0) {
+    const double ssac = clb[SD::NB + b];
+    const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
+    ssat = scat_od / odt;
+    if (scat_od > 0.0) gt = (g_gas * ssa_gas * od_gas + clb[2 * SD::NB + b] * ssac * od_cloud_new) / scat_od;
+  }
+}
+
 // surface spectral and canopy fluxes: radiation_flux.F90:397-577 calc_surface_spectral.  Block-wide (contains barriers);
 // tile: >= 4*rs + 28 doubles of shared memory; dir/dif: per-g direct and diffuse surface fluxes (all-sky, clear-sky).
 template <class SD>

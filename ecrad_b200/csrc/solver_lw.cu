@@ -362,6 +362,7 @@ static int launch_solver_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn
 
 int launch_solver_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   if (cfg.solver_lw == 3) return launch_sp_lw(T, cfg, in, out, w, nc, nlev, st);   // SPARTACUS
+  if (w.layout_b_lw) return launch_solver_lw_scan(T, cfg, in, out, w, nc, nlev, st);   // McICA / Cloudless as warp scans (solver_scan.cu)
   switch (cfg.ng_lw) {
     case NG_LW: return launch_solver_lw_t<LwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
     case 32: return launch_solver_lw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);

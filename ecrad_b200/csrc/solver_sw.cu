@@ -17,22 +17,6 @@ namespace ecb {
 enum { SW_LCH_FLUX = 2, SW_BATCH = 2, SW_NST = 2 };   // sw_flux_kernel: layers per g-point reduction, layers per TMA stage, stages in the ring
 typedef BulkRing<SW_NST, SW_BATCH, 10> SwRing;
 
-// total (gas + scaled cloud) optical properties of a cloudy layer for this g-point: radiation_mcica_sw.F90:249-272
-template <class SD>
-__device__ __forceinline__ void sw_cloudy_props(const CloudMeta& C, const double* pdf_val, uint32_t code, double fsd, const double* clb,
-                                                int b, double od_gas, double ssa_gas, double g_gas, double& odt, double& ssat, double& gt) {
-  const double scal = od_scaling_from_code(C, pdf_val, code, fsd);
-  const double od_cloud_new = scal * clb[b];
-  odt = od_gas + od_cloud_new;
-  ssat = 0.0; gt = 0.0;
-  if (odt > 0.0) {
-    const double ssac = clb[SD::NB + b];
-    const double scat_od = ssa_gas * od_gas + ssac * od_cloud_new;
-    ssat = scat_od / odt;
-    if (scat_od > 0.0) gt = (g_gas * ssa_gas * od_gas + clb[2 * SD::NB + b] * ssac * od_cloud_new) / scat_od;
-  }
-}
-
 struct SwColumn {
   int c, g, gg, b; bool act, cloudy; double mu0, tcc, thr;
   size_t n;
@@ -340,6 +324,7 @@ static int launch_solver_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn
 int launch_solver_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   if (cfg.solver_sw == 4 || cfg.solver_sw == 1) return launch_tc_sw(T, cfg, in, out, w, nc, nlev, st);   // Tripleclouds, Homogeneous
   if (cfg.solver_sw == 3) return launch_sp_sw(T, cfg, in, out, w, nc, nlev, st);   // SPARTACUS
+  if (w.layout_b_sw) return launch_solver_sw_scan(T, cfg, in, out, w, nc, nlev, st);   // McICA / Cloudless as warp scans (solver_scan.cu)
   switch (cfg.ng_sw) {
     case NG_SW: return launch_solver_sw_t<SwRrtmg>(T, cfg, in, out, w, nc, nlev, st);
     case 32: return launch_solver_sw_t<Ckd32>(T, cfg, in, out, w, nc, nlev, st);

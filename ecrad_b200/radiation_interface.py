@@ -18,7 +18,7 @@ from . import abi
 from .config import RadiationConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libecrad_b200.so")
+LIB_PATH = os.environ.get("ECRAD_B200_LIB") or os.path.join(_HERE, "libecrad_b200.so")   # (the override is for A/B builds of the same library)
 DEFAULT_TABLES = os.path.join(_HERE, "data", "rrtmg_tables.bin")
 
 EXPORTS = [
