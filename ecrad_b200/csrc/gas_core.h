@@ -40,6 +40,10 @@ enum { LW_KMAX = 22, SW_KMAX = 14 };
 // Sections of a band's packed table (rows of ng doubles, g-point fastest).
 enum LwSec { L_ABSA, L_ABSB, L_SELF, L_FOR, L_FRACA, L_FRACB, L_M0, L_M1, L_M2, L_M3, L_M4, L_C0, L_C1, L_POST, L_NSEC };
 enum SwSec { S_ABSA, S_ABSB, S_SELF, S_FOR, S_SFLUX, S_RAYA, S_RAYB, S_X0, S_X1, S_ONES, S_NSEC };
+// The packer lays a band out as [ABSA][ABSB][everything else]: the two big major-species tables, which the band-wise kernels
+// stage by pressure window, then the small sections, staged whole.  sec[SEC_SMALL] = first element of the small sections,
+// sec[SEC_END] = one past the band's last element.
+enum { SEC_SMALL = 14, SEC_END = 15 };
 
 struct BandMeta {
   int ng;        // g-points in this band
@@ -59,7 +63,12 @@ struct GasMeta {
   double strrat_sw[NB_SW], rayl_sw[NB_SW], givfac_23, scalekur_27;
   int layreffr_sw[NB_SW], nfor_sw[NB_SW];
   int band_of_g_lw[NG_LW], band_of_g_sw[NG_SW];  // 0-based band of each g-point
+  int lw_rows[NB_LW][2], sw_rows[NB_SW][2];      // rows of ABSA / ABSB per band (0: none); 13 (ABSA) or 47 (ABSB) reference pressures each
 };
+// g-points per band of the RRTMG-IFS reduction (ifsrrtm/rrtm_init_140gp.F90 NGC, srtm_init.F90 NGC): compile-time sizes of the
+// band-wise kernels' register accumulators; ecrad_b200_setup checks the tables against them.
+constexpr int kNgLwBand[NB_LW] = {10, 12, 16, 14, 16, 8, 12, 8, 12, 6, 8, 8, 4, 2, 2, 2};
+constexpr int kNgSwBand[NB_SW] = {6, 12, 8, 8, 10, 10, 2, 10, 8, 6, 6, 8, 6, 12};
 
 // ---------------------------------------------------------------------------------------------------------
 // Per-layer state shared by LW and SW (rrtm_prepare_gases): hPa, K, molecules cm-2
@@ -102,7 +111,8 @@ struct LwLev {
   double fac00, fac01, fac10, fac11, forfac, forfrac, selffac, selffrac, scaleminor, scaleminorn2, minorfrac;
   double colh2o, colco2, colo3, coln2o, colch4, colo2, colbrd, coldry, pavel;
   double wx1, wx2, wx3, wx4;
-  double pad_;   // sizeof = 29 doubles: odd stride => conflict-free shared-memory access across layers
+  double t_top, t_bot;   // half-level temperatures bounding the layer (Planck function of the band-wise kernel)
+  double pad_;   // sizeof = 31 doubles: odd stride => conflict-free shared-memory access across layers
 };
 static_assert(sizeof(LwLev) % 16 == 8, "LwLev stride must be an odd number of doubles");
 
@@ -174,6 +184,7 @@ struct ListOut {
   int stride;
   HD void add(double coef, int off) { Term x; x.c = coef; x.o = off; x.pad = 0; t[n * stride] = x; ++n; }   // one 128-bit store
   HD void pad4() { while (n & 3) add(0.0, 0); }   // zero terms so that consumers can unroll by 4
+  HD void scale_all(double f) { for (int k = 0; k < n; ++k) t[k * stride].c = f * t[k * stride].c; }   // multiply what has been emitted so far
 };
 
 struct Spec { double speccomb, specparm, fs; int js; };
@@ -203,14 +214,14 @@ HD Spec mkspec7(double cola, double rat, double colb, double mult) {
 }
 
 // col * (fac00*T[i0] + fac10*T[i0+1] + fac01*T[i1] + fac11*T[i1+1]);  i0,i1 are the reference's 1-based rows
-HD void emit_major1(ListOut& out, int sec, int ng, int i0, int i1, double col, double f00, double f10, double f01, double f11) {
+template <class Out> HD void emit_major1(Out& out, int sec, int ng, int i0, int i1, double col, double f00, double f10, double f01, double f11) {
   out.add(col * f00, sec + (i0 - 1) * ng);
   out.add(col * f10, sec + i0 * ng);
   out.add(col * f01, sec + (i1 - 1) * ng);
   out.add(col * f11, sec + i1 * ng);
 }
 // lower atmosphere, NSPA=9 (e.g. rrtm_taumol3.F90:170-229): three-point stencils at the ends of the eta range
-HD void emit_low(ListOut& out, int sec, int ng, int ind, const Spec& s, double fa, double fb) {
+template <class Out> HD void emit_low(Out& out, int sec, int ng, int ind, const Spec& s, double fa, double fb) {
   const double sc = s.speccomb;
   if (s.specparm < 0.125) {
     double p = s.fs - 1, p4 = (p * p) * (p * p);
@@ -228,18 +239,18 @@ HD void emit_low(ListOut& out, int sec, int ng, int ind, const Spec& s, double f
   }
 }
 // upper atmosphere, NSPB=5 (e.g. rrtm_taumol3.F90:301-308)
-HD void emit_upp(ListOut& out, int sec, int ng, int ind, const Spec& s, double fa, double fb) {
+template <class Out> HD void emit_upp(Out& out, int sec, int ng, int ind, const Spec& s, double fa, double fb) {
   const double sc = s.speccomb;
   out.add(sc * (1.0 - s.fs) * fa, sec + (ind - 1) * ng);  out.add(sc * s.fs * fa, sec + ind * ng);
   out.add(sc * (1.0 - s.fs) * fb, sec + (ind + 4) * ng);  out.add(sc * s.fs * fb, sec + (ind + 5) * ng);
 }
 // scale * (T[i] + f*(T[i+1]-T[i])), i 1-based
-HD void emit_lin(ListOut& out, int sec, int ng, int i, double f, double scale) {
+template <class Out> HD void emit_lin(Out& out, int sec, int ng, int i, double f, double scale) {
   out.add(scale * (1.0 - f), sec + (i - 1) * ng);
   out.add(scale * f, sec + i * ng);
 }
 // minor species on a (nj, 19) grid: rows (indm-1)*nj + (j-1)   (e.g. rrtm_taumol3.F90:235-239)
-HD void emit_minor2(ListOut& out, int sec, int ng, int nj, int j, double fj, int indm, double mf, double scale) {
+template <class Out> HD void emit_minor2(Out& out, int sec, int ng, int nj, int j, double fj, int indm, double mf, double scale) {
   int r = (indm - 1) * nj + (j - 1);
   out.add(scale * (1.0 - mf) * (1.0 - fj), sec + r * ng);
   out.add(scale * (1.0 - mf) * fj, sec + (r + 1) * ng);
@@ -265,8 +276,10 @@ HD PlanckFrac pf_zero(int sec) { PlanckFrac p; p.c0 = 0.0; p.c1 = 0.0; p.o0 = se
 
 // Build the stencil of LW band `ib` (0-based: 0 = RRTMG band 1) for one layer.  `low` = layer index <= LAYTROP.
 // Returns the Planck-fraction stencil; *post = element offset of a per-g multiplier row or -1.
-HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, ListOut& out, int* post) {
-  const BandMeta& B = M.lw[ib];
+// `B` = the band's section offsets and row stride (B.ng) in the address space `out` reads from: M.lw[ib] for the packed table in
+// global memory, a remapped copy for a shared-memory image.  `Out` = ListOut (materialise the list) or an evaluating sink.
+template <class Out>
+HD PlanckFrac lw_build_list(const GasMeta& M, const BandMeta& B, const LwLev& L, int ib, bool low, Out& out, int* post) {
   const int ng = B.ng;
   const int A = B.sec[L_ABSA], Bb = B.sec[L_ABSB], SF = B.sec[L_SELF], FR = B.sec[L_FOR];
   const int FA = B.sec[L_FRACA], FB = B.sec[L_FRACB];
@@ -301,13 +314,13 @@ HD PlanckFrac lw_build_list(const GasMeta& M, const LwLev& L, int ib, bool low, 
         emit_lin(out, B.sec[L_M1], ng, indm, mf, scalen2);
         pf = pf_const(FB);
       }
-      for (int k = 0; k < out.n; ++k) out.t[k * out.stride].c = corradj * out.t[k * out.stride].c;
+      out.scale_all(corradj);
     } break;
     case 2: {  // rrtm_taumol2.F90: H2O / H2O
       if (low) {
         double corradj = 1.0 - .05 * (L.pavel - 100.0) / 900.0;
         MAJ1A(L.colh2o); SELF_(); FOR_();
-        for (int k = 0; k < out.n; ++k) out.t[k * out.stride].c = corradj * out.t[k * out.stride].c;
+        out.scale_all(corradj);
         pf = pf_const(FA);
       } else {
         MAJ1B(L.colh2o); FOR_();
@@ -579,7 +592,7 @@ HD void sw_setcoef(const GasMeta& M, const LevGas& G, SwLev& L) {
 }
 
 // speccomb*((1-fs)*(T[i0]f00 + T[i0+d]f10 + T[i1]f01 + T[i1+d]f11) + fs*(same rows + 1))
-HD void emit_major2(ListOut& out, int sec, int ng, int i0, int i1, int d, const Spec& s, const SwLev& L) {
+template <class Out> HD void emit_major2(Out& out, int sec, int ng, int i0, int i1, int d, const Spec& s, const SwLev& L) {
   double a = s.speccomb * (1. - s.fs), b = s.speccomb * s.fs;
   out.add(a * L.fac00, sec + (i0 - 1) * ng);  out.add(a * L.fac10, sec + (i0 + d - 1) * ng);
   out.add(a * L.fac01, sec + (i1 - 1) * ng);  out.add(a * L.fac11, sec + (i1 + d - 1) * ng);
@@ -593,8 +606,8 @@ struct SwAux {     // Rayleigh stencil and (if this layer sets it) the solar-sou
 };
 
 // Build the stencil of SW band `ib` (0-based: 0 = band 16) for one layer.  `low` = layer index <= LAYTROP.
-HD void sw_build_list(const GasMeta& M, const SwLev& L, int ib, bool low, ListOut& out, SwAux& aux) {
-  const BandMeta& B = M.sw[ib];
+template <class Out>
+HD void sw_build_list(const GasMeta& M, const BandMeta& B, const SwLev& L, int ib, bool low, Out& out, SwAux& aux) {
   const int jb = ib + 16, ng = B.ng;
   const int A = B.sec[S_ABSA], Bb = B.sec[S_ABSB], SR = B.sec[S_SELF], FR = B.sec[S_FOR], SFX = B.sec[S_SFLUX];
   const int ONES = B.sec[S_ONES];

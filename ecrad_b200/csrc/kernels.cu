@@ -65,7 +65,12 @@ __global__ void gas_prep_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int n
               LD_IN(in.gas[0], c, l), LD_IN(in.gas[1], c, l), LD_IN(in.gas[2], c, l), LD_IN(in.gas[3], c, l),
               LD_IN(in.gas[4], c, l), LD_IN(in.gas[5], c, l), LD_IN(in.gas[6], c, l), LD_IN(in.gas[7], c, l),
               LD_IN(in.gas[8], c, l), G);
-  if (cfg.do_lw) { LwLev L; lw_setcoef(M, G, L); L.pad_ = 0.0; w.lev_lw[(size_t)c * nlev + l] = L; }
+  {
+    LwLev L; lw_setcoef(M, G, L);
+    L.t_top = LD_IN(in.t_hl, c, l); L.t_bot = LD_IN(in.t_hl, c, l + 1); L.pad_ = 0.0;
+    if (cfg.do_lw) w.lev_lw[(size_t)c * nlev + l] = L;
+    w.gas_jp[(size_t)c * nlev + l] = (uint8_t)(L.jp | (L.tropo << 7));   // (jp is the same expression in srtm_setcoef)
+  }
   if (cfg.do_sw && in.cos_sza[c] > 0.0) { SwLev L; sw_setcoef(M, G, L); w.lev_sw[(size_t)c * nlev + l] = L; }
 }
 
@@ -181,7 +186,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         out.t = lt + c_lw_koff[b] * GAS_LC + ll;
         out.n = 0; out.stride = GAS_LC;
         int post;
-        PlanckFrac pf = lw_build_list(M, lev[l], b, il <= laytrop, out, &post);
+        PlanckFrac pf = lw_build_list(M, M.lw[b], lev[l], b, il <= laytrop, out, &post);
         out.pad4();
         ln[ll * NB_LW + b] = out.n;
         lpost[ll * NB_LW + b] = post;
@@ -292,7 +297,7 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         out.t = lt + c_sw_koff[b] * GAS_LC + ll;
         out.n = 0; out.stride = GAS_LC;
         SwAux aux;
-        sw_build_list(M, lev[l], b, il <= laytrop, out, aux);
+        sw_build_list(M, M.sw[b], lev[l], b, il <= laytrop, out, aux);
         out.pad4();
         ln[ll * NB_SW + b] = out.n;
         rc[(ll * NB_SW + b) * 2] = aux.rc0; rc[(ll * NB_SW + b) * 2 + 1] = aux.rc1;

@@ -79,6 +79,10 @@ struct DevCfg {
 
 enum { LW_SCR_ARRAYS = 5, SW_SCR_ARRAYS = 10 };
 
+// Per-column bookkeeping of the RRTMG gas optics (gas_col_kernel): LAYTROP of both spectra, ecRad layer index that supplies the solar
+// source function of each shortwave band (-1: none).
+struct GasCol { int laytrop_lw, laytrop_sw; int lsol[NB_SW]; };
+
 // Per-tile scratch (nc = columns in the tile).
 struct Work {
   double *od_lw, *planck, *emission, *lw_albedo;  // [nc][nlev][140], [nc][nlev+1][140], [nc][140], [nc][140]
@@ -100,6 +104,8 @@ struct Work {
   // lanes-are-g-points kernels), 1 = [column][g][ls] (layer fastest, row stride ls >= nlev+1, a multiple of 4: the scan solvers,
   // whose warps read one contiguous row per g-point)
   int layout_b_lw, layout_b_sw, ls;
+  uint8_t* gas_jp;                                // [nc][nlev] reference-pressure index jp (bits 0-6), longwave "below LAYTROP" flag (bit 7)
+  GasCol* gas_col;                                // [nc]
 };
 
 void init_generator_constants();   // once per process/device, before the first generator launch
@@ -109,6 +115,10 @@ int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, cons
 int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_gas_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+// band-wise RRTMG gas optics from shared-memory table images: gas_band.cu
+int launch_gas_col(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_gas_lw_band(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
+int launch_gas_sw_band(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 // ecCKD gas optics (+ per-g-point aerosol merge), generalised cloud optics: ecckd.cu
 int launch_ckd_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_ckd_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st);

@@ -222,9 +222,13 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     BandMeta& B = M.lw[b];
     B.ng = ngc_lw[b]; B.g0 = g0; g0 += B.ng;
     for (int s = 0; s < 16; ++s) B.sec[s] = -1;
+    if (P.lwtab.size() & 1) P.lwtab.push_back(0.0);   // bands start 16-byte aligned (bulk copies)
     detail::BandPacker pk{T, P.lwtab, B, "lw" + std::to_string(b + 1) + "_"};
     if (pk.has("ABSA")) B.sec[L_ABSA] = pk.rows_fast("ABSA");
     if (pk.has("ABSB")) B.sec[L_ABSB] = pk.rows_fast("ABSB");
+    B.sec[SEC_SMALL] = (int)P.lwtab.size();
+    M.lw_rows[b][0] = B.sec[L_ABSA] >= 0 ? ((B.sec[L_ABSB] >= 0 ? B.sec[L_ABSB] : B.sec[SEC_SMALL]) - B.sec[L_ABSA]) / B.ng : 0;
+    M.lw_rows[b][1] = B.sec[L_ABSB] >= 0 ? (B.sec[SEC_SMALL] - B.sec[L_ABSB]) / B.ng : 0;
     B.sec[L_SELF] = pk.rows_fast("SELFREF");
     B.sec[L_FOR] = pk.rows_fast("FORREF");
     B.sec[L_FRACA] = pk.g_fast("FRACREFA");
@@ -243,6 +247,8 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
       }
       B.sec[L_POST] = off;
     }
+    B.sec[SEC_END] = (int)P.lwtab.size();
+    if (B.ng != kNgLwBand[b]) throw std::runtime_error("lw_NGC is not the 140-g-point reduction this build is compiled for");
   }
   if (g0 != NG_LW) throw std::runtime_error("lw_NGC does not sum to 140");
 
@@ -253,9 +259,13 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     const int jb = b + 16;
     B.ng = ngc_sw[b]; B.g0 = g0; g0 += B.ng;
     for (int s = 0; s < 16; ++s) B.sec[s] = -1;
+    if (P.swtab.size() & 1) P.swtab.push_back(0.0);
     detail::BandPacker pk{T, P.swtab, B, "sw" + std::to_string(jb) + "_"};
     if (pk.has("ABSA")) B.sec[S_ABSA] = pk.rows_fast("ABSA");
     if (pk.has("ABSB")) B.sec[S_ABSB] = pk.rows_fast("ABSB");
+    B.sec[SEC_SMALL] = (int)P.swtab.size();
+    M.sw_rows[b][0] = B.sec[S_ABSA] >= 0 ? ((B.sec[S_ABSB] >= 0 ? B.sec[S_ABSB] : B.sec[SEC_SMALL]) - B.sec[S_ABSA]) / B.ng : 0;
+    M.sw_rows[b][1] = B.sec[S_ABSB] >= 0 ? (B.sec[SEC_SMALL] - B.sec[S_ABSB]) / B.ng : 0;
     if (pk.has("SELFREFC")) B.sec[S_SELF] = pk.rows_fast("SELFREFC");
     if (pk.has("FORREFC")) { B.sec[S_FOR] = pk.rows_fast("FORREFC"); M.nfor_sw[b] = (int)T.req(pk.prefix + "FORREFC").dims[0]; }
     B.sec[S_SFLUX] = pk.g_fast("SFLUXREFC");
@@ -274,6 +284,8 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     M.rayl_sw[b] = rl ? ((const double*)rl->data.data())[0] : 0.0;
     const auto* lr = T.find(pk.prefix + "LAYREFFR");
     M.layreffr_sw[b] = lr ? ((const int32_t*)lr->data.data())[0] : 0;
+    B.sec[SEC_END] = (int)P.swtab.size();
+    if (B.ng != kNgSwBand[b]) throw std::runtime_error("sw_NGC is not the 112-g-point reduction this build is compiled for");
   }
   if (g0 != NG_SW) throw std::runtime_error("sw_NGC does not sum to 112");
   M.givfac_23 = T.d("sw23_GIVFAC")[0];

@@ -51,7 +51,7 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
     for (int b = 0; b < NB_LW; ++b) {
       ListOut out{tt, 0, 1};
       int post;
-      PlanckFrac pf = lw_build_list(M, LL[jl], b, il <= laytrop_lw, out, &post);
+      PlanckFrac pf = lw_build_list(M, M.lw[b], LL[jl], b, il <= laytrop_lw, out, &post);
       if (out.n > *kmax_lw) *kmax_lw = out.n;
       const BandMeta& B = M.lw[b];
       for (int ig = 0; ig < B.ng; ++ig) {
@@ -78,7 +78,7 @@ int hc_gas_column(void* p, int nlev, const double* p_hl, const double* t_hl, con
       const int il = nlev - jl;
       ListOut out{tt, 0, 1};
       SwAux aux;
-      sw_build_list(M, SL[jl], b, il <= laytrop_sw, out, aux);
+      sw_build_list(M, M.sw[b], SL[jl], b, il <= laytrop_sw, out, aux);
       if (out.n > *kmax_sw) *kmax_sw = out.n;
       for (int ig = 0; ig < B.ng; ++ig) {
         double taug = 0.0;

@@ -7,7 +7,7 @@ SRC=$(cd "$(dirname "$0")/../ecrad_b200/csrc" && pwd)
 OBJ=/tmp/ecb_variant_$SUF
 mkdir -p $OBJ
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in api kernels ecckd solver_sw solver_lw solver_tc solver_sp solver_scan; do
+for f in api kernels ecckd solver_sw solver_lw solver_tc solver_sp solver_scan gas_band; do
   ( /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC,-O2 -Xptxas -v "$@" -c $SRC/$f.cu -o $OBJ/$f.o 2> $OBJ/$f.log || (cat $OBJ/$f.log; exit 1) ) &
 done
 wait
