@@ -56,7 +56,10 @@ struct Handle {
   // so the kernels of tile t+1 fill the SMs that the tail of tile t leaves idle.
   cudaStream_t s_comp[2] = {nullptr, nullptr}, s_aux1[2] = {nullptr, nullptr}, s_aux2[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_cloud[2] = {nullptr, nullptr}, ev_sw_done[2] = {nullptr, nullptr};
-  int gas_variant = 1;    // RRTMG gas optics: 1 = band-wise kernels on shared-memory table images (gas_band.cu), 0 = one CTA per column (kernels.cu)
+  // RRTMG gas optics, per spectrum (bit 0 longwave, bit 1 shortwave): band-wise kernel on TMA-staged shared-memory table images
+  // (gas_band.cu) or one CTA per column gathering table rows through L1 (kernels.cu).  Measured on the B200 (10 000 columns):
+  // longwave 3.05 vs 4.05 ms, shortwave 2.25 vs 1.95 ms -> default 1.
+  int gas_variant = 1;
   int scan_solvers = 0;   // McICA / Cloudless solvers as warp scans (solver_scan.cu); 0: the lanes-are-g-points kernels (solver_sw.cu, solver_lw.cu)
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
@@ -130,7 +133,7 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   return 0;
 }
 
-enum { N_WORK = 37 };
+enum { N_WORK = 38 };
 // Which spectra run the scan solvers (and therefore want their gas optical properties laid out [column][g][layer]).
 bool use_scan(const Handle* h, bool sw, int nlev) {
   const ecrad_b200_config& c = h->cfg;
@@ -168,7 +171,7 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       0,                                                                                     // (sw_band_dir: no longer used)
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0,  // tc_reg tc_ods tc_u tc_v tc_cc
-      ckd ? 0 : nc * nl, ckd ? 0 : sizeof(GasCol) * nc};                                     // gas_jp gas_col (RRTMG)
+      ckd ? 0 : nc * nl, ckd ? 0 : sizeof(GasCol) * nc, ckd ? 0 : 4 * (nc + 1)};             // gas_jp gas_col sunlit (RRTMG)
   for (int i = 0; i < N_WORK; ++i) out[i] = sz[i];
 }
 size_t work_bytes_per_column(const Handle* h, int nlev) {
@@ -204,7 +207,7 @@ int ensure_work(Handle* h, int set, int cols, int nlev) {
   w.tc_v = (double*)h->work[set][33].p; w.tc_cc = (double*)h->work[set][34].p;
   w.sw_sums = (double*)h->work[set][19].p; w.sw_carry = (double*)h->work[set][20].p;
   w.lw_sums = (double*)h->work[set][21].p; w.lw_carry = (double*)h->work[set][22].p;
-  w.gas_jp = (uint8_t*)h->work[set][35].p; w.gas_col = (GasCol*)h->work[set][36].p;
+  w.gas_jp = (uint8_t*)h->work[set][35].p; w.gas_col = (GasCol*)h->work[set][36].p; w.sunlit = (int*)h->work[set][37].p;
   w.ls = (nlev + 1 + 3) & ~3;
   h->w_cols[set] = cols; h->w_nlev[set] = nlev;
   return 0;
@@ -225,7 +228,7 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
   if (!ckd) {
     n += launch_gas_prep(h->T, c, in, h->w[set], nc, nlev, st);   // shared by the LW and SW gas-optics kernels
-    if (h->gas_variant) n += launch_gas_col(h->T, c, in, h->w[set], nc, nlev, st);
+    if (h->gas_variant & 3) n += launch_gas_col(h->T, c, in, h->w[set], nc, nlev, st);
     if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w[set], nc, nlev, st);
   }
   if (par) {
@@ -243,12 +246,12 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
   // LW chain
   CK(h, cudaEventRecord(ev[0], s_lw));
-  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : h->gas_variant ? launch_gas_lw_band(h->T, c, in, h->w[set], nc, nlev, s_lw)
+  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : (h->gas_variant & 1) ? launch_gas_lw_band(h->T, c, in, h->w[set], nc, nlev, s_lw)
                                                                                                   : launch_gas_lw(h->T, c, in, h->w[set], nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[1], s_lw));
   // SW chain
   CK(h, cudaEventRecord(ev[2], s_sw));
-  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w[set], nc, nlev, s_sw) : h->gas_variant ? launch_gas_sw_band(h->T, c, in, h->w[set], nc, nlev, s_sw)
+  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w[set], nc, nlev, s_sw) : (h->gas_variant & 2) ? launch_gas_sw_band(h->T, c, in, h->w[set], nc, nlev, s_sw)
                                                                                                   : launch_gas_sw(h->T, c, in, h->w[set], nc, nlev, s_sw);
   CK(h, cudaEventRecord(ev[3], s_sw));
   if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud[set], 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud[set], 0)); }
@@ -514,7 +517,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   }
   if (const char* s2 = getenv("ECRAD_B200_SERIAL")) h->serial = atoi(s2) != 0;
   if (const char* s2 = getenv("ECRAD_B200_SCAN")) h->scan_solvers = atoi(s2) != 0;
-  if (const char* s2 = getenv("ECRAD_B200_GAS")) h->gas_variant = atoi(s2) != 0;
+  if (const char* s2 = getenv("ECRAD_B200_GAS")) h->gas_variant = atoi(s2) & 3;
   init_generator_constants();
   *handle = h;
   return 0;
@@ -566,7 +569,7 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   std::lock_guard<std::mutex> lk(h->mu);
   if (!strcmp(key, "serial")) { h->serial = value != 0; return 0; }
   if (!strcmp(key, "scan_solvers")) { h->scan_solvers = value != 0; return 0; }
-  if (!strcmp(key, "gas_variant")) { h->gas_variant = value != 0; return 0; }
+  if (!strcmp(key, "gas_variant")) { h->gas_variant = value & 3; return 0; }
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
   if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);

@@ -23,7 +23,11 @@
 
 namespace ecb {
 
-enum { GB_LCH = 16, GB_CC = 16, GB_THREADS = GB_LCH * GB_CC, GB_CBLK = 128, GB_IMG_BYTES = 96 * 1024 };
+#ifndef GB_IMG_KB
+#define GB_IMG_KB 96
+#define GB_MINB 2
+#endif
+enum { GB_LCH = 16, GB_CC = 16, GB_THREADS = GB_LCH * GB_CC, GB_CBLK = 128, GB_IMG_BYTES = GB_IMG_KB * 1024 };
 
 // row stride (doubles) of the shared-memory image for rows of ng doubles: stride mod 16 in {2, 6, 10, 14}, so that consecutive rows
 // start 16 bytes x (odd number) apart in the 128-byte bank line and 8 different rows can be read by a warp without conflict
@@ -46,7 +50,11 @@ __global__ void gas_col_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc
     gc.lsol[b] = il > 0 ? nlev - il : -1;
   }
   w.gas_col[c] = gc;
-  if (cfg.do_sw) for (int g = 0; g < NG_SW; ++g) w.incoming[(size_t)c * NG_SW + g] = 0.0;
+  if (cfg.do_sw) {
+    for (int g = 0; g < NG_SW; ++g) w.incoming[(size_t)c * NG_SW + g] = 0.0;
+    // work list of the sunlit columns for the shortwave kernel (order is irrelevant: columns are independent)
+    if (in.cos_sza[c] > 0.0) w.sunlit[1 + atomicAdd(w.sunlit, 1)] = c;
+  }
 }
 
 // incoming_sw = ZINCSOL * solar_irradiance / sum(ZINCSOL): radiation_ifs_rrtm.F90:557-605
@@ -155,8 +163,10 @@ __device__ __forceinline__ void stage_rows(double* img, int rs, int ng, const do
 // ---------------------------------------------------------------------------------------------------------
 template <int IB, bool LAYB>
 __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, const double* img, const double* tp, double pfac, const DevTables& T,
-                                        const DevCfg& cfg, const DevIn& in, const Work& w, int c, int l, int nlev, bool low, const LwLev& L) {
+                                        const DevCfg& cfg, const DevIn& in, const Work& w, int c, int l, int nlev, bool low, const LwLev* __restrict__ Lg, int jw) {
   constexpr int NG = kNgLwBand[IB];
+  LwLev L = *Lg;     // (by value: the compiler keeps the loads of the fields this band reads)
+  if (IB != 15 || low) L.jp = jw;
   EvalSink<NG> sink;
   sink.tab = img; sink.clear();
   int post;
@@ -175,21 +185,28 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
   const size_t sg = LAYB ? (size_t)w.ls : 1, sl = LAYB ? 1 : (size_t)NG_LW;
   double* od_out = w.od_lw + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW) + (size_t)g0 * sg;
   double* pl_out = w.planck + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)(nlev + 1) * NG_LW) + (size_t)g0 * sg;
-  double pfv[NG];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
+  auto pfrac = [&](int g) { return pf.c0 * img[pf.o0 + g] + pf.c1 * img[pf.o1 + g]; };
+  auto odval = [&](int g) {
     double tau = sink.acc[g];
     if (post >= 0) tau *= img[post + g];
-    pfv[g] = pf.c0 * img[pf.o0 + g] + pf.c1 * img[pf.o1 + g];
-    double odv = dmax(tau, cfg.min_gas_od_lw);                           // radiation_ifs_rrtm.F90:506-511
-    if (cfg.use_aerosols) odv = odv + aer;
-    od_out[l * sl + g * sg] = odv;
-    pl_out[(l + 1) * sl + g * sg] = plk_bot * pfv[g];                    // the half-level below uses this layer's PFRAC
+    double o = dmax(tau, cfg.min_gas_od_lw);                             // radiation_ifs_rrtm.F90:506-511
+    if (cfg.use_aerosols) o = o + aer;
+    return o;
+  };
+  if (LAYB) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { od_out[l * sl + g * sg] = odval(g); pl_out[(l + 1) * sl + g * sg] = plk_bot * pfrac(g); }   // the half-level below uses this layer's PFRAC
+  } else {   // rows of the band's g-points: 16-byte stores (g0 is even, rows are 16-byte aligned)
+#pragma unroll
+    for (int g = 0; g < NG; g += 2) {
+      *reinterpret_cast<double2*>(od_out + l * sl + g) = make_double2(odval(g), odval(g + 1));
+      *reinterpret_cast<double2*>(pl_out + (l + 1) * sl + g) = make_double2(plk_bot * pfrac(g), plk_bot * pfrac(g + 1));
+    }
   }
   if (l == 0) {
     const double plk_top = planck(L.t_top);                              // top-of-atmosphere half-level: PFRAC of the top layer
 #pragma unroll
-    for (int g = 0; g < NG; ++g) pl_out[g * sg] = plk_top * pfv[g];
+    for (int g = 0; g < NG; ++g) pl_out[g * sg] = plk_top * pfrac(g);
   }
   if (l == nlev - 1) {
     // surface: planck_function_surf :757-852, lw_emission = planck_surf * (1 - lw_albedo) :466
@@ -207,13 +224,13 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       w.lw_albedo[(size_t)c * NG_LW + g0 + g] = alb;
-      w.emission[(size_t)c * NG_LW + g0 + g] = (plk_surf * pfv[g]) * (1.0 - alb);
+      w.emission[(size_t)c * NG_LW + g0 + g] = (plk_surf * pfrac(g)) * (1.0 - alb);
     }
   }
 }
 
 template <bool LAYB>
-__global__ void __launch_bounds__(GB_THREADS, 2)
+__global__ void __launch_bounds__(GB_THREADS, GB_MINB)
 gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* img = reinterpret_cast<double*>(smem_raw);   // [GB_IMG_BYTES / 8]
@@ -291,10 +308,14 @@ gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
       if (!(v & 512) || jw < jlo || jw > jhi) continue;
       jpv[it] = v & ~512;
       const int c = c_first + it * GB_CC + cc;
-      LwLev L = w.lev_lw[(size_t)c * nlev + l];
+      const LwLev* Lg = w.lev_lw + (size_t)c * nlev + l;
+      if (it + 1 < GB_CBLK / GB_CC && (jpv[it + 1] & 512)) {   // next item's state on its way into L1 while this one is computed
+        const char* nx = reinterpret_cast<const char*>(Lg + (size_t)GB_CC * nlev);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 128));
+      }
       const bool low = (v & 256) != 0;
-      if (L.jp != jw && band != 15) L.jp = jw;
-#define LWB(I) case I: lw_item<I, LAYB>(M, S.B, img, tp, pfac, T, cfg, in, w, c, l, nlev, low, L); break;
+#define LWB(I) case I: lw_item<I, LAYB>(M, S.B, img, tp, pfac, T, cfg, in, w, c, l, nlev, low, Lg, jw); break;
       switch (band) { LWB(0) LWB(1) LWB(2) LWB(3) LWB(4) LWB(5) LWB(6) LWB(7) LWB(8) LWB(9) LWB(10) LWB(11) LWB(12) LWB(13) LWB(14) LWB(15) }
 #undef LWB
     }
@@ -309,8 +330,10 @@ gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
 // ---------------------------------------------------------------------------------------------------------
 template <int IB, bool LAYB>
 __device__ __forceinline__ void sw_item(const GasMeta& M, const BandMeta& Bs, const double* img, const DevCfg& cfg, const Work& w, int c, int l,
-                                        int nlev, bool low, bool solar_layer, const SwLev& L) {
+                                        int nlev, bool low, bool solar_layer, const SwLev* __restrict__ Lg, int jw) {
   constexpr int NG = kNgSwBand[IB];
+  SwLev L = *Lg;
+  L.jp = jw;
   EvalSink<NG> sink;
   sink.tab = img; sink.clear();
   SwAux aux;
@@ -323,32 +346,44 @@ __device__ __forceinline__ void sw_item(const GasMeta& M, const BandMeta& Bs, co
     const double* a = w.aer_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
     od_a = a[IB]; sc_a = a[NB_SW + IB]; sg_a = a[2 * NB_SW + IB];
   }
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
+  auto eval = [&](int g, double& odv, double& ssav, double& gv) {
     const double taug = sink.acc[g];
     const double taur = aux.rc0 * img[aux.ro0 + g] + aux.rc1 * img[aux.ro1 + g];
     const double od = taur + taug;                                        // srtm_gas_optical_depth.F90:314-320
-    double odv = dmax(od, cfg.min_gas_od_sw), ssav = taur / od;          // radiation_ifs_rrtm.F90:593
+    odv = dmax(od, cfg.min_gas_od_sw); ssav = taur / od;                 // radiation_ifs_rrtm.F90:593
+    gv = 0.0;
     if (cfg.use_aerosols) {
       // merge aerosol and gas per g-point: radiation_aerosol_optics.F90:765-781
       const double local_od = odv + od_a;
-      double gv = 0.0;
       if (local_od > 0.0 && od_a > 0.0) {
         const double local_scat = ssav * odv + sc_a;
         if (local_scat > 0.0) gv = sg_a / local_scat;
         ssav = local_scat / local_od;
         odv = local_od;
       }
-      w.g_sw[base + l * sl + g * sg] = gv;
     }
-    w.od_sw[base + l * sl + g * sg] = odv;
-    w.ssa_sw[base + l * sl + g * sg] = ssav;
     if (solar_layer) w.incoming[(size_t)c * NG_SW + g0 + g] = aux.sc0 * img[aux.so0 + g] + aux.sc1 * img[aux.so1 + g];
+  };
+  if (LAYB) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      double o, ss, gv; eval(g, o, ss, gv);
+      w.od_sw[base + l * sl + g * sg] = o; w.ssa_sw[base + l * sl + g * sg] = ss;
+      if (cfg.use_aerosols) w.g_sw[base + l * sl + g * sg] = gv;
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < NG; g += 2) {
+      double o0, s0, v0, o1, s1, v1; eval(g, o0, s0, v0); eval(g + 1, o1, s1, v1);
+      *reinterpret_cast<double2*>(w.od_sw + base + l * sl + g) = make_double2(o0, o1);
+      *reinterpret_cast<double2*>(w.ssa_sw + base + l * sl + g) = make_double2(s0, s1);
+      if (cfg.use_aerosols) *reinterpret_cast<double2*>(w.g_sw + base + l * sl + g) = make_double2(v0, v1);
+    }
   }
 }
 
 template <bool LAYB>
-__global__ void __launch_bounds__(GB_THREADS, 2)
+__global__ void __launch_bounds__(GB_THREADS, GB_MINB)
 gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* img = reinterpret_cast<double*>(smem_raw);
@@ -362,6 +397,9 @@ gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
   const int l = blockIdx.z * GB_LCH + (tid % GB_LCH);
   const int c_first = blockIdx.y * GB_CBLK, cc = tid / GB_LCH;
   const bool lvalid = l < nlev;
+  const int nsun = w.sunlit[0];
+  if (c_first >= nsun) return;   // the grid is sized for "every column sunlit"
+  const int* sun = w.sunlit + 1;
   const BandMeta& G = M.sw[band];
   if (tid == 0) {
     S.ng = G.ng; S.rs = gb_row_stride(G.ng);
@@ -378,9 +416,10 @@ gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
   bool any = false;
 #pragma unroll
   for (int it = 0; it < GB_CBLK / GB_CC; ++it) {
-    const int c = c_first + it * GB_CC + cc;
+    const int ci = c_first + it * GB_CC + cc;
     jpv[it] = 0;
-    if (lvalid && c < nc && in.cos_sza[c] > 0.0) {   // srtm only runs for sunlit columns (radiation_ifs_rrtm.F90:518-542)
+    if (lvalid && ci < nsun) {   // srtm only runs for sunlit columns (radiation_ifs_rrtm.F90:518-542)
+      const int c = sun[ci];
       const int jp = w.gas_jp[(size_t)c * nlev + l] & 127;
       const bool low = (nlev - l) <= w.gas_col[c].laytrop_sw;
       const int jw = low ? imin(jp, 12) : imax(jp, 13);
@@ -420,12 +459,16 @@ gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
       const int v = jpv[it], jw = v & 127;
       if (!(v & 512) || jw < jlo || jw > jhi) continue;
       jpv[it] = v & ~512;
-      const int c = c_first + it * GB_CC + cc;
-      SwLev L = w.lev_sw[(size_t)c * nlev + l];
+      const int c = sun[c_first + it * GB_CC + cc];
+      const SwLev* Lg = w.lev_sw + (size_t)c * nlev + l;
+      if (it + 1 < GB_CBLK / GB_CC && (jpv[it + 1] & 512)) {
+        const char* nx = reinterpret_cast<const char*>(w.lev_sw + (size_t)sun[c_first + (it + 1) * GB_CC + cc] * nlev + l);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 128));
+      }
       const bool low = (v & 256) != 0;
-      L.jp = jw;
       const bool solar_layer = l == w.gas_col[c].lsol[band];
-#define SWB(I) case I: sw_item<I, LAYB>(M, S.B, img, cfg, w, c, l, nlev, low, solar_layer, L); break;
+#define SWB(I) case I: sw_item<I, LAYB>(M, S.B, img, cfg, w, c, l, nlev, low, solar_layer, Lg, jw); break;
       switch (band) { SWB(0) SWB(1) SWB(2) SWB(3) SWB(4) SWB(5) SWB(6) SWB(7) SWB(8) SWB(9) SWB(10) SWB(11) SWB(12) SWB(13) }
 #undef SWB
     }
@@ -439,6 +482,7 @@ gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 int launch_gas_col(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
+  cudaMemsetAsync(w.sunlit, 0, sizeof(int), st);
   gas_col_kernel<<<(nc + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev);
   return 1;
 }

@@ -64,6 +64,8 @@ struct GasMeta {
   int layreffr_sw[NB_SW], nfor_sw[NB_SW];
   int band_of_g_lw[NG_LW], band_of_g_sw[NG_SW];  // 0-based band of each g-point
   int lw_rows[NB_LW][2], sw_rows[NB_SW][2];      // rows of ABSA / ABSB per band (0: none); 13 (ABSA) or 47 (ABSB) reference pressures each
+  short lw_sec_rows[NB_LW][16], sw_sec_rows[NB_SW][16];   // rows of every section of a band's packed table
+  unsigned short lw_sec_low[NB_LW], lw_sec_high[NB_LW];   // small sections the band routine reads below / above LAYTROP (bit = section)
 };
 // g-points per band of the RRTMG-IFS reduction (ifsrrtm/rrtm_init_140gp.F90 NGC, srtm_init.F90 NGC): compile-time sizes of the
 // band-wise kernels' register accumulators; ecrad_b200_setup checks the tables against them.

@@ -106,6 +106,7 @@ struct Work {
   int layout_b_lw, layout_b_sw, ls;
   uint8_t* gas_jp;                                // [nc][nlev] reference-pressure index jp (bits 0-6), longwave "below LAYTROP" flag (bit 7)
   GasCol* gas_col;                                // [nc]
+  int* sunlit;                                    // [1 + nc] number of sunlit columns of the tile, then their indices (any order)
 };
 
 void init_generator_constants();   // once per process/device, before the first generator launch

@@ -248,6 +248,22 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
       B.sec[L_POST] = off;
     }
     B.sec[SEC_END] = (int)P.lwtab.size();
+    {
+      // rows of each section = distance to the next section that starts after it
+      for (int k = 0; k < L_NSEC; ++k) {
+        M.lw_sec_rows[b][k] = 0;
+        if (B.sec[k] < 0) continue;
+        int nxt = B.sec[SEC_END];
+        for (int j = 0; j < L_NSEC; ++j) if (B.sec[j] > B.sec[k] && B.sec[j] < nxt) nxt = B.sec[j];
+        M.lw_sec_rows[b][k] = (short)((nxt - B.sec[k]) / B.ng);
+      }
+      // which small sections the band routine (gas_core.h lw_build_list) reads in the lower / upper atmosphere
+      unsigned lo = (1u << L_SELF) | (1u << L_FOR) | (1u << L_FRACA) | (1u << L_C0) | (1u << L_C1);
+      unsigned hi = (1u << L_FOR) | (1u << L_FRACA) | (1u << L_FRACB) | (1u << L_C0) | (1u << L_C1) | (1u << L_POST);
+      for (int m = 0; m < 5; ++m)
+        if (lw_minor[b][m]) { if (lw_minor[b][m][1] == 'A') lo |= 1u << (L_M0 + m); else hi |= 1u << (L_M0 + m); }
+      M.lw_sec_low[b] = (unsigned short)lo; M.lw_sec_high[b] = (unsigned short)hi;
+    }
     if (B.ng != kNgLwBand[b]) throw std::runtime_error("lw_NGC is not the 140-g-point reduction this build is compiled for");
   }
   if (g0 != NG_LW) throw std::runtime_error("lw_NGC does not sum to 140");
@@ -285,6 +301,13 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
     const auto* lr = T.find(pk.prefix + "LAYREFFR");
     M.layreffr_sw[b] = lr ? ((const int32_t*)lr->data.data())[0] : 0;
     B.sec[SEC_END] = (int)P.swtab.size();
+    for (int k = 0; k < S_NSEC; ++k) {
+      M.sw_sec_rows[b][k] = 0;
+      if (B.sec[k] < 0) continue;
+      int nxt = B.sec[SEC_END];
+      for (int j = 0; j < S_NSEC; ++j) if (B.sec[j] > B.sec[k] && B.sec[j] < nxt) nxt = B.sec[j];
+      M.sw_sec_rows[b][k] = (short)((nxt - B.sec[k]) / B.ng);
+    }
     if (B.ng != kNgSwBand[b]) throw std::runtime_error("sw_NGC is not the 112-g-point reduction this build is compiled for");
   }
   if (g0 != NG_SW) throw std::runtime_error("sw_NGC does not sum to 112");

@@ -561,3 +561,29 @@ def test_error_behaviour(meridian_raw):
     with pytest.raises(RadiationError, match="bad dimensions"):
         h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, istartcol=5, iendcol=40)
     h.finalize()
+
+
+@pytest.mark.parametrize("opts", [dict(gas_variant=0), dict(gas_variant=3), dict(scan_solvers=1), dict(scan_solvers=1, gas_variant=3)])
+@pytest.mark.parametrize("kw", [dict(use_aerosols=True), dict(sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
+                                dict(overlap_scheme_name="Exp-Exp", do_lw_cloud_scattering=False, do_sw_delta_scaling_with_gases=True, use_aerosols=True)])
+def test_selectable_kernel_variants_vs_oracle(meridian_raw, kw, opts):
+    """Every kernel the library can be told to use (set_option): the per-column and the band-wise RRTMG gas optics, the lanes-are-g-points
+    and the warp-scan McICA / Cloudless solvers -- same parity bar against the oracle, with 137 and with 60 levels."""
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+
+    cfg = RadiationConfig(**kw).consolidate()
+    h, orc = setup_radiation(cfg), Oracle(cfg)
+    for k, v in opts.items():
+        h.set_option(k, v)
+    try:
+        for n, nlev in ((300, NLEV), (40, 60)):
+            raw = I.synthetic_columns(meridian_raw, n)
+            if nlev != NLEV:
+                raw = coarsen_levels(raw, nlev)
+            out = h.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+            ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+            compare(out, ref, FLUXES + OTHERS)
+            assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
+    finally:
+        h.finalize()
