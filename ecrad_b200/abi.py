@@ -138,3 +138,81 @@ def make_inputs(arrays, solar_irradiance):
         keep[nm] = a
         setattr(st, nm, a.ctypes.data_as(c_ip if dt == "i4" else c_dp))
     return keep, st
+
+
+class BlockLayout(C.Structure):
+    """struct ecrad_b200_block_layout: where each input / output lives in zrgp(nproma, nfields, nblocks)."""
+    _fields_ = [("struct_bytes", C.c_int32), ("nproma", C.c_int32), ("nblocks", C.c_int32), ("nfields_in", C.c_int32), ("nfields_out", C.c_int32),
+                ("in_field", C.c_int32 * 28), ("out_field", C.c_int32 * 41), ("solar_irradiance", C.c_double)]
+
+
+def pack_blocked(arrays, outputs, ncol, nlev, nproma, cfg, solar_irradiance):
+    """Column-layout inputs (dict keyed like INPUT_ARRAYS) and outputs (dict from alloc_outputs) -> (layout, zrgp_in, zrgp_out) in the
+    blocked layout of driver/ifs_blocking.F90: Fortran (nproma, nfields, nblocks), i.e. C order (nblocks, nfields, nproma)."""
+    nblocks = (ncol + nproma - 1) // nproma
+    lay = BlockLayout()
+    lay.struct_bytes = C.sizeof(BlockLayout)
+    lay.nproma, lay.nblocks, lay.solar_irradiance = nproma, nblocks, float(solar_irradiance)
+    rows_in, f = [], 0
+    for k, (nm, dt, _) in enumerate(INPUT_ARRAYS):
+        a = arrays.get(nm)
+        if a is None:
+            lay.in_field[k] = -1
+            rows_in.append(None)
+            continue
+        a2 = np.asarray(a, dtype=np.float64).reshape(ncol, -1, order="F")   # (ncol, rows): aerosol (ncol, nlev, ntype) -> type slowest
+        lay.in_field[k] = f
+        rows_in.append(a2)
+        f += a2.shape[1]
+    lay.nfields_in = f
+    zin = np.zeros((nblocks, f, nproma))
+    pad = nblocks * nproma - ncol
+    for k, a2 in enumerate(rows_in):
+        if a2 is not None:
+            full = np.concatenate([a2, np.zeros((pad, a2.shape[1]))]) if pad else a2
+            zin[:, lay.in_field[k]:lay.in_field[k] + a2.shape[1], :] = full.reshape(nblocks, nproma, -1).transpose(0, 2, 1)
+    f, views = 0, []
+    for k, (nm, kind) in enumerate(OUTPUT_ARRAYS):
+        a = outputs.get(nm)
+        if a is None:
+            lay.out_field[k] = -1
+            views.append(None)
+            continue
+        if kind in ("h", "c"):
+            a2 = np.asarray(a).reshape(ncol, -1, order="F")                       # (ncol, rows)
+        elif kind in ("pl", "ps"):
+            a2 = np.transpose(np.asarray(a), (1, 2, 0)).reshape(ncol, -1)         # (nb, ncol, nlev+1) -> (ncol, [level][band])
+        else:
+            a2 = np.asarray(a).T                                                  # (n, ncol) -> (ncol, n)
+        lay.out_field[k] = f
+        views.append(a2)
+        f += a2.shape[1]
+    lay.nfields_out = f
+    zout = np.zeros((nblocks, f, nproma))
+    for k, a2 in enumerate(views):
+        if a2 is not None:
+            full = np.concatenate([a2, np.zeros((pad, a2.shape[1]))]) if pad else a2
+            zout[:, lay.out_field[k]:lay.out_field[k] + a2.shape[1], :] = full.reshape(nblocks, nproma, -1).transpose(0, 2, 1)
+    return lay, zin, zout
+
+
+def unpack_blocked(lay, zout, outputs, ncol, nlev):
+    """zrgp_out -> the column-layout flux arrays of `outputs` (in place)."""
+    nproma, nblocks = lay.nproma, lay.nblocks
+    for k, (nm, kind) in enumerate(OUTPUT_ARRAYS):
+        a = outputs.get(nm)
+        if a is None or lay.out_field[k] < 0:
+            continue
+        if kind in ("h", "c"):
+            n = int(np.prod(a.shape[1:])) if a.ndim > 1 else 1
+        elif kind in ("pl", "ps"):
+            n = a.shape[0] * a.shape[2]
+        else:
+            n = a.shape[0]
+        blk = zout[:, lay.out_field[k]:lay.out_field[k] + n, :].transpose(0, 2, 1).reshape(nblocks * nproma, n)[:ncol]
+        if kind in ("h", "c"):
+            a[...] = blk.reshape(a.shape, order="F")
+        elif kind in ("pl", "ps"):
+            a[...] = np.transpose(blk.reshape(ncol, a.shape[2], a.shape[0]), (2, 0, 1))
+        else:
+            a[...] = blk.T

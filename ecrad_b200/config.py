@@ -191,8 +191,8 @@ class RadiationConfig:
                   "clear_to_thick_fraction"):
             setattr(c, k, float(getattr(self, k)))
         c.min_cloud_effective_size = max(1.0e-6, self.min_cloud_effective_size)   # radiation_config.F90:970
-        # radiation_config.F90 consolidate: do_clouds is false only for the Cloudless solvers
-        c.do_clouds = int(not (c.i_solver_sw == 0 and c.i_solver_lw == 0))
+        # radiation_config.F90:1127-1132 consolidate: clouds matter if an active spectrum has a solver other than Cloudless
+        c.do_clouds = int(bool((self.do_sw and c.i_solver_sw != 0) or (self.do_lw and c.i_solver_lw != 0)))
         c.n_g_sw, c.n_g_lw = self.n_g
         c.n_bands_sw, c.n_bands_lw = self.n_bands
         c.n_albedo_sw = self.derived["sw_albedo_weights"].shape[0]

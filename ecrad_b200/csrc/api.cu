@@ -60,10 +60,16 @@ struct Handle {
   // (gas_band.cu) or one CTA per column gathering table rows through L1 (kernels.cu).  Measured on the B200 (10 000 columns):
   // longwave 3.05 vs 4.05 ms, shortwave 2.25 vs 1.95 ms -> default 1.
   int gas_variant = 1;
+  cudaEvent_t ev_dev_done = nullptr;   // end of the last device-entry call: the next call (on any stream) waits for it before reusing the scratch
+  bool dev_pending = false;
+  int register_host = 0;  // host entry: page-lock the caller's arrays (cudaHostRegister, cached per pointer) so that pageable Fortran allocatables
+                          // are copied asynchronously at full PCIe speed like pinned memory
+  std::vector<std::pair<void*, size_t>> registered;
   int scan_solvers = 0;   // McICA / Cloudless solvers as warp scans (solver_scan.cu); 0: the lanes-are-g-points kernels (solver_sw.cu, solver_lw.cu)
   int serial = 0;   // 1: all kernels of a tile on one stream (per-kernel timing); 0: LW chain, SW chain and cloud chain overlap
   Slot slot[2];
   Buf work[2][N_WORK_MAX];
+  Buf blocked;            // blocked entry: device copies of the two zrgp arrays + the column-layout arrays unpacked from / packed into them
   Work w[2];
   int w_cols[2] = {0, 0}, w_nlev[2] = {0, 0}, w_scan[2] = {-1, -1};
   std::mutex mu;
@@ -81,6 +87,38 @@ int fail(Handle* h, const char* fmt, ...) {
   return 1;
 }
 #define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+// Inside the pipelined host entry an error must not leave asynchronous copies into the caller's arrays in flight.
+#define CKD(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { drain(h); return fail(h, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+
+void unregister_all(Handle* h) {
+  for (auto& r : h->registered) cudaHostUnregister(r.first);
+  h->registered.clear();
+  cudaGetLastError();
+}
+// Page-lock [p, p + bytes) once; a later call with the same pointer and a size that fits is free.  Failure is not an error: the
+// copy then takes the (slower, staged) pageable route.
+void register_range(Handle* h, const void* p, size_t bytes) {
+  if (!p || !bytes) return;
+  for (auto& r : h->registered)
+    if (r.first == p) {
+      if (r.second >= bytes) return;
+      cudaHostUnregister(r.first); r.first = nullptr; r.second = 0;
+    }
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    for (auto& r : h->registered) if (!r.first) { r = {const_cast<void*>(p), bytes}; return; }
+    h->registered.push_back({const_cast<void*>(p), bytes});
+  } else {
+    cudaGetLastError();   // already registered by the caller (overlap), or not registrable: leave it
+  }
+}
+
+// Wait for everything this handle has enqueued (error paths of the host entry: no copy may still be writing the caller's arrays
+// or reading them once the call has returned).
+void drain(Handle* h) {
+  for (cudaStream_t q : {h->s_h2d, h->s_d2h, h->s_comp[0], h->s_comp[1], h->s_aux1[0], h->s_aux1[1], h->s_aux2[0], h->s_aux2[1]})
+    if (q) cudaStreamSynchronize(q);
+  cudaGetLastError();
+}
 
 template <class Tp>
 int upload(Handle* h, const Tp* src, size_t n, const Tp** dst) {
@@ -117,6 +155,7 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
     return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
+  if (c.do_sw && !c.do_sw_direct) return fail(h, "do_sw_direct = false is not available in this build (the direct beam is always computed)");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
@@ -287,8 +326,8 @@ int check_args(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const 
   if (!in || !out) return fail(h, "null inputs/outputs");
   if (in->struct_bytes != (int32_t)sizeof(ecrad_b200_inputs) || out->struct_bytes != (int32_t)sizeof(ecrad_b200_outputs))
     return fail(h, "ecrad_b200_inputs/outputs: struct_bytes mismatch (ABI)");
-  if (ncol < 1 || nlev < 2 || nlev > 160 || istartcol < 1 || iendcol > ncol || iendcol < istartcol)
-    return fail(h, "bad dimensions ncol=%d nlev=%d istartcol=%d iendcol=%d (nlev <= 160)", ncol, nlev, istartcol, iendcol);
+  if (ncol < 1 || nlev < 2 || nlev > 256 || istartcol < 1 || iendcol > ncol || iendcol < istartcol)
+    return fail(h, "bad dimensions ncol=%d nlev=%d istartcol=%d iendcol=%d (nlev <= 256)", ncol, nlev, istartcol, iendcol);
   const ecrad_b200_config& c = h->cfg;
   if (!in->pressure_hl || !in->temperature_hl || !in->h2o_mmr || !in->co2_mmr || !in->o3_mmr || !in->n2o_mmr || !in->ch4_mmr ||
       !in->cfc11_mmr || !in->cfc12_mmr || !in->hcfc22_mmr || !in->ccl4_mmr)
@@ -359,25 +398,94 @@ void make_views(void* const* ip, void* const* op, int ld, int ld_out, double sol
 static_assert(sizeof(DevOut) >= N_OUT * sizeof(double*) + sizeof(int), "DevOut layout");
 static_assert(offsetof(DevOut, lw_up_toa_clear_band) == (N_OUT - 1) * sizeof(double*), "DevOut must list the 41 outputs in ABI order");
 
+// ---- blocked (NPROMA) layout: zrgp(nproma, nfields, nblocks) <-> column-fastest arrays -------------------------------------
+struct BlockJob { void* dev; int field0, rows, kind, is_int; };   // kind 0: (ncol, rows); 1: (rows, ncol); 2: (nb = rows, ncol, nlev+1)
+struct BlockJobs { BlockJob j[48]; int n; };
+// one thread per (column, field row): column fastest, so both sides are read / written in runs of nproma
+__global__ void block_unpack_kernel(BlockJobs J, const double* __restrict__ z, int nproma, int nfields, int ncol, int nlev1) {
+  const BlockJob& b = J.j[blockIdx.y];
+  const int nrows = b.kind == 2 ? b.rows * nlev1 : b.rows;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ncol * nrows) return;
+  const int c = (int)(i % ncol), r = (int)(i / ncol);
+  const double v = z[((size_t)(c / nproma) * nfields + b.field0 + r) * nproma + (c % nproma)];
+  if (b.is_int) ((int32_t*)b.dev)[(size_t)r * ncol + c] = (int32_t)v;
+  else if (b.kind == 0) ((double*)b.dev)[(size_t)r * ncol + c] = v;
+  else if (b.kind == 1) ((double*)b.dev)[(size_t)c * b.rows + r] = v;
+  else ((double*)b.dev)[((size_t)(r / b.rows) * ncol + c) * b.rows + (r % b.rows)] = v;
+}
+__global__ void block_pack_kernel(BlockJobs J, double* __restrict__ z, int nproma, int nfields, int ncol, int nlev1) {
+  const BlockJob& b = J.j[blockIdx.y];
+  const int nrows = b.kind == 2 ? b.rows * nlev1 : b.rows;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)ncol * nrows) return;
+  const int c = (int)(i % ncol), r = (int)(i / ncol);
+  const double* src = (const double*)b.dev;
+  double v;
+  if (b.kind == 0) v = src[(size_t)r * ncol + c];
+  else if (b.kind == 1) v = src[(size_t)c * b.rows + r];
+  else v = src[((size_t)(r / b.rows) * ncol + c) * b.rows + (r % b.rows)];   // field r = level * nband + band
+  z[((size_t)(c / nproma) * nfields + b.field0 + r) * nproma + (c % nproma)] = v;
+}
+
+// fp64 multiply-add throughput of the device, measured: 8 independent chains per thread, enough CTAs to fill every SM
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double* out, int iters, double b, double c) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace
 
 // =========================================================================================================
 extern "C" {
 
+int ecrad_b200_measure_fp64(double* tflops) {
+  if (!tflops) return 1;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return fail(nullptr, "ecrad_b200_measure_fp64: no CUDA device");
+  const int blocks = sms * 8, threads = 256, iters = 2048;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return fail(nullptr, "ecrad_b200_measure_fp64: out of memory");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    fp64_fma_probe_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1.0e-6);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (cudaGetLastError() != cudaSuccess) return fail(nullptr, "ecrad_b200_measure_fp64: kernel failed");
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return 0;
+}
+
 ecrad_b200_tables* ecrad_b200_tables_create(void) { return new (std::nothrow) ecrad_b200_tables(); }
 int ecrad_b200_tables_add(ecrad_b200_tables* t, const char* name, int dtype, int ndim, const int64_t* dims, const void* data) {
   if (!t) return 1;
-  return t->add(name, dtype, ndim, dims, data);
+  try { return t->add(name, dtype, ndim, dims, data); } catch (const std::exception& ex) { return fail(nullptr, "ecrad_b200_tables_add('%s'): %s", name ? name : "", ex.what()); }
 }
 int ecrad_b200_tables_load_file(ecrad_b200_tables* t, const char* path) {
   if (!t || !path) return 1;
-  int rc = t->load_file(path);
+  int rc;
+  try { rc = t->load_file(path); } catch (const std::exception& ex) { return fail(nullptr, "cannot load table blob '%s': %s", path, ex.what()); }
   if (rc) fail(nullptr, "cannot load table blob '%s' (rc=%d)", path, rc);
   return rc;
 }
 int ecrad_b200_tables_load_memory(ecrad_b200_tables* t, const void* blob, int64_t nbytes) {
   if (!t || !blob || nbytes < 8) return 1;
-  int rc = t->load_memory((const char*)blob, (size_t)nbytes);
+  int rc;
+  try { rc = t->load_memory((const char*)blob, (size_t)nbytes); } catch (const std::exception& ex) { return fail(nullptr, "table blob in memory: %s", ex.what()); }
   if (rc) fail(nullptr, "table blob in memory is not a valid ETB1 image (rc=%d)", rc);
   return rc;
 }
@@ -429,6 +537,9 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   if (cfg->do_nearest_spectral_lw_emiss ? P.i_emiss_from_band_lw.empty() : (P.lw_emiss_weights.empty() || P.n_emiss_lw != cfg->n_emiss_lw)) {
     fail(nullptr, "table 'i_emiss_from_band_lw' (n_bands_lw) or 'lw_emiss_weights' (n_emiss_lw x n_bands_lw) is required"); delete h; return 1;
   }
+  if (cfg->do_nearest_spectral_lw_emiss)   // the kernels index lw_emissivity(ncol, n_emiss_lw) with this map
+    for (int v : P.i_emiss_from_band_lw)
+      if (v < 1 || v > cfg->n_emiss_lw) { fail(nullptr, "i_emiss_from_band_lw out of range 1..n_emiss_lw = %d", cfg->n_emiss_lw); delete h; return 1; }
   cudaGetDevice(&h->device);
   int rc = 0;
   rc |= upload(h, &P.meta, 1, &h->T.meta);
@@ -515,6 +626,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     cudaEventCreateWithFlags(&h->ev_cloud[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_sw_done[k], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&h->ev_dev_done, cudaEventDisableTiming);
   if (const char* s2 = getenv("ECRAD_B200_SERIAL")) h->serial = atoi(s2) != 0;
   if (const char* s2 = getenv("ECRAD_B200_SCAN")) h->scan_solvers = atoi(s2) != 0;
   if (const char* s2 = getenv("ECRAD_B200_GAS")) h->gas_variant = atoi(s2) & 3;
@@ -528,8 +640,10 @@ void ecrad_b200_finalize(void* handle) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  unregister_all(h);
   for (void* p : h->table_allocs) cudaFree(p);
   for (auto& ws : h->work) for (auto& b : ws) b.release();
+  h->blocked.release();
   for (auto& s : h->slot) {
     for (auto& b : s.in) b.release();
     for (auto& b : s.out) b.release();
@@ -541,6 +655,7 @@ void ecrad_b200_finalize(void* handle) {
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   for (cudaStream_t q : {h->s_comp[0], h->s_comp[1], h->s_aux1[0], h->s_aux1[1], h->s_aux2[0], h->s_aux2[1]}) if (q) cudaStreamDestroy(q);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  if (h->ev_dev_done) cudaEventDestroy(h->ev_dev_done);
   for (cudaEvent_t e : {h->ev_fork[0], h->ev_cloud[0], h->ev_sw_done[0], h->ev_fork[1], h->ev_cloud[1], h->ev_sw_done[1]}) if (e) cudaEventDestroy(e);
   delete h;
 }
@@ -568,6 +683,7 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   if (!h || !key) return 1;
   std::lock_guard<std::mutex> lk(h->mu);
   if (!strcmp(key, "serial")) { h->serial = value != 0; return 0; }
+  if (!strcmp(key, "register_host")) { h->register_host = value != 0; if (!value) unregister_all(h); return 0; }
   if (!strcmp(key, "scan_solvers")) { h->scan_solvers = value != 0; return 0; }
   if (!strcmp(key, "gas_variant")) { h->gas_variant = value & 3; return 0; }
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
@@ -634,64 +750,71 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     }
     return true;
   };
+  if (h->register_host) {
+    for (int k = 0; k < N_IN; ++k) if (id[k].host && id[k].rows > 0) register_range(h, id[k].host, (size_t)id[k].elem * ncol * id[k].rows);
+    for (int k = 0; k < N_OUT; ++k)
+      if (out_active(k)) register_range(h, od[k].host, 8 * (size_t)ncol * od[k].rows * (od[k].kind == 2 ? (size_t)(nlev + 1) : 1));
+  }
   for (auto& s : h->slot) s.used = false;
   for (int t = 0; t < ntiles; ++t) {
     Slot& s = h->slot[t & 1];
     const int c0 = c_first + tile_first[t], nt = tile_n[t];
     void* ip[N_IN]; void* op[N_OUT];
     // ---- H2D (this slot's buffers are free once the kernels and copies of tile t-2 are done) ----
-    if (s.used) { CK(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CK(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }
+    if (s.used) { CKD(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CKD(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }
     for (int k = 0; k < N_IN; ++k) {
       ip[k] = nullptr;
       if (!id[k].host || id[k].rows <= 0) continue;
       const size_t el = (size_t)id[k].elem;
-      CK(h, s.in[k].reserve(el * cap * id[k].rows));
+      CKD(h, s.in[k].reserve(el * cap * id[k].rows));
       ip[k] = s.in[k].p;
-      CK(h, cudaMemcpy2DAsync(s.in[k].p, el * cap, (const char*)id[k].host + el * c0, el * ncol, el * nt, id[k].rows,
+      CKD(h, cudaMemcpy2DAsync(s.in[k].p, el * cap, (const char*)id[k].host + el * c0, el * ncol, el * nt, id[k].rows,
                               cudaMemcpyHostToDevice, h->s_h2d));
     }
     for (int k = 0; k < N_OUT; ++k) {
       op[k] = nullptr;
       if (!out_active(k)) continue;
       const size_t per_col = od[k].kind == 0 ? (size_t)od[k].rows : od[k].kind == 1 ? (size_t)od[k].rows : (size_t)od[k].rows * (nlev + 1);
-      CK(h, s.out[k].reserve(8 * per_col * cap));
+      CKD(h, s.out[k].reserve(8 * per_col * cap));
       op[k] = s.out[k].p;
     }
     // night columns keep the caller's cloud_cover_sw (the reference does not touch it): stage the current values
-    if (op[12]) CK(h, cudaMemcpyAsync(op[12], od[12].host + c0, 8 * (size_t)nt, cudaMemcpyHostToDevice, h->s_h2d));
+    if (op[12]) CKD(h, cudaMemcpyAsync(op[12], od[12].host + c0, 8 * (size_t)nt, cudaMemcpyHostToDevice, h->s_h2d));
     // likewise sw_dn_toa_g / sw_dn_toa_band of night columns (Tripleclouds sets them for sunlit columns only)
     for (int k = 35; k <= 36; ++k)
-      if (op[k]) CK(h, cudaMemcpyAsync(op[k], od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)nt * od[k].rows, cudaMemcpyHostToDevice, h->s_h2d));
-    CK(h, cudaEventRecord(s.h2d_done, h->s_h2d));
+      if (op[k]) CKD(h, cudaMemcpyAsync(op[k], od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)nt * od[k].rows, cudaMemcpyHostToDevice, h->s_h2d));
+    CKD(h, cudaEventRecord(s.h2d_done, h->s_h2d));
     // ---- kernels ----
     DevIn di; DevOut dout;
     make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
     const int set = t & 1;   // staging slot and compute set alternate together
-    CK(h, cudaStreamWaitEvent(h->s_comp[set], s.h2d_done, 0));
-    if (s.used) CK(h, cudaStreamWaitEvent(h->s_comp[set], s.d2h_done, 0));
-    if (run_tile(h, set, di, dout, nt, nlev, h->s_comp[set], &h->ev[t * 2 * N_STAGE])) return 1;
-    CK(h, cudaEventRecord(s.compute_done, h->s_comp[set]));
+    if (h->dev_pending) CKD(h, cudaStreamWaitEvent(h->s_comp[set], h->ev_dev_done, 0));
+    CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.h2d_done, 0));
+    if (s.used) CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.d2h_done, 0));
+    if (run_tile(h, set, di, dout, nt, nlev, h->s_comp[set], &h->ev[t * 2 * N_STAGE])) { drain(h); return 1; }
+    CKD(h, cudaEventRecord(s.compute_done, h->s_comp[set]));
     // ---- D2H ----
-    CK(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
+    CKD(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
     for (int k = 0; k < N_OUT; ++k) {
       if (!op[k]) continue;
       if (od[k].kind == 0)
-        CK(h, cudaMemcpy2DAsync(od[k].host + c0, 8 * (size_t)ncol, op[k], 8 * (size_t)cap, 8 * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+        CKD(h, cudaMemcpy2DAsync(od[k].host + c0, 8 * (size_t)ncol, op[k], 8 * (size_t)cap, 8 * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
       else if (od[k].kind == 1)
-        CK(h, cudaMemcpyAsync(od[k].host + (size_t)c0 * od[k].rows, op[k], 8 * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+        CKD(h, cudaMemcpyAsync(od[k].host + (size_t)c0 * od[k].rows, op[k], 8 * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
       else   // (nband, ncol, nlev+1): row = half-level, nt*nband contiguous values per row
-        CK(h, cudaMemcpy2DAsync(od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)ncol * od[k].rows, op[k], 8 * (size_t)cap * od[k].rows,
+        CKD(h, cudaMemcpy2DAsync(od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)ncol * od[k].rows, op[k], 8 * (size_t)cap * od[k].rows,
                                 8 * (size_t)nt * od[k].rows, nlev + 1, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     if (c.do_clouds && ip[17])   // cropped cloud fraction back into the caller's array (cloud%crop_cloud_fraction)
-      CK(h, cudaMemcpy2DAsync(in->cloud_fraction + c0, 8 * (size_t)ncol, ip[17], 8 * (size_t)cap, 8 * (size_t)nt, nlev, cudaMemcpyDeviceToHost, h->s_d2h));
-    CK(h, cudaEventRecord(s.d2h_done, h->s_d2h));
+      CKD(h, cudaMemcpy2DAsync(in->cloud_fraction + c0, 8 * (size_t)ncol, ip[17], 8 * (size_t)cap, 8 * (size_t)nt, nlev, cudaMemcpyDeviceToHost, h->s_d2h));
+    CKD(h, cudaEventRecord(s.d2h_done, h->s_d2h));
     s.used = true;
   }
-  CK(h, cudaStreamSynchronize(h->s_d2h));
-  CK(h, cudaStreamSynchronize(h->s_comp[0]));
-  CK(h, cudaStreamSynchronize(h->s_comp[1]));
-  CK(h, cudaGetLastError());
+  h->dev_pending = false;   // (the compute streams waited for it, and they are drained below)
+  CKD(h, cudaStreamSynchronize(h->s_d2h));
+  CKD(h, cudaStreamSynchronize(h->s_comp[0]));
+  CKD(h, cudaStreamSynchronize(h->s_comp[1]));
+  CKD(h, cudaGetLastError());
   return 0;
 }
 
@@ -702,11 +825,8 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev, const ecrad_b2
   return ecrad_b200_radiation_device_ld(handle, ncol, nlev, ncol, ncol, in, out, cuda_stream);
 }
 
-int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, int ld_out, const ecrad_b200_inputs* in,
-                                   ecrad_b200_outputs* out, void* cuda_stream) {
-  Handle* h = (Handle*)handle;
-  if (!h) return fail(nullptr, "ecrad_b200_radiation_device: null handle");
-  std::lock_guard<std::mutex> lk(h->mu);
+static int device_entry_locked(Handle* h, int ncol, int nlev, int ld_in, int ld_out, const ecrad_b200_inputs* in, ecrad_b200_outputs* out,
+                               void* cuda_stream) {
   if (check_args(h, ncol, nlev, 1, ncol, in, out)) return 1;
   if (ld_in < ncol || ld_out < ncol) return fail(h, "leading dimensions (%d, %d) smaller than ncol = %d", ld_in, ld_out, ncol);
   CK(h, cudaSetDevice(h->device));
@@ -727,6 +847,8 @@ int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, 
   if (ensure_events(h, ntiles)) return 1;
   InDesc id[N_IN]; OutDesc od[N_OUT];
   fill_descs(c, nlev, in, out, id, od);
+  // the scratch (set 0) may still be in use by an earlier device-entry call on another stream
+  if (h->dev_pending) CK(h, cudaStreamWaitEvent(st, h->ev_dev_done, 0));
   for (int t = 0; t < ntiles; ++t) {
     const int c0 = t * cap, nt = (ncol - c0) < cap ? (ncol - c0) : cap;
     void* ip[N_IN]; void* op[N_OUT];
@@ -740,6 +862,101 @@ int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, 
     make_views(ip, op, ld_in, ld_out, in->solar_irradiance, di, dout);
     if (run_tile(h, 0, di, dout, nt, nlev, st, &h->ev[t * 2 * N_STAGE])) return 1;
   }
+  CK(h, cudaEventRecord(h->ev_dev_done, st));
+  h->dev_pending = true;
+  return 0;
+}
+
+int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, int ld_out, const ecrad_b200_inputs* in,
+                                   ecrad_b200_outputs* out, void* cuda_stream) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_radiation_device: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return device_entry_locked(h, ncol, nlev, ld_in, ld_out, in, out, cuda_stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// blocked (NPROMA) entry
+// ---------------------------------------------------------------------------------------------------------
+int ecrad_b200_radiation_blocked(void* handle, int ncol_total, int nlev, const ecrad_b200_block_layout* lay, const double* zrgp_in, double* zrgp_out) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_radiation_blocked: null handle");
+  if (!lay || !zrgp_in || !zrgp_out) return fail(h, "ecrad_b200_radiation_blocked: null argument");
+  if (lay->struct_bytes != (int32_t)sizeof(ecrad_b200_block_layout)) return fail(h, "ecrad_b200_block_layout: struct_bytes mismatch (ABI)");
+  const int nproma = lay->nproma, nblocks = lay->nblocks;
+  if (nproma < 1 || nblocks < 1 || ncol_total < 1 || ncol_total > (long long)nproma * nblocks || ncol_total <= (long long)nproma * (nblocks - 1))
+    return fail(h, "ecrad_b200_radiation_blocked: ncol_total = %d does not fit %d blocks of %d columns", ncol_total, nblocks, nproma);
+  const ecrad_b200_config& c = h->cfg;
+  // the column-layout view of what the slabs hold: reuse the host-entry descriptors with dummy non-null "host" pointers
+  ecrad_b200_inputs in; ecrad_b200_outputs out;
+  memset(&in, 0, sizeof in); memset(&out, 0, sizeof out);
+  in.struct_bytes = (int32_t)sizeof in; out.struct_bytes = (int32_t)sizeof out;
+  in.solar_irradiance = lay->solar_irradiance;
+  {
+    const void** ip = (const void**)&in.cos_sza;
+    for (int k = 0; k < N_IN; ++k) ip[k] = lay->in_field[k] >= 0 ? (const void*)zrgp_in : nullptr;
+    double** op = (double**)&out.lw_up;
+    for (int k = 0; k < N_OUT; ++k) op[k] = lay->out_field[k] >= 0 ? zrgp_out : nullptr;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (check_args(h, ncol_total, nlev, 1, ncol_total, &in, &out)) return 1;
+  CK(h, cudaSetDevice(h->device));
+  InDesc id[N_IN]; OutDesc od[N_OUT];
+  fill_descs(c, nlev, &in, &out, id, od);
+  const size_t nin = (size_t)nproma * lay->nfields_in * nblocks, nout = (size_t)nproma * lay->nfields_out * nblocks;
+  // device memory: the two slabs + column-layout arrays of every present input / output
+  size_t need = 8 * (nin + nout);
+  for (int k = 0; k < N_IN; ++k) if (id[k].host && id[k].rows > 0) need += ((size_t)id[k].elem * ncol_total * id[k].rows + 255) & ~(size_t)255;
+  for (int k = 0; k < N_OUT; ++k)
+    if (od[k].host) need += (8 * (size_t)ncol_total * od[k].rows * (od[k].kind == 2 ? (size_t)(nlev + 1) : 1) + 255) & ~(size_t)255;
+  CK(h, h->blocked.reserve(need + 512));
+  char* base = (char*)h->blocked.p;
+  double* d_in = (double*)base; base += 8 * nin;
+  double* d_out = (double*)base; base += 8 * nout;
+  base = (char*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  void* ipd[N_IN]; void* opd[N_OUT];
+  BlockJobs Ji, Jo; Ji.n = Jo.n = 0;
+  long long max_in = 0, max_out = 0;
+  for (int k = 0; k < N_IN; ++k) {
+    ipd[k] = nullptr;
+    if (!id[k].host || id[k].rows <= 0) continue;
+    if (lay->in_field[k] + id[k].rows > lay->nfields_in) return fail(h, "ecrad_b200_radiation_blocked: input %d does not fit nfields_in", k);
+    ipd[k] = base; base += ((size_t)id[k].elem * ncol_total * id[k].rows + 255) & ~(size_t)255;
+    Ji.j[Ji.n++] = {ipd[k], lay->in_field[k], id[k].rows, 0, id[k].elem == 4};
+    if ((long long)ncol_total * id[k].rows > max_in) max_in = (long long)ncol_total * id[k].rows;
+  }
+  for (int k = 0; k < N_OUT; ++k) {
+    opd[k] = nullptr;
+    if (!od[k].host) continue;
+    const int nrows = od[k].kind == 2 ? od[k].rows * (nlev + 1) : od[k].rows;
+    if (lay->out_field[k] + nrows > lay->nfields_out) return fail(h, "ecrad_b200_radiation_blocked: output %d does not fit nfields_out", k);
+    opd[k] = base; base += (8 * (size_t)ncol_total * nrows + 255) & ~(size_t)255;
+    Jo.j[Jo.n++] = {opd[k], lay->out_field[k], od[k].rows, od[k].kind, 0};
+    if ((long long)ncol_total * nrows > max_out) max_out = (long long)ncol_total * nrows;
+  }
+  cudaStream_t st = h->s_comp[0];
+  if (h->register_host) { register_range(h, zrgp_in, 8 * nin); register_range(h, zrgp_out, 8 * nout); }
+  CKD(h, cudaMemcpyAsync(d_in, zrgp_in, 8 * nin, cudaMemcpyHostToDevice, st));
+  CKD(h, cudaMemcpyAsync(d_out, zrgp_out, 8 * nout, cudaMemcpyHostToDevice, st));   // outputs the kernels leave alone keep the caller's values
+  block_unpack_kernel<<<dim3((unsigned)((max_in + 255) / 256), Ji.n), 256, 0, st>>>(Ji, d_in, nproma, lay->nfields_in, ncol_total, nlev + 1);
+  // every output array starts from the caller's values: what the kernels leave alone (cloud_cover_sw of night columns, components
+  // the configuration does not produce) comes back unchanged, as with the column-layout entry
+  block_unpack_kernel<<<dim3((unsigned)((max_out + 255) / 256), Jo.n), 256, 0, st>>>(Jo, d_out, nproma, lay->nfields_out, ncol_total, nlev + 1);
+  h->launches += 2;
+  // all columns, leading dimension ncol_total: the device entry does the tiling and the launches
+  ecrad_b200_inputs din = in; ecrad_b200_outputs dout = out;
+  {
+    const void** ip = (const void**)&din.cos_sza;
+    for (int k = 0; k < N_IN; ++k) ip[k] = ipd[k];
+    double** op = (double**)&dout.lw_up;
+    for (int k = 0; k < N_OUT; ++k) op[k] = (double*)opd[k];
+  }
+  if (device_entry_locked(h, ncol_total, nlev, ncol_total, ncol_total, &din, &dout, (void*)st)) { drain(h); return 1; }
+  block_pack_kernel<<<dim3((unsigned)((max_out + 255) / 256), Jo.n), 256, 0, st>>>(Jo, d_out, nproma, lay->nfields_out, ncol_total, nlev + 1);
+  h->launches += 1;
+  CKD(h, cudaMemcpyAsync(zrgp_out, d_out, 8 * nout, cudaMemcpyDeviceToHost, st));
+  CKD(h, cudaStreamSynchronize(st));
+  CKD(h, cudaGetLastError());
   return 0;
 }
 

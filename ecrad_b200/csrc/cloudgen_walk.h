@@ -29,7 +29,7 @@ HD double beta2alpha(double beta, double f1, double f2) {
   return 1.0;
 }
 
-enum { GEN_MAXLEV = 160 };
+enum { GEN_MAXLEV = 256 };
 
 // radiation_cloud_cover.F90:339-623 cum_cloud_cover_exp_exp for one column: cloud "objects" (contiguous layers around a
 // local maximum of cloud fraction) are overlapped exponentially within themselves and merged pairwise, most correlated

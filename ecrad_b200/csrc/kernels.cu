@@ -420,7 +420,7 @@ __global__ void cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, i
 //     "reuse the previous layer's number" chain are further warp scans.
 // Output: code[g][layer] = 0 (clear) or 0x80000000 | rand30, consumed lane-parallel by the solvers (pdf_sample).
 // ---------------------------------------------------------------------------------------------------------
-enum { GW_MAXLEV = 160, GW_LPL = 5 };   // 32 lanes x 5 layers
+enum { GW_MAXLEV = 256, GW_LPL = 8 };   // 32 lanes x up to 8 layers
 
 __constant__ uint32_t c_lfsr_jump[29];   // x^(604 b) mod P, b = 0..28
 
@@ -659,7 +659,9 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
     case 2: gen_walk_warp<2>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
     case 3: gen_walk_warp<3>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
     case 4: gen_walk_warp<4>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
-    default: gen_walk_warp<5>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    case 5: gen_walk_warp<5>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    case 6: gen_walk_warp<6>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
+    default: gen_walk_warp<8>(cfg, ring, rtop, code, ng, nlevp, lane, Lb, Le, tcc, sA1, sT1, sA2, sT2, sCUM, sOPI, tgen, pos); break;
   }
 }
 

@@ -33,7 +33,7 @@ enum { TC_SW_ARRAYS = 20, TC_LW_ARRAYS = 15 };
 enum { TC_PREP_THREADS = 160 };
 __global__ void __launch_bounds__(TC_PREP_THREADS)
 tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
-  __shared__ double v11[TC_PREP_THREADS + 8];
+  __shared__ double v11[264];   // nlev + 1 <= 257 (ecrad_b200_radiation refuses more levels)
   const int c = blockIdx.x;
   double* reg = w.tc_reg + (size_t)c * nlev * 3;
   double* ods = w.tc_ods + (size_t)c * nlev * 3;
@@ -60,7 +60,7 @@ tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
         u[ju * 3 + jw] = fl[jw] >= thr ? M[ju][jw] / fl[jw] : 0.0;
         v[jw * 3 + ju] = fu[ju] >= thr ? M[ju][jw] / fu[ju] : 0.0;
       }
-    if (jlev - 1 < TC_PREP_THREADS + 8) v11[jlev - 1] = v[0];
+    if (jlev - 1 < 264) v11[jlev - 1] = v[0];
   }
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -24,10 +24,14 @@ struct ecrad_b200_tables {
   std::map<std::string, Arr> a;
 
   int add(const char* name, int dtype, int ndim, const int64_t* dims, const void* data) {
-    if (!name || ndim < 1 || ndim > 4 || (dtype != 0 && dtype != 1) || !data) return 1;
+    if (!name || ndim < 1 || ndim > 4 || (dtype != 0 && dtype != 1) || !data || !dims) return 1;
     Arr x; x.dtype = dtype; x.ndim = ndim;
     size_t n = 1;
-    for (int i = 0; i < 4; ++i) { x.dims[i] = i < ndim ? dims[i] : 1; n *= (size_t)x.dims[i]; }
+    for (int i = 0; i < 4; ++i) {
+      x.dims[i] = i < ndim ? dims[i] : 1;
+      if (x.dims[i] < 1 || (uint64_t)x.dims[i] > (uint64_t)1 << 31 || n > ((size_t)1 << 34) / (size_t)x.dims[i]) return 1;   // no table is anywhere near 2^34 elements
+      n *= (size_t)x.dims[i];
+    }
     x.data.assign((const char*)data, (const char*)data + n * (dtype == 0 ? 8 : 4));
     a[name] = std::move(x);
     return 0;
@@ -37,6 +41,7 @@ struct ecrad_b200_tables {
     FILE* f = fopen(path, "rb");
     if (!f) return 1;
     fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    if (sz < 8) { fclose(f); return 2; }   // (ftell failure is -1)
     std::vector<char> buf((size_t)sz);
     if (fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return 2; }
     fclose(f);
@@ -51,7 +56,16 @@ struct ecrad_b200_tables {
     for (uint32_t i = 0; i < n; ++i) {
       Entry e; memcpy(&e, buf + 8 + (size_t)i * sizeof(Entry), sizeof(Entry));
       char nm[49]; memcpy(nm, e.name, 48); nm[48] = 0;
-      if (e.offset < 0 || (size_t)e.offset >= sz) return 4;
+      // the payload must lie behind the directory and inside the blob: validate dims and size BEFORE anything is copied
+      if (e.ndim < 1 || e.ndim > 4 || (e.dtype != 0 && e.dtype != 1)) return 4;
+      size_t cnt = 1;
+      for (int k = 0; k < e.ndim; ++k) {
+        if (e.dims[k] < 1 || (uint64_t)e.dims[k] > (uint64_t)sz || cnt > sz / (size_t)e.dims[k]) return 4;
+        cnt *= (size_t)e.dims[k];
+      }
+      const size_t nbytes = cnt * (e.dtype == 0 ? 8 : 4);
+      if (nbytes / (e.dtype == 0 ? 8 : 4) != cnt) return 4;
+      if (e.offset < (int64_t)(8 + (size_t)n * sizeof(Entry)) || (size_t)e.offset > sz || nbytes > sz - (size_t)e.offset) return 4;
       if (add(nm, e.dtype, e.ndim, e.dims, buf + e.offset)) return 4;
     }
     return 0;

@@ -59,7 +59,10 @@ def to_radiation_inputs(raw, config=None):
         d["aerosol_mmr"] = F(np.transpose(raw["aerosol_mmr"], (0, 2, 1)))
         d["h2o_sat_liq"] = F(saturation_wrt_liquid(raw["pressure_hl"], raw["temperature_hl"]))
     if config is not None and "spartacus" in (config.sw_solver_name.lower(), config.lw_solver_name.lower()):
-        ic, ii = cloud_effective_separation_eta(raw["pressure_hl"], raw["cloud_fraction"])
+        if "inv_cloud_effective_size" in raw:   # given in the input file (driver/ecrad_driver_read_input.F90:334-360), e.g. the I3RC profile
+            ic = ii = np.asarray(raw["inv_cloud_effective_size"], dtype=np.float64)
+        else:
+            ic, ii = cloud_effective_separation_eta(raw["pressure_hl"], raw["cloud_fraction"])
         d["inv_cloud_effective_size"], d["inv_inhom_effective_size"] = F(ic), F(ii)
     return d
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_radiation_device_ld",
     "ecrad_b200_kernel_launches",
     "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
-    "ecrad_b200_version",
+    "ecrad_b200_version", "ecrad_b200_measure_fp64", "ecrad_b200_radiation_blocked",
 ]
 
 _lib = None
@@ -63,6 +63,8 @@ def load_library():
     L.ecrad_b200_last_error.restype = C.c_char_p
     L.ecrad_b200_last_error.argtypes = [C.c_void_p]
     L.ecrad_b200_version.restype = C.c_char_p
+    L.ecrad_b200_measure_fp64.argtypes = [C.POINTER(C.c_double)]
+    L.ecrad_b200_radiation_blocked.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.BlockLayout), abi.c_dp, abi.c_dp]
     _lib = L
     return L
 
@@ -70,7 +72,7 @@ def load_library():
 class RadiationHandle:
     """What `setup_radiation` leaves behind: the config plus the device-side tables (radiation_interface.F90:37-156)."""
 
-    def __init__(self, config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None):
+    def __init__(self, config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None, tables_arrays: dict = None):
         L = load_library()
         self.lib = L
         self.config = config
@@ -78,8 +80,19 @@ class RadiationHandle:
         self.cfg = config.to_struct()
         t = L.ecrad_b200_tables_create()
         try:
-            rc = (L.ecrad_b200_tables_load_memory(t, tables_blob, len(tables_blob)) if tables_blob is not None
-                  else L.ecrad_b200_tables_load_file(t, tables_path.encode()))
+            if tables_arrays is not None:
+                # what the Fortran shim does (fortran/radiation_b200.F90): every array through ecrad_b200_tables_add, no blob
+                for nm, arr in tables_arrays.items():
+                    a = np.asfortranarray(arr)
+                    code = 1 if a.dtype.kind in "iu" else 0
+                    a = a.astype(np.int32 if code else np.float64, order="F")
+                    dims = (C.c_int64 * 4)(*(list(a.shape) + [1] * (4 - a.ndim)))
+                    if L.ecrad_b200_tables_add(t, nm.encode(), code, a.ndim, dims, a.ctypes.data_as(C.c_void_p)):
+                        raise RadiationError(f"cannot add table {nm}")
+                rc = 0
+            else:
+                rc = (L.ecrad_b200_tables_load_memory(t, tables_blob, len(tables_blob)) if tables_blob is not None
+                      else L.ecrad_b200_tables_load_file(t, tables_path.encode()))
             if rc:
                 raise RadiationError(L.ecrad_b200_last_error(None).decode())
             # config%sw_albedo_weights, config%i_emiss_from_band_lw: the part of config_type that is a table
@@ -113,6 +126,17 @@ class RadiationHandle:
         if rc:
             raise RadiationError(self._err())
         outs["cloud_fraction"] = keep.get("cloud_fraction")
+        return outs
+
+    def radiation_blocked(self, inputs, ncol, nlev, nproma, spectral_profiles=False):
+        """The same call through the blocked (NPROMA) entry: inputs are packed into zrgp(nproma, nfields, nblocks) as an IFS-style driver
+        holds them (driver/ifs_blocking.F90), ecrad_b200_radiation_blocked does the rest; returns the flux dict."""
+        outs, _ = abi.alloc_outputs(ncol, nlev, self.cfg, spectral_profiles=spectral_profiles)
+        lay, zin, zout = abi.pack_blocked(inputs, outs, ncol, nlev, nproma, self.cfg, inputs["solar_irradiance"])
+        rc = self.lib.ecrad_b200_radiation_blocked(self.h, ncol, nlev, C.byref(lay), zin.ctypes.data_as(abi.c_dp), zout.ctypes.data_as(abi.c_dp))
+        if rc:
+            raise RadiationError(self._err())
+        abi.unpack_blocked(lay, zout, outs, ncol, nlev)
         return outs
 
     def radiation_device(self, ncol, nlev, ist: abi.Inputs, ost: abi.Outputs, stream=0):
@@ -151,11 +175,12 @@ class RadiationHandle:
             pass
 
 
-def setup_radiation(config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None) -> RadiationHandle:
-    """tables_blob: the ETB1 image as bytes (e.g. received by a broadcast) instead of a file path."""
+def setup_radiation(config: RadiationConfig, tables_path: str = None, tables_blob: bytes = None, tables_arrays: dict = None) -> RadiationHandle:
+    """tables_blob: the ETB1 image as bytes (e.g. received by a broadcast) instead of a file path; tables_arrays: {name: ndarray},
+    each registered with ecrad_b200_tables_add like the Fortran shim does."""
     if not config.derived:
         config.consolidate()
-    return RadiationHandle(config, tables_path, tables_blob)
+    return RadiationHandle(config, tables_path, tables_blob, tables_arrays)
 
 
 def set_gas_units(config: RadiationConfig, gas: dict) -> dict:

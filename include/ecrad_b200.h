@@ -183,9 +183,41 @@ int ecrad_b200_radiation_device(void* handle, int ncol, int nlev,
 int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, int ld_out,
                                    const ecrad_b200_inputs* in, ecrad_b200_outputs* out, void* cuda_stream);
 
-/* Tuning/diagnostic options: "serial" (0/1: run a tile's kernels on one stream instead of the three overlapping chains;
- * needed for per-kernel timing), "tile_cols" (columns per internal tile).  Returns 0 on success. */
+/* Blocked (NPROMA) entry: the layout of the IFS-style drivers (driver/ifs_blocking.F90, driver/ecrad_ifs_driver_blocked.F90:367-481,
+ * ifs/radiation_scheme.F90), in which every variable of a block of `nproma` columns is a group of consecutive "fields" of one array
+ * zrgp(nproma, nfields, nblocks) -- column index fastest, then field, then block.  Here the fields are the arrays of
+ * ecrad_b200_inputs / ecrad_b200_outputs: in_field[k] (k = position of the pointer in ecrad_b200_inputs, 0 = cos_sza ... 27 =
+ * inv_inhom_effective_size) is the 0-based first field of that input in zrgp_in, or -1 if absent; it occupies as many fields as the
+ * array has rows ((ncol, rows) arrays: rows; aerosol_mmr: nlev * n_aerosol_types, type slowest); iseed travels as a real like
+ * every IFS field.  out_field[k] likewise for the 41 outputs in zrgp_out: (ncol, nlev+1) profiles take nlev+1 fields, (n, ncol)
+ * arrays n fields, (nband, ncol, nlev+1) profiles (nlev+1) * nband fields (band fastest).  Columns beyond ncol_total in the last
+ * block are ignored / left untouched.  One host-to-device copy of the whole input array, a device kernel that unpacks it into the
+ * column-fastest arrays the radiation kernels read, the same kernels as ecrad_b200_radiation, a pack kernel, one copy back:
+ * results are bit-identical to ecrad_b200_radiation on the same columns.  (cloud_fraction is cropped on the device only.) */
+typedef struct ecrad_b200_block_layout {
+  int32_t struct_bytes;
+  int32_t nproma, nblocks, nfields_in, nfields_out;
+  int32_t in_field[28];
+  int32_t out_field[41];
+  double  solar_irradiance;
+} ecrad_b200_block_layout;
+int ecrad_b200_radiation_blocked(void* handle, int ncol_total, int nlev, const ecrad_b200_block_layout* layout,
+                                 const double* zrgp_in, double* zrgp_out);
+
+/* Tuning/diagnostic options.  Returns 0 on success.
+ *   "serial"            0/1: run a tile's kernels on one stream instead of the three overlapping chains (per-kernel timing)
+ *   "tile_cols", "tile_cols_device"   columns per internal tile of the host / device entry
+ *   "register_host"     0/1: page-lock the caller's input and output arrays (cudaHostRegister, cached per pointer until
+ *                       ecrad_b200_finalize or register_host = 0), so that ordinary (pageable) Fortran allocatables are copied
+ *                       asynchronously like pinned memory; the arrays must stay allocated while registered
+ *   "gas_variant"       RRTMG gas optics kernel per spectrum (bit 0 longwave, bit 1 shortwave): band-wise on TMA-staged
+ *                       shared-memory table images / one CTA per column
+ *   "scan_solvers"      0/1: McICA / Cloudless solvers with the adding method as warp scans (no scratch) / lanes = g-points */
 int ecrad_b200_set_option(void* handle, const char* key, int value);
+
+/* Measured fp64 multiply-add throughput of the current device in TFLOP/s (2 flops per FMA): the ALU roofline bench.py reports
+ * next to the HBM one.  A measurement helper, not part of the radiation path. */
+int ecrad_b200_measure_fp64(double* tflops);
 
 /* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t ecrad_b200_kernel_launches(void* handle);

@@ -19,9 +19,24 @@ def build():
     return os.path.join(ORACLE_DIR, "liboracle.so")
 
 
+def build_native():
+    """The same C sources built the way the reference's own build compiles its Fortran (Makefile_include.gfortran:25 -O3, CMake adds
+    -march=native; gfortran contracts multiply-adds by default): -O3 -march=native -fopenmp, FMA contraction on.  Only for TIMING the
+    CPU arm of bench.py on the machine it runs on (results differ from the parity oracle in the last bits); built into oracle/_bench/."""
+    out_dir = os.path.join(ORACLE_DIR, "_bench")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "liboracle_native.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith(".c")]
+    newest = max(os.path.getmtime(f) for f in srcs + [os.path.join(ORACLE_DIR, "oracle.h")])
+    if not os.path.exists(out) or os.path.getmtime(out) < newest:
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fopenmp", "-std=c11", "-ffp-contract=fast",
+                               "-I", os.path.join(ROOT, "include"), "-o", out] + srcs + ["-lm"])
+    return out
+
+
 class Oracle:
-    def __init__(self, config):
-        path = os.path.join(ORACLE_DIR, "liboracle.so")
+    def __init__(self, config, lib_path=None):
+        path = lib_path or os.path.join(ORACLE_DIR, "liboracle.so")
         if not os.path.exists(path):
             build()
         self.lib = C.CDLL(path)

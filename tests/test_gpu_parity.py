@@ -587,3 +587,50 @@ def test_selectable_kernel_variants_vs_oracle(meridian_raw, kw, opts):
             assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
     finally:
         h.finalize()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"), dict(scan_solvers=1),
+                                dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, do_3d_lw_multilayer_effects=True,
+                                     sw_entrapment_name="Maximum", overhang_factor=1.0, overhead_sun_factor=0.06),
+                                dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, sw_entrapment_name="Explicit")])
+def test_i3rc_cumulus_profile_164_layers(kw):
+    """More than 160 layers: the reference's I3RC cumulus case (test/i3rc/i3rc_mls_cumulus.nc, 164 layers, eight solar zenith angles),
+    with the options of test/i3rc/configI3RC.nam for SPARTACUS."""
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+
+    kw = dict(kw)
+    scan = kw.pop("scan_solvers", 0)
+    raw = {k: np.array(v, dtype=np.float64) for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "i3rc_mls_cumulus_inputs.npz")).items()}
+    cfg = RadiationConfig(**kw).consolidate()
+    h, orc = setup_radiation(cfg), Oracle(cfg)
+    h.set_option("scan_solvers", scan)
+    try:
+        n, nlev = 8, 164
+        out = h.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+        ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, nlev)
+        compare(out, ref, FLUXES + OTHERS)
+        for nm in ("cloud_cover_lw", "cloud_cover_sw", "cloud_fraction"):
+            assert np.array_equal(out[nm], ref[nm]), nm
+        assert out["sw_dn"][0, 0] > 1300.0 and np.all(out["lw_up"] > 0.0)   # overhead sun: ~1366 W m-2 at the top
+    finally:
+        h.finalize()
+
+
+@pytest.mark.parametrize("kw,nproma", [(dict(use_aerosols=True), 32), (dict(), 13),
+                                       (dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", do_save_spectral_flux=True), 16),
+                                       (dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False), 64)])
+def test_blocked_nproma_entry_is_bit_identical(handles, meridian_raw, kw, nproma):
+    """the IFS-style blocked layout zrgp(nproma, nfields, nblocks) (driver/ifs_blocking.F90) through
+    ecrad_b200_radiation_blocked gives the bits of the column-layout entry, ragged last block included (the reference's own cross-driver
+    check: test/ifs/CMakeLists.txt:139-200 compares the blocked driver with the plain one)."""
+    h, _, cfg = handles(**kw)
+    n = 150
+    raw = I.synthetic_columns(meridian_raw, n)
+    sp = bool(kw.get("do_save_spectral_flux"))
+    a = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV, spectral_profiles=sp)
+    b = h.radiation_blocked(I.to_radiation_inputs(raw, cfg), n, NLEV, nproma, spectral_profiles=sp)
+    for nm in a:
+        if nm == "cloud_fraction" or a[nm] is None:
+            continue
+        assert np.array_equal(a[nm], b[nm], equal_nan=True), nm

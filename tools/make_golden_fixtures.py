@@ -7,7 +7,7 @@ Run in the authoring container (needs /root/reference); the GPU box only sees th
            test/ifs/ecrad_meridian_cloudless_out_REFERENCE.nc  -> tests/golden/ecrad_meridian_cloudless_ref.npz
            ... and the default, expexp, tripleclouds, ecckd_mcica, ecckd_tc reference outputs likewise
 The golden outputs are float32 as written by the reference driver (do_write_double_precision=false); the
-per-band profiles of the cloudless file are kept at 8 half-levels only to keep the fixture small.
+per-band profiles are kept at every half-level.
 """
 import os
 import sys
@@ -20,7 +20,7 @@ from ecrad_b200.inputs import NC_VARS  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
-BAND_LEVELS = [0, 20, 40, 60, 80, 100, 120, 137]
+BAND_LEVELS = list(range(138))   # every half-level (the per-band profiles pin each taumol band at every height)
 
 os.makedirs(OUT, exist_ok=True)
 with netcdf_file(f"{REF}/test/ifs/ecrad_meridian.nc", mmap=False) as f:
@@ -37,3 +37,25 @@ for name in ("noaer", "cloudless", "default", "expexp", "tripleclouds", "ecckd_m
         d["history"] = np.array(getattr(f, "history", b"").decode(errors="replace"))
         np.savez_compressed(f"{OUT}/ecrad_meridian_{name}_ref.npz", **d)
 print(os.listdir(OUT))
+
+# ---- the reference's I3RC cumulus profile (test/i3rc/i3rc_mls_cumulus.nc): 164 layers, the SPARTACUS case of Hogan et al. (2016).
+# Stored in the key format of ecrad_meridian_inputs.npz (what ecrad_b200.inputs.to_radiation_inputs reads), the single profile
+# duplicated for eight of the solar zenith angles of test/i3rc/duplicate_profiles.sh; surface albedo 0.08 and the solar
+# irradiance 1366 W m-2 of test/i3rc/configI3RC.nam in all six albedo intervals of the CY49R1 configuration.
+with netcdf_file("/root/reference/test/i3rc/i3rc_mls_cumulus.nc", mmap=False) as f:
+    V = {k: np.array(v[...], dtype=np.float32) for k, v in f.variables.items()}
+cos_sza = np.array([1.0, 0.939693, 0.788011, 0.615661, 0.438371, 0.241922, 0.104528, 0.01], dtype=np.float32)
+n, nl = len(cos_sza), 164
+rep = lambda a: np.repeat(np.asarray(a, dtype=np.float32).reshape(1, -1), n, axis=0)  # noqa: E731
+full = lambda x: np.full((n, nl), np.float32(x), dtype=np.float32)  # noqa: E731
+i3 = {"solar_irradiance": np.float32(1366.0), "skin_temperature": np.repeat(V["skin_temperature"], n), "cos_solar_zenith_angle": cos_sza,
+      "sw_albedo": np.full((n, 6), np.float32(0.08)), "sw_albedo_direct": np.full((n, 6), np.float32(0.08)),
+      "lw_emissivity": np.full((n, 2), V["lw_emissivity"][0], dtype=np.float32), "iseed": np.arange(1, n + 1, dtype=np.float64),
+      "pressure_hl": rep(V["pressure_hl"]), "temperature_hl": rep(V["temperature_hl"]), "q": rep(V["q"]), "o3_mmr": rep(V["o3_mmr"]),
+      "co2_vmr": full(V["co2_vmr"]), "n2o_vmr": full(V["n2o_vmr"]), "ch4_vmr": full(V["ch4_vmr"]), "cfc11_vmr": full(V["cfc1_vmr"]),
+      "cfc12_vmr": full(V["cfc2_vmr"]), "hcfc22_vmr": full(0.0), "ccl4_vmr": full(0.0),
+      "cloud_fraction": rep(V["cloud_fraction"]), "q_liquid": rep(V["q_liquid"]), "q_ice": rep(V["q_ice"]), "re_liquid": rep(V["re_liquid"]),
+      "re_ice": rep(V["re_ice"]), "overlap_param": rep(V["overlap_param"]), "fractional_std": rep(V["fractional_std"]),
+      "inv_cloud_effective_size": rep(V["inv_cloud_effective_size"])}
+np.savez_compressed(f"{OUT}/i3rc_mls_cumulus_inputs.npz", **i3)
+print("i3rc_mls_cumulus_inputs.npz:", n, "columns,", nl, "layers")
