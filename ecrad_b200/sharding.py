@@ -60,6 +60,23 @@ def gather_profiles(local, ncol_total: int, dist, dst: int = 0):
     return out
 
 
+def gather_slab(local, dist, dst: int = 0, out=None):
+    """ONE collective for all flux profiles: every rank's contiguous slab `local` (any shape, the same on all ranks: e.g.
+    (nprofiles, nlev+1, ncol_local), what the flux kernels wrote) lands in out[rank] of a preallocated (world, *local.shape)
+    tensor on `dst` -- NCCL's grouped send/recv straight into the destination, no padding, no per-profile calls, no copy-out.
+    The result is blocked by rank exactly like the host model's column blocks (out[r] = the columns shard_range(.., r, world))."""
+    import torch
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        if out is None:
+            out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        dist.gather(local, [out[r] for r in range(world)], dst=dst)
+        return out
+    dist.gather(local, None, dst=dst)
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Gather fused into the flux kernels: every rank stores its column slice straight into arrays that live on one GPU
 # ---------------------------------------------------------------------------------------------------------
@@ -127,6 +144,19 @@ class PeerFluxArrays:
         raw = _Raw()
         raw.__cuda_array_interface__ = {"shape": (self.nrows, self.ncol_total), "typestr": "<f8", "version": 3,
                                         "data": (self.base + self.names.index(name) * self.plane, False)}
+        return torch.as_tensor(raw, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def slice_view(self, first_col, ncol_local):
+        """(len(names), nrows, ncol_local) strided view of the columns [first_col, first_col + ncol_local) of ALL arrays, on whatever
+        rank calls it (peer-mapped memory on the non-owners): `view.copy_(local_slab)` pushes a rank's fluxes to the owner with wide
+        coalesced stores over NVLink, rows of ncol_local * 8 bytes at a time."""
+        torch = self._torch
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (len(self.names), self.nrows, int(ncol_local)), "typestr": "<f8", "version": 3,
+                                        "strides": (self.plane, self.ncol_total * 8, 8), "data": (self.base + 8 * int(first_col), False)}
         return torch.as_tensor(raw, device=torch.device("cuda", torch.cuda.current_device()))
 
     def close(self):

@@ -33,7 +33,7 @@ def _worker(rank, world, port, ncol, tmpdir):
     from ecrad_b200 import inputs as I
     from ecrad_b200.config import RadiationConfig
     from ecrad_b200.radiation_interface import DEFAULT_TABLES
-    from ecrad_b200.sharding import broadcast_table_blob, gather_profiles
+    from ecrad_b200.sharding import broadcast_table_blob, gather_profiles, gather_slab
     from oracle_lib import Oracle
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -51,7 +51,16 @@ def _worker(rank, world, port, ncol, tmpdir):
             g = gather_profiles(local, ncol, dist)
             if rank == 0:
                 got[nm] = g.numpy().T
+        # the single-collective route: all profiles in one slab per rank, shards padded to a common width by the caller
+        per = -(-ncol // world)
+        slab = torch.zeros((3, 138, per), dtype=torch.float64)
+        for k, nm in enumerate(("lw_up", "sw_dn", "lw_dn_clear")):
+            slab[k, :, :n_loc] = torch.from_numpy(np.ascontiguousarray(out[nm].T))
+        dest = gather_slab(slab, dist, 0)
         if rank == 0:
+            for k, nm in enumerate(("lw_up", "sw_dn", "lw_dn_clear")):
+                cols = [dest[r, k, :, : shard_range(ncol, r, world)[1] - shard_range(ncol, r, world)[0] + 1] for r in range(world)]
+                got[nm + "_slab"] = torch.cat(cols, dim=1).numpy().T
             np.savez(os.path.join(tmpdir, "gathered.npz"), **got)
     finally:
         dist.destroy_process_group()
@@ -74,3 +83,4 @@ def test_two_rank_shard_and_gather_matches_single_process(tmp_path, meridian_raw
     ref = Oracle(RadiationConfig().consolidate()).radiation(I.to_radiation_inputs(I.synthetic_columns(meridian_raw, ncol)), ncol, 137)
     for nm in ("lw_up", "sw_dn", "lw_dn_clear"):
         assert np.array_equal(got[nm], ref[nm]), nm
+        assert np.array_equal(got[nm + "_slab"], ref[nm]), nm + " (gather_slab)"
