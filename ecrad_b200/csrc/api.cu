@@ -154,7 +154,13 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.i_cloud_pdf_shape != ECRAD_PDF_GAMMA && c.i_cloud_pdf_shape != ECRAD_PDF_LOGNORMAL) return fail(h, "unknown cloud PDF shape");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
     return fail(h, "unknown overlap scheme");
-  if (c.do_lw_aerosol_scattering) return fail(h, "do_lw_aerosol_scattering is not available in this build");
+  if (c.do_lw_aerosol_scattering && c.do_lw) {
+    // radiation_interface.F90:84-88
+    if (!c.do_lw_cloud_scattering) return fail(h, "longwave aerosol scattering requires longwave cloud scattering");
+    const bool plain = c.i_solver_lw == ECRAD_SOLVER_MCICA || c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS;
+    if (!plain || gm != ECRAD_GAS_IFSRRTMG || (c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux))
+      return fail(h, "do_lw_aerosol_scattering is available with the McICA and Cloudless longwave solvers on RRTMG-IFS gas optics");
+  }
   if (c.do_sw && !c.do_sw_direct) return fail(h, "do_sw_direct = false is not available in this build (the direct beam is always computed)");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
@@ -172,10 +178,11 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   return 0;
 }
 
-enum { N_WORK = 38 };
+enum { N_WORK = 40 };
 // Which spectra run the scan solvers (and therefore want their gas optical properties laid out [column][g][layer]).
 bool use_scan(const Handle* h, bool sw, int nlev) {
   const ecrad_b200_config& c = h->cfg;
+  if (!sw && c.do_lw && c.do_lw_aerosol_scattering) return nlev <= scan_max_levels();   // scattering in every layer: the general (scan) adding method
   if (!h->scan_solvers || !(sw ? c.do_sw : c.do_lw)) return false;
   const int sol = sw ? c.i_solver_sw : c.i_solver_lw;
   if (sol != ECRAD_SOLVER_MCICA && sol != ECRAD_SOLVER_CLOUDLESS) return false;
@@ -194,6 +201,7 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const bool tc = tc_lw || tc_sw || sp_lw || sp_sw;   // region fractions and overlap matrices (tc_prep_kernel)
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
   const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
+  const bool lwscat = h->cfg.do_lw && h->cfg.do_lw_aerosol_scattering;
   const size_t sz[N_WORK] = {
       8 * nc * nl * NG_LW, 8 * nc * nl * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,              // od_lw planck emission lw_albedo
       8 * nc * nl * NG_SW, 8 * nc * nl * NG_SW, 8 * nc * NG_SW,                              // od_sw ssa_sw incoming
@@ -207,10 +215,11 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : use_scan(h, true, nlev) ? 0 : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
       ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
-      (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW : 0,                               // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
+      (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW * (lwscat ? 3 : 1) : 0,            // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       0,                                                                                     // (sw_band_dir: no longer used)
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0,  // tc_reg tc_ods tc_u tc_v tc_cc
-      ckd ? 0 : nc * nl, ckd ? 0 : sizeof(GasCol) * nc, ckd ? 0 : 4 * (nc + 1)};             // gas_jp gas_col sunlit (RRTMG)
+      ckd ? 0 : nc * nl, ckd ? 0 : sizeof(GasCol) * nc, ckd ? 0 : 4 * (nc + 1),              // gas_jp gas_col sunlit (RRTMG)
+      lwscat ? 8 * nc * nl * NG_LW : 0, lwscat ? 8 * nc * nl * NG_LW : 0};                   // ssa_lw g_lw (do_lw_aerosol_scattering)
   for (int i = 0; i < N_WORK; ++i) out[i] = sz[i];
 }
 size_t work_bytes_per_column(const Handle* h, int nlev) {
@@ -247,6 +256,7 @@ int ensure_work(Handle* h, int set, int cols, int nlev) {
   w.sw_sums = (double*)h->work[set][19].p; w.sw_carry = (double*)h->work[set][20].p;
   w.lw_sums = (double*)h->work[set][21].p; w.lw_carry = (double*)h->work[set][22].p;
   w.gas_jp = (uint8_t*)h->work[set][35].p; w.gas_col = (GasCol*)h->work[set][36].p; w.sunlit = (int*)h->work[set][37].p;
+  w.ssa_lw = (double*)h->work[set][38].p; w.g_lw = (double*)h->work[set][39].p;
   w.ls = (nlev + 1 + 3) & ~3;
   h->w_cols[set] = cols; h->w_nlev[set] = nlev;
   return 0;
@@ -267,7 +277,7 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
   if (!ckd) {
     n += launch_gas_prep(h->T, c, in, h->w[set], nc, nlev, st);   // shared by the LW and SW gas-optics kernels
-    if (h->gas_variant & 3) n += launch_gas_col(h->T, c, in, h->w[set], nc, nlev, st);
+    if ((h->gas_variant & 3) || c.do_lw_aerosol_scattering) n += launch_gas_col(h->T, c, in, h->w[set], nc, nlev, st);
     if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w[set], nc, nlev, st);
   }
   if (par) {
@@ -285,7 +295,7 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
   // LW chain
   CK(h, cudaEventRecord(ev[0], s_lw));
-  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : (h->gas_variant & 1) ? launch_gas_lw_band(h->T, c, in, h->w[set], nc, nlev, s_lw)
+  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : ((h->gas_variant & 1) || c.do_lw_aerosol_scattering) ? launch_gas_lw_band(h->T, c, in, h->w[set], nc, nlev, s_lw)
                                                                                                   : launch_gas_lw(h->T, c, in, h->w[set], nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[1], s_lw));
   // SW chain
@@ -573,6 +583,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.do_sw = cfg->do_sw; d.do_lw = cfg->do_lw; d.do_clouds = cfg->do_clouds;
   d.do_lw_cloud_scattering = cfg->do_lw_cloud_scattering; d.do_lw_derivatives = cfg->do_lw_derivatives;
   d.do_sw_delta_scaling_with_gases = cfg->do_sw_delta_scaling_with_gases; d.do_fu_lw_ice_optics_bug = cfg->do_fu_lw_ice_optics_bug;
+  d.do_lw_aerosol_scattering = cfg->do_lw && cfg->do_lw_aerosol_scattering;
   d.use_beta_overlap = cfg->use_beta_overlap; d.do_surface_sw_spectral_flux = cfg->do_surface_sw_spectral_flux;
   d.do_canopy_fluxes_sw = cfg->do_canopy_fluxes_sw; d.do_canopy_fluxes_lw = cfg->do_canopy_fluxes_lw; d.do_clear = cfg->do_clear;
   d.n_albedo_sw = cfg->n_albedo_sw; d.n_emiss_lw = cfg->n_emiss_lw;

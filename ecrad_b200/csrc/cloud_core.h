@@ -34,8 +34,8 @@ struct AerMeta {
   int ntype, nrh, n_phobic, n_philic;
   int iclass[32], itype[32];      // per aerosol type of the caller: 0 ignored / 1 hydrophobic / 2 hydrophilic; 1-based table type
   double rh_lower[16];
-  int me_sw_phobic, ssa_sw_phobic, g_sw_phobic, me_lw_phobic, ssa_lw_phobic;
-  int me_sw_philic, ssa_sw_philic, g_sw_philic, me_lw_philic, ssa_lw_philic;
+  int me_sw_phobic, ssa_sw_phobic, g_sw_phobic, me_lw_phobic, ssa_lw_phobic, g_lw_phobic;
+  int me_sw_philic, ssa_sw_philic, g_sw_philic, me_lw_philic, ssa_lw_philic, g_lw_philic;
 };
 
 #define ECB_CO(c, nb, jb, k) ((c)[((k) - 1) * (nb) + (jb)])

@@ -181,7 +181,12 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
     return pfac * (tp[ind - 1] + frac * (tp[ind] - tp[ind - 1]));
   };
   const double plk_bot = planck(L.t_bot);
-  const double aer = cfg.use_aerosols ? w.aer_lw[((size_t)c * nlev + l) * NB_LW + IB] : 0.0;   // radiation_aerosol_optics.F90:806-812
+  const bool lwscat = cfg.do_lw_aerosol_scattering != 0;   // (scan solvers only: LAYB)
+  double aer = 0.0, aer_sc = 0.0, aer_sg = 0.0;
+  if (cfg.use_aerosols) {
+    if (lwscat) { const double* a = w.aer_lw + ((size_t)c * nlev + l) * 3 * NB_LW; aer = a[IB]; aer_sc = a[NB_LW + IB]; aer_sg = a[2 * NB_LW + IB]; }
+    else aer = w.aer_lw[((size_t)c * nlev + l) * NB_LW + IB];   // radiation_aerosol_optics.F90:806-812
+  }
   const size_t sg = LAYB ? (size_t)w.ls : 1, sl = LAYB ? 1 : (size_t)NG_LW;
   double* od_out = w.od_lw + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW) + (size_t)g0 * sg;
   double* pl_out = w.planck + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)(nlev + 1) * NG_LW) + (size_t)g0 * sg;
@@ -190,9 +195,26 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
     double tau = sink.acc[g];
     if (post >= 0) tau *= img[post + g];
     double o = dmax(tau, cfg.min_gas_od_lw);                             // radiation_ifs_rrtm.F90:506-511
-    if (cfg.use_aerosols) o = o + aer;
+    if (cfg.use_aerosols && !lwscat) o = o + aer;
     return o;
   };
+  if (LAYB && lwscat) {
+    // gas + aerosol with scattering (radiation_aerosol_optics.F90:781-796): gases do not scatter, so g is the aerosol's
+    double* ss_out = w.ssa_lw + (size_t)c * NG_LW * w.ls + (size_t)g0 * sg;
+    double* gg_out = w.g_lw + (size_t)c * NG_LW * w.ls + (size_t)g0 * sg;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      double o = odval(g), ssa = 0.0, gg = 0.0;
+      const double local_od = o + aer;
+      if (local_od > 0.0 && aer > 0.0) {
+        if (aer_sc > 0.0) gg = aer_sg / aer_sc;
+        ssa = aer_sc / local_od;
+        o = local_od;
+      }
+      od_out[l * sl + g * sg] = o; ss_out[l + g * sg] = ssa; gg_out[l + g * sg] = gg;
+      pl_out[(l + 1) * sl + g * sg] = plk_bot * pfrac(g);
+    }
+  } else
   if (LAYB) {
 #pragma unroll
     for (int g = 0; g < NG; ++g) { od_out[l * sl + g * sg] = odval(g); pl_out[(l + 1) * sl + g * sg] = plk_bot * pfrac(g); }   // the half-level below uses this layer's PFRAC

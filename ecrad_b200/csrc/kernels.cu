@@ -89,11 +89,12 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
   if (rh > A.rh_lower[A.nrh - 1]) irh = A.nrh;
   else { irh = 1; while (rh > A.rh_lower[irh]) ++irh; }
   const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) * (1.0 / 9.80665);
-  double od_sw[NB_SW], sc_sw[NB_SW], sg_sw[NB_SW], od_lw[NB_LW];
+  const bool lwscat = cfg.do_lw_aerosol_scattering != 0;
+  double od_sw[NB_SW], sc_sw[NB_SW], sg_sw[NB_SW], od_lw[NB_LW], sc_lw[NB_LW], sg_lw[NB_LW];
 #pragma unroll
   for (int b = 0; b < NB_SW; ++b) { od_sw[b] = 0.0; sc_sw[b] = 0.0; sg_sw[b] = 0.0; }
 #pragma unroll
-  for (int b = 0; b < NB_LW; ++b) od_lw[b] = 0.0;
+  for (int b = 0; b < NB_LW; ++b) { od_lw[b] = 0.0; sc_lw[b] = 0.0; sg_lw[b] = 0.0; }
   for (int jt = 0; jt < A.ntype; ++jt) {
     const int iclass = A.iclass[jt];
     if (iclass == 0) continue;
@@ -106,6 +107,7 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
     const double* gg_sw = tab + (iclass == 1 ? A.g_sw_phobic : A.g_sw_philic) + isw;
     const double* me_lw = tab + (iclass == 1 ? A.me_lw_phobic : A.me_lw_philic) + ilw;
     const double* ss_lw = tab + (iclass == 1 ? A.ssa_lw_phobic : A.ssa_lw_philic) + ilw;
+    const double* gg_lw = tab + (iclass == 1 ? A.g_lw_phobic : A.g_lw_philic) + ilw;
 #pragma unroll
     for (int b = 0; b < NB_SW; ++b) {
       const double local_od = factor * mr * me_sw[b];
@@ -113,8 +115,18 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
       sc_sw[b] = sc_sw[b] + local_od * ss_sw[b];
       sg_sw[b] = sg_sw[b] + local_od * ss_sw[b] * gg_sw[b];
     }
+    if (lwscat) {   // radiation_aerosol_optics.F90:657-670, :697-710
 #pragma unroll
-    for (int b = 0; b < NB_LW; ++b) od_lw[b] = od_lw[b] + factor * mr * me_lw[b] * (1.0 - ss_lw[b]);
+      for (int b = 0; b < NB_LW; ++b) {
+        const double local_od = factor * mr * me_lw[b];
+        od_lw[b] = od_lw[b] + local_od;
+        sc_lw[b] = sc_lw[b] + local_od * ss_lw[b];
+        sg_lw[b] = sg_lw[b] + local_od * ss_lw[b] * gg_lw[b];
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < NB_LW; ++b) od_lw[b] = od_lw[b] + factor * mr * me_lw[b] * (1.0 - ss_lw[b]);
+    }
   }
   double* osw = w.aer_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
 #pragma unroll
@@ -129,9 +141,23 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
     }
     osw[b] = od; osw[NB_SW + b] = sc; osw[2 * NB_SW + b] = sg;
   }
-  double* olw = w.aer_lw + ((size_t)c * nlev + l) * NB_LW;
+  if (lwscat) {   // [c][l][3][16]: od, scattering od, scattering od x g after delta_eddington_extensive_vec (:778-779)
+    double* olw = w.aer_lw + ((size_t)c * nlev + l) * 3 * NB_LW;
 #pragma unroll
-  for (int b = 0; b < NB_LW; ++b) olw[b] = od_lw[b];
+    for (int b = 0; b < NB_LW; ++b) {
+      double od = od_lw[b], sc = sc_lw[b], sg = sg_lw[b];
+      const double g = sg / dmax(sc, (double)1.0e-24f);
+      const double f = g * g;
+      od = od - sc * f;
+      sc = sc * (1.0 - f);
+      sg = sc * g / (1.0 + g);
+      olw[b] = od; olw[NB_LW + b] = sc; olw[2 * NB_LW + b] = sg;
+    }
+  } else {
+    double* olw = w.aer_lw + ((size_t)c * nlev + l) * NB_LW;
+#pragma unroll
+    for (int b = 0; b < NB_LW; ++b) olw[b] = od_lw[b];
+  }
 }
 
 // =========================================================================================================

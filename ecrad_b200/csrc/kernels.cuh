@@ -61,6 +61,7 @@ struct DevCfg {
   int solver_sw, solver_lw, overlap_scheme;
   int do_sw, do_lw, do_clouds, do_lw_cloud_scattering, do_lw_derivatives;
   int do_sw_delta_scaling_with_gases, do_fu_lw_ice_optics_bug, use_beta_overlap;
+  int do_lw_aerosol_scattering;   // RRTMG + McICA / Cloudless (scan solvers): gas + aerosol ssa_lw, g_lw per g-point
   int do_surface_sw_spectral_flux, do_canopy_fluxes_sw, do_canopy_fluxes_lw, do_clear;
   int n_albedo_sw, n_emiss_lw, n_canopy_bands_sw, n_canopy_bands_lw;
   int use_aerosols, n_aerosol_types;
@@ -88,6 +89,7 @@ struct Work {
   double *od_lw, *planck, *emission, *lw_albedo;  // [nc][nlev][140], [nc][nlev+1][140], [nc][140], [nc][140]
   double *od_sw, *ssa_sw, *incoming;              // [nc][nlev][112] x2, [nc][112]
   double *g_sw;                                   // [nc][nlev][112] asymmetry factor of gas+aerosol (NULL without aerosols: g = 0)
+  double *ssa_lw, *g_lw;                          // [nc][140][ls] gas + aerosol, do_lw_aerosol_scattering only (layout of od_lw; NULL otherwise)
   double *aer_sw, *aer_lw;                        // aerosol band optics [nc][nlev][3][14] (od, scat, scat*g), [nc][nlev][16] (absorption od)
   double *cl_lw, *cl_sw;                          // cloud optics per band [nc][nlev][3][16], [nc][nlev][3][14]
   double *cum, *pair, *opi;                       // [nlev][nc] column-fastest

@@ -314,9 +314,10 @@ __device__ __forceinline__ void lw_clear_subcolumn(const LwLayer (&L)[LPL], doub
 
 // Cloudy sub-column with or without scattering (fast_adding_ica_lw, radiation_adding_ica_lw.F90:137-263, written for all layers:
 // where the reference takes its cloud-free shortcut above cloud top the layer reflectance is zero and the general step reduces to
-// the same operations).  sums 3: down, 4: up, 5: flux_up(surface) x prod(trans).
+// the same operations; with do_lw_aerosol_scattering it is also the clear-sky sub-column, adding_ica_lw :24-130).
+// sums q0: down, q0+1: up, q0+2: flux_up(surface) x prod(trans).
 template <int LPL>
-__device__ __forceinline__ void lw_cloudy_subcolumn(const LwLayer (&L)[LPL], double emission, double albedo, int lane, int nlev, double* sums,
+__device__ __forceinline__ void lw_cloudy_subcolumn(const LwLayer (&L)[LPL], double emission, double albedo, int lane, int nlev, double* sums, int q0,
                                                     double& dn_surf, double& up_toa) {
   Mob own = mob_id();
 #pragma unroll
@@ -370,16 +371,16 @@ __device__ __forceinline__ void lw_cloudy_subcolumn(const LwLayer (&L)[LPL], dou
 #pragma unroll
   for (int j = LPL - 1; j >= 0; --j) {
     if (L0 + j < nlev) {
-      *sum_slot<LPL>(sums, 3, j, lane) += fdv[j];
-      *sum_slot<LPL>(sums, 4, j, lane) += Ab[j] * fdv[j] + Sb[j];
-      *sum_slot<LPL>(sums, 5, j, lane) += prod;
+      *sum_slot<LPL>(sums, q0, j, lane) += fdv[j];
+      *sum_slot<LPL>(sums, q0 + 1, j, lane) += Ab[j] * fdv[j] + Sb[j];
+      *sum_slot<LPL>(sums, q0 + 2, j, lane) += prod;
     }
     prod = prod * L[j].trans;
   }
   if (lane == 0) {
     up_toa = S;   // flux_dn(TOA) = 0
-    *sum_slot<LPL>(sums, 4, LPL, 0) += S;
-    *sum_slot<LPL>(sums, 5, LPL, 0) += prod;
+    *sum_slot<LPL>(sums, q0 + 1, LPL, 0) += S;
+    *sum_slot<LPL>(sums, q0 + 2, LPL, 0) += prod;
   }
 }
 
@@ -425,6 +426,9 @@ lw_scan_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
     const double* odp = w.od_lw + ((size_t)c * SD::NG + g) * ls;
     const double* plp = w.planck + ((size_t)c * SD::NG + g) * ls;
     const double emission = w.emission[(size_t)c * SD::NG + g], albedo = w.lw_albedo[(size_t)c * SD::NG + g];
+    const bool lwscat = cfg.do_lw_aerosol_scattering != 0;
+    const double* ssp = lwscat ? w.ssa_lw + ((size_t)c * SD::NG + g) * ls : nullptr;
+    const double* ggp = lwscat ? w.g_lw + ((size_t)c * SD::NG + g) * ls : nullptr;
     LwLayer L[LPL];
     {
       double pt = L0 < nl1 ? plp[L0] : 0.0;
@@ -433,7 +437,8 @@ lw_scan_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
         const int l = L0 + j;
         if (l < nlev) {
           const double pb = plp[l + 1];
-          L[j] = lw_no_scat(odp[l], pt, pb);   // radiation_two_stream.F90:342-409
+          // radiation_two_stream.F90:342-409, or with aerosol scattering :246-333 (radiation_mcica_lw.F90:160-165)
+          L[j] = lwscat ? lw_ref_trans(odp[l], ssp[l], ggp[l], pt, pb) : lw_no_scat(odp[l], pt, pb);
           pt = pb;
         } else {
           L[j] = lw_identity_layer();
@@ -441,7 +446,8 @@ lw_scan_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
       }
     }
     double dn_c = 0.0, toa_c = 0.0;
-    lw_clear_subcolumn<LPL>(L, emission, albedo, lane, nlev, wsums, dn_c, toa_c);
+    if (lwscat) lw_cloudy_subcolumn<LPL>(L, emission, albedo, lane, nlev, wsums, 0, dn_c, toa_c);
+    else lw_clear_subcolumn<LPL>(L, emission, albedo, lane, nlev, wsums, dn_c, toa_c);
     if (lane == 0) { gt[g] = dn_c; gt[SD::NG + g] = toa_c; }
     if (cloudy) {
       const uint32_t* codep = w.code_lw + ((size_t)c * SD::NG + g) * nlevp;
@@ -460,9 +466,15 @@ lw_scan_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
             double ssa_total = 0.0, g_total = 0.0;
             if (od_total > 0.0) {
               const double ssac = clb[SD::NB + b];
-              const double scat_od = ssac * od_cloud_new;
-              ssa_total = scat_od / od_total;
-              if (scat_od > 0.0) g_total = clb[2 * SD::NB + b] * ssac * od_cloud_new / scat_od;
+              if (lwscat) {   // :260-280
+                const double ssag = ssp[l], scat_od_total = ssag * odg + ssac * od_cloud_new;
+                ssa_total = scat_od_total / od_total;
+                if (scat_od_total > 0.0) g_total = (ggp[l] * ssag * odg + clb[2 * SD::NB + b] * ssac * od_cloud_new) / scat_od_total;
+              } else {
+                const double scat_od = ssac * od_cloud_new;
+                ssa_total = scat_od / od_total;
+                if (scat_od > 0.0) g_total = clb[2 * SD::NB + b] * ssac * od_cloud_new / scat_od;
+              }
             }
             La = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
           } else {
@@ -486,7 +498,7 @@ lw_scan_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, 
         __syncwarp();
       }
       double dn_a = 0.0, toa_a = 0.0;
-      lw_cloudy_subcolumn<LPL>(L, emission, albedo, lane, nlev, wsums, dn_a, toa_a);
+      lw_cloudy_subcolumn<LPL>(L, emission, albedo, lane, nlev, wsums, 3, dn_a, toa_a);
       if (lane == 0) { gt[2 * SD::NG + g] = dn_a; gt[3 * SD::NG + g] = toa_a; }
     }
   }

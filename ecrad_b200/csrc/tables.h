@@ -381,6 +381,8 @@ inline void pack_common(const ecrad_b200_tables& T, PackedTables& P) {
     const size_t pl_sw = (size_t)NB_SW * A.nrh * A.n_philic, pl_lw = (size_t)NB_LW * A.nrh * A.n_philic;
     A.me_sw_phobic = put("aer_mass_ext_sw_phobic", pb_sw); A.ssa_sw_phobic = put("aer_ssa_sw_phobic", pb_sw); A.g_sw_phobic = put("aer_g_sw_phobic", pb_sw);
     A.me_lw_phobic = put("aer_mass_ext_lw_phobic", pb_lw); A.ssa_lw_phobic = put("aer_ssa_lw_phobic", pb_lw);
+    A.g_lw_phobic = T.find("aer_g_lw_phobic") ? put("aer_g_lw_phobic", pb_lw) : -1;   // (only read with do_lw_aerosol_scattering)
+    A.g_lw_philic = T.find("aer_g_lw_philic") ? put("aer_g_lw_philic", pl_lw) : -1;
     A.me_sw_philic = put("aer_mass_ext_sw_philic", pl_sw); A.ssa_sw_philic = put("aer_ssa_sw_philic", pl_sw); A.g_sw_philic = put("aer_g_sw_philic", pl_sw);
     A.me_lw_philic = put("aer_mass_ext_lw_philic", pl_lw); A.ssa_lw_philic = put("aer_ssa_lw_philic", pl_lw);
     for (int k = 0; k < A.ntype; ++k) {

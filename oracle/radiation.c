@@ -28,6 +28,7 @@
 
 typedef struct {
   double *od_lw, *planck_hl, *lw_emission, *lw_albedo;         /* [nlev][140], [nlev+1][140], [140], [140] */
+  double *ssa_lw, *g_lw;                                       /* [nlev][140] gas + aerosol (do_lw_aerosol_scattering; zero otherwise) */
   double *od_sw, *ssa_sw, *g_sw, *incoming_sw, *alb_dir, *alb_diff;   /* [nlev][112] x3, [112] x3 */
   double *od_lw_cloud, *ssa_lw_cloud, *g_lw_cloud, *od_sw_cloud, *ssa_sw_cloud, *g_sw_cloud; /* [nlev][nb] */
   double *w;  /* scratch pool */
@@ -191,12 +192,13 @@ int orc_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int
 /* add_aerosol_optics, radiation_aerosol_optics.F90:487-826 (band-wise aerosol properties, no LW aerosol scattering,
  * do_cloud_aerosol_per_*_g_point = false).  Modifies od_sw, ssa_sw, g_sw, od_lw of one column in place. */
 static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
-                               const ecrad_b200_inputs* in, double* od_lw, double* od_sw, double* ssa_sw, double* g_sw) {
+                               const ecrad_b200_inputs* in, double* od_lw, double* ssa_lw, double* g_lw, double* od_sw, double* ssa_sw, double* g_sw) {
   const int ntype = cfg->n_aerosol_types, nrh = t->aer_nrh;
   const double OneOverAccelDueToGravity = 1.0 / 9.80665;
-  double* od_sw_aer = (double*)calloc((size_t)nlev * (3 * NB_SW + NB_LW), sizeof(double));
+  double* od_sw_aer = (double*)calloc((size_t)nlev * (3 * NB_SW + 3 * NB_LW), sizeof(double));
   double *scat_sw_aer = od_sw_aer + (size_t)nlev * NB_SW, *scat_g_sw_aer = scat_sw_aer + (size_t)nlev * NB_SW;
   double* od_lw_aer = scat_g_sw_aer + (size_t)nlev * NB_SW;
+  double *scat_lw_aer = od_lw_aer + (size_t)nlev * NB_LW, *scat_g_lw_aer = scat_lw_aer + (size_t)nlev * NB_LW;
   int* irhs = (int*)malloc(sizeof(int) * (size_t)nlev);
   double* factor = (double*)malloc(sizeof(double) * (size_t)nlev);
   for (size_t i = 0; i < (size_t)nlev * NG_SW; ++i) g_sw[i] = 0.0;
@@ -223,12 +225,21 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
       const double *gg_sw = (iclass == 1 ? t->aer_g_sw_phobic : t->aer_g_sw_philic) + isw;
       const double *me_lw = (iclass == 1 ? t->aer_me_lw_phobic : t->aer_me_lw_philic) + ilw;
       const double *ss_lw = (iclass == 1 ? t->aer_ssa_lw_phobic : t->aer_ssa_lw_philic) + ilw;
+      const double *gg_lw = (iclass == 1 ? t->aer_g_lw_phobic : t->aer_g_lw_philic) + ilw;
       for (int jb = 0; jb < NB_SW; ++jb) {
         double local_od_sw = factor[jl] * mixing_ratio * me_sw[jb];
         od_sw_aer[jl * NB_SW + jb] = od_sw_aer[jl * NB_SW + jb] + local_od_sw;
         scat_sw_aer[jl * NB_SW + jb] = scat_sw_aer[jl * NB_SW + jb] + local_od_sw * ss_sw[jb];
         scat_g_sw_aer[jl * NB_SW + jb] = scat_g_sw_aer[jl * NB_SW + jb] + local_od_sw * ss_sw[jb] * gg_sw[jb];
       }
+      if (cfg->do_lw_aerosol_scattering) {   /* radiation_aerosol_optics.F90:657-670, :697-710 */
+        for (int jb = 0; jb < NB_LW; ++jb) {
+          double local_od_lw = factor[jl] * mixing_ratio * me_lw[jb];
+          od_lw_aer[jl * NB_LW + jb] = od_lw_aer[jl * NB_LW + jb] + local_od_lw;
+          scat_lw_aer[jl * NB_LW + jb] = scat_lw_aer[jl * NB_LW + jb] + local_od_lw * ss_lw[jb];
+          scat_g_lw_aer[jl * NB_LW + jb] = scat_g_lw_aer[jl * NB_LW + jb] + local_od_lw * ss_lw[jb] * gg_lw[jb];
+        }
+      } else
       for (int jb = 0; jb < NB_LW; ++jb)
         od_lw_aer[jl * NB_LW + jb] = od_lw_aer[jl * NB_LW + jb] + factor[jl] * mixing_ratio * me_lw[jb] * (1.0 - ss_lw[jb]);
     }
@@ -257,7 +268,28 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
           od_sw[i] = local_od;
         }
       }
-  if (cfg->do_lw)
+  if (cfg->do_lw && cfg->do_lw_aerosol_scattering) {
+    /* radiation_aerosol_optics.F90:778-801: delta-Eddington scaling of the aerosol, then the merge (gases do not scatter) */
+    for (int i = 0; i < nlev * NB_LW; ++i) {
+      double den = scat_lw_aer[i] > (double)1.0e-24f ? scat_lw_aer[i] : (double)1.0e-24f;
+      double g = scat_g_lw_aer[i] / den;
+      double f = g * g;
+      od_lw_aer[i] = od_lw_aer[i] - scat_lw_aer[i] * f;
+      scat_lw_aer[i] = scat_lw_aer[i] * (1.0 - f);
+      scat_g_lw_aer[i] = scat_lw_aer[i] * g / (1.0 + g);
+    }
+    for (int jl = 0; jl < nlev; ++jl)
+      for (int g = 0; g < NG_LW; ++g) {
+        const int ib = t->band_lw[g];
+        const size_t i = (size_t)jl * NG_LW + g;
+        double local_od = od_lw[i] + od_lw_aer[jl * NB_LW + ib];
+        if (local_od > 0.0 && od_lw_aer[jl * NB_LW + ib] > 0.0) {
+          if (scat_lw_aer[jl * NB_LW + ib] > 0.0) g_lw[i] = scat_g_lw_aer[jl * NB_LW + ib] / scat_lw_aer[jl * NB_LW + ib];
+          ssa_lw[i] = scat_lw_aer[jl * NB_LW + ib] / local_od;
+          od_lw[i] = local_od;
+        }
+      }
+  } else if (cfg->do_lw)
     for (int jl = 0; jl < nlev; ++jl)
       for (int g = 0; g < NG_LW; ++g)
         od_lw[(size_t)jl * NG_LW + g] = od_lw[(size_t)jl * NG_LW + g] + od_lw_aer[jl * NB_LW + (t->band_lw[g])];
@@ -313,10 +345,16 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   double *fu = sd + nl, *fd = fu + nl1, *fu_clear = fd + nl1, *fd_clear = fu_clear + nl1;
   double *od_scaling = fd_clear + nl1, *od_total = od_scaling + nl, *ssa_total = od_total + ng, *g_total = ssa_total + ng;
   const double* planck = w->planck_hl;
+  if (cfg->do_lw_aerosol_scattering) {
+    /* radiation_mcica_lw.F90:160-173, radiation_cloudless_lw.F90:102-116: two-stream with scattering in every layer, adding method */
+    orc_calc_ref_trans_lw(ng * nlev, w->od_lw, w->ssa_lw, w->g_lw, planck, planck + ng, ref_clear, trans_clear, su_clear, sd_clear);
+    orc_adding_ica_lw(ng, nlev, ref_clear, trans_clear, su_clear, sd_clear, w->lw_emission, w->lw_albedo, fu_clear, fd_clear);
+  } else {
   /* clear sky: no-scattering (do_lw_aerosol_scattering = false) */
   orc_calc_no_scattering_transmittance_lw(ng * nlev, w->od_lw, planck, planck + ng, trans_clear, su_clear, sd_clear);
   memset(ref_clear, 0, sizeof(double) * nl);
   orc_calc_fluxes_no_scattering_lw(ng, nlev, trans_clear, su_clear, sd_clear, w->lw_emission, w->lw_albedo, fu_clear, fd_clear);
+  }
   sum_g(ng, nlev + 1, fu_clear, ncol, jcol, out->lw_up_clear);
   sum_g(ng, nlev + 1, fd_clear, ncol, jcol, out->lw_dn_clear);
   for (int g = 0; g < ng; ++g) {
@@ -359,7 +397,15 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
           double od_cloud_new = od_scaling[(size_t)jl * ng + g] * w->od_lw_cloud[jl * NB_LW + jb];
           od_total[g] = w->od_lw[(size_t)jl * ng + g] + od_cloud_new;
           ssa_total[g] = 0.0; g_total[g] = 0.0;
-          if (cfg->do_lw_cloud_scattering) {
+          if (cfg->do_lw_cloud_scattering && cfg->do_lw_aerosol_scattering) {   /* radiation_mcica_lw.F90:260-280 */
+            if (od_total[g] > 0.0) {
+              const size_t i = (size_t)jl * ng + g;
+              double scat_od_total = w->ssa_lw[i] * w->od_lw[i] + w->ssa_lw_cloud[jl * NB_LW + jb] * od_cloud_new;
+              ssa_total[g] = scat_od_total / od_total[g];
+              if (scat_od_total > 0.0)
+                g_total[g] = (w->g_lw[i] * w->ssa_lw[i] * w->od_lw[i] + w->g_lw_cloud[jl * NB_LW + jb] * w->ssa_lw_cloud[jl * NB_LW + jb] * od_cloud_new) / scat_od_total;
+            }
+          } else if (cfg->do_lw_cloud_scattering) {
             if (od_total[g] > 0.0) {
               double scat_od = w->ssa_lw_cloud[jl * NB_LW + jb] * od_cloud_new;
               ssa_total[g] = scat_od / od_total[g];
@@ -380,7 +426,9 @@ static void solver_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nco
         }
       }
     }
-    if (cfg->do_lw_cloud_scattering)
+    if (cfg->do_lw_aerosol_scattering)   /* radiation_mcica_lw.F90:324-329: scattering in all layers */
+      orc_adding_ica_lw(ng, nlev, ref, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
+    else if (cfg->do_lw_cloud_scattering)
       orc_fast_adding_ica_lw(ng, nlev, ref, trans, su, sd, w->lw_emission, w->lw_albedo, is_clear, i_cloud_top, fd_clear, fu, fd);
     else
       orc_calc_fluxes_no_scattering_lw(ng, nlev, trans, su, sd, w->lw_emission, w->lw_albedo, fu, fd);
@@ -906,11 +954,13 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
 static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                             const ecrad_b200_inputs* in, ecrad_b200_outputs* out) {
   col_work w;
-  size_t n = (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 3 * (size_t)nlev * NG_SW + 3 * NG_SW +
+  size_t n = 3 * (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 3 * (size_t)nlev * NG_SW + 3 * NG_SW +
              3 * (size_t)nlev * NB_LW + 3 * (size_t)nlev * NB_SW + 6 * (size_t)nlev;
   w.w = (double*)malloc(sizeof(double) * n);
   double* p = w.w;
   w.od_lw = p; p += (size_t)nlev * NG_LW;  w.planck_hl = p; p += (size_t)(nlev + 1) * NG_LW;
+  w.ssa_lw = p; p += (size_t)nlev * NG_LW;  w.g_lw = p; p += (size_t)nlev * NG_LW;
+  for (size_t i = 0; i < 2 * (size_t)nlev * NG_LW; ++i) w.ssa_lw[i] = 0.0;
   w.lw_emission = p; p += NG_LW;           w.lw_albedo = p; p += NG_LW;
   w.od_sw = p; p += (size_t)nlev * NG_SW;  w.ssa_sw = p; p += (size_t)nlev * NG_SW;  w.g_sw = p; p += (size_t)nlev * NG_SW;
   w.incoming_sw = p; p += NG_SW; w.alb_dir = p; p += NG_SW; w.alb_diff = p; p += NG_SW;
@@ -923,7 +973,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   if (rc) { free(w.w); free(phl_full); return rc; }
   gas_optics_column(t, cfg, ncol, nlev, jcol, in, w.lw_albedo, w.od_lw, w.planck_hl, w.lw_emission, w.od_sw, w.ssa_sw, w.incoming_sw);
   for (size_t i = 0; i < (size_t)nlev * NG_SW; ++i) w.g_sw[i] = 0.0;
-  if (cfg->use_aerosols) add_aerosol_optics(t, cfg, ncol, nlev, jcol, in, w.od_lw, w.od_sw, w.ssa_sw, w.g_sw);
+  if (cfg->use_aerosols) add_aerosol_optics(t, cfg, ncol, nlev, jcol, in, w.od_lw, w.ssa_lw, w.g_lw, w.od_sw, w.ssa_sw, w.g_sw);
   for (int jl = 0; jl <= nlev; ++jl) phl_full[jl] = A2(in->pressure_hl, jcol, jl);
   if (cfg->do_clouds) {
     /* crop_cloud_fraction, radiation_cloud.F90:700-740 (mutates the caller's array) */
@@ -958,7 +1008,8 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  if (cfg->do_lw_aerosol_scattering || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
+  const int lw_plain = cfg->i_solver_lw == ECRAD_SOLVER_MCICA || cfg->i_solver_lw == ECRAD_SOLVER_CLOUDLESS;
+  if ((cfg->do_lw_aerosol_scattering && cfg->do_lw && (!lw_plain || t->is_ecckd || !cfg->do_lw_cloud_scattering)) || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
       (cfg->use_vectorizable_generator && cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;

@@ -555,8 +555,10 @@ def test_error_behaviour(meridian_raw):
     """Non-zero status + message instead of the reference's radiation_abort."""
     from ecrad_b200.radiation_interface import RadiationError, setup_radiation
 
-    with pytest.raises(RadiationError, match="do_lw_aerosol_scattering"):
-        setup_radiation(RadiationConfig(do_lw_aerosol_scattering=True).consolidate())
+    with pytest.raises(RadiationError, match="do_lw_aerosol_scattering"):   # built for McICA / Cloudless on RRTMG only
+        setup_radiation(RadiationConfig(do_lw_aerosol_scattering=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds").consolidate())
+    with pytest.raises(RadiationError, match="requires longwave cloud scattering"):   # radiation_interface.F90:84-88
+        setup_radiation(RadiationConfig(do_lw_aerosol_scattering=True, do_lw_cloud_scattering=False).consolidate())
     h = setup_radiation(RadiationConfig().consolidate())
     with pytest.raises(RadiationError, match="bad dimensions"):
         h.radiation(I.to_radiation_inputs(meridian_raw), 32, NLEV, istartcol=5, iendcol=40)
@@ -634,3 +636,26 @@ def test_blocked_nproma_entry_is_bit_identical(handles, meridian_raw, kw, nproma
         if nm == "cloud_fraction" or a[nm] is None:
             continue
         assert np.array_equal(a[nm], b[nm], equal_nan=True), nm
+
+
+@pytest.mark.parametrize("kw", [dict(use_aerosols=True, do_lw_aerosol_scattering=True), dict(do_lw_aerosol_scattering=True),
+                                dict(use_aerosols=True, do_lw_aerosol_scattering=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless",
+                                     do_save_spectral_flux=False),
+                                dict(use_aerosols=True, do_lw_aerosol_scattering=True, overlap_scheme_name="Exp-Exp", do_nearest_spectral_lw_emiss=False)])
+def test_lw_aerosol_scattering(handles, meridian_raw, kw):
+    """do_lw_aerosol_scattering (the default of config_type, radiation_config.F90:260): aerosols scatter in the longwave, so the clear-sky
+    sub-column needs the full adding method as well (radiation_mcica_lw.F90:160-173, :324-329; radiation_aerosol_optics.F90:657-801).
+    McICA and Cloudless on RRTMG; the oracle restates the same branches."""
+    n = 300
+    h, orc, cfg = handles(**kw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert np.array_equal(out["cloud_cover_lw"], ref["cloud_cover_lw"])
+    if kw.get("use_aerosols"):
+        # scattering aerosols change the longwave by a few tenths of a W m-2 against absorption-only aerosols
+        h0, _, cfg0 = handles(**dict(kw, do_lw_aerosol_scattering=False))
+        out0 = h0.radiation(I.to_radiation_inputs(raw, cfg0), n, NLEV)
+        d = np.abs(out["lw_up"] - out0["lw_up"]).max()
+        assert 1e-3 < d < 5.0, d
