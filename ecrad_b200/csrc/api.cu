@@ -213,7 +213,7 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_SW,                                             // sw_sums sw_carry
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
       8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : use_scan(h, true, nlev) ? 0 : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
-      ckd ? 0 : sizeof(LwLev) * nc * nl, ckd ? 0 : sizeof(SwLev) * nc * nl,                  // lev_lw lev_sw (RRTMG)
+      ckd ? 0 : 8 * (size_t)LWLEV_NF * nc * nl, ckd ? 0 : 8 * (size_t)SWLEV_NF * nc * nl,    // lev_lw lev_sw (RRTMG)
       h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
       (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW * (lwscat ? 3 : 1) : 0,            // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       0,                                                                                     // (sw_band_dir: no longer used)
@@ -248,7 +248,7 @@ int ensure_work(Handle* h, int set, int cols, int nlev) {
   w.tcc = (double*)h->work[set][12].p; w.ibegin = (int*)h->work[set][13].p; w.iend = (int*)h->work[set][14].p; w.ict = (int*)h->work[set][15].p;
   w.code_lw = (uint32_t*)h->work[set][16].p; w.code_sw = (uint32_t*)h->work[set][17].p;
   w.scr_lw = (double*)h->work[set][18].p; w.scr_sw = (double*)h->work[set][23].p;
-  w.lev_lw = (LwLev*)h->work[set][24].p; w.lev_sw = (SwLev*)h->work[set][25].p;
+  w.lev_lw = (double*)h->work[set][24].p; w.lev_sw = (double*)h->work[set][25].p;
   w.g_sw = (double*)h->work[set][26].p; w.aer_sw = (double*)h->work[set][27].p; w.aer_lw = (double*)h->work[set][28].p;
   w.sw_band_dir = (double*)h->work[set][29].p;
   w.tc_reg = (double*)h->work[set][30].p; w.tc_ods = (double*)h->work[set][31].p; w.tc_u = (double*)h->work[set][32].p;

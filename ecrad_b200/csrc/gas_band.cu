@@ -163,9 +163,9 @@ __device__ __forceinline__ void stage_rows(double* img, int rs, int ng, const do
 // ---------------------------------------------------------------------------------------------------------
 template <int IB, bool LAYB>
 __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, const double* img, const double* tp, double pfac, const DevTables& T,
-                                        const DevCfg& cfg, const DevIn& in, const Work& w, int c, int l, int nlev, bool low, const LwLev* __restrict__ Lg, int jw) {
+                                        const DevCfg& cfg, const DevIn& in, const Work& w, int c, int l, int nlev, bool low, const double* __restrict__ Lg, int jw) {
   constexpr int NG = kNgLwBand[IB];
-  LwLev L = *Lg;     // (by value: the compiler keeps the loads of the fields this band reads)
+  LwLev L = lwlev_load(Lg, nlev, l);     // (inlined field by field: only the loads of the fields this band reads survive)
   if (IB != 15 || low) L.jp = jw;
   EvalSink<NG> sink;
   sink.tab = img; sink.clear();
@@ -330,12 +330,7 @@ gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
       if (!(v & 512) || jw < jlo || jw > jhi) continue;
       jpv[it] = v & ~512;
       const int c = c_first + it * GB_CC + cc;
-      const LwLev* Lg = w.lev_lw + (size_t)c * nlev + l;
-      if (it + 1 < GB_CBLK / GB_CC && (jpv[it + 1] & 512)) {   // next item's state on its way into L1 while this one is computed
-        const char* nx = reinterpret_cast<const char*>(Lg + (size_t)GB_CC * nlev);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 128));
-      }
+      const double* Lg = w.lev_lw + (size_t)c * LWLEV_NF * nlev;
       const bool low = (v & 256) != 0;
 #define LWB(I) case I: lw_item<I, LAYB>(M, S.B, img, tp, pfac, T, cfg, in, w, c, l, nlev, low, Lg, jw); break;
       switch (band) { LWB(0) LWB(1) LWB(2) LWB(3) LWB(4) LWB(5) LWB(6) LWB(7) LWB(8) LWB(9) LWB(10) LWB(11) LWB(12) LWB(13) LWB(14) LWB(15) }
@@ -352,9 +347,9 @@ gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
 // ---------------------------------------------------------------------------------------------------------
 template <int IB, bool LAYB>
 __device__ __forceinline__ void sw_item(const GasMeta& M, const BandMeta& Bs, const double* img, const DevCfg& cfg, const Work& w, int c, int l,
-                                        int nlev, bool low, bool solar_layer, const SwLev* __restrict__ Lg, int jw) {
+                                        int nlev, bool low, bool solar_layer, const double* __restrict__ Lg, int jw) {
   constexpr int NG = kNgSwBand[IB];
-  SwLev L = *Lg;
+  SwLev L = swlev_load(Lg, nlev, l);
   L.jp = jw;
   EvalSink<NG> sink;
   sink.tab = img; sink.clear();
@@ -482,12 +477,7 @@ gas_sw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
       if (!(v & 512) || jw < jlo || jw > jhi) continue;
       jpv[it] = v & ~512;
       const int c = sun[c_first + it * GB_CC + cc];
-      const SwLev* Lg = w.lev_sw + (size_t)c * nlev + l;
-      if (it + 1 < GB_CBLK / GB_CC && (jpv[it + 1] & 512)) {
-        const char* nx = reinterpret_cast<const char*>(w.lev_sw + (size_t)sun[c_first + (it + 1) * GB_CC + cc] * nlev + l);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 128));
-      }
+      const double* Lg = w.lev_sw + (size_t)c * SWLEV_NF * nlev;
       const bool low = (v & 256) != 0;
       const bool solar_layer = l == w.gas_col[c].lsol[band];
 #define SWB(I) case I: sw_item<I, LAYB>(M, S.B, img, cfg, w, c, l, nlev, low, solar_layer, Lg, jw); break;

@@ -176,6 +176,35 @@ HD void lw_setcoef(const GasMeta& M, const LevGas& G, LwLev& L) {
   L.wx1 = G.wx1; L.wx2 = G.wx2; L.wx3 = G.wx3; L.wx4 = G.wx4;
 }
 
+// Storage of the per-layer state between gas_prep_kernel and the gas-optics kernels: per column a block [field][layer] of doubles
+// (integers stored exactly), layer fastest -- whichever way a kernel maps threads to layers, a field of consecutive layers is one
+// contiguous run (a struct-per-layer array made every field load touch one cache line per lane).
+enum { LWLEV_NF = 33 };
+HD void lwlev_store(double* col, int stride, int l, const LwLev& L) {
+  double* p = col + l;
+  p[0 * stride] = L.jp; p[1 * stride] = L.jt; p[2 * stride] = L.jt1; p[3 * stride] = L.indself; p[4 * stride] = L.indfor;
+  p[5 * stride] = L.indminor; p[6 * stride] = L.tropo;
+  p[7 * stride] = L.fac00; p[8 * stride] = L.fac01; p[9 * stride] = L.fac10; p[10 * stride] = L.fac11; p[11 * stride] = L.forfac;
+  p[12 * stride] = L.forfrac; p[13 * stride] = L.selffac; p[14 * stride] = L.selffrac; p[15 * stride] = L.scaleminor;
+  p[16 * stride] = L.scaleminorn2; p[17 * stride] = L.minorfrac; p[18 * stride] = L.colh2o; p[19 * stride] = L.colco2;
+  p[20 * stride] = L.colo3; p[21 * stride] = L.coln2o; p[22 * stride] = L.colch4; p[23 * stride] = L.colo2; p[24 * stride] = L.colbrd;
+  p[25 * stride] = L.coldry; p[26 * stride] = L.pavel; p[27 * stride] = L.wx1; p[28 * stride] = L.wx2; p[29 * stride] = L.wx3;
+  p[30 * stride] = L.wx4; p[31 * stride] = L.t_top; p[32 * stride] = L.t_bot;
+}
+HD LwLev lwlev_load(const double* col, int stride, int l) {
+  const double* p = col + l;
+  LwLev L;
+  L.jp = (int)p[0 * stride]; L.jt = (int)p[1 * stride]; L.jt1 = (int)p[2 * stride]; L.indself = (int)p[3 * stride];
+  L.indfor = (int)p[4 * stride]; L.indminor = (int)p[5 * stride]; L.tropo = (int)p[6 * stride];
+  L.fac00 = p[7 * stride]; L.fac01 = p[8 * stride]; L.fac10 = p[9 * stride]; L.fac11 = p[10 * stride]; L.forfac = p[11 * stride];
+  L.forfrac = p[12 * stride]; L.selffac = p[13 * stride]; L.selffrac = p[14 * stride]; L.scaleminor = p[15 * stride];
+  L.scaleminorn2 = p[16 * stride]; L.minorfrac = p[17 * stride]; L.colh2o = p[18 * stride]; L.colco2 = p[19 * stride];
+  L.colo3 = p[20 * stride]; L.coln2o = p[21 * stride]; L.colch4 = p[22 * stride]; L.colo2 = p[23 * stride]; L.colbrd = p[24 * stride];
+  L.coldry = p[25 * stride]; L.pavel = p[26 * stride]; L.wx1 = p[27 * stride]; L.wx2 = p[28 * stride]; L.wx3 = p[29 * stride];
+  L.wx4 = p[30 * stride]; L.t_top = p[31 * stride]; L.t_bot = p[32 * stride]; L.pad_ = 0.0;
+  return L;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // list emitters
 // ---------------------------------------------------------------------------------------------------------
@@ -591,6 +620,25 @@ HD void sw_setcoef(const GasMeta& M, const LevGas& G, SwLev& L) {
   double compfp = 1. - fp;
   L.fac10 = compfp * ft; L.fac00 = compfp * (1. - ft);
   L.fac11 = fp * ft1;    L.fac01 = fp * (1. - ft1);
+}
+
+enum { SWLEV_NF = 20 };
+HD void swlev_store(double* col, int stride, int l, const SwLev& L) {
+  double* p = col + l;
+  p[0 * stride] = L.jp; p[1 * stride] = L.jt; p[2 * stride] = L.jt1; p[3 * stride] = L.indself; p[4 * stride] = L.indfor; p[5 * stride] = L.tropo;
+  p[6 * stride] = L.fac00; p[7 * stride] = L.fac01; p[8 * stride] = L.fac10; p[9 * stride] = L.fac11; p[10 * stride] = L.forfac;
+  p[11 * stride] = L.forfrac; p[12 * stride] = L.selffac; p[13 * stride] = L.selffrac; p[14 * stride] = L.colh2o; p[15 * stride] = L.colco2;
+  p[16 * stride] = L.colo3; p[17 * stride] = L.colch4; p[18 * stride] = L.colo2; p[19 * stride] = L.colmol;
+}
+HD SwLev swlev_load(const double* col, int stride, int l) {
+  const double* p = col + l;
+  SwLev L;
+  L.jp = (int)p[0 * stride]; L.jt = (int)p[1 * stride]; L.jt1 = (int)p[2 * stride]; L.indself = (int)p[3 * stride]; L.indfor = (int)p[4 * stride];
+  L.tropo = (int)p[5 * stride];
+  L.fac00 = p[6 * stride]; L.fac01 = p[7 * stride]; L.fac10 = p[8 * stride]; L.fac11 = p[9 * stride]; L.forfac = p[10 * stride];
+  L.forfrac = p[11 * stride]; L.selffac = p[12 * stride]; L.selffrac = p[13 * stride]; L.colh2o = p[14 * stride]; L.colco2 = p[15 * stride];
+  L.colo3 = p[16 * stride]; L.colch4 = p[17 * stride]; L.colo2 = p[18 * stride]; L.colmol = p[19 * stride];
+  return L;
 }
 
 // speccomb*((1-fs)*(T[i0]f00 + T[i0+d]f10 + T[i1]f01 + T[i1+d]f11) + fs*(same rows + 1))

@@ -55,23 +55,45 @@ __device__ __forceinline__ double stencil_dot(const Term* tt, int n, const doubl
 // per-layer state of both spectra (rrtm_prepare_gases + rrtm_setcoef_140gp + srtm_setcoef): one thread per (column, layer),
 // column fastest so that the reference-layout inputs are read coalesced
 // =========================================================================================================
-__global__ void gas_prep_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nc * nlev) return;
-  const int c = i % nc, l = i / nc;
+// A CTA takes a tile of GP_T columns x GP_T layers: inputs are read in runs of GP_T columns (their layout), the state leaves in runs
+// of GP_T layers (its layout) through a shared-memory transpose.
+enum { GP_T = 16 };
+__global__ void __launch_bounds__(GP_T * GP_T)
+gas_prep_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* slw = reinterpret_cast<double*>(smem_raw);            // [GP_T columns][LWLEV_NF][GP_T layers]
+  double* ssw = slw + GP_T * LWLEV_NF * GP_T;                   // [GP_T columns][SWLEV_NF][GP_T layers]
+  const int tc = threadIdx.x % GP_T, tl = threadIdx.x / GP_T;
+  const int c0 = blockIdx.x * GP_T, l0 = blockIdx.y * GP_T;
+  const int c = c0 + tc, l = l0 + tl;
   const GasMeta& M = *T.meta;
-  LevGas G;
-  lev_prepare(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1),
-              LD_IN(in.gas[0], c, l), LD_IN(in.gas[1], c, l), LD_IN(in.gas[2], c, l), LD_IN(in.gas[3], c, l),
-              LD_IN(in.gas[4], c, l), LD_IN(in.gas[5], c, l), LD_IN(in.gas[6], c, l), LD_IN(in.gas[7], c, l),
-              LD_IN(in.gas[8], c, l), G);
-  {
+  const bool valid = c < nc && l < nlev;
+  bool sunlit = false;
+  if (valid) {
+    LevGas G;
+    lev_prepare(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1),
+                LD_IN(in.gas[0], c, l), LD_IN(in.gas[1], c, l), LD_IN(in.gas[2], c, l), LD_IN(in.gas[3], c, l),
+                LD_IN(in.gas[4], c, l), LD_IN(in.gas[5], c, l), LD_IN(in.gas[6], c, l), LD_IN(in.gas[7], c, l),
+                LD_IN(in.gas[8], c, l), G);
     LwLev L; lw_setcoef(M, G, L);
     L.t_top = LD_IN(in.t_hl, c, l); L.t_bot = LD_IN(in.t_hl, c, l + 1); L.pad_ = 0.0;
-    if (cfg.do_lw) w.lev_lw[(size_t)c * nlev + l] = L;
+    lwlev_store(slw + (size_t)tc * LWLEV_NF * GP_T, GP_T, tl, L);
     w.gas_jp[(size_t)c * nlev + l] = (uint8_t)(L.jp | (L.tropo << 7));   // (jp is the same expression in srtm_setcoef)
+    sunlit = cfg.do_sw && in.cos_sza[c] > 0.0;
+    if (sunlit) { SwLev S; sw_setcoef(M, G, S); swlev_store(ssw + (size_t)tc * SWLEV_NF * GP_T, GP_T, tl, S); }
   }
-  if (cfg.do_sw && in.cos_sza[c] > 0.0) { SwLev L; sw_setcoef(M, G, L); w.lev_sw[(size_t)c * nlev + l] = L; }
+  __syncthreads();
+  const int nl = imin((int)GP_T, nlev - l0);
+  if (cfg.do_lw)
+    for (int e = threadIdx.x; e < GP_T * LWLEV_NF * GP_T; e += GP_T * GP_T) {
+      const int k = e % GP_T, f = (e / GP_T) % LWLEV_NF, cc = e / (GP_T * LWLEV_NF);
+      if (c0 + cc < nc && k < nl) w.lev_lw[((size_t)(c0 + cc) * LWLEV_NF + f) * nlev + l0 + k] = slw[e];
+    }
+  if (cfg.do_sw)
+    for (int e = threadIdx.x; e < GP_T * SWLEV_NF * GP_T; e += GP_T * GP_T) {
+      const int k = e % GP_T, f = (e / GP_T) % SWLEV_NF, cc = e / (GP_T * SWLEV_NF);
+      if (c0 + cc < nc && k < nl && in.cos_sza[c0 + cc] > 0.0) w.lev_sw[((size_t)(c0 + cc) * SWLEV_NF + f) * nlev + l0 + k] = ssw[e];
+    }
 }
 
 // =========================================================================================================
@@ -187,8 +209,8 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   float* srn = reinterpret_cast<float*>(sng + NB_LW);                // [16] 1 / g-points per band
 
   // per-layer state was prepared by gas_prep_kernel; LAYTROP = number of layers with plog > 4.56
-  const LwLev* lev = w.lev_lw + (size_t)c * nlev;
-  const int tropo = tid < nlev ? lev[tid].tropo : 0;
+  const double* lev = w.lev_lw + (size_t)c * LWLEV_NF * nlev;
+  const int tropo = tid < nlev ? (int)lev[6 * nlev + tid] : 0;
   for (int g = tid; g < NG_LW; g += GAS_THREADS) { int b = M.band_of_g_lw[g]; bog[g] = b; g0b[g] = g - M.lw[b].g0; }
   if (tid < NB_LW) { sng[tid] = M.lw[tid].ng; srn[tid] = 1.0f / (float)M.lw[tid].ng; }
   if (tid < NB_LW) plk_surf[tid] = planck_band(M, in.skin_t[c], tid);
@@ -200,8 +222,11 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   double* od_out = w.od_lw + (size_t)c * (lb ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW);
   double* pl_out = w.planck + (size_t)c * (lb ? (size_t)NG_LW * w.ls : (size_t)(nlev + 1) * NG_LW);
 
+  __shared__ LwLev s_lev[GAS_LC];
   for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
     const int nl = imin((int)GAS_LC, nlev - l0);
+    if (tid < nl) s_lev[tid] = lwlev_load(lev, nlev, l0 + tid);   // (every band's builder of a layer reads the same state)
+    __syncthreads();
     // ---- stage A: stencils of (layer, band) ----
     {
       const int b = tid >> 4, ll = tid & 15;   // GAS_LC == 16
@@ -212,7 +237,7 @@ gas_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         out.t = lt + c_lw_koff[b] * GAS_LC + ll;
         out.n = 0; out.stride = GAS_LC;
         int post;
-        PlanckFrac pf = lw_build_list(M, M.lw[b], lev[l], b, il <= laytrop, out, &post);
+        PlanckFrac pf = lw_build_list(M, M.lw[b], s_lev[ll], b, il <= laytrop, out, &post);
         out.pad4();
         ln[ll * NB_LW + b] = out.n;
         lpost[ll * NB_LW + b] = post;
@@ -294,9 +319,9 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   int* jps = reinterpret_cast<int*>(srn + NB_SW);                    // [nlev] JP per layer (ecRad order)
   __shared__ double s_scale;
 
-  const SwLev* lev = w.lev_sw + (size_t)c * nlev;
+  const double* lev = w.lev_sw + (size_t)c * SWLEV_NF * nlev;
   int tropo = 0;
-  if (tid < nlev) { jps[tid] = lev[tid].jp; tropo = lev[tid].tropo; }
+  if (tid < nlev) { jps[tid] = (int)lev[tid]; tropo = (int)lev[5 * nlev + tid]; }
   for (int g = tid; g < NG_SW; g += GAS_THREADS) { int b = M.band_of_g_sw[g]; bog[g] = b; g0b[g] = g - M.sw[b].g0; inc[g] = 0.0; }
   if (tid < NB_SW) { sng[tid] = M.sw[tid].ng; srn[tid] = 1.0f / (float)M.sw[tid].ng; }
   const int laytrop = __syncthreads_count(tropo);
@@ -312,8 +337,11 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   double* od_out = w.od_sw + cbase;
   double* ssa_out = w.ssa_sw + cbase;
 
+  __shared__ SwLev s_lev[GAS_LC];
   for (int l0 = 0; l0 < nlev; l0 += GAS_LC) {
     const int nl = imin((int)GAS_LC, nlev - l0);
+    if (tid < nl) s_lev[tid] = swlev_load(lev, nlev, l0 + tid);
+    __syncthreads();
     {
       const int b = tid >> 4, ll = tid & 15;
       if (b < NB_SW && ll < nl) {
@@ -323,7 +351,7 @@ gas_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
         out.t = lt + c_sw_koff[b] * GAS_LC + ll;
         out.n = 0; out.stride = GAS_LC;
         SwAux aux;
-        sw_build_list(M, M.sw[b], lev[l], b, il <= laytrop, out, aux);
+        sw_build_list(M, M.sw[b], s_lev[ll], b, il <= laytrop, out, aux);
         out.pad4();
         ln[ll * NB_SW + b] = out.n;
         rc[(ll * NB_SW + b) * 2] = aux.rc0; rc[(ll * NB_SW + b) * 2 + 1] = aux.rc1;
@@ -803,7 +831,9 @@ static void allow_smem(K kernel, size_t bytes) {
 }
 
 int launch_gas_prep(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
-  gas_prep_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev);
+  const size_t sm = sizeof(double) * GP_T * GP_T * (LWLEV_NF + SWLEV_NF);
+  cudaFuncSetAttribute(gas_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  gas_prep_kernel<<<dim3((nc + GP_T - 1) / GP_T, (nlev + GP_T - 1) / GP_T), GP_T * GP_T, sm, st>>>(T, cfg, in, w, nc, nlev);
   return 1;
 }
 int launch_aerosol(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {

@@ -99,7 +99,7 @@ struct Work {
   double *scr_lw, *scr_sw;                        // [nc][LW_SCR_ARRAYS*nlev*140], [nc][SW_SCR_ARRAYS*nlev*112] (separate: LW and SW chains run concurrently)
   double *sw_band_dir;                            // [nc][nlev+1][14] mu0 * per-band direct-beam sums (spectral flux profiles)
   double *tc_reg, *tc_ods, *tc_u, *tc_v, *tc_cc;  // Tripleclouds: [nc][nlev][3] x2, [nc][nlev+1][9] x2, [nc]
-  LwLev* lev_lw; SwLev* lev_sw;                   // [nc][nlev] per-layer gas-optics state (gas_prep_kernel)
+  double *lev_lw, *lev_sw;                        // [nc][LWLEV_NF / SWLEV_NF][nlev] per-layer gas-optics state (gas_prep_kernel; gas_core.h lwlev_load)
   double *lw_sums, *lw_carry;                     // [nc][6][nlev+1], [nc][4][140] (LW kernels)
   double *sw_sums, *sw_carry;                     // [nc][6][nlev+1] g-point sums per half-level, [nc][4][112] per-g carries between SW kernels
   // Layout of the gas optical properties (od_*, ssa_sw, g_sw, planck), per spectrum: 0 = [column][layer][g] (g fastest: the
