@@ -640,8 +640,10 @@ __device__ __forceinline__ void gen_walk_warp(const DevCfg& cfg, int32_t* ring, 
 }
 
 __global__ void __launch_bounds__(64)
-cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp) {
-  __shared__ double sA1[GW_MAXLEV], sT1[GW_MAXLEV], sA2[GW_MAXLEV], sT2[GW_MAXLEV], sCUM[GW_MAXLEV], sOPI[GW_MAXLEV];
+cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp, int nlev8) {
+  extern __shared__ __align__(16) unsigned char gen_smem[];
+  double* sA1 = reinterpret_cast<double*>(gen_smem);   // six arrays of nlev8 = nlev rounded up to a multiple of 8 (<= GW_MAXLEV)
+  double *sT1 = sA1 + nlev8, *sA2 = sT1 + nlev8, *sT2 = sA2 + nlev8, *sCUM = sT2 + nlev8, *sOPI = sCUM + nlev8;
   __shared__ int32_t sRing[2][1024];
   __shared__ int32_t sTop[2][NG_LW];
   const unsigned FULL = 0xffffffffu;
@@ -650,7 +652,7 @@ cloud_gen_warp_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev, int nlevp)
   if (!(tcc > 0.0)) return;
   const int Lb = w.ibegin[c] - 1, Le = w.iend[c] - 1;   // first / last cloudy layer, 0-based
   // per-layer constants of the two transition tests (same operations, same order as the reference's expressions)
-  for (int L = threadIdx.x; L < GW_MAXLEV; L += 64) {
+  for (int L = threadIdx.x; L < nlev8; L += 64) {
     double a1 = 0.0, t1 = 0.0, a2 = 0.0, t2 = 0.0, cu = 0.0, op = 0.0;
     if (L < nlev) {
       cu = w.cum[(size_t)L * nc + c];
@@ -891,7 +893,8 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
       const int tsw = (cfg.ng_sw + 31) / 32 * 32, tlw = (cfg.ng_lw + 31) / 32 * 32;
       cloud_gen_vec_kernel<<<nc, tsw + tlw, 0, st>>>(cfg, in, w, nc, nlev, nlevp, tsw);
     } else {
-      cloud_gen_warp_kernel<<<nc, 64, 0, st>>>(cfg, in, w, nc, nlev, nlevp);
+      const int nlev8 = (nlev + 7) & ~7;
+      cloud_gen_warp_kernel<<<nc, 64, sizeof(double) * 6 * nlev8, st>>>(cfg, in, w, nc, nlev, nlevp, nlev8);
     }
     ++n;
   }
