@@ -352,6 +352,29 @@ def main():
             dt = (time.perf_counter() - t0) / args.steps
             e2e_extra[key] = {"value": ncol / dt, "ms_per_step": dt * 1e3}
         h.set_option("register_host", 0)
+        # the single-precision boundary (ecrad_b200_radiation_sp): float arrays on the host side, half the PCIe bytes, fp64 kernels
+        f_in = {nm: (t if dt == "i4" else t.to(torch.float32).pin_memory()) for (nm, dt), t in zip(in_arrays, [pinned[nm] for nm, _ in in_arrays])}
+        f_out = {nm: torch.empty_like(t, dtype=torch.float32).pin_memory() for nm, t in host_out.items()}
+        ist_f, ost_f = abi.Inputs(), abi.Outputs()
+        C.memmove(C.byref(ist_f), C.byref(ist_host), C.sizeof(abi.Inputs))
+        C.memmove(C.byref(ost_f), C.byref(ost_host), C.sizeof(abi.Outputs))
+        for nm, dt in in_arrays:
+            setattr(ist_f, nm, C.cast(f_in[nm].data_ptr(), abi.c_ip if dt == "i4" else abi.c_dp))
+        for nm, kind in out_names:
+            setattr(ost_f, nm, C.cast(f_out[nm].data_ptr(), abi.c_dp))
+        for _ in range(2):
+            if h.lib.ecrad_b200_radiation_sp(h.h, ncol, NLEV, 1, ncol, C.byref(ist_f), C.byref(ost_f)):
+                raise RuntimeError(h._err())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h.lib.ecrad_b200_radiation_sp(h.h, ncol, NLEV, 1, ncol, C.byref(ist_f), C.byref(ost_f))
+        torch.cuda.synchronize()
+        dt_sp = (time.perf_counter() - t0) / args.steps
+        sp_err = float((f_out["lw_up"].double() - host_out["lw_up"]).abs().max())
+        assert sp_err <= 1e-3, f"single-precision boundary: lw_up differs from the fp64 result by {sp_err} W m-2"
+        e2e_extra["sp"] = {"value": ncol / dt_sp, "ms_per_step": dt_sp * 1e3, "max_abs_diff_lw_up_vs_fp64": sp_err,
+                           "h2d_bytes_per_step": h2d_bytes // 2, "d2h_bytes_per_step": d2h_bytes // 2}
         assert np.array_equal(page_out["lw_up"], host_out["lw_up"].numpy(), equal_nan=True), "pageable-host results differ from the pinned-host results"
 
     # Exchange step of a host model that wants all fluxes on one GPU.  Not part of `value` (the path itself needs
@@ -540,7 +563,9 @@ def main():
                         "ms_per_step": e2e_s * 1e3, "host_memory": "pinned",
                         # the same call with the host arrays an unmodified Fortran driver has (pageable), without and with
                         # set_option("register_host", 1)
-                        "pageable_host": e2e_extra.get("pageable"), "pageable_host_registered": e2e_extra.get("registered")},
+                        "pageable_host": e2e_extra.get("pageable"), "pageable_host_registered": e2e_extra.get("registered"),
+                        # the same call from a single-precision host (float arrays, ecrad_b200_radiation_sp; kernels still fp64)
+                        "single_precision_host": e2e_extra.get("sp")},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         if gather is not None:
             line["gather"] = gather

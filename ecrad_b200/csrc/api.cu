@@ -38,6 +38,7 @@ const char* kStageNames[N_STAGE] = {"gas_optics_lw", "gas_optics_sw", "cloud_opt
 
 struct Slot {            // device staging of one tile's inputs and outputs
   Buf in[N_IN], out[N_OUT];
+  Buf in32[N_IN], out32[N_OUT];   // single-precision host arrays (ecrad_b200_radiation_sp): staged as float, converted on the device
   cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
   bool used = false;
 };
@@ -438,6 +439,17 @@ __global__ void block_pack_kernel(BlockJobs J, double* __restrict__ z, int nprom
   z[((size_t)(c / nproma) * nfields + b.field0 + r) * nproma + (c % nproma)] = v;
 }
 
+// ---- single-precision boundary: float <-> double conversion of whole staging buffers, one launch for all arrays of a tile ----
+struct CvtJob { const void* src; void* dst; long long n; };
+struct CvtJobs { CvtJob j[48]; int n; };
+__global__ void convert_kernel(CvtJobs J, int to_double) {
+  const CvtJob& b = J.j[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (long long)gridDim.x * blockDim.x) {
+    if (to_double) ((double*)b.dst)[i] = (double)((const float*)b.src)[i];
+    else ((float*)b.dst)[i] = (float)((const double*)b.src)[i];
+  }
+}
+
 // fp64 multiply-add throughput of the device, measured: 8 independent chains per thread, enough CTAs to fill every SM
 __global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double* out, int iters, double b, double c) {
   double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -658,6 +670,8 @@ void ecrad_b200_finalize(void* handle) {
   for (auto& s : h->slot) {
     for (auto& b : s.in) b.release();
     for (auto& b : s.out) b.release();
+    for (auto& b : s.in32) b.release();
+    for (auto& b : s.out32) b.release();
     if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     if (s.compute_done) cudaEventDestroy(s.compute_done);
     if (s.d2h_done) cudaEventDestroy(s.d2h_done);
@@ -705,11 +719,26 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer entry
 // ---------------------------------------------------------------------------------------------------------
+static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in, ecrad_b200_outputs* out, bool sp);
+
 int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in,
                          ecrad_b200_outputs* out) {
   Handle* h = (Handle*)handle;
   if (!h) return fail(nullptr, "ecrad_b200_radiation: null handle");
   std::lock_guard<std::mutex> lk(h->mu);
+  return host_entry(h, ncol, nlev, istartcol, iendcol, in, out, false);
+}
+int ecrad_b200_radiation_sp(void* handle, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in,
+                            ecrad_b200_outputs* out) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_radiation_sp: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return host_entry(h, ncol, nlev, istartcol, iendcol, in, out, true);
+}
+
+// rb = bytes per real of the caller's arrays: 8, or 4 for the single-precision boundary (float arrays behind the struct's pointers)
+static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in, ecrad_b200_outputs* out, bool sp) {
+  const size_t rb = sp ? 4 : 8;
   if (check_args(h, ncol, nlev, istartcol, iendcol, in, out)) return 1;
   CK(h, cudaSetDevice(h->device));
   const ecrad_b200_config& c = h->cfg;
@@ -762,9 +791,9 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     return true;
   };
   if (h->register_host) {
-    for (int k = 0; k < N_IN; ++k) if (id[k].host && id[k].rows > 0) register_range(h, id[k].host, (size_t)id[k].elem * ncol * id[k].rows);
+    for (int k = 0; k < N_IN; ++k) if (id[k].host && id[k].rows > 0) register_range(h, id[k].host, (id[k].elem == 8 ? rb : 4) * ncol * id[k].rows);
     for (int k = 0; k < N_OUT; ++k)
-      if (out_active(k)) register_range(h, od[k].host, 8 * (size_t)ncol * od[k].rows * (od[k].kind == 2 ? (size_t)(nlev + 1) : 1));
+      if (out_active(k)) register_range(h, od[k].host, rb * (size_t)ncol * od[k].rows * (od[k].kind == 2 ? (size_t)(nlev + 1) : 1));
   }
   for (auto& s : h->slot) s.used = false;
   for (int t = 0; t < ntiles; ++t) {
@@ -773,14 +802,24 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     void* ip[N_IN]; void* op[N_OUT];
     // ---- H2D (this slot's buffers are free once the kernels and copies of tile t-2 are done) ----
     if (s.used) { CKD(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CKD(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }
+    CvtJobs jin, jout; jin.n = jout.n = 0;
+    long long cvt_in_max = 0, cvt_out_max = 0;
     for (int k = 0; k < N_IN; ++k) {
       ip[k] = nullptr;
       if (!id[k].host || id[k].rows <= 0) continue;
       const size_t el = (size_t)id[k].elem;
       CKD(h, s.in[k].reserve(el * cap * id[k].rows));
       ip[k] = s.in[k].p;
-      CKD(h, cudaMemcpy2DAsync(s.in[k].p, el * cap, (const char*)id[k].host + el * c0, el * ncol, el * nt, id[k].rows,
-                              cudaMemcpyHostToDevice, h->s_h2d));
+      const bool cvt = sp && el == 8;
+      void* dst = s.in[k].p;
+      const size_t hel = cvt ? 4 : el;   // bytes per element on the host
+      if (cvt) {
+        CKD(h, s.in32[k].reserve(4 * (size_t)cap * id[k].rows));
+        dst = s.in32[k].p;
+        jin.j[jin.n++] = {dst, s.in[k].p, (long long)cap * id[k].rows};
+        if ((long long)cap * id[k].rows > cvt_in_max) cvt_in_max = (long long)cap * id[k].rows;
+      }
+      CKD(h, cudaMemcpy2DAsync(dst, hel * cap, (const char*)id[k].host + hel * c0, hel * ncol, hel * nt, id[k].rows, cudaMemcpyHostToDevice, h->s_h2d));
     }
     for (int k = 0; k < N_OUT; ++k) {
       op[k] = nullptr;
@@ -788,12 +827,21 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
       const size_t per_col = od[k].kind == 0 ? (size_t)od[k].rows : od[k].kind == 1 ? (size_t)od[k].rows : (size_t)od[k].rows * (nlev + 1);
       CKD(h, s.out[k].reserve(8 * per_col * cap));
       op[k] = s.out[k].p;
+      if (sp) {
+        CKD(h, s.out32[k].reserve(4 * per_col * cap));
+        jout.j[jout.n++] = {s.out[k].p, s.out32[k].p, (long long)per_col * cap};
+        if ((long long)per_col * cap > cvt_out_max) cvt_out_max = (long long)per_col * cap;
+      }
     }
-    // night columns keep the caller's cloud_cover_sw (the reference does not touch it): stage the current values
-    if (op[12]) CKD(h, cudaMemcpyAsync(op[12], od[12].host + c0, 8 * (size_t)nt, cudaMemcpyHostToDevice, h->s_h2d));
-    // likewise sw_dn_toa_g / sw_dn_toa_band of night columns (Tripleclouds sets them for sunlit columns only)
-    for (int k = 35; k <= 36; ++k)
-      if (op[k]) CKD(h, cudaMemcpyAsync(op[k], od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)nt * od[k].rows, cudaMemcpyHostToDevice, h->s_h2d));
+    // night columns keep the caller's cloud_cover_sw (the reference does not touch it): stage the current values; likewise
+    // sw_dn_toa_g / sw_dn_toa_band of night columns (Tripleclouds sets them for sunlit columns only)
+    for (int k : {12, 35, 36}) {
+      if (!op[k]) continue;
+      const size_t n = (size_t)nt * od[k].rows;
+      void* dst = sp ? s.out32[k].p : op[k];
+      CKD(h, cudaMemcpyAsync(dst, (const char*)od[k].host + rb * (size_t)c0 * od[k].rows, rb * n, cudaMemcpyHostToDevice, h->s_h2d));
+      if (sp) { jin.j[jin.n++] = {dst, op[k], (long long)n}; if ((long long)n > cvt_in_max) cvt_in_max = (long long)n; }
+    }
     CKD(h, cudaEventRecord(s.h2d_done, h->s_h2d));
     // ---- kernels ----
     DevIn di; DevOut dout;
@@ -802,22 +850,39 @@ int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int ie
     if (h->dev_pending) CKD(h, cudaStreamWaitEvent(h->s_comp[set], h->ev_dev_done, 0));
     CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.h2d_done, 0));
     if (s.used) CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.d2h_done, 0));
+    if (sp && jin.n) {
+      convert_kernel<<<dim3((unsigned)((cvt_in_max + 1023) / 1024 > 592 ? 592 : (cvt_in_max + 1023) / 1024), jin.n), 256, 0, h->s_comp[set]>>>(jin, 1);
+      h->launches += 1;
+    }
     if (run_tile(h, set, di, dout, nt, nlev, h->s_comp[set], &h->ev[t * 2 * N_STAGE])) { drain(h); return 1; }
+    if (sp) {
+      if (c.do_clouds && ip[17]) {   // the cropped cloud fraction goes back as float through the input's float staging buffer
+        jout.j[jout.n++] = {ip[17], s.in32[17].p, (long long)cap * nlev};
+        if ((long long)cap * nlev > cvt_out_max) cvt_out_max = (long long)cap * nlev;
+      }
+      if (jout.n) {
+        convert_kernel<<<dim3((unsigned)((cvt_out_max + 1023) / 1024 > 592 ? 592 : (cvt_out_max + 1023) / 1024), jout.n), 256, 0, h->s_comp[set]>>>(jout, 0);
+        h->launches += 1;
+      }
+    }
     CKD(h, cudaEventRecord(s.compute_done, h->s_comp[set]));
     // ---- D2H ----
     CKD(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
     for (int k = 0; k < N_OUT; ++k) {
       if (!op[k]) continue;
+      const char* src = (const char*)(sp ? s.out32[k].p : op[k]);
+      char* hst = (char*)od[k].host;
       if (od[k].kind == 0)
-        CKD(h, cudaMemcpy2DAsync(od[k].host + c0, 8 * (size_t)ncol, op[k], 8 * (size_t)cap, 8 * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+        CKD(h, cudaMemcpy2DAsync(hst + rb * c0, rb * (size_t)ncol, src, rb * (size_t)cap, rb * (size_t)nt, od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
       else if (od[k].kind == 1)
-        CKD(h, cudaMemcpyAsync(od[k].host + (size_t)c0 * od[k].rows, op[k], 8 * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
+        CKD(h, cudaMemcpyAsync(hst + rb * (size_t)c0 * od[k].rows, src, rb * (size_t)nt * od[k].rows, cudaMemcpyDeviceToHost, h->s_d2h));
       else   // (nband, ncol, nlev+1): row = half-level, nt*nband contiguous values per row
-        CKD(h, cudaMemcpy2DAsync(od[k].host + (size_t)c0 * od[k].rows, 8 * (size_t)ncol * od[k].rows, op[k], 8 * (size_t)cap * od[k].rows,
-                                8 * (size_t)nt * od[k].rows, nlev + 1, cudaMemcpyDeviceToHost, h->s_d2h));
+        CKD(h, cudaMemcpy2DAsync(hst + rb * (size_t)c0 * od[k].rows, rb * (size_t)ncol * od[k].rows, src, rb * (size_t)cap * od[k].rows,
+                                rb * (size_t)nt * od[k].rows, nlev + 1, cudaMemcpyDeviceToHost, h->s_d2h));
     }
     if (c.do_clouds && ip[17])   // cropped cloud fraction back into the caller's array (cloud%crop_cloud_fraction)
-      CKD(h, cudaMemcpy2DAsync(in->cloud_fraction + c0, 8 * (size_t)ncol, ip[17], 8 * (size_t)cap, 8 * (size_t)nt, nlev, cudaMemcpyDeviceToHost, h->s_d2h));
+      CKD(h, cudaMemcpy2DAsync((char*)in->cloud_fraction + rb * c0, rb * (size_t)ncol, sp ? s.in32[17].p : ip[17], rb * (size_t)cap, rb * (size_t)nt, nlev,
+                              cudaMemcpyDeviceToHost, h->s_d2h));
     CKD(h, cudaEventRecord(s.d2h_done, h->s_d2h));
     s.used = true;
   }

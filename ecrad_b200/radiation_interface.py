@@ -26,7 +26,7 @@ EXPORTS = [
     "ecrad_b200_setup", "ecrad_b200_set_option", "ecrad_b200_radiation", "ecrad_b200_radiation_device", "ecrad_b200_radiation_device_ld",
     "ecrad_b200_kernel_launches",
     "ecrad_b200_last_stage_ms", "ecrad_b200_stage_name", "ecrad_b200_finalize", "ecrad_b200_last_error",
-    "ecrad_b200_version", "ecrad_b200_measure_fp64", "ecrad_b200_radiation_blocked",
+    "ecrad_b200_version", "ecrad_b200_measure_fp64", "ecrad_b200_radiation_blocked", "ecrad_b200_radiation_sp",
 ]
 
 _lib = None
@@ -51,6 +51,7 @@ def load_library():
     L.ecrad_b200_tables_free.argtypes = [C.c_void_p]
     L.ecrad_b200_setup.argtypes = [C.POINTER(abi.Config), C.c_void_p, C.POINTER(C.c_void_p)]
     L.ecrad_b200_radiation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
+    L.ecrad_b200_radiation_sp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs)]
     L.ecrad_b200_radiation_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
     L.ecrad_b200_radiation_device_ld.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
     L.ecrad_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -124,6 +125,36 @@ class RadiationHandle:
             outs, ost = outputs
         rc = self.lib.ecrad_b200_radiation(self.h, ncol, nlev, istartcol, iendcol, C.byref(ist), C.byref(ost))
         if rc:
+            raise RadiationError(self._err())
+        outs["cloud_fraction"] = keep.get("cloud_fraction")
+        return outs
+
+    def radiation_sp(self, inputs, ncol, nlev, istartcol=1, iendcol=None, spectral_profiles=False):
+        """The call a single-precision host makes (ecrad_b200_radiation_sp): every real array is float32 on the host side.  Returns the
+        flux dict as float32 arrays (plus the cropped float32 cloud_fraction)."""
+        iendcol = ncol if iendcol is None else iendcol
+        st = abi.Inputs()
+        st.struct_bytes = C.sizeof(abi.Inputs)
+        st.solar_irradiance = float(inputs["solar_irradiance"])
+        keep = {}
+        for nm, dt, _ in abi.INPUT_ARRAYS:
+            a = inputs.get(nm)
+            if a is None:
+                continue
+            a = np.asfortranarray(a, dtype=np.int32 if dt == "i4" else np.float32)
+            keep[nm] = a
+            setattr(st, nm, C.cast(a.ctypes.data, abi.c_ip if dt == "i4" else abi.c_dp))
+        outs, ost = {}, abi.Outputs()
+        ost.struct_bytes = C.sizeof(abi.Outputs)
+        for nm, kind in abi.OUTPUT_ARRAYS:
+            if kind in ("pl", "ps") and not spectral_profiles:
+                continue
+            a = np.full(abi.output_shape(kind, ncol, nlev, self.cfg), np.nan, dtype=np.float32, order="F")
+            if nm.startswith("cloud_cover"):
+                a[...] = -1.0
+            outs[nm] = a
+            setattr(ost, nm, C.cast(a.ctypes.data, abi.c_dp))
+        if self.lib.ecrad_b200_radiation_sp(self.h, ncol, nlev, istartcol, iendcol, C.byref(st), C.byref(ost)):
             raise RadiationError(self._err())
         outs["cloud_fraction"] = keep.get("cloud_fraction")
         return outs

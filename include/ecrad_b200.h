@@ -169,6 +169,14 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
 int ecrad_b200_radiation(void* handle, int ncol, int nlev, int istartcol, int iendcol,
                          const ecrad_b200_inputs* in, ecrad_b200_outputs* out);
 
+/* Single-precision boundary for hosts built with JPRB = JPRM (ifsaux/parkind1.F90:40-49): the same structs, but every `double*`
+ * member points to FLOAT data (iseed stays int32, solar_irradiance a double scalar).  The arrays cross PCIe as float (half the
+ * bytes), are widened on the device, and the kernels compute in double precision exactly as for ecrad_b200_radiation; the outputs
+ * are rounded to float on the device.  Results therefore equal the double-precision path rounded to float (within the 1e-3 W m-2
+ * of the single-precision target by construction); a single-precision COMPUTE path does not exist. */
+int ecrad_b200_radiation_sp(void* handle, int ncol, int nlev, int istartcol, int iendcol,
+                            const ecrad_b200_inputs* in, ecrad_b200_outputs* out);
+
 /* Device-resident entry: every pointer in `in`/`out` is a DEVICE pointer with leading dimension `ncol`,
  * all ncol columns are processed, work is enqueued on `cuda_stream` (a cudaStream_t) and not synchronised. */
 int ecrad_b200_radiation_device(void* handle, int ncol, int nlev,

@@ -659,3 +659,34 @@ def test_lw_aerosol_scattering(handles, meridian_raw, kw):
         out0 = h0.radiation(I.to_radiation_inputs(raw, cfg0), n, NLEV)
         d = np.abs(out["lw_up"] - out0["lw_up"]).max()
         assert 1e-3 < d < 5.0, d
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", do_save_spectral_flux=True)])
+def test_single_precision_boundary(handles, meridian_raw, golden_noaer, kw):
+    """ecrad_b200_radiation_sp: the call of a host built with JPRB = JPRM -- float arrays in, float arrays out, double-precision kernels
+    in between.  Gate of BASELINE.json's north_star for single precision: 1e-3 W m-2 against the double-precision result (the
+    differences are the rounding of the derived inputs -- mass mixing ratios, saturation -- to float on the way in and of the fluxes on
+    the way out)."""
+    h, _, cfg = handles(**kw)
+    sp = bool(kw.get("do_save_spectral_flux"))
+    n = 32
+    d = h.radiation(I.to_radiation_inputs(meridian_raw, cfg), n, NLEV, spectral_profiles=sp)
+    s = h.radiation_sp(I.to_radiation_inputs(meridian_raw, cfg), n, NLEV, spectral_profiles=sp)
+    for nm in FLUXES + OTHERS + (BANDS if sp else []):
+        assert s[nm].dtype == np.float32
+        m = np.isfinite(d[nm])
+        assert np.isfinite(s[nm][m]).all(), nm
+        assert np.abs(s[nm][m].astype(np.float64) - d[nm][m]).max() <= 1e-3, nm
+    assert np.array_equal(s["cloud_fraction"], d["cloud_fraction"].astype(np.float32))
+    assert np.array_equal(s["cloud_cover_sw"], d["cloud_cover_sw"].astype(np.float32))
+    if not kw:   # and the reference's own (float32) golden output
+        assert np.abs(s["sw_dn"].astype(np.float64) - golden_noaer["flux_dn_sw"]).max() <= 1e-3
+    # synthetic columns (inputs rounded to float on the way in) and tiling: still within the single-precision gate of the fp64 run
+    n = 700
+    raw = I.synthetic_columns(meridian_raw, n)
+    d = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    s = h.radiation_sp(I.to_radiation_inputs(raw, cfg), n, NLEV, istartcol=3, iendcol=690)
+    for nm in FLUXES:
+        assert np.isnan(s[nm][:2]).all() and np.isnan(s[nm][690:]).all(), nm
+        err = np.abs(s[nm][2:690].astype(np.float64) - d[nm][2:690]).max()
+        assert err <= 2e-3, (nm, err)   # input rounding (temperature to 2e-5 K) + output rounding (6e-5 W m-2 at 1000 W m-2)

@@ -190,7 +190,9 @@ def main():
     w("! Call sites (two lines in radiation/radiation_interface.F90, see INTEGRATION.md):")
     w("!   end of setup_radiation (:153)            call b200_setup(config)")
     w("!   start of the else branch of radiation (:318)   if (b200_active) then; call b200_radiation(<the arguments of radiation>); else <existing body> end if")
-    w("! Double-precision build only (JPRB = JPRD): the C-ABI takes real(c_double) arrays by pointer, nothing is copied on the host.")
+    w("! The caller's arrays are handed over by pointer, nothing is copied on the host: double-precision builds (JPRB = JPRD) call")
+    w("! ecrad_b200_radiation, single-precision builds (-DPARKIND1_SINGLE, ifsaux/parkind1.F90:46-50) call ecrad_b200_radiation_sp, which takes")
+    w("! the same structs with float arrays behind the pointers (widened on the device; the kernels compute in double precision).")
     w("module radiation_b200")
     w("  use, intrinsic :: iso_c_binding")
     w("  use parkind1, only : jprb, jpim")
@@ -231,6 +233,10 @@ def main():
     w("      import; type(cfg_t) :: cfg; type(c_ptr), value :: tab; type(c_ptr) :: h; integer(c_int) :: rc")
     w("    end function")
     w("    function ecrad_b200_radiation(h, ncol, nlev, istartcol, iendcol, inp, outp) bind(c) result(rc)")
+    w("      import; type(c_ptr), value :: h; integer(c_int), value :: ncol, nlev, istartcol, iendcol")
+    w("      type(in_t) :: inp; type(out_t) :: outp; integer(c_int) :: rc")
+    w("    end function")
+    w("    function ecrad_b200_radiation_sp(h, ncol, nlev, istartcol, iendcol, inp, outp) bind(c) result(rc)")
     w("      import; type(c_ptr), value :: h; integer(c_int), value :: ncol, nlev, istartcol, iendcol")
     w("      type(in_t) :: inp; type(out_t) :: outp; integer(c_int) :: rc")
     w("    end function")
@@ -432,8 +438,13 @@ def main():
             continue
         k += 1
         w(f"    if (allocated(flux%{f})) o%p({k}) = c_loc(flux%{f})")
+    w("#ifdef PARKIND1_SINGLE")
+    w("    if (ecrad_b200_radiation_sp(handle, int(ncol, c_int), int(nlev, c_int), int(istartcol, c_int), int(iendcol, c_int), i, o) /= 0) &")
+    w("         &  call abort_with(ecrad_b200_last_error(handle))")
+    w("#else")
     w("    if (ecrad_b200_radiation(handle, int(ncol, c_int), int(nlev, c_int), int(istartcol, c_int), int(iendcol, c_int), i, o) /= 0) &")
     w("         &  call abort_with(ecrad_b200_last_error(handle))")
+    w("#endif")
     w("  end subroutine")
     w("")
     w("  subroutine b200_set_option(key, val)          ! e.g. call b200_set_option('register_host', 1): page-lock the caller's arrays once")
