@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-sweep", default="", help="tuning aid: 'tile:edge:ramp,...' host-entry tile schedules timed after the e2e measurement (key e2e.sweep)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +321,20 @@ def main():
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e_value = world * ncol / e2e_s
     clocks = sampler.stop()
+
+    if args.e2e_sweep and world == 1:   # tuning aid: the host entry's tile schedule (tile_cols : edge_cols : ramp)
+        sweep = {}
+        for spec in args.e2e_sweep.split(","):
+            tile, edge, ramp = (int(x) for x in spec.split(":"))
+            h.set_option("tile_cols", tile); h.set_option("edge_cols", edge); h.set_option("tile_ramp", ramp)
+            for _ in range(2):
+                step_host()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_host()
+            sweep[spec] = round(ncol / ((time.perf_counter() - t0) / args.steps))
+        print("e2e sweep (columns/s):", json.dumps(sweep), file=sys.stderr)
+        raise SystemExit(0)
 
     # What an unmodified Fortran host passes: ordinary (pageable) allocatables.  Same call, same arrays, copied out of pinned memory
     # into plain numpy arrays: (a) as they are -- cudaMemcpy2DAsync from pageable memory is staged by the driver and serialises with

@@ -12,8 +12,10 @@ c_ip = C.POINTER(C.c_int32)
 SOLVER = {"cloudless": 0, "homogeneous": 1, "mcica": 2, "spartacus": 3, "tripleclouds": 4}
 GAS_MODEL = {"monochromatic": 0, "rrtmg-ifs": 1, "ecckd": 2}
 OVERLAP = {"max-ran": 0, "exp-ran": 1, "exp-exp": 2}
-LIQ_MODEL = {"socrates": 1}
-ICE_MODEL = {"fu-ifs": 1}
+# liquid_model_name / ice_model_name (radiation_config.F90:108-133); Jahangir and Nielsen are in the reference's enumeration but
+# radiation_cloud_optics.F90:345-372 aborts on them, so they are not offered here either
+LIQ_MODEL = {"socrates": 1, "slingo": 2}
+ICE_MODEL = {"fu-ifs": 1, "baran-experimental": 2, "baran2016": 3, "baran2017-experimental": 4, "yi": 5}
 # sw_entrapment_name (radiation_config.F90:69-84)
 PDF_SHAPE = {"lognormal": 0, "gamma": 1}   # cloud_pdf_shape_name (radiation_config.F90:134-142)
 ENTRAPMENT = {"zero": 0, "edge-only": 1, "explicit": 2, "non-fractal": 3, "maximum": 4}

@@ -51,6 +51,8 @@ struct Handle {
   int device = 0;
   int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
   int edge_cols = 1024;          // host entry: at most this many columns in the first and the last tile
+  bool edge_explicit = false;    // edge_cols was set through set_option: not capped at tile_cols / 4
+  int tile_ramp = 0;             // host entry: 1 = tiles double from the edge size up to tile_cols (and halve again at the end)
   int tile_cols_device = 16384;  // device entry: only bounds the scratch (about 3 MB per column); bigger tiles = fewer partial waves
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   // Two compute sets (scratch + three streams + fork/join events): consecutive tiles of the host entry alternate between them,
@@ -167,7 +169,9 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
   if (gm == ECRAD_GAS_IFSRRTMG) {
-    if (c.i_liq_model != ECRAD_LIQ_SOCRATES || c.i_ice_model != ECRAD_ICE_FU) return fail(h, "cloud optics model not available (SOCRATES + Fu-IFS are)");
+    // radiation_cloud_optics.F90:345-372 dispatches SOCRATES and Slingo only; the five ice models of :376-447
+    if (c.i_liq_model != ECRAD_LIQ_SOCRATES && c.i_liq_model != ECRAD_LIQ_SLINGO) return fail(h, "liquid optics model not available (SOCRATES and Slingo are)");
+    if (c.i_ice_model < ECRAD_ICE_FU || c.i_ice_model > ECRAD_ICE_YI) return fail(h, "ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
     if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
   } else {
     // generalised cloud + aerosol optics per g-point (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points
@@ -532,7 +536,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   h->cfg = *cfg;
   if (check_config(h, *cfg)) { delete h; return 1; }
   PackedTables P;
-  try { pack_tables(*tab, P); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
+  try { pack_tables(*tab, P, cfg->i_liq_model, cfg->i_ice_model); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
   if (P.is_ecckd != (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD)) {
     fail(nullptr, "the table directory holds %s tables but the configuration asks for the other gas model", P.is_ecckd ? "ecCKD" : "RRTMG"); delete h; return 1;
   }
@@ -619,10 +623,10 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.sp.min_cloud_effective_size = cfg->min_cloud_effective_size; d.sp.overhead_sun_factor = cfg->overhead_sun_factor;
   d.sp.overhang_factor = cfg->overhang_factor; d.sp.clear_to_thick_fraction = cfg->clear_to_thick_fraction;
   {
-    // host-entry tile (measured, two overlapping compute sets): 2048 columns for the RRTMG-sized spectra, 4096 for the ecCKD
-    // ones (less work per column; their end-to-end time is PCIe-bound and wants more, not bigger, tiles); short first/last tiles
-    const int ngs = (cfg->do_lw ? cfg->n_g_lw : 0) + (cfg->do_sw ? cfg->n_g_sw : 0);
-    int t = ngs >= 200 ? 2048 : 4096;
+    // host-entry tile (measured, two overlapping compute sets; round 2 sweep in DESIGN.md section 4c): 4096 columns, first and
+    // last tile 1024 (10 000 columns: 1024 + 3 x 2651 + 1024).  Smaller tiles lose to partial waves of the 128-column gas blocks,
+    // bigger ones expose the first tile's H2D and the last tile's D2H.
+    int t = 4096;
     // SPARTACUS keeps 3x3 matrices per (layer, g-point) between its kernels: about 5x the scratch per column
     if ((cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS)) t /= 4;
     h->tile_cols = t; h->edge_cols = t / 4;
@@ -712,6 +716,8 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   if (!strcmp(key, "scan_solvers")) { h->scan_solvers = value != 0; return 0; }
   if (!strcmp(key, "gas_variant")) { h->gas_variant = value & 3; return 0; }
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
+  if (!strcmp(key, "edge_cols")) { if (value < 1) return fail(h, "edge_cols must be positive"); h->edge_cols = value; h->edge_explicit = true; return 0; }
+  if (!strcmp(key, "tile_ramp")) { h->tile_ramp = value != 0; return 0; }
   if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);
 }
@@ -747,14 +753,22 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
   // edge tiles are short (a quarter of tile_cols); the columns in between are split into equal tiles of at most tile_cols.
   std::vector<int> tile_first, tile_n;
   {
-    const int edge = h->tile_cols / 4 < h->edge_cols ? h->tile_cols / 4 : h->edge_cols;
+    const int edge_max = h->edge_explicit ? h->tile_cols : h->tile_cols / 4;
+    const int edge = edge_max < h->edge_cols ? edge_max : h->edge_cols;
     int pos = 0;
     auto push = [&](int n) { tile_first.push_back(pos); tile_n.push_back(n); pos += n; };
-    if (edge >= 64 && ntot >= 2 * edge + h->tile_cols / 2) {
-      push(edge);
-      const int rest = ntot - 2 * edge, k = (rest + h->tile_cols - 1) / h->tile_cols;
+    std::vector<int> ramp;   // sizes of the growing tiles at the start (mirrored at the end)
+    if (edge >= 64) {
+      ramp.push_back(edge);
+      if (h->tile_ramp) for (int e = 2 * edge; e < h->tile_cols; e *= 2) ramp.push_back(e);
+    }
+    int nramp = 0;
+    for (int e : ramp) nramp += e;
+    if (!ramp.empty() && ntot >= 2 * nramp + h->tile_cols / 2) {
+      for (size_t i = 0; i < ramp.size(); ++i) push(ramp[i]);
+      const int rest = ntot - 2 * nramp, k = (rest + h->tile_cols - 1) / h->tile_cols;
       for (int i = 0; i < k; ++i) push(rest / k + (i < rest % k ? 1 : 0));
-      push(edge);
+      for (size_t i = ramp.size(); i-- > 0;) push(ramp[i]);
     } else {
       const int k = (ntot + h->tile_cols - 1) / h->tile_cols;
       for (int i = 0; i < k; ++i) push(ntot / k + (i < ntot % k ? 1 : 0));

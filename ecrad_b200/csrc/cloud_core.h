@@ -1,7 +1,10 @@
-// cloud_core.h -- cloud optics (SOCRATES liquid + Fu ice) and the McICA stochastic cloud generator.
+// cloud_core.h -- cloud optics (liquid: SOCRATES, Slingo / Lindner-Li; ice: Fu, Baran, Baran-2016, Baran-2017, Yi) and the McICA
+// stochastic cloud generator.
 //
 // Reference map:  cloud_optics_layer <- radiation/radiation_cloud_optics.F90:218-523,
-//                                       radiation_liquid_optics_socrates.F90:40-80, radiation_ice_optics_fu.F90:42-138,
+//                                       radiation_liquid_optics_socrates.F90:40-80, radiation_liquid_optics_slingo.F90:29-106,
+//                                       radiation_ice_optics_fu.F90:42-138, radiation_ice_optics_baran.F90:34-108,
+//                                       radiation_ice_optics_baran2017.F90:32-68, radiation_ice_optics_yi.F90:37-145,
 //                                       radiation_delta_eddington.h:103-119
 //                 RngMix             <- utilities/radiation_random_numbers_mix.F90:142-309 (30-bit lagged Fibonacci)
 //                 cum_cloud_cover_*  <- radiation/radiation_cloud_cover.F90:169-300
@@ -17,9 +20,15 @@
 
 namespace ecb {
 
+enum { LIQ_SOCRATES = 1, LIQ_SLINGO = 2 };                                       // config%i_liq_model (radiation_config.F90:108-112)
+enum { ICE_FU = 1, ICE_BARAN = 2, ICE_BARAN2016 = 3, ICE_BARAN2017 = 4, ICE_YI = 5 };   // config%i_ice_model (:123-127)
+enum { ICE_MAX_COEFF = 69 };                                                     // Yi: 3 x 23 look-up entries per band
+
 struct CloudMeta {
-  double liq_lw[16 * 16], liq_sw[14 * 16];  // (nb, 16) Fortran order: coeff(jb,k) at [(k-1)*nb + jb]
-  double ice_lw[16 * 11], ice_sw[14 * 10];
+  double liq_lw[16 * 16], liq_sw[14 * 16];  // (nb, ncoeff <= 16) Fortran order: coeff(jb,k) at [(k-1)*nb + jb]
+  double ice_lw[16 * ICE_MAX_COEFF], ice_sw[14 * ICE_MAX_COEFF];
+  double ice_gen[5];                        // Baran-2017: coeff_gen
+  int liq_model, ice_model;
   int pdf_ncdf, pdf_nfsd;
   double pdf_fsd1, pdf_inv_fsd_interval;
   // decoding of the generator's code words into uniform deviates: (code & gen_mask) * gen_scale
@@ -72,6 +81,62 @@ HD void ice_fu_lw(const double* c, int nb, int jb, double iwp, double re, double
   scat = od - iwp_gm_2 * inv_de_um * (ECB_CO(c, nb, jb, 4) + de_um * (ECB_CO(c, nb, jb, 5) + de_um * (ECB_CO(c, nb, jb, 6) + de_um * ECB_CO(c, nb, jb, 7))));
   g = dmin(ECB_CO(c, nb, jb, 8) + de_um * (ECB_CO(c, nb, jb, 9) + de_um * (ECB_CO(c, nb, jb, 10) + de_um * ECB_CO(c, nb, jb, 11))), MaxG);
 }
+// radiation_liquid_optics_slingo.F90:29-63 (Slingo 1989, shortwave) and :69-106 (Lindner & Li 2000, longwave)
+HD void liq_slingo_sw(const double* c, int nb, int jb, double lwp, double re, double& od, double& scat, double& g) {
+  const double lwp_gm_2 = lwp * 1000.0;
+  const double re_um = dmin(dmax(4.2, re * 1.0e6), 16.6);
+  const double inv_re_um = 1.0 / re_um;
+  od = lwp_gm_2 * (ECB_CO(c, nb, jb, 1) + inv_re_um * ECB_CO(c, nb, jb, 2));
+  scat = od * (1.0 - ECB_CO(c, nb, jb, 3) - re_um * ECB_CO(c, nb, jb, 4));
+  g = ECB_CO(c, nb, jb, 5) + re_um * ECB_CO(c, nb, jb, 6);
+}
+HD void liq_lindner_li_lw(const double* c, int nb, int jb, double lwp, double re, double& od, double& scat, double& g) {
+  const double lwp_gm_2 = lwp * 1000.0;
+  const double re_um = dmin(dmax(2.0, re * 1.0e6), 40.0);
+  const double inv_re_um = 1.0 / re_um;
+  od = lwp_gm_2 * (ECB_CO(c, nb, jb, 1) + re_um * ECB_CO(c, nb, jb, 2) +
+                   inv_re_um * (ECB_CO(c, nb, jb, 3) + inv_re_um * (ECB_CO(c, nb, jb, 4) + inv_re_um * ECB_CO(c, nb, jb, 5))));
+  scat = od * (1.0 - (ECB_CO(c, nb, jb, 6) + inv_re_um * ECB_CO(c, nb, jb, 7) + re_um * (ECB_CO(c, nb, jb, 8) + re_um * ECB_CO(c, nb, jb, 9))));
+  g = ECB_CO(c, nb, jb, 10) + inv_re_um * ECB_CO(c, nb, jb, 11) + re_um * (ECB_CO(c, nb, jb, 12) + re_um * ECB_CO(c, nb, jb, 13));
+}
+// radiation_ice_optics_baran.F90:34-60: functions of the ice mixing ratio qi (kg/kg)
+HD void ice_baran(const double* c, int nb, int jb, double iwp, double qi, double& od, double& scat, double& g) {
+  od = iwp * (ECB_CO(c, nb, jb, 1) + ECB_CO(c, nb, jb, 2) / (1.0 + qi * ECB_CO(c, nb, jb, 3)));
+  scat = od * (ECB_CO(c, nb, jb, 4) + ECB_CO(c, nb, jb, 5) / (1.0 + qi * ECB_CO(c, nb, jb, 6)));
+  g = ECB_CO(c, nb, jb, 7) + ECB_CO(c, nb, jb, 8) / (1.0 + qi * ECB_CO(c, nb, jb, 9));
+}
+// radiation_ice_optics_baran.F90:66-108 (Baran et al. 2016): functions of qi and the layer temperature
+HD void ice_baran2016(const double* c, int nb, int jb, double iwp, double qi, double temperature, double& od, double& scat, double& g) {
+  const double T2 = temperature * temperature;
+  const double qi_T = (qi < 1.0e-3 ? qi : 1.0e-3) * temperature;
+  const double qi_over_T4 = 1.0 / (T2 * T2);
+  od = iwp * ECB_CO(c, nb, jb, 1) * qi_over_T4;
+  scat = od * (ECB_CO(c, nb, jb, 2) + ECB_CO(c, nb, jb, 3) * qi_T);
+  g = ECB_CO(c, nb, jb, 4) + ECB_CO(c, nb, jb, 5) * qi_T;
+}
+// radiation_ice_optics_baran2017.F90:32-68
+HD void ice_baran2017(const double* cg, const double* c, int nb, int jb, double iwp, double qi, double temperature, double& od, double& scat, double& g) {
+  const double qi_mod = qi * exp(cg[0] * (temperature - cg[1]));
+  const double qi_mod_od = pow(qi_mod, cg[2]), qi_mod_ssa = pow(qi_mod, cg[3]), qi_mod_g = pow(qi_mod, cg[4]);
+  od = iwp * (ECB_CO(c, nb, jb, 1) + ECB_CO(c, nb, jb, 2) / (1.0 + qi_mod_od * ECB_CO(c, nb, jb, 3)));
+  scat = od * (ECB_CO(c, nb, jb, 4) + ECB_CO(c, nb, jb, 5) / (1.0 + qi_mod_ssa * ECB_CO(c, nb, jb, 6)));
+  g = ECB_CO(c, nb, jb, 7) + ECB_CO(c, nb, jb, 8) / (1.0 + qi_mod_g * ECB_CO(c, nb, jb, 9));
+}
+// radiation_ice_optics_yi.F90:37-89 / :95-145 (Yi et al. 2013): linear interpolation in a 23-entry look-up table over the effective
+// diameter (the shortwave and longwave routines are the same expression on their own coefficients)
+HD void ice_yi(const double* c, int nb, int jb, double iwp, double re, double& od, double& scat, double& g) {
+  const int NSingleCoeffs = 23;
+  const double lu_scale = 0.2, lu_offset = 1.0;
+  double de_um = re * 2.0e6;
+  de_um = dmax(de_um, 10.0);
+  de_um = dmin(de_um, 119.99);
+  const double iwp_gm_2 = iwp * 1000.0;
+  const int lu_idx = (int)floor(de_um * lu_scale - lu_offset);
+  const double wts_2 = (de_um * lu_scale - lu_offset) - lu_idx, wts_1 = 1.0 - wts_2;
+  od = 0.001 * iwp_gm_2 * (wts_1 * ECB_CO(c, nb, jb, lu_idx) + wts_2 * ECB_CO(c, nb, jb, lu_idx + 1));
+  scat = od * (wts_1 * ECB_CO(c, nb, jb, lu_idx + NSingleCoeffs) + wts_2 * ECB_CO(c, nb, jb, lu_idx + NSingleCoeffs + 1));
+  g = wts_1 * ECB_CO(c, nb, jb, lu_idx + 2 * NSingleCoeffs) + wts_2 * ECB_CO(c, nb, jb, lu_idx + 2 * NSingleCoeffs + 1);
+}
 HD void delta_eddington_scat_od(double& od, double& scat, double& g) {
   double f = g * g;
   od = od - scat * f;
@@ -79,12 +144,33 @@ HD void delta_eddington_scat_od(double& od, double& scat, double& g) {
   g = g / (1.0 + g);
 }
 
+// Cloud water of one layer as the parameterisations need it: in-cloud water paths (kg m-2), effective radii (m), ice mixing
+// ratio (kg/kg) and layer-mean temperature (K; radiation_cloud_optics.F90:397-398)
+struct CloudLayerIn { double lwp, iwp, re_liq, re_ice, q_ice, temperature; };
+
+HD void liquid_band(const CloudMeta& C, bool sw, int nb, int jb, const CloudLayerIn& L, double& od, double& scat, double& g) {
+  const double* c = sw ? C.liq_sw : C.liq_lw;
+  if (C.liq_model == LIQ_SLINGO) { if (sw) liq_slingo_sw(c, nb, jb, L.lwp, L.re_liq, od, scat, g); else liq_lindner_li_lw(c, nb, jb, L.lwp, L.re_liq, od, scat, g); }
+  else liq_socrates(c, nb, jb, L.lwp, L.re_liq, od, scat, g);
+}
+HD void ice_band(const CloudMeta& C, bool sw, int nb, int jb, const CloudLayerIn& L, bool fu_lw_bug, double& od, double& scat, double& g) {
+  const double* c = sw ? C.ice_sw : C.ice_lw;
+  switch (C.ice_model) {
+    case ICE_BARAN: ice_baran(c, nb, jb, L.iwp, L.q_ice, od, scat, g); break;
+    case ICE_BARAN2016: ice_baran2016(c, nb, jb, L.iwp, L.q_ice, L.temperature, od, scat, g); break;
+    case ICE_BARAN2017: ice_baran2017(C.ice_gen, c, nb, jb, L.iwp, L.q_ice, L.temperature, od, scat, g); break;
+    case ICE_YI: ice_yi(c, nb, jb, L.iwp, L.re_ice, od, scat, g); break;
+    default:
+      if (sw) ice_fu_sw(c, nb, jb, L.iwp, L.re_ice, od, scat, g);
+      else { ice_fu_lw(c, nb, jb, L.iwp, L.re_ice, od, scat, g); if (fu_lw_bug) scat = od - scat; }
+  }
+}
+
 // SW band jb of a cloudy layer (frac > 0): radiation_cloud_optics.F90:325-514
-HD CloudBandOut cloud_optics_sw(const CloudMeta& C, int jb, double lwp, double iwp, double re_liq, double re_ice,
-                                bool delta_scaling_with_gases) {
+HD CloudBandOut cloud_optics_sw(const CloudMeta& C, int jb, const CloudLayerIn& L, bool delta_scaling_with_gases) {
   double odl = 0, scl = 0, gl = 0, odi = 0, sci = 0, gi = 0;
-  if (lwp > 0.0) { liq_socrates(C.liq_sw, 14, jb, lwp, re_liq, odl, scl, gl); if (!delta_scaling_with_gases) delta_eddington_scat_od(odl, scl, gl); }
-  if (iwp > 0.0) { ice_fu_sw(C.ice_sw, 14, jb, iwp, re_ice, odi, sci, gi); if (!delta_scaling_with_gases) delta_eddington_scat_od(odi, sci, gi); }
+  if (L.lwp > 0.0) { liquid_band(C, true, 14, jb, L, odl, scl, gl); if (!delta_scaling_with_gases) delta_eddington_scat_od(odl, scl, gl); }
+  if (L.iwp > 0.0) { ice_band(C, true, 14, jb, L, false, odi, sci, gi); if (!delta_scaling_with_gases) delta_eddington_scat_od(odi, sci, gi); }
   CloudBandOut o;
   o.od = odl + odi;
   o.g = (gl * scl + gi * sci) / (scl + sci);
@@ -92,13 +178,11 @@ HD CloudBandOut cloud_optics_sw(const CloudMeta& C, int jb, double lwp, double i
   return o;
 }
 // LW band jb of a cloudy layer
-HD CloudBandOut cloud_optics_lw(const CloudMeta& C, int jb, double lwp, double iwp, double re_liq, double re_ice,
-                                bool lw_cloud_scattering, bool fu_lw_bug) {
+HD CloudBandOut cloud_optics_lw(const CloudMeta& C, int jb, const CloudLayerIn& L, bool lw_cloud_scattering, bool fu_lw_bug) {
   double odl = 0, scl = 0, gl = 0, odi = 0, sci = 0, gi = 0;
-  if (lwp > 0.0) liq_socrates(C.liq_lw, 16, jb, lwp, re_liq, odl, scl, gl);
-  if (iwp > 0.0) {
-    ice_fu_lw(C.ice_lw, 16, jb, iwp, re_ice, odi, sci, gi);
-    if (fu_lw_bug) sci = odi - sci;
+  if (L.lwp > 0.0) liquid_band(C, false, 16, jb, L, odl, scl, gl);
+  if (L.iwp > 0.0) {
+    ice_band(C, false, 16, jb, L, fu_lw_bug, odi, sci, gi);
     delta_eddington_scat_od(odi, sci, gi);
   }
   CloudBandOut o;

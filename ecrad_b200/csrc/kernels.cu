@@ -440,19 +440,22 @@ __global__ void cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, i
   // config%is_homogeneous (radiation_cloud_optics.F90:318-327): gridbox-mean water path for the Homogeneous solvers
   const double factor = cfg.is_homogeneous ? (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / 9.80665
                                            : (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) / (9.80665 * frac);
-  const double lwp = factor * LD_IN(in.q_liq, c, l), iwp = factor * LD_IN(in.q_ice, c, l);
-  const double rel = LD_IN(in.re_liq, c, l), rei = LD_IN(in.re_ice, c, l);
+  CloudLayerIn L;
+  L.q_ice = LD_IN(in.q_ice, c, l);
+  L.lwp = factor * LD_IN(in.q_liq, c, l); L.iwp = factor * L.q_ice;
+  L.re_liq = LD_IN(in.re_liq, c, l); L.re_ice = LD_IN(in.re_ice, c, l);
+  L.temperature = 0.5 * (LD_IN(in.t_hl, c, l) + LD_IN(in.t_hl, c, l + 1));
   if (cfg.do_lw) {
     double* o = w.cl_lw + ((size_t)c * nlev + l) * 3 * NB_LW;
     for (int b = 0; b < NB_LW; ++b) {
-      CloudBandOut r = cloud_optics_lw(C, b, lwp, iwp, rel, rei, cfg.do_lw_cloud_scattering != 0, cfg.do_fu_lw_ice_optics_bug != 0);
+      CloudBandOut r = cloud_optics_lw(C, b, L, cfg.do_lw_cloud_scattering != 0, cfg.do_fu_lw_ice_optics_bug != 0);
       o[b] = r.od; o[NB_LW + b] = r.ssa; o[2 * NB_LW + b] = r.g;
     }
   }
   if (cfg.do_sw) {
     double* o = w.cl_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
     for (int b = 0; b < NB_SW; ++b) {
-      CloudBandOut r = cloud_optics_sw(C, b, lwp, iwp, rel, rei, cfg.do_sw_delta_scaling_with_gases != 0);
+      CloudBandOut r = cloud_optics_sw(C, b, L, cfg.do_sw_delta_scaling_with_gases != 0);
       o[b] = r.od; o[NB_SW + b] = r.ssa; o[2 * NB_SW + b] = r.g;
     }
   }

@@ -198,7 +198,8 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
   pack_common(T, P);
 }
 
-inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
+// liq_model / ice_model: config%i_liq_model / i_ice_model (RRTMG-band cloud optics; ignored by the ecCKD tables)
+inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_model = LIQ_SOCRATES, int ice_model = ICE_FU) {
   if (T.find("ckd_lw_meta")) { pack_ecckd(T, P); return; }
   GasMeta& M = P.meta;
   memset(&M, 0, sizeof(M));
@@ -331,8 +332,31 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P) {
   // ---- cloud optics coefficients, PDF look-up table, surface mappings ----
   CloudMeta& C = P.cloud;
   memset(&C, 0, sizeof(C));
-  copy(C.liq_lw, "liq_coeff_lw", 16 * 16); copy(C.liq_sw, "liq_coeff_sw", 14 * 16);
-  copy(C.ice_lw, "ice_coeff_lw", 16 * 11); copy(C.ice_sw, "ice_coeff_sw", 14 * 10);
+  // Coefficients of the configured parameterisations (radiation_cloud_optics.F90:46-216 checks the same coefficient counts).  A host
+  // model registers what it loaded as liq_coeff_* / ice_coeff_* (/ ice_coeff_gen); the stand-alone blob also holds the files of the
+  // other parameterisations under "<name>.<model>".
+  {
+    static const char* liq_tag[] = {"", "", "slingo"};
+    static const int liq_n[][2] = {{0, 0}, {16, 16}, {13, 6}};                       // coefficients per band: longwave, shortwave
+    static const char* ice_tag[] = {"", "", "baran", "baran2016", "baran2017", "yi"};
+    static const int ice_n[][2] = {{0, 0}, {11, 10}, {9, 9}, {5, 5}, {9, 9}, {69, 69}};
+    if (liq_model < LIQ_SOCRATES || liq_model > LIQ_SLINGO) throw std::runtime_error("liquid optics model not available (SOCRATES and Slingo are)");
+    if (ice_model < ICE_FU || ice_model > ICE_YI) throw std::runtime_error("ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
+    auto pick = [&](double* dst, const char* base, const char* tag, int nb, int ncoef) {
+      const std::string tagged = std::string(base) + "." + tag;
+      const std::string name = (tag[0] && T.find(tagged)) ? tagged : std::string(base);
+      const auto& x = T.req(name);
+      if (x.dtype != 0 || x.data.size() != (size_t)nb * ncoef * 8)
+        throw std::runtime_error(name + ": not the (" + std::to_string(nb) + ", " + std::to_string(ncoef) + ") coefficient array of the configured cloud optics model");
+      memcpy(dst, x.data.data(), x.data.size());
+    };
+    pick(C.liq_lw, "liq_coeff_lw", liq_tag[liq_model], 16, liq_n[liq_model][0]);
+    pick(C.liq_sw, "liq_coeff_sw", liq_tag[liq_model], 14, liq_n[liq_model][1]);
+    pick(C.ice_lw, "ice_coeff_lw", ice_tag[ice_model], 16, ice_n[ice_model][0]);
+    pick(C.ice_sw, "ice_coeff_sw", ice_tag[ice_model], 14, ice_n[ice_model][1]);
+    if (ice_model == ICE_BARAN2017) pick(C.ice_gen, "ice_coeff_gen", ice_tag[ice_model], 5, 1);
+    C.liq_model = liq_model; C.ice_model = ice_model;
+  }
   pack_common(T, P);
 }
 

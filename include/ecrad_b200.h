@@ -31,8 +31,10 @@ enum { ECRAD_SOLVER_CLOUDLESS = 0, ECRAD_SOLVER_HOMOGENEOUS = 1, ECRAD_SOLVER_MC
        ECRAD_SOLVER_SPARTACUS = 3, ECRAD_SOLVER_TRIPLECLOUDS = 4 };        /* radiation_config.F90:51-54   */
 enum { ECRAD_GAS_MONOCHROMATIC = 0, ECRAD_GAS_IFSRRTMG = 1, ECRAD_GAS_ECCKD = 2 }; /* radiation_config.F90:86-88 */
 enum { ECRAD_OVERLAP_MAX_RAN = 0, ECRAD_OVERLAP_EXP_RAN = 1, ECRAD_OVERLAP_EXP_EXP = 2 }; /* radiation_cloud_cover.F90:30-33 */
-enum { ECRAD_LIQ_SOCRATES = 1 };                                          /* radiation_config.F90:95-99  */
-enum { ECRAD_ICE_FU = 1 };                                                /* radiation_config.F90:107-111 */
+enum { ECRAD_LIQ_SOCRATES = 1, ECRAD_LIQ_SLINGO = 2 };                    /* radiation_config.F90:108-112 (Jahangir = 3 and Nielsen = 4
+                                                                             are not dispatched by radiation_cloud_optics.F90 either) */
+enum { ECRAD_ICE_FU = 1, ECRAD_ICE_BARAN = 2, ECRAD_ICE_BARAN2016 = 3,
+       ECRAD_ICE_BARAN2017 = 4, ECRAD_ICE_YI = 5 };                       /* radiation_config.F90:123-127 */
 enum { ECRAD_PDF_LOGNORMAL = 0, ECRAD_PDF_GAMMA = 1 };                    /* radiation_config.F90:134-138 */
 /* SPARTACUS shortwave entrapment, config%i_3d_sw_entrapment (radiation_config.F90:69-77) */
 enum { ECRAD_ENTRAPMENT_ZERO = 0, ECRAD_ENTRAPMENT_EDGE_ONLY = 1, ECRAD_ENTRAPMENT_EXPLICIT = 2,

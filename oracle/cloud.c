@@ -1,11 +1,13 @@
 /* cloud.c -- oracle restatement of cloud optics and the McICA stochastic cloud generator.  TEST INFRASTRUCTURE.
  * Follows radiation/radiation_cloud_optics.F90:218-523, radiation_liquid_optics_socrates.F90:40-80,
- * radiation_ice_optics_fu.F90:42-138, radiation_delta_eddington.h:103-119, radiation_cloud_generator.F90:37-390,
+ * radiation_liquid_optics_slingo.F90:29-106, radiation_ice_optics_fu.F90:42-138, radiation_ice_optics_baran.F90:34-108,
+ * radiation_ice_optics_baran2017.F90:32-68, radiation_ice_optics_yi.F90:37-145, radiation_delta_eddington.h:103-119, radiation_cloud_generator.F90:37-390,
  * radiation_cloud_cover.F90:231-300, radiation_pdf_sampler.F90:126-150,
  * utilities/radiation_random_numbers_mix.F90:142-309.
  */
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "oracle.h"
@@ -54,6 +56,74 @@ static void ice_fu_lw(int nb, const double* c, double iwp, double re, double* od
     g[jb] = dmin(CO(c, nb, jb, 8) + de_um * (CO(c, nb, jb, 9) + de_um * (CO(c, nb, jb, 10) + de_um * CO(c, nb, jb, 11))), MaxAsymmetryFactor);
   }
 }
+/* radiation_liquid_optics_slingo.F90:29-63: Slingo (1989), shortwave */
+static void liq_slingo(int nb, const double* c, double lwp, double re, double* od, double* scat_od, double* g) {
+  double lwp_gm_2 = lwp * 1000.0;
+  double re_um = dmin(dmax(4.2, re * 1.0e6), 16.6); /* range of validity 4.2-16.6 microns */
+  double inv_re_um = 1.0 / re_um;
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = lwp_gm_2 * (CO(c, nb, jb, 1) + inv_re_um * CO(c, nb, jb, 2));
+    scat_od[jb] = od[jb] * (1.0 - CO(c, nb, jb, 3) - re_um * CO(c, nb, jb, 4));
+    g[jb] = CO(c, nb, jb, 5) + re_um * CO(c, nb, jb, 6);
+  }
+}
+/* radiation_liquid_optics_slingo.F90:69-106: Lindner & Li (2000), longwave */
+static void liq_lindner_li(int nb, const double* c, double lwp, double re, double* od, double* scat_od, double* g) {
+  double lwp_gm_2 = lwp * 1000.0;
+  double re_um = dmin(dmax(2.0, re * 1.0e6), 40.0); /* range of validity 2-40 microns */
+  double inv_re_um = 1.0 / re_um;
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = lwp_gm_2 * (CO(c, nb, jb, 1) + re_um * CO(c, nb, jb, 2) + inv_re_um * (CO(c, nb, jb, 3) + inv_re_um * (CO(c, nb, jb, 4) + inv_re_um * CO(c, nb, jb, 5))));
+    scat_od[jb] = od[jb] * (1.0 - (CO(c, nb, jb, 6) + inv_re_um * CO(c, nb, jb, 7) + re_um * (CO(c, nb, jb, 8) + re_um * CO(c, nb, jb, 9))));
+    g[jb] = CO(c, nb, jb, 10) + inv_re_um * CO(c, nb, jb, 11) + re_um * (CO(c, nb, jb, 12) + re_um * CO(c, nb, jb, 13));
+  }
+}
+/* radiation_ice_optics_baran.F90:34-60 */
+static void ice_baran(int nb, const double* c, double ice_wp, double qi, double* od, double* scat_od, double* g) {
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = ice_wp * (CO(c, nb, jb, 1) + CO(c, nb, jb, 2) / (1.0 + qi * CO(c, nb, jb, 3)));
+    scat_od[jb] = od[jb] * (CO(c, nb, jb, 4) + CO(c, nb, jb, 5) / (1.0 + qi * CO(c, nb, jb, 6)));
+    g[jb] = CO(c, nb, jb, 7) + CO(c, nb, jb, 8) / (1.0 + qi * CO(c, nb, jb, 9));
+  }
+}
+/* radiation_ice_optics_baran.F90:66-108 */
+static void ice_baran2016(int nb, const double* c, double ice_wp, double qi, double temperature, double* od, double* scat_od, double* g) {
+  double T2 = temperature * temperature, qi_T, qi_over_T4;
+  if (qi < 1.0e-3) { qi_T = qi * temperature; qi_over_T4 = 1.0 / (T2 * T2); }
+  else { qi_T = 1.0e-3 * temperature; qi_over_T4 = 1.0 / (T2 * T2); }
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = ice_wp * CO(c, nb, jb, 1) * qi_over_T4;
+    scat_od[jb] = od[jb] * (CO(c, nb, jb, 2) + CO(c, nb, jb, 3) * qi_T);
+    g[jb] = CO(c, nb, jb, 4) + CO(c, nb, jb, 5) * qi_T;
+  }
+}
+/* radiation_ice_optics_baran2017.F90:32-68 */
+static void ice_baran2017(int nb, const double* coeff_gen, const double* c, double ice_wp, double qi, double temperature, double* od, double* scat_od, double* g) {
+  double qi_mod = qi * exp(coeff_gen[0] * (temperature - coeff_gen[1]));
+  double qi_mod_od = pow(qi_mod, coeff_gen[2]), qi_mod_ssa = pow(qi_mod, coeff_gen[3]), qi_mod_g = pow(qi_mod, coeff_gen[4]);
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = ice_wp * (CO(c, nb, jb, 1) + CO(c, nb, jb, 2) / (1.0 + qi_mod_od * CO(c, nb, jb, 3)));
+    scat_od[jb] = od[jb] * (CO(c, nb, jb, 4) + CO(c, nb, jb, 5) / (1.0 + qi_mod_ssa * CO(c, nb, jb, 6)));
+    g[jb] = CO(c, nb, jb, 7) + CO(c, nb, jb, 8) / (1.0 + qi_mod_g * CO(c, nb, jb, 9));
+  }
+}
+/* radiation_ice_optics_yi.F90:37-89 (shortwave) and :95-145 (longwave): the same statements on either coefficient set */
+static void ice_yi(int nb, const double* c, double ice_wp, double re, double* od, double* scat_od, double* g) {
+  const int NSingleCoeffs = 23;
+  const double lu_scale = 0.2, lu_offset = 1.0;
+  double de_um = re * 2.0e6;
+  de_um = dmax(de_um, 10.0);
+  de_um = dmin(de_um, 119.99);
+  double iwp_gm_2 = ice_wp * 1000.0;
+  int lu_idx = (int)floor(de_um * lu_scale - lu_offset);
+  double wts_2 = (de_um * lu_scale - lu_offset) - lu_idx;
+  double wts_1 = 1.0 - wts_2;
+  for (int jb = 0; jb < nb; ++jb) {
+    od[jb] = 0.001 * iwp_gm_2 * (wts_1 * CO(c, nb, jb, lu_idx) + wts_2 * CO(c, nb, jb, lu_idx + 1));
+    scat_od[jb] = od[jb] * (wts_1 * CO(c, nb, jb, lu_idx + NSingleCoeffs) + wts_2 * CO(c, nb, jb, lu_idx + NSingleCoeffs + 1));
+    g[jb] = wts_1 * CO(c, nb, jb, lu_idx + 2 * NSingleCoeffs) + wts_2 * CO(c, nb, jb, lu_idx + 2 * NSingleCoeffs + 1);
+  }
+}
 /* radiation_delta_eddington.h:103-119 */
 static void delta_eddington_scat_od(int n, double* od, double* scat_od, double* g) {
   for (int i = 0; i < n; ++i) {
@@ -64,12 +134,37 @@ static void delta_eddington_scat_od(int n, double* od, double* scat_od, double* 
   }
 }
 
-/* radiation_cloud_optics.F90:218-523 for one column (SOCRATES liquid + Fu ice).  Outputs [nlev][nb]. */
-void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl,
-                      const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
-                      const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
-                      double* od_sw, double* ssa_sw, double* g_sw) {
+/* coefficient array of the configured model: "<base>.<tag>" of the stand-alone blob, else <base> (what a host model registered),
+ * checked against the coefficient count radiation_cloud_optics.F90:46-216 expects */
+static const double* model_coeff(const orc_tables* t, const char* base, const char* tag, int nb, int ncoef) {
+  char nm[64];
+  const orc_array* a = NULL;
+  if (tag[0]) { snprintf(nm, sizeof nm, "%s.%s", base, tag); a = orc_find(t, nm); }
+  if (!a) a = orc_find(t, base);
+  if (!a || a->dtype != 0) return NULL;
+  int64_t n = 1;
+  for (int k = 0; k < a->ndim; ++k) n *= a->dims[k];
+  return n == (int64_t)nb * ncoef ? (const double*)a->data : NULL;
+}
+
+/* radiation_cloud_optics.F90:218-523 for one column.  Outputs [nlev][nb]. */
+int orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl, const double* t_hl,
+                     const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
+                     const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
+                     double* od_sw, double* ssa_sw, double* g_sw) {
   const double AccelDueToGravity = 9.80665;
+  static const char* liq_tag[] = {"", "", "slingo"};
+  static const int liq_n[][2] = {{0, 0}, {16, 16}, {13, 6}};
+  static const char* ice_tag[] = {"", "", "baran", "baran2016", "baran2017", "yi"};
+  static const int ice_n[][2] = {{0, 0}, {11, 10}, {9, 9}, {5, 5}, {9, 9}, {69, 69}};
+  const int lm = cfg->i_liq_model, im = cfg->i_ice_model;
+  if (lm < ECRAD_LIQ_SOCRATES || lm > ECRAD_LIQ_SLINGO || im < ECRAD_ICE_FU || im > ECRAD_ICE_YI) return -1;
+  const double* liq_coeff_lw = model_coeff(t, "liq_coeff_lw", liq_tag[lm], NB_LW, liq_n[lm][0]);
+  const double* liq_coeff_sw = model_coeff(t, "liq_coeff_sw", liq_tag[lm], NB_SW, liq_n[lm][1]);
+  const double* ice_coeff_lw = model_coeff(t, "ice_coeff_lw", ice_tag[im], NB_LW, ice_n[im][0]);
+  const double* ice_coeff_sw = model_coeff(t, "ice_coeff_sw", ice_tag[im], NB_SW, ice_n[im][1]);
+  const double* ice_coeff_gen = im == ECRAD_ICE_BARAN2017 ? model_coeff(t, "ice_coeff_gen", ice_tag[im], 5, 1) : NULL;
+  if (!liq_coeff_lw || !liq_coeff_sw || !ice_coeff_lw || !ice_coeff_sw || (im == ECRAD_ICE_BARAN2017 && !ice_coeff_gen)) return -1;
   memset(od_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
   memset(ssa_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
   memset(g_lw, 0, sizeof(double) * (size_t)nlev * NB_LW);
@@ -85,17 +180,37 @@ void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nle
     double factor = is_homogeneous ? (p_hl[jl + 1] - p_hl[jl]) / AccelDueToGravity : (p_hl[jl + 1] - p_hl[jl]) / (AccelDueToGravity * frac[jl]);
     double lwp = factor * q_liq[jl], iwp = factor * q_ice[jl];
     if (lwp > 0.0) {
-      liq_socrates(NB_LW, t->liq_coeff_lw, lwp, re_liq[jl], od_lw_liq, scat_lw_liq, g_lw_liq);
-      liq_socrates(NB_SW, t->liq_coeff_sw, lwp, re_liq[jl], od_sw_liq, scat_sw_liq, g_sw_liq);
+      if (lm == ECRAD_LIQ_SOCRATES) {
+        liq_socrates(NB_LW, liq_coeff_lw, lwp, re_liq[jl], od_lw_liq, scat_lw_liq, g_lw_liq);
+        liq_socrates(NB_SW, liq_coeff_sw, lwp, re_liq[jl], od_sw_liq, scat_sw_liq, g_sw_liq);
+      } else {   /* Slingo */
+        liq_lindner_li(NB_LW, liq_coeff_lw, lwp, re_liq[jl], od_lw_liq, scat_lw_liq, g_lw_liq);
+        liq_slingo(NB_SW, liq_coeff_sw, lwp, re_liq[jl], od_sw_liq, scat_sw_liq, g_sw_liq);
+      }
       if (!cfg->do_sw_delta_scaling_with_gases) delta_eddington_scat_od(NB_SW, od_sw_liq, scat_sw_liq, g_sw_liq);
     } else {
       memset(od_lw_liq, 0, sizeof od_lw_liq); memset(scat_lw_liq, 0, sizeof scat_lw_liq); memset(g_lw_liq, 0, sizeof g_lw_liq);
       memset(od_sw_liq, 0, sizeof od_sw_liq); memset(scat_sw_liq, 0, sizeof scat_sw_liq); memset(g_sw_liq, 0, sizeof g_sw_liq);
     }
     if (iwp > 0.0) {
-      ice_fu_lw(NB_LW, t->ice_coeff_lw, iwp, re_ice[jl], od_lw_ice, scat_lw_ice, g_lw_ice);
-      if (cfg->do_fu_lw_ice_optics_bug) for (int b = 0; b < NB_LW; ++b) scat_lw_ice[b] = od_lw_ice[b] - scat_lw_ice[b];
-      ice_fu_sw(NB_SW, t->ice_coeff_sw, iwp, re_ice[jl], od_sw_ice, scat_sw_ice, g_sw_ice);
+      const double temperature = 0.5 * (t_hl[jl] + t_hl[jl + 1]);
+      if (im == ECRAD_ICE_BARAN) {
+        ice_baran(NB_LW, ice_coeff_lw, iwp, q_ice[jl], od_lw_ice, scat_lw_ice, g_lw_ice);
+        ice_baran(NB_SW, ice_coeff_sw, iwp, q_ice[jl], od_sw_ice, scat_sw_ice, g_sw_ice);
+      } else if (im == ECRAD_ICE_BARAN2016) {
+        ice_baran2016(NB_LW, ice_coeff_lw, iwp, q_ice[jl], temperature, od_lw_ice, scat_lw_ice, g_lw_ice);
+        ice_baran2016(NB_SW, ice_coeff_sw, iwp, q_ice[jl], temperature, od_sw_ice, scat_sw_ice, g_sw_ice);
+      } else if (im == ECRAD_ICE_BARAN2017) {
+        ice_baran2017(NB_LW, ice_coeff_gen, ice_coeff_lw, iwp, q_ice[jl], temperature, od_lw_ice, scat_lw_ice, g_lw_ice);
+        ice_baran2017(NB_SW, ice_coeff_gen, ice_coeff_sw, iwp, q_ice[jl], temperature, od_sw_ice, scat_sw_ice, g_sw_ice);
+      } else if (im == ECRAD_ICE_FU) {
+        ice_fu_lw(NB_LW, ice_coeff_lw, iwp, re_ice[jl], od_lw_ice, scat_lw_ice, g_lw_ice);
+        if (cfg->do_fu_lw_ice_optics_bug) for (int b = 0; b < NB_LW; ++b) scat_lw_ice[b] = od_lw_ice[b] - scat_lw_ice[b];
+        ice_fu_sw(NB_SW, ice_coeff_sw, iwp, re_ice[jl], od_sw_ice, scat_sw_ice, g_sw_ice);
+      } else {   /* Yi */
+        ice_yi(NB_LW, ice_coeff_lw, iwp, re_ice[jl], od_lw_ice, scat_lw_ice, g_lw_ice);
+        ice_yi(NB_SW, ice_coeff_sw, iwp, re_ice[jl], od_sw_ice, scat_sw_ice, g_sw_ice);
+      }
       if (!cfg->do_sw_delta_scaling_with_gases) delta_eddington_scat_od(NB_SW, od_sw_ice, scat_sw_ice, g_sw_ice);
       delta_eddington_scat_od(NB_LW, od_lw_ice, scat_lw_ice, g_lw_ice);
     } else {
@@ -119,6 +234,7 @@ void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nle
       ssa_sw[jl * NB_SW + b] = (scat_sw_liq[b] + scat_sw_ice[b]) / (od_sw_liq[b] + od_sw_ice[b]);
     }
   }
+  return 0;
 }
 
 /* ---------------------------------------------------------------------------------------------------

@@ -134,10 +134,11 @@ void orc_fast_adding_ica_lw(int ng, int nlev, const double* ref, const double* t
                        double* flux_up, double* flux_dn);
 
 /* cloud.c */
-void orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl,
-                      const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
-                      const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
-                      double* od_sw, double* ssa_sw, double* g_sw);
+/* returns 0, or -1 when the coefficient arrays of the configured liquid / ice model are not in the table directory */
+int orc_cloud_optics(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl, const double* t_hl,
+                     const double* frac, const double* q_liq, const double* q_ice, const double* re_liq,
+                     const double* re_ice, double* od_lw, double* ssa_lw, double* g_lw,
+                     double* od_sw, double* ssa_sw, double* g_sw);
 void orc_cloud_generator(const orc_tables* t, int ng, int nlev, int i_overlap_scheme, int32_t iseed,
                          double frac_threshold, const double* frac, const double* overlap_param,
                          double decorrelation_scaling, const double* fractional_std, int use_beta_overlap,

@@ -991,8 +991,14 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
       orc_general_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
                                w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
     else
-      orc_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
-                       w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
+    {
+      double* thl_full = (double*)malloc(sizeof(double) * (size_t)(nlev + 1));
+      for (int jl = 0; jl <= nlev; ++jl) thl_full[jl] = A2(in->temperature_hl, jcol, jl);
+      rc = orc_cloud_optics(t, cfg, nlev, phl_full, thl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
+                            w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
+      free(thl_full);
+      if (rc) { free(w.w); free(phl_full); return rc; }
+    }
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }

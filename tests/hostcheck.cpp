@@ -20,6 +20,32 @@ void* hc_load(const char* path) {
   delete T;
   return P;
 }
+// the same with the coefficient arrays of another liquid / ice optics model (config%i_liq_model, i_ice_model)
+void* hc_load_models(const char* path, int liq_model, int ice_model) {
+  auto* T = new ecrad_b200_tables();
+  if (T->load_file(path)) { delete T; return nullptr; }
+  auto* P = new PackedTables();
+  try { pack_tables(*T, *P, liq_model, ice_model); } catch (const std::exception& e) { fprintf(stderr, "hostcheck: %s\n", e.what()); delete T; delete P; return nullptr; }
+  delete T;
+  return P;
+}
+// cloud_core.h on one column: od / ssa / g per band of every cloudy layer, [nlev][nb] (zero where there is no cloud)
+void hc_cloud_optics(void* p, int nlev, const double* p_hl, const double* t_hl, const double* frac, const double* q_liq, const double* q_ice,
+                     const double* re_liq, const double* re_ice, int lw_scattering, int fu_bug, int delta_with_gases, double* od_lw,
+                     double* ssa_lw, double* g_lw, double* od_sw, double* ssa_sw, double* g_sw) {
+  const CloudMeta& C = ((PackedTables*)p)->cloud;
+  for (int l = 0; l < nlev; ++l) {
+    for (int b = 0; b < 16; ++b) { od_lw[l * 16 + b] = 0.0; ssa_lw[l * 16 + b] = 0.0; g_lw[l * 16 + b] = 0.0; }
+    for (int b = 0; b < 14; ++b) { od_sw[l * 14 + b] = 0.0; ssa_sw[l * 14 + b] = 0.0; g_sw[l * 14 + b] = 0.0; }
+    if (!(frac[l] > 0.0)) continue;
+    const double factor = (p_hl[l + 1] - p_hl[l]) / (9.80665 * frac[l]);
+    CloudLayerIn L;
+    L.q_ice = q_ice[l]; L.lwp = factor * q_liq[l]; L.iwp = factor * q_ice[l];
+    L.re_liq = re_liq[l]; L.re_ice = re_ice[l]; L.temperature = 0.5 * (t_hl[l] + t_hl[l + 1]);
+    for (int b = 0; b < 16; ++b) { CloudBandOut r = cloud_optics_lw(C, b, L, lw_scattering != 0, fu_bug != 0); od_lw[l * 16 + b] = r.od; ssa_lw[l * 16 + b] = r.ssa; g_lw[l * 16 + b] = r.g; }
+    for (int b = 0; b < 14; ++b) { CloudBandOut r = cloud_optics_sw(C, b, L, delta_with_gases != 0); od_sw[l * 14 + b] = r.od; ssa_sw[l * 14 + b] = r.ssa; g_sw[l * 14 + b] = r.g; }
+  }
+}
 void hc_free(void* p) { delete (PackedTables*)p; }
 int hc_table_sizes(void* p, int* lw, int* sw) { auto* P = (PackedTables*)p; *lw = (int)P->lwtab.size(); *sw = (int)P->swtab.size(); return (int)sizeof(GasMeta); }
 

@@ -661,6 +661,27 @@ def test_lw_aerosol_scattering(handles, meridian_raw, kw):
         assert 1e-3 < d < 5.0, d
 
 
+@pytest.mark.parametrize("kw", [dict(liquid_model_name="Slingo"), dict(ice_model_name="Baran-EXPERIMENTAL"), dict(ice_model_name="Baran2016", use_aerosols=True),
+                                dict(ice_model_name="Baran2017-EXPERIMENTAL", do_lw_cloud_scattering=False),
+                                dict(ice_model_name="Yi", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(liquid_model_name="Slingo", ice_model_name="Yi", do_sw_delta_scaling_with_gases=True),
+                                dict(ice_model_name="Baran2016", sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)])
+def test_other_liquid_and_ice_optics_models(handles, meridian_raw, kw):
+    """config%i_liq_model / i_ice_model other than SOCRATES + Fu (radiation_cloud_optics.F90:345-447): Slingo / Lindner-Li droplets, Baran,
+    Baran-2016, Baran-2017 and Yi ice, through every solver family.  Oracle: tests/test_cloud_optics_models.py pins its formulas."""
+    n = 200 if "SPARTACUS" in kw.values() else 400
+    h, orc, cfg = handles(**kw)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    assert np.array_equal(out["cloud_cover_sw"], ref["cloud_cover_sw"])
+    # and it is not the default pair's answer
+    h0, _, cfg0 = handles(**{k: v for k, v in kw.items() if k not in ("liquid_model_name", "ice_model_name")})
+    out0 = h0.radiation(I.to_radiation_inputs(raw, cfg0), n, NLEV)
+    assert np.abs(out["sw_up"] - out0["sw_up"]).max() > 1.0
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", do_save_spectral_flux=True)])
 def test_single_precision_boundary(handles, meridian_raw, golden_noaer, kw):
     """ecrad_b200_radiation_sp: the call of a host built with JPRB = JPRM -- float arrays in, float arrays out, double-precision kernels

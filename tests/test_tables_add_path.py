@@ -23,7 +23,9 @@ def test_shim_is_complete_and_current():
     # every array of the RRTMG blob is either registered from ifsrrtm module storage or from config_type
     blob = tables.read_blob(os.path.join(ROOT, "ecrad_b200", "data", "rrtmg_tables.bin"))
     registered = set(re.findall(r"call add_[ri]\d\(t, '([A-Za-z0-9_]+)'", src))
-    assert set(blob) <= registered, sorted(set(blob) - registered)
+    # ("<name>.<model>" entries are the stand-alone blob's copies of the other cloud-optics files; a host registers the configured pair)
+    host_side = {nm.split(".")[0] for nm in blob}
+    assert host_side <= registered, sorted(host_side - registered)
     # all 41 outputs and every input pointer of the header are assigned
     hdr = open(os.path.join(ROOT, "include", "ecrad_b200.h")).read()
     outs = re.search(r"typedef struct ecrad_b200_outputs \{(.*?)\} ecrad_b200_outputs;", hdr, re.S).group(1)

@@ -118,6 +118,19 @@ def nc_tables(ref):
     with netcdf_file(os.path.join(d, "fu_ice_scattering_rrtm.nc"), mmap=False) as f:
         out["ice_coeff_lw"] = np.array(f.variables["coeff_lw"][:], dtype=np.float64)
         out["ice_coeff_sw"] = np.array(f.variables["coeff_sw"][:], dtype=np.float64)
+    # the other parameterisations radiation_cloud_optics.F90 dispatches (file names: radiation_config.F90:1240-1283), stored next to
+    # the default pair as "<name>.<model>"; setup picks the pair of config%i_liq_model / i_ice_model
+    for tag, fn in (("slingo", "slingo_droplet_scattering_rrtm.nc"),):
+        with netcdf_file(os.path.join(d, fn), mmap=False) as f:
+            out[f"liq_coeff_lw.{tag}"] = np.array(f.variables["coeff_lw"][:], dtype=np.float64)
+            out[f"liq_coeff_sw.{tag}"] = np.array(f.variables["coeff_sw"][:], dtype=np.float64)
+    for tag, fn in (("baran", "baran_ice_scattering_rrtm.nc"), ("baran2016", "baran2016_ice_scattering_rrtm.nc"),
+                    ("baran2017", "baran2017_ice_scattering_rrtm.nc"), ("yi", "yi_ice_scattering_rrtm.nc")):
+        with netcdf_file(os.path.join(d, fn), mmap=False) as f:
+            out[f"ice_coeff_lw.{tag}"] = np.array(f.variables["coeff_lw"][:], dtype=np.float64)
+            out[f"ice_coeff_sw.{tag}"] = np.array(f.variables["coeff_sw"][:], dtype=np.float64)
+            if "coeff_gen" in f.variables:
+                out[f"ice_coeff_gen.{tag}"] = np.array(f.variables["coeff_gen"][:], dtype=np.float64)
     # radiation_pdf_sampler.F90:44-107 (setup_pdf_sampler)
     with netcdf_file(os.path.join(d, "mcica_gamma.nc"), mmap=False) as f:
         out["pdf_val"] = np.array(f.variables["x"][:], dtype=np.float64).T.copy()  # val(ncdf, nfsd), radiation_pdf_sampler.F90:83-93

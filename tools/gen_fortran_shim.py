@@ -300,6 +300,8 @@ def main():
     w("    integer :: j")
     w("    call add_r2(t, 'liq_coeff_lw', config%cloud_optics%liq_coeff_lw); call add_r2(t, 'liq_coeff_sw', config%cloud_optics%liq_coeff_sw)")
     w("    call add_r2(t, 'ice_coeff_lw', config%cloud_optics%ice_coeff_lw); call add_r2(t, 'ice_coeff_sw', config%cloud_optics%ice_coeff_sw)")
+    w("    ! (the arrays of the configured liquid_model_name / ice_model_name; the library checks their coefficient counts against i_liq_model / i_ice_model)")
+    w("    if (allocated(config%cloud_optics%ice_coeff_gen)) call add_r1(t, 'ice_coeff_gen', config%cloud_optics%ice_coeff_gen)   ! Baran-2017")
     w("    call add_r2(t, 'pdf_val', config%pdf_sampler%val)                 ! val(ncdf, nfsd), radiation_pdf_sampler.F90:83-93")
     w("    call add_r1(t, 'pdf_fsd', [(config%pdf_sampler%fsd1 + real(j-1,jprb) / config%pdf_sampler%inv_fsd_interval, j = 1, config%pdf_sampler%nfsd)])")
     w("    call add_r2(t, 'sw_albedo_weights', config%sw_albedo_weights)     ! (n_albedo_sw, n_bands_sw)")
