@@ -84,6 +84,32 @@ def set_gas_units(raw, want_vmr):
     return d
 
 
+def ckdmip_raw(fix, mu0, sw_albedo=0.15, lw_emissivity=1.0, solar_irradiance=1361.0, n_albedo=6, n_emiss=2):
+    """The reference's CKDMIP clear-sky test (test/ckdmip/config-*.nam + ckdmip_evaluation1_concentrations_present_reduced.nc) as the
+    raw-variable dict `to_radiation_inputs` reads: what driver/ecrad_driver_read_input.F90 builds from that file -- gases from the
+    `*_mole_fraction_fl` variables (vmr_suffix_str, :566-600), skin temperature = temperature of the lowest half-level (:477-478),
+    cos_solar_zenith_angle / sw_albedo / lw_emissivity / solar irradiance overridden by the namelist, no clouds, no aerosols.
+    `fix`: tests/golden/ckdmip_evaluation1.npz."""
+    f64 = lambda a: np.array(a, dtype=np.float64)   # noqa: E731
+    p = f64(fix["pressure_hl"])
+    ncol, nlev = p.shape[0], p.shape[1] - 1
+    zeros = np.zeros((ncol, nlev))
+    raw = {
+        "solar_irradiance": solar_irradiance, "skin_temperature": f64(fix["temperature_hl"])[:, -1].copy(),
+        "cos_solar_zenith_angle": np.full(ncol, float(mu0)), "sw_albedo": np.full((ncol, n_albedo), sw_albedo),
+        "sw_albedo_direct": np.full((ncol, n_albedo), sw_albedo), "lw_emissivity": np.full((ncol, n_emiss), lw_emissivity),
+        "iseed": np.arange(1, ncol + 1, dtype=np.float64), "pressure_hl": p, "temperature_hl": f64(fix["temperature_hl"]),
+        # H2O and O3 travel as mass mixing ratios in this dict (the IFS file convention); set_gas_units turns them back for ecCKD
+        "q": f64(fix["h2o_mole_fraction_fl"]) * (18.0152833 / AIR_MOLAR_MASS), "o3_mmr": f64(fix["o3_mole_fraction_fl"]) * (47.9982 / AIR_MOLAR_MASS),
+        "hcfc22_vmr": zeros.copy(), "ccl4_vmr": zeros.copy(),
+        "cloud_fraction": zeros.copy(), "q_liquid": zeros.copy(), "q_ice": zeros.copy(), "re_liquid": np.full((ncol, nlev), 1.0e-5),
+        "re_ice": np.full((ncol, nlev), 5.0e-5), "overlap_param": np.ones((ncol, nlev - 1)), "fractional_std": np.ones((ncol, nlev)),
+    }
+    for g in ("co2", "ch4", "n2o", "cfc11", "cfc12"):
+        raw[f"{g}_vmr"] = f64(fix[f"{g}_mole_fraction_fl"])
+    return raw
+
+
 def cloud_effective_separation_eta(pressure_hl, cloud_fraction, separation_surf=2500.0, separation_toa=14000.0, power=3.5,
                                    inhom_separation_factor=0.75):
     """cloud%param_cloud_effective_separation_eta (radiation_cloud.F90:602-690) with the driver's namelist values of

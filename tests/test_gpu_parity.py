@@ -661,6 +661,20 @@ def test_lw_aerosol_scattering(handles, meridian_raw, kw):
         assert 1e-3 < d < 5.0, d
 
 
+def test_ckdmip_profiles_vs_line_by_line(handles):
+    """The reference's CKDMIP clear-sky test (test/ckdmip: 50 profiles x 54 layers, line-by-line fluxes) on the GPU: within 1e-6 W m-2
+    of the oracle and within the published accuracy of each gas-optics model of the line-by-line truth (tests/test_ckdmip_lbl.py)."""
+    import test_ckdmip_lbl as K
+    fix = K.load_fixture()
+    for name, kw, lw_bound, sw_bound in K.MODELS:
+        h, orc, cfg = handles(**K.CLOUDLESS, **kw)
+        K.check_against_lbl(lambda raw: h.radiation(I.to_radiation_inputs(raw, cfg), 50, 54), fix, lw_bound, sw_bound)
+        raw = I.ckdmip_raw(fix, 0.5)
+        out = h.radiation(I.to_radiation_inputs(raw, cfg), 50, 54)
+        ref = orc.radiation(I.to_radiation_inputs(raw, cfg), 50, 54)
+        compare(out, ref, ["lw_up", "lw_dn", "sw_up", "sw_dn", "sw_dn_direct"])
+
+
 @pytest.mark.parametrize("kw", [dict(liquid_model_name="Slingo"), dict(ice_model_name="Baran-EXPERIMENTAL"), dict(ice_model_name="Baran2016", use_aerosols=True),
                                 dict(ice_model_name="Baran2017-EXPERIMENTAL", do_lw_cloud_scattering=False),
                                 dict(ice_model_name="Yi", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
