@@ -537,6 +537,27 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   if (check_config(h, *cfg)) { delete h; return 1; }
   PackedTables P;
   try { pack_tables(*tab, P, cfg->i_liq_model, cfg->i_ice_model); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
+  for (int g = 0; g < NG_LW; ++g) P.meta.rank_lw[g] = (short)g;
+  for (int g = 0; g < NG_SW; ++g) P.meta.rank_sw[g] = (short)g;
+  if (!P.is_ecckd) {
+    // SPARTACUS treats the g-points up to the first one whose gas optical depth exceeds max_gas_od_3d with the matrix exponential,
+    // "assuming that the g-points have been reordered in approximate order of gas optical depth" (radiation_spartacus_sw.F90:462-478):
+    // radiation_ifs_rrtm.F90:122-130 / :167-174 reorder them for this solver only.  The kernels keep the arrays in RRTMG order
+    // and carry each g-point's position in that sequence; the per-g-point outputs are written at that position.
+    for (int sw = 0; sw < 2; ++sw) {
+      if (!(sw ? (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) : (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS))) continue;
+      const char* nm = sw ? "i_g_from_reordered_g_sw" : "i_g_from_reordered_g_lw";
+      const int ng = sw ? NG_SW : NG_LW;
+      const auto* a = tab->find(nm);
+      if (!a || a->dtype != 1 || a->data.size() != (size_t)ng * 4) { fail(nullptr, "SPARTACUS on RRTMG-IFS needs the table '%s' (%d int32)", nm, ng); delete h; return 1; }
+      const int32_t* perm = (const int32_t*)a->data.data();
+      std::vector<int> seen(ng, 0);
+      for (int j = 0; j < ng; ++j) {
+        if (perm[j] < 1 || perm[j] > ng || seen[perm[j] - 1]++) { fail(nullptr, "'%s' is not a permutation of 1..%d", nm, ng); delete h; return 1; }
+        (sw ? P.meta.rank_sw : P.meta.rank_lw)[perm[j] - 1] = (short)j;
+      }
+    }
+  }
   if (P.is_ecckd != (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD)) {
     fail(nullptr, "the table directory holds %s tables but the configuration asks for the other gas model", P.is_ecckd ? "ecCKD" : "RRTMG"); delete h; return 1;
   }

@@ -63,6 +63,9 @@ struct GasMeta {
   double strrat_sw[NB_SW], rayl_sw[NB_SW], givfac_23, scalekur_27;
   int layreffr_sw[NB_SW], nfor_sw[NB_SW];
   int band_of_g_lw[NG_LW], band_of_g_sw[NG_SW];  // 0-based band of each g-point
+  // SPARTACUS on RRTMG: 0-based position of each g-point in the order of approximately increasing gas optical depth
+  // (inverse of config%i_g_from_reordered_g_{lw,sw}, radiation_ifs_rrtm.F90:50-68, :122-130, :167-174); identity otherwise
+  short rank_lw[NG_LW], rank_sw[NG_SW];
   int lw_rows[NB_LW][2], sw_rows[NB_SW][2];      // rows of ABSA / ABSB per band (0: none); 13 (ABSA) or 47 (ABSB) reference pressures each
   short lw_sec_rows[NB_LW][16], sw_sec_rows[NB_SW][16];   // rows of every section of a band's packed table
   unsigned short lw_sec_low[NB_LW], lw_sec_high[NB_LW];   // small sections the band routine reads below / above LAYTROP (bit = section)

@@ -875,7 +875,8 @@ __global__ void toa_spectral_kernel(DevTables T, DevOut out, const double* mu0_o
     if (!src[k] || !dst[k] || (k == 1 && !do_clear) || (k == 2 && !with_dn)) continue;
     if (k == 2 && mu0_of && mu0_of[c] < 1.0e-10) continue;   // night column: sw_dn_toa_g was not set, leave its band sums alone
     double acc = 0.0;
-    for (int g = B.g0; g < B.g0 + B.ng; ++g) acc = acc + src[k][(size_t)c * ng + g];
+    const short* rank = sw ? T.meta->rank_sw : T.meta->rank_lw;   // (SPARTACUS on RRTMG stores its g-point arrays reordered)
+    for (int g = B.g0; g < B.g0 + B.ng; ++g) acc = acc + src[k][(size_t)c * ng + rank[g]];
     dst[k][(size_t)c * nb + b] = acc;
   }
 }

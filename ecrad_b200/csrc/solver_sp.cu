@@ -39,11 +39,12 @@ __device__ __forceinline__ SpGeom sp_geometry(const SpCfg& sc, double mu0) {
   return q;
 }
 
-// first g-point (block-wide) whose clear-region optical depth exceeds max_gas_od_3d; ng if none.  Contains barriers.
-__device__ __forceinline__ int sp_first_thick_g(int* s_first, bool act, int g, int ng, bool thick) {
+// Position (in the sequence the reference scans, `rank`) of the first g-point whose clear-region optical depth exceeds
+// max_gas_od_3d; ng if none (radiation_spartacus_sw.F90:462-478, :486-493).  Block-wide: contains barriers.
+__device__ __forceinline__ int sp_first_thick_g(int* s_first, bool act, int rank, int ng, bool thick) {
   if (threadIdx.x == 0) *s_first = ng;
   __syncthreads();
-  if (act && thick) atomicMin(s_first, g);
+  if (act && thick) atomicMin(s_first, rank);
   __syncthreads();
   return *s_first;
 }
@@ -90,7 +91,8 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     sp_transfer_rates(sc, dz, edge, reg, q.tan_sza, rate_dir);
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate_dif);
   }
-  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
+  const int rank = T.meta->rank_sw[gg];
+  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, rank, SD::NG, odg > sc.max_gas_od_3d) : 0;
   if (!act) return;
   // optical properties of the regions (:606-655)
   const int b = T.meta->band_of_g_sw[g];
@@ -107,7 +109,7 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     g_r[jr] = (scat_od * gas_g + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
     if (od_r[jr] > sc.max_cloud_od) od_r[jr] = sc.max_cloud_od;
   }
-  if (g >= ng3d) {
+  if (rank >= ng3d) {
     // Meador-Weaver per region: diagonal matrices (:783-832)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -502,7 +504,7 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
   }
   const double dif_c = fdc, dir_c = mu0 * ddc;
   if (act) {
-    const size_t i = (size_t)c * SD::NG + g;
+    const size_t i = (size_t)c * SD::NG + T.meta->rank_sw[g];   // flux_type's g-point arrays are in the solver's (reordered) sequence
     if (out.sw_dn_diffuse_surf_g) out.sw_dn_diffuse_surf_g[i] = dif_a;
     if (out.sw_dn_direct_surf_g) out.sw_dn_direct_surf_g[i] = dir_a;
     if (out.sw_dn_diffuse_surf_clear_g) out.sw_dn_diffuse_surf_clear_g[i] = dif_c;
@@ -547,7 +549,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate);
   }
-  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, g, SD::NG, odg > sc.max_gas_od_3d) : 0;
+  const int rank = T.meta->rank_lw[act ? g : 0];
+  const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, rank, SD::NG, odg > sc.max_gas_od_3d) : 0;
   if (!act) return;
   const int b = T.meta->band_of_g_lw[g];
   const double* clb = w.cl_lw + ((size_t)c * nlev + l) * 3 * SD::NB;
@@ -564,7 +567,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     }
     if (od_r[jr] > sc.max_cloud_od) od_r[jr] = sc.max_cloud_od;
   }
-  if (g >= ng3d) {
+  if (rank >= ng3d) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int jr = k / 4;
@@ -901,7 +904,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
     if (want_dv) out.lw_derivatives[o] = l == nlev ? 1.0 : sums[4 * nl1 + l];
   }
   if (act) {
-    const size_t i = (size_t)c * SD::NG + g;
+    const size_t i = (size_t)c * SD::NG + T.meta->rank_lw[g];   // flux_type's g-point arrays are in the solver's (reordered) sequence
     if (out.lw_dn_surf_clear_g) out.lw_dn_surf_clear_g[i] = fdc;
     if (out.lw_up_toa_clear_g) out.lw_up_toa_clear_g[i] = toa_c;
     if (out.lw_dn_surf_g) out.lw_dn_surf_g[i] = dn_surf_g;

@@ -84,6 +84,23 @@ def set_gas_units(raw, want_vmr):
     return d
 
 
+def i3rc_raw(fix, sza_deg, overlap_decorr_length_scaling=1.13):
+    """The reference's I3RC cumulus test (test/i3rc/Makefile + configI3RC.nam) as the raw-variable dict `to_radiation_inputs` reads:
+    the single profile of i3rc_mls_cumulus.nc once per solar zenith angle (duplicate_profiles.sh), and the driver's
+    overlap_decorr_length_scaling applied as driver/ecrad_driver_read_input.F90:247-255 does (overlap_param ** (1 / scaling) where
+    positive).  `fix`: tests/golden/i3rc_mls_cumulus_inputs.npz (surface albedo 0.08 and 1366 W m-2 of the namelist already in it)."""
+    sza = np.atleast_1d(np.asarray(sza_deg, dtype=np.float64))
+    raw = {}
+    for k, v in fix.items():
+        v = np.array(v, dtype=np.float64)
+        raw[k] = v if v.ndim == 0 else np.repeat(v[:1], len(sza), axis=0)
+    raw["cos_solar_zenith_angle"] = np.cos(np.deg2rad(sza))
+    raw["iseed"] = np.arange(1, len(sza) + 1, dtype=np.float64)
+    op = raw["overlap_param"]
+    raw["overlap_param"] = np.where(op > 0.0, np.abs(op) ** (1.0 / overlap_decorr_length_scaling), op)
+    return raw
+
+
 def ckdmip_raw(fix, mu0, sw_albedo=0.15, lw_emissivity=1.0, solar_irradiance=1361.0, n_albedo=6, n_emiss=2):
     """The reference's CKDMIP clear-sky test (test/ckdmip/config-*.nam + ckdmip_evaluation1_concentrations_present_reduced.nc) as the
     raw-variable dict `to_radiation_inputs` reads: what driver/ecrad_driver_read_input.F90 builds from that file -- gases from the

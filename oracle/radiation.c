@@ -1002,13 +1002,57 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
   } else {
     for (int jl = 0; jl < nlev; ++jl) frac[jl] = 0.0;
   }
+  /* SPARTACUS on RRTMG works on g-points reordered by approximately increasing gas optical depth (radiation_ifs_rrtm.F90:50-68,
+   * :122-133, :167-177): the gas-optics arrays leave radiation_ifs_rrtm.F90:481-505, :571-590, :717-737, :838-845 in that order, every
+   * later step (aerosols and albedos are element-wise, so permuting after them is the same thing) indexes bands through
+   * i_band_from_reordered_g, and the per-g-point outputs of flux_type are in the reordered order too. */
+  orc_tables* tp = NULL;
+  if (!t->is_ecckd && ((cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS))) {
+    const orc_array* pl = orc_find(t, "i_g_from_reordered_g_lw");
+    const orc_array* ps = orc_find(t, "i_g_from_reordered_g_sw");
+    if (!pl || !ps) { fprintf(stderr, "oracle: i_g_from_reordered_g_lw/sw missing from the table directory\n"); free(w.w); free(phl_full); return 13; }
+    tp = (orc_tables*)malloc(sizeof(orc_tables));
+    memcpy(tp, t, sizeof(orc_tables));
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(NG_LW > NG_SW ? NG_LW : NG_SW));
+    if (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) {
+      const int32_t* perm = (const int32_t*)pl->data;
+      const int ng = NG_LW;
+      double* rows[4] = {w.od_lw, w.ssa_lw, w.g_lw, w.planck_hl};
+      const int nrows[4] = {nlev, nlev, nlev, nlev + 1};
+      for (int a = 0; a < 4; ++a)
+        for (int r = 0; r < nrows[a]; ++r) {
+          double* x = rows[a] + (size_t)r * ng;
+          for (int j = 0; j < ng; ++j) tmp[j] = x[perm[j] - 1];
+          memcpy(x, tmp, sizeof(double) * ng);
+        }
+      double* one[2] = {w.lw_emission, w.lw_albedo};
+      for (int a = 0; a < 2; ++a) { for (int j = 0; j < ng; ++j) tmp[j] = one[a][perm[j] - 1]; memcpy(one[a], tmp, sizeof(double) * ng); }
+      for (int j = 0; j < ng; ++j) tp->band_lw[j] = t->band_lw[perm[j] - 1];
+    }
+    if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) {
+      const int32_t* perm = (const int32_t*)ps->data;
+      const int ng = NG_SW;
+      double* rows[3] = {w.od_sw, w.ssa_sw, w.g_sw};
+      for (int a = 0; a < 3; ++a)
+        for (int r = 0; r < nlev; ++r) {
+          double* x = rows[a] + (size_t)r * ng;
+          for (int j = 0; j < ng; ++j) tmp[j] = x[perm[j] - 1];
+          memcpy(x, tmp, sizeof(double) * ng);
+        }
+      double* one[3] = {w.incoming_sw, w.alb_dir, w.alb_diff};
+      for (int a = 0; a < 3; ++a) { for (int j = 0; j < ng; ++j) tmp[j] = one[a][perm[j] - 1]; memcpy(one[a], tmp, sizeof(double) * ng); }
+      for (int j = 0; j < ng; ++j) tp->band_sw[j] = t->band_sw[perm[j] - 1];
+    }
+    free(tmp);
+    t = tp;
+  }
   if (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0);
   else if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1);
   else if (cfg->do_sw) { if (cfg->i_solver_sw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1); else solver_sw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   surface_spectral(t, cfg, jcol, out);
   toa_spectral(t, cfg, jcol, (cfg->do_sw && in->cos_sza) ? in->cos_sza[jcol] : 1.0, out);
-  free(w.w); free(phl_full);
+  free(w.w); free(phl_full); free(tp);
   return 0;
 }
 

@@ -175,3 +175,27 @@ def test_spartacus_full_size_properties(meridian_raw):
     for nm in FLUXES:
         assert np.abs(out[nm][idx] - ref[nm]).max() <= TOL, nm
     assert np.array_equal(out["cloud_cover_sw"][idx], ref["cloud_cover_sw"])
+
+
+def test_spartacus_i3rc_vs_mystic_and_oracle():
+    """The reference's I3RC cumulus test (test/i3rc) on the GPU: within the bounds of tests/test_i3rc_libradtran.py of libRadtran's
+    MYSTIC 3D Monte-Carlo fluxes, and within 1e-6 W m-2 of the oracle, per-g-point outputs (in the reordered SPARTACUS sequence of
+    radiation_ifs_rrtm.F90:122-130) included."""
+    import test_i3rc_libradtran as L
+    from ecrad_b200.radiation_interface import setup_radiation
+    from oracle_lib import Oracle
+    fix, lib = L.load()
+    pairs = []
+
+    def run(raw, **kw):
+        cfg = RadiationConfig(**kw).consolidate()
+        h = setup_radiation(cfg)
+        n = len(raw["cos_solar_zenith_angle"])
+        out = h.radiation(I.to_radiation_inputs(raw, cfg), n, 164)
+        h.finalize()
+        pairs.append((out, Oracle(cfg).radiation(I.to_radiation_inputs(raw, cfg), n, 164)))
+        return out
+
+    L.check_against_libradtran(run, fix, lib)
+    for out, ref in pairs:
+        compare(out, ref, FLUXES + OTHERS)

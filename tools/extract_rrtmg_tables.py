@@ -201,6 +201,22 @@ def aerosol_tables(ref):
     return out
 
 
+def gpoint_reordering(ref):
+    """RRTM_GPOINT_REORDERING_SW / _LW (radiation_ifs_rrtm.F90:50-68): the order SPARTACUS wants the g-points in (approximately
+    increasing gas optical depth), i.e. config%i_g_from_reordered_g_{sw,lw} when that spectrum's solver is SPARTACUS
+    (radiation_ifs_rrtm.F90:122-130, :167-174); every other solver gets the identity and does not read these arrays."""
+    import re
+
+    src = open(os.path.join(ref, "radiation", "radiation_ifs_rrtm.F90")).read()
+    out = {}
+    for spec, n in (("SW", 112), ("LW", 140)):
+        m = re.search(r"RRTM_GPOINT_REORDERING_%s\(%d\)\s*=\s*\(/(.*?)/\)" % (spec, n), src, re.S)
+        vals = np.array([int(v) for v in re.findall(r"\d+", m.group(1).replace("&", " "))], dtype=np.int32)
+        assert len(vals) == n and sorted(vals) == list(range(1, n + 1)), spec
+        out[f"i_g_from_reordered_g_{spec.lower()}"] = vals
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -209,6 +225,7 @@ def main():
     tabs = rrtmg_tables(args.ref)
     tabs.update(nc_tables(args.ref))
     tabs.update(aerosol_tables(args.ref))
+    tabs.update(gpoint_reordering(args.ref))
     write_blob(args.out, tabs)
     tot = sum(v.nbytes for v in tabs.values())
     print(f"wrote {args.out}: {len(tabs)} arrays, {tot/1e6:.2f} MB")

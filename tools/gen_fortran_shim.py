@@ -307,6 +307,9 @@ def main():
     w("    call add_r2(t, 'sw_albedo_weights', config%sw_albedo_weights)     ! (n_albedo_sw, n_bands_sw)")
     w("    if (allocated(config%i_albedo_from_band_sw)) call add_i1(t, 'i_albedo_from_band_sw', config%i_albedo_from_band_sw)")
     w("    if (allocated(config%i_emiss_from_band_lw)) call add_i1(t, 'i_emiss_from_band_lw', config%i_emiss_from_band_lw)")
+    w("    ! g-point order of the solvers (radiation_ifs_rrtm.F90:122-130, :167-174): a permutation for SPARTACUS, the identity otherwise")
+    w("    if (allocated(config%i_g_from_reordered_g_sw)) call add_i1(t, 'i_g_from_reordered_g_sw', config%i_g_from_reordered_g_sw)")
+    w("    if (allocated(config%i_g_from_reordered_g_lw)) call add_i1(t, 'i_g_from_reordered_g_lw', config%i_g_from_reordered_g_lw)")
     w("    if (allocated(config%lw_emiss_weights)) call add_r2(t, 'lw_emiss_weights', config%lw_emiss_weights)")
     w("    if (config%use_aerosols) then                                      ! config%aerosol_optics (radiation_aerosol_optics_data.F90:35-120)")
     w("      call add_i1(t, 'aerosol_iclass', config%aerosol_optics%iclass); call add_i1(t, 'aerosol_itype', config%aerosol_optics%itype)")

@@ -7,6 +7,7 @@ Run in the authoring container (needs /root/reference); the GPU box only sees th
            test/ifs/ecrad_meridian_cloudless_out_REFERENCE.nc  -> tests/golden/ecrad_meridian_cloudless_ref.npz
            ... and the default, expexp, tripleclouds, ecckd_mcica, ecckd_tc reference outputs likewise
   i3rc   : test/i3rc/i3rc_mls_cumulus.nc                       -> tests/golden/i3rc_mls_cumulus_inputs.npz
+           test/i3rc/i3rc_mls_cumulus_LIBRADTRAN.mat            -> tests/golden/i3rc_libradtran.npz (DISORT-ICA and MYSTIC-3D fluxes)
   ckdmip : test/ckdmip/ckdmip_evaluation1_*_present_reduced.nc -> tests/golden/ckdmip_evaluation1.npz (50 clear-sky profiles + line-by-line fluxes)
 Usage: make_golden_fixtures.py [reference root] [section ...]   (sections: meridian i3rc ckdmip; default all)
 The golden outputs are float32 as written by the reference driver (do_write_double_precision=false); the
@@ -65,6 +66,17 @@ def i3rc():
           "inv_cloud_effective_size": rep(V["inv_cloud_effective_size"])}
     np.savez_compressed(f"{OUT}/i3rc_mls_cumulus_inputs.npz", **i3)
     print("i3rc_mls_cumulus_inputs.npz:", n, "columns,", nl, "layers")
+    # the benchmark the reference's plot_i3rc.m judges SPARTACUS by (Hogan et al. 2016, Fig. 4): libRadtran on the full 3D cloud field,
+    # DISORT in independent columns ("1D") and the MYSTIC Monte-Carlo model ("3D", with its standard error), nine solar zenith angles
+    from scipy.io import loadmat
+    m = loadmat(f"{REF}/test/i3rc/i3rc_mls_cumulus_LIBRADTRAN.mat")
+    keep = ("sza", "up_toa_1D", "up_toa_3D", "up_toa_std_3D", "dn_surf_1D", "dn_surf_3D", "dn_direct_surf_1D", "dn_direct_surf_3D",
+            "dn_direct_surf_std_3D")
+    lib = {k: np.asarray(m[k], dtype=np.float64).ravel() for k in keep}
+    lib["up_toa_clear"] = np.asarray(m["sw_up_clear"], dtype=np.float64)[-1]
+    lib["dn_surf_clear"] = np.asarray(m["sw_dn_clear"], dtype=np.float64)[0]
+    np.savez_compressed(f"{OUT}/i3rc_libradtran.npz", **lib)
+    print("i3rc_libradtran.npz:", {k: v.shape for k, v in lib.items()})
 
 
 # ---- CKDMIP "evaluation-1" clear-sky data set (test/ckdmip, Hogan & Matricardi 2020): 50 profiles x 54 layers with the line-by-line
