@@ -16,11 +16,13 @@
 // This is the first correct version of the path; nothing here is tuned yet.
 #include "solver_common.cuh"
 #include "sp_core.h"
+#include "sp_coop.cuh"
 #include "tc_shared.cuh"
 
 namespace ecb {
 
 enum { SP_LCH = 4, SP_LCH_LW = 8 };
+enum { SP_SW_NE = 63, SP_LW_NE = 36 };   // entries of a g-point's layer matrix kept in shared memory (shortwave pattern / dense 6x6)
 enum { SP_SW_CLR = 5, SP_SW_MAT = 45, SP_SW_ALB = 20, SP_LW_CLR = 4, SP_LW_MAT = 24, SP_LW_ALB = 14 };
 
 __host__ __device__ inline size_t sp_doubles_sw(int nlev, int ng) { return (size_t)ng * ((size_t)(SP_SW_CLR + SP_SW_MAT) * nlev + (size_t)SP_SW_ALB * (nlev + 1)); }
@@ -52,14 +54,22 @@ __device__ __forceinline__ int sp_first_thick_g(int* s_first, bool act, int rank
 // =========================================================================================================
 // SW: layer properties (radiation_spartacus_sw.F90:420-835)
 // =========================================================================================================
+// mode 0: cloud-free layers (clear-sky arrays only; no shared memory needed); mode 1: the layers that need the region matrices
+// (cloudy ones, or all with use_expm_everywhere).  Two launches of the same grid, so that the many cheap clear-layer CTAs are not
+// throttled by the shared memory the matrix exponentials of the few cloudy ones reserve.
 template <class SD, int MINB>
 __global__ void __launch_bounds__(SD::THREADS, MINB)
-sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
+sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_first;
   const int l = blockIdx.x, c = blockIdx.y, g = threadIdx.x;
+  const SpCfg& sc = cfg.sp;
+  const double frac = LD_IN(in.frac, c, l);
+  const bool cloudy = frac > 0.0;
+  const bool heavy = cloudy || sc.use_expm_everywhere;
+  if (heavy != (mode == 1)) return;
   const double mu0 = in.cos_sza[c];
   if (mu0 < 1.0e-10) return;
-  const SpCfg& sc = cfg.sp;
   const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   const size_t n = (size_t)nlev * SD::NG;
@@ -73,10 +83,8 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   if (act) {
     clr[0 * n + i] = Lc.ref; clr[1 * n + i] = Lc.trans; clr[2 * n + i] = Lc.ref_dir; clr[3 * n + i] = Lc.trans_dir_diff; clr[4 * n + i] = Lc.trans_dir_dir;
   }
-  const double frac = LD_IN(in.frac, c, l);
-  const bool cloudy = frac > 0.0;
   // clear-sky layer: the (1,1) elements are the clear-sky values, unless use_expm_everywhere asks for the matrix exponential there too
-  if (!cloudy && !sc.use_expm_everywhere) return;
+  if (!heavy) return;
   const int nra = cloudy ? 3 : 1;   // nregactive
   // ---- cloudy layer (or a clear one treated with the matrix exponential) ----
   const double* reg = w.tc_reg + ((size_t)c * nlev + l) * 3;
@@ -93,9 +101,8 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   }
   const int rank = T.meta->rank_sw[gg];
   const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, rank, SD::NG, odg > sc.max_gas_od_3d) : 0;
-  if (!act) return;
   // optical properties of the regions (:606-655)
-  const int b = T.meta->band_of_g_sw[g];
+  const int b = T.meta->band_of_g_sw[gg];
   const double* clb = w.cl_sw + ((size_t)c * nlev + l) * 3 * SD::NB;
   double od_r[3], ssa_r[3], g_r[3];
   od_r[0] = odg; ssa_r[0] = ssag; g_r[0] = gas_g;
@@ -109,7 +116,8 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     g_r[jr] = (scat_od * gas_g + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
     if (od_r[jr] > sc.max_cloud_od) od_r[jr] = sc.max_cloud_od;
   }
-  if (rank >= ng3d) {
+  const bool need = act && rank < ng3d;   // this g-point's layer matrices come from the matrix exponential
+  if (act && !need) {
     // Meador-Weaver per region: diagonal matrices (:783-832)
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -122,76 +130,86 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       mats[(size_t)(27 + k) * SD::NG + g] = L.trans_dir_diff;
       mats[(size_t)(36 + k) * SD::NG + g] = L.trans_dir_dir;
     }
-    return;
   }
-  // ---- 9x9 matrix exponential (:658-770) ----
-  const double one_over_mu0 = 1.0 / mu0;
-  double G[81], W[3 * 81];
-  for (int k = 0; k < 81; ++k) G[k] = 0.0;
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+  if (!need_mask) return;   // (warp-uniform)
+  // ---- 9x9 matrix exponential (:658-770), warp-cooperative (sp_coop.cuh) ----
+  // The lanes' matrices live in shared memory, entry e of lane t at Gs[e * 32 + t] (63 entries of the shortwave pattern)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Gs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (SP_SW_NE * 32 + Coop<9>::PER_WARP);
+  double* stage = Gs + SP_SW_NE * 32;
+#define G_(r, cc) Gs[coop_entry<9, true>(r, cc) * 32 + lane]
+  if (need) {
+    const double one_over_mu0 = 1.0 / mu0;
+    for (int k = 0; k < SP_SW_NE; ++k) Gs[k * 32 + lane] = 0.0;
 #pragma unroll
-  for (int jr = 0; jr < 3; ++jr) {
-    if (jr >= nra) continue;
-    const double factor = 0.75 * g_r[jr];   // calc_two_stream_gammas_sw
-    const double gamma1 = 2.0 - ssa_r[jr] * (1.25 + factor), gamma2 = ssa_r[jr] * (0.75 - factor), gamma3 = 0.5 - mu0 * factor;
-    G[jr * 9 + jr] = od_r[jr] * gamma1;
-    G[(jr + 3) * 9 + jr] = od_r[jr] * gamma2;
-    G[jr * 9 + jr + 6] = -od_r[jr] * ssa_r[jr] * gamma3;
-    G[(jr + 3) * 9 + jr + 6] = od_r[jr] * ssa_r[jr] * (1.0 - gamma3);
-    G[(jr + 6) * 9 + jr + 6] = -od_r[jr] * one_over_mu0;
-  }
+    for (int jr = 0; jr < 3; ++jr) {
+      if (jr >= nra) continue;
+      const double factor = 0.75 * g_r[jr];   // calc_two_stream_gammas_sw
+      const double gamma1 = 2.0 - ssa_r[jr] * (1.25 + factor), gamma2 = ssa_r[jr] * (0.75 - factor), gamma3 = 0.5 - mu0 * factor;
+      G_(jr, jr) = od_r[jr] * gamma1;
+      G_(jr + 3, jr) = od_r[jr] * gamma2;
+      G_(jr, jr + 6) = -od_r[jr] * ssa_r[jr] * gamma3;
+      G_(jr + 3, jr + 6) = od_r[jr] * ssa_r[jr] * (1.0 - gamma3);
+      G_(jr + 6, jr + 6) = -od_r[jr] * one_over_mu0;
+    }
 #pragma unroll
-  for (int jr = 0; jr < 2; ++jr) {
-    if (jr + 1 >= nra) continue;
-    G[jr * 9 + jr] = G[jr * 9 + jr] + rate_dif[jr * 3 + jr + 1];
-    G[(jr + 1) * 9 + jr + 1] = G[(jr + 1) * 9 + jr + 1] + rate_dif[(jr + 1) * 3 + jr];
-    G[(jr + 1) * 9 + jr] = -rate_dif[jr * 3 + jr + 1];
-    G[jr * 9 + jr + 1] = -rate_dif[(jr + 1) * 3 + jr];
-    G[(jr + 6) * 9 + jr + 6] = G[(jr + 6) * 9 + jr + 6] - rate_dir[jr * 3 + jr + 1];
-    G[(jr + 7) * 9 + jr + 7] = G[(jr + 7) * 9 + jr + 7] - rate_dir[(jr + 1) * 3 + jr];
-    G[(jr + 7) * 9 + jr + 6] = rate_dir[jr * 3 + jr + 1];
-    G[(jr + 6) * 9 + jr + 7] = rate_dir[(jr + 1) * 3 + jr];
+    for (int jr = 0; jr < 2; ++jr) {
+      if (jr + 1 >= nra) continue;
+      G_(jr, jr) = G_(jr, jr) + rate_dif[jr * 3 + jr + 1];
+      G_(jr + 1, jr + 1) = G_(jr + 1, jr + 1) + rate_dif[(jr + 1) * 3 + jr];
+      G_(jr + 1, jr) = -rate_dif[jr * 3 + jr + 1];
+      G_(jr, jr + 1) = -rate_dif[(jr + 1) * 3 + jr];
+      G_(jr + 6, jr + 6) = G_(jr + 6, jr + 6) - rate_dir[jr * 3 + jr + 1];
+      G_(jr + 7, jr + 7) = G_(jr + 7, jr + 7) - rate_dir[(jr + 1) * 3 + jr];
+      G_(jr + 7, jr + 6) = rate_dir[jr * 3 + jr + 1];
+      G_(jr + 6, jr + 7) = rate_dir[(jr + 1) * 3 + jr];
+    }
+    if (edge[2] > 0.0) {
+      G_(0, 0) = G_(0, 0) + rate_dif[2];
+      G_(2, 2) = G_(2, 2) + rate_dif[6];
+      G_(2, 0) = -rate_dif[2];
+      G_(0, 2) = -rate_dif[6];
+      G_(6, 6) = G_(6, 6) - rate_dir[2];
+      G_(8, 8) = G_(8, 8) - rate_dir[6];
+      G_(8, 6) = rate_dir[2];
+      G_(6, 8) = rate_dir[6];
+    }
+    for (int a = 0; a < nra; ++a)
+      for (int bb = 0; bb < nra; ++bb) G_(3 + a, 3 + bb) = -G_(a, bb);
+    for (int a = 0; a < nra; ++a)
+      for (int bb = 0; bb < nra; ++bb) G_(a, 3 + bb) = -G_(3 + a, bb);
   }
-  if (edge[2] > 0.0) {
-    G[0] = G[0] + rate_dif[2];
-    G[2 * 9 + 2] = G[2 * 9 + 2] + rate_dif[6];
-    G[2 * 9 + 0] = -rate_dif[2];
-    G[0 * 9 + 2] = -rate_dif[6];
-    G[6 * 9 + 6] = G[6 * 9 + 6] - rate_dir[2];
-    G[8 * 9 + 8] = G[8 * 9 + 8] - rate_dir[6];
-    G[8 * 9 + 6] = rate_dir[2];
-    G[6 * 9 + 8] = rate_dir[6];
-  }
-  for (int a = 0; a < nra; ++a)
-    for (int bb = 0; bb < nra; ++bb) G[(3 + a) * 9 + 3 + bb] = -G[a * 9 + bb];
-  for (int a = 0; a < nra; ++a)
-    for (int bb = 0; bb < nra; ++bb) G[a * 9 + 3 + bb] = -G[(3 + a) * 9 + bb];
-  sp_expm<9, true>(G, W);
+  __syncwarp();
+  coop_expm_warp<9, true>(Gs, need_mask, stage);
+  if (!need) return;
   double E11[9], E21[9], X[9], R[9];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int bb = 0; bb < 3; ++bb) { E11[a * 3 + bb] = G[a * 9 + bb]; E21[a * 3 + bb] = G[(3 + a) * 9 + bb]; }
+    for (int bb = 0; bb < 3; ++bb) { E11[a * 3 + bb] = G_(a, bb); E21[a * 3 + bb] = G_(3 + a, bb); }
   // direct transmission
 #pragma unroll
-  for (int k = 0; k < 9; ++k) mats[(size_t)(36 + k) * SD::NG + g] = dmin(1.0, dmax(0.0, G[(6 + k / 3) * 9 + 6 + k % 3]));
+  for (int k = 0; k < 9; ++k) mats[(size_t)(36 + k) * SD::NG + g] = dmin(1.0, dmax(0.0, G_(6 + k / 3, 6 + k % 3)));
   // diffuse reflectance and transmittance
 #pragma unroll
-  for (int k = 0; k < 9; ++k) X[k] = G[(k / 3) * 9 + 3 + k % 3];
+  for (int k = 0; k < 9; ++k) X[k] = G_(k / 3, 3 + k % 3);
   m3_solve_mat(E11, X, X);
 #pragma unroll
   for (int k = 0; k < 9; ++k) { R[k] = dmin(1.0, dmax(0.0, -X[k])); mats[(size_t)k * SD::NG + g] = R[k]; }
   m3_x_m3(E21, R, X);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) mats[(size_t)(9 + k) * SD::NG + g] = dmin(1.0, dmax(0.0, X[k] + G[(3 + k / 3) * 9 + 3 + k % 3]));
+  for (int k = 0; k < 9; ++k) mats[(size_t)(9 + k) * SD::NG + g] = dmin(1.0, dmax(0.0, X[k] + G_(3 + k / 3, 3 + k % 3)));
   // direct -> diffuse up / down
 #pragma unroll
-  for (int k = 0; k < 9; ++k) X[k] = G[(k / 3) * 9 + 6 + k % 3];
+  for (int k = 0; k < 9; ++k) X[k] = G_(k / 3, 6 + k % 3);
   m3_solve_mat(E11, X, X);
 #pragma unroll
   for (int k = 0; k < 9; ++k) { R[k] = dmin(mu0, dmax(0.0, -X[k])); mats[(size_t)(18 + k) * SD::NG + g] = R[k]; }
   m3_x_m3(E21, R, X);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) mats[(size_t)(27 + k) * SD::NG + g] = dmin(mu0, dmax(0.0, X[k] + G[(3 + k / 3) * 9 + 6 + k % 3]));
+  for (int k = 0; k < 9; ++k) mats[(size_t)(27 + k) * SD::NG + g] = dmin(mu0, dmax(0.0, X[k] + G_(3 + k / 3, 6 + k % 3)));
+#undef G_
 }
 
 // per-column shared data of the sweeps on top of the Tripleclouds region data: layer depths and cloud edge lengths
@@ -520,10 +538,15 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
 // =========================================================================================================
 template <class SD, int MINB>
 __global__ void __launch_bounds__(SD::THREADS, MINB)
-sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
+sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode) {   // mode: see sp_sw_layer_kernel
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_first;
   const int l = blockIdx.x, c = blockIdx.y, g = threadIdx.x;
   const SpCfg& sc = cfg.sp;
+  const double frac = LD_IN(in.frac, c, l);
+  const bool cloudy = frac > 0.0;
+  const bool heavy = cloudy || sc.use_expm_everywhere;
+  if (heavy != (mode == 1)) return;
   const bool act = g < SD::NG;
   const int gg = act ? g : 0;
   const size_t n = (size_t)nlev * SD::NG;
@@ -534,9 +557,7 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   double* mats = clr + (size_t)SP_LW_CLR * n + (size_t)l * SP_LW_MAT * SD::NG;
   const LwLayer Lc = lw_ref_trans(odg, 0.0, 0.0, pt, pb);
   if (act) { clr[i] = Lc.ref; clr[n + i] = Lc.trans; clr[2 * n + i] = Lc.source_up; clr[3 * n + i] = Lc.source_dn; }
-  const double frac = LD_IN(in.frac, c, l);
-  const bool cloudy = frac > 0.0;
-  if (!cloudy && !sc.use_expm_everywhere) return;
+  if (!heavy) return;
   const int nra = cloudy ? 3 : 1;   // nregActive
   const double* reg = w.tc_reg + ((size_t)c * nlev + l) * 3;
   const double* ods = w.tc_ods + ((size_t)c * nlev + l) * 3;
@@ -549,10 +570,9 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate);
   }
-  const int rank = T.meta->rank_lw[act ? g : 0];
+  const int rank = T.meta->rank_lw[gg];
   const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, rank, SD::NG, odg > sc.max_gas_od_3d) : 0;
-  if (!act) return;
-  const int b = T.meta->band_of_g_lw[g];
+  const int b = T.meta->band_of_g_lw[gg];
   const double* clb = w.cl_lw + ((size_t)c * nlev + l) * 3 * SD::NB;
   double od_r[3], ssa_r[3] = {0.0, 0.0, 0.0}, g_r[3] = {0.0, 0.0, 0.0};
   od_r[0] = odg;
@@ -567,7 +587,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
     }
     if (od_r[jr] > sc.max_cloud_od) od_r[jr] = sc.max_cloud_od;
   }
-  if (rank >= ng3d) {
+  const bool need = act && rank < ng3d;
+  if (act && !need) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int jr = k / 4;
@@ -581,79 +602,91 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       mats[(size_t)k * SD::NG + g] = L.ref;
       mats[(size_t)(9 + k) * SD::NG + g] = L.trans;
     }
-    return;
   }
-  // ---- 6x6 matrix exponential (:596-727) ----
-  double G[36], W[3 * 36], planck_top[6], planck_diff[6], solution0[6], solution_diff[6];
-  for (int k = 0; k < 36; ++k) G[k] = 0.0;
+  const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+  if (!need_mask) return;   // (warp-uniform)
+  // ---- 6x6 matrix exponential (:596-727), warp-cooperative (sp_coop.cuh): entry e of lane t at Gs[e * 32 + t] ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Gs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (SP_LW_NE * 32 + Coop<6>::PER_WARP);
+  double* stage = Gs + SP_LW_NE * 32;
+#define G_(r, cc) Gs[((r) * 6 + (cc)) * 32 + lane]
+  double solution0[6], solution_diff[6];
+  if (need) {
+    double planck_top[6], planck_diff[6];
+    for (int k = 0; k < 36; ++k) Gs[k * 32 + lane] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { planck_top[k] = 0.0; planck_diff[k] = 0.0; }
+    for (int k = 0; k < 6; ++k) { planck_top[k] = 0.0; planck_diff[k] = 0.0; }
 #pragma unroll
-  for (int jr = 0; jr < 3; ++jr) {
-    if (jr >= nra) continue;
-    const double factor = (ECB_LW_DIFFUSIVITY * 0.5) * ssa_r[jr];   // calc_two_stream_gammas_lw
-    const double gamma1 = ECB_LW_DIFFUSIVITY - factor * (1.0 + g_r[jr]), gamma2 = factor * (1.0 - g_r[jr]);
-    G[jr * 6 + jr] = od_r[jr] * gamma1;
-    G[(jr + 3) * 6 + jr] = od_r[jr] * gamma2;
-    planck_top[3 + jr] = od_r[jr] * (1.0 - ssa_r[jr]) * reg[jr] * pt * ECB_LW_DIFFUSIVITY;
-    planck_top[jr] = -planck_top[3 + jr];
-    planck_diff[3 + jr] = od_r[jr] * (1.0 - ssa_r[jr]) * reg[jr] * (pb - pt) * ECB_LW_DIFFUSIVITY;
-    planck_diff[jr] = -planck_diff[3 + jr];
-  }
-  // non-zeros in the empty cloudy regions of a clear layer, to avoid NaNs (:622-630)
-  for (int jr = nra; jr < 3; ++jr) { G[jr * 6 + jr] = G[0]; G[(3 + jr) * 6 + jr] = G[3 * 6 + 0]; }
-  double side_emiss = 1.0;
-  if (sc.do_lw_side_emissivity && reg[0] > 0.0 && reg[1] > 0.0 && sc.do_3d_effects && inv_size > 0.0) {
-    const double aspect_ratio = 1.0 / (dmin(inv_size, 1.0 / sc.min_cloud_effective_size) * reg[0] * dz);
-    double s = 0.0;
-#pragma unroll
-    for (int jr = 1; jr < 3; ++jr) s = s + od_r[jr] * (1.0 - ssa_r[jr]);
-    const double lateral_od = (aspect_ratio / (3 - 1.0)) * s;
-    const double sqrt_1_minus_ssa = sqrt(1.0 - ssa_r[1]);
-    const double side_emiss_thick = 2.0 * sqrt_1_minus_ssa / (sqrt_1_minus_ssa + sqrt(1.0 - ssa_r[1] * g_r[1]));
-    side_emiss = (1.4107 - side_emiss_thick) / (lateral_od + 1.0) + side_emiss_thick;
-  }
-#pragma unroll
-  for (int jr = 0; jr < 2; ++jr) {
-    if (jr + 1 >= nra) continue;
-    G[jr * 6 + jr] = G[jr * 6 + jr] + rate[jr * 3 + jr + 1];
-    G[(jr + 1) * 6 + jr] = -rate[jr * 3 + jr + 1];
-    if (jr > 0) {
-      G[(jr + 1) * 6 + jr + 1] = G[(jr + 1) * 6 + jr + 1] + rate[(jr + 1) * 3 + jr];
-      G[jr * 6 + jr + 1] = -rate[(jr + 1) * 3 + jr];
-    } else {
-      G[(jr + 1) * 6 + jr + 1] = G[(jr + 1) * 6 + jr + 1] + side_emiss * rate[(jr + 1) * 3 + jr];
-      G[jr * 6 + jr + 1] = -side_emiss * rate[(jr + 1) * 3 + jr];
+    for (int jr = 0; jr < 3; ++jr) {
+      if (jr >= nra) continue;
+      const double factor = (ECB_LW_DIFFUSIVITY * 0.5) * ssa_r[jr];   // calc_two_stream_gammas_lw
+      const double gamma1 = ECB_LW_DIFFUSIVITY - factor * (1.0 + g_r[jr]), gamma2 = factor * (1.0 - g_r[jr]);
+      G_(jr, jr) = od_r[jr] * gamma1;
+      G_(jr + 3, jr) = od_r[jr] * gamma2;
+      planck_top[3 + jr] = od_r[jr] * (1.0 - ssa_r[jr]) * reg[jr] * pt * ECB_LW_DIFFUSIVITY;
+      planck_top[jr] = -planck_top[3 + jr];
+      planck_diff[3 + jr] = od_r[jr] * (1.0 - ssa_r[jr]) * reg[jr] * (pb - pt) * ECB_LW_DIFFUSIVITY;
+      planck_diff[jr] = -planck_diff[3 + jr];
     }
-  }
-  if (edge[2] > 0.0) {
-    G[0] = G[0] + rate[2];
-    G[2 * 6 + 0] = -rate[2];
-    G[2 * 6 + 2] = G[2 * 6 + 2] + side_emiss * rate[6];
-    G[0 * 6 + 2] = -side_emiss * rate[6];
-  }
-  for (int a = 0; a < 3; ++a)
-    for (int bb = 0; bb < 3; ++bb) G[(3 + a) * 6 + 3 + bb] = -G[a * 6 + bb];
-  for (int a = 0; a < 3; ++a)
-    for (int bb = 0; bb < 3; ++bb) G[a * 6 + 3 + bb] = -G[(3 + a) * 6 + bb];
-  // particular solution: solve_vec(Gamma, .) twice with one factorisation
-  for (int k = 0; k < 36; ++k) W[k] = G[k];
-  sp_lu<6>(W);
+    // non-zeros in the empty cloudy regions of a clear layer, to avoid NaNs (:622-630)
+    for (int jr = nra; jr < 3; ++jr) { G_(jr, jr) = G_(0, 0); G_(3 + jr, jr) = G_(3, 0); }
+    double side_emiss = 1.0;
+    if (sc.do_lw_side_emissivity && reg[0] > 0.0 && reg[1] > 0.0 && sc.do_3d_effects && inv_size > 0.0) {
+      const double aspect_ratio = 1.0 / (dmin(inv_size, 1.0 / sc.min_cloud_effective_size) * reg[0] * dz);
+      double sm = 0.0;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) solution_diff[k] = planck_diff[k];
-  sp_lu_subst<6>(W, solution_diff, 1, 1);
+      for (int jr = 1; jr < 3; ++jr) sm = sm + od_r[jr] * (1.0 - ssa_r[jr]);
+      const double lateral_od = (aspect_ratio / (3 - 1.0)) * sm;
+      const double sqrt_1_minus_ssa = sqrt(1.0 - ssa_r[1]);
+      const double side_emiss_thick = 2.0 * sqrt_1_minus_ssa / (sqrt_1_minus_ssa + sqrt(1.0 - ssa_r[1] * g_r[1]));
+      side_emiss = (1.4107 - side_emiss_thick) / (lateral_od + 1.0) + side_emiss_thick;
+    }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { solution_diff[k] = -solution_diff[k]; solution0[k] = solution_diff[k] - planck_top[k]; }
-  sp_lu_subst<6>(W, solution0, 1, 1);
-  sp_expm<6, false>(G, W);
+    for (int jr = 0; jr < 2; ++jr) {
+      if (jr + 1 >= nra) continue;
+      G_(jr, jr) = G_(jr, jr) + rate[jr * 3 + jr + 1];
+      G_(jr + 1, jr) = -rate[jr * 3 + jr + 1];
+      if (jr > 0) {
+        G_(jr + 1, jr + 1) = G_(jr + 1, jr + 1) + rate[(jr + 1) * 3 + jr];
+        G_(jr, jr + 1) = -rate[(jr + 1) * 3 + jr];
+      } else {
+        G_(jr + 1, jr + 1) = G_(jr + 1, jr + 1) + side_emiss * rate[(jr + 1) * 3 + jr];
+        G_(jr, jr + 1) = -side_emiss * rate[(jr + 1) * 3 + jr];
+      }
+    }
+    if (edge[2] > 0.0) {
+      G_(0, 0) = G_(0, 0) + rate[2];
+      G_(2, 0) = -rate[2];
+      G_(2, 2) = G_(2, 2) + side_emiss * rate[6];
+      G_(0, 2) = -side_emiss * rate[6];
+    }
+    for (int a = 0; a < 3; ++a)
+      for (int bb = 0; bb < 3; ++bb) G_(3 + a, 3 + bb) = -G_(a, bb);
+    for (int a = 0; a < 3; ++a)
+      for (int bb = 0; bb < 3; ++bb) G_(a, 3 + bb) = -G_(3 + a, bb);
+    // particular solution: solve_vec(Gamma, .) twice with one factorisation
+    double W[36];
+    for (int k = 0; k < 36; ++k) W[k] = Gs[k * 32 + lane];
+    sp_lu<6>(W);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) solution_diff[k] = planck_diff[k];
+    sp_lu_subst<6>(W, solution_diff, 1, 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { solution_diff[k] = -solution_diff[k]; solution0[k] = solution_diff[k] - planck_top[k]; }
+    sp_lu_subst<6>(W, solution0, 1, 1);
+  }
+  __syncwarp();
+  coop_expm_warp<6, false>(Gs, need_mask, stage);
+  if (!need) return;
   double E11[9], E12[9], E21[9], E22[9], R[9], X[9];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int bb = 0; bb < 3; ++bb) {
-      E11[a * 3 + bb] = G[a * 6 + bb]; E12[a * 3 + bb] = G[a * 6 + 3 + bb];
-      E21[a * 3 + bb] = G[(3 + a) * 6 + bb]; E22[a * 3 + bb] = G[(3 + a) * 6 + 3 + bb];
+      E11[a * 3 + bb] = G_(a, bb); E12[a * 3 + bb] = G_(a, 3 + bb);
+      E21[a * 3 + bb] = G_(3 + a, bb); E22[a * 3 + bb] = G_(3 + a, 3 + bb);
     }
+#undef G_
   m3_solve_mat(E11, E12, X);
 #pragma unroll
   for (int k = 0; k < 9; ++k) { R[k] = -X[k]; mats[(size_t)k * SD::NG + g] = R[k]; }
@@ -918,29 +951,36 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
 static int sp_minb(const char* env, int dflt) {
   const char* s = getenv(env);
   const int v = s ? atoi(s) : dflt;
-  return v <= 2 ? 2 : 4;
+  return v <= 2 ? 2 : v == 3 ? 3 : 4;
 }
 // measured on the B200 (tools/sp_minb_sweep.sh, 20 000 columns): 2/2 -> 97 k, 4/2 -> 104 k, 2/4 -> 107 k, 4/4 -> 115 k columns/s
 #define SP_DISPATCH_MINB(minb, CALL) \
-  switch (minb) { case 2: { constexpr int MB = 2; CALL; } break; default: { constexpr int MB = 4; CALL; } break; }
+  switch (minb) { case 2: { constexpr int MB = 2; CALL; } break; case 3: { constexpr int MB = 3; CALL; } break; default: { constexpr int MB = 4; CALL; } break; }
 
 template <class SD>
 static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
-  SP_DISPATCH_MINB(mb_layer, (sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev)));
+  // cloud-free layers first (no shared memory), then the layers whose g-points need the matrix exponential
+  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_SW_NE * 32 + Coop<9>::PER_WARP);
+  SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_sw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
+                              sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev, 0),
+                              sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, sml, st>>>(T, cfg, in, w, nlev, 1)));
   const size_t sm = sizeof(double) * (6 * (nlev + 1) + 6 * SP_LCH * SD::RS + 2 * SD::NB) + sp_shared_bytes(nlev);
   SP_DISPATCH_MINB(mb_sweep, (cudaFuncSetAttribute(sp_sw_sweep_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
                               sp_sw_sweep_kernel<SD, MB><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev)));
-  return 2;
+  return 3;
 }
 template <class SD>
 static int launch_sp_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
-  SP_DISPATCH_MINB(mb_layer, (sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev)));
+  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_LW_NE * 32 + Coop<6>::PER_WARP);
+  SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_lw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
+                              sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev, 0),
+                              sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, sml, st>>>(T, cfg, in, w, nlev, 1)));
   const size_t sm = sizeof(double) * (5 * (nlev + 1) + 4 * SP_LCH_LW * SD::RS) + tc_shared_bytes(nlev);
   SP_DISPATCH_MINB(mb_sweep, (cudaFuncSetAttribute(sp_lw_sweep_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm),
                               sp_lw_sweep_kernel<SD, MB><<<nc, SD::THREADS, sm, st>>>(T, cfg, in, out, w, nlev)));
-  return 2;
+  return 3;
 }
 int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
   switch (cfg.ng_sw) {
