@@ -134,14 +134,14 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
   const unsigned need_mask = __ballot_sync(0xffffffffu, need);
   if (!need_mask) return;   // (warp-uniform)
   // ---- 9x9 matrix exponential (:658-770), warp-cooperative (sp_coop.cuh) ----
-  // The lanes' matrices live in shared memory, entry e of lane t at Gs[e * 32 + t] (63 entries of the shortwave pattern)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Gs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (SP_SW_NE * 32 + Coop<9>::PER_WARP);
-  double* stage = Gs + SP_SW_NE * 32;
-#define G_(r, cc) Gs[coop_entry<9, true>(r, cc) * 32 + lane]
+  const int warp = threadIdx.x >> 5;
+  double* stage = reinterpret_cast<double*>(smem_raw) + (size_t)warp * Coop<9>::PER_WARP;
+  double Gl[SP_SW_NE];   // this g-point's matrix: the 63 entries of the shortwave pattern
+#define G_(r, cc) Gl[coop_entry<9, true>(r, cc)]
   if (need) {
     const double one_over_mu0 = 1.0 / mu0;
-    for (int k = 0; k < SP_SW_NE; ++k) Gs[k * 32 + lane] = 0.0;
+#pragma unroll 1   // (a run-time index keeps Gl in thread-local memory: it only waits there for its round)
+    for (int k = 0; k < SP_SW_NE; ++k) Gl[k] = 0.0;
 #pragma unroll
     for (int jr = 0; jr < 3; ++jr) {
       if (jr >= nra) continue;
@@ -175,13 +175,16 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
       G_(8, 6) = rate_dir[2];
       G_(6, 8) = rate_dir[6];
     }
-    for (int a = 0; a < nra; ++a)
-      for (int bb = 0; bb < nra; ++bb) G_(3 + a, 3 + bb) = -G_(a, bb);
-    for (int a = 0; a < nra; ++a)
-      for (int bb = 0; bb < nra; ++bb) G_(a, 3 + bb) = -G_(3 + a, bb);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) if (a < nra && bb < nra) G_(3 + a, 3 + bb) = -G_(a, bb);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) if (a < nra && bb < nra) G_(a, 3 + bb) = -G_(3 + a, bb);
   }
-  __syncwarp();
-  coop_expm_warp<9, true>(Gs, need_mask, stage);
+  coop_expm_warp<9, true>(Gl, need_mask, stage);
   if (!need) return;
   double E11[9], E21[9], X[9], R[9];
 #pragma unroll
@@ -605,17 +608,17 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
   }
   const unsigned need_mask = __ballot_sync(0xffffffffu, need);
   if (!need_mask) return;   // (warp-uniform)
-  // ---- 6x6 matrix exponential (:596-727), warp-cooperative (sp_coop.cuh): entry e of lane t at Gs[e * 32 + t] ----
+  // ---- 6x6 matrix exponential (:596-727), warp-cooperative (sp_coop.cuh) ----
+  // the lanes' matrices wait in shared memory, entry e of lane t at Gs[e * SP_LD + t]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Gs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (SP_LW_NE * 32 + Coop<6>::PER_WARP);
-  double* stage = Gs + SP_LW_NE * 32;
-#define G_(r, cc) Gs[((r) * 6 + (cc)) * 32 + lane]
-  double solution0[6], solution_diff[6];
-  if (need) {
-    double planck_top[6], planck_diff[6];
-    for (int k = 0; k < 36; ++k) Gs[k * 32 + lane] = 0.0;
+  double* Gs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (SP_LW_NE * SP_LD + Coop<6>::PER_WARP);
+  double* stage = Gs + SP_LW_NE * SP_LD;
+#define G_(r, cc) Gs[((r) * 6 + (cc)) * SP_LD + lane]
+  double solution0[6], solution_diff[6], planck_top[6], planck_diff[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { planck_top[k] = 0.0; planck_diff[k] = 0.0; }
+  for (int k = 0; k < 6; ++k) { planck_top[k] = 0.0; planck_diff[k] = 0.0; solution0[k] = 0.0; solution_diff[k] = 0.0; }
+  if (need) {
+    for (int k = 0; k < 36; ++k) Gs[k * SP_LD + lane] = 0.0;
 #pragma unroll
     for (int jr = 0; jr < 3; ++jr) {
       if (jr >= nra) continue;
@@ -629,7 +632,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
       planck_diff[jr] = -planck_diff[3 + jr];
     }
     // non-zeros in the empty cloudy regions of a clear layer, to avoid NaNs (:622-630)
-    for (int jr = nra; jr < 3; ++jr) { G_(jr, jr) = G_(0, 0); G_(3 + jr, jr) = G_(3, 0); }
+#pragma unroll
+    for (int jr = 1; jr < 3; ++jr) if (jr >= nra) { G_(jr, jr) = G_(0, 0); G_(3 + jr, jr) = G_(3, 0); }
     double side_emiss = 1.0;
     if (sc.do_lw_side_emissivity && reg[0] > 0.0 && reg[1] > 0.0 && sc.do_3d_effects && inv_size > 0.0) {
       const double aspect_ratio = 1.0 / (dmin(inv_size, 1.0 / sc.min_cloud_effective_size) * reg[0] * dz);
@@ -660,23 +664,18 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
       G_(2, 2) = G_(2, 2) + side_emiss * rate[6];
       G_(0, 2) = -side_emiss * rate[6];
     }
+#pragma unroll
     for (int a = 0; a < 3; ++a)
+#pragma unroll
       for (int bb = 0; bb < 3; ++bb) G_(3 + a, 3 + bb) = -G_(a, bb);
+#pragma unroll
     for (int a = 0; a < 3; ++a)
+#pragma unroll
       for (int bb = 0; bb < 3; ++bb) G_(a, 3 + bb) = -G_(3 + a, bb);
-    // particular solution: solve_vec(Gamma, .) twice with one factorisation
-    double W[36];
-    for (int k = 0; k < 36; ++k) W[k] = Gs[k * 32 + lane];
-    sp_lu<6>(W);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) solution_diff[k] = planck_diff[k];
-    sp_lu_subst<6>(W, solution_diff, 1, 1);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { solution_diff[k] = -solution_diff[k]; solution0[k] = solution_diff[k] - planck_top[k]; }
-    sp_lu_subst<6>(W, solution0, 1, 1);
   }
   __syncwarp();
-  coop_expm_warp<6, false>(Gs, need_mask, stage);
+  // exponential of Gamma and, with the same column distribution, the two solves for the particular solution (:697-707)
+  coop_expm_warp_shared_lw<6>(Gs, need_mask, stage, planck_top, planck_diff, solution0, solution_diff);
   if (!need) return;
   double E11[9], E12[9], E21[9], E22[9], R[9], X[9];
 #pragma unroll
@@ -959,9 +958,9 @@ static int sp_minb(const char* env, int dflt) {
 
 template <class SD>
 static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_SW", 3), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
   // cloud-free layers first (no shared memory), then the layers whose g-points need the matrix exponential
-  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_SW_NE * 32 + Coop<9>::PER_WARP);
+  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * Coop<9>::PER_WARP;
   SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_sw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
                               sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev, 0),
                               sp_sw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, sml, st>>>(T, cfg, in, w, nlev, 1)));
@@ -972,8 +971,8 @@ static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in
 }
 template <class SD>
 static int launch_sp_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
-  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_LW_NE * 32 + Coop<6>::PER_WARP);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_LW", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_LW_NE * SP_LD + Coop<6>::PER_WARP);
   SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_lw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
                               sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev, 0),
                               sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, sml, st>>>(T, cfg, in, w, nlev, 1)));
