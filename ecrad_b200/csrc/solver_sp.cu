@@ -30,6 +30,9 @@ __host__ __device__ inline size_t sp_doubles_lw(int nlev, int ng) { return (size
 size_t sp_scratch_doubles_sw(int nlev, int ng) { return sp_doubles_sw(nlev, ng); }
 size_t sp_scratch_doubles_lw(int nlev, int ng) { return sp_doubles_lw(nlev, ng); }
 
+// correctly rounded reciprocal (one instruction sequence without the slow path the fp64 division takes for zero numerators)
+__device__ __forceinline__ double sp_inv(double x) { return __drcp_rn(x); }
+
 struct SpGeom { double tan_sza, one_over_mu0; };
 __device__ __forceinline__ SpGeom sp_geometry(const SpCfg& sc, double mu0) {
   SpGeom q;
@@ -310,7 +313,7 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       ALB(jl, 18) = tac; ALB(jl, 19) = tdc;
       const double rc = clr[i], trc = clr[n + i], rdc = clr[2 * n + i], tddc = clr[3 * n + i], tdrc = clr[4 * n + i];
       {   // clear-sky column (:879-893)
-        const double inv_denom = 1.0 / (1.0 - tac * rc);
+        const double inv_denom = sp_inv(1.0 - tac * rc);
         const double tac_new = rc + trc * trc * tac * inv_denom;
         tdc = rdc + (tdrc * tdc + tddc * tac) * trc * inv_denom;
         tac = tac_new;
@@ -323,7 +326,7 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         for (int k = 0; k < 9; ++k) { R[k] = 0.0; Tm[k] = 0.0; RD[k] = 0.0; TDD[k] = 0.0; TD[k] = 0.0; }
         if (sc.use_expm_everywhere) { R[0] = MAT(l, 0); Tm[0] = MAT(l, 9); RD[0] = MAT(l, 18); TDD[0] = MAT(l, 27); TD[0] = MAT(l, 36); }
         else { R[0] = rc; Tm[0] = trc; RD[0] = rdc; TDD[0] = tddc; TD[0] = tdrc; }
-        const double inv_denom = 1.0 / (1.0 - TA[0] * R[0]);
+        const double inv_denom = sp_inv(1.0 - TA[0] * R[0]);
         below[0] = R[0] + Tm[0] * Tm[0] * TA[0] * inv_denom;
         belowd[0] = RD[0] + (TD[0] * TAD[0] + TDD[0] * TA[0]) * Tm[0] * inv_denom;
       } else {
@@ -462,7 +465,7 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       {
         const double source_dn_clear = tddc * ddc;
         ddc = tdrc * ddc;
-        fdc = (trc * fdc + rc * tdcb * ddc + source_dn_clear) / (1.0 - rc * tacb);
+        fdc = (trc * fdc + rc * tdcb * ddc + source_dn_clear) * sp_inv(1.0 - rc * tacb);   // (the reciprocal does not wait for the flux recurrence)
         fuc = tdcb * ddc + tacb * fdc;
       }
       if (clear_l) {
@@ -471,7 +474,7 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc, tdd0 = ev ? MAT(l, 27) : tddc, td0 = ev ? MAT(l, 36) : tdrc;
         const double source_dn = tdd0 * ddn[0];
         const double dabove = td0 * ddn[0];
-        fdn[0] = (t0 * fdn[0] + r0 * tad0 * dabove + source_dn) / (1.0 - r0 * ta0);
+        fdn[0] = (t0 * fdn[0] + r0 * tad0 * dabove + source_dn) * sp_inv(1.0 - r0 * ta0);
         fup[0] = tad0 * dabove + ta0 * fdn[0];
         ddn[0] = dabove;
         fdn[1] = 0.0; fdn[2] = 0.0; fup[1] = 0.0; fup[2] = 0.0; ddn[1] = 0.0; ddn[2] = 0.0;
@@ -754,7 +757,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       ALB(jl, 12) = tac; ALB(jl, 13) = tsc;
       const double rc = clr[i], trc = clr[n + i], suc = clr[2 * n + i], sdc = clr[3 * n + i];
       {
-        const double inv_denom = 1.0 / (1.0 - tac * rc);
+        const double inv_denom = sp_inv(1.0 - tac * rc);
         const double tac_new = rc + trc * trc * tac * inv_denom;
         tsc = suc + trc * (tsc + tac * sdc) * inv_denom;
         tac = tac_new;
@@ -766,7 +769,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         const bool ev = sc.use_expm_everywhere != 0;
         const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc;
         const double su0 = ev ? MAT(l, 18) : S.reg[l * 3] * suc, sd0 = ev ? MAT(l, 21) : S.reg[l * 3] * sdc;
-        const double inv_denom = 1.0 / (1.0 - TA[0] * r0);
+        const double inv_denom = sp_inv(1.0 - TA[0] * r0);
         below[0] = r0 + t0 * t0 * TA[0] * inv_denom;
         sbelow[0] = su0 + t0 * (TS[0] + TA[0] * sd0) * inv_denom;
       } else {
@@ -793,7 +796,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         } else {
 #pragma unroll
           for (int jr = 0; jr < 3; ++jr) {
-            const double inv_denom = 1.0 / (1.0 - TA[jr * 4] * R[jr * 4]);
+            const double inv_denom = sp_inv(1.0 - TA[jr * 4] * R[jr * 4]);
             below[jr * 4] = R[jr * 4] + Tm[jr * 4] * Tm[jr * 4] * TA[jr * 4] * inv_denom;
             sbelow[jr] = SU[jr] + Tm[jr * 4] * (TS[jr] + TA[jr * 4] * SDn[jr]) * inv_denom;
           }
@@ -846,13 +849,13 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
       const bool clear_l = S.clear[jl];
       const double rc = clr[i], trc = clr[n + i], sdc = clr[3 * n + i];
       const double tacb = ALB(jl, 12), tscb = ALB(jl, 13);
-      fdc = (trc * fdc + rc * tscb + sdc) / (1.0 - rc * tacb);
+      fdc = (trc * fdc + rc * tscb + sdc) * sp_inv(1.0 - rc * tacb);   // (the reciprocal does not wait for the flux recurrence)
       fuc = tscb + tacb * fdc;
       if (clear_l) {
         const bool ev = sc.use_expm_everywhere != 0;
         const double r0 = ev ? MAT(l, 0) : rc, t0 = ev ? MAT(l, 9) : trc;
         const double ta0 = ALB(jl, 0), ts0 = ALB(jl, 9), sd0 = ev ? MAT(l, 21) : S.reg[l * 3] * sdc;
-        fdn[0] = (t0 * fdn[0] + r0 * ts0 + sd0) / (1.0 - r0 * ta0);
+        fdn[0] = (t0 * fdn[0] + r0 * ts0 + sd0) * sp_inv(1.0 - r0 * ta0);
         fup[0] = ts0 + ta0 * fdn[0];
         fdn[1] = 0.0; fdn[2] = 0.0; fup[1] = 0.0; fup[2] = 0.0;
       } else {
@@ -875,7 +878,7 @@ sp_lw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
         } else {
 #pragma unroll
           for (int jr = 0; jr < 3; ++jr) {
-            fdn[jr] = (Tm[jr * 4] * fdn[jr] + R[jr * 4] * TSb[jr] + SDn[jr]) / (1.0 - R[jr * 4] * TAb[jr * 4]);
+            fdn[jr] = (Tm[jr * 4] * fdn[jr] + R[jr * 4] * TSb[jr] + SDn[jr]) * sp_inv(1.0 - R[jr * 4] * TAb[jr * 4]);
             fup[jr] = TSb[jr] + TAb[jr * 4] * fdn[jr];
           }
         }
@@ -958,7 +961,7 @@ static int sp_minb(const char* env, int dflt) {
 
 template <class SD>
 static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_SW", 3), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_SW", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
   // cloud-free layers first (no shared memory), then the layers whose g-points need the matrix exponential
   const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * Coop<9>::PER_WARP;
   SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_sw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
@@ -971,7 +974,7 @@ static int launch_sp_sw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in
 }
 template <class SD>
 static int launch_sp_lw_t(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st) {
-  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_LW", 4), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
+  static const int mb_layer = sp_minb("ECRAD_B200_SP_MINB_LAYER_LW", 3), mb_sweep = sp_minb("ECRAD_B200_SP_MINB_SWEEP", 4);
   const size_t sml = sizeof(double) * (size_t)(SD::THREADS / 32) * (SP_LW_NE * SP_LD + Coop<6>::PER_WARP);
   SP_DISPATCH_MINB(mb_layer, (cudaFuncSetAttribute(sp_lw_layer_kernel<SD, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml),
                               sp_lw_layer_kernel<SD, MB><<<dim3(nlev, nc), SD::THREADS, 0, st>>>(T, cfg, in, w, nlev, 0),

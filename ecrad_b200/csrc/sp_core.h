@@ -176,20 +176,43 @@ HD void m3_identity_minus_product(const double* A, const double* B, double* C) {
   for (int i = 0; i < 9; ++i) C[i] = -C[i];
   C[0] = 1.0 + C[0]; C[4] = 1.0 + C[4]; C[8] = 1.0 + C[8];
 }
-struct M3LU { double L21, L31, L32, U22, U23, U33; };
+// Division by a value that is used as a divisor several times.  On the device: one correctly rounded reciprocal, then
+// multiplications (within 1 ulp of the quotient; and a zero numerator -- the empty regions of cloud-free layers -- no longer sends
+// the fp64 division through its slow path, which was a fifth of the sweep kernels' instructions).  On the host: the plain division,
+// so the replay of this header stays bit-identical to the oracle (tests/test_core_hostcheck.py).
+struct SpRcp { double b, r; };
+HD SpRcp sp_rcp(double b) {
+  SpRcp x; x.b = b;
+#ifdef __CUDA_ARCH__
+  x.r = __drcp_rn(b);
+#else
+  x.r = 0.0;
+#endif
+  return x;
+}
+HD double operator/(double a, const SpRcp& d) {
+#ifdef __CUDA_ARCH__
+  return a * d.r;
+#else
+  return a / d.b;
+#endif
+}
+struct M3LU { double L21, L31, L32, U23; SpRcp A0, U22, U33; };
 HD M3LU m3_lu(const double* A) {
   M3LU f;
-  f.L21 = A[3] / A[0]; f.L31 = A[6] / A[0];
-  f.U22 = A[4] - f.L21 * A[1]; f.U23 = A[5] - f.L21 * A[2];
+  f.A0 = sp_rcp(A[0]);
+  f.L21 = A[3] / f.A0; f.L31 = A[6] / f.A0;
+  const double u22 = A[4] - f.L21 * A[1];
+  f.U22 = sp_rcp(u22); f.U23 = A[5] - f.L21 * A[2];
   f.L32 = (A[7] - f.L31 * A[1]) / f.U22;
-  f.U33 = A[8] - f.L31 * A[2] - f.L32 * f.U23;
+  f.U33 = sp_rcp(A[8] - f.L31 * A[2] - f.L32 * f.U23);
   return f;
 }
 HD void m3_solve_vec(const double* A, const double* b, double* x) {   // x may alias b
   const M3LU f = m3_lu(A);
   const double y2 = b[1] - f.L21 * b[0], y3 = b[2] - f.L31 * b[0] - f.L32 * y2;
   const double x3 = y3 / f.U33, x2 = (y2 - f.U23 * x3) / f.U22;
-  const double x1 = (b[0] - A[1] * x2 - A[2] * x3) / A[0];
+  const double x1 = (b[0] - A[1] * x2 - A[2] * x3) / f.A0;
   x[0] = x1; x[1] = x2; x[2] = x3;
 }
 HD void m3_solve_mat(const double* A, const double* B, double* X) {   // X may alias B
@@ -200,7 +223,7 @@ HD void m3_solve_mat(const double* A, const double* B, double* X) {   // X may a
     const double y2 = B[3 + j] - f.L21 * B[j], y3 = B[6 + j] - f.L31 * B[j] - f.L32 * y2;
     R[6 + j] = y3 / f.U33;
     R[3 + j] = (y2 - f.U23 * R[6 + j]) / f.U22;
-    R[j] = (B[j] - A[1] * R[3 + j] - A[2] * R[6 + j]) / A[0];
+    R[j] = (B[j] - A[1] * R[3 + j] - A[2] * R[6 + j]) / f.A0;
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) X[i] = R[i];
@@ -213,21 +236,23 @@ HD void m3_u_a_v(const double* U, const double* A, const double* V, double* out)
 }
 
 HD void sp_diag_mat_right_divide_3(const double* A, const double* B, double* X) {
-  const double L21 = A[1] / A[0], L31 = A[2] / A[0];
-  const double U22 = A[4] - L21 * A[3], U23 = A[7] - L21 * A[6];
+  const SpRcp a0 = sp_rcp(A[0]);
+  const double L21 = A[1] / a0, L31 = A[2] / a0;
+  const double u22 = A[4] - L21 * A[3], U23 = A[7] - L21 * A[6];
+  const SpRcp U22 = sp_rcp(u22);
   const double L32 = (A[5] - L31 * A[3]) / U22;
-  const double U33 = A[8] - L31 * A[6] - L32 * U23;
+  const SpRcp U33 = sp_rcp(A[8] - L31 * A[6] - L32 * U23);
   double y2 = -L21 * B[0], y3 = -L31 * B[0] - L32 * y2;
   X[2] = y3 / U33;
   X[1] = (y2 - U23 * X[2]) / U22;
-  X[0] = (B[0] - A[3] * X[1] - A[6] * X[2]) / A[0];
+  X[0] = (B[0] - A[3] * X[1] - A[6] * X[2]) / a0;
   y3 = -L32 * B[1];
   X[5] = y3 / U33;
   X[4] = (B[1] - U23 * X[5]) / U22;
-  X[3] = (-A[3] * X[4] - A[6] * X[5]) / A[0];
+  X[3] = (-A[3] * X[4] - A[6] * X[5]) / a0;
   X[8] = B[2] / U33;
   X[7] = -U23 * X[8] / U22;
-  X[6] = (-A[3] * X[7] - A[6] * X[8]) / A[0];
+  X[6] = (-A[3] * X[7] - A[6] * X[8]) / a0;
 }
 // exp of the exchange matrix [[-a, b, 0], [a, -b-c, d], [0, c, -d]]
 HD void sp_fast_expm_exchange_3(double a, double b, double c, double d, double* R) {
