@@ -651,7 +651,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     // SPARTACUS keeps 3x3 matrices per (layer, g-point) between its kernels: about 5x the scratch per column
     if ((cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS)) {
       t /= 4;
-      h->tile_cols_device = 2048;   // measured at 50 000 columns: 2048 -> 99 k columns/s, 3846 (a third of the free memory) -> 93 k, 1024 -> 90 k
+      h->tile_cols_device = 4096;   // measured (columns/s at 20 000 / 50 000 columns): 2048 -> 100 k / 100 k, 4096 -> 105 k / 104 k, a third of the free memory -> 105 k / 93 k
     }
     h->tile_cols = t; h->edge_cols = t / 4;
   }

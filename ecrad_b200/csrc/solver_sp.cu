@@ -402,8 +402,8 @@ sp_sw_sweep_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nl
                                                       dmax(cfg.cloud_fraction_threshold, S.reg[l * 3 + jr2]);
 #pragma unroll
             for (int jr = 0; jr < 2; ++jr) {
-              rate[jr * 3 + jr + 1] = transfer_scaling * P.edge[(l - 1) * 3 + jr] / dmax(U[jr * 3 + jr2], 1.0e-5);
-              rate[(jr + 1) * 3 + jr] = transfer_scaling * P.edge[(l - 1) * 3 + jr] / dmax(U[(jr + 1) * 3 + jr2], 1.0e-5);
+              rate[jr * 3 + jr + 1] = transfer_scaling * P.edge[(l - 1) * 3 + jr] * sp_inv(dmax(U[jr * 3 + jr2], 1.0e-5));
+              rate[(jr + 1) * 3 + jr] = transfer_scaling * P.edge[(l - 1) * 3 + jr] * sp_inv(dmax(U[(jr + 1) * 3 + jr2], 1.0e-5));
             }
             sp_entrapment_part(sc, rate, xdif[jr2], inv_effective_size, part);
 #pragma unroll

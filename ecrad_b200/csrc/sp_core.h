@@ -262,13 +262,13 @@ HD void sp_fast_expm_exchange_3(double a, double b, double c, double d, double* 
   tmp2 = dmax(tmp2, DBL_EPSILON * tmp1);
   const double lambda1 = -tmp1 + tmp2, lambda2 = -tmp1 - tmp2;
   double V[9], DV[9];
-  V[0] = dmax(my_epsilon, b) / copysign(dmax(my_epsilon, fabs(a + lambda1)), a + lambda1);
-  V[1] = b / copysign(dmax(my_epsilon, fabs(a + lambda2)), a + lambda2);
-  V[2] = b / dmax(my_epsilon, a);
+  V[0] = dmax(my_epsilon, b) / sp_rcp(copysign(dmax(my_epsilon, fabs(a + lambda1)), a + lambda1));
+  V[1] = b / sp_rcp(copysign(dmax(my_epsilon, fabs(a + lambda2)), a + lambda2));   // (b, c = 0 between empty regions: see SpRcp)
+  V[2] = b / sp_rcp(dmax(my_epsilon, a));
   V[3] = 1.0; V[4] = 1.0; V[5] = 1.0;
-  V[6] = c / copysign(dmax(my_epsilon, fabs(d + lambda1)), d + lambda1);
-  V[7] = c / copysign(dmax(my_epsilon, fabs(d + lambda2)), d + lambda2);
-  V[8] = dmax(my_epsilon, c) / dmax(my_epsilon, d);
+  V[6] = c / sp_rcp(copysign(dmax(my_epsilon, fabs(d + lambda1)), d + lambda1));
+  V[7] = c / sp_rcp(copysign(dmax(my_epsilon, fabs(d + lambda2)), d + lambda2));
+  V[8] = dmax(my_epsilon, c) / sp_rcp(dmax(my_epsilon, d));
   const double diag[3] = {exp(lambda1), exp(lambda2), 1.0};
   sp_diag_mat_right_divide_3(V, diag, DV);
 #pragma unroll
