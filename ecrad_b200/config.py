@@ -100,6 +100,7 @@ class RadiationConfig:
     min_gas_od_sw: float = 0.0
     # SPARTACUS (radiation_config.F90:225-411 defaults; test/ifs `test_spartacus` sets do_3d_effects = true)
     do_3d_effects: bool = False
+    n_regions: int = 3               # 2 = one homogeneous cloudy region (SPARTACUS only; test/i3rc `i3rc_spartacus2`)
     sw_entrapment_name: str = "Explicit"
     do_3d_lw_multilayer_effects: bool = False
     do_lw_side_emissivity: bool = True
@@ -184,6 +185,7 @@ class RadiationConfig:
             setattr(c, k, int(getattr(self, k)))
         c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
         c.i_cloud_pdf_shape = abi.PDF_SHAPE[self.cloud_pdf_shape_name.lower()]
+        c.n_regions = int(self.n_regions)
         if c.i_cloud_pdf_shape == 0 and "mcica" in (self.sw_solver_name.lower(), self.lw_solver_name.lower()):
             raise ValueError("the shipped table blob holds the gamma PDF look-up table of the McICA generator (mcica_gamma.nc); "
                              "a lognormal McICA run needs 'pdf_val' from mcica_lognormal.nc")

@@ -155,6 +155,9 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
     return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");
   if (c.i_cloud_pdf_shape != ECRAD_PDF_GAMMA && c.i_cloud_pdf_shape != ECRAD_PDF_LOGNORMAL) return fail(h, "unknown cloud PDF shape");
+  if (c.n_regions != 2 && c.n_regions != 3) return fail(h, "n_regions must be 2 or 3 (radiation_config.F90:268)");
+  if (c.n_regions == 2 && c.do_sw && c.do_lw && (c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) != (c.i_solver_lw == ECRAD_SOLVER_SPARTACUS))
+    return fail(h, "n_regions = 2 needs SPARTACUS in both spectra or in neither (Tripleclouds has three regions by construction and the two solvers share the region properties here)");
   if (c.i_overlap_scheme != ECRAD_OVERLAP_EXP_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_MAX_RAN && c.i_overlap_scheme != ECRAD_OVERLAP_EXP_EXP)
     return fail(h, "unknown overlap scheme");
   if (c.do_lw_aerosol_scattering && c.do_lw) {
@@ -640,6 +643,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.cloud_inhom_decorr_scaling = cfg->cloud_inhom_decorr_scaling;
   d.sp.do_3d_effects = cfg->do_3d_effects; d.sp.entrapment = cfg->i_3d_sw_entrapment;
   d.sp.do_3d_lw_multilayer_effects = cfg->do_3d_lw_multilayer_effects; d.sp.do_lw_side_emissivity = cfg->do_lw_side_emissivity; d.sp.use_expm_everywhere = cfg->use_expm_everywhere;
+  d.sp.two_regions = cfg->n_regions == 2 && ((cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS));
   d.sp.max_gas_od_3d = cfg->max_gas_od_3d; d.sp.max_cloud_od = cfg->max_cloud_od; d.sp.max_3d_transfer_rate = cfg->max_3d_transfer_rate;
   d.sp.min_cloud_effective_size = cfg->min_cloud_effective_size; d.sp.overhead_sun_factor = cfg->overhead_sun_factor;
   d.sp.overhang_factor = cfg->overhang_factor; d.sp.clear_to_thick_fraction = cfg->clear_to_thick_fraction;

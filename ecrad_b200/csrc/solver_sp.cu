@@ -95,7 +95,9 @@ sp_sw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
   double edge[3] = {0.0, 0.0, 0.0}, rate_dir[9], rate_dif[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) { rate_dir[k] = 0.0; rate_dif[k] = 0.0; }
-  const bool has3d = cloudy && in.inv_cloud_size && sp_edge_lengths(sc, reg, LD_IN(in.inv_cloud_size, c, l), in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
+  // (two regions: no lateral transfer in an overcast layer, radiation_spartacus_sw.F90:497-500)
+  const bool overcast2 = sc.two_regions && frac > 1.0 - cfg.cloud_fraction_threshold;
+  const bool has3d = cloudy && !overcast2 && in.inv_cloud_size && sp_edge_lengths(sc, reg, LD_IN(in.inv_cloud_size, c, l), in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
   if (has3d) {
     const SpGeom q = sp_geometry(sc, mu0);
     const double dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
@@ -229,7 +231,7 @@ __device__ __forceinline__ SpGeomShared sp_load_geometry(double* base, const TcS
   for (int l = threadIdx.x; l < nlev; l += nthreads) {
     P.depth[l] = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     double e[3] = {0.0, 0.0, 0.0};
-    if (!S.clear[l + 1] && in.inv_cloud_size) {
+    if (!S.clear[l + 1] && in.inv_cloud_size && !(cfg.sp.two_regions && LD_IN(in.frac, c, l) > 1.0 - cfg.cloud_fraction_threshold)) {
       const double r[3] = {S.reg[l * 3], S.reg[l * 3 + 1], S.reg[l * 3 + 2]};
       sp_edge_lengths(cfg.sp, r, LD_IN(in.inv_cloud_size, c, l), in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, e);
     }
@@ -571,7 +573,8 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
 #pragma unroll
   for (int k = 0; k < 9; ++k) rate[k] = 0.0;
   const double inv_size = in.inv_cloud_size ? LD_IN(in.inv_cloud_size, c, l) : 0.0;
-  const bool has3d = cloudy && in.inv_cloud_size && sp_edge_lengths(sc, reg, inv_size, in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
+  const bool overcast2 = sc.two_regions && frac > 1.0 - cfg.cloud_fraction_threshold;   // radiation_spartacus_lw.F90:423-426
+  const bool has3d = cloudy && !overcast2 && in.inv_cloud_size && sp_edge_lengths(sc, reg, inv_size, in.inv_inhom_size != nullptr, in.inv_inhom_size ? LD_IN(in.inv_inhom_size, c, l) : 0.0, edge);
   if (has3d) {
     dz = sp_layer_depth(LD_IN(in.p_hl, c, l), LD_IN(in.p_hl, c, l + 1), LD_IN(in.t_hl, c, l), LD_IN(in.t_hl, c, l + 1));
     sp_transfer_rates(sc, dz, edge, reg, SP_PI * 0.5, rate);

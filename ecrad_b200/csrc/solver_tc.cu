@@ -46,6 +46,17 @@ tc_prep_kernel(DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
       if (homog) tc_region_homogeneous(LD_IN(in.frac, c, jlev - 1), thr, fl, o_); else tc_region(LD_IN(in.frac, c, jlev - 1), LD_IN(in.fsd, c, jlev - 1), thr, fl, o_, cfg.pdf_gamma != 0);
       for (int r = 0; r < 3; ++r) { reg[(jlev - 1) * 3 + r] = fl[r]; ods[(jlev - 1) * 3 + r] = o_[r]; }
     }
+    if (cfg.sp.two_regions) {
+      // config%nregions = 2 (radiation_regions.F90:105-110): clear sky + one homogeneous cloudy region.  Carried as three regions
+      // with an empty third one: every formula of the three-region path (overlap matrices, radiation_overlap.F90:169-209; edge
+      // lengths; exchange terms) then reduces to the two-region one, the third region exchanges nothing and carries no flux.
+      if (jlev > 1) { const double f = LD_IN(in.frac, c, jlev - 2); fu[0] = 1.0 - f; fu[1] = f; fu[2] = 0.0; }
+      if (jlev <= nlev) {
+        const double f = LD_IN(in.frac, c, jlev - 1);
+        fl[0] = 1.0 - f; fl[1] = f; fl[2] = 0.0;
+        for (int r = 0; r < 3; ++r) { reg[(jlev - 1) * 3 + r] = fl[r]; ods[(jlev - 1) * 3 + r] = r == 0 ? 0.0 : 1.0; }
+      }
+    }
     double op1 = 1.0, op2 = 1.0;
     if (jlev > 1 && jlev <= nlev && !homog) {
       op1 = LD_IN(in.overlap, c, jlev - 2);

@@ -254,6 +254,13 @@ HD void sp_diag_mat_right_divide_3(const double* A, const double* B, double* X) 
   X[7] = -U23 * X[8] / U22;
   X[6] = (-A[3] * X[7] - A[6] * X[8]) / a0;
 }
+// exp of the two-region exchange matrix [[-a, b], [a, -b]] (fast_expm_exchange_2, radiation_matrix.F90:905-925), embedded in the
+// 3x3 form of a two-region run (the empty third region maps to itself)
+HD void sp_fast_expm_exchange_2(double a, double b, double* R) {
+  const double factor = (1.0 - exp(-(a + b))) / dmax(1.0e-12, a + b);
+  R[0] = 1.0 - factor * a; R[3] = factor * a; R[1] = factor * b; R[4] = 1.0 - factor * b;
+  R[2] = 0.0; R[5] = 0.0; R[6] = 0.0; R[7] = 0.0; R[8] = 1.0;
+}
 // exp of the exchange matrix [[-a, b, 0], [a, -b-c, d], [0, c, -d]]
 HD void sp_fast_expm_exchange_3(double a, double b, double c, double d, double* R) {
   const double my_epsilon = 1.0e-12;
@@ -280,6 +287,7 @@ HD void sp_fast_expm_exchange_3(double a, double b, double c, double d, double* 
 // Scalars of config_type the SPARTACUS kernels read.
 struct SpCfg {
   int do_3d_effects, entrapment, do_3d_lw_multilayer_effects, do_lw_side_emissivity, use_expm_everywhere;
+  int two_regions;   // config%nregions == 2: one homogeneous cloudy region; carried as three regions with an empty third one
   double max_gas_od_3d, max_cloud_od, max_3d_transfer_rate, min_cloud_effective_size, overhead_sun_factor, overhang_factor,
       clear_to_thick_fraction;
 };
@@ -374,7 +382,8 @@ HD void sp_entrapment_part(const SpCfg& c, const double* rate, double x, double 
 #pragma unroll
     for (int i = 0; i < 9; ++i) e[i] = e[i] * s;
   }
-  sp_fast_expm_exchange_3(e[3], e[1], e[7], e[5], part);
+  if (c.two_regions) sp_fast_expm_exchange_2(e[3], e[1], part);   // radiation_spartacus_sw.F90:1184-1186
+  else sp_fast_expm_exchange_3(e[3], e[1], e[7], e[5], part);
 }
 
 }  // namespace ecb

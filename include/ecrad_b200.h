@@ -58,7 +58,7 @@ typedef struct ecrad_b200_config {
   int32_t n_emiss_lw;                /* size(single_level%lw_emissivity,2)                               */
   int32_t n_canopy_bands_sw, n_canopy_bands_lw;
   int32_t n_aerosol_types;           /* config%n_aerosol_types == size(aerosol%mixing_ratio,3); 0 without aerosols  */
-  /* SPARTACUS (radiation_config.F90:225-411); nregions is fixed to 3 */
+  /* SPARTACUS (radiation_config.F90:225-411); the number of regions is n_regions at the end of the struct */
   int32_t do_3d_effects, i_3d_sw_entrapment, do_3d_lw_multilayer_effects;
   double cloud_fraction_threshold;   /* config%cloud_fraction_threshold      (default 1e-6)              */
   double cloud_mixing_ratio_threshold; /*                                     (default 1e-9)              */
@@ -70,6 +70,9 @@ typedef struct ecrad_b200_config {
   int32_t do_toa_spectral_flux;      /* config%do_toa_spectral_flux (default 0) */
   int32_t i_cloud_pdf_shape;         /* config%i_cloud_pdf_shape (radiation_config.F90:134-138): 0 lognormal, 1 gamma (default); shapes the
                                       * two cloudy regions of Tripleclouds / SPARTACUS; McICA takes it through the 'pdf_val' table */
+  int32_t n_regions;                 /* config%nregions (radiation_config.F90:268): 3 (default) or 2; read by the SPARTACUS solvers only
+                                      * (Tripleclouds has three regions by construction, radiation_tripleclouds_sw.F90) */
+  int32_t reserved_;                 /* keeps the size a multiple of 8 */
 } ecrad_b200_config;
 
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md

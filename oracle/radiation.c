@@ -815,6 +815,8 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
       extern void orc_region_properties(int, const double*, const double*, double, int, double (*)[3], double (*)[3]);
       extern void orc_overlap_matrices(int, double (*)[3], const double*, double, double, int, double (*)[3][3], double (*)[3][3], double*);
       orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
+      if (spartacus && cfg->n_regions == 2)   /* radiation_regions.F90:105-110 (see two_region_properties in spartacus.c) */
+        for (int jl = 0; jl < nlev; ++jl) { reg[jl][1] = frac[jl]; reg[jl][0] = 1.0 - reg[jl][1]; reg[jl][2] = 0.0; }
       orc_overlap_matrices(nlev, reg, op, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o.cloud_cover);
       free(reg); free(ods); free(U); free(V);
     } else if (spartacus) {

@@ -317,13 +317,25 @@ static void ref_trans_lw(double od, double gamma1, double gamma2, double planck_
   }
 }
 
+/* config%nregions = 2 (radiation_regions.F90:105-110): clear sky + one homogeneous cloudy region, od_scaling = 1.  Restated as three
+ * regions with an empty third one: the three-region formulae of the overlap matrices (radiation_overlap.F90:169-209), the edge
+ * lengths and the exchange terms then reduce to the two-region ones; the third region exchanges nothing and carries no flux.
+ * (Not a separate two-region code path: checked against the three-region solver with two identical cloudy regions, fractional_std = 0,
+ * tests/test_oracle_spartacus.py.) */
+static void two_region_properties(int nlev, const double* frac, double (*reg_fracs)[NREG], double (*od_scaling)[NREG]) {
+  for (int jl = 0; jl < nlev; ++jl) {
+    reg_fracs[jl][1] = frac[jl]; reg_fracs[jl][0] = 1.0 - reg_fracs[jl][1]; reg_fracs[jl][2] = 0.0;
+    od_scaling[jl][0] = 0.0; od_scaling[jl][1] = 1.0; od_scaling[jl][2] = 1.0;
+  }
+}
+
 /* lateral transfer rates of one cloudy layer (radiation_spartacus_sw.F90:495-604 / _lw.F90:415-520).  tan_angle: tan_sza for the
  * direct beam, tan_diffuse_angle_3d for diffuse radiation.  Returns 1 if 3D effects are represented in this layer. */
 static int edge_lengths(const ecrad_b200_config* cfg, double frac, const double* reg, const double* inv_cloud_size,
                         const double* inv_inhom_size, int l, double* edge_length) {
   edge_length[0] = 0.0; edge_length[1] = 0.0; edge_length[2] = 0.0;
-  (void)frac;
   if (!(cfg->do_3d_effects && inv_cloud_size)) return 0;
+  if (cfg->n_regions == 2 && frac > 1.0 - cfg->cloud_fraction_threshold) return 0;   /* radiation_spartacus_sw.F90:497-500, _lw.F90:423-426 */
   if (!(inv_cloud_size[l] > 0.0)) return 0;
   const double four_over_pi = 4.0 / Pi;
   edge_length[0] = four_over_pi * reg[0] * (1.0 - reg[0]) * dmin(inv_cloud_size[l], 1.0 / cfg->min_cloud_effective_size);
@@ -409,7 +421,12 @@ static void entrapment_part(const ecrad_b200_config* cfg, m3 rate, const double 
     const double s = cfg->max_cloud_od / max_entr;
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) e[i][j] = e[i][j] * s;
   }
-  fast_expm_exchange_3(e[1][0], e[0][1], e[2][1], e[1][2], part);
+  if (cfg->n_regions == 2) {   /* fast_expm_exchange_2, radiation_matrix.F90:905-925 (radiation_spartacus_sw.F90:1184-1186) */
+    const double a = e[1][0], b = e[0][1];
+    const double factor = (1.0 - exp(-(a + b))) / dmax(1.0e-12, a + b);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) part[i][j] = 0.0;
+    part[0][0] = 1.0 - factor * a; part[1][0] = factor * a; part[0][1] = factor * b; part[1][1] = 1.0 - factor * b; part[2][2] = 1.0;
+  } else fast_expm_exchange_3(e[1][0], e[0][1], e[2][1], e[1][2], part);
 }
 
 #define L3(p, l, g) ((p) + ((size_t)(l) * ng + (g)) * 9)       /* [lev][g][3][3] */
@@ -429,6 +446,7 @@ void orc_spartacus_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
   orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
+  if (cfg->n_regions == 2) two_region_properties(nlev, frac, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
 
   const double one_over_mu0 = 1.0 / mu0;
@@ -805,6 +823,7 @@ void orc_spartacus_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
   double (*reg)[NREG] = malloc(sizeof(double[NREG]) * nlev), (*ods)[NREG] = malloc(sizeof(double[NREG]) * nlev);
   double (*U)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1)), (*V)[NREG][NREG] = malloc(sizeof(double[NREG][NREG]) * (nlev + 1));
   orc_region_properties(nlev, frac, fsd, cfg->cloud_fraction_threshold, cfg->i_cloud_pdf_shape == ECRAD_PDF_LOGNORMAL, reg, ods);
+  if (cfg->n_regions == 2) two_region_properties(nlev, frac, reg, ods);
   orc_overlap_matrices(nlev, reg, overlap_param, cfg->cloud_inhom_decorr_scaling, cfg->cloud_fraction_threshold, cfg->use_beta_overlap, U, V, &o->cloud_cover);
   int* clear = calloc(nlev + 2, sizeof(int));
   for (int i = 0; i < nlev + 2; ++i) clear[i] = 1;

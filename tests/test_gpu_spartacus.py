@@ -62,7 +62,9 @@ def check_exact(out, ref):
                                 dict(do_3d_effects=False), dict(do_3d_lw_multilayer_effects=True),
                                 dict(do_lw_side_emissivity=False, clear_to_thick_fraction=0.3),
                                 dict(use_aerosols=True, do_lw_cloud_scattering=False),
-                                dict(use_expm_everywhere=True), dict(use_expm_everywhere=True, do_3d_effects=False)])
+                                dict(use_expm_everywhere=True), dict(use_expm_everywhere=True, do_3d_effects=False),
+                                dict(n_regions=2), dict(n_regions=2, sw_entrapment_name="Maximum", do_3d_lw_multilayer_effects=True),
+                                dict(n_regions=2, do_3d_effects=False)])
 def test_spartacus_meridian_vs_oracle(meridian_raw, kw):
     """The reference's own 32-column slice (the input of its `spartacus` / `spartacus_maxentr` ctest targets)."""
     out, ref = run_pair({**SP, **kw}, meridian_raw, 32, spectral_profiles=True)
@@ -136,6 +138,10 @@ def test_spartacus_error_behaviour():
         setup_radiation(RadiationConfig(sw_solver_name="Homogeneous").consolidate())
     with pytest.raises(RadiationError, match="delta-Eddington scaling with gases"):
         setup_radiation(RadiationConfig(do_sw_delta_scaling_with_gases=True, **SP).consolidate())
+    with pytest.raises(RadiationError, match="n_regions must be 2 or 3"):
+        setup_radiation(RadiationConfig(n_regions=4, **SP).consolidate())
+    with pytest.raises(RadiationError, match="n_regions = 2 needs SPARTACUS in both spectra"):
+        setup_radiation(RadiationConfig(n_regions=2, sw_solver_name="SPARTACUS", lw_solver_name="Tripleclouds").consolidate())
 
 
 def test_spartacus_full_size_properties(meridian_raw):
@@ -197,5 +203,6 @@ def test_spartacus_i3rc_vs_mystic_and_oracle():
         return out
 
     L.check_against_libradtran(run, fix, lib)
+    L.check_two_regions(run, fix, lib)
     for out, ref in pairs:
         compare(out, ref, FLUXES + OTHERS)

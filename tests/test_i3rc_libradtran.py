@@ -69,6 +69,25 @@ def test_oracle_spartacus_vs_mystic():
     check_against_libradtran(run, fix, lib)
 
 
+def check_two_regions(run, fix, lib):
+    """test/i3rc `i3rc_spartacus2` (n_regions = 2): the homogeneous-cloud version of the same case; looser agreement with MYSTIC."""
+    raw = I.i3rc_raw(fix, lib["sza"][:8])
+    s2 = run(raw, do_3d_effects=True, n_regions=2, **I3RC)
+    assert np.abs(s2["sw_up"][:, 0] - lib["up_toa_3D"][:8]).max() <= 8.5
+    assert np.abs(s2["sw_dn_direct"][:, -1] - lib["dn_direct_surf_3D"][:8]).max() <= 24.0
+    return s2
+
+
+def test_oracle_two_region_spartacus_vs_mystic():
+    fix, lib = load()
+
+    def run(raw, **kw):
+        cfg = RadiationConfig(**kw).consolidate()
+        return Oracle(cfg).radiation(I.to_radiation_inputs(raw, cfg), len(raw["cos_solar_zenith_angle"]), 164)
+
+    check_two_regions(run, fix, lib)
+
+
 def test_per_g_outputs_are_in_the_reordered_sequence():
     """flux_type's g-point arrays of a SPARTACUS run are in the order the solver works in (config%i_g_from_reordered_g_*): the same
     numbers as a Tripleclouds run's, permuted, in clear sky (both solvers use the same clear-sky two-stream there)."""

@@ -166,3 +166,29 @@ def test_expm_everywhere_reproduces_meador_weaver(meridian_raw):
         assert np.nanmax(np.abs(ev[nm] - mw[nm])) < 5e-6, nm
     for nm in ("lw_up", "lw_dn"):
         assert np.nanmax(np.abs(ev[nm] - mw[nm])) < 5.0, nm
+
+
+def test_two_regions(meridian_raw):
+    """config%nregions = 2 (test/i3rc `i3rc_spartacus2`): clear sky + one homogeneous cloudy region.  Restated (oracle and kernels alike) as
+    three regions with an empty third one plus the reference's two-region branches (no lateral transfer in overcast layers,
+    fast_expm_exchange_2).  No reference output exists; what can be checked: the cloud boundaries overlap exactly as with three regions
+    (same cloud cover, same clear-sky fluxes); the fluxes are those of a three-region run whose two cloudy regions are identical
+    (fractional_std = 0) up to the exchange between those two regions, a few W m-2; and a homogeneous cloud reflects more than an
+    inhomogeneous one of the same mean water content (the plane-parallel albedo bias the third region exists to remove)."""
+    SP3 = dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)
+    two = run(meridian_raw, n_regions=2, **SP3)
+    three = run(meridian_raw, **SP3)
+    raw0 = dict(meridian_raw)
+    raw0["fractional_std"] = np.zeros_like(meridian_raw["fractional_std"])
+    same = run(raw0, **SP3)
+    assert np.array_equal(two["cloud_cover_sw"], three["cloud_cover_sw"]) and np.array_equal(two["cloud_cover_lw"], three["cloud_cover_lw"])
+    for nm in ("sw_up_clear", "sw_dn_clear", "lw_up_clear", "lw_dn_clear"):
+        assert np.array_equal(two[nm], three[nm]), nm
+    for nm, bound in (("sw_up", 5.0), ("sw_dn", 5.0), ("sw_dn_direct", 3.0), ("lw_up", 1.0), ("lw_dn", 1.0)):
+        assert np.isfinite(two[nm]).all()
+        assert np.abs(two[nm] - same[nm]).max() < bound, (nm, float(np.abs(two[nm] - same[nm]).max()))
+    day = np.asarray(meridian_raw["cos_solar_zenith_angle"]) > 0.1
+    cloudy = np.asarray(two["cloud_cover_sw"]) > 0.05
+    assert (two["sw_up"][day & cloudy, 0] - three["sw_up"][day & cloudy, 0]).mean() > 1.0
+    net = two["sw_dn"] - two["sw_up"]
+    assert (np.diff(net[day], axis=1) <= 1e-6).all()

@@ -46,6 +46,8 @@ CFG_SPECIAL = {
     "n_albedo_sw": "size(config%sw_albedo_weights, 1)",
     "n_emiss_lw": "merge(maxval(config%i_emiss_from_band_lw), size(config%lw_emiss_weights, 1), config%do_nearest_spectral_lw_emiss)",
     "n_aerosol_types": "merge(config%n_aerosol_types, 0, config%use_aerosols)",
+    "n_regions": "config%nregions",
+    "reserved_": "0",
 }
 LOGICAL_PREFIXES = ("do_", "use_")
 
