@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="columns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-sweep", default="", help="tuning aid: 'tile:edge:ramp,...' host-entry tile schedules timed after the e2e measurement (key e2e.sweep)")
+    ap.add_argument("--e2e-sweep", default="", help="tuning aid: 'tile:edge:ramp[:tail],...' host-entry tile schedules timed after the e2e measurement (key e2e.sweep)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -325,8 +325,8 @@ def main():
     if args.e2e_sweep and world == 1:   # tuning aid: the host entry's tile schedule (tile_cols : edge_cols : ramp)
         sweep = {}
         for spec in args.e2e_sweep.split(","):
-            tile, edge, ramp = (int(x) for x in spec.split(":"))
-            h.set_option("tile_cols", tile); h.set_option("edge_cols", edge); h.set_option("tile_ramp", ramp)
+            tile, edge, ramp, tail = (int(x) for x in (spec + ":1").split(":")[:4])
+            h.set_option("tile_cols", tile); h.set_option("edge_cols", edge); h.set_option("tile_ramp", ramp); h.set_option("tail_tiles", tail)
             for _ in range(2):
                 step_host()
             t0 = time.perf_counter()

@@ -52,6 +52,7 @@ struct Handle {
   int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
   int edge_cols = 1024;          // host entry: at most this many columns in the first and the last tile
   bool edge_explicit = false;    // edge_cols was set through set_option: not capped at tile_cols / 4
+  int tail_tiles = 1;            // host entry: this many edge-sized tiles at the end of the call
   int tile_ramp = 0;             // host entry: 1 = tiles double from the edge size up to tile_cols (and halve again at the end)
   int tile_cols_device = 16384;  // device entry: only bounds the scratch (about 3 MB per column); bigger tiles = fewer partial waves
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -746,6 +747,7 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   if (!strcmp(key, "tile_cols")) { if (value < 1) return fail(h, "tile_cols must be positive"); h->tile_cols = value; return 0; }
   if (!strcmp(key, "edge_cols")) { if (value < 1) return fail(h, "edge_cols must be positive"); h->edge_cols = value; h->edge_explicit = true; return 0; }
   if (!strcmp(key, "tile_ramp")) { h->tile_ramp = value != 0; return 0; }
+  if (!strcmp(key, "tail_tiles")) { if (value < 1 || value > 8) return fail(h, "tail_tiles must be 1..8"); h->tail_tiles = value; return 0; }
   if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);
 }
@@ -792,11 +794,13 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
     }
     int nramp = 0;
     for (int e : ramp) nramp += e;
-    if (!ramp.empty() && ntot >= 2 * nramp + h->tile_cols / 2) {
+    const int ntail = nramp + (h->tail_tiles - 1) * edge;
+    if (!ramp.empty() && ntot >= nramp + ntail + h->tile_cols / 2) {
       for (size_t i = 0; i < ramp.size(); ++i) push(ramp[i]);
-      const int rest = ntot - 2 * nramp, k = (rest + h->tile_cols - 1) / h->tile_cols;
+      const int rest = ntot - nramp - ntail, k = (rest + h->tile_cols - 1) / h->tile_cols;
       for (int i = 0; i < k; ++i) push(rest / k + (i < rest % k ? 1 : 0));
       for (size_t i = ramp.size(); i-- > 0;) push(ramp[i]);
+      for (int i = 1; i < h->tail_tiles; ++i) push(edge);
     } else {
       const int k = (ntot + h->tile_cols - 1) / h->tile_cols;
       for (int i = 0; i < k; ++i) push(ntot / k + (i < ntot % k ? 1 : 0));
@@ -838,6 +842,10 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
       if (out_active(k)) register_range(h, od[k].host, rb * (size_t)ncol * od[k].rows * (od[k].kind == 2 ? (size_t)(nlev + 1) : 1));
   }
   for (auto& s : h->slot) s.used = false;
+  // ECRAD_B200_TIMELINE=1: per-tile begin/end of H2D, kernels and D2H of this call, printed to stderr (a tuning aid)
+  static const bool timeline = getenv("ECRAD_B200_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  if (timeline) { tl.resize((size_t)ntiles * 6 + 1); for (auto& e : tl) cudaEventCreate(&e); cudaEventRecord(tl[(size_t)ntiles * 6], h->s_h2d); }
   for (int t = 0; t < ntiles; ++t) {
     Slot& s = h->slot[t & 1];
     const int c0 = c_first + tile_first[t], nt = tile_n[t];
@@ -846,6 +854,7 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
     if (s.used) { CKD(h, cudaStreamWaitEvent(h->s_h2d, s.compute_done, 0)); CKD(h, cudaStreamWaitEvent(h->s_h2d, s.d2h_done, 0)); }
     CvtJobs jin, jout; jin.n = jout.n = 0;
     long long cvt_in_max = 0, cvt_out_max = 0;
+    if (timeline) cudaEventRecord(tl[t * 6 + 0], h->s_h2d);
     for (int k = 0; k < N_IN; ++k) {
       ip[k] = nullptr;
       if (!id[k].host || id[k].rows <= 0) continue;
@@ -885,6 +894,7 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
       if (sp) { jin.j[jin.n++] = {dst, op[k], (long long)n}; if ((long long)n > cvt_in_max) cvt_in_max = (long long)n; }
     }
     CKD(h, cudaEventRecord(s.h2d_done, h->s_h2d));
+    if (timeline) cudaEventRecord(tl[t * 6 + 1], h->s_h2d);
     // ---- kernels ----
     DevIn di; DevOut dout;
     make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
@@ -892,6 +902,7 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
     if (h->dev_pending) CKD(h, cudaStreamWaitEvent(h->s_comp[set], h->ev_dev_done, 0));
     CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.h2d_done, 0));
     if (s.used) CKD(h, cudaStreamWaitEvent(h->s_comp[set], s.d2h_done, 0));
+    if (timeline) cudaEventRecord(tl[t * 6 + 2], h->s_comp[set]);
     if (sp && jin.n) {
       convert_kernel<<<dim3((unsigned)((cvt_in_max + 1023) / 1024 > 592 ? 592 : (cvt_in_max + 1023) / 1024), jin.n), 256, 0, h->s_comp[set]>>>(jin, 1);
       h->launches += 1;
@@ -908,8 +919,10 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
       }
     }
     CKD(h, cudaEventRecord(s.compute_done, h->s_comp[set]));
+    if (timeline) cudaEventRecord(tl[t * 6 + 3], h->s_comp[set]);
     // ---- D2H ----
     CKD(h, cudaStreamWaitEvent(h->s_d2h, s.compute_done, 0));
+    if (timeline) cudaEventRecord(tl[t * 6 + 4], h->s_d2h);
     for (int k = 0; k < N_OUT; ++k) {
       if (!op[k]) continue;
       const char* src = (const char*)(sp ? s.out32[k].p : op[k]);
@@ -926,12 +939,23 @@ static int host_entry(Handle* h, int ncol, int nlev, int istartcol, int iendcol,
       CKD(h, cudaMemcpy2DAsync((char*)in->cloud_fraction + rb * c0, rb * (size_t)ncol, sp ? s.in32[17].p : ip[17], rb * (size_t)cap, rb * (size_t)nt, nlev,
                               cudaMemcpyDeviceToHost, h->s_d2h));
     CKD(h, cudaEventRecord(s.d2h_done, h->s_d2h));
+    if (timeline) cudaEventRecord(tl[t * 6 + 5], h->s_d2h);
     s.used = true;
   }
   h->dev_pending = false;   // (the compute streams waited for it, and they are drained below)
   CKD(h, cudaStreamSynchronize(h->s_d2h));
   CKD(h, cudaStreamSynchronize(h->s_comp[0]));
   CKD(h, cudaStreamSynchronize(h->s_comp[1]));
+  if (timeline) {
+    const cudaEvent_t t0 = tl[(size_t)ntiles * 6];
+    fprintf(stderr, "ecrad_b200 timeline (ms after the call's first H2D was queued): tile columns | H2D | kernels | D2H\n");
+    for (int t = 0; t < ntiles; ++t) {
+      float v[6];
+      for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[k], t0, tl[t * 6 + k]);
+      fprintf(stderr, "  %2d %5d | %6.2f-%6.2f | %6.2f-%6.2f | %6.2f-%6.2f\n", t, tile_n[t], v[0], v[1], v[2], v[3], v[4], v[5]);
+    }
+    for (auto& e : tl) cudaEventDestroy(e);
+  }
   CKD(h, cudaGetLastError());
   return 0;
 }
