@@ -164,9 +164,9 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (c.do_lw_aerosol_scattering && c.do_lw) {
     // radiation_interface.F90:84-88
     if (!c.do_lw_cloud_scattering) return fail(h, "longwave aerosol scattering requires longwave cloud scattering");
-    const bool plain = c.i_solver_lw == ECRAD_SOLVER_MCICA || c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS;
+    const bool plain = c.i_solver_lw == ECRAD_SOLVER_MCICA || c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS || c.i_solver_lw == ECRAD_SOLVER_SPARTACUS;
     if (!plain || gm != ECRAD_GAS_IFSRRTMG || (c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux))
-      return fail(h, "do_lw_aerosol_scattering is available with the McICA and Cloudless longwave solvers on RRTMG-IFS gas optics");
+      return fail(h, "do_lw_aerosol_scattering is available with the McICA, Cloudless and SPARTACUS longwave solvers on RRTMG-IFS gas optics");
   }
   if (c.do_sw && !c.do_sw_direct) return fail(h, "do_sw_direct = false is not available in this build (the direct beam is always computed)");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
@@ -191,7 +191,8 @@ enum { N_WORK = 40 };
 // Which spectra run the scan solvers (and therefore want their gas optical properties laid out [column][g][layer]).
 bool use_scan(const Handle* h, bool sw, int nlev) {
   const ecrad_b200_config& c = h->cfg;
-  if (!sw && c.do_lw && c.do_lw_aerosol_scattering) return nlev <= scan_max_levels();   // scattering in every layer: the general (scan) adding method
+  if (!sw && c.do_lw && c.do_lw_aerosol_scattering && c.i_solver_lw != ECRAD_SOLVER_SPARTACUS)
+    return nlev <= scan_max_levels();   // scattering in every layer: the general (scan) adding method
   if (!h->scan_solvers || !(sw ? c.do_sw : c.do_lw)) return false;
   const int sol = sw ? c.i_solver_sw : c.i_solver_lw;
   if (sol != ECRAD_SOLVER_MCICA && sol != ECRAD_SOLVER_CLOUDLESS) return false;

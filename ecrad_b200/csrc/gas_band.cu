@@ -181,7 +181,7 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
     return pfac * (tp[ind - 1] + frac * (tp[ind] - tp[ind - 1]));
   };
   const double plk_bot = planck(L.t_bot);
-  const bool lwscat = cfg.do_lw_aerosol_scattering != 0;   // (scan solvers only: LAYB)
+  const bool lwscat = cfg.do_lw_aerosol_scattering != 0;
   double aer = 0.0, aer_sc = 0.0, aer_sg = 0.0;
   if (cfg.use_aerosols) {
     if (lwscat) { const double* a = w.aer_lw + ((size_t)c * nlev + l) * 3 * NB_LW; aer = a[IB]; aer_sc = a[NB_LW + IB]; aer_sg = a[2 * NB_LW + IB]; }
@@ -198,10 +198,11 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
     if (cfg.use_aerosols && !lwscat) o = o + aer;
     return o;
   };
-  if (LAYB && lwscat) {
-    // gas + aerosol with scattering (radiation_aerosol_optics.F90:781-796): gases do not scatter, so g is the aerosol's
-    double* ss_out = w.ssa_lw + (size_t)c * NG_LW * w.ls + (size_t)g0 * sg;
-    double* gg_out = w.g_lw + (size_t)c * NG_LW * w.ls + (size_t)g0 * sg;
+  if (lwscat) {
+    // gas + aerosol with scattering (radiation_aerosol_optics.F90:781-796): gases do not scatter, so g is the aerosol's.
+    // (ssa_lw / g_lw have the layout of od_lw: [g][ls] for the scan solvers, [layer][g] for SPARTACUS.)
+    double* ss_out = w.ssa_lw + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW) + (size_t)g0 * sg;
+    double* gg_out = w.g_lw + (size_t)c * (LAYB ? (size_t)NG_LW * w.ls : (size_t)nlev * NG_LW) + (size_t)g0 * sg;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       double o = odval(g), ssa = 0.0, gg = 0.0;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
         ssa = aer_sc / local_od;
         o = local_od;
       }
-      od_out[l * sl + g * sg] = o; ss_out[l + g * sg] = ssa; gg_out[l + g * sg] = gg;
+      od_out[l * sl + g * sg] = o; ss_out[l * sl + g * sg] = ssa; gg_out[l * sl + g * sg] = gg;
       pl_out[(l + 1) * sl + g * sg] = plk_bot * pfrac(g);
     }
   } else

@@ -563,7 +563,11 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
   const double pt = w.planck[(size_t)c * (nlev + 1) * SD::NG + i], pb = w.planck[(size_t)c * (nlev + 1) * SD::NG + i + SD::NG];
   double* clr = w.scr_lw + (size_t)c * sp_doubles_lw(nlev, SD::NG);
   double* mats = clr + (size_t)SP_LW_CLR * n + (size_t)l * SP_LW_MAT * SD::NG;
-  const LwLayer Lc = lw_ref_trans(odg, 0.0, 0.0, pt, pb);
+  // gas + aerosol single-scattering albedo and asymmetry factor of the clear region (do_lw_aerosol_scattering,
+  // radiation_spartacus_lw.F90:366-371); zero otherwise
+  const bool lwscat = cfg.do_lw_aerosol_scattering && w.ssa_lw;
+  const double ssa0 = lwscat ? w.ssa_lw[(size_t)c * n + i] : 0.0, g0 = lwscat ? w.g_lw[(size_t)c * n + i] : 0.0;
+  const LwLayer Lc = lw_ref_trans(odg, ssa0, g0, pt, pb);
   if (act) { clr[i] = Lc.ref; clr[n + i] = Lc.trans; clr[2 * n + i] = Lc.source_up; clr[3 * n + i] = Lc.source_dn; }
   if (!heavy) return;
   const int nra = cloudy ? 3 : 1;   // nregActive
@@ -583,16 +587,17 @@ sp_lw_layer_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int mode
   const int ng3d = (has3d || sc.use_expm_everywhere) ? sp_first_thick_g(&s_first, act, rank, SD::NG, odg > sc.max_gas_od_3d) : 0;
   const int b = T.meta->band_of_g_lw[gg];
   const double* clb = w.cl_lw + ((size_t)c * nlev + l) * 3 * SD::NB;
-  double od_r[3], ssa_r[3] = {0.0, 0.0, 0.0}, g_r[3] = {0.0, 0.0, 0.0};
+  double od_r[3], ssa_r[3] = {ssa0, 0.0, 0.0}, g_r[3] = {g0, 0.0, 0.0};
   od_r[0] = odg;
+  const double scat_od = odg * ssa0;   // scattering optical depth of the clear region (:541)
 #pragma unroll
   for (int jr = 1; jr < 3; ++jr) {
     if (!cloudy) { od_r[jr] = 0.0; continue; }
     od_r[jr] = odg + clb[b] * ods[jr];
     if (cfg.do_lw_cloud_scattering) {
-      const double scat_od_cloud = clb[b] * clb[SD::NB + b] * ods[jr];   // scat_od of the clear region is zero
-      ssa_r[jr] = (0.0 + scat_od_cloud) / od_r[jr];
-      if (0.0 + scat_od_cloud > 0.0) g_r[jr] = (0.0 * 0.0 + scat_od_cloud * clb[2 * SD::NB + b]) / (0.0 + scat_od_cloud);
+      const double scat_od_cloud = clb[b] * clb[SD::NB + b] * ods[jr];
+      ssa_r[jr] = (scat_od + scat_od_cloud) / od_r[jr];
+      if (scat_od + scat_od_cloud > 0.0) g_r[jr] = (scat_od * g0 + scat_od_cloud * clb[2 * SD::NB + b]) / (scat_od + scat_od_cloud);
     }
     if (od_r[jr] > sc.max_cloud_od) od_r[jr] = sc.max_cloud_od;
   }

@@ -178,8 +178,9 @@ void orc_spartacus_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
                       const double* alb_dir, orc_tc_out* o);
 void orc_spartacus_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl, const double* t_hl,
                       const double* frac, const double* fsd, const double* overlap_param, const double* inv_cloud_size,
-                      const double* inv_inhom_size, const double* od, const double* planck_hl, const double* od_cloud,
-                      const double* ssa_cloud, const double* g_cloud, const double* emission, const double* albedo, orc_tc_out* o);
+                      const double* inv_inhom_size, const double* od, const double* ssa, const double* g, const double* planck_hl,
+                      const double* od_cloud, const double* ssa_cloud, const double* g_cloud, const double* emission, const double* albedo,
+                      orc_tc_out* o);
 void orc_expm(int m, double* a, int sw_pattern);                                     /* test hooks for the matrix routines */
 void orc_fast_expm_exchange_3(double a, double b, double c, double d, double* r);
 

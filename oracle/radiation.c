@@ -785,8 +785,8 @@ static void solver_tc(const orc_tables* t, const ecrad_b200_config* cfg, int nco
   }
   if (!sw) {
     if (spartacus)
-      orc_spartacus_lw(t, cfg, nlev, p_hl, t_hl, frac, fsd, op, ics, iis, w->od_lw, w->planck_hl, w->od_lw_cloud, w->ssa_lw_cloud,
-                       w->g_lw_cloud, w->lw_emission, w->lw_albedo, &o);
+      orc_spartacus_lw(t, cfg, nlev, p_hl, t_hl, frac, fsd, op, ics, iis, w->od_lw, w->ssa_lw, w->g_lw, w->planck_hl, w->od_lw_cloud,
+                       w->ssa_lw_cloud, w->g_lw_cloud, w->lw_emission, w->lw_albedo, &o);
     else
     orc_tripleclouds_lw(t, cfg, nlev, frac, fsd, op, w->od_lw, w->planck_hl, w->od_lw_cloud, w->ssa_lw_cloud, w->g_lw_cloud,
                         w->lw_emission, w->lw_albedo, &o);
@@ -1060,7 +1060,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
-  const int lw_plain = cfg->i_solver_lw == ECRAD_SOLVER_MCICA || cfg->i_solver_lw == ECRAD_SOLVER_CLOUDLESS;
+  const int lw_plain = cfg->i_solver_lw == ECRAD_SOLVER_MCICA || cfg->i_solver_lw == ECRAD_SOLVER_CLOUDLESS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS;
   if ((cfg->do_lw_aerosol_scattering && cfg->do_lw && (!lw_plain || t->is_ecckd || !cfg->do_lw_cloud_scattering)) || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
       (cfg->use_vectorizable_generator && cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");

@@ -811,12 +811,14 @@ void orc_spartacus_sw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
 #define L6(p, l, g) ((p) + ((size_t)(l) * ng + (g)) * 3)       /* [lev][g][3] */
 
 /* =========================================================================================================
- * solver_spartacus_lw for one column (no LW aerosol scattering: clear-sky ssa = g = 0)
+ * solver_spartacus_lw for one column; ssa, g: gas + aerosol scattering properties [nlev][ng] with do_lw_aerosol_scattering
+ * (radiation_spartacus_lw.F90:366-371), NULL otherwise (clear-sky ssa = g = 0)
  * ========================================================================================================= */
 void orc_spartacus_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nlev, const double* p_hl, const double* t_hl,
                       const double* frac, const double* fsd, const double* overlap_param, const double* inv_cloud_size,
-                      const double* inv_inhom_size, const double* od, const double* planck_hl, const double* od_cloud,
-                      const double* ssa_cloud, const double* g_cloud, const double* emission, const double* albedo, orc_tc_out* o) {
+                      const double* inv_inhom_size, const double* od, const double* ssa, const double* g, const double* planck_hl,
+                      const double* od_cloud, const double* ssa_cloud, const double* g_cloud, const double* emission, const double* albedo,
+                      orc_tc_out* o) {
   const int ng = NG_LW, nreg = NREG;
   const double R_over_g = GasConstantDryAir / AccelDueToGravity;
   const double tan_diffuse_angle_3d = Pi * 0.5, side_emiss_thin = 1.4107;
@@ -851,6 +853,8 @@ void orc_spartacus_lw(const orc_tables* t, const ecrad_b200_config* cfg, int nle
     for (int jg = 0; jg < ng; ++jg)
       for (int r = 0; r < NREG; ++r) { od_region[jg][r] = 0.0; ssa_region[jg][r] = 0.0; g_region[jg][r] = 0.0; gamma1[jg][r] = 0.0; gamma2[jg][r] = 0.0; }
     for (int jg = 0; jg < ng; ++jg) od_region[jg][0] = od[(size_t)l * ng + jg];
+    if (cfg->do_lw_aerosol_scattering && ssa && g)
+      for (int jg = 0; jg < ng; ++jg) { ssa_region[jg][0] = ssa[(size_t)l * ng + jg]; g_region[jg][0] = g[(size_t)l * ng + jg]; }
     int did_3d = 0;
     if (clear[jlev]) {
       nregactive = 1;

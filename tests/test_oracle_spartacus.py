@@ -192,3 +192,17 @@ def test_two_regions(meridian_raw):
     assert (two["sw_up"][day & cloudy, 0] - three["sw_up"][day & cloudy, 0]).mean() > 1.0
     net = two["sw_dn"] - two["sw_up"]
     assert (np.diff(net[day], axis=1) <= 1e-6).all()
+
+
+def test_lw_aerosol_scattering_clear_sky_matches_mcica(meridian_raw):
+    """do_lw_aerosol_scattering with SPARTACUS (radiation_spartacus_lw.F90:366-371): the clear region takes the gas + aerosol
+    single-scattering albedo.  Its clear-sky fluxes come out of SPARTACUS's own albedo / source recurrence and must equal those of the
+    McICA solver's adding method (radiation_mcica_lw.F90:160-173) on the same optical properties -- two separate restatements."""
+    kw = dict(use_aerosols=True, do_lw_aerosol_scattering=True)
+    sp = run(meridian_raw, sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, **kw)
+    mc = run(meridian_raw, **kw)
+    off = run(meridian_raw, sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True, use_aerosols=True)
+    for nm in ("lw_up_clear", "lw_dn_clear"):
+        assert np.abs(sp[nm] - mc[nm]).max() < 1e-9, nm
+        assert 1e-3 < np.abs(sp[nm] - off[nm]).max() < 5.0, nm
+    assert np.array_equal(sp["sw_up"], off["sw_up"])
