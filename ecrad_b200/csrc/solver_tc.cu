@@ -208,16 +208,31 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   }                                                                                                       \
   ++slot;
   PUT_ROWS();
+  // software pipeline: the ten values of the clear-sky column and of region 1 for layer l+1 are requested before the arithmetic of
+  // layer l (the recurrences are two multiply-adds per layer behind a global load: profiles/r2u_tc_sw_kernel_lines.txt)
+  double nx[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) nx[k] = act ? SCR(k / 5, k % 5, g) : 0.0;
   for (int l = 0; l < nlev; ++l) {
     const int jl = l + 1;
     if (act) {
       const size_t i = (size_t)l * SD::NG + g;
-      fdc = SCR(0, 0, i) * fdc + SCR(0, 1, i) * ddc;
-      ddc = SCR(0, 2, i) * ddc;
-      fuc = ddc * SCR(0, 4, i) + fdc * SCR(0, 3, i);
+      double cu[10];
 #pragma unroll
-      for (int jr = 0; jr < 3; ++jr) {
-        if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; ddn[jr] = 0.0; continue; }
+      for (int k = 0; k < 10; ++k) cu[k] = nx[k];
+      if (l + 1 < nlev) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) nx[k] = SCR(k / 5, k % 5, i + SD::NG);
+      }
+      fdc = cu[0] * fdc + cu[1] * ddc;
+      ddc = cu[2] * ddc;
+      fuc = ddc * cu[4] + fdc * cu[3];
+      fdn[0] = cu[5] * fdn[0] + cu[6] * ddn[0];
+      ddn[0] = cu[7] * ddn[0];
+      fup[0] = ddn[0] * cu[9] + fdn[0] * cu[8];
+#pragma unroll
+      for (int jr = 1; jr < 3; ++jr) {
+        if (S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; ddn[jr] = 0.0; continue; }
         fdn[jr] = SCR(1 + jr, 0, i) * fdn[jr] + SCR(1 + jr, 1, i) * ddn[jr];
         ddn[jr] = SCR(1 + jr, 2, i) * ddn[jr];
         fup[jr] = ddn[jr] * SCR(1 + jr, 4, i) + fdn[jr] * SCR(1 + jr, 3, i);
@@ -379,13 +394,23 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     const BandOut bo[2] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0},
                            {cfg.do_save_spectral_flux ? out.lw_dn_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = ict + 1;
+    double nx[4];   // software pipeline: region 1's four values of the next layer are requested one layer ahead
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nx[k] = act ? SCR(0, k, (size_t)ict * SD::NG + g) : 0.0;
     for (int l = ict; l < nlev; ++l) {
       const int jl = l + 1;
       if (act) {
         const size_t i = (size_t)l * SD::NG + g;
+        const double c0 = nx[0], c1 = nx[1], c2 = nx[2], c3 = nx[3];
+        if (l + 1 < nlev) {
 #pragma unroll
-        for (int jr = 0; jr < 3; ++jr) {
-          if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
+          for (int k = 0; k < 4; ++k) nx[k] = SCR(0, k, i + SD::NG);
+        }
+        fdn[0] = c0 * fdn[0] + c1;
+        fup[0] = c3 + fdn[0] * c2;
+#pragma unroll
+        for (int jr = 1; jr < 3; ++jr) {
+          if (S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
           fdn[jr] = SCR(jr, 0, i) * fdn[jr] + SCR(jr, 1, i);
           fup[jr] = SCR(jr, 3, i) + fdn[jr] * SCR(jr, 2, i);
         }
@@ -416,13 +441,18 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     double d[3] = {fus / red[0], 0.0, 0.0};
     double* dst[1] = {s_dv};
     int slot = 0, lfirst = nlev - 1;
+    // (the transmittance of region 1 -- stored below cloud top, exp(-D od) above -- does not depend on d: next layer's value first)
+    auto trans1 = [&](int l) { const size_t i = (size_t)l * SD::NG + g; return l >= ict ? SCR(0, 4, i) : exp(-ECB_LW_DIFFUSIVITY * od[i]); };
+    double t1n = act ? trans1(nlev - 1) : 0.0;
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
         const size_t i = (size_t)l * SD::NG + g;
+        const double t1 = t1n;
+        if (l > 0) t1n = trans1(l - 1);
         mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1)
-        if (l >= ict) { d[0] = d[0] * SCR(0, 4, i); d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
-        else d[0] = d[0] * exp(-ECB_LW_DIFFUSIVITY * od[i]);   // regions 2,3: transmittance = 1 above cloud top
+        if (l >= ict) { d[0] = d[0] * t1; d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
+        else d[0] = d[0] * t1;   // regions 2,3: transmittance = 1 above cloud top
         tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
       }
       ++slot;
