@@ -76,7 +76,7 @@ __device__ __forceinline__ void coop_expm(double (&a)[M], double* bufA, double* 
   const double frac = frexp(normA / 3.925724783138660e+00, &expo);
   if (frac == 0.5) expo = expo - 1;
   if (expo < 0) expo = 0;
-  if (!(normA == normA) || expo > 64) expo = 0;   // (a NaN / overflowed matrix stays what it is; keeps the warp's loop count finite)
+  if (!(normA == normA) || expo > 1100) expo = 0;   // (a NaN matrix stays what it is; keeps the warp's loop count finite)
   const double scaling = ldexp(1.0, -expo);
 #pragma unroll
   for (int i = 0; i < M; ++i) a[i] = a[i] * scaling;
