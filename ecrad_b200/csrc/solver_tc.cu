@@ -394,25 +394,28 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     const BandOut bo[2] = {{cfg.do_save_spectral_flux ? out.lw_up_band : nullptr, out.ld, 0, -1, 1.0, 0.0, nullptr, 0},
                            {cfg.do_save_spectral_flux ? out.lw_dn_band : nullptr, out.ld, 1, -1, 1.0, 0.0, nullptr, 0}};
     int slot = 0, lfirst = ict + 1;
-    double nx[4];   // software pipeline: region 1's four values of the next layer are requested one layer ahead
+    // software pipeline: the four values per region of the next layer are requested one layer ahead (regions 2 and 3 only if that
+    // layer is cloudy: their slots are not written otherwise)
+    double nx[12];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) nx[k] = act ? SCR(0, k, (size_t)ict * SD::NG + g) : 0.0;
+    for (int k = 0; k < 12; ++k) nx[k] = (act && (k < 4 || !S.clear[ict + 1])) ? SCR(k / 4, k % 4, (size_t)ict * SD::NG + g) : 0.0;
     for (int l = ict; l < nlev; ++l) {
       const int jl = l + 1;
       if (act) {
         const size_t i = (size_t)l * SD::NG + g;
-        const double c0 = nx[0], c1 = nx[1], c2 = nx[2], c3 = nx[3];
+        double cu[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) cu[k] = nx[k];
         if (l + 1 < nlev) {
+          const bool cloudy_next = !S.clear[jl + 1];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) nx[k] = SCR(0, k, i + SD::NG);
+          for (int k = 0; k < 12; ++k) if (k < 4 || cloudy_next) nx[k] = SCR(k / 4, k % 4, i + SD::NG);
         }
-        fdn[0] = c0 * fdn[0] + c1;
-        fup[0] = c3 + fdn[0] * c2;
 #pragma unroll
-        for (int jr = 1; jr < 3; ++jr) {
-          if (S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
-          fdn[jr] = SCR(jr, 0, i) * fdn[jr] + SCR(jr, 1, i);
-          fup[jr] = SCR(jr, 3, i) + fdn[jr] * SCR(jr, 2, i);
+        for (int jr = 0; jr < 3; ++jr) {
+          if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
+          fdn[jr] = cu[jr * 4] * fdn[jr] + cu[jr * 4 + 1];
+          fup[jr] = cu[jr * 4 + 3] + fdn[jr] * cu[jr * 4 + 2];
         }
         if (!(S.clear[jl] && S.clear[jl + 1])) mat3_x_vec(S.V + jl * 9, fdn);
         tile[slot * SD::RS + g] = fup[0] + fup[1] + fup[2];
