@@ -220,6 +220,9 @@ int ecrad_b200_radiation_blocked(void* handle, int ncol_total, int nlev, const e
 /* Tuning/diagnostic options.  Returns 0 on success.
  *   "serial"            0/1: run a tile's kernels on one stream instead of the three overlapping chains (per-kernel timing)
  *   "tile_cols", "tile_cols_device"   columns per internal tile of the host / device entry
+ *   "edge_cols", "tail_tiles", "tile_ramp"   host entry: columns in the first / last tile (default tile_cols / 4), number of such short
+ *                       tiles at the end (1), tile sizes doubling from the edge size (0); measured defaults, DESIGN.md section 4c.
+ *                       (Environment ECRAD_B200_TIMELINE=1 prints the H2D / kernel / D2H intervals of every tile of a call.)
  *   "register_host"     0/1: page-lock the caller's input and output arrays (cudaHostRegister, cached per pointer until
  *                       ecrad_b200_finalize or register_host = 0), so that ordinary (pageable) Fortran allocatables are copied
  *                       asynchronously like pinned memory; the arrays must stay allocated while registered
