@@ -89,6 +89,7 @@ __device__ __forceinline__ double ckd_optical_depth(const CkdModel& m, const dou
   const size_t corner = (size_t)(cr.x - 1) * sp + (size_t)(cr.y - 1) * st + g;
   const double* mult = L.mult + (size_t)l * m.ngas;
   double od = 0.0;
+#pragma unroll 8   // (the table loads of several gases in flight: the loop is a chain of L2 hits otherwise)
   for (int j = 0; j < m.ngas; ++j) {
     const CkdGas& G = m.gas[j];
     const double* k00 = tab + G.off + corner;
