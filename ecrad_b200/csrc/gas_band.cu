@@ -161,10 +161,13 @@ __device__ __forceinline__ void stage_rows(double* img, int rs, int ng, const do
 // ---------------------------------------------------------------------------------------------------------
 // longwave
 // ---------------------------------------------------------------------------------------------------------
-template <int IB, bool LAYB>
+// V: kernel variant -- 0: od / Planck in [layer][g]; 1: in [g][ls] (scan solvers; longwave aerosol scattering possible);
+// 2: [layer][g] with longwave aerosol scattering (SPARTACUS).  The default (0) carries no scattering code.
+template <int IB, int V>
 __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, const double* img, const double* tp, double pfac, const DevTables& T,
                                         const DevCfg& cfg, const DevIn& in, const Work& w, int c, int l, int nlev, bool low, const double* __restrict__ Lg, int jw) {
   constexpr int NG = kNgLwBand[IB];
+  constexpr bool LAYB = V == 1;
   LwLev L = lwlev_load(Lg, nlev, l);     // (inlined field by field: only the loads of the fields this band reads survive)
   if (IB != 15 || low) L.jp = jw;
   EvalSink<NG> sink;
@@ -181,7 +184,7 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
     return pfac * (tp[ind - 1] + frac * (tp[ind] - tp[ind - 1]));
   };
   const double plk_bot = planck(L.t_bot);
-  const bool lwscat = cfg.do_lw_aerosol_scattering != 0;
+  const bool lwscat = V != 0 && cfg.do_lw_aerosol_scattering != 0;
   double aer = 0.0, aer_sc = 0.0, aer_sg = 0.0;
   if (cfg.use_aerosols) {
     if (lwscat) { const double* a = w.aer_lw + ((size_t)c * nlev + l) * 3 * NB_LW; aer = a[IB]; aer_sc = a[NB_LW + IB]; aer_sg = a[2 * NB_LW + IB]; }
@@ -252,7 +255,7 @@ __device__ __forceinline__ void lw_item(const GasMeta& M, const BandMeta& Bs, co
   }
 }
 
-template <bool LAYB>
+template <int V>
 __global__ void __launch_bounds__(GB_THREADS, GB_MINB)
 gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -333,7 +336,7 @@ gas_lw_band_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, int nlev) 
       const int c = c_first + it * GB_CC + cc;
       const double* Lg = w.lev_lw + (size_t)c * LWLEV_NF * nlev;
       const bool low = (v & 256) != 0;
-#define LWB(I) case I: lw_item<I, LAYB>(M, S.B, img, tp, pfac, T, cfg, in, w, c, l, nlev, low, Lg, jw); break;
+#define LWB(I) case I: lw_item<I, V>(M, S.B, img, tp, pfac, T, cfg, in, w, c, l, nlev, low, Lg, jw); break;
       switch (band) { LWB(0) LWB(1) LWB(2) LWB(3) LWB(4) LWB(5) LWB(6) LWB(7) LWB(8) LWB(9) LWB(10) LWB(11) LWB(12) LWB(13) LWB(14) LWB(15) }
 #undef LWB
     }
@@ -502,12 +505,19 @@ int launch_gas_col(const DevTables& T, const DevCfg& cfg, const DevIn& in, const
 int launch_gas_lw_band(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   const size_t sm = GB_IMG_BYTES + 181 * sizeof(double) + 16;
   const dim3 grid(NB_LW, (nc + GB_CBLK - 1) / GB_CBLK, (nlev + GB_LCH - 1) / GB_LCH);
-  if (w.layout_b_lw) {
-    cudaFuncSetAttribute(gas_lw_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    gas_lw_band_kernel<true><<<grid, GB_THREADS, sm, st>>>(T, cfg, in, w, nc, nlev);
-  } else {
-    cudaFuncSetAttribute(gas_lw_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    gas_lw_band_kernel<false><<<grid, GB_THREADS, sm, st>>>(T, cfg, in, w, nc, nlev);
+  const int v = w.layout_b_lw ? 1 : cfg.do_lw_aerosol_scattering ? 2 : 0;
+  switch (v) {
+    case 1:
+      cudaFuncSetAttribute(gas_lw_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gas_lw_band_kernel<1><<<grid, GB_THREADS, sm, st>>>(T, cfg, in, w, nc, nlev);
+      break;
+    case 2:
+      cudaFuncSetAttribute(gas_lw_band_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gas_lw_band_kernel<2><<<grid, GB_THREADS, sm, st>>>(T, cfg, in, w, nc, nlev);
+      break;
+    default:
+      cudaFuncSetAttribute(gas_lw_band_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      gas_lw_band_kernel<0><<<grid, GB_THREADS, sm, st>>>(T, cfg, in, w, nc, nlev);
   }
   return 1;
 }
