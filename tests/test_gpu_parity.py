@@ -210,9 +210,16 @@ def test_tiling_is_invisible(meridian_raw):
             del os.environ["ECRAD_B200_TILE"]
         outs.append(h.radiation(I.to_radiation_inputs(raw), n, NLEV))
         h.finalize()
+    # the host entry's schedule options (first / last tile, several short tiles at the end, doubling tile sizes)
+    h = setup_radiation(cfg)
+    for opts in (dict(tile_cols=128, edge_cols=64, tail_tiles=3), dict(tile_cols=256, edge_cols=64, tile_ramp=1), dict(tile_cols=64, edge_cols=64)):
+        for k, v in opts.items():
+            h.set_option(k, v)
+        outs.append(h.radiation(I.to_radiation_inputs(raw), n, NLEV))
+    h.finalize()
     for nm in FLUXES + OTHERS + ["cloud_cover_sw", "cloud_cover_lw", "cloud_fraction"]:
-        assert np.array_equal(outs[0][nm], outs[1][nm], equal_nan=True), nm
-        assert np.array_equal(outs[0][nm], outs[2][nm], equal_nan=True), nm
+        for o in outs[1:]:
+            assert np.array_equal(outs[0][nm], o[nm], equal_nan=True), nm
 
 
 ECCKD = dict(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False)   # test/ifs/configCY49R1_ecckd.nam
