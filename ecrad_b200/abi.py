@@ -49,7 +49,7 @@ class Config(C.Structure):
         ("overhead_sun_factor", C.c_double), ("overhang_factor", C.c_double), ("clear_to_thick_fraction", C.c_double),
         ("do_lw_side_emissivity", C.c_int32), ("use_expm_everywhere", C.c_int32),
         ("do_toa_spectral_flux", C.c_int32), ("i_cloud_pdf_shape", C.c_int32),
-        ("n_regions", C.c_int32), ("reserved_", C.c_int32),
+        ("n_regions", C.c_int32), ("use_general_cloud_optics", C.c_int32),
     ]
 
 

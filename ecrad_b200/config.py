@@ -66,6 +66,9 @@ class RadiationConfig:
     sw_solver_name: str = "McICA"
     lw_solver_name: str = "McICA"
     gas_model_name: str = "RRTMG-IFS"
+    # cloud optics from the generalised look-up tables (config%use_general_cloud_optics).  None = what the reference's namelists of
+    # test/ifs say: false with RRTMG-IFS (configCY49R1.nam:37), true with ecCKD (configCY49R1_ecckd.nam:39)
+    use_general_cloud_optics: bool | None = None
     liquid_model_name: str = "SOCRATES"
     ice_model_name: str = "Fu-IFS"
     overlap_scheme_name: str = "Exp-Ran"
@@ -135,6 +138,9 @@ class RadiationConfig:
         """Tables derived from the config (what `setup_radiation` stores in config_type)."""
         if self.do_canopy_fluxes_sw:   # radiation_config.F90:1119-1124
             self.do_surface_sw_spectral_flux = True
+        if self.is_ecckd and self.use_general_cloud_optics is not None and not self.use_general_cloud_optics:
+            raise ValueError("ecCKD gas optics needs use_general_cloud_optics = true: the band parameterisations are on the RRTMG "
+                             "bands (the reference stops in radiation_cloud_optics.F90:67-79)")
         if self.is_ecckd:
             # consolidate_sw_albedo_intervals / consolidate_lw_emiss_intervals (radiation_config.F90:1947-2100) with the
             # model's own spectral definition, one weight vector per g-point; bands == g-points
@@ -186,6 +192,7 @@ class RadiationConfig:
         c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
         c.i_cloud_pdf_shape = abi.PDF_SHAPE[self.cloud_pdf_shape_name.lower()]
         c.n_regions = int(self.n_regions)
+        c.use_general_cloud_optics = int(self.is_ecckd if self.use_general_cloud_optics is None else bool(self.use_general_cloud_optics))
         if c.i_cloud_pdf_shape == 0 and "mcica" in (self.sw_solver_name.lower(), self.lw_solver_name.lower()):
             raise ValueError("the shipped table blob holds the gamma PDF look-up table of the McICA generator (mcica_gamma.nc); "
                              "a lognormal McICA run needs 'pdf_val' from mcica_lognormal.nc")

@@ -174,8 +174,10 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
   if (gm == ECRAD_GAS_IFSRRTMG) {
     // radiation_cloud_optics.F90:345-372 dispatches SOCRATES and Slingo only; the five ice models of :376-447
-    if (c.i_liq_model != ECRAD_LIQ_SOCRATES && c.i_liq_model != ECRAD_LIQ_SLINGO) return fail(h, "liquid optics model not available (SOCRATES and Slingo are)");
-    if (c.i_ice_model < ECRAD_ICE_FU || c.i_ice_model > ECRAD_ICE_YI) return fail(h, "ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
+    if (!c.use_general_cloud_optics) {   // (with the generalised look-up tables the two model codes are not read)
+      if (c.i_liq_model != ECRAD_LIQ_SOCRATES && c.i_liq_model != ECRAD_LIQ_SLINGO) return fail(h, "liquid optics model not available (SOCRATES and Slingo are)");
+      if (c.i_ice_model < ECRAD_ICE_FU || c.i_ice_model > ECRAD_ICE_YI) return fail(h, "ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
+    }
     if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
   } else {
     // generalised cloud + aerosol optics per g-point (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points
@@ -183,6 +185,8 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     if (!ok(c.n_g_lw) || !ok(c.n_g_sw) || c.n_bands_lw != c.n_g_lw || c.n_bands_sw != c.n_g_sw)
       return fail(h, "ECCKD: models with 32, 64 or 96 g-points and cloud/aerosol optics per g-point (n_bands == n_g) are built in");
     if (c.do_sw_delta_scaling_with_gases) return fail(h, "do_sw_delta_scaling_with_gases is not available in this build");
+    // radiation_cloud_optics.F90:66-79 would abort: the band parameterisations have 16 + 14 RRTMG bands
+    if (!c.use_general_cloud_optics) return fail(h, "ECCKD needs use_general_cloud_optics (the band parameterisations are defined on the RRTMG bands)");
   }
   return 0;
 }
@@ -541,7 +545,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   h->cfg = *cfg;
   if (check_config(h, *cfg)) { delete h; return 1; }
   PackedTables P;
-  try { pack_tables(*tab, P, cfg->i_liq_model, cfg->i_ice_model); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
+  try { pack_tables(*tab, P, cfg->i_liq_model, cfg->i_ice_model, cfg->use_general_cloud_optics != 0); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
   for (int g = 0; g < NG_LW; ++g) P.meta.rank_lw[g] = (short)g;
   for (int g = 0; g < NG_SW; ++g) P.meta.rank_sw[g] = (short)g;
   if (!P.is_ecckd) {
@@ -601,6 +605,10 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
     rc |= upload(h, &P.ckd, 1, &h->T.ckd);
     rc |= upload(h, P.ckdtab.data(), P.ckdtab.size(), &h->T.ckdtab);
   } else {
+    if (cfg->use_general_cloud_optics) {   // look-up tables of the generalised cloud optics per RRTMG band
+      rc |= upload(h, &P.ckd, 1, &h->T.ckd);
+      rc |= upload(h, P.ckdtab.data(), P.ckdtab.size(), &h->T.ckdtab);
+    }
     rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
     rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
   }
@@ -635,6 +643,7 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.use_general_cloud_optics = cfg->use_general_cloud_optics != 0;
   d.do_toa_spectral_flux = cfg->do_toa_spectral_flux;
   d.pdf_gamma = cfg->i_cloud_pdf_shape == ECRAD_PDF_GAMMA;
   d.is_homogeneous = (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) || (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS);   // radiation_config.F90:1351-1356

@@ -890,7 +890,7 @@ int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const W
   const int nlevp = (nlev + 3) & ~3;
   int n = 0;
   cloud_prep_kernel<<<(nc + 127) / 128, 128, 0, st>>>(cfg, in, w, nc, nlev); ++n;
-  if (cfg.gas_model == 2) n += launch_general_cloud_optics(T, cfg, in, w, nc, nlev, st);   // ECRAD_GAS_ECCKD: use_general_cloud_optics
+  if (cfg.use_general_cloud_optics) n += launch_general_cloud_optics(T, cfg, in, w, nc, nlev, st);
   else { cloud_optics_kernel<<<(nc * nlev + 127) / 128, 128, 0, st>>>(T, cfg, in, w, nc, nlev); ++n; }
   if ((cfg.do_lw && cfg.solver_lw == 2) || (cfg.do_sw && cfg.solver_sw == 2)) {
     if (cfg.use_vectorizable_generator) {

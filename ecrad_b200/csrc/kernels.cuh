@@ -69,6 +69,7 @@ struct DevCfg {
   int use_vectorizable_generator;
   int do_nearest_spectral_lw_emiss;
   int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
+  int use_general_cloud_optics;  // cloud optics from the generalised look-up tables (always with ecCKD; an option with RRTMG, per band)
   int do_toa_spectral_flux;
   int pdf_gamma;                 // config%i_cloud_pdf_shape == IPdfShapeGamma (regions of Tripleclouds / SPARTACUS)
   int is_homogeneous;            // config%is_homogeneous: Homogeneous solvers (gridbox-mean cloud water paths, clouds fill the box)

@@ -199,7 +199,8 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
 }
 
 // liq_model / ice_model: config%i_liq_model / i_ice_model (RRTMG-band cloud optics; ignored by the ecCKD tables)
-inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_model = LIQ_SOCRATES, int ice_model = ICE_FU) {
+// general_cloud: config%use_general_cloud_optics with RRTMG-IFS (the look-up tables "gco_*" per RRTMG band instead of the coefficients)
+inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_model = LIQ_SOCRATES, int ice_model = ICE_FU, bool general_cloud = false) {
   if (T.find("ckd_lw_meta")) { pack_ecckd(T, P); return; }
   GasMeta& M = P.meta;
   memset(&M, 0, sizeof(M));
@@ -332,6 +333,29 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_mod
   // ---- cloud optics coefficients, PDF look-up table, surface mappings ----
   CloudMeta& C = P.cloud;
   memset(&C, 0, sizeof(C));
+  memset(&P.ckd, 0, sizeof(P.ckd));
+  if (general_cloud) {
+    // generalised cloud optics on the RRTMG bands (radiation_general_cloud_optics.F90:39-110 with use_bands = .true.): the same
+    // look-up tables the ecCKD path uses per g-point, one row per band here; read by general_cloud_optics_kernel through T.ckd / T.ckdtab
+    for (int sw = 0; sw < 2; ++sw)
+      for (int jt = 0; jt < 2; ++jt) {
+        const int nb = sw ? NB_SW : NB_LW;
+        GcoType& c = sw ? P.ckd.gco_sw[jt] : P.ckd.gco_lw[jt];
+        const std::string gp = std::string("gco_") + (sw ? "sw_" : "lw_") + std::to_string(jt) + "_";
+        const double* cm = T.d(gp + "meta");
+        c.nre = (int)cm[0]; c.re0 = cm[1]; c.dre = cm[2];
+        auto put = [&](const std::string& nm) {
+          const auto& x = T.req(nm);
+          if (x.dtype != 0 || x.data.size() != (size_t)nb * c.nre * 8) throw std::runtime_error(nm + ": not a (n_bands, n_effective_radius) table");
+          const size_t off = P.ckdtab.size();
+          P.ckdtab.insert(P.ckdtab.end(), (const double*)x.data.data(), (const double*)x.data.data() + (size_t)nb * c.nre);
+          return off;
+        };
+        c.off_me = put(gp + "mass_ext"); c.off_ssa = put(gp + "ssa"); c.off_g = put(gp + "asymmetry");
+      }
+    memset(&C, 0, sizeof(C));   // (the band parameterisations are not used)
+    C.liq_model = liq_model; C.ice_model = ice_model;
+  } else
   // Coefficients of the configured parameterisations (radiation_cloud_optics.F90:46-216 checks the same coefficient counts).  A host
   // model registers what it loaded as liq_coeff_* / ice_coeff_* (/ ice_coeff_gen); the stand-alone blob also holds the files of the
   // other parameterisations under "<name>.<model>".

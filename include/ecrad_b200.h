@@ -72,7 +72,9 @@ typedef struct ecrad_b200_config {
                                       * two cloudy regions of Tripleclouds / SPARTACUS; McICA takes it through the 'pdf_val' table */
   int32_t n_regions;                 /* config%nregions (radiation_config.F90:268): 3 (default) or 2; read by the SPARTACUS solvers only
                                       * (Tripleclouds has three regions by construction, radiation_tripleclouds_sw.F90) */
-  int32_t reserved_;                 /* keeps the size a multiple of 8 */
+  int32_t use_general_cloud_optics;  /* config%use_general_cloud_optics (radiation_config.F90:185): cloud optics from the look-up tables of
+                                      * radiation_general_cloud_optics.F90 ("gco_*" tables) instead of the band parameterisations selected
+                                      * by i_liq_model / i_ice_model.  Must be 1 with ecCKD; 0 or 1 with RRTMG-IFS (tables per band) */
 } ecrad_b200_config;
 
 /* Read-only tables: a directory of named arrays, Fortran element order.  Names are listed in DESIGN.md

@@ -989,7 +989,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
       qliq[jl] = A2(in->q_liq, jcol, jl); qice[jl] = A2(in->q_ice, jcol, jl);
       rel[jl] = A2(in->re_liq, jcol, jl); rei[jl] = A2(in->re_ice, jcol, jl);
     }
-    if (t->is_ecckd)   /* use_general_cloud_optics */
+    if (cfg->use_general_cloud_optics)   /* radiation_interface.F90:378-392 */
       orc_general_cloud_optics(t, cfg, nlev, phl_full, frac, qliq, qice, rel, rei, w.od_lw_cloud, w.ssa_lw_cloud, w.g_lw_cloud,
                                w.od_sw_cloud, w.ssa_sw_cloud, w.g_sw_cloud);
     else

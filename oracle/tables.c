@@ -63,27 +63,35 @@ static void resolve_ckd_model(orc_tables* t, const char* pre, orc_ckd_model* m, 
   }
 }
 
+/* general cloud optics tables, "gco_{lw,sw}_{0,1}_*": on the g-points' bands for ecCKD, on the 16/14 RRTMG bands in the
+ * RRTMG blob (tools/extract_rrtmg_tables.py general_cloud_tables; radiation_general_cloud_optics.F90:36-141) */
+static void resolve_gco(orc_tables* t, int required, int* err) {
+  for (int jt = 0; jt < 2; ++jt)
+    for (int sw = 0; sw < 2; ++sw) {
+      orc_gco* c = sw ? &t->gco_sw[jt] : &t->gco_lw[jt];
+      char nm[64];
+      snprintf(nm, sizeof nm, "gco_%s_%d_meta", sw ? "sw" : "lw", jt);
+      if (!required && !orc_find(t, nm)) { c->nre = 0; c->mass_ext = c->ssa = c->asymmetry = NULL; continue; }
+      const double* meta = Dreq(t, nm, err);
+      if (meta) { c->nre = (int)meta[0]; c->re0 = meta[1]; c->dre = meta[2]; }
+      snprintf(nm, sizeof nm, "gco_%s_%d_mass_ext", sw ? "sw" : "lw", jt); c->mass_ext = Dreq(t, nm, err);
+      snprintf(nm, sizeof nm, "gco_%s_%d_ssa", sw ? "sw" : "lw", jt); c->ssa = Dreq(t, nm, err);
+      snprintf(nm, sizeof nm, "gco_%s_%d_asymmetry", sw ? "sw" : "lw", jt); c->asymmetry = Dreq(t, nm, err);
+    }
+}
+
 int orc_tables_resolve(orc_tables* t) {
   int err = 0;
   t->is_ecckd = orc_find(t, "ckd_lw_meta") != NULL;
   if (t->is_ecckd) {
     resolve_ckd_model(t, "ckd_lw_", &t->ckd_lw, &err);
     resolve_ckd_model(t, "ckd_sw_", &t->ckd_sw, &err);
-    for (int jt = 0; jt < 2; ++jt)
-      for (int sw = 0; sw < 2; ++sw) {
-        orc_gco* c = sw ? &t->gco_sw[jt] : &t->gco_lw[jt];
-        char nm[64];
-        snprintf(nm, sizeof nm, "gco_%s_%d_meta", sw ? "sw" : "lw", jt);
-        const double* meta = Dreq(t, nm, &err);
-        if (meta) { c->nre = (int)meta[0]; c->re0 = meta[1]; c->dre = meta[2]; }
-        snprintf(nm, sizeof nm, "gco_%s_%d_mass_ext", sw ? "sw" : "lw", jt); c->mass_ext = Dreq(t, nm, &err);
-        snprintf(nm, sizeof nm, "gco_%s_%d_ssa", sw ? "sw" : "lw", jt); c->ssa = Dreq(t, nm, &err);
-        snprintf(nm, sizeof nm, "gco_%s_%d_asymmetry", sw ? "sw" : "lw", jt); c->asymmetry = Dreq(t, nm, &err);
-      }
+    resolve_gco(t, 1, &err);
     for (int g = 0; g < 256; ++g) { t->band_lw[g] = g; t->band_sw[g] = g; }   /* radiation_ecckd_interface.F90:60-63 */
     resolve_common(t, &err);
     return err;
   }
+  resolve_gco(t, 0, &err);
   for (int b = 1; b <= 16; ++b) {
     t->absa_lw[b] = D(t, "lw%d_ABSA", b);  t->absb_lw[b] = D(t, "lw%d_ABSB", b);
     t->selfref_lw[b] = D(t, "lw%d_SELFREF", b); t->forref_lw[b] = D(t, "lw%d_FORREF", b);

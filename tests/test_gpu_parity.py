@@ -161,7 +161,11 @@ def test_cloudless_vs_oracle_and_golden(handles, meridian_raw, golden_cloudless)
                                 dict(do_sw_delta_scaling_with_gases=True), dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
-                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous")])
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"),
+                                # use_general_cloud_optics with RRTMG-IFS (radiation_config.F90:185, :1078-1090): look-up tables per band
+                                dict(use_general_cloud_optics=True), dict(use_general_cloud_optics=True, use_aerosols=True, do_lw_cloud_scattering=False),
+                                dict(use_general_cloud_optics=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(use_general_cloud_optics=True, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", do_sw_delta_scaling_with_gases=True)])
 def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """600 perturbed columns (BASELINE.md section 4 generator): different cloud profiles, seeds, sun angles."""
     n = 600

@@ -65,7 +65,8 @@ def check_exact(out, ref):
                                 dict(use_expm_everywhere=True), dict(use_expm_everywhere=True, do_3d_effects=False),
                                 dict(n_regions=2), dict(n_regions=2, sw_entrapment_name="Maximum", do_3d_lw_multilayer_effects=True),
                                 dict(n_regions=2, do_3d_effects=False),
-                                dict(use_aerosols=True, do_lw_aerosol_scattering=True), dict(do_lw_aerosol_scattering=True, n_regions=2)])
+                                dict(use_aerosols=True, do_lw_aerosol_scattering=True), dict(do_lw_aerosol_scattering=True, n_regions=2),
+                                dict(use_general_cloud_optics=True)])
 def test_spartacus_meridian_vs_oracle(meridian_raw, kw):
     """The reference's own 32-column slice (the input of its `spartacus` / `spartacus_maxentr` ctest targets)."""
     out, ref = run_pair({**SP, **kw}, meridian_raw, 32, spectral_profiles=True)

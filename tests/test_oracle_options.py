@@ -81,3 +81,26 @@ def test_lognormal_regions(meridian_raw):
     assert np.isfinite(logn["sw_up"]).all() and 0.0 < np.abs(logn["sw_up"] - gam["sw_up"]).max() < 60.0
     with pytest.raises(ValueError, match="gamma PDF"):
         RadiationConfig(cloud_pdf_shape_name="Lognormal").consolidate().to_struct()
+
+
+@pytest.mark.parametrize("kw", [dict(), TC, dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)])
+def test_general_cloud_optics_with_rrtmg(meridian_raw, kw):
+    """config%use_general_cloud_optics = true with RRTMG-IFS (radiation_interface.F90:378-392, radiation_config.F90:1078-1090: cloud
+    properties per band): Mie droplets + Baum ice from the look-up tables instead of SOCRATES + Fu-IFS.  No reference output exists
+    for the combination: the clear-sky fluxes cannot change, the cloudy ones move by what two cloud-optics models differ by."""
+    base = run(meridian_raw, **kw)
+    gen = run(meridian_raw, use_general_cloud_optics=True, **kw)
+    for nm in ("sw_up_clear", "sw_dn_clear", "lw_up_clear", "lw_dn_clear"):
+        assert np.array_equal(gen[nm], base[nm]), nm
+    for nm, bound in (("sw_up", 60.0), ("sw_dn", 80.0), ("lw_up", 15.0), ("lw_dn", 15.0)):
+        d = np.abs(gen[nm] - base[nm])
+        assert 0.0 < d.max() < bound and d.mean() < 0.1 * bound, (nm, d.max(), d.mean())
+    assert np.array_equal(gen["cloud_cover_sw"], base["cloud_cover_sw"])
+
+
+def test_general_cloud_optics_flag_is_required_by_ecckd(meridian_raw):
+    """ecCKD has no band parameterisations to fall back to (the reference warns, radiation_config.F90:1155-1157, then stops on the band
+    count in radiation_cloud_optics.F90:67-79)."""
+    cfg = RadiationConfig(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_general_cloud_optics=False)
+    with pytest.raises(ValueError, match="use_general_cloud_optics"):
+        cfg.consolidate()

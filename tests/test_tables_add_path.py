@@ -25,6 +25,9 @@ def test_shim_is_complete_and_current():
     registered = set(re.findall(r"call add_[ri]\d\(t, '([A-Za-z0-9_]+)'", src))
     # ("<name>.<model>" entries are the stand-alone blob's copies of the other cloud-optics files; a host registers the configured pair)
     host_side = {nm.split(".")[0] for nm in blob}
+    # the general cloud optics tables go through register_gco(t, '<prefix>', config%cloud_optics_xx(jtype)), for RRTMG-IFS too
+    for pre in set(re.findall(r"call register_gco\(t, '(gco_[ls]w_[01]_)'", src)):
+        registered |= {pre + f for f in ("meta", "mass_ext", "ssa", "asymmetry")}
     assert host_side <= registered, sorted(host_side - registered)
     # all 41 outputs and every input pointer of the header are assigned
     hdr = open(os.path.join(ROOT, "include", "ecrad_b200.h")).read()

@@ -201,6 +201,32 @@ def aerosol_tables(ref):
     return out
 
 
+def general_cloud_tables(ref):
+    """use_general_cloud_optics = true with RRTMG-IFS (the config_type default, radiation_config.F90:185): the look-up tables of
+    radiation_general_cloud_optics.F90:39-110 (cloud types 1 = mie_droplet, 2 = baum-general-habit-mixture_ice) averaged to the 14 + 16
+    RRTMG bands -- setup_general_cloud_optics with use_bands = .true. (RRTMG supports cloud properties per band only,
+    radiation_config.F90:1078-1090) on the bands-only spectral definitions of radiation_ifs_rrtm.F90:108-114, :156-162, "thick"
+    averaging (radiation_config.F90:352).  Same names as in the ecCKD blobs: gco_{sw,lw}_{0,1}_{meta,mass_ext,ssa,asymmetry}."""
+    from extract_ecckd_tables import general_cloud_optics
+    from ecrad_b200.config import LW_WN1, LW_WN2, SOLAR_REF_T, SW_WN1, SW_WN2, TERRESTRIAL_REF_T
+
+    class Bands:
+        def __init__(self, wn1, wn2, tref):
+            self.wn1, self.wn2, self.tref = wn1, wn2, tref
+
+        def calc_mapping(self, wavenumber):
+            return calc_mapping_bands(wavenumber, self.wn1, self.wn2, self.tref)
+
+    out = {}
+    d = os.path.join(ref, "data")
+    for jt, nm in enumerate(("mie_droplet", "baum-general-habit-mixture_ice")):
+        for spec, sd in (("sw", Bands(SW_WN1, SW_WN2, SOLAR_REF_T)), ("lw", Bands(LW_WN1, LW_WN2, TERRESTRIAL_REF_T))):
+            meta, me, ss, gg = general_cloud_optics(os.path.join(d, nm + "_scattering.nc"), sd, thick=True)
+            out[f"gco_{spec}_{jt}_meta"] = meta
+            out[f"gco_{spec}_{jt}_mass_ext"], out[f"gco_{spec}_{jt}_ssa"], out[f"gco_{spec}_{jt}_asymmetry"] = me, ss, gg
+    return out
+
+
 def gpoint_reordering(ref):
     """RRTM_GPOINT_REORDERING_SW / _LW (radiation_ifs_rrtm.F90:50-68): the order SPARTACUS wants the g-points in (approximately
     increasing gas optical depth), i.e. config%i_g_from_reordered_g_{sw,lw} when that spectrum's solver is SPARTACUS
@@ -226,6 +252,7 @@ def main():
     tabs.update(nc_tables(args.ref))
     tabs.update(aerosol_tables(args.ref))
     tabs.update(gpoint_reordering(args.ref))
+    tabs.update(general_cloud_tables(args.ref))
     write_blob(args.out, tabs)
     tot = sum(v.nbytes for v in tabs.values())
     print(f"wrote {args.out}: {len(tabs)} arrays, {tot/1e6:.2f} MB")

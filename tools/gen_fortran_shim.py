@@ -47,7 +47,6 @@ CFG_SPECIAL = {
     "n_emiss_lw": "merge(maxval(config%i_emiss_from_band_lw), size(config%lw_emiss_weights, 1), config%do_nearest_spectral_lw_emiss)",
     "n_aerosol_types": "merge(config%n_aerosol_types, 0, config%use_aerosols)",
     "n_regions": "config%nregions",
-    "reserved_": "0",
 }
 LOGICAL_PREFIXES = ("do_", "use_")
 
@@ -300,10 +299,12 @@ def main():
     w("    use radiation_config, only : config_type")
     w("    type(c_ptr), intent(in) :: t; type(config_type), intent(in) :: config")
     w("    integer :: j")
-    w("    call add_r2(t, 'liq_coeff_lw', config%cloud_optics%liq_coeff_lw); call add_r2(t, 'liq_coeff_sw', config%cloud_optics%liq_coeff_sw)")
-    w("    call add_r2(t, 'ice_coeff_lw', config%cloud_optics%ice_coeff_lw); call add_r2(t, 'ice_coeff_sw', config%cloud_optics%ice_coeff_sw)")
-    w("    ! (the arrays of the configured liquid_model_name / ice_model_name; the library checks their coefficient counts against i_liq_model / i_ice_model)")
-    w("    if (allocated(config%cloud_optics%ice_coeff_gen)) call add_r1(t, 'ice_coeff_gen', config%cloud_optics%ice_coeff_gen)   ! Baran-2017")
+    w("    if (.not. config%use_general_cloud_optics) then   ! setup_cloud_optics ran (radiation_interface.F90:116-120)")
+    w("      call add_r2(t, 'liq_coeff_lw', config%cloud_optics%liq_coeff_lw); call add_r2(t, 'liq_coeff_sw', config%cloud_optics%liq_coeff_sw)")
+    w("      call add_r2(t, 'ice_coeff_lw', config%cloud_optics%ice_coeff_lw); call add_r2(t, 'ice_coeff_sw', config%cloud_optics%ice_coeff_sw)")
+    w("      ! (the arrays of the configured liquid_model_name / ice_model_name; the library checks their coefficient counts against i_liq_model / i_ice_model)")
+    w("      if (allocated(config%cloud_optics%ice_coeff_gen)) call add_r1(t, 'ice_coeff_gen', config%cloud_optics%ice_coeff_gen)   ! Baran-2017")
+    w("    end if")
     w("    call add_r2(t, 'pdf_val', config%pdf_sampler%val)                 ! val(ncdf, nfsd), radiation_pdf_sampler.F90:83-93")
     w("    call add_r1(t, 'pdf_fsd', [(config%pdf_sampler%fsd1 + real(j-1,jprb) / config%pdf_sampler%inv_fsd_interval, j = 1, config%pdf_sampler%nfsd)])")
     w("    call add_r2(t, 'sw_albedo_weights', config%sw_albedo_weights)     ! (n_albedo_sw, n_bands_sw)")
@@ -377,6 +378,10 @@ def main():
     w("      call register_ecckd(t, config)")
     w("    else")
     w("      call register_rrtmg(t)")
+    w("      if (config%use_general_cloud_optics) then   ! look-up tables per RRTMG band (radiation_config.F90:1078-1090)")
+    w("        call register_gco(t, 'gco_lw_0_', config%cloud_optics_lw(1)); call register_gco(t, 'gco_lw_1_', config%cloud_optics_lw(2))")
+    w("        call register_gco(t, 'gco_sw_0_', config%cloud_optics_sw(1)); call register_gco(t, 'gco_sw_1_', config%cloud_optics_sw(2))")
+    w("      end if")
     w("    end if")
     w("    call register_config_tables(t, config)")
     missing = []
