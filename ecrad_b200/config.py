@@ -66,6 +66,10 @@ class RadiationConfig:
     sw_solver_name: str = "McICA"
     lw_solver_name: str = "McICA"
     gas_model_name: str = "RRTMG-IFS"
+    # one gas model per spectrum (sw_gas_model_name / lw_gas_model_name, radiation_config.F90:712-713); None = gas_model_name.
+    # RRTMG-IFS in one spectrum and ECCKD in the other is the mixed configuration of test/ifs/configCY49R1_mixed.nam
+    sw_gas_model_name: str | None = None
+    lw_gas_model_name: str | None = None
     # cloud optics from the generalised look-up tables (config%use_general_cloud_optics).  None = what the reference's namelists of
     # test/ifs say: false with RRTMG-IFS (configCY49R1.nam:37), true with ecCKD (configCY49R1_ecckd.nam:39)
     use_general_cloud_optics: bool | None = None
@@ -124,39 +128,79 @@ class RadiationConfig:
     n_bands: tuple = (14, 16)    # (n_bands_sw, n_bands_lw)
 
     @property
+    def is_ecckd_sw(self):
+        return (self.sw_gas_model_name or self.gas_model_name).lower() == "ecckd"
+
+    @property
+    def is_ecckd_lw(self):
+        return (self.lw_gas_model_name or self.gas_model_name).lower() == "ecckd"
+
+    @property
     def is_ecckd(self):
-        return self.gas_model_name.lower() == "ecckd"
+        """Both spectra on ecCKD: the gas arrays are volume mixing ratios then (set_gas_units, radiation_interface.F90:164-186)."""
+        return self.is_ecckd_sw and self.is_ecckd_lw
+
+    @property
+    def is_mixed(self):
+        return self.is_ecckd_sw != self.is_ecckd_lw
+
+    def _data_path(self, name):
+        here = os.path.dirname(os.path.abspath(__file__))
+        return name if os.path.isabs(name) else os.path.join(here, "data", name)
 
     def tables_path(self):
         """The table blob `setup_radiation` loads for this configuration."""
-        here = os.path.dirname(os.path.abspath(__file__))
-        if not self.is_ecckd:
-            return os.path.join(here, "data", "rrtmg_tables.bin")
-        return self.ecckd_tables if os.path.isabs(self.ecckd_tables) else os.path.join(here, "data", self.ecckd_tables)
+        if self.is_ecckd:
+            return self._data_path(self.ecckd_tables)
+        if not self.is_mixed:
+            return self._data_path("rrtmg_tables.bin")
+        # mixed gas models: the RRTMG directory plus the ecCKD spectrum's model, cloud and aerosol tables (their names carry the
+        # spectrum), what a host that ran both setup_gas_optics would register.  Written once next to the shipped blobs.
+        from .tables import read_blob, write_blob
+        spec = "sw" if self.is_ecckd_sw else "lw"
+        src = self._data_path(self.ecckd_tables)
+        out = self._data_path(os.path.join("_mixed", f"rrtmg_{spec}_{os.path.basename(src)}"))
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(self._data_path("rrtmg_tables.bin"))):
+            tabs = read_blob(self._data_path("rrtmg_tables.bin"))
+            for nm, arr in read_blob(src).items():
+                if f"_{spec}_" in nm:
+                    tabs[nm] = arr
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            tmp = f"{out}.{os.getpid()}.tmp"
+            write_blob(tmp, tabs)
+            os.replace(tmp, out)
+        return out
 
     def consolidate(self):
         """Tables derived from the config (what `setup_radiation` stores in config_type)."""
         if self.do_canopy_fluxes_sw:   # radiation_config.F90:1119-1124
             self.do_surface_sw_spectral_flux = True
-        if self.is_ecckd and self.use_general_cloud_optics is not None and not self.use_general_cloud_optics:
+        any_ckd = self.is_ecckd_sw or self.is_ecckd_lw
+        if any_ckd and self.use_general_cloud_optics is not None and not self.use_general_cloud_optics:
             raise ValueError("ecCKD gas optics needs use_general_cloud_optics = true: the band parameterisations are on the RRTMG "
                              "bands (the reference stops in radiation_cloud_optics.F90:67-79)")
-        if self.is_ecckd:
+        if any_ckd:
             # consolidate_sw_albedo_intervals / consolidate_lw_emiss_intervals (radiation_config.F90:1947-2100) with the
             # model's own spectral definition, one weight vector per g-point; bands == g-points
             # (radiation_ecckd_interface.F90:46-76)
             from .spectral import SpectralDefinition
             from .tables import read_blob
-            tabs = read_blob(self.tables_path())
-            sd_sw, sd_lw = SpectralDefinition.from_tables(tabs, "ckd_sw_"), SpectralDefinition.from_tables(tabs, "ckd_lw_")
+            tabs = read_blob(self._data_path(self.ecckd_tables))
+        if self.is_ecckd_sw:
+            sd_sw = SpectralDefinition.from_tables(tabs, "ckd_sw_")
             w = sd_sw.calc_mapping_from_bands(self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
-            e = sd_lw.calc_mapping_from_bands(self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
-            self.n_g = (sd_sw.ng, sd_lw.ng)
-            self.n_bands = (sd_sw.ng, sd_lw.ng)
+            ng_sw = nb_sw = sd_sw.ng
         else:
             w = mapping_from_bands(SW_WN1, SW_WN2, SOLAR_REF_T, self.sw_albedo_wavelength_bound, self.i_sw_albedo_index)
+            ng_sw, nb_sw = 112, 14
+        if self.is_ecckd_lw:
+            sd_lw = SpectralDefinition.from_tables(tabs, "ckd_lw_")
+            e = sd_lw.calc_mapping_from_bands(self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
+            ng_lw = nb_lw = sd_lw.ng
+        else:
             e = mapping_from_bands(LW_WN1, LW_WN2, TERRESTRIAL_REF_T, self.lw_emiss_wavelength_bound, self.i_lw_emiss_index)
-            self.n_g, self.n_bands = (112, 140), (14, 16)
+            ng_lw, nb_lw = 140, 16
+        self.n_g, self.n_bands = (ng_sw, ng_lw), (nb_sw, nb_lw)
         self.derived = {
             "sw_albedo_weights": np.asfortranarray(w),                                   # (n_albedo, 14)
             "i_emiss_from_band_lw": (np.argmax(e, axis=0) + 1).astype(np.int32),         # maxloc(dim=1)
@@ -178,7 +222,8 @@ class RadiationConfig:
         c.struct_bytes = C.sizeof(abi.Config)
         c.i_solver_sw = abi.SOLVER[self.sw_solver_name.lower()]
         c.i_solver_lw = abi.SOLVER[self.lw_solver_name.lower()]
-        c.i_gas_model_sw = c.i_gas_model_lw = abi.GAS_MODEL[self.gas_model_name.lower()]
+        c.i_gas_model_sw = abi.GAS_MODEL[(self.sw_gas_model_name or self.gas_model_name).lower()]
+        c.i_gas_model_lw = abi.GAS_MODEL[(self.lw_gas_model_name or self.gas_model_name).lower()]
         c.i_overlap_scheme = abi.OVERLAP[self.overlap_scheme_name.lower()]
         c.i_liq_model = abi.LIQ_MODEL[self.liquid_model_name.lower()]
         c.i_ice_model = abi.ICE_MODEL[self.ice_model_name.lower()]
@@ -192,7 +237,7 @@ class RadiationConfig:
         c.i_3d_sw_entrapment = abi.ENTRAPMENT[self.sw_entrapment_name.lower()]
         c.i_cloud_pdf_shape = abi.PDF_SHAPE[self.cloud_pdf_shape_name.lower()]
         c.n_regions = int(self.n_regions)
-        c.use_general_cloud_optics = int(self.is_ecckd if self.use_general_cloud_optics is None else bool(self.use_general_cloud_optics))
+        c.use_general_cloud_optics = int((self.is_ecckd_sw or self.is_ecckd_lw) if self.use_general_cloud_optics is None else bool(self.use_general_cloud_optics))
         if c.i_cloud_pdf_shape == 0 and "mcica" in (self.sw_solver_name.lower(), self.lw_solver_name.lower()):
             raise ValueError("the shipped table blob holds the gamma PDF look-up table of the McICA generator (mcica_gamma.nc); "
                              "a lognormal McICA run needs 'pdf_val' from mcica_lognormal.nc")

@@ -152,9 +152,10 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     if (c.i_3d_sw_entrapment < ECRAD_ENTRAPMENT_ZERO || c.i_3d_sw_entrapment > ECRAD_ENTRAPMENT_MAXIMUM) return fail(h, "unknown sw_entrapment");
     if (!(c.min_cloud_effective_size > 0.0) || !(c.max_cloud_od > 0.0)) return fail(h, "SPARTACUS: min_cloud_effective_size and max_cloud_od must be positive");
   }
-  const int gm = c.do_lw ? c.i_gas_model_lw : c.i_gas_model_sw;
-  if ((gm != ECRAD_GAS_IFSRRTMG && gm != ECRAD_GAS_ECCKD) || (c.do_sw && c.do_lw && c.i_gas_model_sw != c.i_gas_model_lw))
-    return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD, the same in the longwave and the shortwave)");
+  // one gas model per spectrum (radiation_interface.F90:333-355); RRTMG-IFS in one and ECCKD in the other = test/ifs/configCY49R1_mixed.nam
+  auto known = [](int m) { return m == ECRAD_GAS_IFSRRTMG || m == ECRAD_GAS_ECCKD; };
+  if (!known(c.i_gas_model_lw) || !known(c.i_gas_model_sw)) return fail(h, "gas model not available in this build (RRTMG-IFS or ECCKD)");
+  const bool ckd_lw = c.i_gas_model_lw == ECRAD_GAS_ECCKD, ckd_sw = c.i_gas_model_sw == ECRAD_GAS_ECCKD;
   if (c.i_cloud_pdf_shape != ECRAD_PDF_GAMMA && c.i_cloud_pdf_shape != ECRAD_PDF_LOGNORMAL) return fail(h, "unknown cloud PDF shape");
   if (c.n_regions != 2 && c.n_regions != 3) return fail(h, "n_regions must be 2 or 3 (radiation_config.F90:268)");
   if (c.n_regions == 2 && c.do_sw && c.do_lw && (c.i_solver_sw == ECRAD_SOLVER_SPARTACUS) != (c.i_solver_lw == ECRAD_SOLVER_SPARTACUS))
@@ -165,29 +166,29 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     // radiation_interface.F90:84-88
     if (!c.do_lw_cloud_scattering) return fail(h, "longwave aerosol scattering requires longwave cloud scattering");
     const bool plain = c.i_solver_lw == ECRAD_SOLVER_MCICA || c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS || c.i_solver_lw == ECRAD_SOLVER_SPARTACUS;
-    if (!plain || gm != ECRAD_GAS_IFSRRTMG || (c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux))
+    if (!plain || ckd_lw || (c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux))
       return fail(h, "do_lw_aerosol_scattering is available with the McICA, Cloudless and SPARTACUS longwave solvers on RRTMG-IFS gas optics");
   }
   if (c.do_sw && !c.do_sw_direct) return fail(h, "do_sw_direct = false is not available in this build (the direct beam is always computed)");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
-  if (gm == ECRAD_GAS_IFSRRTMG) {
+  if (!ckd_lw && !ckd_sw && !c.use_general_cloud_optics) {
     // radiation_cloud_optics.F90:345-372 dispatches SOCRATES and Slingo only; the five ice models of :376-447
-    if (!c.use_general_cloud_optics) {   // (with the generalised look-up tables the two model codes are not read)
-      if (c.i_liq_model != ECRAD_LIQ_SOCRATES && c.i_liq_model != ECRAD_LIQ_SLINGO) return fail(h, "liquid optics model not available (SOCRATES and Slingo are)");
-      if (c.i_ice_model < ECRAD_ICE_FU || c.i_ice_model > ECRAD_ICE_YI) return fail(h, "ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
-    }
-    if (c.n_g_lw != NG_LW || c.n_g_sw != NG_SW || c.n_bands_lw != NB_LW || c.n_bands_sw != NB_SW) return fail(h, "unexpected RRTMG spectral dimensions");
-  } else {
-    // generalised cloud + aerosol optics per g-point (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points
-    auto ok = [](int n) { return n == 32 || n == 64 || n == 96; };
-    if (!ok(c.n_g_lw) || !ok(c.n_g_sw) || c.n_bands_lw != c.n_g_lw || c.n_bands_sw != c.n_g_sw)
-      return fail(h, "ECCKD: models with 32, 64 or 96 g-points and cloud/aerosol optics per g-point (n_bands == n_g) are built in");
-    if (c.do_sw_delta_scaling_with_gases) return fail(h, "do_sw_delta_scaling_with_gases is not available in this build");
-    // radiation_cloud_optics.F90:66-79 would abort: the band parameterisations have 16 + 14 RRTMG bands
-    if (!c.use_general_cloud_optics) return fail(h, "ECCKD needs use_general_cloud_optics (the band parameterisations are defined on the RRTMG bands)");
+    // (with the generalised look-up tables the two model codes are not read)
+    if (c.i_liq_model != ECRAD_LIQ_SOCRATES && c.i_liq_model != ECRAD_LIQ_SLINGO) return fail(h, "liquid optics model not available (SOCRATES and Slingo are)");
+    if (c.i_ice_model < ECRAD_ICE_FU || c.i_ice_model > ECRAD_ICE_YI) return fail(h, "ice optics model not available (Fu-IFS, Baran, Baran2016, Baran2017 and Yi are)");
   }
+  // RRTMG: 140 / 112 g-points in 16 / 14 bands.  ecCKD: generalised cloud + aerosol optics per g-point
+  // (do_cloud_aerosol_per_{sw,lw}_g_point): bands == g-points
+  auto ok = [](int n) { return n == 32 || n == 64 || n == 96; };
+  if (!ckd_lw && (c.n_g_lw != NG_LW || c.n_bands_lw != NB_LW)) return fail(h, "unexpected RRTMG spectral dimensions");
+  if (!ckd_sw && (c.n_g_sw != NG_SW || c.n_bands_sw != NB_SW)) return fail(h, "unexpected RRTMG spectral dimensions");
+  if ((ckd_lw && (!ok(c.n_g_lw) || c.n_bands_lw != c.n_g_lw)) || (ckd_sw && (!ok(c.n_g_sw) || c.n_bands_sw != c.n_g_sw)))
+    return fail(h, "ECCKD: models with 32, 64 or 96 g-points and cloud/aerosol optics per g-point (n_bands == n_g) are built in");
+  if (ckd_sw && c.do_sw_delta_scaling_with_gases) return fail(h, "do_sw_delta_scaling_with_gases is not available with ECCKD in this build");
+  // radiation_cloud_optics.F90:66-79 would abort: the band parameterisations have 16 + 14 RRTMG bands
+  if ((ckd_lw || ckd_sw) && !c.use_general_cloud_optics) return fail(h, "ECCKD needs use_general_cloud_optics (the band parameterisations are defined on the RRTMG bands)");
   return 0;
 }
 
@@ -201,7 +202,7 @@ bool use_scan(const Handle* h, bool sw, int nlev) {
   const int sol = sw ? c.i_solver_sw : c.i_solver_lw;
   if (sol != ECRAD_SOLVER_MCICA && sol != ECRAD_SOLVER_CLOUDLESS) return false;
   if (sol == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux) return false;   // per-band profiles: the band-summing kernels
-  if (h->dcfg.gas_model != ECRAD_GAS_IFSRRTMG) return false;
+  if (sw ? h->dcfg.ckd_sw : h->dcfg.ckd_lw) return false;
   return nlev <= scan_max_levels();
 }
 // bytes of every per-tile scratch array for `cols` columns (all linear in cols)
@@ -214,7 +215,7 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
   const bool sp_lw = h->cfg.do_lw && h->cfg.i_solver_lw == ECRAD_SOLVER_SPARTACUS, sp_sw = h->cfg.do_sw && h->cfg.i_solver_sw == ECRAD_SOLVER_SPARTACUS;
   const bool tc = tc_lw || tc_sw || sp_lw || sp_sw;   // region fractions and overlap matrices (tc_prep_kernel)
   const size_t NG_LW = (size_t)h->cfg.n_g_lw, NG_SW = (size_t)h->cfg.n_g_sw, NB_LW = (size_t)h->cfg.n_bands_lw, NB_SW = (size_t)h->cfg.n_bands_sw;
-  const bool ckd = h->dcfg.gas_model == ECRAD_GAS_ECCKD;
+  const bool ckd_lw = h->dcfg.ckd_lw, ckd_sw = h->dcfg.ckd_sw, ckd = ckd_lw && ckd_sw;   // ckd: no RRTMG spectrum at all
   const bool lwscat = h->cfg.do_lw && h->cfg.do_lw_aerosol_scattering;
   const size_t sz[N_WORK] = {
       8 * nc * nl * NG_LW, 8 * nc * nl * NG_LW, 8 * nc * NG_LW, 8 * nc * NG_LW,              // od_lw planck emission lw_albedo
@@ -228,8 +229,8 @@ void work_sizes(const Handle* h, int cols, int nlev, size_t* out) {
       8 * nc * 6 * (nl + 1), 8 * nc * 4 * NG_LW,                                             // lw_sums lw_carry
       8 * nc * (sp_sw ? sp_scratch_doubles_sw(nlev, (int)NG_SW) : tc_sw ? tc_scratch_doubles_sw(nlev, (int)NG_SW) : use_scan(h, true, nlev) ? 0 : SW_SCR_ARRAYS * nl * NG_SW),            // scr_sw
       ckd ? 0 : 8 * (size_t)LWLEV_NF * nc * nl, ckd ? 0 : 8 * (size_t)SWLEV_NF * nc * nl,    // lev_lw lev_sw (RRTMG)
-      h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
-      (h->cfg.use_aerosols && !ckd) ? 8 * nc * nl * NB_LW * (lwscat ? 3 : 1) : 0,            // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
+      h->cfg.use_aerosols ? 8 * nc * nl * NG_SW : 0, (h->cfg.use_aerosols && !ckd_sw) ? 8 * nc * nl * 3 * NB_SW : 0,   // g_sw aer_sw
+      (h->cfg.use_aerosols && !ckd_lw) ? 8 * nc * nl * NB_LW * (lwscat ? 3 : 1) : 0,            // aer_lw (ecCKD merges aerosols per g-point inside its gas kernels)
       0,                                                                                     // (sw_band_dir: no longer used)
       tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * nl * 3 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc * (nl + 1) * 9 : 0, tc ? 8 * nc : 0,  // tc_reg tc_ods tc_u tc_v tc_cc
       ckd ? 0 : nc * nl, ckd ? 0 : sizeof(GasCol) * nc, ckd ? 0 : 4 * (nc + 1),              // gas_jp gas_col sunlit (RRTMG)
@@ -288,11 +289,14 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   h->w[set].layout_b_lw = use_scan(h, false, nlev);
   h->w[set].layout_b_sw = use_scan(h, true, nlev);
   cudaStream_t s_lw = st, s_sw = par ? h->s_aux1[set] : st, s_cl = par ? h->s_aux2[set] : st;
-  const bool ckd = c.gas_model == ECRAD_GAS_ECCKD;
-  if (!ckd) {
-    n += launch_gas_prep(h->T, c, in, h->w[set], nc, nlev, st);   // shared by the LW and SW gas-optics kernels
-    if ((h->gas_variant & 3) || c.do_lw_aerosol_scattering) n += launch_gas_col(h->T, c, in, h->w[set], nc, nlev, st);
-    if (c.use_aerosols) n += launch_aerosol(h->T, c, in, h->w[set], nc, nlev, st);
+  const bool ckd_lw = c.ckd_lw != 0, ckd_sw = c.ckd_sw != 0;
+  // what the RRTMG kernels see: with mixed gas models only the RRTMG spectrum is theirs (the other one has other spectral sizes)
+  DevCfg crr = c;
+  crr.do_lw = c.do_lw && !ckd_lw; crr.do_sw = c.do_sw && !ckd_sw;
+  if (!(ckd_lw && ckd_sw)) {
+    n += launch_gas_prep(h->T, crr, in, h->w[set], nc, nlev, st);   // shared by the LW and SW gas-optics kernels
+    if ((h->gas_variant & 3) || c.do_lw_aerosol_scattering) n += launch_gas_col(h->T, crr, in, h->w[set], nc, nlev, st);
+    if (c.use_aerosols) n += launch_aerosol(h->T, crr, in, h->w[set], nc, nlev, st);
   }
   if (par) {
     CK(h, cudaEventRecord(h->ev_fork[set], st));
@@ -309,13 +313,13 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   if (par) CK(h, cudaEventRecord(h->ev_cloud[set], s_cl));
   // LW chain
   CK(h, cudaEventRecord(ev[0], s_lw));
-  if (c.do_lw) n += ckd ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : ((h->gas_variant & 1) || c.do_lw_aerosol_scattering) ? launch_gas_lw_band(h->T, c, in, h->w[set], nc, nlev, s_lw)
-                                                                                                  : launch_gas_lw(h->T, c, in, h->w[set], nc, nlev, s_lw);
+  if (c.do_lw) n += ckd_lw ? launch_ckd_lw(h->T, c, in, h->w[set], nc, nlev, s_lw) : ((h->gas_variant & 1) || c.do_lw_aerosol_scattering) ? launch_gas_lw_band(h->T, crr, in, h->w[set], nc, nlev, s_lw)
+                                                                                                  : launch_gas_lw(h->T, crr, in, h->w[set], nc, nlev, s_lw);
   CK(h, cudaEventRecord(ev[1], s_lw));
   // SW chain
   CK(h, cudaEventRecord(ev[2], s_sw));
-  if (c.do_sw) n += ckd ? launch_ckd_sw(h->T, c, in, h->w[set], nc, nlev, s_sw) : (h->gas_variant & 2) ? launch_gas_sw_band(h->T, c, in, h->w[set], nc, nlev, s_sw)
-                                                                                                  : launch_gas_sw(h->T, c, in, h->w[set], nc, nlev, s_sw);
+  if (c.do_sw) n += ckd_sw ? launch_ckd_sw(h->T, c, in, h->w[set], nc, nlev, s_sw) : (h->gas_variant & 2) ? launch_gas_sw_band(h->T, crr, in, h->w[set], nc, nlev, s_sw)
+                                                                                                  : launch_gas_sw(h->T, crr, in, h->w[set], nc, nlev, s_sw);
   CK(h, cudaEventRecord(ev[3], s_sw));
   if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud[set], 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud[set], 0)); }
   CK(h, cudaEventRecord(ev[6], s_lw));
@@ -548,13 +552,14 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   try { pack_tables(*tab, P, cfg->i_liq_model, cfg->i_ice_model, cfg->use_general_cloud_optics != 0); } catch (const std::exception& ex) { fail(nullptr, "table directory incomplete: %s", ex.what()); delete h; return 1; }
   for (int g = 0; g < NG_LW; ++g) P.meta.rank_lw[g] = (short)g;
   for (int g = 0; g < NG_SW; ++g) P.meta.rank_sw[g] = (short)g;
-  if (!P.is_ecckd) {
+  {
     // SPARTACUS treats the g-points up to the first one whose gas optical depth exceeds max_gas_od_3d with the matrix exponential,
     // "assuming that the g-points have been reordered in approximate order of gas optical depth" (radiation_spartacus_sw.F90:462-478):
     // radiation_ifs_rrtm.F90:122-130 / :167-174 reorder them for this solver only.  The kernels keep the arrays in RRTMG order
     // and carry each g-point's position in that sequence; the per-g-point outputs are written at that position.
     for (int sw = 0; sw < 2; ++sw) {
       if (!(sw ? (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) : (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS))) continue;
+      if (sw ? P.ckd_sw : P.ckd_lw) continue;   // (an ecCKD spectrum stays in its own order)
       const char* nm = sw ? "i_g_from_reordered_g_sw" : "i_g_from_reordered_g_lw";
       const int ng = sw ? NG_SW : NG_LW;
       const auto* a = tab->find(nm);
@@ -567,10 +572,11 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
       }
     }
   }
-  if (P.is_ecckd != (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD)) {
-    fail(nullptr, "the table directory holds %s tables but the configuration asks for the other gas model", P.is_ecckd ? "ecCKD" : "RRTMG"); delete h; return 1;
+  if (P.ckd_lw != (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) || P.ckd_sw != (cfg->i_gas_model_sw == ECRAD_GAS_ECCKD)) {
+    fail(nullptr, "the table directory holds %s / %s tables (longwave / shortwave) but the configuration names other gas models",
+         P.ckd_lw ? "ecCKD" : "RRTMG", P.ckd_sw ? "ecCKD" : "RRTMG"); delete h; return 1;
   }
-  if (P.is_ecckd && ((cfg->do_lw && P.ng_lw != cfg->n_g_lw) || (cfg->do_sw && P.ng_sw != cfg->n_g_sw))) {
+  if ((P.ckd_lw && cfg->do_lw && P.ng_lw != cfg->n_g_lw) || (P.ckd_sw && cfg->do_sw && P.ng_sw != cfg->n_g_sw)) {
     fail(nullptr, "ecCKD tables have %d/%d g-points (LW/SW), the configuration says %d/%d", P.ng_lw, P.ng_sw, cfg->n_g_lw, cfg->n_g_sw); delete h; return 1;
   }
   if (cfg->do_nearest_spectral_sw_albedo) {
@@ -601,14 +607,11 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   rc |= upload(h, &P.meta, 1, &h->T.meta);
   h->T.lwtab = h->T.swtab = nullptr; h->T.ckd = nullptr; h->T.ckdtab = nullptr;
   h->T.i_emiss_from_band_lw = nullptr; h->T.lw_emiss_weights = nullptr;
-  if (P.is_ecckd) {
+  if (P.ckd_lw || P.ckd_sw || cfg->use_general_cloud_optics) {   // ecCKD models and/or the generalised cloud optics look-up tables (per g-point or per RRTMG band)
     rc |= upload(h, &P.ckd, 1, &h->T.ckd);
     rc |= upload(h, P.ckdtab.data(), P.ckdtab.size(), &h->T.ckdtab);
-  } else {
-    if (cfg->use_general_cloud_optics) {   // look-up tables of the generalised cloud optics per RRTMG band
-      rc |= upload(h, &P.ckd, 1, &h->T.ckd);
-      rc |= upload(h, P.ckdtab.data(), P.ckdtab.size(), &h->T.ckdtab);
-    }
+  }
+  if (!P.is_ecckd) {
     rc |= upload(h, P.lwtab.data(), P.lwtab.size(), &h->T.lwtab);
     rc |= upload(h, P.swtab.data(), P.swtab.size(), &h->T.swtab);
   }
@@ -642,7 +645,8 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.do_save_spectral_flux = cfg->do_save_spectral_flux;
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
-  d.gas_model = cfg->do_lw ? cfg->i_gas_model_lw : cfg->i_gas_model_sw;
+  d.ckd_lw = P.ckd_lw; d.ckd_sw = P.ckd_sw;
+  d.gas_mmr = !(P.ckd_lw && P.ckd_sw);
   d.use_general_cloud_optics = cfg->use_general_cloud_optics != 0;
   d.do_toa_spectral_flux = cfg->do_toa_spectral_flux;
   d.pdf_gamma = cfg->i_cloud_pdf_shape == ECRAD_PDF_GAMMA;

@@ -43,7 +43,7 @@ __device__ __forceinline__ unsigned char* ckd_layers_carve(unsigned char* base, 
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(L.ic1 + (size_t)nlev * m.nlut) + 15) & ~(uintptr_t)15);
 }
 
-__device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double* __restrict__ tab, const DevIn& in, int c, int l, const CkdLayers& L) {
+__device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double* __restrict__ tab, const DevIn& in, int c, int l, const CkdLayers& L, bool gas_mmr) {
   const double global_multiplier = 1.0 / (9.80665 * 0.001 * 28.970);   // 1 / (AccelDueToGravity * 0.001 * AirMolarMass)
   const double p1 = LD_IN(in.p_hl, c, l), p2 = LD_IN(in.p_hl, c, l + 1);
   const double t1 = LD_IN(in.t_hl, c, l), t2 = LD_IN(in.t_hl, c, l + 1);
@@ -65,17 +65,18 @@ __device__ __forceinline__ void ckd_layer_state(const CkdModel& m, const double*
   for (int j = 0; j < m.ngas; ++j) {
     const CkdGas& G = m.gas[j];
     const double mf = G.slot >= 0 ? LD_IN(in.gas[G.slot], c, l) : 0.0;
+    const double scaling = gas_mmr ? G.mmr_scaling : 1.0;   // local_concentration_scaling(igascode), radiation_ecckd.F90:518-519
     double mult;
-    if (G.dep == CKD_CONC_LINEAR) mult = simple_multiplier * mf * 1.0;
-    else if (G.dep == CKD_CONC_RELATIVE_LINEAR) mult = simple_multiplier * (mf * 1.0 - G.reference_mole_frac);
+    if (G.dep == CKD_CONC_LINEAR) mult = simple_multiplier * mf * scaling;
+    else if (G.dep == CKD_CONC_RELATIVE_LINEAR) mult = simple_multiplier * (mf * scaling - G.reference_mole_frac);
     else if (G.dep == CKD_CONC_LUT) {
-      const double log_conc = log(dmax(mf * 1.0, G.mole_frac1));
+      const double log_conc = log(dmax(mf * scaling, G.mole_frac1));
       double cindex1 = (log_conc - G.log_mole_frac1) / G.d_log_mole_frac;
       cindex1 = 1.0 + dmax(0.0, dmin(cindex1, G.n_mole_frac - 1.0001));
       const int ic1 = (int)cindex1;
       L.ic1[(size_t)l * m.nlut + G.lut] = ic1;
       L.cw2[(size_t)l * m.nlut + G.lut] = cindex1 - ic1;
-      mult = simple_multiplier * mf * 1.0;
+      mult = simple_multiplier * mf * scaling;
     } else mult = simple_multiplier;
     L.mult[(size_t)l * m.ngas + j] = mult;
   }
@@ -116,9 +117,9 @@ __device__ __forceinline__ void aer_layers_carve(unsigned char* base, int nlev, 
   a.fm = reinterpret_cast<double*>(base);
   a.irh = reinterpret_cast<int*>(a.fm + (size_t)nlev * ntype);
 }
-__device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& in, int c, int l, int nlev, const AerLayers& a) {
+__device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& in, int c, int l, int nlev, const AerLayers& a, bool gas_mmr) {
   // gas%mixing_ratio(:,:,IH2O) is a mole fraction under ecCKD: gas%get(IH2O, IMassMixingRatio) (:611, radiation_gas.F90:603-616)
-  const double h2o_mmr = LD_IN(in.gas[0], c, l) * (18.0152833 / 28.970);
+  const double h2o_mmr = gas_mmr ? LD_IN(in.gas[0], c, l) : LD_IN(in.gas[0], c, l) * (18.0152833 / 28.970);
   const double rh = h2o_mmr / LD_IN(in.h2o_sat_liq, c, l);
   int irh;
   if (rh > A.rh_lower[A.nrh - 1]) irh = A.nrh;
@@ -144,8 +145,8 @@ ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   AerLayers aer;
   if (do_aer) aer_layers_carve(reinterpret_cast<unsigned char*>(ptw + 2 * (nlev + 2)), nlev, T.aer->ntype, aer);
   for (int l = tid; l < nlev; l += CKD_THREADS) {
-    ckd_layer_state(m, tab, in, c, l, lay);
-    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer);
+    ckd_layer_state(m, tab, in, c, l, lay, cfg.gas_mmr != 0);
+    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer, cfg.gas_mmr != 0);
   }
   for (int k = tid; k < nlev + 2; k += CKD_THREADS) {   // half-levels 0..nlev, then the skin temperature
     const double temperature = k <= nlev ? LD_IN(in.t_hl, c, k) : in.skin_t[c];
@@ -224,8 +225,8 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   AerLayers aer;
   if (do_aer) aer_layers_carve(rest, nlev, T.aer->ntype, aer);
   for (int l = tid; l < nlev; l += CKD_THREADS) {
-    ckd_layer_state(m, tab, in, c, l, lay);
-    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer);
+    ckd_layer_state(m, tab, in, c, l, lay, cfg.gas_mmr != 0);
+    if (do_aer) aer_layer_state(*T.aer, in, c, l, nlev, aer, cfg.gas_mmr != 0);
   }
   __syncthreads();
   const size_t n = (size_t)nlev * SD::NG;

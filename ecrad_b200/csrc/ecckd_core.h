@@ -22,6 +22,7 @@ struct CkdGas {
   int lut;            // index among the look-up-table gases of the model (dep == CKD_CONC_LUT), else -1
   double reference_mole_frac, log_mole_frac1, d_log_mole_frac;
   double mole_frac1;  // exp(log_mole_frac1), evaluated once on the host (radiation_ecckd.F90:586)
+  double mmr_scaling; // local_concentration_scaling of this gas when the gas arrays are mass mixing ratios (mixed gas models)
   size_t off;         // molar_abs
 };
 

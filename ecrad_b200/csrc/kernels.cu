@@ -112,6 +112,7 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
   else { irh = 1; while (rh > A.rh_lower[irh]) ++irh; }
   const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) * (1.0 / 9.80665);
   const bool lwscat = cfg.do_lw_aerosol_scattering != 0;
+  const bool psw = !cfg.ckd_sw, plw = !cfg.ckd_lw;   // mixed gas models: an ecCKD spectrum merges its aerosols per g-point in its own gas kernel
   double od_sw[NB_SW], sc_sw[NB_SW], sg_sw[NB_SW], od_lw[NB_LW], sc_lw[NB_LW], sg_lw[NB_LW];
 #pragma unroll
   for (int b = 0; b < NB_SW; ++b) { od_sw[b] = 0.0; sc_sw[b] = 0.0; sg_sw[b] = 0.0; }
@@ -130,13 +131,16 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
     const double* me_lw = tab + (iclass == 1 ? A.me_lw_phobic : A.me_lw_philic) + ilw;
     const double* ss_lw = tab + (iclass == 1 ? A.ssa_lw_phobic : A.ssa_lw_philic) + ilw;
     const double* gg_lw = tab + (iclass == 1 ? A.g_lw_phobic : A.g_lw_philic) + ilw;
+    if (psw) {
 #pragma unroll
-    for (int b = 0; b < NB_SW; ++b) {
-      const double local_od = factor * mr * me_sw[b];
-      od_sw[b] = od_sw[b] + local_od;
-      sc_sw[b] = sc_sw[b] + local_od * ss_sw[b];
-      sg_sw[b] = sg_sw[b] + local_od * ss_sw[b] * gg_sw[b];
+      for (int b = 0; b < NB_SW; ++b) {
+        const double local_od = factor * mr * me_sw[b];
+        od_sw[b] = od_sw[b] + local_od;
+        sc_sw[b] = sc_sw[b] + local_od * ss_sw[b];
+        sg_sw[b] = sg_sw[b] + local_od * ss_sw[b] * gg_sw[b];
+      }
     }
+    if (!plw) continue;
     if (lwscat) {   // radiation_aerosol_optics.F90:657-670, :697-710
 #pragma unroll
       for (int b = 0; b < NB_LW; ++b) {
@@ -151,6 +155,7 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
     }
   }
   double* osw = w.aer_sw + ((size_t)c * nlev + l) * 3 * NB_SW;
+  if (psw) {
 #pragma unroll
   for (int b = 0; b < NB_SW; ++b) {
     double od = od_sw[b], sc = sc_sw[b], sg = sg_sw[b];
@@ -163,6 +168,8 @@ __global__ void aerosol_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w,
     }
     osw[b] = od; osw[NB_SW + b] = sc; osw[2 * NB_SW + b] = sg;
   }
+  }
+  if (!plw) return;
   if (lwscat) {   // [c][l][3][16]: od, scattering od, scattering od x g after delta_eddington_extensive_vec (:778-779)
     double* olw = w.aer_lw + ((size_t)c * nlev + l) * 3 * NB_LW;
 #pragma unroll

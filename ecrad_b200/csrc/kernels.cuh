@@ -68,7 +68,8 @@ struct DevCfg {
   int do_save_spectral_flux;
   int use_vectorizable_generator;
   int do_nearest_spectral_lw_emiss;
-  int gas_model;                 // ECRAD_GAS_IFSRRTMG / ECRAD_GAS_ECCKD
+  int ckd_lw, ckd_sw;            // this spectrum's gas optics is ecCKD (else RRTMG-IFS); one of each = mixed gas models
+  int gas_mmr;                   // the gas arrays hold mass mixing ratios (any RRTMG spectrum, set_gas_units radiation_interface.F90:164-186): ecCKD scales them itself
   int use_general_cloud_optics;  // cloud optics from the generalised look-up tables (always with ecCKD; an option with RRTMG, per band)
   int do_toa_spectral_flux;
   int pdf_gamma;                 // config%i_cloud_pdf_shape == IPdfShapeGamma (regions of Tripleclouds / SPARTACUS)

@@ -92,7 +92,8 @@ struct PackedTables {
   std::vector<int32_t> i_emiss_from_band_lw;  // (n_bands_lw) 1-based
   std::vector<double> lw_emiss_weights;   // (n_emiss_lw, n_bands_lw)
   int n_emiss_lw = 0;
-  bool is_ecckd = false;
+  bool is_ecckd = false;              // both spectra on ecCKD
+  bool ckd_lw = false, ckd_sw = false;   // per spectrum (mixed gas models: one of the two)
   int ng_lw = NG_LW, ng_sw = NG_SW, nb_lw = NB_LW, nb_sw = NB_SW;
   CkdMeta ckd{};                      // ecCKD gas optics + generalised cloud optics
   std::vector<double> ckdtab;
@@ -138,9 +139,8 @@ inline void pack_common(const ecrad_b200_tables& T, PackedTables& P);
 
 // ecCKD blob of tools/extract_ecckd_tables.py: "ckd_{lw,sw}_*" (read_ckd_model, radiation_ecckd.F90:128-226) and
 // "gco_{lw,sw}_{0,1}_*" (setup_general_cloud_optics, radiation_general_cloud_optics_data.F90:71-243)
-inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
-  memset(&P.meta, 0, sizeof(P.meta));
-  memset(&P.ckd, 0, sizeof(P.ckd));
+// one spectrum's ecCKD model + its per-g-point cloud look-up tables; bands == g-points in that spectrum
+inline void pack_ckd_spectrum(const ecrad_b200_tables& T, PackedTables& P, int sw) {
   auto put = [&](const std::string& nm, size_t expect) {
     const auto& x = T.req(nm);
     if (x.dtype != 0 || x.data.size() != expect * 8) throw std::runtime_error(nm + ": unexpected size");
@@ -149,7 +149,9 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
     return off;
   };
   static const int slot_of_code[13] = {-1, 0, 1, 8, 3, -1, 2, -1, 4, 5, 6, 7, -1};   // DevIn::gas order: h2o co2 ch4 n2o cfc11 cfc12 hcfc22 ccl4 o3
-  for (int sw = 0; sw < 2; ++sw) {
+  // GasMolarMass(0:12), radiation_gas_constants.F90:43-56: AirMolarMass / GasMolarMass turns a mass mixing ratio into a mole fraction
+  static const double gas_molar_mass[13] = {0.0, 18.0152833, 44.011, 47.9982, 44.013, 28.0101, 16.043, 31.9988, 137.3686, 120.914, 86.469, 153.823, 46.0055};
+  {
     const std::string pre = sw ? "ckd_sw_" : "ckd_lw_";
     CkdModel& m = sw ? P.ckd.sw : P.ckd.lw;
     const double* meta = T.d(pre + "meta");
@@ -175,6 +177,7 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
       g.mole_frac1 = exp(g.log_mole_frac1);
       g.lut = g.dep == CKD_CONC_LUT ? m.nlut++ : -1;
       g.slot = (code >= 0 && code <= 12) ? slot_of_code[code] : -1;
+      g.mmr_scaling = (code >= 1 && code <= 12) ? 1.0 * 28.970 / gas_molar_mass[code] : 1.0;   // gas%get_scaling, radiation_gas.F90:471-486
       const size_t n = (size_t)m.ng * m.npress * m.ntemp * (g.dep == CKD_CONC_LUT ? g.n_mole_frac : 1);
       g.off = put(pre + "gas" + std::to_string(j) + "_molar_abs", n);
     }
@@ -187,13 +190,25 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
       c.off_ssa = put(gp + "ssa", (size_t)m.ng * c.nre);
       c.off_g = put(gp + "asymmetry", (size_t)m.ng * c.nre);
     }
+    // bands == g-points (radiation_ecckd_interface.F90:60-63, :95-98)
+    if (sw) {
+      P.ckd_sw = true; P.ng_sw = P.nb_sw = m.ng;
+      memset(P.meta.band_of_g_sw, 0, sizeof(P.meta.band_of_g_sw)); memset(P.meta.sw, 0, sizeof(P.meta.sw));
+      for (int g = 0; g < m.ng; ++g) { P.meta.band_of_g_sw[g] = g; P.meta.sw[g].ng = 1; P.meta.sw[g].g0 = g; }
+    } else {
+      P.ckd_lw = true; P.ng_lw = P.nb_lw = m.ng;
+      memset(P.meta.band_of_g_lw, 0, sizeof(P.meta.band_of_g_lw)); memset(P.meta.lw, 0, sizeof(P.meta.lw));
+      for (int g = 0; g < m.ng; ++g) { P.meta.band_of_g_lw[g] = g; P.meta.lw[g].ng = 1; P.meta.lw[g].g0 = g; }
+    }
   }
+}
+
+inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
+  memset(&P.meta, 0, sizeof(P.meta));
+  memset(&P.ckd, 0, sizeof(P.ckd));
+  pack_ckd_spectrum(T, P, 0);
+  pack_ckd_spectrum(T, P, 1);
   P.is_ecckd = true;
-  P.ng_lw = P.nb_lw = P.ckd.lw.ng;
-  P.ng_sw = P.nb_sw = P.ckd.sw.ng;
-  // bands == g-points (radiation_ecckd_interface.F90:60-63, :95-98)
-  for (int g = 0; g < P.ng_lw; ++g) { P.meta.band_of_g_lw[g] = g; P.meta.lw[g].ng = 1; P.meta.lw[g].g0 = g; }
-  for (int g = 0; g < P.ng_sw; ++g) { P.meta.band_of_g_sw[g] = g; P.meta.sw[g].ng = 1; P.meta.sw[g].g0 = g; }
   memset(&P.cloud, 0, sizeof(P.cloud));
   pack_common(T, P);
 }
@@ -201,7 +216,12 @@ inline void pack_ecckd(const ecrad_b200_tables& T, PackedTables& P) {
 // liq_model / ice_model: config%i_liq_model / i_ice_model (RRTMG-band cloud optics; ignored by the ecCKD tables)
 // general_cloud: config%use_general_cloud_optics with RRTMG-IFS (the look-up tables "gco_*" per RRTMG band instead of the coefficients)
 inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_model = LIQ_SOCRATES, int ice_model = ICE_FU, bool general_cloud = false) {
-  if (T.find("ckd_lw_meta")) { pack_ecckd(T, P); return; }
+  // a spectrum runs ecCKD when its model is in the directory; one ecCKD spectrum next to the RRTMG tables = mixed gas models
+  // (radiation_interface.F90:333-355, test/ifs/configCY49R1_mixed.nam)
+  const bool has_ckd_lw = T.find("ckd_lw_meta") != nullptr, has_ckd_sw = T.find("ckd_sw_meta") != nullptr;
+  if (has_ckd_lw && has_ckd_sw) { pack_ecckd(T, P); return; }
+  const bool mixed = has_ckd_lw || has_ckd_sw;
+  if (mixed && !general_cloud) throw std::runtime_error("an ecCKD spectrum needs use_general_cloud_optics");
   GasMeta& M = P.meta;
   memset(&M, 0, sizeof(M));
   auto copy = [&](double* dst, const char* name, size_t n) {
@@ -337,7 +357,8 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_mod
   if (general_cloud) {
     // generalised cloud optics on the RRTMG bands (radiation_general_cloud_optics.F90:39-110 with use_bands = .true.): the same
     // look-up tables the ecCKD path uses per g-point, one row per band here; read by general_cloud_optics_kernel through T.ckd / T.ckdtab
-    for (int sw = 0; sw < 2; ++sw)
+    for (int sw = 0; sw < 2; ++sw) {
+      if (sw ? has_ckd_sw : has_ckd_lw) { pack_ckd_spectrum(T, P, sw); continue; }   // mixed: this spectrum per g-point
       for (int jt = 0; jt < 2; ++jt) {
         const int nb = sw ? NB_SW : NB_LW;
         GcoType& c = sw ? P.ckd.gco_sw[jt] : P.ckd.gco_lw[jt];
@@ -353,6 +374,7 @@ inline void pack_tables(const ecrad_b200_tables& T, PackedTables& P, int liq_mod
         };
         c.off_me = put(gp + "mass_ext"); c.off_ssa = put(gp + "ssa"); c.off_g = put(gp + "asymmetry");
       }
+    }
     memset(&C, 0, sizeof(C));   // (the band parameterisations are not used)
     C.liq_model = liq_model; C.ice_model = ice_model;
   } else

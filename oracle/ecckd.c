@@ -28,8 +28,13 @@ static const double* gas_array(const ecrad_b200_inputs* in, int code) {
 }
 
 /* calc_optical_depth_ckd_model for one column; od (and rayleigh for SW) are [nlev][ng] */
+/* GasMolarMass(0:12), radiation_gas_constants.F90:43-56 */
+static const double GasMolarMass[13] = {0.0, 18.0152833, 44.011, 47.9982, 44.013, 28.0101, 16.043, 31.9988, 137.3686, 120.914, 86.469, 153.823, 46.0055};
+
+/* concentration_scaling: NULL when the gas arrays hold volume mixing ratios; else gas%get_scaling(IVolumeMixingRatio)
+ * (radiation_gas.F90:471-486: AirMolarMass / GasMolarMass for arrays in mass mixing ratio), indexed by gas code */
 static void ckd_optical_depth(const orc_ckd_model* m, int ncol, int nlev, int jcol, const ecrad_b200_inputs* in,
-                              const double* temperature_fl, double* od, double* rayleigh) {
+                              const double* temperature_fl, const double* concentration_scaling, double* od, double* rayleigh) {
   const int ng = m->ng;
   const size_t sp = (size_t)ng, st = (size_t)ng * m->npress, sc = st * m->ntemp;   /* strides of pressure, temperature, concentration */
   const double global_multiplier = 1.0 / (AccelDueToGravity * 0.001 * AirMolarMass);
@@ -52,17 +57,18 @@ static void ckd_optical_depth(const orc_ckd_model* m, int ncol, int nlev, int jc
       const orc_ckd_gas* gas = &m->gas[jg];
       const double* src = gas_array(in, gas->code);
       const double mf = src ? A2(src, jcol, jl) : 0.0;
+      const double scaling = concentration_scaling ? concentration_scaling[gas->code] : 1.0;   /* local_concentration_scaling(igascode) */
       const double* k00 = gas->molar_abs + (size_t)(ip1 - 1) * sp + (size_t)(it1 - 1) * st;   /* (:, ip1, it1) */
       const double *k10 = k00 + sp, *k01 = k00 + st, *k11 = k00 + sp + st;
       if (gas->dep == ORC_CONC_LUT) {
         const double mole_frac1 = exp(gas->log_mole_frac1);
-        const double log_conc = log(dmax(mf * 1.0, mole_frac1));
+        const double log_conc = log(dmax(mf * scaling, mole_frac1));
         double cindex1 = (log_conc - gas->log_mole_frac1) / gas->d_log_mole_frac;
         cindex1 = 1.0 + dmax(0.0, dmin(cindex1, gas->n_mole_frac - 1.0001));
         const int ic1 = (int)cindex1;
         const double cw2 = cindex1 - ic1, cw1 = 1.0 - cw2;
         const size_t c0 = (size_t)(ic1 - 1) * sc, c1 = c0 + sc;
-        const double mult = simple_multiplier * mf * 1.0;
+        const double mult = simple_multiplier * mf * scaling;
         const double w000 = cw1 * tw1 * pw1, w100 = cw1 * tw1 * pw2, w010 = cw1 * tw2 * pw1, w110 = cw1 * tw2 * pw2;
         const double w001 = cw2 * tw1 * pw1, w101 = cw2 * tw1 * pw2, w011 = cw2 * tw2 * pw1, w111 = cw2 * tw2 * pw2;
         for (int g = 0; g < ng; ++g)
@@ -70,8 +76,8 @@ static void ckd_optical_depth(const orc_ckd_model* m, int ncol, int nlev, int jc
                                 w001 * k00[c1 + g] + w101 * k10[c1 + g] + w011 * k01[c1 + g] + w111 * k11[c1 + g]);
       } else {
         double multiplier;
-        if (gas->dep == ORC_CONC_LINEAR) multiplier = simple_multiplier * mf * 1.0;
-        else if (gas->dep == ORC_CONC_RELATIVE_LINEAR) multiplier = simple_multiplier * (mf * 1.0 - gas->reference_mole_frac);
+        if (gas->dep == ORC_CONC_LINEAR) multiplier = simple_multiplier * mf * scaling;   /* :560-562 */
+        else if (gas->dep == ORC_CONC_RELATIVE_LINEAR) multiplier = simple_multiplier * (mf * scaling - gas->reference_mole_frac);
         else multiplier = simple_multiplier;
         for (int g = 0; g < ng; ++g)
           o[g] = o[g] + multiplier * (tw1 * (pw1 * k00[g] + pw2 * k10[g]) + tw2 * (pw1 * k01[g] + pw2 * k11[g]));
@@ -106,20 +112,29 @@ void orc_ecckd_gas_optics_column(const orc_tables* t, const ecrad_b200_config* c
     const double p1 = A2(in->pressure_hl, jcol, jl), p2 = A2(in->pressure_hl, jcol, jl + 1);
     temperature_fl[jl] = (A2(in->temperature_hl, jcol, jl) * p1 + A2(in->temperature_hl, jcol, jl + 1) * p2) / (p1 + p2);
   }
-  if (cfg->do_sw) {
+  /* set_gas_units (radiation_interface.F90:164-186): mass mixing ratios as soon as one spectrum uses RRTMG; ecCKD then scales
+   * (radiation_ecckd_interface.F90:249-255) */
+  double scaling_buf[13];
+  const double* scaling = NULL;
+  if (cfg->i_gas_model_sw != ECRAD_GAS_ECCKD || cfg->i_gas_model_lw != ECRAD_GAS_ECCKD) {
+    scaling_buf[0] = 1.0;
+    for (int j = 1; j <= 12; ++j) scaling_buf[j] = 1.0 * AirMolarMass / GasMolarMass[j];
+    scaling = scaling_buf;
+  }
+  if (cfg->do_sw && cfg->i_gas_model_sw == ECRAD_GAS_ECCKD) {
     const orc_ckd_model* m = &t->ckd_sw;
     const int ng = m->ng;
-    ckd_optical_depth(m, ncol, nlev, jcol, in, temperature_fl, od_sw, ssa_sw);
+    ckd_optical_depth(m, ncol, nlev, jcol, in, temperature_fl, scaling, od_sw, ssa_sw);
     for (size_t i = 0; i < (size_t)nlev * ng; ++i) {   /* :272-279 */
       od_sw[i] = od_sw[i] + ssa_sw[i];
       ssa_sw[i] = ssa_sw[i] / od_sw[i];
     }
     for (int g = 0; g < ng; ++g) incoming_sw[g] = in->solar_irradiance * m->norm_solar_irradiance[g];
   }
-  if (cfg->do_lw) {
+  if (cfg->do_lw && cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) {
     const orc_ckd_model* m = &t->ckd_lw;
     const int ng = m->ng;
-    ckd_optical_depth(m, ncol, nlev, jcol, in, temperature_fl, od_lw, NULL);
+    ckd_optical_depth(m, ncol, nlev, jcol, in, temperature_fl, scaling, od_lw, NULL);
     for (int jl = 0; jl <= nlev; ++jl) ckd_planck(m, A2(in->temperature_hl, jcol, jl), planck_hl + (size_t)jl * ng);
     ckd_planck(m, in->skin_temperature[jcol], lw_emission);
     for (int g = 0; g < ng; ++g) lw_emission[g] = lw_emission[g] * (1.0 - lw_albedo[g]);

@@ -67,7 +67,7 @@ typedef struct orc_tables {
   /* 0-based band of each g-point: RRTMG ngb-1 / ngb-16; ecCKD with per-g-point cloud/aerosol optics: identity */
   int32_t band_lw[256], band_sw[256];
   /* ecCKD gas optics + generalised cloud optics (blob of tools/extract_ecckd_tables.py) */
-  int is_ecckd;
+  int is_ecckd, is_ecckd_lw, is_ecckd_sw;   /* both spectra / this spectrum (mixed gas models: one of the two) */
   orc_ckd_model ckd_lw, ckd_sw;
   orc_gco gco_lw[2], gco_sw[2];         /* cloud types: 0 liquid (mie_droplet), 1 ice (baum-general-habit-mixture) */
 } orc_tables;

@@ -105,10 +105,14 @@ static void planck_bands(const orc_tables* t, double temperature, double* store)
 static void gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                               const ecrad_b200_inputs* in, const double* lw_albedo, double* od_lw, double* planck_hl,
                               double* lw_emission, double* od_sw, double* ssa_sw, double* incoming_sw) {
-  if (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) {
+  /* radiation_interface.F90:333-355: each gas model fills the spectra it is configured for */
+  const int ckd_lw = cfg->i_gas_model_lw == ECRAD_GAS_ECCKD, ckd_sw = cfg->i_gas_model_sw == ECRAD_GAS_ECCKD;
+  if (ckd_lw || ckd_sw)
     orc_ecckd_gas_optics_column(t, cfg, ncol, nlev, jcol, in, lw_albedo, od_lw, planck_hl, lw_emission, od_sw, ssa_sw, incoming_sw);
-    return;
-  }
+  if (ckd_lw && ckd_sw) return;
+  ecrad_b200_config cfg_rrtmg = *cfg;
+  cfg_rrtmg.do_lw = cfg->do_lw && !ckd_lw; cfg_rrtmg.do_sw = cfg->do_sw && !ckd_sw;
+  cfg = &cfg_rrtmg;
   double* buf = (double*)malloc(sizeof(double) * (size_t)(nlev + 1) * 16);
   double *p_hl = buf, *t_hl = p_hl + (nlev + 1), *p_fl = t_hl + (nlev + 1), *t_fl = p_fl + nlev;
   double* gas[9];
@@ -205,7 +209,7 @@ static void add_aerosol_optics(const orc_tables* t, const ecrad_b200_config* cfg
   for (int jl = 0; jl < nlev; ++jl) {
     /* gas%mixing_ratio(:,:,IH2O) is a volume mixing ratio under ecCKD: radiation_aerosol_optics.F90:590-600 converts */
     double h2o = A2(in->h2o_mmr, jcol, jl);
-    if (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) h2o = h2o * (18.0152833 / 28.970);
+    if (cfg->i_gas_model_lw == ECRAD_GAS_ECCKD && cfg->i_gas_model_sw == ECRAD_GAS_ECCKD) h2o = h2o * (18.0152833 / 28.970);
     double rh = h2o / A2(in->h2o_sat_liq, jcol, jl);
     int irh;   /* calc_rh_index, radiation_aerosol_optics_data.F90:640-664 (1-based) */
     if (rh > t->aer_rh_lower[nrh - 1]) irh = nrh;
@@ -1009,14 +1013,16 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
    * later step (aerosols and albedos are element-wise, so permuting after them is the same thing) indexes bands through
    * i_band_from_reordered_g, and the per-g-point outputs of flux_type are in the reordered order too. */
   orc_tables* tp = NULL;
-  if (!t->is_ecckd && ((cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) || (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS))) {
+  const int reorder_lw = !t->is_ecckd_lw && cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS;
+  const int reorder_sw = !t->is_ecckd_sw && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS;
+  if (reorder_lw || reorder_sw) {
     const orc_array* pl = orc_find(t, "i_g_from_reordered_g_lw");
     const orc_array* ps = orc_find(t, "i_g_from_reordered_g_sw");
-    if (!pl || !ps) { fprintf(stderr, "oracle: i_g_from_reordered_g_lw/sw missing from the table directory\n"); free(w.w); free(phl_full); return 13; }
+    if ((reorder_lw && !pl) || (reorder_sw && !ps)) { fprintf(stderr, "oracle: i_g_from_reordered_g_lw/sw missing from the table directory\n"); free(w.w); free(phl_full); return 13; }
     tp = (orc_tables*)malloc(sizeof(orc_tables));
     memcpy(tp, t, sizeof(orc_tables));
     double* tmp = (double*)malloc(sizeof(double) * (size_t)(NG_LW > NG_SW ? NG_LW : NG_SW));
-    if (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) {
+    if (reorder_lw) {
       const int32_t* perm = (const int32_t*)pl->data;
       const int ng = NG_LW;
       double* rows[4] = {w.od_lw, w.ssa_lw, w.g_lw, w.planck_hl};
@@ -1031,7 +1037,7 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
       for (int a = 0; a < 2; ++a) { for (int j = 0; j < ng; ++j) tmp[j] = one[a][perm[j] - 1]; memcpy(one[a], tmp, sizeof(double) * ng); }
       for (int j = 0; j < ng; ++j) tp->band_lw[j] = t->band_lw[perm[j] - 1];
     }
-    if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) {
+    if (reorder_sw) {
       const int32_t* perm = (const int32_t*)ps->data;
       const int ng = NG_SW;
       double* rows[3] = {w.od_sw, w.ssa_sw, w.g_sw};
@@ -1061,11 +1067,16 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads) {
   const int lw_plain = cfg->i_solver_lw == ECRAD_SOLVER_MCICA || cfg->i_solver_lw == ECRAD_SOLVER_CLOUDLESS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS;
-  if ((cfg->do_lw_aerosol_scattering && cfg->do_lw && (!lw_plain || t->is_ecckd || !cfg->do_lw_cloud_scattering)) || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
+  if ((cfg->do_lw_aerosol_scattering && cfg->do_lw && (!lw_plain || t->is_ecckd_lw || !cfg->do_lw_cloud_scattering)) || (cfg->do_sw_delta_scaling_with_gases && cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_SPARTACUS) ||
       (cfg->use_vectorizable_generator && cfg->i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)) {
     fprintf(stderr, "oracle: configuration outside the restated path\n");
     return 10;
   }
+  if ((cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) != (t->is_ecckd_lw != 0) || (cfg->i_gas_model_sw == ECRAD_GAS_ECCKD) != (t->is_ecckd_sw != 0)) {
+    fprintf(stderr, "oracle: the table directory does not hold the gas models the configuration names\n");
+    return 14;
+  }
+  if ((t->is_ecckd_lw || t->is_ecckd_sw) && !cfg->use_general_cloud_optics) { fprintf(stderr, "oracle: ecCKD needs use_general_cloud_optics\n"); return 14; }
   if (!out->lw_up_clear || !out->lw_dn_clear || !out->sw_up_clear || !out->sw_dn_clear || !out->sw_dn_direct_clear) {
     fprintf(stderr, "oracle: clear-sky flux outputs are required (do_clear)\n");
     return 11;

@@ -82,10 +82,14 @@ static void resolve_gco(orc_tables* t, int required, int* err) {
 
 int orc_tables_resolve(orc_tables* t) {
   int err = 0;
-  t->is_ecckd = orc_find(t, "ckd_lw_meta") != NULL;
+  /* a spectrum uses ecCKD when its model is in the directory; a directory with one ecCKD spectrum next to the RRTMG tables is the
+   * mixed configuration of radiation_interface.F90:333-355 (test/ifs/configCY49R1_mixed.nam) */
+  t->is_ecckd_lw = orc_find(t, "ckd_lw_meta") != NULL;
+  t->is_ecckd_sw = orc_find(t, "ckd_sw_meta") != NULL;
+  t->is_ecckd = t->is_ecckd_lw && t->is_ecckd_sw;
+  if (t->is_ecckd_lw) resolve_ckd_model(t, "ckd_lw_", &t->ckd_lw, &err);
+  if (t->is_ecckd_sw) resolve_ckd_model(t, "ckd_sw_", &t->ckd_sw, &err);
   if (t->is_ecckd) {
-    resolve_ckd_model(t, "ckd_lw_", &t->ckd_lw, &err);
-    resolve_ckd_model(t, "ckd_sw_", &t->ckd_sw, &err);
     resolve_gco(t, 1, &err);
     for (int g = 0; g < 256; ++g) { t->band_lw[g] = g; t->band_sw[g] = g; }   /* radiation_ecckd_interface.F90:60-63 */
     resolve_common(t, &err);
@@ -139,6 +143,8 @@ int orc_tables_resolve(orc_tables* t) {
   t->ice_coeff_lw = Dreq(t, "ice_coeff_lw", &err); t->ice_coeff_sw = Dreq(t, "ice_coeff_sw", &err);
   if (t->ngb_lw) for (int g = 0; g < NG_LW; ++g) t->band_lw[g] = t->ngb_lw[g] - 1;
   if (t->ngb_sw) for (int g = 0; g < NG_SW; ++g) t->band_sw[g] = t->ngb_sw[g] - 16;
+  if (t->is_ecckd_lw) for (int g = 0; g < 256; ++g) t->band_lw[g] = g;
+  if (t->is_ecckd_sw) for (int g = 0; g < 256; ++g) t->band_sw[g] = g;
   resolve_common(t, &err);
   return err;
 }

@@ -179,6 +179,43 @@ def test_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     assert np.array_equal(out["cloud_fraction"], ref["cloud_fraction"])
 
 
+MIXED = [dict(), dict(use_aerosols=True), dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True),
+         dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True),
+         dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"), dict(sw_solver_name="Cloudless", lw_solver_name="Cloudless", use_aerosols=True),
+         dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True, overlap_scheme_name="Exp-Exp", do_lw_cloud_scattering=False)]
+
+
+@pytest.mark.parametrize("ckd_spectrum", ["sw", "lw"])
+@pytest.mark.parametrize("kw", MIXED)
+def test_mixed_gas_models_vs_oracle(handles, meridian_raw, kw, ckd_spectrum):
+    """RRTMG-IFS in one spectrum, ecCKD in the other (radiation_interface.F90:333-355; test/ifs `test_mixed_gas` with
+    configCY49R1_mixed.nam): mass mixing ratios in, ecCKD scales them itself, cloud optics from the generalised look-up tables per
+    band (RRTMG spectrum) and per g-point (ecCKD spectrum).  Each spectrum must also reproduce the run that uses its model twice."""
+    n = 300
+    E = dict(do_nearest_spectral_lw_emiss=False, **kw)
+    h, orc, cfg = handles(**{ckd_spectrum + "_gas_model_name": "ECCKD"}, **E)
+    raw = I.synthetic_columns(meridian_raw, n)
+    out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+    compare(out, ref, FLUXES + OTHERS)
+    for nm in ("cloud_cover_lw", "cloud_cover_sw", "cloud_fraction"):
+        assert np.array_equal(out[nm], ref[nm]), nm
+    nck = 64 if "64b" in str(kw) else 32
+    assert (h.cfg.n_g_sw, h.cfg.n_g_lw) == ((nck, 140) if ckd_spectrum == "sw" else (112, nck))
+    # the RRTMG spectrum of the mixed run == the same spectrum of the all-RRTMG run with the generalised cloud optics (bit for bit:
+    # the same kernels on the same inputs); the ecCKD spectrum == the all-ecCKD run up to the rounding of the unit conversion
+    hr, _, cr = handles(use_general_cloud_optics=True, **E)
+    hc, _, cc = handles(gas_model_name="ECCKD", **E)
+    rr = hr.radiation(I.to_radiation_inputs(raw, cr), n, NLEV)
+    ck = hc.radiation(I.to_radiation_inputs(raw, cc), n, NLEV)
+    lw, sw = ("lw_up", "lw_dn", "lw_up_clear", "lw_dn_clear"), ("sw_up", "sw_dn", "sw_dn_direct", "sw_up_clear", "sw_dn_clear")
+    for nm in (lw if ckd_spectrum == "sw" else sw):
+        assert np.array_equal(out[nm], rr[nm]), nm
+    for nm in (sw if ckd_spectrum == "sw" else lw):
+        m = np.isfinite(ck[nm])
+        assert np.abs(out[nm][m] - ck[nm][m]).max() < TOL, nm   # (SPARTACUS amplifies the conversion's rounding to 2e-7)
+
+
 def test_column_range_and_untouched_columns(handles, meridian_raw):
     """istartcol/iendcol semantics of radiation(): only that range is written (1-based inclusive)."""
     h, orc, _ = handles()

@@ -104,3 +104,23 @@ def test_general_cloud_optics_flag_is_required_by_ecckd(meridian_raw):
     cfg = RadiationConfig(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_general_cloud_optics=False)
     with pytest.raises(ValueError, match="use_general_cloud_optics"):
         cfg.consolidate()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_aerosols=True, **TC), dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)])
+def test_mixed_gas_models(meridian_raw, kw):
+    """One gas model per spectrum (radiation_interface.F90:333-355; the four runs of test/ifs `test_mixed_gas`).  The gas arrays are
+    mass mixing ratios as soon as one spectrum uses RRTMG (set_gas_units, :164-186) and ecCKD scales them itself
+    (radiation_ecckd.F90:518-623), so each spectrum of a mixed run reproduces the same spectrum of the run with that model in both:
+    exactly for RRTMG, to the rounding of the unit conversion for ecCKD."""
+    E = dict(do_nearest_spectral_lw_emiss=False, **kw)
+    rrtmg = run(meridian_raw, use_general_cloud_optics=True, **E)
+    ecckd = run(meridian_raw, gas_model_name="ECCKD", **E)
+    sw_ckd = run(meridian_raw, sw_gas_model_name="ECCKD", **E)
+    lw_ckd = run(meridian_raw, lw_gas_model_name="ECCKD", **E)
+    for nm in ("lw_up", "lw_dn", "lw_up_clear", "lw_dn_clear"):
+        assert np.array_equal(sw_ckd[nm], rrtmg[nm]), nm
+        assert np.abs(lw_ckd[nm] - ecckd[nm]).max() < 1e-7, nm   # (SPARTACUS amplifies the rounding to a few 1e-9)
+    for nm in ("sw_up", "sw_dn", "sw_dn_direct", "sw_up_clear", "sw_dn_clear"):
+        assert np.array_equal(lw_ckd[nm], rrtmg[nm]), nm
+        assert np.abs(sw_ckd[nm] - ecckd[nm]).max() < 1e-7, nm
+    assert sw_ckd["sw_up_toa_g"].shape[0] == 32 and sw_ckd["lw_up_toa_g"].shape[0] == 140

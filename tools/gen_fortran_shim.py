@@ -324,16 +324,8 @@ def main():
     w("    end if")
     w("  end subroutine")
     w("")
-    w("  ! ---- ecCKD: config%gas_optics_lw/sw (ckd_model_type, radiation_ecckd.F90:60-126) and the generalised cloud optics")
-    w("  !      config%cloud_optics_lw/sw(1:2) (general_cloud_optics_type, radiation_general_cloud_optics_data.F90:30-68)")
-    w("  subroutine register_ecckd(t, config)")
-    w("    use radiation_config, only : config_type")
-    w("    type(c_ptr), intent(in) :: t; type(config_type), intent(in), target :: config")
-    w("    call register_ckd_model(t, 'ckd_lw_', config%gas_optics_lw, .false.)")
-    w("    call register_ckd_model(t, 'ckd_sw_', config%gas_optics_sw, .true.)")
-    w("    call register_gco(t, 'gco_lw_0_', config%cloud_optics_lw(1)); call register_gco(t, 'gco_lw_1_', config%cloud_optics_lw(2))")
-    w("    call register_gco(t, 'gco_sw_0_', config%cloud_optics_sw(1)); call register_gco(t, 'gco_sw_1_', config%cloud_optics_sw(2))")
-    w("  end subroutine")
+    w("  ! ---- ecCKD: config%gas_optics_lw/sw (ckd_model_type, radiation_ecckd.F90:60-126), registered per spectrum in b200_setup, and the")
+    w("  !      generalised cloud optics config%cloud_optics_lw/sw(1:2) (general_cloud_optics_type, radiation_general_cloud_optics_data.F90:30-68)")
     w("  subroutine register_ckd_model(t, pre, go, is_sw)")
     w("    use radiation_ecckd, only : ckd_model_type")
     w("    use radiation_ecckd_gas, only : IConcDependenceLUT")
@@ -374,14 +366,14 @@ def main():
     w("    type(config_type), intent(in) :: config")
     w("    type(cfg_t) :: c; type(c_ptr) :: t")
     w("    t = ecrad_b200_tables_create()")
-    w("    if (config%i_gas_model_lw == IGasModelECCKD .or. config%i_gas_model_sw == IGasModelECCKD) then")
-    w("      call register_ecckd(t, config)")
-    w("    else")
-    w("      call register_rrtmg(t)")
-    w("      if (config%use_general_cloud_optics) then   ! look-up tables per RRTMG band (radiation_config.F90:1078-1090)")
-    w("        call register_gco(t, 'gco_lw_0_', config%cloud_optics_lw(1)); call register_gco(t, 'gco_lw_1_', config%cloud_optics_lw(2))")
-    w("        call register_gco(t, 'gco_sw_0_', config%cloud_optics_sw(1)); call register_gco(t, 'gco_sw_1_', config%cloud_optics_sw(2))")
-    w("      end if")
+    w("    ! one gas model per spectrum (radiation_interface.F90:333-355): the ifsrrtm module storage as soon as one spectrum runs RRTMG-IFS,")
+    w("    ! the ckd_model_type of each ecCKD spectrum; the library tells the spectra apart by which tables it finds")
+    w("    if (config%i_gas_model_lw /= IGasModelECCKD .or. config%i_gas_model_sw /= IGasModelECCKD) call register_rrtmg(t)")
+    w("    if (config%i_gas_model_lw == IGasModelECCKD) call register_ckd_model(t, 'ckd_lw_', config%gas_optics_lw, .false.)")
+    w("    if (config%i_gas_model_sw == IGasModelECCKD) call register_ckd_model(t, 'ckd_sw_', config%gas_optics_sw, .true.)")
+    w("    if (config%use_general_cloud_optics) then   ! look-up tables per g-point (ecCKD) or per RRTMG band (radiation_config.F90:1078-1090)")
+    w("      call register_gco(t, 'gco_lw_0_', config%cloud_optics_lw(1)); call register_gco(t, 'gco_lw_1_', config%cloud_optics_lw(2))")
+    w("      call register_gco(t, 'gco_sw_0_', config%cloud_optics_sw(1)); call register_gco(t, 'gco_sw_1_', config%cloud_optics_sw(2))")
     w("    end if")
     w("    call register_config_tables(t, config)")
     missing = []
