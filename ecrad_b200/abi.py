@@ -101,6 +101,31 @@ class Outputs(C.Structure):
     _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32)] + [(nm, c_dp) for nm, _ in OUTPUT_ARRAYS]
 
 
+# ecrad_b200_radiative_properties (include/ecrad_b200.h): name, shape kind -- the argument list of save_radiative_properties
+# (radiation_save.F90:716-726)
+RADPROP_ARRAYS = [
+    ("planck_hl", "glh"), ("lw_emission", "gl"), ("lw_albedo", "gl"), ("sw_albedo_direct", "gs"), ("sw_albedo_diffuse", "gs"),
+    ("incoming_sw", "gs"), ("od_lw", "glf"), ("ssa_lw", "glf"), ("g_lw", "glf"), ("od_sw", "gsf"), ("ssa_sw", "gsf"), ("g_sw", "gsf"),
+    ("od_lw_cloud", "blf"), ("ssa_lw_cloud", "blf"), ("g_lw_cloud", "blf"), ("od_sw_cloud", "bsf"), ("ssa_sw_cloud", "bsf"), ("g_sw_cloud", "bsf"),
+]
+
+
+class RadiativeProperties(C.Structure):
+    _fields_ = [(nm, c_dp) for nm, _ in RADPROP_ARRAYS]
+
+
+def alloc_radiative_properties(ncol, nlev, cfg):
+    """NaN-filled Fortran-ordered arrays (spectral index fastest, column slowest) + the struct that points at them."""
+    shapes = {"glh": (cfg.n_g_lw, nlev + 1, ncol), "gl": (cfg.n_g_lw, ncol), "gs": (cfg.n_g_sw, ncol), "glf": (cfg.n_g_lw, nlev, ncol),
+              "gsf": (cfg.n_g_sw, nlev, ncol), "blf": (cfg.n_bands_lw, nlev, ncol), "bsf": (cfg.n_bands_sw, nlev, ncol)}
+    arrs, st = {}, RadiativeProperties()
+    for nm, kind in RADPROP_ARRAYS:
+        a = np.full(shapes[kind], np.nan, dtype=np.float64, order="F")
+        arrs[nm] = a
+        setattr(st, nm, a.ctypes.data_as(c_dp))
+    return arrs, st
+
+
 def output_shape(kind, ncol, nlev, cfg):
     """Fortran shape of a flux_type component (radiation_flux.F90:147-300)."""
     return {

@@ -282,7 +282,7 @@ int ensure_work(Handle* h, int set, int cols, int nlev) {
 // adding -> flux); the solvers wait for the cloud chain.  With serial == 0 they run on three streams forked from and
 // joined into `st`, so that latency-bound and fp64-bound kernels share the SMs.
 // ev: 2 events per stage (start, end), stages = gas_lw, gas_sw, cloud, solver_lw, solver_sw.
-int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev) {
+int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int nlev, cudaStream_t st, cudaEvent_t* ev, bool optics_only = false) {
   const DevCfg& c = h->dcfg;
   int n = 0;
   const bool par = !h->serial;
@@ -323,12 +323,12 @@ int run_tile(Handle* h, int set, const DevIn& in, const DevOut& out, int nc, int
   CK(h, cudaEventRecord(ev[3], s_sw));
   if (par) { CK(h, cudaStreamWaitEvent(s_lw, h->ev_cloud[set], 0)); CK(h, cudaStreamWaitEvent(s_sw, h->ev_cloud[set], 0)); }
   CK(h, cudaEventRecord(ev[6], s_lw));
-  if (c.do_lw) n += launch_solver_lw(h->T, c, in, out, h->w[set], nc, nlev, s_lw);
-  if (c.do_lw && c.do_toa_spectral_flux) n += launch_toa_spectral(h->T, c, in, out, nc, false, s_lw);
+  if (c.do_lw && !optics_only) n += launch_solver_lw(h->T, c, in, out, h->w[set], nc, nlev, s_lw);
+  if (c.do_lw && c.do_toa_spectral_flux && !optics_only) n += launch_toa_spectral(h->T, c, in, out, nc, false, s_lw);
   CK(h, cudaEventRecord(ev[7], s_lw));
   CK(h, cudaEventRecord(ev[8], s_sw));
-  if (c.do_sw) n += launch_solver_sw(h->T, c, in, out, h->w[set], nc, nlev, s_sw);
-  if (c.do_sw && c.do_toa_spectral_flux) n += launch_toa_spectral(h->T, c, in, out, nc, true, s_sw);
+  if (c.do_sw && !optics_only) n += launch_solver_sw(h->T, c, in, out, h->w[set], nc, nlev, s_sw);
+  if (c.do_sw && c.do_toa_spectral_flux && !optics_only) n += launch_toa_spectral(h->T, c, in, out, nc, true, s_sw);
   CK(h, cudaEventRecord(ev[9], s_sw));
   if (par) {
     CK(h, cudaEventRecord(h->ev_sw_done[set], s_sw));
@@ -1029,6 +1029,89 @@ int ecrad_b200_radiation_device_ld(void* handle, int ncol, int nlev, int ld_in, 
   if (!h) return fail(nullptr, "ecrad_b200_radiation_device: null handle");
   std::lock_guard<std::mutex> lk(h->mu);
   return device_entry_locked(h, ncol, nlev, ld_in, ld_out, in, out, cuda_stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// save_radiative_properties (radiation_interface.F90:405-425): the optics stages only, then a gather into the reference's layout.
+// A diagnostic: plain synchronous copies, tiles of at most 2048 columns on compute set 0.
+// ---------------------------------------------------------------------------------------------------------
+int ecrad_b200_save_radiative_properties(void* handle, int ncol, int nlev, int istartcol, int iendcol, const ecrad_b200_inputs* in,
+                                         const ecrad_b200_radiative_properties* props) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_save_radiative_properties: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!in || !props) return fail(h, "ecrad_b200_save_radiative_properties: null argument");
+  ecrad_b200_outputs none; memset(&none, 0, sizeof(none));
+  InDesc id[N_IN]; OutDesc od[N_OUT];
+  if (ncol < 1 || nlev < 2 || nlev > 256 || istartcol < 1 || iendcol > ncol || istartcol > iendcol) return fail(h, "ecrad_b200_save_radiative_properties: bad dimensions or column range");
+  fill_descs(h->cfg, nlev, in, &none, id, od);
+  {
+    // the arrays radiation() requires (check_args), minus the outputs
+    const ecrad_b200_config& c = h->cfg;
+    const bool need[N_IN] = {c.do_sw != 0, c.do_lw != 0, c.do_sw != 0, false, c.do_lw != 0, c.do_clouds != 0, true, true,
+                             true, true, true, true, true, true, true, true, true,
+                             c.do_clouds != 0, c.do_clouds != 0, c.do_clouds != 0, c.do_clouds != 0, c.do_clouds != 0, c.do_clouds != 0, c.do_clouds != 0,
+                             c.use_aerosols != 0, c.use_aerosols != 0, false, false};
+    for (int k = 0; k < N_IN; ++k) if (need[k] && !id[k].host) return fail(h, "ecrad_b200_save_radiative_properties: a required input array (index %d of ecrad_b200_inputs) is null", k);
+  }
+  CK(h, cudaSetDevice(h->device));
+  drain(h);
+  const ecrad_b200_config& c = h->cfg;
+  const int n = iendcol - istartcol + 1, first = istartcol - 1;
+  const int cap = n < 2048 ? n : 2048;
+  if (ensure_work(h, 0, cap, nlev)) return 1;
+  if (ensure_events(h, 1)) return 1;
+  cudaStream_t st = h->s_comp[0];
+  if (h->dev_pending) CK(h, cudaStreamWaitEvent(st, h->ev_dev_done, 0));
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
+  auto release = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
+  void* ip[N_IN]; void* op[N_OUT];
+  for (int k = 0; k < N_OUT; ++k) op[k] = nullptr;
+  for (int k = 0; k < N_IN; ++k) {
+    ip[k] = nullptr;
+    if (!id[k].host) continue;
+    ip[k] = dalloc((size_t)id[k].rows * cap * id[k].elem);
+    if (!ip[k]) { release(); return fail(h, "ecrad_b200_save_radiative_properties: out of device memory"); }
+  }
+  struct PD { double* host; size_t per_col; double* dev; };
+  const size_t gl = (size_t)c.n_g_lw, gs = (size_t)c.n_g_sw, bl = (size_t)c.n_bands_lw, bs = (size_t)c.n_bands_sw, nl = (size_t)nlev;
+  PD pd[18] = {{props->planck_hl, gl * (nl + 1)}, {props->lw_emission, gl}, {props->lw_albedo, gl}, {props->sw_albedo_direct, gs},
+               {props->sw_albedo_diffuse, gs}, {props->incoming_sw, gs}, {props->od_lw, gl * nl}, {props->ssa_lw, gl * nl}, {props->g_lw, gl * nl},
+               {props->od_sw, gs * nl}, {props->ssa_sw, gs * nl}, {props->g_sw, gs * nl}, {props->od_lw_cloud, bl * nl}, {props->ssa_lw_cloud, bl * nl},
+               {props->g_lw_cloud, bl * nl}, {props->od_sw_cloud, bs * nl}, {props->ssa_sw_cloud, bs * nl}, {props->g_sw_cloud, bs * nl}};
+  const bool is_lw[18] = {true, true, true, false, false, false, true, true, true, false, false, false, true, true, true, false, false, false};
+  for (int k = 0; k < 18; ++k) {
+    pd[k].dev = nullptr;
+    if (!pd[k].host || !(is_lw[k] ? c.do_lw : c.do_sw)) continue;
+    pd[k].dev = (double*)dalloc(pd[k].per_col * cap * 8);
+    if (!pd[k].dev) { release(); return fail(h, "ecrad_b200_save_radiative_properties: out of device memory"); }
+  }
+  int rc = 0;
+  for (int c0 = 0; c0 < n && !rc; c0 += cap) {
+    const int nt = (n - c0) < cap ? (n - c0) : cap;
+    for (int k = 0; k < N_IN && !rc; ++k) {
+      if (!ip[k]) continue;
+      const size_t rb = (size_t)id[k].elem;
+      if (cudaMemcpy2D(ip[k], rb * cap, (const char*)id[k].host + rb * (first + c0), rb * (size_t)ncol, rb * nt, id[k].rows, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1;
+    }
+    if (rc || cudaDeviceSynchronize() != cudaSuccess) { rc = 1; break; }   // (pageable sources: the DMA may trail the call's return)
+    DevIn di; DevOut dout;
+    make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
+    if (run_tile(h, 0, di, dout, nt, nlev, st, &h->ev[0], true)) { rc = 2; break; }
+    DevProps dp = {pd[0].dev, pd[1].dev, pd[2].dev, pd[3].dev, pd[4].dev, pd[5].dev, pd[6].dev, pd[7].dev, pd[8].dev,
+                   pd[9].dev, pd[10].dev, pd[11].dev, pd[12].dev, pd[13].dev, pd[14].dev, pd[15].dev, pd[16].dev, pd[17].dev};
+    launch_radprops_gather(h->T, h->dcfg, di, h->w[0], dp, nt, nlev, st);
+    h->launches += 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 1; break; }
+    for (int k = 0; k < 18 && !rc; ++k)
+      if (pd[k].dev && cudaMemcpy(pd[k].host + pd[k].per_col * (size_t)(first + c0), pd[k].dev, pd[k].per_col * nt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+  }
+  const cudaError_t e = cudaGetLastError();
+  release();
+  if (rc == 2) return 1;   // (run_tile recorded the message)
+  if (rc || e != cudaSuccess) return fail(h, "ecrad_b200_save_radiative_properties: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaErrorUnknown));
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -325,7 +325,10 @@ general_cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, i
   const int l = blockIdx.y * CKD_WARPS + warp;
   if (l >= nlev) return;
   const double frac = LD_IN(in.frac, c, l);
-  if (!(frac > 0.0)) return;
+  // The no-scattering longwave form adds absorption wherever there is condensate, cropped (frac = 0) layers included
+  // (radiation_general_cloud_optics_data.F90:311-325); no solver reads those layers, save_radiative_properties shows them.
+  const bool cloudy = frac > 0.0;
+  if (!cloudy && !(cfg.do_lw && !cfg.do_lw_cloud_scattering)) return;
   const CkdMeta& M = *T.ckd;
   const double* tab = T.ckdtab;
   const double dp = LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l);
@@ -348,7 +351,7 @@ general_cloud_optics_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nc, i
       o[g] = a.od; o[ng + g] = a.scat; o[2 * ng + g] = a.scat_g;
     }
   }
-  if (cfg.do_sw) {
+  if (cfg.do_sw && cloudy) {
     const int ng = cfg.nb_sw;
     double* o = w.cl_sw + ((size_t)c * nlev + l) * 3 * ng;
     for (int g = lane; g < ng; g += 32) {

@@ -893,6 +893,87 @@ int launch_toa_spectral(const DevTables& T, const DevCfg& cfg, const DevIn& in, 
   toa_spectral_kernel<<<(nc * nb + 127) / 128, 128, 0, st>>>(T, out, sw ? in.cos_sza : nullptr, nc, ng, nb, sw ? 1 : 0, cfg.do_clear, sw && cfg.solver_sw == 4);
   return 1;
 }
+// ---------------------------------------------------------------------------------------------------------
+// save_radiative_properties (radiation_interface.F90:405-425): the optics stages' scratch, whatever its layout, rewritten in the
+// reference's element order (spectral index fastest, column slowest), g-points at their position in the solver's sequence
+// (T.meta->rank_*: the SPARTACUS reordering on RRTMG-IFS, identity otherwise).  Block = (half-level, column), threads = spectral index.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void radprops_gather_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, DevProps p, int nc, int nlev) {
+  const int l = blockIdx.x, c = blockIdx.y, t = threadIdx.x;
+  const int ng_lw = cfg.ng_lw, ng_sw = cfg.ng_sw, nb_lw = cfg.nb_lw, nb_sw = cfg.nb_sw;
+  const int ls = w.ls;
+  if (cfg.do_lw && t < ng_lw) {
+    const int g = t, gd = T.meta->rank_lw[g];
+    const bool lb = w.layout_b_lw != 0;
+    const size_t hl = lb ? ((size_t)c * ng_lw + g) * ls + l : ((size_t)c * (nlev + 1) + l) * ng_lw + g;   // arrays with nlev + 1 rows
+    const size_t fl = lb ? hl : ((size_t)c * nlev + l) * ng_lw + g;                                        // arrays with nlev rows
+    if (p.planck_hl) p.planck_hl[((size_t)c * (nlev + 1) + l) * ng_lw + gd] = w.planck[hl];
+    if (l < nlev) {
+      const size_t o = ((size_t)c * nlev + l) * ng_lw + gd;
+      if (p.od_lw) p.od_lw[o] = w.od_lw[fl];
+      const bool sc = cfg.do_lw_aerosol_scattering && w.ssa_lw && w.g_lw;
+      if (p.ssa_lw) p.ssa_lw[o] = sc ? w.ssa_lw[fl] : 0.0;
+      if (p.g_lw) p.g_lw[o] = sc ? w.g_lw[fl] : 0.0;
+    }
+    if (l == 0) {
+      if (p.lw_emission) p.lw_emission[(size_t)c * ng_lw + gd] = w.emission[(size_t)c * ng_lw + g];
+      if (p.lw_albedo) p.lw_albedo[(size_t)c * ng_lw + gd] = w.lw_albedo[(size_t)c * ng_lw + g];
+    }
+  }
+  if (cfg.do_sw && t < ng_sw) {
+    const int g = t, gd = T.meta->rank_sw[g];
+    const bool sunlit = in.cos_sza[c] > 0.0;
+    const bool lb = w.layout_b_sw != 0;
+    if (l < nlev) {
+      const size_t fl = lb ? ((size_t)c * ng_sw + g) * ls + l : ((size_t)c * nlev + l) * ng_sw + g;
+      const size_t o = ((size_t)c * nlev + l) * ng_sw + gd;
+      if (p.od_sw) p.od_sw[o] = sunlit ? w.od_sw[fl] : 0.0;
+      if (p.ssa_sw) p.ssa_sw[o] = sunlit ? w.ssa_sw[fl] : 0.0;
+      if (p.g_sw) p.g_sw[o] = (sunlit && w.g_sw) ? w.g_sw[fl] : 0.0;   // (no aerosols: the gases' asymmetry factor is zero)
+    }
+    if (l == 0) {
+      if (p.incoming_sw) p.incoming_sw[(size_t)c * ng_sw + gd] = sunlit ? w.incoming[(size_t)c * ng_sw + g] : 0.0;
+      // get_albedos, radiation_single_level.F90:216-301 (the nearest-interval mapping arrives as 0/1 weights)
+      const int jb = T.meta->band_of_g_sw[g];
+      double bd = 0.0, bdir = 0.0;
+      for (int ja = 0; ja < cfg.n_albedo_sw; ++ja) {
+        const double wgt = T.sw_albedo_weights[jb * cfg.n_albedo_sw + ja];
+        if (wgt != 0.0) {
+          bd = bd + wgt * LD_IN(in.sw_albedo, c, ja);
+          if (in.sw_albedo_direct) bdir = bdir + wgt * LD_IN(in.sw_albedo_direct, c, ja);
+        }
+      }
+      if (p.sw_albedo_diffuse) p.sw_albedo_diffuse[(size_t)c * ng_sw + gd] = bd;
+      if (p.sw_albedo_direct) p.sw_albedo_direct[(size_t)c * ng_sw + gd] = in.sw_albedo_direct ? bdir : bd;
+    }
+  }
+  if (l < nlev) {
+    // cloud optics per band, zero where the (cropped) layer holds no cloud (radiation_cloud_optics.F90:263-270 initialises to zero)
+    const bool cloudy = cfg.do_clouds && LD_IN(in.frac, c, l) > 0.0;
+    if (cfg.do_lw && t < nb_lw) {
+      const double* s = w.cl_lw + ((size_t)c * nlev + l) * 3 * nb_lw;
+      const size_t o = ((size_t)c * nlev + l) * nb_lw + t;
+      // (the generalised no-scattering form leaves absorption in cropped layers that hold condensate, see general_cloud_optics_kernel)
+      const bool od_any = cfg.do_clouds && cfg.use_general_cloud_optics && !cfg.do_lw_cloud_scattering &&
+                          (LD_IN(in.q_liq, c, l) > 0.0 || LD_IN(in.q_ice, c, l) > 0.0);
+      if (p.od_lw_cloud) p.od_lw_cloud[o] = (cloudy || od_any) ? s[t] : 0.0;
+      if (p.ssa_lw_cloud) p.ssa_lw_cloud[o] = cloudy ? s[nb_lw + t] : 0.0;
+      if (p.g_lw_cloud) p.g_lw_cloud[o] = cloudy ? s[2 * nb_lw + t] : 0.0;
+    }
+    if (cfg.do_sw && t < nb_sw) {
+      const double* s = w.cl_sw + ((size_t)c * nlev + l) * 3 * nb_sw;
+      const size_t o = ((size_t)c * nlev + l) * nb_sw + t;
+      if (p.od_sw_cloud) p.od_sw_cloud[o] = cloudy ? s[t] : 0.0;
+      if (p.ssa_sw_cloud) p.ssa_sw_cloud[o] = cloudy ? s[nb_sw + t] : 0.0;
+      if (p.g_sw_cloud) p.g_sw_cloud[o] = cloudy ? s[2 * nb_sw + t] : 0.0;
+    }
+  }
+}
+int launch_radprops_gather(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, const DevProps& p, int nc, int nlev, cudaStream_t st) {
+  const int n = cfg.ng_lw > cfg.ng_sw ? cfg.ng_lw : cfg.ng_sw;
+  radprops_gather_kernel<<<dim3(nlev + 1, nc), (n + 31) / 32 * 32, 0, st>>>(T, cfg, in, w, p, nc, nlev);
+  return 1;
+}
 int launch_cloud(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, int nc, int nlev, cudaStream_t st) {
   const int nlevp = (nlev + 3) & ~3;
   int n = 0;

@@ -139,6 +139,13 @@ size_t sp_scratch_doubles_lw(int nlev, int ng);
 size_t sp_scratch_doubles_sw(int nlev, int ng);
 int launch_sp_lw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
 int launch_sp_sw(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);
+// Device view of ecrad_b200_radiative_properties for one tile: the reference's element order, column slowest; NULL = skipped.
+struct DevProps {
+  double *planck_hl, *lw_emission, *lw_albedo, *sw_albedo_direct, *sw_albedo_diffuse, *incoming_sw;
+  double *od_lw, *ssa_lw, *g_lw, *od_sw, *ssa_sw, *g_sw;
+  double *od_lw_cloud, *ssa_lw_cloud, *g_lw_cloud, *od_sw_cloud, *ssa_sw_cloud, *g_sw_cloud;
+};
+int launch_radprops_gather(const DevTables& T, const DevCfg& cfg, const DevIn& in, const Work& w, const DevProps& p, int nc, int nlev, cudaStream_t st);   // save_radiative_properties
 int launch_toa_spectral(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, int nc, bool sw, cudaStream_t st);   // flux%calc_toa_spectral
 int scan_max_levels();   // most layers the scan solvers take (32 lanes x layers per lane)
 int launch_solver_lw_scan(const DevTables& T, const DevCfg& cfg, const DevIn& in, const DevOut& out, const Work& w, int nc, int nlev, cudaStream_t st);

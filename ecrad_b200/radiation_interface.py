@@ -65,6 +65,7 @@ def load_library():
     L.ecrad_b200_last_error.argtypes = [C.c_void_p]
     L.ecrad_b200_version.restype = C.c_char_p
     L.ecrad_b200_measure_fp64.argtypes = [C.POINTER(C.c_double)]
+    L.ecrad_b200_save_radiative_properties.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.RadiativeProperties)]
     L.ecrad_b200_radiation_blocked.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.BlockLayout), abi.c_dp, abi.c_dp]
     _lib = L
     return L
@@ -113,6 +114,17 @@ class RadiationHandle:
 
     def _err(self):
         return self.lib.ecrad_b200_last_error(self.h).decode()
+
+    def radiative_properties(self, inputs, ncol, nlev, istartcol=1, iendcol=None):
+        """What radiation() passes to save_radiative_properties (radiation_interface.F90:405-425): the optical properties the gas,
+        aerosol and cloud optics hand to the solvers, as a dict of Fortran-ordered arrays (g-point or band, level, column).  The
+        caller's cloud_fraction is left uncropped."""
+        iendcol = ncol if iendcol is None else iendcol
+        keep, ist = abi.make_inputs(dict(inputs, cloud_fraction=np.array(inputs["cloud_fraction"], order="F")), inputs["solar_irradiance"])
+        arrs, pst = abi.alloc_radiative_properties(ncol, nlev, self.cfg)
+        if self.lib.ecrad_b200_save_radiative_properties(self.h, ncol, nlev, istartcol, iendcol, C.byref(ist), C.byref(pst)):
+            raise RadiationError(self._err())
+        return arrs
 
     def radiation(self, inputs, ncol, nlev, istartcol=1, iendcol=None, outputs=None, spectral_profiles=False):
         """inputs: dict keyed like abi.INPUT_ARRAYS (+ 'solar_irradiance'); cloud_fraction is cropped in place like

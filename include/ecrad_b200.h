@@ -219,6 +219,32 @@ typedef struct ecrad_b200_block_layout {
 int ecrad_b200_radiation_blocked(void* handle, int ncol_total, int nlev, const ecrad_b200_block_layout* layout,
                                  const double* zrgp_in, double* zrgp_out);
 
+/* The intermediate optical properties radiation() hands to save_radiative_properties when config%do_save_radiative_properties is
+ * set (radiation_interface.F90:405-425, radiation_save.F90:716-1100): what the gas, aerosol and cloud optics produced for the
+ * solvers.  All arrays are host arrays in the reference's element order, spectral index fastest, column slowest, and are written for
+ * columns istartcol..iendcol only; a NULL member is skipped.  The g-point order is the solver's (reordered for SPARTACUS on RRTMG-IFS,
+ * like every per-g-point array of flux_type).  ssa_lw / g_lw are defined with do_lw_aerosol_scattering only (zero otherwise, as the
+ * reference leaves them); the cloud properties of layers without cloud are zero (except where the reference's no-scattering
+ * generalised cloud optics leaves absorption in cropped layers that hold condensate: reproduced).  One deviation: the shortwave properties (od_sw,
+ * ssa_sw, g_sw, incoming_sw) of night columns (cos_sza <= 0) are written as zero -- no solver reads them and the library does not
+ * compute them, whereas the reference stores aerosol-only (RRTMG-IFS, radiation_ifs_rrtm.F90:531-594) or full (ecCKD) values there. */
+typedef struct ecrad_b200_radiative_properties {
+  double* planck_hl;          /* (n_g_lw, nlev+1, ncol) */
+  double* lw_emission;        /* (n_g_lw, ncol) */
+  double* lw_albedo;          /* (n_g_lw, ncol) */
+  double* sw_albedo_direct;   /* (n_g_sw, ncol) */
+  double* sw_albedo_diffuse;  /* (n_g_sw, ncol) */
+  double* incoming_sw;        /* (n_g_sw, ncol) */
+  double* od_lw;  double* ssa_lw;  double* g_lw;                      /* (n_g_lw, nlev, ncol) gases + aerosols */
+  double* od_sw;  double* ssa_sw;  double* g_sw;                      /* (n_g_sw, nlev, ncol) */
+  double* od_lw_cloud;  double* ssa_lw_cloud;  double* g_lw_cloud;    /* (n_bands_lw, nlev, ncol) in-cloud, delta-Eddington scaled */
+  double* od_sw_cloud;  double* ssa_sw_cloud;  double* g_sw_cloud;    /* (n_bands_sw, nlev, ncol) */
+} ecrad_b200_radiative_properties;
+/* Runs the optics stages of radiation() (no solver) on the same inputs and copies the properties out.  A diagnostic: synchronous,
+ * not pipelined.  cloud_fraction is NOT cropped in the caller's array by this call.  Returns 0 or an error (ecrad_b200_last_error). */
+int ecrad_b200_save_radiative_properties(void* handle, int ncol, int nlev, int istartcol, int iendcol,
+                                         const ecrad_b200_inputs* inputs, const ecrad_b200_radiative_properties* props);
+
 /* Tuning/diagnostic options.  Returns 0 on success.
  *   "serial"            0/1: run a tile's kernels on one stream instead of the three overlapping chains (per-kernel timing)
  *   "tile_cols", "tile_cols_device"   columns per internal tile of the host / device entry

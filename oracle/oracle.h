@@ -187,6 +187,8 @@ void orc_fast_expm_exchange_3(double a, double b, double c, double d, double* r)
 /* radiation.c */
 int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
                   const ecrad_b200_inputs* in, ecrad_b200_outputs* out, int nthreads);
+int orc_radiative_properties(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
+                             const ecrad_b200_inputs* in, const ecrad_b200_radiative_properties* props);
 /* stage dump for localising differences: gas optics of ONE column (1-based jcol), ecRad level order */
 int orc_gas_optics_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
                   const ecrad_b200_inputs* in, double* od_lw, double* planck_hl, double* lw_emission,

@@ -957,8 +957,10 @@ static void surface_spectral(const orc_tables* t, const ecrad_b200_config* cfg, 
   }
 }
 
+/* props != NULL: stop where radiation() calls save_radiative_properties (radiation_interface.F90:405-425) and copy the optical
+ * properties out instead of solving */
 static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int jcol,
-                            const ecrad_b200_inputs* in, ecrad_b200_outputs* out) {
+                            const ecrad_b200_inputs* in, ecrad_b200_outputs* out, const ecrad_b200_radiative_properties* props) {
   col_work w;
   size_t n = 3 * (size_t)nlev * NG_LW + (size_t)(nlev + 1) * NG_LW + 2 * NG_LW + 3 * (size_t)nlev * NG_SW + 3 * NG_SW +
              3 * (size_t)nlev * NB_LW + 3 * (size_t)nlev * NB_SW + 6 * (size_t)nlev;
@@ -1054,6 +1056,23 @@ static int radiation_column(const orc_tables* t, const ecrad_b200_config* cfg, i
     free(tmp);
     t = tp;
   }
+  if (props) {
+    const size_t c = (size_t)jcol;
+#define PUT(dst, src, n) do { if (props->dst) memcpy(props->dst + c * (size_t)(n), (src), sizeof(double) * (size_t)(n)); } while (0)
+    if (cfg->do_lw) {
+      PUT(planck_hl, w.planck_hl, (size_t)(nlev + 1) * NG_LW); PUT(lw_emission, w.lw_emission, NG_LW); PUT(lw_albedo, w.lw_albedo, NG_LW);
+      PUT(od_lw, w.od_lw, (size_t)nlev * NG_LW); PUT(ssa_lw, w.ssa_lw, (size_t)nlev * NG_LW); PUT(g_lw, w.g_lw, (size_t)nlev * NG_LW);
+      PUT(od_lw_cloud, w.od_lw_cloud, (size_t)nlev * NB_LW); PUT(ssa_lw_cloud, w.ssa_lw_cloud, (size_t)nlev * NB_LW); PUT(g_lw_cloud, w.g_lw_cloud, (size_t)nlev * NB_LW);
+    }
+    if (cfg->do_sw) {
+      PUT(sw_albedo_direct, w.alb_dir, NG_SW); PUT(sw_albedo_diffuse, w.alb_diff, NG_SW); PUT(incoming_sw, w.incoming_sw, NG_SW);
+      PUT(od_sw, w.od_sw, (size_t)nlev * NG_SW); PUT(ssa_sw, w.ssa_sw, (size_t)nlev * NG_SW); PUT(g_sw, w.g_sw, (size_t)nlev * NG_SW);
+      PUT(od_sw_cloud, w.od_sw_cloud, (size_t)nlev * NB_SW); PUT(ssa_sw_cloud, w.ssa_sw_cloud, (size_t)nlev * NB_SW); PUT(g_sw_cloud, w.g_sw_cloud, (size_t)nlev * NB_SW);
+    }
+#undef PUT
+    free(w.w); free(phl_full); free(tp);
+    return 0;
+  }
   if (cfg->do_lw && cfg->i_solver_lw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0);
   else if (cfg->do_lw) { if (cfg->i_solver_lw == ECRAD_SOLVER_TRIPLECLOUDS || cfg->i_solver_lw == ECRAD_SOLVER_SPARTACUS) solver_tc(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 0); else solver_lw(t, cfg, ncol, nlev, jcol, in, out, &w, frac); }
   if (cfg->do_sw && cfg->i_solver_sw == ECRAD_SOLVER_HOMOGENEOUS) solver_homog(t, cfg, ncol, nlev, jcol, in, out, &w, frac, 1);
@@ -1090,7 +1109,18 @@ int orc_radiation(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, i
   if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(| : err)
 #endif
-  for (int jcol = istartcol - 1; jcol < iendcol; ++jcol) err |= radiation_column(t, cfg, ncol, nlev, jcol, in, out);
+  for (int jcol = istartcol - 1; jcol < iendcol; ++jcol) err |= radiation_column(t, cfg, ncol, nlev, jcol, in, out, NULL);
   (void)nthreads;
+  return err;
+}
+
+/* the optical properties radiation() would hand to save_radiative_properties (radiation_interface.F90:405-425, radiation_save.F90:716-726),
+ * columns istartcol..iendcol; in->cloud_fraction is cropped in place like in orc_radiation */
+int orc_radiative_properties(const orc_tables* t, const ecrad_b200_config* cfg, int ncol, int nlev, int istartcol, int iendcol,
+                             const ecrad_b200_inputs* in, const ecrad_b200_radiative_properties* props) {
+  if (!props) return 12;
+  if ((cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) != (t->is_ecckd_lw != 0) || (cfg->i_gas_model_sw == ECRAD_GAS_ECCKD) != (t->is_ecckd_sw != 0)) return 14;
+  int err = 0;
+  for (int jcol = istartcol - 1; jcol < iendcol; ++jcol) err |= radiation_column(t, cfg, ncol, nlev, jcol, in, NULL, props);
   return err;
 }

@@ -48,6 +48,8 @@ class Oracle:
         L.orc_tables_free.argtypes = [C.c_void_p]
         L.orc_radiation.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_int]
+        L.orc_radiative_properties.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(abi.Inputs), C.POINTER(abi.RadiativeProperties)]
         L.orc_gas_optics_column.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int,
                                             C.POINTER(abi.Inputs)] + [abi.c_dp] * 6
         L.orc_expm.argtypes = [C.c_int, abi.c_dp, C.c_int]
@@ -68,6 +70,16 @@ class Oracle:
             L.orc_tables_add(self.t, nm.encode(), code, a.ndim, dims, a.ctypes.data_as(C.c_void_p))
         if L.orc_tables_resolve(self.t):
             raise RuntimeError("oracle: table blob incomplete")
+
+    def radiative_properties(self, inputs, ncol, nlev, istartcol=1, iendcol=None):
+        """What radiation() hands to save_radiative_properties (radiation_interface.F90:405-425); cloud_fraction of `inputs` is cropped."""
+        iendcol = ncol if iendcol is None else iendcol
+        keep, ist = abi.make_inputs(inputs, inputs["solar_irradiance"])
+        arrs, pst = abi.alloc_radiative_properties(ncol, nlev, self.cfg)
+        rc = self.lib.orc_radiative_properties(self.t, C.byref(self.cfg), ncol, nlev, istartcol, iendcol, C.byref(ist), C.byref(pst))
+        if rc:
+            raise RuntimeError(f"oracle radiative_properties failed rc={rc}")
+        return arrs
 
     def radiation(self, inputs, ncol, nlev, istartcol=1, iendcol=None, nthreads=0, spectral_profiles=False):
         """inputs: dict from ecrad_b200.inputs.to_radiation_inputs (cloud_fraction is modified in place)."""

@@ -124,3 +124,27 @@ def test_mixed_gas_models(meridian_raw, kw):
         assert np.array_equal(lw_ckd[nm], rrtmg[nm]), nm
         assert np.abs(sw_ckd[nm] - ecckd[nm]).max() < 1e-7, nm
     assert sw_ckd["sw_up_toa_g"].shape[0] == 32 and sw_ckd["lw_up_toa_g"].shape[0] == 140
+
+
+def test_radiative_properties(meridian_raw):
+    """orc_radiative_properties = the arrays radiation() hands to save_radiative_properties (radiation_interface.F90:405-425): without
+    aerosols the gas part is the gas-optics stage dump, the SPARTACUS order is the permutation of radiation_ifs_rrtm.F90:50-68, a
+    column range leaves the other columns alone, and the incoming flux sums to the solar irradiance."""
+    cfg = RadiationConfig().consolidate()
+    o = Oracle(cfg)
+    p = o.radiative_properties(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV, istartcol=3, iendcol=30)
+    for nm, a in p.items():
+        assert np.isnan(a[..., :2]).all() and np.isnan(a[..., 30:]).all() and np.isfinite(a[..., 2:30]).all(), nm
+    g = o.gas_optics_column(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV, 11)
+    for nm in ("od_lw", "planck_hl", "lw_emission", "od_sw", "ssa_sw", "incoming_sw"):
+        assert np.array_equal(p[nm][..., 10], np.asarray(g[nm]).T), nm   # (the stage dump is C-ordered [level][g])
+    sun = meridian_raw["cos_solar_zenith_angle"][2:30] > 0.0
+    assert np.abs(p["incoming_sw"][:, 2:30][:, sun].sum(axis=0) - float(meridian_raw["solar_irradiance"])).max() < 1e-9
+    assert not p["g_sw"][..., 2:30].any() and not p["ssa_lw"][..., 2:30].any()
+    # SPARTACUS on RRTMG: the same numbers at the reordered positions
+    from ecrad_b200.tables import read_blob
+    perm = read_blob(cfg.tables_path())["i_g_from_reordered_g_lw"].astype(int) - 1
+    sp = RadiationConfig(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True).consolidate()
+    q = Oracle(sp).radiative_properties(I.to_radiation_inputs(meridian_raw, sp), 32, NLEV, istartcol=3, iendcol=30)
+    assert np.array_equal(q["od_lw"][..., 2:30], p["od_lw"][perm][..., 2:30])
+    assert np.array_equal(q["od_lw_cloud"][..., 2:30], p["od_lw_cloud"][..., 2:30])

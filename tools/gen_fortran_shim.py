@@ -199,7 +199,7 @@ def main():
     w("  use parkind1, only : jprb, jpim")
     w("  implicit none")
     w("  private")
-    w("  public :: b200_setup, b200_radiation, b200_finalize, b200_set_option, b200_active")
+    w("  public :: b200_setup, b200_radiation, b200_save_radiative_properties, b200_finalize, b200_set_option, b200_active")
     w("")
     w("  logical     :: b200_active = .false.")
     w("  type(c_ptr) :: handle = c_null_ptr")
@@ -217,6 +217,9 @@ def main():
     w("  type, bind(c) :: out_t                       ! == struct ecrad_b200_outputs: %d pointers in the header's order, c_null_ptr = not allocated" % (len(outp) - 2))
     w("    integer(c_int32_t) :: struct_bytes, reserved")
     w(f"    type(c_ptr)        :: p({len(outp) - 2})")
+    w("  end type")
+    w("  type, bind(c) :: props_t                     ! == struct ecrad_b200_radiative_properties: 18 pointers in the header's order")
+    w("    type(c_ptr) :: p(18)")
     w("  end type")
     w("")
     w("  interface")
@@ -240,6 +243,10 @@ def main():
     w("    function ecrad_b200_radiation_sp(h, ncol, nlev, istartcol, iendcol, inp, outp) bind(c) result(rc)")
     w("      import; type(c_ptr), value :: h; integer(c_int), value :: ncol, nlev, istartcol, iendcol")
     w("      type(in_t) :: inp; type(out_t) :: outp; integer(c_int) :: rc")
+    w("    end function")
+    w("    function ecrad_b200_save_radiative_properties(h, ncol, nlev, istartcol, iendcol, inp, props) bind(c) result(rc)")
+    w("      import; type(c_ptr), value :: h; integer(c_int), value :: ncol, nlev, istartcol, iendcol")
+    w("      type(in_t) :: inp; type(props_t) :: props; integer(c_int) :: rc")
     w("    end function")
     w("    function ecrad_b200_set_option(h, key, val) bind(c) result(rc)")
     w("      import; type(c_ptr), value :: h; character(kind=c_char) :: key(*); integer(c_int), value :: val; integer(c_int) :: rc")
@@ -416,26 +423,29 @@ def main():
     w("    type(in_t) :: i; type(out_t) :: o")
     w("    i%struct_bytes = int(c_sizeof(i), c_int32_t); i%reserved = 0")
     w("    o%struct_bytes = int(c_sizeof(o), c_int32_t); o%reserved = 0; o%p = c_null_ptr")
-    w("    i%solar_irradiance = real(single_level%solar_irradiance, c_double)")
+    in_lines = ["    i%struct_bytes = int(c_sizeof(i), c_int32_t); i%reserved = 0",
+                "    i%solar_irradiance = real(single_level%solar_irradiance, c_double)"]
     unmapped = []
     for tname, f in inp:
         if f in ("struct_bytes", "reserved", "solar_irradiance"):
             continue
         if f in IN_MAP:
-            w(f"    i%{f} = {IN_MAP[f]}")
+            in_lines.append(f"    i%{f} = {IN_MAP[f]}")
         elif f in IN_OPTIONAL:
             cond, expr = IN_OPTIONAL[f]
-            w(f"    i%{f} = c_null_ptr")
+            in_lines.append(f"    i%{f} = c_null_ptr")
             if "present(aerosol)" in cond:
-                w("    if (present(aerosol)) then")
-                w(f"      if (config%use_aerosols) i%{f} = {expr}")
-                w("    end if")
+                in_lines.append("    if (present(aerosol)) then")
+                in_lines.append(f"      if (config%use_aerosols) i%{f} = {expr}")
+                in_lines.append("    end if")
             else:
-                w(f"    if ({cond}) i%{f} = {expr}")
+                in_lines.append(f"    if ({cond}) i%{f} = {expr}")
         else:
             unmapped.append(f)
     if unmapped:
         raise SystemExit("ecrad_b200_inputs fields without a mapping: " + ", ".join(unmapped))
+    for ln in in_lines[1:]:
+        w(ln)
     k = 0
     for tname, f in outp:
         if f in ("struct_bytes", "reserved"):
@@ -449,6 +459,43 @@ def main():
     w("    if (ecrad_b200_radiation(handle, int(ncol, c_int), int(nlev, c_int), int(istartcol, c_int), int(iendcol, c_int), i, o) /= 0) &")
     w("         &  call abort_with(ecrad_b200_last_error(handle))")
     w("#endif")
+    w("  end subroutine")
+    w("")
+    props = ["planck_hl", "lw_emission", "lw_albedo", "sw_albedo_direct", "sw_albedo_diffuse", "incoming_sw", "od_lw", "ssa_lw", "g_lw",
+             "od_sw", "ssa_sw", "g_sw", "od_lw_cloud", "ssa_lw_cloud", "g_lw_cloud", "od_sw_cloud", "ssa_sw_cloud", "g_sw_cloud"]
+    hdr_props = re.search(r"typedef struct ecrad_b200_radiative_properties \{(.*?)\} ecrad_b200_radiative_properties;", hdr, re.S).group(1)
+    hdr_props = re.findall(r"double\*\s*(\w+);", re.sub(r"/\*.*?\*/", "", hdr_props, flags=re.S))
+    if hdr_props != props:
+        raise SystemExit("ecrad_b200_radiative_properties changed: " + ", ".join(hdr_props))
+    w("  ! The arrays radiation() passes to save_radiative_properties (radiation_interface.F90:405-425), filled by the library from the same")
+    w("  ! inputs; call it where config%do_save_radiative_properties is tested and hand the arrays on to radiation_save.  Double precision only.")
+    w("  subroutine b200_save_radiative_properties(ncol, nlev, istartcol, iendcol, config, single_level, thermodynamics, gas, cloud, &")
+    w("       &  planck_hl, lw_emission, lw_albedo, sw_albedo_direct, sw_albedo_diffuse, incoming_sw, od_lw, ssa_lw, g_lw, od_sw, ssa_sw, g_sw, &")
+    w("       &  od_lw_cloud, ssa_lw_cloud, g_lw_cloud, od_sw_cloud, ssa_sw_cloud, g_sw_cloud, aerosol)")
+    w("    use radiation_config, only : config_type")
+    w("    use radiation_single_level, only : single_level_type")
+    w("    use radiation_thermodynamics, only : thermodynamics_type")
+    w("    use radiation_gas, only : gas_type, IH2O, ICO2, IO3, IN2O, ICH4, ICFC11, ICFC12, IHCFC22, ICCl4")
+    w("    use radiation_cloud, only : cloud_type")
+    w("    use radiation_aerosol, only : aerosol_type")
+    w("    integer, intent(in) :: ncol, nlev, istartcol, iendcol")
+    w("    type(config_type), intent(in) :: config")
+    w("    type(single_level_type), intent(in), target :: single_level")
+    w("    type(thermodynamics_type), intent(in), target :: thermodynamics")
+    w("    type(gas_type), intent(in), target :: gas")
+    w("    type(cloud_type), intent(in), target :: cloud")
+    w("    ! (spectral index, level, column) with ALL ncol columns, like the library's other arrays; columns istartcol:iendcol are written")
+    w("    real(jprb), intent(inout), target, contiguous, dimension(:,:,:) :: planck_hl, od_lw, ssa_lw, g_lw, od_sw, ssa_sw, g_sw, &")
+    w("         &  od_lw_cloud, ssa_lw_cloud, g_lw_cloud, od_sw_cloud, ssa_sw_cloud, g_sw_cloud")
+    w("    real(jprb), intent(inout), target, contiguous, dimension(:,:) :: lw_emission, lw_albedo, sw_albedo_direct, sw_albedo_diffuse, incoming_sw")
+    w("    type(aerosol_type), intent(in), target, optional :: aerosol")
+    w("    type(in_t) :: i; type(props_t) :: p")
+    for ln in in_lines:
+        w(ln)
+    for k, nm in enumerate(props, 1):
+        w(f"    p%p({k}) = c_loc({nm})")
+    w("    if (ecrad_b200_save_radiative_properties(handle, int(ncol, c_int), int(nlev, c_int), int(istartcol, c_int), int(iendcol, c_int), i, p) /= 0) &")
+    w("         &  call abort_with(ecrad_b200_last_error(handle))")
     w("  end subroutine")
     w("")
     w("  subroutine b200_set_option(key, val)          ! e.g. call b200_set_option('register_host', 1): page-lock the caller's arrays once")
