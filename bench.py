@@ -143,6 +143,9 @@ WORKLOADS = {
                              "configCY49R1_ecckd.nam + 64-term models, use_aerosols=false", "BASELINE.json configs[2]"),
     "tripleclouds_rrtmg": (dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"), 10000, "Tripleclouds LW+SW, RRTMG 140+112 g-points",
                            "configCY49R1.nam, Tripleclouds, use_aerosols=false", "extra"),
+    "tripleclouds_mixed": (dict(sw_gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds",
+                                use_aerosols=True), 10000, "Tripleclouds, SW ecCKD 32 g-points + LW RRTMG 140 g-points (mixed gas models), aerosols",
+                           "configCY49R1_mixed.nam, lw_gas_model_name=RRTMG-IFS (test/ifs `test_mixed_gas`, second run)", "extra"),
     "spartacus_rrtmg": (dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True), 50000,
                         "SPARTACUS LW+SW 3 regions with 3D effects, RRTMG 140+112 g-points",
                         "configCY49R1.nam, SPARTACUS, do_3d_effects=true, use_aerosols=false (ctest `spartacus`)", "BASELINE.json configs[4]"),
