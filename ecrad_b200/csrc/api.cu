@@ -1088,6 +1088,12 @@ int ecrad_b200_save_radiative_properties(void* handle, int ncol, int nlev, int i
     if (!pd[k].dev) { release(); return fail(h, "ecrad_b200_save_radiative_properties: out of device memory"); }
   }
   int rc = 0;
+  double* ones = nullptr;
+  if (c.do_sw && h->dcfg.ckd_sw) {
+    ones = (double*)dalloc((size_t)cap * 8);
+    const std::vector<double> one((size_t)cap, 1.0);
+    if (!ones || cudaMemcpy(ones, one.data(), (size_t)cap * 8, cudaMemcpyHostToDevice) != cudaSuccess) { release(); return fail(h, "ecrad_b200_save_radiative_properties: out of device memory"); }
+  }
   for (int c0 = 0; c0 < n && !rc; c0 += cap) {
     const int nt = (n - c0) < cap ? (n - c0) : cap;
     for (int k = 0; k < N_IN && !rc; ++k) {
@@ -1098,6 +1104,9 @@ int ecrad_b200_save_radiative_properties(void* handle, int ncol, int nlev, int i
     if (rc || cudaDeviceSynchronize() != cudaSuccess) { rc = 1; break; }   // (pageable sources: the DMA may trail the call's return)
     DevIn di; DevOut dout;
     make_views(ip, op, cap, cap, in->solar_irradiance, di, dout);
+    // ecCKD computes the shortwave properties of every column, sunlit or not (radiation_ecckd_interface.F90:257-292); the kernels skip
+    // night columns because no solver reads them, so this pass marks every column sunlit.  (RRTMG-IFS skips them in the reference too.)
+    if (ones) di.cos_sza = ones;
     if (run_tile(h, 0, di, dout, nt, nlev, st, &h->ev[0], true)) { rc = 2; break; }
     DevProps dp = {pd[0].dev, pd[1].dev, pd[2].dev, pd[3].dev, pd[4].dev, pd[5].dev, pd[6].dev, pd[7].dev, pd[8].dev,
                    pd[9].dev, pd[10].dev, pd[11].dev, pd[12].dev, pd[13].dev, pd[14].dev, pd[15].dev, pd[16].dev, pd[17].dev};

@@ -927,9 +927,31 @@ __global__ void radprops_gather_kernel(DevTables T, DevCfg cfg, DevIn in, Work w
     if (l < nlev) {
       const size_t fl = lb ? ((size_t)c * ng_sw + g) * ls + l : ((size_t)c * nlev + l) * ng_sw + g;
       const size_t o = ((size_t)c * nlev + l) * ng_sw + gd;
-      if (p.od_sw) p.od_sw[o] = sunlit ? w.od_sw[fl] : 0.0;
-      if (p.ssa_sw) p.ssa_sw[o] = sunlit ? w.ssa_sw[fl] : 0.0;
-      if (p.g_sw) p.g_sw[o] = (sunlit && w.g_sw) ? w.g_sw[fl] : 0.0;   // (no aerosols: the gases' asymmetry factor is zero)
+      double odv = 0.0, ssav = 0.0, gv = 0.0;
+      if (sunlit) {
+        odv = w.od_sw[fl]; ssav = w.ssa_sw[fl];
+        gv = w.g_sw ? w.g_sw[fl] : 0.0;   // (no aerosols: the gases' asymmetry factor is zero)
+      } else {
+        // Night column with RRTMG-IFS (an ecCKD spectrum arrives here with every column marked sunlit): the gas kernels skip it like
+        // srtm_gas_optical_depth does, so the reference's arrays hold max(min_gas_od_sw, 0) and ssa = 0 (radiation_ifs_rrtm.F90:531-594)
+        // merged with the aerosols (radiation_aerosol_optics.F90:753-790), which are computed for every column
+        odv = dmax(cfg.min_gas_od_sw, 0.0);
+        if (cfg.use_aerosols && T.aer && w.aer_sw) {
+          const int jb = T.meta->band_of_g_sw[g];
+          const double* a = w.aer_sw + ((size_t)c * nlev + l) * 3 * nb_sw;
+          const double od_aer = a[jb], scat_aer = a[nb_sw + jb], scat_g_aer = a[2 * nb_sw + jb];
+          const double local_od = odv + od_aer;
+          if (local_od > 0.0 && od_aer > 0.0) {
+            const double local_scat = ssav * odv + scat_aer;
+            if (local_scat > 0.0) gv = scat_g_aer / local_scat;
+            ssav = local_scat / local_od;
+            odv = local_od;
+          }
+        }
+      }
+      if (p.od_sw) p.od_sw[o] = odv;
+      if (p.ssa_sw) p.ssa_sw[o] = ssav;
+      if (p.g_sw) p.g_sw[o] = gv;
     }
     if (l == 0) {
       if (p.incoming_sw) p.incoming_sw[(size_t)c * ng_sw + gd] = sunlit ? w.incoming[(size_t)c * ng_sw + g] : 0.0;

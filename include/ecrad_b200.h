@@ -225,9 +225,8 @@ int ecrad_b200_radiation_blocked(void* handle, int ncol_total, int nlev, const e
  * columns istartcol..iendcol only; a NULL member is skipped.  The g-point order is the solver's (reordered for SPARTACUS on RRTMG-IFS,
  * like every per-g-point array of flux_type).  ssa_lw / g_lw are defined with do_lw_aerosol_scattering only (zero otherwise, as the
  * reference leaves them); the cloud properties of layers without cloud are zero (except where the reference's no-scattering
- * generalised cloud optics leaves absorption in cropped layers that hold condensate: reproduced).  One deviation: the shortwave properties (od_sw,
- * ssa_sw, g_sw, incoming_sw) of night columns (cos_sza <= 0) are written as zero -- no solver reads them and the library does not
- * compute them, whereas the reference stores aerosol-only (RRTMG-IFS, radiation_ifs_rrtm.F90:531-594) or full (ecCKD) values there. */
+ * generalised cloud optics leaves absorption in cropped layers that hold condensate: reproduced).  Night columns hold what the
+ * reference holds: aerosols on zero gas optical depth with RRTMG-IFS (radiation_ifs_rrtm.F90:531-594), full values with ecCKD. */
 typedef struct ecrad_b200_radiative_properties {
   double* planck_hl;          /* (n_g_lw, nlev+1, ncol) */
   double* lw_emission;        /* (n_g_lw, ncol) */
