@@ -49,6 +49,7 @@ struct Handle {
   DevTables T;
   std::vector<void*> table_allocs;
   int device = 0;
+  bool has_solar_cycle = false;  // the ecCKD shortwave model came with norm_amplitude_solar_irradiance
   int tile_cols = 4096;          // host entry: columns per tile (H2D / kernels / D2H of consecutive tiles overlap)
   int edge_cols = 1024;          // host entry: at most this many columns in the first and the last tile
   bool edge_explicit = false;    // edge_cols was set through set_option: not capped at tile_cols / 4
@@ -646,6 +647,8 @@ int ecrad_b200_setup(const ecrad_b200_config* cfg, const ecrad_b200_tables* tab,
   d.use_vectorizable_generator = cfg->use_vectorizable_generator;
   d.do_nearest_spectral_lw_emiss = cfg->do_nearest_spectral_lw_emiss;
   d.ckd_lw = P.ckd_lw; d.ckd_sw = P.ckd_sw;
+  d.solar_cycle_multiplier = 0.0;
+  h->has_solar_cycle = P.ckd_sw && P.ckd.sw.off_solar_amp >= 0;
   d.gas_mmr = !(P.ckd_lw && P.ckd_sw);
   d.use_general_cloud_optics = cfg->use_general_cloud_optics != 0;
   d.do_toa_spectral_flux = cfg->do_toa_spectral_flux;
@@ -764,6 +767,21 @@ int ecrad_b200_set_option(void* handle, const char* key, int value) {
   if (!strcmp(key, "tail_tiles")) { if (value < 1 || value > 8) return fail(h, "tail_tiles must be 1..8"); h->tail_tiles = value; return 0; }
   if (!strcmp(key, "tile_cols_device")) { if (value < 1) return fail(h, "tile_cols_device must be positive"); h->tile_cols_device = value; return 0; }
   return fail(h, "unknown option '%s'", key);
+}
+
+// single_level%spectral_solar_cycle_multiplier (radiation_single_level.F90:71) for the calls that follow: -1 solar minimum .. +1 maximum.
+// calc_incoming_sw (radiation_ecckd.F90:946-962) stops when it is non-zero and the model carries no solar-cycle amplitude.
+int ecrad_b200_set_solar_cycle_multiplier(void* handle, double multiplier) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(nullptr, "ecrad_b200_set_solar_cycle_multiplier: null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (multiplier != 0.0) {
+    if (!h->dcfg.ckd_sw) return fail(h, "solar cycle only available with ecCKD gas optics model");   // radiation_config.F90:1200-1203
+    if (!h->has_solar_cycle) return fail(h, "calc_incoming_sw: no information present on solar cycle (table 'ckd_sw_norm_amplitude_solar_irradiance')");
+  }
+  drain(h);
+  h->dcfg.solar_cycle_multiplier = multiplier;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

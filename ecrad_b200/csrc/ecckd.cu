@@ -277,8 +277,15 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       if (g_out) g_out[(size_t)l * SD::NG + g] = gg;
     }
   }
+  // calc_incoming_sw, radiation_ecckd.F90:935-964 (the multiplier is zero unless use_spectral_solar_cycle)
   const double* solar = tab + m.off_solar;
-  for (int g = tid; g < SD::NG; g += CKD_THREADS) w.incoming[(size_t)c * SD::NG + g] = in.solar_irradiance * __ldg(solar + g);
+  if (cfg.solar_cycle_multiplier != 0.0 && m.off_solar_amp >= 0) {
+    const double* amp = tab + m.off_solar_amp;
+    for (int g = tid; g < SD::NG; g += CKD_THREADS)
+      w.incoming[(size_t)c * SD::NG + g] = in.solar_irradiance * (__ldg(solar + g) + cfg.solar_cycle_multiplier * __ldg(amp + g));
+  } else {
+    for (int g = tid; g < SD::NG; g += CKD_THREADS) w.incoming[(size_t)c * SD::NG + g] = in.solar_irradiance * __ldg(solar + g);
+  }
 }
 
 // =========================================================================================================

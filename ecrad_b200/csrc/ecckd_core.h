@@ -30,6 +30,7 @@ struct CkdModel {
   int ng, npress, ntemp, nplanck, ngas, nlut;
   double log_pressure1, d_log_pressure, d_temperature, temperature1_planck, d_temperature_planck;
   size_t off_temperature1, off_planck, off_solar, off_rayleigh;
+  long long off_solar_amp;   // norm_amplitude_solar_irradiance (read_spectral_solar_cycle, radiation_ecckd.F90:421-431), -1 if not registered
   CkdGas gas[CKD_MAXGAS];
 };
 

@@ -77,6 +77,7 @@ struct DevCfg {
   int ckd_ngas_lw, ckd_nlut_lw, ckd_ngas_sw, ckd_nlut_sw;   // ecCKD: gases / look-up-table gases per model (shared-memory sizing)
   int ng_lw, ng_sw, nb_lw, nb_sw;   // spectral sizes: RRTMG 140/112/16/14; ecCKD ng = nb = 32/64/96
   double cloud_fraction_threshold, cloud_mixing_ratio_threshold, min_gas_od_lw, min_gas_od_sw, cloud_inhom_decorr_scaling;
+  double solar_cycle_multiplier;   // single_level%spectral_solar_cycle_multiplier (ecCKD shortwave, use_spectral_solar_cycle); 0 = mean spectrum
   SpCfg sp;                      // SPARTACUS scalars
 };
 

@@ -165,6 +165,7 @@ inline void pack_ckd_spectrum(const ecrad_b200_tables& T, PackedTables& P, int s
     if (sw) {
       m.off_solar = put(pre + "norm_solar_irradiance", (size_t)m.ng);
       m.off_rayleigh = put(pre + "rayleigh_molar_scat", (size_t)m.ng);
+      m.off_solar_amp = T.find(pre + "norm_amplitude_solar_irradiance") ? (long long)put(pre + "norm_amplitude_solar_irradiance", (size_t)m.ng) : -1;
     } else {
       m.off_planck = put(pre + "planck_function", (size_t)m.ng * m.nplanck);
     }

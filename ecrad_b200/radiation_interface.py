@@ -55,6 +55,7 @@ def load_library():
     L.ecrad_b200_radiation_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
     L.ecrad_b200_radiation_device_ld.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_void_p]
     L.ecrad_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.ecrad_b200_set_solar_cycle_multiplier.argtypes = [C.c_void_p, C.c_double]
     L.ecrad_b200_kernel_launches.restype = C.c_int64
     L.ecrad_b200_kernel_launches.argtypes = [C.c_void_p]
     L.ecrad_b200_last_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
@@ -192,6 +193,11 @@ class RadiationHandle:
         """As radiation_device with separate leading dimensions (outputs may be a column slice of peer-GPU arrays)."""
         rc = self.lib.ecrad_b200_radiation_device_ld(self.h, ncol, nlev, ld_in, ld_out, C.byref(ist), C.byref(ost), C.c_void_p(stream))
         if rc:
+            raise RadiationError(self._err())
+
+    def set_solar_cycle_multiplier(self, multiplier):
+        """single_level%spectral_solar_cycle_multiplier for the calls that follow (-1 solar minimum .. +1 maximum; ecCKD shortwave)."""
+        if self.lib.ecrad_b200_set_solar_cycle_multiplier(self.h, float(multiplier)):
             raise RadiationError(self._err())
 
     def set_option(self, key, value):

@@ -244,6 +244,13 @@ typedef struct ecrad_b200_radiative_properties {
 int ecrad_b200_save_radiative_properties(void* handle, int ncol, int nlev, int istartcol, int iendcol,
                                          const ecrad_b200_inputs* inputs, const ecrad_b200_radiative_properties* props);
 
+/* single_level%spectral_solar_cycle_multiplier (radiation_single_level.F90:71; config%use_spectral_solar_cycle, radiation_config.F90:174)
+ * for the radiation calls that follow: -1 = solar minimum, +1 = solar maximum, 0 (the default) = the mean spectrum.  ecCKD shortwave only:
+ * incoming_sw = solar_irradiance * (norm_solar_irradiance + multiplier * norm_amplitude_solar_irradiance), calc_incoming_sw
+ * radiation_ecckd.F90:935-964; the amplitude is the table 'ckd_sw_norm_amplitude_solar_irradiance' (read_spectral_solar_cycle, :295-451).
+ * A non-zero multiplier without that table, or with RRTMG-IFS in the shortwave, is an error like in the reference. */
+int ecrad_b200_set_solar_cycle_multiplier(void* handle, double multiplier);
+
 /* Tuning/diagnostic options.  Returns 0 on success.
  *   "serial"            0/1: run a tile's kernels on one stream instead of the three overlapping chains (per-kernel timing)
  *   "tile_cols", "tile_cols_device"   columns per internal tile of the host / device entry

@@ -129,7 +129,11 @@ void orc_ecckd_gas_optics_column(const orc_tables* t, const ecrad_b200_config* c
       od_sw[i] = od_sw[i] + ssa_sw[i];
       ssa_sw[i] = ssa_sw[i] / od_sw[i];
     }
-    for (int g = 0; g < ng; ++g) incoming_sw[g] = in->solar_irradiance * m->norm_solar_irradiance[g];
+    if (t->solar_cycle_multiplier != 0.0 && m->norm_amplitude_solar_irradiance)   /* calc_incoming_sw, radiation_ecckd.F90:950-954 */
+      for (int g = 0; g < ng; ++g)
+        incoming_sw[g] = in->solar_irradiance * (m->norm_solar_irradiance[g] + t->solar_cycle_multiplier * m->norm_amplitude_solar_irradiance[g]);
+    else
+      for (int g = 0; g < ng; ++g) incoming_sw[g] = in->solar_irradiance * m->norm_solar_irradiance[g];
   }
   if (cfg->do_lw && cfg->i_gas_model_lw == ECRAD_GAS_ECCKD) {
     const orc_ckd_model* m = &t->ckd_lw;

@@ -31,6 +31,7 @@ typedef struct {
   int ng, npress, ntemp, nplanck, ngas, is_sw;
   double log_pressure1, d_log_pressure, d_temperature, temperature1_planck, d_temperature_planck;
   const double *temperature1, *planck_function /*(ng, nplanck)*/, *norm_solar_irradiance, *rayleigh_molar_scat;
+  const double* norm_amplitude_solar_irradiance;   /* read_spectral_solar_cycle, radiation_ecckd.F90:421-431; NULL if not in the directory */
   orc_ckd_gas gas[16];
 } orc_ckd_model;
 /* generalised cloud optics of one cloud type (radiation_general_cloud_optics_data.F90:33-62) */
@@ -67,6 +68,7 @@ typedef struct orc_tables {
   /* 0-based band of each g-point: RRTMG ngb-1 / ngb-16; ecCKD with per-g-point cloud/aerosol optics: identity */
   int32_t band_lw[256], band_sw[256];
   /* ecCKD gas optics + generalised cloud optics (blob of tools/extract_ecckd_tables.py) */
+  double solar_cycle_multiplier;        /* single_level%spectral_solar_cycle_multiplier (orc_set_solar_cycle_multiplier), default 0 */
   int is_ecckd, is_ecckd_lw, is_ecckd_sw;   /* both spectra / this spectrum (mixed gas models: one of the two) */
   orc_ckd_model ckd_lw, ckd_sw;
   orc_gco gco_lw[2], gco_sw[2];         /* cloud types: 0 liquid (mie_droplet), 1 ice (baum-general-habit-mixture) */
@@ -76,6 +78,7 @@ orc_tables* orc_tables_load(const char* path);
 int  orc_tables_add(orc_tables* t, const char* name, int dtype, int ndim, const int64_t* dims, const void* data);
 int  orc_tables_resolve(orc_tables* t);
 void orc_tables_free(orc_tables* t);
+int  orc_set_solar_cycle_multiplier(orc_tables* t, double multiplier);   /* non-zero needs an ecCKD shortwave model with the amplitude table */
 const orc_array* orc_find(const orc_tables* t, const char* name);
 
 /* ---- per-column gas-optics state (RRTMG layer order: 1 = bottom) ---- */

@@ -50,6 +50,8 @@ static void resolve_ckd_model(orc_tables* t, const char* pre, orc_ckd_model* m, 
   if (m->is_sw) {
     snprintf(nm, sizeof nm, "%snorm_solar_irradiance", pre); m->norm_solar_irradiance = Dreq(t, nm, err);
     snprintf(nm, sizeof nm, "%srayleigh_molar_scat", pre); m->rayleigh_molar_scat = Dreq(t, nm, err);
+    snprintf(nm, sizeof nm, "%snorm_amplitude_solar_irradiance", pre);
+    { const orc_array* a = orc_find(t, nm); m->norm_amplitude_solar_irradiance = a ? (const double*)a->data : NULL; }
   } else {
     snprintf(nm, sizeof nm, "%splanck_function", pre); m->planck_function = Dreq(t, nm, err);
   }
@@ -78,6 +80,13 @@ static void resolve_gco(orc_tables* t, int required, int* err) {
       snprintf(nm, sizeof nm, "gco_%s_%d_ssa", sw ? "sw" : "lw", jt); c->ssa = Dreq(t, nm, err);
       snprintf(nm, sizeof nm, "gco_%s_%d_asymmetry", sw ? "sw" : "lw", jt); c->asymmetry = Dreq(t, nm, err);
     }
+}
+
+/* calc_incoming_sw, radiation_ecckd.F90:946-962: a non-zero multiplier needs the solar-cycle amplitude */
+int orc_set_solar_cycle_multiplier(orc_tables* t, double multiplier) {
+  if (multiplier != 0.0 && !(t->is_ecckd_sw && t->ckd_sw.norm_amplitude_solar_irradiance)) return 1;
+  t->solar_cycle_multiplier = multiplier;
+  return 0;
 }
 
 int orc_tables_resolve(orc_tables* t) {

@@ -46,6 +46,7 @@ class Oracle:
         L.orc_tables_add.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p]
         L.orc_tables_resolve.argtypes = [C.c_void_p]
         L.orc_tables_free.argtypes = [C.c_void_p]
+        L.orc_set_solar_cycle_multiplier.argtypes = [C.c_void_p, C.c_double]
         L.orc_radiation.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(abi.Inputs), C.POINTER(abi.Outputs), C.c_int]
         L.orc_radiative_properties.argtypes = [C.c_void_p, C.POINTER(abi.Config), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -70,6 +71,10 @@ class Oracle:
             L.orc_tables_add(self.t, nm.encode(), code, a.ndim, dims, a.ctypes.data_as(C.c_void_p))
         if L.orc_tables_resolve(self.t):
             raise RuntimeError("oracle: table blob incomplete")
+
+    def set_solar_cycle_multiplier(self, multiplier):
+        if self.lib.orc_set_solar_cycle_multiplier(self.t, float(multiplier)):
+            raise RuntimeError("oracle: no information present on solar cycle")
 
     def radiative_properties(self, inputs, ncol, nlev, istartcol=1, iendcol=None):
         """What radiation() hands to save_radiative_properties (radiation_interface.F90:405-425); cloud_fraction of `inputs` is cropped."""

@@ -216,6 +216,46 @@ def test_mixed_gas_models_vs_oracle(handles, meridian_raw, kw, ckd_spectrum):
         assert np.abs(out[nm][m] - ck[nm][m]).max() < TOL, nm   # (SPARTACUS amplifies the conversion's rounding to 2e-7)
 
 
+@pytest.mark.parametrize("kw", [dict(gas_model_name="ECCKD"), dict(sw_gas_model_name="ECCKD", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", use_aerosols=True),
+                                dict(gas_model_name="ECCKD", ecckd_tables="ecckd_tables_lw32_sw96.bin", sw_solver_name="Cloudless", lw_solver_name="Cloudless")])
+def test_spectral_solar_cycle(meridian_raw, kw):
+    """single_level%spectral_solar_cycle_multiplier (use_spectral_solar_cycle; calc_incoming_sw, radiation_ecckd.F90:935-964)."""
+    from ecrad_b200.radiation_interface import RadiationError, setup_radiation
+    from ecrad_b200.tables import read_blob
+    from oracle_lib import Oracle
+
+    n = 200
+    cfg = RadiationConfig(do_nearest_spectral_lw_emiss=False, **kw).consolidate()
+    raw = I.synthetic_columns(meridian_raw, n)
+    h, orc = setup_radiation(cfg), Oracle(cfg)
+    try:
+        base = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+        for mult in (1.0, -0.37):
+            h.set_solar_cycle_multiplier(mult); orc.set_solar_cycle_multiplier(mult)
+            out = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+            ref = orc.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+            compare(out, ref, FLUXES + OTHERS)
+            assert np.abs(out["sw_dn"] - base["sw_dn"]).max() > 1e-4
+            inc = h.radiative_properties(I.to_radiation_inputs(raw, cfg), n, NLEV)["incoming_sw"]
+            assert np.abs(inc.sum(axis=0) - float(raw["solar_irradiance"])).max() < 1e-9
+        h.set_solar_cycle_multiplier(0.0)
+        again = h.radiation(I.to_radiation_inputs(raw, cfg), n, NLEV)
+        assert np.array_equal(again["sw_dn"], base["sw_dn"]) and np.array_equal(again["sw_up"], base["sw_up"])
+    finally:
+        h.finalize()
+    # no solar-cycle information: RRTMG-IFS in the shortwave, or an ecCKD model registered without the amplitude
+    hr = setup_radiation(RadiationConfig().consolidate())
+    with pytest.raises(RadiationError, match="solar cycle only available with ecCKD"):
+        hr.set_solar_cycle_multiplier(1.0)
+    hr.set_solar_cycle_multiplier(0.0)
+    hr.finalize()
+    arrays = {k: v for k, v in read_blob(cfg.tables_path()).items() if k != "ckd_sw_norm_amplitude_solar_irradiance"}
+    hn = setup_radiation(cfg, tables_arrays=arrays)
+    with pytest.raises(RadiationError, match="no information present on solar cycle"):
+        hn.set_solar_cycle_multiplier(-1.0)
+    hn.finalize()
+
+
 def test_column_range_and_untouched_columns(handles, meridian_raw):
     """istartcol/iendcol semantics of radiation(): only that range is written (1-based inclusive)."""
     h, orc, _ = handles()

@@ -148,3 +148,33 @@ def test_radiative_properties(meridian_raw):
     q = Oracle(sp).radiative_properties(I.to_radiation_inputs(meridian_raw, sp), 32, NLEV, istartcol=3, iendcol=30)
     assert np.array_equal(q["od_lw"][..., 2:30], p["od_lw"][perm][..., 2:30])
     assert np.array_equal(q["od_lw_cloud"][..., 2:30], p["od_lw_cloud"][..., 2:30])
+
+
+def test_spectral_solar_cycle(meridian_raw):
+    """use_spectral_solar_cycle (radiation_config.F90:174, read_spectral_solar_cycle radiation_ecckd.F90:295-451, calc_incoming_sw :935-964):
+    the multiplier redistributes the incoming flux among the g-points (more ultraviolet at solar maximum) without changing its sum."""
+    cfg = RadiationConfig(gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False).consolidate()
+    o = Oracle(cfg)
+    base = o.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+    p0 = o.radiative_properties(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)["incoming_sw"]
+    o.set_solar_cycle_multiplier(1.0)
+    smax = o.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+    p1 = o.radiative_properties(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)["incoming_sw"]
+    o.set_solar_cycle_multiplier(-1.0)
+    pm = o.radiative_properties(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)["incoming_sw"]
+    o.set_solar_cycle_multiplier(0.0)
+    again = o.radiation(I.to_radiation_inputs(meridian_raw, cfg), 32, NLEV)
+    assert np.array_equal(again["sw_dn"], base["sw_dn"])
+    tsi = float(meridian_raw["solar_irradiance"])
+    assert np.abs(p1.sum(axis=0) - tsi).max() < 1e-9 and np.abs(pm.sum(axis=0) - tsi).max() < 1e-9
+    rel = p1[:, 0] / p0[:, 0] - 1.0
+    assert 0.002 < rel.max() < 0.05 and -0.001 < rel.min() < 0.0      # a few 0.1 % more in the ultraviolet terms, slightly less elsewhere
+    assert np.allclose(p1 + pm, 2.0 * p0, rtol=0, atol=1e-12)         # linear in the multiplier
+    sun = meridian_raw["cos_solar_zenith_angle"] > 0.0
+    assert np.abs(smax["sw_dn"][sun, 0] - base["sw_dn"][sun, 0]).max() < 1e-9     # the same flux enters ...
+    d = np.abs(smax["sw_dn"][sun, -1] - base["sw_dn"][sun, -1])
+    assert 0.0 < d.max() < 1.0                                                     # ... a little less of it reaches the surface
+    assert np.array_equal(smax["lw_up"], base["lw_up"])
+    # RRTMG-IFS has no solar-cycle information (radiation_config.F90:1200-1203)
+    with pytest.raises(RuntimeError):
+        Oracle(RadiationConfig().consolidate()).set_solar_cycle_multiplier(0.5)

@@ -158,12 +158,37 @@ def aerosol_tables(path, sd_sw, sd_lw):
     return out
 
 
+def solar_cycle_amplitude(path, sd, norm_solar_irradiance):
+    """read_spectral_solar_cycle (radiation_ecckd.F90:295-451, use_updated_solar_spectrum = false): the solar-cycle amplitude of the
+    spectral solar irradiance (data/ssi_nrl2.nc) interpolated to the model's wavenumber grid, mapped to the g-points, and shifted so that
+    it does not change the total (the caller scales by the total solar irradiance).  calc_incoming_sw (:935-964) then gives
+    incoming = TSI * (norm_solar_irradiance + spectral_solar_cycle_multiplier * norm_amplitude_solar_irradiance)."""
+    with netcdf_file(path, mmap=False) as f:
+        wavenumber = f64(f.variables["wavenumber"])
+        ssi = f64(f.variables["mean_solar_spectral_irradiance"])
+        ssi_amplitude = f64(f.variables["ssi_solar_cycle_amplitude"])
+    grid = 0.5 * (sd.wavenumber1 + sd.wavenumber2)
+    dwav = sd.wavenumber2[0] - sd.wavenumber1[0]
+    ssi_grid, amp_grid = np.zeros(sd.nwav), np.zeros(sd.nwav)
+    for j, wn in enumerate(grid):   # linear interpolation, first bracketing pair (:379-393)
+        k = np.nonzero((wavenumber[:-1] < wn) & (wavenumber[1:] >= wn))[0]
+        if len(k):
+            k = k[0]
+            dw = wavenumber[k + 1] - wavenumber[k]
+            ssi_grid[j] = (ssi[k] * (wavenumber[k + 1] - wn) + ssi[k + 1] * (wn - wavenumber[k])) * dwav / dw
+            amp_grid[j] = (ssi_amplitude[k] * (wavenumber[k + 1] - wn) + ssi_amplitude[k + 1] * (wn - wavenumber[k])) * dwav / dw
+    amp = norm_solar_irradiance * (amp_grid @ sd.gpoint_fraction) / (ssi_grid @ sd.gpoint_fraction)   # :421-424
+    return (norm_solar_irradiance + amp) / (norm_solar_irradiance + amp).sum() - norm_solar_irradiance   # :428-431
+
+
 def build(ref, lw_file, sw_file):
     d = os.path.join(ref, "data")
     tabs = {}
     lw, sd_lw = read_ckd_model(os.path.join(d, lw_file), "ckd_lw_")
     sw, sd_sw = read_ckd_model(os.path.join(d, sw_file), "ckd_sw_")
     tabs.update(lw); tabs.update(sw)
+    # use_spectral_solar_cycle (radiation_ecckd_interface.F90:79-82): ssi_nrl2.nc, radiation_config.F90:1200-1203
+    tabs["ckd_sw_norm_amplitude_solar_irradiance"] = solar_cycle_amplitude(os.path.join(d, "ssi_nrl2.nc"), sd_sw, tabs["ckd_sw_norm_solar_irradiance"])
     # cloud types 1 (liquid) and 2 (ice): radiation_general_cloud_optics.F90:62-71, thick averaging (radiation_config.F90:352)
     for jt, nm in enumerate(("mie_droplet", "baum-general-habit-mixture_ice")):
         for spec, sd in (("sw", sd_sw), ("lw", sd_lw)):

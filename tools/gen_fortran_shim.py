@@ -248,6 +248,9 @@ def main():
     w("      import; type(c_ptr), value :: h; integer(c_int), value :: ncol, nlev, istartcol, iendcol")
     w("      type(in_t) :: inp; type(props_t) :: props; integer(c_int) :: rc")
     w("    end function")
+    w("    function ecrad_b200_set_solar_cycle_multiplier(h, multiplier) bind(c) result(rc)")
+    w("      import; type(c_ptr), value :: h; real(c_double), value :: multiplier; integer(c_int) :: rc")
+    w("    end function")
     w("    function ecrad_b200_set_option(h, key, val) bind(c) result(rc)")
     w("      import; type(c_ptr), value :: h; character(kind=c_char) :: key(*); integer(c_int), value :: val; integer(c_int) :: rc")
     w("    end function")
@@ -343,6 +346,8 @@ def main():
     w("    call add_r1(t, pre//'temperature1', go%temperature1)")
     w("    if (is_sw) then")
     w("      call add_r1(t, pre//'norm_solar_irradiance', go%norm_solar_irradiance); call add_r1(t, pre//'rayleigh_molar_scat', go%rayleigh_molar_scat)")
+    w("      ! read_spectral_solar_cycle ran (config%use_spectral_solar_cycle, radiation_ecckd_interface.F90:79-82)")
+    w("      if (allocated(go%norm_amplitude_solar_irradiance)) call add_r1(t, pre//'norm_amplitude_solar_irradiance', go%norm_amplitude_solar_irradiance)")
     w("    else")
     w("      call add_r2(t, pre//'planck_function', go%planck_function)       ! (ng, nplanck)")
     w("    end if")
@@ -452,6 +457,10 @@ def main():
             continue
         k += 1
         w(f"    if (allocated(flux%{f})) o%p({k}) = c_loc(flux%{f})")
+    w("    if (config%use_spectral_solar_cycle) then   ! calc_incoming_sw with the multiplier, radiation_ecckd_interface.F90:284-290")
+    w("      if (ecrad_b200_set_solar_cycle_multiplier(handle, real(single_level%spectral_solar_cycle_multiplier, c_double)) /= 0) &")
+    w("           &  call abort_with(ecrad_b200_last_error(handle))")
+    w("    end if")
     w("#ifdef PARKIND1_SINGLE")
     w("    if (ecrad_b200_radiation_sp(handle, int(ncol, c_int), int(nlev, c_int), int(istartcol, c_int), int(iendcol, c_int), i, o) /= 0) &")
     w("         &  call abort_with(ecrad_b200_last_error(handle))")
