@@ -110,12 +110,15 @@ __device__ __forceinline__ double ckd_optical_depth(const CkdModel& m, const dou
 }
 
 // aerosol state of one layer: humidity bin and (layer mass) x (mixing ratio) of every type (add_aerosol_optics :623-700)
-struct AerLayers { int* irh; double* fm; int ntype; };   // [nlev], [nlev][ntype]
-__host__ __device__ inline size_t aer_layers_bytes(int nlev, int ntype) { return (size_t)nlev * (sizeof(int) + ntype * sizeof(double)) + 16; }
+// `row`: table row of each type in this layer (bit 15: hydrophilic table), resolved once per layer so that the per-g-point merge is a
+// branch-free chain of independent loads; ignored types get mass 0 and row 0 (adds exact zeros).
+struct AerLayers { int* irh; double* fm; unsigned short* row; int ntype; };   // [nlev], [nlev][ntype], [nlev][ntype]
+__host__ __device__ inline size_t aer_layers_bytes(int nlev, int ntype) { return (size_t)nlev * (sizeof(int) + ntype * (sizeof(double) + sizeof(unsigned short))) + 16; }
 __device__ __forceinline__ void aer_layers_carve(unsigned char* base, int nlev, int ntype, AerLayers& a) {
   a.ntype = ntype;
   a.fm = reinterpret_cast<double*>(base);
   a.irh = reinterpret_cast<int*>(a.fm + (size_t)nlev * ntype);
+  a.row = reinterpret_cast<unsigned short*>(a.irh + nlev);
 }
 __device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& in, int c, int l, int nlev, const AerLayers& a, bool gas_mmr) {
   // gas%mixing_ratio(:,:,IH2O) is a mole fraction under ecCKD: gas%get(IH2O, IMassMixingRatio) (:611, radiation_gas.F90:603-616)
@@ -126,7 +129,12 @@ __device__ __forceinline__ void aer_layer_state(const AerMeta& A, const DevIn& i
   else { irh = 1; while (rh > A.rh_lower[irh]) ++irh; }
   a.irh[l] = irh;
   const double factor = (LD_IN(in.p_hl, c, l + 1) - LD_IN(in.p_hl, c, l)) * (1.0 / 9.80665);
-  for (int jt = 0; jt < A.ntype; ++jt) a.fm[(size_t)l * A.ntype + jt] = factor * in.aerosol_mmr[((size_t)jt * nlev + l) * in.ld + c];
+  for (int jt = 0; jt < A.ntype; ++jt) {
+    const int iclass = A.iclass[jt];
+    a.fm[(size_t)l * A.ntype + jt] = iclass ? factor * in.aerosol_mmr[((size_t)jt * nlev + l) * in.ld + c] : 0.0;
+    a.row[(size_t)l * A.ntype + jt] = iclass == 2 ? (unsigned short)(0x8000u | (unsigned)((A.itype[jt] - 1) * A.nrh + (irh - 1)))
+                                    : iclass == 1 ? (unsigned short)(A.itype[jt] - 1) : (unsigned short)0;
+  }
 }
 
 // =========================================================================================================
@@ -169,21 +177,24 @@ ckd_lw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   };
   double* od_out = w.od_lw + (size_t)c * nlev * SD::NG;
   double* pl_out = w.planck + (size_t)c * (nlev + 1) * SD::NG;
+  const int me_pb = do_aer ? T.aer->me_lw_phobic : 0, me_pl = do_aer ? T.aer->me_lw_philic : 0;
+  const int ss_pb = do_aer ? T.aer->ssa_lw_phobic : 0, ss_pl = do_aer ? T.aer->ssa_lw_philic : 0;
   for (int l = warp; l <= nlev; l += CKD_WARPS) {
     for (int g = lane; g < SD::NG; g += 32) {
       pl_out[(size_t)l * SD::NG + g] = planck(l, g);
       if (l < nlev) {
         double od = ckd_optical_depth(m, tab, lay, l, g);
         if (do_aer) {   // absorption optical depth of the aerosol mixture in this g-point (:700-722, no LW aerosol scattering)
-          const AerMeta& A = *T.aer;
           double od_aer = 0.0;
-          for (int jt = 0; jt < A.ntype; ++jt) {
-            const int iclass = A.iclass[jt];
-            if (iclass == 0) continue;
-            const int row = iclass == 1 ? (A.itype[jt] - 1) : ((A.itype[jt] - 1) * A.nrh + (aer.irh[l] - 1));
-            const double me = __ldg(T.aertab + (iclass == 1 ? A.me_lw_phobic : A.me_lw_philic) + (size_t)row * SD::NB + g);
-            const double ss = __ldg(T.aertab + (iclass == 1 ? A.ssa_lw_phobic : A.ssa_lw_philic) + (size_t)row * SD::NB + g);
-            od_aer = od_aer + aer.fm[(size_t)l * A.ntype + jt] * me * (1.0 - ss);
+          const double* fm = aer.fm + (size_t)l * aer.ntype;
+          const unsigned short* rw = aer.row + (size_t)l * aer.ntype;
+#pragma unroll 4
+          for (int jt = 0; jt < aer.ntype; ++jt) {
+            const unsigned r = rw[jt];
+            const size_t off = (size_t)(r & 0x7FFFu) * SD::NB + g;
+            const double me = __ldg(T.aertab + ((r & 0x8000u) ? me_pl : me_pb) + off);
+            const double ss = __ldg(T.aertab + ((r & 0x8000u) ? ss_pl : ss_pb) + off);
+            od_aer = od_aer + fm[jt] * me * (1.0 - ss);
           }
           od = od + od_aer;
         }
@@ -234,6 +245,9 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
   double* ssa_out = w.ssa_sw + (size_t)c * n;
   double* g_out = w.g_sw ? w.g_sw + (size_t)c * n : nullptr;
   const double* rayl = tab + m.off_rayleigh;
+  const int me_pb = do_aer ? T.aer->me_sw_phobic : 0, me_pl = do_aer ? T.aer->me_sw_philic : 0;
+  const int ss_pb = do_aer ? T.aer->ssa_sw_phobic : 0, ss_pl = do_aer ? T.aer->ssa_sw_philic : 0;
+  const int ga_pb = do_aer ? T.aer->g_sw_phobic : 0, ga_pl = do_aer ? T.aer->g_sw_philic : 0;
   for (int l = warp; l < nlev; l += CKD_WARPS) {
     for (int g = lane; g < SD::NG; g += 32) {
       double od = ckd_optical_depth(m, tab, lay, l, g);
@@ -242,16 +256,18 @@ ckd_sw_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev) {
       double ssa = rayleigh / od;
       double gg = 0.0;
       if (do_aer) {
-        const AerMeta& A = *T.aer;
         double od_aer = 0.0, scat = 0.0, scat_g = 0.0;
-        for (int jt = 0; jt < A.ntype; ++jt) {
-          const int iclass = A.iclass[jt];
-          if (iclass == 0) continue;
-          const size_t row = iclass == 1 ? (size_t)(A.itype[jt] - 1) : (size_t)((A.itype[jt] - 1) * A.nrh + (aer.irh[l] - 1));
-          const double me = __ldg(T.aertab + (iclass == 1 ? A.me_sw_phobic : A.me_sw_philic) + row * SD::NB + g);
-          const double ss = __ldg(T.aertab + (iclass == 1 ? A.ssa_sw_phobic : A.ssa_sw_philic) + row * SD::NB + g);
-          const double ga = __ldg(T.aertab + (iclass == 1 ? A.g_sw_phobic : A.g_sw_philic) + row * SD::NB + g);
-          const double local_od = aer.fm[(size_t)l * A.ntype + jt] * me;
+        const double* fm = aer.fm + (size_t)l * aer.ntype;
+        const unsigned short* rw = aer.row + (size_t)l * aer.ntype;
+#pragma unroll 4
+        for (int jt = 0; jt < aer.ntype; ++jt) {
+          const unsigned r = rw[jt];
+          const bool pl = (r & 0x8000u) != 0;
+          const size_t off = (size_t)(r & 0x7FFFu) * SD::NB + g;
+          const double me = __ldg(T.aertab + (pl ? me_pl : me_pb) + off);
+          const double ss = __ldg(T.aertab + (pl ? ss_pl : ss_pb) + off);
+          const double ga = __ldg(T.aertab + (pl ? ga_pl : ga_pb) + off);
+          const double local_od = fm[jt] * me;
           od_aer = od_aer + local_od;
           scat = scat + local_od * ss;
           scat_g = scat_g + local_od * ss * ga;
