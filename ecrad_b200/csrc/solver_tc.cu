@@ -305,6 +305,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
   const double fd_ict = ict < nlev ? carry[gg] : fd_surf_clear;   // clear-sky flux_dn at the cloud-top half-level
   double* s_up_c = sums, *s_up = sums + nl1, *s_dn = sums + 2 * nl1, *s_dv = sums + 3 * nl1;
 
+  const bool keep_trans = cfg.do_lw_derivatives && out.lw_derivatives;
   // ---- upward sweep (radiation_tripleclouds_lw.F90:215-420) ----
   double ta[3] = {albedo, albedo, albedo}, ts[3];
 #pragma unroll
@@ -373,6 +374,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           if (l == ict) fu = ts[0] + ta[0] * fd_ict;   // flux_up(:,1) at cloud top
         } else {
           fu = Lc.trans * fu + Lc.source_up;            // above cloud top
+          if (keep_trans) SCR(0, 4, i) = Lc.trans;       // (the LW derivatives multiply by it again)
         }
         pb = pt;
         tile[slot * SD::RS + g] = fuc; tile[(TC_LCH_LW + slot) * SD::RS + g] = l <= ict ? fu : 0.0;
@@ -444,8 +446,8 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     double d[3] = {fus / red[0], 0.0, 0.0};
     double* dst[1] = {s_dv};
     int slot = 0, lfirst = nlev - 1;
-    // (the transmittance of region 1 -- stored below cloud top, exp(-D od) above -- does not depend on d: next layer's value first)
-    auto trans1 = [&](int l) { const size_t i = (size_t)l * SD::NG + g; return l >= ict ? SCR(0, 4, i) : exp(-ECB_LW_DIFFUSIVITY * od[i]); };
+    // (the transmittance of region 1 does not depend on d: next layer's value first)
+    auto trans1 = [&](int l) { return SCR(0, 4, (size_t)l * SD::NG + g); };   // (exp(-D od) of the clear-sky region, kept by the upward sweep)
     double t1n = act ? trans1(nlev - 1) : 0.0;
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
@@ -453,7 +455,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
         const size_t i = (size_t)l * SD::NG + g;
         const double t1 = t1n;
         if (l > 0) t1n = trans1(l - 1);
-        mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1)
+        if (jl >= ict) mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1); the identity between two layers above cloud top (1*d + 0 + 0 is exact)
         if (l >= ict) { d[0] = d[0] * t1; d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
         else d[0] = d[0] * t1;   // regions 2,3: transmittance = 1 above cloud top
         tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
