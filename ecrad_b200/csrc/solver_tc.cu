@@ -334,7 +334,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
           double below[3] = {0.0, 0.0, 0.0}, sbelow[3] = {0.0, 0.0, 0.0};
 #pragma unroll
           for (int jr = 0; jr < 3; ++jr) {
-            if (jr > 0 && !cloudy_layer) { SCR(jr, 4, i) = 1.0; continue; }
+            if (jr > 0 && !cloudy_layer) continue;   // (nothing reads the slots of regions 2 and 3 in a clear layer)
             LwLayer L = Lc;
             if (jr > 0) {   // radiation_tripleclouds_lw.F90:247-300
               const double* clb = cl + (size_t)l * 3 * SD::NB;
@@ -446,18 +446,23 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     double d[3] = {fus / red[0], 0.0, 0.0};
     double* dst[1] = {s_dv};
     int slot = 0, lfirst = nlev - 1;
-    // (the transmittance of region 1 does not depend on d: next layer's value first)
-    auto trans1 = [&](int l) { return SCR(0, 4, (size_t)l * SD::NG + g); };   // (exp(-D od) of the clear-sky region, kept by the upward sweep)
-    double t1n = act ? trans1(nlev - 1) : 0.0;
+    // Transmittances of the three regions in layer l: exp(-D od) of the clear-sky region kept by the upward sweep; regions 2 and 3 exist
+    // in cloudy layers only and transmit everything elsewhere (x * 1.0 is exact).  They do not depend on d: next layer's values first.
+    auto trans = [&](int l, double* t) {
+      const size_t i = (size_t)l * SD::NG + g;
+      t[0] = SCR(0, 4, i);
+      const bool cloudy = l >= ict && !S.clear[l + 1];
+      t[1] = cloudy ? SCR(1, 4, i) : 1.0; t[2] = cloudy ? SCR(2, 4, i) : 1.0;
+    };
+    double tn[3] = {0.0, 1.0, 1.0};
+    if (act) trans(nlev - 1, tn);
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
-        const size_t i = (size_t)l * SD::NG + g;
-        const double t1 = t1n;
-        if (l > 0) t1n = trans1(l - 1);
+        const double t[3] = {tn[0], tn[1], tn[2]};
+        if (l > 0) trans(l - 1, tn);
         if (jl >= ict) mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1); the identity between two layers above cloud top (1*d + 0 + 0 is exact)
-        if (l >= ict) { d[0] = d[0] * t1; d[1] = d[1] * SCR(1, 4, i); d[2] = d[2] * SCR(2, 4, i); }
-        else d[0] = d[0] * t1;   // regions 2,3: transmittance = 1 above cloud top
+        d[0] = d[0] * t[0]; d[1] = d[1] * t[1]; d[2] = d[2] * t[2];
         tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
       }
       ++slot;
