@@ -321,12 +321,19 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
     ++slot;
     double pb = act ? pl[(size_t)nlev * SD::NG + g] : 0.0;
     double od_n = act ? od[(size_t)(nlev - 1) * SD::NG + g] : 0.0, pt_n = act ? pl[(size_t)(nlev - 1) * SD::NG + g] : 0.0;   // software pipeline
+    // (the band's cloud properties of the next layer up are requested with them when that layer is cloudy)
+    double cl_n[3] = {0.0, 0.0, 0.0};
+    if (act && !S.clear[nlev]) { const double* q = cl + (size_t)(nlev - 1) * 3 * SD::NB; cl_n[0] = q[b]; cl_n[1] = q[SD::NB + b]; cl_n[2] = q[2 * SD::NB + b]; }
     for (int l = nlev - 1; l >= 0; --l) {
       const int jl = l + 1;
       if (act) {
         const size_t i = (size_t)l * SD::NG + g;
         const double odg = od_n, pt = pt_n;
-        if (l > 0) { od_n = od[i - SD::NG]; pt_n = pl[i - SD::NG]; }
+        const double clb0 = cl_n[0], clb1 = cl_n[1], clb2 = cl_n[2];
+        if (l > 0) {
+          od_n = od[i - SD::NG]; pt_n = pl[i - SD::NG];
+          if (l - 1 >= ict && !S.clear[jl - 1]) { const double* q = cl + (size_t)(l - 1) * 3 * SD::NB; cl_n[0] = q[b]; cl_n[1] = q[SD::NB + b]; cl_n[2] = q[2 * SD::NB + b]; }
+        }
         const LwLayer Lc = lw_no_scat(odg, pt, pb);
         fuc = Lc.trans * fuc + Lc.source_up;
         if (l >= ict) {
@@ -337,13 +344,12 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
             if (jr > 0 && !cloudy_layer) continue;   // (nothing reads the slots of regions 2 and 3 in a clear layer)
             LwLayer L = Lc;
             if (jr > 0) {   // radiation_tripleclouds_lw.F90:247-300
-              const double* clb = cl + (size_t)l * 3 * SD::NB;
-              const double od_cloud_new = clb[b] * S.ods[l * 3 + jr];
+              const double od_cloud_new = clb0 * S.ods[l * 3 + jr];
               const double od_total = odg + od_cloud_new;
               if (cfg.do_lw_cloud_scattering) {
                 double ssa_total = 0.0, g_total = 0.0;
-                if (od_total > 0.0) ssa_total = clb[SD::NB + b] * od_cloud_new / od_total;
-                if (ssa_total > 0.0 && od_total > 0.0) g_total = clb[2 * SD::NB + b] * clb[SD::NB + b] * od_cloud_new / (ssa_total * od_total);
+                if (od_total > 0.0) ssa_total = clb1 * od_cloud_new / od_total;
+                if (ssa_total > 0.0 && od_total > 0.0) g_total = clb2 * clb1 * od_cloud_new / (ssa_total * od_total);
                 L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
               } else {
                 L = lw_no_scat(od_total, pt, pb);
