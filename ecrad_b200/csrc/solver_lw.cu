@@ -122,6 +122,8 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
   if (s.act) { tile[g] = fu; tile[LW_LCH_UP * SD::RS + g] = prod; tile[2 * LW_LCH_UP * SD::RS + g] = 0.0; }
   ++slot;
   uint4 cq = make_uint4(0, 0, 0, 0);
+  double cl_n[3] = {0.0, 0.0, 0.0};
+  if (s.act && cloudy && fracs[nlev - 1] >= s.thr) { const double* q = cl + (size_t)(nlev - 1) * 3 * SD::NB; cl_n[0] = q[b]; cl_n[1] = q[SD::NB + b]; cl_n[2] = q[2 * SD::NB + b]; }
   double pb = s.act ? s.pl[(size_t)nlev * SD::NG + g] : 0.0;
   // optical depth and Planck function (top of layer) come through a ring of shared-memory stages filled by the TMA unit
   // (bulk_pipe.cuh), LW_UP_NL layers per stage from the surface upwards, requested two stages ahead
@@ -148,20 +150,22 @@ lw_up_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev, in
         if (l >= ict) {
           if (l == nlev - 1 || (l & 3) == 3) cq = __ldg(codep + (l >> 2));
           double a_, b_, t_;
+          // the band's cloud properties: this layer's were requested one layer ago, the next layer's are requested now
+          const double clb0 = cl_n[0], clb1 = cl_n[1], clb2 = cl_n[2];
+          if (l > ict && fracs[l - 1] >= s.thr) { const double* q = cl + (size_t)(l - 1) * 3 * SD::NB; cl_n[0] = q[b]; cl_n[1] = q[SD::NB + b]; cl_n[2] = q[2 * SD::NB + b]; }
           if (fracs[l] >= s.thr) {
             // radiation_mcica_lw.F90:248-294: gas + scaled cloud
             const double scal = od_scaling_from_code(C, T.pdf_val, pick4(cq, l & 3), fsds[l]);
-            const double* clb = cl + (size_t)l * 3 * SD::NB;
-            const double od_cloud_new = scal * clb[b];
+            const double od_cloud_new = scal * clb0;
             const double od_total = odg + od_cloud_new;
             LwLayer L;
             if (cfg.do_lw_cloud_scattering) {
               double ssa_total = 0.0, g_total = 0.0;
               if (od_total > 0.0) {
-                const double ssac = clb[SD::NB + b];
+                const double ssac = clb1;
                 const double scat_od = ssac * od_cloud_new;
                 ssa_total = scat_od / od_total;
-                if (scat_od > 0.0) g_total = clb[2 * SD::NB + b] * ssac * od_cloud_new / scat_od;
+                if (scat_od > 0.0) g_total = clb2 * ssac * od_cloud_new / scat_od;
               }
               L = lw_ref_trans(od_total, ssa_total, g_total, pt, pb);
             } else {
