@@ -187,7 +187,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
   if (!ckd_sw && (c.n_g_sw != NG_SW || c.n_bands_sw != NB_SW)) return fail(h, "unexpected RRTMG spectral dimensions");
   if ((ckd_lw && (!ok(c.n_g_lw) || c.n_bands_lw != c.n_g_lw)) || (ckd_sw && (!ok(c.n_g_sw) || c.n_bands_sw != c.n_g_sw)))
     return fail(h, "ECCKD: models with 32, 64 or 96 g-points and cloud/aerosol optics per g-point (n_bands == n_g) are built in");
-  if (ckd_sw && c.do_sw_delta_scaling_with_gases) return fail(h, "do_sw_delta_scaling_with_gases is not available with ECCKD in this build");
   // radiation_cloud_optics.F90:66-79 would abort: the band parameterisations have 16 + 14 RRTMG bands
   if ((ckd_lw || ckd_sw) && !c.use_general_cloud_optics) return fail(h, "ECCKD needs use_general_cloud_optics (the band parameterisations are defined on the RRTMG bands)");
   return 0;

@@ -346,7 +346,12 @@ def test_ecckd_mcica_vs_reference_golden(handles, meridian_raw, golden_ecckd_mci
                                 dict(ecckd_tables="ecckd_tables_64b.bin", use_aerosols=True), dict(use_vectorizable_generator=True),
                                 dict(ecckd_tables="ecckd_tables_64b.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
                                 dict(ecckd_tables="ecckd_tables_lw32_sw96.bin", use_aerosols=True),
-                                dict(ecckd_tables="ecckd_tables_lw32_sw96.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds")])
+                                dict(ecckd_tables="ecckd_tables_lw32_sw96.bin", sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                # do_sw_delta_scaling_with_gases on the ecCKD spectra (radiation_mcica_sw.F90:156-180, :274-278 and the other solvers)
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True),
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds"),
+                                dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, sw_solver_name="Cloudless", lw_solver_name="Cloudless"),
+                                dict(do_sw_delta_scaling_with_gases=True, sw_solver_name="Homogeneous", lw_solver_name="Homogeneous", ecckd_tables="ecckd_tables_64b.bin")])
 def test_ecckd_synthetic_columns_vs_oracle(handles, meridian_raw, kw):
     """ecCKD configurations (32- and 64-term models; BASELINE configs 1 and 3 have no golden file) on 300 perturbed columns."""
     n = 300

@@ -54,7 +54,7 @@ def check(out, ref, cos_sza, cfg, cols=slice(None)):
     (dict(use_aerosols=True, **CKD, **TC), None), (dict(ecckd_tables="ecckd_tables_64b.bin", **CKD), None),
     (dict(sw_gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_aerosols=True), None),
     (dict(lw_gas_model_name="ECCKD", do_nearest_spectral_lw_emiss=False, use_aerosols=True, **SP), None),
-    (dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"), None), (dict(do_nearest_spectral_sw_albedo=True), None)])
+    (dict(sw_solver_name="Homogeneous", lw_solver_name="Homogeneous"), None), (dict(do_sw_delta_scaling_with_gases=True, use_aerosols=True, **CKD), None), (dict(do_nearest_spectral_sw_albedo=True), None)])
 def test_radiative_properties_vs_oracle(meridian_raw, kw, opts):
     n = 96
     raw = I.synthetic_columns(meridian_raw, n)
