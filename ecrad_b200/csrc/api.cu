@@ -170,7 +170,6 @@ int check_config(Handle* h, const ecrad_b200_config& c) {
     if (!plain || ckd_lw || (c.i_solver_lw == ECRAD_SOLVER_CLOUDLESS && c.do_save_spectral_flux))
       return fail(h, "do_lw_aerosol_scattering is available with the McICA, Cloudless and SPARTACUS longwave solvers on RRTMG-IFS gas optics");
   }
-  if (c.do_sw && !c.do_sw_direct) return fail(h, "do_sw_direct = false is not available in this build (the direct beam is always computed)");
   if (c.use_aerosols && (c.n_aerosol_types < 1 || c.n_aerosol_types > 32)) return fail(h, "use_aerosols needs 1..32 aerosol types");
   if (c.use_vectorizable_generator && c.i_overlap_scheme == ECRAD_OVERLAP_EXP_EXP)   // radiation_cloud_generator.F90:239-242
     return fail(h, "the vectorizable cloud generator is not available with Exp-Exp overlap");
@@ -406,6 +405,11 @@ void fill_descs(const ecrad_b200_config& c, int nlev, const ecrad_b200_inputs* i
       {out->sw_dn_toa_g, 1, c.n_g_sw}, {out->sw_dn_toa_band, 1, c.n_bands_sw}, {out->sw_up_toa_band, 1, c.n_bands_sw},
       {out->sw_up_toa_clear_band, 1, c.n_bands_sw}, {out->lw_up_toa_band, 1, c.n_bands_lw}, {out->lw_up_toa_clear_band, 1, c.n_bands_lw}};
   for (int i = 0; i < N_OUT; ++i) od[i] = outs[i];
+  // config%do_sw_direct = false: flux%sw_dn_direct, sw_dn_direct_clear and sw_dn_direct_band are not allocated (radiation_flux.F90:208-240)
+  // and every solver tests allocated() before storing them; the direct beam itself is always part of the solution
+  if (!c.do_sw_direct)
+    for (int i = 0; i < N_OUT; ++i)
+      if (od[i].host && (od[i].host == out->sw_dn_direct || od[i].host == out->sw_dn_direct_clear || od[i].host == out->sw_dn_direct_band)) od[i].host = nullptr;
 }
 
 // Build the kernel-facing views from 28 input / 41 output base pointers (device) with leading dimension ld.

@@ -256,6 +256,28 @@ def test_spectral_solar_cycle(meridian_raw, kw):
     hn.finalize()
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(sw_solver_name="Tripleclouds", lw_solver_name="Tripleclouds", do_save_spectral_flux=True),
+                                dict(sw_solver_name="SPARTACUS", lw_solver_name="SPARTACUS", do_3d_effects=True)])
+def test_do_sw_direct_false(handles, meridian_raw, kw):
+    """config%do_sw_direct = false (radiation_flux.F90:208-240): sw_dn_direct, sw_dn_direct_clear and sw_dn_direct_band do not exist for the
+    solvers (they test allocated()); every other output is what it is with the direct arrays."""
+    n = 100
+    raw = I.synthetic_columns(meridian_raw, n)
+    h1, _, cfg1 = handles(**kw)
+    h0, _, cfg0 = handles(do_sw_direct=False, **kw)
+    prof = bool(kw.get("do_save_spectral_flux"))
+    a = h1.radiation(I.to_radiation_inputs(raw, cfg1), n, NLEV, spectral_profiles=prof)
+    b = h0.radiation(I.to_radiation_inputs(raw, cfg0), n, NLEV, spectral_profiles=prof)
+    for nm in a:
+        if a[nm] is None:
+            continue
+        if nm in ("sw_dn_direct", "sw_dn_direct_clear", "sw_dn_direct_band"):
+            assert np.isnan(b[nm]).all(), nm           # alloc_outputs fills with NaN: left untouched
+            assert np.isfinite(a[nm]).any(), nm
+        else:
+            assert np.array_equal(a[nm], b[nm], equal_nan=True), nm
+
+
 def test_column_range_and_untouched_columns(handles, meridian_raw):
     """istartcol/iendcol semantics of radiation(): only that range is written (1-based inclusive)."""
     h, orc, _ = handles()
