@@ -52,6 +52,7 @@ __device__ __forceinline__ SwColumn sw_column(const DevTables& T, const DevCfg& 
 // evaluation of the cloudy layers' optical properties.  Stored per layer and sub-column (clear / cloudy):
 //   a = T/(1-A*R), b = (Tdir*D*R + Tdirdif)/(1-A*R), t = Tdir, A, D      (A, D: of everything below the layer)
 // ---------------------------------------------------------------------------------------------------------
+enum { SW_PF_DIST = 4 };
 template <class SD, bool CLOUDLESS, bool AER, bool DELTA>   // AER: gas + aerosol asymmetry factor g_sw is non-zero and read from memory; DELTA: do_sw_delta_scaling_with_gases
 __global__ void __launch_bounds__(SD::THREADS, scaled_min_blocks(SD::THREADS, 128, 6))
 sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp) {
@@ -99,6 +100,10 @@ sw_adding_kernel(DevTables T, DevCfg cfg, DevIn in, Work w, int nlev, int nlevp)
       const size_t ip = i - SD::NG;
       od_n = s.od[ip]; ssa_n = s.ssa[ip];
       if (AER) gg_n = s.gas_g[ip];
+      if (l > SW_PF_DIST) {   // (the rows of a few layers further up: into L2 now, no register held)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.od + i - (size_t)SW_PF_DIST * SD::NG));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.ssa + i - (size_t)SW_PF_DIST * SD::NG));
+      }
     }
     SwLayer Lc;
     if (DELTA && AER) {   // radiation_mcica_sw.F90:165-180 (a no-op when g = 0, i.e. without aerosols)
