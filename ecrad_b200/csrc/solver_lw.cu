@@ -12,6 +12,7 @@
 #include "solver_common.cuh"
 
 namespace ecb {
+enum { LW_PF_DIST = 4 };
 
 enum { LW_LCH_FLUX = 8, LW_LCH_UP = 8, LW_FLUX_NL = 2, LW_FLUX_NST = 2 };   // lw_flux_kernel: layers per TMA stage, stages in the ring
 typedef BulkRing<LW_FLUX_NST, LW_FLUX_NL, 4> LwRing;
@@ -69,6 +70,11 @@ lw_down_kernel(DevTables T, DevCfg cfg, DevOut out, Work w, int nlev) {
       if (l == s.ict) fd_ict = fd;
       const double odg = od_n, pb = pb_n;
       if (l + 1 < nlev) { const size_t i1 = (size_t)(l + 1) * SD::NG + g; od_n = s.od[i1]; pb_n = s.pl[i1 + SD::NG]; }
+      if (l + LW_PF_DIST < nlev) {   // (rows a few layers further down: into L2 now, no register held)
+        const size_t ipf = (size_t)(l + LW_PF_DIST) * SD::NG + g;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.od + ipf));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.pl + ipf + SD::NG));
+      }
       const LwLayer L = lw_no_scat(odg, pt, pb);
       pt = pb;
       fd = L.trans * fd + L.source_dn;
