@@ -229,6 +229,10 @@ tc_sw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
 #pragma unroll
         for (int k = 0; k < 10; ++k) nx[k] = SCR(k / 5, k % 5, i + SD::NG);
       }
+      if (l + TC_PF_DIST < nlev) {   // (the same ten rows a few layers further down: into L2 now)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(&SCR(k / 5, k % 5, i + (size_t)TC_PF_DIST * SD::NG)));
+      }
       fdc = cu[0] * fdc + cu[1] * ddc;
       ddc = cu[2] * ddc;
       fuc = ddc * cu[4] + fdc * cu[3];
@@ -428,6 +432,10 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
 #pragma unroll
           for (int k = 0; k < 12; ++k) if (k < 4 || cloudy_next) nx[k] = SCR(k / 4, k % 4, i + SD::NG);
         }
+        if (l + TC_PF_DIST < nlev) {   // (region 1's four rows a few layers further down: into L2 now)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(&SCR(0, k, i + (size_t)TC_PF_DIST * SD::NG)));
+        }
 #pragma unroll
         for (int jr = 0; jr < 3; ++jr) {
           if (jr > 0 && S.clear[jl]) { fdn[jr] = 0.0; fup[jr] = 0.0; continue; }
@@ -476,6 +484,7 @@ tc_lw_kernel(DevTables T, DevCfg cfg, DevIn in, DevOut out, Work w, int nlev) {
       if (act) {
         const double t[3] = {tn[0], tn[1], tn[2]};
         if (l > 0) trans(l - 1, tn);
+        if (l > TC_PF_DIST) asm volatile("prefetch.global.L2 [%0];" ::"l"(&SCR(0, 4, (size_t)(l - TC_PF_DIST) * SD::NG + g)));
         if (jl >= ict) mat3_x_vec(S.U + jl * 9, d);   // u_matrix(:,:,jlev+1); the identity between two layers above cloud top (1*d + 0 + 0 is exact)
         d[0] = d[0] * t[0]; d[1] = d[1] * t[1]; d[2] = d[2] * t[2];
         tile[slot * SD::RS + g] = d[0] + d[1] + d[2];
