@@ -70,3 +70,17 @@ def test_config_derived_tables():
     w = cfg.derived["sw_albedo_weights"]
     assert w.shape == (6, 14) and np.allclose(w.sum(axis=0), 1.0)
     assert list(cfg.derived["i_emiss_from_band_lw"]) == [1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1]
+
+
+def test_radiative_properties_struct_matches_the_header():
+    """abi.RadiativeProperties lists the 18 pointers of struct ecrad_b200_radiative_properties in the header's order
+    (= the argument list of save_radiative_properties, radiation_save.F90:716-726)."""
+    import re
+
+    from ecrad_b200 import abi
+
+    hdr = open(os.path.join(ROOT, "include", "ecrad_b200.h")).read()
+    body = re.search(r"typedef struct ecrad_b200_radiative_properties \{(.*?)\} ecrad_b200_radiative_properties;", hdr, re.S).group(1)
+    names = re.findall(r"double\*\s*(\w+);", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    assert names == [nm for nm, _ in abi.RADPROP_ARRAYS] and len(names) == 18
+    assert C.sizeof(abi.RadiativeProperties) == 18 * C.sizeof(C.c_void_p)
